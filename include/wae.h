@@ -1,0 +1,353 @@
+/*
+ * wae.h — C ABI of the B200 render-quantum engine ("wae" = web-audio engine).
+ *
+ * This is the drop-in boundary for web-audio-api-rs's OfflineAudioContext hot path.
+ * The reference has NO FFI today: its plug-in point is the Rust trait
+ *     AudioProcessor::process(inputs, outputs, params, scope) -> bool   (src/render/processor.rs:131-196)
+ * driven one 128-frame quantum at a time by Graph::render (src/render/graph.rs:490-591) inside
+ * RenderThread::render_audiobuffer_sync (src/render/thread.rs:260-302).  A per-quantum FFI is useless
+ * for a GPU, so the boundary is graph-level and batch-level: the Rust side keeps its AudioNode /
+ * AudioProcessor surface, forwards node construction / connect / param events / start-stop to the
+ * calls below (they mirror the ControlMessage enum, src/message.rs:13-87), and replaces the quantum
+ * loop of render_audiobuffer_sync with ONE call to wae_render_batch for many contexts at once.
+ *
+ * Conventions
+ *   - every function returns wae_status (0 = ok); nothing unwinds across the boundary;
+ *     wae_last_error() returns a thread-local, NUL-terminated description of the last failure.
+ *     Reference behaviour being mirrored: argument validation panics on the control thread with
+ *     DOMException-style messages (e.g. src/node/convolver.rs:264-275) -> WAE_INVALID_ARGUMENT /
+ *     WAE_INVALID_STATE / WAE_NOT_SUPPORTED with the same message text.
+ *   - plain pointers and sizes only; inputs are borrowed for the duration of the call and copied;
+ *     outputs are caller-allocated.
+ *   - node ids follow the reference's allocation exactly (src/context/concrete_base.rs:240,
+ *     src/context/mod.rs:24-40): destination = 0, listener = 1, listener params = 2..=10, first user
+ *     node = 11; a node takes its id BEFORE its AudioParams (oscillator N -> frequency N+1, detune N+2).
+ *     The render order and therefore the f32 summation order of the mixer depend on these ids
+ *     (src/render/graph.rs:443-479).
+ *   - one host thread per engine at a time (the reference renders a context on the calling thread,
+ *     src/context/offline.rs:157-185).
+ *
+ * The oracle (oracle/, test infrastructure only) exports the same graph-building surface with the
+ * prefix wao_ so that parity tests can build one graph twice.
+ */
+#ifndef WAE_H
+#define WAE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef WAE_API
+#define WAE_API __attribute__((visibility("default")))
+#endif
+
+#define WAE_RENDER_QUANTUM_SIZE 128u /* src/lib.rs:18 */
+#define WAE_MAX_CHANNELS 32u         /* src/lib.rs:21 */
+
+typedef int32_t wae_status;
+enum {
+    WAE_OK = 0,
+    WAE_INVALID_ARGUMENT = 1, /* RangeError / IndexSizeError / TypeError style panics          */
+    WAE_INVALID_STATE = 2,    /* InvalidStateError (start twice, stop before start, ...)       */
+    WAE_NOT_SUPPORTED = 3,    /* NotSupportedError in the reference (e.g. 3-channel IR)        */
+    WAE_UNSUPPORTED = 4,      /* valid in the reference, not lowered to the GPU yet -> caller  */
+                              /* falls back to the CPU renderer                                */
+    WAE_CUDA_ERROR = 5,
+    WAE_OUT_OF_MEMORY = 6,
+    WAE_NO_DEVICE = 7
+};
+
+typedef struct wae_engine wae_engine; /* one per GPU / per process rank                        */
+typedef struct wae_graph wae_graph;   /* one OfflineAudioContext (src/context/offline.rs:78)   */
+typedef uint32_t wae_node_id;
+
+/* ChannelCountMode / ChannelInterpretation, src/node/audio_node.rs (enum order kept) */
+enum { WAE_COUNT_MODE_MAX = 0, WAE_COUNT_MODE_CLAMPED_MAX = 1, WAE_COUNT_MODE_EXPLICIT = 2 };
+enum { WAE_INTERPRETATION_SPEAKERS = 0, WAE_INTERPRETATION_DISCRETE = 1 };
+
+/* AudioNodeOptions (src/node/audio_node.rs:54-71). count == 0 means "node default". */
+typedef struct wae_channel_config {
+    uint32_t count;
+    uint32_t count_mode;
+    uint32_t interpretation;
+} wae_channel_config;
+
+/* AudioBuffer: planar f32 channels (src/buffer.rs:69-72). */
+typedef struct wae_audio_buffer {
+    uint32_t number_of_channels;
+    uint64_t length; /* frames per channel */
+    float sample_rate;
+    const float* const* channels; /* [number_of_channels] pointers to `length` floats */
+} wae_audio_buffer;
+
+/* ---- node option structs: one per renderer of SURVEY §8(a) ------------------------------------- */
+
+/* OscillatorType, src/node/oscillator.rs:74-87 */
+enum { WAE_OSC_SINE = 0, WAE_OSC_SQUARE = 1, WAE_OSC_SAWTOOTH = 2, WAE_OSC_TRIANGLE = 3, WAE_OSC_CUSTOM = 4 };
+/* OscillatorOptions, src/node/oscillator.rs:48-70. Params: 0 = frequency, 1 = detune. */
+typedef struct wae_oscillator_options {
+    uint32_t type;
+    float frequency;
+    float detune;
+    const float* periodic_wave; /* custom only: precomputed wavetable (src/periodic_wave.rs:163-209) */
+    uint32_t periodic_wave_len;
+} wae_oscillator_options;
+enum { WAE_OSC_PARAM_FREQUENCY = 0, WAE_OSC_PARAM_DETUNE = 1 };
+
+/* BiquadFilterType, src/node/biquad_filter.rs:392-403 */
+enum {
+    WAE_BIQUAD_LOWPASS = 0, WAE_BIQUAD_HIGHPASS = 1, WAE_BIQUAD_BANDPASS = 2, WAE_BIQUAD_NOTCH = 3,
+    WAE_BIQUAD_ALLPASS = 4, WAE_BIQUAD_PEAKING = 5, WAE_BIQUAD_LOWSHELF = 6, WAE_BIQUAD_HIGHSHELF = 7
+};
+/* BiquadFilterOptions, src/node/biquad_filter.rs:430-450. Params in creation order
+ * (src/node/biquad_filter.rs:555-593): 0 = Q, 1 = detune, 2 = frequency, 3 = gain. */
+typedef struct wae_biquad_options {
+    uint32_t type;
+    float q;
+    float detune;
+    float frequency;
+    float gain;
+    wae_channel_config channel_config;
+} wae_biquad_options;
+enum { WAE_BIQUAD_PARAM_Q = 0, WAE_BIQUAD_PARAM_DETUNE = 1, WAE_BIQUAD_PARAM_FREQUENCY = 2, WAE_BIQUAD_PARAM_GAIN = 3 };
+
+/* IIRFilterOptions, src/node/iir_filter.rs (feedforward/feedback, 1..=20 coefficients, f64) */
+typedef struct wae_iir_options {
+    const double* feedforward;
+    uint32_t feedforward_len;
+    const double* feedback;
+    uint32_t feedback_len;
+    wae_channel_config channel_config;
+} wae_iir_options;
+
+/* GainOptions, src/node/gain.rs. Param 0 = gain. */
+typedef struct wae_gain_options {
+    float gain;
+    wae_channel_config channel_config;
+} wae_gain_options;
+
+/* AudioBufferSourceOptions, src/node/audio_buffer_source.rs. Params: 0 = detune, 1 = playbackRate
+ * (creation order). */
+typedef struct wae_buffer_source_options {
+    const wae_audio_buffer* buffer; /* may be NULL */
+    float detune;
+    float playback_rate;
+    uint32_t loop;
+    double loop_start;
+    double loop_end;
+} wae_buffer_source_options;
+enum { WAE_ABSN_PARAM_DETUNE = 0, WAE_ABSN_PARAM_PLAYBACK_RATE = 1 };
+
+/* ConstantSourceOptions, src/node/constant_source.rs. Param 0 = offset. */
+typedef struct wae_constant_source_options {
+    float offset;
+} wae_constant_source_options;
+
+/* ConvolverOptions, src/node/convolver.rs:55-81 (default channel config ClampedMax / 2 / Speakers) */
+typedef struct wae_convolver_options {
+    const wae_audio_buffer* buffer; /* may be NULL: pass-through (convolver.rs:368-375) */
+    uint32_t disable_normalization;
+    wae_channel_config channel_config;
+} wae_convolver_options;
+
+/* OverSampleType, src/node/waveshaper.rs */
+enum { WAE_OVERSAMPLE_NONE = 0, WAE_OVERSAMPLE_X2 = 1, WAE_OVERSAMPLE_X4 = 2 };
+typedef struct wae_wave_shaper_options {
+    const float* curve; /* may be NULL: pass-through */
+    uint32_t curve_len;
+    uint32_t oversample;
+    wae_channel_config channel_config;
+} wae_wave_shaper_options;
+
+/* DelayOptions, src/node/delay.rs. Param 0 = delayTime. */
+typedef struct wae_delay_options {
+    double max_delay_time; /* default 1.0 */
+    double delay_time;
+    wae_channel_config channel_config;
+} wae_delay_options;
+
+/* StereoPannerOptions, src/node/stereo_panner.rs. Param 0 = pan. */
+typedef struct wae_stereo_panner_options {
+    float pan;
+    wae_channel_config channel_config;
+} wae_stereo_panner_options;
+
+/* PannerOptions, src/node/panner.rs. Params in creation order:
+ * 0..2 = positionX/Y/Z, 3..5 = orientationX/Y/Z. */
+enum { WAE_PANNING_EQUALPOWER = 0, WAE_PANNING_HRTF = 1 };
+enum { WAE_DISTANCE_LINEAR = 0, WAE_DISTANCE_INVERSE = 1, WAE_DISTANCE_EXPONENTIAL = 2 };
+typedef struct wae_panner_options {
+    uint32_t panning_model;
+    uint32_t distance_model;
+    float position_x, position_y, position_z;
+    float orientation_x, orientation_y, orientation_z;
+    double ref_distance, max_distance, rolloff_factor;
+    double cone_inner_angle, cone_outer_angle, cone_outer_gain;
+    wae_channel_config channel_config;
+} wae_panner_options;
+
+/* AnalyserOptions, src/node/analyser.rs */
+typedef struct wae_analyser_options {
+    uint32_t fft_size; /* 32..32768, power of two, default 2048 */
+    double smoothing_time_constant; /* default 0.8 */
+    double min_decibels;            /* default -100 */
+    double max_decibels;            /* default -30 */
+    wae_channel_config channel_config;
+} wae_analyser_options;
+
+/* DynamicsCompressorOptions, src/node/dynamics_compressor.rs. Params in creation order:
+ * 0 = attack, 1 = knee, 2 = ratio, 3 = release, 4 = threshold. */
+typedef struct wae_dynamics_compressor_options {
+    float attack, knee, ratio, release, threshold;
+    wae_channel_config channel_config;
+} wae_dynamics_compressor_options;
+
+typedef struct wae_channel_merger_options {
+    uint32_t number_of_inputs; /* default 6 */
+} wae_channel_merger_options;
+typedef struct wae_channel_splitter_options {
+    uint32_t number_of_outputs; /* default 6 */
+} wae_channel_splitter_options;
+
+/* AudioParamEventType, src/param.rs:160-170 (enum order kept) */
+enum {
+    WAE_EVENT_SET_VALUE = 0,
+    WAE_EVENT_SET_VALUE_AT_TIME = 1,
+    WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME = 2,
+    WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME = 3,
+    WAE_EVENT_CANCEL_SCHEDULED_VALUES = 4,
+    WAE_EVENT_SET_TARGET_AT_TIME = 5,
+    WAE_EVENT_CANCEL_AND_HOLD_AT_TIME = 6,
+    WAE_EVENT_SET_VALUE_CURVE_AT_TIME = 7
+};
+enum { WAE_AUTOMATION_RATE_A = 0, WAE_AUTOMATION_RATE_K = 1 };
+
+/* AudioParam automation call (src/param.rs:403-640): `time` is start/end/cancel time as in the
+ * method of the same name; `aux` = timeConstant (set_target) or duration (set_value_curve);
+ * `values` only for set_value_curve. */
+typedef struct wae_param_event {
+    uint32_t type;
+    float value;
+    double time;
+    double aux;
+    const float* values;
+    uint32_t values_len;
+} wae_param_event;
+
+/* ---- engine ------------------------------------------------------------------------------------ */
+
+/* device_ordinal: CUDA device of this process rank. Fails with WAE_NO_DEVICE when no sm_100 GPU is
+ * usable — there is NO CPU fallback in this library. */
+WAE_API wae_status wae_engine_create(int32_t device_ordinal, wae_engine** out_engine);
+WAE_API wae_status wae_engine_destroy(wae_engine* engine);
+WAE_API const char* wae_last_error(void);
+WAE_API const char* wae_version(void);
+
+/* Engine tunables (all optional). */
+enum {
+    WAE_OPT_CHUNK_FRAMES = 1,   /* frames rendered per time chunk (multiple of 128; 0 = auto)      */
+    WAE_OPT_FUSE = 2,           /* 1 (default): fuse source->filter->gain chains; 0: one stage/node */
+    WAE_OPT_SERIAL_FILTERS = 3  /* 1: bit-faithful serial recurrences (thread per channel)          */
+};
+WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
+
+/* ---- graph construction = OfflineAudioContext::new + BaseAudioContext::create_* ----------------- */
+
+/* OfflineAudioContext::new(number_of_channels, length, sample_rate), src/context/offline.rs:78. */
+WAE_API wae_status wae_graph_create(wae_engine* engine, uint32_t number_of_channels, uint64_t length,
+                                    float sample_rate, wae_graph** out_graph);
+WAE_API wae_status wae_graph_destroy(wae_graph* graph);
+
+/* BaseAudioContext::create_* (src/context/base.rs:26-361) / XxxNode::new(context, options). */
+WAE_API wae_status wae_create_oscillator(wae_graph*, const wae_oscillator_options*, wae_node_id* out);
+WAE_API wae_status wae_create_biquad_filter(wae_graph*, const wae_biquad_options*, wae_node_id* out);
+WAE_API wae_status wae_create_iir_filter(wae_graph*, const wae_iir_options*, wae_node_id* out);
+WAE_API wae_status wae_create_gain(wae_graph*, const wae_gain_options*, wae_node_id* out);
+WAE_API wae_status wae_create_buffer_source(wae_graph*, const wae_buffer_source_options*, wae_node_id* out);
+WAE_API wae_status wae_create_constant_source(wae_graph*, const wae_constant_source_options*, wae_node_id* out);
+WAE_API wae_status wae_create_convolver(wae_graph*, const wae_convolver_options*, wae_node_id* out);
+WAE_API wae_status wae_create_wave_shaper(wae_graph*, const wae_wave_shaper_options*, wae_node_id* out);
+WAE_API wae_status wae_create_delay(wae_graph*, const wae_delay_options*, wae_node_id* out);
+WAE_API wae_status wae_create_stereo_panner(wae_graph*, const wae_stereo_panner_options*, wae_node_id* out);
+WAE_API wae_status wae_create_panner(wae_graph*, const wae_panner_options*, wae_node_id* out);
+WAE_API wae_status wae_create_analyser(wae_graph*, const wae_analyser_options*, wae_node_id* out);
+WAE_API wae_status wae_create_dynamics_compressor(wae_graph*, const wae_dynamics_compressor_options*, wae_node_id* out);
+WAE_API wae_status wae_create_channel_merger(wae_graph*, const wae_channel_merger_options*, wae_node_id* out);
+WAE_API wae_status wae_create_channel_splitter(wae_graph*, const wae_channel_splitter_options*, wae_node_id* out);
+
+/* AudioNode::connect_from_output_to_input (src/node/audio_node.rs:259-289); destination is node 0. */
+WAE_API wae_status wae_connect(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t input);
+/* AudioNode::connect(&param): audio-rate modulation of a param (src/param.rs:762-796). */
+WAE_API wae_status wae_connect_param(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index);
+/* AudioNode::disconnect() — removes all outgoing connections of `from`. */
+WAE_API wae_status wae_disconnect(wae_graph*, wae_node_id from);
+
+/* AudioParam methods (src/param.rs:336-662). */
+WAE_API wae_status wae_param_event_push(wae_graph*, wae_node_id node, uint32_t param_index, const wae_param_event* event);
+WAE_API wae_status wae_param_set_automation_rate(wae_graph*, wae_node_id node, uint32_t param_index, uint32_t rate);
+/* AudioListener params (src/spatial.rs): index 0..8 = position xyz, forward xyz, up xyz. */
+WAE_API wae_status wae_listener_param_event_push(wae_graph*, uint32_t param_index, const wae_param_event* event);
+
+/* AudioScheduledSourceNode (src/node/scheduled_source.rs:12-54): start_at / stop_at, and
+ * AudioBufferSourceNode::start_at_with_offset_and_duration. Pass offset = 0, duration = +inf
+ * (or any value >= 1e300) for the plain start_at. */
+WAE_API wae_status wae_source_start(wae_graph*, wae_node_id node, double when, double offset, double duration);
+WAE_API wae_status wae_source_stop(wae_graph*, wae_node_id node, double when);
+
+/* Setters that exist as control messages in the reference. */
+WAE_API wae_status wae_oscillator_set_type(wae_graph*, wae_node_id node, uint32_t type);
+WAE_API wae_status wae_biquad_set_type(wae_graph*, wae_node_id node, uint32_t type);
+
+/* ---- rendering = OfflineAudioContext::start_rendering_sync for a whole batch ------------------- */
+
+enum {
+    WAE_RENDER_OUT_HOST = 0,   /* `out` is host memory (pageable or pinned)                         */
+    WAE_RENDER_OUT_DEVICE = 1  /* `out` is device memory on the engine's GPU                       */
+};
+
+/* Renders every graph of the batch from frame 0 to its length. All graphs of one batch must have
+ * the same number_of_channels, length and sample_rate (independent OfflineAudioContexts that only
+ * differ in their node graphs / assets).  Output layout: planar [n_graphs][number_of_channels][length]
+ * f32, i.e. the AudioBuffer each start_rendering_sync would return (src/render/thread.rs:298-301),
+ * back to back.  The call is synchronous: on return `out` is complete. */
+WAE_API wae_status wae_render_batch(wae_engine* engine, wae_graph* const* graphs, uint32_t n_graphs,
+                                    float* out, uint32_t flags);
+
+/* Two-phase variant used by bench.py and by callers that render the same batch repeatedly or keep
+ * PCM on the device for the NCCL gather: prepare uploads assets and compiles the stage schedule,
+ * run renders (device-resident output owned by the engine), fetch copies to the host. */
+typedef struct wae_batch wae_batch;
+WAE_API wae_status wae_batch_prepare(wae_engine* engine, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out_batch);
+WAE_API wae_status wae_batch_run(wae_batch* batch);                       /* async on the engine stream   */
+WAE_API wae_status wae_batch_sync(wae_batch* batch);                      /* wait for the stream           */
+WAE_API wae_status wae_batch_output_device_ptr(wae_batch* batch, float** out_dev, uint64_t* out_floats);
+WAE_API wae_status wae_batch_fetch(wae_batch* batch, float* host_out);   /* D2H of the whole output       */
+WAE_API wae_status wae_batch_destroy(wae_batch* batch);
+
+/* Introspection used by bench.py / tests (counts since prepare). */
+typedef struct wae_batch_stats {
+    uint64_t kernel_launches_per_run; /* launches of OUR kernels per wae_batch_run                  */
+    uint64_t stages;                  /* stages in the compiled schedule                            */
+    uint64_t chunks;                  /* time chunks per run                                        */
+    uint64_t arena_bytes;             /* device bytes of edge buffers + state                        */
+    uint64_t asset_bytes;             /* device bytes of uploaded assets (buffers, IR spectra, ...)  */
+    uint64_t algorithmic_bytes;       /* SURVEY §8(d) compulsory HBM bytes per run                   */
+    uint64_t graph_quanta;            /* n_graphs * ceil(length / 128)                               */
+    float last_run_ms;                /* CUDA-event time of the last completed run                   */
+    float dominant_kernel_ms;         /* CUDA-event time of the dominant stage kernel in last run    */
+    char dominant_kernel[64];
+} wae_batch_stats;
+WAE_API wae_status wae_batch_get_stats(wae_batch* batch, wae_batch_stats* out);
+
+/* AnalyserNode read-out after a render (src/node/analyser.rs:246-264, src/analysis.rs:347-401):
+ * state of the analyser at the end of the render. */
+WAE_API wae_status wae_analyser_get_float_time_domain_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
+WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAE_H */

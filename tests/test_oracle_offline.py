@@ -1,0 +1,133 @@
+"""Pins the oracle's graph / mixer / scheduling semantics against the reference's integration tests
+(/root/reference/tests/offline.rs).  Each test restates one reference `#[test]` (name + line cited)."""
+import numpy as np
+
+RQ = 128
+
+
+def ctx(pkg, oracle, ch, length, sr):
+    return pkg.OfflineAudioContext(ch, length, sr, oracle)
+
+
+def test_offline_render(pkg, oracle):
+    # tests/offline.rs:10-46 test_offline_render: 2 + (-4) = -2 exactly, partial last quantum
+    LENGTH = 555
+    c = ctx(pkg, oracle, 2, LENGTH, 44100.0)
+    c1 = c.create_constant_source()
+    c1.offset.set_value(2.0)
+    c1.connect(c.destination())
+    c2 = c.create_constant_source()
+    c2.offset.set_value(-4.0)
+    c2.connect(c.destination())
+    c1.start()
+    c2.start()
+    out = c.start_rendering_sync()
+    assert out.number_of_channels() == 2 and out.length() == LENGTH
+    assert np.array_equal(out.get_channel_data(0), np.full(LENGTH, -2.0, np.float32))
+    assert np.array_equal(out.get_channel_data(1), np.full(LENGTH, -2.0, np.float32))
+
+
+def test_start_stop(pkg, oracle):
+    # tests/offline.rs:48-81 test_start_stop
+    sr = 48000.0
+    c = ctx(pkg, oracle, 1, RQ * 4, sr)
+    osc = c.create_oscillator(type_=pkg.SQUARE, frequency=0.0)
+    osc.connect(c.destination())
+    osc.start_at(128.0 / sr)
+    osc.stop_at(128.0 * 3.0 / sr)
+    out = c.start_rendering_sync().get_channel_data(0)
+    expected = np.concatenate([np.zeros(RQ), np.ones(2 * RQ), np.zeros(RQ)]).astype(np.float32)
+    assert np.array_equal(out, expected)
+
+
+def test_delayed_constant_source(pkg, oracle):
+    # tests/offline.rs:83-112 test_delayed_constant_source
+    sr = 48000.0
+    c = ctx(pkg, oracle, 1, RQ * 4, sr)
+    delay = c.create_delay(1.0)
+    delay.delay_time.set_value(128.0 * 2.0 / sr)
+    delay.connect(c.destination())
+    src = c.create_constant_source()
+    src.connect(delay)
+    src.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    expected = np.concatenate([np.zeros(2 * RQ), np.ones(2 * RQ)]).astype(np.float32)
+    assert np.abs(out - expected).max() <= 0.00001
+
+
+def test_audio_param_graph(pkg, oracle):
+    # tests/offline.rs:114-149 test_audio_param_graph: param intrinsic value + two audio-rate inputs
+    c = ctx(pkg, oracle, 1, RQ, 48000.0)
+    gain = c.create_gain()
+    gain.gain.set_value(0.5)
+    gain.connect(c.destination())
+    source = c.create_constant_source()
+    source.offset.set_value(0.8)
+    source.connect(gain)
+    p1 = c.create_constant_source()
+    p1.offset.set_value(0.1)
+    p1.connect(gain.gain)
+    p2 = c.create_constant_source()
+    p2.offset.set_value(0.3)
+    p2.connect(gain.gain)
+    source.start()
+    p1.start()
+    p2.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    expected = np.full(RQ, np.float32(0.8) * np.float32(0.9), np.float32)
+    assert np.array_equal(out, expected)
+
+
+def test_cycle(pkg, oracle):
+    # tests/offline.rs:170-203 test_cycle: nodes in an unbroken cycle are muted
+    c = ctx(pkg, oracle, 1, RQ, 48000.0)
+    cycle1 = c.create_gain()
+    cycle1.connect(c.destination())
+    cycle2 = c.create_gain()
+    cycle2.connect(cycle1)
+    cycle1.connect(cycle2)
+    source_cycle = c.create_constant_source()
+    source_cycle.offset.set_value(1.0)
+    source_cycle.connect(cycle1)
+    other = c.create_constant_source()
+    other.offset.set_value(2.0)
+    other.connect(c.destination())
+    source_cycle.start()
+    other.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out, np.full(RQ, 2.0, np.float32))
+
+
+def test_cycle_breaker(pkg, oracle):
+    # tests/offline.rs:205-244 test_cycle_breaker: DelayNode breaks the cycle, feedback of 1 quantum
+    sr = 48000.0
+    c = ctx(pkg, oracle, 1, RQ * 3, sr)
+    delay = c.create_delay(1.0 / sr)
+    delay.delay_time.set_value(1.0 / sr)
+    delay.connect(c.destination())
+    delay.connect(delay)
+    source = c.create_constant_source()
+    source.offset.set_value(1.0)
+    source.connect(delay)
+    source.connect(c.destination())
+    source.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out[:RQ], np.full(RQ, 1.0, np.float32))
+    assert np.array_equal(out[RQ:2 * RQ], np.full(RQ, 2.0, np.float32))
+    assert np.array_equal(out[2 * RQ:], np.full(RQ, 3.0, np.float32))
+
+
+def test_render_order_matches_reference(pkg, oracle):
+    # src/render/graph.rs:443-479 + SURVEY §3.3: reverse post-order over ascending ids — the last-created
+    # branch is processed first.  ids: dest 0; osc1 11 (+12,13); osc2 14 (+15,16)
+    import ctypes
+    c = ctx(pkg, oracle, 1, RQ, 48000.0)
+    o1 = c.create_oscillator()
+    o2 = c.create_oscillator()
+    o1.connect(c.destination())
+    o2.connect(c.destination())
+    assert (o1.id, o2.id) == (11, 14)
+    ids = (ctypes.c_uint32 * 64)()
+    n = oracle.api.render_order(c._g, ids, 64)
+    order = list(ids[:n])
+    assert order == [16, 15, 14, 13, 12, 11, 0]

@@ -1,0 +1,468 @@
+"""Host-side mirror of the reference's control API for the OfflineAudioContext path.
+
+Same names and argument meaning as web-audio-api-rs:
+  OfflineAudioContext::new / create_* / destination / start_rendering_sync   (src/context/offline.rs, base.rs)
+  AudioNode::connect / connect_from_output_to_input / disconnect               (src/node/audio_node.rs:224-466)
+  AudioScheduledSourceNode::start / start_at / stop / stop_at                  (src/node/scheduled_source.rs)
+  AudioParam::value / set_value / *_at_time                                    (src/param.rs:336-662)
+so that the parity tests read like the reference's own `#[test]`s.  Everything is forwarded through the
+C ABI of include/wae.h; errors surface as WaeError carrying the reference's panic text.
+
+One addition that the reference does not have: `render_batch([ctx, ...])` renders many independent
+OfflineAudioContexts in ONE engine call — the whole point of the GPU engine.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _binding as B
+
+F64_MAX = 1.7976931348623157e308
+
+# enums, same order as the reference
+SINE, SQUARE, SAWTOOTH, TRIANGLE, CUSTOM = range(5)
+LOWPASS, HIGHPASS, BANDPASS, NOTCH, ALLPASS, PEAKING, LOWSHELF, HIGHSHELF = range(8)
+MAX, CLAMPED_MAX, EXPLICIT = range(3)
+SPEAKERS, DISCRETE = range(2)
+EQUALPOWER, HRTF = range(2)
+LINEAR, INVERSE, EXPONENTIAL = range(3)
+OVERSAMPLE_NONE, OVERSAMPLE_X2, OVERSAMPLE_X4 = range(3)
+
+
+class Backend:
+    """An Api plus (for the product) an engine handle."""
+
+    def __init__(self, api, engine=None):
+        self.api = api
+        self.engine = engine
+
+
+class AudioBuffer:
+    """Planar f32 PCM (src/buffer.rs:69-72)."""
+
+    def __init__(self, channels, sample_rate):
+        self.channels = [B.as_f32(c) for c in channels]
+        self.sample_rate = float(np.float32(sample_rate))
+
+    @classmethod
+    def zeros(cls, number_of_channels, length, sample_rate):
+        return cls([np.zeros(length, np.float32) for _ in range(number_of_channels)], sample_rate)
+
+    def number_of_channels(self):
+        return len(self.channels)
+
+    def length(self):
+        return len(self.channels[0]) if self.channels else 0
+
+    def duration(self):
+        return self.length() / self.sample_rate
+
+    def get_channel_data(self, i):
+        return self.channels[i]
+
+    def copy_to_channel(self, data, i):
+        d = B.as_f32(data)
+        self.channels[i][: len(d)] = d
+
+    def _desc(self):
+        return B.buffer_desc(self.channels, self.sample_rate)
+
+
+def channel_config(count=0, count_mode=MAX, interpretation=SPEAKERS):
+    """AudioNodeOptions; count == 0 selects the node's default config."""
+    return B.ChannelConfig(count, count_mode, interpretation)
+
+
+class AudioParam:
+    def __init__(self, ctx, node_id, index, value, min_value=-3.4028234663852886e38, max_value=3.4028234663852886e38):
+        self._ctx, self._node, self._index = ctx, node_id, index
+        self._value = float(np.float32(value))
+        self._min, self._max = min_value, max_value
+
+    def _push(self, type_, value=0.0, time=0.0, aux=0.0, values=None):
+        ev = B.ParamEvent(type_, float(value), float(time), float(aux), None, 0)
+        keep = None
+        if values is not None:
+            keep = B.as_f32(values)
+            ev.values = B.fptr(keep)
+            ev.values_len = len(keep)
+        api = self._ctx._api
+        if self._node == "listener":
+            api.check(api.listener_param_event_push(self._ctx._g, self._index, C.byref(ev)))
+        else:
+            api.check(api.param_event_push(self._ctx._g, self._node, self._index, C.byref(ev)))
+        return self
+
+    def value(self):
+        return self._value
+
+    def set_value(self, v):
+        self._push(0, v)
+        self._value = min(max(float(np.float32(v)), self._min), self._max)
+        return self
+
+    def set_value_at_time(self, v, start_time):
+        return self._push(1, v, start_time)
+
+    def linear_ramp_to_value_at_time(self, v, end_time):
+        return self._push(2, v, end_time)
+
+    def exponential_ramp_to_value_at_time(self, v, end_time):
+        return self._push(3, v, end_time)
+
+    def cancel_scheduled_values(self, cancel_time):
+        return self._push(4, 0.0, cancel_time)
+
+    def set_target_at_time(self, v, start_time, time_constant):
+        return self._push(5, v, start_time, time_constant)
+
+    def cancel_and_hold_at_time(self, cancel_time):
+        return self._push(6, 0.0, cancel_time)
+
+    def set_value_curve_at_time(self, values, start_time, duration):
+        return self._push(7, 0.0, start_time, duration, values)
+
+    def set_automation_rate(self, rate):
+        api = self._ctx._api
+        api.check(api.param_set_automation_rate(self._ctx._g, self._node, self._index, 0 if rate in ("a", "A", 0) else 1))
+
+
+class AudioNode:
+    def __init__(self, ctx, node_id, n_inputs=1, n_outputs=1):
+        self._ctx, self.id = ctx, node_id
+        self._n_inputs, self._n_outputs = n_inputs, n_outputs
+
+    def number_of_inputs(self):
+        return self._n_inputs
+
+    def number_of_outputs(self):
+        return self._n_outputs
+
+    def connect(self, dest):
+        return self.connect_from_output_to_input(dest, 0, 0)
+
+    def connect_from_output_to_input(self, dest, output, input):
+        api = self._ctx._api
+        if isinstance(dest, AudioParam):
+            api.check(api.connect_param(self._ctx._g, self.id, output, dest._node, dest._index))
+        else:
+            if dest._ctx is not self._ctx:
+                raise B.WaeError(1, "InvalidAccessError - Attempting to connect nodes from different contexts")
+            api.check(api.connect(self._ctx._g, self.id, output, dest.id, input))
+        return dest
+
+    def disconnect(self):
+        api = self._ctx._api
+        api.check(api.disconnect(self._ctx._g, self.id))
+
+
+class AudioScheduledSourceNode(AudioNode):
+    def start(self):
+        self.start_at(0.0)  # context.current_time() is 0 before an offline render
+
+    def start_at(self, when):
+        api = self._ctx._api
+        api.check(api.source_start(self._ctx._g, self.id, when, 0.0, F64_MAX))
+
+    def stop(self):
+        self.stop_at(0.0)
+
+    def stop_at(self, when):
+        api = self._ctx._api
+        api.check(api.source_stop(self._ctx._g, self.id, when))
+
+
+class OscillatorNode(AudioScheduledSourceNode):
+    def set_type(self, type_):
+        api = self._ctx._api
+        api.check(api.oscillator_set_type(self._ctx._g, self.id, type_))
+
+
+class AudioBufferSourceNode(AudioScheduledSourceNode):
+    def start_at_with_offset(self, start, offset):
+        self.start_at_with_offset_and_duration(start, offset, F64_MAX)
+
+    def start_at_with_offset_and_duration(self, start, offset, duration):
+        api = self._ctx._api
+        api.check(api.source_start(self._ctx._g, self.id, start, offset, duration))
+
+
+class BiquadFilterNode(AudioNode):
+    def set_type(self, type_):
+        api = self._ctx._api
+        api.check(api.biquad_set_type(self._ctx._g, self.id, type_))
+
+
+class AnalyserNode(AudioNode):
+    def __init__(self, ctx, node_id, fft_size):
+        super().__init__(ctx, node_id)
+        self.fft_size = fft_size
+
+    def frequency_bin_count(self):
+        return self.fft_size // 2
+
+    def get_float_time_domain_data(self, n=None):
+        return self._ctx._analyser_read(self, "time", n or self.fft_size)
+
+    def get_float_frequency_data(self, n=None):
+        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2)
+
+
+class AudioListener:
+    def __init__(self, ctx):
+        names = ["position_x", "position_y", "position_z", "forward_x", "forward_y", "forward_z", "up_x", "up_y", "up_z"]
+        defaults = [0, 0, 0, 0, 0, -1, 0, 1, 0]
+        for i, (n, d) in enumerate(zip(names, defaults)):
+            setattr(self, n, AudioParam(ctx, "listener", i, d))
+
+
+class OfflineAudioContext:
+    """OfflineAudioContext::new(number_of_channels, length, sample_rate), src/context/offline.rs:78."""
+
+    def __init__(self, number_of_channels, length, sample_rate, backend):
+        self._backend = backend
+        self._api = backend.api
+        self._channels, self._length = int(number_of_channels), int(length)
+        self._sample_rate = float(np.float32(sample_rate))
+        g = C.c_void_p()
+        if self._api.is_product:
+            self._api.check(self._api.graph_create(backend.engine, self._channels, self._length, self._sample_rate, C.byref(g)))
+        else:
+            self._api.check(self._api.graph_create(self._channels, self._length, self._sample_rate, C.byref(g)))
+        self._g = g
+        self._keep = []
+        self._dest = AudioNode(self, 0, 1, 1)
+        self._batch = None
+        self._batch_index = 0
+        self._listener = None
+
+    def __del__(self):
+        try:
+            if self._g:
+                self._api.graph_destroy(self._g)
+                self._g = None
+        except Exception:
+            pass
+
+    # ---- BaseAudioContext
+    def destination(self):
+        return self._dest
+
+    def sample_rate(self):
+        return self._sample_rate
+
+    def length(self):
+        return self._length
+
+    def listener(self):
+        if self._listener is None:
+            self._listener = AudioListener(self)
+        return self._listener
+
+    def create_buffer(self, number_of_channels, length, sample_rate):
+        return AudioBuffer.zeros(number_of_channels, length, sample_rate)
+
+    def _create(self, fn, opts):
+        nid = C.c_uint32()
+        self._api.check(getattr(self._api, fn)(self._g, C.byref(opts), C.byref(nid)))
+        return nid.value
+
+    def create_oscillator(self, type_=SINE, frequency=440.0, detune=0.0, periodic_wave=None):
+        o = B.OscillatorOptions(type_, frequency, detune, None, 0)
+        if periodic_wave is not None:
+            pw = B.as_f32(periodic_wave)
+            self._keep.append(pw)
+            o.periodic_wave, o.periodic_wave_len, o.type = B.fptr(pw), len(pw), CUSTOM
+        nid = self._create("create_oscillator", o)
+        n = OscillatorNode(self, nid, 0, 1)
+        nyq = self._sample_rate / 2
+        n.frequency = AudioParam(self, nid, 0, frequency, -nyq, nyq)
+        n.detune = AudioParam(self, nid, 1, detune, -153600.0, 153600.0)
+        return n
+
+    def create_biquad_filter(self, type_=LOWPASS, frequency=350.0, q=1.0, detune=0.0, gain=0.0, cfg=None):
+        o = B.BiquadOptions(type_, q, detune, frequency, gain, cfg or channel_config())
+        nid = self._create("create_biquad_filter", o)
+        n = BiquadFilterNode(self, nid)
+        n.q = AudioParam(self, nid, 0, q)
+        n.detune = AudioParam(self, nid, 1, detune, -153600.0, 153600.0)
+        n.frequency = AudioParam(self, nid, 2, frequency, 0.0, self._sample_rate / 2)
+        n.gain = AudioParam(self, nid, 3, gain)
+        return n
+
+    def create_iir_filter(self, feedforward, feedback, cfg=None):
+        ff = np.ascontiguousarray(feedforward, dtype=np.float64)
+        fb = np.ascontiguousarray(feedback, dtype=np.float64)
+        o = B.IirOptions(ff.ctypes.data_as(B.c_double_p), len(ff), fb.ctypes.data_as(B.c_double_p), len(fb),
+                         cfg or channel_config())
+        return AudioNode(self, self._create("create_iir_filter", o))
+
+    def create_gain(self, gain=1.0, cfg=None):
+        nid = self._create("create_gain", B.GainOptions(gain, cfg or channel_config()))
+        n = AudioNode(self, nid)
+        n.gain = AudioParam(self, nid, 0, gain)
+        return n
+
+    def create_buffer_source(self, buffer=None, detune=0.0, playback_rate=1.0, loop=False, loop_start=0.0, loop_end=0.0):
+        o = B.BufferSourceOptions(None, detune, playback_rate, 1 if loop else 0, loop_start, loop_end)
+        if buffer is not None:
+            d, keep = buffer._desc()
+            self._keep.append((d, keep))
+            o.buffer = C.pointer(d)
+        nid = self._create("create_buffer_source", o)
+        n = AudioBufferSourceNode(self, nid, 0, 1)
+        n.detune = AudioParam(self, nid, 0, detune)
+        n.playback_rate = AudioParam(self, nid, 1, playback_rate)
+        return n
+
+    def create_constant_source(self, offset=1.0):
+        nid = self._create("create_constant_source", B.ConstantSourceOptions(offset))
+        n = AudioScheduledSourceNode(self, nid, 0, 1)
+        n.offset = AudioParam(self, nid, 0, offset)
+        return n
+
+    def create_convolver(self, buffer=None, disable_normalization=False, cfg=None):
+        o = B.ConvolverOptions(None, 1 if disable_normalization else 0, cfg or channel_config())
+        if buffer is not None:
+            d, keep = buffer._desc()
+            self._keep.append((d, keep))
+            o.buffer = C.pointer(d)
+        return AudioNode(self, self._create("create_convolver", o))
+
+    def create_wave_shaper(self, curve=None, oversample=OVERSAMPLE_NONE, cfg=None):
+        o = B.WaveShaperOptions(None, 0, oversample, cfg or channel_config())
+        if curve is not None:
+            c = B.as_f32(curve)
+            self._keep.append(c)
+            o.curve, o.curve_len = B.fptr(c), len(c)
+        return AudioNode(self, self._create("create_wave_shaper", o))
+
+    def create_delay(self, max_delay_time=1.0, delay_time=0.0, cfg=None):
+        nid = self._create("create_delay", B.DelayOptions(max_delay_time, delay_time, cfg or channel_config()))
+        n = AudioNode(self, nid)
+        n.delay_time = AudioParam(self, nid, 0, delay_time, 0.0, max_delay_time)
+        return n
+
+    def create_stereo_panner(self, pan=0.0, cfg=None):
+        nid = self._create("create_stereo_panner", B.StereoPannerOptions(pan, cfg or channel_config()))
+        n = AudioNode(self, nid)
+        n.pan = AudioParam(self, nid, 0, pan, -1.0, 1.0)
+        return n
+
+    def create_panner(self, panning_model=EQUALPOWER, distance_model=INVERSE, position=(0.0, 0.0, 0.0),
+                      orientation=(1.0, 0.0, 0.0), ref_distance=1.0, max_distance=10000.0, rolloff_factor=1.0,
+                      cone_inner_angle=360.0, cone_outer_angle=360.0, cone_outer_gain=0.0, cfg=None):
+        o = B.PannerOptions(panning_model, distance_model, *position, *orientation, ref_distance, max_distance,
+                            rolloff_factor, cone_inner_angle, cone_outer_angle, cone_outer_gain, cfg or channel_config())
+        nid = self._create("create_panner", o)
+        n = AudioNode(self, nid)
+        for i, name in enumerate(["position_x", "position_y", "position_z", "orientation_x", "orientation_y", "orientation_z"]):
+            setattr(n, name, AudioParam(self, nid, i, (list(position) + list(orientation))[i]))
+        return n
+
+    def create_analyser(self, fft_size=2048, smoothing_time_constant=0.8, min_decibels=-100.0, max_decibels=-30.0, cfg=None):
+        o = B.AnalyserOptions(fft_size, smoothing_time_constant, min_decibels, max_decibels, cfg or channel_config())
+        return AnalyserNode(self, self._create("create_analyser", o), fft_size)
+
+    def create_dynamics_compressor(self, attack=0.003, knee=30.0, ratio=12.0, release=0.25, threshold=-24.0, cfg=None):
+        o = B.DynamicsCompressorOptions(attack, knee, ratio, release, threshold, cfg or channel_config())
+        nid = self._create("create_dynamics_compressor", o)
+        n = AudioNode(self, nid)
+        for i, (name, v) in enumerate([("attack", attack), ("knee", knee), ("ratio", ratio), ("release", release), ("threshold", threshold)]):
+            setattr(n, name, AudioParam(self, nid, i, v))
+        return n
+
+    def create_channel_merger(self, number_of_inputs=6):
+        return AudioNode(self, self._create("create_channel_merger", B.ChannelMergerOptions(number_of_inputs)), number_of_inputs, 1)
+
+    def create_channel_splitter(self, number_of_outputs=6):
+        return AudioNode(self, self._create("create_channel_splitter", B.ChannelSplitterOptions(number_of_outputs)), 1, number_of_outputs)
+
+    # ---- rendering
+    def start_rendering_sync(self):
+        """OfflineAudioContext::start_rendering_sync (src/context/offline.rs:157-185): a batch of one."""
+        return render_batch([self])[0]
+
+    def _analyser_read(self, node, kind, n):
+        out = np.zeros(n, np.float32)
+        api = self._api
+        if api.is_product:
+            if self._batch is None:
+                raise B.WaeError(2, "analyser data is available after rendering")
+            fn = api.analyser_get_float_time_domain_data if kind == "time" else api.analyser_get_float_frequency_data
+            api.check(fn(self._batch.handle, self._batch_index, node.id, B.fptr(out), n))
+        else:
+            fn = api.analyser_get_float_time_domain_data if kind == "time" else api.analyser_get_float_frequency_data
+            api.check(fn(self._g, node.id, B.fptr(out), n))
+        return out
+
+
+class Batch:
+    """wae_batch_prepare / run / fetch: a compiled batch of contexts (product only)."""
+
+    def __init__(self, contexts):
+        ctx0 = contexts[0]
+        self.api = ctx0._api
+        self.contexts = contexts
+        self.n = len(contexts)
+        self.channels, self.length = ctx0._channels, ctx0._length
+        arr = (C.c_void_p * self.n)(*[c._g for c in contexts])
+        h = C.c_void_p()
+        self.api.check(self.api.batch_prepare(ctx0._backend.engine, arr, self.n, C.byref(h)))
+        self.handle = h
+        for i, c in enumerate(contexts):
+            c._batch, c._batch_index = self, i
+
+    def run(self):
+        self.api.check(self.api.batch_run(self.handle))
+
+    def sync(self):
+        self.api.check(self.api.batch_sync(self.handle))
+
+    def fetch(self, out=None):
+        if out is None:
+            out = np.empty((self.n, self.channels, self.length), np.float32)
+        self.api.check(self.api.batch_fetch(self.handle, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self.api.check(self.api.batch_output_device_ptr(self.handle, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stats(self):
+        s = B.BatchStats()
+        self.api.check(self.api.batch_get_stats(self.handle, C.byref(s)))
+        return s
+
+    def destroy(self):
+        if self.handle:
+            self.api.batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def render_batch(contexts, threads=1):
+    """Render many OfflineAudioContexts. Returns a list of AudioBuffer (one per context).
+
+    Product: one wae_render_batch call.  Oracle (tests only): wao_render per context (optionally threaded)."""
+    ctx0 = contexts[0]
+    api = ctx0._api
+    n, ch, length = len(contexts), ctx0._channels, ctx0._length
+    out = np.empty((n, ch, length), np.float32)
+    arr = (C.c_void_p * n)(*[c._g for c in contexts])
+    if api.is_product:
+        b = Batch(contexts)
+        b.run()
+        b.sync()
+        b.fetch(out)
+    else:
+        secs = C.c_double()
+        api.check(api.render_many(arr, n, B.fptr(out), threads, C.byref(secs)))
+    return [AudioBuffer([out[i, c] for c in range(ch)], ctx0._sample_rate) for i in range(n)]
