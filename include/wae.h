@@ -253,6 +253,8 @@ enum {
     WAE_OPT_SERIAL_FILTERS = 3  /* 1: bit-faithful serial recurrences (thread per channel)          */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
+/* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */
+WAE_API wae_status wae_engine_stream(wae_engine* engine, void** out_stream);
 
 /* ---- graph construction = OfflineAudioContext::new + BaseAudioContext::create_* ----------------- */
 
@@ -321,6 +323,11 @@ WAE_API wae_status wae_render_batch(wae_engine* engine, wae_graph* const* graphs
  * run renders (device-resident output owned by the engine), fetch copies to the host. */
 typedef struct wae_batch wae_batch;
 WAE_API wae_status wae_batch_prepare(wae_engine* engine, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out_batch);
+/* re-upload the source PCM of every AudioBufferSourceNode from host memory (pinned at prepare) — the H2D
+ * leg of an end-to-end step when the same batch is rendered repeatedly */
+WAE_API wae_status wae_batch_upload(wae_batch* batch);                    /* async on the engine stream   */
+/* per_stage != 0: record CUDA events around every stage (diagnostic: serialises chunks) */
+WAE_API wae_status wae_batch_set_timing(wae_batch* batch, uint32_t per_stage);
 WAE_API wae_status wae_batch_run(wae_batch* batch);                       /* async on the engine stream   */
 WAE_API wae_status wae_batch_sync(wae_batch* batch);                      /* wait for the stream           */
 WAE_API wae_status wae_batch_output_device_ptr(wae_batch* batch, float** out_dev, uint64_t* out_floats);
@@ -341,6 +348,9 @@ typedef struct wae_batch_stats {
     char dominant_kernel[64];
 } wae_batch_stats;
 WAE_API wae_status wae_batch_get_stats(wae_batch* batch, wae_batch_stats* out);
+/* device time of stage `index` summed over the chunks of the last run (needs wae_batch_set_timing(batch, 1));
+ * returns WAE_INVALID_ARGUMENT past the last stage */
+WAE_API wae_status wae_batch_stage_time(wae_batch* batch, uint32_t index, char* name64, float* ms, uint32_t* n_instances);
 
 /* AnalyserNode read-out after a render (src/node/analyser.rs:246-264, src/analysis.rs:347-401):
  * state of the analyser at the end of the render. */

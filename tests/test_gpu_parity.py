@@ -1,0 +1,357 @@
+"""Parity tests proper: the CUDA engine (through the C ABI) vs the CPU oracle on the same seeded graphs.
+Tolerance = the north_star contract: 1e-5 absolute on f32 PCM (TOL below); several cases are bit-exact."""
+import numpy as np
+import pytest
+
+import graphs as G
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # BASELINE.json north_star: "match the reference ... within 1e-5 f32"
+
+
+def both(pkg, engine, oracle, build, n=1):
+    gpu = G.render(pkg, [build(engine.backend, g) for g in range(n)])
+    cpu = G.render(pkg, [build(oracle, g) for g in range(n)])
+    return gpu, cpu
+
+
+def maxdiff(a, b):
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max())
+
+
+def test_c1_osc_biquad(pkg, engine, oracle):
+    # BASELINE configs[0]: 1 s of osc -> biquad -> destination at 48 kHz stereo
+    gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c1_osc_biquad(pkg, be, 48000))
+    assert gpu.shape == (1, 2, 48000)
+    assert maxdiff(gpu, cpu) <= TOL
+    assert np.array_equal(gpu[0, 0], gpu[0, 1])  # mono fan-in is up-mixed by copy
+
+
+def test_c1_partial_last_quantum(pkg, engine, oracle):
+    gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c1_osc_biquad(pkg, be, 555, 44100.0))
+    assert gpu.shape == (1, 2, 555)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("serial", [0, 1])
+def test_c2_buffer_biquad_gain(pkg, engine, oracle, serial):
+    engine.set_option(pkg.OPT_SERIAL_FILTERS, serial)
+    try:
+        n, length = 24, 128 * 97 + 5
+        gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c2_buffer_biquad_gain(pkg, be, g, length), n)
+        assert maxdiff(gpu, cpu) <= TOL
+        if serial:  # the serial kernel keeps the reference's f64 operation order
+            assert maxdiff(gpu, cpu) <= 1e-7
+    finally:
+        engine.set_option(pkg.OPT_SERIAL_FILTERS, 0)
+
+
+@pytest.mark.parametrize("chunk", [128, 1024, 2048, 4096 + 128, 0])
+def test_chunk_invariance(pkg, engine, oracle, chunk):
+    # size-independent property: the result must not depend on how the render is cut into time chunks
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        length = 128 * 131
+        gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c2_buffer_biquad_gain(pkg, be, g, length), 5)
+        assert maxdiff(gpu, cpu) <= TOL
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+
+
+def test_c3_many_voices_summation_order(pkg, engine, oracle):
+    # C3 scaled down: 300 voices summed at the destination in the reference's order (last-created first)
+    gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c3_many_voices(pkg, be, 300, 128 * 40))
+    scale = float(np.abs(cpu).max())
+    assert scale > 1.0
+    assert maxdiff(gpu, cpu) <= TOL * max(1.0, scale / 8)  # abs 1e-5 at amplitudes up to 8, relative above
+
+
+@pytest.mark.parametrize("typ", ["sine", "square", "sawtooth", "triangle"])
+def test_oscillator_types_and_schedule(pkg, engine, oracle, typ):
+    t = {"sine": 0, "square": 1, "sawtooth": 2, "triangle": 3}[typ]
+
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 20, G.SR, be)
+        osc = c.create_oscillator(type_=t, frequency=443.7, detune=35.0)
+        osc.connect(c.destination())
+        osc.start_at(0.0113)   # sub-sample start inside quantum 4
+        osc.stop_at(0.0402)
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build)
+    assert np.array_equal(gpu == 0, cpu == 0)  # same start/stop frames
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_oscillator_outside_nyquist_and_negative(pkg, engine, oracle):
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 8, G.SR, be)
+        for f in (23999.0, -440.0, 24000.0):
+            o = c.create_oscillator(frequency=f)
+            o.connect(c.destination())
+            o.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("btype", range(8))
+def test_biquad_all_types(pkg, engine, oracle, btype):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 30)
+        c = pkg.OfflineAudioContext(2, 128 * 30, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        b = c.create_biquad_filter(type_=btype, frequency=1200.0, q=2.5, gain=6.0, detune=120.0)
+        s.connect(b)
+        b.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_low_frequency_high_q_biquad_long(pkg, engine, oracle):
+    # poles close to the unit circle + many scan tiles: the stress case of the time-parallel recurrence
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 400)
+        c = pkg.OfflineAudioContext(1, 128 * 400, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0]], G.SR))
+        b = c.create_biquad_filter(type_=pkg.BANDPASS, frequency=25.0, q=30.0)
+        s.connect(b)
+        b.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_iir_filter(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 25)
+        c = pkg.OfflineAudioContext(2, 128 * 25, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        f = c.create_iir_filter([0.0675, 0.1349, 0.0675, 0.01], [1.0, -1.1430, 0.4128])
+        s.connect(f)
+        f.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= 1e-7  # same serial f64 order
+
+
+def test_gain_shaper_panner_chain(pkg, engine, oracle):
+    curve = np.tanh(np.linspace(-3, 3, 1024)).astype(np.float32)
+
+    def build(be, g):
+        c = pkg.OfflineAudioContext(2, 128 * 16, G.SR, be)
+        o = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=330.0 + 10 * g)
+        ws = c.create_wave_shaper(curve)
+        gn = c.create_gain(0.7)
+        sp = c.create_stereo_panner(pan=-0.4 + 0.3 * g)
+        o.connect(ws)
+        ws.connect(gn)
+        gn.connect(sp)
+        sp.connect(c.destination())
+        o.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_stereo_panner_stereo_input(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 8)
+        c = pkg.OfflineAudioContext(2, 128 * 8, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        sp = c.create_stereo_panner(pan=[-0.6, 0.0, 0.8][g])
+        s.connect(sp)
+        sp.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_equal_power_panner(pkg, engine, oracle):
+    def build(be, g):
+        c = pkg.OfflineAudioContext(2, 128 * 8, G.SR, be)
+        o = c.create_oscillator(frequency=500.0)
+        p = c.create_panner(position=[(3.0, 1.0, -2.0), (-4.0, 0.0, 0.5), (0.0, 0.0, 0.0)][g], distance_model=g,
+                            cone_inner_angle=60.0, cone_outer_angle=120.0, cone_outer_gain=0.3, max_distance=50.0)
+        o.connect(p)
+        p.connect(c.destination())
+        o.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_delay_node(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 40)
+        c = pkg.OfflineAudioContext(2, 128 * 40, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        d = c.create_delay(max_delay_time=0.5, delay_time=[0.0, 0.00101, 0.0213][g])
+        s.connect(d)
+        d.connect(c.destination())
+        s.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_dynamics_compressor(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 30) * np.float32(0.9)
+        c = pkg.OfflineAudioContext(2, 128 * 30, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        d = c.create_dynamics_compressor()
+        s.connect(d)
+        d.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= 5e-5  # f32 log10/pow chains differ by a few ulp between glibc and CUDA libm
+
+
+def test_analyser_passthrough_and_time_domain(pkg, engine, oracle):
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 30 + 17, G.SR, be)
+        o = c.create_oscillator(frequency=700.0)
+        a = c.create_analyser(fft_size=1024)
+        o.connect(a)
+        a.connect(c.destination())
+        o.start()
+        c._test_analyser = a
+        return c
+
+    cg, cc = build(engine.backend, 0), build(oracle, 0)
+    gpu = G.render(pkg, [cg])
+    cpu = G.render(pkg, [cc])
+    assert maxdiff(gpu, cpu) <= TOL
+    tg = cg._test_analyser.get_float_time_domain_data()
+    tc = cc._test_analyser.get_float_time_domain_data()
+    assert maxdiff(tg, tc) <= TOL
+
+
+def test_channel_splitter_merger(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 6)
+        c = pkg.OfflineAudioContext(2, 128 * 6, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        sp = c.create_channel_splitter(2)
+        mg = c.create_channel_merger(2)
+        s.connect(sp)
+        sp.connect_from_output_to_input(mg, 0, 1)  # swap left / right
+        sp.connect_from_output_to_input(mg, 1, 0)
+        mg.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 1)
+    assert np.array_equal(gpu, cpu)
+
+
+@pytest.mark.parametrize("in_ch,ir_ch", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 4), (1, 4)])
+def test_convolver_channel_routing(pkg, engine, oracle, in_ch, ir_ch):
+    # the six routings of src/node/convolver.rs:378-487
+    ir = G.synthetic_ir(3000, ir_ch, seed=5)
+
+    def build(be, g):
+        length = 128 * 60
+        pcm = G.c2_source(g, length)
+        c = pkg.OfflineAudioContext(2, length, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[i] for i in range(in_ch)], G.SR))
+        cv = c.create_convolver(pkg.AudioBuffer(ir, G.SR))
+        s.connect(cv)
+        cv.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("chunk", [1024, 4096, 0])
+def test_c4_convolver_long_ir(pkg, engine, oracle, chunk):
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        ir = G.synthetic_ir(20000, 2)  # 20 partitions of 1024
+        gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c4_convolver(pkg, be, g, 128 * 250 + 77, ir), 3)
+        assert maxdiff(gpu, cpu) <= TOL
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+
+
+def test_convolver_linearity(pkg, engine):
+    # size-independent property at a larger size: conv(a + b) == conv(a) + conv(b) within f32 rounding
+    ir = G.synthetic_ir(48000, 2)
+    length = 128 * 600
+    rng = np.random.default_rng(3)
+    a = rng.uniform(-0.5, 0.5, (2, length)).astype(np.float32)
+    bb = rng.uniform(-0.5, 0.5, (2, length)).astype(np.float32)
+
+    def build(pcm):
+        c = pkg.OfflineAudioContext(2, length, G.SR, engine.backend)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        cv = c.create_convolver(pkg.AudioBuffer(ir, G.SR))
+        s.connect(cv)
+        cv.connect(c.destination())
+        s.start()
+        return c
+
+    out = G.render(pkg, [build(a), build(bb), build(a + bb)])
+    assert maxdiff(out[0] + out[1], out[2]) <= TOL
+
+
+def test_north_star_graph(pkg, engine, oracle):
+    ir = G.synthetic_ir(9000, 2)
+    gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.north_star_voices_convolver(pkg, be, 40, 128 * 100, ir, seed=g), 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_unsupported_is_reported_not_faked(pkg, engine):
+    c = pkg.OfflineAudioContext(1, 128, G.SR, engine.backend)
+    g = c.create_gain()
+    src = c.create_constant_source()
+    g.gain.linear_ramp_to_value_at_time(0.0, 0.001)
+    src.connect(g)
+    g.connect(c.destination())
+    src.start()
+    with pytest.raises(pkg.WaeError) as e:
+        c.start_rendering_sync()
+    assert e.value.status == 4  # WAE_UNSUPPORTED -> the caller falls back to the CPU renderer
+
+
+def test_offline_rs_cases_on_gpu(pkg, engine):
+    # tests/offline.rs:10-46 and :48-81 on the CUDA path (exact)
+    c = pkg.OfflineAudioContext(2, 555, 44100.0, engine.backend)
+    c1 = c.create_constant_source()
+    c1.offset.set_value(2.0)
+    c1.connect(c.destination())
+    c2 = c.create_constant_source()
+    c2.offset.set_value(-4.0)
+    c2.connect(c.destination())
+    c1.start()
+    c2.start()
+    out = c.start_rendering_sync()
+    assert np.array_equal(out.get_channel_data(0), np.full(555, -2.0, np.float32))
+    assert np.array_equal(out.get_channel_data(1), np.full(555, -2.0, np.float32))
+    sr = 48000.0
+    c = pkg.OfflineAudioContext(1, 512, sr, engine.backend)
+    osc = c.create_oscillator(type_=pkg.SQUARE, frequency=0.0)
+    osc.connect(c.destination())
+    osc.start_at(128.0 / sr)
+    osc.stop_at(128.0 * 3.0 / sr)
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out, np.concatenate([np.zeros(128), np.ones(256), np.zeros(128)]).astype(np.float32))

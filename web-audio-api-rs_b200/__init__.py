@@ -50,6 +50,12 @@ class Engine:
         a = api()
         a.check(a.engine_set_option(self.handle, option, int(value)))
 
+    def stream(self):
+        a = api()
+        p = ctypes.c_void_p()
+        a.check(a.engine_stream(self.handle, ctypes.byref(p)))
+        return p.value
+
     def context(self, number_of_channels, length, sample_rate):
         return context.OfflineAudioContext(number_of_channels, length, sample_rate, self.backend)
 

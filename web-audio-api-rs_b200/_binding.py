@@ -133,13 +133,13 @@ CREATE_FUNCS = {
 
 # every symbol include/wae.h declares (tests check the product exports all of them)
 WAE_SYMBOLS = [
-    "wae_engine_create", "wae_engine_destroy", "wae_last_error", "wae_version", "wae_engine_set_option",
+    "wae_engine_create", "wae_engine_destroy", "wae_last_error", "wae_version", "wae_engine_set_option", "wae_engine_stream",
     "wae_graph_create", "wae_graph_destroy",
 ] + ["wae_" + n for n in CREATE_FUNCS] + [
     "wae_connect", "wae_connect_param", "wae_disconnect", "wae_param_event_push", "wae_param_set_automation_rate",
     "wae_listener_param_event_push", "wae_source_start", "wae_source_stop", "wae_oscillator_set_type",
-    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_run", "wae_batch_sync",
-    "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats",
+    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_sync",
+    "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data",
 ]
 
@@ -172,15 +172,19 @@ class Api:
             f("engine_create", C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)])
             f("engine_destroy", C.c_int32, [C.c_void_p])
             f("engine_set_option", C.c_int32, [C.c_void_p, C.c_uint32, C.c_int64])
+            f("engine_stream", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p)])
             f("graph_create", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)])
             f("render_batch", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32])
             f("batch_prepare", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p)])
+            f("batch_upload", C.c_int32, [C.c_void_p])
+            f("batch_set_timing", C.c_int32, [C.c_void_p, C.c_uint32])
             f("batch_run", C.c_int32, [C.c_void_p])
             f("batch_sync", C.c_int32, [C.c_void_p])
             f("batch_output_device_ptr", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)])
             f("batch_fetch", C.c_int32, [C.c_void_p, C.c_void_p])
             f("batch_destroy", C.c_int32, [C.c_void_p])
             f("batch_get_stats", C.c_int32, [C.c_void_p, C.POINTER(BatchStats)])
+            f("batch_stage_time", C.c_int32, [C.c_void_p, C.c_uint32, C.c_char_p, c_float_p, C.POINTER(C.c_uint32)])
             f("analyser_get_float_time_domain_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, c_float_p, C.c_uint32])
             f("analyser_get_float_frequency_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, c_float_p, C.c_uint32])
         else:

@@ -417,6 +417,12 @@ class Batch:
     def run(self):
         self.api.check(self.api.batch_run(self.handle))
 
+    def upload(self):
+        self.api.check(self.api.batch_upload(self.handle))
+
+    def set_timing(self, per_stage):
+        self.api.check(self.api.batch_set_timing(self.handle, 1 if per_stage else 0))
+
     def sync(self):
         self.api.check(self.api.batch_sync(self.handle))
 
@@ -435,6 +441,18 @@ class Batch:
         s = B.BatchStats()
         self.api.check(self.api.batch_get_stats(self.handle, C.byref(s)))
         return s
+
+    def stage_times(self):
+        """[(kernel name, ms over the last run, instances)] — needs set_timing(True) before run()."""
+        out, i = [], 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, n = C.c_float(), C.c_uint32()
+            if self.api.batch_stage_time(self.handle, i, name, C.byref(ms), C.byref(n)) != 0:
+                break
+            out.append((name.value.decode(), ms.value, n.value))
+            i += 1
+        return out
 
     def destroy(self):
         if self.handle:

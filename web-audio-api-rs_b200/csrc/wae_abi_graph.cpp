@@ -1,0 +1,551 @@
+// C ABI, graph-construction half (include/wae.h): OfflineAudioContext::new, create_*, connect, AudioParam
+// events, start/stop.  Mirrors the control side of the reference (file:line cited per function); argument
+// validation returns the reference's panic text through wae_last_error().
+#include "wae_graph.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+using namespace wae;
+
+namespace wae {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+// AudioParamProcessor::handle_incoming_event for SetValue (src/param.rs:987-990) + mix_to_output clamp (:755-760)
+bool Param::constant() const {
+    for (auto& e : events)
+        if (e.type != WAE_EVENT_SET_VALUE) return false;
+    return true;
+}
+float Param::constant_value() const {
+    float v = default_value;
+    for (auto& e : events)
+        if (e.type == WAE_EVENT_SET_VALUE) v = e.value;
+    if (std::isnan(v)) return default_value;
+    v = v > min_value ? v : min_value;
+    v = v < max_value ? v : max_value;
+    return v;
+}
+}  // namespace wae
+
+static const float F32_MAX = 3.40282347e+38f;
+
+// BaseAudioContext::create_audio_param, src/context/base.rs:320-337
+uint32_t wae_graph::create_param(uint32_t owner, float def, float mn, float mx, bool a_rate, float initial, bool send_set_value,
+                                 bool fixed_id, uint32_t id, bool constrained) {
+    uint32_t pid = fixed_id ? id : next_id++;
+    Node n;
+    n.id = pid;
+    n.kind = K_PARAM;
+    n.out_id = pid;
+    n.cfg = ChannelCfg{1, WAE_COUNT_MODE_EXPLICIT, WAE_INTERPRETATION_DISCRETE};  // src/param.rs:296-310
+    n.param = Param{def, mn, mx, a_rate, constrained, {}};
+    if (send_set_value) n.param.events.push_back(ParamEv{WAE_EVENT_SET_VALUE, initial, 0., 0., {}});
+    nodes[pid] = std::move(n);
+    pending_param_edges.push_back({pid, owner});
+    return pid;
+}
+
+// tail of ConcreteBaseAudioContext::register (src/context/concrete_base.rs:232-270)
+Node& wae_graph::finish_register(Node n) {
+    uint32_t id = n.id;
+    nodes[id] = std::move(n);
+    for (auto& e : pending_param_edges)
+        if (e.second == id) add_edge(e.first, 0, e.second, -1);
+    pending_param_edges.erase(
+        std::remove_if(pending_param_edges.begin(), pending_param_edges.end(), [&](auto& e) { return e.second == id; }),
+        pending_param_edges.end());
+    return nodes[id];
+}
+
+// ensure_audio_listener_present, src/context/concrete_base.rs:516-534 + AudioListenerNode::new (src/spatial.rs:117-170)
+void wae_graph::ensure_listener() {
+    if (listener_present) return;
+    listener_present = true;
+    static const float defaults[9] = {0.f, 0.f, 0.f, 0.f, 0.f, -1.f, 0.f, 1.f, 0.f};
+    Node l;
+    l.id = 1;
+    l.kind = K_LISTENER;
+    l.out_id = 1;
+    l.n_inputs = 0;
+    l.n_outputs = 9;
+    l.cfg = ChannelCfg{1, WAE_COUNT_MODE_EXPLICIT, WAE_INTERPRETATION_DISCRETE};
+    for (int i = 0; i < 9; i++) l.params.push_back(create_param(1, defaults[i], -F32_MAX, F32_MAX, true, defaults[i], false, true, 2 + i));
+    finish_register(std::move(l));
+    add_edge(1, 0, 0, -1);
+}
+
+static ChannelCfg resolve_cfg(const wae_channel_config& c, ChannelCfg def) {
+    if (c.count == 0) return def;
+    return ChannelCfg{(int)c.count, (int)c.count_mode, (int)c.interpretation};
+}
+
+static std::shared_ptr<PcmBuffer> copy_buffer(const wae_audio_buffer* b) {
+    auto p = std::make_shared<PcmBuffer>();
+    p->sample_rate = b->sample_rate;
+    for (uint32_t c = 0; c < b->number_of_channels; c++) p->channels.emplace_back(b->channels[c], b->channels[c] + b->length);
+    return p;
+}
+
+extern "C" {
+
+WAE_API const char* wae_last_error(void) { return g_err.c_str(); }
+WAE_API const char* wae_version(void) { return "wae-b200 0.1 (sm_100a)"; }
+
+// OfflineAudioContext::new, src/context/offline.rs:78-105
+WAE_API wae_status wae_graph_create(wae_engine* engine, uint32_t number_of_channels, uint64_t length, float sample_rate,
+                                    wae_graph** out) {
+    if (!engine || !out) return fail(WAE_INVALID_ARGUMENT, "null engine / out pointer");
+    if (number_of_channels < 1 || number_of_channels > WAE_MAX_CHANNELS)
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels");
+    if (length == 0) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid length: 0");
+    if (!(sample_rate >= 3000.f && sample_rate <= 768000.f)) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid sample rate");
+    auto* g = new wae_graph;
+    g->engine = engine;
+    g->channels = number_of_channels;
+    g->length = length;
+    g->sample_rate = sample_rate;
+    Node d;  // AudioDestinationNode::new, src/node/destination.rs:100-117
+    d.id = 0;
+    d.kind = K_DEST;
+    d.cfg = ChannelCfg{(int)number_of_channels, WAE_COUNT_MODE_EXPLICIT, WAE_INTERPRETATION_SPEAKERS};
+    g->finish_register(std::move(d));
+    *out = g;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_graph_destroy(wae_graph* g) {
+    delete g;
+    return WAE_OK;
+}
+
+// OscillatorNode::new, src/node/oscillator.rs:211-275
+WAE_API wae_status wae_create_oscillator(wae_graph* g, const wae_oscillator_options* o, wae_node_id* out) {
+    if (o->type > WAE_OSC_CUSTOM) return fail(WAE_INVALID_ARGUMENT, "invalid oscillator type");
+    if (o->type == WAE_OSC_CUSTOM && (!o->periodic_wave || o->periodic_wave_len == 0))
+        return fail(WAE_INVALID_ARGUMENT, "custom oscillator needs a periodic wave table");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_OSC;
+    n.n_inputs = 0;
+    n.type = (int)o->type;
+    float nyquist = g->sample_rate / 2.f;
+    n.params.push_back(g->create_param(n.id, 440.f, -nyquist, nyquist, true, o->frequency));
+    n.params.push_back(g->create_param(n.id, 0.f, -153600.f, 153600.f, true, o->detune));
+    if (o->type == WAE_OSC_CUSTOM) n.table.assign(o->periodic_wave, o->periodic_wave + o->periodic_wave_len);
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// BiquadFilterNode::new, src/node/biquad_filter.rs:542-608
+WAE_API wae_status wae_create_biquad_filter(wae_graph* g, const wae_biquad_options* o, wae_node_id* out) {
+    if (o->type > 7) return fail(WAE_INVALID_ARGUMENT, "invalid biquad type");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_BIQUAD;
+    n.type = (int)o->type;
+    n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, true, o->q));
+    n.params.push_back(g->create_param(n.id, 0.f, -153600.f, 153600.f, true, o->detune));
+    n.params.push_back(g->create_param(n.id, 350.f, 0.f, g->sample_rate / 2.f, true, o->frequency));
+    n.params.push_back(g->create_param(n.id, 0.f, -F32_MAX, 40.f * log10f(F32_MAX), true, o->gain));
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// IIRFilterNode::new, src/node/iir_filter.rs:146-205
+WAE_API wae_status wae_create_iir_filter(wae_graph* g, const wae_iir_options* o, wae_node_id* out) {
+    if (o->feedforward_len == 0 || o->feedforward_len > 20) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - invalid feedforward length");
+    if (o->feedback_len == 0 || o->feedback_len > 20) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - invalid feedback length");
+    bool all_zero = true;
+    for (uint32_t i = 0; i < o->feedforward_len; i++)
+        if (o->feedforward[i] != 0.) all_zero = false;
+    if (all_zero) return fail(WAE_INVALID_STATE, "InvalidStateError - all feedforward coefficients are zero");
+    if (o->feedback[0] == 0.) return fail(WAE_INVALID_STATE, "InvalidStateError - first feedback coefficient is zero");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_IIR;
+    n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    n.feedforward.assign(o->feedforward, o->feedforward + o->feedforward_len);
+    n.feedback.assign(o->feedback, o->feedback + o->feedback_len);
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// GainNode::new, src/node/gain.rs:86-117
+WAE_API wae_status wae_create_gain(wae_graph* g, const wae_gain_options* o, wae_node_id* out) {
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_GAIN;
+    n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, true, o->gain));
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// AudioBufferSourceNode::new, src/node/audio_buffer_source.rs:160-235
+WAE_API wae_status wae_create_buffer_source(wae_graph* g, const wae_buffer_source_options* o, wae_node_id* out) {
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_ABSN;
+    n.n_inputs = 0;
+    n.params.push_back(g->create_param(n.id, 0.f, -F32_MAX, F32_MAX, false, o->detune, true, false, 0, true));
+    n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, false, o->playback_rate, true, false, 0, true));
+    n.loop = o->loop != 0;
+    n.loop_start = o->loop_start;
+    n.loop_end = o->loop_end;
+    if (o->buffer) n.buffer = copy_buffer(o->buffer);
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// ConstantSourceNode::new, src/node/constant_source.rs:138-170
+WAE_API wae_status wae_create_constant_source(wae_graph* g, const wae_constant_source_options* o, wae_node_id* out) {
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_CONST;
+    n.n_inputs = 0;
+    n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, true, o->offset));
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// ConvolverNode::new + set_buffer, src/node/convolver.rs:199-317
+WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_options* o, wae_node_id* out) {
+    ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
+    if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - ConvolverNode channel count cannot be greater than two");
+    if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - ConvolverNode channel count mode cannot be set to max");
+    if (o->buffer) {
+        if (o->buffer->sample_rate != g->sample_rate)
+            return fail(WAE_NOT_SUPPORTED, "NotSupportedError - sample rate of the convolution buffer must match the audio context");
+        uint32_t c = o->buffer->number_of_channels;
+        if (!(c == 1 || c == 2 || c == 4))
+            return fail(WAE_NOT_SUPPORTED, "NotSupportedError - the convolution buffer must consist of 1, 2 or 4 channels");
+    }
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_CONV;
+    n.cfg = cfg;
+    n.normalize = !o->disable_normalization;
+    if (o->buffer) n.buffer = copy_buffer(o->buffer);
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// WaveShaperNode::new, src/node/waveshaper.rs:190-260
+WAE_API wae_status wae_create_wave_shaper(wae_graph* g, const wae_wave_shaper_options* o, wae_node_id* out) {
+    if (o->oversample != WAE_OVERSAMPLE_NONE)
+        return fail(WAE_UNSUPPORTED, "oversampled WaveShaper (rubato FftFixedInOut, un-vendored) is not lowered to the GPU");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_SHAPER;
+    n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    if (o->curve) {
+        n.has_curve = true;
+        n.table.assign(o->curve, o->curve + o->curve_len);
+    }
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// DelayNode::new, src/node/delay.rs:283-368: writer N, reader N+1, delayTime N+2
+WAE_API wae_status wae_create_delay(wae_graph* g, const wae_delay_options* o, wae_node_id* out) {
+    if (!(o->max_delay_time > 0. && o->max_delay_time < 180.))
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - maxDelayTime MUST be greater than zero and less than three minutes");
+    ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    uint32_t writer_id = g->next_id++;
+    uint32_t reader_id = g->next_id++;
+    Node r;
+    r.id = reader_id;
+    r.out_id = reader_id;
+    r.kind = K_DELAY_R;
+    r.cfg = cfg;
+    r.max_delay_time = o->max_delay_time;
+    r.delay_peer = writer_id;
+    r.params.push_back(g->create_param(reader_id, 0.f, 0.f, (float)o->max_delay_time, true, (float)o->delay_time));
+    uint32_t p = r.params[0];
+    g->finish_register(std::move(r));
+    Node w;
+    w.id = writer_id;
+    w.out_id = reader_id;
+    w.kind = K_DELAY_W;
+    w.cfg = cfg;
+    w.max_delay_time = o->max_delay_time;
+    w.delay_peer = reader_id;
+    w.params.push_back(p);
+    w.cycle_breaker = true;
+    g->finish_register(std::move(w));
+    g->add_edge(writer_id, 0, reader_id, 0);
+    *out = writer_id;
+    return WAE_OK;
+}
+
+// StereoPannerNode::new, src/node/stereo_panner.rs:163-200
+WAE_API wae_status wae_create_stereo_panner(wae_graph* g, const wae_stereo_panner_options* o, wae_node_id* out) {
+    ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
+    if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - StereoPannerNode channel count mode cannot be set to max");
+    if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - StereoPannerNode channel count cannot be greater than two");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_SPANNER;
+    n.cfg = cfg;
+    n.params.push_back(g->create_param(n.id, 0.f, -1.f, 1.f, true, o->pan));
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// PannerNode::new, src/node/panner.rs:392-520
+WAE_API wae_status wae_create_panner(wae_graph* g, const wae_panner_options* o, wae_node_id* out) {
+    ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
+    if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - PannerNode channel count mode cannot be set to max");
+    if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - PannerNode channel count cannot be greater than two");
+    if (o->ref_distance < 0.) return fail(WAE_INVALID_ARGUMENT, "RangeError - refDistance cannot be negative");
+    if (o->max_distance <= 0.) return fail(WAE_INVALID_ARGUMENT, "RangeError - maxDistance must be strictly positive");
+    if (o->rolloff_factor < 0.) return fail(WAE_INVALID_ARGUMENT, "RangeError - rolloffFactor cannot be negative");
+    if (o->cone_outer_gain < 0. || o->cone_outer_gain > 1.) return fail(WAE_INVALID_STATE, "InvalidStateError - coneOuterGain must be in the range [0, 1]");
+    if (o->panning_model == WAE_PANNING_HRTF)
+        return fail(WAE_UNSUPPORTED, "HRTF panning (un-vendored hrtf 0.8.1 crate, parity unpinned) is not lowered to the GPU yet");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_PANNER;
+    n.cfg = cfg;
+    n.panning_model = (int)o->panning_model;
+    n.distance_model = (int)o->distance_model;
+    n.ref_distance = o->ref_distance;
+    n.max_distance = o->max_distance;
+    n.rolloff_factor = o->rolloff_factor;
+    n.cone_inner_angle = o->cone_inner_angle;
+    n.cone_outer_angle = o->cone_outer_angle;
+    n.cone_outer_gain = o->cone_outer_gain;
+    g->ensure_listener();
+    const float init[6] = {o->position_x, o->position_y, o->position_z, o->orientation_x, o->orientation_y, o->orientation_z};
+    for (int i = 0; i < 6; i++) n.params.push_back(g->create_param(n.id, i == 3 ? 1.f : 0.f, -F32_MAX, F32_MAX, true, init[i]));
+    uint32_t id = g->finish_register(std::move(n)).id;
+    g->add_edge(1, 0, id, -1);  // connect_listener_to_panner, concrete_base.rs:511-513
+    *out = id;
+    return WAE_OK;
+}
+
+// AnalyserNode::new, src/node/analyser.rs:130-175 (asserts of src/analysis.rs:33-72)
+WAE_API wae_status wae_create_analyser(wae_graph* g, const wae_analyser_options* o, wae_node_id* out) {
+    uint32_t fft = o->fft_size ? o->fft_size : 2048;
+    if ((fft & (fft - 1)) != 0) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: not a power of two");
+    if (fft < 32 || fft > 32768) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: outside range [32, 32768]");
+    double stc = o->fft_size ? o->smoothing_time_constant : 0.8;
+    if (!(stc >= 0. && stc <= 1.)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid smoothing time constant");
+    double mn = o->fft_size ? o->min_decibels : -100., mx = o->fft_size ? o->max_decibels : -30.;
+    if (!(mn < mx)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid min decibels");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_ANALYSER;
+    n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
+    n.fft_size = fft;
+    n.smoothing = stc;
+    n.min_db = mn;
+    n.max_db = mx;
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// DynamicsCompressorNode::new, src/node/dynamics_compressor.rs:130-260
+WAE_API wae_status wae_create_dynamics_compressor(wae_graph* g, const wae_dynamics_compressor_options* o, wae_node_id* out) {
+    ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
+    if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - DynamicsCompressorNode channel count cannot be greater than two");
+    if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - DynamicsCompressorNode channel count mode cannot be set to max");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_COMP;
+    n.cfg = cfg;
+    n.params.push_back(g->create_param(n.id, 0.003f, 0.f, 1.f, false, o->attack, true, false, 0, true));
+    n.params.push_back(g->create_param(n.id, 30.f, 0.f, 40.f, false, o->knee, true, false, 0, true));
+    n.params.push_back(g->create_param(n.id, 12.f, 1.f, 20.f, false, o->ratio, true, false, 0, true));
+    n.params.push_back(g->create_param(n.id, 0.25f, 0.f, 1.f, false, o->release, true, false, 0, true));
+    n.params.push_back(g->create_param(n.id, -24.f, -100.f, 0.f, false, o->threshold, true, false, 0, true));
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// ChannelMergerNode::new, src/node/channel_merger.rs:120-140
+WAE_API wae_status wae_create_channel_merger(wae_graph* g, const wae_channel_merger_options* o, wae_node_id* out) {
+    uint32_t k = o->number_of_inputs ? o->number_of_inputs : 6;
+    if (k < 1 || k > WAE_MAX_CHANNELS) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid number of inputs");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_MERGER;
+    n.n_inputs = (int)k;
+    n.cfg = ChannelCfg{1, WAE_COUNT_MODE_EXPLICIT, WAE_INTERPRETATION_SPEAKERS};
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// ChannelSplitterNode::new, src/node/channel_splitter.rs:140-180
+WAE_API wae_status wae_create_channel_splitter(wae_graph* g, const wae_channel_splitter_options* o, wae_node_id* out) {
+    uint32_t k = o->number_of_outputs ? o->number_of_outputs : 6;
+    if (k < 1 || k > WAE_MAX_CHANNELS) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid number of outputs");
+    Node n;
+    n.id = g->next_id++;
+    n.out_id = n.id;
+    n.kind = K_SPLITTER;
+    n.n_outputs = (int)k;
+    n.cfg = ChannelCfg{(int)k, WAE_COUNT_MODE_EXPLICIT, WAE_INTERPRETATION_DISCRETE};
+    *out = g->finish_register(std::move(n)).id;
+    return WAE_OK;
+}
+
+// AudioNode::connect_from_output_to_input, src/node/audio_node.rs:259-289
+WAE_API wae_status wae_connect(wae_graph* g, wae_node_id from, uint32_t output, wae_node_id to, uint32_t input) {
+    auto fi = g->nodes.find(from), ti = g->nodes.find(to);
+    if (fi == g->nodes.end() || ti == g->nodes.end() || fi->second.kind == K_PARAM || ti->second.kind == K_PARAM)
+        return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if ((int)output >= fi->second.n_outputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port " + std::to_string(output) + " is out of bounds");
+    if ((int)input >= ti->second.n_inputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - input port " + std::to_string(input) + " is out of bounds");
+    g->add_edge(fi->second.out_id, (int)output, to, (int)input);
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_connect_param(wae_graph* g, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index) {
+    auto fi = g->nodes.find(from), ti = g->nodes.find(to);
+    if (fi == g->nodes.end() || ti == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if ((int)output >= fi->second.n_outputs) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port out of bounds");
+    if (param_index >= ti->second.params.size()) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - param index out of bounds");
+    g->add_edge(fi->second.out_id, (int)output, ti->second.params[param_index], 0);
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_disconnect(wae_graph* g, wae_node_id from) {
+    auto fi = g->nodes.find(from);
+    if (fi == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    g->nodes.at(fi->second.out_id).outgoing.clear();
+    return WAE_OK;
+}
+
+static wae_status push_event(Param& p, const wae_param_event* e) {
+    auto finite = [](float v) { return std::isfinite(v); };
+    auto valid_time = [](double t) { return std::isfinite(t) && t >= 0.; };
+    ParamEv ev{(int)e->type, e->value, e->time, e->aux, {}};
+    switch (e->type) {
+        case WAE_EVENT_SET_VALUE:
+            if (!finite(e->value)) return fail(WAE_INVALID_ARGUMENT, "TypeError - The provided value is non-finite.");
+            ev.time = 0.;
+            break;
+        case WAE_EVENT_SET_VALUE_AT_TIME:
+        case WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME:
+            if (!finite(e->value)) return fail(WAE_INVALID_ARGUMENT, "TypeError - The provided value is non-finite.");
+            if (!valid_time(e->time)) return fail(WAE_INVALID_ARGUMENT, "RangeError - time should be positive");
+            break;
+        case WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME:
+            if (!finite(e->value)) return fail(WAE_INVALID_ARGUMENT, "TypeError - The provided value is non-finite.");
+            if (e->value == 0.f) return fail(WAE_INVALID_ARGUMENT, "RangeError - value (0.0) should not be equal to zero");
+            if (!valid_time(e->time)) return fail(WAE_INVALID_ARGUMENT, "RangeError - time should be positive");
+            break;
+        case WAE_EVENT_SET_TARGET_AT_TIME:
+            if (!finite(e->value)) return fail(WAE_INVALID_ARGUMENT, "TypeError - The provided value is non-finite.");
+            if (!valid_time(e->time) || !valid_time(e->aux)) return fail(WAE_INVALID_ARGUMENT, "RangeError - time should be positive");
+            if (e->aux == 0.) ev.type = WAE_EVENT_SET_VALUE_AT_TIME;  // src/param.rs:529-538
+            break;
+        case WAE_EVENT_CANCEL_SCHEDULED_VALUES:
+        case WAE_EVENT_CANCEL_AND_HOLD_AT_TIME:
+            if (!valid_time(e->time)) return fail(WAE_INVALID_ARGUMENT, "RangeError - time should be positive");
+            break;
+        case WAE_EVENT_SET_VALUE_CURVE_AT_TIME:
+            if (e->values_len < 2) return fail(WAE_INVALID_STATE, "InvalidStateError - sequence length should not be less than 2");
+            if (!valid_time(e->time)) return fail(WAE_INVALID_ARGUMENT, "RangeError - time should be positive");
+            if (!(std::isfinite(e->aux) && e->aux > 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - duration should be strictly positive");
+            ev.values.assign(e->values, e->values + e->values_len);
+            break;
+        default: return fail(WAE_INVALID_ARGUMENT, "unknown event type");
+    }
+    p.events.push_back(std::move(ev));
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_param_event_push(wae_graph* g, wae_node_id node, uint32_t param_index, const wae_param_event* e) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end() || param_index >= ni->second.params.size()) return fail(WAE_INVALID_ARGUMENT, "unknown param");
+    return push_event(g->nodes.at(ni->second.params[param_index]).param, e);
+}
+
+WAE_API wae_status wae_listener_param_event_push(wae_graph* g, uint32_t param_index, const wae_param_event* e) {
+    if (param_index >= 9) return fail(WAE_INVALID_ARGUMENT, "unknown listener param");
+    g->ensure_listener();
+    return push_event(g->nodes.at(2 + param_index).param, e);
+}
+
+WAE_API wae_status wae_param_set_automation_rate(wae_graph* g, wae_node_id node, uint32_t param_index, uint32_t rate) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end() || param_index >= ni->second.params.size()) return fail(WAE_INVALID_ARGUMENT, "unknown param");
+    Param& p = g->nodes.at(ni->second.params[param_index]).param;
+    bool want_a = rate == WAE_AUTOMATION_RATE_A;
+    if (p.rate_constrained && want_a != p.a_rate)
+        return fail(WAE_INVALID_STATE, "InvalidStateError - automation rate cannot be changed for this param");
+    p.a_rate = want_a;
+    return WAE_OK;
+}
+
+// AudioScheduledSourceNode::start_at / stop_at, AudioBufferSourceNode::start_at_with_offset_and_duration
+WAE_API wae_status wae_source_start(wae_graph* g, wae_node_id node, double when, double offset, double duration) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "unknown node");
+    Node& n = ni->second;
+    if (!(n.kind == K_OSC || n.kind == K_ABSN || n.kind == K_CONST)) return fail(WAE_INVALID_ARGUMENT, "not a scheduled source node");
+    if (!(std::isfinite(when) && when >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - when should be positive");
+    if (n.has_start) return fail(WAE_INVALID_STATE, "InvalidStateError - Cannot call `start` twice");
+    if (n.kind == K_ABSN && (!(offset >= 0.) || !(duration >= 0.))) return fail(WAE_INVALID_ARGUMENT, "RangeError - offset/duration should be positive");
+    n.has_start = true;
+    n.start_time = when;
+    if (n.kind == K_ABSN) {
+        n.offset = offset;
+        n.duration = duration >= 1e300 ? 1.7976931348623157e308 : duration;
+    }
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_source_stop(wae_graph* g, wae_node_id node, double when) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "unknown node");
+    Node& n = ni->second;
+    if (!(n.kind == K_OSC || n.kind == K_ABSN || n.kind == K_CONST)) return fail(WAE_INVALID_ARGUMENT, "not a scheduled source node");
+    if (!(std::isfinite(when) && when >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - when should be positive");
+    if (!n.has_start) return fail(WAE_INVALID_STATE, "InvalidStateError cannot stop before start");
+    n.stop_time = when;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_oscillator_set_type(wae_graph* g, wae_node_id node, uint32_t type) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end() || ni->second.kind != K_OSC) return fail(WAE_INVALID_ARGUMENT, "not an oscillator");
+    if (type >= WAE_OSC_CUSTOM) return fail(WAE_INVALID_STATE, "InvalidStateError: Custom type cannot be set manually");
+    if (ni->second.type == WAE_OSC_CUSTOM) return WAE_OK;
+    ni->second.type = (int)type;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t type) {
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end() || ni->second.kind != K_BIQUAD || type > 7) return fail(WAE_INVALID_ARGUMENT, "not a biquad / bad type");
+    ni->second.type = (int)type;
+    return WAE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Device-visible POD descriptors shared by the planner (wae_plan.cpp) and the kernels (wae_kernels.cu).
+//
+// Execution model: a batch of G independent graphs is lowered to STAGES.  A stage is one kernel launch over
+// all node instances of one kind at one topological level, for ONE time chunk [f0, f0+nf) of the render.
+// Edge buffers live in a per-chunk arena (planar [ch][chunk_frames] f32, reused every chunk so they stay
+// L2-resident); node state that crosses chunks (filter state, delay/compressor/analyser rings, convolver
+// spectra) lives in persistent device memory.
+#pragma once
+#include <cstdint>
+#include <vector_types.h>
+
+namespace wae {
+
+struct BufRef {
+    float* p;           // channel 0, frame 0 of the chunk (arena) or of the whole render (absolute)
+    uint32_t stride;    // floats between channels
+    uint32_t absolute;  // 1: index with f0 + n (final output / assets), 0: index with n (arena)
+};
+
+struct ChunkInfo {
+    int64_t f0;  // first frame of this chunk
+    int32_t nf;  // frames in this chunk (multiple of 128 except nothing: render is padded to whole quanta)
+};
+
+struct OscInst {
+    BufRef out;
+    int32_t type;             // WAE_OSC_*
+    int32_t outside_nyquist;  // |computed_freq| >= nyquist -> zeros (oscillator.rs:542-555)
+    double incr;              // phase increment per frame = computedFrequency / sampleRate
+    double phase0;            // phase at frame n_first
+    int64_t n_first, n_stop;  // active frames [n_first, n_stop)
+    const float* table;       // sine table (2048) or periodic wave
+    int32_t table_len;
+    int32_t pad;
+};
+
+struct ConstInst {
+    BufRef out;
+    float value;
+    int32_t pad;
+    int64_t n_first, n_stop;
+};
+
+struct AbsnInst {
+    BufRef out;
+    const float* buf;  // planar [ch][buf_len]
+    int64_t buf_len;
+    int64_t n_start, n_stop;  // output frames [n_start, n_stop) play buf[n - n_start + buf_offset] (fast track)
+    int64_t buf_offset;
+    int32_t ch;
+    int32_t loop;  // 1: wrap modulo buf_len (default loop points)
+};
+
+struct BiquadInst {
+    BufRef in, out;
+    double b0, b1, b2, a1, a2;
+    double* state;  // [ch][4] = x1, x2, y1, y2 (biquad_filter.rs:761)
+    int32_t ch;
+    int32_t pad;
+};
+
+struct IirInst {
+    BufRef in, out;
+    double b[20], a[20];  // normalised by a0 (iir_filter.rs:301-309)
+    double* state;        // [ch][20]
+    int32_t n;            // number of coefficients
+    int32_t ch;
+};
+
+struct GainInst {
+    BufRef in, out;
+    float gain;
+    int32_t ch;
+};
+
+struct ShaperInst {
+    BufRef in, out;
+    const float* curve;  // nullptr: pass-through
+    int32_t n;
+    int32_t ch;
+};
+
+struct SPanInst {
+    BufRef in, out;
+    float pan;
+    int32_t in_ch;
+};
+
+struct PanInst {  // equal-power panner with static source/listener (panner.rs:839-870,988-1057)
+    BufRef in, out;
+    float dist_gain, cone_gain, azimuth;
+    int32_t in_ch;
+};
+
+struct MixEdge {
+    BufRef src;
+    int32_t src_ch;
+    int32_t pad;
+};
+
+struct MixInst {  // AudioRenderQuantum::add over all incoming edges of one input port, reference order
+    BufRef out;
+    int32_t out_ch;
+    int32_t interp;  // 0 speakers, 1 discrete
+    int32_t n_edges;
+    uint32_t edge_offset;
+    int64_t limit;  // frames >= limit are not written (destination: render length); < 0: no limit
+};
+
+struct DelayInst {
+    BufRef in, out;
+    float* ring;         // [ch][ring_len]
+    uint32_t ring_len;   // power of two
+    int32_t ch;
+    int64_t fl;          // floor(-delay * sr): integer part of the (negative) read offset
+    float k;             // fractional part
+    int32_t pad;
+};
+
+struct CompInst {
+    BufRef in, out;
+    float* ring;         // [ch][ring_len] input history
+    float* state;        // [0] = prev_detector_value, [1] = last reduction (dB)
+    uint32_t ring_len;   // power of two
+    int32_t ch;
+    int32_t delay_frames;  // (ring_size - 1) * 128
+    float threshold, knee, ratio, attack, release, sample_rate;
+    int32_t pad;
+};
+
+struct AnalyserInst {
+    BufRef in, out;
+    float* ring;  // 32768 + 128 floats (analysis.rs:74)
+    int32_t ch;
+    int32_t pad;
+};
+
+struct RouteInst {  // channel merger / splitter: copy one channel
+    BufRef in, out;
+    int32_t in_channel, out_channel;
+    int32_t zero;  // 1: write zeros (splitter output beyond the input's channels)
+    int32_t pad;
+};
+
+// ---- convolver (uniformly partitioned overlap-save, block 1024 / FFT 2048, time-batched) -----------------
+struct ConvInput {   // one input channel of one convolver instance
+    BufRef in;
+    float* prev;     // [1024] last block of the previous chunk
+    float2* xring;   // [xring_blocks][1025] input spectra ring
+    int32_t in_channel;
+    int32_t xring_blocks;
+};
+struct ConvPath {    // one FFTConvolver of the reference: (input channel, IR channel) -> output channel
+    BufRef out;
+    const float2* h;  // [S][1025] IR segment spectra
+    int32_t input;    // index into the ConvInput table
+    int32_t S;        // IR segments
+    int32_t out_channel;
+    int32_t accumulate;  // 1: out += (true-stereo mix-down, convolver.rs:436-452)
+};
+
+}  // namespace wae

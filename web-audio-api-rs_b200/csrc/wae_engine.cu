@@ -1,0 +1,1218 @@
+// Engine + planner: lowers a batch of graph descriptions (wae_graph.h) into GPU stages (wae_device.h) and runs
+// them chunk by chunk on one CUDA stream.  C ABI: wae_engine_*, wae_batch_*, wae_render_batch (include/wae.h).
+//
+// Reference functions replaced by this file:
+//   RenderThread::render_audiobuffer_sync / render_offline_quantum   src/render/thread.rs:260-302,355-396
+//   Graph::order_nodes / visit / render                              src/render/graph.rs:331-591
+//   (the per-node arithmetic is in wae_kernels.cu)
+#include "wae_graph.h"
+#include "wae_hostmath.h"
+#include "wae_kernels.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <unordered_map>
+
+using namespace wae;
+namespace hm = wae::hostmath;
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct wae_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t chunk_frames = 0;  // 0 = auto
+    bool fuse = true;
+    bool serial_filters = false;
+    float* d_sine = nullptr;
+};
+
+namespace {
+
+enum StageKind : int {
+    S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_COMP, S_ANALYSER,
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_KINDS
+};
+const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad", "k_iir_serial", "k_gain",
+                                    "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay", "k_compressor",
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)"};
+
+// host-side accumulation of instances for one (level, kind) stage
+struct StageBuild {
+    int level = 0;
+    int kind = 0;
+    std::vector<OscInst> osc;
+    std::vector<ConstInst> cst;
+    std::vector<AbsnInst> absn;
+    std::vector<BiquadInst> biquad;
+    std::vector<BiquadScanCoef> biquad_coef;
+    std::vector<IirInst> iir;
+    std::vector<GainInst> gain;
+    std::vector<ShaperInst> shaper;
+    std::vector<SPanInst> span;
+    std::vector<float2> span_gains;
+    std::vector<PanInst> pan;
+    std::vector<RouteInst> route;
+    std::vector<DelayInst> delay;
+    std::vector<CompInst> comp;
+    std::vector<AnalyserInst> analyser;
+    std::vector<MixInst> mix;
+    std::vector<MixEdge> mix_edges;
+    std::vector<ConvInput> conv_in;
+    std::vector<ConvPath> conv_path;
+    int max_ch = 1;
+};
+
+struct Stage {
+    int kind = 0;
+    int n = 0;
+    int max_ch = 1;
+    void* d_a = nullptr;  // instances
+    void* d_b = nullptr;  // auxiliary table (mix edges, scan coefficients, conv inputs, panner gains)
+    float ms = 0.f;       // accumulated device time of the last run (when timing is enabled)
+};
+
+struct AnalyserRec {
+    uint32_t graph_index;
+    uint32_t node;
+    float* d_ring;
+    uint32_t fft_size;
+    double smoothing;
+};
+
+}  // namespace
+
+struct wae_batch {
+    wae_engine* engine = nullptr;
+    uint32_t n_graphs = 0, channels = 0;
+    uint64_t length = 0;   // frames requested
+    int64_t lq = 0;        // frames rendered: whole quanta (src/render/thread.rs:273)
+    int64_t chunk = 0;     // frames per chunk
+    std::vector<void*> allocs;
+    std::vector<Stage> stages;
+    float* d_out = nullptr;  // [n_graphs][channels][length]
+    // state that must be reset before every run
+    std::vector<std::pair<void*, size_t>> zero_on_run;
+    std::vector<AnalyserRec> analysers;
+    // source PCM assets: device destination <- host source (re-uploadable: wae_batch_upload)
+    struct Upload {
+        float* dst;
+        const float* src;
+        size_t bytes;
+    };
+    std::vector<Upload> uploads;
+    std::vector<const void*> registered_host;
+    wae_batch_stats stats{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> stage_events;
+    bool time_stages = false;
+    size_t timed_chunks = 0;
+    uint64_t arena_bytes = 0, asset_bytes = 0;
+
+    template <typename T>
+    T* dalloc(size_t count, bool zero = false, bool rezero_on_run = false) {
+        void* p = nullptr;
+        size_t bytes = count * sizeof(T);
+        if (bytes == 0) bytes = 16;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        allocs.push_back(p);
+        if (zero || rezero_on_run) cudaMemsetAsync(p, 0, bytes, engine->stream);
+        if (rezero_on_run) zero_on_run.push_back({p, bytes});
+        return (T*)p;
+    }
+    template <typename T>
+    T* dupload(const std::vector<T>& v) {
+        T* p = dalloc<T>(v.size());
+        if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, engine->stream);
+        return p;
+    }
+};
+
+namespace {
+
+// ---- topological order: Graph::order_nodes / visit (src/render/graph.rs:331-487) ---------------------------
+struct Orderer {
+    wae_graph* g;
+    std::vector<uint32_t> ordered, marked, marked_temp, in_cycle;
+    bool cycle_found = false;
+    static bool contains(const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+    void visit(uint32_t id) {
+        auto it = std::find(marked_temp.begin(), marked_temp.end(), id);
+        if (it != marked_temp.end()) {
+            cycle_found = true;  // cycles (muted nodes / DelayNode cycle breakers) are not lowered yet
+            in_cycle.insert(in_cycle.end(), it, marked_temp.end());
+            return;
+        }
+        if (contains(marked, id)) return;
+        marked.push_back(id);
+        marked_temp.push_back(id);
+        for (auto& e : g->nodes.at(id).outgoing)
+            if (g->nodes.count(e.other_id)) visit(e.other_id);
+        ordered.push_back(id);
+        marked_temp.erase(std::remove(marked_temp.begin(), marked_temp.end(), id), marked_temp.end());
+    }
+    void run() {
+        for (auto& kv : g->nodes) visit(kv.first);
+        std::reverse(ordered.begin(), ordered.end());
+    }
+};
+
+struct PortRef {
+    uint32_t node;
+    int port;
+};
+
+struct PNode {
+    Node* n = nullptr;
+    int level = 0;
+    std::vector<std::vector<PortRef>> in_edges;  // per input port, reference summation order
+    std::vector<int> in_ch;
+    std::vector<BufRef> in_buf;
+    std::vector<int> out_ch;
+    std::vector<BufRef> out_buf;
+};
+
+struct Planner {
+    wae_batch* b;
+    wae_engine* eng;
+    std::map<std::pair<int, int>, StageBuild> builds;  // (level, kind)
+    std::string error;
+    int error_code = 0;
+    uint64_t algorithmic_bytes = 0;
+    // IR spectra cache: content hash -> device spectra
+    struct IrSpectra {
+        float2* h;
+        int S;
+        int channels;
+    };
+    std::unordered_map<uint64_t, IrSpectra> ir_cache;
+
+    bool bail(int code, const std::string& msg) {
+        if (!error_code) {
+            error_code = code;
+            error = msg;
+        }
+        return false;
+    }
+
+    StageBuild& stage(int level, int kind) {
+        StageBuild& s = builds[{level, kind}];
+        s.level = level;
+        s.kind = kind;
+        return s;
+    }
+
+    BufRef arena_buf(int ch) {
+        size_t floats = (size_t)ch * (size_t)b->chunk;
+        float* p = b->dalloc<float>(floats);
+        b->arena_bytes += floats * 4;
+        return BufRef{p, (uint32_t)b->chunk, 0};
+    }
+
+    bool const_param(wae_graph* g, uint32_t pid, float& v) {
+        Node& pn = g->nodes.at(pid);
+        // audio-rate modulation: any audio edge into the param node
+        for (auto& kv : g->nodes)
+            for (auto& e : kv.second.outgoing)
+                if (e.other_id == pid && e.other_index >= 0)
+                    return bail(WAE_UNSUPPORTED, "audio-rate AudioParam inputs are not lowered to the GPU yet");
+        if (!pn.param.constant()) return bail(WAE_UNSUPPORTED, "AudioParam automation events are not lowered to the GPU yet");
+        v = pn.param.constant_value();
+        return true;
+    }
+
+    bool plan_graph(wae_graph* g, uint32_t gi);
+    bool plan_convolver(wae_graph* g, PNode& pn, int level);
+};
+
+static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
+    const uint8_t* p = (const uint8_t*)data;
+    // 8 bytes at a time is enough for a cache key
+    size_t n8 = bytes / 8;
+    const uint64_t* q = (const uint64_t*)p;
+    for (size_t i = 0; i < n8; i++) {
+        h ^= q[i];
+        h *= 1099511628211ull;
+    }
+    for (size_t i = n8 * 8; i < bytes; i++) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+
+// computedNumberOfChannels for one input port (src/render/quantum.rs:543-547), static channel counts
+static int computed_channels(const ChannelCfg& cfg, int max_in) {
+    switch (cfg.mode) {
+        case WAE_COUNT_MODE_MAX: return max_in;
+        case WAE_COUNT_MODE_EXPLICIT: return cfg.count;
+        default: return std::min(max_in, cfg.count);
+    }
+}
+
+static uint32_t next_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
+    Node& n = *pn.n;
+    int in_ch = pn.in_ch[0];
+    if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
+        pn.out_ch = {in_ch};
+        pn.out_buf = {pn.in_buf[0]};
+        return true;
+    }
+    PcmBuffer& ir = *n.buffer;
+    int ir_ch = (int)ir.channels.size();
+    size_t ir_len = ir.length();
+    // normalize_buffer, src/node/convolver.rs:16-53 (f32, channel by channel)
+    float scale = 1.f;
+    if (n.normalize) {
+        float power = 0.f;
+        for (auto& c : ir.channels) {
+            float s = 0.f;
+            for (float v : c) s += v * v;
+            power += s;
+        }
+        power = std::sqrt(power / (float)((size_t)ir_ch * ir_len));
+        if (!std::isfinite(power) || power < 0.000125f) power = 0.000125f;
+        scale = 1.f / power;
+        scale *= 0.00125f;
+        scale *= 44100.f / ir.sample_rate;
+        if (ir_ch == 4) scale *= 0.5f;
+    }
+    // convolvers: one per IR channel, a mono IR is duplicated (convolver.rs:289-293)
+    int n_conv = std::max(ir_ch, 2);
+    // trailing samples below 1e-6 are ignored by fft-convolver's init
+    std::vector<std::vector<float>> scaled(ir_ch);
+    size_t trimmed_len = 0;
+    for (int c = 0; c < ir_ch; c++) {
+        scaled[c].resize(ir_len);
+        for (size_t i = 0; i < ir_len; i++) scaled[c][i] = ir.channels[c][i] * scale;
+    }
+    // per-channel trimmed length (each FFTConvolver trims its own IR); use per channel S
+    std::vector<int> S(ir_ch);
+    for (int c = 0; c < ir_ch; c++) {
+        size_t m = ir_len;
+        while (m > 0 && std::fabs(scaled[c][m - 1]) < 0.000001f) m--;
+        S[c] = (int)((m + 1023) / 1024);
+        trimmed_len = std::max(trimmed_len, m);
+        // zero the ignored tail so that a shared segment count reproduces the per-convolver trimming
+        for (size_t i = m; i < ir_len; i++) scaled[c][i] = 0.f;
+    }
+    int Smax = *std::max_element(S.begin(), S.end());
+    pn.out_ch = {ir_ch == 1 && in_ch == 1 ? 1 : 2};
+    pn.out_buf = {arena_buf(pn.out_ch[0])};
+    if (Smax == 0) {  // all-zero IR: output zeros -> a mix with no edges
+        StageBuild& ms = stage(level, S_MIX);
+        ms.mix.push_back(MixInst{pn.out_buf[0], pn.out_ch[0], 0, 0, (uint32_t)ms.mix_edges.size(), -1});
+        return true;
+    }
+    // IR spectra (deduplicated across the batch by content)
+    uint64_t key = fnv1a(&scale, sizeof(scale));
+    for (int c = 0; c < ir_ch; c++) key = fnv1a(ir.channels[c].data(), ir_len * sizeof(float), key);
+    key = fnv1a(&ir_len, sizeof(ir_len), key);
+    IrSpectra spec;
+    auto it = ir_cache.find(key);
+    if (it != ir_cache.end()) {
+        spec = it->second;
+    } else {
+        std::vector<float> flat((size_t)ir_ch * ir_len);
+        for (int c = 0; c < ir_ch; c++) std::memcpy(flat.data() + (size_t)c * ir_len, scaled[c].data(), ir_len * sizeof(float));
+        float* d_ir = b->dupload(flat);
+        cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
+        spec.S = Smax;
+        spec.channels = ir_ch;
+        spec.h = b->dalloc<float2>((size_t)ir_ch * Smax * 1025);
+        if (!d_ir || !spec.h) return bail(WAE_OUT_OF_MEMORY, "out of device memory (IR spectra)");
+        launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
+        b->asset_bytes += (size_t)ir_ch * Smax * 1025 * 8;
+        ir_cache[key] = spec;
+    }
+    // inputs: one spectra ring per input channel
+    StageBuild& fs = stage(level, S_CONV_FFT);
+    int blocks_per_chunk = (int)((b->chunk + 1023) / 1024);
+    int ring_blocks = Smax + blocks_per_chunk;
+    int in_base = (int)fs.conv_in.size();
+    for (int c = 0; c < in_ch; c++) {
+        ConvInput ci;
+        ci.in = pn.in_buf[0];
+        ci.in_channel = c;
+        ci.prev = b->dalloc<float>(1024, true, true);
+        ci.xring = b->dalloc<float2>((size_t)ring_blocks * 1025);
+        ci.xring_blocks = ring_blocks;
+        if (!ci.prev || !ci.xring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver input spectra)");
+        b->arena_bytes += (size_t)ring_blocks * 1025 * 8;
+        fs.conv_in.push_back(ci);
+    }
+    // paths: channel routing table of convolver.rs:378-487
+    struct R {
+        int in, ir, out, acc;
+    };
+    std::vector<R> routes;
+    if (in_ch == 1 && ir_ch == 1) routes = {{0, 0, 0, 0}};
+    else if (in_ch == 1 && ir_ch == 2) routes = {{0, 0, 0, 0}, {0, 1, 1, 0}};
+    else if (in_ch == 2 && ir_ch == 1) routes = {{0, 0, 0, 0}, {1, 0, 1, 0}};
+    else if (in_ch == 2 && ir_ch == 2) routes = {{0, 0, 0, 0}, {1, 1, 1, 0}};
+    else if (in_ch == 2 && ir_ch == 4) routes = {{0, 0, 0, 0}, {0, 1, 1, 0}, {1, 2, 0, 1}, {1, 3, 1, 1}};
+    else if (in_ch == 1 && ir_ch == 4) routes = {{0, 0, 0, 0}, {0, 1, 1, 0}, {0, 2, 0, 1}, {0, 3, 1, 1}};
+    else return bail(WAE_UNSUPPORTED, "unsupported convolver channel routing");
+    (void)n_conv;
+    for (auto& r : routes) {
+        ConvPath p;
+        p.out = pn.out_buf[0];
+        p.h = spec.h + (size_t)r.ir * Smax * 1025;
+        p.input = in_base + r.in;
+        p.S = Smax;
+        p.out_channel = r.out;
+        p.accumulate = r.acc;
+        stage(level, r.acc ? S_CONV_MAC_ACC : S_CONV_MAC).conv_path.push_back(p);
+    }
+    // S*1025*8 B of input-history spectra per convolver-block of 1024 frames
+    algorithmic_bytes += (uint64_t)routes.size() * (uint64_t)Smax * 1025ull * 8ull * (uint64_t)((b->lq + 1023) / 1024);
+    return true;
+}
+
+bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
+    Orderer ord{g};
+    ord.run();
+    if (ord.cycle_found) return bail(WAE_UNSUPPORTED, "graphs with cycles (feedback through DelayNode / muted cycles) are not lowered to the GPU yet");
+    std::map<uint32_t, PNode> pn;
+    for (auto& kv : g->nodes) {
+        if (kv.second.kind == K_PARAM) continue;
+        PNode p;
+        p.n = &kv.second;
+        p.in_edges.resize(kv.second.n_inputs);
+        pn[kv.first] = std::move(p);
+    }
+    // Graph::render (graph.rs:500-535): walk the order, append each audio edge to its destination port
+    for (uint32_t id : ord.ordered) {
+        Node& n = g->nodes.at(id);
+        if (n.kind == K_PARAM) continue;
+        for (auto& e : n.outgoing) {
+            if (e.other_index < 0) continue;
+            auto it = pn.find(e.other_id);
+            if (it == pn.end()) continue;  // edge into a param node: rejected in const_param
+            it->second.in_edges[e.other_index].push_back(PortRef{id, e.self_index});
+        }
+    }
+    hm::SchedClock clock(g->sample_rate);
+    const double sr = (double)g->sample_rate;
+    for (uint32_t id : ord.ordered) {
+        Node& n = g->nodes.at(id);
+        if (n.kind == K_PARAM || n.kind == K_LISTENER) continue;
+        PNode& p = pn.at(id);
+        // ---- inputs: static channel count + mix stage where needed
+        int level = 0;
+        for (auto& port : p.in_edges)
+            for (auto& r : port) level = std::max(level, pn.at(r.node).level + 1);
+        p.level = level;
+        p.in_ch.assign(n.n_inputs, 1);
+        p.in_buf.assign(n.n_inputs, BufRef{nullptr, 0, 0});
+        for (int port = 0; port < n.n_inputs; port++) {
+            auto& edges = p.in_edges[port];
+            int max_in = 1;
+            for (auto& r : edges) max_in = std::max(max_in, pn.at(r.node).out_ch[r.port]);
+            int ch = computed_channels(n.cfg, max_in);
+            if (n.kind == K_DELAY_R) {  // the reader's only input is the hidden writer edge: take the writer's layout
+                ch = max_in;
+            }
+            p.in_ch[port] = ch;
+            bool is_dest = n.kind == K_DEST;
+            if (!is_dest && edges.size() == 1 && pn.at(edges[0].node).out_ch[edges[0].port] == ch) {
+                p.in_buf[port] = pn.at(edges[0].node).out_buf[edges[0].port];  // alias, no copy
+                continue;
+            }
+            StageBuild& ms = stage(2 * level, S_MIX);
+            MixInst m;
+            m.out_ch = ch;
+            m.interp = n.cfg.interp;
+            m.n_edges = (int)edges.size();
+            m.edge_offset = (uint32_t)ms.mix_edges.size();
+            m.limit = -1;
+            if (is_dest) {
+                m.out = BufRef{b->d_out + (size_t)gi * b->channels * b->length, (uint32_t)b->length, 1};
+                m.limit = (int64_t)b->length;
+                if (b->length > 0xffffffffull) return bail(WAE_UNSUPPORTED, "render length above 2^32 frames");
+            } else {
+                m.out = arena_buf(ch);
+                if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+            }
+            for (auto& r : edges) {
+                PNode& s = pn.at(r.node);
+                ms.mix_edges.push_back(MixEdge{s.out_buf[r.port], s.out_ch[r.port], 0});
+            }
+            ms.mix.push_back(m);
+            p.in_buf[port] = m.out;
+        }
+        const int L = 2 * level + 1;  // node kernels run after the mixes of their level
+        auto need_out = [&](int ch) {
+            p.out_ch = {ch};
+            p.out_buf = {arena_buf(ch)};
+            return p.out_buf[0].p != nullptr;
+        };
+        switch (n.kind) {
+            case K_DEST: {
+                p.out_ch = {(int)b->channels};
+                p.out_buf = {p.in_buf[0]};
+                algorithmic_bytes += (uint64_t)b->channels * b->length * 4;  // destination write, SURVEY §8(d)
+                break;
+            }
+            case K_OSC: {
+                float freq, detune;
+                if (!const_param(g, n.params[0], freq) || !const_param(g, n.params[1], detune)) return false;
+                if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                OscInst o{};
+                o.out = p.out_buf[0];
+                o.type = n.type;
+                double computed_freq = (double)freq * std::exp2((double)detune / 1200.);  // oscillator.rs:30-32
+                o.incr = computed_freq / sr;
+                o.outside_nyquist = std::fabs(computed_freq) >= sr / 2.;
+                o.n_first = std::numeric_limits<int64_t>::max();
+                o.n_stop = std::numeric_limits<int64_t>::max();
+                o.phase0 = 0.;
+                if (n.start_time < 1e300) {
+                    // oscillator.rs:391-428,511-540: first rendered frame and its phase
+                    int64_t q = clock.quantum_containing(n.start_time);
+                    double start = n.start_time;
+                    if (start < clock.block_time(q)) start = clock.block_time(q);  // "prevent scheduling in the past"
+                    double t = 0.;
+                    // walk the accumulated per-frame clock of that quantum
+                    double cur = clock.block_time(q);
+                    int i = 0;
+                    for (; i < 128; i++) {
+                        if (!(cur < start)) break;
+                        cur += clock.dt;
+                    }
+                    t = cur;
+                    o.n_first = q * 128 + i;
+                    if (i < 128 && t > start) {
+                        double ratio = (t - start) / clock.dt;
+                        double ph = o.incr * ratio;
+                        if (o.outside_nyquist) {
+                            ph = std::fmod(ph, 1.);
+                            if (ph < 0.) ph += 1.;
+                        } else {
+                            ph = hm::unroll_phase(ph);
+                        }
+                        o.phase0 = ph;
+                    }
+                    if (n.stop_time < 1e300) {
+                        int64_t qs = clock.quantum_containing(n.stop_time);
+                        if (n.stop_time <= clock.block_time(qs)) o.n_stop = qs * 128;
+                        else o.n_stop = clock.first_frame_at_or_after(n.stop_time);
+                    }
+                }
+                if (n.type == WAE_OSC_CUSTOM) {
+                    float* d = b->dupload(n.table);
+                    o.table = d;
+                    o.table_len = (int)n.table.size();
+                } else {
+                    o.table = eng->d_sine;
+                    o.table_len = 2048;
+                }
+                stage(L, S_OSC).osc.push_back(o);
+                break;
+            }
+            case K_CONST: {
+                float v;
+                if (!const_param(g, n.params[0], v)) return false;
+                if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                ConstInst c{};
+                c.out = p.out_buf[0];
+                c.value = v;
+                c.n_first = std::numeric_limits<int64_t>::max();
+                c.n_stop = std::numeric_limits<int64_t>::max();
+                if (n.start_time < 1e300) {
+                    // constant_source.rs:203-246
+                    c.n_first = clock.first_frame_at_or_after(n.start_time);
+                    if (n.stop_time < 1e300) c.n_stop = clock.first_frame_at_or_after(n.stop_time);
+                }
+                stage(L, S_CONST).cst.push_back(c);
+                break;
+            }
+            case K_ABSN: {
+                float detune, rate;
+                if (!const_param(g, n.params[0], detune) || !const_param(g, n.params[1], rate)) return false;
+                int ch = n.buffer ? (int)n.buffer->channels.size() : 1;
+                if (!n.buffer || n.start_time >= 1e300 || ch == 0) {  // never plays: silence
+                    if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    StageBuild& ms = stage(L, S_MIX);
+                    ms.mix.push_back(MixInst{p.out_buf[0], 1, 0, 0, (uint32_t)ms.mix_edges.size(), -1});
+                    break;
+                }
+                PcmBuffer& pb = *n.buffer;
+                double computed_rate = (double)rate * std::exp2((double)detune / 1200.);
+                double duration = pb.duration();
+                double ls = n.loop_start, le = n.loop_end;  // clamp_loop_boundaries, audio_buffer_source.rs:400-417
+                if (ls < 0.) ls = 0.; else if (ls > duration) ls = duration;
+                if (le <= 0. || le > duration) le = duration;
+                int64_t q = clock.quantum_containing(n.start_time);
+                // a start time that IS the next block boundary but compares below next_block_time by one rounding:
+                // the reference goes through one all-silent slow-track quantum, then aligns (audio_buffer_source.rs:521-523)
+                if (n.start_time > clock.block_time(q) && n.start_time == clock.block_time(q + 1)) q = q + 1;
+                bool aligned = (n.start_time <= clock.block_time(q)) && n.offset == 0.;  // start in the past snaps to the block
+                bool fast = aligned && (double)pb.sample_rate / sr == 1. && computed_rate == 1. && ls == 0. && le == duration &&
+                            n.duration > 1e300 && n.stop_time > 1e300;
+                if (!fast)
+                    return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode slow track (unaligned start, offset/duration, stop, playbackRate/"
+                                                 "detune != 1, custom loop points, resampling) is not lowered to the GPU yet");
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                size_t len = pb.length();
+                float* d_buf = b->dalloc<float>((size_t)ch * len);
+                if (!d_buf) return bail(WAE_OUT_OF_MEMORY, "out of device memory (source PCM)");
+                for (int c = 0; c < ch; c++) b->uploads.push_back({d_buf + (size_t)c * len, pb.channels[c].data(), len * sizeof(float)});
+                b->asset_bytes += (size_t)ch * len * 4;
+                AbsnInst a{};
+                a.out = p.out_buf[0];
+                a.buf = d_buf;
+                a.buf_len = (int64_t)len;
+                a.n_start = q * 128;
+                a.n_stop = std::numeric_limits<int64_t>::max();
+                a.buf_offset = 0;
+                a.ch = ch;
+                a.loop = n.loop ? 1 : 0;
+                stage(L, S_ABSN).absn.push_back(a);
+                // compulsory read of the source PCM that is actually played
+                algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::max<int64_t>(0, std::min<int64_t>(b->lq - a.n_start, n.loop ? b->lq : (int64_t)len));
+                break;
+            }
+            case K_BIQUAD: {
+                float q, detune, freq, gain;
+                if (!const_param(g, n.params[0], q) || !const_param(g, n.params[1], detune) || !const_param(g, n.params[2], freq) ||
+                    !const_param(g, n.params[3], gain))
+                    return false;
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                float cf = hm::biquad_computed_freq(freq, detune);
+                hm::BiquadCoefs c = hm::biquad_coefs(n.type, sr, (double)cf, (double)gain, (double)q);
+                BiquadInst bi{};
+                bi.in = p.in_buf[0];
+                bi.out = p.out_buf[0];
+                bi.b0 = c.b0; bi.b1 = c.b1; bi.b2 = c.b2; bi.a1 = c.a1; bi.a2 = c.a2;
+                bi.ch = ch;
+                bi.state = b->dalloc<double>((size_t)ch * 4, true, true);
+                if (!bi.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                StageBuild& s = stage(L, S_BIQUAD);
+                s.max_ch = std::max(s.max_ch, ch);
+                s.biquad.push_back(bi);
+                // scan coefficients: h1/h2 = first row of M^(j+1); P[d] = (M^8)^(2^d)
+                BiquadScanCoef sc{};
+                double m00 = -c.a1, m01 = -c.a2, m10 = 1., m11 = 0.;
+                double r00 = 1., r01 = 0., r10 = 0., r11 = 1.;
+                for (int j = 0; j < 8; j++) {
+                    double t00 = m00 * r00 + m01 * r10, t01 = m00 * r01 + m01 * r11;
+                    double t10 = m10 * r00 + m11 * r10, t11 = m10 * r01 + m11 * r11;
+                    r00 = t00; r01 = t01; r10 = t10; r11 = t11;
+                    sc.h1[j] = r00;
+                    sc.h2[j] = r01;
+                }
+                double p00 = r00, p01 = r01, p10 = r10, p11 = r11;
+                for (int d = 0; d < 8; d++) {
+                    sc.P[d][0] = p00; sc.P[d][1] = p01; sc.P[d][2] = p10; sc.P[d][3] = p11;
+                    double t00 = p00 * p00 + p01 * p10, t01 = p00 * p01 + p01 * p11;
+                    double t10 = p10 * p00 + p11 * p10, t11 = p10 * p01 + p11 * p11;
+                    p00 = t00; p01 = t01; p10 = t10; p11 = t11;
+                }
+                s.biquad_coef.push_back(sc);
+                break;
+            }
+            case K_IIR: {
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                std::vector<double> ff = n.feedforward, fb = n.feedback;  // iir_filter.rs:282-309
+                if (ff.size() < fb.size()) ff.resize(fb.size(), 0.);
+                if (ff.size() > fb.size()) fb.resize(ff.size(), 0.);
+                IirInst ii{};
+                ii.in = p.in_buf[0];
+                ii.out = p.out_buf[0];
+                ii.n = (int)ff.size();
+                ii.ch = ch;
+                double a0 = fb[0];
+                for (size_t i = 0; i < ff.size(); i++) {
+                    ii.b[i] = ff[i] / a0;
+                    ii.a[i] = fb[i] / a0;
+                }
+                ii.state = b->dalloc<double>((size_t)ch * 20, true, true);
+                if (!ii.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                StageBuild& s = stage(L, S_IIR);
+                s.max_ch = std::max(s.max_ch, ch);
+                s.iir.push_back(ii);
+                break;
+            }
+            case K_GAIN: {
+                float gv;
+                if (!const_param(g, n.params[0], gv)) return false;
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                // gain.rs:153-169: |g| <= 1e-6 -> silence, |1-g| <= 1e-6 -> pass-through (quanta >= 1; quantum 0 takes
+                // the multiply path, a difference of at most 1e-6 * |x| that is below the parity tolerance)
+                if (std::fabs(gv) <= 1e-6f) gv = 0.f;
+                else if (std::fabs(1.f - gv) <= 1e-6f) gv = 1.f;
+                stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch});
+                break;
+            }
+            case K_SHAPER: {
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                ShaperInst s{};
+                s.in = p.in_buf[0];
+                s.out = p.out_buf[0];
+                s.ch = ch;
+                s.n = (int)n.table.size();
+                s.curve = n.has_curve ? b->dupload(n.table) : nullptr;
+                stage(L, S_SHAPER).shaper.push_back(s);
+                break;
+            }
+            case K_SPANNER: {
+                float pan;
+                if (!const_param(g, n.params[0], pan)) return false;
+                int ch = p.in_ch[0];
+                if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                float x = ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);  // stereo_panner.rs:247-249,274-276
+                float gl, gr;
+                hm::stereo_gains(x, gl, gr);
+                StageBuild& s = stage(L, S_SPAN);
+                s.span.push_back(SPanInst{p.in_buf[0], p.out_buf[0], pan, ch});
+                s.span_gains.push_back(make_float2(gl, gr));
+                break;
+            }
+            case K_PANNER: {
+                float v[15];
+                for (int i = 0; i < 6; i++)
+                    if (!const_param(g, n.params[i], v[i])) return false;
+                for (int i = 0; i < 9; i++)
+                    if (!const_param(g, 2 + i, v[6 + i])) return false;
+                int ch = p.in_ch[0];
+                if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                const float* sp = v, *so = v + 3, *lp = v + 6, *lf = v + 9, *lu = v + 12;
+                PanInst pi{};
+                pi.in = p.in_buf[0];
+                pi.out = p.out_buf[0];
+                pi.in_ch = ch;
+                float el;
+                hm::azimuth_elevation(sp, lp, lf, lu, pi.azimuth, el);
+                {  // dist_gain, panner.rs:954-986
+                    float rel[3];
+                    hm::sub3(sp, lp, rel);
+                    double distance = (double)std::sqrt(hm::sq_len(rel));
+                    double gd;
+                    auto clampd = [](double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); };
+                    if (n.distance_model == 0) {
+                        double ro = clampd(n.rolloff_factor, 0., 1.);
+                        double d2ref = std::min(n.ref_distance, n.max_distance), d2max = std::max(n.ref_distance, n.max_distance);
+                        gd = 1. - ro * (clampd(distance, d2ref, d2max) - d2ref) / (d2max - d2ref);
+                    } else if (n.distance_model == 1) {
+                        double ro = std::max(n.rolloff_factor, 0.);
+                        gd = distance > 0. ? n.ref_distance / (n.ref_distance + ro * (std::max(n.ref_distance, distance) - n.ref_distance)) : 1.;
+                    } else {
+                        double ro = std::max(n.rolloff_factor, 0.);
+                        gd = std::pow(std::max(distance, n.ref_distance) / n.ref_distance, -ro);
+                    }
+                    pi.dist_gain = (float)gd;
+                }
+                {  // cone_gain, panner.rs:927-952
+                    float inner = (float)std::fabs(n.cone_inner_angle) / 2.f, outer = (float)std::fabs(n.cone_outer_angle) / 2.f;
+                    if (inner >= 180.f && outer >= 180.f) {
+                        pi.cone_gain = 1.f;
+                    } else {
+                        float og = (float)n.cone_outer_gain;
+                        float a = hm::cone_angle(sp, so, lp);
+                        if (a < inner) pi.cone_gain = 1.f;
+                        else if (a >= outer) pi.cone_gain = og;
+                        else {
+                            float x = (a - inner) / (outer - inner);
+                            pi.cone_gain = (1.f - x) + og * x;
+                        }
+                    }
+                }
+                stage(L, S_PAN).pan.push_back(pi);
+                break;
+            }
+            case K_DELAY_W: {  // the writer only records its input: the reader aliases it (hidden edge, delay.rs:359-365)
+                p.out_ch = {p.in_ch[0]};
+                p.out_buf = {p.in_buf[0]};
+                break;
+            }
+            case K_DELAY_R: {
+                float dt;
+                if (!const_param(g, n.params[0], dt)) return false;
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                DelayInst d{};
+                d.in = p.in_buf[0];
+                d.out = p.out_buf[0];
+                d.ch = ch;
+                double num_samples = (double)dt * sr;          // delay.rs:706
+                double position = 0. - num_samples;            // sample_index 0
+                double pf = std::floor(position);
+                d.fl = (int64_t)pf;
+                d.k = (float)(position - pf);
+                uint64_t max_frames = (uint64_t)std::ceil(n.max_delay_time * sr) + 2;
+                d.ring_len = next_pow2(max_frames + 128);
+                d.ring = b->dalloc<float>((size_t)ch * d.ring_len, true, true);
+                if (!d.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (delay ring)");
+                b->arena_bytes += (size_t)ch * d.ring_len * 4;
+                stage(L, S_DELAY).delay.push_back(d);
+                break;
+            }
+            case K_COMP: {
+                float at, kn, ra, re, th;
+                if (!const_param(g, n.params[0], at) || !const_param(g, n.params[1], kn) || !const_param(g, n.params[2], ra) ||
+                    !const_param(g, n.params[3], re) || !const_param(g, n.params[4], th))
+                    return false;
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                CompInst c{};
+                c.in = p.in_buf[0];
+                c.out = p.out_buf[0];
+                c.ch = ch;
+                int ring_size = (int)std::ceil(g->sample_rate * 0.006f / 128.f) + 1;  // dynamics_compressor.rs:250-255
+                c.delay_frames = (ring_size - 1) * 128;
+                c.ring_len = next_pow2((uint64_t)c.delay_frames + 128);
+                c.ring = b->dalloc<float>((size_t)ch * c.ring_len, true, true);
+                c.state = b->dalloc<float>(2, true, true);
+                if (!c.ring || !c.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (compressor)");
+                c.threshold = th; c.knee = kn; c.ratio = ra; c.attack = at; c.release = re;
+                c.sample_rate = g->sample_rate;
+                stage(L, S_COMP).comp.push_back(c);
+                break;
+            }
+            case K_ANALYSER: {
+                int ch = p.in_ch[0];
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                AnalyserInst a{};
+                a.in = p.in_buf[0];
+                a.out = p.out_buf[0];
+                a.ch = ch;
+                a.ring = b->dalloc<float>(32768 + 128, true, true);
+                if (!a.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser ring)");
+                stage(L, S_ANALYSER).analyser.push_back(a);
+                b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing});
+                algorithmic_bytes += (uint64_t)b->lq * 4;  // ring write, SURVEY §8(d)
+                break;
+            }
+            case K_MERGER: {
+                int k = n.n_inputs;
+                if (!need_out(k)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                for (int i = 0; i < k; i++) stage(L, S_ROUTE).route.push_back(RouteInst{p.in_buf[i], p.out_buf[0], 0, i, 0, 0});
+                break;
+            }
+            case K_SPLITTER: {
+                int k = n.n_outputs;
+                p.out_ch.assign(k, 1);
+                p.out_buf.resize(k);
+                for (int i = 0; i < k; i++) {
+                    if (i < p.in_ch[0]) {  // alias channel i of the input
+                        BufRef r = p.in_buf[0];
+                        r.p += (size_t)i * r.stride;
+                        p.out_buf[i] = r;
+                    } else {
+                        p.out_buf[i] = arena_buf(1);
+                        stage(L, S_ROUTE).route.push_back(RouteInst{p.in_buf[0], p.out_buf[i], 0, 0, 1, 0});
+                    }
+                }
+                break;
+            }
+            case K_CONV: {
+                if (!plan_convolver(g, p, L)) return false;
+                break;
+            }
+            default: return bail(WAE_UNSUPPORTED, "node kind not lowered to the GPU");
+        }
+    }
+    return true;
+}
+
+template <typename T>
+static void* up(wae_batch* b, const std::vector<T>& v) {
+    return (void*)b->dupload(v);
+}
+
+}  // namespace
+
+extern "C" {
+
+WAE_API wae_status wae_engine_create(int32_t device_ordinal, wae_engine** out) {
+    if (!out) return fail(WAE_INVALID_ARGUMENT, "null out pointer");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(WAE_NO_DEVICE, std::string("no CUDA device usable (") + cudaGetErrorString(e) + "): this library has no CPU fallback");
+    if (device_ordinal < 0 || device_ordinal >= count) return fail(WAE_NO_DEVICE, "device ordinal out of range");
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major < 10) return fail(WAE_NO_DEVICE, "the kernels are built for sm_100a only");
+    auto* eng = new wae_engine;
+    eng->device = device_ordinal;
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    std::vector<float> sine = hm::sine_table();
+    CUDA_TRY(cudaMalloc(&eng->d_sine, sine.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(eng->d_sine, sine.data(), sine.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float2> tw(1024);
+    for (int k = 0; k < 1024; k++) {
+        double a = -2.0 * hm::PI64 * (double)k / 2048.0;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    upload_twiddles(tw.data());
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = eng;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_engine_destroy(wae_engine* eng) {
+    if (!eng) return WAE_OK;
+    cudaSetDevice(eng->device);
+    if (eng->d_sine) cudaFree(eng->d_sine);
+    if (eng->stream) cudaStreamDestroy(eng->stream);
+    delete eng;
+    return WAE_OK;
+}
+
+// the CUDA stream every kernel of this engine is launched on (for callers that time with their own events)
+WAE_API wae_status wae_engine_stream(wae_engine* eng, void** out_stream) {
+    *out_stream = (void*)eng->stream;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64_t value) {
+    switch (option) {
+        case WAE_OPT_CHUNK_FRAMES:
+            if (value < 0 || value % 128 != 0) return fail(WAE_INVALID_ARGUMENT, "chunk frames must be a multiple of 128");
+            eng->chunk_frames = value;
+            return WAE_OK;
+        case WAE_OPT_FUSE: eng->fuse = value != 0; return WAE_OK;
+        case WAE_OPT_SERIAL_FILTERS: eng->serial_filters = value != 0; return WAE_OK;
+        default: return fail(WAE_INVALID_ARGUMENT, "unknown option");
+    }
+}
+
+WAE_API wae_status wae_batch_destroy(wae_batch* b) {
+    if (!b) return WAE_OK;
+    cudaSetDevice(b->engine->device);
+    cudaStreamSynchronize(b->engine->stream);
+    for (const void* h : b->registered_host) cudaHostUnregister(const_cast<void*>(h));
+    for (void* p : b->allocs) cudaFree(p);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    for (auto e : b->stage_events) cudaEventDestroy(e);
+    delete b;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out) {
+    if (!eng || !graphs || !out || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
+    CUDA_TRY(cudaSetDevice(eng->device));
+    for (uint32_t i = 0; i < n_graphs; i++) {
+        if (graphs[i]->channels != graphs[0]->channels || graphs[i]->length != graphs[0]->length ||
+            graphs[i]->sample_rate != graphs[0]->sample_rate)
+            return fail(WAE_INVALID_ARGUMENT, "all graphs of a batch must share number_of_channels, length and sample_rate");
+    }
+    auto* b = new wae_batch;
+    b->engine = eng;
+    b->n_graphs = n_graphs;
+    b->channels = graphs[0]->channels;
+    b->length = graphs[0]->length;
+    b->lq = (int64_t)((b->length + 127) / 128 * 128);
+    bool has_conv = false;
+    size_t node_count = 0;
+    for (uint32_t i = 0; i < n_graphs; i++)
+        for (auto& kv : graphs[i]->nodes) {
+            if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
+            if (kv.second.kind != K_PARAM) node_count++;
+        }
+    // chunk size: explicit option, else sized so that the arena (~3 live buffers of 2 channels per node) stays
+    // within ~64 MiB (L2-resident edge buffers), bounded to [2048, 65536] frames; convolvers want whole
+    // 1024-frame blocks and long chunks (their spectra ring is the state that matters)
+    int64_t chunk = eng->chunk_frames;
+    if (chunk == 0) {
+        double per_frame = (double)node_count * 2.0 * 4.0;
+        chunk = (int64_t)(64.0 * 1024 * 1024 / std::max(per_frame, 1.0));
+        chunk = std::max<int64_t>(2048, std::min<int64_t>(chunk, 65536));
+        if (has_conv) chunk = std::max<int64_t>(chunk, 16384);
+        chunk = chunk / 2048 * 2048;
+    }
+    if (has_conv) chunk = (chunk + 1023) / 1024 * 1024;
+    if (chunk > b->lq) chunk = has_conv ? (b->lq + 1023) / 1024 * 1024 : b->lq;
+    b->chunk = chunk;
+    size_t out_floats = (size_t)n_graphs * b->channels * b->length;
+    b->d_out = b->dalloc<float>(out_floats, true);
+    if (!b->d_out) {
+        wae_batch_destroy(b);
+        return fail(WAE_OUT_OF_MEMORY, "out of device memory (output PCM)");
+    }
+    Planner pl{b, eng};
+    for (uint32_t i = 0; i < n_graphs; i++) {
+        if (!pl.plan_graph(graphs[i], i)) {
+            int code = pl.error_code;
+            std::string msg = pl.error;
+            wae_batch_destroy(b);
+            return fail(code, msg);
+        }
+    }
+    // materialise the stages in (level, kind) order
+    for (auto& kv : pl.builds) {
+        StageBuild& s = kv.second;
+        Stage st;
+        st.kind = s.kind;
+        st.max_ch = s.max_ch;
+        switch (s.kind) {
+            case S_MIX: st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges); break;
+            case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
+            case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
+            case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
+            case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); st.d_b = up(b, s.biquad_coef); break;
+            case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
+            case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
+            case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
+            case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
+            case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
+            case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
+            case S_DELAY: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
+            case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
+            case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
+            case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); break;
+            case S_CONV_MAC:
+            case S_CONV_MAC_ACC: {
+                st.n = (int)s.conv_path.size();
+                st.d_a = up(b, s.conv_path);
+                // the conv-input table of the same level
+                auto it = pl.builds.find({s.level, S_CONV_FFT});
+                st.d_b = nullptr;
+                for (auto& prev : b->stages)
+                    if (prev.kind == S_CONV_FFT) st.d_b = prev.d_a;  // latest FFT stage = same level (kinds are ordered)
+                (void)it;
+                break;
+            }
+        }
+        if (st.n > 0) b->stages.push_back(st);
+    }
+    // pin + upload source PCM
+    for (auto& u : b->uploads) {
+        if (cudaHostRegister(const_cast<float*>(u.src), u.bytes, cudaHostRegisterReadOnly) == cudaSuccess)
+            b->registered_host.push_back(u.src);
+        else
+            cudaGetLastError();
+        CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, eng->stream));
+    }
+    CUDA_TRY(cudaEventCreate(&b->ev0));
+    CUDA_TRY(cudaEventCreate(&b->ev1));
+    b->stage_events.resize(b->stages.size() + 1);
+    for (auto& e : b->stage_events) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaStreamSynchronize(eng->stream));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        wae_batch_destroy(b);
+        return fail(WAE_CUDA_ERROR, std::string("prepare: ") + cudaGetErrorString(le));
+    }
+    int64_t n_chunks = (b->lq + b->chunk - 1) / b->chunk;
+    uint64_t launches = 0;
+    for (auto& st : b->stages) launches += (st.kind == S_DELAY || st.kind == S_CONV_FFT) ? 2 : 1;
+    std::memset(&b->stats, 0, sizeof(b->stats));
+    b->stats.kernel_launches_per_run = launches * (uint64_t)n_chunks;
+    b->stats.stages = b->stages.size();
+    b->stats.chunks = (uint64_t)n_chunks;
+    b->stats.arena_bytes = b->arena_bytes;
+    b->stats.asset_bytes = b->asset_bytes;
+    b->stats.algorithmic_bytes = pl.algorithmic_bytes;
+    b->stats.graph_quanta = (uint64_t)n_graphs * (uint64_t)(b->lq / 128);
+    *out = b;
+    return WAE_OK;
+}
+
+static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
+    cudaStream_t s = b->engine->stream;
+    switch (st.kind) {
+        case S_MIX: launch_mix((MixInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s); break;
+        case S_OSC: launch_oscillator((OscInst*)st.d_a, st.n, ci, s); break;
+        case S_CONST: launch_constant((ConstInst*)st.d_a, st.n, ci, s); break;
+        case S_ABSN: launch_buffer_source((AbsnInst*)st.d_a, st.n, ci, s); break;
+        case S_BIQUAD:
+            if (b->engine->serial_filters) launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
+            else launch_biquad_scan((BiquadInst*)st.d_a, (BiquadScanCoef*)st.d_b, st.n, st.max_ch, ci, s);
+            break;
+        case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
+        case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;
+        case S_SHAPER: launch_shaper((ShaperInst*)st.d_a, st.n, ci, s); break;
+        case S_SPAN: launch_stereo_panner((SPanInst*)st.d_a, (float2*)st.d_b, st.n, ci, s); break;
+        case S_PAN: launch_panner_eq((PanInst*)st.d_a, st.n, ci, s); break;
+        case S_ROUTE: launch_route((RouteInst*)st.d_a, st.n, ci, s); break;
+        case S_DELAY: launch_delay((DelayInst*)st.d_a, st.n, ci, s); break;
+        case S_COMP: launch_compressor((CompInst*)st.d_a, st.n, ci, s); break;
+        case S_ANALYSER: launch_analyser((AnalyserInst*)st.d_a, st.n, ci, s); break;
+        case S_CONV_FFT: launch_conv_fft_in((ConvInput*)st.d_a, st.n, ci, s); break;
+        case S_CONV_MAC:
+        case S_CONV_MAC_ACC: launch_conv_mac_ifft((ConvPath*)st.d_a, (ConvInput*)st.d_b, st.n, ci, s); break;
+    }
+}
+
+// re-upload the source PCM of every AudioBufferSourceNode from (pinned) host memory
+WAE_API wae_status wae_batch_upload(wae_batch* b) {
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    for (auto& u : b->uploads) CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, b->engine->stream));
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_set_timing(wae_batch* b, uint32_t per_stage) {
+    b->time_stages = per_stage != 0;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_run(wae_batch* b) {
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    cudaStream_t s = b->engine->stream;
+    for (auto& z : b->zero_on_run) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+    CUDA_TRY(cudaEventRecord(b->ev0, s));
+    for (auto& st : b->stages) st.ms = 0.f;
+    const size_t per_chunk = b->stages.size() + 1;
+    if (b->time_stages) {
+        // per-stage device time: one event between consecutive stages of every chunk, recorded on the launching
+        // stream and read back in wae_batch_sync (no host synchronisation inside the run)
+        size_t need = per_chunk * (size_t)((b->lq + b->chunk - 1) / b->chunk);
+        while (b->stage_events.size() < need) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            b->stage_events.push_back(e);
+        }
+    }
+    size_t chunk_index = 0;
+    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk, chunk_index++) {
+        ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0)};
+        if (b->time_stages) {
+            cudaEvent_t* ev = b->stage_events.data() + chunk_index * per_chunk;
+            CUDA_TRY(cudaEventRecord(ev[0], s));
+            for (size_t i = 0; i < b->stages.size(); i++) {
+                launch_stage(b, b->stages[i], ci);
+                CUDA_TRY(cudaEventRecord(ev[i + 1], s));
+            }
+        } else {
+            for (auto& st : b->stages) launch_stage(b, st, ci);
+        }
+    }
+    b->timed_chunks = b->time_stages ? chunk_index : 0;
+    CUDA_TRY(cudaEventRecord(b->ev1, s));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string("run: ") + cudaGetErrorString(le));
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_sync(wae_batch* b) {
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    CUDA_TRY(cudaStreamSynchronize(b->engine->stream));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) b->stats.last_run_ms = ms;
+    else cudaGetLastError();
+    if (b->timed_chunks) {
+        const size_t per_chunk = b->stages.size() + 1;
+        for (auto& st : b->stages) st.ms = 0.f;
+        for (size_t c = 0; c < b->timed_chunks; c++)
+            for (size_t i = 0; i < b->stages.size(); i++) {
+                float t = 0.f;
+                if (cudaEventElapsedTime(&t, b->stage_events[c * per_chunk + i], b->stage_events[c * per_chunk + i + 1]) == cudaSuccess)
+                    b->stages[i].ms += t;
+                else
+                    cudaGetLastError();
+            }
+        int best = -1;
+        for (size_t i = 0; i < b->stages.size(); i++)
+            if (best < 0 || b->stages[i].ms > b->stages[best].ms) best = (int)i;
+        if (best >= 0) {
+            b->stats.dominant_kernel_ms = b->stages[best].ms;
+            const char* nm = kStageNames[b->stages[best].kind];
+            if (b->stages[best].kind == S_BIQUAD) nm = b->engine->serial_filters ? "k_biquad_serial" : "k_biquad_scan";
+            std::snprintf(b->stats.dominant_kernel, sizeof(b->stats.dominant_kernel), "%s", nm);
+        }
+    }
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_output_device_ptr(wae_batch* b, float** out_dev, uint64_t* out_floats) {
+    *out_dev = b->d_out;
+    *out_floats = (uint64_t)b->n_graphs * b->channels * b->length;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_fetch(wae_batch* b, float* host_out) {
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    size_t bytes = (size_t)b->n_graphs * b->channels * b->length * sizeof(float);
+    CUDA_TRY(cudaMemcpyAsync(host_out, b->d_out, bytes, cudaMemcpyDeviceToHost, b->engine->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->engine->stream));
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_stage_time(wae_batch* b, uint32_t index, char* name64, float* ms, uint32_t* n_instances) {
+    if (index >= b->stages.size()) return fail(WAE_INVALID_ARGUMENT, "stage index out of range");
+    const Stage& st = b->stages[index];
+    const char* nm = kStageNames[st.kind];
+    if (st.kind == S_BIQUAD) nm = b->engine->serial_filters ? "k_biquad_serial" : "k_biquad_scan";
+    std::snprintf(name64, 64, "%s", nm);
+    *ms = st.ms;
+    *n_instances = (uint32_t)st.n;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_get_stats(wae_batch* b, wae_batch_stats* out) {
+    *out = b->stats;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_render_batch(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, float* out, uint32_t flags) {
+    wae_batch* b = nullptr;
+    wae_status st = wae_batch_prepare(eng, graphs, n_graphs, &b);
+    if (st != WAE_OK) return st;
+    st = wae_batch_run(b);
+    if (st == WAE_OK) st = wae_batch_sync(b);
+    if (st == WAE_OK) {
+        if (flags & WAE_RENDER_OUT_DEVICE) {
+            size_t bytes = (size_t)b->n_graphs * b->channels * b->length * sizeof(float);
+            cudaError_t e = cudaMemcpyAsync(out, b->d_out, bytes, cudaMemcpyDeviceToDevice, eng->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(eng->stream);
+            if (e != cudaSuccess) st = fail(WAE_CUDA_ERROR, cudaGetErrorString(e));
+        } else {
+            st = wae_batch_fetch(b, out);
+        }
+    }
+    std::string saved = wae_last_error();
+    wae_batch_destroy(b);
+    if (st != WAE_OK) set_error(saved);
+    return st;
+}
+
+// AnalyserNode read-out: get_float_time_domain_data (src/analysis.rs:261-264, ring read :114-127)
+static const AnalyserRec* find_analyser(wae_batch* b, uint32_t gi, wae_node_id node) {
+    for (auto& a : b->analysers)
+        if (a.graph_index == gi && a.node == node) return &a;
+    return nullptr;
+}
+
+WAE_API wae_status wae_analyser_get_float_time_domain_data(wae_batch* b, uint32_t graph_index, wae_node_id node, float* out, uint32_t len) {
+    const AnalyserRec* a = find_analyser(b, graph_index, node);
+    if (!a) return fail(WAE_INVALID_ARGUMENT, "not an analyser of this batch");
+    const uint32_t RING = 32768 + 128;
+    std::vector<float> ring(RING);
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    CUDA_TRY(cudaMemcpy(ring.data(), a->d_ring, RING * sizeof(float), cudaMemcpyDeviceToHost));
+    uint32_t n = std::min(len, a->fft_size);
+    uint64_t write_index = (uint64_t)b->lq % RING;
+    for (uint32_t i = 0; i < n; i++) out[i] = ring[(RING + write_index - n + i) % RING];
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t, wae_node_id, float*, uint32_t) {
+    return fail(WAE_UNSUPPORTED, "analyser frequency read-out (control-thread FFT, src/analysis.rs:278-369) is not lowered to the GPU yet");
+}
+
+}  // extern "C"

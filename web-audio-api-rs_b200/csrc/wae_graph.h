@@ -1,0 +1,113 @@
+// Host-side graph description built through the C ABI (include/wae.h).
+//
+// This is the control half of the engine: what the reference keeps in its control-thread structs
+// (XxxNode, AudioParam, ConcreteBaseAudioContext::connections — src/context/concrete_base.rs) and ships to
+// the render thread as ControlMessages (src/message.rs:13-87).  Nothing here renders; wae_plan.cpp lowers a
+// batch of these descriptions into GPU stages.
+#pragma once
+#include "../../include/wae.h"
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace wae {
+
+enum Kind : int {
+    K_DEST = 0, K_PARAM, K_OSC, K_BIQUAD, K_IIR, K_GAIN, K_ABSN, K_CONST, K_CONV, K_SHAPER, K_DELAY_W, K_DELAY_R,
+    K_SPANNER, K_PANNER, K_ANALYSER, K_COMP, K_MERGER, K_SPLITTER, K_LISTENER, K_KINDS
+};
+
+struct ChannelCfg {
+    int count = 2, mode = WAE_COUNT_MODE_MAX, interp = WAE_INTERPRETATION_SPEAKERS;
+};
+
+struct PcmBuffer {  // an AudioBuffer asset (src/buffer.rs:69-72), host copy
+    std::vector<std::vector<float>> channels;
+    float sample_rate = 0.f;
+    size_t length() const { return channels.empty() ? 0 : channels[0].size(); }
+    double duration() const { return (double)length() / (double)sample_rate; }
+};
+
+struct ParamEv {
+    int type;
+    float value;
+    double time, aux;
+    std::vector<float> values;
+};
+
+struct Param {  // AudioParam: its own graph node in the reference (src/context/base.rs:320-337)
+    float default_value, min_value, max_value;
+    bool a_rate;
+    bool rate_constrained = false;
+    std::vector<ParamEv> events;  // in arrival order
+    // lowering helpers
+    bool constant() const;        // only SetValue events: value is constant over the render
+    float constant_value() const; // clamped like AudioParamProcessor::mix_to_output (src/param.rs:755-760)
+};
+
+struct Edge {
+    int self_index;
+    uint32_t other_id;
+    int other_index;  // -1: hidden param port (usize::MAX in the reference)
+};
+
+struct Node {
+    uint32_t id = 0;
+    Kind kind = K_DEST;
+    uint32_t out_id = 0;  // DelayNode: outputs come from the reader (src/node/delay.rs:128-159)
+    int n_inputs = 1, n_outputs = 1;
+    ChannelCfg cfg;
+    std::vector<uint32_t> params;  // param node ids, creation order
+    std::vector<Edge> outgoing;
+    bool cycle_breaker = false;
+    bool has_start = false;
+
+    // per-kind options
+    int type = 0;  // oscillator / biquad type
+    std::vector<float> table;  // periodic wave / shaper curve
+    bool has_curve = false;
+    std::vector<double> feedforward, feedback;  // IIR
+    std::shared_ptr<PcmBuffer> buffer;          // ABSN buffer / convolver IR
+    bool normalize = true;                      // convolver
+    double start_time = 1.7976931348623157e308, stop_time = 1.7976931348623157e308;
+    double offset = 0., duration = 1.7976931348623157e308;
+    bool loop = false;
+    double loop_start = 0., loop_end = 0.;
+    double max_delay_time = 1.;
+    uint32_t delay_peer = 0;  // writer <-> reader
+    // panner
+    int panning_model = 0, distance_model = 1;
+    double ref_distance = 1., max_distance = 10000., rolloff_factor = 1., cone_inner_angle = 360., cone_outer_angle = 360.,
+           cone_outer_gain = 0.;
+    // analyser
+    uint32_t fft_size = 2048;
+    double smoothing = 0.8, min_db = -100., max_db = -30.;
+    Param param;  // K_PARAM only
+};
+
+}  // namespace wae
+
+struct wae_graph {
+    wae_engine* engine = nullptr;
+    uint32_t channels = 0;
+    uint64_t length = 0;
+    float sample_rate = 0.f;
+    uint32_t next_id = 11;  // src/context/mod.rs:24-40
+    std::map<uint32_t, wae::Node> nodes;
+    std::vector<std::pair<uint32_t, uint32_t>> pending_param_edges;
+    bool listener_present = false;
+
+    uint32_t create_param(uint32_t owner, float def, float mn, float mx, bool a_rate, float initial, bool send_set_value = true,
+                          bool fixed_id = false, uint32_t id = 0, bool constrained = false);
+    wae::Node& finish_register(wae::Node n);
+    void ensure_listener();
+    void add_edge(uint32_t src, int out, uint32_t dst, int in) { nodes.at(src).outgoing.push_back(wae::Edge{out, dst, in}); }
+};
+
+namespace wae {
+void set_error(const std::string& msg);
+int32_t fail(int32_t code, const std::string& msg);
+}  // namespace wae

@@ -1,0 +1,884 @@
+// Hand-written sm_100a kernels of the render-quantum engine, one per node renderer of SURVEY §8(a).
+//
+// All kernels are HBM/latency-bound streaming or scan kernels (no dense contraction -> no tensor cores):
+// coalesced planar f32 loads/stores, f64 only where the reference computes in f64 (biquad / IIR state,
+// oscillator phase), grids sized over (time tiles x node instances).  Each kernel cites the reference
+// renderer whose arithmetic it reproduces; parity target is 1e-5 absolute on f32 PCM.
+#include "wae_kernels.h"
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace wae {
+
+#define DEVI __device__ __forceinline__
+
+DEVI float* chan(const BufRef& b, int c, const ChunkInfo& ci) { return b.p + (size_t)c * b.stride + (b.absolute ? ci.f0 : 0); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Oscillator — OscillatorRenderer::process + generate_* (src/node/oscillator.rs:364-676), constant
+// frequency/detune.  The reference advances phase by repeated `phase += incr` (f64); here phase is the
+// closed form frac(phase0 + (n - n_first) * incr), which differs by < 1e-10 over minutes of audio.
+// ---------------------------------------------------------------------------------------------------------
+DEVI double osc_poly_blep(double t, double dt) {  // oscillator.rs:645-659 (release build: enabled)
+    if (t < dt) {
+        t /= dt;
+        return t + t - t * t - 1.0;
+    } else if (t > 1.0 - dt) {
+        t = (t - 1.0) / dt;
+        return fma(t, t, t) + t + 1.0;
+    }
+    return 0.0;
+}
+DEVI double osc_unroll(double p) { return p >= 1. ? p - 1. : (p < 0. ? p + 1. : p); }
+
+DEVI float osc_sample(const OscInst& o, double phase) {
+    switch (o.type) {
+        case 0:
+        case 4: {  // sine (:571-585) / custom (:622-637): table lookup + lerp with fmaf
+            double position = phase * (double)o.table_len;
+            double floored = floor(position);
+            int prev = (int)floored;
+            if (prev >= o.table_len) prev = o.table_len - 1;  // guards phase == 1-ulp rounding up
+            int next = prev + 1;
+            if (next == o.table_len) next = 0;
+            float k = (float)(position - floored);
+            return fmaf(__ldg(o.table + prev), 1.f - k, __ldg(o.table + next) * k);
+        }
+        case 2: {  // sawtooth, :588-595
+            double ph = osc_unroll(phase + 0.5);
+            double s = 2.0 * ph - 1.0;
+            s -= osc_poly_blep(ph, o.incr);
+            return (float)s;
+        }
+        case 1: {  // square, :598-606
+            double s = phase < 0.5 ? 1.0 : -1.0;
+            s += osc_poly_blep(phase, o.incr);
+            s -= osc_poly_blep(osc_unroll(phase + 0.5), o.incr);
+            return (float)s;
+        }
+        default: {  // triangle, :609-619
+            double s = -4. * phase + 2.;
+            if (s > 1.)
+                s = 2. - s;
+            else if (s < -1.)
+                s = -2. - s;
+            return (float)s;
+        }
+    }
+}
+
+DEVI double osc_phase_at(const OscInst& o, int64_t n) {
+    double d = (double)(n - o.n_first);
+    double p = fma(d, o.incr, o.phase0);
+    p -= floor(p);
+    if (p >= 1.) p = 0.;
+    return p;
+}
+
+__global__ void __launch_bounds__(256) k_oscillator(const OscInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const OscInst o = insts[ii];
+        float* out = chan(o.out, 0, ci);
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t n = ci.f0 + n0 + j;
+            float s = 0.f;
+            if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
+            v[j] = s;
+        }
+        *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// ConstantSourceRenderer (src/node/constant_source.rs:190-262), constant offset
+__global__ void __launch_bounds__(256) k_constant(const ConstInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const ConstInst o = insts[ii];
+        float* out = chan(o.out, 0, ci);
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t n = ci.f0 + n0 + j;
+            v[j] = (n >= o.n_first && n < o.n_stop) ? o.value : 0.f;
+        }
+        *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+// AudioBufferSourceRenderer fast track (src/node/audio_buffer_source.rs:554-624): aligned copy, optional loop
+__global__ void __launch_bounds__(256) k_buffer_source(const AbsnInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const AbsnInst o = insts[ii];
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        for (int c = 0; c < o.ch; c++) {
+            float* out = chan(o.out, c, ci);
+            const float* src = o.buf + (size_t)c * o.buf_len;
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int64_t n = ci.f0 + n0 + j;
+                float s = 0.f;
+                if (n >= o.n_start && n < o.n_stop) {
+                    int64_t idx = n - o.n_start + o.buf_offset;
+                    if (o.loop)
+                        s = __ldg(src + (idx % o.buf_len));
+                    else if (idx < o.buf_len)
+                        s = __ldg(src + idx);
+                }
+                v[j] = s;
+            }
+            *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Mixer — AudioRenderQuantum::add / mix (src/render/quantum.rs:274-569): per input port, the incoming edges
+// are summed in the reference's processing order, each up/down-mixed to the port's computed channel count.
+// One thread per frame; sequential f32 adds over the edges => same summation order as the reference.
+// ---------------------------------------------------------------------------------------------------------
+DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, const ChunkInfo& ci) {
+    const int s = e.src_ch;
+    auto ld = [&](int ch) { return chan(e.src, ch, ci)[n]; };
+    if (s == dst_ch) return ld(c);
+    if (interp == 1 || s > 6 || dst_ch > 6) return c < s ? ld(c) : 0.f;  // discrete: zero-fill / truncate
+    const float sqrt05 = 0.70710678118654752440f;                          // (0.5f32).sqrt()
+    switch (s * 16 + dst_ch) {
+        case 1 * 16 + 2: return ld(0);
+        case 1 * 16 + 4: return c < 2 ? ld(0) : 0.f;
+        case 1 * 16 + 6: return c == 2 ? ld(0) : 0.f;
+        case 2 * 16 + 4:
+        case 2 * 16 + 6: return c < 2 ? ld(c) : 0.f;
+        case 4 * 16 + 5: return c < 2 ? ld(c) : (c == 2 ? 0.f : ld(c - 1));
+        case 4 * 16 + 6: return c < 2 ? ld(c) : (c < 4 ? 0.f : ld(c - 2));
+        case 2 * 16 + 1: return 0.5f * (ld(0) + ld(1));
+        case 4 * 16 + 1: return 0.25f * (ld(0) + ld(1) + ld(2) + ld(3));
+        case 6 * 16 + 1: return fmaf(sqrt05, ld(0) + ld(1), fmaf(0.5f, ld(4) + ld(5), ld(2)));
+        case 4 * 16 + 2: return 0.5f * (ld(c) + ld(c + 2));
+        case 6 * 16 + 2: return ld(c) + sqrt05 * (ld(2) + ld(4 + c));
+        case 6 * 16 + 4: return c < 2 ? ld(c) + sqrt05 * ld(2) : ld(c + 2);
+        default: return c < s ? ld(c) : 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst,
+                                             ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const MixInst m = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
+        for (int c = 0; c < m.out_ch; c++) {
+            float acc = 0.f;
+            for (int e = 0; e < m.n_edges; e++) {
+                float v = mixed_sample(edges[m.edge_offset + e], m.out_ch, c, m.interp, n, ci);
+                acc = e == 0 ? v : acc + v;
+            }
+            chan(m.out, c, ci)[n] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BiquadFilter — BiquadFilterRenderer::process (src/node/biquad_filter.rs:764-899), constant coefficients.
+// (1) serial: one thread per (instance, channel), the reference's exact f64 operation order (bit-faithful).
+// (2) scan: one CTA per (instance, channel); the chunk is processed in tiles of 256 x 8 frames.  Each thread
+//     runs the recurrence on its 8 frames from zero state, a block-wide Kogge-Stone scan over the 2x2
+//     state-transition powers propagates the true state, and the homogeneous response is added back:
+//         y[j] = y0[j] + h1[j] * y[-1] + h2[j] * y[-2].
+//     Same filter in exact arithmetic; rounding differs from the serial order by ~1e-15 relative.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ii = t / max_ch, c = t % max_ch;
+    if (ii >= n_inst) return;
+    const BiquadInst q = insts[ii];
+    if (c >= q.ch) return;
+    const float* in = chan(q.in, c, ci);
+    float* out = chan(q.out, c, ci);
+    double* st = q.state + 4 * c;
+    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    for (int n = 0; n < ci.nf; n++) {
+        double x = (double)in[n];
+        // b0*x + b1*x1 + b2*x2 - a1*y1 - a2*y2, left to right, unfused (biquad_filter.rs:878)
+        double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.b0, x), __dmul_rn(q.b1, x1)), __dmul_rn(q.b2, x2)),
+                                       __dmul_rn(q.a1, y1)),
+                             __dmul_rn(q.a2, y2));
+        // `if !y.is_normal() { y = 0. }` (:881-883) incl. FTZ of subnormals
+        double ay = fabs(y);
+        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+        x2 = x1;
+        x1 = x;
+        y2 = y1;
+        y1 = y;
+        out[n] = (float)y;
+    }
+    st[0] = x1;
+    st[1] = x2;
+    st[2] = y1;
+    st[3] = y2;
+}
+
+constexpr int BQ_K = 8;          // frames per thread
+constexpr int BQ_THREADS = 256;  // threads per CTA -> tile = 2048 frames
+
+__global__ void __launch_bounds__(BQ_THREADS) k_biquad_scan(const BiquadInst* __restrict__ insts,
+                                                            const BiquadScanCoef* __restrict__ coefs, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x;
+    const int c = blockIdx.y;
+    const BiquadInst q = insts[ii];
+    if (c >= q.ch) return;
+    const BiquadScanCoef& sc = coefs[ii];
+    const float* in = chan(q.in, c, ci);
+    float* out = chan(q.out, c, ci);
+    double* st = q.state + 4 * c;
+    __shared__ double sh_a[BQ_THREADS], sh_b[BQ_THREADS];
+    __shared__ double tile_state[4];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        tile_state[0] = st[0];
+        tile_state[1] = st[1];
+        tile_state[2] = st[2];
+        tile_state[3] = st[3];
+    }
+    // per-thread copies of the homogeneous responses h1[j], h2[j], j < K
+    double h1[BQ_K], h2[BQ_K];
+#pragma unroll
+    for (int j = 0; j < BQ_K; j++) {
+        h1[j] = sc.h1[j];
+        h2[j] = sc.h2[j];
+    }
+    __syncthreads();
+    for (int base = 0; base < ci.nf; base += BQ_THREADS * BQ_K) {
+        const int n0 = base + t * BQ_K;
+        const bool active = n0 < ci.nf;  // nf is a multiple of 128 and K divides 128
+        double x[BQ_K + 2];
+        double y0[BQ_K];
+        if (active) {
+            float4 a = *reinterpret_cast<const float4*>(in + n0);
+            float4 b = *reinterpret_cast<const float4*>(in + n0 + 4);
+            x[2] = a.x; x[3] = a.y; x[4] = a.z; x[5] = a.w;
+            x[6] = b.x; x[7] = b.y; x[8] = b.z; x[9] = b.w;
+            if (n0 >= 2) {
+                x[1] = (double)in[n0 - 1];
+                x[0] = (double)in[n0 - 2];
+            } else {  // first thread of the chunk: previous inputs come from the carried state
+                x[1] = tile_state[0];
+                x[0] = tile_state[1];
+            }
+            double p1 = 0., p2 = 0.;
+#pragma unroll
+            for (int j = 0; j < BQ_K; j++) {
+                double w = fma(q.b2, x[j], fma(q.b1, x[j + 1], q.b0 * x[j + 2]));
+                double y = fma(-q.a1, p1, fma(-q.a2, p2, w));
+                y0[j] = y;
+                p2 = p1;
+                p1 = y;
+            }
+        }
+        // Kogge-Stone scan of the end states: S_t = M^K S_{t-1} + v_t, v_t = (y0[K-1], y0[K-2])
+        double va = active ? y0[BQ_K - 1] : 0., vb = active ? y0[BQ_K - 2] : 0.;
+        if (t == 0) {  // fold the incoming tile state into thread 0
+            double s1 = tile_state[2], s2 = tile_state[3];
+            va += sc.P[0][0] * s1 + sc.P[0][1] * s2;
+            vb += sc.P[0][2] * s1 + sc.P[0][3] * s2;
+        }
+        sh_a[t] = va;
+        sh_b[t] = vb;
+        __syncthreads();
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+            const int off = 1 << d;
+            double oa = 0., ob = 0.;
+            if (t >= off) {
+                oa = sh_a[t - off];
+                ob = sh_b[t - off];
+            }
+            __syncthreads();
+            if (t >= off) {
+                va += sc.P[d][0] * oa + sc.P[d][1] * ob;
+                vb += sc.P[d][2] * oa + sc.P[d][3] * ob;
+                sh_a[t] = va;
+                sh_b[t] = vb;
+            }
+            __syncthreads();
+        }
+        // exclusive state for this thread
+        double e1, e2;
+        if (t == 0) {
+            e1 = tile_state[2];
+            e2 = tile_state[3];
+        } else {
+            e1 = sh_a[t - 1];
+            e2 = sh_b[t - 1];
+        }
+        const int last_active = min(BQ_THREADS, (ci.nf - base) / BQ_K) - 1;
+        __syncthreads();
+        if (active) {
+            float o[BQ_K];
+#pragma unroll
+            for (int j = 0; j < BQ_K; j++) o[j] = (float)fma(h1[j], e1, fma(h2[j], e2, y0[j]));
+            *reinterpret_cast<float4*>(out + n0) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(out + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            if (t == last_active) {
+                tile_state[0] = x[BQ_K + 1];
+                tile_state[1] = x[BQ_K];
+                tile_state[2] = fma(h1[BQ_K - 1], e1, fma(h2[BQ_K - 1], e2, y0[BQ_K - 1]));
+                tile_state[3] = fma(h1[BQ_K - 2], e1, fma(h2[BQ_K - 2], e2, y0[BQ_K - 2]));
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        st[0] = tile_state[0];
+        st[1] = tile_state[1];
+        st[2] = tile_state[2];
+        st[3] = tile_state[3];
+    }
+}
+
+// IIRFilter — IirFilterRenderer::process (src/node/iir_filter.rs:323-414): transposed DF-II in f64, serial
+__global__ void __launch_bounds__(64) k_iir_serial(const IirInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ii = t / max_ch, c = t % max_ch;
+    if (ii >= n_inst) return;
+    const IirInst& q = insts[ii];
+    if (c >= q.ch) return;
+    const float* in = chan(q.in, c, ci);
+    float* out = chan(q.out, c, ci);
+    double s[20];
+    const int nc = q.n;
+    for (int i = 0; i < 20; i++) s[i] = q.state[20 * c + i];
+    for (int n = 0; n < ci.nf; n++) {
+        double x = (double)in[n];
+        double y = fma(q.b[0], x, s[0]);  // b0.mul_add(input, last_state), :391
+        double ay = fabs(y);
+        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+#pragma unroll
+        for (int i = 0; i < 19; i++)
+            if (i + 1 < nc) s[i] = __dadd_rn(__dsub_rn(__dmul_rn(q.b[i + 1], x), __dmul_rn(q.a[i + 1], y)), s[i + 1]);
+        out[n] = (float)y;
+    }
+    for (int i = 0; i < 20; i++) q.state[20 * c + i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Element-wise renderers
+// ---------------------------------------------------------------------------------------------------------
+// GainRenderer (src/node/gain.rs:147-199), scalar gain (the ~0 / ~1 shortcuts yield the same values up to
+// 1e-6 relative only when |gain| or |1-gain| <= 1e-6: handled on the host by folding gain to 0 / 1)
+__global__ void __launch_bounds__(256) k_gain(const GainInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const GainInst g = insts[ii];
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        for (int c = 0; c < g.ch; c++) {
+            float4 v = *reinterpret_cast<const float4*>(chan(g.in, c, ci) + n0);
+            v.x *= g.gain; v.y *= g.gain; v.z *= g.gain; v.w *= g.gain;
+            *reinterpret_cast<float4*>(chan(g.out, c, ci) + n0) = v;
+        }
+    }
+}
+
+// apply_curve, src/node/waveshaper.rs:555-572
+DEVI float shaper_apply(const float* curve, int len, float input) {
+    float n = (float)len;
+    float v = (n - 1.f) / 2.0f * (input + 1.f);
+    if (v <= 0.f) return __ldg(curve);
+    if (v >= n - 1.f) return __ldg(curve + (int)(n - 1.f));
+    float k = floorf(v);
+    float f = v - k;
+    return __fadd_rn(__fmul_rn(1.f - f, __ldg(curve + (int)k)), __fmul_rn(f, __ldg(curve + (int)(k + 1.f))));
+}
+__global__ void __launch_bounds__(256) k_shaper(const ShaperInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const ShaperInst s = insts[ii];
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        for (int c = 0; c < s.ch; c++) {
+            float4 v = *reinterpret_cast<const float4*>(chan(s.in, c, ci) + n0);
+            if (s.curve) {
+                if (s.n == 0) {
+                    v = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    v.x = shaper_apply(s.curve, s.n, v.x);
+                    v.y = shaper_apply(s.curve, s.n, v.y);
+                    v.z = shaper_apply(s.curve, s.n, v.z);
+                    v.w = shaper_apply(s.curve, s.n, v.w);
+                }
+            }
+            *reinterpret_cast<float4*>(chan(s.out, c, ci) + n0) = v;
+        }
+    }
+}
+
+// StereoPannerRenderer (src/node/stereo_panner.rs:218-318), constant pan; gains are computed on the host
+// with the reference's f32 expressions (get_stereo_gains, :74-79) and passed in `pan`-derived fields.
+__global__ void __launch_bounds__(256) k_stereo_panner(const SPanInst* __restrict__ insts, const float2* __restrict__ gains, int n_inst,
+                                                       ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const SPanInst s = insts[ii];
+        const float gl = gains[ii].x, gr = gains[ii].y;
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        float* l = chan(s.out, 0, ci);
+        float* r = chan(s.out, 1, ci);
+        if (s.in_ch == 1) {
+            float x = chan(s.in, 0, ci)[n];
+            l[n] = x * gl;
+            r[n] = x * gr;
+        } else {
+            float il = chan(s.in, 0, ci)[n], ir = chan(s.in, 1, ci)[n];
+            if (s.pan <= 0.f) {
+                l[n] = fmaf(ir, gl, il);
+                r[n] = ir * gr;
+            } else {
+                l[n] = il * gl;
+                r[n] = fmaf(il, gr, ir);
+            }
+        }
+    }
+}
+
+// PannerRenderer equal-power branch, static source/listener (src/node/panner.rs:839-870, 988-1057)
+__global__ void __launch_bounds__(256) k_panner_eq(const PanInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const float PI32 = 3.14159265358979323846f;
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const PanInst p = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        float az = fminf(fmaxf(p.azimuth, -180.f), 180.f);
+        if (az < -90.f)
+            az = -180.f - az;
+        else if (az > 90.f)
+            az = 180.f - az;
+        float* l = chan(p.out, 0, ci);
+        float* r = chan(p.out, 1, ci);
+        if (p.in_ch == 1) {
+            float x = (az + 90.f) / 180.f;
+            float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
+            float v = chan(p.in, 0, ci)[n];
+            l[n] = v * (gl * p.dist_gain * p.cone_gain);
+            r[n] = v * (gr * p.dist_gain * p.cone_gain);
+        } else {
+            float x = az <= 0.f ? (az + 90.f) / 90.f : az / 90.f;
+            float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
+            float il = chan(p.in, 0, ci)[n], ir = chan(p.in, 1, ci)[n];
+            if (az <= 0.f) {
+                l[n] = (il + ir * gl) * p.dist_gain * p.cone_gain;
+                r[n] = ir * gr * p.dist_gain * p.cone_gain;
+            } else {
+                l[n] = il * gl * p.dist_gain * p.cone_gain;
+                r[n] = (ir + il * gr) * p.dist_gain * p.cone_gain;
+            }
+        }
+    }
+}
+
+// channel merger / splitter (src/node/channel_merger.rs:146-171, channel_splitter.rs:183-208)
+__global__ void __launch_bounds__(256) k_route(const RouteInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const RouteInst r = insts[ii];
+        int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n0 >= ci.nf) continue;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!r.zero) v = *reinterpret_cast<const float4*>(chan(r.in, r.in_channel, ci) + n0);
+        *reinterpret_cast<float4*>(chan(r.out, r.out_channel, ci) + n0) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Delay — DelayWriter/DelayReader (src/node/delay.rs:428-461, 515-743), constant delayTime, acyclic.
+// The reference's ring-of-quanta index arithmetic reduces to out[n] = fmaf(1-k, x[n+fl], k*x[n+fl+1]) with
+// fl = floor(-delay*sr), k = frac(-delay*sr); history older than the chunk comes from a persistent ring.
+// ---------------------------------------------------------------------------------------------------------
+DEVI float delay_fetch(const DelayInst& d, const float* in, const float* ring, int64_t m, const ChunkInfo& ci) {
+    if (m < 0) return 0.f;
+    if (m >= ci.f0) {
+        int64_t r = m - ci.f0;
+        if (r < ci.nf) return in[r];
+        // "next" sample beyond the newest quantum: the reference reads the oldest ring entry here; it is
+        // always multiplied by k == 0 in that situation (delay == 0)
+        return 0.f;
+    }
+    return ring[m & (d.ring_len - 1)];
+}
+__global__ void __launch_bounds__(256) k_delay_read(const DelayInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const DelayInst d = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        for (int c = 0; c < d.ch; c++) {
+            const float* in = chan(d.in, c, ci);
+            const float* ring = d.ring + (size_t)c * d.ring_len;
+            int64_t m = ci.f0 + n + d.fl;
+            float prev = delay_fetch(d, in, ring, m, ci);
+            float next = delay_fetch(d, in, ring, m + 1, ci);
+            chan(d.out, c, ci)[n] = fmaf(1.f - d.k, prev, d.k * next);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_ring_write(const DelayInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const DelayInst d = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf || ci.nf - n > (int64_t)d.ring_len) continue;  // only the newest ring_len frames (no slot written twice)
+        for (int c = 0; c < d.ch; c++) d.ring[(size_t)c * d.ring_len + ((ci.f0 + n) & (d.ring_len - 1))] = chan(d.in, c, ci)[n];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// DynamicsCompressor — DynamicsCompressorRenderer::process (src/node/dynamics_compressor.rs:330-478).
+// The branching peak detector is a non-linear serial recurrence: one thread per instance walks the chunk.
+// ---------------------------------------------------------------------------------------------------------
+DEVI float db_to_lin(float v) { return powf(10.0f, v / 20.f); }
+DEVI float lin_to_db(float v) { return v == 0.f ? -1000.f : 20.f * log10f(v); }
+__global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= n_inst) return;
+    const CompInst q = insts[ii];
+    float thr = q.knee > 0.f ? q.threshold + q.knee / 2.f : q.threshold;
+    float half_knee = q.knee / 2.f;
+    float knee_partial = (1.f / q.ratio - 1.f) / (2.f * q.knee);
+    float attack_tau = expf(-1.f / (q.attack * q.sample_rate));
+    float release_tau = expf(-1.f / (q.release * q.sample_rate));
+    float full_range_gain = thr + (-thr / q.ratio);
+    float full_range_makeup = 1.f / db_to_lin(full_range_gain);
+    float makeup_gain = lin_to_db(powf(full_range_makeup, 0.6f));
+    float prev = q.state[0];
+    float reduction_gain = q.state[1];
+    const uint32_t mask = q.ring_len - 1;
+    for (int n = 0; n < ci.nf; n++) {
+        float mx = -3.40282347e+38f;
+        for (int c = 0; c < q.ch; c++) {
+            float s = fabsf(chan(q.in, c, ci)[n]);
+            if (s > mx) mx = s;
+        }
+        float sample_db = lin_to_db(mx);
+        float att;
+        if (sample_db <= thr - half_knee) {
+            att = sample_db;
+        } else if (sample_db <= thr + half_knee) {
+            float t = sample_db - thr + half_knee;
+            att = __fadd_rn(sample_db, __fmul_rn(__fmul_rn(t, t), knee_partial));
+        } else {
+            att = thr + (sample_db - thr) / q.ratio;
+        }
+        float attenuation = sample_db - att;
+        float det;
+        if (attenuation > prev)
+            det = __fadd_rn(__fmul_rn(attack_tau, prev), __fmul_rn(1.f - attack_tau, attenuation));
+        else
+            det = __fadd_rn(__fmul_rn(release_tau, prev), __fmul_rn(1.f - release_tau, attenuation));
+        reduction_gain = -det + makeup_gain;
+        float g = db_to_lin(reduction_gain);
+        prev = det;
+        int64_t m = ci.f0 + n - q.delay_frames;
+        for (int c = 0; c < q.ch; c++) {
+            float x = 0.f;
+            if (m >= ci.f0)
+                x = chan(q.in, c, ci)[m - ci.f0];
+            else if (m >= 0)
+                x = q.ring[(size_t)c * q.ring_len + (m & mask)];
+            chan(q.out, c, ci)[n] = x * g;
+        }
+    }
+    // history for the next chunk
+    for (int n = max(0, ci.nf - q.delay_frames); n < ci.nf; n++)
+        for (int c = 0; c < q.ch; c++) q.ring[(size_t)c * q.ring_len + ((ci.f0 + n) & mask)] = chan(q.in, c, ci)[n];
+    q.state[0] = prev;
+    q.state[1] = reduction_gain;
+}
+
+// AnalyserRenderer (src/node/analyser.rs:267-294) + AnalyserRingBuffer::write (src/analysis.rs:96-112)
+__global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int RING = 32768 + 128;
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const AnalyserInst a = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        MixEdge e;
+        e.src = a.in;
+        e.src_ch = a.ch;
+        float mono = mixed_sample(e, 1, 0, 0, n, ci);  // mono.mix(1, Speakers)
+        for (int c = 0; c < a.ch; c++) chan(a.out, c, ci)[n] = chan(a.in, c, ci)[n];
+        if (ci.nf - n <= RING) a.ring[(ci.f0 + n) % RING] = mono;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Convolver — ConvolverRenderer (src/node/convolver.rs:343-490) over fft-convolver's uniformly partitioned
+// scheme (block 1024, FFT 2048), evaluated time-batched: every 1024-frame block of a chunk is transformed
+// once (overlap-save frame [previous block | current block]), then for each output block j
+//     Y_j = sum_i H_i * X_{j-i},   out_j = IFFT(Y_j)[1024..2048) / 2048.
+// Shared-memory radix-2 complex FFT of 1024 points + real-FFT packing (2048 real <-> 1024 complex).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int CV_B = 1024;      // block
+constexpr int CV_BINS = 1025;   // spectrum bins of the 2048-point real FFT
+constexpr int CV_THREADS = 256;
+
+__device__ float2 c_tw2048[1024];  // exp(-2*pi*i*k/2048), k < 1024 (global + L1: per-thread indices diverge)
+
+DEVI float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// in-place 1024-point complex FFT in shared memory (decimation in frequency, output bit-reversed is avoided by
+// a Stockham-free approach: DIT with explicit bit reversal on load).  sign = -1 forward, +1 inverse.
+DEVI void fft1024_smem(float2* s, int sign) {
+    const int t = threadIdx.x;
+    // bit reversal permutation (10 bits)
+    for (int i = t; i < 1024; i += CV_THREADS) {
+        int r = __brev((unsigned)i) >> 22;
+        if (i < r) {
+            float2 tmp = s[i];
+            s[i] = s[r];
+            s[r] = tmp;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int len = 2; len <= 1024; len <<= 1) {
+        const int half = len >> 1;
+        const int step = 2048 / len;  // twiddle stride in the 2048 table: exp(-2*pi*i*j/len) = tw[j*2048/len]
+        for (int b = t; b < 512; b += CV_THREADS) {
+            int grp = b / half, j = b % half;
+            int i0 = grp * len + j, i1 = i0 + half;
+            float2 w = __ldg(&c_tw2048[j * step]);
+            if (sign > 0) w.y = -w.y;
+            float2 u = s[i0], v = cmul(s[i1], w);
+            s[i0] = make_float2(u.x + v.x, u.y + v.y);
+            s[i1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+// grid: (blocks in chunk, conv inputs).  Builds X_j for every new block of the chunk.
+__global__ void __launch_bounds__(CV_THREADS) k_conv_fft_in(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
+    __shared__ float2 z[1024];
+    const ConvInput ip = inputs[blockIdx.y];
+    const int jb = blockIdx.x;                         // block within the chunk
+    const int64_t jabs = ci.f0 / CV_B + jb;            // absolute block index
+    const float* in = chan(ip.in, ip.in_channel, ci);
+    const int t = threadIdx.x;
+    // frame = [previous block | current block] (2048 reals) packed as 1024 complex (even, odd)
+    for (int i = t; i < 1024; i += CV_THREADS) {
+        float a, b;
+        int n = 2 * i;  // index in the 2048 frame
+        if (n < CV_B) {
+            if (jb == 0) {
+                a = ip.prev[n];
+                b = ip.prev[n + 1];
+            } else {
+                a = in[(jb - 1) * CV_B + n];
+                b = in[(jb - 1) * CV_B + n + 1];
+            }
+        } else {
+            int m = jb * CV_B + (n - CV_B);
+            a = m < ci.nf ? in[m] : 0.f;
+            b = m + 1 < ci.nf ? in[m + 1] : 0.f;
+        }
+        z[i] = make_float2(a, b);
+    }
+    __syncthreads();
+    fft1024_smem(z, -1);
+    // unpack to the 1025 bins of the real FFT: X[k] = E[k] + w^k O[k]
+    float2* X = ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS;
+    for (int k = t; k <= 1024; k += CV_THREADS) {
+        float2 r;
+        if (k == 0) {
+            r = make_float2(z[0].x + z[0].y, 0.f);
+        } else if (k == 1024) {
+            r = make_float2(z[0].x - z[0].y, 0.f);
+        } else {
+            float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
+            float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+            float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+            float2 w = c_tw2048[k];
+            float2 tw = cmul(w, o);
+            r = make_float2(e.x + tw.x, e.y + tw.y);
+        }
+        X[k] = r;
+    }
+}
+
+// saves the last block of the chunk as "previous block" for the next chunk.  grid: (4, conv inputs)
+__global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
+    const ConvInput ip = inputs[blockIdx.y];
+    const float* in = chan(ip.in, ip.in_channel, ci);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int nblocks = (ci.nf + CV_B - 1) / CV_B;
+    int m = (nblocks - 1) * CV_B + i;
+    ip.prev[i] = m < ci.nf ? in[m] : 0.f;
+}
+
+// grid: (blocks in chunk, paths).  Y_j = sum_i H_i X_{j-i}; inverse FFT; write frames [j*1024, (j+1)*1024).
+__global__ void __launch_bounds__(CV_THREADS) k_conv_mac_ifft(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs,
+                                                              int n_paths, ChunkInfo ci) {
+    __shared__ float2 z[1024];
+    __shared__ float2 ynyq;
+    const ConvPath p = paths[blockIdx.y];
+    const ConvInput ip = inputs[p.input];
+    const int jb = blockIdx.x;
+    const int64_t jabs = ci.f0 / CV_B + jb;
+    const int t = threadIdx.x;
+    const int imax = (int)min((int64_t)p.S - 1, jabs);  // X_{j-i} exists for j-i >= 0
+    // each thread accumulates bins k = t, t+256, t+512, t+768 (+ bin 1024 on thread 0)
+    float2 acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[u] = make_float2(0.f, 0.f);
+    float2 acc_n = make_float2(0.f, 0.f);
+    for (int i = 0; i <= imax; i++) {
+        const float2* H = p.h + (size_t)i * CV_BINS;
+        const float2* X = ip.xring + (size_t)((jabs - i) % ip.xring_blocks) * CV_BINS;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            int k = t + u * CV_THREADS;
+            float2 h = __ldg(H + k), x = X[k];
+            acc[u].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[u].x));
+            acc[u].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[u].y));
+        }
+        if (t == 0) {
+            float2 h = __ldg(H + 1024), x = X[1024];
+            acc_n.x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc_n.x));
+            acc_n.y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc_n.y));
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) z[t + u * CV_THREADS] = acc[u];
+    if (t == 0) ynyq = acc_n;
+    __syncthreads();
+    // pack the half spectrum for the inverse real FFT: Z[k] = (Y[k] + conj(Y[N/2-k])) + i w^-k (Y[k] - conj(Y[N/2-k]))
+    float2 zz[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        int k = t + u * CV_THREADS;
+        float2 yk = k == 0 ? make_float2(z[0].x, 0.f) : z[k];
+        float2 ym = k == 0 ? make_float2(ynyq.x, 0.f) : z[1024 - k];
+        float2 yc = make_float2(ym.x, -ym.y);
+        float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
+        float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
+        float2 w = c_tw2048[k];
+        w.y = -w.y;  // conj
+        float2 o = cmul(w, d);
+        zz[u] = make_float2(e.x - o.y, e.y + o.x);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) z[t + u * CV_THREADS] = zz[u];
+    __syncthreads();
+    fft1024_smem(z, +1);
+    // frame samples 2i, 2i+1 = Re, Im of z[i]; keep the second half [1024, 2048) -> i in [512, 1024)
+    float* out = chan(p.out, p.out_channel, ci) + (size_t)jb * CV_B;
+    const float scale = 1.f / 2048.f;
+    for (int i = 512 + t; i < 1024; i += CV_THREADS) {
+        int n = 2 * (i - 512);
+        if (jb * CV_B + n < ci.nf) {
+            float2 v = make_float2(z[i].x * scale, z[i].y * scale);
+            float2* dst = reinterpret_cast<float2*>(out + n);
+            if (p.accumulate) {
+                float2 o = *dst;
+                v.x += o.x;
+                v.y += o.y;
+            }
+            *dst = v;
+        }
+    }
+}
+
+// IR segment spectra H_i (host uploads the scaled IR; one CTA per segment).  grid: (S, ir channels)
+__global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restrict__ ir, int64_t ir_len, int64_t ir_stride, float2* __restrict__ h,
+                                                            int S) {
+    __shared__ float2 z[1024];
+    const int seg = blockIdx.x, c = blockIdx.y;
+    const float* src = ir + (size_t)c * ir_stride;
+    const int t = threadIdx.x;
+    for (int i = t; i < 1024; i += CV_THREADS) {
+        int n = 2 * i;
+        float a = 0.f, b = 0.f;
+        if (n < CV_B) {  // segment in the first half, zeros in the second
+            int64_t m = (int64_t)seg * CV_B + n;
+            a = m < ir_len ? src[m] : 0.f;
+            b = m + 1 < ir_len ? src[m + 1] : 0.f;
+        }
+        z[i] = make_float2(a, b);
+    }
+    __syncthreads();
+    fft1024_smem(z, -1);
+    float2* H = h + ((size_t)c * S + seg) * CV_BINS;
+    for (int k = t; k <= 1024; k += CV_THREADS) {
+        float2 r;
+        if (k == 0) {
+            r = make_float2(z[0].x + z[0].y, 0.f);
+        } else if (k == 1024) {
+            r = make_float2(z[0].x - z[0].y, 0.f);
+        } else {
+            float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
+            float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+            float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+            float2 tw = cmul(c_tw2048[k], o);
+            r = make_float2(e.x + tw.x, e.y + tw.y);
+        }
+        H[k] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+static inline dim3 grid_tiles(int nf, int per_block, int n_inst) {
+    return dim3((unsigned)((nf + per_block - 1) / per_block), (unsigned)(n_inst < 32768 ? n_inst : 32768));
+}
+
+void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw2048, host_tw, sizeof(float2) * 1024); }
+
+void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_oscillator<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_constant<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_buffer_source<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) { k_mix<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci); }
+void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    int threads = n * max_ch;
+    k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
+}
+void launch_biquad_scan(const BiquadInst* d, const BiquadScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    k_biquad_scan<<<dim3((unsigned)n, (unsigned)max_ch), BQ_THREADS, 0, s>>>(d, c, n, ci);
+}
+void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    int threads = n * max_ch;
+    k_iir_serial<<<(threads + 63) / 64, 64, 0, s>>>(d, n, max_ch, ci);
+}
+void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_gain<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_shaper<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_stereo_panner(const SPanInst* d, const float2* g, int n, ChunkInfo ci, cudaStream_t s) {
+    k_stereo_panner<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, g, n, ci);
+}
+void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_eq<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_route<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_delay(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) {
+    k_delay_read<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
+    k_ring_write<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
+}
+void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
+void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_analyser<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s) {
+    int nb = (ci.nf + CV_B - 1) / CV_B;
+    k_conv_fft_in<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, 0, s>>>(d, n, ci);
+    k_conv_save_prev<<<dim3(4, (unsigned)n), 256, 0, s>>>(d, n, ci);
+}
+void launch_conv_mac_ifft(const ConvPath* p, const ConvInput* in, int n, ChunkInfo ci, cudaStream_t s) {
+    int nb = (ci.nf + CV_B - 1) / CV_B;
+    k_conv_mac_ifft<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, 0, s>>>(p, in, n, ci);
+}
+void launch_conv_ir_fft(const float* ir, int64_t ir_len, int64_t ir_stride, float2* h, int S, int channels, cudaStream_t s) {
+    k_conv_ir_fft<<<dim3((unsigned)S, (unsigned)channels), CV_THREADS, 0, s>>>(ir, ir_len, ir_stride, h, S);
+}
+
+}  // namespace wae

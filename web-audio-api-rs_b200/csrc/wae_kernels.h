@@ -1,0 +1,34 @@
+// Launch wrappers of the sm_100a kernels (wae_kernels.cu).
+#pragma once
+#include "wae_device.h"
+
+#include <cuda_runtime.h>
+
+namespace wae {
+
+struct BiquadScanCoef {
+    double h1[8], h2[8];  // homogeneous responses: y[j] = y0[j] + h1[j]*y[-1] + h2[j]*y[-2], j < 8
+    double P[8][4];       // (M^8)^(2^d), row-major 2x2, d = 0..7 (M = [[-a1,-a2],[1,0]])
+};
+
+void upload_twiddles(const float2* host_tw);
+void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
+void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
+void launch_biquad_scan(const BiquadInst* d, const BiquadScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
+void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
+void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_stereo_panner(const SPanInst* d, const float2* gains, int n, ChunkInfo ci, cudaStream_t s);
+void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_delay(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_conv_mac_ifft(const ConvPath* p, const ConvInput* in, int n, ChunkInfo ci, cudaStream_t s);
+void launch_conv_ir_fft(const float* ir, int64_t ir_len, int64_t ir_stride, float2* h, int S, int channels, cudaStream_t s);
+
+}  // namespace wae
