@@ -250,7 +250,8 @@ WAE_API const char* wae_version(void);
 enum {
     WAE_OPT_CHUNK_FRAMES = 1,   /* frames rendered per time chunk (multiple of 128; 0 = auto)      */
     WAE_OPT_FUSE = 2,           /* 1 (default): fuse source->filter->gain chains; 0: one stage/node */
-    WAE_OPT_SERIAL_FILTERS = 3  /* 1: bit-faithful serial recurrences (thread per channel)          */
+    WAE_OPT_SERIAL_FILTERS = 3, /* 1: bit-faithful serial recurrences (thread per channel)          */
+    WAE_OPT_PIPELINE_GROUPS = 4 /* graph groups of the H2D/render/D2H pipeline (0 = auto: 8)        */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
 /* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */
@@ -329,6 +330,10 @@ WAE_API wae_status wae_batch_upload(wae_batch* batch);                    /* asy
 /* per_stage != 0: record CUDA events around every stage (diagnostic: serialises chunks) */
 WAE_API wae_status wae_batch_set_timing(wae_batch* batch, uint32_t per_stage);
 WAE_API wae_status wae_batch_run(wae_batch* batch);                       /* async on the engine stream   */
+/* End-to-end render with HOST buffers: per graph group H2D(source PCM, pinned mirror) -> render -> D2H into host_out
+ * ([n_graphs][channels][length] f32, ideally pinned), the three legs of neighbouring groups overlapped on three
+ * streams.  Synchronous.  wae_render_batch(..., WAE_RENDER_OUT_HOST) is prepare + this + destroy. */
+WAE_API wae_status wae_batch_run_pipelined(wae_batch* batch, float* host_out);
 WAE_API wae_status wae_batch_sync(wae_batch* batch);                      /* wait for the stream           */
 WAE_API wae_status wae_batch_output_device_ptr(wae_batch* batch, float** out_dev, uint64_t* out_floats);
 WAE_API wae_status wae_batch_fetch(wae_batch* batch, float* host_out);   /* D2H of the whole output       */

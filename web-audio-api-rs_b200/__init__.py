@@ -17,6 +17,7 @@ from . import _binding
 from ._binding import Api, WaeError
 from .context import *  # noqa: F401,F403
 from . import context
+from . import parallel
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwae_b200.so")
@@ -65,4 +66,4 @@ class Engine:
             self.handle = None
 
 
-OPT_CHUNK_FRAMES, OPT_FUSE, OPT_SERIAL_FILTERS = 1, 2, 3
+OPT_CHUNK_FRAMES, OPT_FUSE, OPT_SERIAL_FILTERS, OPT_PIPELINE_GROUPS = 1, 2, 3, 4

@@ -138,7 +138,7 @@ WAE_SYMBOLS = [
 ] + ["wae_" + n for n in CREATE_FUNCS] + [
     "wae_connect", "wae_connect_param", "wae_disconnect", "wae_param_event_push", "wae_param_set_automation_rate",
     "wae_listener_param_event_push", "wae_source_start", "wae_source_stop", "wae_oscillator_set_type",
-    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_sync",
+    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync",
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data",
 ]
@@ -179,6 +179,7 @@ class Api:
             f("batch_upload", C.c_int32, [C.c_void_p])
             f("batch_set_timing", C.c_int32, [C.c_void_p, C.c_uint32])
             f("batch_run", C.c_int32, [C.c_void_p])
+            f("batch_run_pipelined", C.c_int32, [C.c_void_p, C.c_void_p])
             f("batch_sync", C.c_int32, [C.c_void_p])
             f("batch_output_device_ptr", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)])
             f("batch_fetch", C.c_int32, [C.c_void_p, C.c_void_p])

@@ -426,6 +426,10 @@ class Batch:
     def sync(self):
         self.api.check(self.api.batch_sync(self.handle))
 
+    def run_pipelined(self, host_out_ptr):
+        """H2D + render + D2H, overlapped per graph group; `host_out_ptr` = address of [n][ch][length] f32 (pinned)."""
+        self.api.check(self.api.batch_run_pipelined(self.handle, host_out_ptr))
+
     def fetch(self, out=None):
         if out is None:
             out = np.empty((self.n, self.channels, self.length), np.float32)

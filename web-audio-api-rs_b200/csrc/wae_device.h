@@ -44,7 +44,8 @@ struct ConstInst {
 struct AbsnInst {
     BufRef out;
     const float* buf;  // planar [ch][buf_len]
-    int64_t buf_len;
+    int64_t buf_len;     // frames per channel
+    int64_t buf_stride;  // floats between channels (>= buf_len, multiple of 4)
     int64_t n_start, n_stop;  // output frames [n_start, n_stop) play buf[n - n_start + buf_offset] (fast track)
     int64_t buf_offset;
     int32_t ch;
@@ -140,6 +141,34 @@ struct RouteInst {  // channel merger / splitter: copy one channel
     int32_t in_channel, out_channel;
     int32_t zero;  // 1: write zeros (splitter output beyond the input's channels)
     int32_t pad;
+};
+
+// ---- fused chain: source -> {biquad | gain | shaper}* -> buffer or destination, one pass over the PCM -------
+enum ChainSrc : int32_t { CHAIN_SRC_BUFFER = 0, CHAIN_SRC_ABSN = 1, CHAIN_SRC_OSC = 2, CHAIN_SRC_CONST = 3 };
+enum ChainStepKind : int32_t { CHAIN_BIQUAD = 0, CHAIN_GAIN = 1, CHAIN_SHAPER = 2 };
+struct ChainStep {
+    int32_t kind;
+    int32_t n;            // shaper: curve length
+    float gain;           // gain
+    int32_t coef;         // biquad: index into the ScanCoef table
+    const float* curve;   // shaper (nullptr: pass-through)
+    double* state;        // biquad: [ch][4]
+    double b0, b1, b2, a1, a2;
+};
+constexpr int CHAIN_MAX_STEPS = 6;
+constexpr int CHAIN_MAX_BIQUADS = 2;
+struct ChainInst {
+    int32_t src_kind;
+    int32_t ch;        // channels processed (one CTA each)
+    int32_t n_steps;
+    int32_t out_dup;   // >1: the (mono) result is written to channels 0..out_dup-1 (speaker up-mix 1->2 by copy)
+    BufRef in;         // CHAIN_SRC_BUFFER
+    AbsnInst absn;     // CHAIN_SRC_ABSN (out unused)
+    OscInst osc;       // CHAIN_SRC_OSC (out unused)
+    ConstInst cst;     // CHAIN_SRC_CONST (out unused)
+    BufRef out;
+    int64_t limit;     // frames >= limit are not written (destination); < 0: none
+    ChainStep steps[CHAIN_MAX_STEPS];
 };
 
 // ---- convolver (uniformly partitioned overlap-save, block 1024 / FFT 2048, time-batched) -----------------

@@ -34,6 +34,7 @@ struct wae_engine {
     int64_t chunk_frames = 0;  // 0 = auto
     bool fuse = true;
     bool serial_filters = false;
+    int pipeline_groups = 0;  // 0 = auto
     float* d_sine = nullptr;
 };
 
@@ -41,11 +42,11 @@ namespace {
 
 enum StageKind : int {
     S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_KINDS
 };
-const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad", "k_iir_serial", "k_gain",
+const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -55,7 +56,8 @@ struct StageBuild {
     std::vector<ConstInst> cst;
     std::vector<AbsnInst> absn;
     std::vector<BiquadInst> biquad;
-    std::vector<BiquadScanCoef> biquad_coef;
+    std::vector<ChainInst> chain;
+    std::vector<ScanCoef> scan_coef;
     std::vector<IirInst> iir;
     std::vector<GainInst> gain;
     std::vector<ShaperInst> shaper;
@@ -75,6 +77,7 @@ struct StageBuild {
 
 struct Stage {
     int kind = 0;
+    int group = 0;
     int n = 0;
     int max_ch = 1;
     void* d_a = nullptr;  // instances
@@ -105,22 +108,57 @@ struct wae_batch {
     std::vector<std::pair<void*, size_t>> zero_on_run;
     std::vector<AnalyserRec> analysers;
     // source PCM assets: device destination <- host source (re-uploadable: wae_batch_upload)
-    struct Upload {
-        float* dst;
-        const float* src;
-        size_t bytes;
+    // Graph groups: the batch is cut into contiguous groups of graphs; a group's source PCM lives in one device slab
+    // mirrored by one pinned host slab, so that H2D(group k+1), render(group k) and D2H(group k-1) overlap on three
+    // streams (wae_batch_run_pipelined).  All groups share the arena-sizing chunk.
+    struct Group {
+        uint32_t g0 = 0, g1 = 0;        // graphs [g0, g1)
+        size_t stage0 = 0, stage1 = 0;  // stages [stage0, stage1) of `stages`
+        float* d_src = nullptr;         // device slab of source PCM
+        float* h_src = nullptr;         // pinned host mirror
+        size_t src_floats = 0;
+        cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     };
-    std::vector<Upload> uploads;
-    std::vector<const void*> registered_host;
+    std::vector<Group> groups;
+    std::vector<void*> pinned;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    struct Timed {
+        size_t stage, e0, e1;
+    };
+    std::vector<Timed> timed;
     wae_batch_stats stats{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> stage_events;
     bool time_stages = false;
-    size_t timed_chunks = 0;
+    size_t timed_events_used = 0;
     uint64_t arena_bytes = 0, asset_bytes = 0;
 
+    // small per-node state that is zeroed before every run lives in slabs: one memset per slab, not per node
+    char* slab = nullptr;
+    size_t slab_used = 0, slab_cap = 0;
+    void* slab_alloc(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        if (bytes > (1u << 20)) return nullptr;
+        if (!slab || slab_used + bytes > slab_cap) {
+            slab_cap = 8u << 20;
+            void* p = nullptr;
+            if (cudaMalloc(&p, slab_cap) != cudaSuccess) return nullptr;
+            allocs.push_back(p);
+            cudaMemsetAsync(p, 0, slab_cap, engine->stream);
+            zero_on_run.push_back({p, slab_cap});
+            slab = (char*)p;
+            slab_used = 0;
+        }
+        void* r = slab + slab_used;
+        slab_used += bytes;
+        return r;
+    }
     template <typename T>
     T* dalloc(size_t count, bool zero = false, bool rezero_on_run = false) {
+        if (rezero_on_run && count * sizeof(T) <= (1u << 20)) {
+            void* r = slab_alloc(count * sizeof(T));
+            if (r) return (T*)r;
+        }
         void* p = nullptr;
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
@@ -197,6 +235,29 @@ struct Planner {
     };
     std::unordered_map<uint64_t, IrSpectra> ir_cache;
 
+    bool dry = false;                     // sizing pass: count arena floats per frame, touch no device memory
+    uint64_t arena_floats_per_frame = 0;
+    // source PCM slab of the group being planned (device pointer, pinned host mirror, cursor in floats)
+    float* d_src = nullptr;
+    float* h_src = nullptr;
+    size_t src_cursor = 0;
+    struct PendingChain {
+        ChainInst inst;
+        std::vector<ScanCoef> coefs;
+        int ch = 1;
+    };
+
+    template <typename T>
+    T* alloc(size_t count, bool zero = false, bool rezero_on_run = false) {
+        if (dry) return reinterpret_cast<T*>(uintptr_t(256));
+        return b->dalloc<T>(count, zero, rezero_on_run);
+    }
+    template <typename T>
+    T* upload(const std::vector<T>& v) {
+        if (dry) return reinterpret_cast<T*>(uintptr_t(256));
+        return b->dupload(v);
+    }
+
     bool bail(int code, const std::string& msg) {
         if (!error_code) {
             error_code = code;
@@ -213,6 +274,8 @@ struct Planner {
     }
 
     BufRef arena_buf(int ch) {
+        arena_floats_per_frame += (uint64_t)ch;
+        if (dry) return BufRef{reinterpret_cast<float*>(uintptr_t(256)), (uint32_t)b->chunk, 0};
         size_t floats = (size_t)ch * (size_t)b->chunk;
         float* p = b->dalloc<float>(floats);
         b->arena_bytes += floats * 4;
@@ -264,6 +327,35 @@ static uint32_t next_pow2(uint64_t v) {
     uint32_t p = 1;
     while (p < v) p <<= 1;
     return p;
+}
+
+// constants of the time-parallel biquad recurrence (see ScanCoef in wae_kernels.h), f64 on the host
+static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
+    ScanCoef sc{};
+    struct M2 {
+        double a, b, c, d;
+    };
+    auto mul = [](const M2& x, const M2& y) { return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; };
+    const M2 M{-c.a1, -c.a2, 1., 0.};
+    M2 r{1., 0., 0., 1.};
+    for (int j = 0; j < 8; j++) {
+        r = mul(M, r);
+        sc.h1[j] = r.a;
+        sc.h2[j] = r.b;
+    }
+    const M2 A = r;  // M^8
+    M2 pw = A;
+    for (int d = 0; d < 5; d++) {
+        sc.Pshfl[d][0] = pw.a; sc.Pshfl[d][1] = pw.b; sc.Pshfl[d][2] = pw.c; sc.Pshfl[d][3] = pw.d;
+        pw = mul(pw, pw);
+    }
+    sc.Pwarp[0] = pw.a; sc.Pwarp[1] = pw.b; sc.Pwarp[2] = pw.c; sc.Pwarp[3] = pw.d;  // A^32
+    M2 pl = A;
+    for (int l = 0; l < 32; l++) {
+        sc.Plane[l][0] = pl.a; sc.Plane[l][1] = pl.b; sc.Plane[l][2] = pl.c; sc.Plane[l][3] = pl.d;
+        pl = mul(A, pl);
+    }
+    return sc;
 }
 
 bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
@@ -331,13 +423,13 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     } else {
         std::vector<float> flat((size_t)ir_ch * ir_len);
         for (int c = 0; c < ir_ch; c++) std::memcpy(flat.data() + (size_t)c * ir_len, scaled[c].data(), ir_len * sizeof(float));
-        float* d_ir = b->dupload(flat);
-        cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
+        float* d_ir = upload(flat);
+        if (!dry) cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
         spec.S = Smax;
         spec.channels = ir_ch;
-        spec.h = b->dalloc<float2>((size_t)ir_ch * Smax * 1025);
+        spec.h = alloc<float2>((size_t)ir_ch * Smax * 1025);
         if (!d_ir || !spec.h) return bail(WAE_OUT_OF_MEMORY, "out of device memory (IR spectra)");
-        launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
+        if (!dry) launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
         b->asset_bytes += (size_t)ir_ch * Smax * 1025 * 8;
         ir_cache[key] = spec;
     }
@@ -350,8 +442,8 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         ConvInput ci;
         ci.in = pn.in_buf[0];
         ci.in_channel = c;
-        ci.prev = b->dalloc<float>(1024, true, true);
-        ci.xring = b->dalloc<float2>((size_t)ring_blocks * 1025);
+        ci.prev = alloc<float>(1024, true, true);
+        ci.xring = alloc<float2>((size_t)ring_blocks * 1025);
         ci.xring_blocks = ring_blocks;
         if (!ci.prev || !ci.xring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver input spectra)");
         b->arena_bytes += (size_t)ring_blocks * 1025 * 8;
@@ -410,6 +502,48 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     }
     hm::SchedClock clock(g->sample_rate);
     const double sr = (double)g->sample_rate;
+    // ---- chain fusion (WAE_OPT_FUSE): sources and biquad/gain/shaper nodes are not emitted one stage each; a node
+    // with exactly one consumer stays PENDING, the consumer either extends the chain (same channel count, single
+    // edge) or forces it to be materialised into an arena buffer.  A chain that ends at a destination whose only
+    // input it is writes the final PCM directly.
+    const bool fuse = eng->fuse;
+    std::map<uint32_t, PendingChain> pending;
+    auto consumers = [&](const Node& nd) {
+        int k = 0;
+        for (auto& e : nd.outgoing)
+            if (e.other_index >= 0) k++;
+        return k;
+    };
+    auto emit_chain = [&](PendingChain& pc, int L) {
+        StageBuild& cs = stage(L, S_CHAIN);
+        for (int i = 0, k = 0; i < pc.inst.n_steps; i++)
+            if (pc.inst.steps[i].kind == CHAIN_BIQUAD) {
+                pc.inst.steps[i].coef = (int32_t)cs.scan_coef.size();
+                cs.scan_coef.push_back(pc.coefs[k++]);
+            }
+        cs.max_ch = std::max(cs.max_ch, pc.ch);
+        cs.chain.push_back(pc.inst);
+    };
+    auto materialize = [&](uint32_t nid) -> bool {
+        auto it = pending.find(nid);
+        if (it == pending.end()) return true;
+        PNode& sp = pn.at(nid);
+        BufRef buf = arena_buf(it->second.ch);
+        if (!buf.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+        it->second.inst.out = buf;
+        it->second.inst.limit = -1;
+        it->second.inst.out_dup = 0;
+        emit_chain(it->second, 2 * sp.level + 1);
+        sp.out_buf = {buf};
+        pending.erase(it);
+        return true;
+    };
+    auto chain_steps_ok = [&](const ChainInst& ci, bool adding_biquad) {
+        int nb = 0;
+        for (int i = 0; i < ci.n_steps; i++)
+            if (ci.steps[i].kind == CHAIN_BIQUAD) nb++;
+        return ci.n_steps < CHAIN_MAX_STEPS && (!adding_biquad || nb < CHAIN_MAX_BIQUADS);
+    };
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
         if (n.kind == K_PARAM || n.kind == K_LISTENER) continue;
@@ -419,6 +553,28 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         for (auto& port : p.in_edges)
             for (auto& r : port) level = std::max(level, pn.at(r.node).level + 1);
         p.level = level;
+        // does this node extend the pending chain of its only producer / take it as the destination's only input?
+        uint32_t fuse_src = 0;
+        bool extend = false, dest_direct = false;
+        const bool chain_kind = (n.kind == K_BIQUAD && !eng->serial_filters) || (fuse && (n.kind == K_GAIN || n.kind == K_SHAPER));
+        if (fuse && n.n_inputs == 1 && p.in_edges[0].size() == 1 && p.in_edges[0][0].port == 0) {
+            auto it = pending.find(p.in_edges[0][0].node);
+            if (it != pending.end()) {
+                int sch = pn.at(it->first).out_ch[0];
+                if (chain_kind && computed_channels(n.cfg, sch) == sch && chain_steps_ok(it->second.inst, n.kind == K_BIQUAD)) {
+                    extend = true;
+                    fuse_src = it->first;
+                } else if (n.kind == K_DEST && b->length <= 0xffffffffull &&
+                           (sch == (int)b->channels || (sch == 1 && b->channels == 2 && n.cfg.interp == WAE_INTERPRETATION_SPEAKERS))) {
+                    dest_direct = true;
+                    fuse_src = it->first;
+                }
+            }
+        }
+        for (auto& port : p.in_edges)
+            for (auto& r : port)
+                if (!((extend || dest_direct) && r.node == fuse_src))
+                    if (!materialize(r.node)) return false;
         p.in_ch.assign(n.n_inputs, 1);
         p.in_buf.assign(n.n_inputs, BufRef{nullptr, 0, 0});
         for (int port = 0; port < n.n_inputs; port++) {
@@ -431,6 +587,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             }
             p.in_ch[port] = ch;
             bool is_dest = n.kind == K_DEST;
+            if (extend || dest_direct) continue;  // the producer's chain is consumed in registers / written directly
             if (!is_dest && edges.size() == 1 && pn.at(edges[0].node).out_ch[edges[0].port] == ch) {
                 p.in_buf[port] = pn.at(edges[0].node).out_buf[edges[0].port];  // alias, no copy
                 continue;
@@ -463,9 +620,48 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             p.out_buf = {arena_buf(ch)};
             return p.out_buf[0].p != nullptr;
         };
+        // registers this node as the tail of a chain: pending while exactly one consumer may still fuse with it
+        auto finish_chain = [&](PendingChain&& pc) -> bool {
+            p.out_ch = {pc.ch};
+            p.out_buf = {BufRef{nullptr, 0, 0}};
+            pending[id] = std::move(pc);
+            if (!(fuse && consumers(n) == 1)) return materialize(id);
+            return true;
+        };
+        auto source_chain = [&](int kind, int ch) {
+            PendingChain pc;
+            std::memset(&pc.inst, 0, sizeof(pc.inst));
+            pc.inst.src_kind = kind;
+            pc.inst.ch = ch;
+            pc.inst.limit = -1;
+            pc.ch = ch;
+            return pc;
+        };
+        // chain that this biquad / gain / shaper node joins: its producer's pending chain, or a new one reading in_buf
+        auto open_chain = [&]() {
+            if (extend) {
+                PendingChain pc = std::move(pending.at(fuse_src));
+                pending.erase(fuse_src);
+                return pc;
+            }
+            PendingChain pc = source_chain(CHAIN_SRC_BUFFER, p.in_ch[0]);
+            pc.inst.in = p.in_buf[0];
+            return pc;
+        };
         switch (n.kind) {
             case K_DEST: {
                 p.out_ch = {(int)b->channels};
+                if (dest_direct) {  // the chain writes the rendered PCM itself (speaker up-mix 1->2 = copy, quantum.rs:301-305)
+                    PendingChain pc = std::move(pending.at(fuse_src));
+                    pending.erase(fuse_src);
+                    BufRef fin{b->d_out + (size_t)gi * b->channels * b->length, (uint32_t)b->length, 1};
+                    pc.inst.out = fin;
+                    pc.inst.limit = (int64_t)b->length;
+                    pc.inst.out_dup = (pc.ch == 1 && b->channels == 2) ? 2 : 0;
+                    emit_chain(pc, L);
+                    pn.at(fuse_src).out_buf = {fin};
+                    p.in_buf[0] = fin;
+                }
                 p.out_buf = {p.in_buf[0]};
                 algorithmic_bytes += (uint64_t)b->channels * b->length * 4;  // destination write, SURVEY §8(d)
                 break;
@@ -473,9 +669,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             case K_OSC: {
                 float freq, detune;
                 if (!const_param(g, n.params[0], freq) || !const_param(g, n.params[1], detune)) return false;
-                if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (!fuse && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 OscInst o{};
-                o.out = p.out_buf[0];
+                if (!fuse) o.out = p.out_buf[0];
                 o.type = n.type;
                 double computed_freq = (double)freq * std::exp2((double)detune / 1200.);  // oscillator.rs:30-32
                 o.incr = computed_freq / sr;
@@ -516,22 +712,28 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     }
                 }
                 if (n.type == WAE_OSC_CUSTOM) {
-                    float* d = b->dupload(n.table);
+                    float* d = upload(n.table);
                     o.table = d;
                     o.table_len = (int)n.table.size();
                 } else {
                     o.table = eng->d_sine;
                     o.table_len = 2048;
                 }
-                stage(L, S_OSC).osc.push_back(o);
+                if (fuse) {
+                    PendingChain pc = source_chain(CHAIN_SRC_OSC, 1);
+                    pc.inst.osc = o;
+                    if (!finish_chain(std::move(pc))) return false;
+                } else {
+                    stage(L, S_OSC).osc.push_back(o);
+                }
                 break;
             }
             case K_CONST: {
                 float v;
                 if (!const_param(g, n.params[0], v)) return false;
-                if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (!fuse && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 ConstInst c{};
-                c.out = p.out_buf[0];
+                if (!fuse) c.out = p.out_buf[0];
                 c.value = v;
                 c.n_first = std::numeric_limits<int64_t>::max();
                 c.n_stop = std::numeric_limits<int64_t>::max();
@@ -540,7 +742,13 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     c.n_first = clock.first_frame_at_or_after(n.start_time);
                     if (n.stop_time < 1e300) c.n_stop = clock.first_frame_at_or_after(n.stop_time);
                 }
-                stage(L, S_CONST).cst.push_back(c);
+                if (fuse) {
+                    PendingChain pc = source_chain(CHAIN_SRC_CONST, 1);
+                    pc.inst.cst = c;
+                    if (!finish_chain(std::move(pc))) return false;
+                } else {
+                    stage(L, S_CONST).cst.push_back(c);
+                }
                 break;
             }
             case K_ABSN: {
@@ -569,22 +777,35 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (!fast)
                     return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode slow track (unaligned start, offset/duration, stop, playbackRate/"
                                                  "detune != 1, custom loop points, resampling) is not lowered to the GPU yet");
-                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (!fuse && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
-                float* d_buf = b->dalloc<float>((size_t)ch * len);
-                if (!d_buf) return bail(WAE_OUT_OF_MEMORY, "out of device memory (source PCM)");
-                for (int c = 0; c < ch; c++) b->uploads.push_back({d_buf + (size_t)c * len, pb.channels[c].data(), len * sizeof(float)});
+                size_t stride = (len + 3) / 4 * 4;  // every channel starts 16 B aligned (LDG.128)
+                float* d_buf = d_src + src_cursor;
+                if (!dry)
+                    for (int c = 0; c < ch; c++) {
+                        float* dst = h_src + src_cursor + (size_t)c * stride;
+                        std::memcpy(dst, pb.channels[c].data(), len * sizeof(float));
+                        for (size_t i = len; i < stride; i++) dst[i] = 0.f;
+                    }
+                src_cursor += (size_t)ch * stride;
                 b->asset_bytes += (size_t)ch * len * 4;
                 AbsnInst a{};
-                a.out = p.out_buf[0];
+                if (!fuse) a.out = p.out_buf[0];
                 a.buf = d_buf;
                 a.buf_len = (int64_t)len;
+                a.buf_stride = (int64_t)stride;
                 a.n_start = q * 128;
                 a.n_stop = std::numeric_limits<int64_t>::max();
                 a.buf_offset = 0;
                 a.ch = ch;
                 a.loop = n.loop ? 1 : 0;
-                stage(L, S_ABSN).absn.push_back(a);
+                if (fuse) {
+                    PendingChain pc = source_chain(CHAIN_SRC_ABSN, ch);
+                    pc.inst.absn = a;
+                    if (!finish_chain(std::move(pc))) return false;
+                } else {
+                    stage(L, S_ABSN).absn.push_back(a);
+                }
                 // compulsory read of the source PCM that is actually played
                 algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::max<int64_t>(0, std::min<int64_t>(b->lq - a.n_start, n.loop ? b->lq : (int64_t)len));
                 break;
@@ -595,38 +816,30 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     !const_param(g, n.params[3], gain))
                     return false;
                 int ch = p.in_ch[0];
-                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 float cf = hm::biquad_computed_freq(freq, detune);
                 hm::BiquadCoefs c = hm::biquad_coefs(n.type, sr, (double)cf, (double)gain, (double)q);
-                BiquadInst bi{};
-                bi.in = p.in_buf[0];
-                bi.out = p.out_buf[0];
-                bi.b0 = c.b0; bi.b1 = c.b1; bi.b2 = c.b2; bi.a1 = c.a1; bi.a2 = c.a2;
-                bi.ch = ch;
-                bi.state = b->dalloc<double>((size_t)ch * 4, true, true);
-                if (!bi.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
-                StageBuild& s = stage(L, S_BIQUAD);
-                s.max_ch = std::max(s.max_ch, ch);
-                s.biquad.push_back(bi);
-                // scan coefficients: h1/h2 = first row of M^(j+1); P[d] = (M^8)^(2^d)
-                BiquadScanCoef sc{};
-                double m00 = -c.a1, m01 = -c.a2, m10 = 1., m11 = 0.;
-                double r00 = 1., r01 = 0., r10 = 0., r11 = 1.;
-                for (int j = 0; j < 8; j++) {
-                    double t00 = m00 * r00 + m01 * r10, t01 = m00 * r01 + m01 * r11;
-                    double t10 = m10 * r00 + m11 * r10, t11 = m10 * r01 + m11 * r11;
-                    r00 = t00; r01 = t01; r10 = t10; r11 = t11;
-                    sc.h1[j] = r00;
-                    sc.h2[j] = r01;
+                double* state = alloc<double>((size_t)ch * 4, true, true);
+                if (!state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                if (eng->serial_filters) {  // bit-faithful serial recurrence, one stage per biquad
+                    if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    BiquadInst bi{};
+                    bi.in = p.in_buf[0];
+                    bi.out = p.out_buf[0];
+                    bi.b0 = c.b0; bi.b1 = c.b1; bi.b2 = c.b2; bi.a1 = c.a1; bi.a2 = c.a2;
+                    bi.ch = ch;
+                    bi.state = state;
+                    StageBuild& s = stage(L, S_BIQUAD);
+                    s.max_ch = std::max(s.max_ch, ch);
+                    s.biquad.push_back(bi);
+                    break;
                 }
-                double p00 = r00, p01 = r01, p10 = r10, p11 = r11;
-                for (int d = 0; d < 8; d++) {
-                    sc.P[d][0] = p00; sc.P[d][1] = p01; sc.P[d][2] = p10; sc.P[d][3] = p11;
-                    double t00 = p00 * p00 + p01 * p10, t01 = p00 * p01 + p01 * p11;
-                    double t10 = p10 * p00 + p11 * p10, t11 = p10 * p01 + p11 * p11;
-                    p00 = t00; p01 = t01; p10 = t10; p11 = t11;
-                }
-                s.biquad_coef.push_back(sc);
+                PendingChain pc = open_chain();
+                ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
+                st.kind = CHAIN_BIQUAD;
+                st.state = state;
+                st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
+                pc.coefs.push_back(make_scan_coef(c));
+                if (!finish_chain(std::move(pc))) return false;
                 break;
             }
             case K_IIR: {
@@ -645,7 +858,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     ii.b[i] = ff[i] / a0;
                     ii.a[i] = fb[i] / a0;
                 }
-                ii.state = b->dalloc<double>((size_t)ch * 20, true, true);
+                ii.state = alloc<double>((size_t)ch * 20, true, true);
                 if (!ii.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
                 StageBuild& s = stage(L, S_IIR);
                 s.max_ch = std::max(s.max_ch, ch);
@@ -656,24 +869,42 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 float gv;
                 if (!const_param(g, n.params[0], gv)) return false;
                 int ch = p.in_ch[0];
-                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 // gain.rs:153-169: |g| <= 1e-6 -> silence, |1-g| <= 1e-6 -> pass-through (quanta >= 1; quantum 0 takes
                 // the multiply path, a difference of at most 1e-6 * |x| that is below the parity tolerance)
                 if (std::fabs(gv) <= 1e-6f) gv = 0.f;
                 else if (std::fabs(1.f - gv) <= 1e-6f) gv = 1.f;
+                if (fuse) {
+                    PendingChain pc = open_chain();
+                    ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
+                    st.kind = CHAIN_GAIN;
+                    st.gain = gv;
+                    if (!finish_chain(std::move(pc))) return false;
+                    break;
+                }
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch});
                 break;
             }
             case K_SHAPER: {
                 int ch = p.in_ch[0];
+                const float* curve = n.has_curve ? upload(n.table) : nullptr;
+                if (fuse) {
+                    PendingChain pc = open_chain();
+                    ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
+                    st.kind = CHAIN_SHAPER;
+                    st.curve = curve;
+                    st.n = (int)n.table.size();
+                    if (!finish_chain(std::move(pc))) return false;
+                    break;
+                }
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                ShaperInst s{};
-                s.in = p.in_buf[0];
-                s.out = p.out_buf[0];
-                s.ch = ch;
-                s.n = (int)n.table.size();
-                s.curve = n.has_curve ? b->dupload(n.table) : nullptr;
-                stage(L, S_SHAPER).shaper.push_back(s);
+                ShaperInst sh{};
+                sh.in = p.in_buf[0];
+                sh.out = p.out_buf[0];
+                sh.ch = ch;
+                sh.n = (int)n.table.size();
+                sh.curve = curve;
+                stage(L, S_SHAPER).shaper.push_back(sh);
                 break;
             }
             case K_SPANNER: {
@@ -762,7 +993,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 d.k = (float)(position - pf);
                 uint64_t max_frames = (uint64_t)std::ceil(n.max_delay_time * sr) + 2;
                 d.ring_len = next_pow2(max_frames + 128);
-                d.ring = b->dalloc<float>((size_t)ch * d.ring_len, true, true);
+                d.ring = alloc<float>((size_t)ch * d.ring_len, true, true);
                 if (!d.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (delay ring)");
                 b->arena_bytes += (size_t)ch * d.ring_len * 4;
                 stage(L, S_DELAY).delay.push_back(d);
@@ -782,8 +1013,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 int ring_size = (int)std::ceil(g->sample_rate * 0.006f / 128.f) + 1;  // dynamics_compressor.rs:250-255
                 c.delay_frames = (ring_size - 1) * 128;
                 c.ring_len = next_pow2((uint64_t)c.delay_frames + 128);
-                c.ring = b->dalloc<float>((size_t)ch * c.ring_len, true, true);
-                c.state = b->dalloc<float>(2, true, true);
+                c.ring = alloc<float>((size_t)ch * c.ring_len, true, true);
+                c.state = alloc<float>(2, true, true);
                 if (!c.ring || !c.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (compressor)");
                 c.threshold = th; c.knee = kn; c.ratio = ra; c.attack = at; c.release = re;
                 c.sample_rate = g->sample_rate;
@@ -797,10 +1028,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 a.in = p.in_buf[0];
                 a.out = p.out_buf[0];
                 a.ch = ch;
-                a.ring = b->dalloc<float>(32768 + 128, true, true);
+                a.ring = alloc<float>(32768 + 128, true, true);
                 if (!a.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser ring)");
                 stage(L, S_ANALYSER).analyser.push_back(a);
-                b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing});
+                if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing});
                 algorithmic_bytes += (uint64_t)b->lq * 4;  // ring write, SURVEY §8(d)
                 break;
             }
@@ -833,6 +1064,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             default: return bail(WAE_UNSUPPORTED, "node kind not lowered to the GPU");
         }
     }
+    // chains whose single consumer never showed up as an audio input (e.g. it feeds an AudioParam): materialise
+    while (!pending.empty())
+        if (!materialize(pending.begin()->first)) return false;
     return true;
 }
 
@@ -896,6 +1130,10 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             return WAE_OK;
         case WAE_OPT_FUSE: eng->fuse = value != 0; return WAE_OK;
         case WAE_OPT_SERIAL_FILTERS: eng->serial_filters = value != 0; return WAE_OK;
+        case WAE_OPT_PIPELINE_GROUPS:
+            if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "pipeline groups must be in [0, 1024]");
+            eng->pipeline_groups = (int)value;
+            return WAE_OK;
         default: return fail(WAE_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -904,7 +1142,13 @@ WAE_API wae_status wae_batch_destroy(wae_batch* b) {
     if (!b) return WAE_OK;
     cudaSetDevice(b->engine->device);
     cudaStreamSynchronize(b->engine->stream);
-    for (const void* h : b->registered_host) cudaHostUnregister(const_cast<void*>(h));
+    for (void* h : b->pinned) cudaFreeHost(h);
+    for (auto& g : b->groups) {
+        if (g.ev_h2d) cudaEventDestroy(g.ev_h2d);
+        if (g.ev_done) cudaEventDestroy(g.ev_done);
+    }
+    if (b->s_h2d) cudaStreamDestroy(b->s_h2d);
+    if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
     for (void* p : b->allocs) cudaFree(p);
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
@@ -928,90 +1172,137 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     b->length = graphs[0]->length;
     b->lq = (int64_t)((b->length + 127) / 128 * 128);
     bool has_conv = false;
-    size_t node_count = 0;
     for (uint32_t i = 0; i < n_graphs; i++)
-        for (auto& kv : graphs[i]->nodes) {
+        for (auto& kv : graphs[i]->nodes)
             if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
-            if (kv.second.kind != K_PARAM) node_count++;
-        }
-    // chunk size: explicit option, else sized so that the arena (~3 live buffers of 2 channels per node) stays
-    // within ~64 MiB (L2-resident edge buffers), bounded to [2048, 65536] frames; convolvers want whole
-    // 1024-frame blocks and long chunks (their spectra ring is the state that matters)
-    int64_t chunk = eng->chunk_frames;
-    if (chunk == 0) {
-        double per_frame = (double)node_count * 2.0 * 4.0;
-        chunk = (int64_t)(64.0 * 1024 * 1024 / std::max(per_frame, 1.0));
-        chunk = std::max<int64_t>(2048, std::min<int64_t>(chunk, 65536));
-        if (has_conv) chunk = std::max<int64_t>(chunk, 16384);
-        chunk = chunk / 2048 * 2048;
-    }
-    if (has_conv) chunk = (chunk + 1023) / 1024 * 1024;
-    if (chunk > b->lq) chunk = has_conv ? (b->lq + 1023) / 1024 * 1024 : b->lq;
-    b->chunk = chunk;
     size_t out_floats = (size_t)n_graphs * b->channels * b->length;
     b->d_out = b->dalloc<float>(out_floats, true);
     if (!b->d_out) {
         wae_batch_destroy(b);
         return fail(WAE_OUT_OF_MEMORY, "out of device memory (output PCM)");
     }
-    Planner pl{b, eng};
-    for (uint32_t i = 0; i < n_graphs; i++) {
-        if (!pl.plan_graph(graphs[i], i)) {
-            int code = pl.error_code;
-            std::string msg = pl.error;
-            wae_batch_destroy(b);
-            return fail(code, msg);
-        }
+    // graph groups for the H2D / render / D2H pipeline
+    int n_groups = eng->pipeline_groups;
+    if (n_groups == 0) n_groups = n_graphs >= 64 ? 8 : 1;
+    n_groups = std::max(1, std::min<int>(n_groups, (int)n_graphs));
+    b->groups.resize(n_groups);
+    for (int k = 0; k < n_groups; k++) {
+        b->groups[k].g0 = (uint32_t)((uint64_t)n_graphs * k / n_groups);
+        b->groups[k].g1 = (uint32_t)((uint64_t)n_graphs * (k + 1) / n_groups);
     }
-    // materialise the stages in (level, kind) order
-    for (auto& kv : pl.builds) {
-        StageBuild& s = kv.second;
-        Stage st;
-        st.kind = s.kind;
-        st.max_ch = s.max_ch;
-        switch (s.kind) {
-            case S_MIX: st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges); break;
-            case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
-            case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
-            case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
-            case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); st.d_b = up(b, s.biquad_coef); break;
-            case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
-            case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
-            case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
-            case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
-            case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
-            case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
-            case S_DELAY: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
-            case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
-            case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
-            case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); break;
-            case S_CONV_MAC:
-            case S_CONV_MAC_ACC: {
-                st.n = (int)s.conv_path.size();
-                st.d_a = up(b, s.conv_path);
-                // the conv-input table of the same level
-                auto it = pl.builds.find({s.level, S_CONV_FFT});
-                st.d_b = nullptr;
-                for (auto& prev : b->stages)
-                    if (prev.kind == S_CONV_FFT) st.d_b = prev.d_a;  // latest FFT stage = same level (kinds are ordered)
-                (void)it;
-                break;
+    // Sizing pass (no device memory touched): arena floats per frame of the largest group and the source-PCM slab of
+    // every group.  Chunk size: explicit option, else chosen so that a group's arena stays around 48 MiB — edge
+    // buffers are rewritten every chunk and stay L2-resident (126 MB L2).  A plan without any arena buffer (fully
+    // fused source->...->destination chains) renders the whole length in one launch per group.  Convolvers work on
+    // whole 1024-frame blocks and prefer long chunks (their spectra ring, not the arena, is the traffic that matters).
+    b->chunk = 2048;
+    uint64_t fpf = 0;
+    for (int k = 0; k < n_groups; k++) {
+        Planner sizing{b, eng};
+        sizing.dry = true;
+        sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
+        for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
+            if (!sizing.plan_graph(graphs[i], i)) {
+                int code = sizing.error_code;
+                std::string msg = sizing.error;
+                wae_batch_destroy(b);
+                return fail(code, msg);
             }
         }
-        if (st.n > 0) b->stages.push_back(st);
+        fpf = std::max(fpf, sizing.arena_floats_per_frame);
+        b->groups[k].src_floats = sizing.src_cursor;
     }
-    // pin + upload source PCM
-    for (auto& u : b->uploads) {
-        if (cudaHostRegister(const_cast<float*>(u.src), u.bytes, cudaHostRegisterReadOnly) == cudaSuccess)
-            b->registered_host.push_back(u.src);
-        else
-            cudaGetLastError();
-        CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, eng->stream));
+    b->arena_bytes = 0;
+    b->asset_bytes = 0;
+    int64_t chunk = eng->chunk_frames;
+    if (chunk == 0) {
+        if (fpf == 0) {
+            chunk = b->lq;
+        } else {
+            chunk = (int64_t)(48.0 * 1024 * 1024 / (4.0 * (double)fpf));
+            chunk = std::max<int64_t>(2048, std::min<int64_t>(chunk, 1 << 20));
+            chunk = chunk / 2048 * 2048;
+        }
+        if (has_conv) chunk = std::max<int64_t>(chunk, 16384);
+    }
+    if (has_conv) chunk = (chunk + 1023) / 1024 * 1024;
+    if (chunk > b->lq) chunk = has_conv ? (b->lq + 1023) / 1024 * 1024 : b->lq;
+    b->chunk = chunk;
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
+    uint64_t algorithmic_bytes = 0;
+    std::unordered_map<uint64_t, Planner::IrSpectra> ir_cache;
+    for (int k = 0; k < n_groups; k++) {
+        wae_batch::Group& grp = b->groups[k];
+        CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_h2d, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_done, cudaEventDisableTiming));
+        if (grp.src_floats) {
+            grp.d_src = b->dalloc<float>(grp.src_floats);
+            void* hp = nullptr;
+            if (!grp.d_src || cudaHostAlloc(&hp, grp.src_floats * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                wae_batch_destroy(b);
+                return fail(WAE_OUT_OF_MEMORY, "out of memory (source PCM slab / pinned mirror)");
+            }
+            b->pinned.push_back(hp);
+            grp.h_src = (float*)hp;
+        }
+        Planner pl{b, eng};
+        pl.d_src = grp.d_src;
+        pl.h_src = grp.h_src;
+        pl.ir_cache.swap(ir_cache);
+        for (uint32_t i = grp.g0; i < grp.g1; i++) {
+            if (!pl.plan_graph(graphs[i], i)) {
+                int code = pl.error_code;
+                std::string msg = pl.error;
+                wae_batch_destroy(b);
+                return fail(code, msg);
+            }
+        }
+        ir_cache.swap(pl.ir_cache);
+        algorithmic_bytes += pl.algorithmic_bytes;
+        // materialise the group's stages in (level, kind) order
+        grp.stage0 = b->stages.size();
+        void* last_conv_inputs = nullptr;
+        for (auto& kv : pl.builds) {
+            StageBuild& s = kv.second;
+            Stage st;
+            st.kind = s.kind;
+            st.group = k;
+            st.max_ch = s.max_ch;
+            switch (s.kind) {
+                case S_MIX: st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges); break;
+                case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
+                case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
+                case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
+                case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
+                case S_CHAIN: st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); break;
+                case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
+                case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
+                case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
+                case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
+                case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
+                case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
+                case S_DELAY: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
+                case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
+                case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
+                case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
+                case S_CONV_MAC:
+                case S_CONV_MAC_ACC:
+                    st.n = (int)s.conv_path.size();
+                    st.d_a = up(b, s.conv_path);
+                    st.d_b = last_conv_inputs;  // conv-input table of the same level (kinds are ordered FFT < MAC < MAC_ACC)
+                    break;
+            }
+            if (st.n > 0) b->stages.push_back(st);
+        }
+        grp.stage1 = b->stages.size();
+        // first upload of the group's source PCM
+        if (grp.src_floats)
+            CUDA_TRY(cudaMemcpyAsync(grp.d_src, grp.h_src, grp.src_floats * sizeof(float), cudaMemcpyHostToDevice, eng->stream));
     }
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
-    b->stage_events.resize(b->stages.size() + 1);
-    for (auto& e : b->stage_events) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaStreamSynchronize(eng->stream));
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
@@ -1027,7 +1318,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     b->stats.chunks = (uint64_t)n_chunks;
     b->stats.arena_bytes = b->arena_bytes;
     b->stats.asset_bytes = b->asset_bytes;
-    b->stats.algorithmic_bytes = pl.algorithmic_bytes;
+    b->stats.algorithmic_bytes = algorithmic_bytes;
     b->stats.graph_quanta = (uint64_t)n_graphs * (uint64_t)(b->lq / 128);
     *out = b;
     return WAE_OK;
@@ -1041,9 +1332,9 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_CONST: launch_constant((ConstInst*)st.d_a, st.n, ci, s); break;
         case S_ABSN: launch_buffer_source((AbsnInst*)st.d_a, st.n, ci, s); break;
         case S_BIQUAD:
-            if (b->engine->serial_filters) launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
-            else launch_biquad_scan((BiquadInst*)st.d_a, (BiquadScanCoef*)st.d_b, st.n, st.max_ch, ci, s);
+            launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
             break;
+        case S_CHAIN: launch_chain((ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;
         case S_SHAPER: launch_shaper((ShaperInst*)st.d_a, st.n, ci, s); break;
@@ -1059,10 +1350,12 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
     }
 }
 
-// re-upload the source PCM of every AudioBufferSourceNode from (pinned) host memory
+// re-upload the source PCM of every AudioBufferSourceNode from the pinned host mirror (one copy per group)
 WAE_API wae_status wae_batch_upload(wae_batch* b) {
     CUDA_TRY(cudaSetDevice(b->engine->device));
-    for (auto& u : b->uploads) CUDA_TRY(cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, b->engine->stream));
+    for (auto& g : b->groups)
+        if (g.src_floats)
+            CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->engine->stream));
     return WAE_OK;
 }
 
@@ -1071,41 +1364,89 @@ WAE_API wae_status wae_batch_set_timing(wae_batch* b, uint32_t per_stage) {
     return WAE_OK;
 }
 
-WAE_API wae_status wae_batch_run(wae_batch* b) {
+// renders one group (all its chunks, all its stages) on the engine stream
+static wae_status run_group(wae_batch* b, const wae_batch::Group& g) {
+    cudaStream_t s = b->engine->stream;
+    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk) {
+        ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0)};
+        if (b->time_stages) {
+            // per-stage device time: one event between consecutive launches, recorded on the launching stream and
+            // read back in wae_batch_sync (no host synchronisation inside the run)
+            auto next_event = [&]() -> size_t {
+                if (b->timed_events_used == b->stage_events.size()) {
+                    cudaEvent_t e;
+                    if (cudaEventCreate(&e) != cudaSuccess) return (size_t)-1;
+                    b->stage_events.push_back(e);
+                }
+                return b->timed_events_used++;
+            };
+            size_t e_prev = next_event();
+            if (e_prev == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+            CUDA_TRY(cudaEventRecord(b->stage_events[e_prev], s));
+            for (size_t i = g.stage0; i < g.stage1; i++) {
+                launch_stage(b, b->stages[i], ci);
+                size_t e = next_event();
+                if (e == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+                CUDA_TRY(cudaEventRecord(b->stage_events[e], s));
+                b->timed.push_back({i, e_prev, e});
+                e_prev = e;
+            }
+        } else {
+            for (size_t i = g.stage0; i < g.stage1; i++) launch_stage(b, b->stages[i], ci);
+        }
+    }
+    return WAE_OK;
+}
+
+static wae_status begin_run(wae_batch* b) {
     CUDA_TRY(cudaSetDevice(b->engine->device));
     cudaStream_t s = b->engine->stream;
     for (auto& z : b->zero_on_run) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
+    b->timed.clear();
+    b->timed_events_used = 0;
     CUDA_TRY(cudaEventRecord(b->ev0, s));
-    for (auto& st : b->stages) st.ms = 0.f;
-    const size_t per_chunk = b->stages.size() + 1;
-    if (b->time_stages) {
-        // per-stage device time: one event between consecutive stages of every chunk, recorded on the launching
-        // stream and read back in wae_batch_sync (no host synchronisation inside the run)
-        size_t need = per_chunk * (size_t)((b->lq + b->chunk - 1) / b->chunk);
-        while (b->stage_events.size() < need) {
-            cudaEvent_t e;
-            CUDA_TRY(cudaEventCreate(&e));
-            b->stage_events.push_back(e);
-        }
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_run(wae_batch* b) {
+    wae_status st = begin_run(b);
+    if (st != WAE_OK) return st;
+    for (auto& g : b->groups) {
+        st = run_group(b, g);
+        if (st != WAE_OK) return st;
     }
-    size_t chunk_index = 0;
-    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk, chunk_index++) {
-        ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0)};
-        if (b->time_stages) {
-            cudaEvent_t* ev = b->stage_events.data() + chunk_index * per_chunk;
-            CUDA_TRY(cudaEventRecord(ev[0], s));
-            for (size_t i = 0; i < b->stages.size(); i++) {
-                launch_stage(b, b->stages[i], ci);
-                CUDA_TRY(cudaEventRecord(ev[i + 1], s));
-            }
-        } else {
-            for (auto& st : b->stages) launch_stage(b, st, ci);
-        }
-    }
-    b->timed_chunks = b->time_stages ? chunk_index : 0;
-    CUDA_TRY(cudaEventRecord(b->ev1, s));
+    CUDA_TRY(cudaEventRecord(b->ev1, b->engine->stream));
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string("run: ") + cudaGetErrorString(le));
+    return WAE_OK;
+}
+
+// End-to-end render with HOST buffers: for every group, H2D of its source PCM (pinned mirror), render, D2H of its
+// rendered PCM into `host_out` ([n_graphs][channels][length] f32; pinned memory gives full PCIe speed) — on three
+// streams, so the copies of neighbouring groups overlap the render.  Synchronous: returns when host_out is complete.
+WAE_API wae_status wae_batch_run_pipelined(wae_batch* b, float* host_out) {
+    wae_status st = begin_run(b);
+    if (st != WAE_OK) return st;
+    cudaStream_t s = b->engine->stream;
+    const size_t per_graph = (size_t)b->channels * b->length;
+    for (auto& g : b->groups) {
+        if (g.src_floats) {
+            CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->s_h2d));
+            CUDA_TRY(cudaEventRecord(g.ev_h2d, b->s_h2d));
+            CUDA_TRY(cudaStreamWaitEvent(s, g.ev_h2d, 0));
+        }
+        st = run_group(b, g);
+        if (st != WAE_OK) return st;
+        CUDA_TRY(cudaEventRecord(g.ev_done, s));
+        CUDA_TRY(cudaStreamWaitEvent(b->s_d2h, g.ev_done, 0));
+        CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)g.g0 * per_graph, b->d_out + (size_t)g.g0 * per_graph,
+                                 (size_t)(g.g1 - g.g0) * per_graph * sizeof(float), cudaMemcpyDeviceToHost, b->s_d2h));
+    }
+    CUDA_TRY(cudaEventRecord(b->ev1, s));
+    CUDA_TRY(cudaStreamSynchronize(b->s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string("run_pipelined: ") + cudaGetErrorString(le));
     return WAE_OK;
 }
 
@@ -1115,24 +1456,19 @@ WAE_API wae_status wae_batch_sync(wae_batch* b) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, b->ev0, b->ev1) == cudaSuccess) b->stats.last_run_ms = ms;
     else cudaGetLastError();
-    if (b->timed_chunks) {
-        const size_t per_chunk = b->stages.size() + 1;
+    if (!b->timed.empty()) {
         for (auto& st : b->stages) st.ms = 0.f;
-        for (size_t c = 0; c < b->timed_chunks; c++)
-            for (size_t i = 0; i < b->stages.size(); i++) {
-                float t = 0.f;
-                if (cudaEventElapsedTime(&t, b->stage_events[c * per_chunk + i], b->stage_events[c * per_chunk + i + 1]) == cudaSuccess)
-                    b->stages[i].ms += t;
-                else
-                    cudaGetLastError();
-            }
+        for (auto& t : b->timed) {
+            float v = 0.f;
+            if (cudaEventElapsedTime(&v, b->stage_events[t.e0], b->stage_events[t.e1]) == cudaSuccess) b->stages[t.stage].ms += v;
+            else cudaGetLastError();
+        }
         int best = -1;
         for (size_t i = 0; i < b->stages.size(); i++)
             if (best < 0 || b->stages[i].ms > b->stages[best].ms) best = (int)i;
         if (best >= 0) {
             b->stats.dominant_kernel_ms = b->stages[best].ms;
             const char* nm = kStageNames[b->stages[best].kind];
-            if (b->stages[best].kind == S_BIQUAD) nm = b->engine->serial_filters ? "k_biquad_serial" : "k_biquad_scan";
             std::snprintf(b->stats.dominant_kernel, sizeof(b->stats.dominant_kernel), "%s", nm);
         }
     }
@@ -1157,7 +1493,6 @@ WAE_API wae_status wae_batch_stage_time(wae_batch* b, uint32_t index, char* name
     if (index >= b->stages.size()) return fail(WAE_INVALID_ARGUMENT, "stage index out of range");
     const Stage& st = b->stages[index];
     const char* nm = kStageNames[st.kind];
-    if (st.kind == S_BIQUAD) nm = b->engine->serial_filters ? "k_biquad_serial" : "k_biquad_scan";
     std::snprintf(name64, 64, "%s", nm);
     *ms = st.ms;
     *n_instances = (uint32_t)st.n;
@@ -1173,6 +1508,13 @@ WAE_API wae_status wae_render_batch(wae_engine* eng, wae_graph* const* graphs, u
     wae_batch* b = nullptr;
     wae_status st = wae_batch_prepare(eng, graphs, n_graphs, &b);
     if (st != WAE_OK) return st;
+    if (!(flags & WAE_RENDER_OUT_DEVICE)) {
+        st = wae_batch_run_pipelined(b, out);  // source PCM was uploaded at prepare; the pipeline re-sends it per group
+        std::string saved0 = wae_last_error();
+        wae_batch_destroy(b);
+        if (st != WAE_OK) set_error(saved0);
+        return st;
+    }
     st = wae_batch_run(b);
     if (st == WAE_OK) st = wae_batch_sync(b);
     if (st == WAE_OK) {

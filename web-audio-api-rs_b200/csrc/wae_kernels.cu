@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(256) k_buffer_source(const AbsnInst* __restric
         if (n0 >= ci.nf) continue;
         for (int c = 0; c < o.ch; c++) {
             float* out = chan(o.out, c, ci);
-            const float* src = o.buf + (size_t)c * o.buf_len;
+            const float* src = o.buf + (size_t)c * o.buf_stride;
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -226,121 +226,285 @@ __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restr
     st[3] = y2;
 }
 
-constexpr int BQ_K = 8;          // frames per thread
-constexpr int BQ_THREADS = 256;  // threads per CTA -> tile = 2048 frames
+DEVI float shaper_apply(const float* curve, int len, float input);
 
-__global__ void __launch_bounds__(BQ_THREADS) k_biquad_scan(const BiquadInst* __restrict__ insts,
-                                                            const BiquadScanCoef* __restrict__ coefs, int n_inst, ChunkInfo ci) {
-    const int ii = blockIdx.x;
-    const int c = blockIdx.y;
-    const BiquadInst q = insts[ii];
-    if (c >= q.ch) return;
-    const BiquadScanCoef& sc = coefs[ii];
-    const float* in = chan(q.in, c, ci);
-    float* out = chan(q.out, c, ci);
-    double* st = q.state + 4 * c;
-    __shared__ double sh_a[BQ_THREADS], sh_b[BQ_THREADS];
-    __shared__ double tile_state[4];
-    const int t = threadIdx.x;
-    if (t == 0) {
-        tile_state[0] = st[0];
-        tile_state[1] = st[1];
-        tile_state[2] = st[2];
-        tile_state[3] = st[3];
-    }
-    // per-thread copies of the homogeneous responses h1[j], h2[j], j < K
-    double h1[BQ_K], h2[BQ_K];
+constexpr int CH_K = 8;          // frames per thread
+constexpr int CH_THREADS = 256;  // threads per CTA -> tile = 2048 frames
+constexpr int CH_WARPS = CH_THREADS / 32;
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused chain — source -> {BiquadFilter | Gain | WaveShaper}* -> buffer / destination in ONE pass over the PCM.
+// One CTA per (instance, channel); the chunk is walked in tiles of 256 threads x 8 frames, the next tile's
+// source frames are prefetched while the current tile is filtered.  Replaces, for chain-shaped sub-graphs,
+// AudioBufferSourceRenderer / OscillatorRenderer / ConstantSourceRenderer + BiquadFilterRenderer + GainRenderer +
+// WaveShaperRenderer + the destination copy (src/node/{audio_buffer_source,oscillator,constant_source,
+// biquad_filter,gain,waveshaper,destination}.rs), so that a graph-quantum costs its compulsory HBM bytes only
+// (source read + destination write).
+//
+// Biquad step = the time-parallel recurrence: each thread runs its 8 frames from zero state (y0), the end states
+// are scanned — 5 shuffle steps inside a warp with A^(2^d), then the 8 warp totals are chained with A^32 — and
+// the homogeneous response is added back:  y[j] = y0[j] + h1[j]*y[-1] + h2[j]*y[-2]   (f64, fma).
+// ---------------------------------------------------------------------------------------------------------
+DEVI void mat2_apply(const double* P, double a, double b, double& oa, double& ob) {
+    oa = fma(P[0], a, P[1] * b);
+    ob = fma(P[2], a, P[3] * b);
+}
+
+DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int n0, float v[CH_K]) {
+    // n0: first frame (chunk-relative) of this thread's 8 frames; caller guarantees n0 < ci.nf
+    switch (q.src_kind) {
+        case CHAIN_SRC_BUFFER: {
+            const float* in = chan(q.in, c, ci) + n0;
+            float4 a = *reinterpret_cast<const float4*>(in);
+            float4 b = *reinterpret_cast<const float4*>(in + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            break;
+        }
+        case CHAIN_SRC_ABSN: {
+            const AbsnInst& o = q.absn;
+            const float* src = o.buf + (size_t)c * o.buf_stride;
+            int64_t n = ci.f0 + n0;
+            int64_t idx = n - o.n_start + o.buf_offset;
+            if (!o.loop && n >= o.n_start && idx + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) {  // aligned interior: 2 x LDG.128
+                float4 a = __ldg(reinterpret_cast<const float4*>(src + idx));
+                float4 b = __ldg(reinterpret_cast<const float4*>(src + idx + 4));
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
 #pragma unroll
-    for (int j = 0; j < BQ_K; j++) {
-        h1[j] = sc.h1[j];
-        h2[j] = sc.h2[j];
+                for (int j = 0; j < CH_K; j++) {
+                    int64_t m = n + j;
+                    float s = 0.f;
+                    if (m >= o.n_start && m < o.n_stop) {
+                        int64_t id = m - o.n_start + o.buf_offset;
+                        if (o.loop) s = __ldg(src + (id % o.buf_len));
+                        else if (id < o.buf_len) s = __ldg(src + id);
+                    }
+                    v[j] = s;
+                }
+            }
+            break;
+        }
+        case CHAIN_SRC_OSC: {
+            const OscInst& o = q.osc;
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) {
+                int64_t n = ci.f0 + n0 + j;
+                float s = 0.f;
+                if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
+                v[j] = s;
+            }
+            break;
+        }
+        default: {
+            const ConstInst& o = q.cst;
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) {
+                int64_t n = ci.f0 + n0 + j;
+                v[j] = (n >= o.n_first && n < o.n_stop) ? o.value : 0.f;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs, int n_inst,
+                                                     ChunkInfo ci) {
+    __shared__ ChainInst q;
+    __shared__ double s_state[CHAIN_MAX_BIQUADS][4];         // x1, x2, y1, y2 carried from tile to tile
+    __shared__ double s_wtot[CH_WARPS][2];                    // per-warp end state (zero incoming state)
+    __shared__ float s_edge[CH_WARPS][2];                     // last two step inputs of every warp
+    __shared__ double s_h[CHAIN_MAX_BIQUADS][2 * CH_K + 24];  // h1[8], h2[8], Pshfl[5][4], Pwarp[4]
+    const int c = blockIdx.y;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    {
+        const int* src = reinterpret_cast<const int*>(insts + blockIdx.x);
+        int* dst = reinterpret_cast<int*>(&q);
+        for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    for (int base = 0; base < ci.nf; base += BQ_THREADS * BQ_K) {
-        const int n0 = base + t * BQ_K;
-        const bool active = n0 < ci.nf;  // nf is a multiple of 128 and K divides 128
-        double x[BQ_K + 2];
-        double y0[BQ_K];
-        if (active) {
-            float4 a = *reinterpret_cast<const float4*>(in + n0);
-            float4 b = *reinterpret_cast<const float4*>(in + n0 + 4);
-            x[2] = a.x; x[3] = a.y; x[4] = a.z; x[5] = a.w;
-            x[6] = b.x; x[7] = b.y; x[8] = b.z; x[9] = b.w;
-            if (n0 >= 2) {
-                x[1] = (double)in[n0 - 1];
-                x[0] = (double)in[n0 - 2];
-            } else {  // first thread of the chunk: previous inputs come from the carried state
-                x[1] = tile_state[0];
-                x[0] = tile_state[1];
-            }
-            double p1 = 0., p2 = 0.;
-#pragma unroll
-            for (int j = 0; j < BQ_K; j++) {
-                double w = fma(q.b2, x[j], fma(q.b1, x[j + 1], q.b0 * x[j + 2]));
-                double y = fma(-q.a1, p1, fma(-q.a2, p2, w));
-                y0[j] = y;
-                p2 = p1;
-                p1 = y;
-            }
+    if (c >= q.ch) return;
+    // biquad bookkeeping
+    int n_bq = 0;
+    for (int s = 0; s < q.n_steps; s++) {
+        if (q.steps[s].kind != CHAIN_BIQUAD) continue;
+        const ScanCoef& sc = coefs[q.steps[s].coef];
+        if (t < CH_K) {
+            s_h[n_bq][t] = sc.h1[t];
+            s_h[n_bq][CH_K + t] = sc.h2[t];
         }
-        // Kogge-Stone scan of the end states: S_t = M^K S_{t-1} + v_t, v_t = (y0[K-1], y0[K-2])
-        double va = active ? y0[BQ_K - 1] : 0., vb = active ? y0[BQ_K - 2] : 0.;
-        if (t == 0) {  // fold the incoming tile state into thread 0
-            double s1 = tile_state[2], s2 = tile_state[3];
-            va += sc.P[0][0] * s1 + sc.P[0][1] * s2;
-            vb += sc.P[0][2] * s1 + sc.P[0][3] * s2;
+        if (t < 20) s_h[n_bq][2 * CH_K + t] = (&sc.Pshfl[0][0])[t];
+        if (t < 4) {
+            s_h[n_bq][2 * CH_K + 20 + t] = sc.Pwarp[t];
+            s_state[n_bq][t] = q.steps[s].state[4 * c + t];
         }
-        sh_a[t] = va;
-        sh_b[t] = vb;
-        __syncthreads();
-#pragma unroll
-        for (int d = 0; d < 8; d++) {
-            const int off = 1 << d;
-            double oa = 0., ob = 0.;
-            if (t >= off) {
-                oa = sh_a[t - off];
-                ob = sh_b[t - off];
-            }
-            __syncthreads();
-            if (t >= off) {
-                va += sc.P[d][0] * oa + sc.P[d][1] * ob;
-                vb += sc.P[d][2] * oa + sc.P[d][3] * ob;
-                sh_a[t] = va;
-                sh_b[t] = vb;
-            }
-            __syncthreads();
-        }
-        // exclusive state for this thread
-        double e1, e2;
-        if (t == 0) {
-            e1 = tile_state[2];
-            e2 = tile_state[3];
-        } else {
-            e1 = sh_a[t - 1];
-            e2 = sh_b[t - 1];
-        }
-        const int last_active = min(BQ_THREADS, (ci.nf - base) / BQ_K) - 1;
-        __syncthreads();
-        if (active) {
-            float o[BQ_K];
-#pragma unroll
-            for (int j = 0; j < BQ_K; j++) o[j] = (float)fma(h1[j], e1, fma(h2[j], e2, y0[j]));
-            *reinterpret_cast<float4*>(out + n0) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(out + n0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-            if (t == last_active) {
-                tile_state[0] = x[BQ_K + 1];
-                tile_state[1] = x[BQ_K];
-                tile_state[2] = fma(h1[BQ_K - 1], e1, fma(h2[BQ_K - 1], e2, y0[BQ_K - 1]));
-                tile_state[3] = fma(h1[BQ_K - 2], e1, fma(h2[BQ_K - 2], e2, y0[BQ_K - 2]));
-            }
-        }
-        __syncthreads();
+        n_bq++;
     }
-    if (t == 0) {
-        st[0] = tile_state[0];
-        st[1] = tile_state[1];
-        st[2] = tile_state[2];
-        st[3] = tile_state[3];
+    __syncthreads();
+
+    const int tile = CH_THREADS * CH_K;
+    float v[CH_K], vnext[CH_K];
+    {
+        const int n0 = t * CH_K;
+        if (n0 < ci.nf) chain_load_source(q, c, ci, n0, v);
+    }
+    for (int base = 0; base < ci.nf; base += tile) {
+        const int n0 = base + t * CH_K;
+        const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
+        const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
+        // prefetch the next tile's source frames
+        const int n1 = n0 + tile;
+        const bool have_next = n1 < ci.nf;
+        if (have_next) chain_load_source(q, c, ci, n1, vnext);
+        int bq = 0;
+        for (int s = 0; s < q.n_steps; s++) {
+            const ChainStep& st = q.steps[s];
+            if (st.kind == CHAIN_GAIN) {
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) v[j] *= st.gain;
+            } else if (st.kind == CHAIN_SHAPER) {
+                if (st.curve) {
+#pragma unroll
+                    for (int j = 0; j < CH_K; j++) v[j] = st.n == 0 ? 0.f : shaper_apply(st.curve, st.n, v[j]);
+                }
+            } else {
+                const double* H = s_h[bq];
+                const double* Psh = H + 2 * CH_K;
+                const double* Pw = H + 2 * CH_K + 20;
+                // previous two step inputs: neighbour lane, previous warp, or the carried state
+                float xl1 = active ? v[CH_K - 1] : 0.f, xl2 = active ? v[CH_K - 2] : 0.f;
+                if (lane == 31) {
+                    s_edge[warp][0] = xl1;
+                    s_edge[warp][1] = xl2;
+                }
+                float p1 = __shfl_up_sync(0xffffffffu, xl1, 1);
+                float p2 = __shfl_up_sync(0xffffffffu, xl2, 1);
+                __syncthreads();
+                double xm1, xm2;
+                if (lane == 0) {
+                    if (warp == 0) {
+                        xm1 = s_state[bq][0];
+                        xm2 = s_state[bq][1];
+                    } else {
+                        xm1 = (double)s_edge[warp - 1][0];
+                        xm2 = (double)s_edge[warp - 1][1];
+                    }
+                } else {
+                    xm1 = (double)p1;
+                    xm2 = (double)p2;
+                }
+                // zero-state response of the thread's 8 frames
+                double y0[CH_K];
+                {
+                    double x1 = xm1, x2 = xm2, r1 = 0., r2 = 0.;
+#pragma unroll
+                    for (int j = 0; j < CH_K; j++) {
+                        double x = (double)v[j];
+                        double w = fma(st.b2, x2, fma(st.b1, x1, st.b0 * x));
+                        double y = fma(-st.a1, r1, fma(-st.a2, r2, w));
+                        y0[j] = y;
+                        x2 = x1;
+                        x1 = x;
+                        r2 = r1;
+                        r1 = y;
+                    }
+                }
+                // warp-level inclusive scan of end states: S_t = A S_{t-1} + (y0[7], y0[6])
+                double va = active ? y0[CH_K - 1] : 0., vb = active ? y0[CH_K - 2] : 0.;
+#pragma unroll
+                for (int d = 0; d < 5; d++) {
+                    double oa = __shfl_up_sync(0xffffffffu, va, 1 << d);
+                    double ob = __shfl_up_sync(0xffffffffu, vb, 1 << d);
+                    if (lane >= (1 << d)) {
+                        double ta, tb;
+                        mat2_apply(Psh + 4 * d, oa, ob, ta, tb);
+                        va += ta;
+                        vb += tb;
+                    }
+                }
+                if (lane == 31) {
+                    s_wtot[warp][0] = va;
+                    s_wtot[warp][1] = vb;
+                }
+                // inclusive value of the previous lane (exclusive prefix inside the warp)
+                double ea = __shfl_up_sync(0xffffffffu, va, 1);
+                double eb = __shfl_up_sync(0xffffffffu, vb, 1);
+                __syncthreads();
+                // state entering this warp: chain the previous warps' totals through A^32
+                double wa = s_state[bq][2], wb = s_state[bq][3];
+                for (int k = 0; k < warp; k++) {
+                    double ta, tb;
+                    mat2_apply(Pw, wa, wb, ta, tb);
+                    wa = ta + s_wtot[k][0];
+                    wb = tb + s_wtot[k][1];
+                }
+                // state entering this thread
+                double e1, e2;
+                if (lane == 0) {
+                    e1 = wa;
+                    e2 = wb;
+                } else {
+                    const double* Pl = coefs[st.coef].Plane[lane - 1];
+                    double ta, tb;
+                    mat2_apply(Pl, wa, wb, ta, tb);
+                    e1 = ea + ta;
+                    e2 = eb + tb;
+                }
+                double yl1 = 0., yl2 = 0.;
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) {
+                    double y = fma(H[j], e1, fma(H[CH_K + j], e2, y0[j]));
+                    if (j == CH_K - 1) yl1 = y;
+                    if (j == CH_K - 2) yl2 = y;
+                    v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
+                }
+                __syncthreads();  // everyone has read s_state / s_wtot / s_edge of this step
+                if (active && t == n_active - 1) {
+                    s_state[bq][0] = (double)xl1;
+                    s_state[bq][1] = (double)xl2;
+                    s_state[bq][2] = yl1;
+                    s_state[bq][3] = yl2;
+                }
+                bq++;
+            }
+        }
+        if (active) {
+            const int64_t nabs = ci.f0 + n0;
+            const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + n0) & 15) == 0 &&
+                                 (q.out_dup <= 1 || (q.out.stride & 3) == 0);
+            if (aligned && (q.limit < 0 || nabs + CH_K <= q.limit)) {
+                const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
+                if (q.out_dup > 1) {
+                    for (int oc = 0; oc < q.out_dup; oc++) {
+                        float* out = chan(q.out, oc, ci) + n0;
+                        *reinterpret_cast<float4*>(out) = a;
+                        *reinterpret_cast<float4*>(out + 4) = b;
+                    }
+                } else {
+                    float* out = chan(q.out, c, ci) + n0;
+                    *reinterpret_cast<float4*>(out) = a;
+                    *reinterpret_cast<float4*>(out + 4) = b;
+                }
+            } else {  // unaligned channel base (odd render length) or the last, partial quantum: scalar stores
+                for (int oc = 0; oc < (q.out_dup > 1 ? q.out_dup : 1); oc++) {
+                    float* out = chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0;
+                    for (int j = 0; j < CH_K; j++)
+                        if (q.limit < 0 || nabs + j < q.limit) out[j] = v[j];
+                }
+            }
+        }
+        if (have_next) {
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) v[j] = vnext[j];
+        }
+        __syncthreads();  // s_state of this tile is visible before the next tile reads it
+    }
+    // carry the filter state to the next chunk
+    int bq = 0;
+    for (int s = 0; s < q.n_steps; s++) {
+        if (q.steps[s].kind != CHAIN_BIQUAD) continue;
+        if (t < 4) q.steps[s].state[4 * c + t] = s_state[bq][t];
+        bq++;
     }
 }
 
@@ -848,8 +1012,8 @@ void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, 
     int threads = n * max_ch;
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
 }
-void launch_biquad_scan(const BiquadInst* d, const BiquadScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
-    k_biquad_scan<<<dim3((unsigned)n, (unsigned)max_ch), BQ_THREADS, 0, s>>>(d, c, n, ci);
+void launch_chain(const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    k_chain<<<dim3((unsigned)n, (unsigned)max_ch), CH_THREADS, 0, s>>>(d, c, n, ci);
 }
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;
