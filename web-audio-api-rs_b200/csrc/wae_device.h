@@ -145,30 +145,30 @@ struct RouteInst {  // channel merger / splitter: copy one channel
 
 // ---- fused chain: source -> {biquad | gain | shaper}* -> buffer or destination, one pass over the PCM -------
 enum ChainSrc : int32_t { CHAIN_SRC_BUFFER = 0, CHAIN_SRC_ABSN = 1, CHAIN_SRC_OSC = 2, CHAIN_SRC_CONST = 3 };
-enum ChainStepKind : int32_t { CHAIN_BIQUAD = 0, CHAIN_GAIN = 1, CHAIN_SHAPER = 2 };
-struct ChainStep {
-    int32_t kind;
-    int32_t n;            // shaper: curve length
-    float gain;           // gain
-    int32_t coef;         // biquad: index into the ScanCoef table
-    const float* curve;   // shaper (nullptr: pass-through)
-    double* state;        // biquad: [ch][4]
+struct ChainBiquad {
     double b0, b1, b2, a1, a2;
+    double* state;  // [ch][4] = x1, x2, y1, y2
+    int32_t coef;   // index into the ScanCoef table of the stage
+    int32_t pad;
 };
-constexpr int CHAIN_MAX_STEPS = 6;
 constexpr int CHAIN_MAX_BIQUADS = 2;
+// canonical chain: src -> *g[0] -> [biquad A] -> *g[1] -> [biquad B] -> *g[2] -> [shaper] -> *g[3] -> out
 struct ChainInst {
     int32_t src_kind;
-    int32_t ch;        // channels processed (one CTA each)
-    int32_t n_steps;
-    int32_t out_dup;   // >1: the (mono) result is written to channels 0..out_dup-1 (speaker up-mix 1->2 by copy)
-    BufRef in;         // CHAIN_SRC_BUFFER
-    AbsnInst absn;     // CHAIN_SRC_ABSN (out unused)
-    OscInst osc;       // CHAIN_SRC_OSC (out unused)
-    ConstInst cst;     // CHAIN_SRC_CONST (out unused)
+    int32_t ch;          // channels processed (one CTA each)
+    int32_t n_biquad;    // 0..2
+    int32_t has_shaper;
+    float g[4];
+    int32_t out_dup;     // >1: the (mono) result is written to channels 0..out_dup-1 (speaker up-mix 1->2 by copy)
+    int32_t shaper_n;    // curve length
+    const float* curve;  // nullptr: pass-through
+    BufRef in;           // CHAIN_SRC_BUFFER
+    AbsnInst absn;       // CHAIN_SRC_ABSN (out unused)
+    OscInst osc;         // CHAIN_SRC_OSC (out unused)
+    ConstInst cst;       // CHAIN_SRC_CONST (out unused)
     BufRef out;
-    int64_t limit;     // frames >= limit are not written (destination); < 0: none
-    ChainStep steps[CHAIN_MAX_STEPS];
+    int64_t limit;       // frames >= limit are not written (destination); < 0: none
+    ChainBiquad bq[CHAIN_MAX_BIQUADS];
 };
 
 // ---- convolver (uniformly partitioned overlap-save, block 1024 / FFT 2048, time-batched) -----------------

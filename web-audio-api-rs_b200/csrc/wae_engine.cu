@@ -52,6 +52,7 @@ const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_bu
 struct StageBuild {
     int level = 0;
     int kind = 0;
+    int variant = 0;
     std::vector<OscInst> osc;
     std::vector<ConstInst> cst;
     std::vector<AbsnInst> absn;
@@ -77,6 +78,7 @@ struct StageBuild {
 
 struct Stage {
     int kind = 0;
+    int variant = 0;
     int group = 0;
     int n = 0;
     int max_ch = 1;
@@ -223,7 +225,7 @@ struct PNode {
 struct Planner {
     wae_batch* b;
     wae_engine* eng;
-    std::map<std::pair<int, int>, StageBuild> builds;  // (level, kind)
+    std::map<std::pair<int, int>, StageBuild> builds;  // (level, kind * 64 + variant)
     std::string error;
     int error_code = 0;
     uint64_t algorithmic_bytes = 0;
@@ -245,6 +247,7 @@ struct Planner {
         ChainInst inst;
         std::vector<ScanCoef> coefs;
         int ch = 1;
+        int phase = 0;  // 0: before biquad A, 1: after A, 3: after B, 5: after the shaper (canonical chain order)
     };
 
     template <typename T>
@@ -266,10 +269,11 @@ struct Planner {
         return false;
     }
 
-    StageBuild& stage(int level, int kind) {
-        StageBuild& s = builds[{level, kind}];
+    StageBuild& stage(int level, int kind, int variant = 0) {
+        StageBuild& s = builds[{level, kind * 64 + variant}];
         s.level = level;
         s.kind = kind;
+        s.variant = variant;
         return s;
     }
 
@@ -338,12 +342,8 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
     auto mul = [](const M2& x, const M2& y) { return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; };
     const M2 M{-c.a1, -c.a2, 1., 0.};
     M2 r{1., 0., 0., 1.};
-    for (int j = 0; j < 8; j++) {
-        r = mul(M, r);
-        sc.h1[j] = r.a;
-        sc.h2[j] = r.b;
-    }
-    const M2 A = r;  // M^8
+    for (int j = 0; j < WAE_CHAIN_K; j++) r = mul(M, r);
+    const M2 A = r;  // M^K: one thread of k_chain
     M2 pw = A;
     for (int d = 0; d < 5; d++) {
         sc.Pshfl[d][0] = pw.a; sc.Pshfl[d][1] = pw.b; sc.Pshfl[d][2] = pw.c; sc.Pshfl[d][3] = pw.d;
@@ -515,12 +515,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         return k;
     };
     auto emit_chain = [&](PendingChain& pc, int L) {
-        StageBuild& cs = stage(L, S_CHAIN);
-        for (int i = 0, k = 0; i < pc.inst.n_steps; i++)
-            if (pc.inst.steps[i].kind == CHAIN_BIQUAD) {
-                pc.inst.steps[i].coef = (int32_t)cs.scan_coef.size();
-                cs.scan_coef.push_back(pc.coefs[k++]);
-            }
+        const int variant = pc.inst.src_kind * 6 + pc.inst.n_biquad * 2 + (pc.inst.has_shaper ? 1 : 0);
+        StageBuild& cs = stage(L, S_CHAIN, variant);
+        for (int k = 0; k < pc.inst.n_biquad; k++) {
+            pc.inst.bq[k].coef = (int32_t)cs.scan_coef.size();
+            cs.scan_coef.push_back(pc.coefs[k]);
+        }
         cs.max_ch = std::max(cs.max_ch, pc.ch);
         cs.chain.push_back(pc.inst);
     };
@@ -538,11 +538,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         pending.erase(it);
         return true;
     };
-    auto chain_steps_ok = [&](const ChainInst& ci, bool adding_biquad) {
-        int nb = 0;
-        for (int i = 0; i < ci.n_steps; i++)
-            if (ci.steps[i].kind == CHAIN_BIQUAD) nb++;
-        return ci.n_steps < CHAIN_MAX_STEPS && (!adding_biquad || nb < CHAIN_MAX_BIQUADS);
+    // can a node of this kind still be appended to the canonical chain gain, A, gain, B, gain, shaper, gain?
+    auto chain_accepts = [&](const PendingChain& pc, Kind kind) {
+        if (kind == K_GAIN) return true;
+        if (kind == K_BIQUAD) return pc.phase <= 1;
+        if (kind == K_SHAPER) return pc.phase < 5;
+        return false;
     };
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
@@ -561,7 +562,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             auto it = pending.find(p.in_edges[0][0].node);
             if (it != pending.end()) {
                 int sch = pn.at(it->first).out_ch[0];
-                if (chain_kind && computed_channels(n.cfg, sch) == sch && chain_steps_ok(it->second.inst, n.kind == K_BIQUAD)) {
+                if (chain_kind && computed_channels(n.cfg, sch) == sch && chain_accepts(it->second, n.kind)) {
                     extend = true;
                     fuse_src = it->first;
                 } else if (n.kind == K_DEST && b->length <= 0xffffffffull &&
@@ -634,6 +635,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             pc.inst.src_kind = kind;
             pc.inst.ch = ch;
             pc.inst.limit = -1;
+            for (int i = 0; i < 4; i++) pc.inst.g[i] = 1.f;
             pc.ch = ch;
             return pc;
         };
@@ -834,11 +836,11 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     break;
                 }
                 PendingChain pc = open_chain();
-                ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
-                st.kind = CHAIN_BIQUAD;
+                ChainBiquad& st = pc.inst.bq[pc.inst.n_biquad++];
                 st.state = state;
                 st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
                 pc.coefs.push_back(make_scan_coef(c));
+                pc.phase = pc.phase == 0 ? 1 : 3;
                 if (!finish_chain(std::move(pc))) return false;
                 break;
             }
@@ -875,9 +877,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 else if (std::fabs(1.f - gv) <= 1e-6f) gv = 1.f;
                 if (fuse) {
                     PendingChain pc = open_chain();
-                    ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
-                    st.kind = CHAIN_GAIN;
-                    st.gain = gv;
+                    // consecutive gains of one slot are folded (differs from two f32 multiplies by <= 1 ulp)
+                    pc.inst.g[pc.phase == 0 ? 0 : (pc.phase == 1 ? 1 : (pc.phase == 3 ? 2 : 3))] *= gv;
                     if (!finish_chain(std::move(pc))) return false;
                     break;
                 }
@@ -890,10 +891,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 const float* curve = n.has_curve ? upload(n.table) : nullptr;
                 if (fuse) {
                     PendingChain pc = open_chain();
-                    ChainStep& st = pc.inst.steps[pc.inst.n_steps++];
-                    st.kind = CHAIN_SHAPER;
-                    st.curve = curve;
-                    st.n = (int)n.table.size();
+                    pc.inst.has_shaper = 1;
+                    pc.inst.curve = curve;
+                    pc.inst.shaper_n = (int)n.table.size();
+                    pc.phase = 5;
                     if (!finish_chain(std::move(pc))) return false;
                     break;
                 }
@@ -1268,6 +1269,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             StageBuild& s = kv.second;
             Stage st;
             st.kind = s.kind;
+            st.variant = s.variant;
             st.group = k;
             st.max_ch = s.max_ch;
             switch (s.kind) {
@@ -1334,7 +1336,7 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_BIQUAD:
             launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
             break;
-        case S_CHAIN: launch_chain((ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
+        case S_CHAIN: launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;
         case S_SHAPER: launch_shaper((ShaperInst*)st.d_a, st.n, ci, s); break;

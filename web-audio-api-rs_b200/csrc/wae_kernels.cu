@@ -228,266 +228,269 @@ __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restr
 
 DEVI float shaper_apply(const float* curve, int len, float input);
 
-constexpr int CH_K = 8;          // frames per thread
-constexpr int CH_THREADS = 256;  // threads per CTA -> tile = 2048 frames
+constexpr int CH_K = WAE_CHAIN_K;  // frames per thread
+constexpr int CH_THREADS = 128;  // threads per CTA -> tile = 2048 frames
 constexpr int CH_WARPS = CH_THREADS / 32;
 
 // ---------------------------------------------------------------------------------------------------------
-// Fused chain — source -> {BiquadFilter | Gain | WaveShaper}* -> buffer / destination in ONE pass over the PCM.
-// One CTA per (instance, channel); the chunk is walked in tiles of 256 threads x 8 frames, the next tile's
-// source frames are prefetched while the current tile is filtered.  Replaces, for chain-shaped sub-graphs,
-// AudioBufferSourceRenderer / OscillatorRenderer / ConstantSourceRenderer + BiquadFilterRenderer + GainRenderer +
-// WaveShaperRenderer + the destination copy (src/node/{audio_buffer_source,oscillator,constant_source,
-// biquad_filter,gain,waveshaper,destination}.rs), so that a graph-quantum costs its compulsory HBM bytes only
-// (source read + destination write).
+// Fused chain — source -> gain -> [biquad A] -> gain -> [biquad B] -> gain -> [wave-shaper] -> gain -> buffer or
+// destination, in ONE pass over the PCM.  One CTA per (instance, channel); the chunk is walked in tiles of
+// 128 threads x 16 frames, the next tile's source frames are prefetched while the current tile is filtered.
+// Replaces, for chain-shaped sub-graphs, AudioBufferSourceRenderer / OscillatorRenderer / ConstantSourceRenderer +
+// BiquadFilterRenderer + GainRenderer + WaveShaperRenderer + the destination copy (src/node/{audio_buffer_source,
+// oscillator,constant_source,biquad_filter,gain,waveshaper,destination}.rs), so that a graph-quantum costs only its
+// compulsory HBM bytes (source read + destination write).  The kernel is compiled per chain shape
+// <source kind, number of biquads, shaper> so that the per-step dispatch costs no instructions.
 //
-// Biquad step = the time-parallel recurrence: each thread runs its 8 frames from zero state (y0), the end states
-// are scanned — 5 shuffle steps inside a warp with A^(2^d), then the 8 warp totals are chained with A^32 — and
-// the homogeneous response is added back:  y[j] = y0[j] + h1[j]*y[-1] + h2[j]*y[-2]   (f64, fma).
+// Biquad = time-parallel recurrence in f64: pass 1 runs the thread's 16 frames from zero state to get its end
+// state, the end states are scanned (5 shuffle steps with A^(2^d) inside a warp, then the 4 warp totals are chained
+// with A^32), pass 2 re-runs the recurrence from the true incoming state.  Same filter as the reference's serial
+// loop (biquad_filter.rs:876-891) in exact arithmetic; rounding differs by ~1e-15 relative.
 // ---------------------------------------------------------------------------------------------------------
-DEVI void mat2_apply(const double* P, double a, double b, double& oa, double& ob) {
-    oa = fma(P[0], a, P[1] * b);
-    ob = fma(P[2], a, P[3] * b);
+DEVI void mat2_fma(const double* P, double a, double b, double& accA, double& accB) {
+    accA = fma(P[0], a, fma(P[1], b, accA));
+    accB = fma(P[2], a, fma(P[3], b, accB));
 }
 
+template <int SRC>
 DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int n0, float v[CH_K]) {
-    // n0: first frame (chunk-relative) of this thread's 8 frames; caller guarantees n0 < ci.nf
-    switch (q.src_kind) {
-        case CHAIN_SRC_BUFFER: {
-            const float* in = chan(q.in, c, ci) + n0;
-            float4 a = *reinterpret_cast<const float4*>(in);
-            float4 b = *reinterpret_cast<const float4*>(in + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            break;
-        }
-        case CHAIN_SRC_ABSN: {
-            const AbsnInst& o = q.absn;
-            const float* src = o.buf + (size_t)c * o.buf_stride;
-            int64_t n = ci.f0 + n0;
-            int64_t idx = n - o.n_start + o.buf_offset;
-            if (!o.loop && n >= o.n_start && idx + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) {  // aligned interior: 2 x LDG.128
-                float4 a = __ldg(reinterpret_cast<const float4*>(src + idx));
-                float4 b = __ldg(reinterpret_cast<const float4*>(src + idx + 4));
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            } else {
+    // n0: first frame (chunk-relative) of this thread's 16 frames; caller guarantees n0 < ci.nf
+    if (SRC == CHAIN_SRC_BUFFER) {
+        const float4* in = reinterpret_cast<const float4*>(chan(q.in, c, ci) + n0);
 #pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    int64_t m = n + j;
-                    float s = 0.f;
-                    if (m >= o.n_start && m < o.n_stop) {
-                        int64_t id = m - o.n_start + o.buf_offset;
-                        if (o.loop) s = __ldg(src + (id % o.buf_len));
-                        else if (id < o.buf_len) s = __ldg(src + id);
-                    }
-                    v[j] = s;
-                }
-            }
-            break;
+        for (int u = 0; u < CH_K / 4; u++) {
+            float4 a = in[u];
+            v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
         }
-        case CHAIN_SRC_OSC: {
-            const OscInst& o = q.osc;
+    } else if (SRC == CHAIN_SRC_ABSN) {
+        const AbsnInst& o = q.absn;
+        const float* src = o.buf + (size_t)c * o.buf_stride;
+        const int64_t n = ci.f0 + n0;
+        const int64_t idx = n - o.n_start + o.buf_offset;
+        if (!o.loop && n >= o.n_start && idx + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) {
+            const float4* in = reinterpret_cast<const float4*>(src + idx);  // aligned interior: 4 x LDG.128
+#pragma unroll
+            for (int u = 0; u < CH_K / 4; u++) {
+                float4 a = __ldg(in + u);
+                v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
+            }
+        } else {
 #pragma unroll
             for (int j = 0; j < CH_K; j++) {
-                int64_t n = ci.f0 + n0 + j;
+                int64_t m = n + j;
                 float s = 0.f;
-                if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
+                if (m >= o.n_start && m < o.n_stop) {
+                    int64_t id = m - o.n_start + o.buf_offset;
+                    if (o.loop) s = __ldg(src + (id % o.buf_len));
+                    else if (id < o.buf_len) s = __ldg(src + id);
+                }
                 v[j] = s;
             }
-            break;
         }
-        default: {
-            const ConstInst& o = q.cst;
+    } else if (SRC == CHAIN_SRC_OSC) {
+        const OscInst& o = q.osc;
 #pragma unroll
-            for (int j = 0; j < CH_K; j++) {
-                int64_t n = ci.f0 + n0 + j;
-                v[j] = (n >= o.n_first && n < o.n_stop) ? o.value : 0.f;
-            }
+        for (int j = 0; j < CH_K; j++) {
+            int64_t n = ci.f0 + n0 + j;
+            float s = 0.f;
+            if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
+            v[j] = s;
+        }
+    } else {
+        const ConstInst& o = q.cst;
+#pragma unroll
+        for (int j = 0; j < CH_K; j++) {
+            int64_t n = ci.f0 + n0 + j;
+            v[j] = (n >= o.n_first && n < o.n_stop) ? o.value : 0.f;
         }
     }
 }
 
+struct ChainSmem {
+    ChainInst q;
+    double state[CHAIN_MAX_BIQUADS][4];  // x1, x2, y1, y2 carried from tile to tile
+    double P[CHAIN_MAX_BIQUADS][24];     // Pshfl[5][4], Pwarp[4]
+    double wtot[CH_WARPS][2];            // per-warp end state (zero incoming state)
+    float edge[CH_WARPS][2];             // last two step inputs of every warp
+};
+
+// one biquad over the thread's 16 frames (v in/out), see the header comment
+DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, const double b2, const double a1, const double a2,
+                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp) {
+    const double* Psh = sm.P[bq];
+    const double* Pw = sm.P[bq] + 20;
+    // previous two step inputs: neighbour lane, previous warp, or the carried state
+    const float xl1 = active ? v[CH_K - 1] : 0.f, xl2 = active ? v[CH_K - 2] : 0.f;
+    if (lane == 31) {
+        sm.edge[warp][0] = xl1;
+        sm.edge[warp][1] = xl2;
+    }
+    const float p1 = __shfl_up_sync(0xffffffffu, xl1, 1);
+    const float p2 = __shfl_up_sync(0xffffffffu, xl2, 1);
+    __syncthreads();
+    double x1, x2;
+    if (lane == 0) {
+        if (warp == 0) {
+            x1 = sm.state[bq][0];
+            x2 = sm.state[bq][1];
+        } else {
+            x1 = (double)sm.edge[warp - 1][0];
+            x2 = (double)sm.edge[warp - 1][1];
+        }
+    } else {
+        x1 = (double)p1;
+        x2 = (double)p2;
+    }
+    // FIR part and pass 1 (zero incoming state): end state only
+    double w[CH_K];
+    double r1 = 0., r2 = 0.;
+    const double na1 = -a1, na2 = -a2;
+#pragma unroll
+    for (int j = 0; j < CH_K; j++) {
+        const double x = (double)v[j];
+        w[j] = fma(b2, x2, fma(b1, x1, b0 * x));
+        const double y = fma(na1, r1, fma(na2, r2, w[j]));
+        x2 = x1;
+        x1 = x;
+        r2 = r1;
+        r1 = y;
+    }
+    // warp-level inclusive scan of end states: S_t = A S_{t-1} + (r1, r2)
+    double va = active ? r1 : 0., vb = active ? r2 : 0.;
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+        const double oa = __shfl_up_sync(0xffffffffu, va, 1 << d);
+        const double ob = __shfl_up_sync(0xffffffffu, vb, 1 << d);
+        if (lane >= (1 << d)) mat2_fma(Psh + 4 * d, oa, ob, va, vb);
+    }
+    if (lane == 31) {
+        sm.wtot[warp][0] = va;
+        sm.wtot[warp][1] = vb;
+    }
+    const double ea = __shfl_up_sync(0xffffffffu, va, 1);  // inclusive value of the previous lane
+    const double eb = __shfl_up_sync(0xffffffffu, vb, 1);
+    __syncthreads();
+    // state entering this warp: chain the previous warps' totals through A^32
+    double wa = sm.state[bq][2], wb = sm.state[bq][3];
+#pragma unroll
+    for (int k = 0; k < CH_WARPS - 1; k++) {
+        if (k < warp) {
+            double ta = sm.wtot[k][0], tb = sm.wtot[k][1];
+            mat2_fma(Pw, wa, wb, ta, tb);
+            wa = ta;
+            wb = tb;
+        }
+    }
+    // state entering this thread: warp-incoming state carried over `lane` threads + exclusive prefix inside the warp
+    double e1 = wa, e2 = wb;
+    if (lane != 0) {
+        e1 = ea;
+        e2 = eb;
+        mat2_fma(Plane, wa, wb, e1, e2);
+    }
+    // pass 2: the recurrence from the true state
+    r1 = e1;
+    r2 = e2;
+#pragma unroll
+    for (int j = 0; j < CH_K; j++) {
+        const double y = fma(na1, r1, fma(na2, r2, w[j]));
+        r2 = r1;
+        r1 = y;
+        v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
+    }
+    __syncthreads();  // everyone has read state / wtot / edge of this step
+    if (active && t == n_active - 1) {
+        sm.state[bq][0] = (double)xl1;
+        sm.state[bq][1] = (double)xl2;
+        sm.state[bq][2] = r1;
+        sm.state[bq][3] = r2;
+    }
+}
+
+template <int SRC, int NB, bool SHAPER>
 __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs, int n_inst,
                                                      ChunkInfo ci) {
-    __shared__ ChainInst q;
-    __shared__ double s_state[CHAIN_MAX_BIQUADS][4];         // x1, x2, y1, y2 carried from tile to tile
-    __shared__ double s_wtot[CH_WARPS][2];                    // per-warp end state (zero incoming state)
-    __shared__ float s_edge[CH_WARPS][2];                     // last two step inputs of every warp
-    __shared__ double s_h[CHAIN_MAX_BIQUADS][2 * CH_K + 24];  // h1[8], h2[8], Pshfl[5][4], Pwarp[4]
+    __shared__ ChainSmem sm;
     const int c = blockIdx.y;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     {
         const int* src = reinterpret_cast<const int*>(insts + blockIdx.x);
-        int* dst = reinterpret_cast<int*>(&q);
+        int* dst = reinterpret_cast<int*>(&sm.q);
         for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = src[i];
     }
     __syncthreads();
+    const ChainInst& q = sm.q;
     if (c >= q.ch) return;
-    // biquad bookkeeping
-    int n_bq = 0;
-    for (int s = 0; s < q.n_steps; s++) {
-        if (q.steps[s].kind != CHAIN_BIQUAD) continue;
-        const ScanCoef& sc = coefs[q.steps[s].coef];
-        if (t < CH_K) {
-            s_h[n_bq][t] = sc.h1[t];
-            s_h[n_bq][CH_K + t] = sc.h2[t];
-        }
-        if (t < 20) s_h[n_bq][2 * CH_K + t] = (&sc.Pshfl[0][0])[t];
+    // per-CTA constants -> registers / shared
+    double cb[NB > 0 ? NB : 1][5];
+    double plane[NB > 0 ? NB : 1][4];
+#pragma unroll
+    for (int k = 0; k < NB; k++) {
+        const ChainBiquad& bq = q.bq[k];
+        cb[k][0] = bq.b0; cb[k][1] = bq.b1; cb[k][2] = bq.b2; cb[k][3] = bq.a1; cb[k][4] = bq.a2;
+        const ScanCoef& sc = coefs[bq.coef];
+        if (t < 20) sm.P[k][t] = (&sc.Pshfl[0][0])[t];
         if (t < 4) {
-            s_h[n_bq][2 * CH_K + 20 + t] = sc.Pwarp[t];
-            s_state[n_bq][t] = q.steps[s].state[4 * c + t];
+            sm.P[k][20 + t] = sc.Pwarp[t];
+            sm.state[k][t] = bq.state[4 * c + t];
         }
-        n_bq++;
+#pragma unroll
+        for (int i = 0; i < 4; i++) plane[k][i] = lane > 0 ? sc.Plane[lane - 1][i] : 0.;
     }
+    const float g0 = q.g[0], g1 = q.g[1], g2 = q.g[2], g3 = q.g[3];
     __syncthreads();
 
-    const int tile = CH_THREADS * CH_K;
+    constexpr int tile = CH_THREADS * CH_K;
     float v[CH_K], vnext[CH_K];
     {
         const int n0 = t * CH_K;
-        if (n0 < ci.nf) chain_load_source(q, c, ci, n0, v);
+        if (n0 < ci.nf) chain_load_source<SRC>(q, c, ci, n0, v);
     }
     for (int base = 0; base < ci.nf; base += tile) {
         const int n0 = base + t * CH_K;
         const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
         const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
-        // prefetch the next tile's source frames
         const int n1 = n0 + tile;
         const bool have_next = n1 < ci.nf;
-        if (have_next) chain_load_source(q, c, ci, n1, vnext);
-        int bq = 0;
-        for (int s = 0; s < q.n_steps; s++) {
-            const ChainStep& st = q.steps[s];
-            if (st.kind == CHAIN_GAIN) {
+        if (have_next) chain_load_source<SRC>(q, c, ci, n1, vnext);  // prefetch the next tile
 #pragma unroll
-                for (int j = 0; j < CH_K; j++) v[j] *= st.gain;
-            } else if (st.kind == CHAIN_SHAPER) {
-                if (st.curve) {
+        for (int j = 0; j < CH_K; j++) v[j] *= g0;
+        if (NB >= 1) {
+            chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp);
 #pragma unroll
-                    for (int j = 0; j < CH_K; j++) v[j] = st.n == 0 ? 0.f : shaper_apply(st.curve, st.n, v[j]);
-                }
-            } else {
-                const double* H = s_h[bq];
-                const double* Psh = H + 2 * CH_K;
-                const double* Pw = H + 2 * CH_K + 20;
-                // previous two step inputs: neighbour lane, previous warp, or the carried state
-                float xl1 = active ? v[CH_K - 1] : 0.f, xl2 = active ? v[CH_K - 2] : 0.f;
-                if (lane == 31) {
-                    s_edge[warp][0] = xl1;
-                    s_edge[warp][1] = xl2;
-                }
-                float p1 = __shfl_up_sync(0xffffffffu, xl1, 1);
-                float p2 = __shfl_up_sync(0xffffffffu, xl2, 1);
-                __syncthreads();
-                double xm1, xm2;
-                if (lane == 0) {
-                    if (warp == 0) {
-                        xm1 = s_state[bq][0];
-                        xm2 = s_state[bq][1];
-                    } else {
-                        xm1 = (double)s_edge[warp - 1][0];
-                        xm2 = (double)s_edge[warp - 1][1];
-                    }
-                } else {
-                    xm1 = (double)p1;
-                    xm2 = (double)p2;
-                }
-                // zero-state response of the thread's 8 frames
-                double y0[CH_K];
-                {
-                    double x1 = xm1, x2 = xm2, r1 = 0., r2 = 0.;
+            for (int j = 0; j < CH_K; j++) v[j] *= g1;
+        }
+        if (NB >= 2) {
+            chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], plane[NB - 1], v, active,
+                         n_active, t, lane, warp);
 #pragma unroll
-                    for (int j = 0; j < CH_K; j++) {
-                        double x = (double)v[j];
-                        double w = fma(st.b2, x2, fma(st.b1, x1, st.b0 * x));
-                        double y = fma(-st.a1, r1, fma(-st.a2, r2, w));
-                        y0[j] = y;
-                        x2 = x1;
-                        x1 = x;
-                        r2 = r1;
-                        r1 = y;
-                    }
-                }
-                // warp-level inclusive scan of end states: S_t = A S_{t-1} + (y0[7], y0[6])
-                double va = active ? y0[CH_K - 1] : 0., vb = active ? y0[CH_K - 2] : 0.;
+            for (int j = 0; j < CH_K; j++) v[j] *= g2;
+        }
+        if (SHAPER) {
+            const float* curve = q.curve;
+            const int cn = q.shaper_n;
+            if (curve) {
 #pragma unroll
-                for (int d = 0; d < 5; d++) {
-                    double oa = __shfl_up_sync(0xffffffffu, va, 1 << d);
-                    double ob = __shfl_up_sync(0xffffffffu, vb, 1 << d);
-                    if (lane >= (1 << d)) {
-                        double ta, tb;
-                        mat2_apply(Psh + 4 * d, oa, ob, ta, tb);
-                        va += ta;
-                        vb += tb;
-                    }
-                }
-                if (lane == 31) {
-                    s_wtot[warp][0] = va;
-                    s_wtot[warp][1] = vb;
-                }
-                // inclusive value of the previous lane (exclusive prefix inside the warp)
-                double ea = __shfl_up_sync(0xffffffffu, va, 1);
-                double eb = __shfl_up_sync(0xffffffffu, vb, 1);
-                __syncthreads();
-                // state entering this warp: chain the previous warps' totals through A^32
-                double wa = s_state[bq][2], wb = s_state[bq][3];
-                for (int k = 0; k < warp; k++) {
-                    double ta, tb;
-                    mat2_apply(Pw, wa, wb, ta, tb);
-                    wa = ta + s_wtot[k][0];
-                    wb = tb + s_wtot[k][1];
-                }
-                // state entering this thread
-                double e1, e2;
-                if (lane == 0) {
-                    e1 = wa;
-                    e2 = wb;
-                } else {
-                    const double* Pl = coefs[st.coef].Plane[lane - 1];
-                    double ta, tb;
-                    mat2_apply(Pl, wa, wb, ta, tb);
-                    e1 = ea + ta;
-                    e2 = eb + tb;
-                }
-                double yl1 = 0., yl2 = 0.;
-#pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    double y = fma(H[j], e1, fma(H[CH_K + j], e2, y0[j]));
-                    if (j == CH_K - 1) yl1 = y;
-                    if (j == CH_K - 2) yl2 = y;
-                    v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
-                }
-                __syncthreads();  // everyone has read s_state / s_wtot / s_edge of this step
-                if (active && t == n_active - 1) {
-                    s_state[bq][0] = (double)xl1;
-                    s_state[bq][1] = (double)xl2;
-                    s_state[bq][2] = yl1;
-                    s_state[bq][3] = yl2;
-                }
-                bq++;
+                for (int j = 0; j < CH_K; j++) v[j] = cn == 0 ? 0.f : shaper_apply(curve, cn, v[j]);
             }
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) v[j] *= g3;
         }
         if (active) {
             const int64_t nabs = ci.f0 + n0;
+            const int n_out = q.out_dup > 1 ? q.out_dup : 1;
             const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + n0) & 15) == 0 &&
                                  (q.out_dup <= 1 || (q.out.stride & 3) == 0);
             if (aligned && (q.limit < 0 || nabs + CH_K <= q.limit)) {
-                const float4 a = make_float4(v[0], v[1], v[2], v[3]), b = make_float4(v[4], v[5], v[6], v[7]);
-                if (q.out_dup > 1) {
-                    for (int oc = 0; oc < q.out_dup; oc++) {
-                        float* out = chan(q.out, oc, ci) + n0;
-                        *reinterpret_cast<float4*>(out) = a;
-                        *reinterpret_cast<float4*>(out + 4) = b;
-                    }
-                } else {
-                    float* out = chan(q.out, c, ci) + n0;
-                    *reinterpret_cast<float4*>(out) = a;
-                    *reinterpret_cast<float4*>(out + 4) = b;
+                for (int oc = 0; oc < n_out; oc++) {
+                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0);
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++) out[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 }
             } else {  // unaligned channel base (odd render length) or the last, partial quantum: scalar stores
-                for (int oc = 0; oc < (q.out_dup > 1 ? q.out_dup : 1); oc++) {
+                for (int oc = 0; oc < n_out; oc++) {
                     float* out = chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0;
+#pragma unroll
                     for (int j = 0; j < CH_K; j++)
                         if (q.limit < 0 || nabs + j < q.limit) out[j] = v[j];
                 }
@@ -497,15 +500,12 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] = vnext[j];
         }
-        __syncthreads();  // s_state of this tile is visible before the next tile reads it
+        if (NB > 0) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
     }
     // carry the filter state to the next chunk
-    int bq = 0;
-    for (int s = 0; s < q.n_steps; s++) {
-        if (q.steps[s].kind != CHAIN_BIQUAD) continue;
-        if (t < 4) q.steps[s].state[4 * c + t] = s_state[bq][t];
-        bq++;
-    }
+#pragma unroll
+    for (int k = 0; k < NB; k++)
+        if (t < 4) q.bq[k].state[4 * c + t] = sm.state[k][t];
 }
 
 // IIRFilter — IirFilterRenderer::process (src/node/iir_filter.rs:323-414): transposed DF-II in f64, serial
@@ -1012,8 +1012,28 @@ void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, 
     int threads = n * max_ch;
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
 }
-void launch_chain(const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
-    k_chain<<<dim3((unsigned)n, (unsigned)max_ch), CH_THREADS, 0, s>>>(d, c, n, ci);
+template <int SRC, int NB>
+static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    dim3 grid((unsigned)n, (unsigned)max_ch);
+    if (shaper) k_chain<SRC, NB, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
+    else k_chain<SRC, NB, false><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
+}
+template <int SRC>
+static void launch_chain_s(int nb, bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    if (nb == 0) launch_chain_v<SRC, 0>(shaper, d, c, n, max_ch, ci, s);
+    else if (nb == 1) launch_chain_v<SRC, 1>(shaper, d, c, n, max_ch, ci, s);
+    else launch_chain_v<SRC, 2>(shaper, d, c, n, max_ch, ci, s);
+}
+// variant = src_kind * 6 + n_biquad * 2 + has_shaper (all instances of one launch share the chain shape)
+void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    const int src = variant / 6, nb = (variant % 6) / 2;
+    const bool shaper = (variant & 1) != 0;
+    switch (src) {
+        case CHAIN_SRC_BUFFER: launch_chain_s<CHAIN_SRC_BUFFER>(nb, shaper, d, c, n, max_ch, ci, s); break;
+        case CHAIN_SRC_ABSN: launch_chain_s<CHAIN_SRC_ABSN>(nb, shaper, d, c, n, max_ch, ci, s); break;
+        case CHAIN_SRC_OSC: launch_chain_s<CHAIN_SRC_OSC>(nb, shaper, d, c, n, max_ch, ci, s); break;
+        default: launch_chain_s<CHAIN_SRC_CONST>(nb, shaper, d, c, n, max_ch, ci, s); break;
+    }
 }
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;

@@ -7,9 +7,9 @@
 namespace wae {
 
 // Per-biquad constants of the time-parallel recurrence (host-computed in f64).  M = [[-a1,-a2],[1,0]] advances the
-// state (y[n-1], y[n-2]) by one frame; A = M^8 advances it by one thread (8 frames).
+// state (y[n-1], y[n-2]) by one frame; A = M^WAE_CHAIN_K advances it by one thread (WAE_CHAIN_K frames).
+constexpr int WAE_CHAIN_K = 16;  // frames per thread of k_chain
 struct ScanCoef {
-    double h1[8], h2[8];   // homogeneous responses: y[j] = y0[j] + h1[j]*y[-1] + h2[j]*y[-2], j < 8 (first row of M^(j+1))
     double Pshfl[5][4];    // A^(2^d), d = 0..4: warp-level Kogge-Stone steps
     double Plane[32][4];   // A^(lane+1): carries a warp's incoming state to each lane
     double Pwarp[4];       // A^32: one warp
@@ -21,7 +21,7 @@ void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
-void launch_chain(const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
+void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
