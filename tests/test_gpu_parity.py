@@ -322,9 +322,9 @@ def test_north_star_graph(pkg, engine, oracle):
 
 def test_unsupported_is_reported_not_faked(pkg, engine):
     c = pkg.OfflineAudioContext(1, 128, G.SR, engine.backend)
-    g = c.create_gain()
+    g = c.create_dynamics_compressor()
     src = c.create_constant_source()
-    g.gain.linear_ramp_to_value_at_time(0.0, 0.001)
+    g.threshold.linear_ramp_to_value_at_time(-50.0, 0.001)  # automated compressor params: not lowered yet
     src.connect(g)
     g.connect(c.destination())
     src.start()
@@ -355,3 +355,179 @@ def test_offline_rs_cases_on_gpu(pkg, engine):
     osc.stop_at(128.0 * 3.0 / sr)
     out = c.start_rendering_sync().get_channel_data(0)
     assert np.array_equal(out, np.concatenate([np.zeros(128), np.ones(256), np.zeros(128)]).astype(np.float32))
+
+
+def test_cycle_is_muted_and_cycle_breaker_feeds_back(pkg, engine, oracle):
+    # tests/offline.rs:170-203 test_cycle and :205-244 test_cycle_breaker on the CUDA path
+    c = pkg.OfflineAudioContext(1, 128, 48000.0, engine.backend)
+    cycle1 = c.create_gain()
+    cycle1.connect(c.destination())
+    cycle2 = c.create_gain()
+    cycle2.connect(cycle1)
+    cycle1.connect(cycle2)
+    sc = c.create_constant_source()
+    sc.offset.set_value(1.0)
+    sc.connect(cycle1)
+    other = c.create_constant_source()
+    other.offset.set_value(2.0)
+    other.connect(c.destination())
+    sc.start()
+    other.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out, np.full(128, 2.0, np.float32))
+
+    sr = 48000.0
+    c = pkg.OfflineAudioContext(1, 128 * 3, sr, engine.backend)
+    delay = c.create_delay(1.0 / sr)
+    delay.delay_time.set_value(1.0 / sr)
+    delay.connect(c.destination())
+    delay.connect(delay)
+    source = c.create_constant_source()
+    source.offset.set_value(1.0)
+    source.connect(delay)
+    source.connect(c.destination())
+    source.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out[:128], np.full(128, 1.0, np.float32))
+    assert np.array_equal(out[128:256], np.full(128, 2.0, np.float32))
+    assert np.array_equal(out[256:], np.full(128, 3.0, np.float32))
+
+
+def test_feedback_delay_echo(pkg, engine, oracle):
+    # a classic feedback echo: source -> delay -> gain(0.6) -> back into the delay; stereo source, 25 quanta
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 25)
+        pcm[:, 128 * 3:] = 0
+        c = pkg.OfflineAudioContext(2, 128 * 25, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        d = c.create_delay(max_delay_time=0.05, delay_time=0.0071)
+        fb = c.create_gain(0.6)
+        s.connect(d)
+        d.connect(fb)
+        fb.connect(d)
+        d.connect(c.destination())
+        s.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+# ---- AudioParam automation and audio-rate modulation ------------------------------------------
+AUTOMATIONS = {
+    "linear": lambda p: (p.set_value(0.2), p.linear_ramp_to_value_at_time(1.0, 0.013)),
+    "exponential": lambda p: (p.set_value(0.01), p.exponential_ramp_to_value_at_time(0.9, 0.021)),
+    "set_value_at_time": lambda p: (p.set_value(0.1), p.set_value_at_time(0.7, 0.0051), p.set_value_at_time(0.3, 0.0102)),
+    "set_target": lambda p: (p.set_value(0.0), p.set_target_at_time(1.0, 0.003, 0.004)),
+    "set_target_then_ramp": lambda p: (p.set_value(1.0), p.set_target_at_time(0.0, 0.002, 0.003), p.linear_ramp_to_value_at_time(0.8, 0.02)),
+    "value_curve": lambda p: p.set_value_curve_at_time([0.0, 1.0, 0.25, 0.75, 0.0], 0.004, 0.017),
+    "cancel_and_hold": lambda p: (p.set_value(0.0), p.linear_ramp_to_value_at_time(1.0, 0.02), p.cancel_and_hold_at_time(0.011)),
+    "cancel_scheduled": lambda p: (p.set_value(0.5), p.set_value_at_time(0.9, 0.004), p.linear_ramp_to_value_at_time(0.1, 0.02),
+                                   p.cancel_scheduled_values(0.01)),
+    "k_rate_ramp": lambda p: (p.set_automation_rate("k"), p.set_value(0.0), p.linear_ramp_to_value_at_time(1.0, 0.02)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(AUTOMATIONS))
+def test_param_automation_on_gain(pkg, engine, oracle, name):
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 12 + 50, G.SR, be)
+        src = c.create_oscillator(frequency=700.0)
+        gn = c.create_gain()
+        AUTOMATIONS[name](gn.gain)
+        src.connect(gn)
+        gn.connect(c.destination())
+        src.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("name", ["linear", "set_target", "value_curve"])
+def test_param_automation_on_constant_source(pkg, engine, oracle, name):
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 12, G.SR, be)
+        src = c.create_constant_source()
+        AUTOMATIONS[name](src.offset)
+        src.connect(c.destination())
+        src.start_at(0.0007)
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build)
+    assert maxdiff(gpu, cpu) <= 2e-6
+
+
+def test_audio_rate_param_inputs_offline_rs(pkg, engine):
+    # tests/offline.rs:114-149 test_audio_param_graph on the CUDA path: intrinsic 0.5 + two audio-rate inputs
+    c = pkg.OfflineAudioContext(1, 128, 48000.0, engine.backend)
+    gain = c.create_gain()
+    gain.gain.set_value(0.5)
+    gain.connect(c.destination())
+    source = c.create_constant_source()
+    source.offset.set_value(0.8)
+    source.connect(gain)
+    for v in (0.1, 0.3):
+        s2 = c.create_constant_source()
+        s2.offset.set_value(v)
+        s2.connect(gain.gain)
+        s2.start()
+    source.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out, np.full(128, np.float32(0.8) * np.float32(0.9), np.float32))
+
+
+def test_fm_synthesis_audio_rate_frequency(pkg, engine, oracle):
+    # an LFO / FM patch: modulator -> gain (depth) -> carrier.frequency, plus a detune ramp on the carrier
+    def build(be, g):
+        c = pkg.OfflineAudioContext(1, 128 * 40, G.SR, be)
+        car = c.create_oscillator(type_=[pkg.SINE, pkg.SAWTOOTH][g], frequency=440.0)
+        mod = c.create_oscillator(frequency=110.0)
+        depth = c.create_gain(150.0)
+        mod.connect(depth)
+        depth.connect(car.frequency)
+        car.detune.linear_ramp_to_value_at_time(700.0, 0.08)
+        car.connect(c.destination())
+        mod.start()
+        car.start_at(0.0021)
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_biquad_frequency_sweep(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 30)
+        c = pkg.OfflineAudioContext(2, 128 * 30, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        f = c.create_biquad_filter(type_=[pkg.LOWPASS, pkg.PEAKING][g], frequency=200.0, q=4.0, gain=6.0)
+        f.frequency.exponential_ramp_to_value_at_time(6000.0, 0.06)
+        f.q.linear_ramp_to_value_at_time(0.7, 0.05)
+        s.connect(f)
+        f.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_panner_and_delay_time_automation(pkg, engine, oracle):
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 30)
+        c = pkg.OfflineAudioContext(2, 128 * 30, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]] if g else [pcm[0]], G.SR))
+        sp = c.create_stereo_panner(pan=-1.0)
+        sp.pan.linear_ramp_to_value_at_time(1.0, 0.07)
+        d = c.create_delay(max_delay_time=0.1, delay_time=0.001)
+        d.delay_time.linear_ramp_to_value_at_time(0.02, 0.06)
+        s.connect(sp)
+        sp.connect(d)
+        d.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= TOL

@@ -32,6 +32,7 @@ struct OscInst {
     const float* table;       // sine table (2048) or periodic wave
     int32_t table_len;
     int32_t pad;
+    double inv_incr;          // 1 / incr (polyBLEP of constant-frequency oscillators)
 };
 
 struct ConstInst {
@@ -39,6 +40,7 @@ struct ConstInst {
     float value;
     int32_t pad;
     int64_t n_first, n_stop;
+    BufRef track;  // p != nullptr: automated offset
 };
 
 struct AbsnInst {
@@ -72,6 +74,7 @@ struct GainInst {
     BufRef in, out;
     float gain;
     int32_t ch;
+    BufRef gain_track;  // p != nullptr: a-rate / automated gain, one value per frame (k_param output)
 };
 
 struct ShaperInst {
@@ -85,6 +88,7 @@ struct SPanInst {
     BufRef in, out;
     float pan;
     int32_t in_ch;
+    BufRef pan_track;  // p != nullptr: automated pan
 };
 
 struct PanInst {  // equal-power panner with static source/listener (panner.rs:839-870,988-1057)
@@ -106,6 +110,8 @@ struct MixInst {  // AudioRenderQuantum::add over all incoming edges of one inpu
     int32_t n_edges;
     uint32_t edge_offset;
     int64_t limit;  // frames >= limit are not written (destination: render length); < 0: no limit
+    int32_t simple;    // every edge has out_ch channels or is mono up-mixed by copy (speakers 1 -> 2): vector fast path
+    int32_t all_mono;  // simple and every edge is mono: sum once, write to all channels
 };
 
 struct DelayInst {
@@ -115,6 +121,9 @@ struct DelayInst {
     int32_t ch;
     int64_t fl;          // floor(-delay * sr): integer part of the (negative) read offset
     float k;             // fractional part
+    int32_t in_cycle;    // 1: the reader runs before the writer (cycle breaker applied): history comes from the ring only
+    BufRef delay_track;  // p != nullptr: automated delayTime (seconds per frame)
+    float sample_rate;
     int32_t pad;
 };
 
@@ -140,6 +149,62 @@ struct RouteInst {  // channel merger / splitter: copy one channel
     BufRef in, out;
     int32_t in_channel, out_channel;
     int32_t zero;  // 1: write zeros (splitter output beyond the input's channels)
+    int32_t pad;
+};
+
+// oscillator with automated / audio-rate frequency or detune (oscillator.rs:447-459): phase = running sum of the
+// per-frame increments
+struct OscArInst {
+    OscInst base;        // type, table, n_first, n_stop (incr / phase0 unused)
+    BufRef freq, detune; // p == nullptr: constant f_val / d_val
+    float f_val, d_val;
+    double start_ratio;  // (t_first - start_time) / dt: sub-sample start (oscillator.rs:527-540)
+    double* phase;       // carried phase (before the first frame of the next chunk)
+    float sample_rate;
+    int32_t pad;
+};
+
+// biquad with automated parameters: coefficients per frame (biquad_filter.rs:837-855), serial recurrence
+struct BiquadArInst {
+    BufRef in, out;
+    BufRef q, detune, freq, gain;  // p == nullptr: constant *_val
+    float q_val, detune_val, freq_val, gain_val;
+    double* state;
+    float sample_rate;
+    int32_t type;
+    int32_t ch;
+    int32_t pad;
+};
+
+// ---- AudioParam automation (AudioParamProcessor, src/param.rs:664-1600) -------------------------------------
+struct ParamEvDev {  // AudioParamEvent (param.rs:172-181) after handle_incoming_event
+    int32_t type;    // WAE_EVENT_*
+    float value;
+    double time;
+    double aux;          // time constant (setTarget) / duration (value curve)
+    double cancel_time;  // cancel_and_hold
+    int32_t has_cancel;
+    int32_t values_off, values_len;  // value curve samples in the curve pool
+    int32_t pad;
+};
+struct ParamState {  // render-side state of one param, carried across chunks
+    float intrinsic;
+    int32_t head;        // events [0, head) have been popped
+    int32_t has_last;
+    int32_t override_valid;  // replace_peek(): the event at `head` is `override_ev`
+    ParamEvDev last;
+    ParamEvDev override_ev;
+};
+struct ParamInst {
+    const ParamEvDev* events;
+    const float* curves;
+    ParamState* state;
+    BufRef in;   // summed audio-rate input (mono), p == nullptr: none
+    BufRef out;  // 1 channel: the computed value of every frame
+    float def, mn, mx, intrinsic0;
+    float sample_rate;
+    int32_t n_events;
+    int32_t a_rate;
     int32_t pad;
 };
 

@@ -8,6 +8,7 @@
 #include "wae_graph.h"
 #include "wae_hostmath.h"
 #include "wae_kernels.h"
+#include "wae_param_host.h"
 
 #include <cuda_runtime.h>
 
@@ -41,12 +42,12 @@ struct wae_engine {
 namespace {
 
 enum StageKind : int {
-    S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_KINDS
+    S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
-                                    "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain"};
+                                    "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -58,6 +59,9 @@ struct StageBuild {
     std::vector<AbsnInst> absn;
     std::vector<BiquadInst> biquad;
     std::vector<ChainInst> chain;
+    std::vector<ParamInst> param;
+    std::vector<OscArInst> osc_ar;
+    std::vector<BiquadArInst> biquad_ar;
     std::vector<ScanCoef> scan_coef;
     std::vector<IirInst> iir;
     std::vector<GainInst> gain;
@@ -183,26 +187,47 @@ namespace {
 // ---- topological order: Graph::order_nodes / visit (src/render/graph.rs:331-487) ---------------------------
 struct Orderer {
     wae_graph* g;
-    std::vector<uint32_t> ordered, marked, marked_temp, in_cycle;
-    bool cycle_found = false;
+    std::map<uint32_t, std::vector<Edge>> edges;  // working copy: cycle breakers clear a DelayWriter's edges
+    std::vector<uint32_t> ordered, marked, marked_temp, in_cycle, cycle_breakers, broken;
     static bool contains(const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); }
-    void visit(uint32_t id) {
+    // returns true when a cycle breaker was applied (the ordering is then restarted), graph.rs:331-403
+    bool visit(uint32_t id) {
         auto it = std::find(marked_temp.begin(), marked_temp.end(), id);
         if (it != marked_temp.end()) {
-            cycle_found = true;  // cycles (muted nodes / DelayNode cycle breakers) are not lowered yet
-            in_cycle.insert(in_cycle.end(), it, marked_temp.end());
-            return;
+            for (auto jt = it; jt != marked_temp.end(); ++jt)
+                if (g->nodes.at(*jt).cycle_breaker) {
+                    cycle_breakers.push_back(*jt);
+                    return true;
+                }
+            in_cycle.insert(in_cycle.end(), it, marked_temp.end());  // no DelayNode in the cycle: its nodes are muted
+            return false;
         }
-        if (contains(marked, id)) return;
+        if (contains(marked, id)) return false;
         marked.push_back(id);
         marked_temp.push_back(id);
-        for (auto& e : g->nodes.at(id).outgoing)
-            if (g->nodes.count(e.other_id)) visit(e.other_id);
+        const std::vector<Edge>& out = edges.at(id);
+        for (size_t i = 0; i < out.size(); i++)
+            if (g->nodes.count(out[i].other_id) && visit(out[i].other_id)) return true;
         ordered.push_back(id);
         marked_temp.erase(std::remove(marked_temp.begin(), marked_temp.end(), id), marked_temp.end());
+        return false;
     }
-    void run() {
-        for (auto& kv : g->nodes) visit(kv.first);
+    void run() {  // graph.rs:418-487
+        for (auto& kv : g->nodes) edges[kv.first] = kv.second.outgoing;
+        for (;;) {
+            ordered.clear(); marked.clear(); marked_temp.clear(); in_cycle.clear(); cycle_breakers.clear();
+            bool applied = false;
+            for (auto& kv : g->nodes) {
+                applied = visit(kv.first);
+                if (applied) break;
+            }
+            if (!applied) break;
+            for (uint32_t id : cycle_breakers) {
+                edges[id].clear();
+                if (!contains(broken, id)) broken.push_back(id);
+            }
+        }
+        ordered.erase(std::remove_if(ordered.begin(), ordered.end(), [&](uint32_t o) { return contains(in_cycle, o); }), ordered.end());
         std::reverse(ordered.begin(), ordered.end());
     }
 };
@@ -237,6 +262,15 @@ struct Planner {
     };
     std::unordered_map<uint64_t, IrSpectra> ir_cache;
 
+    bool has_feedback = false;            // some graph has a cycle broken by a DelayNode
+    std::map<std::pair<uint32_t, uint32_t>, int>* delay_ch_hint = nullptr;  // (graph, reader id) -> channels of an in-cycle delay
+    std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_seen;
+    struct DelayRing {
+        float* ring;
+        uint32_t ring_len;
+        int ch;
+    };
+    std::map<std::pair<uint32_t, uint32_t>, DelayRing> delay_rings;       // (graph, writer id)
     bool dry = false;                     // sizing pass: count arena floats per frame, touch no device memory
     uint64_t arena_floats_per_frame = 0;
     // source PCM slab of the group being planned (device pointer, pinned host mirror, cursor in floats)
@@ -286,15 +320,18 @@ struct Planner {
         return BufRef{p, (uint32_t)b->chunk, 0};
     }
 
+    std::map<uint32_t, PNode>* cur_pn = nullptr;
+    struct PRef {
+        bool dyn = false;  // automated / audio-rate driven: one value per frame in `track`
+        float v = 0.f;
+        BufRef track{nullptr, 0, 0};
+    };
+    PRef param_ref(wae_graph* g, uint32_t pid);
+    // for renderers whose automated parameters are not lowered yet
     bool const_param(wae_graph* g, uint32_t pid, float& v) {
-        Node& pn = g->nodes.at(pid);
-        // audio-rate modulation: any audio edge into the param node
-        for (auto& kv : g->nodes)
-            for (auto& e : kv.second.outgoing)
-                if (e.other_id == pid && e.other_index >= 0)
-                    return bail(WAE_UNSUPPORTED, "audio-rate AudioParam inputs are not lowered to the GPU yet");
-        if (!pn.param.constant()) return bail(WAE_UNSUPPORTED, "AudioParam automation events are not lowered to the GPU yet");
-        v = pn.param.constant_value();
+        PRef r = param_ref(g, pid);
+        if (r.dyn) return bail(WAE_UNSUPPORTED, "AudioParam automation / audio-rate input on this parameter is not lowered to the GPU yet");
+        v = r.v;
         return true;
     }
 
@@ -427,10 +464,10 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         if (!dry) cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
         spec.S = Smax;
         spec.channels = ir_ch;
-        spec.h = alloc<float2>((size_t)ir_ch * Smax * 1025);
+        spec.h = alloc<float2>((size_t)ir_ch * Smax * WAE_CONV_SPEC);
         if (!d_ir || !spec.h) return bail(WAE_OUT_OF_MEMORY, "out of device memory (IR spectra)");
         if (!dry) launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
-        b->asset_bytes += (size_t)ir_ch * Smax * 1025 * 8;
+        b->asset_bytes += (size_t)ir_ch * Smax * WAE_CONV_SPEC * 8;
         ir_cache[key] = spec;
     }
     // inputs: one spectra ring per input channel
@@ -443,10 +480,10 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         ci.in = pn.in_buf[0];
         ci.in_channel = c;
         ci.prev = alloc<float>(1024, true, true);
-        ci.xring = alloc<float2>((size_t)ring_blocks * 1025);
+        ci.xring = alloc<float2>((size_t)ring_blocks * WAE_CONV_SPEC);
         ci.xring_blocks = ring_blocks;
         if (!ci.prev || !ci.xring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver input spectra)");
-        b->arena_bytes += (size_t)ring_blocks * 1025 * 8;
+        b->arena_bytes += (size_t)ring_blocks * WAE_CONV_SPEC * 8;
         fs.conv_in.push_back(ci);
     }
     // paths: channel routing table of convolver.rs:378-487
@@ -465,7 +502,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     for (auto& r : routes) {
         ConvPath p;
         p.out = pn.out_buf[0];
-        p.h = spec.h + (size_t)r.ir * Smax * 1025;
+        p.h = spec.h + (size_t)r.ir * Smax * WAE_CONV_SPEC;
         p.input = in_base + r.in;
         p.S = Smax;
         p.out_channel = r.out;
@@ -477,13 +514,24 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     return true;
 }
 
+Planner::PRef Planner::param_ref(wae_graph* g, uint32_t pid) {
+    PRef r;
+    r.v = g->nodes.at(pid).param.constant_value();
+    auto it = cur_pn->find(pid);
+    if (it != cur_pn->end() && !it->second.out_buf.empty()) {
+        r.dyn = true;
+        r.track = it->second.out_buf[0];
+    }
+    return r;
+}
+
 bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     Orderer ord{g};
     ord.run();
-    if (ord.cycle_found) return bail(WAE_UNSUPPORTED, "graphs with cycles (feedback through DelayNode / muted cycles) are not lowered to the GPU yet");
+    if (!ord.broken.empty()) has_feedback = true;  // feedback through a DelayNode: rendered quantum by quantum (chunk = 128)
     std::map<uint32_t, PNode> pn;
+    cur_pn = &pn;
     for (auto& kv : g->nodes) {
-        if (kv.second.kind == K_PARAM) continue;
         PNode p;
         p.n = &kv.second;
         p.in_edges.resize(kv.second.n_inputs);
@@ -492,11 +540,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     // Graph::render (graph.rs:500-535): walk the order, append each audio edge to its destination port
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
-        if (n.kind == K_PARAM) continue;
-        for (auto& e : n.outgoing) {
+        for (auto& e : ord.edges.at(id)) {
             if (e.other_index < 0) continue;
             auto it = pn.find(e.other_id);
-            if (it == pn.end()) continue;  // edge into a param node: rejected in const_param
+            if (it == pn.end()) continue;
             it->second.in_edges[e.other_index].push_back(PortRef{id, e.self_index});
         }
     }
@@ -510,7 +557,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     std::map<uint32_t, PendingChain> pending;
     auto consumers = [&](const Node& nd) {
         int k = 0;
-        for (auto& e : nd.outgoing)
+        for (auto& e : ord.edges.at(nd.id))
             if (e.other_index >= 0) k++;
         return k;
     };
@@ -547,17 +594,73 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     };
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
-        if (n.kind == K_PARAM || n.kind == K_LISTENER) continue;
+        if (n.kind == K_LISTENER) continue;
         PNode& p = pn.at(id);
+        if (n.kind == K_PARAM) {
+            // AudioParamProcessor (param.rs:685-797): only params with automation events or audio-rate inputs become
+            // GPU work; a constant param is a scalar in its owner's instance
+            auto& edges = p.in_edges[0];
+            if (n.param.constant() && edges.empty()) continue;
+            int level = 0;
+            for (auto& r : edges) level = std::max(level, pn.at(r.node).level + 1);
+            p.level = level;
+            for (auto& r : edges)
+                if (!materialize(r.node)) return false;
+            ParamTimeline tl = build_param_timeline(n.param);
+            if (!tl.error.empty()) return bail(WAE_NOT_SUPPORTED, tl.error);
+            ParamInst pi{};
+            if (!edges.empty()) {  // sum of the connected signals, first channel each (1 / explicit / discrete, param.rs:296-310)
+                StageBuild& ms = stage(2 * level, S_MIX);
+                MixInst m;
+                m.out = arena_buf(1);
+                if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                m.out_ch = 1;
+                m.interp = WAE_INTERPRETATION_DISCRETE;
+                m.n_edges = (int)edges.size();
+                m.edge_offset = (uint32_t)ms.mix_edges.size();
+                m.limit = -1;
+                for (auto& r : edges) ms.mix_edges.push_back(MixEdge{pn.at(r.node).out_buf[r.port], pn.at(r.node).out_ch[r.port], 0});
+                ms.mix.push_back(m);
+                pi.in = m.out;
+            }
+            pi.events = tl.events.empty() ? nullptr : upload(tl.events);
+            pi.curves = tl.curves.empty() ? nullptr : upload(tl.curves);
+            pi.state = alloc<ParamState>(1, true, true);
+            pi.out = arena_buf(1);
+            if (!pi.state || !pi.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (param)");
+            pi.def = n.param.default_value;
+            pi.mn = n.param.min_value;
+            pi.mx = n.param.max_value;
+            pi.intrinsic0 = tl.intrinsic;
+            pi.sample_rate = g->sample_rate;
+            pi.n_events = (int32_t)tl.events.size();
+            pi.a_rate = n.param.a_rate ? 1 : 0;
+            stage(2 * level + 1, S_PARAM).param.push_back(pi);
+            p.out_ch = {1};
+            p.out_buf = {pi.out};
+            continue;
+        }
         // ---- inputs: static channel count + mix stage where needed
         int level = 0;
         for (auto& port : p.in_edges)
             for (auto& r : port) level = std::max(level, pn.at(r.node).level + 1);
+        bool dyn_params = false;
+        for (uint32_t pid : n.params) {
+            PNode& pp = pn.at(pid);
+            if (!pp.out_buf.empty()) {
+                dyn_params = true;
+                level = std::max(level, pp.level + 1);
+            }
+        }
+        if (n.kind == K_PANNER)
+            for (uint32_t pid = 2; pid <= 10; pid++)
+                if (pn.count(pid) && !pn.at(pid).out_buf.empty()) level = std::max(level, pn.at(pid).level + 1);
         p.level = level;
+        const bool fuse_n = fuse && !dyn_params;  // nodes with automated params run their own a-rate kernels
         // does this node extend the pending chain of its only producer / take it as the destination's only input?
         uint32_t fuse_src = 0;
         bool extend = false, dest_direct = false;
-        const bool chain_kind = (n.kind == K_BIQUAD && !eng->serial_filters) || (fuse && (n.kind == K_GAIN || n.kind == K_SHAPER));
+        const bool chain_kind = !dyn_params && ((n.kind == K_BIQUAD && !eng->serial_filters) || (fuse && (n.kind == K_GAIN || n.kind == K_SHAPER)));
         if (fuse && n.n_inputs == 1 && p.in_edges[0].size() == 1 && p.in_edges[0][0].port == 0) {
             auto it = pending.find(p.in_edges[0][0].node);
             if (it != pending.end()) {
@@ -669,14 +772,16 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_OSC: {
-                float freq, detune;
-                if (!const_param(g, n.params[0], freq) || !const_param(g, n.params[1], detune)) return false;
-                if (!fuse && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                PRef pf = param_ref(g, n.params[0]), pd = param_ref(g, n.params[1]);
+                float freq = pf.v, detune = pd.v;
+                if (!fuse_n && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 OscInst o{};
-                if (!fuse) o.out = p.out_buf[0];
+                double start_ratio = 0.;
+                if (!fuse_n) o.out = p.out_buf[0];
                 o.type = n.type;
                 double computed_freq = (double)freq * std::exp2((double)detune / 1200.);  // oscillator.rs:30-32
                 o.incr = computed_freq / sr;
+                o.inv_incr = o.incr != 0. ? 1. / o.incr : 0.;
                 o.outside_nyquist = std::fabs(computed_freq) >= sr / 2.;
                 o.n_first = std::numeric_limits<int64_t>::max();
                 o.n_stop = std::numeric_limits<int64_t>::max();
@@ -698,6 +803,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     o.n_first = q * 128 + i;
                     if (i < 128 && t > start) {
                         double ratio = (t - start) / clock.dt;
+                        start_ratio = ratio;
                         double ph = o.incr * ratio;
                         if (o.outside_nyquist) {
                             ph = std::fmod(ph, 1.);
@@ -721,7 +827,19 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     o.table = eng->d_sine;
                     o.table_len = 2048;
                 }
-                if (fuse) {
+                if (dyn_params) {  // automated / audio-rate frequency or detune: running-sum phase
+                    OscArInst oa{};
+                    oa.base = o;
+                    oa.freq = pf.dyn ? pf.track : BufRef{nullptr, 0, 0};
+                    oa.detune = pd.dyn ? pd.track : BufRef{nullptr, 0, 0};
+                    oa.f_val = freq;
+                    oa.d_val = detune;
+                    oa.start_ratio = start_ratio;
+                    oa.phase = alloc<double>(1, true, true);
+                    oa.sample_rate = g->sample_rate;
+                    if (!oa.phase) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    stage(L, S_OSC_AR).osc_ar.push_back(oa);
+                } else if (fuse_n) {
                     PendingChain pc = source_chain(CHAIN_SRC_OSC, 1);
                     pc.inst.osc = o;
                     if (!finish_chain(std::move(pc))) return false;
@@ -731,11 +849,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_CONST: {
-                float v;
-                if (!const_param(g, n.params[0], v)) return false;
-                if (!fuse && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                PRef po = param_ref(g, n.params[0]);
+                float v = po.v;
+                if (!fuse_n && !need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 ConstInst c{};
-                if (!fuse) c.out = p.out_buf[0];
+                if (!fuse_n) c.out = p.out_buf[0];
+                if (po.dyn) c.track = po.track;
                 c.value = v;
                 c.n_first = std::numeric_limits<int64_t>::max();
                 c.n_stop = std::numeric_limits<int64_t>::max();
@@ -744,7 +863,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     c.n_first = clock.first_frame_at_or_after(n.start_time);
                     if (n.stop_time < 1e300) c.n_stop = clock.first_frame_at_or_after(n.stop_time);
                 }
-                if (fuse) {
+                if (fuse_n) {
                     PendingChain pc = source_chain(CHAIN_SRC_CONST, 1);
                     pc.inst.cst = c;
                     if (!finish_chain(std::move(pc))) return false;
@@ -779,7 +898,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (!fast)
                     return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode slow track (unaligned start, offset/duration, stop, playbackRate/"
                                                  "detune != 1, custom loop points, resampling) is not lowered to the GPU yet");
-                if (!fuse && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (!fuse_n && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
                 size_t stride = (len + 3) / 4 * 4;  // every channel starts 16 B aligned (LDG.128)
                 float* d_buf = d_src + src_cursor;
@@ -792,7 +911,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 src_cursor += (size_t)ch * stride;
                 b->asset_bytes += (size_t)ch * len * 4;
                 AbsnInst a{};
-                if (!fuse) a.out = p.out_buf[0];
+                if (!fuse_n) a.out = p.out_buf[0];
                 a.buf = d_buf;
                 a.buf_len = (int64_t)len;
                 a.buf_stride = (int64_t)stride;
@@ -801,7 +920,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 a.buf_offset = 0;
                 a.ch = ch;
                 a.loop = n.loop ? 1 : 0;
-                if (fuse) {
+                if (fuse_n) {
                     PendingChain pc = source_chain(CHAIN_SRC_ABSN, ch);
                     pc.inst.absn = a;
                     if (!finish_chain(std::move(pc))) return false;
@@ -813,11 +932,30 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_BIQUAD: {
-                float q, detune, freq, gain;
-                if (!const_param(g, n.params[0], q) || !const_param(g, n.params[1], detune) || !const_param(g, n.params[2], freq) ||
-                    !const_param(g, n.params[3], gain))
-                    return false;
+                PRef pq = param_ref(g, n.params[0]), pdt = param_ref(g, n.params[1]), pfr = param_ref(g, n.params[2]), pg = param_ref(g, n.params[3]);
+                float q = pq.v, detune = pdt.v, freq = pfr.v, gain = pg.v;
                 int ch = p.in_ch[0];
+                if (dyn_params) {  // per-frame coefficients (biquad_filter.rs:837-855): serial a-rate kernel
+                    if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    BiquadArInst ba{};
+                    ba.in = p.in_buf[0];
+                    ba.out = p.out_buf[0];
+                    const BufRef none{nullptr, 0, 0};
+                    ba.q = pq.dyn ? pq.track : none;
+                    ba.detune = pdt.dyn ? pdt.track : none;
+                    ba.freq = pfr.dyn ? pfr.track : none;
+                    ba.gain = pg.dyn ? pg.track : none;
+                    ba.q_val = q; ba.detune_val = detune; ba.freq_val = freq; ba.gain_val = gain;
+                    ba.state = alloc<double>((size_t)ch * 4, true, true);
+                    if (!ba.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    ba.sample_rate = g->sample_rate;
+                    ba.type = n.type;
+                    ba.ch = ch;
+                    StageBuild& sb = stage(L, S_BIQUAD_AR);
+                    sb.max_ch = std::max(sb.max_ch, ch);
+                    sb.biquad_ar.push_back(ba);
+                    break;
+                }
                 float cf = hm::biquad_computed_freq(freq, detune);
                 hm::BiquadCoefs c = hm::biquad_coefs(n.type, sr, (double)cf, (double)gain, (double)q);
                 double* state = alloc<double>((size_t)ch * 4, true, true);
@@ -868,14 +1006,19 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_GAIN: {
-                float gv;
-                if (!const_param(g, n.params[0], gv)) return false;
+                PRef pgn = param_ref(g, n.params[0]);
+                float gv = pgn.v;
                 int ch = p.in_ch[0];
+                if (pgn.dyn) {  // a-rate gain (gain.rs:189-197)
+                    if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch, pgn.track});
+                    break;
+                }
                 // gain.rs:153-169: |g| <= 1e-6 -> silence, |1-g| <= 1e-6 -> pass-through (quanta >= 1; quantum 0 takes
                 // the multiply path, a difference of at most 1e-6 * |x| that is below the parity tolerance)
                 if (std::fabs(gv) <= 1e-6f) gv = 0.f;
                 else if (std::fabs(1.f - gv) <= 1e-6f) gv = 1.f;
-                if (fuse) {
+                if (fuse_n) {
                     PendingChain pc = open_chain();
                     // consecutive gains of one slot are folded (differs from two f32 multiplies by <= 1 ulp)
                     pc.inst.g[pc.phase == 0 ? 0 : (pc.phase == 1 ? 1 : (pc.phase == 3 ? 2 : 3))] *= gv;
@@ -883,13 +1026,13 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     break;
                 }
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch});
+                stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch, BufRef{nullptr, 0, 0}});
                 break;
             }
             case K_SHAPER: {
                 int ch = p.in_ch[0];
                 const float* curve = n.has_curve ? upload(n.table) : nullptr;
-                if (fuse) {
+                if (fuse_n) {
                     PendingChain pc = open_chain();
                     pc.inst.has_shaper = 1;
                     pc.inst.curve = curve;
@@ -909,15 +1052,15 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_SPANNER: {
-                float pan;
-                if (!const_param(g, n.params[0], pan)) return false;
+                PRef ppan = param_ref(g, n.params[0]);
+                float pan = ppan.v;
                 int ch = p.in_ch[0];
                 if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 float x = ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);  // stereo_panner.rs:247-249,274-276
                 float gl, gr;
                 hm::stereo_gains(x, gl, gr);
                 StageBuild& s = stage(L, S_SPAN);
-                s.span.push_back(SPanInst{p.in_buf[0], p.out_buf[0], pan, ch});
+                s.span.push_back(SPanInst{p.in_buf[0], p.out_buf[0], pan, ch, ppan.dyn ? ppan.track : BufRef{nullptr, 0, 0}});
                 s.span_gains.push_back(make_float2(gl, gr));
                 break;
             }
@@ -973,31 +1116,63 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 stage(L, S_PAN).pan.push_back(pi);
                 break;
             }
-            case K_DELAY_W: {  // the writer only records its input: the reader aliases it (hidden edge, delay.rs:359-365)
+            case K_DELAY_W: {
                 p.out_ch = {p.in_ch[0]};
                 p.out_buf = {p.in_buf[0]};
+                if (Orderer::contains(ord.broken, id)) {
+                    // cycle breaker applied (graph.rs:458-466): the hidden writer->reader edge is gone, the reader ran
+                    // earlier in this quantum from the ring; record this quantum's input now
+                    delay_ch_seen[{gi, n.delay_peer}] = p.in_ch[0];
+                    auto it = delay_rings.find({gi, id});
+                    if (it == delay_rings.end()) return bail(WAE_UNSUPPORTED, "DelayNode writer processed before its reader inside a cycle");
+                    if (it->second.ch != p.in_ch[0]) {
+                        if (!dry) return bail(WAE_UNSUPPORTED, "channel layout of a DelayNode in a feedback cycle did not converge");
+                        break;  // sizing pass: the hint is corrected and the pass repeated
+                    }
+                    DelayInst d{};
+                    d.in = p.in_buf[0];
+                    d.ch = it->second.ch;
+                    d.ring = it->second.ring;
+                    d.ring_len = it->second.ring_len;
+                    stage(L, S_DELAY_WRITE).delay.push_back(d);
+                }
                 break;
             }
             case K_DELAY_R: {
-                float dt;
-                if (!const_param(g, n.params[0], dt)) return false;
+                PRef pdl = param_ref(g, n.params[0]);
+                float dt = pdl.v;
+                const bool in_cycle = Orderer::contains(ord.broken, n.delay_peer);
                 int ch = p.in_ch[0];
+                if (in_cycle) {
+                    ch = 1;
+                    if (delay_ch_hint) {
+                        auto it = delay_ch_hint->find({gi, id});
+                        if (it != delay_ch_hint->end()) ch = it->second;
+                    }
+                }
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 DelayInst d{};
                 d.in = p.in_buf[0];
                 d.out = p.out_buf[0];
                 d.ch = ch;
-                double num_samples = (double)dt * sr;          // delay.rs:706
+                d.in_cycle = in_cycle ? 1 : 0;
+                if (pdl.dyn) d.delay_track = pdl.track;
+                d.sample_rate = g->sample_rate;
+                double delay = (double)dt;
+                if (in_cycle) delay = std::max(delay, 128. / sr);  // delay.rs:699-703: at least one quantum inside a cycle
+                double num_samples = delay * sr;               // delay.rs:706
                 double position = 0. - num_samples;            // sample_index 0
                 double pf = std::floor(position);
                 d.fl = (int64_t)pf;
                 d.k = (float)(position - pf);
-                uint64_t max_frames = (uint64_t)std::ceil(n.max_delay_time * sr) + 2;
+                uint64_t max_frames = (uint64_t)std::ceil(std::max(n.max_delay_time, 128. / sr) * sr) + 2;
                 d.ring_len = next_pow2(max_frames + 128);
                 d.ring = alloc<float>((size_t)ch * d.ring_len, true, true);
                 if (!d.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (delay ring)");
                 b->arena_bytes += (size_t)ch * d.ring_len * 4;
                 stage(L, S_DELAY).delay.push_back(d);
+                if (in_cycle) delay_rings[{gi, n.delay_peer}] = DelayRing{d.ring, d.ring_len, ch};
+                else stage(L, S_DELAY_WRITE).delay.push_back(d);  // acyclic: history is recorded right after the read
                 break;
             }
             case K_COMP: {
@@ -1198,20 +1373,37 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     // whole 1024-frame blocks and prefer long chunks (their spectra ring, not the arena, is the traffic that matters).
     b->chunk = 2048;
     uint64_t fpf = 0;
-    for (int k = 0; k < n_groups; k++) {
-        Planner sizing{b, eng};
-        sizing.dry = true;
-        sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
-        for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
-            if (!sizing.plan_graph(graphs[i], i)) {
-                int code = sizing.error_code;
-                std::string msg = sizing.error;
-                wae_batch_destroy(b);
-                return fail(code, msg);
+    bool has_feedback = false;
+    std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_hint;
+    for (int iter = 0; iter < 8; iter++) {  // repeated only while the channel layout of in-cycle delays changes
+        bool hints_changed = false;
+        fpf = 0;
+        for (int k = 0; k < n_groups; k++) {
+            Planner sizing{b, eng};
+            sizing.dry = true;
+            sizing.delay_ch_hint = &delay_ch_hint;
+            sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
+            for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
+                if (!sizing.plan_graph(graphs[i], i)) {
+                    int code = sizing.error_code;
+                    std::string msg = sizing.error;
+                    wae_batch_destroy(b);
+                    return fail(code, msg);
+                }
+            }
+            fpf = std::max(fpf, sizing.arena_floats_per_frame);
+            b->groups[k].src_floats = sizing.src_cursor;
+            has_feedback = has_feedback || sizing.has_feedback;
+            for (auto& kv : sizing.delay_ch_seen) {
+                auto it = delay_ch_hint.find(kv.first);
+                int cur = it == delay_ch_hint.end() ? 1 : it->second;
+                if (cur != kv.second) {
+                    delay_ch_hint[kv.first] = kv.second;
+                    hints_changed = true;
+                }
             }
         }
-        fpf = std::max(fpf, sizing.arena_floats_per_frame);
-        b->groups[k].src_floats = sizing.src_cursor;
+        if (!hints_changed) break;
     }
     b->arena_bytes = 0;
     b->asset_bytes = 0;
@@ -1220,11 +1412,19 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         if (fpf == 0) {
             chunk = b->lq;
         } else {
-            chunk = (int64_t)(48.0 * 1024 * 1024 / (4.0 * (double)fpf));
-            chunk = std::max<int64_t>(2048, std::min<int64_t>(chunk, 1 << 20));
+            chunk = (int64_t)(1024.0 * 1024 * 1024 / (4.0 * (double)fpf));  // arena budget 1 GiB
+            chunk = std::max<int64_t>(8192, std::min<int64_t>(chunk, 1 << 20));  // >= 8192: keeps per-chunk launches and serial tails amortised
             chunk = chunk / 2048 * 2048;
         }
         if (has_conv) chunk = std::max<int64_t>(chunk, 16384);
+    }
+    if (has_feedback) {
+        // feedback through a DelayNode is resolved one render quantum at a time, like the reference's render loop
+        if (has_conv) {
+            wae_batch_destroy(b);
+            return fail(WAE_UNSUPPORTED, "a ConvolverNode in a batch with DelayNode feedback cycles is not lowered to the GPU yet");
+        }
+        chunk = 128;
     }
     if (has_conv) chunk = (chunk + 1023) / 1024 * 1024;
     if (chunk > b->lq) chunk = has_conv ? (b->lq + 1023) / 1024 * 1024 : b->lq;
@@ -1251,6 +1451,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         Planner pl{b, eng};
         pl.d_src = grp.d_src;
         pl.h_src = grp.h_src;
+        pl.delay_ch_hint = &delay_ch_hint;
         pl.ir_cache.swap(ir_cache);
         for (uint32_t i = grp.g0; i < grp.g1; i++) {
             if (!pl.plan_graph(graphs[i], i)) {
@@ -1273,19 +1474,40 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             st.group = k;
             st.max_ch = s.max_ch;
             switch (s.kind) {
-                case S_MIX: st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges); break;
+                case S_MIX: {
+                    for (auto& m : s.mix) {  // classify: vector fast path of k_mix
+                        bool simple = true, all_mono = m.n_edges > 0;
+                        for (int e = 0; e < m.n_edges; e++) {
+                            const MixEdge& ed = s.mix_edges[m.edge_offset + e];
+                            bool same = ed.src_ch == m.out_ch;
+                            bool dup = ed.src_ch == 1 && m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS;
+                            if (!(same || dup)) simple = false;
+                            if (ed.src_ch != 1) all_mono = false;
+                            // sources must allow 16-byte loads: arena buffers do; asset / output aliases may not
+                            if (ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) simple = false;
+                        }
+                        m.simple = simple ? 1 : 0;
+                        m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
+                    }
+                    st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
+                    break;
+                }
                 case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
                 case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
                 case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
                 case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
                 case S_CHAIN: st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); break;
+                case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
+                case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
+                case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
                 case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
                 case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
                 case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
                 case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
                 case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
                 case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
-                case S_DELAY: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
+                case S_DELAY:
+                case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
                 case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
                 case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
                 case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
@@ -1313,7 +1535,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     }
     int64_t n_chunks = (b->lq + b->chunk - 1) / b->chunk;
     uint64_t launches = 0;
-    for (auto& st : b->stages) launches += (st.kind == S_DELAY || st.kind == S_CONV_FFT) ? 2 : 1;
+    for (auto& st : b->stages) launches += st.kind == S_CONV_FFT ? 2 : 1;
     std::memset(&b->stats, 0, sizeof(b->stats));
     b->stats.kernel_launches_per_run = launches * (uint64_t)n_chunks;
     b->stats.stages = b->stages.size();
@@ -1336,6 +1558,9 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_BIQUAD:
             launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
             break;
+        case S_PARAM: launch_param((ParamInst*)st.d_a, st.n, ci, s); break;
+        case S_OSC_AR: launch_osc_arate((OscArInst*)st.d_a, st.n, ci, s); break;
+        case S_BIQUAD_AR: launch_biquad_arate((BiquadArInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_CHAIN: launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;
@@ -1343,7 +1568,8 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_SPAN: launch_stereo_panner((SPanInst*)st.d_a, (float2*)st.d_b, st.n, ci, s); break;
         case S_PAN: launch_panner_eq((PanInst*)st.d_a, st.n, ci, s); break;
         case S_ROUTE: launch_route((RouteInst*)st.d_a, st.n, ci, s); break;
-        case S_DELAY: launch_delay((DelayInst*)st.d_a, st.n, ci, s); break;
+        case S_DELAY: launch_delay_read((DelayInst*)st.d_a, st.n, ci, s); break;
+        case S_DELAY_WRITE: launch_ring_write((DelayInst*)st.d_a, st.n, ci, s); break;
         case S_COMP: launch_compressor((CompInst*)st.d_a, st.n, ci, s); break;
         case S_ANALYSER: launch_analyser((AnalyserInst*)st.d_a, st.n, ci, s); break;
         case S_CONV_FFT: launch_conv_fft_in((ConvInput*)st.d_a, st.n, ci, s); break;

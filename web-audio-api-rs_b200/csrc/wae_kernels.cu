@@ -5,6 +5,7 @@
 // oscillator phase), grids sized over (time tiles x node instances).  Each kernel cites the reference
 // renderer whose arithmetic it reproduces; parity target is 1e-5 absolute on f32 PCM.
 #include "wae_kernels.h"
+#include "../../include/wae.h"
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -30,9 +31,20 @@ DEVI double osc_poly_blep(double t, double dt) {  // oscillator.rs:645-659 (rele
     }
     return 0.0;
 }
+// same with a precomputed 1/dt (constant-frequency oscillators): t * (1/dt) differs from t / dt by <= 1 ulp of f64
+DEVI double osc_poly_blep_r(double t, double dt, double inv_dt) {
+    if (t < dt) {
+        t *= inv_dt;
+        return t + t - t * t - 1.0;
+    } else if (t > 1.0 - dt) {
+        t = (t - 1.0) * inv_dt;
+        return fma(t, t, t) + t + 1.0;
+    }
+    return 0.0;
+}
 DEVI double osc_unroll(double p) { return p >= 1. ? p - 1. : (p < 0. ? p + 1. : p); }
 
-DEVI float osc_sample(const OscInst& o, double phase) {
+DEVI float osc_sample(const OscInst& o, double phase, double incr) {
     switch (o.type) {
         case 0:
         case 4: {  // sine (:571-585) / custom (:622-637): table lookup + lerp with fmaf
@@ -43,18 +55,18 @@ DEVI float osc_sample(const OscInst& o, double phase) {
             int next = prev + 1;
             if (next == o.table_len) next = 0;
             float k = (float)(position - floored);
-            return fmaf(__ldg(o.table + prev), 1.f - k, __ldg(o.table + next) * k);
+            return fmaf(o.table[prev], 1.f - k, o.table[next] * k);  // generic loads: the table may sit in shared memory
         }
         case 2: {  // sawtooth, :588-595
             double ph = osc_unroll(phase + 0.5);
             double s = 2.0 * ph - 1.0;
-            s -= osc_poly_blep(ph, o.incr);
+            s -= osc_poly_blep(ph, incr);
             return (float)s;
         }
         case 1: {  // square, :598-606
             double s = phase < 0.5 ? 1.0 : -1.0;
-            s += osc_poly_blep(phase, o.incr);
-            s -= osc_poly_blep(osc_unroll(phase + 0.5), o.incr);
+            s += osc_poly_blep(phase, incr);
+            s -= osc_poly_blep(osc_unroll(phase + 0.5), incr);
             return (float)s;
         }
         default: {  // triangle, :609-619
@@ -87,7 +99,7 @@ __global__ void __launch_bounds__(256) k_oscillator(const OscInst* __restrict__ 
         for (int j = 0; j < 4; j++) {
             int64_t n = ci.f0 + n0 + j;
             float s = 0.f;
-            if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
+            if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n), o.incr);
             v[j] = s;
         }
         *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(256) k_constant(const ConstInst* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int64_t n = ci.f0 + n0 + j;
-            v[j] = (n >= o.n_first && n < o.n_stop) ? o.value : 0.f;
+            v[j] = (n >= o.n_first && n < o.n_stop) ? (o.track.p ? chan(o.track, 0, ci)[n0 + j] : o.value) : 0.f;
         }
         *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -168,20 +180,94 @@ DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, 
     }
 }
 
+// Fast path (MixInst::simple): every edge either has the port's channel count or is a mono signal up-mixed by
+// copy (speakers 1 -> 2).  One thread owns 4 consecutive frames; the edge loop issues 8 independent 16-byte loads
+// before the 8 dependent adds, so a 4096-edge fan-in (config C3) is bandwidth-, not latency-bound, while the f32
+// summation order stays the reference's.  When all edges are mono the sum is computed once and written to every
+// output channel (the reference's "all channels identical" fast path, quantum.rs:549-558).
+constexpr int MIX_BATCH = 8;
+template <int VEC>
+struct MixVec;
+template <>
+struct MixVec<4> {
+    float4 v;
+    DEVI void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+    DEVI void add(const MixVec& o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    DEVI void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    DEVI float get(int j) const { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+};
+template <>
+struct MixVec<1> {
+    float v;
+    DEVI void load(const float* p) { v = *p; }
+    DEVI void add(const MixVec& o) { v += o.v; }
+    DEVI void zero() { v = 0.f; }
+    DEVI float get(int) const { return v; }
+};
+
+template <int VEC>
+DEVI void mix_simple(const MixInst& m, const MixEdge* __restrict__ edges, int c, int n0, const ChunkInfo& ci, MixVec<VEC>& acc) {
+    const MixEdge* e = edges + m.edge_offset;
+    acc.zero();
+    int k = 0;
+    for (; k + MIX_BATCH <= m.n_edges; k += MIX_BATCH) {
+        MixVec<VEC> v[MIX_BATCH];
+#pragma unroll
+        for (int u = 0; u < MIX_BATCH; u++) {
+            const MixEdge& ed = e[k + u];
+            v[u].load(chan(ed.src, ed.src_ch == 1 ? 0 : c, ci) + n0);
+        }
+#pragma unroll
+        for (int u = 0; u < MIX_BATCH; u++) {
+            if (k + u == 0) acc = v[u];
+            else acc.add(v[u]);
+        }
+    }
+    for (; k < m.n_edges; k++) {
+        const MixEdge& ed = e[k];
+        MixVec<VEC> v;
+        v.load(chan(ed.src, ed.src_ch == 1 ? 0 : c, ci) + n0);
+        if (k == 0) acc = v;
+        else acc.add(v);
+    }
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst,
                                              ChunkInfo ci) {
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const MixInst m = insts[ii];
-        int n = blockIdx.x * blockDim.x + threadIdx.x;
-        if (n >= ci.nf) continue;
-        if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
-        for (int c = 0; c < m.out_ch; c++) {
-            float acc = 0.f;
-            for (int e = 0; e < m.n_edges; e++) {
-                float v = mixed_sample(edges[m.edge_offset + e], m.out_ch, c, m.interp, n, ci);
-                acc = e == 0 ? v : acc + v;
+        const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+        if (n0 >= ci.nf) continue;
+        if (m.simple) {
+            const int n_sum = m.all_mono ? 1 : m.out_ch;
+            for (int c = 0; c < n_sum; c++) {
+                MixVec<VEC> acc;
+                mix_simple<VEC>(m, edges, c, n0, ci, acc);
+                for (int oc = c; oc < (m.all_mono ? m.out_ch : c + 1); oc++) {
+                    float* out = chan(m.out, oc, ci) + n0;
+                    const bool vec = VEC == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (m.limit < 0 || ci.f0 + n0 + 4 <= m.limit);
+                    if (vec) {
+                        *reinterpret_cast<float4*>(out) = make_float4(acc.get(0), acc.get(1), acc.get(2), acc.get(3));
+                    } else {
+                        for (int j = 0; j < VEC; j++)
+                            if (m.limit < 0 || ci.f0 + n0 + j < m.limit) out[j] = acc.get(j);
+                    }
+                }
             }
-            chan(m.out, c, ci)[n] = acc;
+            continue;
+        }
+        for (int j = 0; j < VEC; j++) {
+            const int n = n0 + j;
+            if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
+            for (int c = 0; c < m.out_ch; c++) {
+                float acc = 0.f;
+                for (int e = 0; e < m.n_edges; e++) {
+                    float v = mixed_sample(edges[m.edge_offset + e], m.out_ch, c, m.interp, n, ci);
+                    acc = e == 0 ? v : acc + v;
+                }
+                chan(m.out, c, ci)[n] = acc;
+            }
         }
     }
 }
@@ -289,12 +375,40 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
         }
     } else if (SRC == CHAIN_SRC_OSC) {
         const OscInst& o = q.osc;
+        const int64_t na = ci.f0 + n0;
+        if (na >= o.n_first && na + CH_K <= o.n_stop && !o.outside_nyquist && o.incr > 0. && o.incr < 0.5) {
+            // fully active run: closed-form phase for the first frame, then 15 increments with the reference's wrap
+            double ph = osc_phase_at(o, na);
+            const double inc = o.incr, inv = o.inv_incr;
+            const int type = o.type;
 #pragma unroll
-        for (int j = 0; j < CH_K; j++) {
-            int64_t n = ci.f0 + n0 + j;
-            float s = 0.f;
-            if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n));
-            v[j] = s;
+            for (int j = 0; j < CH_K; j++) {
+                float s;
+                if (type == 0 || type == 4) {
+                    s = osc_sample(o, ph, inc);
+                } else if (type == 2) {
+                    double p2 = ph + 0.5;
+                    p2 = p2 >= 1. ? p2 - 1. : p2;
+                    s = (float)(2.0 * p2 - 1.0 - osc_poly_blep_r(p2, inc, inv));
+                } else if (type == 1) {
+                    double p2 = ph + 0.5;
+                    p2 = p2 >= 1. ? p2 - 1. : p2;
+                    s = (float)((ph < 0.5 ? 1.0 : -1.0) + osc_poly_blep_r(ph, inc, inv) - osc_poly_blep_r(p2, inc, inv));
+                } else {
+                    s = osc_sample(o, ph, inc);
+                }
+                v[j] = s;
+                ph += inc;
+                ph = ph >= 1. ? ph - 1. : ph;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) {
+                int64_t n = na + j;
+                float s = 0.f;
+                if (n >= o.n_first && n < o.n_stop && !o.outside_nyquist) s = osc_sample(o, osc_phase_at(o, n), o.incr);
+                v[j] = s;
+            }
         }
     } else {
         const ConstInst& o = q.cst;
@@ -419,6 +533,17 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
         for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = src[i];
     }
     __syncthreads();
+    // oscillator wavetable -> shared memory: the 128 threads of a CTA are 16 frames apart, so their table indices fall
+    // in different 128-byte lines (a 32-wavefront global gather per load); shared memory only pays bank conflicts
+    __shared__ float s_table[SRC == CHAIN_SRC_OSC ? 2048 : 1];
+    if (SRC == CHAIN_SRC_OSC && sm.q.osc.table_len <= 2048 && (sm.q.osc.type == 0 || sm.q.osc.type == 4)) {
+        const float* gt = sm.q.osc.table;
+        const int len = sm.q.osc.table_len;
+        for (int i = t; i < len; i += CH_THREADS) s_table[i] = __ldg(gt + i);
+        __syncthreads();
+        if (t == 0) sm.q.osc.table = s_table;
+        __syncthreads();
+    }
     const ChainInst& q = sm.q;
     if (c >= q.ch) return;
     // per-CTA constants -> registers / shared
@@ -441,18 +566,59 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
     __syncthreads();
 
     constexpr int tile = CH_THREADS * CH_K;
-    float v[CH_K], vnext[CH_K];
-    {
-        const int n0 = t * CH_K;
-        if (n0 < ci.nf) chain_load_source<SRC>(q, c, ci, n0, v);
+    constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;  // PCM read from memory: prefetch with cp.async
+    // double-buffered staging of the source frames, [buffer][float4 u of the thread][thread]: every thread stages
+    // and later reads only its own 64 bytes (no barrier needed), conflict-free 16-byte shared accesses
+    __shared__ float4 s_in[STREAMED ? 2 : 1][STREAMED ? CH_K / 4 : 1][STREAMED ? CH_THREADS : 1];
+    auto stage_source = [&](int buf, int nfirst) {
+        if (!STREAMED || nfirst >= ci.nf) return;
+        const float* gp = nullptr;
+        if (SRC == CHAIN_SRC_BUFFER) {
+            gp = chan(q.in, c, ci) + nfirst;
+        } else {
+            const AbsnInst& o = q.absn;
+            const float* src = o.buf + (size_t)c * o.buf_stride;
+            const int64_t n = ci.f0 + nfirst;
+            const int64_t idx = n - o.n_start + o.buf_offset;
+            if (!o.loop && n >= o.n_start && idx + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) gp = src + idx;
+        }
+        if (gp) {
+#pragma unroll
+            for (int u = 0; u < CH_K / 4; u++) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_in[buf][u][t]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * u) : "memory");
+            }
+        } else {  // ragged start / end of the buffer, loops, unaligned channel: scalar gather, then stage
+            float tmp[CH_K];
+            chain_load_source<SRC>(q, c, ci, nfirst, tmp);
+#pragma unroll
+            for (int u = 0; u < CH_K / 4; u++) s_in[buf][u][t] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
+        }
+    };
+    float v[CH_K];
+    if (STREAMED) {
+        stage_source(0, t * CH_K);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int base = 0; base < ci.nf; base += tile) {
+    int tile_index = 0;
+    for (int base = 0; base < ci.nf; base += tile, tile_index++) {
         const int n0 = base + t * CH_K;
         const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
         const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
-        const int n1 = n0 + tile;
-        const bool have_next = n1 < ci.nf;
-        if (have_next) chain_load_source<SRC>(q, c, ci, n1, vnext);  // prefetch the next tile
+        if (STREAMED) {
+            stage_source((tile_index + 1) & 1, n0 + tile);  // prefetch the next tile while this one is filtered
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's group has landed
+            if (active) {
+#pragma unroll
+                for (int u = 0; u < CH_K / 4; u++) {
+                    const float4 a = s_in[tile_index & 1][u][t];
+                    v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
+                }
+            }
+        } else if (active) {
+            chain_load_source<SRC>(q, c, ci, n0, v);
+        }
 #pragma unroll
         for (int j = 0; j < CH_K; j++) v[j] *= g0;
         if (NB >= 1) {
@@ -496,16 +662,188 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
                 }
             }
         }
-        if (have_next) {
-#pragma unroll
-            for (int j = 0; j < CH_K; j++) v[j] = vnext[j];
-        }
         if (NB > 0) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
     }
     // carry the filter state to the next chunk
 #pragma unroll
     for (int k = 0; k < NB; k++)
         if (t < 4) q.bq[k].state[4 * c + t] = sm.state[k][t];
+}
+
+// Oscillator with automated / audio-rate frequency or detune (oscillator.rs:447-459,511-557): the phase of frame n is
+// the running sum of the per-frame increments f[n] * 2^(d[n]/1200) / sr.  One CTA per oscillator; tiles of 256 x 8
+// frames, Kogge-Stone scan of the tile's increments in f64, the phase is carried from tile to tile and chunk to chunk.
+__global__ void __launch_bounds__(256) k_osc_arate(const OscArInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ double s_sum[256];
+    __shared__ double s_carry;
+    const OscArInst q = insts[blockIdx.x];
+    const OscInst& o = q.base;
+    float* out = chan(o.out, 0, ci);
+    const float* ft = q.freq.p ? chan(q.freq, 0, ci) : nullptr;
+    const float* dtk = q.detune.p ? chan(q.detune, 0, ci) : nullptr;
+    const int t = threadIdx.x;
+    const double sr = (double)q.sample_rate, nyq = sr / 2.;
+    if (t == 0) s_carry = ci.f0 == 0 ? 0. : *q.phase;
+    __syncthreads();
+    for (int base = 0; base < ci.nf; base += 2048) {
+        const int n0 = base + t * 8;
+        double inc[8];
+        bool act[8], oob[8];
+        double local = 0.;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int n = n0 + j;
+            const int64_t na = ci.f0 + n;
+            act[j] = n < ci.nf && na >= o.n_first && na < o.n_stop;
+            double cf = 0.;
+            if (n < ci.nf) {
+                float f = ft ? ft[n] : q.f_val, d = dtk ? dtk[n] : q.d_val;
+                cf = (double)f * exp2((double)d / 1200.);  // get_computed_freq, oscillator.rs:30-32
+            }
+            oob[j] = fabs(cf) >= nyq;
+            inc[j] = cf / sr;
+            double add = act[j] ? inc[j] : 0.;
+            if (act[j] && na == o.n_first) add += q.start_ratio * inc[j];  // sub-sample start: phase = incr * ratio
+            local += add;
+        }
+        s_sum[t] = local;
+        __syncthreads();
+        for (int off = 1; off < 256; off <<= 1) {
+            double v = t >= off ? s_sum[t - off] : 0.;
+            __syncthreads();
+            s_sum[t] += v;
+            __syncthreads();
+        }
+        double ph = s_carry + (t > 0 ? s_sum[t - 1] : 0.);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int64_t na = ci.f0 + n0 + j;
+            double p = ph;
+            if (act[j] && na == o.n_first) p += q.start_ratio * inc[j];
+            p -= floor(p);
+            if (p >= 1.) p = 0.;
+            v[j] = (act[j] && !oob[j]) ? osc_sample(o, p, inc[j]) : 0.f;
+            if (act[j]) ph = p + inc[j];
+        }
+        if (n0 < ci.nf) {
+            *reinterpret_cast<float4*>(out + n0) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(out + n0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncthreads();
+        if (t == 255) {
+            double c = s_carry + s_sum[255];
+            s_carry = c - floor(c);
+        }
+        __syncthreads();
+    }
+    if (t == 0) *q.phase = s_carry;
+}
+
+// calculate_coefs on the device (src/node/biquad_filter.rs:28-390) for per-frame coefficients
+struct BqC {
+    double b0, b1, b2, a1, a2;
+};
+DEVI BqC bq_norm(double b0, double b1, double b2, double a0, double a1, double a2) {
+    double s = 1. / a0;
+    return BqC{b0 * s, b1 * s, b2 * s, a1 * s, a2 * s};
+}
+DEVI BqC bq_coefs(int type, double sample_rate, double f0, double gain, double q) {
+    const BqC wire{1., 0., 0., 0., 0.}, zero{0., 0., 0., 0., 0.};
+    const double PI64 = 3.14159265358979323846;
+    double f = f0 / (sample_rate / 2.);
+    f = f < 0. ? 0. : (f > 1. ? 1. : f);
+    const double w0 = PI64 * f, sn = sin(w0), c = cos(w0);
+    const double A = pow(10., gain / 40.);
+    switch (type) {
+        case 0: {
+            if (f == 1.) return wire;
+            double a = sn / (2. * pow(10., q / 20.)), beta = (1. - c) / 2.;
+            return bq_norm(beta, 2. * beta, beta, 1. + a, -2. * c, 1. - a);
+        }
+        case 1: {
+            if (f == 1.) return zero;
+            if (f == 0.) return wire;
+            double a = sn / (2. * pow(10., q / 20.)), beta = (1. + c) / 2.;
+            return bq_norm(beta, -2. * beta, beta, 1. + a, -2. * c, 1. - a);
+        }
+        case 2: {
+            if (!(f > 0. && f < 1.)) return zero;
+            if (!(q > 0.)) return wire;
+            double a = sn / (2. * q);
+            return bq_norm(a, 0., -a, 1. + a, -2. * c, 1. - a);
+        }
+        case 3: {
+            if (!(f > 0. && f < 1.)) return wire;
+            if (!(q > 0.)) return zero;
+            double a = sn / (2. * q);
+            return bq_norm(1., -2. * c, 1., 1. + a, -2. * c, 1. - a);
+        }
+        case 4: {
+            if (!(f > 0. && f < 1.)) return wire;
+            if (!(q > 0.)) return BqC{-1., 0., 0., 0., 0.};
+            double a = sn / (2. * q);
+            return bq_norm(1. - a, -2. * c, 1. + a, 1. + a, -2. * c, 1. - a);
+        }
+        case 5: {
+            if (!(f > 0. && f < 1.)) return wire;
+            if (!(q > 0.)) return BqC{A * A, 0., 0., 0., 0.};
+            double a = sn / (2. * q);
+            return bq_norm(1. + a * A, -2. * c, 1. - a * A, 1. + a / A, -2. * c, 1. - a / A);
+        }
+        case 6: {
+            if (f == 1.) return BqC{A * A, 0., 0., 0., 0.};
+            if (f == 0.) return wire;
+            double as = sn / 2. * 1.41421356237309504880168872420969808;
+            double tt = 2. * as * sqrt(A), ap = A + 1., am = A - 1.;
+            return bq_norm(A * (ap - am * c + tt), 2. * A * (am - ap * c), A * (ap - am * c - tt), ap + am * c + tt, -2. * (am + ap * c),
+                           ap + am * c - tt);
+        }
+        default: {
+            if (f == 1.) return wire;
+            if (!(f > 0.)) return BqC{A * A, 0., 0., 0., 0.};
+            double as = sn / 2. * 1.41421356237309504880168872420969808;
+            double tt = 2. * as * sqrt(A), ap = A + 1., am = A - 1.;
+            return bq_norm(A * (ap + am * c + tt), -2. * A * (am + ap * c), A * (ap + am * c - tt), ap - am * c + tt, 2. * (am - ap * c),
+                           ap - am * c - tt);
+        }
+    }
+}
+
+// BiquadFilter with automated parameters: per-frame coefficients + the reference's serial f64 recurrence
+__global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int ii = t / max_ch, c = t % max_ch;
+    if (ii >= n_inst) return;
+    const BiquadArInst q = insts[ii];
+    if (c >= q.ch) return;
+    const float* in = chan(q.in, c, ci);
+    float* out = chan(q.out, c, ci);
+    const float* tq = q.q.p ? chan(q.q, 0, ci) : nullptr;
+    const float* td = q.detune.p ? chan(q.detune, 0, ci) : nullptr;
+    const float* tf = q.freq.p ? chan(q.freq, 0, ci) : nullptr;
+    const float* tg = q.gain.p ? chan(q.gain, 0, ci) : nullptr;
+    double* st = q.state + 4 * c;
+    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    float pq = 0.f, pd = 0.f, pf = 0.f, pg = 0.f;
+    BqC cf{};
+    for (int n = 0; n < ci.nf; n++) {
+        float vq = tq ? tq[n] : q.q_val, vd = td ? td[n] : q.detune_val, vf = tf ? tf[n] : q.freq_val, vg = tg ? tg[n] : q.gain_val;
+        if (n == 0 || vq != pq || vd != pd || vf != pf || vg != pg) {
+            float computed = vd != 0.f ? vf * exp2f(vd / 1200.f) : vf;  // get_computed_freq, biquad_filter.rs:393-399
+            cf = bq_coefs(q.type, (double)q.sample_rate, (double)computed, (double)vg, (double)vq);
+            pq = vq; pd = vd; pf = vf; pg = vg;
+        }
+        double x = (double)in[n];
+        double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf.b0, x), __dmul_rn(cf.b1, x1)), __dmul_rn(cf.b2, x2)),
+                                       __dmul_rn(cf.a1, y1)),
+                             __dmul_rn(cf.a2, y2));
+        double ay = fabs(y);
+        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+        x2 = x1; x1 = x; y2 = y1; y1 = y;
+        out[n] = (float)y;
+    }
+    st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
 }
 
 // IIRFilter — IirFilterRenderer::process (src/node/iir_filter.rs:323-414): transposed DF-II in f64, serial
@@ -545,7 +883,12 @@ __global__ void __launch_bounds__(256) k_gain(const GainInst* __restrict__ insts
         if (n0 >= ci.nf) continue;
         for (int c = 0; c < g.ch; c++) {
             float4 v = *reinterpret_cast<const float4*>(chan(g.in, c, ci) + n0);
-            v.x *= g.gain; v.y *= g.gain; v.z *= g.gain; v.w *= g.gain;
+            if (g.gain_track.p) {  // a-rate gain (gain.rs:189-197)
+                float4 t = *reinterpret_cast<const float4*>(chan(g.gain_track, 0, ci) + n0);
+                v.x *= t.x; v.y *= t.y; v.z *= t.z; v.w *= t.w;
+            } else {
+                v.x *= g.gain; v.y *= g.gain; v.z *= g.gain; v.w *= g.gain;
+            }
             *reinterpret_cast<float4*>(chan(g.out, c, ci) + n0) = v;
         }
     }
@@ -589,9 +932,17 @@ __global__ void __launch_bounds__(256) k_stereo_panner(const SPanInst* __restric
                                                        ChunkInfo ci) {
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const SPanInst s = insts[ii];
-        const float gl = gains[ii].x, gr = gains[ii].y;
+        float gl = gains[ii].x, gr = gains[ii].y;
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
+        float pan = s.pan;
+        if (s.pan_track.p) {  // a-rate pan: gains per frame (stereo_panner.rs:259-271, 293-313)
+            pan = chan(s.pan_track, 0, ci)[n];
+            const float PI32 = 3.14159265358979323846f;
+            float x = s.in_ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);
+            gl = sinf((1.f - x) * PI32 / 2.f);
+            gr = sinf(x * PI32 / 2.f);
+        }
         float* l = chan(s.out, 0, ci);
         float* r = chan(s.out, 1, ci);
         if (s.in_ch == 1) {
@@ -600,7 +951,7 @@ __global__ void __launch_bounds__(256) k_stereo_panner(const SPanInst* __restric
             r[n] = x * gr;
         } else {
             float il = chan(s.in, 0, ci)[n], ir = chan(s.in, 1, ci)[n];
-            if (s.pan <= 0.f) {
+            if (pan <= 0.f) {
                 l[n] = fmaf(ir, gl, il);
                 r[n] = ir * gr;
             } else {
@@ -665,6 +1016,7 @@ __global__ void __launch_bounds__(256) k_route(const RouteInst* __restrict__ ins
 // ---------------------------------------------------------------------------------------------------------
 DEVI float delay_fetch(const DelayInst& d, const float* in, const float* ring, int64_t m, const ChunkInfo& ci) {
     if (m < 0) return 0.f;
+    if (d.in_cycle) return m >= ci.f0 ? 0.f : ring[m & (d.ring_len - 1)];
     if (m >= ci.f0) {
         int64_t r = m - ci.f0;
         if (r < ci.nf) return in[r];
@@ -680,12 +1032,23 @@ __global__ void __launch_bounds__(256) k_delay_read(const DelayInst* __restrict_
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
         for (int c = 0; c < d.ch; c++) {
-            const float* in = chan(d.in, c, ci);
+            const float* in = d.in_cycle ? nullptr : chan(d.in, c, ci);
             const float* ring = d.ring + (size_t)c * d.ring_len;
             int64_t m = ci.f0 + n + d.fl;
+            float k = d.k;
+            if (d.delay_track.p) {  // a-rate delayTime: get_playback_infos per frame (delay.rs:688-743)
+                double delay = (double)chan(d.delay_track, 0, ci)[n];
+                const double sr = (double)d.sample_rate;
+                if (d.in_cycle) delay = fmax(delay, 128. / sr);
+                const int i = (int)((ci.f0 + n) & 127);
+                double position = (double)i - delay * sr;
+                double pf = floor(position);
+                m = (ci.f0 + n - i) + (int64_t)pf;
+                k = (float)(position - pf);
+            }
             float prev = delay_fetch(d, in, ring, m, ci);
             float next = delay_fetch(d, in, ring, m + 1, ci);
-            chan(d.out, c, ci)[n] = fmaf(1.f - d.k, prev, d.k * next);
+            chan(d.out, c, ci)[n] = fmaf(1.f - k, prev, k * next);
         }
     }
 }
@@ -778,6 +1141,286 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// AudioParam automation — AudioParamProcessor::compute_buffer + mix_to_output (src/param.rs:739-797, 1038-1600).
+// One thread per param instance walks the chunk quantum by quantum through the (host-prepared) event timeline,
+// exactly like the reference's per-quantum state machine (set_value / linear & exponential ramps / setTarget with
+// snap-to-target / value curves / cancel_and_hold), adds the summed audio-rate input, maps NaN to the default and
+// clamps to [min, max].  The output is the param's value for EVERY frame (k-rate and constant blocks are
+// replicated), which is what the a-rate consumers read.
+// ---------------------------------------------------------------------------------------------------------
+struct ParamCursor {
+    const ParamInst& p;
+    ParamState& s;
+    DEVI bool empty() const { return s.head >= p.n_events; }
+    DEVI ParamEvDev peek() const { return s.override_valid ? s.override_ev : p.events[s.head]; }
+    DEVI bool has_next() const { return s.head + 1 < p.n_events; }
+    DEVI ParamEvDev next() const { return p.events[s.head + 1]; }
+    DEVI ParamEvDev pop() {
+        ParamEvDev e = peek();
+        s.head++;
+        s.override_valid = 0;
+        return e;
+    }
+    DEVI void replace_peek(const ParamEvDev& e) {
+        s.override_ev = e;
+        s.override_valid = 1;
+    }
+};
+
+DEVI float par_linear(double t0, double dur, float v0, float diff, double t) { return fmaf(diff, (float)((t - t0) / dur), v0); }
+DEVI float par_exp(double t0, double dur, float v0, float ratio, double t) { return v0 * powf(ratio, (float)((t - t0) / dur)); }
+DEVI float par_target(double t0, double tau, float v1, float diff, double t) { return fmaf(diff, (float)exp(-((t - t0) / tau)), v1); }
+DEVI float par_curve(double t0, double dur, const float* values, int n, double t) {
+    if (t - t0 >= dur) return values[n - 1];
+    double position = (double)(n - 1) * (t - t0) / dur;
+    int k = (int)position;
+    float phase = (float)(position - floor(position));
+    return fmaf(values[k + 1] - values[k], phase, values[k]);
+}
+DEVI int par_end_index(double end_time, double block_time, double dt, int count) {
+    double r = round(fmax(end_time - block_time, 0.) / dt);
+    if (!(r < 4.0e9)) return count;
+    int idx = (int)r;
+    return idx < count ? idx : count;
+}
+
+__global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= n_inst) return;
+    const ParamInst p = insts[ii];
+    ParamState st = *p.state;
+    if (ci.f0 == 0) {  // start of a render
+        st.intrinsic = p.intrinsic0;
+        st.head = 0;
+        st.has_last = 0;
+        st.override_valid = 0;
+    }
+    ParamCursor tl{p, st};
+    const double dt = 1. / (double)p.sample_rate;
+    const int count = 128;
+    float* out = chan(p.out, 0, ci);
+    const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
+    float buf[128];
+    for (int q0 = 0; q0 < ci.nf; q0 += 128) {
+        const double block_time = (double)(ci.f0 + q0) / (double)p.sample_rate;
+        const double next_block_time = fma(dt, (double)count, block_time);
+        int len = 0;
+        // ---- compute_buffer (param.rs:1500-1600)
+        bool is_constant_block;
+        if (tl.empty()) {
+            is_constant_block = true;
+        } else {
+            ParamEvDev e = tl.peek();
+            is_constant_block = (e.type != WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME && e.type != WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME)
+                                    ? e.time >= next_block_time
+                                    : false;
+        }
+        if (!p.a_rate || is_constant_block) buf[len++] = st.intrinsic;
+        if (!is_constant_block) {
+            for (;;) {
+                bool exit_loop;
+                if (tl.empty()) {
+                    if (p.a_rate)
+                        while (len < count) buf[len++] = st.intrinsic;
+                    exit_loop = true;
+                } else {
+                    ParamEvDev ev = tl.peek();
+                    switch (ev.type) {
+                        case WAE_EVENT_SET_VALUE:
+                        case WAE_EVENT_SET_VALUE_AT_TIME: {  // param.rs:1038-1091
+                            double time = ev.time == 0. ? block_time : ev.time;
+                            if (p.a_rate) {
+                                int e = par_end_index(time, block_time, dt, count);
+                                while (len < e) buf[len++] = st.intrinsic;
+                            }
+                            if (time > next_block_time) {
+                                exit_loop = true;
+                                break;
+                            }
+                            st.intrinsic = ev.value;
+                            ParamEvDev l = tl.pop();
+                            l.time = time;
+                            st.last = l;
+                            st.has_last = 1;
+                            exit_loop = false;
+                            break;
+                        }
+                        case WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME:
+                        case WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME: {  // param.rs:1093-1272
+                            const bool lin = ev.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME;
+                            const double start_time = st.last.time;
+                            double end_time = ev.time;
+                            const double duration = end_time - start_time;
+                            if (ev.has_cancel) end_time = ev.cancel_time;
+                            const float v0 = st.last.value, v1 = ev.value;
+                            const float k = lin ? v1 - v0 : v1 / v0;
+                            if (!lin && (v0 == 0.f || v0 * v1 < 0.f)) {  // degenerate exponential ramp -> SetValueAtTime
+                                ParamEvDev r{};
+                                r.type = WAE_EVENT_SET_VALUE_AT_TIME;
+                                r.time = end_time;
+                                r.value = v1;
+                                tl.replace_peek(r);
+                                exit_loop = false;
+                                break;
+                            }
+                            if (p.a_rate) {
+                                int e = par_end_index(end_time, block_time, dt, count);
+                                if (e > len) {
+                                    double time = fma((double)len, dt, block_time);
+                                    float value = 0.f;
+                                    while (len < e) {
+                                        value = lin ? par_linear(start_time, duration, v0, k, time) : par_exp(start_time, duration, v0, k, time);
+                                        buf[len++] = value;
+                                        time += dt;
+                                    }
+                                    st.intrinsic = value;
+                                }
+                            }
+                            if (end_time >= next_block_time) {
+                                st.intrinsic = lin ? par_linear(start_time, duration, v0, k, next_block_time)
+                                                   : par_exp(start_time, duration, v0, k, next_block_time);
+                                exit_loop = true;
+                                break;
+                            }
+                            if (ev.has_cancel) {
+                                float value = lin ? par_linear(start_time, duration, v0, k, end_time) : par_exp(start_time, duration, v0, k, end_time);
+                                st.intrinsic = value;
+                                ParamEvDev l = tl.pop();
+                                l.time = end_time;
+                                l.value = value;
+                                st.last = l;
+                            } else {
+                                st.intrinsic = v1;
+                                st.last = tl.pop();
+                            }
+                            st.has_last = 1;
+                            exit_loop = false;
+                            break;
+                        }
+                        case WAE_EVENT_SET_TARGET_AT_TIME: {  // param.rs:1274-1427
+                            double end_time = next_block_time;
+                            bool ended = false;
+                            if (tl.has_next()) {
+                                ParamEvDev nx = tl.next();
+                                if (nx.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME || nx.type == WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME) {
+                                    end_time = block_time;
+                                    ended = true;
+                                } else if (nx.time < next_block_time) {
+                                    end_time = nx.time;
+                                    ended = true;
+                                }
+                            }
+                            if (ev.has_cancel && ev.cancel_time < next_block_time) {
+                                end_time = ev.cancel_time;
+                                ended = true;
+                            }
+                            const double start_time = ev.time;
+                            const float v0 = st.last.value, v1 = ev.value;
+                            const float diff = v0 - v1;
+                            const double tau = ev.aux;
+                            if (p.a_rate) {
+                                int e = par_end_index(end_time, block_time, dt, count);
+                                if (e > len) {
+                                    double time = fma((double)len, dt, block_time);
+                                    float value = 0.f;
+                                    while (len < e) {
+                                        value = (time - start_time < 0.) ? st.intrinsic : par_target(start_time, tau, v1, diff, time);
+                                        buf[len++] = value;
+                                        time += dt;
+                                    }
+                                    st.intrinsic = value;
+                                }
+                            }
+                            if (!ended) {
+                                float value = par_target(start_time, tau, v1, diff, next_block_time);
+                                if (fabsf(v1 - value) < 1e-10f) {  // SNAP_TO_TARGET, param.rs:22
+                                    st.intrinsic = v1;
+                                    if (v1 == 0.f)
+                                        for (int i = 0; i < len; i++)
+                                            if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
+                                    ParamEvDev r{};
+                                    r.type = WAE_EVENT_SET_VALUE_AT_TIME;
+                                    r.time = next_block_time;
+                                    r.value = v1;
+                                    tl.replace_peek(r);
+                                } else {
+                                    st.intrinsic = value;
+                                }
+                                exit_loop = true;
+                                break;
+                            }
+                            float value = par_target(start_time, tau, v1, diff, end_time);
+                            st.intrinsic = value;
+                            ParamEvDev l = tl.pop();
+                            l.time = end_time;
+                            l.value = value;
+                            st.last = l;
+                            st.has_last = 1;
+                            exit_loop = false;
+                            break;
+                        }
+                        case WAE_EVENT_SET_VALUE_CURVE_AT_TIME: {  // param.rs:1429-1498
+                            const double start_time = ev.time, duration = ev.aux;
+                            const float* values = p.curves + ev.values_off;
+                            const int nv = ev.values_len;
+                            double end_time = start_time + duration;
+                            if (ev.has_cancel) end_time = ev.cancel_time;
+                            if (p.a_rate) {
+                                int e = par_end_index(end_time, block_time, dt, count);
+                                if (e > len) {
+                                    double time = fma((double)len, dt, block_time);
+                                    float value = 0.f;
+                                    while (len < e) {
+                                        value = time < start_time ? st.intrinsic : par_curve(start_time, duration, values, nv, time);
+                                        buf[len++] = value;
+                                        time += dt;
+                                    }
+                                    st.intrinsic = value;
+                                }
+                            }
+                            if (end_time >= next_block_time) {
+                                st.intrinsic = par_curve(start_time, duration, values, nv, next_block_time);
+                                exit_loop = true;
+                                break;
+                            }
+                            float value = ev.has_cancel ? par_curve(start_time, duration, values, nv, end_time) : values[nv - 1];
+                            ParamEvDev l = tl.pop();
+                            l.time = end_time;
+                            l.value = value;
+                            st.intrinsic = value;
+                            st.last = l;
+                            st.has_last = 1;
+                            exit_loop = false;
+                            break;
+                        }
+                        default: exit_loop = true;
+                    }
+                }
+                if (exit_loop) break;
+            }
+        }
+        // ---- mix_to_output (param.rs:739-797): + input signal, NaN -> default, clamp
+        auto fix = [&](float v) {
+            if (v != v) return p.def;
+            v = v > p.mn ? v : p.mn;
+            return v < p.mx ? v : p.mx;
+        };
+        if (len == 1 || !p.a_rate) {
+            const float value = buf[0];
+            if (!in || !p.a_rate) {
+                float v = fix(value + (in ? in[q0] : 0.f));
+                for (int i = 0; i < 128; i++) out[q0 + i] = v;
+            } else {
+                for (int i = 0; i < 128; i++) out[q0 + i] = fix(in[q0 + i] + value);
+            }
+        } else {
+            for (int i = 0; i < 128; i++) out[q0 + i] = fix((in ? in[q0 + i] : 0.f) + buf[i]);
+        }
+    }
+    *p.state = st;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Convolver — ConvolverRenderer (src/node/convolver.rs:343-490) over fft-convolver's uniformly partitioned
 // scheme (block 1024, FFT 2048), evaluated time-batched: every 1024-frame block of a chunk is transformed
 // once (overlap-save frame [previous block | current block]), then for each output block j
@@ -785,7 +1428,7 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
 // Shared-memory radix-2 complex FFT of 1024 points + real-FFT packing (2048 real <-> 1024 complex).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CV_B = 1024;      // block
-constexpr int CV_BINS = 1025;   // spectrum bins of the 2048-point real FFT
+constexpr int CV_BINS = WAE_CONV_SPEC;  // packed half spectrum: bin 0 = (DC, Nyquist), bins 1..1023 complex
 constexpr int CV_THREADS = 256;
 
 __device__ float2 c_tw2048[1024];  // exp(-2*pi*i*k/2048), k < 1024 (global + L1: per-thread indices diverge)
@@ -854,12 +1497,10 @@ __global__ void __launch_bounds__(CV_THREADS) k_conv_fft_in(const ConvInput* __r
     fft1024_smem(z, -1);
     // unpack to the 1025 bins of the real FFT: X[k] = E[k] + w^k O[k]
     float2* X = ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS;
-    for (int k = t; k <= 1024; k += CV_THREADS) {
+    for (int k = t; k < 1024; k += CV_THREADS) {
         float2 r;
         if (k == 0) {
-            r = make_float2(z[0].x + z[0].y, 0.f);
-        } else if (k == 1024) {
-            r = make_float2(z[0].x - z[0].y, 0.f);
+            r = make_float2(z[0].x + z[0].y, z[0].x - z[0].y);  // packed (DC, Nyquist)
         } else {
             float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
             float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
@@ -883,77 +1524,137 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
     ip.prev[i] = m < ci.nf ? in[m] : 0.f;
 }
 
-// grid: (blocks in chunk, paths).  Y_j = sum_i H_i X_{j-i}; inverse FFT; write frames [j*1024, (j+1)*1024).
-__global__ void __launch_bounds__(CV_THREADS) k_conv_mac_ifft(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs,
-                                                              int n_paths, ChunkInfo ci) {
-    __shared__ float2 z[1024];
-    __shared__ float2 ynyq;
+// grid: (ceil(blocks in chunk / CV_J), paths), 512 threads.  For CV_J consecutive output blocks j at once:
+//     Y_j = sum_i H_i X_{j-i};  out_j = IFFT(Y_j)[1024..2048) / 2048.
+// Register tiling over the block axis: the input blocks are walked in groups of CV_J; a group needs 2*CV_J-1 IR
+// spectra values and CV_J input spectra values per bin for CV_J^2 complex MACs (0.36 loads per MAC instead of 2),
+// which turns the L2-bound MAC loop into an FP32-FMA-bound one.  Y_j (CV_J x 8 KB) is kept in shared memory and
+// transformed back block by block.
+constexpr int CV_J = 8;
+constexpr int CV_MAC_THREADS = 512;
+
+DEVI void fft1024_smem_n(float2* s, int sign, int nthreads) {
+    const int t = threadIdx.x;
+    for (int i = t; i < 1024; i += nthreads) {
+        int r = __brev((unsigned)i) >> 22;
+        if (i < r) {
+            float2 tmp = s[i];
+            s[i] = s[r];
+            s[r] = tmp;
+        }
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int len = 2; len <= 1024; len <<= 1) {
+        const int half = len >> 1;
+        const int step = 2048 / len;
+        for (int b = t; b < 512; b += nthreads) {
+            int grp = b / half, j = b % half;
+            int i0 = grp * len + j, i1 = i0 + half;
+            float2 w = __ldg(&c_tw2048[j * step]);
+            if (sign > 0) w.y = -w.y;
+            float2 u = s[i0], v = cmul(s[i1], w);
+            s[i0] = make_float2(u.x + v.x, u.y + v.y);
+            s[i1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac_ifft(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs,
+                                                                  int n_paths, ChunkInfo ci) {
+    extern __shared__ float2 sY[];  // [CV_J][1024]
     const ConvPath p = paths[blockIdx.y];
     const ConvInput ip = inputs[p.input];
-    const int jb = blockIdx.x;
-    const int64_t jabs = ci.f0 / CV_B + jb;
+    const int nb = (ci.nf + CV_B - 1) / CV_B;
+    const int j0 = blockIdx.x * CV_J;                  // first output block of this CTA (chunk-relative)
+    const int64_t jabs0 = ci.f0 / CV_B + j0;
+    const int64_t jabs_last = ci.f0 / CV_B + nb - 1;   // newest input block transformed so far
     const int t = threadIdx.x;
-    const int imax = (int)min((int64_t)p.S - 1, jabs);  // X_{j-i} exists for j-i >= 0
-    // each thread accumulates bins k = t, t+256, t+512, t+768 (+ bin 1024 on thread 0)
-    float2 acc[4];
+    const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;  // i runs up to S-1: i_base - (J-1) <= S-1
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const int k = t + pass * CV_MAC_THREADS;
+        float2 acc[CV_J];
 #pragma unroll
-    for (int u = 0; u < 4; u++) acc[u] = make_float2(0.f, 0.f);
-    float2 acc_n = make_float2(0.f, 0.f);
-    for (int i = 0; i <= imax; i++) {
-        const float2* H = p.h + (size_t)i * CV_BINS;
-        const float2* X = ip.xring + (size_t)((jabs - i) % ip.xring_blocks) * CV_BINS;
+        for (int jj = 0; jj < CV_J; jj++) acc[jj] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int g = 0; g < groups; g++) {
+            const int i_base = g * CV_J;
+            const int64_t b0 = jabs0 - i_base;
+            float2 hw[2 * CV_J - 1];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            int k = t + u * CV_THREADS;
-            float2 h = __ldg(H + k), x = X[k];
-            acc[u].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[u].x));
-            acc[u].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[u].y));
-        }
-        if (t == 0) {
-            float2 h = __ldg(H + 1024), x = X[1024];
-            acc_n.x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc_n.x));
-            acc_n.y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc_n.y));
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) z[t + u * CV_THREADS] = acc[u];
-    if (t == 0) ynyq = acc_n;
-    __syncthreads();
-    // pack the half spectrum for the inverse real FFT: Z[k] = (Y[k] + conj(Y[N/2-k])) + i w^-k (Y[k] - conj(Y[N/2-k]))
-    float2 zz[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-        int k = t + u * CV_THREADS;
-        float2 yk = k == 0 ? make_float2(z[0].x, 0.f) : z[k];
-        float2 ym = k == 0 ? make_float2(ynyq.x, 0.f) : z[1024 - k];
-        float2 yc = make_float2(ym.x, -ym.y);
-        float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
-        float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
-        float2 w = c_tw2048[k];
-        w.y = -w.y;  // conj
-        float2 o = cmul(w, d);
-        zz[u] = make_float2(e.x - o.y, e.y + o.x);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 4; u++) z[t + u * CV_THREADS] = zz[u];
-    __syncthreads();
-    fft1024_smem(z, +1);
-    // frame samples 2i, 2i+1 = Re, Im of z[i]; keep the second half [1024, 2048) -> i in [512, 1024)
-    float* out = chan(p.out, p.out_channel, ci) + (size_t)jb * CV_B;
-    const float scale = 1.f / 2048.f;
-    for (int i = 512 + t; i < 1024; i += CV_THREADS) {
-        int n = 2 * (i - 512);
-        if (jb * CV_B + n < ci.nf) {
-            float2 v = make_float2(z[i].x * scale, z[i].y * scale);
-            float2* dst = reinterpret_cast<float2*>(out + n);
-            if (p.accumulate) {
-                float2 o = *dst;
-                v.x += o.x;
-                v.y += o.y;
+            for (int u = 0; u < 2 * CV_J - 1; u++) {
+                const int i = i_base - (CV_J - 1) + u;
+                hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
             }
-            *dst = v;
+#pragma unroll
+            for (int r = 0; r < CV_J; r++) {
+                const int64_t b = b0 + r;
+                float2 x = make_float2(0.f, 0.f);
+                if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)(b % ip.xring_blocks) * CV_BINS + k];
+                if (k == 0) {  // packed real bins: (DC, Nyquist) multiply component-wise
+#pragma unroll
+                    for (int jj = 0; jj < CV_J; jj++) {
+                        const float2 h = hw[(CV_J - 1) + jj - r];
+                        acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
+                        acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
+                    }
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < CV_J; jj++) {
+                        const float2 h = hw[(CV_J - 1) + jj - r];
+                        acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
+                        acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
+                    }
+                }
+            }
         }
+#pragma unroll
+        for (int jj = 0; jj < CV_J; jj++) sY[jj * 1024 + k] = acc[jj];
+    }
+    __syncthreads();
+    const float scale = 1.f / 2048.f;
+#pragma unroll 1
+    for (int jj = 0; jj < CV_J; jj++) {
+        if (j0 + jj >= nb) break;  // uniform
+        float2* z = sY + jj * 1024;
+        // half spectrum -> packed complex input of the 1024-point inverse transform
+        float2 zz[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int k = t + u * CV_MAC_THREADS;
+            float2 yk = k == 0 ? make_float2(z[0].x, 0.f) : z[k];
+            float2 ym = k == 0 ? make_float2(z[0].y, 0.f) : z[1024 - k];
+            float2 yc = make_float2(ym.x, -ym.y);
+            float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
+            float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
+            float2 w = __ldg(&c_tw2048[k]);
+            w.y = -w.y;
+            float2 o = cmul(w, d);
+            zz[u] = make_float2(e.x - o.y, e.y + o.x);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 2; u++) z[t + u * CV_MAC_THREADS] = zz[u];
+        __syncthreads();
+        fft1024_smem_n(z, +1, CV_MAC_THREADS);
+        float* out = chan(p.out, p.out_channel, ci) + (size_t)(j0 + jj) * CV_B;
+        {
+            const int i = 512 + t;  // second half of the 2048 frame: complex i in [512, 1024)
+            const int n = 2 * t;
+            if ((j0 + jj) * CV_B + n < ci.nf) {
+                float2 v = make_float2(z[i].x * scale, z[i].y * scale);
+                float2* dst = reinterpret_cast<float2*>(out + n);
+                if (p.accumulate) {
+                    float2 o = *dst;
+                    v.x += o.x;
+                    v.y += o.y;
+                }
+                *dst = v;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -977,12 +1678,10 @@ __global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restr
     __syncthreads();
     fft1024_smem(z, -1);
     float2* H = h + ((size_t)c * S + seg) * CV_BINS;
-    for (int k = t; k <= 1024; k += CV_THREADS) {
+    for (int k = t; k < 1024; k += CV_THREADS) {
         float2 r;
         if (k == 0) {
-            r = make_float2(z[0].x + z[0].y, 0.f);
-        } else if (k == 1024) {
-            r = make_float2(z[0].x - z[0].y, 0.f);
+            r = make_float2(z[0].x + z[0].y, z[0].x - z[0].y);  // packed (DC, Nyquist)
         } else {
             float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
             float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
@@ -1007,7 +1706,12 @@ void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw2048, host_
 void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_oscillator<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_constant<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_buffer_source<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
-void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) { k_mix<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci); }
+void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) {
+    // few instances x few frames (one graph with a huge fan-in): one frame per thread keeps more loads in flight
+    const long ctas4 = (long)((ci.nf + 1023) / 1024) * n;
+    if (ctas4 < 2 * 148) k_mix<1><<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci);
+    else k_mix<4><<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, e, n, ci);
+}
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
@@ -1046,10 +1750,14 @@ void launch_stereo_panner(const SPanInst* d, const float2* g, int n, ChunkInfo c
 }
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_eq<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_route<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
-void launch_delay(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) {
-    k_delay_read<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
-    k_ring_write<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
+void launch_delay_read(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_delay_read<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_ring_write<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_osc_arate<<<n, 256, 0, s>>>(d, n, ci); }
+void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    int threads = n * max_ch;
+    k_biquad_arate<<<(threads + 63) / 64, 64, 0, s>>>(d, n, max_ch, ci);
 }
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_param<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_analyser<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s) {
@@ -1058,8 +1766,14 @@ void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s)
     k_conv_save_prev<<<dim3(4, (unsigned)n), 256, 0, s>>>(d, n, ci);
 }
 void launch_conv_mac_ifft(const ConvPath* p, const ConvInput* in, int n, ChunkInfo ci, cudaStream_t s) {
+    static bool configured = false;
+    const int smem = CV_J * 1024 * (int)sizeof(float2);
+    if (!configured) {
+        cudaFuncSetAttribute(k_conv_mac_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
     int nb = (ci.nf + CV_B - 1) / CV_B;
-    k_conv_mac_ifft<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, 0, s>>>(p, in, n, ci);
+    k_conv_mac_ifft<<<dim3((unsigned)((nb + CV_J - 1) / CV_J), (unsigned)n), CV_MAC_THREADS, smem, s>>>(p, in, n, ci);
 }
 void launch_conv_ir_fft(const float* ir, int64_t ir_len, int64_t ir_stride, float2* h, int S, int channels, cudaStream_t s) {
     k_conv_ir_fft<<<dim3((unsigned)S, (unsigned)channels), CV_THREADS, 0, s>>>(ir, ir_len, ir_stride, h, S);

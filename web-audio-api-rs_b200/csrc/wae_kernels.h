@@ -9,6 +9,7 @@ namespace wae {
 // Per-biquad constants of the time-parallel recurrence (host-computed in f64).  M = [[-a1,-a2],[1,0]] advances the
 // state (y[n-1], y[n-2]) by one frame; A = M^WAE_CHAIN_K advances it by one thread (WAE_CHAIN_K frames).
 constexpr int WAE_CHAIN_K = 16;  // frames per thread of k_chain
+constexpr int WAE_CONV_SPEC = 1024;  // float2 per block spectrum (packed real FFT of 2048: bin 0 = (DC, Nyquist))
 struct ScanCoef {
     double Pshfl[5][4];    // A^(2^d), d = 0..4: warp-level Kogge-Stone steps
     double Plane[32][4];   // A^(lane+1): carries a warp's incoming state to each lane
@@ -28,7 +29,11 @@ void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_stereo_panner(const SPanInst* d, const float2* gains, int n, ChunkInfo ci, cudaStream_t s);
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
-void launch_delay(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_delay_read(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s);
