@@ -567,37 +567,49 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
 
     constexpr int tile = CH_THREADS * CH_K;
     constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;  // PCM read from memory: prefetch with cp.async
-    // double-buffered staging of the source frames, [buffer][float4 u of the thread][thread]: every thread stages
-    // and later reads only its own 64 bytes (no barrier needed), conflict-free 16-byte shared accesses
-    __shared__ float4 s_in[STREAMED ? 2 : 1][STREAMED ? CH_K / 4 : 1][STREAMED ? CH_THREADS : 1];
-    auto stage_source = [&](int buf, int nfirst) {
-        if (!STREAMED || nfirst >= ci.nf) return;
-        const float* gp = nullptr;
+    // Per-warp staging of source / result frames, double buffered.  A warp owns 512 consecutive frames (2 KB) of the
+    // tile; global memory is touched with fully coalesced 512-byte warp accesses (lane l moves the 16-byte piece
+    // f = 32*u + l), while thread tt works on the contiguous pieces f = 4*tt + uu.  The XOR swizzle makes both
+    // access patterns conflict-free for 128-bit shared accesses.
+    constexpr int WF = 32 * CH_K / 4;  // float4 pieces per warp region (128)
+    __shared__ float4 s_io[2][CH_WARPS][WF];
+    auto swz = [](int f) { return f ^ ((f >> 3) & 3); };
+    const int wbase = warp * 32 * CH_K;  // first frame of the warp region inside a tile
+    auto stage_source = [&](int buf, int tile_base) {
+        if (!STREAMED) return;
+        const int nw = tile_base + wbase;  // chunk-relative first frame of this warp's region
+        if (nw >= ci.nf) return;
+        const float* gp = nullptr;  // warp-uniform: whole region readable with aligned 16-byte pieces
         if (SRC == CHAIN_SRC_BUFFER) {
-            gp = chan(q.in, c, ci) + nfirst;
+            gp = chan(q.in, c, ci) + nw;  // nf is a multiple of 128 = 8 threads: the warp region may be ragged at the end
+            if (nw + 32 * CH_K > ci.nf) gp = nullptr;
         } else {
             const AbsnInst& o = q.absn;
             const float* src = o.buf + (size_t)c * o.buf_stride;
-            const int64_t n = ci.f0 + nfirst;
+            const int64_t n = ci.f0 + nw;
             const int64_t idx = n - o.n_start + o.buf_offset;
-            if (!o.loop && n >= o.n_start && idx + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) gp = src + idx;
+            if (!o.loop && n >= o.n_start && idx + 32 * CH_K <= o.buf_len && nw + 32 * CH_K <= ci.nf &&
+                ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0))
+                gp = src + idx;
         }
         if (gp) {
 #pragma unroll
             for (int u = 0; u < CH_K / 4; u++) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_in[buf][u][t]);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * u) : "memory");
+                const int f = 32 * u + lane;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_io[buf][warp][swz(f)]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * f) : "memory");
             }
-        } else {  // ragged start / end of the buffer, loops, unaligned channel: scalar gather, then stage
+        } else if (nw + lane * CH_K < ci.nf) {  // ragged start / end, loops, unaligned channel: per-thread gather
             float tmp[CH_K];
-            chain_load_source<SRC>(q, c, ci, nfirst, tmp);
+            chain_load_source<SRC>(q, c, ci, nw + lane * CH_K, tmp);
 #pragma unroll
-            for (int u = 0; u < CH_K / 4; u++) s_in[buf][u][t] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
+            for (int u = 0; u < CH_K / 4; u++)
+                s_io[buf][warp][swz(4 * lane + u)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
         }
     };
     float v[CH_K];
     if (STREAMED) {
-        stage_source(0, t * CH_K);
+        stage_source(0, 0);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     int tile_index = 0;
@@ -605,14 +617,16 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
         const int n0 = base + t * CH_K;
         const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
         const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
+        const int buf = tile_index & 1;
         if (STREAMED) {
-            stage_source((tile_index + 1) & 1, n0 + tile);  // prefetch the next tile while this one is filtered
+            stage_source(buf ^ 1, base + tile);  // prefetch the next tile while this one is filtered
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's group has landed
+            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's pieces have landed ...
+            __syncwarp();                                            // ... for every lane of the warp
             if (active) {
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++) {
-                    const float4 a = s_in[tile_index & 1][u][t];
+                    const float4 a = s_io[buf][warp][swz(4 * lane + u)];
                     v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
                 }
             }
@@ -642,18 +656,32 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g3;
         }
-        if (active) {
-            const int64_t nabs = ci.f0 + n0;
+        {
+            // results: through the warp's staging region (the source pieces of this tile are consumed), so that global
+            // memory sees coalesced 512-byte stores; per-thread stores for ragged / unaligned / length-limited regions
+            const int nw = base + wbase;
             const int n_out = q.out_dup > 1 ? q.out_dup : 1;
-            const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + n0) & 15) == 0 &&
+            const bool region_full = nw + 32 * CH_K <= ci.nf;
+            const bool in_limit = q.limit < 0 || ci.f0 + nw + 32 * CH_K <= q.limit;
+            const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + nw) & 15) == 0 &&
                                  (q.out_dup <= 1 || (q.out.stride & 3) == 0);
-            if (aligned && (q.limit < 0 || nabs + CH_K <= q.limit)) {
-                for (int oc = 0; oc < n_out; oc++) {
-                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0);
+            if (region_full && in_limit && aligned) {  // warp-uniform
+                __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < CH_K / 4; u++) out[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                for (int u = 0; u < CH_K / 4; u++)
+                    s_io[buf][warp][swz(4 * lane + u)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                __syncwarp();
+                for (int oc = 0; oc < n_out; oc++) {
+                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++) {
+                        const int f = 32 * u + lane;
+                        out[f] = s_io[buf][warp][swz(f)];
+                    }
                 }
-            } else {  // unaligned channel base (odd render length) or the last, partial quantum: scalar stores
+                __syncwarp();
+            } else if (active) {
+                const int64_t nabs = ci.f0 + n0;
                 for (int oc = 0; oc < n_out; oc++) {
                     float* out = chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0;
 #pragma unroll
