@@ -414,6 +414,45 @@ def test_feedback_delay_echo(pkg, engine, oracle):
     assert maxdiff(gpu, cpu) <= TOL
 
 
+# ---- AudioBufferSource slow track ---------------------------------------------------------------
+SLOW_CASES = {
+    "rate_half": dict(playback_rate=0.5),
+    "rate_1p7_detune": dict(playback_rate=1.7, detune=-130.0),
+    "subsample_start": dict(start=0.00123),
+    "offset_duration": dict(start=0.004, offset=0.0112, duration=0.0305),
+    "stop": dict(stop=0.0391),
+    "loop_custom_points": dict(loop=True, loop_start=0.0103, loop_end=0.0377, playback_rate=1.3),
+    "loop_default_rate": dict(loop=True, playback_rate=0.77),
+    "buffer_44k1_in_48k": dict(buffer_sr=44100.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SLOW_CASES))
+def test_buffer_source_slow_track(pkg, engine, oracle, name):
+    o = SLOW_CASES[name]
+
+    def build(be, g):
+        rng = np.random.default_rng(50 + g)
+        t = np.arange(2600) / 48000.0
+        pcm = [(np.sin(2 * np.pi * (300 + 90 * g) * t + c) * 0.7 + 0.05 * rng.standard_normal(2600)).astype(np.float32) for c in range(2)]
+        c = pkg.OfflineAudioContext(2, 128 * 60, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer(pcm, o.get("buffer_sr", G.SR)), detune=o.get("detune", 0.0),
+                                   playback_rate=o.get("playback_rate", 1.0), loop=o.get("loop", False),
+                                   loop_start=o.get("loop_start", 0.0), loop_end=o.get("loop_end", 0.0))
+        s.connect(c.destination())
+        if "offset" in o:
+            s.start_at_with_offset_and_duration(o["start"], o["offset"], o["duration"])
+        else:
+            s.start_at(o.get("start", 0.0))
+        if "stop" in o:
+            s.stop_at(o["stop"])
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert float(np.abs(cpu).max()) > 0.3
+    assert maxdiff(gpu, cpu) <= TOL
+
+
 # ---- AudioParam automation and audio-rate modulation ------------------------------------------
 AUTOMATIONS = {
     "linear": lambda p: (p.set_value(0.2), p.linear_ramp_to_value_at_time(1.0, 0.013)),

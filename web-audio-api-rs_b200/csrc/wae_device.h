@@ -54,6 +54,30 @@ struct AbsnInst {
     int32_t loop;  // 1: wrap modulo buf_len (default loop points)
 };
 
+// AudioBufferSourceRenderer slow track (audio_buffer_source.rs:625-823): fractional playhead, offset / duration / stop,
+// custom loop points, buffer sample rate != context sample rate; constant positive playback rate
+struct AbsnSlowInst {
+    BufRef out;
+    const float* buf;
+    int64_t buf_len, buf_stride;
+    int64_t n_first, n_stop;     // frames [n_first, n_stop) may play
+    double offset0;              // buffer time (s) at n_first
+    double step;                 // dt * computed_playback_rate
+    double elapsed0, duration;   // buffer_time_elapsed at n_first / explicit duration (f64::MAX: none)
+    double buffer_duration;
+    double pos_scale;            // sampling_ratio * sample_rate: playhead (frames) = buffer_time * pos_scale
+    double loop_start, loop_end; // actual loop points (s)
+    double sample_rate;
+    int32_t ch;
+    int32_t loop;
+    // playhead segments: buffer_time(n) = seg_bt[k] + (n - seg_n[k]) * step for seg_n[k] <= n < seg_n[k+1]; a new
+    // segment starts wherever the reference modifies buffer_time (loop wrap, sticky snap to a loop point)
+    const int64_t* seg_n;
+    const double* seg_bt;
+    int32_t n_seg;
+    int32_t pad;
+};
+
 struct BiquadInst {
     BufRef in, out;
     double b0, b1, b2, a1, a2;

@@ -43,11 +43,11 @@ namespace {
 
 enum StageKind : int {
     S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -62,6 +62,7 @@ struct StageBuild {
     std::vector<ParamInst> param;
     std::vector<OscArInst> osc_ar;
     std::vector<BiquadArInst> biquad_ar;
+    std::vector<AbsnSlowInst> absn_slow;
     std::vector<ScanCoef> scan_coef;
     std::vector<IirInst> iir;
     std::vector<GainInst> gain;
@@ -895,10 +896,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 bool aligned = (n.start_time <= clock.block_time(q)) && n.offset == 0.;  // start in the past snaps to the block
                 bool fast = aligned && (double)pb.sample_rate / sr == 1. && computed_rate == 1. && ls == 0. && le == duration &&
                             n.duration > 1e300 && n.stop_time > 1e300;
-                if (!fast)
-                    return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode slow track (unaligned start, offset/duration, stop, playbackRate/"
-                                                 "detune != 1, custom loop points, resampling) is not lowered to the GPU yet");
-                if (!fuse_n && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (!fast && !(computed_rate > 0.))
+                    return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode with a zero or negative playback rate is not lowered to the GPU yet");
+                const bool fuse_src = fuse_n && fast;
+                if (!fuse_src && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
                 size_t stride = (len + 3) / 4 * 4;  // every channel starts 16 B aligned (LDG.128)
                 float* d_buf = d_src + src_cursor;
@@ -910,8 +911,123 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     }
                 src_cursor += (size_t)ch * stride;
                 b->asset_bytes += (size_t)ch * len * 4;
+                if (!fast) {
+                    // ---- slow track (audio_buffer_source.rs:625-823): fractional playhead
+                    auto almost_equal = [](double x, double y) {
+                        if (x == y) return true;
+                        const double tol = 1.4901161193847656e-8;
+                        double d = std::fabs(y - x);
+                        return d <= tol || d <= std::max(std::fabs(x), std::fabs(y)) * tol;
+                    };
+                    AbsnSlowInst a{};
+                    a.out = p.out_buf[0];
+                    a.buf = d_buf;
+                    a.buf_len = (int64_t)len;
+                    a.buf_stride = (int64_t)stride;
+                    a.ch = ch;
+                    a.loop = n.loop ? 1 : 0;
+                    a.sample_rate = sr;
+                    a.buffer_duration = duration;
+                    a.pos_scale = ((double)pb.sample_rate / sr) * sr;  // position = buffer_time * sampling_ratio; playhead = position * sr
+                    a.step = clock.dt * computed_rate;
+                    a.duration = n.duration;
+                    // actual loop points (:627-636)
+                    if (n.loop && ls >= 0. && le > 0. && ls < le) {
+                        a.loop_start = ls;
+                        a.loop_end = le;
+                    } else {
+                        a.loop_start = 0.;
+                        a.loop_end = duration;
+                    }
+                    // first frame at / after the start time: current_time = block_time + i * dt (:648), sticky within
+                    // almost::equal (:652-654)
+                    double start = n.start_time;
+                    int64_t qq = clock.quantum_containing(start);
+                    int64_t n_first = -1;
+                    double t_first = 0.;
+                    for (int guard = 0; guard < 3 && n_first < 0; guard++, qq++) {
+                        double bt0 = clock.block_time(qq);
+                        for (int i = 0; i < 128; i++) {
+                            double t = bt0 + (double)i * clock.dt;
+                            if (almost_equal(t, start)) start = t;
+                            if (!(t < start)) {
+                                n_first = qq * 128 + i;
+                                t_first = t;
+                                break;
+                            }
+                        }
+                    }
+                    if (n_first < 0) n_first = qq * 128;
+                    double delta = t_first - start;
+                    double off = n.offset + delta * computed_rate;  // :672-674
+                    off = std::min(std::max(off, 0.), duration);
+                    if (n.loop && off > a.loop_end) off = a.loop_end;  // :676-678 (rate >= 0)
+                    a.offset0 = off;
+                    a.elapsed0 = std::fabs(delta * computed_rate);
+                    a.n_first = n_first;
+                    a.n_stop = std::numeric_limits<int64_t>::max();
+                    if (n.stop_time < 1e300) {  // first frame with current_time >= stop_time (:663)
+                        int64_t qs = clock.quantum_containing(n.stop_time);
+                        int64_t ns = (qs + 1) * 128;
+                        double bt0 = clock.block_time(qs);
+                        for (int i = 0; i < 128; i++)
+                            if (bt0 + (double)i * clock.dt >= n.stop_time) {
+                                ns = qs * 128 + i;
+                                break;
+                            }
+                        a.n_stop = ns;
+                    }
+                    // playhead schedule: walk the reference's per-frame bookkeeping (:730-770) from event to event — a
+                    // frame where buffer_time is snapped to a loop point (almost::equal) or wrapped starts a new segment
+                    std::vector<int64_t> seg_n{n_first};
+                    std::vector<double> seg_bt{off};
+                    if (n.loop && off < a.loop_end) {
+                        const double ls2 = a.loop_start, le2 = a.loop_end, len2 = le2 - ls2, step = a.step;
+                        if (!(len2 > 4. * step)) return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode loop shorter than four output frames is not lowered to the GPU");
+                        const int64_t n_end = std::min<int64_t>(b->lq, a.n_stop);
+                        int64_t m = 0;   // frames since n_first
+                        double v = off;  // buffer_time of frame m
+                        bool entered = false;
+                        auto tz = [&](double x) { return 3.0e-8 * (1.0 + std::fabs(x)); };  // a little wider than almost::equal
+                        while (n_first + m < n_end) {
+                            // frames until the playhead can touch the tolerance zone of a loop point
+                            double to_ls = v < ls2 - tz(ls2) ? (ls2 - tz(ls2) - v) / step : 0.;
+                            double to_le = v < le2 - tz(le2) ? (le2 - tz(le2) - v) / step : 0.;
+                            double skip = (!entered && to_ls > 0.) ? std::min(to_ls, to_le) : to_le;
+                            int64_t adv = (int64_t)std::floor(skip);
+                            if (adv > 0) {
+                                v += (double)adv * step;
+                                m += adv;
+                                continue;
+                            }
+                            // exact per-frame logic of the reference
+                            double w = v;
+                            if (almost_equal(w, le2)) w = le2;
+                            if (almost_equal(w, ls2)) w = ls2;
+                            if (!entered && w >= ls2) entered = true;
+                            if (entered) {
+                                while (w >= le2) w -= len2;
+                                while (w < ls2) w += len2;
+                            }
+                            if (w != v && n_first + m > seg_n.back()) {
+                                seg_n.push_back(n_first + m);
+                                seg_bt.push_back(w);
+                            } else if (w != v) {
+                                seg_bt.back() = w;
+                            }
+                            v = w + step;
+                            m += 1;
+                        }
+                    }
+                    a.n_seg = (int32_t)seg_n.size();
+                    a.seg_n = upload(seg_n);
+                    a.seg_bt = upload(seg_bt);
+                    stage(L, S_ABSN_SLOW).absn_slow.push_back(a);
+                    algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::min<int64_t>(b->lq, (int64_t)len);
+                    break;
+                }
                 AbsnInst a{};
-                if (!fuse_n) a.out = p.out_buf[0];
+                if (!fuse_src) a.out = p.out_buf[0];
                 a.buf = d_buf;
                 a.buf_len = (int64_t)len;
                 a.buf_stride = (int64_t)stride;
@@ -920,7 +1036,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 a.buf_offset = 0;
                 a.ch = ch;
                 a.loop = n.loop ? 1 : 0;
-                if (fuse_n) {
+                if (fuse_src) {
                     PendingChain pc = source_chain(CHAIN_SRC_ABSN, ch);
                     pc.inst.absn = a;
                     if (!finish_chain(std::move(pc))) return false;
@@ -1500,6 +1616,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                 case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
                 case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
                 case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
+                case S_ABSN_SLOW: st.n = (int)s.absn_slow.size(); st.d_a = up(b, s.absn_slow); break;
                 case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
                 case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
                 case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
@@ -1560,6 +1677,7 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
             break;
         case S_PARAM: launch_param((ParamInst*)st.d_a, st.n, ci, s); break;
         case S_OSC_AR: launch_osc_arate((OscArInst*)st.d_a, st.n, ci, s); break;
+        case S_ABSN_SLOW: launch_buffer_source_slow((AbsnSlowInst*)st.d_a, st.n, ci, s); break;
         case S_BIQUAD_AR: launch_biquad_arate((BiquadArInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_CHAIN: launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;

@@ -151,6 +151,73 @@ __global__ void __launch_bounds__(256) k_buffer_source(const AbsnInst* __restric
     }
 }
 
+// AudioBufferSourceRenderer slow track (src/node/audio_buffer_source.rs:625-823) for a constant positive playback
+// rate.  The reference advances `buffer_time += dt * rate` per frame; here the playhead of frame n is the closed form
+// offset0 + (n - n_first) * step (loop wrap applied arithmetically), which differs by rounding only; the linear
+// interpolation is continuous across frame boundaries, so the PCM agrees to ~1e-7.
+DEVI bool almost_eq(double a, double b) {  // `almost` crate 0.2: absolute or relative sqrt(eps)
+    if (a == b) return true;
+    const double tol = 1.4901161193847656e-8;
+    double d = fabs(b - a);
+    if (d <= tol) return true;
+    return d <= fmax(fabs(a), fabs(b)) * tol;
+}
+__global__ void __launch_bounds__(256) k_buffer_source_slow(const AbsnSlowInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const AbsnSlowInst o = insts[ii];
+        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        const int64_t na = ci.f0 + n;
+        bool play = na >= o.n_first && na < o.n_stop;
+        int64_t pfi = 0;
+        double k = 0.;
+        if (play) {
+            const double m = (double)(na - o.n_first);
+            double elapsed = fma(m, fabs(o.step), o.elapsed0);
+            if (almost_eq(elapsed, o.duration)) elapsed = o.duration;
+            if (elapsed >= o.duration) play = false;
+            // segment of the playhead schedule that contains this frame (binary search), then the linear playhead
+            int lo = 0, hi = o.n_seg - 1;
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (o.seg_n[mid] <= na) lo = mid;
+                else hi = mid - 1;
+            }
+            double bt = fma((double)(na - o.seg_n[lo]), o.step, o.seg_bt[lo]);
+            if (fabs(bt) < 1.4901161193847656e-8) bt = 0.;
+            if (play && bt >= 0. && bt < o.buffer_duration) {
+                double playhead = bt * o.pos_scale;
+                double fl = floor(playhead);
+                pfi = (int64_t)fl;
+                k = playhead - fl;
+                if (pfi >= o.buf_len) play = false;
+            } else {
+                play = false;
+            }
+        }
+        for (int c = 0; c < o.ch; c++) {
+            float v = 0.f;
+            if (play) {
+                const float* b = o.buf + (size_t)c * o.buf_stride;
+                double prev = (double)__ldg(b + pfi), next;
+                if (pfi + 1 < o.buf_len) {
+                    next = (double)__ldg(b + pfi + 1);
+                } else if (o.loop) {  // :788-800 (rate >= 0): first frame at / after the loop start
+                    double sp = o.loop_start * o.sample_rate;
+                    int64_t si = floor(sp) == sp ? (int64_t)sp : (int64_t)sp + 1;
+                    next = (double)__ldg(b + (si < o.buf_len ? si : o.buf_len - 1));
+                } else if (almost_eq(k, 1.) || pfi == 0) {
+                    next = 0.;
+                } else {
+                    next = 2. * prev - (double)__ldg(b + pfi - 1);  // extrapolate past the end (:815-819)
+                }
+                v = (float)fma(1. - k, prev, k * next);
+            }
+            chan(o.out, c, ci)[n] = v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Mixer — AudioRenderQuantum::add / mix (src/render/quantum.rs:274-569): per input port, the incoming edges
 // are summed in the reference's processing order, each up/down-mixed to the port's computed channel count.
@@ -1734,6 +1801,9 @@ void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw2048, host_
 void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_oscillator<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_constant<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_buffer_source<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
+void launch_buffer_source_slow(const AbsnSlowInst* d, int n, ChunkInfo ci, cudaStream_t s) {
+    k_buffer_source_slow<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
+}
 void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) {
     // few instances x few frames (one graph with a huge fan-in): one frame per thread keeps more loads in flight
     const long ctas4 = (long)((ci.nf + 1023) / 1024) * n;
