@@ -362,6 +362,14 @@ WAE_API wae_status wae_batch_stage_time(wae_batch* batch, uint32_t index, char* 
 WAE_API wae_status wae_analyser_get_float_time_domain_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
 WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
 
+/* DynamicsCompressorNode::reduction (src/node/dynamics_compressor.rs:204-206): gain reduction (dB) at the end of the render */
+WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_index, wae_node_id node, float* out);
+
+/* AudioBuffer::resample (src/buffer.rs:311-363) on the GPU: linear interpolation keeping the first and last frame; the
+ * input side of the path (decode_audio_data resamples buffers to the context rate).  Host pointers. */
+WAE_API wae_status wae_resample_linear(wae_engine* engine, const float* in, uint64_t len, float from_rate, float to_rate, float* out,
+                                       uint64_t out_cap, uint64_t* out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -348,6 +348,8 @@ WAO_API wae_status wao_create_panner(wae_graph* g, const wae_panner_options* o, 
     if (o->panning_model == WAE_PANNING_HRTF) {
         std::string err;
         if (!hrtf_sphere_available(err)) return fail(WAE_UNSUPPORTED, err);
+        if (!hrtf_state_new(g->sample_rate))
+            return fail(WAE_UNSUPPORTED, "HRTF panning: the context sample rate differs from the HRIR sphere's (resampling the sphere is not restated)");
     }
     // the node id is taken first, then ensure_audio_listener_present (panner.rs:432), then the params
     uint32_t id = g->next_id++;
@@ -715,6 +717,16 @@ WAO_API wae_status wao_analyser_get_byte_time_domain_data(wae_graph* g, wae_node
     return WAE_OK;
 }
 
+// load_hrtf_processor (src/node/panner.rs:39-68): the HRIR sphere bytes (resources/IRC_1003_C.bin in the reference)
+WAO_API wae_status wao_set_hrir_sphere(const void* data, uint64_t len) {
+    std::string err;
+    if (!hrtf_set_sphere(data, len, err)) return fail(WAE_INVALID_ARGUMENT, err);
+    return WAE_OK;
+}
+// test hook: triangle + barycentric weights for a direction in the sphere's own coordinates
+WAO_API int32_t wao_hrtf_locate(const float* pos, const uint32_t* faces, uint32_t n_faces, const float* dir, uint32_t* idx, float* k) {
+    return hrtf_locate(pos, faces, n_faces, dir, idx, k) ? 1 : 0;
+}
 // DynamicsCompressorNode::reduction
 WAO_API wae_status wao_compressor_reduction(wae_graph* g, wae_node_id node, float* out) {
     auto ni = g->info.find(node);

@@ -20,6 +20,8 @@ float spatial_distance(const float sp[3], const float lp[3]);
 float spatial_angle(const float sp[3], const float so[3], const float lp[3]);
 
 bool hrtf_sphere_available(std::string& why);
+bool hrtf_set_sphere(const void* data, uint64_t len, std::string& err);
+bool hrtf_locate(const float* pos, const uint32_t* faces, size_t n_faces, const float dir[3], uint32_t idx[3], float k[3]);
 
 struct HrtfState;  // defined in wao_hrtf.cpp
 

@@ -218,10 +218,14 @@ def test_dynamics_compressor(pkg, engine, oracle):
         s.connect(d)
         d.connect(c.destination())
         s.start()
+        c._test_comp = d
         return c
 
     gpu, cpu = both(pkg, engine, oracle, build, 2)
     assert maxdiff(gpu, cpu) <= 5e-5  # f32 log10/pow chains differ by a few ulp between glibc and CUDA libm
+    cg, cc = build(engine.backend, 1), build(oracle, 1)
+    G.render(pkg, [cg]), G.render(pkg, [cc])
+    assert abs(cg._test_comp.reduction() - cc._test_comp.reduction()) <= 1e-3  # dB
 
 
 def test_analyser_passthrough_and_time_domain(pkg, engine, oracle):
@@ -242,6 +246,51 @@ def test_analyser_passthrough_and_time_domain(pkg, engine, oracle):
     tg = cg._test_analyser.get_float_time_domain_data()
     tc = cc._test_analyser.get_float_time_domain_data()
     assert maxdiff(tg, tc) <= TOL
+
+
+@pytest.mark.parametrize("fft_size,smoothing", [(32, 0.8), (1024, 0.0), (2048, 0.8), (32768, 0.3)])
+def test_analyser_frequency_data(pkg, engine, oracle, fft_size, smoothing):
+    """Analyser::compute_fft + get_float_frequency_data (src/analysis.rs:278-369) after the render."""
+    def build(be):
+        c = pkg.OfflineAudioContext(1, 128 * 300 + 5, G.SR, be)
+        o1 = c.create_oscillator(frequency=700.0)
+        o2 = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=3111.0)
+        g = c.create_gain(gain=0.25)
+        a = c.create_analyser(fft_size=fft_size, smoothing_time_constant=smoothing)
+        o1.connect(a)
+        o2.connect(g)
+        g.connect(a)
+        a.connect(c.destination())
+        o1.start()
+        o2.start()
+        c._test_analyser = a
+        return c
+
+    cg, cc = build(engine.backend), build(oracle)
+    assert maxdiff(G.render(pkg, [cg]), G.render(pkg, [cc])) <= TOL
+    fg = cg._test_analyser.get_float_frequency_data()
+    fc = cc._test_analyser.get_float_frequency_data()
+    assert fg.shape == fc.shape == (fft_size // 2,)
+    lin_g, lin_c = 10.0 ** (fg.astype(np.float64) / 20), 10.0 ** (fc.astype(np.float64) / 20)
+    assert np.abs(lin_g - lin_c).max() <= 1e-6          # magnitudes (the quantity the FFT produces)
+    loud = lin_c > 1e-4
+    assert loud.any() and np.abs(fg[loud] - fc[loud]).max() <= 1e-2   # dB where the bin is above the noise floor
+    # a second read at the same current_time returns the cached spectrum (analysis.rs:353-361)
+    assert np.array_equal(cg._test_analyser.get_float_frequency_data(), fg)
+
+
+@pytest.mark.parametrize("n,src,dst", [(1, 44100, 48000), (5, 48000, 44100), (1000, 44100, 48000), (48000, 96000, 48000),
+                                       (12345, 8000, 48000), (777, 48000, 48000.05)])
+def test_resample_linear(pkg, engine, oracle, n, src, dst):
+    """AudioBuffer::resample (src/buffer.rs:311-363) on the GPU vs the oracle."""
+    import ctypes as C
+    x = np.random.default_rng(n).standard_normal(n).astype(np.float32)
+    got = engine.resample(x, src, dst)
+    want = np.zeros(len(got) + 8, np.float32)
+    fp = C.POINTER(C.c_float)
+    m = oracle.api.resample_linear(x.ctypes.data_as(fp), n, float(src), float(dst), want.ctypes.data_as(fp), len(want))
+    assert m == len(got)
+    assert maxdiff(got, want[:m]) <= 1e-6
 
 
 def test_channel_splitter_merger(pkg, engine, oracle):

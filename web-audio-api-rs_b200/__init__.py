@@ -60,6 +60,20 @@ class Engine:
     def context(self, number_of_channels, length, sample_rate):
         return context.OfflineAudioContext(number_of_channels, length, sample_rate, self.backend)
 
+    def resample(self, samples, from_rate, to_rate):
+        """AudioBuffer::resample of one channel on the GPU (wae_resample_linear; src/buffer.rs:311-363)."""
+        import math
+        import numpy as np
+        a = api()
+        x = np.ascontiguousarray(samples, np.float32)
+        cap = max(len(x), int(math.ceil(len(x) * (float(to_rate) / float(from_rate)))) + 1)
+        out = np.zeros(cap, np.float32)
+        n = ctypes.c_uint64(0)
+        fp = ctypes.POINTER(ctypes.c_float)
+        a.check(a.resample_linear(self.handle, x.ctypes.data_as(fp), len(x), float(from_rate), float(to_rate),
+                                  out.ctypes.data_as(fp), cap, ctypes.byref(n)))
+        return out[:n.value]
+
     def close(self):
         if self.handle:
             api().engine_destroy(self.handle)

@@ -194,6 +194,20 @@ class BiquadFilterNode(AudioNode):
         api.check(api.biquad_set_type(self._ctx._g, self.id, type_))
 
 
+class DynamicsCompressorNode(AudioNode):
+    def reduction(self):
+        """DynamicsCompressorNode::reduction (src/node/dynamics_compressor.rs:204-206) after the render."""
+        ctx, api = self._ctx, self._ctx._api
+        out = C.c_float(0)
+        if api.is_product:
+            if ctx._batch is None:
+                raise B.WaeError(2, "reduction is available after rendering")
+            api.check(api.compressor_reduction(ctx._batch.handle, ctx._batch_index, self.id, C.byref(out)))
+        else:
+            api.check(api.compressor_reduction(ctx._g, self.id, C.byref(out)))
+        return out.value
+
+
 class AnalyserNode(AudioNode):
     def __init__(self, ctx, node_id, fft_size):
         super().__init__(ctx, node_id)
@@ -368,7 +382,7 @@ class OfflineAudioContext:
     def create_dynamics_compressor(self, attack=0.003, knee=30.0, ratio=12.0, release=0.25, threshold=-24.0, cfg=None):
         o = B.DynamicsCompressorOptions(attack, knee, ratio, release, threshold, cfg or channel_config())
         nid = self._create("create_dynamics_compressor", o)
-        n = AudioNode(self, nid)
+        n = DynamicsCompressorNode(self, nid)
         for i, (name, v) in enumerate([("attack", attack), ("knee", knee), ("ratio", ratio), ("release", release), ("threshold", threshold)]):
             setattr(n, name, AudioParam(self, nid, i, v))
         return n

@@ -98,6 +98,9 @@ struct AnalyserRec {
     float* d_ring;
     uint32_t fft_size;
     double smoothing;
+    float* d_last_fft;  // last_fft_output (analysis.rs:168), zeroed per run
+    float* d_db;        // read-out scratch
+    bool computed;      // frequency data already computed for the end-of-render time (analysis.rs:353-361)
 };
 
 }  // namespace
@@ -114,6 +117,8 @@ struct wae_batch {
     // state that must be reset before every run
     std::vector<std::pair<void*, size_t>> zero_on_run;
     std::vector<AnalyserRec> analysers;
+    struct CompRec { uint32_t graph; wae_node_id node; const float* d_state; };
+    std::vector<CompRec> compressors;
     // source PCM assets: device destination <- host source (re-uploadable: wae_batch_upload)
     // Graph groups: the batch is cut into contiguous groups of graphs; a group's source PCM lives in one device slab
     // mirrored by one pinned host slab, so that H2D(group k+1), render(group k) and D2H(group k-1) overlap on three
@@ -1311,6 +1316,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 c.threshold = th; c.knee = kn; c.ratio = ra; c.attack = at; c.release = re;
                 c.sample_rate = g->sample_rate;
                 stage(L, S_COMP).comp.push_back(c);
+                if (!dry) b->compressors.push_back(wae_batch::CompRec{gi, id, c.state});
                 break;
             }
             case K_ANALYSER: {
@@ -1323,7 +1329,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 a.ring = alloc<float>(32768 + 128, true, true);
                 if (!a.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser ring)");
                 stage(L, S_ANALYSER).analyser.push_back(a);
-                if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing});
+                {
+                    float* last = alloc<float>(16384, true, true);
+                    float* db = alloc<float>(16384);
+                    if (!last || !db) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser)");
+                    if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false});
+                }
                 algorithmic_bytes += (uint64_t)b->lq * 4;  // ring write, SURVEY §8(d)
                 break;
             }
@@ -1750,6 +1761,7 @@ static wae_status begin_run(wae_batch* b) {
     for (auto& z : b->zero_on_run) CUDA_TRY(cudaMemsetAsync(z.first, 0, z.second, s));
     b->timed.clear();
     b->timed_events_used = 0;
+    for (auto& a : b->analysers) a.computed = false;
     CUDA_TRY(cudaEventRecord(b->ev0, s));
     return WAE_OK;
 }
@@ -1899,8 +1911,64 @@ WAE_API wae_status wae_analyser_get_float_time_domain_data(wae_batch* b, uint32_
     return WAE_OK;
 }
 
-WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t, wae_node_id, float*, uint32_t) {
-    return fail(WAE_UNSUPPORTED, "analyser frequency read-out (control-thread FFT, src/analysis.rs:278-369) is not lowered to the GPU yet");
+WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch* b, uint32_t graph_index, wae_node_id node, float* out, uint32_t len) {
+    AnalyserRec* a = const_cast<AnalyserRec*>(find_analyser(b, graph_index, node));
+    if (!a) return fail(WAE_INVALID_ARGUMENT, "not an analyser of this batch");
+    CUDA_TRY(cudaSetDevice(b->engine->device));
+    const uint32_t RING = 32768 + 128;
+    const uint32_t bins = a->fft_size / 2;
+    if (!a->computed) {  // one FFT per distinct current_time (analysis.rs:353-361): the read-out happens after the render
+        launch_analyser_fft(a->d_ring, (uint32_t)((uint64_t)b->lq % RING), (int)a->fft_size, (float)a->smoothing, a->d_last_fft, a->d_db,
+                            b->engine->stream);
+        a->computed = true;
+    }
+    uint32_t n = std::min(len, bins);
+    CUDA_TRY(cudaMemcpyAsync(out, a->d_db, n * sizeof(float), cudaMemcpyDeviceToHost, b->engine->stream));
+    CUDA_TRY(cudaStreamSynchronize(b->engine->stream));
+    return WAE_OK;
+}
+
+// DynamicsCompressorNode::reduction (src/node/dynamics_compressor.rs:204-206,448): the reduction (dB) of the last frame
+WAE_API wae_status wae_compressor_reduction(wae_batch* b, uint32_t graph_index, wae_node_id node, float* out) {
+    if (!b || !out) return fail(WAE_INVALID_ARGUMENT, "null argument");
+    for (auto& c : b->compressors)
+        if (c.graph == graph_index && c.node == node) {
+            CUDA_TRY(cudaSetDevice(b->engine->device));
+            CUDA_TRY(cudaMemcpyAsync(out, c.d_state + 1, sizeof(float), cudaMemcpyDeviceToHost, b->engine->stream));
+            CUDA_TRY(cudaStreamSynchronize(b->engine->stream));
+            return WAE_OK;
+        }
+    return fail(WAE_INVALID_ARGUMENT, "not a dynamics compressor of this batch");
+}
+
+// AudioBuffer::resample on the GPU (src/buffer.rs:311-363): `in` / `out` are host pointers, out_cap >= ceil(len * to/from)
+WAE_API wae_status wae_resample_linear(wae_engine* eng, const float* in, uint64_t len, float from_rate, float to_rate, float* out,
+                                       uint64_t out_cap, uint64_t* out_len) {
+    if (!eng || !in || !out || !out_len) return fail(WAE_INVALID_ARGUMENT, "null argument");
+    if (std::fabs(from_rate - to_rate) <= 0.1f || len == 0) {  // "very similar sample rate: do not resample"
+        if (out_cap < len) return fail(WAE_INVALID_ARGUMENT, "output capacity too small");
+        std::memcpy(out, in, len * sizeof(float));
+        *out_len = len;
+        return WAE_OK;
+    }
+    uint64_t target = (uint64_t)std::ceil((double)len * ((double)to_rate / (double)from_rate));
+    if (out_cap < target) return fail(WAE_INVALID_ARGUMENT, "output capacity too small");
+    CUDA_TRY(cudaSetDevice(eng->device));
+    float *d_in = nullptr, *d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_in, len * sizeof(float)));
+    if (cudaMalloc(&d_out, target * sizeof(float)) != cudaSuccess) {
+        cudaFree(d_in);
+        return fail(WAE_OUT_OF_MEMORY, "out of device memory (resample)");
+    }
+    cudaMemcpyAsync(d_in, in, len * sizeof(float), cudaMemcpyHostToDevice, eng->stream);
+    launch_resample_linear(d_in, (int64_t)len, d_out, (int64_t)target, eng->stream);
+    cudaMemcpyAsync(out, d_out, target * sizeof(float), cudaMemcpyDeviceToHost, eng->stream);
+    cudaError_t e = cudaStreamSynchronize(eng->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(WAE_CUDA_ERROR, cudaGetErrorString(e));
+    *out_len = target;
+    return WAE_OK;
 }
 
 }  // extern "C"

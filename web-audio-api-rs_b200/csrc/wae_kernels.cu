@@ -1790,6 +1790,82 @@ __global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Analyser frequency read-out — Analyser::compute_fft + get_float_frequency_data (src/analysis.rs:278-369): the most
+// recent fftSize frames of the ring x Blackman window (alpha 0.16, :13-24) -> real FFT -> |X[k]| / N -> exponential
+// smoothing with the previous read-out -> 20 log10.  One CTA per analyser, radix-2 complex FFT of fftSize/2 points in
+// shared memory (fftSize up to 32768 -> 128 KB), the real-FFT split done on the fly.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_analyser_fft(const float* __restrict__ ring, uint32_t write_index, int fft_size, float smoothing,
+                                                      float* __restrict__ last_fft, float* __restrict__ out_db) {
+    extern __shared__ float2 zf[];
+    const int RING = 32768 + 128;
+    const int n = fft_size / 2;
+    const int t = threadIdx.x;
+    const float PI32 = 3.14159265358979323846f;
+    int bits = 0;
+    while ((1 << bits) < n) bits++;
+    for (int i = t; i < n; i += blockDim.x) {
+        float v[2];
+        for (int h = 0; h < 2; h++) {
+            int idx = 2 * i + h;
+            float x = ring[(RING + write_index - fft_size + idx) % RING];
+            float w = 0.42f - 0.5f * cosf(2.f * PI32 * (float)idx / (float)fft_size) + 0.08f * cosf(4.f * PI32 * (float)idx / (float)fft_size);
+            v[h] = x * w;
+        }
+        int r = (int)(__brev((unsigned)i) >> (32 - bits));
+        zf[bits == 0 ? 0 : r] = make_float2(v[0], v[1]);
+    }
+    __syncthreads();
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1;
+        for (int b = t; b < n / 2; b += blockDim.x) {
+            int grp = b / half, j = b % half;
+            int i0 = grp * len + j, i1 = i0 + half;
+            float sn, cs;
+            sincospif(-2.f * (float)j / (float)len, &sn, &cs);
+            float2 u = zf[i0], x = zf[i1];
+            float2 v = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+            zf[i0] = make_float2(u.x + v.x, u.y + v.y);
+            zf[i1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+    const float norm = 1.f / (float)fft_size;
+    for (int k = t; k < n; k += blockDim.x) {  // bins 0 .. N/2-1 (the Nyquist bin is ignored, analysis.rs:303-333)
+        float2 X;
+        if (k == 0) {
+            X = make_float2(zf[0].x + zf[0].y, 0.f);
+        } else {
+            float2 zk = zf[k], zc = make_float2(zf[n - k].x, -zf[n - k].y);
+            float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+            float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+            float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+            float sn, cs;
+            sincospif(-2.f * (float)k / (float)fft_size, &sn, &cs);
+            X = make_float2(e.x + (o.x * cs - o.y * sn), e.y + (o.x * sn + o.y * cs));
+        }
+        float mag = hypotf(X.x, X.y) * norm;
+        float value = smoothing * last_fft[k] + (1.f - smoothing) * mag;
+        if (!isfinite(value)) value = 0.f;
+        last_fft[k] = value;
+        out_db[k] = 20.f * log10f(value);
+    }
+}
+
+// AudioBuffer::resample (src/buffer.rs:311-363): linear interpolation that keeps the first and the last frame
+__global__ void __launch_bounds__(256) k_resample_linear(const float* __restrict__ in, int64_t len, float* __restrict__ out, int64_t target_len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= target_len) return;
+    double position = (double)i / (double)(target_len - 1);
+    double playhead = position * (double)(len - 1);
+    double fl = floor(playhead);
+    int64_t prev = (int64_t)fl;
+    int64_t next = prev + 1 < len - 1 ? prev + 1 : len - 1;
+    float k = (float)(playhead - fl);
+    out[i] = __fadd_rn(__fmul_rn(1.f - k, in[prev]), __fmul_rn(k, in[next]));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 static inline dim3 grid_tiles(int nf, int per_block, int n_inst) {
@@ -1854,6 +1930,17 @@ void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s) {
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;
     k_biquad_arate<<<(threads + 63) / 64, 64, 0, s>>>(d, n, max_ch, ci);
+}
+void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, float smoothing, float* last_fft, float* out_db, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_analyser_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * (int)sizeof(float2));
+        configured = true;
+    }
+    k_analyser_fft<<<1, 256, (size_t)(fft_size / 2) * sizeof(float2), s>>>(ring, write_index, fft_size, smoothing, last_fft, out_db);
+}
+void launch_resample_linear(const float* in, int64_t len, float* out, int64_t target_len, cudaStream_t s) {
+    k_resample_linear<<<(unsigned)((target_len + 255) / 256), 256, 0, s>>>(in, len, out, target_len);
 }
 void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_param<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
