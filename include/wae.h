@@ -284,6 +284,7 @@ WAE_API wae_status wae_create_channel_splitter(wae_graph*, const wae_channel_spl
 /* AudioNode::connect_from_output_to_input (src/node/audio_node.rs:259-289); destination is node 0. */
 WAE_API wae_status wae_connect(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t input);
 /* AudioNode::connect(&param): audio-rate modulation of a param (src/param.rs:762-796). */
+/* `to` = 1 (WAE_LISTENER_NODE) addresses the AudioListener's params: 0..8 = position xyz, forward xyz, up xyz */
 WAE_API wae_status wae_connect_param(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index);
 /* AudioNode::disconnect() — removes all outgoing connections of `from`. */
 WAE_API wae_status wae_disconnect(wae_graph*, wae_node_id from);
@@ -361,6 +362,12 @@ WAE_API wae_status wae_batch_stage_time(wae_batch* batch, uint32_t index, char* 
  * state of the analyser at the end of the render. */
 WAE_API wae_status wae_analyser_get_float_time_domain_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
 WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t graph_index, wae_node_id node, float* out, uint32_t len);
+
+/* load_hrtf_processor (src/node/panner.rs:39-68): the HRIR sphere the reference embeds with include_bytes!
+ * ("resources/IRC_1003_C.bin": "HRIR" | u32 rate | u32 taps | u32 #vertices | u32 #indices | indices | per vertex xyz,
+ * left[taps], right[taps]).  Must be set before a batch with PanningModelType::HRTF panners is prepared; contexts whose
+ * sample rate differs from the sphere's are WAE_UNSUPPORTED (the hrtf crate's rubato resampling is not lowered). */
+WAE_API wae_status wae_engine_set_hrir_sphere(wae_engine* engine, const void* data, uint64_t len);
 
 /* DynamicsCompressorNode::reduction (src/node/dynamics_compressor.rs:204-206): gain reduction (dB) at the end of the render */
 WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_index, wae_node_id node, float* out);

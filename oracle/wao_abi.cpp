@@ -457,6 +457,7 @@ WAO_API wae_status wao_connect(wae_graph* g, wae_node_id from, uint32_t output, 
 }
 
 WAO_API wae_status wao_connect_param(wae_graph* g, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index) {
+    if (to == 1) g->ensure_listener();  // BaseAudioContext::listener() creates it on first access (context/mod.rs)
     auto fi = g->info.find(from), ti = g->info.find(to);
     if (fi == g->info.end() || ti == g->info.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
     if ((int)output >= fi->second.n_outputs) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port out of bounds");

@@ -100,6 +100,53 @@ def north_star_voices_convolver(pkg, backend, voices, length, ir, sr=SR, seed=0)
     return c
 
 
+def synthetic_hrir_sphere(sample_rate=48000, taps=256, subdivisions=2, seed=5):
+    """An HRIR sphere in the container format of the reference's resources/IRC_1003_C.bin (see include/wae.h):
+    a subdivided octahedron (z up) whose vertex responses are decaying noise with a direction-dependent inter-aural
+    delay and level.  Test data only: the real sphere cannot travel to the GPU box."""
+    import struct
+    verts = [(1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    faces = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    verts = [np.array(v, np.float64) for v in verts]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+        def mid(i, j):
+            key = (min(i, j), max(i, j))
+            if key not in cache:
+                m = verts[i] + verts[j]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nf
+    rng = np.random.default_rng(seed)
+    t = np.arange(taps)
+    out = [b"HRIR", struct.pack("<IIII", int(sample_rate), taps, len(verts), 3 * len(faces))]
+    out.append(np.asarray(faces, "<u4").tobytes())
+    for v in verts:
+        out.append(np.asarray(v, "<f4").tobytes())
+        for ear in (-1.0, 1.0):  # left ear at -x, right ear at +x
+            lateral = ear * v[0]
+            delay = 12.0 * (1.0 - lateral)
+            env = np.where(t >= delay, np.exp(-(t - delay) / (10.0 + 6.0 * (1.0 + v[2]))), 0.0)
+            h = (0.35 + 0.25 * lateral) * env * (0.6 * rng.standard_normal(taps) + np.where(np.abs(t - delay) < 1, 1.0, 0.0))
+            out.append(h.astype("<f4").tobytes())
+    return b"".join(out)
+
+
+def parse_hrir_sphere(data):
+    """(sample_rate, positions [v][3], faces [f][3], left [v][taps], right [v][taps]) of an HRIR container."""
+    import struct
+    sr, taps, nv, ni = struct.unpack("<IIII", data[4:20])
+    off = 20
+    faces = np.frombuffer(data, "<u4", ni, off).reshape(-1, 3)
+    off += 4 * ni
+    rec = np.frombuffer(data, "<f4", nv * (3 + 2 * taps), off).reshape(nv, 3 + 2 * taps)
+    return sr, rec[:, :3], faces, rec[:, 3:3 + taps], rec[:, 3 + taps:]
+
+
 def render(pkg, contexts, threads=1):
     bufs = pkg.render_batch(contexts, threads=threads)
     return np.stack([np.stack(b.channels) for b in bufs])

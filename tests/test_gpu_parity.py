@@ -193,6 +193,97 @@ def test_equal_power_panner(pkg, engine, oracle):
     assert maxdiff(gpu, cpu) <= TOL
 
 
+@pytest.mark.parametrize("taps,chunk", [(256, 0), (512, 0), (250, 0), (256, 128), (256, 1024)])
+def test_hrtf_panner(pkg, engine, oracle, taps, chunk):
+    """PanningModelType::HRTF (panner.rs:215-271,781-830): static source / listener, mono and stereo inputs, all
+    distance models, cone gain; synthetic HRIR sphere at the context rate (the real one cannot travel)."""
+    data = G.synthetic_hrir_sphere(int(G.SR), taps)
+    oracle.set_hrir_sphere(data)
+    engine.backend.set_hrir_sphere(data)
+    positions = [(3.0, 1.0, -2.0), (-4.0, 0.0, 0.5), (0.0, 0.0, 0.0), (0.2, -6.0, 0.1), (1.0, 0.0, 0.0), (0.0, 0.0, -1.0)]
+
+    def build(be, g):
+        n = 128 * 21 + 40
+        pcm = G.c2_source(g, n) * np.float32(0.5)
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]] if g % 2 else [pcm[0]], G.SR))
+        p = c.create_panner(panning_model=pkg.context.HRTF, position=positions[g], distance_model=g % 3,
+                            cone_inner_angle=60.0, cone_outer_angle=120.0, cone_outer_gain=0.3, max_distance=50.0,
+                            orientation=(0.0, 1.0, 0.5))
+        s.connect(p)
+        p.connect(c.destination())
+        s.start()
+        return c
+
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        gpu, cpu = both(pkg, engine, oracle, build, len(positions))
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+    assert float(np.abs(cpu).max()) > 0.05
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("model", ["equalpower", "hrtf"])
+@pytest.mark.parametrize("who", ["source", "listener", "both", "audio_rate"])
+def test_panner_moving_source_and_listener(pkg, engine, oracle, model, who):
+    """Automated panner / listener params (panner.rs:714-780): a-rate spatial params for equal-power panning — including
+    the reference's rule that only the LISTENER params decide between the single-valued and the per-frame path
+    (panner.rs:833-841) — and first-value-per-quantum (k-rate) for HRTF (panner.rs:781-788)."""
+    if model == "hrtf":
+        data = G.synthetic_hrir_sphere(int(G.SR), 128, subdivisions=1)
+        oracle.set_hrir_sphere(data)
+        engine.backend.set_hrir_sphere(data)
+
+    def build(be, g):
+        n = 128 * 24
+        pcm = G.c2_source(g, n) * np.float32(0.5)
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]] if g % 2 else [pcm[0]], G.SR))
+        p = c.create_panner(panning_model=pkg.context.HRTF if model == "hrtf" else pkg.context.EQUALPOWER,
+                            position=(-3.0, 0.5, 1.0), distance_model=g % 3, max_distance=40.0,
+                            cone_inner_angle=50.0, cone_outer_angle=140.0, cone_outer_gain=0.2, orientation=(0.0, 0.2, -1.0))
+        if who in ("source", "both"):
+            p.position_x.linear_ramp_to_value_at_time(4.0, 0.05)
+            p.position_z.set_target_at_time(-6.0, 0.01, 0.02)
+            p.orientation_x.set_value_at_time(1.0, 0.03)
+        if who in ("listener", "both"):
+            l = c.listener()
+            l.position_x.linear_ramp_to_value_at_time(2.0, 0.04)
+            l.forward_x.set_value_at_time(0.6, 0.02)
+            l.up_z.linear_ramp_to_value_at_time(0.3, 0.06)
+        if who == "audio_rate":
+            lfo = c.create_oscillator(frequency=13.0)
+            amp = c.create_gain(gain=2.5)
+            lfo.connect(amp)
+            amp.connect(p.position_x)
+            amp.connect(c.listener().position_y)
+            lfo.start()
+        s.connect(p)
+        p.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert float(np.abs(cpu).max()) > 0.02
+    assert maxdiff(gpu, cpu) <= (3e-5 if model == "equalpower" else TOL)  # acosf / atan chains: few-ulp libm differences on angles
+
+
+def test_hrtf_panner_needs_matching_sphere(pkg, engine):
+    engine.backend.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 64))
+    c = pkg.OfflineAudioContext(2, 256, G.SR, engine.backend)
+    o = c.create_oscillator()
+    p = c.create_panner(panning_model=pkg.context.HRTF)
+    o.connect(p)
+    p.connect(c.destination())
+    o.start()
+    with pytest.raises(pkg.WaeError) as e:
+        c.start_rendering_sync()
+    assert e.value.status == 4 and "sample rate" in str(e.value)   # WAE_UNSUPPORTED
+    with pytest.raises(pkg.WaeError):
+        engine.backend.set_hrir_sphere(b"HRIX" + bytes(64))
+
+
 def test_delay_node(pkg, engine, oracle):
     def build(be, g):
         pcm = G.c2_source(g, 128 * 40)

@@ -76,6 +76,7 @@ class Engine:
 
     def close(self):
         if self.handle:
+            self.backend.close_batches()
             api().engine_destroy(self.handle)
             self.handle = None
 

@@ -34,8 +34,24 @@ class Backend:
     """An Api plus (for the product) an engine handle."""
 
     def __init__(self, api, engine=None):
+        import weakref
         self.api = api
         self.engine = engine
+        self.batches = weakref.WeakSet()  # live wae_batch handles: destroyed before their engine (Engine.close)
+        self.closed = False
+
+    def close_batches(self):
+        for b in list(self.batches):
+            b.destroy()
+        self.closed = True
+
+    def set_hrir_sphere(self, data):
+        """load_hrtf_processor (src/node/panner.rs:39-68): hand over the bytes of the HRIR sphere (IRC_1003_C.bin format)."""
+        buf = C.create_string_buffer(bytes(data), len(data))
+        if self.api.is_product:
+            self.api.check(self.api.engine_set_hrir_sphere(self.engine, C.cast(buf, C.c_void_p), len(data)))
+        else:
+            self.api.check(self.api.set_hrir_sphere(C.cast(buf, C.c_void_p), len(data)))
 
 
 class AudioBuffer:
@@ -145,7 +161,7 @@ class AudioNode:
     def connect_from_output_to_input(self, dest, output, input):
         api = self._ctx._api
         if isinstance(dest, AudioParam):
-            api.check(api.connect_param(self._ctx._g, self.id, output, dest._node, dest._index))
+            api.check(api.connect_param(self._ctx._g, self.id, output, 1 if dest._node == "listener" else dest._node, dest._index))
         else:
             if dest._ctx is not self._ctx:
                 raise B.WaeError(1, "InvalidAccessError - Attempting to connect nodes from different contexts")
@@ -425,6 +441,8 @@ class Batch:
         h = C.c_void_p()
         self.api.check(self.api.batch_prepare(ctx0._backend.engine, arr, self.n, C.byref(h)))
         self.handle = h
+        self._backend = ctx0._backend
+        self._backend.batches.add(self)
         for i, c in enumerate(contexts):
             c._batch, c._batch_index = self, i
 
@@ -474,7 +492,8 @@ class Batch:
 
     def destroy(self):
         if self.handle:
-            self.api.batch_destroy(self.handle)
+            if not self._backend.closed:  # a batch must not outlive its engine
+                self.api.batch_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -318,8 +318,6 @@ WAE_API wae_status wae_create_panner(wae_graph* g, const wae_panner_options* o, 
     if (o->max_distance <= 0.) return fail(WAE_INVALID_ARGUMENT, "RangeError - maxDistance must be strictly positive");
     if (o->rolloff_factor < 0.) return fail(WAE_INVALID_ARGUMENT, "RangeError - rolloffFactor cannot be negative");
     if (o->cone_outer_gain < 0. || o->cone_outer_gain > 1.) return fail(WAE_INVALID_STATE, "InvalidStateError - coneOuterGain must be in the range [0, 1]");
-    if (o->panning_model == WAE_PANNING_HRTF)
-        return fail(WAE_UNSUPPORTED, "HRTF panning (un-vendored hrtf 0.8.1 crate, parity unpinned) is not lowered to the GPU yet");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
@@ -425,6 +423,7 @@ WAE_API wae_status wae_connect(wae_graph* g, wae_node_id from, uint32_t output, 
 }
 
 WAE_API wae_status wae_connect_param(wae_graph* g, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index) {
+    if (to == 1) g->ensure_listener();  // BaseAudioContext::listener() creates it on first access (context/mod.rs)
     auto fi = g->nodes.find(from), ti = g->nodes.find(to);
     if (fi == g->nodes.end() || ti == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
     if ((int)output >= fi->second.n_outputs) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port out of bounds");

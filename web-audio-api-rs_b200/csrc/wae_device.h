@@ -9,6 +9,8 @@
 #include <cstdint>
 #include <vector_types.h>
 
+#include "wae_spatial.h"
+
 namespace wae {
 
 struct BufRef {
@@ -119,6 +121,51 @@ struct PanInst {  // equal-power panner with static source/listener (panner.rs:8
     BufRef in, out;
     float dist_gain, cone_gain, azimuth;
     int32_t in_ch;
+};
+
+// HRTF panner (panner.rs:215-271,781-830 + the hrtf crate's process_samples with interpolation_steps = 1): per quantum a
+// sphere triangle (v) and blend weights (w) select the L-tap left / right responses; out = gain * FIR(in)
+struct HrtfSel {
+    uint32_t v[3];
+    float w[3];
+    float gain;  // cone_gain * dist_gain
+    float pad;
+};
+struct HrtfInst {
+    BufRef in, out;
+    const float* sphere_ir;  // [vertex][2][L]
+    float* hist;             // [L-1] mono input before the chunk
+    const HrtfSel* sel;      // per-quantum table of the chunk (moving source / listener) or nullptr: static_sel
+    HrtfSel static_sel;
+    int32_t L;
+    int32_t in_ch;
+    float correction;        // 2 for stereo input (panner.rs:805-812)
+    int32_t pad;
+};
+
+// the 15 spatial params of a panner (source position / orientation, listener position / forward / up); an automated one
+// is a k_param track: channel 0 = value per frame, channel 1 [first frame of a quantum] = 1 if the reference's param
+// buffer is single-valued in that quantum (panner.rs:833-841 branches on the listener params' lengths)
+struct SpatialTracks {
+    BufRef track[15];  // p == nullptr: value[i]
+    float value[15];
+    int32_t pad;
+};
+struct PanDynInst {  // equal-power panner with moving source / listener (panner.rs:833-897)
+    BufRef in, out;
+    SpatialTracks sp;
+    spatial::PanModel model;
+    int32_t in_ch;
+    int32_t pad;
+};
+struct HrtfSelInst {  // per-quantum triangle / weights / gain of an HRTF panner with moving source / listener
+    SpatialTracks sp;
+    spatial::PanModel model;
+    const float* pos;     // sphere vertices [v][3]
+    const uint32_t* tri;  // sphere faces
+    int32_t n_faces;
+    int32_t pad;
+    HrtfSel* sel;         // [quanta per chunk]
 };
 
 struct MixEdge {

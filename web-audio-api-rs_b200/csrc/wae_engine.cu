@@ -7,6 +7,7 @@
 //   (the per-node arithmetic is in wae_kernels.cu)
 #include "wae_graph.h"
 #include "wae_hostmath.h"
+#include "wae_hrtf_host.h"
 #include "wae_kernels.h"
 #include "wae_param_host.h"
 
@@ -37,17 +38,21 @@ struct wae_engine {
     bool serial_filters = false;
     int pipeline_groups = 0;  // 0 = auto
     float* d_sine = nullptr;
+    wae::HrirSphere* sphere = nullptr;  // wae_engine_set_hrir_sphere
+    float* d_sphere_ir = nullptr;
+    float* d_sphere_pos = nullptr;
+    uint32_t* d_sphere_tri = nullptr;
 };
 
 namespace {
 
 enum StageKind : int {
     S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -70,6 +75,9 @@ struct StageBuild {
     std::vector<SPanInst> span;
     std::vector<float2> span_gains;
     std::vector<PanInst> pan;
+    std::vector<HrtfInst> hrtf;
+    std::vector<HrtfSelInst> hrtf_sel;
+    std::vector<PanDynInst> pan_dyn;
     std::vector<RouteInst> route;
     std::vector<DelayInst> delay;
     std::vector<CompInst> comp;
@@ -86,6 +94,7 @@ struct Stage {
     int variant = 0;
     int group = 0;
     int n = 0;
+    int n_b = 0;
     int max_ch = 1;
     void* d_a = nullptr;  // instances
     void* d_b = nullptr;  // auxiliary table (mix edges, scan coefficients, conv inputs, panner gains)
@@ -632,7 +641,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             pi.events = tl.events.empty() ? nullptr : upload(tl.events);
             pi.curves = tl.curves.empty() ? nullptr : upload(tl.curves);
             pi.state = alloc<ParamState>(1, true, true);
-            pi.out = arena_buf(1);
+            pi.out = arena_buf(2);  // channel 0: value per frame, channel 1: single-valued flag per quantum
             if (!pi.state || !pi.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (param)");
             pi.def = n.param.default_value;
             pi.mn = n.param.min_value;
@@ -1186,54 +1195,86 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_PANNER: {
-                float v[15];
-                for (int i = 0; i < 6; i++)
-                    if (!const_param(g, n.params[i], v[i])) return false;
-                for (int i = 0; i < 9; i++)
-                    if (!const_param(g, 2 + i, v[6 + i])) return false;
+                // the 15 spatial params (panner.rs:714-780): 6 of the node, 9 of the AudioListener (graph ids 2..10)
+                PRef pr[15];
+                bool moving = false;
+                for (int i = 0; i < 15; i++) {
+                    pr[i] = param_ref(g, i < 6 ? n.params[i] : (uint32_t)(2 + i - 6));
+                    moving = moving || pr[i].dyn;
+                }
                 int ch = p.in_ch[0];
                 if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                const float* sp = v, *so = v + 3, *lp = v + 6, *lf = v + 9, *lu = v + 12;
+                spatial::PanModel model{};
+                model.distance_model = n.distance_model;
+                model.ref_distance = n.ref_distance;
+                model.max_distance = n.max_distance;
+                model.rolloff_factor = n.rolloff_factor;
+                model.cone_inner_angle = n.cone_inner_angle;
+                model.cone_outer_angle = n.cone_outer_angle;
+                model.cone_outer_gain = n.cone_outer_gain;
+                SpatialTracks tr{};
+                float v[15];
+                for (int i = 0; i < 15; i++) {
+                    v[i] = tr.value[i] = pr[i].v;
+                    tr.track[i] = pr[i].dyn ? pr[i].track : BufRef{nullptr, 0, 0};
+                }
+                const spatial::SpatialParams sp0 = spatial::spatial_params(model, v);  // static source and listener
+                if (n.panning_model == WAE_PANNING_HRTF) {  // panner.rs:781-830
+                    const HrirSphere* sph = eng->sphere;
+                    if (!sph) return bail(WAE_UNSUPPORTED, "HRTF panning needs an HRIR sphere: call wae_engine_set_hrir_sphere first");
+                    uint32_t sr = (uint32_t)g->sample_rate;
+                    if (sr < 27000) sr = 27000;  // panner.rs:46
+                    if (sr != sph->sample_rate)
+                        return bail(WAE_UNSUPPORTED, "HRTF panning: the context sample rate differs from the HRIR sphere's (resampling the sphere is not lowered)");
+                    HrtfInst h{};
+                    h.in = p.in_buf[0];
+                    h.out = p.out_buf[0];
+                    h.in_ch = ch;
+                    h.L = (int)sph->taps;
+                    h.sphere_ir = eng->d_sphere_ir;
+                    h.sel = nullptr;
+                    h.correction = ch == 2 ? 2.f : 1.f;
+                    h.hist = alloc<float>(sph->taps, true, true);
+                    if (!h.hist) return bail(WAE_OUT_OF_MEMORY, "out of device memory (hrtf history)");
+                    StageBuild& hs = stage(L, S_HRTF);
+                    if (moving) {
+                        HrtfSelInst si{};
+                        si.sp = tr;
+                        si.model = model;
+                        si.pos = eng->d_sphere_pos;
+                        si.tri = eng->d_sphere_tri;
+                        si.n_faces = (int)(sph->tri.size() / 3);
+                        si.sel = alloc<HrtfSel>((size_t)(b->chunk / 128 + 1));
+                        if (!si.sel) return bail(WAE_OUT_OF_MEMORY, "out of device memory (hrtf selection)");
+                        h.sel = si.sel;
+                        hs.hrtf_sel.push_back(si);
+                    } else {
+                        float proj[3];
+                        spatial::projected_source(sp0, proj);
+                        const float dir[3] = {proj[0], proj[2], proj[1]};  // HrtfState::process swaps y / z (panner.rs:248-252)
+                        h.static_sel = HrtfSel{{0, 0, 0}, {0.f, 0.f, 0.f}, sp0.cone_gain * sp0.dist_gain, 0.f};
+                        sph->locate(dir, h.static_sel.v, h.static_sel.w);  // no face: all-zero weights (silence)
+                    }
+                    hs.hrtf.push_back(h);
+                    break;
+                }
+                if (moving) {
+                    PanDynInst d{};
+                    d.in = p.in_buf[0];
+                    d.out = p.out_buf[0];
+                    d.sp = tr;
+                    d.model = model;
+                    d.in_ch = ch;
+                    stage(L, S_PAN_DYN).pan_dyn.push_back(d);
+                    break;
+                }
                 PanInst pi{};
                 pi.in = p.in_buf[0];
                 pi.out = p.out_buf[0];
                 pi.in_ch = ch;
-                float el;
-                hm::azimuth_elevation(sp, lp, lf, lu, pi.azimuth, el);
-                {  // dist_gain, panner.rs:954-986
-                    float rel[3];
-                    hm::sub3(sp, lp, rel);
-                    double distance = (double)std::sqrt(hm::sq_len(rel));
-                    double gd;
-                    auto clampd = [](double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); };
-                    if (n.distance_model == 0) {
-                        double ro = clampd(n.rolloff_factor, 0., 1.);
-                        double d2ref = std::min(n.ref_distance, n.max_distance), d2max = std::max(n.ref_distance, n.max_distance);
-                        gd = 1. - ro * (clampd(distance, d2ref, d2max) - d2ref) / (d2max - d2ref);
-                    } else if (n.distance_model == 1) {
-                        double ro = std::max(n.rolloff_factor, 0.);
-                        gd = distance > 0. ? n.ref_distance / (n.ref_distance + ro * (std::max(n.ref_distance, distance) - n.ref_distance)) : 1.;
-                    } else {
-                        double ro = std::max(n.rolloff_factor, 0.);
-                        gd = std::pow(std::max(distance, n.ref_distance) / n.ref_distance, -ro);
-                    }
-                    pi.dist_gain = (float)gd;
-                }
-                {  // cone_gain, panner.rs:927-952
-                    float inner = (float)std::fabs(n.cone_inner_angle) / 2.f, outer = (float)std::fabs(n.cone_outer_angle) / 2.f;
-                    if (inner >= 180.f && outer >= 180.f) {
-                        pi.cone_gain = 1.f;
-                    } else {
-                        float og = (float)n.cone_outer_gain;
-                        float a = hm::cone_angle(sp, so, lp);
-                        if (a < inner) pi.cone_gain = 1.f;
-                        else if (a >= outer) pi.cone_gain = og;
-                        else {
-                            float x = (a - inner) / (outer - inner);
-                            pi.cone_gain = (1.f - x) + og * x;
-                        }
-                    }
-                }
+                pi.azimuth = sp0.azimuth;
+                pi.dist_gain = sp0.dist_gain;
+                pi.cone_gain = sp0.cone_gain;
                 stage(L, S_PAN).pan.push_back(pi);
                 break;
             }
@@ -1414,8 +1455,51 @@ WAE_API wae_status wae_engine_destroy(wae_engine* eng) {
     if (!eng) return WAE_OK;
     cudaSetDevice(eng->device);
     if (eng->d_sine) cudaFree(eng->d_sine);
+    if (eng->d_sphere_ir) cudaFree(eng->d_sphere_ir);
+    if (eng->d_sphere_pos) cudaFree(eng->d_sphere_pos);
+    if (eng->d_sphere_tri) cudaFree(eng->d_sphere_tri);
+    delete eng->sphere;
     if (eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
+    return WAE_OK;
+}
+
+// load_hrtf_processor (src/node/panner.rs:39-68): the reference embeds resources/IRC_1003_C.bin; the binding hands the same
+// bytes to the engine once.  Batches prepared afterwards may contain PanningModelType::HRTF panners.
+WAE_API wae_status wae_engine_set_hrir_sphere(wae_engine* eng, const void* data, uint64_t len) {
+    if (!eng) return fail(WAE_INVALID_ARGUMENT, "null engine");
+    auto* sp = new HrirSphere();
+    std::string err;
+    if (!sp->parse(static_cast<const uint8_t*>(data), len, err)) {
+        delete sp;
+        return fail(WAE_INVALID_ARGUMENT, err.c_str());
+    }
+    CUDA_TRY(cudaSetDevice(eng->device));
+    float* d = nullptr;
+    if (cudaMalloc(&d, sp->ir.size() * sizeof(float)) != cudaSuccess) {
+        delete sp;
+        return fail(WAE_OUT_OF_MEMORY, "out of device memory (HRIR sphere)");
+    }
+    float* dpos = nullptr;
+    uint32_t* dtri = nullptr;
+    if (cudaMalloc(&dpos, sp->pos.size() * sizeof(float)) != cudaSuccess || cudaMalloc(&dtri, sp->tri.size() * sizeof(uint32_t)) != cudaSuccess) {
+        cudaFree(d);
+        if (dpos) cudaFree(dpos);
+        delete sp;
+        return fail(WAE_OUT_OF_MEMORY, "out of device memory (HRIR sphere)");
+    }
+    cudaMemcpy(d, sp->ir.data(), sp->ir.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(dpos, sp->pos.data(), sp->pos.size() * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemcpy(dtri, sp->tri.data(), sp->tri.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    CUDA_TRY(cudaStreamSynchronize(eng->stream));  // batches in flight may still read the previous sphere
+    if (eng->d_sphere_ir) cudaFree(eng->d_sphere_ir);
+    if (eng->d_sphere_pos) cudaFree(eng->d_sphere_pos);
+    if (eng->d_sphere_tri) cudaFree(eng->d_sphere_tri);
+    eng->d_sphere_pos = dpos;
+    eng->d_sphere_tri = dtri;
+    delete eng->sphere;
+    eng->sphere = sp;
+    eng->d_sphere_ir = d;
     return WAE_OK;
 }
 
@@ -1633,6 +1717,9 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                 case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
                 case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
                 case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
+                case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
+                    st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
+                case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
                 case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
                 case S_DELAY:
                 case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
@@ -1696,6 +1783,8 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_SHAPER: launch_shaper((ShaperInst*)st.d_a, st.n, ci, s); break;
         case S_SPAN: launch_stereo_panner((SPanInst*)st.d_a, (float2*)st.d_b, st.n, ci, s); break;
         case S_PAN: launch_panner_eq((PanInst*)st.d_a, st.n, ci, s); break;
+        case S_HRTF: launch_hrtf((HrtfInst*)st.d_a, st.n, (HrtfSelInst*)st.d_b, st.n_b, st.max_ch, ci, s); break;
+        case S_PAN_DYN: launch_panner_dyn((PanDynInst*)st.d_a, st.n, ci, s); break;
         case S_ROUTE: launch_route((RouteInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY: launch_delay_read((DelayInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY_WRITE: launch_ring_write((DelayInst*)st.d_a, st.n, ci, s); break;

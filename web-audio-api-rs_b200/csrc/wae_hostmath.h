@@ -7,6 +7,8 @@
 #include <limits>
 #include <vector>
 
+#include "wae_spatial.h"
+
 namespace wae {
 namespace hostmath {
 
@@ -138,61 +140,8 @@ inline void stereo_gains(float x, float& gl, float& gr) {
     gr = sinf(x * PI32 / 2.f);
 }
 
-// ---- spatial helpers, src/spatial.rs:205-299 (vecmath restated: dot / cross / normalised = v * (1/len)) ------
-inline float sq_len(const float a[3]) { return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]; }
-inline float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-inline void sub3(const float a[3], const float b[3], float o[3]) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
-inline void norm3(const float a[3], float o[3]) {
-    float inv = 1.f / std::sqrt(sq_len(a));
-    o[0] = a[0] * inv; o[1] = a[1] * inv; o[2] = a[2] * inv;
-}
-inline void cross3(const float a[3], const float b[3], float o[3]) {
-    o[0] = a[1] * b[2] - a[2] * b[1];
-    o[1] = a[2] * b[0] - a[0] * b[2];
-    o[2] = a[0] * b[1] - a[1] * b[0];
-}
-inline void azimuth_elevation(const float sp[3], const float lp[3], const float lf[3], const float lu[3], float& az, float& el) {
-    const float MINP = 1.17549435e-38f;
-    az = 0.f;
-    el = 0.f;
-    float rel[3];
-    sub3(sp, lp, rel);
-    if (sq_len(rel) <= MINP) return;
-    float sl[3], right[3];
-    norm3(rel, sl);
-    cross3(lf, lu, right);
-    if (sq_len(right) == 0.f) return;
-    float rn[3], fn[3], up[3];
-    norm3(right, rn);
-    norm3(lf, fn);
-    cross3(rn, fn, up);
-    float elevation = 90.f - 180.f * acosf(dot3(sl, up)) / PI32;
-    if (elevation > 90.f) elevation = 180.f - elevation;
-    else if (elevation < -90.f) elevation = -180.f - elevation;
-    float upp = dot3(sl, up);
-    float proj[3] = {sl[0] - up[0] * upp, sl[1] - up[1] * upp, sl[2] - up[2] * upp};
-    if (sq_len(proj) == 0.f) {
-        el = elevation;
-        return;
-    }
-    float pn[3];
-    norm3(proj, pn);
-    float azimuth = 180.f * acosf(dot3(pn, rn)) / PI32;
-    if (dot3(pn, fn) < 0.f) azimuth = 360.f - azimuth;
-    azimuth = (azimuth >= 0.f && azimuth <= 270.f) ? 90.f - azimuth : 450.f - azimuth;
-    az = azimuth;
-    el = elevation;
-}
-inline float cone_angle(const float sp[3], const float so[3], const float lp[3]) {
-    const float MINP = 1.17549435e-38f;
-    if (sq_len(so) == 0.f) return 0.f;
-    float nso[3], rel[3], sl[3];
-    norm3(so, nso);
-    sub3(sp, lp, rel);
-    if (sq_len(rel) <= MINP) return 0.f;
-    norm3(rel, sl);
-    return std::fabs(180.f * acosf(dot3(sl, nso)) / PI32);
-}
+// spatial helpers (src/spatial.rs:205-299) live in wae_spatial.h, shared with the device code
+using namespace ::wae::spatial;
 
 }  // namespace hostmath
 }  // namespace wae

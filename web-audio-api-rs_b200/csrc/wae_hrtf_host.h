@@ -3,6 +3,8 @@
 // per-direction blend of the three vertex responses of the sphere triangle the source direction crosses — the job of the
 // third-party `hrtf` 0.8.1 crate's HrirSphere / sample_bilinear.  The convolution itself runs on the GPU (k_hrtf_fir).
 #pragma once
+#include "wae_spatial.h"
+
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -52,57 +54,18 @@ struct HrirSphere {
             if (!rd.take(vx.p, 12) || !rd.take(&ir[vx.left], 4ull * taps) || !rd.take(&ir[vx.right], 4ull * taps))
                 return err = "HRIR sphere: truncated vertex data", false;
         }
+        finish();
         return true;
     }
 
-    // Blend weights of direction d (sphere coordinates): the face whose plane the segment 0 -> 10 d crosses inside the
-    // triangle; hits on an edge / vertex resolve to the face where the hit is most interior.
+    std::vector<float> pos;  // [vertex][3]
+    void finish() {
+        pos.resize(3 * vertices.size());
+        for (size_t v = 0; v < vertices.size(); v++) std::memcpy(&pos[3 * v], vertices[v].p, 12);
+    }
+    // blend weights of direction d (sphere coordinates)
     bool locate(const float d[3], uint32_t v[3], float w[3]) const {
-        const float r[3] = {d[0] * 10.f, d[1] * 10.f, d[2] * 10.f};
-        auto dot = [](const float* x, const float* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; };
-        bool any = false;
-        float best = -3.0e38f;
-        for (size_t f = 0; f + 2 < tri.size(); f += 3) {
-            const float *A = vertices[tri[f]].p, *B = vertices[tri[f + 1]].p, *C = vertices[tri[f + 2]].p;
-            const float e0[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
-            const float e1[3] = {C[0] - A[0], C[1] - A[1], C[2] - A[2]};
-            const float n[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-            const float plane_d = -dot(A, n);
-            const float rn = dot(r, n);
-            if (rn == 0.f) continue;
-            const float t = -plane_d / rn;
-            if (!(t >= 0.f && t <= 1.f)) continue;
-            const float hit[3] = {r[0] * t, r[1] * t, r[2] * t};
-            const float q[3] = {hit[0] - A[0], hit[1] - A[1], hit[2] - A[2]};
-            const float d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1), d20 = dot(q, e0), d21 = dot(q, e1);
-            const float den = d00 * d11 - d01 * d01;
-            if (den == 0.f) continue;
-            const float wb = (d11 * d20 - d01 * d21) / den;
-            const float wc = (d00 * d21 - d01 * d20) / den;
-            const float wa = 1.f - wb - wc;
-            const float inside = std::fmin(wa, std::fmin(wb, wc));
-            if (inside > best) {
-                best = inside;
-                any = true;
-                v[0] = tri[f], v[1] = tri[f + 1], v[2] = tri[f + 2];
-                w[0] = wa, w[1] = wb, w[2] = wc;
-            }
-        }
-        return any;
-    }
-
-    // blended (left | right) responses for direction d -> out[2 * taps]; false: no face found
-    bool blend(const float d[3], float* out) const {
-        uint32_t v[3];
-        float w[3];
-        if (!locate(d, v, w)) return false;
-        for (int ear = 0; ear < 2; ear++) {
-            const float* a = &ir[ear ? vertices[v[0]].right : vertices[v[0]].left];
-            const float* b = &ir[ear ? vertices[v[1]].right : vertices[v[1]].left];
-            const float* c = &ir[ear ? vertices[v[2]].right : vertices[v[2]].left];
-            for (uint32_t i = 0; i < taps; i++) out[ear * taps + i] = a[i] * w[0] + b[i] * w[1] + c[i] * w[2];
-        }
-        return true;
+        return spatial::hrir_locate(pos.data(), tri.data(), (int)(tri.size() / 3), d, v, w);
     }
 };
 

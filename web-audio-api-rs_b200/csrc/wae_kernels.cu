@@ -1057,39 +1057,201 @@ __global__ void __launch_bounds__(256) k_stereo_panner(const SPanInst* __restric
     }
 }
 
+// equal-power gains of one frame (panner.rs:988-1057)
+__device__ __forceinline__ void pan_eq_frame(const spatial::SpatialParams& sp, int in_ch, float il, float ir, float& l, float& r) {
+    const float PI32 = 3.14159265358979323846f;
+    float az = fminf(fmaxf(sp.azimuth, -180.f), 180.f);
+    if (az < -90.f)
+        az = -180.f - az;
+    else if (az > 90.f)
+        az = 180.f - az;
+    if (in_ch == 1) {
+        float x = (az + 90.f) / 180.f;
+        float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
+        l = il * (gl * sp.dist_gain * sp.cone_gain);
+        r = il * (gr * sp.dist_gain * sp.cone_gain);
+    } else {
+        float x = az <= 0.f ? (az + 90.f) / 90.f : az / 90.f;
+        float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
+        if (az <= 0.f) {
+            l = (il + ir * gl) * sp.dist_gain * sp.cone_gain;
+            r = ir * gr * sp.dist_gain * sp.cone_gain;
+        } else {
+            l = il * gl * sp.dist_gain * sp.cone_gain;
+            r = (ir + il * gr) * sp.dist_gain * sp.cone_gain;
+        }
+    }
+}
+
 // PannerRenderer equal-power branch, static source/listener (src/node/panner.rs:839-870, 988-1057)
 __global__ void __launch_bounds__(256) k_panner_eq(const PanInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
-    const float PI32 = 3.14159265358979323846f;
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const PanInst p = insts[ii];
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
-        float az = fminf(fmaxf(p.azimuth, -180.f), 180.f);
-        if (az < -90.f)
-            az = -180.f - az;
-        else if (az > 90.f)
-            az = 180.f - az;
-        float* l = chan(p.out, 0, ci);
-        float* r = chan(p.out, 1, ci);
-        if (p.in_ch == 1) {
-            float x = (az + 90.f) / 180.f;
-            float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
-            float v = chan(p.in, 0, ci)[n];
-            l[n] = v * (gl * p.dist_gain * p.cone_gain);
-            r[n] = v * (gr * p.dist_gain * p.cone_gain);
-        } else {
-            float x = az <= 0.f ? (az + 90.f) / 90.f : az / 90.f;
-            float gl = cosf(x * PI32 / 2.f), gr = sinf(x * PI32 / 2.f);
-            float il = chan(p.in, 0, ci)[n], ir = chan(p.in, 1, ci)[n];
-            if (az <= 0.f) {
-                l[n] = (il + ir * gl) * p.dist_gain * p.cone_gain;
-                r[n] = ir * gr * p.dist_gain * p.cone_gain;
-            } else {
-                l[n] = il * gl * p.dist_gain * p.cone_gain;
-                r[n] = (ir + il * gr) * p.dist_gain * p.cone_gain;
+        spatial::SpatialParams sp{p.dist_gain, p.cone_gain, p.azimuth, 0.f};
+        float il = chan(p.in, 0, ci)[n], ir = p.in_ch == 2 ? chan(p.in, 1, ci)[n] : 0.f;
+        float l, r;
+        pan_eq_frame(sp, p.in_ch, il, ir, l, r);
+        chan(p.out, 0, ci)[n] = l;
+        chan(p.out, 1, ci)[n] = r;
+    }
+}
+
+// the 15 spatial params at frame n of the chunk; `first_of_quantum`: take the quantum's first value of every param
+__device__ __forceinline__ void spatial_fetch(const SpatialTracks& t, int n, bool first_of_quantum, const ChunkInfo& ci, float v[15]) {
+    const int pf = first_of_quantum ? (n & ~127) : n;
+#pragma unroll
+    for (int i = 0; i < 15; i++) v[i] = t.track[i].p ? chan(t.track[i], 0, ci)[pf] : t.value[i];
+}
+// panner.rs:833-841: all nine listener params single-valued in this quantum?
+__device__ __forceinline__ bool listener_single_valued(const SpatialTracks& t, int n, const ChunkInfo& ci) {
+    const int q0 = n & ~127;
+    bool single = true;
+#pragma unroll
+    for (int i = 6; i < 15; i++)
+        if (t.track[i].p && chan(t.track[i], 1, ci)[q0] == 0.f) single = false;
+    return single;
+}
+
+// PannerRenderer equal-power branch with automated source / listener params (panner.rs:714-780, 833-897)
+__global__ void __launch_bounds__(128) k_panner_dyn(const PanDynInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const PanDynInst& p = insts[ii];
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        float v[15];
+        spatial_fetch(p.sp, n, listener_single_valued(p.sp, n, ci), ci, v);
+        const spatial::SpatialParams sp = spatial::spatial_params(p.model, v);
+        const int in_ch = p.in_ch;
+        float il = chan(p.in, 0, ci)[n], ir = in_ch == 2 ? chan(p.in, 1, ci)[n] : 0.f;
+        float l, r;
+        pan_eq_frame(sp, in_ch, il, ir, l, r);
+        chan(p.out, 0, ci)[n] = l;
+        chan(p.out, 1, ci)[n] = r;
+    }
+}
+
+// HRTF panner with automated params: k-rate, first value of every quantum (panner.rs:781-802)
+__global__ void __launch_bounds__(64) k_hrtf_sel(const HrtfSelInst* __restrict__ insts, ChunkInfo ci) {
+    const HrtfSelInst& p = insts[blockIdx.y];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q * 128 >= ci.nf) return;
+    float v[15];
+    spatial_fetch(p.sp, q * 128, true, ci, v);
+    const spatial::SpatialParams sp = spatial::spatial_params(p.model, v);
+    float proj[3];
+    spatial::projected_source(sp, proj);
+    const float dir[3] = {proj[0], proj[2], proj[1]};  // HrtfState::process swaps y / z (panner.rs:248-252)
+    HrtfSel s{{0, 0, 0}, {0.f, 0.f, 0.f}, sp.cone_gain * sp.dist_gain, 0.f};
+    spatial::hrir_locate(p.pos, p.tri, p.n_faces, dir, s.v, s.w);
+    p.sel[q] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// HRTF panner: out[n] = gain * sum_k h[k] x[n-k] for the left and the right blended response (L taps, L = 512 for the
+// reference's IRC_1003_C sphere).  One warp per render quantum, 4 consecutive frames x 2 ears per lane with the input window
+// sliding through registers: per 4 taps 4 shared loads of x + 2 float4 broadcasts of h feed 32 FMAs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int HRTF_TILE = 512;  // frames per CTA (4 warps x 128)
+__device__ __forceinline__ int hrtf_pad(int i) { return i + (i >> 5); }  // stride-4 lane access -> distinct banks
+
+__device__ __forceinline__ float hrtf_input(const HrtfInst& p, int m, const ChunkInfo& ci) {
+    float v = chan(p.in, 0, ci)[m];
+    if (p.in_ch == 2) v = 0.5f * (v + chan(p.in, 1, ci)[m]);  // output.mix(1, Speakers), quantum.rs 2 -> 1
+    return v;
+}
+
+__global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ insts, ChunkInfo ci) {
+    extern __shared__ __align__(16) float hsm[];
+    const HrtfInst p = insts[blockIdx.y];
+    const int L = p.L, L4 = (L + 3) & ~3;
+    const int tile0 = blockIdx.x * HRTF_TILE;
+    const int nx = 4 + (L4 - 1) + HRTF_TILE;  // 4 leading slots keep the 4-tap unroll in range
+    float* xs = hsm;                           // padded input window: xs[pad(4 + (L4-1) + n)] = x[tile0 + n]
+    float* hs = hsm + ((hrtf_pad(nx) + 4) & ~3);  // [4 warps][2][L4]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < nx; i += 128) {
+        int m = tile0 + i - 4 - (L4 - 1);  // chunk-relative frame
+        float v = 0.f;
+        if (m >= 0) {
+            if (m < ci.nf) v = hrtf_input(p, m, ci);
+        } else if (m >= -(L - 1)) {
+            v = p.hist[(L - 1) + m];
+        }
+        xs[hrtf_pad(i)] = v;
+    }
+    const int q0 = tile0 + warp * 128;  // first frame of this warp's quantum
+    const bool active = q0 < ci.nf;
+    HrtfSel sel = p.static_sel;
+    if (active) {
+        if (p.sel) sel = p.sel[q0 >> 7];
+        float* hl = hs + warp * 2 * L4;
+        float* hr = hl + L4;
+        const float* A = p.sphere_ir + (size_t)sel.v[0] * 2 * L;
+        const float* B = p.sphere_ir + (size_t)sel.v[1] * 2 * L;
+        const float* C = p.sphere_ir + (size_t)sel.v[2] * 2 * L;
+        for (int k = lane; k < L4; k += 32) {
+            float l = 0.f, r = 0.f;
+            if (k < L) {
+                l = __fadd_rn(__fadd_rn(__fmul_rn(A[k], sel.w[0]), __fmul_rn(B[k], sel.w[1])), __fmul_rn(C[k], sel.w[2]));
+                r = __fadd_rn(__fadd_rn(__fmul_rn(A[L + k], sel.w[0]), __fmul_rn(B[L + k], sel.w[1])), __fmul_rn(C[L + k], sel.w[2]));
             }
+            hl[k] = l;
+            hr[k] = r;
         }
     }
+    __syncthreads();
+    if (!active) return;
+    const float* hl = hs + warp * 2 * L4;
+    const float* hr = hl + L4;
+    const int nrel = warp * 128 + lane * 4;       // tile-relative first frame of this lane
+    const int base = 4 + (L4 - 1) + nrel;          // xs index of x[n0]
+    float w0 = xs[hrtf_pad(base)], w1 = xs[hrtf_pad(base + 1)], w2 = xs[hrtf_pad(base + 2)], w3 = xs[hrtf_pad(base + 3)];
+    float al0 = 0.f, al1 = 0.f, al2 = 0.f, al3 = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, ar3 = 0.f;
+#pragma unroll 2
+    for (int k = 0; k < L4; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(hl + k);
+        const float4 b = *reinterpret_cast<const float4*>(hr + k);
+        // tap k: window (w0..w3) = x[n0-k .. n0-k+3]
+        al0 = fmaf(a.x, w0, al0); al1 = fmaf(a.x, w1, al1); al2 = fmaf(a.x, w2, al2); al3 = fmaf(a.x, w3, al3);
+        ar0 = fmaf(b.x, w0, ar0); ar1 = fmaf(b.x, w1, ar1); ar2 = fmaf(b.x, w2, ar2); ar3 = fmaf(b.x, w3, ar3);
+        const float m1 = xs[hrtf_pad(base - k - 1)];
+        al0 = fmaf(a.y, m1, al0); al1 = fmaf(a.y, w0, al1); al2 = fmaf(a.y, w1, al2); al3 = fmaf(a.y, w2, al3);
+        ar0 = fmaf(b.y, m1, ar0); ar1 = fmaf(b.y, w0, ar1); ar2 = fmaf(b.y, w1, ar2); ar3 = fmaf(b.y, w2, ar3);
+        const float m2 = xs[hrtf_pad(base - k - 2)];
+        al0 = fmaf(a.z, m2, al0); al1 = fmaf(a.z, m1, al1); al2 = fmaf(a.z, w0, al2); al3 = fmaf(a.z, w1, al3);
+        ar0 = fmaf(b.z, m2, ar0); ar1 = fmaf(b.z, m1, ar1); ar2 = fmaf(b.z, w0, ar2); ar3 = fmaf(b.z, w1, ar3);
+        const float m3 = xs[hrtf_pad(base - k - 3)];
+        al0 = fmaf(a.w, m3, al0); al1 = fmaf(a.w, m2, al1); al2 = fmaf(a.w, m1, al2); al3 = fmaf(a.w, w0, al3);
+        ar0 = fmaf(b.w, m3, ar0); ar1 = fmaf(b.w, m2, ar1); ar2 = fmaf(b.w, m1, ar2); ar3 = fmaf(b.w, w0, ar3);
+        const float m4 = xs[hrtf_pad(base - k - 4)];
+        w3 = m1; w2 = m2; w1 = m3; w0 = m4;
+    }
+    const int n = tile0 + nrel;
+    float* ol = chan(p.out, 0, ci);
+    float* orr = chan(p.out, 1, ci);
+    const float g = sel.gain, c = p.correction;
+    const float l4[4] = {al0, al1, al2, al3}, r4[4] = {ar0, ar1, ar2, ar3};
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (n + j < ci.nf) {
+            ol[n + j] = __fmul_rn(c, __fmul_rn(l4[j], g));
+            orr[n + j] = __fmul_rn(c, __fmul_rn(r4[j], g));
+        }
+}
+
+// input history for the next chunk (runs after every k_hrtf_fir CTA of the chunk has read the old one)
+__global__ void __launch_bounds__(128) k_hrtf_hist(const HrtfInst* __restrict__ insts, ChunkInfo ci) {
+    extern __shared__ float hh[];
+    const HrtfInst p = insts[blockIdx.x];
+    const int H = p.L - 1;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        int m = ci.nf - H + i;
+        hh[i] = m >= 0 ? hrtf_input(p, m, ci) : p.hist[H + m];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < H; i += blockDim.x) p.hist[i] = hh[i];
 }
 
 // channel merger / splitter (src/node/channel_merger.rs:146-171, channel_splitter.rs:183-208)
@@ -1294,6 +1456,7 @@ __global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ inst
     const double dt = 1. / (double)p.sample_rate;
     const int count = 128;
     float* out = chan(p.out, 0, ci);
+    float* single = chan(p.out, 1, ci);  // [first frame of a quantum] = 1: the reference's output buffer is single-valued
     const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
     float buf[128];
     for (int q0 = 0; q0 < ci.nf; q0 += 128) {
@@ -1505,11 +1668,14 @@ __global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ inst
             if (!in || !p.a_rate) {
                 float v = fix(value + (in ? in[q0] : 0.f));
                 for (int i = 0; i < 128; i++) out[q0 + i] = v;
+                single[q0] = 1.f;
             } else {
                 for (int i = 0; i < 128; i++) out[q0 + i] = fix(in[q0 + i] + value);
+                single[q0] = 0.f;
             }
         } else {
             for (int i = 0; i < 128; i++) out[q0 + i] = fix((in ? in[q0 + i] : 0.f) + buf[i]);
+            single[q0] = 0.f;
         }
     }
     *p.state = st;
@@ -1921,6 +2087,20 @@ void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_gai
 void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_shaper<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_stereo_panner(const SPanInst* d, const float2* g, int n, ChunkInfo ci, cudaStream_t s) {
     k_stereo_panner<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, g, n, ci);
+}
+void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_dyn<<<grid_tiles(ci.nf, 128, n), 128, 0, s>>>(d, n, ci); }
+void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s) {
+    if (n_sel > 0) k_hrtf_sel<<<dim3((ci.nf / 128 + 63) / 64 + 1, n_sel), 64, 0, s>>>(sel, ci);
+    const int L4 = (max_taps + 3) & ~3;
+    const int nx = 4 + (L4 - 1) + HRTF_TILE;
+    const size_t smem = (size_t)(((nx + (nx >> 5) + 4) & ~3) + 4 * 2 * L4) * sizeof(float);
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        cudaFuncSetAttribute(k_hrtf_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    k_hrtf_fir<<<dim3((ci.nf + HRTF_TILE - 1) / HRTF_TILE, n), 128, smem, s>>>(d, ci);
+    k_hrtf_hist<<<n, 128, (size_t)max_taps * sizeof(float), s>>>(d, ci);
 }
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_eq<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_route<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }

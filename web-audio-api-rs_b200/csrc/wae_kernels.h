@@ -28,6 +28,8 @@ void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t 
 void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_stereo_panner(const SPanInst* d, const float2* gains, int n, ChunkInfo ci, cudaStream_t s);
+void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s);
+void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_delay_read(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
