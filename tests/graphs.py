@@ -100,6 +100,31 @@ def north_star_voices_convolver(pkg, backend, voices, length, ir, sr=SR, seed=0)
     return c
 
 
+def c5_full_chain(pkg, backend, g, length, ir, sr=SR):
+    """C5 (configs[4]): Oscillator -> WaveShaper -> Biquad -> Convolver -> PannerNode(HRTF) -> Analyser -> destination.
+    The backend must have an HRIR sphere at the context rate (synthetic_hrir_sphere)."""
+    rng = np.random.default_rng(5000 + g)
+    c = pkg.OfflineAudioContext(2, length, sr, backend)
+    osc = c.create_oscillator(type_=[pkg.SAWTOOTH, pkg.SINE, pkg.SQUARE, pkg.TRIANGLE][g % 4], frequency=float(110.0 * 2.0 ** rng.uniform(0, 4)))
+    x = np.linspace(-1.0, 1.0, 257)
+    sh = c.create_wave_shaper(curve=np.tanh(x * (1.5 + g % 3)).astype(np.float32))
+    bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=float(rng.uniform(800, 6000)), q=float(rng.uniform(0.7, 4.0)))
+    cv = c.create_convolver(pkg.AudioBuffer(ir, sr))
+    az = rng.uniform(0, 2 * np.pi)
+    pn = c.create_panner(panning_model=pkg.context.HRTF, distance_model=1,
+                         position=(float(3 * np.sin(az)), float(rng.uniform(-1, 1)), float(-3 * np.cos(az))))
+    an = c.create_analyser(fft_size=2048)
+    osc.connect(sh)
+    sh.connect(bq)
+    bq.connect(cv)
+    cv.connect(pn)
+    pn.connect(an)
+    an.connect(c.destination())
+    osc.start()
+    c._test_analyser = an
+    return c
+
+
 def synthetic_hrir_sphere(sample_rate=48000, taps=256, subdivisions=2, seed=5):
     """An HRIR sphere in the container format of the reference's resources/IRC_1003_C.bin (see include/wae.h):
     a subdivided octahedron (z up) whose vertex responses are decaying noise with a direction-dependent inter-aural

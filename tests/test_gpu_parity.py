@@ -269,6 +269,23 @@ def test_panner_moving_source_and_listener(pkg, engine, oracle, model, who):
     assert maxdiff(gpu, cpu) <= (3e-5 if model == "equalpower" else TOL)  # acosf / atan chains: few-ulp libm differences on angles
 
 
+def test_c5_full_chain(pkg, engine, oracle):
+    """configs[4] scaled down: Oscillator -> WaveShaper -> Biquad -> Convolver -> Panner(HRTF) -> Analyser -> destination."""
+    data = G.synthetic_hrir_sphere(int(G.SR), 512)
+    oracle.set_hrir_sphere(data)
+    engine.backend.set_hrir_sphere(data)
+    ir = G.synthetic_ir(5000, 2, decay=0.05)
+    n = 128 * 100 + 77
+    cg = [G.c5_full_chain(pkg, engine.backend, g, n, ir) for g in range(4)]
+    cc = [G.c5_full_chain(pkg, oracle, g, n, ir) for g in range(4)]
+    gpu, cpu = G.render(pkg, cg), G.render(pkg, cc)
+    assert float(np.abs(cpu).max()) > 1e-3
+    assert maxdiff(gpu, cpu) <= TOL
+    for a, b in zip(cg, cc):
+        fa, fb = a._test_analyser.get_float_frequency_data(), b._test_analyser.get_float_frequency_data()
+        assert np.abs(10.0 ** (fa / 20) - 10.0 ** (fb / 20)).max() <= 1e-6
+
+
 def test_hrtf_panner_needs_matching_sphere(pkg, engine):
     engine.backend.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 64))
     c = pkg.OfflineAudioContext(2, 256, G.SR, engine.backend)
@@ -317,6 +334,28 @@ def test_dynamics_compressor(pkg, engine, oracle):
     cg, cc = build(engine.backend, 1), build(oracle, 1)
     G.render(pkg, [cg]), G.render(pkg, [cc])
     assert abs(cg._test_comp.reduction() - cc._test_comp.reduction()) <= 1e-3  # dB
+
+
+def test_dynamics_compressor_automated_params(pkg, engine, oracle):
+    """k-rate automation of threshold / knee / ratio / attack / release (dynamics_compressor.rs:352-391)."""
+    def build(be, g):
+        n = 128 * 40
+        pcm = G.c2_source(g, n) * np.float32(0.9)
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        d = c.create_dynamics_compressor()
+        d.threshold.linear_ramp_to_value_at_time(-50.0, 0.08)
+        d.ratio.set_value_at_time(4.0, 0.02)
+        d.knee.set_target_at_time(5.0, 0.01, 0.02)
+        d.attack.set_value_at_time(0.05, 0.03)
+        d.release.exponential_ramp_to_value_at_time(0.05, 0.1)
+        s.connect(d)
+        d.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert maxdiff(gpu, cpu) <= 5e-5
 
 
 def test_analyser_passthrough_and_time_domain(pkg, engine, oracle):
@@ -462,13 +501,12 @@ def test_north_star_graph(pkg, engine, oracle):
 
 def test_unsupported_is_reported_not_faked(pkg, engine):
     c = pkg.OfflineAudioContext(1, 128, G.SR, engine.backend)
-    g = c.create_dynamics_compressor()
-    src = c.create_constant_source()
-    g.threshold.linear_ramp_to_value_at_time(-50.0, 0.001)  # automated compressor params: not lowered yet
-    src.connect(g)
-    g.connect(c.destination())
-    src.start()
-    with pytest.raises(pkg.WaeError) as e:
+    with pytest.raises(pkg.WaeError) as e:  # rubato resampling: not lowered; reported, never approximated
+        g = c.create_wave_shaper(curve=np.linspace(-1, 1, 5), oversample=pkg.context.OVERSAMPLE_X2)
+        src = c.create_constant_source()
+        src.connect(g)
+        g.connect(c.destination())
+        src.start()
         c.start_rendering_sync()
     assert e.value.status == 4  # WAE_UNSUPPORTED -> the caller falls back to the CPU renderer
 
@@ -564,6 +602,15 @@ SLOW_CASES = {
     "loop_custom_points": dict(loop=True, loop_start=0.0103, loop_end=0.0377, playback_rate=1.3),
     "loop_default_rate": dict(loop=True, playback_rate=0.77),
     "buffer_44k1_in_48k": dict(buffer_sr=44100.0),
+    # renderer frame loop on the GPU (k_buffer_source_serial): what the closed-form tracks do not cover
+    "reverse": dict(playback_rate=-1.0, offset=0.05, start=0.0, duration=1e308),
+    "reverse_loop": dict(playback_rate=-0.8, loop=True, loop_start=0.0103, loop_end=0.0377, offset=0.03, start=0.002, duration=1e308),
+    "rate_zero": dict(playback_rate=0.0, offset=0.01, start=0.0, duration=1e308),
+    "tiny_loop": dict(loop=True, loop_start=0.0100, loop_end=0.01004, playback_rate=1.1),
+    "rate_ramp": dict(auto="rate_ramp"),
+    "detune_steps_loop": dict(auto="detune_steps", loop=True),
+    "rate_lfo_krate": dict(auto="rate_lfo", loop=True, loop_start=0.005, loop_end=0.04),
+    "rate_back_to_one": dict(auto="rate_back_to_one"),
 }
 
 
@@ -580,6 +627,23 @@ def test_buffer_source_slow_track(pkg, engine, oracle, name):
                                    playback_rate=o.get("playback_rate", 1.0), loop=o.get("loop", False),
                                    loop_start=o.get("loop_start", 0.0), loop_end=o.get("loop_end", 0.0))
         s.connect(c.destination())
+        auto = o.get("auto")
+        if auto == "rate_ramp":
+            s.playback_rate.set_value(0.5)
+            s.playback_rate.linear_ramp_to_value_at_time(2.0, 0.05)
+        elif auto == "detune_steps":
+            s.detune.set_value_at_time(700.0, 0.01)
+            s.detune.set_value_at_time(-500.0, 0.03)
+            s.detune.exponential_ramp_to_value_at_time(-100.0, 0.09)
+        elif auto == "rate_lfo":
+            lfo = c.create_oscillator(frequency=9.0)
+            amp = c.create_gain(gain=0.6)
+            lfo.connect(amp)
+            amp.connect(s.playback_rate)
+            lfo.start()
+        elif auto == "rate_back_to_one":
+            s.playback_rate.set_value_at_time(1.5, 0.01)
+            s.playback_rate.set_value_at_time(1.0, 0.02)
         if "offset" in o:
             s.start_at_with_offset_and_duration(o["start"], o["offset"], o["duration"])
         else:

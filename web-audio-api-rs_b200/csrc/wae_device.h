@@ -80,6 +80,26 @@ struct AbsnSlowInst {
     int32_t pad;
 };
 
+// AudioBufferSourceRenderer::process restated frame by frame (audio_buffer_source.rs:422-845) for everything the two
+// closed-form tracks do not cover: automated playbackRate / detune (k-rate), zero / negative rates, very short loops.
+// One warp per instance: lane 0 walks the renderer's state machine of a quantum, all lanes interpolate.
+struct AbsnSerialState {
+    double start_time, offset, buffer_time, buffer_time_elapsed;
+    int32_t started, entered_loop, ended, is_aligned;
+};
+struct AbsnSerialInst {
+    BufRef out;
+    const float* buf;
+    int64_t buf_len, buf_stride;
+    double start_time, stop_time, offset, duration;  // start(when, offset, duration) / stop(when)
+    double loop_start, loop_end;                     // after clamp_loop_boundaries (:400-417)
+    double buffer_duration, buffer_sample_rate, sample_rate;
+    BufRef rate_track, detune_track;                 // p != nullptr: automated (first value of every quantum)
+    float rate, detune;
+    int32_t ch, loop;
+    AbsnSerialState* state;
+};
+
 struct BiquadInst {
     BufRef in, out;
     double b0, b1, b2, a1, a2;
@@ -207,6 +227,7 @@ struct CompInst {
     int32_t delay_frames;  // (ring_size - 1) * 128
     float threshold, knee, ratio, attack, release, sample_rate;
     int32_t pad;
+    BufRef track[5];  // attack, knee, ratio, release, threshold: p != nullptr -> automated (k-rate: first value of a quantum)
 };
 
 struct AnalyserInst {
@@ -307,17 +328,18 @@ struct ChainInst {
     ChainBiquad bq[CHAIN_MAX_BIQUADS];
 };
 
-// ---- convolver (uniformly partitioned overlap-save, block 1024 / FFT 2048, time-batched) -----------------
+// ---- convolver (uniformly partitioned overlap-save, block WAE_CONV_BLOCK, time-batched) -----------------
 struct ConvInput {   // one input channel of one convolver instance
     BufRef in;
-    float* prev;     // [1024] last block of the previous chunk
-    float2* xring;   // [xring_blocks][1025] input spectra ring
+    float* prev;     // [block] last block of the previous chunk
+    float2* xring;   // [xring_blocks][block] input spectra ring
     int32_t in_channel;
     int32_t xring_blocks;
 };
 struct ConvPath {    // one FFTConvolver of the reference: (input channel, IR channel) -> output channel
     BufRef out;
-    const float2* h;  // [S][1025] IR segment spectra
+    const float2* h;  // [S][block] IR segment spectra
+    float2* y;        // [blocks per chunk][block] output spectra of the chunk (scratch between k_conv_mac and k_conv_ifft)
     int32_t input;    // index into the ConvInput table
     int32_t S;        // IR segments
     int32_t out_channel;

@@ -48,11 +48,11 @@ namespace {
 
 enum StageKind : int {
     S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -78,6 +78,7 @@ struct StageBuild {
     std::vector<HrtfInst> hrtf;
     std::vector<HrtfSelInst> hrtf_sel;
     std::vector<PanDynInst> pan_dyn;
+    std::vector<AbsnSerialInst> absn_serial;
     std::vector<RouteInst> route;
     std::vector<DelayInst> delay;
     std::vector<CompInst> comp;
@@ -451,7 +452,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     for (int c = 0; c < ir_ch; c++) {
         size_t m = ir_len;
         while (m > 0 && std::fabs(scaled[c][m - 1]) < 0.000001f) m--;
-        S[c] = (int)((m + 1023) / 1024);
+        S[c] = (int)((m + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK);
         trimmed_len = std::max(trimmed_len, m);
         // zero the ignored tail so that a shared segment count reproduces the per-convolver trimming
         for (size_t i = m; i < ir_len; i++) scaled[c][i] = 0.f;
@@ -487,14 +488,14 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     }
     // inputs: one spectra ring per input channel
     StageBuild& fs = stage(level, S_CONV_FFT);
-    int blocks_per_chunk = (int)((b->chunk + 1023) / 1024);
+    int blocks_per_chunk = (int)((b->chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK);
     int ring_blocks = Smax + blocks_per_chunk;
     int in_base = (int)fs.conv_in.size();
     for (int c = 0; c < in_ch; c++) {
         ConvInput ci;
         ci.in = pn.in_buf[0];
         ci.in_channel = c;
-        ci.prev = alloc<float>(1024, true, true);
+        ci.prev = alloc<float>(WAE_CONV_BLOCK, true, true);
         ci.xring = alloc<float2>((size_t)ring_blocks * WAE_CONV_SPEC);
         ci.xring_blocks = ring_blocks;
         if (!ci.prev || !ci.xring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver input spectra)");
@@ -522,10 +523,14 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         p.S = Smax;
         p.out_channel = r.out;
         p.accumulate = r.acc;
+        p.y = alloc<float2>((size_t)blocks_per_chunk * WAE_CONV_SPEC);
+        if (!p.y) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver output spectra)");
+        b->arena_bytes += (size_t)blocks_per_chunk * WAE_CONV_SPEC * 8;
         stage(level, r.acc ? S_CONV_MAC_ACC : S_CONV_MAC).conv_path.push_back(p);
     }
     // S*1025*8 B of input-history spectra per convolver-block of 1024 frames
-    algorithmic_bytes += (uint64_t)routes.size() * (uint64_t)Smax * 1025ull * 8ull * (uint64_t)((b->lq + 1023) / 1024);
+    // (the reference's 1024-frame partitioning defines the algorithmic figure, whatever block size the kernels use)
+    algorithmic_bytes += (uint64_t)routes.size() * (uint64_t)((trimmed_len + 1023) / 1024) * 1025ull * 8ull * (uint64_t)((b->lq + 1023) / 1024);
     return true;
 }
 
@@ -888,8 +893,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_ABSN: {
-                float detune, rate;
-                if (!const_param(g, n.params[0], detune) || !const_param(g, n.params[1], rate)) return false;
+                PRef pdet = param_ref(g, n.params[0]), prate = param_ref(g, n.params[1]);
+                const float detune = pdet.v, rate = prate.v;
+                const bool rate_automated = pdet.dyn || prate.dyn;
                 int ch = n.buffer ? (int)n.buffer->channels.size() : 1;
                 if (!n.buffer || n.start_time >= 1e300 || ch == 0) {  // never plays: silence
                     if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
@@ -908,10 +914,15 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 // the reference goes through one all-silent slow-track quantum, then aligns (audio_buffer_source.rs:521-523)
                 if (n.start_time > clock.block_time(q) && n.start_time == clock.block_time(q + 1)) q = q + 1;
                 bool aligned = (n.start_time <= clock.block_time(q)) && n.offset == 0.;  // start in the past snaps to the block
-                bool fast = aligned && (double)pb.sample_rate / sr == 1. && computed_rate == 1. && ls == 0. && le == duration &&
+                bool fast = !rate_automated && aligned && (double)pb.sample_rate / sr == 1. && computed_rate == 1. && ls == 0. && le == duration &&
                             n.duration > 1e300 && n.stop_time > 1e300;
-                if (!fast && !(computed_rate > 0.))
-                    return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode with a zero or negative playback rate is not lowered to the GPU yet");
+                // everything the closed-form tracks do not cover runs the renderer's own frame loop (one warp per source)
+                bool serial = rate_automated || (!fast && !(computed_rate > 0.));
+                if (!fast && !serial && n.loop) {
+                    const bool custom = ls >= 0. && le > 0. && ls < le;
+                    const double loop_len = custom ? le - ls : duration;
+                    if (!(loop_len > 4. * clock.dt * computed_rate)) serial = true;  // loop shorter than four output frames
+                }
                 const bool fuse_src = fuse_n && fast;
                 if (!fuse_src && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
@@ -925,6 +936,34 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     }
                 src_cursor += (size_t)ch * stride;
                 b->asset_bytes += (size_t)ch * len * 4;
+                if (serial) {
+                    AbsnSerialInst a{};
+                    a.out = p.out_buf[0];
+                    a.buf = d_buf;
+                    a.buf_len = (int64_t)len;
+                    a.buf_stride = (int64_t)stride;
+                    a.start_time = n.start_time;
+                    a.stop_time = n.stop_time;
+                    a.offset = n.offset;
+                    a.duration = n.duration;
+                    a.loop_start = ls;
+                    a.loop_end = le;
+                    a.buffer_duration = duration;
+                    a.buffer_sample_rate = (double)pb.sample_rate;
+                    a.sample_rate = sr;
+                    const BufRef none{nullptr, 0, 0};
+                    a.rate_track = prate.dyn ? prate.track : none;
+                    a.detune_track = pdet.dyn ? pdet.track : none;
+                    a.rate = rate;
+                    a.detune = detune;
+                    a.ch = ch;
+                    a.loop = n.loop ? 1 : 0;
+                    a.state = alloc<AbsnSerialState>(1, true, true);
+                    if (!a.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (buffer source state)");
+                    stage(L, S_ABSN_SERIAL).absn_serial.push_back(a);
+                    algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::min<int64_t>(b->lq, (int64_t)len);
+                    break;
+                }
                 if (!fast) {
                     // ---- slow track (audio_buffer_source.rs:625-823): fractional playhead
                     auto almost_equal = [](double x, double y) {
@@ -997,7 +1036,6 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     std::vector<double> seg_bt{off};
                     if (n.loop && off < a.loop_end) {
                         const double ls2 = a.loop_start, le2 = a.loop_end, len2 = le2 - ls2, step = a.step;
-                        if (!(len2 > 4. * step)) return bail(WAE_UNSUPPORTED, "AudioBufferSourceNode loop shorter than four output frames is not lowered to the GPU");
                         const int64_t n_end = std::min<int64_t>(b->lq, a.n_stop);
                         int64_t m = 0;   // frames since n_first
                         double v = off;  // buffer_time of frame m
@@ -1338,10 +1376,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_COMP: {
-                float at, kn, ra, re, th;
-                if (!const_param(g, n.params[0], at) || !const_param(g, n.params[1], kn) || !const_param(g, n.params[2], ra) ||
-                    !const_param(g, n.params[3], re) || !const_param(g, n.params[4], th))
-                    return false;
+                PRef cp[5];
+                for (int i = 0; i < 5; i++) cp[i] = param_ref(g, n.params[i]);
+                const float at = cp[0].v, kn = cp[1].v, ra = cp[2].v, re = cp[3].v, th = cp[4].v;
                 int ch = p.in_ch[0];
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 CompInst c{};
@@ -1355,6 +1392,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 c.state = alloc<float>(2, true, true);
                 if (!c.ring || !c.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (compressor)");
                 c.threshold = th; c.knee = kn; c.ratio = ra; c.attack = at; c.release = re;
+                for (int i = 0; i < 5; i++) c.track[i] = cp[i].dyn ? cp[i].track : BufRef{nullptr, 0, 0};
                 c.sample_rate = g->sample_rate;
                 stage(L, S_COMP).comp.push_back(c);
                 if (!dry) b->compressors.push_back(wae_batch::CompRec{gi, id, c.state});
@@ -1440,9 +1478,9 @@ WAE_API wae_status wae_engine_create(int32_t device_ordinal, wae_engine** out) {
     std::vector<float> sine = hm::sine_table();
     CUDA_TRY(cudaMalloc(&eng->d_sine, sine.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(eng->d_sine, sine.data(), sine.size() * sizeof(float), cudaMemcpyHostToDevice));
-    std::vector<float2> tw(1024);
-    for (int k = 0; k < 1024; k++) {
-        double a = -2.0 * hm::PI64 * (double)k / 2048.0;
+    std::vector<float2> tw(WAE_CONV_BLOCK);
+    for (int k = 0; k < WAE_CONV_BLOCK; k++) {
+        double a = -2.0 * hm::PI64 * (double)k / (2.0 * WAE_CONV_BLOCK);
         tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     upload_twiddles(tw.data());
@@ -1627,7 +1665,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             chunk = std::max<int64_t>(8192, std::min<int64_t>(chunk, 1 << 20));  // >= 8192: keeps per-chunk launches and serial tails amortised
             chunk = chunk / 2048 * 2048;
         }
-        if (has_conv) chunk = std::max<int64_t>(chunk, 16384);
+        if (has_conv) chunk = std::max<int64_t>(chunk, 8 * WAE_CONV_BLOCK);  // k_conv_mac tiles 8 output blocks
     }
     if (has_feedback) {
         // feedback through a DelayNode is resolved one render quantum at a time, like the reference's render loop
@@ -1637,8 +1675,8 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         }
         chunk = 128;
     }
-    if (has_conv) chunk = (chunk + 1023) / 1024 * 1024;
-    if (chunk > b->lq) chunk = has_conv ? (b->lq + 1023) / 1024 * 1024 : b->lq;
+    if (has_conv) chunk = (chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK;
+    if (chunk > b->lq) chunk = has_conv ? (b->lq + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK : b->lq;
     b->chunk = chunk;
     CUDA_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
@@ -1720,6 +1758,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                 case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
                     st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
                 case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
+                case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
                 case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
                 case S_DELAY:
                 case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
@@ -1750,7 +1789,8 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     }
     int64_t n_chunks = (b->lq + b->chunk - 1) / b->chunk;
     uint64_t launches = 0;
-    for (auto& st : b->stages) launches += st.kind == S_CONV_FFT ? 2 : 1;
+    for (auto& st : b->stages)
+        launches += (st.kind == S_CONV_FFT || st.kind == S_CONV_MAC || st.kind == S_CONV_MAC_ACC) ? 2 : st.kind == S_HRTF ? (st.n_b > 0 ? 3 : 2) : 1;
     std::memset(&b->stats, 0, sizeof(b->stats));
     b->stats.kernel_launches_per_run = launches * (uint64_t)n_chunks;
     b->stats.stages = b->stages.size();
@@ -1785,6 +1825,7 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_PAN: launch_panner_eq((PanInst*)st.d_a, st.n, ci, s); break;
         case S_HRTF: launch_hrtf((HrtfInst*)st.d_a, st.n, (HrtfSelInst*)st.d_b, st.n_b, st.max_ch, ci, s); break;
         case S_PAN_DYN: launch_panner_dyn((PanDynInst*)st.d_a, st.n, ci, s); break;
+        case S_ABSN_SERIAL: launch_buffer_source_serial((AbsnSerialInst*)st.d_a, st.n, ci, s); break;
         case S_ROUTE: launch_route((RouteInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY: launch_delay_read((DelayInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY_WRITE: launch_ring_write((DelayInst*)st.d_a, st.n, ci, s); break;

@@ -218,6 +218,185 @@ __global__ void __launch_bounds__(256) k_buffer_source_slow(const AbsnSlowInst* 
     }
 }
 
+// AudioBufferSourceRenderer::process, general form (audio_buffer_source.rs:422-845): one warp per instance, lane 0 runs
+// the renderer's per-frame bookkeeping for a quantum (exactly the reference's sequence of f64 operations), then the 32
+// lanes produce the 128 samples of every channel.
+constexpr int ABSN_SERIAL_WARPS = 4;
+__global__ void __launch_bounds__(32 * ABSN_SERIAL_WARPS) k_buffer_source_serial(const AbsnSerialInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ long long s_idx[ABSN_SERIAL_WARPS][128];  // frame of the buffer to read, -1: silence
+    __shared__ double s_k[ABSN_SERIAL_WARPS][128];      // interpolation weight, < 0: plain copy (fast track)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ii = blockIdx.x * ABSN_SERIAL_WARPS + warp;
+    if (ii >= n_inst) return;
+    const AbsnSerialInst& o = insts[ii];
+    long long* idx = s_idx[warp];
+    double* kk = s_k[warp];
+    AbsnSerialState st;
+    if (lane == 0) {
+        st = *o.state;
+        if (ci.f0 == 0) st = AbsnSerialState{o.start_time, o.offset, 0., 0., 0, 0, 0, 0};
+    }
+    const double sample_rate = o.sample_rate, dt = 1. / sample_rate, block_duration = dt * 128.;
+    const double buffer_duration = o.buffer_duration;
+    const double sampling_ratio = o.buffer_sample_rate / sample_rate;
+    const bool is_looping = o.loop != 0;
+    for (int q0 = 0; q0 < ci.nf; q0 += 128) {
+        float playback_rate_f = o.rate_track.p ? chan(o.rate_track, 0, ci)[q0] : o.rate;
+        double actual_loop_start = 0., actual_loop_end = 0.;
+        if (is_looping) {  // :627-636 (only read by the slow track)
+            if (o.loop_start >= 0. && o.loop_end > 0. && o.loop_start < o.loop_end) {
+                actual_loop_start = o.loop_start;
+                actual_loop_end = o.loop_end;
+            } else {
+                actual_loop_end = buffer_duration;
+            }
+        }
+        if (lane == 0) {
+            for (int i = 0; i < 128; i++) idx[i] = -1;
+            const double block_time = (double)(ci.f0 + q0) / sample_rate;
+            const double next_block_time = block_time + block_duration;
+            bool run = !st.ended;
+            if (run && st.start_time >= next_block_time) {  // :470-481
+                if (o.stop_time <= next_block_time) st.ended = 1;
+                run = false;
+            }
+            if (run) {
+                const double detune_v = (double)(o.detune_track.p ? chan(o.detune_track, 0, ci)[q0] : o.detune);
+                const double computed_playback_rate = (double)playback_rate_f * exp2(detune_v / 1200.);
+                double buffer_time = st.buffer_time;
+                if (!st.started && st.start_time < block_time) st.start_time = block_time;  // :519-523
+                if (st.start_time == block_time && st.offset == 0.) st.is_aligned = 1;
+                if (sampling_ratio != 1. || computed_playback_rate != 1.) st.is_aligned = 0;
+                if (o.loop_start != 0. || o.loop_end != buffer_duration) st.is_aligned = 0;
+                if (buffer_time + block_duration > o.duration || block_time + block_duration > o.stop_time) st.is_aligned = 0;
+                if (st.is_aligned) {  // fast track (:554-624)
+                    if (st.start_time == block_time) st.started = 1;
+                    long long start_index = llround(buffer_time * sample_rate);
+                    if (buffer_time + block_duration > buffer_duration) {
+                        const long long end_index = o.buf_len;
+                        bool has_loop_point = false;
+                        int loop_point_index = 0;
+                        long long off = 0;
+                        for (int i = 0; i < 128; i++) {
+                            long long bi = start_index + i - off;
+                            if (bi >= end_index) {
+                                if (is_looping) {
+                                    has_loop_point = true;
+                                    loop_point_index = i;
+                                    start_index = 0;
+                                    off = i;
+                                    bi = 0;
+                                } else {
+                                    bi = -1;
+                                }
+                            }
+                            idx[i] = bi;
+                            kk[i] = -1.;
+                        }
+                        if (has_loop_point)
+                            buffer_time = fmod((double)(128 - loop_point_index) / sample_rate, buffer_duration);
+                        else
+                            buffer_time += block_duration;
+                    } else {
+                        for (int i = 0; i < 128; i++) {
+                            idx[i] = start_index + i;
+                            kk[i] = -1.;
+                        }
+                        buffer_time += block_duration;
+                    }
+                    st.buffer_time_elapsed += block_duration;
+                } else {  // slow track (:625-823)
+                    if (!is_looping) st.entered_loop = 0;
+                    for (int i = 0; i < 128; i++) {
+                        const double current_time = block_time + (double)i * dt;
+                        if (!st.started && almost_eq(current_time, st.start_time)) st.start_time = current_time;
+                        if (almost_eq(st.buffer_time_elapsed, o.duration)) st.buffer_time_elapsed = o.duration;
+                        if (current_time < st.start_time || current_time >= o.stop_time || st.buffer_time_elapsed >= o.duration) continue;
+                        if (!st.started) {
+                            const double delta = current_time - st.start_time;
+                            st.offset += delta * computed_playback_rate;
+                            st.offset = fmin(fmax(st.offset, 0.), buffer_duration);
+                            if (is_looping && computed_playback_rate >= 0. && st.offset > actual_loop_end) st.offset = actual_loop_end;
+                            if (is_looping && computed_playback_rate < 0. && st.offset < actual_loop_start) st.offset = actual_loop_start;
+                            buffer_time = st.offset;
+                            st.buffer_time_elapsed = fabs(delta * computed_playback_rate);
+                            st.started = 1;
+                        }
+                        if (is_looping) {
+                            if (almost_eq(buffer_time, actual_loop_end)) buffer_time = actual_loop_end;
+                            if (almost_eq(buffer_time, actual_loop_start)) buffer_time = actual_loop_start;
+                            if (!st.entered_loop) {
+                                if (st.offset < actual_loop_end && buffer_time >= actual_loop_start) st.entered_loop = 1;
+                                if (st.offset >= actual_loop_end && buffer_time < actual_loop_end) st.entered_loop = 1;
+                            }
+                            if (st.entered_loop) {
+                                while (buffer_time >= actual_loop_end) buffer_time -= actual_loop_end - actual_loop_start;
+                                while (buffer_time < actual_loop_start) buffer_time += actual_loop_end - actual_loop_start;
+                            }
+                        }
+                        if (fabs(buffer_time) < 1.4901161193847656e-8) buffer_time = 0.;
+                        if (buffer_time >= 0. && buffer_time < buffer_duration) {
+                            const double position = buffer_time * sampling_ratio;
+                            const double playhead = position * sample_rate;
+                            const double fl = floor(playhead);
+                            const long long pfi = (long long)fl;
+                            if (pfi < o.buf_len) {
+                                idx[i] = pfi;
+                                kk[i] = playhead - fl;
+                            }
+                        }
+                        const double time_incr = dt * computed_playback_rate;
+                        buffer_time += time_incr;
+                        st.buffer_time_elapsed += fabs(time_incr);
+                    }
+                }
+                st.buffer_time = buffer_time;
+                if (next_block_time >= o.stop_time || st.buffer_time_elapsed >= o.duration ||
+                    (!is_looping && ((computed_playback_rate > 0. && buffer_time >= buffer_duration) || (computed_playback_rate < 0. && buffer_time < 0.))))
+                    st.ended = 1;  // :826-838
+            }
+        }
+        __syncwarp();
+        for (int c = 0; c < o.ch; c++) {
+            const float* b = o.buf + (size_t)c * o.buf_stride;
+            float* out = chan(o.out, c, ci) + q0;
+            for (int i = lane; i < 128; i += 32) {
+                const long long pfi = idx[i];
+                float v = 0.f;
+                if (pfi >= 0) {
+                    const double k = kk[i];
+                    if (k < 0.) {
+                        v = __ldg(b + pfi);
+                    } else {
+                        const double prev = (double)__ldg(b + pfi);
+                        double next;
+                        if (pfi + 1 < o.buf_len) {
+                            next = (double)__ldg(b + pfi + 1);
+                        } else if (is_looping) {  // :788-800
+                            long long j;
+                            if (playback_rate_f >= 0.f) {
+                                const double sp = actual_loop_start * sample_rate;
+                                j = floor(sp) == sp ? (long long)sp : (long long)sp + 1;
+                            } else {
+                                j = (long long)(actual_loop_end * sample_rate);
+                            }
+                            next = (double)__ldg(b + (j < o.buf_len ? j : o.buf_len - 1));
+                        } else if (almost_eq(k, 1.) || pfi == 0) {
+                            next = 0.;
+                        } else {
+                            next = 2. * prev - (double)__ldg(b + pfi - 1);
+                        }
+                        v = (float)fma(1. - k, prev, k * next);
+                    }
+                }
+                out[i] = v;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *o.state = st;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Mixer — AudioRenderQuantum::add / mix (src/render/quantum.rs:274-569): per input port, the incoming edges
 // are summed in the reference's processing order, each up/down-mixed to the port's computed channel count.
@@ -1328,18 +1507,27 @@ __global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ 
     int ii = blockIdx.x * blockDim.x + threadIdx.x;
     if (ii >= n_inst) return;
     const CompInst q = insts[ii];
-    float thr = q.knee > 0.f ? q.threshold + q.knee / 2.f : q.threshold;
-    float half_knee = q.knee / 2.f;
-    float knee_partial = (1.f / q.ratio - 1.f) / (2.f * q.knee);
-    float attack_tau = expf(-1.f / (q.attack * q.sample_rate));
-    float release_tau = expf(-1.f / (q.release * q.sample_rate));
-    float full_range_gain = thr + (-thr / q.ratio);
-    float full_range_makeup = 1.f / db_to_lin(full_range_gain);
-    float makeup_gain = lin_to_db(powf(full_range_makeup, 0.6f));
+    float thr = 0.f, half_knee = 0.f, knee_partial = 0.f, attack_tau = 0.f, release_tau = 0.f, makeup_gain = 0.f, ratio = 1.f;
+    const bool automated = q.track[0].p || q.track[1].p || q.track[2].p || q.track[3].p || q.track[4].p;
     float prev = q.state[0];
     float reduction_gain = q.state[1];
     const uint32_t mask = q.ring_len - 1;
     for (int n = 0; n < ci.nf; n++) {
+        if (n == 0 || (automated && (n & 127) == 0)) {  // per-quantum constants (dynamics_compressor.rs:352-391), params are k-rate
+            const float attack = q.track[0].p ? chan(q.track[0], 0, ci)[n] : q.attack;
+            const float knee = q.track[1].p ? chan(q.track[1], 0, ci)[n] : q.knee;
+            ratio = q.track[2].p ? chan(q.track[2], 0, ci)[n] : q.ratio;
+            const float release = q.track[3].p ? chan(q.track[3], 0, ci)[n] : q.release;
+            const float threshold = q.track[4].p ? chan(q.track[4], 0, ci)[n] : q.threshold;
+            thr = knee > 0.f ? threshold + knee / 2.f : threshold;
+            half_knee = knee / 2.f;
+            knee_partial = (1.f / ratio - 1.f) / (2.f * knee);
+            attack_tau = expf(-1.f / (attack * q.sample_rate));
+            release_tau = expf(-1.f / (release * q.sample_rate));
+            const float full_range_gain = thr + (-thr / ratio);
+            const float full_range_makeup = 1.f / db_to_lin(full_range_gain);
+            makeup_gain = lin_to_db(powf(full_range_makeup, 0.6f));
+        }
         float mx = -3.40282347e+38f;
         for (int c = 0; c < q.ch; c++) {
             float s = fabsf(chan(q.in, c, ci)[n]);
@@ -1353,7 +1541,7 @@ __global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ 
             float t = sample_db - thr + half_knee;
             att = __fadd_rn(sample_db, __fmul_rn(__fmul_rn(t, t), knee_partial));
         } else {
-            att = thr + (sample_db - thr) / q.ratio;
+            att = thr + (sample_db - thr) / ratio;
         }
         float attenuation = sample_db - att;
         float det;
@@ -1682,277 +1870,308 @@ __global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ inst
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Convolver — ConvolverRenderer (src/node/convolver.rs:343-490) over fft-convolver's uniformly partitioned
-// scheme (block 1024, FFT 2048), evaluated time-batched: every 1024-frame block of a chunk is transformed
-// once (overlap-save frame [previous block | current block]), then for each output block j
-//     Y_j = sum_i H_i * X_{j-i},   out_j = IFFT(Y_j)[1024..2048) / 2048.
-// Shared-memory radix-2 complex FFT of 1024 points + real-FFT packing (2048 real <-> 1024 complex).
+// Convolver — ConvolverRenderer (src/node/convolver.rs:343-490).  The reference runs fft-convolver's uniformly
+// partitioned overlap-save with 1024-frame partitions because it must answer every 128 frames; an offline batch has no
+// such deadline, so the same linear convolution is evaluated time-batched with B = 8192-frame partitions (FFT 16384):
+// 8x fewer partitions => 8x less spectrum traffic and MAC work per output frame.  Per chunk:
+//   k_conv_fft_in : X_j = FFT([block j-1 | block j])                         CTA per (input channel, block), smem FFT
+//   k_conv_mac    : Y_j = sum_i H_i * X_{j-i}  for CV_J output blocks at once  thread per bin, register tiled over j
+//   k_conv_ifft   : out_j = IFFT(Y_j)[B..2B) / 2B                              CTA per (path, block), smem FFT
+// Real FFTs of 2B points are computed as complex FFTs of B points (packed even/odd) in shared memory (64 KB).
 // ---------------------------------------------------------------------------------------------------------
-constexpr int CV_B = 1024;      // block
-constexpr int CV_BINS = WAE_CONV_SPEC;  // packed half spectrum: bin 0 = (DC, Nyquist), bins 1..1023 complex
-constexpr int CV_THREADS = 256;
+constexpr int CV_B = WAE_CONV_BLOCK;    // frames per partition
+constexpr int CV_LOGB = 13;
+static_assert((1 << CV_LOGB) == CV_B, "CV_LOGB");
+constexpr int CV_BINS = CV_B;           // packed half spectrum: bin 0 = (DC, Nyquist), bins 1..B-1 complex
+constexpr int CV_THREADS = 512;
 
-__device__ float2 c_tw2048[1024];  // exp(-2*pi*i*k/2048), k < 1024 (global + L1: per-thread indices diverge)
+__device__ float2 c_tw[CV_B];  // exp(-2*pi*i*k/(2B)), k < B
 
 DEVI float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
-// in-place 1024-point complex FFT in shared memory (decimation in frequency, output bit-reversed is avoided by
-// a Stockham-free approach: DIT with explicit bit reversal on load).  sign = -1 forward, +1 inverse.
-DEVI void fft1024_smem(float2* s, int sign) {
-    const int t = threadIdx.x;
-    // bit reversal permutation (10 bits)
-    for (int i = t; i < 1024; i += CV_THREADS) {
-        int r = __brev((unsigned)i) >> 22;
-        if (i < r) {
-            float2 tmp = s[i];
-            s[i] = s[r];
-            s[r] = tmp;
+// In-place B-point (8192) complex FFT in shared memory, decimation in frequency, radix 8 x 8 x 8 x 16 with the
+// butterflies in registers: 4 passes / 3 barriers instead of 13 radix-2 stages.  The result is left in bit-reversed
+// order (element k at position brev13(k)); consumers index through cv_pos().  Storage is padded by one float2 per 16
+// so that the contiguous radix-16 pass is free of bank conflicts.  sign = -1 forward, +1 inverse (unnormalised).
+constexpr int CV_SMEM_ELEMS = CV_B + CV_B / 16;
+DEVI int cv_pad(int i) { return i + (i >> 4); }
+DEVI int cv_pos(int k) { return cv_pad((int)(__brev((unsigned)k) >> (32 - CV_LOGB))); }  // where element k of an FFT result lives
+DEVI float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+DEVI float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by exp(sign * 2*pi*i * m / 16)
+template <int M>
+DEVI float2 rot16(float2 v, int sign) {
+    constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, R = 0.70710678118654752440f;
+    constexpr int m = M & 15;
+    float c, sn;
+    if (m == 0) return v;
+    if (m == 4) return sign > 0 ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+    if (m == 8) return make_float2(-v.x, -v.y);
+    if (m == 12) return sign > 0 ? make_float2(v.y, -v.x) : make_float2(-v.y, v.x);
+    // cos / sin of 2*pi*m/16
+    if (m == 1) c = C1, sn = S1;
+    else if (m == 2) c = R, sn = R;
+    else if (m == 3) c = S1, sn = C1;
+    else if (m == 5) c = -S1, sn = C1;
+    else if (m == 6) c = -R, sn = R;
+    else if (m == 7) c = -C1, sn = S1;
+    else if (m == 9) c = -C1, sn = -S1;
+    else if (m == 10) c = -R, sn = -R;
+    else if (m == 11) c = -S1, sn = -C1;
+    else if (m == 13) c = S1, sn = -C1;
+    else if (m == 14) c = R, sn = -R;
+    else c = C1, sn = -S1;
+    if (sign < 0) sn = -sn;
+    return make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+}
+// one radix-8 DIF butterfly on elements base + m*q (three radix-2 stages with spans 4q, 2q, q)
+DEVI void fft_radix8_pass(float2* s, int q, int log_q, int sign) {
+    for (int bf = threadIdx.x; bf < CV_B / 8; bf += CV_THREADS) {
+        const int lo = bf & (q - 1), hi = bf >> log_q;
+        const int base = (hi << (log_q + 3)) + lo;
+        float2 a[8];
+#pragma unroll
+        for (int m = 0; m < 8; m++) a[m] = s[cv_pad(base + m * q)];
+        // twiddles exp(-2*pi*i*lo/(8q)), /(4q), /(2q) from the exp(-2*pi*i*k/(2B)) table
+        float2 t1 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 3))]);
+        float2 t2 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 2))]);
+        float2 t3 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 1))]);
+        if (sign > 0) t1.y = -t1.y, t2.y = -t2.y, t3.y = -t3.y;
+        float2 u, v;
+        // span 4: twiddle t1 * W8^m
+        u = cadd(a[0], a[4]); v = csub(a[0], a[4]); a[0] = u; a[4] = cmul(v, t1);
+        u = cadd(a[1], a[5]); v = csub(a[1], a[5]); a[1] = u; a[5] = cmul(rot16<2>(v, sign), t1);
+        u = cadd(a[2], a[6]); v = csub(a[2], a[6]); a[2] = u; a[6] = cmul(rot16<4>(v, sign), t1);
+        u = cadd(a[3], a[7]); v = csub(a[3], a[7]); a[3] = u; a[7] = cmul(rot16<6>(v, sign), t1);
+        // span 2: twiddle t2 * W4^m
+#pragma unroll
+        for (int g = 0; g < 8; g += 4) {
+            u = cadd(a[g], a[g + 2]); v = csub(a[g], a[g + 2]); a[g] = u; a[g + 2] = cmul(v, t2);
+            u = cadd(a[g + 1], a[g + 3]); v = csub(a[g + 1], a[g + 3]); a[g + 1] = u; a[g + 3] = cmul(rot16<4>(v, sign), t2);
         }
+        // span 1: twiddle t3
+#pragma unroll
+        for (int m = 0; m < 8; m += 2) {
+            u = cadd(a[m], a[m + 1]); v = csub(a[m], a[m + 1]); a[m] = u; a[m + 1] = cmul(v, t3);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) s[cv_pad(base + m * q)] = a[m];
     }
+}
+// the last four radix-2 stages on 16 contiguous elements: all twiddles are 16th roots of unity
+DEVI void fft_radix16_last(float2* s, int sign) {
+    for (int bf = threadIdx.x; bf < CV_B / 16; bf += CV_THREADS) {
+        float2 a[16];
+        float2* p = s + cv_pad(bf * 16);  // 16 contiguous elements never straddle a pad slot
+#pragma unroll
+        for (int m = 0; m < 16; m++) a[m] = p[m];
+        float2 u, v;
+#define WAE_BF(i, j, M) u = cadd(a[i], a[j]); v = csub(a[i], a[j]); a[i] = u; a[j] = rot16<M>(v, sign);
+        WAE_BF(0, 8, 0) WAE_BF(1, 9, 1) WAE_BF(2, 10, 2) WAE_BF(3, 11, 3) WAE_BF(4, 12, 4) WAE_BF(5, 13, 5) WAE_BF(6, 14, 6) WAE_BF(7, 15, 7)
+#pragma unroll
+        for (int g = 0; g < 16; g += 8) {
+            WAE_BF(g, g + 4, 0) WAE_BF(g + 1, g + 5, 2) WAE_BF(g + 2, g + 6, 4) WAE_BF(g + 3, g + 7, 6)
+        }
+#pragma unroll
+        for (int g = 0; g < 16; g += 4) {
+            WAE_BF(g, g + 2, 0) WAE_BF(g + 1, g + 3, 4)
+        }
+#pragma unroll
+        for (int g = 0; g < 16; g += 2) {
+            WAE_BF(g, g + 1, 0)
+        }
+#undef WAE_BF
+#pragma unroll
+        for (int m = 0; m < 16; m++) p[m] = a[m];
+    }
+}
+DEVI void fft_smem(float2* s, int sign) {
+    static_assert(CV_LOGB == 13, "pass schedule below is 8 x 8 x 8 x 16");
+    fft_radix8_pass(s, CV_B / 8, CV_LOGB - 3, sign);
     __syncthreads();
-#pragma unroll 1
-    for (int len = 2; len <= 1024; len <<= 1) {
-        const int half = len >> 1;
-        const int step = 2048 / len;  // twiddle stride in the 2048 table: exp(-2*pi*i*j/len) = tw[j*2048/len]
-        for (int b = t; b < 512; b += CV_THREADS) {
-            int grp = b / half, j = b % half;
-            int i0 = grp * len + j, i1 = i0 + half;
-            float2 w = __ldg(&c_tw2048[j * step]);
-            if (sign > 0) w.y = -w.y;
-            float2 u = s[i0], v = cmul(s[i1], w);
-            s[i0] = make_float2(u.x + v.x, u.y + v.y);
-            s[i1] = make_float2(u.x - v.x, u.y - v.y);
-        }
-        __syncthreads();
+    fft_radix8_pass(s, CV_B / 64, CV_LOGB - 6, sign);
+    __syncthreads();
+    fft_radix8_pass(s, CV_B / 512, CV_LOGB - 9, sign);
+    __syncthreads();
+    fft_radix16_last(s, sign);
+    __syncthreads();
+}
+// FFT result z (bit-reversed, padded) -> the B packed bins of the 2B-point real FFT: X[k] = E[k] + w^k O[k]
+DEVI float2 rfft_bin(const float2* z, int k) {
+    if (k == 0) {
+        const float2 z0 = z[0];
+        return make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
     }
+    const float2 zk = z[cv_pos(k)], zm = z[cv_pos(CV_B - k)];
+    const float2 zc = make_float2(zm.x, -zm.y);
+    const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+    const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
+    const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
+    const float2 tw = cmul(__ldg(&c_tw[k]), o);
+    return make_float2(e.x + tw.x, e.y + tw.y);
 }
 
 // grid: (blocks in chunk, conv inputs).  Builds X_j for every new block of the chunk.
 __global__ void __launch_bounds__(CV_THREADS) k_conv_fft_in(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
-    __shared__ float2 z[1024];
+    extern __shared__ float2 z[];
     const ConvInput ip = inputs[blockIdx.y];
     const int jb = blockIdx.x;                         // block within the chunk
     const int64_t jabs = ci.f0 / CV_B + jb;            // absolute block index
     const float* in = chan(ip.in, ip.in_channel, ci);
     const int t = threadIdx.x;
-    // frame = [previous block | current block] (2048 reals) packed as 1024 complex (even, odd)
-    for (int i = t; i < 1024; i += CV_THREADS) {
+    // frame = [previous block | current block] (2B reals) packed as B complex (even, odd)
+    for (int i = t; i < CV_B; i += CV_THREADS) {
         float a, b;
-        int n = 2 * i;  // index in the 2048 frame
+        const int n = 2 * i;
         if (n < CV_B) {
             if (jb == 0) {
                 a = ip.prev[n];
                 b = ip.prev[n + 1];
             } else {
-                a = in[(jb - 1) * CV_B + n];
-                b = in[(jb - 1) * CV_B + n + 1];
+                a = in[(size_t)(jb - 1) * CV_B + n];
+                b = in[(size_t)(jb - 1) * CV_B + n + 1];
             }
         } else {
-            int m = jb * CV_B + (n - CV_B);
+            const int64_t m = (int64_t)jb * CV_B + (n - CV_B);
             a = m < ci.nf ? in[m] : 0.f;
             b = m + 1 < ci.nf ? in[m + 1] : 0.f;
         }
-        z[i] = make_float2(a, b);
+        z[cv_pad(i)] = make_float2(a, b);
     }
     __syncthreads();
-    fft1024_smem(z, -1);
-    // unpack to the 1025 bins of the real FFT: X[k] = E[k] + w^k O[k]
+    fft_smem(z, -1);
     float2* X = ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS;
-    for (int k = t; k < 1024; k += CV_THREADS) {
-        float2 r;
-        if (k == 0) {
-            r = make_float2(z[0].x + z[0].y, z[0].x - z[0].y);  // packed (DC, Nyquist)
-        } else {
-            float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
-            float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-            float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
-            float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
-            float2 w = c_tw2048[k];
-            float2 tw = cmul(w, o);
-            r = make_float2(e.x + tw.x, e.y + tw.y);
-        }
-        X[k] = r;
-    }
+    for (int k = t; k < CV_B; k += CV_THREADS) X[k] = rfft_bin(z, k);
 }
 
-// saves the last block of the chunk as "previous block" for the next chunk.  grid: (4, conv inputs)
+// saves the last block of the chunk as "previous block" for the next chunk.  grid: (B / 256, conv inputs)
 __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
     const ConvInput ip = inputs[blockIdx.y];
     const float* in = chan(ip.in, ip.in_channel, ci);
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nblocks = (ci.nf + CV_B - 1) / CV_B;
-    int m = (nblocks - 1) * CV_B + i;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nblocks = (ci.nf + CV_B - 1) / CV_B;
+    const int64_t m = (int64_t)(nblocks - 1) * CV_B + i;
     ip.prev[i] = m < ci.nf ? in[m] : 0.f;
 }
 
-// grid: (ceil(blocks in chunk / CV_J), paths), 512 threads.  For CV_J consecutive output blocks j at once:
-//     Y_j = sum_i H_i X_{j-i};  out_j = IFFT(Y_j)[1024..2048) / 2048.
-// Register tiling over the block axis: the input blocks are walked in groups of CV_J; a group needs 2*CV_J-1 IR
-// spectra values and CV_J input spectra values per bin for CV_J^2 complex MACs (0.36 loads per MAC instead of 2),
-// which turns the L2-bound MAC loop into an FP32-FMA-bound one.  Y_j (CV_J x 8 KB) is kept in shared memory and
-// transformed back block by block.
+// grid: (B / 256 * ceil(blocks in chunk / CV_J), paths), 256 threads, one bin per thread.  For CV_J consecutive output
+// blocks j at once: Y_j = sum_i H_i X_{j-i}.  Register tiling over the block axis: the input blocks are walked in
+// groups of CV_J; a group needs 2*CV_J-1 IR spectrum values and CV_J input spectrum values per bin for CV_J^2 complex
+// MACs (0.36 loads per MAC instead of 2).  No shared memory => many resident warps hide the L2 latency of the loads.
 constexpr int CV_J = 8;
-constexpr int CV_MAC_THREADS = 512;
-
-DEVI void fft1024_smem_n(float2* s, int sign, int nthreads) {
-    const int t = threadIdx.x;
-    for (int i = t; i < 1024; i += nthreads) {
-        int r = __brev((unsigned)i) >> 22;
-        if (i < r) {
-            float2 tmp = s[i];
-            s[i] = s[r];
-            s[r] = tmp;
-        }
-    }
-    __syncthreads();
-#pragma unroll 1
-    for (int len = 2; len <= 1024; len <<= 1) {
-        const int half = len >> 1;
-        const int step = 2048 / len;
-        for (int b = t; b < 512; b += nthreads) {
-            int grp = b / half, j = b % half;
-            int i0 = grp * len + j, i1 = i0 + half;
-            float2 w = __ldg(&c_tw2048[j * step]);
-            if (sign > 0) w.y = -w.y;
-            float2 u = s[i0], v = cmul(s[i1], w);
-            s[i0] = make_float2(u.x + v.x, u.y + v.y);
-            s[i1] = make_float2(u.x - v.x, u.y - v.y);
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac_ifft(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs,
-                                                                  int n_paths, ChunkInfo ci) {
-    extern __shared__ float2 sY[];  // [CV_J][1024]
+constexpr int CV_MAC_THREADS = 256;
+__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
+                                                             ChunkInfo ci) {
     const ConvPath p = paths[blockIdx.y];
     const ConvInput ip = inputs[p.input];
     const int nb = (ci.nf + CV_B - 1) / CV_B;
-    const int j0 = blockIdx.x * CV_J;                  // first output block of this CTA (chunk-relative)
+    constexpr int TILES = CV_B / CV_MAC_THREADS;
+    const int k = (blockIdx.x % TILES) * CV_MAC_THREADS + threadIdx.x;  // bin
+    const int j0 = (blockIdx.x / TILES) * CV_J;                         // first output block of this CTA (chunk-relative)
     const int64_t jabs0 = ci.f0 / CV_B + j0;
-    const int64_t jabs_last = ci.f0 / CV_B + nb - 1;   // newest input block transformed so far
-    const int t = threadIdx.x;
-    const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;  // i runs up to S-1: i_base - (J-1) <= S-1
+    const int64_t jabs_last = ci.f0 / CV_B + nb - 1;                    // newest input block transformed so far
+    const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;                 // i runs up to S-1: i_base - (J-1) <= S-1
+    float2 acc[CV_J];
+#pragma unroll
+    for (int jj = 0; jj < CV_J; jj++) acc[jj] = make_float2(0.f, 0.f);
 #pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const int k = t + pass * CV_MAC_THREADS;
-        float2 acc[CV_J];
+    for (int g = 0; g < groups; g++) {
+        const int i_base = g * CV_J;
+        const int64_t b0 = jabs0 - i_base;
+        float2 hw[2 * CV_J - 1];
 #pragma unroll
-        for (int jj = 0; jj < CV_J; jj++) acc[jj] = make_float2(0.f, 0.f);
-#pragma unroll 1
-        for (int g = 0; g < groups; g++) {
-            const int i_base = g * CV_J;
-            const int64_t b0 = jabs0 - i_base;
-            float2 hw[2 * CV_J - 1];
+        for (int u = 0; u < 2 * CV_J - 1; u++) {
+            const int i = i_base - (CV_J - 1) + u;
+            hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
+        }
 #pragma unroll
-            for (int u = 0; u < 2 * CV_J - 1; u++) {
-                const int i = i_base - (CV_J - 1) + u;
-                hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
-            }
+        for (int r = 0; r < CV_J; r++) {
+            const int64_t b = b0 + r;
+            float2 x = make_float2(0.f, 0.f);
+            if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)(b % ip.xring_blocks) * CV_BINS + k];
+            if (k == 0) {  // packed real bins: (DC, Nyquist) multiply component-wise
 #pragma unroll
-            for (int r = 0; r < CV_J; r++) {
-                const int64_t b = b0 + r;
-                float2 x = make_float2(0.f, 0.f);
-                if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)(b % ip.xring_blocks) * CV_BINS + k];
-                if (k == 0) {  // packed real bins: (DC, Nyquist) multiply component-wise
+                for (int jj = 0; jj < CV_J; jj++) {
+                    const float2 h = hw[(CV_J - 1) + jj - r];
+                    acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
+                    acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
+                }
+            } else {
 #pragma unroll
-                    for (int jj = 0; jj < CV_J; jj++) {
-                        const float2 h = hw[(CV_J - 1) + jj - r];
-                        acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
-                        acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
-                    }
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < CV_J; jj++) {
-                        const float2 h = hw[(CV_J - 1) + jj - r];
-                        acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
-                        acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
-                    }
+                for (int jj = 0; jj < CV_J; jj++) {
+                    const float2 h = hw[(CV_J - 1) + jj - r];
+                    acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
+                    acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
                 }
             }
         }
+    }
 #pragma unroll
-        for (int jj = 0; jj < CV_J; jj++) sY[jj * 1024 + k] = acc[jj];
+    for (int jj = 0; jj < CV_J; jj++)
+        if (j0 + jj < nb) p.y[(size_t)(j0 + jj) * CV_BINS + k] = acc[jj];
+}
+
+// grid: (blocks in chunk, paths): out_j = IFFT(Y_j)[B..2B) / 2B
+__global__ void __launch_bounds__(CV_THREADS) k_conv_ifft(const ConvPath* __restrict__ paths, int n_paths, ChunkInfo ci) {
+    extern __shared__ float2 z[];
+    const ConvPath p = paths[blockIdx.y];
+    const int jb = blockIdx.x;
+    const float2* Y = p.y + (size_t)jb * CV_BINS;
+    const int t = threadIdx.x;
+    // half spectrum -> packed complex input of the B-point inverse transform
+    for (int k = t; k < CV_B; k += CV_THREADS) {
+        const float2 y0 = Y[0];
+        const float2 yk = k == 0 ? make_float2(y0.x, 0.f) : Y[k];
+        const float2 ym = k == 0 ? make_float2(y0.y, 0.f) : Y[CV_B - k];
+        const float2 yc = make_float2(ym.x, -ym.y);
+        const float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
+        const float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
+        float2 w = __ldg(&c_tw[k]);
+        w.y = -w.y;
+        const float2 o = cmul(w, d);
+        z[cv_pad(k)] = make_float2(e.x - o.y, e.y + o.x);
     }
     __syncthreads();
-    const float scale = 1.f / 2048.f;
-#pragma unroll 1
-    for (int jj = 0; jj < CV_J; jj++) {
-        if (j0 + jj >= nb) break;  // uniform
-        float2* z = sY + jj * 1024;
-        // half spectrum -> packed complex input of the 1024-point inverse transform
-        float2 zz[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int k = t + u * CV_MAC_THREADS;
-            float2 yk = k == 0 ? make_float2(z[0].x, 0.f) : z[k];
-            float2 ym = k == 0 ? make_float2(z[0].y, 0.f) : z[1024 - k];
-            float2 yc = make_float2(ym.x, -ym.y);
-            float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
-            float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
-            float2 w = __ldg(&c_tw2048[k]);
-            w.y = -w.y;
-            float2 o = cmul(w, d);
-            zz[u] = make_float2(e.x - o.y, e.y + o.x);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 2; u++) z[t + u * CV_MAC_THREADS] = zz[u];
-        __syncthreads();
-        fft1024_smem_n(z, +1, CV_MAC_THREADS);
-        float* out = chan(p.out, p.out_channel, ci) + (size_t)(j0 + jj) * CV_B;
-        {
-            const int i = 512 + t;  // second half of the 2048 frame: complex i in [512, 1024)
-            const int n = 2 * t;
-            if ((j0 + jj) * CV_B + n < ci.nf) {
-                float2 v = make_float2(z[i].x * scale, z[i].y * scale);
-                float2* dst = reinterpret_cast<float2*>(out + n);
-                if (p.accumulate) {
-                    float2 o = *dst;
-                    v.x += o.x;
-                    v.y += o.y;
-                }
-                *dst = v;
+    fft_smem(z, +1);
+    const float scale = 1.f / (float)(2 * CV_B);
+    float* out = chan(p.out, p.out_channel, ci) + (size_t)jb * CV_B;
+    for (int i = t; i < CV_B / 2; i += CV_THREADS) {  // second half of the 2B frame: complex i in [B/2, B)
+        const int n = 2 * i;
+        if ((int64_t)jb * CV_B + n < ci.nf) {
+            const float2 c = z[cv_pos(CV_B / 2 + i)];
+            float2 v = make_float2(c.x * scale, c.y * scale);
+            float2* dst = reinterpret_cast<float2*>(out + n);
+            if (p.accumulate) {
+                const float2 o = *dst;
+                v.x += o.x;
+                v.y += o.y;
             }
+            *dst = v;
         }
-        __syncthreads();
     }
 }
 
 // IR segment spectra H_i (host uploads the scaled IR; one CTA per segment).  grid: (S, ir channels)
 __global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restrict__ ir, int64_t ir_len, int64_t ir_stride, float2* __restrict__ h,
                                                             int S) {
-    __shared__ float2 z[1024];
+    extern __shared__ float2 z[];
     const int seg = blockIdx.x, c = blockIdx.y;
     const float* src = ir + (size_t)c * ir_stride;
     const int t = threadIdx.x;
-    for (int i = t; i < 1024; i += CV_THREADS) {
-        int n = 2 * i;
+    for (int i = t; i < CV_B; i += CV_THREADS) {
+        const int n = 2 * i;
         float a = 0.f, b = 0.f;
         if (n < CV_B) {  // segment in the first half, zeros in the second
-            int64_t m = (int64_t)seg * CV_B + n;
+            const int64_t m = (int64_t)seg * CV_B + n;
             a = m < ir_len ? src[m] : 0.f;
             b = m + 1 < ir_len ? src[m + 1] : 0.f;
         }
-        z[i] = make_float2(a, b);
+        z[cv_pad(i)] = make_float2(a, b);
     }
     __syncthreads();
-    fft1024_smem(z, -1);
+    fft_smem(z, -1);
     float2* H = h + ((size_t)c * S + seg) * CV_BINS;
-    for (int k = t; k < 1024; k += CV_THREADS) {
-        float2 r;
-        if (k == 0) {
-            r = make_float2(z[0].x + z[0].y, z[0].x - z[0].y);  // packed (DC, Nyquist)
-        } else {
-            float2 zk = z[k], zc = make_float2(z[1024 - k].x, -z[1024 - k].y);
-            float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
-            float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
-            float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
-            float2 tw = cmul(c_tw2048[k], o);
-            r = make_float2(e.x + tw.x, e.y + tw.y);
-        }
-        H[k] = r;
-    }
+    for (int k = t; k < CV_B; k += CV_THREADS) H[k] = rfft_bin(z, k);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2038,7 +2257,7 @@ static inline dim3 grid_tiles(int nf, int per_block, int n_inst) {
     return dim3((unsigned)((nf + per_block - 1) / per_block), (unsigned)(n_inst < 32768 ? n_inst : 32768));
 }
 
-void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw2048, host_tw, sizeof(float2) * 1024); }
+void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw, host_tw, sizeof(float2) * CV_B); }
 
 void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_oscillator<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_constant<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
@@ -2088,6 +2307,9 @@ void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s) { k
 void launch_stereo_panner(const SPanInst* d, const float2* g, int n, ChunkInfo ci, cudaStream_t s) {
     k_stereo_panner<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, g, n, ci);
 }
+void launch_buffer_source_serial(const AbsnSerialInst* d, int n, ChunkInfo ci, cudaStream_t s) {
+    k_buffer_source_serial<<<(n + ABSN_SERIAL_WARPS - 1) / ABSN_SERIAL_WARPS, 32 * ABSN_SERIAL_WARPS, 0, s>>>(d, n, ci);
+}
 void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_dyn<<<grid_tiles(ci.nf, 128, n), 128, 0, s>>>(d, n, ci); }
 void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s) {
     if (n_sel > 0) k_hrtf_sel<<<dim3((ci.nf / 128 + 63) / 64 + 1, n_sel), 64, 0, s>>>(sel, ci);
@@ -2125,23 +2347,30 @@ void launch_resample_linear(const float* in, int64_t len, float* out, int64_t ta
 void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_param<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_analyser<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+static void conv_configure() {
+    static bool configured = false;
+    if (configured) return;
+    const int smem = CV_SMEM_ELEMS * (int)sizeof(float2);
+    cudaFuncSetAttribute(k_conv_fft_in, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_conv_ir_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+}
 void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s) {
-    int nb = (ci.nf + CV_B - 1) / CV_B;
-    k_conv_fft_in<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, 0, s>>>(d, n, ci);
-    k_conv_save_prev<<<dim3(4, (unsigned)n), 256, 0, s>>>(d, n, ci);
+    conv_configure();
+    const int nb = (ci.nf + CV_B - 1) / CV_B;
+    k_conv_fft_in<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, CV_SMEM_ELEMS * sizeof(float2), s>>>(d, n, ci);
+    k_conv_save_prev<<<dim3(CV_B / 256, (unsigned)n), 256, 0, s>>>(d, n, ci);
 }
 void launch_conv_mac_ifft(const ConvPath* p, const ConvInput* in, int n, ChunkInfo ci, cudaStream_t s) {
-    static bool configured = false;
-    const int smem = CV_J * 1024 * (int)sizeof(float2);
-    if (!configured) {
-        cudaFuncSetAttribute(k_conv_mac_ifft, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
-    int nb = (ci.nf + CV_B - 1) / CV_B;
-    k_conv_mac_ifft<<<dim3((unsigned)((nb + CV_J - 1) / CV_J), (unsigned)n), CV_MAC_THREADS, smem, s>>>(p, in, n, ci);
+    conv_configure();
+    const int nb = (ci.nf + CV_B - 1) / CV_B;
+    k_conv_mac<<<dim3((unsigned)((CV_B / CV_MAC_THREADS) * ((nb + CV_J - 1) / CV_J)), (unsigned)n), CV_MAC_THREADS, 0, s>>>(p, in, n, ci);
+    k_conv_ifft<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, CV_SMEM_ELEMS * sizeof(float2), s>>>(p, n, ci);
 }
 void launch_conv_ir_fft(const float* ir, int64_t ir_len, int64_t ir_stride, float2* h, int S, int channels, cudaStream_t s) {
-    k_conv_ir_fft<<<dim3((unsigned)S, (unsigned)channels), CV_THREADS, 0, s>>>(ir, ir_len, ir_stride, h, S);
+    conv_configure();
+    k_conv_ir_fft<<<dim3((unsigned)S, (unsigned)channels), CV_THREADS, CV_SMEM_ELEMS * sizeof(float2), s>>>(ir, ir_len, ir_stride, h, S);
 }
 
 }  // namespace wae

@@ -9,7 +9,8 @@ namespace wae {
 // Per-biquad constants of the time-parallel recurrence (host-computed in f64).  M = [[-a1,-a2],[1,0]] advances the
 // state (y[n-1], y[n-2]) by one frame; A = M^WAE_CHAIN_K advances it by one thread (WAE_CHAIN_K frames).
 constexpr int WAE_CHAIN_K = 16;  // frames per thread of k_chain
-constexpr int WAE_CONV_SPEC = 1024;  // float2 per block spectrum (packed real FFT of 2048: bin 0 = (DC, Nyquist))
+constexpr int WAE_CONV_BLOCK = 8192;            // frames per convolver partition (the reference's 1024 is a latency choice, see wae_kernels.cu)
+constexpr int WAE_CONV_SPEC = WAE_CONV_BLOCK;   // float2 per block spectrum (packed real FFT of 2 * block: bin 0 = (DC, Nyquist))
 struct ScanCoef {
     double Pshfl[5][4];    // A^(2^d), d = 0..4: warp-level Kogge-Stone steps
     double Plane[32][4];   // A^(lane+1): carries a warp's incoming state to each lane
@@ -29,6 +30,7 @@ void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_stereo_panner(const SPanInst* d, const float2* gains, int n, ChunkInfo ci, cudaStream_t s);
 void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s);
+void launch_buffer_source_serial(const AbsnSerialInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
