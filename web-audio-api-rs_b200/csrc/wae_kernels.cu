@@ -42,6 +42,15 @@ DEVI double osc_poly_blep_r(double t, double dt, double inv_dt) {
     }
     return 0.0;
 }
+// the rare frames inside a polyBLEP window, out of line so that the common path of the fused chain stays small
+__device__ __noinline__ float osc_saw_blep(unsigned long long p2, double inc, double inv) {
+    const double t = (double)p2 * 5.42101086242752217e-20;  // 2^-64
+    return (float)(2.0 * t - 1.0 - osc_poly_blep_r(t, inc, inv));
+}
+__device__ __noinline__ float osc_square_blep(unsigned long long ph, unsigned long long p2, double inc, double inv) {
+    const double t = (double)ph * 5.42101086242752217e-20, t2 = (double)p2 * 5.42101086242752217e-20;
+    return (float)((t < 0.5 ? 1.0 : -1.0) + osc_poly_blep_r(t, inc, inv) - osc_poly_blep_r(t2, inc, inv));
+}
 DEVI double osc_unroll(double p) { return p >= 1. ? p - 1. : (p < 0. ? p + 1. : p); }
 
 DEVI float osc_sample(const OscInst& o, double phase, double incr) {
@@ -451,20 +460,20 @@ struct MixVec<1> {
     DEVI float get(int) const { return v; }
 };
 
-template <int VEC>
+template <int VEC, int BATCH>
 DEVI void mix_simple(const MixInst& m, const MixEdge* __restrict__ edges, int c, int n0, const ChunkInfo& ci, MixVec<VEC>& acc) {
     const MixEdge* e = edges + m.edge_offset;
     acc.zero();
     int k = 0;
-    for (; k + MIX_BATCH <= m.n_edges; k += MIX_BATCH) {
-        MixVec<VEC> v[MIX_BATCH];
+    for (; k + BATCH <= m.n_edges; k += BATCH) {
+        MixVec<VEC> v[BATCH];
 #pragma unroll
-        for (int u = 0; u < MIX_BATCH; u++) {
+        for (int u = 0; u < BATCH; u++) {
             const MixEdge& ed = e[k + u];
             v[u].load(chan(ed.src, ed.src_ch == 1 ? 0 : c, ci) + n0);
         }
 #pragma unroll
-        for (int u = 0; u < MIX_BATCH; u++) {
+        for (int u = 0; u < BATCH; u++) {
             if (k + u == 0) acc = v[u];
             else acc.add(v[u]);
         }
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
             const int n_sum = m.all_mono ? 1 : m.out_ch;
             for (int c = 0; c < n_sum; c++) {
                 MixVec<VEC> acc;
-                mix_simple<VEC>(m, edges, c, n0, ci, acc);
+                mix_simple<VEC, MIX_BATCH>(m, edges, c, n0, ci, acc);  // (32 loads in flight measured slower than 8 on C3)
                 for (int oc = c; oc < (m.all_mono ? m.out_ch : c + 1); oc++) {
                     float* out = chan(m.out, oc, ci) + n0;
                     const bool vec = VEC == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (m.limit < 0 || ci.f0 + n0 + 4 <= m.limit);
@@ -622,30 +631,56 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
     } else if (SRC == CHAIN_SRC_OSC) {
         const OscInst& o = q.osc;
         const int64_t na = ci.f0 + n0;
-        if (na >= o.n_first && na + CH_K <= o.n_stop && !o.outside_nyquist && o.incr > 0. && o.incr < 0.5) {
-            // fully active run: closed-form phase for the first frame, then 15 increments with the reference's wrap
-            double ph = osc_phase_at(o, na);
+        if (na >= o.n_first && na + CH_K <= o.n_stop && !o.outside_nyquist && o.incr > 0. && o.incr < 0.5 && (o.table_len == 2048 || (o.type != 0 && o.type != 4))) {
+            // Fully active run.  The reference accumulates `phase += incr` (wrapping at 1) in f64; here the phase of the
+            // first frame comes from the closed form and then runs as a 64-bit fixed-point fraction of a cycle (wraps for
+            // free, 2^-64 resolution): |phase - reference phase| stays ~1e-14, far below the f32 output resolution, and the
+            // per-frame work is integer / f32 instead of f64 compare-and-wrap + f64 <-> f32 conversions.
             const double inc = o.incr, inv = o.inv_incr;
+            unsigned long long ph = __double2ull_rn(osc_phase_at(o, na) * 9223372036854775808.0) << 1;
+            const unsigned long long dph = __double2ull_rn(inc * 18446744073709551616.0);
+            const unsigned long long HALF = 0x8000000000000000ull;
             const int type = o.type;
+            if (type == 0 || type == 4) {  // sine (:571-585) / custom (:622-637): 2048-entry table + lerp with fmaf
 #pragma unroll
-            for (int j = 0; j < CH_K; j++) {
-                float s;
-                if (type == 0 || type == 4) {
-                    s = osc_sample(o, ph, inc);
-                } else if (type == 2) {
-                    double p2 = ph + 0.5;
-                    p2 = p2 >= 1. ? p2 - 1. : p2;
-                    s = (float)(2.0 * p2 - 1.0 - osc_poly_blep_r(p2, inc, inv));
-                } else if (type == 1) {
-                    double p2 = ph + 0.5;
-                    p2 = p2 >= 1. ? p2 - 1. : p2;
-                    s = (float)((ph < 0.5 ? 1.0 : -1.0) + osc_poly_blep_r(ph, inc, inv) - osc_poly_blep_r(p2, inc, inv));
-                } else {
-                    s = osc_sample(o, ph, inc);
+                for (int j = 0; j < CH_K; j++) {
+                    const unsigned hi = (unsigned)(ph >> 32), lo = (unsigned)ph;
+                    const int prev = (int)(hi >> 21);
+                    const int next = (prev + 1) & 2047;
+                    const float k = __uint_as_float(0x3f800000u | ((hi << 11 | lo >> 21) >> 9)) - 1.0f;
+                    v[j] = fmaf(o.table[prev], 1.f - k, o.table[next] * k);
+                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
                 }
-                v[j] = s;
-                ph += inc;
-                ph = ph >= 1. ? ph - 1. : ph;
+            } else if (type == 2) {  // sawtooth (:588-595): 2 * unroll(phase + 0.5) - 1 - polyBLEP
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) {
+                    const unsigned long long p2 = ph + HALF;
+                    float s;
+                    if (p2 < dph || p2 > 0ull - dph) {  // inside the polyBLEP window (a 2 * incr fraction of the frames)
+                        s = osc_saw_blep(p2, inc, inv);
+                    } else {
+                        s = __ll2float_rn((long long)ph) * 1.08420217248550443e-19f;  // (2 p2 - 1) = signed(ph) / 2^63
+                    }
+                    v[j] = s;
+                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
+                }
+            } else if (type == 1) {  // square (:598-606)
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) {
+                    const unsigned long long p2 = ph + HALF;
+                    float s = (long long)ph >= 0 ? 1.0f : -1.0f;
+                    if (ph < dph || ph > 0ull - dph || p2 < dph || p2 > 0ull - dph) s = osc_square_blep(ph, p2, inc, inv);
+                    v[j] = s;
+                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
+                }
+            } else {  // triangle (:609-619): fold(-4 phase + 2) = 1 - 4 |phase - 1/4| with the difference taken modulo 1
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) {
+                    long long q = (long long)(ph - 0x4000000000000000ull);
+                    q = q < 0 ? -q : q;  // |q| * 2^64, < 2^63 (q = -2^63 maps to itself: phase 3/4, value -1)
+                    v[j] = fmaf(__ull2float_rn((unsigned long long)q), -2.16840434497100887e-19f, 1.0f);  // 1 - 4 |q| / 2^64
+                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
+                }
             }
         } else {
 #pragma unroll
