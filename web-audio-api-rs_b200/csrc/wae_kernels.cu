@@ -854,7 +854,10 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
     // access patterns conflict-free for 128-bit shared accesses.
     constexpr int WF = 32 * CH_K / 4;  // float4 pieces per warp region (128)
     __shared__ float4 s_io[2][CH_WARPS][WF];
-    auto swz = [](int f) { return f ^ ((f >> 3) & 3); };
+    // swizzle f -> f ^ ((f >> 3) & 3).  For the coalesced pieces f = 32u + lane it only touches the lane part, for the
+    // thread's own pieces f = 4 lane + u only the u part: both reduce to one per-thread constant plus a compile-time offset
+    const int lane_sw = lane ^ ((lane >> 3) & 3);  // coalesced piece 32u + lane lives at 32u + lane_sw
+    const int xq = (lane >> 1) & 3;                // own piece 4 lane + u lives at 4 lane + (u ^ xq)
     const int wbase = warp * 32 * CH_K;  // first frame of the warp region inside a tile
     auto stage_source = [&](int buf, int tile_base) {
         if (!STREAMED) return;
@@ -877,7 +880,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
 #pragma unroll
             for (int u = 0; u < CH_K / 4; u++) {
                 const int f = 32 * u + lane;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_io[buf][warp][swz(f)]);
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_io[buf][warp][32 * u + lane_sw]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * f) : "memory");
             }
         } else if (nw + lane * CH_K < ci.nf) {  // ragged start / end, loops, unaligned channel: per-thread gather
@@ -885,7 +888,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
             chain_load_source<SRC>(q, c, ci, nw + lane * CH_K, tmp);
 #pragma unroll
             for (int u = 0; u < CH_K / 4; u++)
-                s_io[buf][warp][swz(4 * lane + u)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
+                s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
         }
     };
     float v[CH_K];
@@ -907,25 +910,31 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
             if (active) {
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++) {
-                    const float4 a = s_io[buf][warp][swz(4 * lane + u)];
+                    const float4 a = s_io[buf][warp][4 * lane + (u ^ xq)];
                     v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
                 }
             }
         } else if (active) {
             chain_load_source<SRC>(q, c, ci, n0, v);
         }
+        if (g0 != 1.f) {  // x * 1.0f == x bit for bit: skip the multiply (uniform branch)
 #pragma unroll
-        for (int j = 0; j < CH_K; j++) v[j] *= g0;
+            for (int j = 0; j < CH_K; j++) v[j] *= g0;
+        }
         if (NB >= 1) {
             chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp);
+            if (g1 != 1.f) {
 #pragma unroll
-            for (int j = 0; j < CH_K; j++) v[j] *= g1;
+                for (int j = 0; j < CH_K; j++) v[j] *= g1;
+            }
         }
         if (NB >= 2) {
             chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], plane[NB - 1], v, active,
                          n_active, t, lane, warp);
+            if (g2 != 1.f) {
 #pragma unroll
-            for (int j = 0; j < CH_K; j++) v[j] *= g2;
+                for (int j = 0; j < CH_K; j++) v[j] *= g2;
+            }
         }
         if (SHAPER) {
             const float* curve = q.curve;
@@ -950,14 +959,13 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++)
-                    s_io[buf][warp][swz(4 * lane + u)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 __syncwarp();
                 for (int oc = 0; oc < n_out; oc++) {
                     float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
 #pragma unroll
                     for (int u = 0; u < CH_K / 4; u++) {
-                        const int f = 32 * u + lane;
-                        out[f] = s_io[buf][warp][swz(f)];
+                        out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
                     }
                 }
                 __syncwarp();
