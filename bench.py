@@ -327,8 +327,17 @@ def main():
     alg_bytes_launch = alg_bytes_step / n_chunks
     dom_ms_launch = dom[1] / n_chunks if n_chunks else 0.0
     achieved = alg_bytes_launch / (dom_ms_launch * 1e-3) / 1e9 if dom_ms_launch > 0 else 0.0
+    # DRAM traffic of the same launch from an `ncu` capture of this very command (measured/dram_traffic.json, written by
+    # tools/record_traffic.py on the GPU box); null when no capture matches the workload size
+    traffic = None
+    try:
+        rec = json.load(open(os.path.join(ROOT, "web-audio-api-rs_b200", "measured", "dram_traffic.json")))
+        if rec.get("kernel") == dom[0] and rec.get("graphs") == n_graphs and rec.get("frames_per_graph") == length:
+            traffic = rec["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "kernel_ms_per_launch": dom_ms_launch, "kernel_share_of_step": dom[1] / ms_per_step if ms_per_step else None,
                 "step_achieved_gbs": alg_bytes_step / (ms_per_step * 1e-3) / 1e9,
                 "launches_per_step": n_chunks, "stages_ms_per_step": {n: round(ms, 4) for n, ms in agg.items()}}
