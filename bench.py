@@ -309,8 +309,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = total_quanta / e2e_s
-    h2d = stats.asset_bytes
-    d2h = out_floats * 4
+    h2d = stats.asset_bytes * world  # whole job, like `value`: every rank copies its own shard over its own PCIe link
+    d2h = out_floats * 4 * world
 
     # ---- roofline of the dominant kernel (CUDA events around every stage launch, on the launching stream)
     peak, peak_src = load_peaks()
