@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--ref-graphs", type=int, default=512, help="graphs per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-sample-graphs", type=int, default=512)
     ap.add_argument("--chunk", type=int, default=0)
-    ap.add_argument("--groups", type=int, default=8, help="graph groups of the e2e pipeline")
+    ap.add_argument("--groups", type=int, default=32, help="graph groups of the e2e pipeline (H2D | render | D2H overlap)")
     ap.add_argument("--serial-filters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra", type=int, default=1, help="also measure C3 / C4 / north_star (rank 0, N=1 only)")

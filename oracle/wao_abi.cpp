@@ -284,11 +284,12 @@ WAO_API wae_status wao_create_convolver(wae_graph* g, const wae_convolver_option
 
 // WaveShaperNode::new, src/node/waveshaper.rs:190-260
 WAO_API wae_status wao_create_wave_shaper(wae_graph* g, const wae_wave_shaper_options* o, wae_node_id* out) {
-    if (o->oversample != WAE_OVERSAMPLE_NONE)
-        return fail(WAE_UNSUPPORTED, "oversampled WaveShaper goes through the un-vendored rubato crate: parity unpinned, not restated");
+    if (o->oversample > WAE_OVERSAMPLE_X4) return fail(WAE_INVALID_ARGUMENT, "unknown oversample type");
     uint32_t id = g->next_id++;
     auto r = std::make_unique<WaveShaperRenderer>();
     if (o->curve) r->set_curve(o->curve, o->curve_len);
+    r->oversample = (int)o->oversample;
+    r->sample_rate = (size_t)g->sample_rate;  // `sample_rate as usize`, waveshaper.rs:148-150
     g->finish_register(id, std::move(r), K_SHAPER, 1, 1, resolve_cfg(o->channel_config, ChannelConfig()), {}, id);
     *out = id;
     return WAE_OK;

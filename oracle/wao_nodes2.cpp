@@ -50,10 +50,28 @@ bool WaveShaperRenderer::process(std::vector<Quantum>& inputs, std::vector<Quant
         return false;
     }
     output = input;
-    if (has_curve) {
+    if (has_curve && oversample == 0) {
         for (int c = 0; c < output.number_of_channels(); c++) {
             float* o = output.channel_mut(c).make_mut();
             for (int i = 0; i < RQ; i++) o[i] = waveshaper_apply_curve(curve, o[i]);
+        }
+    } else if (has_curve) {  // X2 / X4 (:409-480): up-sample, shape, down-sample; samplers rebuilt when the channel count changes
+        const size_t factor = oversample == 1 ? 2 : 4;
+        const size_t channels = (size_t)output.number_of_channels();
+        if (channels != os_channels) {
+            os_channels = channels;
+            upsampler = FftFixedInOut(sample_rate, sample_rate * factor, RQ, channels);
+            downsampler = FftFixedInOut(sample_rate * factor, sample_rate, RQ * factor, channels);
+        }
+        std::vector<std::vector<float>> in(channels), up, down;
+        for (size_t c = 0; c < channels; c++) in[c].assign(output.channel((int)c).data(), output.channel((int)c).data() + RQ);
+        upsampler.process(in, up);
+        for (auto& ch : up)
+            for (float& s : ch) s = waveshaper_apply_curve(curve, s);
+        downsampler.process(up, down);
+        for (size_t c = 0; c < channels; c++) {
+            float* o = output.channel_mut((int)c).make_mut();
+            for (int i = 0; i < RQ; i++) o[i] = down[c][i];
         }
     }
     return false;

@@ -2,6 +2,7 @@
 // WaveShaper, Delay (writer/reader), StereoPanner, DynamicsCompressor, Analyser, ChannelMerger/Splitter.
 #pragma once
 #include "wao_core.h"
+#include "wao_resampler.h"
 #include "wao_fft.h"
 
 namespace wao {
@@ -12,6 +13,10 @@ struct WaveShaperRenderer : Processor {
     bool has_curve = false;
     std::vector<float> curve;
     bool can_propagate_silence = true;
+    int oversample = 0;      // 0 none, 1 X2, 2 X4 (waveshaper.rs:18-36)
+    size_t sample_rate = 0;
+    size_t os_channels = 0;  // channels the up / down samplers were built for (:411-424)
+    FftFixedInOut upsampler, downsampler;
     void set_curve(const float* c, size_t n);  // onmessage, :480-503
     bool process(std::vector<Quantum>&, std::vector<Quantum>&, const ParamValues&, const Scope&) override;
     const char* name() const override { return "WaveShaperRenderer"; }

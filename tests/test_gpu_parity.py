@@ -500,15 +500,41 @@ def test_north_star_graph(pkg, engine, oracle):
 
 
 def test_unsupported_is_reported_not_faked(pkg, engine):
-    c = pkg.OfflineAudioContext(1, 128, G.SR, engine.backend)
-    with pytest.raises(pkg.WaeError) as e:  # rubato resampling: not lowered; reported, never approximated
-        g = c.create_wave_shaper(curve=np.linspace(-1, 1, 5), oversample=pkg.context.OVERSAMPLE_X2)
+    c = pkg.OfflineAudioContext(2, 256, G.SR, engine.backend)
+    with pytest.raises(pkg.WaeError) as e:  # no HRIR sphere at this rate: reported, never approximated
+        engine.backend.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 64))
+        p = c.create_panner(panning_model=pkg.context.HRTF)
         src = c.create_constant_source()
-        src.connect(g)
-        g.connect(c.destination())
+        src.connect(p)
+        p.connect(c.destination())
         src.start()
         c.start_rendering_sync()
     assert e.value.status == 4  # WAE_UNSUPPORTED -> the caller falls back to the CPU renderer
+
+
+@pytest.mark.parametrize("oversample", [1, 2])
+@pytest.mark.parametrize("chunk", [0, 128, 1024])
+def test_waveshaper_oversampled(pkg, engine, oracle, oversample, chunk):
+    """OverSampleType::X2 / X4 (waveshaper.rs:409-480): FFT up-sampler -> curve -> FFT down-sampler, mono and stereo."""
+    def build(be, g):
+        n = 128 * 24
+        pcm = G.c2_source(g, n) * np.float32(1.4)
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]] if g else [pcm[0]], G.SR))
+        x = np.linspace(-1.0, 1.0, 33)
+        sh = c.create_wave_shaper(curve=np.tanh(3.0 * x).astype(np.float32), oversample=oversample)
+        s.connect(sh)
+        sh.connect(c.destination())
+        s.start()
+        return c
+
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        gpu, cpu = both(pkg, engine, oracle, build, 2)
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+    assert float(np.abs(cpu).max()) > 0.3
+    assert maxdiff(gpu, cpu) <= TOL
 
 
 def test_offline_rs_cases_on_gpu(pkg, engine):

@@ -247,12 +247,12 @@ WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_option
 
 // WaveShaperNode::new, src/node/waveshaper.rs:190-260
 WAE_API wae_status wae_create_wave_shaper(wae_graph* g, const wae_wave_shaper_options* o, wae_node_id* out) {
-    if (o->oversample != WAE_OVERSAMPLE_NONE)
-        return fail(WAE_UNSUPPORTED, "oversampled WaveShaper (rubato FftFixedInOut, un-vendored) is not lowered to the GPU");
+    if (o->oversample > WAE_OVERSAMPLE_X4) return fail(WAE_INVALID_ARGUMENT, "unknown oversample type");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_SHAPER;
+    n.oversample = (int)o->oversample;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     if (o->curve) {
         n.has_curve = true;

@@ -130,6 +130,19 @@ struct ShaperInst {
     int32_t ch;
 };
 
+// over-sampled WaveShaper (waveshaper.rs:409-480): 128 -> 128 * factor frames up (FFT resampler), curve, back down
+struct ShaperOsInst {
+    BufRef in, out;
+    const float* curve;
+    const float2* f_up;  // [128] filter bins of the up-sampler
+    const float2* f_dn;  // [128] filter bins of the down-sampler
+    float* hist;         // [ch][256] the two input quanta before the chunk
+    int32_t n;           // curve length
+    int32_t ch;
+    int32_t factor;      // 2 or 4
+    int32_t pad;
+};
+
 struct SPanInst {
     BufRef in, out;
     float pan;

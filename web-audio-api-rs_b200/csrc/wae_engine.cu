@@ -8,6 +8,7 @@
 #include "wae_graph.h"
 #include "wae_hostmath.h"
 #include "wae_hrtf_host.h"
+#include "wae_resample_host.h"
 #include "wae_kernels.h"
 #include "wae_param_host.h"
 
@@ -48,11 +49,11 @@ namespace {
 
 enum StageKind : int {
     S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_SHAPER_OS, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial", "k_shaper_os"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -79,6 +80,7 @@ struct StageBuild {
     std::vector<HrtfSelInst> hrtf_sel;
     std::vector<PanDynInst> pan_dyn;
     std::vector<AbsnSerialInst> absn_serial;
+    std::vector<ShaperOsInst> shaper_os;
     std::vector<RouteInst> route;
     std::vector<DelayInst> delay;
     std::vector<CompInst> comp;
@@ -277,6 +279,7 @@ struct Planner {
         int channels;
     };
     std::unordered_map<uint64_t, IrSpectra> ir_cache;
+    std::map<int, std::pair<const float2*, const float2*>> os_filters;  // over-sampled shaper: factor -> (up, down) filter bins
 
     bool has_feedback = false;            // some graph has a cycle broken by a DelayNode
     std::map<std::pair<uint32_t, uint32_t>, int>* delay_ch_hint = nullptr;  // (graph, reader id) -> channels of an in-cycle delay
@@ -680,7 +683,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         // does this node extend the pending chain of its only producer / take it as the destination's only input?
         uint32_t fuse_src = 0;
         bool extend = false, dest_direct = false;
-        const bool chain_kind = !dyn_params && ((n.kind == K_BIQUAD && !eng->serial_filters) || (fuse && (n.kind == K_GAIN || n.kind == K_SHAPER)));
+        const bool chain_kind = !dyn_params && ((n.kind == K_BIQUAD && !eng->serial_filters) || (fuse && (n.kind == K_GAIN || (n.kind == K_SHAPER && !(n.oversample && n.has_curve)))));
         if (fuse && n.n_inputs == 1 && p.in_edges[0].size() == 1 && p.in_edges[0][0].port == 0) {
             auto it = pending.find(p.in_edges[0][0].node);
             if (it != pending.end()) {
@@ -1200,6 +1203,33 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             case K_SHAPER: {
                 int ch = p.in_ch[0];
                 const float* curve = n.has_curve ? upload(n.table) : nullptr;
+                if (n.oversample && n.has_curve) {  // waveshaper.rs:409-480: up-sample, shape, down-sample
+                    if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    const int factor = n.oversample == WAE_OVERSAMPLE_X2 ? 2 : 4;
+                    auto& filt = os_filters[factor];
+                    if (!filt.first) {
+                        const std::vector<float2> fu = resampler_filter_bins(128, 128 * factor, 128);
+                        const std::vector<float2> fd = resampler_filter_bins(128 * factor, 128, 128);
+                        filt.first = upload(fu);
+                        filt.second = upload(fd);
+                        if (!dry) cudaStreamSynchronize(eng->stream);  // the host vectors go out of scope
+                    }
+                    ShaperOsInst so{};
+                    so.in = p.in_buf[0];
+                    so.out = p.out_buf[0];
+                    so.curve = curve;
+                    so.n = (int)n.table.size();
+                    so.ch = ch;
+                    so.factor = factor;
+                    so.f_up = filt.first;
+                    so.f_dn = filt.second;
+                    so.hist = alloc<float>((size_t)256 * ch, true, true);
+                    if (!so.hist || !so.f_up || !so.f_dn) return bail(WAE_OUT_OF_MEMORY, "out of device memory (over-sampled shaper)");
+                    StageBuild& os = stage(L, S_SHAPER_OS);
+                    os.max_ch = std::max(os.max_ch, ch);
+                    os.shaper_os.push_back(so);
+                    break;
+                }
                 if (fuse_n) {
                     PendingChain pc = open_chain();
                     pc.inst.has_shaper = 1;
@@ -1608,7 +1638,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     }
     // graph groups for the H2D / render / D2H pipeline
     int n_groups = eng->pipeline_groups;
-    if (n_groups == 0) n_groups = n_graphs >= 64 ? 8 : 1;
+    if (n_groups == 0) n_groups = n_graphs >= 512 ? 32 : (n_graphs >= 64 ? 8 : 1);  // measured on C2: 8 groups 88 ms, 16: 83.7, 32: 80.6 (fill / drain of the 3-stage pipeline)
     n_groups = std::max(1, std::min<int>(n_groups, (int)n_graphs));
     b->groups.resize(n_groups);
     for (int k = 0; k < n_groups; k++) {
@@ -1759,6 +1789,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                     st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
                 case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
                 case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
+                case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
                 case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
                 case S_DELAY:
                 case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
@@ -1826,6 +1857,7 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_HRTF: launch_hrtf((HrtfInst*)st.d_a, st.n, (HrtfSelInst*)st.d_b, st.n_b, st.max_ch, ci, s); break;
         case S_PAN_DYN: launch_panner_dyn((PanDynInst*)st.d_a, st.n, ci, s); break;
         case S_ABSN_SERIAL: launch_buffer_source_serial((AbsnSerialInst*)st.d_a, st.n, ci, s); break;
+        case S_SHAPER_OS: launch_shaper_os((ShaperOsInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_ROUTE: launch_route((RouteInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY: launch_delay_read((DelayInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY_WRITE: launch_ring_write((DelayInst*)st.d_a, st.n, ci, s); break;

@@ -69,6 +69,7 @@ struct Node {
     int type = 0;  // oscillator / biquad type
     std::vector<float> table;  // periodic wave / shaper curve
     bool has_curve = false;
+    int oversample = 0;  // WaveShaper: WAE_OVERSAMPLE_*
     std::vector<double> feedforward, feedback;  // IIR
     std::shared_ptr<PcmBuffer> buffer;          // ABSN buffer / convolver IR
     bool normalize = true;                      // convolver

@@ -49,7 +49,9 @@ __device__ __noinline__ float osc_saw_blep(unsigned long long p2, double inc, do
 }
 __device__ __noinline__ float osc_square_blep(unsigned long long ph, unsigned long long p2, double inc, double inv) {
     const double t = (double)ph * 5.42101086242752217e-20, t2 = (double)p2 * 5.42101086242752217e-20;
-    return (float)((t < 0.5 ? 1.0 : -1.0) + osc_poly_blep_r(t, inc, inv) - osc_poly_blep_r(t2, inc, inv));
+    // the half-cycle sign comes from the fixed-point phase itself: `t` may round to exactly 0.5 (or 1.0) while p2 is still
+    // just below the wrap, and deciding the sign from the rounded value would pair +-1 with the wrong polyBLEP branch
+    return (float)(((long long)ph >= 0 ? 1.0 : -1.0) + osc_poly_blep_r(t, inc, inv) - osc_poly_blep_r(t2, inc, inv));
 }
 DEVI double osc_unroll(double p) { return p >= 1. ? p - 1. : (p < 0. ? p + 1. : p); }
 
@@ -678,7 +680,7 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
                 for (int j = 0; j < CH_K; j++) {
                     long long q = (long long)(ph - 0x4000000000000000ull);
                     q = q < 0 ? -q : q;  // |q| * 2^64, < 2^63 (q = -2^63 maps to itself: phase 3/4, value -1)
-                    v[j] = fmaf(__ull2float_rn((unsigned long long)q), -2.16840434497100887e-19f, 1.0f);  // 1 - 4 |q| / 2^64
+                    v[j] = (float)fma((double)(unsigned long long)q, -2.16840434497100887e-19, 1.0);  // 1 - 4 |q| / 2^64, one f32 rounding
                     asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
                 }
             }
@@ -1317,6 +1319,118 @@ __global__ void __launch_bounds__(256) k_panner_eq(const PanInst* __restrict__ i
         pan_eq_frame(sp, p.in_ch, il, ir, l, r);
         chan(p.out, 0, ci)[n] = l;
         chan(p.out, 1, ci)[n] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Over-sampled WaveShaper (waveshaper.rs:409-480 over rubato::FftFixedInOut): per render quantum q
+//     up_j   = irFFT_{2 fo}( rFFT_256([x_j | 0]) * F_up )            fo = 128 * factor
+//     u_j    = curve( up_j[0 .. fo) + up_{j-1}[fo .. 2 fo) )
+//     dn_j   = irFFT_256( rFFT_{2 fo}([u_j | 0])[0 .. 128) * F_dn )
+//     out_q  = dn_q[0 .. 128) + dn_{q-1}[128 .. 256)
+// One CTA per (quantum, channel, instance) recomputes the three up-transforms and two down-transforms its output
+// depends on, so the only state between chunks is two quanta of input.  Plain complex FFTs (<= 1024 points) in smem.
+// ---------------------------------------------------------------------------------------------------------
+DEVI void fft_small(float2* s, int n, int logn, int sign) {  // 128 threads, in place, natural order in and out
+    const int t = threadIdx.x;
+    for (int i = t; i < n; i += 128) {
+        const int r = (int)(__brev((unsigned)i) >> (32 - logn));
+        if (i < r) {
+            const float2 tmp = s[i];
+            s[i] = s[r];
+            s[r] = tmp;
+        }
+    }
+    __syncthreads();
+    for (int len = 2; len <= n; len <<= 1) {
+        const int half = len >> 1;
+        for (int b = t; b < n / 2; b += 128) {
+            const int j = b & (half - 1);
+            const int i0 = ((b - j) << 1) + j, i1 = i0 + half;
+            float sn, cs;
+            sincospif((float)sign * 2.f * (float)j / (float)len, &sn, &cs);
+            const float2 u = s[i0], x = s[i1];
+            const float2 v = make_float2(x.x * cs - x.y * sn, x.x * sn + x.y * cs);
+            s[i0] = make_float2(u.x + v.x, u.y + v.y);
+            s[i1] = make_float2(u.x - v.x, u.y - v.y);
+        }
+        __syncthreads();
+    }
+}
+// z <- irFFT_{n_out}( rFFT_{n_in}(real input in z[0 .. n_in)) [0 .. 128) * F ): the real result is left in z[i].x
+DEVI void os_resample(float2* z, int n_in, int log_in, int n_out, int log_out, const float2* __restrict__ F) {
+    const int t = threadIdx.x;
+    fft_small(z, n_in, log_in, -1);
+    float2 y = make_float2(0.f, 0.f);
+    {
+        const float2 x = z[t], f = __ldg(F + t);  // bins 0 .. 127 (n_in >= 256)
+        y = make_float2(x.x * f.x - x.y * f.y, x.x * f.y + x.y * f.x);
+        if (t == 0) y.y = 0.f;  // realfft ignores the imaginary part of the DC bin
+    }
+    __syncthreads();
+    for (int i = t; i < n_out; i += 128) z[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+    z[t] = y;
+    if (t > 0) z[n_out - t] = make_float2(y.x, -y.y);  // Hermitian half
+    __syncthreads();
+    fft_small(z, n_out, log_out, +1);
+}
+__global__ void __launch_bounds__(128) k_shaper_os(const ShaperOsInst* __restrict__ insts, ChunkInfo ci) {
+    __shared__ float2 z[1024];
+    __shared__ float keep[4][512];  // up_{q-2} second half, up_{q-1} both halves, up_q first half
+    __shared__ float dn_prev[128];
+    const ShaperOsInst& p = insts[blockIdx.z];
+    const int c = blockIdx.y;
+    if (c >= p.ch) return;
+    const int q = blockIdx.x;  // quantum inside the chunk
+    const int t = threadIdx.x;
+    const int fo = 128 * p.factor, n2 = 2 * fo, log2n = p.factor == 2 ? 9 : 10;
+    const float* in = chan(p.in, c, ci);
+    const float* hist = p.hist + 256 * c;
+    // three up-transforms: quanta q-2, q-1, q
+    for (int r = 0; r < 3; r++) {
+        const int qq = q - 2 + r;
+        float x = qq >= 0 ? in[qq * 128 + t] : hist[(qq + 2) * 128 + t];
+        z[t] = make_float2(x, 0.f);
+        z[128 + t] = make_float2(0.f, 0.f);
+        __syncthreads();
+        os_resample(z, 256, 8, n2, log2n, p.f_up);
+        for (int i = t; i < fo; i += 128) {
+            if (r == 0) keep[0][i] = z[fo + i].x;
+            if (r == 1) keep[1][i] = z[i].x, keep[2][i] = z[fo + i].x;
+            if (r == 2) keep[3][i] = z[i].x;
+        }
+        __syncthreads();
+    }
+    // two down-transforms: u_{q-1} and u_q
+    float result = 0.f;
+    for (int r = 0; r < 2; r++) {
+        for (int i = t; i < n2; i += 128) {
+            float u = 0.f;
+            if (i < fo) {
+                u = r == 0 ? keep[1][i] + keep[0][i] : keep[3][i] + keep[2][i];
+                u = p.n == 0 ? 0.f : shaper_apply(p.curve, p.n, u);
+            }
+            z[i] = make_float2(u, 0.f);
+        }
+        __syncthreads();
+        os_resample(z, n2, log2n, 256, 8, p.f_dn);
+        if (r == 0) dn_prev[t] = z[128 + t].x;
+        else result = z[t].x;
+        __syncthreads();
+    }
+    chan(p.out, c, ci)[q * 128 + t] = result + dn_prev[t];
+}
+// the two input quanta before the next chunk
+__global__ void __launch_bounds__(256) k_shaper_os_hist(const ShaperOsInst* __restrict__ insts, ChunkInfo ci) {
+    const ShaperOsInst& p = insts[blockIdx.x];
+    const int t = threadIdx.x;
+    for (int c = 0; c < p.ch; c++) {
+        const int m = ci.nf - 256 + t;
+        const float v = m >= 0 ? chan(p.in, c, ci)[m] : p.hist[256 * c + 128 + t - (128 - ci.nf)];  // nf == 128: shift by one quantum
+        __syncthreads();
+        p.hist[256 * c + t] = v;
+        __syncthreads();
     }
 }
 
@@ -2352,6 +2466,10 @@ void launch_stereo_panner(const SPanInst* d, const float2* g, int n, ChunkInfo c
 }
 void launch_buffer_source_serial(const AbsnSerialInst* d, int n, ChunkInfo ci, cudaStream_t s) {
     k_buffer_source_serial<<<(n + ABSN_SERIAL_WARPS - 1) / ABSN_SERIAL_WARPS, 32 * ABSN_SERIAL_WARPS, 0, s>>>(d, n, ci);
+}
+void launch_shaper_os(const ShaperOsInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    k_shaper_os<<<dim3((unsigned)(ci.nf / 128), (unsigned)max_ch, (unsigned)n), 128, 0, s>>>(d, ci);
+    k_shaper_os_hist<<<n, 256, 0, s>>>(d, ci);
 }
 void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_dyn<<<grid_tiles(ci.nf, 128, n), 128, 0, s>>>(d, n, ci); }
 void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s) {

@@ -31,6 +31,7 @@ void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_stereo_panner(const SPanInst* d, const float2* gains, int n, ChunkInfo ci, cudaStream_t s);
 void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, int max_taps, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source_serial(const AbsnSerialInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_shaper_os(const ShaperOsInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
