@@ -618,6 +618,68 @@ def test_feedback_delay_echo(pkg, engine, oracle):
     assert maxdiff(gpu, cpu) <= TOL
 
 
+@pytest.mark.parametrize("chunk", [0, 1024])
+def test_feedback_echo_into_reverb_and_mixed_batch(pkg, engine, oracle, chunk):
+    """A DelayNode feedback loop followed by a ConvolverNode, a biquad and an HRTF panner, in one batch with feedback-free
+    graphs: the cyclic levels are replayed quantum by quantum inside a chunk, everything downstream runs on whole chunks."""
+    data = G.synthetic_hrir_sphere(int(G.SR), 128, subdivisions=1)
+    oracle.set_hrir_sphere(data)
+    engine.backend.set_hrir_sphere(data)
+    ir = G.synthetic_ir(3000, 2, decay=0.03)
+    n = 128 * 70 + 33
+
+    def build(be, g):
+        if g == 2:
+            return G.c4_convolver(pkg, be, g, n, ir)
+        if g == 3:
+            return G.c2_buffer_biquad_gain(pkg, be, g, n)
+        pcm = G.c2_source(g, n)
+        pcm[:, 128 * 5:] = 0
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        lp = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=3000.0)
+        d = c.create_delay(max_delay_time=0.05, delay_time=[0.0071, 0.0029][g])
+        fb = c.create_gain(0.55)
+        s.connect(lp)
+        lp.connect(d)
+        d.connect(fb)
+        fb.connect(d)
+        cv = c.create_convolver(pkg.AudioBuffer(ir, G.SR))
+        d.connect(cv)
+        hp = c.create_biquad_filter(type_=pkg.HIGHPASS, frequency=150.0)
+        cv.connect(hp)
+        pn = c.create_panner(panning_model=pkg.context.HRTF, position=(2.0, 0.5, -1.0))
+        hp.connect(pn)
+        pn.connect(c.destination())
+        s.connect(c.destination())
+        s.start()
+        return c
+
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        gpu, cpu = both(pkg, engine, oracle, build, 4)
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_convolver_upstream_of_feedback_is_reported(pkg, engine):
+    c = pkg.OfflineAudioContext(1, 128 * 4, G.SR, engine.backend)
+    s = c.create_constant_source()
+    cv = c.create_convolver(pkg.AudioBuffer([np.ones(4, np.float32)], G.SR))
+    d = c.create_delay(max_delay_time=0.05, delay_time=0.004)
+    fb = c.create_gain(0.5)
+    s.connect(cv)
+    cv.connect(d)
+    d.connect(fb)
+    fb.connect(d)
+    d.connect(c.destination())
+    s.start()
+    with pytest.raises(pkg.WaeError) as e:
+        c.start_rendering_sync()
+    assert e.value.status == 4 and "feedback" in str(e.value)
+
+
 # ---- AudioBufferSource slow track (SURVEY §8 a17 / f2) ---------------------------------------------------------------
 SLOW_CASES = {
     "rate_half": dict(playback_rate=0.5),

@@ -22,6 +22,8 @@ struct BufRef {
 struct ChunkInfo {
     int64_t f0;  // first frame of this chunk
     int32_t nf;  // frames in this chunk (multiple of 128 except nothing: render is padded to whole quanta)
+    int32_t sub;  // offset of these frames inside the chunk's arena buffers: 0 for a whole chunk, q * 128 when the stages of
+                  // a DelayNode feedback cycle are replayed quantum by quantum inside a chunk (f0 then includes it)
 };
 
 struct OscInst {

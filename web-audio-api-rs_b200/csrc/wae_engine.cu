@@ -20,6 +20,8 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <map>
+#include <set>
 #include <unordered_map>
 
 using namespace wae;
@@ -57,6 +59,7 @@ const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_bu
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
+    int cls = 0;
     int level = 0;
     int kind = 0;
     int variant = 0;
@@ -93,6 +96,7 @@ struct StageBuild {
 };
 
 struct Stage {
+    int cls = 0;  // see Planner::stage_class
     int kind = 0;
     int variant = 0;
     int group = 0;
@@ -301,6 +305,7 @@ struct Planner {
         std::vector<ScanCoef> coefs;
         int ch = 1;
         int phase = 0;  // 0: before biquad A, 1: after A, 3: after B, 5: after the shaper (canonical chain order)
+        int cls = 0;    // scheduling class of the node that opened the chain (see stage())
     };
 
     template <typename T>
@@ -322,8 +327,15 @@ struct Planner {
         return false;
     }
 
+    // Scheduling class of a stage: 0 = graph without DelayNode feedback (whole chunks); for a graph with feedback, 1 = the
+    // node is an ancestor of a cycle-breaking DelayWriter, i.e. inside or upstream of a feedback cycle (replayed quantum by
+    // quantum inside the chunk, like the reference's render loop), 2 = everything else of that graph: downstream of the
+    // cycles only, whole chunks again (e.g. a reverb after an echo loop).
+    int cur_cls = 0;  // class of the node being planned
     StageBuild& stage(int level, int kind, int variant = 0) {
-        StageBuild& s = builds[{level, kind * 64 + variant}];
+        const int cls = cur_cls;
+        StageBuild& s = builds[{cls * 1000000 + level, kind * 64 + variant}];
+        s.cls = cls;
         s.level = level;
         s.kind = kind;
         s.variant = variant;
@@ -417,6 +429,8 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
 bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
+    if (!dry && n.buffer && cur_cls == 1)
+        return bail(WAE_UNSUPPORTED, "a ConvolverNode inside or upstream of a DelayNode feedback cycle is not lowered to the GPU (after the cycle it is)");
     if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
         pn.out_ch = {in_ch};
         pn.out_buf = {pn.in_buf[0]};
@@ -551,7 +565,23 @@ Planner::PRef Planner::param_ref(wae_graph* g, uint32_t pid) {
 bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     Orderer ord{g};
     ord.run();
-    if (!ord.broken.empty()) has_feedback = true;  // feedback through a DelayNode: rendered quantum by quantum (chunk = 128)
+    if (!ord.broken.empty()) has_feedback = true;  // feedback through a DelayNode: its levels are replayed quantum by quantum
+    // nodes from which a broken DelayWriter is reachable (reverse reachability over the ordered graph's edges, AudioParam ->
+    // owner edges included): they have to be rendered quantum by quantum
+    std::set<uint32_t> feeds_cycle;
+    if (!ord.broken.empty()) {
+        std::map<uint32_t, std::vector<uint32_t>> rev;
+        for (auto& kv : ord.edges)
+            for (auto& e : kv.second) rev[e.other_id].push_back(kv.first);
+        std::vector<uint32_t> todo(ord.broken.begin(), ord.broken.end());
+        while (!todo.empty()) {
+            uint32_t x = todo.back();
+            todo.pop_back();
+            if (!feeds_cycle.insert(x).second) continue;
+            for (uint32_t y : rev[x]) todo.push_back(y);
+        }
+    }
+    auto node_class = [&](uint32_t id) { return ord.broken.empty() ? 0 : (feeds_cycle.count(id) ? 1 : 2); };
     std::map<uint32_t, PNode> pn;
     cur_pn = &pn;
     for (auto& kv : g->nodes) {
@@ -586,7 +616,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     };
     auto emit_chain = [&](PendingChain& pc, int L) {
         const int variant = pc.inst.src_kind * 6 + pc.inst.n_biquad * 2 + (pc.inst.has_shaper ? 1 : 0);
+        const int consumer_cls = cur_cls;  // a chain is emitted while its consumer is planned, but runs with its own nodes' class
+        cur_cls = pc.cls;
         StageBuild& cs = stage(L, S_CHAIN, variant);
+        cur_cls = consumer_cls;
         for (int k = 0; k < pc.inst.n_biquad; k++) {
             pc.inst.bq[k].coef = (int32_t)cs.scan_coef.size();
             cs.scan_coef.push_back(pc.coefs[k]);
@@ -619,6 +652,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         Node& n = g->nodes.at(id);
         if (n.kind == K_LISTENER) continue;
         PNode& p = pn.at(id);
+        cur_cls = node_class(id);
         if (n.kind == K_PARAM) {
             // AudioParamProcessor (param.rs:685-797): only params with automation events or audio-rate inputs become
             // GPU work; a constant param is a scalar in its owner's instance
@@ -763,6 +797,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             pc.inst.limit = -1;
             for (int i = 0; i < 4; i++) pc.inst.g[i] = 1.f;
             pc.ch = ch;
+            pc.cls = cur_cls;
             return pc;
         };
         // chain that this biquad / gain / shaper node joins: its producer's pending chain, or a new one reading in_buf
@@ -1697,14 +1732,9 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         }
         if (has_conv) chunk = std::max<int64_t>(chunk, 8 * WAE_CONV_BLOCK);  // k_conv_mac tiles 8 output blocks
     }
-    if (has_feedback) {
-        // feedback through a DelayNode is resolved one render quantum at a time, like the reference's render loop
-        if (has_conv) {
-            wae_batch_destroy(b);
-            return fail(WAE_UNSUPPORTED, "a ConvolverNode in a batch with DelayNode feedback cycles is not lowered to the GPU yet");
-        }
-        chunk = 128;
-    }
+    // feedback through a DelayNode: the stages up to the cycle are replayed one render quantum at a time INSIDE each chunk
+    // (run_group), so the chunk size does not depend on it
+    (void)has_feedback;
     if (has_conv) chunk = (chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK;
     if (chunk > b->lq) chunk = has_conv ? (b->lq + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK : b->lq;
     b->chunk = chunk;
@@ -1748,6 +1778,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         for (auto& kv : pl.builds) {
             StageBuild& s = kv.second;
             Stage st;
+            st.cls = s.cls;
             st.kind = s.kind;
             st.variant = s.variant;
             st.group = k;
@@ -1820,10 +1851,14 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     }
     int64_t n_chunks = (b->lq + b->chunk - 1) / b->chunk;
     uint64_t launches = 0;
-    for (auto& st : b->stages)
-        launches += (st.kind == S_CONV_FFT || st.kind == S_CONV_MAC || st.kind == S_CONV_MAC_ACC) ? 2 : st.kind == S_HRTF ? (st.n_b > 0 ? 3 : 2) : 1;
+    for (auto& st : b->stages) {
+        const uint64_t k = (st.kind == S_CONV_FFT || st.kind == S_CONV_MAC || st.kind == S_CONV_MAC_ACC || st.kind == S_SHAPER_OS) ? 2
+                           : st.kind == S_HRTF ? (st.n_b > 0 ? 3 : 2) : 1;
+        // per-quantum stages (class 1) launch once per render quantum, the others once per chunk
+        launches += st.cls == 1 ? k * (uint64_t)(b->lq / 128) : k * (uint64_t)n_chunks;
+    }
     std::memset(&b->stats, 0, sizeof(b->stats));
-    b->stats.kernel_launches_per_run = launches * (uint64_t)n_chunks;
+    b->stats.kernel_launches_per_run = launches;
     b->stats.stages = b->stages.size();
     b->stats.chunks = (uint64_t)n_chunks;
     b->stats.arena_bytes = b->arena_bytes;
@@ -1886,33 +1921,50 @@ WAE_API wae_status wae_batch_set_timing(wae_batch* b, uint32_t per_stage) {
 // renders one group (all its chunks, all its stages) on the engine stream
 static wae_status run_group(wae_batch* b, const wae_batch::Group& g) {
     cudaStream_t s = b->engine->stream;
-    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk) {
-        ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0)};
+    // per-stage device time: one event between consecutive launches, recorded on the launching stream and read back in
+    // wae_batch_sync (no host synchronisation inside the run)
+    size_t e_prev = (size_t)-1;
+    auto next_event = [&]() -> size_t {
+        if (b->timed_events_used == b->stage_events.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return (size_t)-1;
+            b->stage_events.push_back(e);
+        }
+        return b->timed_events_used++;
+    };
+    auto run = [&](size_t i, const ChunkInfo& ci) -> bool {
+        launch_stage(b, b->stages[i], ci);
         if (b->time_stages) {
-            // per-stage device time: one event between consecutive launches, recorded on the launching stream and
-            // read back in wae_batch_sync (no host synchronisation inside the run)
-            auto next_event = [&]() -> size_t {
-                if (b->timed_events_used == b->stage_events.size()) {
-                    cudaEvent_t e;
-                    if (cudaEventCreate(&e) != cudaSuccess) return (size_t)-1;
-                    b->stage_events.push_back(e);
-                }
-                return b->timed_events_used++;
-            };
-            size_t e_prev = next_event();
+            size_t e = next_event();
+            if (e == (size_t)-1) return false;
+            if (cudaEventRecord(b->stage_events[e], s) != cudaSuccess) return false;
+            b->timed.push_back({i, e_prev, e});
+            e_prev = e;
+        }
+        return true;
+    };
+    // stages are sorted by class: [whole-chunk stages of feedback-free graphs | per-quantum stages | whole-chunk stages after cycles]
+    size_t c1 = g.stage0, c2 = g.stage0;
+    while (c1 < g.stage1 && b->stages[c1].cls == 0) c1++;
+    c2 = c1;
+    while (c2 < g.stage1 && b->stages[c2].cls == 1) c2++;
+    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk) {
+        const ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0), 0};
+        if (b->time_stages) {
+            e_prev = next_event();
             if (e_prev == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
             CUDA_TRY(cudaEventRecord(b->stage_events[e_prev], s));
-            for (size_t i = g.stage0; i < g.stage1; i++) {
-                launch_stage(b, b->stages[i], ci);
-                size_t e = next_event();
-                if (e == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
-                CUDA_TRY(cudaEventRecord(b->stage_events[e], s));
-                b->timed.push_back({i, e_prev, e});
-                e_prev = e;
-            }
-        } else {
-            for (size_t i = g.stage0; i < g.stage1; i++) launch_stage(b, b->stages[i], ci);
         }
+        for (size_t i = g.stage0; i < c1; i++)
+            if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+        if (c2 > c1)
+            for (int32_t sub = 0; sub < ci.nf; sub += 128) {  // the reference's render loop, for the cyclic part only
+                const ChunkInfo cq{f0 + sub, 128, sub};
+                for (size_t i = c1; i < c2; i++)
+                    if (!run(i, cq)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+            }
+        for (size_t i = c2; i < g.stage1; i++)
+            if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
     }
     return WAE_OK;
 }

@@ -14,7 +14,7 @@ namespace wae {
 
 #define DEVI __device__ __forceinline__
 
-DEVI float* chan(const BufRef& b, int c, const ChunkInfo& ci) { return b.p + (size_t)c * b.stride + (b.absolute ? ci.f0 : 0); }
+DEVI float* chan(const BufRef& b, int c, const ChunkInfo& ci) { return b.p + (size_t)c * b.stride + (b.absolute ? ci.f0 : ci.sub); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Oscillator — OscillatorRenderer::process + generate_* (src/node/oscillator.rs:364-676), constant
@@ -1481,7 +1481,7 @@ __global__ void __launch_bounds__(64) k_hrtf_sel(const HrtfSelInst* __restrict__
     const float dir[3] = {proj[0], proj[2], proj[1]};  // HrtfState::process swaps y / z (panner.rs:248-252)
     HrtfSel s{{0, 0, 0}, {0.f, 0.f, 0.f}, sp.cone_gain * sp.dist_gain, 0.f};
     spatial::hrir_locate(p.pos, p.tri, p.n_faces, dir, s.v, s.w);
-    p.sel[q] = s;
+    p.sel[(ci.sub >> 7) + q] = s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1521,7 +1521,7 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
     const bool active = q0 < ci.nf;
     HrtfSel sel = p.static_sel;
     if (active) {
-        if (p.sel) sel = p.sel[q0 >> 7];
+        if (p.sel) sel = p.sel[(ci.sub + q0) >> 7];
         float* hl = hs + warp * 2 * L4;
         float* hr = hl + L4;
         const float* A = p.sphere_ir + (size_t)sel.v[0] * 2 * L;
