@@ -369,6 +369,10 @@ WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch*, uint32_t gr
  * sample rate differs from the sphere's are WAE_UNSUPPORTED (the hrtf crate's rubato resampling is not lowered). */
 WAE_API wae_status wae_engine_set_hrir_sphere(wae_engine* engine, const void* data, uint64_t len);
 
+/* Analyser::get_byte_time_domain_data / get_byte_frequency_data (src/analysis.rs:266-276, 371-401) */
+WAE_API wae_status wae_analyser_get_byte_time_domain_data(wae_batch* batch, uint32_t graph_index, wae_node_id node, uint8_t* out, uint32_t len);
+WAE_API wae_status wae_analyser_get_byte_frequency_data(wae_batch* batch, uint32_t graph_index, wae_node_id node, uint8_t* out, uint32_t len);
+
 /* DynamicsCompressorNode::reduction (src/node/dynamics_compressor.rs:204-206): gain reduction (dB) at the end of the render */
 WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_index, wae_node_id node, float* out);
 

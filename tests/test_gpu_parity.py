@@ -407,6 +407,11 @@ def test_analyser_frequency_data(pkg, engine, oracle, fft_size, smoothing):
     assert loud.any() and np.abs(fg[loud] - fc[loud]).max() <= 1e-2   # dB where the bin is above the noise floor
     # a second read at the same current_time returns the cached spectrum (analysis.rs:353-361)
     assert np.array_equal(cg._test_analyser.get_float_frequency_data(), fg)
+    # byte read-outs (analysis.rs:266-276, 371-401): floor() of a scaled value, so allow one count where the float sits on a step
+    bg, bc = cg._test_analyser.get_byte_frequency_data(), cc._test_analyser.get_byte_frequency_data()
+    assert np.abs(bg.astype(int) - bc.astype(int)).max() <= 1 and int(bc.max()) > 0
+    tg, tc = cg._test_analyser.get_byte_time_domain_data(), cc._test_analyser.get_byte_time_domain_data()
+    assert np.abs(tg.astype(int) - tc.astype(int)).max() <= 1 and tg.std() > 1
 
 
 @pytest.mark.parametrize("n,src,dst", [(1, 44100, 48000), (5, 48000, 44100), (1000, 44100, 48000), (48000, 96000, 48000),

@@ -140,7 +140,7 @@ WAE_SYMBOLS = [
     "wae_listener_param_event_push", "wae_source_start", "wae_source_stop", "wae_oscillator_set_type",
     "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync",
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
-    "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_engine_set_hrir_sphere",
+    "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere",
 ]
 
 
@@ -189,6 +189,8 @@ class Api:
             f("analyser_get_float_time_domain_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, c_float_p, C.c_uint32])
             f("analyser_get_float_frequency_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, c_float_p, C.c_uint32])
             f("compressor_reduction", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, c_float_p])
+            f("analyser_get_byte_time_domain_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])
+            f("analyser_get_byte_frequency_data", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])
             f("engine_set_hrir_sphere", C.c_int32, [C.c_void_p, C.c_void_p, C.c_uint64])
             f("resample_linear", C.c_int32, [C.c_void_p, c_float_p, C.c_uint64, C.c_float, C.c_float, c_float_p, C.c_uint64, C.POINTER(C.c_uint64)])
         else:

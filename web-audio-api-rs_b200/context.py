@@ -238,6 +238,12 @@ class AnalyserNode(AudioNode):
     def get_float_frequency_data(self, n=None):
         return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2)
 
+    def get_byte_time_domain_data(self, n=None):
+        return self._ctx._analyser_read(self, "time", n or self.fft_size, byte=True)
+
+    def get_byte_frequency_data(self, n=None):
+        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2, byte=True)
+
 
 class AudioListener:
     def __init__(self, ctx):
@@ -414,17 +420,18 @@ class OfflineAudioContext:
         """OfflineAudioContext::start_rendering_sync (src/context/offline.rs:157-185): a batch of one."""
         return render_batch([self])[0]
 
-    def _analyser_read(self, node, kind, n):
-        out = np.zeros(n, np.float32)
+    def _analyser_read(self, node, kind, n, byte=False):
+        out = np.zeros(n, np.uint8 if byte else np.float32)
+        ptr = out.ctypes.data_as(C.POINTER(C.c_uint8)) if byte else B.fptr(out)
         api = self._api
+        name = "analyser_get_%s_%s_data" % ("byte" if byte else "float", "time_domain" if kind == "time" else "frequency")
+        fn = getattr(api, name)
         if api.is_product:
             if self._batch is None:
                 raise B.WaeError(2, "analyser data is available after rendering")
-            fn = api.analyser_get_float_time_domain_data if kind == "time" else api.analyser_get_float_frequency_data
-            api.check(fn(self._batch.handle, self._batch_index, node.id, B.fptr(out), n))
+            api.check(fn(self._batch.handle, self._batch_index, node.id, ptr, n))
         else:
-            fn = api.analyser_get_float_time_domain_data if kind == "time" else api.analyser_get_float_frequency_data
-            api.check(fn(self._g, node.id, B.fptr(out), n))
+            api.check(fn(self._g, node.id, ptr, n))
         return out
 
 

@@ -117,6 +117,7 @@ struct AnalyserRec {
     float* d_last_fft;  // last_fft_output (analysis.rs:168), zeroed per run
     float* d_db;        // read-out scratch
     bool computed;      // frequency data already computed for the end-of-render time (analysis.rs:353-361)
+    double min_db, max_db;
 };
 
 }  // namespace
@@ -1477,7 +1478,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     float* last = alloc<float>(16384, true, true);
                     float* db = alloc<float>(16384);
                     if (!last || !db) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser)");
-                    if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false});
+                    if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false, n.min_db, n.max_db});
                 }
                 algorithmic_bytes += (uint64_t)b->lq * 4;  // ring write, SURVEY §8(d)
                 break;
@@ -2139,6 +2140,38 @@ WAE_API wae_status wae_analyser_get_float_frequency_data(wae_batch* b, uint32_t 
     uint32_t n = std::min(len, bins);
     CUDA_TRY(cudaMemcpyAsync(out, a->d_db, n * sizeof(float), cudaMemcpyDeviceToHost, b->engine->stream));
     CUDA_TRY(cudaStreamSynchronize(b->engine->stream));
+    return WAE_OK;
+}
+
+// Analyser::get_byte_time_domain_data (src/analysis.rs:266-276): 128 (1 + x) clamped to a byte
+WAE_API wae_status wae_analyser_get_byte_time_domain_data(wae_batch* b, uint32_t graph_index, wae_node_id node, uint8_t* out, uint32_t len) {
+    std::vector<float> tmp(len, 0.f);
+    wae_status st = wae_analyser_get_float_time_domain_data(b, graph_index, node, tmp.data(), len);
+    if (st != WAE_OK) return st;
+    const AnalyserRec* a = find_analyser(b, graph_index, node);
+    const uint32_t n = std::min(len, a->fft_size);
+    for (uint32_t i = 0; i < n; i++) {
+        float scaled = 128.f * (1.f + tmp[i]);
+        scaled = scaled < 0.f ? 0.f : (scaled > 255.f ? 255.f : scaled);
+        out[i] = (uint8_t)scaled;
+    }
+    return WAE_OK;
+}
+
+// Analyser::get_byte_frequency_data (src/analysis.rs:371-401): dB scaled into [minDecibels, maxDecibels] -> 0..255
+WAE_API wae_status wae_analyser_get_byte_frequency_data(wae_batch* b, uint32_t graph_index, wae_node_id node, uint8_t* out, uint32_t len) {
+    const AnalyserRec* a = find_analyser(b, graph_index, node);
+    if (!a) return fail(WAE_INVALID_ARGUMENT, "not an analyser of this batch");
+    const uint32_t n = std::min(len, a->fft_size / 2);
+    std::vector<float> db(n, 0.f);
+    wae_status st = wae_analyser_get_float_frequency_data(b, graph_index, node, db.data(), n);
+    if (st != WAE_OK) return st;
+    const float mn = (float)a->min_db, mx = (float)a->max_db;
+    for (uint32_t i = 0; i < n; i++) {
+        float scaled = 255.f / (mx - mn) * (db[i] - mn);
+        scaled = !(scaled > 0.f) ? 0.f : (scaled > 255.f ? 255.f : scaled);  // -inf dB (silence) and NaN -> 0
+        out[i] = (uint8_t)scaled;
+    }
     return WAE_OK;
 }
 
