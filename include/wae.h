@@ -284,6 +284,11 @@ WAE_API wae_status wae_create_channel_splitter(wae_graph*, const wae_channel_spl
 /* AudioNode::connect_from_output_to_input (src/node/audio_node.rs:259-289); destination is node 0. */
 WAE_API wae_status wae_connect(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t input);
 /* AudioNode::connect(&param): audio-rate modulation of a param (src/param.rs:762-796). */
+/* OfflineAudioContext::suspend_sync(suspend_time, callback) (src/context/offline.rs:330-387): call this, then run the
+ * callback; graph mutations issued afterwards (new nodes, connections, param events, start / stop) take effect at the
+ * suspend frame (suspend_time quantised up to a render quantum).  Suspend points must be taken in increasing time order. */
+WAE_API wae_status wae_graph_suspend(wae_graph* graph, double suspend_time);
+
 /* `to` = 1 (WAE_LISTENER_NODE) addresses the AudioListener's params: 0..8 = position xyz, forward xyz, up xyz */
 WAE_API wae_status wae_connect_param(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index);
 /* AudioNode::disconnect() — removes all outgoing connections of `from`. */

@@ -55,6 +55,8 @@ struct wae_graph {  // the oracle's OfflineAudioContext
     std::vector<std::pair<uint32_t, std::shared_ptr<Analyser>>> analysers;
     bool rendered = false;
     uint64_t frames_played = 0;
+    std::vector<float> partial;           // [channels][length] PCM rendered before a suspend point
+    std::vector<uint64_t> suspend_quanta;  // OfflineAudioContext::suspend_sync points already taken
 
     // BaseAudioContext::create_audio_param, src/context/base.rs:320-337: the param is its own graph node
     uint32_t create_param(uint32_t owner, const ParamDescriptor& d, float initial, bool fixed_id = false, uint32_t id = 0, bool send_set_value = true) {
@@ -625,13 +627,11 @@ struct NoDenormals {  // crate no_denormals: FTZ + DAZ while rendering (src/rend
 
 // render_audiobuffer_sync + render_offline_quantum, src/render/thread.rs:260-302,355-396.
 // out: planar [channels][length]
-WAO_API wae_status wao_render(wae_graph* g, float* out) {
-    if (g->rendered) return fail(WAE_INVALID_STATE, "InvalidStateError - Cannot call `startRendering` twice");
-    g->rendered = true;
-    uint64_t length = g->length;
-    uint64_t num_quanta = (length + RQ - 1) / RQ;
-    uint64_t written = 0;
-    for (uint64_t q = 0; q < num_quanta; q++) {
+// render quanta until `until_frame` into dst ([channels][length] planar) — render_audiobuffer_sync's loop body
+// (src/render/thread.rs:260-302,355-396)
+static void render_until(wae_graph* g, float* dst, uint64_t until_frame) {
+    const uint64_t length = g->length;
+    while (g->frames_played < until_frame) {
         uint64_t current_frame = g->frames_played;
         g->frames_played += RQ;
         Scope scope{current_frame, (double)current_frame / (double)g->sample_rate, g->sample_rate};
@@ -640,16 +640,41 @@ WAO_API wae_status wao_render(wae_graph* g, float* out) {
             NoDenormals guard;
             rendered = &g->graph.render(scope);
         }
-        uint64_t remaining = std::min<uint64_t>(length - written, RQ);
+        uint64_t remaining = std::min<uint64_t>(length - current_frame, RQ);
         for (uint32_t c = 0; c < g->channels; c++) {
-            float* dst = out + (size_t)c * length + written;
+            float* d = dst + (size_t)c * length + current_frame;
             if ((int)c < rendered->number_of_channels())
-                std::memcpy(dst, rendered->channel((int)c).data(), remaining * sizeof(float));
+                std::memcpy(d, rendered->channel((int)c).data(), remaining * sizeof(float));
             else
-                std::memset(dst, 0, remaining * sizeof(float));
+                std::memset(d, 0, remaining * sizeof(float));
         }
-        written += remaining;
     }
+}
+
+// OfflineAudioContext::suspend_sync (src/context/offline.rs:330-387; render loop: src/render/thread.rs:271-290): rendering
+// pauses at the quantised frame, the caller then mutates the graph (that is the callback) and rendering resumes.  The oracle
+// is a live graph, so it simply renders up to the suspend point now.
+WAO_API wae_status wao_graph_suspend(wae_graph* g, double suspend_time) {
+    if (g->rendered) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend when rendering has already started");
+    if (!(suspend_time >= 0.)) return fail(WAE_INVALID_STATE, "InvalidStateError - suspendTime cannot be negative");
+    const uint64_t quantum = (uint64_t)std::ceil(suspend_time * (double)g->sample_rate / (double)RQ);  // offline.rs:248-251
+    const uint64_t total = (g->length + RQ - 1) / RQ;
+    if (quantum * RQ <= g->frames_played && !(quantum == 0 && g->frames_played == 0))
+        return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend at a time that is not after the current time");
+    if (quantum >= total) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend after the end of the rendering");
+    for (uint64_t q : g->suspend_quanta)
+        if (q == quantum) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend multiple times at the same render quantum");
+    g->suspend_quanta.push_back(quantum);
+    if (g->partial.empty()) g->partial.assign((size_t)g->channels * g->length, 0.f);
+    render_until(g, g->partial.data(), quantum * RQ);
+    return WAE_OK;
+}
+
+WAO_API wae_status wao_render(wae_graph* g, float* out) {
+    if (g->rendered) return fail(WAE_INVALID_STATE, "InvalidStateError - Cannot call `startRendering` twice");
+    g->rendered = true;
+    if (!g->partial.empty()) std::memcpy(out, g->partial.data(), g->partial.size() * sizeof(float));
+    render_until(g, out, (g->length + RQ - 1) / RQ * RQ);
     return WAE_OK;
 }
 

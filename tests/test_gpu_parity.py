@@ -685,6 +685,68 @@ def test_convolver_upstream_of_feedback_is_reported(pkg, engine):
     assert e.value.status == 4 and "feedback" in str(e.value)
 
 
+# ---- OfflineAudioContext::suspend_sync: graph mutation at render time -----------------------------------------
+def test_suspend_sync_reference_case(pkg, engine):
+    import test_oracle_offline as O
+    O.test_suspend_sync(pkg, engine.backend)          # src/context/offline.rs:469-511 on the CUDA path
+    O.test_suspend_argument_errors(pkg, engine.backend)
+
+
+@pytest.mark.parametrize("chunk", [0, 256])
+def test_suspend_sync_mutations_keep_node_state(pkg, engine, oracle, chunk):
+    """Nodes that live across a suspend point keep their state (filter memory, delay line, oscillator phase, automation);
+    nodes, connections, param events and sources added or removed in the callbacks take effect at the suspend frame."""
+    n = 128 * 40
+
+    def build(be, g):
+        pcm = G.c2_source(g, n)
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        bq = c.create_biquad_filter(type_=pkg.BANDPASS, frequency=900.0, q=12.0)
+        dl = c.create_delay(max_delay_time=0.05, delay_time=0.013)
+        gn = c.create_gain(0.8)
+        gn.gain.linear_ramp_to_value_at_time(0.2, 0.09)
+        osc = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=333.0)
+        og = c.create_gain(0.1)
+        src.connect(bq)
+        bq.connect(dl)
+        dl.connect(gn)
+        gn.connect(c.destination())
+        osc.connect(og)
+        og.connect(c.destination())
+        src.start()
+        osc.start()
+
+        def first(ctx):   # new branch: a second filter in parallel, an automation event on a running ramp, a new source
+            hp = ctx.create_biquad_filter(type_=pkg.HIGHPASS, frequency=2500.0)
+            bq.connect(hp)
+            hp.connect(ctx.destination())
+            gn.gain.set_value_at_time(0.9, ctx.current_time() + 0.004)
+            k = ctx.create_constant_source(offset=0.05)
+            k.connect(ctx.destination())
+            k.start_at(ctx.current_time())
+            k.stop_at(ctx.current_time() + 0.01)
+
+        def second(ctx):  # remove the oscillator branch, re-route the delay
+            og.disconnect()
+            dl.disconnect()
+            dl.connect(ctx.destination())
+
+        if g == 0:
+            c.suspend_sync(128 * 7 / G.SR, first)
+            c.suspend_sync(128 * 19 / G.SR + 1e-4, second)   # quantised up: frame 128 * 20
+        elif g == 1:
+            c.suspend_sync(128 * 11 / G.SR, second)
+        return c                                             # g == 2: no suspend point, same batch
+
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        gpu, cpu = both(pkg, engine, oracle, build, 3)
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
 # ---- AudioBufferSource slow track (SURVEY §8 a17 / f2) ---------------------------------------------------------------
 SLOW_CASES = {
     "rate_half": dict(playback_rate=0.5),

@@ -1,6 +1,7 @@
 """Pins the oracle's graph / mixer / scheduling semantics against the reference's integration tests
 (/root/reference/tests/offline.rs).  Each test restates one reference `#[test]` (name + line cited)."""
 import numpy as np
+import pytest
 
 RQ = 128
 
@@ -131,3 +132,34 @@ def test_render_order_matches_reference(pkg, oracle):
     n = oracle.api.render_order(c._g, ids, 64)
     order = list(ids[:n])
     assert order == [16, 15, 14, 13, 12, 11, 0]
+
+
+def test_suspend_sync(pkg, oracle):
+    # src/context/offline.rs:469-511 test_suspend_sync: a source created and started inside the first callback, disconnected
+    # inside the second one
+    sr = 48000.0
+    c = ctx(pkg, oracle, 1, RQ * 4, sr)
+    box = {}
+
+    def first(context):
+        src = context.create_constant_source()
+        src.connect(context.destination())
+        src.start_at(context.current_time())
+        box["src"] = src
+
+    c.suspend_sync(RQ / sr, first)
+    c.suspend_sync(3 * RQ / sr, lambda context: box["src"].disconnect())
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out[:RQ], np.zeros(RQ, np.float32))
+    assert np.array_equal(out[RQ:3 * RQ], np.ones(2 * RQ, np.float32))
+    assert np.array_equal(out[3 * RQ:], np.zeros(RQ, np.float32))
+
+
+def test_suspend_argument_errors(pkg, oracle):
+    # src/context/offline.rs:547-575: negative time, after the duration, twice at the same quantum
+    for times in ([-1.0], [1.0], [0.0, 0.0]):
+        c = ctx(pkg, oracle, 2, RQ, 44100.0)
+        for t in times:
+            c.suspend_sync(t, lambda context: None)
+        with pytest.raises(pkg.WaeError):
+            c.start_rendering_sync()

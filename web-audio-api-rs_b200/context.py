@@ -272,6 +272,8 @@ class OfflineAudioContext:
         self._batch = None
         self._batch_index = 0
         self._listener = None
+        self._suspends = []
+        self._current_time = 0.0
 
     def __del__(self):
         try:
@@ -415,6 +417,24 @@ class OfflineAudioContext:
     def create_channel_splitter(self, number_of_outputs=6):
         return AudioNode(self, self._create("create_channel_splitter", B.ChannelSplitterOptions(number_of_outputs)), 1, number_of_outputs)
 
+    def current_time(self):
+        """BaseAudioContext::current_time: 0 before rendering, the suspend time inside a suspend_sync callback."""
+        return self._current_time
+
+    def suspend_sync(self, suspend_time, callback):
+        """OfflineAudioContext::suspend_sync (src/context/offline.rs:330-387): `callback(context)` runs when the render reaches
+        suspend_time (quantised up to a render quantum) and may mutate the graph."""
+        self._suspends.append((float(suspend_time), callback))
+
+    def _run_suspend_callbacks(self):
+        """The control half of the render loop (src/render/thread.rs:271-290): take the suspend points in time order."""
+        todo, self._suspends = sorted(self._suspends, key=lambda sc: sc[0]), []
+        for t, cb in todo:
+            self._api.check(self._api.graph_suspend(self._g, t))
+            self._current_time = math.ceil(t * self._sample_rate / 128.0) * 128.0 / self._sample_rate
+            cb(self)
+        self._current_time = 0.0
+
     # ---- rendering
     def start_rendering_sync(self):
         """OfflineAudioContext::start_rendering_sync (src/context/offline.rs:157-185): a batch of one."""
@@ -444,6 +464,8 @@ class Batch:
         self.contexts = contexts
         self.n = len(contexts)
         self.channels, self.length = ctx0._channels, ctx0._length
+        for c in contexts:
+            c._run_suspend_callbacks()
         arr = (C.c_void_p * self.n)(*[c._g for c in contexts])
         h = C.c_void_p()
         self.api.check(self.api.batch_prepare(ctx0._backend.engine, arr, self.n, C.byref(h)))
@@ -517,6 +539,8 @@ def render_batch(contexts, threads=1):
     ctx0 = contexts[0]
     api = ctx0._api
     n, ch, length = len(contexts), ctx0._channels, ctx0._length
+    for c in contexts:
+        c._run_suspend_callbacks()
     out = np.empty((n, ch, length), np.float32)
     arr = (C.c_void_p * n)(*[c._g for c in contexts])
     if api.is_product:

@@ -432,6 +432,23 @@ WAE_API wae_status wae_connect_param(wae_graph* g, wae_node_id from, uint32_t ou
     return WAE_OK;
 }
 
+// OfflineAudioContext::suspend_sync (src/context/offline.rs:330-387).  The binding runs the user's callback right after this
+// call: every graph mutation issued from here on takes effect at the quantised suspend frame.
+WAE_API wae_status wae_graph_suspend(wae_graph* g, double suspend_time) {
+    if (!g) return fail(WAE_INVALID_ARGUMENT, "null graph");
+    if (!(suspend_time >= 0.)) return fail(WAE_INVALID_STATE, "InvalidStateError - suspendTime cannot be negative");
+    const uint64_t quantum = (uint64_t)std::ceil(suspend_time * (double)g->sample_rate / 128.);  // offline.rs:248-251
+    const uint64_t total = (g->length + 127) / 128;
+    const uint64_t last = g->epochs.empty() ? 0 : g->epochs.back().frame / 128;
+    if (!g->epochs.empty() && quantum == last)
+        return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend multiple times at the same render quantum");
+    if (!g->epochs.empty() && quantum < last)
+        return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend at a time that is not after the current time");
+    if (quantum >= total) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot suspend after the end of the rendering");
+    g->epochs.push_back(wae_graph::Epoch{quantum * 128, g->nodes});
+    return WAE_OK;
+}
+
 WAE_API wae_status wae_disconnect(wae_graph* g, wae_node_id from) {
     auto fi = g->nodes.find(from);
     if (fi == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");

@@ -88,6 +88,7 @@ struct AbsnSlowInst {
 struct AbsnSerialState {
     double start_time, offset, buffer_time, buffer_time_elapsed;
     int32_t started, entered_loop, ended, is_aligned;
+    int32_t inited, pad;  // 0 after the per-run memset
 };
 struct AbsnSerialInst {
     BufRef out;
@@ -299,6 +300,8 @@ struct ParamState {  // render-side state of one param, carried across chunks
     int32_t head;        // events [0, head) have been popped
     int32_t has_last;
     int32_t override_valid;  // replace_peek(): the event at `head` is `override_ev`
+    int32_t inited;          // 0 after the per-run memset: the first quantum this param is rendered initialises the state
+    int32_t pad;
     ParamEvDev last;
     ParamEvDev override_ev;
 };
@@ -312,7 +315,8 @@ struct ParamInst {
     float sample_rate;
     int32_t n_events;
     int32_t a_rate;
-    int32_t pad;
+    int32_t has_last0;  // render-side `last_event` the state starts with (params whose events were extended at a suspend point)
+    ParamEvDev last0;
 };
 
 // ---- fused chain: source -> {biquad | gain | shaper}* -> buffer or destination, one pass over the PCM -------

@@ -10,6 +10,7 @@
 #include "wae_hrtf_host.h"
 #include "wae_resample_host.h"
 #include "wae_kernels.h"
+#include "wae_param_core.h"
 #include "wae_param_host.h"
 
 #include <cuda_runtime.h>
@@ -22,6 +23,7 @@
 #include <limits>
 #include <map>
 #include <set>
+#include <tuple>
 #include <unordered_map>
 
 using namespace wae;
@@ -96,7 +98,8 @@ struct StageBuild {
 };
 
 struct Stage {
-    int cls = 0;  // see Planner::stage_class
+    int cls = 0;  // see Planner::stage()
+    int seg = 0;  // render segment (between two suspend points) this stage belongs to
     int kind = 0;
     int variant = 0;
     int group = 0;
@@ -142,13 +145,23 @@ struct wae_batch {
     // streams (wae_batch_run_pipelined).  All groups share the arena-sizing chunk.
     struct Group {
         uint32_t g0 = 0, g1 = 0;        // graphs [g0, g1)
-        size_t stage0 = 0, stage1 = 0;  // stages [stage0, stage1) of `stages`
+        size_t stage0 = 0, stage1 = 0;  // stages [stage0, stage1) of `stages` (all segments)
+        std::vector<std::pair<size_t, size_t>> seg_stages;  // per render segment: its stages
         float* d_src = nullptr;         // device slab of source PCM
         float* h_src = nullptr;         // pinned host mirror
         size_t src_floats = 0;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     };
     std::vector<Group> groups;
+    // OfflineAudioContext::suspend_sync: the render is cut at the suspend frames of all graphs; every segment has its own
+    // plan, node state is shared between the plans through `state_map` (graph, node, allocation sequence, salt)
+    std::vector<int64_t> seg_bounds;  // 0 = b0 < b1 < ... < lq
+    struct StateKey {
+        uint32_t graph, node, seq;
+        uint64_t salt;
+        bool operator<(const StateKey& o) const { return std::tie(graph, node, seq, salt) < std::tie(o.graph, o.node, o.seq, o.salt); }
+    };
+    std::map<StateKey, std::pair<void*, size_t>> state_map;
     std::vector<void*> pinned;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     struct Timed {
@@ -309,10 +322,78 @@ struct Planner {
         int cls = 0;    // scheduling class of the node that opened the chain (see stage())
     };
 
+    // Node state is allocated through a key (graph, node, n-th allocation of that node, salt): the plans of consecutive
+    // render segments (suspend_sync) find the state of a node that lives on, new nodes get fresh (zeroed) state.
+    uint32_t key_graph = 0, key_node = 0, key_seq = 0;
+    uint64_t key_salt = 0;
     template <typename T>
     T* alloc(size_t count, bool zero = false, bool rezero_on_run = false) {
         if (dry) return reinterpret_cast<T*>(uintptr_t(256));
-        return b->dalloc<T>(count, zero, rezero_on_run);
+        const wae_batch::StateKey key{key_graph, key_node, key_seq++, key_salt};
+        const size_t bytes = count * sizeof(T);
+        auto it = b->state_map.find(key);
+        if (it != b->state_map.end() && it->second.second == bytes) return (T*)it->second.first;
+        T* p = b->dalloc<T>(count, zero, rezero_on_run);
+        if (p) b->state_map[key] = {(void*)p, bytes};
+        return p;
+    }
+    // arena buffers are chunk-local scratch: every segment's plan draws from the same pool
+    std::map<int, std::vector<float*>> arena_pool;
+    std::map<int, size_t> arena_used;
+    std::map<std::pair<uint32_t, uint32_t>, size_t> src_offsets;  // (graph, buffer source node) -> offset in the group's PCM slab
+    // render-side view of every AudioParam: the event queue it (re)started with at `init_frame`.  When a suspend callback
+    // pushed more events, the state machine is replayed on the host up to the suspend frame and the new events are folded
+    // into what is left of the queue — handle_incoming_event against the live state, like the reference's render thread.
+    struct ParamRecord {
+        size_t n_source_events = 0;  // arrival-order events of the Param already folded in
+        ParamTimeline tl;
+        int64_t init_frame = 0;
+    };
+    std::map<std::pair<uint32_t, uint32_t>, ParamRecord> param_records;
+    const ParamTimeline* param_timeline(uint32_t gi, uint32_t pid, const Param& prm, float sample_rate) {
+        auto it = param_records.find({gi, pid});
+        if (it == param_records.end()) {
+            ParamRecord r;
+            r.tl = build_param_timeline(prm);
+            r.n_source_events = prm.events.size();
+            r.init_frame = seg_start;
+            return &param_records.emplace(std::make_pair(gi, pid), std::move(r)).first->second.tl;
+        }
+        ParamRecord& r = it->second;
+        if (r.n_source_events == prm.events.size() || !r.tl.error.empty()) return &r.tl;
+        // replay compute_buffer from the record's start to this segment's start
+        ParamInst host{};
+        host.events = r.tl.events.data();
+        host.curves = r.tl.curves.data();
+        host.n_events = (int32_t)r.tl.events.size();
+        host.a_rate = prm.a_rate ? 1 : 0;
+        host.sample_rate = sample_rate;
+        ParamState st{};
+        st.intrinsic = r.tl.intrinsic;
+        st.has_last = r.tl.has_last ? 1 : 0;
+        st.last = r.tl.last;
+        st.inited = 1;
+        float buf[128];
+        for (int64_t f = r.init_frame; f < seg_start; f += 128) param_compute_buffer(host, st, (double)f / (double)sample_rate, buf);
+        ParamTimeline next;
+        next.curves = r.tl.curves;
+        for (int i = st.head; i < host.n_events; i++) next.events.push_back(i == st.head && st.override_valid ? st.override_ev : r.tl.events[i]);
+        next.intrinsic = st.intrinsic;
+        next.has_last = st.has_last != 0;
+        next.last = st.last;
+        fold_param_events(next, prm.events.data() + r.n_source_events, prm.events.size() - r.n_source_events);
+        r.tl = std::move(next);
+        r.n_source_events = prm.events.size();
+        r.init_frame = seg_start;
+        return &r.tl;
+    }
+    int64_t seg_start = 0, seg_end = 0;
+    void begin_segment(int64_t f0, int64_t f1) {
+        seg_start = f0;
+        seg_end = f1;
+        builds.clear();
+        arena_used.clear();
+        arena_floats_per_frame = 0;
     }
     template <typename T>
     T* upload(const std::vector<T>& v) {
@@ -346,9 +427,16 @@ struct Planner {
     BufRef arena_buf(int ch) {
         arena_floats_per_frame += (uint64_t)ch;
         if (dry) return BufRef{reinterpret_cast<float*>(uintptr_t(256)), (uint32_t)b->chunk, 0};
+        std::vector<float*>& pool = arena_pool[ch];
+        size_t& used = arena_used[ch];
+        if (used < pool.size()) return BufRef{pool[used++], (uint32_t)b->chunk, 0};
         size_t floats = (size_t)ch * (size_t)b->chunk;
         float* p = b->dalloc<float>(floats);
         b->arena_bytes += floats * 4;
+        if (p) {
+            pool.push_back(p);
+            used++;
+        }
         return BufRef{p, (uint32_t)b->chunk, 0};
     }
 
@@ -654,17 +742,22 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         if (n.kind == K_LISTENER) continue;
         PNode& p = pn.at(id);
         cur_cls = node_class(id);
+        key_graph = gi;
+        key_node = id;
+        key_seq = 0;
+        key_salt = n.kind == K_PARAM ? (uint64_t)n.param.events.size() : 0;  // a param whose event list grew restarts its timeline
         if (n.kind == K_PARAM) {
             // AudioParamProcessor (param.rs:685-797): only params with automation events or audio-rate inputs become
             // GPU work; a constant param is a scalar in its owner's instance
             auto& edges = p.in_edges[0];
+            const ParamTimeline* tlp = param_timeline(gi, id, n.param, g->sample_rate);
             if (n.param.constant() && edges.empty()) continue;
             int level = 0;
             for (auto& r : edges) level = std::max(level, pn.at(r.node).level + 1);
             p.level = level;
             for (auto& r : edges)
                 if (!materialize(r.node)) return false;
-            ParamTimeline tl = build_param_timeline(n.param);
+            const ParamTimeline& tl = *tlp;
             if (!tl.error.empty()) return bail(WAE_NOT_SUPPORTED, tl.error);
             ParamInst pi{};
             if (!edges.empty()) {  // sum of the connected signals, first channel each (1 / explicit / discrete, param.rs:296-310)
@@ -690,6 +783,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             pi.mn = n.param.min_value;
             pi.mx = n.param.max_value;
             pi.intrinsic0 = tl.intrinsic;
+            pi.has_last0 = tl.has_last ? 1 : 0;
+            pi.last0 = tl.last;
             pi.sample_rate = g->sample_rate;
             pi.n_events = (int32_t)tl.events.size();
             pi.a_rate = n.param.a_rate ? 1 : 0;
@@ -966,15 +1061,21 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (!fuse_src && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
                 size_t stride = (len + 3) / 4 * 4;  // every channel starts 16 B aligned (LDG.128)
-                float* d_buf = d_src + src_cursor;
-                if (!dry)
-                    for (int c = 0; c < ch; c++) {
-                        float* dst = h_src + src_cursor + (size_t)c * stride;
-                        std::memcpy(dst, pb.channels[c].data(), len * sizeof(float));
-                        for (size_t i = len; i < stride; i++) dst[i] = 0.f;
-                    }
-                src_cursor += (size_t)ch * stride;
-                b->asset_bytes += (size_t)ch * len * 4;
+                // one copy of the PCM per (graph, node) in the group's slab, shared by the plans of all render segments
+                auto so = src_offsets.find({gi, id});
+                const bool first_use = so == src_offsets.end();
+                if (first_use) so = src_offsets.emplace(std::make_pair(gi, id), src_cursor).first;
+                float* d_buf = d_src + so->second;
+                if (first_use) {
+                    if (!dry)
+                        for (int c = 0; c < ch; c++) {
+                            float* dst = h_src + src_cursor + (size_t)c * stride;
+                            std::memcpy(dst, pb.channels[c].data(), len * sizeof(float));
+                            for (size_t i = len; i < stride; i++) dst[i] = 0.f;
+                        }
+                    src_cursor += (size_t)ch * stride;
+                    b->asset_bytes += (size_t)ch * len * 4;
+                }
                 if (serial) {
                     AbsnSerialInst a{};
                     a.out = p.out_buf[0];
@@ -1461,7 +1562,11 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 for (int i = 0; i < 5; i++) c.track[i] = cp[i].dyn ? cp[i].track : BufRef{nullptr, 0, 0};
                 c.sample_rate = g->sample_rate;
                 stage(L, S_COMP).comp.push_back(c);
-                if (!dry) b->compressors.push_back(wae_batch::CompRec{gi, id, c.state});
+                if (!dry) {
+                    bool known = false;
+                    for (auto& r : b->compressors) known = known || (r.graph == gi && r.node == id);
+                    if (!known) b->compressors.push_back(wae_batch::CompRec{gi, id, c.state});
+                }
                 break;
             }
             case K_ANALYSER: {
@@ -1478,7 +1583,11 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     float* last = alloc<float>(16384, true, true);
                     float* db = alloc<float>(16384);
                     if (!last || !db) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser)");
-                    if (!dry) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false, n.min_db, n.max_db});
+                    if (!dry) {
+                        bool known = false;
+                        for (auto& r : b->analysers) known = known || (r.graph_index == gi && r.node == id);
+                        if (!known) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false, n.min_db, n.max_db});
+                    }
                 }
                 algorithmic_bytes += (uint64_t)b->lq * 4;  // ring write, SURVEY §8(d)
                 break;
@@ -1522,6 +1631,22 @@ template <typename T>
 static void* up(wae_batch* b, const std::vector<T>& v) {
     return (void*)b->dupload(v);
 }
+
+// While alive, `g->nodes` is the graph description that is valid at `frame` (the snapshot taken at the first suspend point
+// after it, or the live graph when none follows): the planner reads g->nodes without knowing about suspend points.
+struct EpochView {
+    wae_graph* g;
+    size_t e;
+    EpochView(wae_graph* g_, int64_t frame) : g(g_), e(0) {
+        while (e < g->epochs.size() && (int64_t)g->epochs[e].frame <= frame) e++;
+        if (e < g->epochs.size()) std::swap(g->nodes, g->epochs[e].nodes);
+    }
+    ~EpochView() {
+        if (e < g->epochs.size()) std::swap(g->nodes, g->epochs[e].nodes);
+    }
+    EpochView(const EpochView&) = delete;
+    EpochView& operator=(const EpochView&) = delete;
+};
 
 }  // namespace
 
@@ -1663,9 +1788,25 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     b->length = graphs[0]->length;
     b->lq = (int64_t)((b->length + 127) / 128 * 128);
     bool has_conv = false;
-    for (uint32_t i = 0; i < n_graphs; i++)
+    std::set<int64_t> cuts{0, b->lq};
+    for (uint32_t i = 0; i < n_graphs; i++) {
         for (auto& kv : graphs[i]->nodes)
             if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
+        for (auto& ep : graphs[i]->epochs) {
+            if ((int64_t)ep.frame > 0 && (int64_t)ep.frame < b->lq) cuts.insert((int64_t)ep.frame);
+            for (auto& kv : ep.nodes)
+                if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
+        }
+    }
+    b->seg_bounds.assign(cuts.begin(), cuts.end());
+    const int n_seg = (int)b->seg_bounds.size() - 1;
+    if (has_conv)
+        for (int64_t f : b->seg_bounds)
+            if (f != b->lq && f % WAE_CONV_BLOCK != 0)
+                return [&]() {
+                    wae_batch_destroy(b);
+                    return fail(WAE_UNSUPPORTED, "a suspend point that is not a multiple of the convolver partition (8192 frames) in a batch with ConvolverNodes is not lowered to the GPU");
+                }();
     size_t out_floats = (size_t)n_graphs * b->channels * b->length;
     b->d_out = b->dalloc<float>(out_floats, true);
     if (!b->d_out) {
@@ -1698,15 +1839,19 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             sizing.dry = true;
             sizing.delay_ch_hint = &delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
-            for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
-                if (!sizing.plan_graph(graphs[i], i)) {
-                    int code = sizing.error_code;
-                    std::string msg = sizing.error;
-                    wae_batch_destroy(b);
-                    return fail(code, msg);
+            for (int sg = 0; sg < n_seg; sg++) {
+                sizing.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
+                for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
+                    EpochView view(graphs[i], b->seg_bounds[sg]);
+                    if (!sizing.plan_graph(graphs[i], i)) {
+                        int code = sizing.error_code;
+                        std::string msg = sizing.error;
+                        wae_batch_destroy(b);
+                        return fail(code, msg);
+                    }
                 }
+                fpf = std::max(fpf, sizing.arena_floats_per_frame);
             }
-            fpf = std::max(fpf, sizing.arena_floats_per_frame);
             b->groups[k].src_floats = sizing.src_cursor;
             has_feedback = has_feedback || sizing.has_feedback;
             for (auto& kv : sizing.delay_ch_seen) {
@@ -1763,7 +1908,12 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         pl.h_src = grp.h_src;
         pl.delay_ch_hint = &delay_ch_hint;
         pl.ir_cache.swap(ir_cache);
+        grp.stage0 = b->stages.size();
+        for (int sg = 0; sg < n_seg; sg++) {
+        pl.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
+        const uint64_t alg_before = pl.algorithmic_bytes;
         for (uint32_t i = grp.g0; i < grp.g1; i++) {
+            EpochView view(graphs[i], b->seg_bounds[sg]);
             if (!pl.plan_graph(graphs[i], i)) {
                 int code = pl.error_code;
                 std::string msg = pl.error;
@@ -1771,14 +1921,15 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                 return fail(code, msg);
             }
         }
-        ir_cache.swap(pl.ir_cache);
-        algorithmic_bytes += pl.algorithmic_bytes;
-        // materialise the group's stages in (level, kind) order
-        grp.stage0 = b->stages.size();
+        // the per-node byte counts assume the whole render: scale to this segment's share of it
+        algorithmic_bytes += (uint64_t)((double)(pl.algorithmic_bytes - alg_before) * (double)(pl.seg_end - pl.seg_start) / (double)b->lq);
+        // materialise the segment's stages in (class, level, kind) order
+        const size_t seg_stage0 = b->stages.size();
         void* last_conv_inputs = nullptr;
         for (auto& kv : pl.builds) {
             StageBuild& s = kv.second;
             Stage st;
+            st.seg = sg;
             st.cls = s.cls;
             st.kind = s.kind;
             st.variant = s.variant;
@@ -1837,6 +1988,9 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             }
             if (st.n > 0) b->stages.push_back(st);
         }
+        grp.seg_stages.push_back({seg_stage0, b->stages.size()});
+        }  // segments
+        ir_cache.swap(pl.ir_cache);
         grp.stage1 = b->stages.size();
         // first upload of the group's source PCM
         if (grp.src_floats)
@@ -1850,13 +2004,15 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         wae_batch_destroy(b);
         return fail(WAE_CUDA_ERROR, std::string("prepare: ") + cudaGetErrorString(le));
     }
-    int64_t n_chunks = (b->lq + b->chunk - 1) / b->chunk;
+    int64_t n_chunks = 0;
+    for (size_t sg = 0; sg + 1 < b->seg_bounds.size(); sg++) n_chunks += (b->seg_bounds[sg + 1] - b->seg_bounds[sg] + b->chunk - 1) / b->chunk;
     uint64_t launches = 0;
     for (auto& st : b->stages) {
         const uint64_t k = (st.kind == S_CONV_FFT || st.kind == S_CONV_MAC || st.kind == S_CONV_MAC_ACC || st.kind == S_SHAPER_OS) ? 2
                            : st.kind == S_HRTF ? (st.n_b > 0 ? 3 : 2) : 1;
-        // per-quantum stages (class 1) launch once per render quantum, the others once per chunk
-        launches += st.cls == 1 ? k * (uint64_t)(b->lq / 128) : k * (uint64_t)n_chunks;
+        // per-quantum stages (class 1) launch once per render quantum of their segment, the others once per chunk of it
+        const int64_t seg_len = b->seg_bounds[st.seg + 1] - b->seg_bounds[st.seg];
+        launches += st.cls == 1 ? k * (uint64_t)(seg_len / 128) : k * (uint64_t)((seg_len + b->chunk - 1) / b->chunk);
     }
     std::memset(&b->stats, 0, sizeof(b->stats));
     b->stats.kernel_launches_per_run = launches;
@@ -1944,28 +2100,32 @@ static wae_status run_group(wae_batch* b, const wae_batch::Group& g) {
         }
         return true;
     };
-    // stages are sorted by class: [whole-chunk stages of feedback-free graphs | per-quantum stages | whole-chunk stages after cycles]
-    size_t c1 = g.stage0, c2 = g.stage0;
-    while (c1 < g.stage1 && b->stages[c1].cls == 0) c1++;
-    c2 = c1;
-    while (c2 < g.stage1 && b->stages[c2].cls == 1) c2++;
-    for (int64_t f0 = 0; f0 < b->lq; f0 += b->chunk) {
-        const ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, b->lq - f0), 0};
-        if (b->time_stages) {
-            e_prev = next_event();
-            if (e_prev == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
-            CUDA_TRY(cudaEventRecord(b->stage_events[e_prev], s));
-        }
-        for (size_t i = g.stage0; i < c1; i++)
-            if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
-        if (c2 > c1)
-            for (int32_t sub = 0; sub < ci.nf; sub += 128) {  // the reference's render loop, for the cyclic part only
-                const ChunkInfo cq{f0 + sub, 128, sub};
-                for (size_t i = c1; i < c2; i++)
-                    if (!run(i, cq)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+    for (size_t sg = 0; sg + 1 < b->seg_bounds.size(); sg++) {  // render segments between suspend points (usually one)
+        const size_t s0 = g.seg_stages[sg].first, s1 = g.seg_stages[sg].second;
+        // stages are sorted by class: [whole-chunk stages of feedback-free graphs | per-quantum stages | whole-chunk stages after cycles]
+        size_t c1 = s0, c2 = s0;
+        while (c1 < s1 && b->stages[c1].cls == 0) c1++;
+        c2 = c1;
+        while (c2 < s1 && b->stages[c2].cls == 1) c2++;
+        const int64_t seg_end = b->seg_bounds[sg + 1];
+        for (int64_t f0 = b->seg_bounds[sg]; f0 < seg_end; f0 += b->chunk) {
+            const ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, seg_end - f0), 0};
+            if (b->time_stages) {
+                e_prev = next_event();
+                if (e_prev == (size_t)-1) return fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+                CUDA_TRY(cudaEventRecord(b->stage_events[e_prev], s));
             }
-        for (size_t i = c2; i < g.stage1; i++)
-            if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+            for (size_t i = s0; i < c1; i++)
+                if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+            if (c2 > c1)
+                for (int32_t sub = 0; sub < ci.nf; sub += 128) {  // the reference's render loop, for the cyclic part only
+                    const ChunkInfo cq{f0 + sub, 128, sub};
+                    for (size_t i = c1; i < c2; i++)
+                        if (!run(i, cq)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+                }
+            for (size_t i = c2; i < s1; i++)
+                if (!run(i, ci)) return fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+        }
     }
     return WAE_OK;
 }

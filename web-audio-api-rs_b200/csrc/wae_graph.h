@@ -100,6 +100,13 @@ struct wae_graph {
     std::map<uint32_t, wae::Node> nodes;
     std::vector<std::pair<uint32_t, uint32_t>> pending_param_edges;
     bool listener_present = false;
+    // OfflineAudioContext::suspend_sync (src/context/offline.rs:330-387): `epochs[k]` is the graph as it was before the k-th
+    // suspend point, valid for the frames before `frame`; the live `nodes` describe the frames after the last suspend point
+    struct Epoch {
+        uint64_t frame;
+        std::map<uint32_t, wae::Node> nodes;
+    };
+    std::vector<Epoch> epochs;
 
     uint32_t create_param(uint32_t owner, float def, float mn, float mx, bool a_rate, float initial, bool send_set_value = true,
                           bool fixed_id = false, uint32_t id = 0, bool constrained = false);

@@ -5,6 +5,7 @@
 // oscillator phase), grids sized over (time tiles x node instances).  Each kernel cites the reference
 // renderer whose arithmetic it reproduces; parity target is 1e-5 absolute on f32 PCM.
 #include "wae_kernels.h"
+#include "wae_param_core.h"
 #include "../../include/wae.h"
 
 #include <cuda_runtime.h>
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(32 * ABSN_SERIAL_WARPS) k_buffer_source_serial
     AbsnSerialState st;
     if (lane == 0) {
         st = *o.state;
-        if (ci.f0 == 0) st = AbsnSerialState{o.start_time, o.offset, 0., 0., 0, 0, 0, 0};
+        if (!st.inited) st = AbsnSerialState{o.start_time, o.offset, 0., 0., 0, 0, 0, 0, 1, 0};  // first quantum of this source in this run
     }
     const double sample_rate = o.sample_rate, dt = 1. / sample_rate, block_duration = dt * 128.;
     const double buffer_duration = o.buffer_duration;
@@ -1002,7 +1003,7 @@ __global__ void __launch_bounds__(256) k_osc_arate(const OscArInst* __restrict__
     const float* dtk = q.detune.p ? chan(q.detune, 0, ci) : nullptr;
     const int t = threadIdx.x;
     const double sr = (double)q.sample_rate, nyq = sr / 2.;
-    if (t == 0) s_carry = ci.f0 == 0 ? 0. : *q.phase;
+    if (t == 0) s_carry = *q.phase;  // zeroed before every run
     __syncthreads();
     for (int base = 0; base < ci.nf; base += 2048) {
         const int n0 = base + t * 8;
@@ -1750,258 +1751,26 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
 // clamps to [min, max].  The output is the param's value for EVERY frame (k-rate and constant blocks are
 // replicated), which is what the a-rate consumers read.
 // ---------------------------------------------------------------------------------------------------------
-struct ParamCursor {
-    const ParamInst& p;
-    ParamState& s;
-    DEVI bool empty() const { return s.head >= p.n_events; }
-    DEVI ParamEvDev peek() const { return s.override_valid ? s.override_ev : p.events[s.head]; }
-    DEVI bool has_next() const { return s.head + 1 < p.n_events; }
-    DEVI ParamEvDev next() const { return p.events[s.head + 1]; }
-    DEVI ParamEvDev pop() {
-        ParamEvDev e = peek();
-        s.head++;
-        s.override_valid = 0;
-        return e;
-    }
-    DEVI void replace_peek(const ParamEvDev& e) {
-        s.override_ev = e;
-        s.override_valid = 1;
-    }
-};
-
-DEVI float par_linear(double t0, double dur, float v0, float diff, double t) { return fmaf(diff, (float)((t - t0) / dur), v0); }
-DEVI float par_exp(double t0, double dur, float v0, float ratio, double t) { return v0 * powf(ratio, (float)((t - t0) / dur)); }
-DEVI float par_target(double t0, double tau, float v1, float diff, double t) { return fmaf(diff, (float)exp(-((t - t0) / tau)), v1); }
-DEVI float par_curve(double t0, double dur, const float* values, int n, double t) {
-    if (t - t0 >= dur) return values[n - 1];
-    double position = (double)(n - 1) * (t - t0) / dur;
-    int k = (int)position;
-    float phase = (float)(position - floor(position));
-    return fmaf(values[k + 1] - values[k], phase, values[k]);
-}
-DEVI int par_end_index(double end_time, double block_time, double dt, int count) {
-    double r = round(fmax(end_time - block_time, 0.) / dt);
-    if (!(r < 4.0e9)) return count;
-    int idx = (int)r;
-    return idx < count ? idx : count;
-}
-
 __global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
     const int ii = blockIdx.x * blockDim.x + threadIdx.x;
     if (ii >= n_inst) return;
     const ParamInst p = insts[ii];
     ParamState st = *p.state;
-    if (ci.f0 == 0) {  // start of a render
+    if (!st.inited) {  // first quantum of this param in this run (start of the render, or of the segment that created it / changed its events)
         st.intrinsic = p.intrinsic0;
         st.head = 0;
-        st.has_last = 0;
+        st.has_last = p.has_last0;
+        st.last = p.last0;
         st.override_valid = 0;
+        st.inited = 1;
     }
-    ParamCursor tl{p, st};
-    const double dt = 1. / (double)p.sample_rate;
-    const int count = 128;
     float* out = chan(p.out, 0, ci);
     float* single = chan(p.out, 1, ci);  // [first frame of a quantum] = 1: the reference's output buffer is single-valued
     const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
     float buf[128];
     for (int q0 = 0; q0 < ci.nf; q0 += 128) {
         const double block_time = (double)(ci.f0 + q0) / (double)p.sample_rate;
-        const double next_block_time = fma(dt, (double)count, block_time);
-        int len = 0;
-        // ---- compute_buffer (param.rs:1500-1600)
-        bool is_constant_block;
-        if (tl.empty()) {
-            is_constant_block = true;
-        } else {
-            ParamEvDev e = tl.peek();
-            is_constant_block = (e.type != WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME && e.type != WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME)
-                                    ? e.time >= next_block_time
-                                    : false;
-        }
-        if (!p.a_rate || is_constant_block) buf[len++] = st.intrinsic;
-        if (!is_constant_block) {
-            for (;;) {
-                bool exit_loop;
-                if (tl.empty()) {
-                    if (p.a_rate)
-                        while (len < count) buf[len++] = st.intrinsic;
-                    exit_loop = true;
-                } else {
-                    ParamEvDev ev = tl.peek();
-                    switch (ev.type) {
-                        case WAE_EVENT_SET_VALUE:
-                        case WAE_EVENT_SET_VALUE_AT_TIME: {  // param.rs:1038-1091
-                            double time = ev.time == 0. ? block_time : ev.time;
-                            if (p.a_rate) {
-                                int e = par_end_index(time, block_time, dt, count);
-                                while (len < e) buf[len++] = st.intrinsic;
-                            }
-                            if (time > next_block_time) {
-                                exit_loop = true;
-                                break;
-                            }
-                            st.intrinsic = ev.value;
-                            ParamEvDev l = tl.pop();
-                            l.time = time;
-                            st.last = l;
-                            st.has_last = 1;
-                            exit_loop = false;
-                            break;
-                        }
-                        case WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME:
-                        case WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME: {  // param.rs:1093-1272
-                            const bool lin = ev.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME;
-                            const double start_time = st.last.time;
-                            double end_time = ev.time;
-                            const double duration = end_time - start_time;
-                            if (ev.has_cancel) end_time = ev.cancel_time;
-                            const float v0 = st.last.value, v1 = ev.value;
-                            const float k = lin ? v1 - v0 : v1 / v0;
-                            if (!lin && (v0 == 0.f || v0 * v1 < 0.f)) {  // degenerate exponential ramp -> SetValueAtTime
-                                ParamEvDev r{};
-                                r.type = WAE_EVENT_SET_VALUE_AT_TIME;
-                                r.time = end_time;
-                                r.value = v1;
-                                tl.replace_peek(r);
-                                exit_loop = false;
-                                break;
-                            }
-                            if (p.a_rate) {
-                                int e = par_end_index(end_time, block_time, dt, count);
-                                if (e > len) {
-                                    double time = fma((double)len, dt, block_time);
-                                    float value = 0.f;
-                                    while (len < e) {
-                                        value = lin ? par_linear(start_time, duration, v0, k, time) : par_exp(start_time, duration, v0, k, time);
-                                        buf[len++] = value;
-                                        time += dt;
-                                    }
-                                    st.intrinsic = value;
-                                }
-                            }
-                            if (end_time >= next_block_time) {
-                                st.intrinsic = lin ? par_linear(start_time, duration, v0, k, next_block_time)
-                                                   : par_exp(start_time, duration, v0, k, next_block_time);
-                                exit_loop = true;
-                                break;
-                            }
-                            if (ev.has_cancel) {
-                                float value = lin ? par_linear(start_time, duration, v0, k, end_time) : par_exp(start_time, duration, v0, k, end_time);
-                                st.intrinsic = value;
-                                ParamEvDev l = tl.pop();
-                                l.time = end_time;
-                                l.value = value;
-                                st.last = l;
-                            } else {
-                                st.intrinsic = v1;
-                                st.last = tl.pop();
-                            }
-                            st.has_last = 1;
-                            exit_loop = false;
-                            break;
-                        }
-                        case WAE_EVENT_SET_TARGET_AT_TIME: {  // param.rs:1274-1427
-                            double end_time = next_block_time;
-                            bool ended = false;
-                            if (tl.has_next()) {
-                                ParamEvDev nx = tl.next();
-                                if (nx.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME || nx.type == WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME) {
-                                    end_time = block_time;
-                                    ended = true;
-                                } else if (nx.time < next_block_time) {
-                                    end_time = nx.time;
-                                    ended = true;
-                                }
-                            }
-                            if (ev.has_cancel && ev.cancel_time < next_block_time) {
-                                end_time = ev.cancel_time;
-                                ended = true;
-                            }
-                            const double start_time = ev.time;
-                            const float v0 = st.last.value, v1 = ev.value;
-                            const float diff = v0 - v1;
-                            const double tau = ev.aux;
-                            if (p.a_rate) {
-                                int e = par_end_index(end_time, block_time, dt, count);
-                                if (e > len) {
-                                    double time = fma((double)len, dt, block_time);
-                                    float value = 0.f;
-                                    while (len < e) {
-                                        value = (time - start_time < 0.) ? st.intrinsic : par_target(start_time, tau, v1, diff, time);
-                                        buf[len++] = value;
-                                        time += dt;
-                                    }
-                                    st.intrinsic = value;
-                                }
-                            }
-                            if (!ended) {
-                                float value = par_target(start_time, tau, v1, diff, next_block_time);
-                                if (fabsf(v1 - value) < 1e-10f) {  // SNAP_TO_TARGET, param.rs:22
-                                    st.intrinsic = v1;
-                                    if (v1 == 0.f)
-                                        for (int i = 0; i < len; i++)
-                                            if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
-                                    ParamEvDev r{};
-                                    r.type = WAE_EVENT_SET_VALUE_AT_TIME;
-                                    r.time = next_block_time;
-                                    r.value = v1;
-                                    tl.replace_peek(r);
-                                } else {
-                                    st.intrinsic = value;
-                                }
-                                exit_loop = true;
-                                break;
-                            }
-                            float value = par_target(start_time, tau, v1, diff, end_time);
-                            st.intrinsic = value;
-                            ParamEvDev l = tl.pop();
-                            l.time = end_time;
-                            l.value = value;
-                            st.last = l;
-                            st.has_last = 1;
-                            exit_loop = false;
-                            break;
-                        }
-                        case WAE_EVENT_SET_VALUE_CURVE_AT_TIME: {  // param.rs:1429-1498
-                            const double start_time = ev.time, duration = ev.aux;
-                            const float* values = p.curves + ev.values_off;
-                            const int nv = ev.values_len;
-                            double end_time = start_time + duration;
-                            if (ev.has_cancel) end_time = ev.cancel_time;
-                            if (p.a_rate) {
-                                int e = par_end_index(end_time, block_time, dt, count);
-                                if (e > len) {
-                                    double time = fma((double)len, dt, block_time);
-                                    float value = 0.f;
-                                    while (len < e) {
-                                        value = time < start_time ? st.intrinsic : par_curve(start_time, duration, values, nv, time);
-                                        buf[len++] = value;
-                                        time += dt;
-                                    }
-                                    st.intrinsic = value;
-                                }
-                            }
-                            if (end_time >= next_block_time) {
-                                st.intrinsic = par_curve(start_time, duration, values, nv, next_block_time);
-                                exit_loop = true;
-                                break;
-                            }
-                            float value = ev.has_cancel ? par_curve(start_time, duration, values, nv, end_time) : values[nv - 1];
-                            ParamEvDev l = tl.pop();
-                            l.time = end_time;
-                            l.value = value;
-                            st.intrinsic = value;
-                            st.last = l;
-                            st.has_last = 1;
-                            exit_loop = false;
-                            break;
-                        }
-                        default: exit_loop = true;
-                    }
-                }
-                if (exit_loop) break;
-            }
-        }
+        const int len = param_compute_buffer(p, st, block_time, buf);  // wae_param_core.h
         // ---- mix_to_output (param.rs:739-797): + input signal, NaN -> default, clamp
         auto fix = [&](float v) {
             if (v != v) return p.def;

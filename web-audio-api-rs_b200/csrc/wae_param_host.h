@@ -14,15 +14,17 @@
 namespace wae {
 
 struct ParamTimeline {
-    std::vector<ParamEvDev> events;  // sorted, values_off indexes `curves`
+    std::vector<ParamEvDev> events;  // the render side's event queue: sorted, values_off indexes `curves`
     std::vector<float> curves;
     float intrinsic = 0.f;
-    std::string error;  // the reference's panic text when the event stream is invalid
+    bool has_last = false;  // AudioParamProcessor::last_event: the last event the render side popped (none before rendering
+    ParamEvDev last{};      // started; after a suspend point: what the replay of the state machine says)
+    std::string error;      // the reference's panic text when the event stream is invalid
 };
 
-inline ParamTimeline build_param_timeline(const Param& p) {
-    ParamTimeline tl;
-    tl.intrinsic = p.default_value;
+// handle_incoming_event (param.rs:799-1036) for `n` events in arrival order, against the queue / last event / intrinsic
+// value in `tl`
+inline void fold_param_events(ParamTimeline& tl, const ParamEv* evs, size_t n) {
     std::vector<ParamEvDev>& q = tl.events;
     auto make = [&](const ParamEv& e) {
         ParamEvDev d{};
@@ -42,11 +44,15 @@ inline ParamTimeline build_param_timeline(const Param& p) {
         return d;
     };
     auto sort_q = [&]() { std::stable_sort(q.begin(), q.end(), [](const ParamEvDev& a, const ParamEvDev& b) { return a.time < b.time; }); };
-    // no event has been *processed* yet while the control messages are drained (offline: before the first quantum),
-    // so `last_event` is None throughout (param.rs:852-856 only matters after rendering started)
-    for (const ParamEv& in : p.events) {
+    for (size_t ei = 0; ei < n; ei++) {
+        const ParamEv& in = evs[ei];
         ParamEvDev ev = make(in);
         if (ev.type == WAE_EVENT_CANCEL_SCHEDULED_VALUES) {  // param.rs:812-866
+            // in the middle of a ramp (only possible once rendering has started): the value from before the ramp is restored
+            if (!q.empty() && tl.has_last &&
+                (q.front().type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME || q.front().type == WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME) &&
+                q.front().time >= ev.time)
+                tl.intrinsic = tl.last.value;
             q.erase(std::remove_if(q.begin(), q.end(), [&](const ParamEvDev& x) { return !(x.time < ev.time); }), q.end());
             continue;
         }
@@ -90,7 +96,7 @@ inline ParamTimeline build_param_timeline(const Param& p) {
             for (auto& x : q)
                 if (!(x.time <= t0 || x.time >= t1)) {
                     tl.error = "NotSupportedError - scheduling SetValueCurveAtTime at time of another automation event";
-                    return tl;
+                    return;
                 }
         } else {  // param.rs:964-986
             for (auto& x : q)
@@ -98,13 +104,13 @@ inline ParamTimeline build_param_timeline(const Param& p) {
                     double t0 = x.time, t1 = t0 + x.aux;
                     if (!(ev.time <= t0 || ev.time >= t1)) {
                         tl.error = "NotSupportedError - scheduling automation event during SetValueCurveAtTime";
-                        return tl;
+                        return;
                     }
                 }
         }
         if (ev.type == WAE_EVENT_SET_VALUE) tl.intrinsic = ev.value;  // param.rs:988-990
         bool ramp = ev.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME || ev.type == WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME;
-        if (q.empty() && (ramp || ev.type == WAE_EVENT_SET_TARGET_AT_TIME)) {  // param.rs:992-1030: implicit SetValue
+        if (q.empty() && ((ramp && !tl.has_last) || ev.type == WAE_EVENT_SET_TARGET_AT_TIME)) {  // param.rs:992-1030: implicit SetValue
             ParamEvDev sv{};
             sv.type = WAE_EVENT_SET_VALUE;
             sv.value = tl.intrinsic;
@@ -114,6 +120,13 @@ inline ParamTimeline build_param_timeline(const Param& p) {
         q.push_back(ev);
         sort_q();
     }
+}
+
+// the timeline a param starts the render with: every control message is drained before the first quantum
+inline ParamTimeline build_param_timeline(const Param& p) {
+    ParamTimeline tl;
+    tl.intrinsic = p.default_value;
+    fold_param_events(tl, p.events.data(), p.events.size());
     return tl;
 }
 
