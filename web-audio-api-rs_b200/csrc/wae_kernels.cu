@@ -8,6 +8,7 @@
 #include "wae_param_core.h"
 #include "../../include/wae.h"
 
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -1809,7 +1810,7 @@ constexpr int CV_B = WAE_CONV_BLOCK;    // frames per partition
 constexpr int CV_LOGB = 13;
 static_assert((1 << CV_LOGB) == CV_B, "CV_LOGB");
 constexpr int CV_BINS = CV_B;           // packed half spectrum: bin 0 = (DC, Nyquist), bins 1..B-1 complex
-constexpr int CV_THREADS = 512;
+constexpr int CV_THREADS = 256;
 
 __device__ float2 c_tw[CV_B];  // exp(-2*pi*i*k/(2B)), k < B
 
@@ -1852,6 +1853,7 @@ DEVI float2 rot16(float2 v, int sign) {
 }
 // one radix-8 DIF butterfly on elements base + m*q (three radix-2 stages with spans 4q, 2q, q)
 DEVI void fft_radix8_pass(float2* s, int q, int log_q, int sign) {
+#pragma unroll 2
     for (int bf = threadIdx.x; bf < CV_B / 8; bf += CV_THREADS) {
         const int lo = bf & (q - 1), hi = bf >> log_q;
         const int base = (hi << (log_q + 3)) + lo;
@@ -1938,7 +1940,7 @@ DEVI float2 rfft_bin(const float2* z, int k) {
 }
 
 // grid: (blocks in chunk, conv inputs).  Builds X_j for every new block of the chunk.
-__global__ void __launch_bounds__(CV_THREADS) k_conv_fft_in(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
+__global__ void __launch_bounds__(CV_THREADS, 3) k_conv_fft_in(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
     extern __shared__ float2 z[];
     const ConvInput ip = inputs[blockIdx.y];
     const int jb = blockIdx.x;                         // block within the chunk
@@ -1986,20 +1988,13 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 // MACs (0.36 loads per MAC instead of 2).  No shared memory => many resident warps hide the L2 latency of the loads.
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
-__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
-                                                             ChunkInfo ci) {
-    const ConvPath p = paths[blockIdx.y];
-    const ConvInput ip = inputs[p.input];
-    const int nb = (ci.nf + CV_B - 1) / CV_B;
-    constexpr int TILES = CV_B / CV_MAC_THREADS;
-    const int k = (blockIdx.x % TILES) * CV_MAC_THREADS + threadIdx.x;  // bin
-    const int j0 = (blockIdx.x / TILES) * CV_J;                         // first output block of this CTA (chunk-relative)
-    const int64_t jabs0 = ci.f0 / CV_B + j0;
-    const int64_t jabs_last = ci.f0 / CV_B + nb - 1;                    // newest input block transformed so far
-    const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;                 // i runs up to S-1: i_base - (J-1) <= S-1
-    float2 acc[CV_J];
-#pragma unroll
-    for (int jj = 0; jj < CV_J; jj++) acc[jj] = make_float2(0.f, 0.f);
+// PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
+template <bool PACKED>
+DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t jabs0, int64_t jabs_last, float2 acc[CV_J]) {
+    const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;  // i runs up to S-1: i_base - (J-1) <= S-1
+    const int ring = ip.xring_blocks;
+    // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
+    int slot0 = (int)(jabs0 % ring);
 #pragma unroll 1
     for (int g = 0; g < groups; g++) {
         const int i_base = g * CV_J;
@@ -2014,31 +2009,48 @@ __global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac(const ConvPath* __r
         for (int r = 0; r < CV_J; r++) {
             const int64_t b = b0 + r;
             float2 x = make_float2(0.f, 0.f);
-            if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)(b % ip.xring_blocks) * CV_BINS + k];
-            if (k == 0) {  // packed real bins: (DC, Nyquist) multiply component-wise
+            int slot = slot0 + r;
+            slot = slot >= ring ? slot - ring : slot;
+            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
+            if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)slot * CV_BINS + k];
 #pragma unroll
-                for (int jj = 0; jj < CV_J; jj++) {
-                    const float2 h = hw[(CV_J - 1) + jj - r];
+            for (int jj = 0; jj < CV_J; jj++) {
+                const float2 h = hw[(CV_J - 1) + jj - r];
+                if (PACKED) {
                     acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
                     acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
-                }
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < CV_J; jj++) {
-                    const float2 h = hw[(CV_J - 1) + jj - r];
+                } else {
                     acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
                     acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
                 }
             }
         }
+        slot0 -= CV_J;
+        while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
     }
+}
+__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
+                                                             ChunkInfo ci) {
+    const ConvPath p = paths[blockIdx.y];
+    const ConvInput ip = inputs[p.input];
+    const int nb = (ci.nf + CV_B - 1) / CV_B;
+    constexpr int TILES = CV_B / CV_MAC_THREADS;
+    const int k = (blockIdx.x % TILES) * CV_MAC_THREADS + threadIdx.x;  // bin
+    const int j0 = (blockIdx.x / TILES) * CV_J;                         // first output block of this CTA (chunk-relative)
+    const int64_t jabs0 = ci.f0 / CV_B + j0;
+    const int64_t jabs_last = ci.f0 / CV_B + nb - 1;                    // newest input block transformed so far
+    float2 acc[CV_J];
+#pragma unroll
+    for (int jj = 0; jj < CV_J; jj++) acc[jj] = make_float2(0.f, 0.f);
+    if (k == 0) conv_mac_bin<true>(p, ip, k, jabs0, jabs_last, acc);
+    else conv_mac_bin<false>(p, ip, k, jabs0, jabs_last, acc);
 #pragma unroll
     for (int jj = 0; jj < CV_J; jj++)
         if (j0 + jj < nb) p.y[(size_t)(j0 + jj) * CV_BINS + k] = acc[jj];
 }
 
 // grid: (blocks in chunk, paths): out_j = IFFT(Y_j)[B..2B) / 2B
-__global__ void __launch_bounds__(CV_THREADS) k_conv_ifft(const ConvPath* __restrict__ paths, int n_paths, ChunkInfo ci) {
+__global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __restrict__ paths, int n_paths, ChunkInfo ci) {
     extern __shared__ float2 z[];
     const ConvPath p = paths[blockIdx.y];
     const int jb = blockIdx.x;
