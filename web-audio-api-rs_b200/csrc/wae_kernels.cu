@@ -1491,15 +1491,18 @@ __global__ void __launch_bounds__(64) k_hrtf_sel(const HrtfSelInst* __restrict__
 // reference's IRC_1003_C sphere).  One warp per render quantum, 4 consecutive frames x 2 ears per lane with the input window
 // sliding through registers: per 4 taps 4 shared loads of x + 2 float4 broadcasts of h feed 32 FMAs.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int HRTF_TILE = 512;  // frames per CTA (4 warps x 128)
-__device__ __forceinline__ int hrtf_pad(int i) { return i + (i >> 5); }  // stride-4 lane access -> distinct banks
+constexpr int HRTF_TILE = 1024;  // frames per CTA: 4 warps x 32 lanes x 8 frames = 8 render quanta
+DEVI int hrtf_pad(int i) { return i + (i >> 3); }  // stride-8 lane access -> 32 distinct banks
 
-__device__ __forceinline__ float hrtf_input(const HrtfInst& p, int m, const ChunkInfo& ci) {
+DEVI float hrtf_input(const HrtfInst& p, int m, const ChunkInfo& ci) {
     float v = chan(p.in, 0, ci)[m];
     if (p.in_ch == 2) v = 0.5f * (v + chan(p.in, 1, ci)[m]);  // output.mix(1, Speakers), quantum.rs 2 -> 1
     return v;
 }
 
+// One lane = 8 consecutive frames x 2 ears (16 accumulators); the input window slides through registers, so 4 taps cost
+// 4 shared loads of x + 2 float4 loads of h for 64 FMAs.  A warp covers two render quanta (lanes 0-15 / 16-31), each with
+// its own blended response (moving sources: the response changes per quantum).
 __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ insts, ChunkInfo ci) {
     extern __shared__ __align__(16) float hsm[];
     const HrtfInst p = insts[blockIdx.y];
@@ -1507,7 +1510,7 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
     const int tile0 = blockIdx.x * HRTF_TILE;
     const int nx = 4 + (L4 - 1) + HRTF_TILE;  // 4 leading slots keep the 4-tap unroll in range
     float* xs = hsm;                           // padded input window: xs[pad(4 + (L4-1) + n)] = x[tile0 + n]
-    float* hs = hsm + ((hrtf_pad(nx) + 4) & ~3);  // [4 warps][2][L4]
+    float* hs = hsm + ((hrtf_pad(nx) + 4) & ~3);  // [8 quanta][2][L4]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < nx; i += 128) {
         int m = tile0 + i - 4 - (L4 - 1);  // chunk-relative frame
@@ -1519,17 +1522,21 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
         }
         xs[hrtf_pad(i)] = v;
     }
-    const int q0 = tile0 + warp * 128;  // first frame of this warp's quantum
-    const bool active = q0 < ci.nf;
-    HrtfSel sel = p.static_sel;
-    if (active) {
-        if (p.sel) sel = p.sel[(ci.sub + q0) >> 7];
-        float* hl = hs + warp * 2 * L4;
+    // blended responses: one per quantum of the tile for a moving source / listener (warp w blends quanta 2w and 2w + 1),
+    // a single shared one for a static panner (each warp blends a quarter of it)
+    const bool moving = p.sel != nullptr;
+    for (int h = 0; h < 2; h++) {
+        const int qi = moving ? warp * 2 + h : 0;
+        const int q0 = tile0 + qi * 128;
+        if (moving && q0 >= ci.nf) break;
+        if (!moving && h == 1) break;
+        const HrtfSel sel = moving ? p.sel[(ci.sub + q0) >> 7] : p.static_sel;
+        float* hl = hs + qi * 2 * L4;
         float* hr = hl + L4;
         const float* A = p.sphere_ir + (size_t)sel.v[0] * 2 * L;
         const float* B = p.sphere_ir + (size_t)sel.v[1] * 2 * L;
         const float* C = p.sphere_ir + (size_t)sel.v[2] * 2 * L;
-        for (int k = lane; k < L4; k += 32) {
+        for (int k = moving ? lane : tid; k < L4; k += moving ? 32 : 128) {
             float l = 0.f, r = 0.f;
             if (k < L) {
                 l = __fadd_rn(__fadd_rn(__fmul_rn(A[k], sel.w[0]), __fmul_rn(B[k], sel.w[1])), __fmul_rn(C[k], sel.w[2]));
@@ -1540,42 +1547,70 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
         }
     }
     __syncthreads();
-    if (!active) return;
-    const float* hl = hs + warp * 2 * L4;
+    const int qi = warp * 2 + (lane >> 4);
+    const int q0 = tile0 + qi * 128;
+    if (q0 >= ci.nf) return;
+    const HrtfSel sel = moving ? p.sel[(ci.sub + q0) >> 7] : p.static_sel;
+    const float* hl = hs + (moving ? qi : 0) * 2 * L4;
     const float* hr = hl + L4;
-    const int nrel = warp * 128 + lane * 4;       // tile-relative first frame of this lane
+    const int nrel = warp * 256 + lane * 8;        // tile-relative first frame of this lane
     const int base = 4 + (L4 - 1) + nrel;          // xs index of x[n0]
-    float w0 = xs[hrtf_pad(base)], w1 = xs[hrtf_pad(base + 1)], w2 = xs[hrtf_pad(base + 2)], w3 = xs[hrtf_pad(base + 3)];
-    float al0 = 0.f, al1 = 0.f, al2 = 0.f, al3 = 0.f, ar0 = 0.f, ar1 = 0.f, ar2 = 0.f, ar3 = 0.f;
-#pragma unroll 2
+    float w[8], al[8], ar[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        w[j] = xs[hrtf_pad(base + j)];
+        al[j] = 0.f;
+        ar[j] = 0.f;
+    }
+#pragma unroll 1
     for (int k = 0; k < L4; k += 4) {
         const float4 a = *reinterpret_cast<const float4*>(hl + k);
         const float4 b = *reinterpret_cast<const float4*>(hr + k);
-        // tap k: window (w0..w3) = x[n0-k .. n0-k+3]
-        al0 = fmaf(a.x, w0, al0); al1 = fmaf(a.x, w1, al1); al2 = fmaf(a.x, w2, al2); al3 = fmaf(a.x, w3, al3);
-        ar0 = fmaf(b.x, w0, ar0); ar1 = fmaf(b.x, w1, ar1); ar2 = fmaf(b.x, w2, ar2); ar3 = fmaf(b.x, w3, ar3);
-        const float m1 = xs[hrtf_pad(base - k - 1)];
-        al0 = fmaf(a.y, m1, al0); al1 = fmaf(a.y, w0, al1); al2 = fmaf(a.y, w1, al2); al3 = fmaf(a.y, w2, al3);
-        ar0 = fmaf(b.y, m1, ar0); ar1 = fmaf(b.y, w0, ar1); ar2 = fmaf(b.y, w1, ar2); ar3 = fmaf(b.y, w2, ar3);
-        const float m2 = xs[hrtf_pad(base - k - 2)];
-        al0 = fmaf(a.z, m2, al0); al1 = fmaf(a.z, m1, al1); al2 = fmaf(a.z, w0, al2); al3 = fmaf(a.z, w1, al3);
-        ar0 = fmaf(b.z, m2, ar0); ar1 = fmaf(b.z, m1, ar1); ar2 = fmaf(b.z, w0, ar2); ar3 = fmaf(b.z, w1, ar3);
-        const float m3 = xs[hrtf_pad(base - k - 3)];
-        al0 = fmaf(a.w, m3, al0); al1 = fmaf(a.w, m2, al1); al2 = fmaf(a.w, m1, al2); al3 = fmaf(a.w, w0, al3);
-        ar0 = fmaf(b.w, m3, ar0); ar1 = fmaf(b.w, m2, ar1); ar2 = fmaf(b.w, m1, ar2); ar3 = fmaf(b.w, w0, ar3);
-        const float m4 = xs[hrtf_pad(base - k - 4)];
-        w3 = m1; w2 = m2; w1 = m3; w0 = m4;
+        const float m1 = xs[hrtf_pad(base - k - 1)], m2 = xs[hrtf_pad(base - k - 2)];
+        const float m3 = xs[hrtf_pad(base - k - 3)], m4 = xs[hrtf_pad(base - k - 4)];
+        // tap k: x[n0 - k + j] = w[j]
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            al[j] = fmaf(a.x, w[j], al[j]);
+            ar[j] = fmaf(b.x, w[j], ar[j]);
+        }
+        // tap k + 1: (m1, w0 .. w6)
+        al[0] = fmaf(a.y, m1, al[0]); ar[0] = fmaf(b.y, m1, ar[0]);
+#pragma unroll
+        for (int j = 1; j < 8; j++) {
+            al[j] = fmaf(a.y, w[j - 1], al[j]);
+            ar[j] = fmaf(b.y, w[j - 1], ar[j]);
+        }
+        // tap k + 2: (m2, m1, w0 .. w5)
+        al[0] = fmaf(a.z, m2, al[0]); ar[0] = fmaf(b.z, m2, ar[0]);
+        al[1] = fmaf(a.z, m1, al[1]); ar[1] = fmaf(b.z, m1, ar[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j++) {
+            al[j] = fmaf(a.z, w[j - 2], al[j]);
+            ar[j] = fmaf(b.z, w[j - 2], ar[j]);
+        }
+        // tap k + 3: (m3, m2, m1, w0 .. w4)
+        al[0] = fmaf(a.w, m3, al[0]); ar[0] = fmaf(b.w, m3, ar[0]);
+        al[1] = fmaf(a.w, m2, al[1]); ar[1] = fmaf(b.w, m2, ar[1]);
+        al[2] = fmaf(a.w, m1, al[2]); ar[2] = fmaf(b.w, m1, ar[2]);
+#pragma unroll
+        for (int j = 3; j < 8; j++) {
+            al[j] = fmaf(a.w, w[j - 3], al[j]);
+            ar[j] = fmaf(b.w, w[j - 3], ar[j]);
+        }
+        // next window: x[n0 - k - 4 + j]
+        w[7] = w[3]; w[6] = w[2]; w[5] = w[1]; w[4] = w[0];
+        w[3] = m1; w[2] = m2; w[1] = m3; w[0] = m4;
     }
     const int n = tile0 + nrel;
     float* ol = chan(p.out, 0, ci);
     float* orr = chan(p.out, 1, ci);
     const float g = sel.gain, c = p.correction;
-    const float l4[4] = {al0, al1, al2, al3}, r4[4] = {ar0, ar1, ar2, ar3};
 #pragma unroll
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 8; j++)
         if (n + j < ci.nf) {
-            ol[n + j] = __fmul_rn(c, __fmul_rn(l4[j], g));
-            orr[n + j] = __fmul_rn(c, __fmul_rn(r4[j], g));
+            ol[n + j] = __fmul_rn(c, __fmul_rn(al[j], g));
+            orr[n + j] = __fmul_rn(c, __fmul_rn(ar[j], g));
         }
 }
 
@@ -2257,7 +2292,8 @@ void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, in
     if (n_sel > 0) k_hrtf_sel<<<dim3((ci.nf / 128 + 63) / 64 + 1, n_sel), 64, 0, s>>>(sel, ci);
     const int L4 = (max_taps + 3) & ~3;
     const int nx = 4 + (L4 - 1) + HRTF_TILE;
-    const size_t smem = (size_t)(((nx + (nx >> 5) + 4) & ~3) + 4 * 2 * L4) * sizeof(float);
+    const int copies = n_sel > 0 ? 8 : 1;  // blended responses kept in shared memory: one per quantum only for moving sources
+    const size_t smem = (size_t)(((nx + (nx >> 3) + 4) & ~3) + copies * 2 * L4) * sizeof(float);
     static size_t configured = 48 * 1024;
     if (smem > configured) {
         cudaFuncSetAttribute(k_hrtf_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
