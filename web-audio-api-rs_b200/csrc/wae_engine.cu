@@ -1571,10 +1571,13 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             }
             case K_ANALYSER: {
                 int ch = p.in_ch[0];
-                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                // pass-through (analyser.rs:267-294): the output IS the input buffer (nobody writes an edge buffer after its
+                // producer), only the ring is written
+                p.out_ch = {ch};
+                p.out_buf = {p.in_buf[0]};
                 AnalyserInst a{};
                 a.in = p.in_buf[0];
-                a.out = p.out_buf[0];
+                a.out = BufRef{nullptr, 0, 0};
                 a.ch = ch;
                 a.ring = alloc<float>(32768 + 128, true, true);
                 if (!a.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser ring)");

@@ -1770,11 +1770,13 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
         const AnalyserInst a = insts[ii];
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
+        if (!a.out.p && ci.nf - n > RING) continue;  // older than the ring: overwritten by this very chunk
         MixEdge e;
         e.src = a.in;
         e.src_ch = a.ch;
         float mono = mixed_sample(e, 1, 0, 0, n, ci);  // mono.mix(1, Speakers)
-        for (int c = 0; c < a.ch; c++) chan(a.out, c, ci)[n] = chan(a.in, c, ci)[n];
+        if (a.out.p)
+            for (int c = 0; c < a.ch; c++) chan(a.out, c, ci)[n] = chan(a.in, c, ci)[n];
         if (ci.nf - n <= RING) a.ring[(ci.f0 + n) % RING] = mono;
     }
 }
