@@ -1913,85 +1913,85 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         pl.ir_cache.swap(ir_cache);
         grp.stage0 = b->stages.size();
         for (int sg = 0; sg < n_seg; sg++) {
-        pl.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
-        const uint64_t alg_before = pl.algorithmic_bytes;
-        for (uint32_t i = grp.g0; i < grp.g1; i++) {
-            EpochView view(graphs[i], b->seg_bounds[sg]);
-            if (!pl.plan_graph(graphs[i], i)) {
-                int code = pl.error_code;
-                std::string msg = pl.error;
-                wae_batch_destroy(b);
-                return fail(code, msg);
-            }
-        }
-        // the per-node byte counts assume the whole render: scale to this segment's share of it
-        algorithmic_bytes += (uint64_t)((double)(pl.algorithmic_bytes - alg_before) * (double)(pl.seg_end - pl.seg_start) / (double)b->lq);
-        // materialise the segment's stages in (class, level, kind) order
-        const size_t seg_stage0 = b->stages.size();
-        void* last_conv_inputs = nullptr;
-        for (auto& kv : pl.builds) {
-            StageBuild& s = kv.second;
-            Stage st;
-            st.seg = sg;
-            st.cls = s.cls;
-            st.kind = s.kind;
-            st.variant = s.variant;
-            st.group = k;
-            st.max_ch = s.max_ch;
-            switch (s.kind) {
-                case S_MIX: {
-                    for (auto& m : s.mix) {  // classify: vector fast path of k_mix
-                        bool simple = true, all_mono = m.n_edges > 0;
-                        for (int e = 0; e < m.n_edges; e++) {
-                            const MixEdge& ed = s.mix_edges[m.edge_offset + e];
-                            bool same = ed.src_ch == m.out_ch;
-                            bool dup = ed.src_ch == 1 && m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS;
-                            if (!(same || dup)) simple = false;
-                            if (ed.src_ch != 1) all_mono = false;
-                            // sources must allow 16-byte loads: arena buffers do; asset / output aliases may not
-                            if (ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) simple = false;
-                        }
-                        m.simple = simple ? 1 : 0;
-                        m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
-                    }
-                    st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
-                    break;
+            pl.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
+            const uint64_t alg_before = pl.algorithmic_bytes;
+            for (uint32_t i = grp.g0; i < grp.g1; i++) {
+                EpochView view(graphs[i], b->seg_bounds[sg]);
+                if (!pl.plan_graph(graphs[i], i)) {
+                    int code = pl.error_code;
+                    std::string msg = pl.error;
+                    wae_batch_destroy(b);
+                    return fail(code, msg);
                 }
-                case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
-                case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
-                case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
-                case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
-                case S_CHAIN: st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); break;
-                case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
-                case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
-                case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
-                case S_ABSN_SLOW: st.n = (int)s.absn_slow.size(); st.d_a = up(b, s.absn_slow); break;
-                case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
-                case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
-                case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
-                case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
-                case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
-                case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
-                    st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
-                case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
-                case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
-                case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
-                case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
-                case S_DELAY:
-                case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
-                case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
-                case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
-                case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
-                case S_CONV_MAC:
-                case S_CONV_MAC_ACC:
-                    st.n = (int)s.conv_path.size();
-                    st.d_a = up(b, s.conv_path);
-                    st.d_b = last_conv_inputs;  // conv-input table of the same level (kinds are ordered FFT < MAC < MAC_ACC)
-                    break;
             }
-            if (st.n > 0) b->stages.push_back(st);
-        }
-        grp.seg_stages.push_back({seg_stage0, b->stages.size()});
+            // the per-node byte counts assume the whole render: scale to this segment's share of it
+            algorithmic_bytes += (uint64_t)((double)(pl.algorithmic_bytes - alg_before) * (double)(pl.seg_end - pl.seg_start) / (double)b->lq);
+            // materialise the segment's stages in (class, level, kind) order
+            const size_t seg_stage0 = b->stages.size();
+            void* last_conv_inputs = nullptr;
+            for (auto& kv : pl.builds) {
+                StageBuild& s = kv.second;
+                Stage st;
+                st.seg = sg;
+                st.cls = s.cls;
+                st.kind = s.kind;
+                st.variant = s.variant;
+                st.group = k;
+                st.max_ch = s.max_ch;
+                switch (s.kind) {
+                    case S_MIX: {
+                        for (auto& m : s.mix) {  // classify: vector fast path of k_mix
+                            bool simple = true, all_mono = m.n_edges > 0;
+                            for (int e = 0; e < m.n_edges; e++) {
+                                const MixEdge& ed = s.mix_edges[m.edge_offset + e];
+                                bool same = ed.src_ch == m.out_ch;
+                                bool dup = ed.src_ch == 1 && m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS;
+                                if (!(same || dup)) simple = false;
+                                if (ed.src_ch != 1) all_mono = false;
+                                // sources must allow 16-byte loads: arena buffers do; asset / output aliases may not
+                                if (ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) simple = false;
+                            }
+                            m.simple = simple ? 1 : 0;
+                            m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
+                        }
+                        st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
+                        break;
+                    }
+                    case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
+                    case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
+                    case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
+                    case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
+                    case S_CHAIN: st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); break;
+                    case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
+                    case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
+                    case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
+                    case S_ABSN_SLOW: st.n = (int)s.absn_slow.size(); st.d_a = up(b, s.absn_slow); break;
+                    case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
+                    case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
+                    case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
+                    case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
+                    case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
+                    case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
+                        st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
+                    case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
+                    case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
+                    case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
+                    case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
+                    case S_DELAY:
+                    case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
+                    case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
+                    case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
+                    case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
+                    case S_CONV_MAC:
+                    case S_CONV_MAC_ACC:
+                        st.n = (int)s.conv_path.size();
+                        st.d_a = up(b, s.conv_path);
+                        st.d_b = last_conv_inputs;  // conv-input table of the same level (kinds are ordered FFT < MAC < MAC_ACC)
+                        break;
+                }
+                if (st.n > 0) b->stages.push_back(st);
+            }
+            grp.seg_stages.push_back({seg_stage0, b->stages.size()});
         }  // segments
         ir_cache.swap(pl.ir_cache);
         grp.stage1 = b->stages.size();
