@@ -59,6 +59,9 @@ class AudioBuffer:
 
     def __init__(self, channels, sample_rate):
         self.channels = [B.as_f32(c) for c in channels]
+        # AudioBuffer::from (src/buffer.rs:96-117) panics on ragged channels
+        if any(len(c) != len(self.channels[0]) for c in self.channels):
+            raise B.WaeError(2, "all channels of an AudioBuffer must have the same length")
         self.sample_rate = float(np.float32(sample_rate))
 
     @classmethod

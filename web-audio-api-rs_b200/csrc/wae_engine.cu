@@ -147,15 +147,16 @@ struct wae_batch {
         uint32_t g0 = 0, g1 = 0;        // graphs [g0, g1)
         size_t stage0 = 0, stage1 = 0;  // stages [stage0, stage1) of `stages` (all segments)
         std::vector<std::pair<size_t, size_t>> seg_stages;  // per render segment: its stages
+        std::vector<int64_t> seg_bounds;                    // 0 = b0 < b1 < ... < lq: the suspend frames of this group's graphs
         float* d_src = nullptr;         // device slab of source PCM
         float* h_src = nullptr;         // pinned host mirror
         size_t src_floats = 0;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     };
     std::vector<Group> groups;
-    // OfflineAudioContext::suspend_sync: the render is cut at the suspend frames of all graphs; every segment has its own
-    // plan, node state is shared between the plans through `state_map` (graph, node, allocation sequence, salt)
-    std::vector<int64_t> seg_bounds;  // 0 = b0 < b1 < ... < lq
+    // OfflineAudioContext::suspend_sync: a group's render is cut at the suspend frames of its graphs (graphs with different
+    // suspend points are put in different groups); every segment has its own plan, node state is shared between the plans
+    // through `state_map` (graph, node, allocation sequence, salt)
     struct StateKey {
         uint32_t graph, node, seq;
         uint64_t salt;
@@ -1791,25 +1792,18 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     b->length = graphs[0]->length;
     b->lq = (int64_t)((b->length + 127) / 128 * 128);
     bool has_conv = false;
-    std::set<int64_t> cuts{0, b->lq};
+    std::vector<char> graph_has_conv(n_graphs, 0);
+    std::vector<std::vector<int64_t>> cuts(n_graphs);  // per graph: its suspend frames inside the render
     for (uint32_t i = 0; i < n_graphs; i++) {
         for (auto& kv : graphs[i]->nodes)
-            if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
+            if (kv.second.kind == K_CONV && kv.second.buffer) graph_has_conv[i] = 1;
         for (auto& ep : graphs[i]->epochs) {
-            if ((int64_t)ep.frame > 0 && (int64_t)ep.frame < b->lq) cuts.insert((int64_t)ep.frame);
+            if ((int64_t)ep.frame > 0 && (int64_t)ep.frame < b->lq) cuts[i].push_back((int64_t)ep.frame);
             for (auto& kv : ep.nodes)
-                if (kv.second.kind == K_CONV && kv.second.buffer) has_conv = true;
+                if (kv.second.kind == K_CONV && kv.second.buffer) graph_has_conv[i] = 1;
         }
+        has_conv = has_conv || graph_has_conv[i];
     }
-    b->seg_bounds.assign(cuts.begin(), cuts.end());
-    const int n_seg = (int)b->seg_bounds.size() - 1;
-    if (has_conv)
-        for (int64_t f : b->seg_bounds)
-            if (f != b->lq && f % WAE_CONV_BLOCK != 0)
-                return [&]() {
-                    wae_batch_destroy(b);
-                    return fail(WAE_UNSUPPORTED, "a suspend point that is not a multiple of the convolver partition (8192 frames) in a batch with ConvolverNodes is not lowered to the GPU");
-                }();
     size_t out_floats = (size_t)n_graphs * b->channels * b->length;
     b->d_out = b->dalloc<float>(out_floats, true);
     if (!b->d_out) {
@@ -1820,10 +1814,33 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     int n_groups = eng->pipeline_groups;
     if (n_groups == 0) n_groups = n_graphs >= 512 ? 32 : (n_graphs >= 64 ? 8 : 1);  // measured on C2: 8 groups 88 ms, 16: 83.7, 32: 80.6 (fill / drain of the 3-stage pipeline)
     n_groups = std::max(1, std::min<int>(n_groups, (int)n_graphs));
-    b->groups.resize(n_groups);
-    for (int k = 0; k < n_groups; k++) {
-        b->groups[k].g0 = (uint32_t)((uint64_t)n_graphs * k / n_groups);
-        b->groups[k].g1 = (uint32_t)((uint64_t)n_graphs * (k + 1) / n_groups);
+    {
+        // contiguous runs of graphs with the same suspend frames, cut further into about n_groups pieces
+        const uint32_t target = (n_graphs + (uint32_t)n_groups - 1) / (uint32_t)n_groups;
+        uint32_t g0 = 0;
+        for (uint32_t i = 1; i <= n_graphs; i++)
+            if (i == n_graphs || cuts[i] != cuts[g0] || i - g0 >= target) {
+                wae_batch::Group grp;
+                grp.g0 = g0;
+                grp.g1 = i;
+                grp.seg_bounds.push_back(0);
+                for (int64_t f : cuts[g0]) grp.seg_bounds.push_back(f);
+                grp.seg_bounds.push_back(b->lq);
+                b->groups.push_back(grp);
+                g0 = i;
+            }
+        n_groups = (int)b->groups.size();
+    }
+    // the convolver kernels work on whole partitions: a chunk (and so a render segment) has to start on one
+    for (auto& grp : b->groups) {
+        bool conv = false;
+        for (uint32_t i = grp.g0; i < grp.g1; i++) conv = conv || graph_has_conv[i];
+        if (!conv) continue;
+        for (int64_t f : grp.seg_bounds)
+            if (f != b->lq && f % WAE_CONV_BLOCK != 0) {
+                wae_batch_destroy(b);
+                return fail(WAE_UNSUPPORTED, "a suspend point that is not a multiple of the convolver partition (8192 frames) in a graph with a ConvolverNode is not lowered to the GPU");
+            }
     }
     // Sizing pass (no device memory touched): arena floats per frame of the largest group and the source-PCM slab of
     // every group.  Chunk size: explicit option, else chosen so that a group's arena stays around 48 MiB — edge
@@ -1842,10 +1859,11 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             sizing.dry = true;
             sizing.delay_ch_hint = &delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
-            for (int sg = 0; sg < n_seg; sg++) {
-                sizing.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
+            const std::vector<int64_t>& bounds = b->groups[k].seg_bounds;
+            for (size_t sg = 0; sg + 1 < bounds.size(); sg++) {
+                sizing.begin_segment(bounds[sg], bounds[sg + 1]);
                 for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
-                    EpochView view(graphs[i], b->seg_bounds[sg]);
+                    EpochView view(graphs[i], bounds[sg]);
                     if (!sizing.plan_graph(graphs[i], i)) {
                         int code = sizing.error_code;
                         std::string msg = sizing.error;
@@ -1912,11 +1930,11 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         pl.delay_ch_hint = &delay_ch_hint;
         pl.ir_cache.swap(ir_cache);
         grp.stage0 = b->stages.size();
-        for (int sg = 0; sg < n_seg; sg++) {
-            pl.begin_segment(b->seg_bounds[sg], b->seg_bounds[sg + 1]);
+        for (int sg = 0; sg + 1 < (int)grp.seg_bounds.size(); sg++) {
+            pl.begin_segment(grp.seg_bounds[sg], grp.seg_bounds[sg + 1]);
             const uint64_t alg_before = pl.algorithmic_bytes;
             for (uint32_t i = grp.g0; i < grp.g1; i++) {
-                EpochView view(graphs[i], b->seg_bounds[sg]);
+                EpochView view(graphs[i], grp.seg_bounds[sg]);
                 if (!pl.plan_graph(graphs[i], i)) {
                     int code = pl.error_code;
                     std::string msg = pl.error;
@@ -2008,13 +2026,19 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         return fail(WAE_CUDA_ERROR, std::string("prepare: ") + cudaGetErrorString(le));
     }
     int64_t n_chunks = 0;
-    for (size_t sg = 0; sg + 1 < b->seg_bounds.size(); sg++) n_chunks += (b->seg_bounds[sg + 1] - b->seg_bounds[sg] + b->chunk - 1) / b->chunk;
+    for (auto& grp : b->groups)  // the largest number of chunks any group renders
+    {
+        int64_t c = 0;
+        for (size_t sg = 0; sg + 1 < grp.seg_bounds.size(); sg++) c += (grp.seg_bounds[sg + 1] - grp.seg_bounds[sg] + b->chunk - 1) / b->chunk;
+        n_chunks = std::max(n_chunks, c);
+    }
     uint64_t launches = 0;
     for (auto& st : b->stages) {
         const uint64_t k = (st.kind == S_CONV_FFT || st.kind == S_CONV_MAC || st.kind == S_CONV_MAC_ACC || st.kind == S_SHAPER_OS) ? 2
                            : st.kind == S_HRTF ? (st.n_b > 0 ? 3 : 2) : 1;
         // per-quantum stages (class 1) launch once per render quantum of their segment, the others once per chunk of it
-        const int64_t seg_len = b->seg_bounds[st.seg + 1] - b->seg_bounds[st.seg];
+        const std::vector<int64_t>& sb = b->groups[st.group].seg_bounds;
+        const int64_t seg_len = sb[st.seg + 1] - sb[st.seg];
         launches += st.cls == 1 ? k * (uint64_t)(seg_len / 128) : k * (uint64_t)((seg_len + b->chunk - 1) / b->chunk);
     }
     std::memset(&b->stats, 0, sizeof(b->stats));
@@ -2103,15 +2127,15 @@ static wae_status run_group(wae_batch* b, const wae_batch::Group& g) {
         }
         return true;
     };
-    for (size_t sg = 0; sg + 1 < b->seg_bounds.size(); sg++) {  // render segments between suspend points (usually one)
+    for (size_t sg = 0; sg + 1 < g.seg_bounds.size(); sg++) {  // render segments between suspend points (usually one)
         const size_t s0 = g.seg_stages[sg].first, s1 = g.seg_stages[sg].second;
         // stages are sorted by class: [whole-chunk stages of feedback-free graphs | per-quantum stages | whole-chunk stages after cycles]
         size_t c1 = s0, c2 = s0;
         while (c1 < s1 && b->stages[c1].cls == 0) c1++;
         c2 = c1;
         while (c2 < s1 && b->stages[c2].cls == 1) c2++;
-        const int64_t seg_end = b->seg_bounds[sg + 1];
-        for (int64_t f0 = b->seg_bounds[sg]; f0 < seg_end; f0 += b->chunk) {
+        const int64_t seg_end = g.seg_bounds[sg + 1];
+        for (int64_t f0 = g.seg_bounds[sg]; f0 < seg_end; f0 += b->chunk) {
             const ChunkInfo ci{f0, (int32_t)std::min<int64_t>(b->chunk, seg_end - f0), 0};
             if (b->time_stages) {
                 e_prev = next_event();
