@@ -126,7 +126,7 @@ def random_graph(pkg, be, seed, tap=None):
         lfo.start()
         outs.append((tgt, 4.0))
     # ---- a feedback loop through a DelayNode
-    if rng.random() < 0.4 and not has_conv:  # (a ConvolverNode upstream of a feedback loop is WAE_UNSUPPORTED)
+    if rng.random() < 0.4:
         d = c.create_delay(max_delay_time=0.05, delay_time=float(rng.uniform(0.003, 0.02)))
         fb = c.create_gain(float(rng.uniform(0.2, 0.6)))
         pick()[0].connect(d)

@@ -668,16 +668,38 @@ def test_feedback_echo_into_reverb_and_mixed_batch(pkg, engine, oracle, chunk):
     assert maxdiff(gpu, cpu) <= TOL
 
 
-def test_convolver_upstream_of_feedback_is_reported(pkg, engine):
+def test_convolver_around_feedback(pkg, engine, oracle):
+    """A reverb FEEDING an echo loop runs time-batched before the per-quantum part; a ConvolverNode INSIDE the loop is reported."""
+    ir = G.synthetic_ir(2000, 1, decay=0.02)
+    n = 128 * 70
+
+    def build(be, g):
+        pcm = G.c2_source(g, n)
+        pcm[:, 128 * 4:] = 0
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0]], G.SR), loop=True)
+        cv = c.create_convolver(pkg.AudioBuffer(ir, G.SR))
+        d = c.create_delay(max_delay_time=0.05, delay_time=[0.004, 0.0113][g])
+        fb = c.create_gain(0.5)
+        s.connect(cv)
+        cv.connect(d)
+        d.connect(fb)
+        fb.connect(d)
+        d.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert float(np.abs(cpu).max()) > 1e-3
+    assert maxdiff(gpu, cpu) <= TOL
+
     c = pkg.OfflineAudioContext(1, 128 * 4, G.SR, engine.backend)
     s = c.create_constant_source()
     cv = c.create_convolver(pkg.AudioBuffer([np.ones(4, np.float32)], G.SR))
     d = c.create_delay(max_delay_time=0.05, delay_time=0.004)
-    fb = c.create_gain(0.5)
-    s.connect(cv)
+    s.connect(d)
+    d.connect(cv)
     cv.connect(d)
-    d.connect(fb)
-    fb.connect(d)
     d.connect(c.destination())
     s.start()
     with pytest.raises(pkg.WaeError) as e:

@@ -410,10 +410,11 @@ struct Planner {
         return false;
     }
 
-    // Scheduling class of a stage: 0 = graph without DelayNode feedback (whole chunks); for a graph with feedback, 1 = the
-    // node is an ancestor of a cycle-breaking DelayWriter, i.e. inside or upstream of a feedback cycle (replayed quantum by
-    // quantum inside the chunk, like the reference's render loop), 2 = everything else of that graph: downstream of the
-    // cycles only, whole chunks again (e.g. a reverb after an echo loop).
+    // Scheduling class of a stage.  Graphs without DelayNode feedback: 0 (whole chunks).  Graphs with feedback: 0 = strictly
+    // upstream of every cycle (whole chunks, rendered first: sources, a reverb feeding an echo loop), 1 = on a path from a
+    // cycle to a cycle-breaking DelayWriter, i.e. inside a feedback cycle or between two of them (replayed quantum by quantum
+    // inside the chunk, like the reference's render loop), 2 = the rest: downstream of the cycles only (whole chunks again,
+    // e.g. a reverb after an echo loop).
     int cur_cls = 0;  // class of the node being planned
     StageBuild& stage(int level, int kind, int variant = 0) {
         const int cls = cur_cls;
@@ -520,7 +521,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
     if (!dry && n.buffer && cur_cls == 1)
-        return bail(WAE_UNSUPPORTED, "a ConvolverNode inside or upstream of a DelayNode feedback cycle is not lowered to the GPU (after the cycle it is)");
+        return bail(WAE_UNSUPPORTED, "a ConvolverNode inside a DelayNode feedback cycle is not lowered to the GPU (before or after the cycle it is)");
     if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
         pn.out_ch = {in_ch};
         pn.out_buf = {pn.in_buf[0]};
@@ -671,7 +672,25 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             for (uint32_t y : rev[x]) todo.push_back(y);
         }
     }
-    auto node_class = [&](uint32_t id) { return ord.broken.empty() ? 0 : (feeds_cycle.count(id) ? 1 : 2); };
+    // ... and of those, the ones a cycle feeds (descendants of the readers of the broken delays): only they depend on
+    // audio that is produced quantum by quantum
+    std::set<uint32_t> fed_by_cycle;
+    if (!ord.broken.empty()) {
+        std::vector<uint32_t> todo;
+        for (uint32_t w : ord.broken) todo.push_back(g->nodes.at(w).delay_peer);
+        while (!todo.empty()) {
+            uint32_t x = todo.back();
+            todo.pop_back();
+            if (!fed_by_cycle.insert(x).second) continue;
+            auto it = ord.edges.find(x);
+            if (it == ord.edges.end()) continue;
+            for (auto& e : it->second) todo.push_back(e.other_id);
+        }
+    }
+    auto node_class = [&](uint32_t id) {
+        if (ord.broken.empty() || !feeds_cycle.count(id)) return ord.broken.empty() ? 0 : 2;
+        return fed_by_cycle.count(id) ? 1 : 0;
+    };
     std::map<uint32_t, PNode> pn;
     cur_pn = &pn;
     for (auto& kv : g->nodes) {
