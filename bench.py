@@ -246,7 +246,9 @@ def main():
     ctxs = build_c2_batch(pkg, eng.backend, n_graphs, length, seed_base=rank * n_graphs)
     batch = pkg.Batch(ctxs)
     eng.set_option(pkg.OPT_PIPELINE_GROUPS, args.groups)
-    batch_e2e = pkg.Batch(ctxs)
+    t_prep = time.perf_counter()
+    batch_e2e = pkg.Batch(ctxs)  # wae_batch_prepare: planning + allocation + the first upload of the source PCM
+    prepare_ms = (time.perf_counter() - t_prep) * 1e3
     stats0 = batch.stats()
     out_floats = n_graphs * 2 * length
     host_out = torch.empty(out_floats, dtype=torch.float32, pin_memory=True)
@@ -396,7 +398,7 @@ def main():
                        "graphs_per_gpu": n_graphs, "frames_per_graph": length, "chunk_frames": int(stats0.chunks and (length + 127) // 128 * 128 // stats0.chunks),
                        "l2": "inputs (%.2f GB/GPU) larger than L2, no flush" % (stats.asset_bytes / 1e9),
                        "sharding": "independent graphs per rank, no data-path collective", "e2e_pipeline_groups": args.groups},
-            "samples_per_sec": value * 128, "gpu_launches": int(stats.kernel_launches_per_run) * args.steps,
+            "samples_per_sec": value * 128, "prepare_ms_once": prepare_ms, "gpu_launches": int(stats.kernel_launches_per_run) * args.steps,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "graph-quanta/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3},

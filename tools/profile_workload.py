@@ -27,7 +27,13 @@ def main():
         eng.backend.set_hrir_sphere(G.synthetic_hrir_sphere(48000, 512))
         build = lambda g: G.c5_full_chain(pkg, eng.backend, g, n, ir3)
     eng.set_option(pkg.OPT_PIPELINE_GROUPS, 1)
-    batch = pkg.Batch([build(g) for g in range(graphs)])
+    import time
+    t0 = time.perf_counter()
+    ctxs = [build(g) for g in range(graphs)]
+    t1 = time.perf_counter()
+    batch = pkg.Batch(ctxs)
+    t2 = time.perf_counter()
+    print(f"graph building (ctypes) {1e3 * (t1 - t0):.1f} ms, wae_batch_prepare {1e3 * (t2 - t1):.1f} ms")
     batch.set_timing(True)
     for _ in range(3):
         batch.run()

@@ -25,6 +25,7 @@
 #include <set>
 #include <tuple>
 #include <unordered_map>
+#include <unordered_set>
 
 using namespace wae;
 namespace hm = wae::hostmath;
@@ -227,10 +228,12 @@ struct Orderer {
     std::map<uint32_t, std::vector<Edge>> edges;  // working copy: cycle breakers clear a DelayWriter's edges
     std::vector<uint32_t> ordered, marked, marked_temp, in_cycle, cycle_breakers, broken;
     static bool contains(const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); }
-    // returns true when a cycle breaker was applied (the ordering is then restarted), graph.rs:331-403
+    // returns true when a cycle breaker was applied (the ordering is then restarted), graph.rs:331-403.  Same visiting order
+    // as the reference; membership tests use hash sets instead of its linear `contains` (O(n^2) on 10^4-node graphs).
+    std::unordered_set<uint32_t> marked_set, temp_set;
     bool visit(uint32_t id) {
-        auto it = std::find(marked_temp.begin(), marked_temp.end(), id);
-        if (it != marked_temp.end()) {
+        if (temp_set.count(id)) {
+            auto it = std::find(marked_temp.begin(), marked_temp.end(), id);
             for (auto jt = it; jt != marked_temp.end(); ++jt)
                 if (g->nodes.at(*jt).cycle_breaker) {
                     cycle_breakers.push_back(*jt);
@@ -239,20 +242,25 @@ struct Orderer {
             in_cycle.insert(in_cycle.end(), it, marked_temp.end());  // no DelayNode in the cycle: its nodes are muted
             return false;
         }
-        if (contains(marked, id)) return false;
-        marked.push_back(id);
+        if (!marked_set.insert(id).second) return false;
         marked_temp.push_back(id);
+        temp_set.insert(id);
         const std::vector<Edge>& out = edges.at(id);
         for (size_t i = 0; i < out.size(); i++)
             if (g->nodes.count(out[i].other_id) && visit(out[i].other_id)) return true;
         ordered.push_back(id);
-        marked_temp.erase(std::remove(marked_temp.begin(), marked_temp.end(), id), marked_temp.end());
+        // `id` is the innermost node still being visited: it is the last entry of the stack unless an unbroken cycle was
+        // recorded below it, in which case the reference's `retain` removes it wherever it is
+        if (!marked_temp.empty() && marked_temp.back() == id) marked_temp.pop_back();
+        else marked_temp.erase(std::remove(marked_temp.begin(), marked_temp.end(), id), marked_temp.end());
+        temp_set.erase(id);
         return false;
     }
     void run() {  // graph.rs:418-487
         for (auto& kv : g->nodes) edges[kv.first] = kv.second.outgoing;
         for (;;) {
             ordered.clear(); marked.clear(); marked_temp.clear(); in_cycle.clear(); cycle_breakers.clear();
+            marked_set.clear(); temp_set.clear();
             bool applied = false;
             for (auto& kv : g->nodes) {
                 applied = visit(kv.first);
@@ -264,7 +272,10 @@ struct Orderer {
                 if (!contains(broken, id)) broken.push_back(id);
             }
         }
-        ordered.erase(std::remove_if(ordered.begin(), ordered.end(), [&](uint32_t o) { return contains(in_cycle, o); }), ordered.end());
+        if (!in_cycle.empty()) {
+            std::unordered_set<uint32_t> muted(in_cycle.begin(), in_cycle.end());
+            ordered.erase(std::remove_if(ordered.begin(), ordered.end(), [&](uint32_t o) { return muted.count(o) != 0; }), ordered.end());
+        }
         std::reverse(ordered.begin(), ordered.end());
     }
 };
