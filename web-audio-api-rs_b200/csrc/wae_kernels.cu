@@ -2066,7 +2066,7 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
         while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
     }
 }
-__global__ void __launch_bounds__(CV_MAC_THREADS) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
+__global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
                                                              ChunkInfo ci) {
     const ConvPath p = paths[blockIdx.y];
     const ConvInput ip = inputs[p.input];
