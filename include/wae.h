@@ -338,7 +338,9 @@ WAE_API wae_status wae_batch_set_timing(wae_batch* batch, uint32_t per_stage);
 WAE_API wae_status wae_batch_run(wae_batch* batch);                       /* async on the engine stream   */
 /* End-to-end render with HOST buffers: per graph group H2D(source PCM, pinned mirror) -> render -> D2H into host_out
  * ([n_graphs][channels][length] f32, ideally pinned), the three legs of neighbouring groups overlapped on three
- * streams.  Synchronous.  wae_render_batch(..., WAE_RENDER_OUT_HOST) is prepare + this + destroy. */
+ * streams.  Synchronous.  The pinned host mirror of the source PCM is built on the first call.  wae_render_batch(...,
+ * WAE_RENDER_OUT_HOST) is prepare (which uploads the sources straight from the graphs' buffers) + group-wise render with
+ * overlapped D2H + destroy. */
 WAE_API wae_status wae_batch_run_pipelined(wae_batch* batch, float* host_out);
 WAE_API wae_status wae_batch_sync(wae_batch* batch);                      /* wait for the stream           */
 WAE_API wae_status wae_batch_output_device_ptr(wae_batch* batch, float** out_dev, uint64_t* out_floats);

@@ -58,6 +58,25 @@ def test_chunk_invariance(pkg, engine, oracle, chunk):
         engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
 
 
+def test_one_shot_render_batch_abi(pkg, engine, oracle):
+    """wae_render_batch(HOST): prepare + render + D2H in ONE call, the entry point the Rust binding uses."""
+    import ctypes as C
+    n_graphs, length = 5, 128 * 37 + 11
+    ctxs = [G.c2_buffer_biquad_gain(pkg, engine.backend, g, length) for g in range(n_graphs)]
+    out = np.zeros((n_graphs, 2, length), np.float32)
+    arr = (C.c_void_p * n_graphs)(*[c._g for c in ctxs])
+    api = engine.backend.api
+    api.check(api.render_batch(engine.backend.engine, arr, n_graphs, out.ctypes.data_as(C.c_void_p), 0))
+    cpu = G.render(pkg, [G.c2_buffer_biquad_gain(pkg, oracle, g, length) for g in range(n_graphs)])
+    assert maxdiff(out, cpu) <= TOL
+    # the pipelined path (pinned mirror built on first use) gives the same PCM
+    b = pkg.Batch([G.c2_buffer_biquad_gain(pkg, engine.backend, g, length) for g in range(n_graphs)])
+    out2 = np.zeros_like(out)
+    b.run_pipelined(out2.ctypes.data_as(C.c_void_p))
+    b.run_pipelined(out2.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(out, out2)
+
+
 def test_c3_many_voices_summation_order(pkg, engine, oracle):
     # C3 scaled down: 300 voices summed at the destination in the reference's order (last-created first)
     gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c3_many_voices(pkg, be, 300, 128 * 40))

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -150,7 +152,13 @@ struct wae_batch {
         std::vector<std::pair<size_t, size_t>> seg_stages;  // per render segment: its stages
         std::vector<int64_t> seg_bounds;                    // 0 = b0 < b1 < ... < lq: the suspend frames of this group's graphs
         float* d_src = nullptr;         // device slab of source PCM
-        float* h_src = nullptr;         // pinned host mirror
+        float* h_src = nullptr;         // pinned host mirror, built on first use (wae_batch_upload / wae_batch_run_pipelined)
+        struct SrcCopy {                // one channel of one AudioBufferSourceNode's PCM inside the slab
+            std::shared_ptr<PcmBuffer> buf;
+            int channel;
+            size_t offset, len;         // floats
+        };
+        std::vector<SrcCopy> src_copies;
         size_t src_floats = 0;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     };
@@ -176,6 +184,7 @@ struct wae_batch {
     bool time_stages = false;
     size_t timed_events_used = 0;
     uint64_t arena_bytes = 0, asset_bytes = 0;
+    uint64_t n_cuda_malloc = 0;  // prepare-time diagnostics (WAE_PREPARE_PROFILE=1)
 
     // small per-node state that is zeroed before every run lives in slabs: one memset per slab, not per node
     char* slab = nullptr;
@@ -207,6 +216,7 @@ struct wae_batch {
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
         if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        n_cuda_malloc++;
         allocs.push_back(p);
         if (zero || rezero_on_run) cudaMemsetAsync(p, 0, bytes, engine->stream);
         if (rezero_on_run) zero_on_run.push_back({p, bytes});
@@ -324,7 +334,7 @@ struct Planner {
     uint64_t arena_floats_per_frame = 0;
     // source PCM slab of the group being planned (device pointer, pinned host mirror, cursor in floats)
     float* d_src = nullptr;
-    float* h_src = nullptr;
+    std::vector<wae_batch::Group::SrcCopy>* src_copies = nullptr;
     size_t src_cursor = 0;
     struct PendingChain {
         ChainInst inst;
@@ -1098,12 +1108,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (first_use) so = src_offsets.emplace(std::make_pair(gi, id), src_cursor).first;
                 float* d_buf = d_src + so->second;
                 if (first_use) {
-                    if (!dry)
-                        for (int c = 0; c < ch; c++) {
-                            float* dst = h_src + src_cursor + (size_t)c * stride;
-                            std::memcpy(dst, pb.channels[c].data(), len * sizeof(float));
-                            for (size_t i = len; i < stride; i++) dst[i] = 0.f;
-                        }
+                    if (!dry && src_copies)  // uploaded straight from the graph's buffer after planning (no staging copy)
+                        for (int c = 0; c < ch; c++)
+                            src_copies->push_back(wae_batch::Group::SrcCopy{n.buffer, c, src_cursor + (size_t)c * stride, len});
                     src_cursor += (size_t)ch * stride;
                     b->asset_bytes += (size_t)ch * len * 4;
                 }
@@ -1815,6 +1822,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
             graphs[i]->sample_rate != graphs[0]->sample_rate)
             return fail(WAE_INVALID_ARGUMENT, "all graphs of a batch must share number_of_channels, length and sample_rate");
     }
+    const auto t_prep0 = std::chrono::steady_clock::now();
     auto* b = new wae_batch;
     b->engine = eng;
     b->n_graphs = n_graphs;
@@ -1916,6 +1924,7 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         }
         if (!hints_changed) break;
     }
+    const auto t_prep1 = std::chrono::steady_clock::now();  // sizing pass done
     b->arena_bytes = 0;
     b->asset_bytes = 0;
     int64_t chunk = eng->chunk_frames;
@@ -1944,19 +1953,15 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_h2d, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_done, cudaEventDisableTiming));
         if (grp.src_floats) {
-            grp.d_src = b->dalloc<float>(grp.src_floats);
-            void* hp = nullptr;
-            if (!grp.d_src || cudaHostAlloc(&hp, grp.src_floats * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
+            grp.d_src = b->dalloc<float>(grp.src_floats, true);  // zeroed: the channel paddings stay zero
+            if (!grp.d_src) {
                 wae_batch_destroy(b);
-                return fail(WAE_OUT_OF_MEMORY, "out of memory (source PCM slab / pinned mirror)");
+                return fail(WAE_OUT_OF_MEMORY, "out of device memory (source PCM slab)");
             }
-            b->pinned.push_back(hp);
-            grp.h_src = (float*)hp;
         }
         Planner pl{b, eng};
         pl.d_src = grp.d_src;
-        pl.h_src = grp.h_src;
+        pl.src_copies = &grp.src_copies;
         pl.delay_ch_hint = &delay_ch_hint;
         pl.ir_cache.swap(ir_cache);
         grp.stage0 = b->stages.size();
@@ -2043,13 +2048,22 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         }  // segments
         ir_cache.swap(pl.ir_cache);
         grp.stage1 = b->stages.size();
-        // first upload of the group's source PCM
-        if (grp.src_floats)
-            CUDA_TRY(cudaMemcpyAsync(grp.d_src, grp.h_src, grp.src_floats * sizeof(float), cudaMemcpyHostToDevice, eng->stream));
+        // first upload of the group's source PCM, straight from the graphs' buffers (a one-shot render never pays for a
+        // pinned staging copy; the pinned mirror of the pipelined path is built on first use)
+        for (auto& sc : grp.src_copies)
+            CUDA_TRY(cudaMemcpyAsync(grp.d_src + sc.offset, sc.buf->channels[sc.channel].data(), sc.len * sizeof(float), cudaMemcpyHostToDevice,
+                                     eng->stream));
     }
+    const auto t_prep2 = std::chrono::steady_clock::now();  // planned, allocated, uploads enqueued
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
     CUDA_TRY(cudaStreamSynchronize(eng->stream));
+    if (getenv("WAE_PREPARE_PROFILE")) {
+        const auto t_prep3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+        std::fprintf(stderr, "[wae prepare] sizing %.1f ms, plan+alloc+upload %.1f ms, sync %.1f ms, cudaMalloc calls %llu, stages %zu\n", ms(t_prep0, t_prep1),
+                     ms(t_prep1, t_prep2), ms(t_prep2, t_prep3), (unsigned long long)b->n_cuda_malloc, b->stages.size());
+    }
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) {
         wae_batch_destroy(b);
@@ -2118,9 +2132,28 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
     }
 }
 
+// pinned host mirror of every group's source-PCM slab: built once, when the PCM is uploaded a second time
+static wae_status ensure_host_mirror(wae_batch* b) {
+    for (auto& g : b->groups) {
+        if (!g.src_floats || g.h_src) continue;
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, g.src_floats * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(WAE_OUT_OF_MEMORY, "out of memory (pinned mirror of the source PCM)");
+        }
+        b->pinned.push_back(hp);
+        g.h_src = (float*)hp;
+        std::memset(hp, 0, g.src_floats * sizeof(float));
+        for (auto& sc : g.src_copies) std::memcpy(g.h_src + sc.offset, sc.buf->channels[sc.channel].data(), sc.len * sizeof(float));
+    }
+    return WAE_OK;
+}
+
 // re-upload the source PCM of every AudioBufferSourceNode from the pinned host mirror (one copy per group)
 WAE_API wae_status wae_batch_upload(wae_batch* b) {
     CUDA_TRY(cudaSetDevice(b->engine->device));
+    wae_status ms = ensure_host_mirror(b);
+    if (ms != WAE_OK) return ms;
     for (auto& g : b->groups)
         if (g.src_floats)
             CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->engine->stream));
@@ -2214,13 +2247,15 @@ WAE_API wae_status wae_batch_run(wae_batch* b) {
 // End-to-end render with HOST buffers: for every group, H2D of its source PCM (pinned mirror), render, D2H of its
 // rendered PCM into `host_out` ([n_graphs][channels][length] f32; pinned memory gives full PCIe speed) — on three
 // streams, so the copies of neighbouring groups overlap the render.  Synchronous: returns when host_out is complete.
-WAE_API wae_status wae_batch_run_pipelined(wae_batch* b, float* host_out) {
-    wae_status st = begin_run(b);
+static wae_status run_pipelined(wae_batch* b, float* host_out, bool resend_sources) {
+    wae_status st = resend_sources ? ensure_host_mirror(b) : WAE_OK;
+    if (st != WAE_OK) return st;
+    st = begin_run(b);
     if (st != WAE_OK) return st;
     cudaStream_t s = b->engine->stream;
     const size_t per_graph = (size_t)b->channels * b->length;
     for (auto& g : b->groups) {
-        if (g.src_floats) {
+        if (g.src_floats && resend_sources) {
             CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->s_h2d));
             CUDA_TRY(cudaEventRecord(g.ev_h2d, b->s_h2d));
             CUDA_TRY(cudaStreamWaitEvent(s, g.ev_h2d, 0));
@@ -2239,6 +2274,8 @@ WAE_API wae_status wae_batch_run_pipelined(wae_batch* b, float* host_out) {
     if (le != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string("run_pipelined: ") + cudaGetErrorString(le));
     return WAE_OK;
 }
+
+WAE_API wae_status wae_batch_run_pipelined(wae_batch* b, float* host_out) { return run_pipelined(b, host_out, true); }
 
 WAE_API wae_status wae_batch_sync(wae_batch* b) {
     CUDA_TRY(cudaSetDevice(b->engine->device));
@@ -2299,7 +2336,7 @@ WAE_API wae_status wae_render_batch(wae_engine* eng, wae_graph* const* graphs, u
     wae_status st = wae_batch_prepare(eng, graphs, n_graphs, &b);
     if (st != WAE_OK) return st;
     if (!(flags & WAE_RENDER_OUT_DEVICE)) {
-        st = wae_batch_run_pipelined(b, out);  // source PCM was uploaded at prepare; the pipeline re-sends it per group
+        st = run_pipelined(b, out, false);  // source PCM was uploaded at prepare: render group by group, D2H overlapped
         std::string saved0 = wae_last_error();
         wae_batch_destroy(b);
         if (st != WAE_OK) set_error(saved0);
