@@ -39,3 +39,36 @@ def test_convolver_channel_config_on_gpu(pkg, engine, case):
     # the reference asserts abs <= 1e-7 with its 2048-point FFTs; the engine's 16384-point f32 FFT (8192-frame partitions)
     # returns 1 - 2^-23 for a unit tap: one f32 ulp at 1.0, so the bound here is 2 ulp
     K.test_convolver_channel_config(pkg, engine.backend, case, tol=2.4e-7)
+
+
+# ---- src/node/audio_buffer_source.rs:974-1890, restated in tests/test_oracle_absn.py -------------------------------------
+import test_oracle_absn as A  # noqa: E402
+
+ABSN_CASES = [
+    A.test_sub_quantum_start_1, A.test_sub_quantum_start_2, A.test_sub_sample_start, A.test_sub_quantum_stop, A.test_sub_sample_stop,
+    A.test_start_in_the_past, A.test_playback_rate_and_detune, A.test_negative_playback_rate, A.test_end_of_file,
+    A.test_with_duration_and_offset, A.test_reverse_playback_with_duration, A.test_offset_larger_than_buffer_duration,
+    A.test_reverse_loop_boundaries,
+]
+
+
+@pytest.mark.parametrize("case", ABSN_CASES, ids=lambda f: f.__name__)
+def test_buffer_source_reference_case_on_gpu(pkg, engine, case):
+    case(pkg, engine.backend)
+
+
+@pytest.mark.parametrize("buf_sr", [22500, 38000, 43800, 48000, 96000])
+def test_buffer_source_resampling_on_gpu(pkg, engine, buf_sr):
+    A.test_audio_buffer_resampling(pkg, engine.backend, buf_sr)
+
+
+@pytest.mark.parametrize("buffer_len", A.LOOP_LENS)
+def test_buffer_source_loops_on_gpu(pkg, engine, buffer_len):
+    A.test_track_loop_mono(pkg, engine.backend, buffer_len)
+    A.test_track_loop_stereo(pkg, engine.backend, buffer_len)
+
+
+@pytest.mark.parametrize("bounds", [(-2.0, -1.0, 0.0), (-1.0, -2.0, 0.0), (0.0, 0.0, 0.0), (-1.0, 2.0, 0.0), (2.0, -1.0, 1e-10), (1.0, 1.0, 1e-10),
+                                    (2.0, 3.0, 1e-10), (3.0, 2.0, 1e-10)])
+def test_buffer_source_loop_out_of_bounds_on_gpu(pkg, engine, bounds):
+    A.test_loop_out_of_bounds(pkg, engine.backend, *bounds)
