@@ -72,3 +72,16 @@ def test_buffer_source_loops_on_gpu(pkg, engine, buffer_len):
                                     (2.0, 3.0, 1e-10), (3.0, 2.0, 1e-10)])
 def test_buffer_source_loop_out_of_bounds_on_gpu(pkg, engine, bounds):
     A.test_loop_out_of_bounds(pkg, engine.backend, *bounds)
+
+
+# ---- src/node/delay.rs:766-1200, restated in tests/test_oracle_delay.py ----------------------------------------------------
+import test_oracle_delay as D  # noqa: E402
+
+DELAY_CASES = [D.test_sample_accurate, D.test_sub_sample_accurate, D.test_multichannel, D.test_input_number_of_channels_change,
+               D.test_node_stays_alive_long_enough, D.test_subquantum_delay, D.test_min_delay_when_in_loop, D.test_max_delay,
+               D.test_max_delay_smaller_than_quantum_size, D.test_max_delay_multiple_of_quantum_size, D.test_subquantum_delay_dynamic_lifetime]
+
+
+@pytest.mark.parametrize("case", DELAY_CASES, ids=lambda f: f.__name__)
+def test_delay_reference_case_on_gpu(pkg, engine, case):
+    case(pkg, engine.backend)
