@@ -85,3 +85,16 @@ DELAY_CASES = [D.test_sample_accurate, D.test_sub_sample_accurate, D.test_multic
 @pytest.mark.parametrize("case", DELAY_CASES, ids=lambda f: f.__name__)
 def test_delay_reference_case_on_gpu(pkg, engine, case):
     case(pkg, engine.backend)
+
+
+# ---- src/node/oscillator.rs:806-1455, restated in tests/test_oracle_osc.py ---------------------------------------------------
+import test_oracle_osc as OS  # noqa: E402
+
+OSC_CASES = [OS.test_sine_raw, OS.test_square_and_sawtooth_raw_away_from_the_steps, OS.test_periodic_wave, OS.test_sub_quantum_and_sub_sample_start,
+             OS.test_sub_quantum_and_sub_sample_stop, OS.test_stop_disarms_future_start, OS.test_start_in_the_past,
+             OS.test_computed_frequency_outside_nyquist_is_silent, OS.test_delayed_start_and_negative_frequency]
+
+
+@pytest.mark.parametrize("case", OSC_CASES, ids=lambda f: f.__name__)
+def test_oscillator_reference_case_on_gpu(pkg, engine, case):
+    case(pkg, engine.backend)

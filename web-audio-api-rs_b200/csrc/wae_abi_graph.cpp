@@ -529,10 +529,10 @@ WAE_API wae_status wae_source_start(wae_graph* g, wae_node_id node, double when,
     if (n.has_start) return fail(WAE_INVALID_STATE, "InvalidStateError - Cannot call `start` twice");
     if (n.kind == K_ABSN && (!(offset >= 0.) || !(duration >= 0.))) return fail(WAE_INVALID_ARGUMENT, "RangeError - offset/duration should be positive");
     n.has_start = true;
-    // issued from a suspend_sync callback: an AudioBufferSource start time in the past snaps to the quantum the render is
-    // suspended at, the first one that sees the message (audio_buffer_source.rs:519-523; test_start_in_the_past :1151-1172).
-    // An oscillator instead starts with the phase it would have reached (oscillator.rs:527-537): its start time is kept.
-    if (!g->epochs.empty() && n.kind != K_OSC) when = std::max(when, (double)g->epochs.back().frame / (double)g->sample_rate);
+    // issued from a suspend_sync callback: a start time in the past snaps to the quantum the render is suspended at, the first
+    // one that sees the message (oscillator.rs `if !started && start_time < current_time`, audio_buffer_source.rs:519-523;
+    // the reference's test_start_in_the_past for both nodes)
+    if (!g->epochs.empty()) when = std::max(when, (double)g->epochs.back().frame / (double)g->sample_rate);
     n.start_time = when;
     if (n.kind == K_ABSN) {
         n.offset = offset;
