@@ -284,6 +284,17 @@ WAE_API wae_status wae_create_channel_splitter(wae_graph*, const wae_channel_spl
 /* AudioNode::connect_from_output_to_input (src/node/audio_node.rs:259-289); destination is node 0. */
 WAE_API wae_status wae_connect(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t input);
 /* AudioNode::connect(&param): audio-rate modulation of a param (src/param.rs:762-796). */
+/* Host-side simulation of ONE AudioParam, block by block (no GPU involved): the engine's event folding and per-quantum state
+ * machine — the code the planner and the k_param kernel run — driven like the reference's unit tests drive
+ * AudioParamProcessor (src/param.rs:1766-3545: handle_incoming_event, then compute_intrinsic_values(block_time, dt, count)).
+ * `out` holds `count` (<= 128) floats; *len = 1 for a single-valued block, else count. */
+typedef struct wae_param_sim wae_param_sim;
+WAE_API wae_status wae_param_sim_create(uint32_t a_rate, float default_value, float min_value, float max_value, wae_param_sim** out);
+WAE_API wae_status wae_param_sim_destroy(wae_param_sim* sim);
+WAE_API wae_status wae_param_sim_push(wae_param_sim* sim, const wae_param_event* event);
+WAE_API wae_status wae_param_sim_set_automation_rate(wae_param_sim* sim, uint32_t a_rate);
+WAE_API wae_status wae_param_sim_compute(wae_param_sim* sim, double block_time, double dt, uint32_t count, float* out, uint32_t* len);
+
 /* OfflineAudioContext::suspend_sync(suspend_time, callback) (src/context/offline.rs:330-387): call this, then run the
  * callback; graph mutations issued afterwards (new nodes, connections, param events, start / stop) take effect at the
  * suspend frame (suspend_time quantised up to a render quantum).  Suspend points must be taken in increasing time order. */

@@ -537,6 +537,28 @@ WAO_API wae_status wao_param_event_push(wae_graph* g, wae_node_id node, uint32_t
     return push_event(p, e);
 }
 
+// test hooks: one AudioParamProcessor driven like the reference's unit tests (param.rs:1766-3545)
+WAO_API wae_status wao_param_sim_create(uint32_t a_rate, float default_value, float min_value, float max_value, void** out) {
+    *out = new ParamProcessor(ParamDescriptor{default_value, min_value, max_value, a_rate != 0});
+    return WAE_OK;
+}
+WAO_API wae_status wao_param_sim_destroy(void* s) {
+    delete static_cast<ParamProcessor*>(s);
+    return WAE_OK;
+}
+WAO_API wae_status wao_param_sim_push(void* s, const wae_param_event* e) { return push_event(static_cast<ParamProcessor*>(s), e); }
+WAO_API wae_status wao_param_sim_set_automation_rate(void* s, uint32_t a_rate) {
+    static_cast<ParamProcessor*>(s)->a_rate = a_rate != 0;
+    return WAE_OK;
+}
+WAO_API wae_status wao_param_sim_compute(void* s, double block_time, double dt, uint32_t count, float* out, uint32_t* len) {
+    auto* p = static_cast<ParamProcessor*>(s);
+    p->compute_buffer(block_time, dt, (int)count);
+    for (int i = 0; i < p->buffer_len; i++) out[i] = p->buffer[i];
+    *len = (uint32_t)p->buffer_len;
+    return WAE_OK;
+}
+
 WAO_API wae_status wao_listener_param_event_push(wae_graph* g, uint32_t param_index, const wae_param_event* e) {
     if (param_index >= 9) return fail(WAE_INVALID_ARGUMENT, "unknown listener param");
     g->ensure_listener();

@@ -1,0 +1,408 @@
+"""The reference's AudioParamProcessor unit tests (src/param.rs:1765-3300: handle_incoming_event + compute_intrinsic_values on
+one processor, block by block) restated as data and run against BOTH param implementations of this repo on the CPU:
+
+* "oracle"  — oracle/wao_param.cpp (the parity checker), through its wao_param_sim_* test hooks;
+* "engine"  — the product's own host code: the event folding of csrc/wae_param_host.h and the state machine of
+  csrc/wae_param_core.h, which is the code the planner replays at suspend points AND the code the k_param CUDA kernel
+  executes (same header, __host__ __device__), through wae_param_sim_* (include/wae.h).  No GPU is involved.
+
+Expected values that the reference computes with powf / exp are recomputed here with numpy; they are compared at 2 f32 ulp
+instead of the reference's exact 0 (libm vs numpy), everything else keeps the reference's tolerance."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+A, K = 1, 0
+F = np.float32
+
+
+class Sim:
+    def __init__(self, api, rate, default, mn, mx, pkg):
+        self.api, self.pkg = api, pkg
+        self.h = C.c_void_p()
+        api.check(api.param_sim_create(rate, default, mn, mx, C.byref(self.h)))
+        self.keep = []
+
+    def _push(self, type_, value=0.0, time=0.0, aux=0.0, values=None):
+        B = self.pkg._binding
+        ev = B.ParamEvent(type_, float(value), float(time), float(aux), None, 0)
+        if values is not None:
+            arr = np.ascontiguousarray(values, np.float32)
+            self.keep.append(arr)
+            ev.values, ev.values_len = arr.ctypes.data_as(C.POINTER(C.c_float)), len(arr)
+        self.api.check(self.api.param_sim_push(self.h, C.byref(ev)))
+
+    def set_value_at_time(self, v, t):
+        self._push(1, v, t)
+
+    def linear(self, v, t):
+        self._push(2, v, t)
+
+    def exponential(self, v, t):
+        self._push(3, v, t)
+
+    def cancel(self, t):
+        self._push(4, 0.0, t)
+
+    def target(self, v, t, tc):
+        self._push(5, v, t, tc)
+
+    def cancel_and_hold(self, t):
+        self._push(6, 0.0, t)
+
+    def curve(self, values, t, duration):
+        self._push(7, 0.0, t, duration, values)
+
+    def set_rate(self, rate):
+        self.api.check(self.api.param_sim_set_automation_rate(self.h, rate))
+
+    def run(self, block_time, count=10, dt=1.0):
+        out = np.zeros(count, np.float32)
+        n = C.c_uint32(0)
+        self.api.check(self.api.param_sim_compute(self.h, float(block_time), float(dt), count, out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n)))
+        return out[:n.value].copy()
+
+    def close(self):
+        self.api.param_sim_destroy(self.h)
+
+
+@pytest.fixture(params=["oracle", "engine"])
+def sim(request, pkg, oracle):
+    if request.param == "oracle":
+        api = oracle.api
+    else:
+        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+        if not os.path.exists(so):
+            pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+        api = pkg.api()
+    made = []
+
+    def make(rate, default, mn, mx):
+        s = Sim(api, rate, default, mn, mx, pkg)
+        made.append(s)
+        return s
+
+    yield make
+    for s in made:
+        s.close()
+
+
+def eq(got, want, tol=0.0):
+    want = np.asarray(want, np.float32)
+    assert got.shape == want.shape, (got, want)
+    assert np.abs(got.astype(np.float64) - want).max() <= tol, (got, want)
+
+
+def ulp2(want):
+    return 2.4e-7 * max(1.0, float(np.abs(np.asarray(want)).max()))
+
+
+def exp_ramp(start, end, n, total):
+    return [F(start) * np.power(F(end) / F(start), F(t) / F(total), dtype=np.float32) for t in range(n)]
+
+
+def target_curve(v0, v1, t0, tc, ts):
+    return [F(v1) + (F(v0) - F(v1)) * F(np.exp(-((float(t) - t0) / tc))) for t in ts]
+
+
+def test_steps_a_rate(sim):  # param.rs:1814-1872
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(5.0, 2.0)
+    p.set_value_at_time(12.0, 8.0)  # (clamped later, in mix_to_output)
+    p.set_value_at_time(8.0, 10.0)
+    eq(p.run(0.0), [0, 0, 5, 5, 5, 5, 5, 5, 12, 12])
+    eq(p.run(10.0), [8.0])
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(5.0, 2.0)
+    p.set_value_at_time(8.0, 12.0)
+    eq(p.run(0.0), [0, 0, 5, 5, 5, 5, 5, 5, 5, 5])
+    eq(p.run(10.0), [5, 5, 8, 8, 8, 8, 8, 8, 8, 8])
+
+
+def test_steps_k_rate(sim):  # :1874-1899
+    p = sim(K, 0.0, -10.0, 10.0)
+    for v, t in [(5.0, 2.0), (12.0, 8.0), (8.0, 10.0), (3.0, 14.0)]:
+        p.set_value_at_time(v, t)
+    eq(p.run(0.0), [0.0])
+    eq(p.run(10.0), [8.0])
+    eq(p.run(20.0), [3.0])
+
+
+def test_linear_ramps_a_rate(sim):  # :1901-2033 linear_ramp_arate, _end_of_block, _implicit_set_value, _multiple_blocks
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(5.0, 2.0)
+    p.linear(8.0, 5.0)
+    p.linear(0.0, 13.0)
+    eq(p.run(0.0), [0, 0, 5, 6, 7, 8, 7, 6, 5, 4])
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.linear(9.0, 9.0)
+    eq(p.run(0.0), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+    p = sim(A, 0.0, -10.0, 10.0)
+    eq(p.run(0.0), [0.0])
+    p.linear(10.0, 20.0)  # arrives while rendering: ramps from the last event (time 0 of the implicit start) ... :1960-1992
+    eq(p.run(10.0), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+    eq(p.run(20.0), [10.0] * 10)
+    p = sim(A, 0.0, -20.0, 20.0)
+    p.linear(20.0, 20.0)
+    eq(p.run(0.0), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+    eq(p.run(10.0), [10, 11, 12, 13, 14, 15, 16, 17, 18, 19])
+    eq(p.run(20.0), [20.0] * 10)
+
+
+def test_linear_ramp_k_rate_and_start_time(sim):  # :2035-2128
+    for end, last in [(20.0, 20.0), (15.0, 15.0)]:
+        p = sim(K, 0.0, -20.0, 20.0)
+        p.linear(end, end)
+        eq(p.run(0.0), [0.0])
+        eq(p.run(10.0), [10.0])
+        eq(p.run(20.0), [last])
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(1.0, 0.0)
+    p.linear(-1.0, 10.0)
+    eq(p.run(0.0), [1, 0.8, 0.6, 0.4, 0.2, 0, -0.2, -0.4, -0.6, -0.8], 1e-7)
+    eq(p.run(10.0), [-1.0] * 10)
+    p.linear(1.0, 30.0)  # starts from the previous event (t = 10), not from "now"
+    eq(p.run(20.0), [0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9], 1e-7)
+
+
+def test_exponential_ramps(sim):  # :2130-2400
+    p = sim(A, 0.0, 0.0, 1.0)
+    p.set_value_at_time(0.0001, 0.0)
+    p.exponential(1.0, 10.0)
+    want = exp_ramp(0.0001, 1.0, 10, 10)
+    eq(p.run(0.0), want, ulp2(want))
+    eq(p.run(10.0), [1.0] * 10)
+    p = sim(A, 0.0, 0.0, 1.0)
+    p.set_value_at_time(0.0001, 3.0)
+    p.exponential(1.0, 13.0)
+    res = [0.0] * 3 + exp_ramp(0.0001, 1.0, 10, 10) + [1.0] * 7
+    eq(p.run(0.0), res[:10], ulp2(res))
+    eq(p.run(10.0), res[10:], ulp2(res))
+    # zero start value / opposite sign: the ramp degenerates into a step at its end time
+    p = sim(A, 0.0, 0.0, 1.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.exponential(1.0, 5.0)
+    eq(p.run(0.0), [0, 0, 0, 0, 0, 1, 1, 1, 1, 1])
+    p = sim(A, 0.0, -1.0, 1.0)
+    p.set_value_at_time(-1.0, 0.0)
+    p.exponential(1.0, 5.0)
+    eq(p.run(0.0), [-1, -1, -1, -1, -1, 1, 1, 1, 1, 1])
+    # k-rate
+    p = sim(K, 0.0, 0.0, 1.0)
+    p.set_value_at_time(0.0001, 3.0)
+    p.exponential(1.0, 13.0)
+    eq(p.run(0.0), [res[0]], ulp2(res))
+    eq(p.run(10.0), [res[10]], ulp2(res))
+    eq(p.run(20.0), [1.0])
+    for default in (0.0, -1.0):
+        p = sim(K, default, -1.0, 1.0)
+        p.exponential(1.0, 5.0)
+        eq(p.run(0.0), [default])
+        eq(p.run(10.0), [1.0])
+    # an exponential ramp pushed after a finished linear one starts from that one's end (:2362-2400)
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.linear(1.0, 10.0)
+    eq(p.run(0.0), [0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9], 1e-7)
+    eq(p.run(10.0), [1.0] * 10)
+    p.exponential(0.0001, 30.0)
+    eq(p.run(20.0), exp_ramp(1.0, 0.0001, 20, 20)[10:], 1e-7)
+
+
+def test_exponential_ramp_to_zero_is_rejected(sim, pkg):  # :2262-2272 #[should_panic]
+    p = sim(A, 1.0, 0.0, 1.0)
+    with pytest.raises(pkg.WaeError):
+        p.exponential(0.0, 10.0)
+
+
+def test_set_target(sim):  # :2402-2775
+    for pre in (True, False):  # with an explicit SetValueAtTime before it, or the implicit one
+        p = sim(A, 0.0, 0.0, 1.0)
+        if pre:
+            p.set_value_at_time(0.0, 0.0)
+        p.target(1.0, 0.0, 1.0)
+        want = target_curve(0.0, 1.0, 0.0, 1.0, range(10))
+        eq(p.run(0.0), want, ulp2(want))
+    p = sim(A, 0.0, 0.0, 100.0)
+    p.set_value_at_time(1.0, 1.0)
+    p.target(42.0, 1.0, 2.1)
+    want = target_curve(1.0, 42.0, 1.0, 2.1, range(10))
+    want[0] = 0.0
+    eq(p.run(0.0), want, ulp2(want))
+    p = sim(A, 0.0, 0.0, 100.0)
+    p.target(1.0, 1.0, 0.0)  # zero time constant == set_value_at_time
+    eq(p.run(0.0), [0.0] + [1.0] * 9)
+    # several blocks, then followed by a SetValueAtTime
+    p = sim(A, 0.0, 0.0, 2.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.target(2.0, 0.0, 1.0)
+    res = target_curve(0.0, 2.0, 0.0, 1.0, range(20))
+    eq(p.run(0.0), res[:10], ulp2(res))
+    eq(p.run(10.0), res[10:], ulp2(res))
+    p = sim(A, 0.0, 0.0, 2.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.target(2.0, 0.0, 1.0)
+    p.set_value_at_time(0.5, 15.0)
+    res = target_curve(0.0, 2.0, 0.0, 1.0, range(15)) + [0.5] * 5
+    eq(p.run(0.0), res[:10], ulp2(res))
+    eq(p.run(10.0), res[10:], ulp2(res))
+    # ends at the threshold: no subnormals, then exactly the target (:2589-2619)
+    p = sim(A, 0.0, 0.0, 2.0)
+    p.set_value_at_time(1.0, 0.0)
+    p.target(0.0, 1.0, 0.2)
+    vs = p.run(0.0, 128)
+    assert np.all((vs == 0.0) | (np.abs(vs) >= np.finfo(np.float32).tiny))
+    eq(p.run(10.0, 128), [0.0] * 128)
+    # waits for its start time (:2621-2643)
+    p = sim(A, 0.0, 0.0, 2.0)
+    p.set_value_at_time(1.0, 0.0)
+    p.target(0.0, 5.0, 1.0)
+    assert np.all(p.run(0.0)[:6] == 1.0)
+    # followed by a ramp that starts from the value the SetTarget reached (:2645-2697)
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.target(2.0, 0.0, 10.0)
+    res = target_curve(0.0, 2.0, 0.0, 10.0, range(11))
+    eq(p.run(0.0), res[:10], ulp2(res))
+    v0 = res[10]
+    p.linear(10.0, 20.0)
+    ramp = [v0 + (F(10.0) - v0) * F(t - 10.0) / F(10.0) for t in range(10, 20)]
+    eq(p.run(10.0), ramp, 1e-6)
+    eq(p.run(20.0), [10.0] * 10)
+    # k-rate
+    p = sim(K, 0.0, 0.0, 2.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.target(2.0, 0.0, 1.0)
+    res = target_curve(0.0, 2.0, 0.0, 1.0, range(20))
+    eq(p.run(0.0), [res[0]], ulp2(res))
+    eq(p.run(10.0), [res[10]], ulp2(res))
+    # snaps to the target once close enough (:2731-2775)
+    p = sim(A, 0.0, 0.0, 1.0)
+    p.set_value_at_time(1.0, 0.0)
+    p.target(0.0, 0.0, 1.0)
+    res = target_curve(1.0, 0.0, 0.0, 1.0, range(30))
+    eq(p.run(0.0), res[:10], ulp2(res))
+    eq(p.run(10.0), res[10:20], ulp2(res))
+    eq(p.run(20.0), res[20:30], ulp2(res))
+    eq(p.run(30.0), [0.0] * 10)
+
+
+def test_cancel_scheduled_values(sim):  # :2777-2902
+    p = sim(A, 0.0, 0.0, 10.0)
+    for t in range(10):
+        p.set_value_at_time(float(t), float(t))
+    p.cancel(5.0)
+    eq(p.run(0.0), [0, 1, 2, 3, 4, 4, 4, 4, 4, 4])
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.linear(10.0, 10.0)
+    p.cancel(10.0)
+    eq(p.run(0.0), [0.0] * 10)
+    for explicit in (True, False):  # cancelling a ramp that is under way restores the value from before the ramp
+        p = sim(A, 0.0, 0.0, 20.0)
+        if explicit:
+            p.set_value_at_time(0.0, 0.0)
+        p.linear(20.0, 20.0)
+        eq(p.run(0.0), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+        p.cancel(10.0)
+        eq(p.run(10.0), [0.0])
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.linear(10.0, 10.0)
+    p.cancel(10.0)
+    eq(p.run(0.0), [0.0] * 10)
+
+
+def test_cancel_and_hold(sim):  # :2904-3142
+    p = sim(A, 0.0, 0.0, 10.0)
+    for t in (1.0, 2.0, 3.0, 4.0):
+        p.set_value_at_time(t, t)
+    p.cancel_and_hold(2.5)
+    eq(p.run(0.0), [0, 1, 2, 2, 2, 2, 2, 2, 2, 2])
+    p = sim(A, 0.0, 0.0, 2.0)
+    p.set_value_at_time(0.0, 0.0)
+    p.target(2.0, 0.0, 1.0)
+    p.cancel_and_hold(15.0)
+    res = target_curve(0.0, 2.0, 0.0, 1.0, range(16))
+    res = res[:15] + [res[15]] * 5
+    eq(p.run(0.0), res[:10], ulp2(res))
+    eq(p.run(10.0), res[10:], ulp2(res))
+    for hold, want in [(5.0, [0, 1, 2, 3, 4, 5, 5, 5, 5, 5]), (4.5, [0, 1, 2, 3, 4, 4.5, 4.5, 4.5, 4.5, 4.5])]:
+        p = sim(A, 0.0, 0.0, 10.0)
+        p.linear(10.0, 10.0)
+        p.cancel_and_hold(hold)
+        eq(p.run(0.0), want)
+    ramp = exp_ramp(0.0001, 1.0, 6, 10)
+    for hold, want in [(5.0, ramp[:5] + [ramp[5]] * 5),
+                       (4.5, ramp[:5] + [F(0.0001) * np.power(F(1.0) / F(0.0001), F(4.5) / F(10.0), dtype=np.float32)] * 5)]:
+        p = sim(A, 0.0, 0.0, 10.0)
+        p.set_value_at_time(0.0001, 0.0)
+        p.exponential(1.0, 10.0)
+        p.cancel_and_hold(hold)
+        eq(p.run(0.0), want, ulp2(want))
+    for hold, want in [(5.0, [0, 0.2, 0.4, 0.6, 0.8, 1, 1, 1, 1, 1]), (4.5, [0, 0.2, 0.4, 0.6, 0.8, 0.9, 0.9, 0.9, 0.9, 0.9])]:
+        p = sim(A, 0.0, 0.0, 2.0)
+        p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 0.0, 10.0)
+        p.cancel_and_hold(hold)
+        eq(p.run(0.0), want, 1e-7)
+
+
+def test_set_value_curve(sim, pkg):  # :3144-3275
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 0.0, 10.0)
+    eq(p.run(0.0), [0, 0.2, 0.4, 0.6, 0.8, 1, 0.8, 0.6, 0.4, 0.2], 1e-7)
+    eq(p.run(10.0), [0.0] * 10)
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 0.0, 20.0)
+    eq(p.run(0.0), [0, 0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9], 1e-7)
+    eq(p.run(10.0), [1, 0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.3, 0.2, 0.1], 1e-7)
+    eq(p.run(20.0), [0.0] * 10)
+    p = sim(A, 0.0, 0.0, 10.0)
+    p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 5.0, 10.0)
+    eq(p.run(0.0), [0, 0, 0, 0, 0, 0, 0.2, 0.4, 0.6, 0.8])
+    # overlapping another event is rejected, whichever comes first (#[should_panic] :3203-3250)
+    p = sim(A, 1.0, 0.0, 1.0)
+    p.set_value_at_time(0.0, 5.0)
+    with pytest.raises(pkg.WaeError):
+        p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 0.0, 10.0)
+        p.run(0.0)
+    p = sim(A, 1.0, 0.0, 1.0)
+    p.curve([0.0, 0.5, 1.0, 0.5, 0.0], 0.0, 10.0)
+    with pytest.raises(pkg.WaeError):
+        p.set_value_at_time(0.0, 5.0)
+        p.run(0.0)
+
+
+def test_update_automation_rate(sim):  # :3277-3314
+    p = sim(A, 0.0, -10.0, 10.0)
+    p.set_rate(K)
+    p.set_value_at_time(2.0, 0.000001)
+    eq(p.run(0.0), [0.0])
+    p = sim(K, 0.0, -10.0, 10.0)
+    p.set_rate(A)
+    p.set_value_at_time(2.0, 0.000001)
+    eq(p.run(0.0), [2.0] * 10)
+
+
+def test_varying_param_size(sim):  # :3316-3392 — the block is single-valued exactly when no event touches it
+    for online in (True, False):
+        p = sim(A, 0.0, 0.0, 10.0)
+        p.set_value_at_time(0.0, 0.0)
+        p.linear(9.0, 9.0)
+        if not online:
+            p.set_value_at_time(1.0, 25.0)
+        eq(p.run(0.0), [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+        eq(p.run(10.0), [9.0])
+        if online:
+            p.set_value_at_time(1.0, 25.0)
+        eq(p.run(20.0), [9, 9, 9, 9, 9, 1, 1, 1, 1, 1])
+        eq(p.run(30.0), [1.0])
+
+
+def test_full_block_ramp_from_set_value(sim):  # :3503-3528 (the intrinsic half of test_full_render_chain)
+    p = sim(A, 2.0, 2.0, 42.0)
+    p._push(0, 128.0)  # SetValue: stored unclamped, clamped only in mix_to_output
+    p.linear(0.0, 128.0)
+    eq(p.run(0.0, 128), 128.0 - np.arange(128, dtype=np.float32))

@@ -140,7 +140,8 @@ WAE_SYMBOLS = [
     "wae_listener_param_event_push", "wae_source_start", "wae_source_stop", "wae_oscillator_set_type",
     "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync",
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
-    "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend",
+    "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
+    "wae_param_sim_set_automation_rate", "wae_param_sim_compute",
 ]
 
 
@@ -158,6 +159,11 @@ class Api:
             f(name, C.c_int32, [gp, C.POINTER(opt), C.POINTER(C.c_uint32)])
         f("graph_destroy", C.c_int32, [gp])
         f("graph_suspend", C.c_int32, [gp, C.c_double])
+        f("param_sim_create", C.c_int32, [C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_void_p)])
+        f("param_sim_destroy", C.c_int32, [C.c_void_p])
+        f("param_sim_push", C.c_int32, [C.c_void_p, C.POINTER(ParamEvent)])
+        f("param_sim_set_automation_rate", C.c_int32, [C.c_void_p, C.c_uint32])
+        f("param_sim_compute", C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_uint32, c_float_p, C.POINTER(C.c_uint32)])
         f("connect", C.c_int32, [gp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32])
         f("connect_param", C.c_int32, [gp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32])
         f("disconnect", C.c_int32, [gp, C.c_uint32])

@@ -2,6 +2,8 @@
 // events, start/stop.  Mirrors the control side of the reference (file:line cited per function); argument
 // validation returns the reference's panic text through wae_last_error().
 #include "wae_graph.h"
+#include "wae_param_core.h"
+#include "wae_param_host.h"
 
 #include <algorithm>
 #include <cmath>
@@ -493,6 +495,76 @@ static wae_status push_event(Param& p, const wae_param_event* e) {
         default: return fail(WAE_INVALID_ARGUMENT, "unknown event type");
     }
     p.events.push_back(std::move(ev));
+    return WAE_OK;
+}
+
+// ---- host-side simulation of ONE AudioParam (diagnostics / tests, no GPU): the event folding of wae_param_host.h and the
+// state machine of wae_param_core.h — the very code the planner and the k_param kernel run — driven block by block like the
+// reference's unit tests drive AudioParamProcessor (src/param.rs:1766-3545: handle_incoming_event + compute_intrinsic_values).
+struct wae_param_sim {
+    Param prm;
+    size_t folded = 0;
+    ParamTimeline tl;
+    ParamState st{};
+    bool started = false;
+};
+WAE_API wae_status wae_param_sim_create(uint32_t a_rate, float default_value, float min_value, float max_value, wae_param_sim** out) {
+    auto* s = new wae_param_sim;
+    s->prm.default_value = default_value;
+    s->prm.min_value = min_value;
+    s->prm.max_value = max_value;
+    s->prm.a_rate = a_rate != 0;
+    *out = s;
+    return WAE_OK;
+}
+WAE_API wae_status wae_param_sim_destroy(wae_param_sim* s) {
+    delete s;
+    return WAE_OK;
+}
+WAE_API wae_status wae_param_sim_push(wae_param_sim* s, const wae_param_event* e) { return push_event(s->prm, e); }
+WAE_API wae_status wae_param_sim_set_automation_rate(wae_param_sim* s, uint32_t a_rate) {
+    s->prm.a_rate = a_rate != 0;
+    return WAE_OK;
+}
+// out must hold `count` floats; *len = 1 (single-valued block) or count
+WAE_API wae_status wae_param_sim_compute(wae_param_sim* s, double block_time, double dt, uint32_t count, float* out, uint32_t* len) {
+    if (count == 0 || count > 128) return fail(WAE_INVALID_ARGUMENT, "count must be in [1, 128]");
+    if (s->folded < s->prm.events.size()) {  // events that arrived since the last block: handle_incoming_event against the live state
+        ParamTimeline next;
+        if (!s->started) {
+            next.intrinsic = s->prm.default_value;
+        } else {
+            next.curves = s->tl.curves;
+            for (int i = s->st.head; i < (int)s->tl.events.size(); i++)
+                next.events.push_back(i == s->st.head && s->st.override_valid ? s->st.override_ev : s->tl.events[i]);
+            next.intrinsic = s->st.intrinsic;
+            next.has_last = s->st.has_last != 0;
+            next.last = s->st.last;
+        }
+        fold_param_events(next, s->prm.events.data() + s->folded, s->prm.events.size() - s->folded);
+        if (!next.error.empty()) return fail(WAE_NOT_SUPPORTED, next.error);
+        s->tl = std::move(next);
+        s->folded = s->prm.events.size();
+        s->st.intrinsic = s->tl.intrinsic;
+        s->st.head = 0;
+        s->st.override_valid = 0;
+        s->st.has_last = s->tl.has_last ? 1 : 0;
+        s->st.last = s->tl.last;
+        s->started = true;
+    } else if (!s->started) {
+        s->st.intrinsic = s->prm.default_value;
+        s->started = true;
+    }
+    ParamInst host{};
+    host.events = s->tl.events.data();
+    host.curves = s->tl.curves.data();
+    host.n_events = (int32_t)s->tl.events.size();
+    host.a_rate = s->prm.a_rate ? 1 : 0;
+    host.sample_rate = (float)(1. / dt);
+    float buf[128];
+    const int n = param_compute_buffer(host, s->st, block_time, buf, (int)count);
+    for (int i = 0; i < n; i++) out[i] = buf[i];
+    *len = (uint32_t)n;
     return WAE_OK;
 }
 

@@ -49,11 +49,10 @@ WAE_HD int par_end_index(double end_time, double block_time, double dt, int coun
 
 
 // Fills buf with the intrinsic values of the quantum starting at block_time; returns how many were written: 1 (constant
-// / k-rate block) or 128.  Advances the state (events popped, last event, intrinsic value).
-WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block_time, float* buf) {
+// / k-rate block) or `count` (128 in the render path; the reference's unit tests use shorter blocks).  Advances the state (events popped, last event, intrinsic value).
+WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block_time, float* buf, const int count = 128) {
     ParamCursor tl{p, st};
     const double dt = 1. / (double)p.sample_rate;
-    const int count = 128;
     const double next_block_time = fma(dt, (double)count, block_time);
     int len = 0;
         // ---- compute_buffer (param.rs:1500-1600)
