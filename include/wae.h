@@ -399,6 +399,17 @@ WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_ind
 WAE_API wae_status wae_resample_linear(wae_engine* engine, const float* in, uint64_t len, float from_rate, float to_rate, float* out,
                                        uint64_t out_cap, uint64_t* out_len);
 
+/* Control-side read-outs of the filter nodes; host math only, no engine needed.
+ * wae_biquad_frequency_response = BiquadFilterNode::get_frequency_response (src/node/biquad_filter.rs:657-735): the node's type and the
+ * current value of its frequency / detune / q / gain params; frequencies outside [0, sample_rate / 2] answer NaN.
+ * wae_iir_frequency_response = IIRFilterNode::get_frequency_response (src/node/iir_filter.rs:215-265).
+ * wae_biquad_coefs = calculate_coefs (src/node/biquad_filter.rs:42-390): {b0, b1, b2, a1, a2} normalised by a0, as the kernels use them. */
+WAE_API void wae_biquad_coefs(uint32_t type, double sample_rate, double computed_frequency, double gain, double q, double* out5);
+WAE_API void wae_biquad_frequency_response(uint32_t type, float sample_rate, float frequency, float detune, float q, float gain,
+                                           const float* frequency_hz, float* mag_response, float* phase_response, uint32_t n);
+WAE_API void wae_iir_frequency_response(const double* feedforward, uint32_t n_feedforward, const double* feedback, uint32_t n_feedback,
+                                        float sample_rate, const float* frequency_hz, float* mag_response, float* phase_response, uint32_t n);
+
 #ifdef __cplusplus
 }
 #endif

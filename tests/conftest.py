@@ -43,6 +43,18 @@ def oracle(pkg):
     return pkg.context.Backend(api)
 
 
+@pytest.fixture(params=["oracle", "engine"])
+def host_api(request, pkg, oracle):
+    """Host-only entry points (no device work) that BOTH libraries export: the oracle's and the product's own host code
+    (libwae_b200.so loads without a GPU).  Tests using it pin the product's control-side math on the CPU."""
+    if request.param == "oracle":
+        return oracle.api
+    so = os.path.join(ROOT, "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    return pkg.api()
+
+
 @pytest.fixture(scope="session")
 def engine(pkg, oracle):
     if os.environ.get("WAE_DRYRUN_ORACLE_AS_ENGINE"):  # local dry run of the test plumbing only (no parity meaning)

@@ -19,7 +19,8 @@ CASES = [
     K.test_convolver_argument_errors, K.test_convolver_matches_direct_convolution, K.test_mixing_channel_count_modes,
     K.test_denormals_are_flushed, K.test_waveshaper_curves, K.test_delay_integer_and_fractional, K.test_stereo_panner_mono_and_stereo,
     K.test_equal_power_panner_positions, K.test_compressor_lookahead_delay, K.test_buffer_source_fast_and_slow_track,
-    K.test_param_automation_vectors,
+    K.test_param_automation_vectors, K.test_filter_node_frequency_response_methods, K.test_iir_coefficient_validation,
+    K.test_iir_one_zero_different_lengths,
 ]
 
 
@@ -97,4 +98,18 @@ OSC_CASES = [OS.test_sine_raw, OS.test_square_and_sawtooth_raw_away_from_the_ste
 
 @pytest.mark.parametrize("case", OSC_CASES, ids=lambda f: f.__name__)
 def test_oscillator_reference_case_on_gpu(pkg, engine, case):
+    case(pkg, engine.backend)
+
+
+# ---- panner / constant source / merger / splitter / stereo panner / wave shaper unit tests, restated in tests/test_oracle_nodes.py ---
+import test_oracle_nodes as N  # noqa: E402
+
+NODE_CASES = [N.test_equal_power_mono_to_stereo, N.test_equal_power_azimuth_mono_to_stereo, N.test_equal_power_stereo_to_stereo,
+              N.test_constant_source_start_stop, N.test_constant_source_start_in_the_past, N.test_constant_source_start_in_the_future_while_dropped,
+              N.test_channel_merger, N.test_channel_merger_disconnect, N.test_channel_merger_splitter_option_errors, N.test_channel_splitter,
+              N.test_stereo_panner_mono_panning, N.test_stereo_panner_stereo_panning, N.test_wave_shaper_boundaries, N.test_wave_shaper_interpolation]
+
+
+@pytest.mark.parametrize("case", NODE_CASES, ids=lambda f: f.__name__)
+def test_node_reference_case_on_gpu(pkg, engine, case):
     case(pkg, engine.backend)

@@ -9,7 +9,6 @@ one processor, block by block) restated as data and run against BOTH param imple
 Expected values that the reference computes with powf / exp are recomputed here with numpy; they are compared at 2 f32 ulp
 instead of the reference's exact 0 (libm vs numpy), everything else keeps the reference's tolerance."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
@@ -68,15 +67,9 @@ class Sim:
         self.api.param_sim_destroy(self.h)
 
 
-@pytest.fixture(params=["oracle", "engine"])
-def sim(request, pkg, oracle):
-    if request.param == "oracle":
-        api = oracle.api
-    else:
-        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
-        if not os.path.exists(so):
-            pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
-        api = pkg.api()
+@pytest.fixture
+def sim(host_api, pkg):
+    api = host_api
     made = []
 
     def make(rate, default, mn, mx):

@@ -141,7 +141,7 @@ WAE_SYMBOLS = [
     "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync",
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
-    "wae_param_sim_set_automation_rate", "wae_param_sim_compute",
+    "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
 ]
 
 
@@ -174,6 +174,11 @@ class Api:
         f("source_stop", C.c_int32, [gp, C.c_uint32, C.c_double])
         f("oscillator_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
         f("biquad_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
+        f("biquad_coefs", None, [C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p])
+        f("biquad_frequency_response", None, [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                              c_float_p, c_float_p, c_float_p, C.c_uint32])
+        f("iir_frequency_response", None, [c_double_p, C.c_uint32, c_double_p, C.c_uint32, C.c_float,
+                                           c_float_p, c_float_p, c_float_p, C.c_uint32])
         if self.is_product:
             f("version", C.c_char_p, [])
             f("engine_create", C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)])
@@ -210,11 +215,6 @@ class Api:
             f("analyser_get_byte_frequency_data", C.c_int32, [gp, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])
             f("analyser_get_byte_time_domain_data", C.c_int32, [gp, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])
             f("compressor_reduction", C.c_int32, [gp, C.c_uint32, c_float_p])
-            f("biquad_coefs", None, [C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p])
-            f("biquad_frequency_response", None, [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                                  c_float_p, c_float_p, c_float_p, C.c_uint32])
-            f("iir_frequency_response", None, [c_double_p, C.c_uint32, c_double_p, C.c_uint32, C.c_float,
-                                               c_float_p, c_float_p, c_float_p, C.c_uint32])
             f("blackman", None, [C.c_uint32, c_float_p])
             f("set_hrir_sphere", C.c_int32, [C.c_void_p, C.c_uint64])
             f("hrtf_locate", C.c_int32, [c_float_p, C.POINTER(C.c_uint32), C.c_uint32, c_float_p, C.POINTER(C.c_uint32), c_float_p])

@@ -207,10 +207,34 @@ class AudioBufferSourceNode(AudioScheduledSourceNode):
         api.check(api.source_start(self._ctx._g, self.id, start, offset, duration))
 
 
+def _response_arrays(frequency_hz):
+    f = np.ascontiguousarray(frequency_hz, dtype=np.float32)
+    return f, np.zeros(len(f), np.float32), np.zeros(len(f), np.float32)
+
+
 class BiquadFilterNode(AudioNode):
     def set_type(self, type_):
         api = self._ctx._api
         api.check(api.biquad_set_type(self._ctx._g, self.id, type_))
+        self.type_ = type_
+
+    def get_frequency_response(self, frequency_hz):
+        """BiquadFilterNode::get_frequency_response (src/node/biquad_filter.rs:657-735) -> (mag_response, phase_response)."""
+        f, mag, phase = _response_arrays(frequency_hz)
+        self._ctx._api.biquad_frequency_response(self.type_, self._ctx._sample_rate, self.frequency.value(), self.detune.value(), self.q.value(),
+                                                 self.gain.value(), f.ctypes.data_as(B.c_float_p), mag.ctypes.data_as(B.c_float_p),
+                                                 phase.ctypes.data_as(B.c_float_p), len(f))
+        return mag, phase
+
+
+class IIRFilterNode(AudioNode):
+    def get_frequency_response(self, frequency_hz):
+        """IIRFilterNode::get_frequency_response (src/node/iir_filter.rs:215-265) -> (mag_response, phase_response)."""
+        f, mag, phase = _response_arrays(frequency_hz)
+        ff, fb = self.feedforward, self.feedback
+        self._ctx._api.iir_frequency_response(ff.ctypes.data_as(B.c_double_p), len(ff), fb.ctypes.data_as(B.c_double_p), len(fb), self._ctx._sample_rate,
+                                              f.ctypes.data_as(B.c_float_p), mag.ctypes.data_as(B.c_float_p), phase.ctypes.data_as(B.c_float_p), len(f))
+        return mag, phase
 
 
 class DynamicsCompressorNode(AudioNode):
@@ -326,6 +350,7 @@ class OfflineAudioContext:
         o = B.BiquadOptions(type_, q, detune, frequency, gain, cfg or channel_config())
         nid = self._create("create_biquad_filter", o)
         n = BiquadFilterNode(self, nid)
+        n.type_ = type_
         n.q = AudioParam(self, nid, 0, q)
         n.detune = AudioParam(self, nid, 1, detune, -153600.0, 153600.0)
         n.frequency = AudioParam(self, nid, 2, frequency, 0.0, self._sample_rate / 2)
@@ -337,7 +362,9 @@ class OfflineAudioContext:
         fb = np.ascontiguousarray(feedback, dtype=np.float64)
         o = B.IirOptions(ff.ctypes.data_as(B.c_double_p), len(ff), fb.ctypes.data_as(B.c_double_p), len(fb),
                          cfg or channel_config())
-        return AudioNode(self, self._create("create_iir_filter", o))
+        n = IIRFilterNode(self, self._create("create_iir_filter", o))
+        n.feedforward, n.feedback = ff, fb
+        return n
 
     def create_gain(self, gain=1.0, cfg=None):
         nid = self._create("create_gain", B.GainOptions(gain, cfg or channel_config()))

@@ -2,11 +2,13 @@
 // events, start/stop.  Mirrors the control side of the reference (file:line cited per function); argument
 // validation returns the reference's panic text through wae_last_error().
 #include "wae_graph.h"
+#include "wae_hostmath.h"
 #include "wae_param_core.h"
 #include "wae_param_host.h"
 
 #include <algorithm>
 #include <cmath>
+#include <complex>
 #include <cstring>
 
 using namespace wae;
@@ -638,6 +640,51 @@ WAE_API wae_status wae_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t 
     if (ni == g->nodes.end() || ni->second.kind != K_BIQUAD || type > 7) return fail(WAE_INVALID_ARGUMENT, "not a biquad / bad type");
     ni->second.type = (int)type;
     return WAE_OK;
+}
+
+// ---- control-side read-outs of the filter nodes (no device work) ---------------------------------------------------------
+// calculate_coefs (src/node/biquad_filter.rs:42-390): the normalised coefficients the k_biquad / k_chain kernels are fed with
+WAE_API void wae_biquad_coefs(uint32_t type, double sample_rate, double f0, double gain, double q, double* out5) {
+    hostmath::BiquadCoefs c = hostmath::biquad_coefs((int)type, sample_rate, f0, gain, q);
+    out5[0] = c.b0; out5[1] = c.b1; out5[2] = c.b2; out5[3] = c.a1; out5[4] = c.a2;
+}
+// BiquadFilterNode::get_frequency_response (src/node/biquad_filter.rs:657-735)
+WAE_API void wae_biquad_frequency_response(uint32_t type, float sample_rate, float frequency, float detune, float q, float gain,
+                                           const float* freq_hz, float* mag, float* phase, uint32_t n) {
+    const float nyquist = sample_rate / 2.f;
+    const float computed = hostmath::biquad_computed_freq(frequency, detune);
+    const hostmath::BiquadCoefs c = hostmath::biquad_coefs((int)type, (double)sample_rate, (double)computed, (double)gain, (double)q);
+    for (uint32_t i = 0; i < n; i++) {
+        const float f = freq_hz[i];
+        if (!(f >= 0.f && f <= nyquist)) {
+            mag[i] = phase[i] = std::numeric_limits<float>::quiet_NaN();
+            continue;
+        }
+        const double omega = -hostmath::PI64 * (double)(f / nyquist);
+        const std::complex<double> z(std::cos(omega), std::sin(omega));
+        const std::complex<double> h = (c.b0 + (c.b1 + c.b2 * z) * z) / (std::complex<double>(1., 0.) + (c.a1 + c.a2 * z) * z);
+        mag[i] = (float)std::abs(h);
+        phase[i] = (float)std::arg(h);
+    }
+}
+// IIRFilterNode::get_frequency_response (src/node/iir_filter.rs:215-265)
+WAE_API void wae_iir_frequency_response(const double* ff, uint32_t nff, const double* fb, uint32_t nfb, float sample_rate,
+                                        const float* freq_hz, float* mag, float* phase, uint32_t n) {
+    const float nyquist = sample_rate / 2.f;
+    for (uint32_t i = 0; i < n; i++) {
+        const float f = freq_hz[i];
+        if (!(f >= 0.f && f <= nyquist)) {
+            mag[i] = phase[i] = std::numeric_limits<float>::quiet_NaN();
+            continue;
+        }
+        const double z = -2.0 * hostmath::PI64 * (double)f / (double)sample_rate;
+        std::complex<double> num(0., 0.), den(0., 0.);
+        for (uint32_t k = 0; k < nff; k++) num += std::polar(1.0, (double)k * z) * ff[k];  // Complex::from_polar(b, idx * z)
+        for (uint32_t k = 0; k < nfb; k++) den += std::polar(1.0, (double)k * z) * fb[k];
+        const std::complex<double> h = num / den;
+        mag[i] = (float)std::abs(h);
+        phase[i] = (float)std::arg(h);
+    }
 }
 
 }  // extern "C"
