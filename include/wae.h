@@ -399,6 +399,15 @@ WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_ind
 WAE_API wae_status wae_resample_linear(wae_engine* engine, const float* in, uint64_t len, float from_rate, float to_rate, float* out,
                                        uint64_t out_cap, uint64_t* out_len);
 
+/* AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation (src/node/audio_node.rs:417-441), with the
+ * constraints of the nodes that narrow them (destination.rs:55-96, channel_merger.rs:39-110, channel_splitter.rs:36-134, convolver.rs:187-197,
+ * dynamics_compressor.rs:168-178, stereo_panner.rs:143-152, panner.rs:363-372, param.rs:325-333, spatial.rs:113-121): a value the reference
+ * panics on answers WAE_NOT_SUPPORTED with the panic text.  `node` is the id create_* returned; 0 addresses the destination.  Called
+ * between wae_graph_suspend points the change applies from that point on, like the reference's control message. */
+WAE_API wae_status wae_node_set_channel_count(wae_graph* graph, wae_node_id node, uint32_t count);
+WAE_API wae_status wae_node_set_channel_count_mode(wae_graph* graph, wae_node_id node, uint32_t count_mode);
+WAE_API wae_status wae_node_set_channel_interpretation(wae_graph* graph, wae_node_id node, uint32_t interpretation);
+
 /* Control-side read-outs of the filter nodes; host math only, no engine needed.
  * wae_biquad_frequency_response = BiquadFilterNode::get_frequency_response (src/node/biquad_filter.rs:657-735): the node's type and the
  * current value of its frequency / detune / q / gain params; frequencies outside [0, sample_rate / 2] answer NaN.

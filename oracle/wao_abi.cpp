@@ -635,6 +635,59 @@ WAO_API wae_status wao_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t 
     return WAE_OK;
 }
 
+// AudioNode::set_channel_count / _mode / _interpretation (src/node/audio_node.rs:417-441) with the per-node overrides:
+// param.rs:325-333, spatial.rs:113-121, destination.rs:55-96, channel_merger.rs:39-110, channel_splitter.rs:36-134,
+// convolver.rs:187-197, dynamics_compressor.rs:168-178, stereo_panner.rs:143-152, panner.rs:363-372.
+// The render side applies them to the node's ChannelConfig (src/render/graph.rs:306-320).
+static wae_status set_cfg_field(wae_graph* g, wae_node_id node, int field, uint32_t v) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    const NodeInfo& n = ni->second;
+    static const char* what[3] = {"channel count", "channel count mode", "channel interpretation"};
+    if (field == 1 && v > 2) return fail(WAE_INVALID_ARGUMENT, "unknown channel count mode");
+    if (field == 2 && v > 1) return fail(WAE_INVALID_ARGUMENT, "unknown channel interpretation");
+    bool store = true;
+    switch (n.kind) {
+        case K_PARAM: return fail(WAE_NOT_SUPPORTED, std::string("NotSupportedError - AudioParam has ") + what[field] + " constraints");
+        case K_LISTENER: return fail(WAE_NOT_SUPPORTED, std::string("NotSupportedError - AudioListenerNode has ") + what[field] + " constraints");
+        case K_DEST:
+            if (field == 0 && v != g->channels)
+                return fail(WAE_NOT_SUPPORTED, "NotSupportedError - not allowed to change OfflineAudioContext destination channel count");
+            if (field == 1 && v != MODE_EXPLICIT) return fail(WAE_NOT_SUPPORTED, "InvalidStateError - AudioDestinationNode has channel count mode constraints");
+            break;
+        case K_MERGER:
+            if (field == 0 && v != 1) return fail(WAE_NOT_SUPPORTED, "InvalidStateError - channel count of ChannelMergerNode must be equal to 1");
+            if (field == 1 && v != MODE_EXPLICIT) return fail(WAE_NOT_SUPPORTED, "InvalidStateError - channel count of ChannelMergerNode must be set to Explicit");
+            store = field != 0;
+            break;
+        case K_SPLITTER:
+            if (field == 0 && v != (uint32_t)n.n_outputs)
+                return fail(WAE_NOT_SUPPORTED, "InvalidStateError - channel count of ChannelSplitterNode must be equal to number of outputs");
+            if (field == 1 && v != MODE_EXPLICIT) return fail(WAE_NOT_SUPPORTED, "InvalidStateError - channel count mode of ChannelSplitterNode must be set to Explicit");
+            if (field == 2 && v != DISCRETE) return fail(WAE_NOT_SUPPORTED, "InvalidStateError - channel interpretation of ChannelSplitterNode must be set to Discrete");
+            store = field != 0;
+            break;
+        case K_CONV: case K_COMP: case K_SPANNER: case K_PANNER: {
+            const char* name = n.kind == K_CONV ? "ConvolverNode" : n.kind == K_COMP ? "DynamicsCompressorNode" : n.kind == K_SPANNER ? "StereoPannerNode" : "PannerNode";
+            if (field == 0 && v > 2) return fail(WAE_NOT_SUPPORTED, std::string("NotSupportedError - ") + name + " channel count cannot be greater than two");
+            if (field == 1 && v == MODE_MAX) return fail(WAE_NOT_SUPPORTED, std::string("NotSupportedError - ") + name + " channel count mode cannot be set to max");
+            break;
+        }
+        default: break;
+    }
+    if (field == 0 && (v < 1 || v > 32))
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(v) + " is outside range [1, 32]");
+    if (!store) return WAE_OK;
+    ChannelConfig& cfg = g->graph.get(node)->cfg;
+    if (field == 0) cfg.count = (int)v;
+    else if (field == 1) cfg.mode = (int)v;
+    else cfg.interp = (int)v;
+    return WAE_OK;
+}
+WAO_API wae_status wao_node_set_channel_count(wae_graph* g, wae_node_id node, uint32_t count) { return set_cfg_field(g, node, 0, count); }
+WAO_API wae_status wao_node_set_channel_count_mode(wae_graph* g, wae_node_id node, uint32_t mode) { return set_cfg_field(g, node, 1, mode); }
+WAO_API wae_status wao_node_set_channel_interpretation(wae_graph* g, wae_node_id node, uint32_t v) { return set_cfg_field(g, node, 2, v); }
+
 // ---- rendering --------------------------------------------------------------------------------------
 
 struct NoDenormals {  // crate no_denormals: FTZ + DAZ while rendering (src/render/thread.rs:373-380)

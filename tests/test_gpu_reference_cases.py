@@ -107,9 +107,28 @@ import test_oracle_nodes as N  # noqa: E402
 NODE_CASES = [N.test_equal_power_mono_to_stereo, N.test_equal_power_azimuth_mono_to_stereo, N.test_equal_power_stereo_to_stereo,
               N.test_constant_source_start_stop, N.test_constant_source_start_in_the_past, N.test_constant_source_start_in_the_future_while_dropped,
               N.test_channel_merger, N.test_channel_merger_disconnect, N.test_channel_merger_splitter_option_errors, N.test_channel_splitter,
-              N.test_stereo_panner_mono_panning, N.test_stereo_panner_stereo_panning, N.test_wave_shaper_boundaries, N.test_wave_shaper_interpolation]
+              N.test_stereo_panner_mono_panning, N.test_stereo_panner_stereo_panning, N.test_wave_shaper_boundaries, N.test_wave_shaper_interpolation,
+              N.test_up_down_mix_rules_through_a_graph, N.test_mixing_integration_cases,
+              N.test_channel_config_setters_take_effect_at_a_suspend_point, N.test_channel_config_constraints]
 
 
 @pytest.mark.parametrize("case", NODE_CASES, ids=lambda f: f.__name__)
 def test_node_reference_case_on_gpu(pkg, engine, case):
     case(pkg, engine.backend)
+
+
+# ---- src/analysis.rs:414-868, restated in tests/test_oracle_analyser.py ---------------------------------------------------------
+import test_oracle_analyser as AN  # noqa: E402
+
+ANALYSER_CASES = [AN.test_time_domain_data_vs_fft_size, AN.test_time_domain_data_is_the_most_recent_window, AN.test_byte_time_domain_data,
+                  AN.test_frequency_data_vs_frequency_bin_count, AN.test_option_constraints]
+
+
+@pytest.mark.parametrize("case", ANALYSER_CASES, ids=lambda f: f.__name__)
+def test_analyser_reference_case_on_gpu(pkg, engine, case):
+    case(pkg, engine.backend)
+
+
+@pytest.mark.parametrize("bins", [range(1, 128, 9), range(5, 128, 9)], ids=["a", "b"])
+def test_analyser_sine_bins_on_gpu(pkg, engine, bins):
+    AN.test_float_frequency_data_peaks_at_the_sine_bin(pkg, engine.backend, bins)

@@ -211,3 +211,113 @@ def test_wave_shaper_boundaries(pkg, oracle):  # waveshaper.rs:671-707 test_shap
 def test_wave_shaper_interpolation(pkg, oracle):  # waveshaper.rs:709-739 test_shape_interpolation
     data = (np.arange(RQ, dtype=np.float32) / np.float32(RQ) * np.float32(2.0) - np.float32(1.0)).astype(np.float32)
     assert np.array_equal(_shape(pkg, oracle, data, RQ), data / np.float32(2.0))
+
+
+def test_up_down_mix_rules_through_a_graph(pkg, oracle):
+    # src/render/quantum.rs:803-1440 test_audiobuffer_upmix_speakers / _downmix_speakers, :745-785 _mix_discrete: the same tables,
+    # applied by the input mixer of an explicit-count node (src/render/graph.rs:507-521) instead of AudioRenderQuantum::mix directly
+    s = np.float32(0.5) ** np.float32(0.5)
+    f = np.float32
+    table = [
+        ([1], 2, 0, [1, 1]), ([1], 4, 0, [1, 1, 0, 0]), ([1], 6, 0, [0, 0, 1, 0, 0, 0]), ([1, 2], 4, 0, [1, 2, 0, 0]),
+        ([1, 2], 6, 0, [1, 2, 0, 0, 0, 0]), ([1, 2, 3, 4], 6, 0, [1, 2, 0, 0, 3, 4]), ([1, 2], 1, 0, [1.5]), ([1, 2, 3, 4], 1, 0, [2.5]),
+        ([1, 2, 3, 4, 5, 6], 1, 0, [s * (f(1) + f(2)) + f(3) + f(0.5) * (f(5) + f(6))]), ([1, 2, 3, 4], 2, 0, [2.0, 3.0]),
+        ([1, 2, 3, 4, 5, 6], 2, 0, [f(1) + s * (f(3) + f(5)), f(2) + s * (f(3) + f(6))]),
+        ([1, 2, 3, 4, 5, 6], 4, 0, [f(1) + s * f(3), f(2) + s * f(3), 5, 6]),
+        ([1, 2, 3], 5, 1, [1, 2, 3, 0, 0]), ([1, 2, 3], 2, 1, [1, 2]), ([1, 2, 3], 4, 0, [1, 2, 3, 0]),  # 3 -> 4 has no speaker rule: discrete
+    ]
+    sr = 48000.0
+    for vals, to, interp, want in table:
+        c = pkg.OfflineAudioContext(to, RQ, sr, oracle)
+        src = c.create_buffer_source(pkg.AudioBuffer([np.full(RQ, v, np.float32) for v in vals], sr))
+        g = c.create_gain(1.0, cfg=pkg.channel_config(to, pkg.EXPLICIT, pkg.DISCRETE if interp else pkg.SPEAKERS))
+        src.connect(g)
+        g.connect(c.destination())
+        src.start()
+        out = c.start_rendering_sync()
+        got = np.array([out.get_channel_data(i) for i in range(to)])
+        assert np.all(got == got[:, :1]), (vals, to)
+        assert np.abs(got[:, 0].astype(np.float64) - np.asarray(want, np.float64)).max() <= 2.4e-7 * max(1.0, max(vals)), (vals, to, got[:, 0], want)
+
+
+def _mixing_case(pkg, be, dest_channels, dest_interp, count, mode, interp):
+    # tests/mixing.rs:11-44 setup_with_destination_channel_config + run_with_intermediate_channel_config
+    c = pkg.OfflineAudioContext(dest_channels, RQ, 44100.0, be)
+    c.destination().set_channel_interpretation(dest_interp)
+    constant = c.create_constant_source()
+    constant.start()
+    gain = c.create_gain()  # only added for mixing
+    gain.set_channel_count(count)
+    gain.set_channel_count_mode(mode)
+    gain.set_channel_interpretation(interp)
+    constant.connect(gain)
+    gain.connect(c.destination())
+    out = c.start_rendering_sync()
+    assert out.number_of_channels() == dest_channels
+    return [out.get_channel_data(i) for i in range(dest_channels)]
+
+
+def test_mixing_integration_cases(pkg, oracle):  # tests/mixing.rs:48-106 (all six)
+    ones, zeroes = np.ones(RQ, np.float32), np.zeros(RQ, np.float32)
+    for dest, dest_interp, count, want in [
+        (1, pkg.SPEAKERS, 1, [ones]),                       # test_mono_speakers
+        (2, pkg.SPEAKERS, 2, [ones, ones]),                 # test_stereo_speakers
+        (4, pkg.SPEAKERS, 4, [ones, ones, zeroes, zeroes]),  # test_quad_speakers
+        (2, pkg.DISCRETE, 1, [ones, zeroes]),               # test_mono_to_discrete_stereo
+        (2, pkg.DISCRETE, 2, [ones, zeroes]),               # test_stereo_to_discrete_stereo
+        (1, pkg.DISCRETE, 2, [ones]),                       # test_stereo_to_discrete_mono
+    ]:
+        got = _mixing_case(pkg, oracle, dest, dest_interp, count, pkg.MAX, pkg.SPEAKERS)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w), (dest, dest_interp, count)
+
+
+def test_channel_config_setters_take_effect_at_a_suspend_point(pkg, oracle):
+    # the control message reaches the graph between two quanta (src/render/thread.rs:229-248): stereo source into a gain whose
+    # count mode goes Max -> Explicit(1) half-way: [1, -0.5] before, the down-mix 0.25 on both destination channels after
+    sr = 48000.0
+    c = pkg.OfflineAudioContext(2, 4 * RQ, sr, oracle)
+    src = c.create_buffer_source(pkg.AudioBuffer([np.full(4 * RQ, 1.0, np.float32), np.full(4 * RQ, -0.5, np.float32)], sr))
+    g = c.create_gain()
+    src.connect(g)
+    g.connect(c.destination())
+    src.start()
+
+    def narrow(_ctx):
+        g.set_channel_count(1)
+        g.set_channel_count_mode(pkg.EXPLICIT)
+
+    c.suspend_sync(2 * RQ / sr, narrow)
+    out = c.start_rendering_sync()
+    left, right = out.get_channel_data(0), out.get_channel_data(1)
+    assert np.all(left[:2 * RQ] == 1.0) and np.all(right[:2 * RQ] == -0.5)
+    assert np.all(left[2 * RQ:] == 0.25) and np.all(right[2 * RQ:] == 0.25)
+
+
+def test_channel_config_constraints(pkg, oracle):
+    # channel_merger.rs:195-204, channel_splitter.rs:250-259 (#[should_panic]) and the other per-node overrides of the three setters
+    import pytest
+    c = pkg.OfflineAudioContext(2, RQ, 48000.0, oracle)
+    ok = [
+        (c.create_gain(), "set_channel_count", 32), (c.create_gain(), "set_channel_count_mode", pkg.EXPLICIT),
+        (c.create_channel_merger(2), "set_channel_count", 1), (c.create_channel_splitter(3), "set_channel_count", 3),
+        (c.create_panner(), "set_channel_count", 1), (c.create_stereo_panner(), "set_channel_count_mode", pkg.EXPLICIT),
+        (c.destination(), "set_channel_count", 2), (c.destination(), "set_channel_interpretation", pkg.DISCRETE),
+        (c.create_convolver(), "set_channel_count", 1), (c.create_dynamics_compressor(), "set_channel_count_mode", pkg.EXPLICIT),
+    ]
+    for node, setter, v in ok:
+        getattr(node, setter)(v)
+    bad = [
+        (c.create_gain(), "set_channel_count", 0), (c.create_gain(), "set_channel_count", 33),
+        (c.create_channel_merger(2), "set_channel_count", 3), (c.create_channel_merger(2), "set_channel_count_mode", pkg.MAX),
+        (c.create_channel_splitter(2), "set_channel_count", 3), (c.create_channel_splitter(2), "set_channel_count_mode", pkg.MAX),
+        (c.create_channel_splitter(2), "set_channel_interpretation", pkg.SPEAKERS),
+        (c.create_panner(), "set_channel_count", 3), (c.create_panner(), "set_channel_count_mode", pkg.MAX),
+        (c.create_stereo_panner(), "set_channel_count", 3), (c.create_stereo_panner(), "set_channel_count_mode", pkg.MAX),
+        (c.create_convolver(), "set_channel_count", 3), (c.create_convolver(), "set_channel_count_mode", pkg.MAX),
+        (c.create_dynamics_compressor(), "set_channel_count", 3), (c.create_dynamics_compressor(), "set_channel_count_mode", pkg.MAX),
+        (c.destination(), "set_channel_count", 1), (c.destination(), "set_channel_count_mode", pkg.MAX),
+    ]
+    for node, setter, v in bad:
+        with pytest.raises(pkg.WaeError):
+            getattr(node, setter)(v)

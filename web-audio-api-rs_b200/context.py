@@ -158,6 +158,19 @@ class AudioNode:
     def number_of_outputs(self):
         return self._n_outputs
 
+    # AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation (src/node/audio_node.rs:417-441)
+    def set_channel_count(self, count):
+        api = self._ctx._api
+        api.check(api.node_set_channel_count(self._ctx._g, self.id, int(count)))
+
+    def set_channel_count_mode(self, mode):
+        api = self._ctx._api
+        api.check(api.node_set_channel_count_mode(self._ctx._g, self.id, int(mode)))
+
+    def set_channel_interpretation(self, interpretation):
+        api = self._ctx._api
+        api.check(api.node_set_channel_interpretation(self._ctx._g, self.id, int(interpretation)))
+
     def connect(self, dest):
         return self.connect_from_output_to_input(dest, 0, 0)
 
@@ -259,17 +272,19 @@ class AnalyserNode(AudioNode):
     def frequency_bin_count(self):
         return self.fft_size // 2
 
-    def get_float_time_domain_data(self, n=None):
-        return self._ctx._analyser_read(self, "time", n or self.fft_size)
+    # `out`: a caller-owned array (like the reference's `&mut [f32]` / `&mut [u8]`): only the first min(len, fft_size or
+    # frequency_bin_count) entries are written, the rest is left as it was
+    def get_float_time_domain_data(self, n=None, out=None):
+        return self._ctx._analyser_read(self, "time", n or self.fft_size, out=out)
 
-    def get_float_frequency_data(self, n=None):
-        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2)
+    def get_float_frequency_data(self, n=None, out=None):
+        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2, out=out)
 
-    def get_byte_time_domain_data(self, n=None):
-        return self._ctx._analyser_read(self, "time", n or self.fft_size, byte=True)
+    def get_byte_time_domain_data(self, n=None, out=None):
+        return self._ctx._analyser_read(self, "time", n or self.fft_size, byte=True, out=out)
 
-    def get_byte_frequency_data(self, n=None):
-        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2, byte=True)
+    def get_byte_frequency_data(self, n=None, out=None):
+        return self._ctx._analyser_read(self, "freq", n or self.fft_size // 2, byte=True, out=out)
 
 
 class AudioListener:
@@ -470,8 +485,12 @@ class OfflineAudioContext:
         """OfflineAudioContext::start_rendering_sync (src/context/offline.rs:157-185): a batch of one."""
         return render_batch([self])[0]
 
-    def _analyser_read(self, node, kind, n, byte=False):
-        out = np.zeros(n, np.uint8 if byte else np.float32)
+    def _analyser_read(self, node, kind, n, byte=False, out=None):
+        if out is None:
+            out = np.zeros(n, np.uint8 if byte else np.float32)
+        else:
+            assert out.dtype == (np.uint8 if byte else np.float32) and out.flags.c_contiguous
+            n = len(out)
         ptr = out.ctypes.data_as(C.POINTER(C.c_uint8)) if byte else B.fptr(out)
         api = self._api
         name = "analyser_get_%s_%s_data" % ("byte" if byte else "float", "time_domain" if kind == "time" else "frequency")

@@ -642,6 +642,73 @@ WAE_API wae_status wae_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t 
     return WAE_OK;
 }
 
+// ---- AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation -------------------------------------
+// src/node/audio_node.rs:417-441 and the per-node overrides that narrow them.  `node` is the id create_* returned (a DelayNode
+// is addressed by its writer, delay.rs:108-115, which is the half that has the mixed input).
+namespace {
+enum CfgField { F_COUNT, F_MODE, F_INTERP };
+// returns "" when the value is allowed for this kind of node, else the reference's panic text
+std::string channel_config_constraint(const wae_graph* g, const Node& n, CfgField f, uint32_t v) {
+    switch (n.kind) {
+        case K_PARAM:  // src/param.rs:325-333
+            return f == F_COUNT ? "NotSupportedError - AudioParam has channel count constraints"
+                 : f == F_MODE  ? "NotSupportedError - AudioParam has channel count mode constraints"
+                                : "NotSupportedError - AudioParam has channel interpretation constraints";
+        case K_LISTENER:  // src/spatial.rs:113-121
+            return f == F_COUNT ? "NotSupportedError - AudioListenerNode has channel count constraints"
+                 : f == F_MODE  ? "NotSupportedError - AudioListenerNode has channel count mode constraints"
+                                : "NotSupportedError - AudioListenerNode has channel interpretation constraints";
+        case K_DEST:  // src/node/destination.rs:55-96 (offline context)
+            if (f == F_COUNT && v != g->channels) return "NotSupportedError - not allowed to change OfflineAudioContext destination channel count";
+            if (f == F_MODE && v != WAE_COUNT_MODE_EXPLICIT) return "InvalidStateError - AudioDestinationNode has channel count mode constraints";
+            return "";
+        case K_MERGER:  // src/node/channel_merger.rs:39-62
+            if (f == F_COUNT && v != 1) return "InvalidStateError - channel count of ChannelMergerNode must be equal to 1";
+            if (f == F_MODE && v != WAE_COUNT_MODE_EXPLICIT) return "InvalidStateError - channel count of ChannelMergerNode must be set to Explicit";
+            return "";
+        case K_SPLITTER:  // src/node/channel_splitter.rs:36-78
+            if (f == F_COUNT && v != (uint32_t)n.n_outputs) return "InvalidStateError - channel count of ChannelSplitterNode must be equal to number of outputs";
+            if (f == F_MODE && v != WAE_COUNT_MODE_EXPLICIT) return "InvalidStateError - channel count mode of ChannelSplitterNode must be set to Explicit";
+            if (f == F_INTERP && v != WAE_INTERPRETATION_DISCRETE) return "InvalidStateError - channel interpretation of ChannelSplitterNode must be set to Discrete";
+            return "";
+        case K_CONV: case K_COMP: case K_SPANNER: case K_PANNER: {  // convolver.rs:48-78, dynamics_compressor.rs:21-50, stereo_panner.rs:23-53, panner.rs
+            const char* name = n.kind == K_CONV ? "ConvolverNode" : n.kind == K_COMP ? "DynamicsCompressorNode" : n.kind == K_SPANNER ? "StereoPannerNode" : "PannerNode";
+            if (f == F_COUNT && v > 2) return std::string("NotSupportedError - ") + name + " channel count cannot be greater than two";
+            if (f == F_MODE && v == WAE_COUNT_MODE_MAX) return std::string("NotSupportedError - ") + name + " channel count mode cannot be set to max";
+            return "";
+        }
+        default:
+            return "";
+    }
+}
+wae_status set_channel_config_field(wae_graph* g, wae_node_id node, CfgField f, uint32_t v) {
+    if (!g) return fail(WAE_INVALID_ARGUMENT, "null graph");
+    auto ni = g->nodes.find(node);
+    if (ni == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    Node& n = ni->second;
+    if (f == F_MODE && v > WAE_COUNT_MODE_EXPLICIT) return fail(WAE_INVALID_ARGUMENT, "unknown channel count mode");
+    if (f == F_INTERP && v > WAE_INTERPRETATION_DISCRETE) return fail(WAE_INVALID_ARGUMENT, "unknown channel interpretation");
+    std::string why = channel_config_constraint(g, n, f, v);
+    if (!why.empty()) return fail(WAE_NOT_SUPPORTED, why);
+    if (f == F_COUNT) {
+        if (v < 1 || v > WAE_MAX_CHANNELS)  // assert_valid_number_of_channels, src/lib.rs:185-192
+            return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(v) + " is outside range [1, 32]");
+        if (n.kind != K_MERGER && n.kind != K_SPLITTER) n.cfg.count = (int)v;  // those two only validate (channel_merger.rs:102-104)
+    } else if (f == F_MODE) {
+        n.cfg.mode = (int)v;
+    } else {
+        n.cfg.interp = (int)v;
+    }
+    return WAE_OK;
+}
+}  // namespace
+
+WAE_API wae_status wae_node_set_channel_count(wae_graph* g, wae_node_id node, uint32_t count) { return set_channel_config_field(g, node, F_COUNT, count); }
+WAE_API wae_status wae_node_set_channel_count_mode(wae_graph* g, wae_node_id node, uint32_t mode) { return set_channel_config_field(g, node, F_MODE, mode); }
+WAE_API wae_status wae_node_set_channel_interpretation(wae_graph* g, wae_node_id node, uint32_t interpretation) {
+    return set_channel_config_field(g, node, F_INTERP, interpretation);
+}
+
 // ---- control-side read-outs of the filter nodes (no device work) ---------------------------------------------------------
 // calculate_coefs (src/node/biquad_filter.rs:42-390): the normalised coefficients the k_biquad / k_chain kernels are fed with
 WAE_API void wae_biquad_coefs(uint32_t type, double sample_rate, double f0, double gain, double q, double* out5) {
