@@ -259,9 +259,15 @@ WAE_API wae_status wae_engine_stream(wae_engine* engine, void** out_stream);
 
 /* ---- graph construction = OfflineAudioContext::new + BaseAudioContext::create_* ----------------- */
 
-/* OfflineAudioContext::new(number_of_channels, length, sample_rate), src/context/offline.rs:78. */
+/* OfflineAudioContext::new(number_of_channels, length, sample_rate), src/context/offline.rs:78.
+ * `engine` may be NULL: graph construction is host work (validation, id allocation, the event queues), the graph meets a
+ * device only when it is handed to wae_batch_prepare / wae_render_batch, which take the engine themselves. */
 WAE_API wae_status wae_graph_create(wae_engine* engine, uint32_t number_of_channels, uint64_t length,
                                     float sample_rate, wae_graph** out_graph);
+/* The order the graph's nodes are processed in within one quantum, as the planner derives it: Graph::order_nodes
+ * (src/render/graph.rs:331-487: depth-first over ascending ids, reversed post-order, DelayWriters of a cycle lose their
+ * outgoing edges, nodes of a cycle without a delay are dropped).  Fills at most `cap` ids, *n = the full count. Host work. */
+WAE_API wae_status wae_graph_render_order(wae_graph* graph, wae_node_id* ids, uint32_t cap, uint32_t* n);
 WAE_API wae_status wae_graph_destroy(wae_graph* graph);
 
 /* BaseAudioContext::create_* (src/context/base.rs:26-361) / XxxNode::new(context, options). */

@@ -55,6 +55,18 @@ def host_api(request, pkg, oracle):
     return pkg.api()
 
 
+@pytest.fixture(params=["oracle", "engine"])
+def builder(request, pkg, oracle):
+    """A backend for tests that only BUILD graphs (validation, ids, processing order): the oracle, and the product's own graph
+    half with no engine attached (wae_graph_create(NULL, ...): host work, runs without a GPU; rendering it raises)."""
+    if request.param == "oracle":
+        return oracle
+    so = os.path.join(ROOT, "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    return pkg.context.Backend(pkg.api(), None)
+
+
 @pytest.fixture(scope="session")
 def engine(pkg, oracle):
     if os.environ.get("WAE_DRYRUN_ORACLE_AS_ENGINE"):  # local dry run of the test plumbing only (no parity meaning)

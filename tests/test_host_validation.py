@@ -1,0 +1,78 @@
+"""The graph-building half of the product (csrc/wae_abi_graph.cpp: option validation, id allocation, constraint checks, processing
+order) is host code and runs without a GPU: wae_graph_create accepts a NULL engine.  The argument-error tests restated from the
+reference are therefore executed here against libwae_b200.so itself, on the CPU — not only against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import test_oracle_analyser as AN
+import test_oracle_kat as K
+import test_oracle_nodes as N
+
+RQ = 128
+
+
+@pytest.fixture
+def product(pkg):
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    return pkg.context.Backend(pkg.api(), None)
+
+
+@pytest.mark.parametrize("case", [N.test_channel_config_constraints, N.test_channel_merger_splitter_option_errors, K.test_iir_coefficient_validation,
+                                  K.test_convolver_argument_errors, AN.test_option_constraints], ids=lambda f: f.__name__)
+def test_reference_argument_errors_on_the_product(pkg, product, case):
+    case(pkg, product)
+
+
+@pytest.mark.parametrize("which", ["product", "oracle"])
+def test_node_and_param_ids_follow_the_reference(pkg, product, oracle, which):
+    # src/context/concrete_base.rs:240 + SURVEY Appendix A.1: ids 0..=10 reserved, a node's id is taken before its params'
+    c = pkg.OfflineAudioContext(2, RQ, 48000.0, product if which == "product" else oracle)
+    osc = c.create_oscillator()       # 11, frequency 12, detune 13
+    bq = c.create_biquad_filter()     # 14, q 15, detune 16, frequency 17, gain 18
+    d = c.create_delay(1.0, 0.1)      # writer 19, reader 20, delayTime 21
+    g = c.create_gain()               # 22, gain 23
+    assert (osc.id, bq.id, d.id, g.id) == (11, 14, 19, 22)
+    osc.connect(bq)
+    bq.connect(d)
+    d.connect(g)
+    g.connect(c.destination())
+    # depth-first from ascending ids (graph.rs:443-479): 0 | 11 -> 14 -> 19 -> 20 -> 22 | 12 | 13 | 15..18 | 21 | 23, post-order reversed
+    assert c.render_order() == [23, 21, 18, 17, 16, 15, 13, 12, 11, 14, 19, 20, 22, 0]
+
+
+def test_rendering_without_an_engine_fails_loudly(pkg, product):
+    c = pkg.OfflineAudioContext(1, RQ, 48000.0, product)
+    src = c.create_constant_source()
+    src.connect(c.destination())
+    src.start()
+    with pytest.raises(pkg.WaeError):
+        c.start_rendering_sync()
+
+
+def test_context_option_errors(pkg, product):
+    # src/context/offline.rs:78-105 / src/lib.rs:185-260: channel count, length and sample-rate ranges
+    for ch, length, sr in [(0, RQ, 48000.0), (33, RQ, 48000.0), (1, 0, 48000.0), (1, RQ, 2999.0), (1, RQ, 768001.0)]:
+        with pytest.raises(pkg.WaeError):
+            pkg.OfflineAudioContext(ch, length, sr, product)
+    pkg.OfflineAudioContext(32, 1, 3000.0, product)
+
+
+def test_param_event_argument_errors(pkg, product):
+    # src/param.rs:560-657 assert_* : negative times, zero exponential target, non-positive curve duration, short curves
+    c = pkg.OfflineAudioContext(1, RQ, 48000.0, product)
+    g = c.create_gain().gain
+    g.set_value_at_time(1.0, 0.0)
+    g.linear_ramp_to_value_at_time(2.0, 0.5)
+    for bad in [lambda: g.set_value_at_time(1.0, -1.0), lambda: g.linear_ramp_to_value_at_time(1.0, -0.1),
+                lambda: g.exponential_ramp_to_value_at_time(0.0, 1.0), lambda: g.exponential_ramp_to_value_at_time(1.0, -1.0),
+                lambda: g.set_target_at_time(1.0, -1.0, 0.1), lambda: g.set_target_at_time(1.0, 1.0, -0.1),
+                lambda: g.cancel_scheduled_values(-1.0), lambda: g.cancel_and_hold_at_time(-1.0),
+                lambda: g.set_value_curve_at_time(np.array([1.0], np.float32), 1.0, 1.0),
+                lambda: g.set_value_curve_at_time(np.array([1.0, 2.0], np.float32), -1.0, 1.0),
+                lambda: g.set_value_curve_at_time(np.array([1.0, 2.0], np.float32), 1.0, 0.0)]:
+        with pytest.raises(pkg.WaeError):
+            bad()

@@ -118,20 +118,67 @@ def test_cycle_breaker(pkg, oracle):
     assert np.array_equal(out[2 * RQ:], np.full(RQ, 3.0, np.float32))
 
 
-def test_render_order_matches_reference(pkg, oracle):
+def test_render_order_matches_reference(pkg, builder):
     # src/render/graph.rs:443-479 + SURVEY §3.3: reverse post-order over ascending ids — the last-created
     # branch is processed first.  ids: dest 0; osc1 11 (+12,13); osc2 14 (+15,16)
-    import ctypes
-    c = ctx(pkg, oracle, 1, RQ, 48000.0)
+    c = ctx(pkg, builder, 1, RQ, 48000.0)
     o1 = c.create_oscillator()
     o2 = c.create_oscillator()
     o1.connect(c.destination())
     o2.connect(c.destination())
     assert (o1.id, o2.id) == (11, 14)
-    ids = (ctypes.c_uint32 * 64)()
-    n = oracle.api.render_order(c._g, ids, 64)
-    order = list(ids[:n])
-    assert order == [16, 15, 14, 13, 12, 11, 0]
+    assert c.render_order() == [16, 15, 14, 13, 12, 11, 0]
+
+
+def _gain_graph(pkg, be, n):
+    """n + 1 plain nodes like the reference's graph tests: destination = 0, gains g[1..n] (each gain id is followed by its param)."""
+    c = ctx(pkg, be, 1, RQ, 48000.0)
+    nodes = [c.destination()] + [c.create_gain() for _ in range(n)]
+    return c, nodes
+
+
+def test_graph_order_add_remove(pkg, builder):  # src/render/graph.rs:659-706 test_add_remove
+    c, n = _gain_graph(pkg, builder, 3)
+    n[1].connect(n[0])
+    n[2].connect(n[1])
+    n[3].connect(n[0])
+    order = c.render_order()
+    ids = [x.id for x in n]
+    assert all(i in order for i in ids) and order[-1] == 0  # all nodes present, the root comes last
+    assert order.index(ids[2]) < order.index(ids[1])        # node 1 depends on node 2
+    n[1].disconnect()                                       # detach node 1 (and thus node 2) from the root
+    order = c.render_order()
+    assert all(i in order for i in ids)
+    assert order.index(ids[2]) < order.index(ids[1])
+
+
+def test_graph_order_cycle_without_delay_is_muted(pkg, builder):  # src/render/graph.rs:708-741 test_cycle
+    c, n = _gain_graph(pkg, builder, 4)
+    n[4].connect(n[2])
+    n[2].connect(n[1])
+    n[1].connect(n[0])
+    n[1].connect(n[2])
+    n[3].connect(n[0])
+    order = c.render_order()
+    assert n[1].id not in order and n[2].id not in order    # the cycle 1 <> 2 is removed
+    assert n[4].id in order                                 # the leg feeding the cycle is still rendered
+    assert order.index(n[3].id) < order.index(0)            # the acyclic part is present
+
+
+def test_graph_order_cycle_breaker(pkg, builder):  # src/render/graph.rs:458-479: a DelayWriter inside a cycle loses its outgoing edge
+    c = ctx(pkg, builder, 1, RQ, 48000.0)
+    src = c.create_constant_source()
+    g = c.create_gain()
+    d = c.create_delay(1.0, 0.5)
+    src.connect(g)
+    g.connect(d)
+    d.connect(g)
+    g.connect(c.destination())
+    order = c.render_order()
+    writer, reader = d.id, d.id + 1
+    assert writer in order and reader in order and g.id in order
+    # reader (the cycle's source after the break) -> gain -> writer; without the break the writer would precede the reader
+    assert order.index(reader) < order.index(g.id) < order.index(writer)
 
 
 def test_suspend_sync(pkg, oracle):

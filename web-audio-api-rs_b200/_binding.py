@@ -142,7 +142,7 @@ WAE_SYMBOLS = [
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
-    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation",
+    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order",
 ]
 
 
@@ -159,6 +159,10 @@ class Api:
         for name, opt in CREATE_FUNCS.items():
             f(name, C.c_int32, [gp, C.POINTER(opt), C.POINTER(C.c_uint32)])
         f("graph_destroy", C.c_int32, [gp])
+        if self.is_product:
+            f("graph_render_order", C.c_int32, [gp, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)])
+        else:
+            f("render_order", C.c_uint32, [gp, C.POINTER(C.c_uint32), C.c_uint32])
         f("graph_suspend", C.c_int32, [gp, C.c_double])
         f("param_sim_create", C.c_int32, [C.c_uint32, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_void_p)])
         f("param_sim_destroy", C.c_int32, [C.c_void_p])
@@ -212,7 +216,6 @@ class Api:
             f("graph_create", C.c_int32, [C.c_uint32, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)])
             f("render", C.c_int32, [gp, c_float_p])
             f("render_many", C.c_int32, [C.POINTER(C.c_void_p), C.c_uint32, c_float_p, C.c_uint32, c_double_p])
-            f("render_order", C.c_uint32, [gp, C.POINTER(C.c_uint32), C.c_uint32])
             f("analyser_get_float_time_domain_data", C.c_int32, [gp, C.c_uint32, c_float_p, C.c_uint32])
             f("analyser_get_float_frequency_data", C.c_int32, [gp, C.c_uint32, c_float_p, C.c_uint32])
             f("analyser_get_byte_frequency_data", C.c_int32, [gp, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])

@@ -325,6 +325,17 @@ class OfflineAudioContext:
         except Exception:
             pass
 
+    def render_order(self):
+        """Ids in per-quantum processing order (Graph::order_nodes, src/render/graph.rs:331-487); host work on both libraries."""
+        ids = (C.c_uint32 * 4096)()
+        if self._api.is_product:
+            n = C.c_uint32(0)
+            self._api.check(self._api.graph_render_order(self._g, ids, 4096, C.byref(n)))
+            n = n.value
+        else:
+            n = self._api.render_order(self._g, ids, 4096)
+        return list(ids[:min(n, 4096)])
+
     # ---- BaseAudioContext
     def destination(self):
         return self._dest

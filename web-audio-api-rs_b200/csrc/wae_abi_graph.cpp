@@ -105,7 +105,7 @@ WAE_API const char* wae_version(void) { return "wae-b200 0.1 (sm_100a)"; }
 // OfflineAudioContext::new, src/context/offline.rs:78-105
 WAE_API wae_status wae_graph_create(wae_engine* engine, uint32_t number_of_channels, uint64_t length, float sample_rate,
                                     wae_graph** out) {
-    if (!engine || !out) return fail(WAE_INVALID_ARGUMENT, "null engine / out pointer");
+    if (!out) return fail(WAE_INVALID_ARGUMENT, "null out pointer");  // a NULL engine is fine: planning and rendering name their own
     if (number_of_channels < 1 || number_of_channels > WAE_MAX_CHANNELS)
         return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels");
     if (length == 0) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid length: 0");

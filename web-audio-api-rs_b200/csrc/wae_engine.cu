@@ -1814,6 +1814,17 @@ WAE_API wae_status wae_batch_destroy(wae_batch* b) {
     return WAE_OK;
 }
 
+// Graph::order_nodes as the planner runs it (host only): lets the CPU tests pin the ordering against the reference's tests
+WAE_API wae_status wae_graph_render_order(wae_graph* g, wae_node_id* ids, uint32_t cap, uint32_t* n) {
+    if (!g || !n || (cap && !ids)) return fail(WAE_INVALID_ARGUMENT, "null argument");
+    Orderer o;
+    o.g = g;
+    o.run();
+    *n = (uint32_t)o.ordered.size();
+    for (uint32_t i = 0; i < *n && i < cap; i++) ids[i] = o.ordered[i];
+    return WAE_OK;
+}
+
 WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out) {
     if (!eng || !graphs || !out || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
     CUDA_TRY(cudaSetDevice(eng->device));
