@@ -132,3 +132,17 @@ def test_analyser_reference_case_on_gpu(pkg, engine, case):
 @pytest.mark.parametrize("bins", [range(1, 128, 9), range(5, 128, 9)], ids=["a", "b"])
 def test_analyser_sine_bins_on_gpu(pkg, engine, bins):
     AN.test_float_frequency_data_peaks_at_the_sine_bin(pkg, engine.backend, bins)
+
+
+# ---- src/buffer.rs:716-816 AudioBuffer::resample, restated in tests/test_oracle_buffer.py; here through wae_resample_linear -------
+import test_oracle_buffer as BU  # noqa: E402
+
+
+def test_resample_up_down_and_edges_on_gpu(pkg, engine):
+    BU.check_up_and_downsample(engine.resample)
+    BU.check_resample_edge_cases(engine.resample)
+
+
+@pytest.mark.parametrize("source_sr", [22500, 38000, 48000, 96000])
+def test_resample_stereo_on_gpu(pkg, engine, source_sr):
+    BU.check_resample_stereo(engine.resample, source_sr)

@@ -76,3 +76,26 @@ def test_param_event_argument_errors(pkg, product):
                 lambda: g.set_value_curve_at_time(np.array([1.0, 2.0], np.float32), 1.0, 0.0)]:
         with pytest.raises(pkg.WaeError):
             bad()
+
+
+@pytest.mark.parametrize("kind", ["constant", "buffer", "oscillator"])
+def test_scheduled_source_state_machine(pkg, builder, kind):
+    # src/node/scheduled_source.rs:267-338: start twice panics, stop before start panics, stop twice is allowed (issue #579)
+    def make():
+        c = pkg.OfflineAudioContext(2, 1, 44100.0, builder)
+        return c, {"constant": c.create_constant_source, "buffer": c.create_buffer_source, "oscillator": c.create_oscillator}[kind]()
+
+    c, src = make()
+    src.start()
+    with pytest.raises(pkg.WaeError):
+        src.start()
+    c, src = make()
+    with pytest.raises(pkg.WaeError):
+        src.stop()
+    c, src = make()
+    src.start()
+    src.stop()
+    src.stop()
+    c, src = make()
+    with pytest.raises(pkg.WaeError):
+        src.start_at(-1.0)  # scheduled_source.rs:12-30 assert_valid_time_value / RangeError
