@@ -41,3 +41,26 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 text = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in text and "oracle/" not in text and "wao_core" not in text, f
+
+
+def test_header_is_plain_c99_and_struct_layouts_match_the_binding(pkg, tmp_path):
+    # the boundary is a C ABI: include/wae.h must compile as C (no C++-isms), and the ctypes structures of the binding must have
+    # the sizes the C compiler gives the header's structs (a field added on one side only would silently shift arguments)
+    import subprocess
+    pairs = [("wae_channel_config", "ChannelConfig"), ("wae_audio_buffer", "AudioBufferDesc"), ("wae_param_event", "ParamEvent"),
+             ("wae_oscillator_options", "OscillatorOptions"), ("wae_biquad_options", "BiquadOptions"), ("wae_iir_options", "IirOptions"),
+             ("wae_gain_options", "GainOptions"), ("wae_delay_options", "DelayOptions"), ("wae_stereo_panner_options", "StereoPannerOptions"),
+             ("wae_panner_options", "PannerOptions"), ("wae_analyser_options", "AnalyserOptions"),
+             ("wae_dynamics_compressor_options", "DynamicsCompressorOptions"), ("wae_channel_merger_options", "ChannelMergerOptions"),
+             ("wae_channel_splitter_options", "ChannelSplitterOptions"), ("wae_batch_stats", "BatchStats")]
+    B = pkg._binding
+    pairs = [(c, p) for c, p in pairs if hasattr(B, p)]
+    assert len(pairs) >= 10
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "wae.h"\nint main(void) {\n' +
+                   "".join('  printf("%s %%zu\\n", sizeof(%s));\n' % (c, c) for c, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for c, p in pairs:
+        assert int(sizes[c]) == ctypes.sizeof(getattr(B, p)), (c, p)
