@@ -414,6 +414,11 @@ WAE_API wae_status wae_node_set_channel_count(wae_graph* graph, wae_node_id node
 WAE_API wae_status wae_node_set_channel_count_mode(wae_graph* graph, wae_node_id node, uint32_t count_mode);
 WAE_API wae_status wae_node_set_channel_interpretation(wae_graph* graph, wae_node_id node, uint32_t interpretation);
 
+/* HrirSphere::new(reader, context_rate) of the hrtf crate (src/node/panner.rs:39-68 is the call site): when the context rate differs from
+ * the sphere's, every impulse response is resampled once with an asynchronous windowed-sinc resampler (ratio = context_rate / sphere_rate).
+ * The engine does this to the whole sphere on first use of a rate; this entry point applies it to one response (host work, for tests). */
+WAE_API wae_status wae_hrir_resample(const float* hrir, uint32_t len, double ratio, float* out, uint32_t cap, uint32_t* out_len);
+
 /* Control-side read-outs of the filter nodes; host math only, no engine needed.
  * wae_biquad_frequency_response = BiquadFilterNode::get_frequency_response (src/node/biquad_filter.rs:657-735): the node's type and the
  * current value of its frequency / detune / q / gain params; frequencies outside [0, sample_rate / 2] answer NaN.

@@ -868,4 +868,12 @@ WAO_API void wao_mix(const float* in, uint32_t from, uint32_t to, uint32_t inter
     for (uint32_t c = 0; c < to; c++) std::memcpy(out + 128 * c, q.channel((int)c).data(), 128 * sizeof(float));
 }
 
+// test hook: one impulse response through the restated sphere resampler (wao_hrtf.cpp)
+WAO_API wae_status wao_hrir_resample(const float* hrir, uint32_t len, double ratio, float* out, uint32_t cap, uint32_t* n) {
+    std::vector<float> r = wao::resample_hrir(std::vector<float>(hrir, hrir + len), ratio);
+    *n = (uint32_t)r.size();
+    for (uint32_t i = 0; i < *n && i < cap; i++) out[i] = r[i];
+    return WAE_OK;
+}
+
 }  // extern "C"

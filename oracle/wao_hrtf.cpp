@@ -14,10 +14,14 @@
 //     history (the crate: complex FFT of L+127 points, scaled by distance_gain / pad_length), i.e. a plain L-tap FIR:
 //         out[n] = distance_gain * sum_k h[k] * x[n - k]
 //     evaluated here in the time domain with f64 accumulation.
-// NOT restated: the crate resamples the sphere with rubato's SincFixedIn when the context rate differs from the
-// sphere's (44.1 kHz data at 48 kHz).  Contexts whose sample rate differs from the loaded sphere's get
-// WAE_UNSUPPORTED.  Degenerate rays (through a mesh vertex / edge) pick the face with the largest minimum
-// barycentric coordinate instead of the crate's first-hit order.
+// When the context rate differs from the sphere's (the embedded sphere is 44.1 kHz data, contexts are usually 48 kHz) the
+// crate resamples every impulse response once, at load time, with rubato's asynchronous sinc resampler (SincFixedIn, one
+// `process` call over the whole response, parameters sinc_len 256 / f_cutoff 0.95 / oversampling 160 / cubic / BlackmanHarris2).
+// resample_hrir() below restates that algorithm from rubato's published description (windowed-sinc bank, 4 neighbouring sinc
+// phases, cubic polynomial between them, start index -sinc_len/2, stop at chunk - sinc_len - 1).  Neither crate is in
+// /root/reference, so the tap values of a resampled sphere are unpinned like the rest of this file.
+// Degenerate rays (through a mesh vertex / edge) pick the face with the largest minimum barycentric coordinate instead of
+// the crate's first-hit order.
 // PARITY UNPINNED: the only reference test (panner.rs:1225-1269) asserts "output != input" and "tail is non-zero"
 // (both checked in tests/test_oracle_kat.py when the sphere is present); there are no golden vectors for this path.
 #include "wao_panner.h"
@@ -91,6 +95,107 @@ static std::shared_ptr<const HrirSphereData> current_sphere() {
     return g_sphere;
 }
 
+// ---- rubato (asynchronous sinc resampler), as hrtf 0.8.1 drives it over one impulse response -----------------------------
+namespace {
+const float kPi = 3.14159265358979323846f;
+
+float sinc_pi(float x) { return x == 0.f ? 1.f : std::sin(x * kPi) / (x * kPi); }
+
+// make_sincs(npoints, factor, f_cutoff, BlackmanHarris2): `factor` phase-shifted copies of a windowed sinc, each `npoints` long
+std::vector<std::vector<float>> make_sinc_bank(size_t npoints, size_t factor, float f_cutoff) {
+    const size_t tot = npoints * factor;
+    std::vector<float> y(tot);
+    const float np_f = (float)tot;
+    float sum = 0.f;
+    for (size_t x = 0; x < tot; x++) {
+        const float xf = (float)x;
+        const float bh = 0.35875f - 0.48829f * std::cos(2.f * kPi * xf / np_f) + 0.14128f * std::cos(4.f * kPi * xf / np_f) -
+                         0.01168f * std::cos(6.f * kPi * xf / np_f);
+        const float val = bh * bh * sinc_pi((xf - (float)(tot / 2)) * f_cutoff / (float)factor);
+        sum += val;
+        y[x] = val;
+    }
+    sum /= (float)factor;
+    std::vector<std::vector<float>> bank(factor, std::vector<float>(npoints));
+    for (size_t p = 0; p < npoints; p++)
+        for (size_t n = 0; n < factor; n++) bank[factor - n - 1][p] = y[factor * p + n] / sum;
+    return bank;
+}
+
+float cubic(float x, const float y[4]) {
+    const float a0 = y[1];
+    const float a1 = -(1.f / 3.f) * y[0] - 0.5f * y[1] + y[2] - (1.f / 6.f) * y[3];
+    const float a2 = 0.5f * (y[0] + y[2]) - y[1];
+    const float a3 = 0.5f * (y[1] - y[2]) + (1.f / 6.f) * (y[3] - y[0]);
+    const float x2 = x * x;
+    return a0 + a1 * x + a2 * x2 + a3 * x2 * x;
+}
+}  // namespace
+
+std::vector<float> resample_hrir(const std::vector<float>& hrir, double ratio) {
+    const size_t sinc_len = 256, factor = 160, chunk = hrir.size();
+    const float cutoff = ratio >= 1.0 ? 0.95f : 0.95f * (float)ratio;
+    const std::vector<std::vector<float>> bank = make_sinc_bank(sinc_len, factor, cutoff);
+    std::vector<float> buf(chunk + 2 * sinc_len, 0.f);  // [2 * sinc_len zeros of history | the response]
+    std::memcpy(buf.data() + 2 * sinc_len, hrir.data(), chunk * sizeof(float));
+    const double t_ratio = 1.0 / ratio;
+    const double end_idx = (double)((ptrdiff_t)chunk - (ptrdiff_t)(sinc_len + 1));
+    double idx = -(double)(sinc_len / 2);
+    std::vector<float> out;
+    while (idx < end_idx) {
+        idx += t_ratio;
+        const double fl = std::floor(idx);
+        ptrdiff_t index = (ptrdiff_t)fl;
+        ptrdiff_t sub = (ptrdiff_t)std::floor((idx - fl) * (double)factor);
+        const double scaled = idx * (double)factor;
+        const float frac = (float)(scaled - std::floor(scaled));
+        float pts[4];
+        for (int k = 0; k < 4; k++) {
+            ptrdiff_t i = index, s2 = sub - 1 + k;
+            if (s2 < 0) { s2 += (ptrdiff_t)factor; i -= 1; }
+            else if (s2 >= (ptrdiff_t)factor) { s2 -= (ptrdiff_t)factor; i += 1; }
+            const float* w = buf.data() + (i + 2 * (ptrdiff_t)sinc_len);
+            const float* sc = bank[(size_t)s2].data();
+            float acc = 0.f;
+            for (size_t j = 0; j < sinc_len; j++) acc += w[j] * sc[j];
+            pts[k] = acc;
+        }
+        out.push_back(cubic(frac, pts));
+    }
+    return out;
+}
+
+static std::mutex g_resampled_mutex;
+static std::vector<std::pair<std::pair<const HrirSphereData*, uint32_t>, std::shared_ptr<const HrirSphereData>>> g_resampled;
+
+// HrirSphere::new(reader, sample_rate): every response of the sphere at the context's rate
+static std::shared_ptr<const HrirSphereData> sphere_at_rate(const std::shared_ptr<const HrirSphereData>& sp, uint32_t rate) {
+    if (rate == sp->sample_rate) return sp;
+    std::lock_guard<std::mutex> lk(g_resampled_mutex);
+    for (auto& e : g_resampled)
+        if (e.first.first == sp.get() && e.first.second == rate) return e.second;
+    auto r = std::make_shared<HrirSphereData>();
+    r->sample_rate = rate;
+    r->pos = sp->pos;
+    r->faces = sp->faces;
+    const double ratio = (double)rate / (double)sp->sample_rate;
+    const size_t nv = sp->pos.size() / 3, L = sp->length;
+    for (size_t v = 0; v < nv; v++) {
+        for (int ear = 0; ear < 2; ear++) {
+            const std::vector<float>& src = ear ? sp->right : sp->left;
+            std::vector<float> one(src.begin() + v * L, src.begin() + (v + 1) * L);
+            std::vector<float> res = resample_hrir(one, ratio);
+            if (v == 0 && ear == 0) r->length = (uint32_t)res.size();
+            res.resize(r->length, 0.f);
+            std::vector<float>& dst = ear ? r->right : r->left;
+            dst.insert(dst.end(), res.begin(), res.end());
+        }
+    }
+    if (g_resampled.size() > 8) g_resampled.erase(g_resampled.begin());
+    g_resampled.push_back({{sp.get(), rate}, r});
+    return r;
+}
+
 struct HrtfState {
     std::shared_ptr<const HrirSphereData> sphere;
     size_t len = 0;
@@ -108,10 +213,11 @@ size_t hrtf_tail_time_samples(const HrtfState& s) { return s.len; }
 std::shared_ptr<HrtfState> hrtf_state_new(float sample_rate) {
     auto sp = current_sphere();
     if (!sp) return nullptr;
-    // load_hrtf_processor clamps the rate to >= 27 kHz (panner.rs:46) and resamples when it differs — not restated
+    // load_hrtf_processor clamps the rate to >= 27 kHz (panner.rs:46); HrirSphere::new resamples when it differs
     uint32_t sr = (uint32_t)sample_rate;
     if (sr < 27000) sr = 27000;
-    if (sr != sp->sample_rate) return nullptr;
+    sp = sphere_at_rate(sp, sr);
+    if (sp->length < 2) return nullptr;
     auto st = std::make_shared<HrtfState>();
     st->sphere = sp;
     st->len = sp->length;

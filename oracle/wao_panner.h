@@ -44,5 +44,7 @@ size_t hrtf_tail_time_samples(const HrtfState&);
 // source: 128 mono samples; out: 128 interleaved (l, r) pairs
 void hrtf_process(HrtfState&, const float* source, float new_distance_gain, const float projected_source[3], float* out_lr);
 std::shared_ptr<HrtfState> hrtf_state_new(float sample_rate);
+// one impulse response resampled as HrirSphere::new does for a context rate other than the data's (ratio = context / data)
+std::vector<float> resample_hrir(const std::vector<float>& hrir, double ratio);
 
 }  // namespace wao

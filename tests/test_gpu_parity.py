@@ -305,17 +305,32 @@ def test_c5_full_chain(pkg, engine, oracle):
         assert np.abs(10.0 ** (fa / 20) - 10.0 ** (fb / 20)).max() <= 1e-6
 
 
-def test_hrtf_panner_needs_matching_sphere(pkg, engine):
-    engine.backend.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 64))
-    c = pkg.OfflineAudioContext(2, 256, G.SR, engine.backend)
-    o = c.create_oscillator()
-    p = c.create_panner(panning_model=pkg.context.HRTF)
-    o.connect(p)
-    p.connect(c.destination())
-    o.start()
-    with pytest.raises(pkg.WaeError) as e:
-        c.start_rendering_sync()
-    assert e.value.status == 4 and "sample rate" in str(e.value)   # WAE_UNSUPPORTED
+@pytest.mark.parametrize("sphere_rate,ctx_rate", [(44100, 48000.0), (44100, 96000.0), (48000, 32000.0)])
+def test_hrtf_panner_resamples_the_sphere_to_the_context_rate(pkg, engine, oracle, sphere_rate, ctx_rate):
+    """HrirSphere::new(reader, context_rate): the reference's embedded sphere is 44.1 kHz data, its contexts usually 48 kHz — every
+    response is resampled once (asynchronous sinc resampler; csrc/wae_hrtf_host.h vs oracle/wao_hrtf.cpp) before the panner runs."""
+    data = G.synthetic_hrir_sphere(sphere_rate, 384)
+    oracle.set_hrir_sphere(data)
+    engine.backend.set_hrir_sphere(data)
+    positions = [(3.0, 1.0, -2.0), (-4.0, 0.0, 0.5), (0.2, -6.0, 0.1)]
+
+    def build(be, g):
+        n = 128 * 15 + 7
+        pcm = G.c2_source(g, n) * np.float32(0.5)
+        c = pkg.OfflineAudioContext(2, n, ctx_rate, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]] if g % 2 else [pcm[0]], ctx_rate))
+        p = c.create_panner(panning_model=pkg.context.HRTF, position=positions[g])
+        s.connect(p)
+        p.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, len(positions))
+    assert float(np.abs(cpu).max()) > 0.01
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_hrtf_panner_rejects_a_malformed_sphere(pkg, engine):
     with pytest.raises(pkg.WaeError):
         engine.backend.set_hrir_sphere(b"HRIX" + bytes(64))
 
@@ -524,14 +539,19 @@ def test_north_star_graph(pkg, engine, oracle):
 
 
 def test_unsupported_is_reported_not_faked(pkg, engine):
+    # a ConvolverNode inside a DelayNode feedback loop is not lowered: reported, never approximated
     c = pkg.OfflineAudioContext(2, 256, G.SR, engine.backend)
-    with pytest.raises(pkg.WaeError) as e:  # no HRIR sphere at this rate: reported, never approximated
-        engine.backend.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 64))
-        p = c.create_panner(panning_model=pkg.context.HRTF)
-        src = c.create_constant_source()
-        src.connect(p)
-        p.connect(c.destination())
-        src.start()
+    src = c.create_constant_source()
+    g = c.create_gain(0.5)
+    d = c.create_delay(1.0, 0.01)
+    conv = c.create_convolver(pkg.AudioBuffer([np.ones(8, np.float32)], G.SR))
+    src.connect(g)
+    g.connect(d)
+    d.connect(conv)
+    conv.connect(g)
+    g.connect(c.destination())
+    src.start()
+    with pytest.raises(pkg.WaeError) as e:
         c.start_rendering_sync()
     assert e.value.status == 4  # WAE_UNSUPPORTED -> the caller falls back to the CPU renderer
 

@@ -142,7 +142,7 @@ WAE_SYMBOLS = [
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
-    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order",
+    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample",
 ]
 
 
@@ -179,6 +179,7 @@ class Api:
         f("source_stop", C.c_int32, [gp, C.c_uint32, C.c_double])
         f("oscillator_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
         f("biquad_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
+        f("hrir_resample", C.c_int32, [c_float_p, C.c_uint32, C.c_double, c_float_p, C.c_uint32, C.POINTER(C.c_uint32)])
         for name in ("node_set_channel_count", "node_set_channel_count_mode", "node_set_channel_interpretation"):
             f(name, C.c_int32, [gp, C.c_uint32, C.c_uint32])
         f("biquad_coefs", None, [C.c_uint32, C.c_double, C.c_double, C.c_double, C.c_double, c_double_p])

@@ -3,6 +3,7 @@
 // validation returns the reference's panic text through wae_last_error().
 #include "wae_graph.h"
 #include "wae_hostmath.h"
+#include "wae_hrtf_host.h"
 #include "wae_param_core.h"
 #include "wae_param_host.h"
 
@@ -752,6 +753,17 @@ WAE_API void wae_iir_frequency_response(const double* ff, uint32_t nff, const do
         mag[i] = (float)std::abs(h);
         phase[i] = (float)std::arg(h);
     }
+}
+
+// One impulse response of the HRIR sphere resampled the way HrirSphere::new of the hrtf crate does when the context rate differs from the
+// data's (csrc/wae_hrtf_host.h); the engine applies it to the whole sphere on first use of a rate.  Host work.
+WAE_API wae_status wae_hrir_resample(const float* hrir, uint32_t len, double ratio, float* out, uint32_t cap, uint32_t* n) {
+    if (!hrir || !n || !(ratio > 0.)) return fail(WAE_INVALID_ARGUMENT, "null argument / non-positive ratio");
+    const SincBank bank(ratio >= 1.0 ? 0.95f : 0.95f * (float)ratio);
+    const std::vector<float> r = hrir_resample(bank, hrir, len, ratio);
+    *n = (uint32_t)r.size();
+    for (uint32_t i = 0; i < *n && i < cap; i++) out[i] = r[i];
+    return WAE_OK;
 }
 
 }  // extern "C"

@@ -50,6 +50,16 @@ struct wae_engine {
     float* d_sphere_ir = nullptr;
     float* d_sphere_pos = nullptr;
     uint32_t* d_sphere_tri = nullptr;
+    struct RateSphere {  // the sphere's responses resampled to a context rate (HrirSphere::new of the crate), built on first use
+        float* d_ir = nullptr;
+        uint32_t taps = 0;
+    };
+    std::map<uint32_t, RateSphere> sphere_rates;
+    void drop_rate_spheres() {
+        for (auto& kv : sphere_rates)
+            if (kv.second.d_ir) cudaFree(kv.second.d_ir);
+        sphere_rates.clear();
+    }
 };
 
 namespace {
@@ -1467,17 +1477,31 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     if (!sph) return bail(WAE_UNSUPPORTED, "HRTF panning needs an HRIR sphere: call wae_engine_set_hrir_sphere first");
                     uint32_t sr = (uint32_t)g->sample_rate;
                     if (sr < 27000) sr = 27000;  // panner.rs:46
-                    if (sr != sph->sample_rate)
-                        return bail(WAE_UNSUPPORTED, "HRTF panning: the context sample rate differs from the HRIR sphere's (resampling the sphere is not lowered)");
+                    uint32_t taps = sph->taps;
+                    const float* d_ir = eng->d_sphere_ir;
+                    if (sr != sph->sample_rate) {  // the crate resamples the responses to the context rate once (wae_hrtf_host.h)
+                        auto it = eng->sphere_rates.find(sr);
+                        if (it == eng->sphere_rates.end()) {
+                            const HrirSphere rs = sph->at_rate(sr);
+                            wae_engine::RateSphere r;
+                            r.taps = rs.taps;
+                            if (r.taps < 2) return bail(WAE_UNSUPPORTED, "HRTF panning: the HRIR sphere is too short to be resampled to the context rate");
+                            if (cudaMalloc(&r.d_ir, rs.ir.size() * sizeof(float)) != cudaSuccess) return bail(WAE_OUT_OF_MEMORY, "out of device memory (resampled HRIR sphere)");
+                            cudaMemcpy(r.d_ir, rs.ir.data(), rs.ir.size() * sizeof(float), cudaMemcpyHostToDevice);
+                            it = eng->sphere_rates.emplace(sr, r).first;
+                        }
+                        taps = it->second.taps;
+                        d_ir = it->second.d_ir;
+                    }
                     HrtfInst h{};
                     h.in = p.in_buf[0];
                     h.out = p.out_buf[0];
                     h.in_ch = ch;
-                    h.L = (int)sph->taps;
-                    h.sphere_ir = eng->d_sphere_ir;
+                    h.L = (int)taps;
+                    h.sphere_ir = d_ir;
                     h.sel = nullptr;
                     h.correction = ch == 2 ? 2.f : 1.f;
-                    h.hist = alloc<float>(sph->taps, true, true);
+                    h.hist = alloc<float>(taps, true, true);
                     if (!h.hist) return bail(WAE_OUT_OF_MEMORY, "out of device memory (hrtf history)");
                     StageBuild& hs = stage(L, S_HRTF);
                     if (moving) {
@@ -1728,6 +1752,7 @@ WAE_API wae_status wae_engine_destroy(wae_engine* eng) {
     if (eng->d_sphere_ir) cudaFree(eng->d_sphere_ir);
     if (eng->d_sphere_pos) cudaFree(eng->d_sphere_pos);
     if (eng->d_sphere_tri) cudaFree(eng->d_sphere_tri);
+    eng->drop_rate_spheres();
     delete eng->sphere;
     if (eng->stream) cudaStreamDestroy(eng->stream);
     delete eng;
@@ -1765,6 +1790,7 @@ WAE_API wae_status wae_engine_set_hrir_sphere(wae_engine* eng, const void* data,
     if (eng->d_sphere_ir) cudaFree(eng->d_sphere_ir);
     if (eng->d_sphere_pos) cudaFree(eng->d_sphere_pos);
     if (eng->d_sphere_tri) cudaFree(eng->d_sphere_tri);
+    eng->drop_rate_spheres();
     eng->d_sphere_pos = dpos;
     eng->d_sphere_tri = dtri;
     delete eng->sphere;
