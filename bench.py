@@ -152,14 +152,16 @@ def run_extra_workloads(pkg, eng, oracle, cores, steps=2):
     res.append(measure_workload(pkg, eng, oracle, "north_star", lambda be, g: G.north_star_voices_convolver(pkg, be, 1000, 480000, ir3, seed=g),
                                 8, 8, 480000, steps, cores,
                                 "north_star: 8 graphs/GPU, each 1000 voices (Oscillator -> Biquad -> Gain) summed into one Convolver(3 s IR) -> destination, 10 s"))
-    sphere = G.synthetic_hrir_sphere(48000, 512)  # the reference's 44.1 kHz IRC sphere cannot travel: same size, synthetic data
+    # the reference's IRC_1003_C sphere (44.1 kHz, 512 taps, 187 vertices) cannot travel: synthetic data of the same rate and size,
+    # resampled to the 48 kHz context rate by the library exactly as the embedded one would be (~417 taps)
+    sphere = G.synthetic_hrir_sphere(44100, 512)
     eng.backend.set_hrir_sphere(sphere)
     if oracle is not None:
         oracle.set_hrir_sphere(sphere)
     res.append(measure_workload(pkg, eng, oracle, "C5", lambda be, g: G.c5_full_chain(pkg, be, g, 192000, ir3), 256, min(cores, 64), 192000,
                                 steps, cores,
                                 "configs[4] per-GPU share (2048 graphs / 8 GPUs): Oscillator -> WaveShaper -> Biquad -> Convolver(3 s IR) -> "
-                                "Panner(HRTF, 512 taps) -> Analyser -> destination, 4 s"))
+                                "Panner(HRTF, 44.1 kHz / 512-tap sphere resampled to 48 kHz) -> Analyser -> destination, 4 s"))
     return res
 
 

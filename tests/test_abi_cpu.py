@@ -64,3 +64,27 @@ def test_header_is_plain_c99_and_struct_layouts_match_the_binding(pkg, tmp_path)
     sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
     for c, p in pairs:
         assert int(sizes[c]) == ctypes.sizeof(getattr(B, p)), (c, p)
+
+
+def build_c_client(tmp_path):
+    import subprocess
+    exe = tmp_path / "c_client"
+    pkg_dir = os.path.join(ROOT, "web-audio-api-rs_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "c_client.c"), "-L", pkg_dir, "-lwae_b200", "-Wl,-rpath," + pkg_dir, "-lm", "-o", str(exe)])
+    return str(exe)
+
+
+def test_plain_c_client_links_and_fails_loudly_without_a_gpu(pkg, tmp_path):
+    # examples/c_client.c: the boundary used from C, no Python / torch in the process.  Without a device it must stop at
+    # wae_engine_create with WAE_NO_DEVICE (exit code 2) — never render on the CPU
+    import subprocess
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    exe = build_c_client(tmp_path)
+    r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert r.returncode == 0, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr

@@ -990,3 +990,25 @@ def test_panner_and_delay_time_automation(pkg, engine, oracle):
 
     gpu, cpu = both(pkg, engine, oracle, build, 2)
     assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_plain_c_client_renders_what_the_oracle_renders(pkg, engine, oracle, tmp_path):
+    """examples/c_client.c drives the C ABI from C (own process, no Python): its per-graph RMS must be the oracle's for the same graphs."""
+    import subprocess
+    from test_abi_cpu import build_c_client
+    r = subprocess.run([build_c_client(tmp_path), "3"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    got = [float(line.split("rms")[1]) for line in r.stdout.splitlines() if "rms" in line]
+    assert len(got) == 3
+    for g in range(3):
+        c = pkg.OfflineAudioContext(2, 48000, 48000.0, oracle)
+        osc = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=110.0 * (g + 1))
+        bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=900.0, q=2.0)
+        gn = c.create_gain(0.5)
+        osc.connect(bq)
+        bq.connect(gn)
+        gn.connect(c.destination())
+        gn.gain.linear_ramp_to_value_at_time(0.0, 1.0)
+        osc.start()
+        left = c.start_rendering_sync().get_channel_data(0).astype(np.float64)
+        assert abs(got[g] - float(np.sqrt(np.mean(left * left)))) <= 2e-6
