@@ -831,6 +831,17 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
     }
     const ChainInst& q = sm.q;
     if (c >= q.ch) return;
+    // A chain without a filter carries nothing from tile to tile (the sources are closed forms of the frame index), so a launch
+    // with few chains but a long chunk is also split along time: gridDim.z slabs of whole tiles.  Filtered chains (NB > 0) carry
+    // their state through the chunk and are always launched with one slab.
+    int slab_begin = 0, slab_end = ci.nf;
+    if (NB == 0 && gridDim.z > 1) {
+        const int n_tiles = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+        const int per = (n_tiles + (int)gridDim.z - 1) / (int)gridDim.z;
+        slab_begin = (int)blockIdx.z * per * (CH_THREADS * CH_K);
+        slab_end = min(ci.nf, slab_begin + per * (CH_THREADS * CH_K));
+        if (slab_begin >= ci.nf) return;
+    }
     // per-CTA constants -> registers / shared
     double cb[NB > 0 ? NB : 1][5];
     double plane[NB > 0 ? NB : 1][4];
@@ -897,11 +908,11 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
     };
     float v[CH_K];
     if (STREAMED) {
-        stage_source(0, 0);
+        stage_source(0, slab_begin);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
     int tile_index = 0;
-    for (int base = 0; base < ci.nf; base += tile, tile_index++) {
+    for (int base = slab_begin; base < slab_end; base += tile, tile_index++) {
         const int n0 = base + t * CH_K;
         const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
         const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
@@ -1783,54 +1794,71 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
 
 // ---------------------------------------------------------------------------------------------------------
 // AudioParam automation — AudioParamProcessor::compute_buffer + mix_to_output (src/param.rs:739-797, 1038-1600).
-// One thread per param instance walks the chunk quantum by quantum through the (host-prepared) event timeline,
+// Lane 0 of a warp per param instance walks the chunk quantum by quantum through the (host-prepared) event timeline,
 // exactly like the reference's per-quantum state machine (set_value / linear & exponential ramps / setTarget with
 // snap-to-target / value curves / cancel_and_hold), adds the summed audio-rate input, maps NaN to the default and
 // clamps to [min, max].  The output is the param's value for EVERY frame (k-rate and constant blocks are
 // replicated), which is what the a-rate consumers read.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32) k_param(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
-    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ii >= n_inst) return;
+constexpr int PARAM_WARPS = 4;
+// One WARP per param instance: lane 0 walks the state machine of the quantum (wae_param_core.h, the code the host also runs), the 32
+// lanes then add the audio-rate input, map NaN to the default, clamp and store the 128 frames with coalesced accesses.
+__global__ void __launch_bounds__(32 * PARAM_WARPS) k_param(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ float s_buf[PARAM_WARPS][128];
+    __shared__ int s_len[PARAM_WARPS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ii = blockIdx.x * PARAM_WARPS + w;
+    if (ii >= n_inst) return;  // whole warps leave; the loop below only uses warp-level synchronisation
     const ParamInst p = insts[ii];
-    ParamState st = *p.state;
-    if (!st.inited) {  // first quantum of this param in this run (start of the render, or of the segment that created it / changed its events)
-        st.intrinsic = p.intrinsic0;
-        st.head = 0;
-        st.has_last = p.has_last0;
-        st.last = p.last0;
-        st.override_valid = 0;
-        st.inited = 1;
+    ParamState st{};
+    if (lane == 0) {
+        st = *p.state;
+        if (!st.inited) {  // first quantum of this param in this run (start of the render, or of the segment that created it / changed its events)
+            st.intrinsic = p.intrinsic0;
+            st.head = 0;
+            st.has_last = p.has_last0;
+            st.last = p.last0;
+            st.override_valid = 0;
+            st.inited = 1;
+        }
     }
     float* out = chan(p.out, 0, ci);
     float* single = chan(p.out, 1, ci);  // [first frame of a quantum] = 1: the reference's output buffer is single-valued
     const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
-    float buf[128];
+    float* buf = s_buf[w];
+    // ---- mix_to_output (param.rs:739-797): + input signal, NaN -> default, clamp
+    auto fix = [&](float v) {
+        if (v != v) return p.def;
+        v = v > p.mn ? v : p.mn;
+        return v < p.mx ? v : p.mx;
+    };
     for (int q0 = 0; q0 < ci.nf; q0 += 128) {
-        const double block_time = (double)(ci.f0 + q0) / (double)p.sample_rate;
-        const int len = param_compute_buffer(p, st, block_time, buf);  // wae_param_core.h
-        // ---- mix_to_output (param.rs:739-797): + input signal, NaN -> default, clamp
-        auto fix = [&](float v) {
-            if (v != v) return p.def;
-            v = v > p.mn ? v : p.mn;
-            return v < p.mx ? v : p.mx;
-        };
+        if (lane == 0) {
+            const double block_time = (double)(ci.f0 + q0) / (double)p.sample_rate;
+            s_len[w] = param_compute_buffer(p, st, block_time, buf);
+        }
+        __syncwarp();
+        const int len = s_len[w];
         if (len == 1 || !p.a_rate) {
             const float value = buf[0];
             if (!in || !p.a_rate) {
-                float v = fix(value + (in ? in[q0] : 0.f));
-                for (int i = 0; i < 128; i++) out[q0 + i] = v;
-                single[q0] = 1.f;
+                const float v = fix(value + (in ? in[q0] : 0.f));
+#pragma unroll
+                for (int i = lane; i < 128; i += 32) out[q0 + i] = v;
+                if (lane == 0) single[q0] = 1.f;
             } else {
-                for (int i = 0; i < 128; i++) out[q0 + i] = fix(in[q0 + i] + value);
-                single[q0] = 0.f;
+#pragma unroll
+                for (int i = lane; i < 128; i += 32) out[q0 + i] = fix(in[q0 + i] + value);
+                if (lane == 0) single[q0] = 0.f;
             }
         } else {
-            for (int i = 0; i < 128; i++) out[q0 + i] = fix((in ? in[q0 + i] : 0.f) + buf[i]);
-            single[q0] = 0.f;
+#pragma unroll
+            for (int i = lane; i < 128; i += 32) out[q0 + i] = fix((in ? in[q0 + i] : 0.f) + buf[i]);
+            if (lane == 0) single[q0] = 0.f;
         }
+        __syncwarp();  // the quantum's values are consumed before lane 0 overwrites them
     }
-    *p.state = st;
+    if (lane == 0) *p.state = st;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2253,6 +2281,12 @@ void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, 
 template <int SRC, int NB>
 static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     dim3 grid((unsigned)n, (unsigned)max_ch);
+    if (NB == 0) {  // stateless chain: also split along time until the launch fills the machine (4 CTAs per SM)
+        const long ctas = (long)n * max_ch, tiles = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+        long slabs = (4L * 148 + ctas - 1) / ctas;
+        if (slabs > tiles) slabs = tiles;
+        if (slabs > 1) grid.z = (unsigned)slabs;
+    }
     if (shaper) k_chain<SRC, NB, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
     else k_chain<SRC, NB, false><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
 }
@@ -2324,7 +2358,9 @@ void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, 
 void launch_resample_linear(const float* in, int64_t len, float* out, int64_t target_len, cudaStream_t s) {
     k_resample_linear<<<(unsigned)((target_len + 255) / 256), 256, 0, s>>>(in, len, out, target_len);
 }
-void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_param<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) {
+    k_param<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
+}
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_analyser<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 static void conv_configure() {
