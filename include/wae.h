@@ -405,6 +405,22 @@ WAE_API wae_status wae_compressor_reduction(wae_batch* batch, uint32_t graph_ind
 WAE_API wae_status wae_resample_linear(wae_engine* engine, const float* in, uint64_t len, float from_rate, float to_rate, float* out,
                                        uint64_t out_cap, uint64_t* out_len);
 
+/* What wae_batch_prepare would lower `graphs` to, computed on the host only (no engine, no device, default engine options): the planner's
+ * sizing pass.  Errors are the ones prepare would report (WAE_UNSUPPORTED for what is not lowered, WAE_INVALID_ARGUMENT ...), except
+ * the refusal of a ConvolverNode inside a DelayNode feedback loop, which only the full planning pass detects. */
+typedef struct wae_plan_info {
+    uint32_t groups;                 /* graph groups of the H2D / render / D2H pipeline                                  */
+    uint32_t segments;               /* render segments over all groups (1 per group without wae_graph_suspend points)    */
+    uint32_t stages;                 /* kernel launches per chunk, summed over groups and segments                        */
+    uint32_t has_feedback;           /* some graph has a cycle broken by a DelayNode                                      */
+    uint64_t chunk_frames;           /* frames rendered per time chunk                                                    */
+    uint64_t chunks;                 /* chunks per render                                                                 */
+    uint64_t arena_floats_per_frame; /* edge buffers of the largest group, floats per frame                               */
+    uint64_t source_floats;          /* AudioBuffer PCM resident on the device, floats                                    */
+    char stage_kinds[512];           /* "k_chain x 1, k_mix x 1": the stages by kernel                                    */
+} wae_plan_info;
+WAE_API wae_status wae_batch_plan(wae_graph* const* graphs, uint32_t n_graphs, wae_plan_info* info);
+
 /* AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation (src/node/audio_node.rs:417-441), with the
  * constraints of the nodes that narrow them (destination.rs:55-96, channel_merger.rs:39-110, channel_splitter.rs:36-134, convolver.rs:187-197,
  * dynamics_compressor.rs:168-178, stereo_panner.rs:143-152, panner.rs:363-372, param.rs:325-333, spatial.rs:113-121): a value the reference

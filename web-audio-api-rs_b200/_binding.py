@@ -100,6 +100,12 @@ class ParamEvent(C.Structure):
                 ("values", c_float_p), ("values_len", C.c_uint32)]
 
 
+class PlanInfo(C.Structure):
+    _fields_ = [("groups", C.c_uint32), ("segments", C.c_uint32), ("stages", C.c_uint32), ("has_feedback", C.c_uint32),
+                ("chunk_frames", C.c_uint64), ("chunks", C.c_uint64), ("arena_floats_per_frame", C.c_uint64), ("source_floats", C.c_uint64),
+                ("stage_kinds", C.c_char * 512)]
+
+
 class BatchStats(C.Structure):
     _fields_ = [("kernel_launches_per_run", C.c_uint64), ("stages", C.c_uint64), ("chunks", C.c_uint64),
                 ("arena_bytes", C.c_uint64), ("asset_bytes", C.c_uint64), ("algorithmic_bytes", C.c_uint64),
@@ -142,7 +148,7 @@ WAE_SYMBOLS = [
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
-    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample",
+    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample", "wae_batch_plan",
 ]
 
 
@@ -196,6 +202,7 @@ class Api:
             f("graph_create", C.c_int32, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.POINTER(C.c_void_p)])
             f("render_batch", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_uint32])
             f("batch_prepare", C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p)])
+            f("batch_plan", C.c_int32, [C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(PlanInfo)])
             f("batch_upload", C.c_int32, [C.c_void_p])
             f("batch_set_timing", C.c_int32, [C.c_void_p, C.c_uint32])
             f("batch_run", C.c_int32, [C.c_void_p])

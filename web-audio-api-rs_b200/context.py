@@ -592,6 +592,25 @@ class Batch:
             pass
 
 
+def plan_batch(contexts):
+    """wae_batch_plan: what the contexts would be lowered to (host only, no GPU) -> dict; raises what prepare would raise."""
+    api = contexts[0]._api
+    assert api.is_product
+    for c in contexts:
+        c._run_suspend_callbacks()
+    arr = (C.c_void_p * len(contexts))(*[c._g for c in contexts])
+    info = B.PlanInfo()
+    api.check(api.batch_plan(arr, len(contexts), C.byref(info)))
+    kinds = {}
+    for part in info.stage_kinds.decode().split(", "):
+        if part:
+            name, n = part.rsplit(" x ", 1)
+            kinds[name] = int(n)
+    return {"groups": info.groups, "segments": info.segments, "stages": info.stages, "has_feedback": bool(info.has_feedback),
+            "chunk_frames": info.chunk_frames, "chunks": info.chunks, "arena_floats_per_frame": info.arena_floats_per_frame,
+            "source_floats": info.source_floats, "kinds": kinds}
+
+
 def render_batch(contexts, threads=1):
     """Render many OfflineAudioContexts. Returns a list of AudioBuffer (one per context).
 

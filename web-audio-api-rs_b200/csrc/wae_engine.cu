@@ -1851,9 +1851,11 @@ WAE_API wae_status wae_graph_render_order(wae_graph* g, wae_node_id* ids, uint32
     return WAE_OK;
 }
 
-WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out) {
-    if (!eng || !graphs || !out || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
-    CUDA_TRY(cudaSetDevice(eng->device));
+// `plan` != nullptr: planning only — grouping, the sizing pass of the planner (which touches no device memory) and the chunk choice,
+// reported through *plan; nothing is allocated and no CUDA call is made (wae_batch_plan: runs without a GPU).
+static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out, wae_plan_info* plan) {
+    if (!eng || !graphs || (!out && !plan) || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
+    if (!plan) CUDA_TRY(cudaSetDevice(eng->device));
     for (uint32_t i = 0; i < n_graphs; i++) {
         if (graphs[i]->channels != graphs[0]->channels || graphs[i]->length != graphs[0]->length ||
             graphs[i]->sample_rate != graphs[0]->sample_rate)
@@ -1880,10 +1882,12 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
         has_conv = has_conv || graph_has_conv[i];
     }
     size_t out_floats = (size_t)n_graphs * b->channels * b->length;
-    b->d_out = b->dalloc<float>(out_floats, true);
-    if (!b->d_out) {
-        wae_batch_destroy(b);
-        return fail(WAE_OUT_OF_MEMORY, "out of device memory (output PCM)");
+    if (!plan) {
+        b->d_out = b->dalloc<float>(out_floats, true);
+        if (!b->d_out) {
+            wae_batch_destroy(b);
+            return fail(WAE_OUT_OF_MEMORY, "out of device memory (output PCM)");
+        }
     }
     // graph groups for the H2D / render / D2H pipeline
     int n_groups = eng->pipeline_groups;
@@ -1926,9 +1930,11 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     uint64_t fpf = 0;
     bool has_feedback = false;
     std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_hint;
+    std::vector<std::vector<int>> plan_stage_lists;  // plan-only: stage kinds per (group, segment) of the last iteration
     for (int iter = 0; iter < 8; iter++) {  // repeated only while the channel layout of in-cycle delays changes
         bool hints_changed = false;
         fpf = 0;
+        plan_stage_lists.clear();
         for (int k = 0; k < n_groups; k++) {
             Planner sizing{b, eng};
             sizing.dry = true;
@@ -1947,6 +1953,11 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
                     }
                 }
                 fpf = std::max(fpf, sizing.arena_floats_per_frame);
+                if (plan) {  // the stages (= kernel launches per chunk) this segment of this group lowers to
+                    std::vector<int> kinds;
+                    for (auto& kv : sizing.builds) kinds.push_back(kv.second.kind);
+                    plan_stage_lists.push_back(std::move(kinds));
+                }
             }
             b->groups[k].src_floats = sizing.src_cursor;
             has_feedback = has_feedback || sizing.has_feedback;
@@ -1981,6 +1992,29 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     if (has_conv) chunk = (chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK;
     if (chunk > b->lq) chunk = has_conv ? (b->lq + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK : b->lq;
     b->chunk = chunk;
+    if (plan) {
+        std::memset(plan, 0, sizeof *plan);
+        plan->groups = (uint32_t)n_groups;
+        plan->chunk_frames = (uint64_t)chunk;
+        plan->chunks = (uint64_t)((b->lq + chunk - 1) / chunk);
+        plan->arena_floats_per_frame = fpf;
+        plan->has_feedback = has_feedback ? 1u : 0u;
+        uint32_t per_kind[S_KINDS] = {0};
+        for (auto& grp : b->groups) {
+            plan->source_floats += grp.src_floats;
+            plan->segments += (uint32_t)grp.seg_bounds.size() - 1;
+        }
+        for (auto& kinds : plan_stage_lists) {
+            plan->stages += (uint32_t)kinds.size();
+            for (int k : kinds) per_kind[k]++;
+        }
+        std::string txt;  // "k_chain x 1, k_mix x 1": stages by kernel, summed over groups and segments
+        for (int k = 0; k < S_KINDS; k++)
+            if (per_kind[k]) txt += (txt.empty() ? "" : ", ") + std::string(kStageNames[k]) + " x " + std::to_string(per_kind[k]);
+        std::snprintf(plan->stage_kinds, sizeof plan->stage_kinds, "%s", txt.c_str());
+        delete b;  // nothing was allocated on the device
+        return WAE_OK;
+    }
     CUDA_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
     uint64_t algorithmic_bytes = 0;
@@ -2132,6 +2166,18 @@ WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, 
     b->stats.graph_quanta = (uint64_t)n_graphs * (uint64_t)(b->lq / 128);
     *out = b;
     return WAE_OK;
+}
+
+WAE_API wae_status wae_batch_prepare(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out) {
+    if (!out) return fail(WAE_INVALID_ARGUMENT, "null out pointer");
+    return prepare_impl(eng, graphs, n_graphs, out, nullptr);
+}
+
+// What wae_batch_prepare would lower the graphs to, without a device: the planner's sizing pass under the default engine options.
+WAE_API wae_status wae_batch_plan(wae_graph* const* graphs, uint32_t n_graphs, wae_plan_info* info) {
+    if (!info) return fail(WAE_INVALID_ARGUMENT, "null info pointer");
+    wae_engine host_only;  // default options; no stream, no sphere: HRTF panners answer WAE_UNSUPPORTED ("needs an HRIR sphere")
+    return prepare_impl(&host_only, graphs, n_graphs, nullptr, info);
 }
 
 static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
