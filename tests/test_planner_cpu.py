@@ -116,3 +116,109 @@ def test_batch_shape_errors(pkg, be):
     b = pkg.OfflineAudioContext(1, 256, 48000.0, be)
     with pytest.raises(pkg.WaeError):
         plan(pkg, [a, b])  # all graphs of a batch share channels / length / sample rate
+
+
+def _one(pkg, be, build, length=RQ * 8, channels=2, sr=48000.0):
+    c = pkg.OfflineAudioContext(channels, length, sr, be)
+    build(c)
+    return plan(pkg, [c])["kinds"]
+
+
+def test_which_kernel_a_node_variant_is_lowered_to(pkg, be):
+    noise = np.random.default_rng(3).uniform(-1, 1, 4096).astype(np.float32)
+
+    def src_to(c, node):
+        s = c.create_buffer_source(pkg.AudioBuffer([noise, noise], 48000.0))
+        s.connect(node)
+        node.connect(c.destination())
+        s.start()
+        return s
+
+    # canonical chain order: source -> gain -> biquad -> gain -> biquad -> gain -> shaper -> gain is ONE fused launch
+    def long_chain(c):
+        s = c.create_buffer_source(pkg.AudioBuffer([noise, noise], 48000.0))
+        nodes = [c.create_gain(0.9), c.create_biquad_filter(), c.create_gain(0.8), c.create_biquad_filter(type_=pkg.HIGHPASS), c.create_gain(0.7),
+                 c.create_wave_shaper(curve=np.linspace(-1, 1, 9).astype(np.float32)), c.create_gain(0.6)]
+        prev = s
+        for n in nodes:
+            prev.connect(n)
+            prev = n
+        prev.connect(c.destination())
+        s.start()
+    assert _one(pkg, be, long_chain) == {"k_chain": 1}
+    # a third biquad does not fit the chain shape: the chain is materialised and a second one starts
+    def three_biquads(c):
+        s = c.create_buffer_source(pkg.AudioBuffer([noise, noise], 48000.0))
+        prev = s
+        for _ in range(3):
+            b = c.create_biquad_filter()
+            prev.connect(b)
+            prev = b
+        prev.connect(c.destination())
+        s.start()
+    k = _one(pkg, be, three_biquads)
+    assert k.get("k_chain", 0) == 2 and "k_biquad_serial" not in k
+    # IIR filter, compressor, analyser, stereo panner, delay: their own stages
+    assert "k_iir_serial" in _one(pkg, be, lambda c: src_to(c, c.create_iir_filter([0.5, 0.5], [1.0, -0.2])))
+    assert "k_compressor" in _one(pkg, be, lambda c: src_to(c, c.create_dynamics_compressor()))
+    assert "k_analyser" in _one(pkg, be, lambda c: src_to(c, c.create_analyser()))
+    assert "k_stereo_panner" in _one(pkg, be, lambda c: src_to(c, c.create_stereo_panner(0.3)))
+    k = _one(pkg, be, lambda c: src_to(c, c.create_delay(1.0, 0.01)))
+    assert "k_delay_read" in k and "k_ring_write" in k
+    # equal-power panner: static source and listener -> k_panner_eq; an automated position -> k_param + k_panner_dyn
+    assert "k_panner_eq" in _one(pkg, be, lambda c: src_to(c, c.create_panner(position=(1.0, 0.0, -1.0))))
+
+    def moving(c):
+        p = c.create_panner(position=(1.0, 0.0, -1.0))
+        p.position_x.linear_ramp_to_value_at_time(-3.0, 0.01)
+        src_to(c, p)
+    k = _one(pkg, be, moving)
+    assert "k_panner_dyn" in k and "k_param" in k and "k_panner_eq" not in k
+    # over-sampled shaper
+    assert "k_shaper_os" in _one(pkg, be, lambda c: src_to(c, c.create_wave_shaper(curve=np.linspace(-1, 1, 9).astype(np.float32), oversample=pkg.OVERSAMPLE_X2)))
+
+
+def test_automation_selects_the_a_rate_kernels(pkg, be):
+    def osc_fm(c):  # an LFO on the carrier's frequency: audio-rate param input -> k_param + k_osc_arate
+        lfo = c.create_oscillator(frequency=5.0)
+        depth = c.create_gain(30.0)
+        car = c.create_oscillator(frequency=440.0)
+        lfo.connect(depth)
+        depth.connect(car.frequency)
+        car.connect(c.destination())
+        lfo.start()
+        car.start()
+    k = _one(pkg, be, osc_fm)
+    assert "k_osc_arate" in k and "k_param" in k
+
+    def filter_sweep(c):
+        o = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=110.0)
+        f = c.create_biquad_filter()
+        f.frequency.exponential_ramp_to_value_at_time(4000.0, 0.02)
+        o.connect(f)
+        f.connect(c.destination())
+        o.start()
+    k = _one(pkg, be, filter_sweep)
+    assert "k_biquad_arate" in k and "k_param" in k
+
+    def rate_automation(c):  # playbackRate automation: the renderer's own frame loop, one warp per source
+        s = c.create_buffer_source(pkg.AudioBuffer([np.ones(4096, np.float32)], 48000.0))
+        s.playback_rate.linear_ramp_to_value_at_time(2.0, 0.02)
+        s.connect(c.destination())
+        s.start()
+    assert "k_buffer_source_serial" in _one(pkg, be, rate_automation)
+
+    def resampled(c):  # a 38 kHz asset in a 48 kHz context: the closed-form slow track
+        s = c.create_buffer_source(pkg.AudioBuffer([np.ones(4096, np.float32)], 38000.0), loop=True)
+        s.connect(c.destination())
+        s.start()
+    assert "k_buffer_source_slow" in _one(pkg, be, resampled)
+
+
+def test_chunk_sizing_follows_the_arena(pkg, be):
+    # no arena (fully fused): one chunk; 64 mono voices at 1 GiB / (4 B x 64 floats per frame) would be 4 M frames -> capped to the render;
+    # a long render with many edges is cut into chunks of >= 8192 frames, multiples of 2048
+    p = plan(pkg, [G.c3_many_voices(pkg, be, 300, 48000 * 40)])
+    assert p["arena_floats_per_frame"] == 300 and p["chunks"] > 1
+    assert p["chunk_frames"] % 2048 == 0 and p["chunk_frames"] >= 8192
+    assert p["chunk_frames"] * 4 * p["arena_floats_per_frame"] <= 1 << 30
