@@ -252,3 +252,131 @@ SCENARIOS = [
     ("IIR filter", iir_filter),
     ("Biquad filter", biquad_filter),
 ]
+
+
+# ---- benches/my_benchmark.rs (criterion / iai): 10 s at 48 kHz stereo (1 s for the HRTF one); `seconds` scales the 10 ------------
+def _bench_ctx(pkg, be, seconds, short=False):
+    return pkg.OfflineAudioContext(2, int((seconds / 10.0 if short else seconds) * SR), SR, be)
+
+
+def bench_ctor(pkg, be, seconds):  # :43-46
+    return _bench_ctx(pkg, be, seconds)
+
+
+def bench_constant_source(pkg, be, seconds):  # :56-65 (start at 1 s, stop at 9 s of 10)
+    c = _bench_ctx(pkg, be, seconds)
+    src = c.create_constant_source()
+    src.connect(c.destination())
+    src.start_at(0.1 * seconds)
+    src.stop_at(0.9 * seconds)
+    return c
+
+
+def bench_sine(pkg, be, seconds):  # :67-75
+    c = _bench_ctx(pkg, be, seconds)
+    osc = c.create_oscillator()
+    osc.connect(c.destination())
+    osc.start()
+    return c
+
+
+def bench_detuned_sine(pkg, be, seconds):  # :77-87
+    c = _bench_ctx(pkg, be, seconds)
+    osc = c.create_oscillator()
+    osc.detune.linear_ramp_to_value_at_time(1000.0, seconds)
+    osc.connect(c.destination())
+    osc.start()
+    return c
+
+
+def bench_sine_gain(pkg, be, seconds, delay=False):  # :89-101, :103-119
+    c = _bench_ctx(pkg, be, seconds)
+    osc = c.create_oscillator()
+    gain = c.create_gain()
+    if delay:
+        d = c.create_delay(0.3)
+        d.delay_time.set_value(0.2)
+        osc.connect(d)
+        d.connect(gain)
+    else:
+        gain.gain.set_value(0.5)  # "avoid happy path"
+        osc.connect(gain)
+    gain.connect(c.destination())
+    osc.start()
+    return c
+
+
+def _bench_buffer_src(to):
+    def build(pkg, be, seconds):  # :121-196, :222-257: the looped stereo asset into one node
+        c = _bench_ctx(pkg, be, seconds)
+        src = c.create_buffer_source(pkg.AudioBuffer(think(SR, 2, 2.1), SR), loop=True)  # think-stereo-48000.wav is 101 129 frames
+        node = to(pkg, c)
+        if node is None:
+            src.connect(c.destination())
+        else:
+            node.connect(c.destination())
+            src.connect(node)
+        src.start()
+        return c
+    return build
+
+
+def _delay_02(pkg, c):
+    d = c.create_delay(0.3)
+    d.delay_time.set_value(0.2)
+    return d
+
+
+def _iir_200(pkg, c):
+    return c.create_iir_filter([0.0002029799640409502, 0.0004059599280819004, 0.0002029799640409502],
+                               [1.0126964557853775, -1.9991880801438362, 0.9873035442146225])
+
+
+def _biquad_200(pkg, c):
+    b = c.create_biquad_filter()
+    b.frequency.set_value(200.0)
+    return b
+
+
+def _panning_automation(pkg, c):
+    p = c.create_stereo_panner()
+    p.pan.set_value_at_time(-1.0, 0.0)
+    p.pan.set_value_at_time(0.2, 0.5)
+    return p
+
+
+def bench_hrtf_panners(pkg, be, seconds):  # :259-278: one oscillator into two HRTF panners at x = +-10, 1 s (the backend needs an HRIR sphere)
+    c = _bench_ctx(pkg, be, seconds, short=True)
+    osc = c.create_oscillator()
+    for x in (10.0, -10.0):
+        p = c.create_panner(panning_model=pkg.context.HRTF)
+        p.position_x.set_value(x)
+        p.connect(c.destination())
+        osc.connect(p)
+    osc.start()
+    return c
+
+
+CRITERION = [
+    ("bench_ctor", bench_ctor),
+    ("bench_constant_source", bench_constant_source),
+    ("bench_sine", bench_sine),
+    ("bench_detuned_sine", bench_detuned_sine),
+    ("bench_sine_gain", bench_sine_gain),
+    ("bench_sine_gain_delay", lambda pkg, be, seconds: bench_sine_gain(pkg, be, seconds, delay=True)),
+    ("bench_buffer_src", _bench_buffer_src(lambda pkg, c: None)),
+    ("bench_buffer_src_delay", _bench_buffer_src(_delay_02)),
+    ("bench_buffer_src_iir", _bench_buffer_src(_iir_200)),
+    ("bench_buffer_src_biquad", _bench_buffer_src(_biquad_200)),
+    ("bench_stereo_positional", _bench_buffer_src(lambda pkg, c: _positional_node(pkg, c))),
+    ("bench_stereo_panning_automation", _bench_buffer_src(_panning_automation)),
+    ("bench_analyser_node", _bench_buffer_src(lambda pkg, c: c.create_analyser())),
+    ("bench_hrtf_panners", bench_hrtf_panners),
+]
+
+
+def _positional_node(pkg, c):  # :198-220 (the panner of _positional, not yet connected)
+    p = c.create_panner()
+    for name, v in [("position_x", 1.0), ("position_y", 2.0), ("position_z", 3.0), ("orientation_x", 1.0), ("orientation_y", 2.0), ("orientation_z", 3.0)]:
+        getattr(p, name).set_value(v)
+    return p

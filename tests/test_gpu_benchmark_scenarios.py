@@ -20,3 +20,19 @@ def test_scenario_matches_the_oracle(pkg, engine, oracle, name, build):
         # "Simple mixing (100x ...)" sums 100 voices: its samples reach ~50, where 1e-5 is below one f32 ulp; the bound scales there
         tol = 1e-5 * max(1.0, float(np.abs(w).max()))
         assert d.max() <= tol, (name, ch, int(d.argmax()), float(d.max()), float(np.abs(w).max()))
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU time was spent: not yet run on a B200 (the graphs are variations of validated ones)")
+@pytest.mark.parametrize("name,build", BS.CRITERION, ids=[n for n, _ in BS.CRITERION])
+def test_criterion_bench_matches_the_oracle(pkg, engine, oracle, name, build):
+    """benches/my_benchmark.rs (criterion / iai), GPU vs oracle at 1e-5."""
+    import graphs as G
+    if "hrtf" in name:
+        sphere = G.synthetic_hrir_sphere(44100, 256)
+        oracle.set_hrir_sphere(sphere)
+        engine.backend.set_hrir_sphere(sphere)
+    got = build(pkg, engine.backend, 2.0).start_rendering_sync()
+    want = build(pkg, oracle, 2.0).start_rendering_sync()
+    for ch in range(2):
+        d = np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch))
+        assert d.max() <= 1e-5, (name, ch, float(d.max()))

@@ -222,3 +222,17 @@ def test_chunk_sizing_follows_the_arena(pkg, be):
     assert p["arena_floats_per_frame"] == 300 and p["chunks"] > 1
     assert p["chunk_frames"] % 2048 == 0 and p["chunk_frames"] >= 8192
     assert p["chunk_frames"] * 4 * p["arena_floats_per_frame"] <= 1 << 30
+
+
+@pytest.mark.parametrize("name,build", BS.CRITERION, ids=[n for n, _ in BS.CRITERION])
+def test_every_criterion_bench_graph_is_lowered(pkg, be, name, build):
+    # benches/my_benchmark.rs: planned without a GPU; the HRTF one stops at "needs an HRIR sphere" (the sphere belongs to an engine)
+    if "hrtf" in name:
+        with pytest.raises(pkg.WaeError) as e:
+            plan(pkg, [build(pkg, be, 2.0)])
+        assert e.value.status == 4 and "HRIR sphere" in str(e.value)
+        return
+    p = plan(pkg, [build(pkg, be, 2.0) for _ in range(3)])
+    assert p["stages"] >= 1
+    if name in ("bench_sine", "bench_sine_gain", "bench_buffer_src", "bench_buffer_src_biquad", "bench_constant_source"):
+        assert p["kinds"] == {"k_chain": 1}  # fully fused into the destination
