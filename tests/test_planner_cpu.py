@@ -236,3 +236,13 @@ def test_every_criterion_bench_graph_is_lowered(pkg, be, name, build):
     assert p["stages"] >= 1
     if name in ("bench_sine", "bench_sine_gain", "bench_buffer_src", "bench_buffer_src_biquad", "bench_constant_source"):
         assert p["kinds"] == {"k_chain": 1}  # fully fused into the destination
+
+
+@pytest.mark.parametrize("block", range(8))
+def test_planner_accepts_random_graphs(pkg, be, block):
+    # the generator of tests/test_gpu_fuzz.py (random DAGs of every lowered node kind, automation, feedback loops, suspend points) on the
+    # CPU: 8 x 40 seeds through the planner's sizing pass — no crash, no refusal, a sane plan; the GPU suite renders 120 of them
+    import test_gpu_fuzz as F
+    for seed in range(1000 + 40 * block, 1000 + 40 * (block + 1)):
+        p = plan(pkg, [F.random_graph(pkg, be, seed)])
+        assert 1 <= p["stages"] <= 400 and p["segments"] >= 1 and p["chunk_frames"] >= 128, seed
