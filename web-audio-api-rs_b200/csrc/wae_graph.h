@@ -32,15 +32,15 @@ struct PcmBuffer {  // an AudioBuffer asset (src/buffer.rs:69-72), host copy
 };
 
 struct ParamEv {
-    int type;
-    float value;
-    double time, aux;
+    int type = 0;
+    float value = 0.f;
+    double time = 0., aux = 0.;
     std::vector<float> values;
 };
 
 struct Param {  // AudioParam: its own graph node in the reference (src/context/base.rs:320-337)
-    float default_value, min_value, max_value;
-    bool a_rate;
+    float default_value = 0.f, min_value = 0.f, max_value = 0.f;  // (initialised: every Node carries a Param, only K_PARAM nodes use it)
+    bool a_rate = false;
     bool rate_constrained = false;
     std::vector<ParamEv> events;  // in arrival order
     // lowering helpers
