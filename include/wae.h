@@ -421,6 +421,30 @@ typedef struct wae_plan_info {
 } wae_plan_info;
 WAE_API wae_status wae_batch_plan(wae_graph* const* graphs, uint32_t n_graphs, wae_plan_info* info);
 
+/* ---- attributes set after construction (the reference posts one control message per setter) --------------------------------
+ * AudioBufferSourceNode::set_buffer (once; src/node/audio_buffer_source.rs:278-288), ConvolverNode::set_buffer (convolver.rs:259-317; the
+ * normalisation is decided at this call from the current `normalize` attribute), WaveShaperNode::set_curve (once; waveshaper.rs:203-213),
+ * OscillatorNode::set_periodic_wave (oscillator.rs:334-337; `table` = the wavetable of PeriodicWave::new, the type becomes Custom). */
+WAE_API wae_status wae_buffer_source_set_buffer(wae_graph* graph, wae_node_id node, const wae_audio_buffer* buffer);
+WAE_API wae_status wae_convolver_set_buffer(wae_graph* graph, wae_node_id node, const wae_audio_buffer* buffer);
+WAE_API wae_status wae_wave_shaper_set_curve(wae_graph* graph, wae_node_id node, const float* curve, uint32_t len);
+WAE_API wae_status wae_oscillator_set_periodic_wave(wae_graph* graph, wae_node_id node, const float* table, uint32_t len);
+/* the scalar setters: AudioBufferSourceNode::set_loop / set_loop_start / set_loop_end (audio_buffer_source.rs:324-349),
+ * ConvolverNode::set_normalize (convolver.rs:325-328), WaveShaperNode::set_oversample (waveshaper.rs:226-229), PannerNode::set_*
+ * (panner.rs:545-657), AnalyserNode::set_* (analyser.rs:148-222).  Enumerated values (models, oversample) are passed as their enum
+ * value, booleans as 0 / 1.  Range errors answer the reference's panic text.  Called after wae_graph_suspend the change applies from
+ * that point on; two changes at a suspend point are answered WAE_UNSUPPORTED (the graph keeps the CPU renderer): the loop attributes of
+ * a source that was already started, and a second impulse response for a ConvolverNode. */
+enum {
+    WAE_ATTR_LOOP = 1, WAE_ATTR_LOOP_START = 2, WAE_ATTR_LOOP_END = 3,
+    WAE_ATTR_NORMALIZE = 4,
+    WAE_ATTR_OVERSAMPLE = 5,
+    WAE_ATTR_PANNING_MODEL = 6, WAE_ATTR_DISTANCE_MODEL = 7, WAE_ATTR_REF_DISTANCE = 8, WAE_ATTR_MAX_DISTANCE = 9,
+    WAE_ATTR_ROLLOFF_FACTOR = 10, WAE_ATTR_CONE_INNER_ANGLE = 11, WAE_ATTR_CONE_OUTER_ANGLE = 12, WAE_ATTR_CONE_OUTER_GAIN = 13,
+    WAE_ATTR_FFT_SIZE = 14, WAE_ATTR_SMOOTHING_TIME_CONSTANT = 15, WAE_ATTR_MIN_DECIBELS = 16, WAE_ATTR_MAX_DECIBELS = 17
+};
+WAE_API wae_status wae_node_set_attribute(wae_graph* graph, wae_node_id node, uint32_t attribute, double value);
+
 /* AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation (src/node/audio_node.rs:417-441), with the
  * constraints of the nodes that narrow them (destination.rs:55-96, channel_merger.rs:39-110, channel_splitter.rs:36-134, convolver.rs:187-197,
  * dynamics_compressor.rs:168-178, stereo_panner.rs:143-152, panner.rs:363-372, param.rs:325-333, spatial.rs:113-121): a value the reference

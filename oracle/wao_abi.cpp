@@ -39,6 +39,8 @@ struct NodeInfo {
     std::vector<uint32_t> params;
     bool has_start = false;
     Processor* proc = nullptr;
+    bool normalize = true;   // ConvolverNode::normalize (control side; used by the next set_buffer)
+    bool has_buffer = false;  // AudioBufferSourceNode: a buffer was given
 };
 
 }  // namespace
@@ -280,6 +282,7 @@ WAO_API wae_status wao_create_convolver(wae_graph* g, const wae_convolver_option
         r->set_buffer(*ab, !o->disable_normalization);
     }
     g->finish_register(id, std::move(r), K_CONV, 1, 1, cfg, {}, id);
+    g->info[id].normalize = !o->disable_normalization;
     *out = id;
     return WAE_OK;
 }
@@ -687,6 +690,137 @@ static wae_status set_cfg_field(wae_graph* g, wae_node_id node, int field, uint3
 WAO_API wae_status wao_node_set_channel_count(wae_graph* g, wae_node_id node, uint32_t count) { return set_cfg_field(g, node, 0, count); }
 WAO_API wae_status wao_node_set_channel_count_mode(wae_graph* g, wae_node_id node, uint32_t mode) { return set_cfg_field(g, node, 1, mode); }
 WAO_API wae_status wao_node_set_channel_interpretation(wae_graph* g, wae_node_id node, uint32_t v) { return set_cfg_field(g, node, 2, v); }
+
+static Analyser* find_analyser(wae_graph* g, wae_node_id node);
+// ---- node attributes set after construction: the onmessage handlers of the renderers ----------------------------------------
+// AudioBufferSourceNode::set_buffer (audio_buffer_source.rs:278-288, onmessage :856-872)
+WAO_API wae_status wao_buffer_source_set_buffer(wae_graph* g, wae_node_id node, const wae_audio_buffer* buffer) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end() || ni->second.kind != K_ABSN || !buffer) return fail(WAE_INVALID_ARGUMENT, "not an AudioBufferSourceNode / null buffer");
+    auto* r = static_cast<AudioBufferSourceRenderer*>(ni->second.proc);
+    if (r->buffer) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign buffer twice");
+    r->buffer = copy_buffer(buffer);
+    r->clamp_loop_boundaries();
+    return WAE_OK;
+}
+// ConvolverNode::set_buffer (convolver.rs:259-317)
+WAO_API wae_status wao_convolver_set_buffer(wae_graph* g, wae_node_id node, const wae_audio_buffer* buffer) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end() || ni->second.kind != K_CONV || !buffer) return fail(WAE_INVALID_ARGUMENT, "not a ConvolverNode / null buffer");
+    if (buffer->sample_rate != g->sample_rate)
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - sample rate of the convolution buffer must match the audio context");
+    const uint32_t c = buffer->number_of_channels;
+    if (!(c == 1 || c == 2 || c == 4)) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - the convolution buffer must consist of 1, 2 or 4 channels");
+    auto ab = copy_buffer(buffer);
+    static_cast<ConvolverRenderer*>(ni->second.proc)->set_buffer(*ab, ni->second.normalize);
+    return WAE_OK;
+}
+// WaveShaperNode::set_curve (waveshaper.rs:203-213)
+WAO_API wae_status wao_wave_shaper_set_curve(wae_graph* g, wae_node_id node, const float* curve, uint32_t len) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end() || ni->second.kind != K_SHAPER || (!curve && len)) return fail(WAE_INVALID_ARGUMENT, "not a WaveShaperNode / null curve");
+    auto* r = static_cast<WaveShaperRenderer*>(ni->second.proc);
+    if (r->has_curve) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign curve twice");
+    r->set_curve(curve, len);
+    return WAE_OK;
+}
+// OscillatorNode::set_periodic_wave (oscillator.rs:334-337, onmessage :350-361)
+WAO_API wae_status wao_oscillator_set_periodic_wave(wae_graph* g, wae_node_id node, const float* table, uint32_t len) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end() || ni->second.kind != K_OSC || !table || len == 0) return fail(WAE_INVALID_ARGUMENT, "not an OscillatorNode / empty wavetable");
+    auto* r = static_cast<OscillatorRenderer*>(ni->second.proc);
+    r->type = WAE_OSC_CUSTOM;
+    r->periodic_wave.assign(table, table + len);
+    return WAE_OK;
+}
+WAO_API wae_status wao_node_set_attribute(wae_graph* g, wae_node_id node, uint32_t attribute, double value) {
+    auto ni = g->info.find(node);
+    if (ni == g->info.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    NodeInfo& n = ni->second;
+    auto wrong = [&]() { return fail(WAE_INVALID_ARGUMENT, "this node has no such attribute"); };
+    switch (attribute) {
+        case WAE_ATTR_LOOP: case WAE_ATTR_LOOP_START: case WAE_ATTR_LOOP_END: {  // ControlMessage::Loop / LoopStart / LoopEnd, :873-893
+            if (n.kind != K_ABSN) return wrong();
+            auto* r = static_cast<AudioBufferSourceRenderer*>(n.proc);
+            if (attribute == WAE_ATTR_LOOP) r->is_looping = value != 0.;
+            else if (attribute == WAE_ATTR_LOOP_START) r->loop_start = value;
+            else r->loop_end = value;
+            if (attribute != WAE_ATTR_LOOP && r->buffer) r->clamp_loop_boundaries();
+            return WAE_OK;
+        }
+        case WAE_ATTR_NORMALIZE:
+            if (n.kind != K_CONV) return wrong();
+            n.normalize = value != 0.;
+            return WAE_OK;
+        case WAE_ATTR_OVERSAMPLE:
+            if (n.kind != K_SHAPER) return wrong();
+            if (!(value == 0. || value == 1. || value == 2.)) return fail(WAE_INVALID_ARGUMENT, "unknown oversample type");
+            static_cast<WaveShaperRenderer*>(n.proc)->oversample = (int)value;
+            return WAE_OK;
+        case WAE_ATTR_PANNING_MODEL: case WAE_ATTR_DISTANCE_MODEL: case WAE_ATTR_REF_DISTANCE: case WAE_ATTR_MAX_DISTANCE:
+        case WAE_ATTR_ROLLOFF_FACTOR: case WAE_ATTR_CONE_INNER_ANGLE: case WAE_ATTR_CONE_OUTER_ANGLE: case WAE_ATTR_CONE_OUTER_GAIN: {
+            if (n.kind != K_PANNER) return wrong();
+            auto* r = static_cast<PannerRenderer*>(n.proc);
+            switch (attribute) {
+                case WAE_ATTR_PANNING_MODEL:
+                    if (value == 1.) {
+                        std::string err;
+                        if (!hrtf_sphere_available(err)) return fail(WAE_UNSUPPORTED, err);
+                        r->set_hrtf(g->sample_rate);
+                        if (!r->hrtf_state) return fail(WAE_UNSUPPORTED, "HRTF panning: the HRIR sphere cannot be used at this sample rate");
+                    } else if (value == 0.) {
+                        r->hrtf_state.reset();
+                    } else {
+                        return fail(WAE_INVALID_ARGUMENT, "unknown panning model");
+                    }
+                    break;
+                case WAE_ATTR_DISTANCE_MODEL:
+                    if (!(value == 0. || value == 1. || value == 2.)) return fail(WAE_INVALID_ARGUMENT, "unknown distance model");
+                    r->distance_model = (int)value;
+                    break;
+                case WAE_ATTR_REF_DISTANCE:
+                    if (!(value >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - refDistance cannot be negative");
+                    r->ref_distance = value;
+                    break;
+                case WAE_ATTR_MAX_DISTANCE:
+                    if (!(value > 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - maxDistance must be strictly positive");
+                    r->max_distance = value;
+                    break;
+                case WAE_ATTR_ROLLOFF_FACTOR:
+                    if (!(value >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - rolloffFactor cannot be negative");
+                    r->rolloff_factor = value;
+                    break;
+                case WAE_ATTR_CONE_INNER_ANGLE: r->cone_inner_angle = value; break;
+                case WAE_ATTR_CONE_OUTER_ANGLE: r->cone_outer_angle = value; break;
+                default:
+                    if (!(value >= 0. && value <= 1.)) return fail(WAE_INVALID_STATE, "InvalidStateError - coneOuterGain must be in the range [0, 1]");
+                    r->cone_outer_gain = value;
+            }
+            return WAE_OK;
+        }
+        case WAE_ATTR_FFT_SIZE: case WAE_ATTR_SMOOTHING_TIME_CONSTANT: case WAE_ATTR_MIN_DECIBELS: case WAE_ATTR_MAX_DECIBELS: {
+            if (n.kind != K_ANALYSER) return wrong();
+            Analyser* a = find_analyser(g, node);
+            if (attribute == WAE_ATTR_FFT_SIZE) {
+                const uint64_t f = (uint64_t)value;
+                if (!((double)f == value && f >= 32 && f <= 32768 && (f & (f - 1)) == 0))
+                    return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: must be a power of two in [32, 32768]");
+                a->set_fft_size((size_t)f);
+            } else if (attribute == WAE_ATTR_SMOOTHING_TIME_CONSTANT) {
+                if (!(value >= 0. && value <= 1.)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid smoothing time constant: must be in [0, 1]");
+                a->smoothing_time_constant = value;
+            } else if (attribute == WAE_ATTR_MIN_DECIBELS) {
+                if (!(value < a->max_decibels)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid min decibels: must be less than max decibels");
+                a->min_decibels = value;
+            } else {
+                if (!(value > a->min_decibels)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid max decibels: must be greater than min decibels");
+                a->max_decibels = value;
+            }
+            return WAE_OK;
+        }
+        default: return fail(WAE_INVALID_ARGUMENT, "unknown attribute");
+    }
+}
 
 // ---- rendering --------------------------------------------------------------------------------------
 

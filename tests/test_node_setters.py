@@ -1,0 +1,172 @@
+"""The reference's post-construction setters (one control message each): AudioBufferSourceNode::set_buffer / set_loop / set_loop_start /
+set_loop_end, ConvolverNode::set_buffer / set_normalize, WaveShaperNode::set_curve / set_oversample, OscillatorNode::set_periodic_wave,
+PannerNode::set_*, AnalyserNode::set_* — the way the reference's own examples and benchmarks build graphs
+(`create_buffer_source()` then `set_buffer(..)`, `create_panner()` then `set_panning_model(HRTF)`).
+A node configured through the setters must be THE node its options would have built: same PCM on the oracle, same plan in the library
+(host only here; tests/test_gpu_reference_cases.py renders the graph-level functions on CUDA)."""
+import numpy as np
+import pytest
+
+import graphs as G
+
+RQ = 128
+SR = 48000.0
+
+
+def _noise(n, ch=1, seed=11):
+    return list(np.random.default_rng(seed).uniform(-0.8, 0.8, (ch, n)).astype(np.float32))
+
+
+def _variants(pkg, be, with_setters):
+    """One context that uses every setter (with_setters) or the equivalent construction options."""
+    c = pkg.OfflineAudioContext(2, RQ * 24, SR, be)
+    buf = pkg.AudioBuffer(_noise(1500, 2), SR)
+    ir = pkg.AudioBuffer(_noise(700, 2, seed=12), SR)
+    curve = np.tanh(np.linspace(-2, 2, 33)).astype(np.float32)
+    table = np.sin(np.arange(2048) / 2048.0 * 2 * np.pi * 3).astype(np.float32)
+    if with_setters:
+        src = c.create_buffer_source()
+        src.set_buffer(buf)
+        src.set_loop(True)
+        src.set_loop_start(0.004)
+        src.set_loop_end(0.02)
+        conv = c.create_convolver()
+        conv.set_normalize(False)
+        conv.set_buffer(ir)
+        conv.set_normalize(True)  # only the NEXT set_buffer would see it (convolver.rs:325-328)
+        sh = c.create_wave_shaper()
+        sh.set_curve(curve)
+        sh.set_oversample(pkg.OVERSAMPLE_X2)
+        osc = c.create_oscillator(frequency=300.0)
+        osc.set_periodic_wave(table)
+        pan = c.create_panner()
+        pan.set_distance_model(pkg.context.EXPONENTIAL)
+        pan.set_ref_distance(2.0)
+        pan.set_max_distance(50.0)
+        pan.set_rolloff_factor(1.5)
+        pan.set_cone_inner_angle(40.0)
+        pan.set_cone_outer_angle(100.0)
+        pan.set_cone_outer_gain(0.25)
+        pan.position_x.set_value(3.0)
+        pan.position_z.set_value(-2.0)
+        an = c.create_analyser()
+        an.set_fft_size(512)
+        an.set_smoothing_time_constant(0.3)
+        an.set_min_decibels(-90.0)
+        an.set_max_decibels(-10.0)
+    else:
+        src = c.create_buffer_source(buf, loop=True, loop_start=0.004, loop_end=0.02)
+        conv = c.create_convolver(ir, disable_normalization=True)
+        sh = c.create_wave_shaper(curve=curve, oversample=pkg.OVERSAMPLE_X2)
+        osc = c.create_oscillator(frequency=300.0, periodic_wave=table)
+        pan = c.create_panner(distance_model=pkg.context.EXPONENTIAL, ref_distance=2.0, max_distance=50.0, rolloff_factor=1.5,
+                              cone_inner_angle=40.0, cone_outer_angle=100.0, cone_outer_gain=0.25, position=(3.0, 0.0, -2.0))
+        an = c.create_analyser(fft_size=512, smoothing_time_constant=0.3, min_decibels=-90.0, max_decibels=-10.0)
+    src.connect(conv)
+    conv.connect(sh)
+    osc.connect(sh)
+    sh.connect(pan)
+    pan.connect(an)
+    an.connect(c.destination())
+    src.start()
+    osc.start()
+    c._analyser = an
+    return c
+
+
+def test_setters_build_the_node_the_options_build(pkg, oracle):
+    a = _variants(pkg, oracle, True)
+    b = _variants(pkg, oracle, False)
+    pa, pb = a.start_rendering_sync(), b.start_rendering_sync()
+    assert np.abs(pa.get_channel_data(0)).max() > 1e-3
+    for ch in range(2):
+        assert np.array_equal(pa.get_channel_data(ch), pb.get_channel_data(ch))
+    assert np.array_equal(a._analyser.get_float_frequency_data(), b._analyser.get_float_frequency_data())
+    assert np.array_equal(a._analyser.get_byte_frequency_data(), b._analyser.get_byte_frequency_data())
+
+
+def test_setters_give_the_library_the_same_plan(pkg, builder):
+    if not builder.api.is_product:
+        pytest.skip("plan is the library's")
+    pa = pkg.context.plan_batch([_variants(pkg, builder, True)])
+    pb = pkg.context.plan_batch([_variants(pkg, builder, False)])
+    assert pa == pb and "k_shaper_os" in pa["kinds"] and "k_conv_mac_ifft" in pa["kinds"]
+
+
+def test_setter_errors(pkg, builder):
+    # audio_buffer_source.rs:283-286, waveshaper.rs:204-207 "cannot assign ... twice"; convolver.rs:520-548; panner.rs:560-640; analysis.rs:592-653
+    c = pkg.OfflineAudioContext(2, RQ, SR, builder)
+    buf = pkg.AudioBuffer(_noise(64), SR)
+    s = c.create_buffer_source(buf)
+    with pytest.raises(pkg.WaeError) as e:
+        s.set_buffer(buf)
+    assert "cannot assign buffer twice" in str(e.value)
+    s = c.create_buffer_source()
+    s.set_buffer(buf)
+    with pytest.raises(pkg.WaeError):
+        s.set_buffer(buf)
+    sh = c.create_wave_shaper(curve=np.array([1.0], np.float32))
+    with pytest.raises(pkg.WaeError) as e:  # waveshaper.rs:624-647 change_a_curve_for_another_curve_should_panic
+        sh.set_curve(np.array([2.0], np.float32))
+    assert "cannot assign curve twice" in str(e.value)
+    sh = c.create_wave_shaper()             # waveshaper.rs:649-669 change_none_for_curve_after_build
+    sh.set_curve(np.array([2.0], np.float32))
+    sh.set_oversample(pkg.OVERSAMPLE_X4)
+    cv = c.create_convolver()
+    with pytest.raises(pkg.WaeError):
+        cv.set_buffer(pkg.AudioBuffer(_noise(64), 44100.0))
+    with pytest.raises(pkg.WaeError):
+        cv.set_buffer(pkg.AudioBuffer(_noise(64, 3), SR))
+    cv.set_buffer(buf)
+    cv.set_buffer(pkg.AudioBuffer(_noise(32, 2), SR))  # a convolver may get another response
+    p = c.create_panner()
+    for setter, bad in [("set_ref_distance", -1.0), ("set_max_distance", 0.0), ("set_rolloff_factor", -0.5), ("set_cone_outer_gain", 1.5),
+                        ("set_cone_outer_gain", -0.1), ("set_distance_model", 7), ("set_panning_model", 5)]:
+        with pytest.raises(pkg.WaeError):
+            getattr(p, setter)(bad)
+    a = c.create_analyser()
+    for setter, bad in [("set_fft_size", 13), ("set_fft_size", 16), ("set_fft_size", 65536), ("set_smoothing_time_constant", -1.0),
+                        ("set_smoothing_time_constant", 2.0), ("set_min_decibels", -30.0), ("set_max_decibels", -100.0)]:
+        with pytest.raises(pkg.WaeError):
+            getattr(a, setter)(bad)
+    a.set_min_decibels(-20.0 - 30.0)
+    a.set_max_decibels(10.0)   # analysis.rs:592-597 test_set_decibels
+    g = c.create_gain()
+    with pytest.raises(pkg.WaeError):
+        g._set_attribute(pkg._binding.ATTR_LOOP, 1.0)  # a gain has no loop
+
+
+def test_buffer_source_configured_the_way_the_reference_examples_do(pkg, oracle):
+    # examples/benchmarks.rs:97-105 (and every test of audio_buffer_source.rs): create_buffer_source(); set_buffer(..); set_loop(true); start()
+    c = pkg.OfflineAudioContext(1, RQ * 4, SR, oracle)
+    pcm = _noise(100)[0]
+    src = c.create_buffer_source()
+    src.set_buffer(pkg.AudioBuffer([pcm], SR))
+    src.set_loop(True)
+    src.connect(c.destination())
+    src.start()
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.array_equal(out, np.tile(pcm, 6)[:RQ * 4])
+
+
+def test_hrtf_selected_with_set_panning_model(pkg, oracle):
+    # benches/my_benchmark.rs:262-263: create_panner() then set_panning_model(HRTF)
+    oracle.set_hrir_sphere(G.synthetic_hrir_sphere(44100, 384))  # (>= 258 taps: shorter responses vanish in the resampler)
+
+    def build(setter):
+        c = pkg.OfflineAudioContext(2, RQ * 6, SR, oracle)
+        osc = c.create_oscillator()
+        if setter:
+            p = c.create_panner()
+            p.set_panning_model(pkg.context.HRTF)
+        else:
+            p = c.create_panner(panning_model=pkg.context.HRTF)
+        p.position_x.set_value(10.0)
+        osc.connect(p)
+        p.connect(c.destination())
+        osc.start()
+        return c.start_rendering_sync()
+
+    a, b = build(True), build(False)
+    assert np.array_equal(a.get_channel_data(0), b.get_channel_data(0)) and np.array_equal(a.get_channel_data(1), b.get_channel_data(1))
+    assert np.abs(a.get_channel_data(1)).max() > 1e-3

@@ -100,6 +100,11 @@ class ParamEvent(C.Structure):
                 ("values", c_float_p), ("values_len", C.c_uint32)]
 
 
+(ATTR_LOOP, ATTR_LOOP_START, ATTR_LOOP_END, ATTR_NORMALIZE, ATTR_OVERSAMPLE, ATTR_PANNING_MODEL, ATTR_DISTANCE_MODEL, ATTR_REF_DISTANCE,
+ ATTR_MAX_DISTANCE, ATTR_ROLLOFF_FACTOR, ATTR_CONE_INNER_ANGLE, ATTR_CONE_OUTER_ANGLE, ATTR_CONE_OUTER_GAIN, ATTR_FFT_SIZE,
+ ATTR_SMOOTHING_TIME_CONSTANT, ATTR_MIN_DECIBELS, ATTR_MAX_DECIBELS) = range(1, 18)
+
+
 class PlanInfo(C.Structure):
     _fields_ = [("groups", C.c_uint32), ("segments", C.c_uint32), ("stages", C.c_uint32), ("has_feedback", C.c_uint32),
                 ("chunk_frames", C.c_uint64), ("chunks", C.c_uint64), ("arena_floats_per_frame", C.c_uint64), ("source_floats", C.c_uint64),
@@ -148,7 +153,8 @@ WAE_SYMBOLS = [
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
-    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample", "wae_batch_plan",
+    "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample", "wae_batch_plan", "wae_buffer_source_set_buffer", "wae_convolver_set_buffer", "wae_wave_shaper_set_curve",
+    "wae_oscillator_set_periodic_wave", "wae_node_set_attribute",
 ]
 
 
@@ -185,6 +191,11 @@ class Api:
         f("source_stop", C.c_int32, [gp, C.c_uint32, C.c_double])
         f("oscillator_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
         f("biquad_set_type", C.c_int32, [gp, C.c_uint32, C.c_uint32])
+        f("buffer_source_set_buffer", C.c_int32, [gp, C.c_uint32, C.POINTER(AudioBufferDesc)])
+        f("convolver_set_buffer", C.c_int32, [gp, C.c_uint32, C.POINTER(AudioBufferDesc)])
+        f("wave_shaper_set_curve", C.c_int32, [gp, C.c_uint32, c_float_p, C.c_uint32])
+        f("oscillator_set_periodic_wave", C.c_int32, [gp, C.c_uint32, c_float_p, C.c_uint32])
+        f("node_set_attribute", C.c_int32, [gp, C.c_uint32, C.c_uint32, C.c_double])
         f("hrir_resample", C.c_int32, [c_float_p, C.c_uint32, C.c_double, c_float_p, C.c_uint32, C.POINTER(C.c_uint32)])
         for name in ("node_set_channel_count", "node_set_channel_count_mode", "node_set_channel_interpretation"):
             f(name, C.c_int32, [gp, C.c_uint32, C.c_uint32])

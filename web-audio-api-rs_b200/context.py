@@ -158,6 +158,16 @@ class AudioNode:
     def number_of_outputs(self):
         return self._n_outputs
 
+    def _set_attribute(self, attribute, value):
+        api = self._ctx._api
+        api.check(api.node_set_attribute(self._ctx._g, self.id, attribute, float(value)))
+
+    def _set_buffer(self, fn, buffer):
+        d, keep = buffer._desc()
+        self._ctx._keep.append((d, keep))
+        api = self._ctx._api
+        api.check(getattr(api, fn)(self._ctx._g, self.id, C.byref(d)))
+
     # AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation (src/node/audio_node.rs:417-441)
     def set_channel_count(self, count):
         api = self._ctx._api
@@ -206,12 +216,31 @@ class AudioScheduledSourceNode(AudioNode):
 
 
 class OscillatorNode(AudioScheduledSourceNode):
+    def set_periodic_wave(self, table):
+        """OscillatorNode::set_periodic_wave (oscillator.rs:334-337); `table` = PeriodicWave's wavetable (periodic_wave.rs:163-209)."""
+        t = B.as_f32(table)
+        api = self._ctx._api
+        api.check(api.oscillator_set_periodic_wave(self._ctx._g, self.id, B.fptr(t), len(t)))
+
     def set_type(self, type_):
         api = self._ctx._api
         api.check(api.oscillator_set_type(self._ctx._g, self.id, type_))
 
 
 class AudioBufferSourceNode(AudioScheduledSourceNode):
+    # audio_buffer_source.rs:278-349
+    def set_buffer(self, buffer):
+        self._set_buffer("buffer_source_set_buffer", buffer)
+
+    def set_loop(self, value):
+        self._set_attribute(B.ATTR_LOOP, 1.0 if value else 0.0)
+
+    def set_loop_start(self, value):
+        self._set_attribute(B.ATTR_LOOP_START, value)
+
+    def set_loop_end(self, value):
+        self._set_attribute(B.ATTR_LOOP_END, value)
+
     def start_at_with_offset(self, start, offset):
         self.start_at_with_offset_and_duration(start, offset, F64_MAX)
 
@@ -223,6 +252,53 @@ class AudioBufferSourceNode(AudioScheduledSourceNode):
 def _response_arrays(frequency_hz):
     f = np.ascontiguousarray(frequency_hz, dtype=np.float32)
     return f, np.zeros(len(f), np.float32), np.zeros(len(f), np.float32)
+
+
+class ConvolverNode(AudioNode):
+    # convolver.rs:259-328
+    def set_buffer(self, buffer):
+        self._set_buffer("convolver_set_buffer", buffer)
+
+    def set_normalize(self, value):
+        self._set_attribute(B.ATTR_NORMALIZE, 1.0 if value else 0.0)
+
+
+class WaveShaperNode(AudioNode):
+    # waveshaper.rs:203-229
+    def set_curve(self, curve):
+        c = B.as_f32(curve)
+        api = self._ctx._api
+        api.check(api.wave_shaper_set_curve(self._ctx._g, self.id, B.fptr(c), len(c)))
+
+    def set_oversample(self, oversample):
+        self._set_attribute(B.ATTR_OVERSAMPLE, oversample)
+
+
+class PannerNode(AudioNode):
+    # panner.rs:545-657
+    def set_panning_model(self, v):
+        self._set_attribute(B.ATTR_PANNING_MODEL, v)
+
+    def set_distance_model(self, v):
+        self._set_attribute(B.ATTR_DISTANCE_MODEL, v)
+
+    def set_ref_distance(self, v):
+        self._set_attribute(B.ATTR_REF_DISTANCE, v)
+
+    def set_max_distance(self, v):
+        self._set_attribute(B.ATTR_MAX_DISTANCE, v)
+
+    def set_rolloff_factor(self, v):
+        self._set_attribute(B.ATTR_ROLLOFF_FACTOR, v)
+
+    def set_cone_inner_angle(self, v):
+        self._set_attribute(B.ATTR_CONE_INNER_ANGLE, v)
+
+    def set_cone_outer_angle(self, v):
+        self._set_attribute(B.ATTR_CONE_OUTER_ANGLE, v)
+
+    def set_cone_outer_gain(self, v):
+        self._set_attribute(B.ATTR_CONE_OUTER_GAIN, v)
 
 
 class BiquadFilterNode(AudioNode):
@@ -268,6 +344,20 @@ class AnalyserNode(AudioNode):
     def __init__(self, ctx, node_id, fft_size):
         super().__init__(ctx, node_id)
         self.fft_size = fft_size
+
+    # analyser.rs:148-222
+    def set_fft_size(self, fft_size):
+        self._set_attribute(B.ATTR_FFT_SIZE, fft_size)
+        self.fft_size = int(fft_size)
+
+    def set_smoothing_time_constant(self, v):
+        self._set_attribute(B.ATTR_SMOOTHING_TIME_CONSTANT, v)
+
+    def set_min_decibels(self, v):
+        self._set_attribute(B.ATTR_MIN_DECIBELS, v)
+
+    def set_max_decibels(self, v):
+        self._set_attribute(B.ATTR_MAX_DECIBELS, v)
 
     def frequency_bin_count(self):
         return self.fft_size // 2
@@ -422,7 +512,7 @@ class OfflineAudioContext:
             d, keep = buffer._desc()
             self._keep.append((d, keep))
             o.buffer = C.pointer(d)
-        return AudioNode(self, self._create("create_convolver", o))
+        return ConvolverNode(self, self._create("create_convolver", o))
 
     def create_wave_shaper(self, curve=None, oversample=OVERSAMPLE_NONE, cfg=None):
         o = B.WaveShaperOptions(None, 0, oversample, cfg or channel_config())
@@ -430,7 +520,7 @@ class OfflineAudioContext:
             c = B.as_f32(curve)
             self._keep.append(c)
             o.curve, o.curve_len = B.fptr(c), len(c)
-        return AudioNode(self, self._create("create_wave_shaper", o))
+        return WaveShaperNode(self, self._create("create_wave_shaper", o))
 
     def create_delay(self, max_delay_time=1.0, delay_time=0.0, cfg=None):
         nid = self._create("create_delay", B.DelayOptions(max_delay_time, delay_time, cfg or channel_config()))
@@ -450,7 +540,7 @@ class OfflineAudioContext:
         o = B.PannerOptions(panning_model, distance_model, *position, *orientation, ref_distance, max_distance,
                             rolloff_factor, cone_inner_angle, cone_outer_angle, cone_outer_gain, cfg or channel_config())
         nid = self._create("create_panner", o)
-        n = AudioNode(self, nid)
+        n = PannerNode(self, nid)
         for i, name in enumerate(["position_x", "position_y", "position_z", "orientation_x", "orientation_y", "orientation_z"]):
             setattr(n, name, AudioParam(self, nid, i, (list(position) + list(orientation))[i]))
         return n

@@ -244,7 +244,7 @@ WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_option
     n.out_id = n.id;
     n.kind = K_CONV;
     n.cfg = cfg;
-    n.normalize = !o->disable_normalization;
+    n.normalize = n.normalize_next = !o->disable_normalization;
     if (o->buffer) n.buffer = copy_buffer(o->buffer);
     *out = g->finish_register(std::move(n)).id;
     return WAE_OK;
@@ -641,6 +641,145 @@ WAE_API wae_status wae_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t 
     if (ni == g->nodes.end() || ni->second.kind != K_BIQUAD || type > 7) return fail(WAE_INVALID_ARGUMENT, "not a biquad / bad type");
     ni->second.type = (int)type;
     return WAE_OK;
+}
+
+// ---- node attributes set after construction (the reference posts a control message per setter) ------------------------------
+namespace {
+Node* node_of_kind(wae_graph* g, wae_node_id id, Kind kind) {
+    if (!g) return nullptr;
+    auto it = g->nodes.find(id);
+    return it == g->nodes.end() || it->second.kind != kind ? nullptr : &it->second;
+}
+}  // namespace
+
+// AudioBufferSourceNode::set_buffer (src/node/audio_buffer_source.rs:278-288): once
+WAE_API wae_status wae_buffer_source_set_buffer(wae_graph* g, wae_node_id node, const wae_audio_buffer* buffer) {
+    Node* n = node_of_kind(g, node, K_ABSN);
+    if (!n || !buffer) return fail(WAE_INVALID_ARGUMENT, "not an AudioBufferSourceNode / null buffer");
+    if (n->buffer) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign buffer twice");
+    n->buffer = copy_buffer(buffer);
+    return WAE_OK;
+}
+
+// ConvolverNode::set_buffer (src/node/convolver.rs:259-317): may replace the response; the normalisation is decided now
+WAE_API wae_status wae_convolver_set_buffer(wae_graph* g, wae_node_id node, const wae_audio_buffer* buffer) {
+    Node* n = node_of_kind(g, node, K_CONV);
+    if (!n || !buffer) return fail(WAE_INVALID_ARGUMENT, "not a ConvolverNode / null buffer");
+    if (buffer->sample_rate != g->sample_rate)
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - sample rate of the convolution buffer must match the audio context");
+    const uint32_t c = buffer->number_of_channels;
+    if (!(c == 1 || c == 2 || c == 4)) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - the convolution buffer must consist of 1, 2 or 4 channels");
+    if (!g->epochs.empty() && n->buffer)  // the reference swaps in fresh convolvers (tail dropped): not lowered mid-render
+        return fail(WAE_UNSUPPORTED, "replacing the impulse response of a ConvolverNode at a suspend point is not lowered to the GPU");
+    n->buffer = copy_buffer(buffer);
+    n->normalize = n->normalize_next;
+    return WAE_OK;
+}
+
+// WaveShaperNode::set_curve (src/node/waveshaper.rs:203-213): once
+WAE_API wae_status wae_wave_shaper_set_curve(wae_graph* g, wae_node_id node, const float* curve, uint32_t len) {
+    Node* n = node_of_kind(g, node, K_SHAPER);
+    if (!n || (!curve && len)) return fail(WAE_INVALID_ARGUMENT, "not a WaveShaperNode / null curve");
+    if (n->has_curve) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign curve twice");
+    n->has_curve = true;
+    n->table.assign(curve, curve + len);
+    return WAE_OK;
+}
+
+// OscillatorNode::set_periodic_wave (src/node/oscillator.rs:334-337): the type becomes Custom for good; `table` is the wavetable the
+// binding generated (PeriodicWave::new, src/periodic_wave.rs:163-209)
+WAE_API wae_status wae_oscillator_set_periodic_wave(wae_graph* g, wae_node_id node, const float* table, uint32_t len) {
+    Node* n = node_of_kind(g, node, K_OSC);
+    if (!n || !table || len == 0) return fail(WAE_INVALID_ARGUMENT, "not an OscillatorNode / empty wavetable");
+    n->type = WAE_OSC_CUSTOM;
+    n->table.assign(table, table + len);
+    return WAE_OK;
+}
+
+// the scalar setters of AudioBufferSourceNode (audio_buffer_source.rs:324-349), ConvolverNode (convolver.rs:325-328), WaveShaperNode
+// (waveshaper.rs:226-229), PannerNode (panner.rs:545-657) and AnalyserNode (analyser.rs:148-222)
+WAE_API wae_status wae_node_set_attribute(wae_graph* g, wae_node_id node, uint32_t attribute, double value) {
+    if (!g) return fail(WAE_INVALID_ARGUMENT, "null graph");
+    auto it = g->nodes.find(node);
+    if (it == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    Node& n = it->second;
+    auto wrong = [&]() { return fail(WAE_INVALID_ARGUMENT, "this node has no such attribute"); };
+    switch (attribute) {
+        case WAE_ATTR_LOOP: case WAE_ATTR_LOOP_START: case WAE_ATTR_LOOP_END:
+            if (n.kind != K_ABSN) return wrong();
+            // the renderer keeps playing from its current playhead when the loop changes under it; the closed-form tracks of the
+            // engine are planned per segment from the start time, so a change at a suspend point of a started source is refused
+            if (!g->epochs.empty() && n.has_start)
+                return fail(WAE_UNSUPPORTED, "changing the loop attributes of a started AudioBufferSourceNode at a suspend point is not lowered to the GPU");
+            if (attribute == WAE_ATTR_LOOP) n.loop = value != 0.;
+            else if (attribute == WAE_ATTR_LOOP_START) n.loop_start = value;
+            else n.loop_end = value;
+            return WAE_OK;
+        case WAE_ATTR_NORMALIZE:
+            if (n.kind != K_CONV) return wrong();
+            n.normalize_next = value != 0.;
+            return WAE_OK;
+        case WAE_ATTR_OVERSAMPLE:
+            if (n.kind != K_SHAPER) return wrong();
+            if (!(value == 0. || value == 1. || value == 2.)) return fail(WAE_INVALID_ARGUMENT, "unknown oversample type");
+            n.oversample = (int)value;
+            return WAE_OK;
+        case WAE_ATTR_PANNING_MODEL: case WAE_ATTR_DISTANCE_MODEL: case WAE_ATTR_REF_DISTANCE: case WAE_ATTR_MAX_DISTANCE:
+        case WAE_ATTR_ROLLOFF_FACTOR: case WAE_ATTR_CONE_INNER_ANGLE: case WAE_ATTR_CONE_OUTER_ANGLE: case WAE_ATTR_CONE_OUTER_GAIN:
+            if (n.kind != K_PANNER) return wrong();
+            switch (attribute) {
+                case WAE_ATTR_PANNING_MODEL:
+                    if (!(value == 0. || value == 1.)) return fail(WAE_INVALID_ARGUMENT, "unknown panning model");
+                    n.panning_model = (int)value;
+                    break;
+                case WAE_ATTR_DISTANCE_MODEL:
+                    if (!(value == 0. || value == 1. || value == 2.)) return fail(WAE_INVALID_ARGUMENT, "unknown distance model");
+                    n.distance_model = (int)value;
+                    break;
+                case WAE_ATTR_REF_DISTANCE:
+                    if (!(value >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - refDistance cannot be negative");
+                    n.ref_distance = value;
+                    break;
+                case WAE_ATTR_MAX_DISTANCE:
+                    if (!(value > 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - maxDistance must be strictly positive");
+                    n.max_distance = value;
+                    break;
+                case WAE_ATTR_ROLLOFF_FACTOR:
+                    if (!(value >= 0.)) return fail(WAE_INVALID_ARGUMENT, "RangeError - rolloffFactor cannot be negative");
+                    n.rolloff_factor = value;
+                    break;
+                case WAE_ATTR_CONE_INNER_ANGLE: n.cone_inner_angle = value; break;
+                case WAE_ATTR_CONE_OUTER_ANGLE: n.cone_outer_angle = value; break;
+                default:
+                    if (!(value >= 0. && value <= 1.)) return fail(WAE_INVALID_STATE, "InvalidStateError - coneOuterGain must be in the range [0, 1]");
+                    n.cone_outer_gain = value;
+            }
+            return WAE_OK;
+        case WAE_ATTR_FFT_SIZE: {
+            if (n.kind != K_ANALYSER) return wrong();
+            const uint64_t f = (uint64_t)value;
+            if (!((double)f == value && f >= 32 && f <= 32768 && (f & (f - 1)) == 0))
+                return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: must be a power of two in [32, 32768]");
+            n.fft_size = (uint32_t)f;
+            return WAE_OK;
+        }
+        case WAE_ATTR_SMOOTHING_TIME_CONSTANT:
+            if (n.kind != K_ANALYSER) return wrong();
+            if (!(value >= 0. && value <= 1.)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid smoothing time constant: must be in [0, 1]");
+            n.smoothing = value;
+            return WAE_OK;
+        case WAE_ATTR_MIN_DECIBELS:
+            if (n.kind != K_ANALYSER) return wrong();
+            if (!(value < n.max_db)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid min decibels: must be less than max decibels");
+            n.min_db = value;
+            return WAE_OK;
+        case WAE_ATTR_MAX_DECIBELS:
+            if (n.kind != K_ANALYSER) return wrong();
+            if (!(value > n.min_db)) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid max decibels: must be greater than min decibels");
+            n.max_db = value;
+            return WAE_OK;
+        default: return fail(WAE_INVALID_ARGUMENT, "unknown attribute");
+    }
 }
 
 // ---- AudioNode::set_channel_count / set_channel_count_mode / set_channel_interpretation -------------------------------------

@@ -72,7 +72,8 @@ struct Node {
     int oversample = 0;  // WaveShaper: WAE_OVERSAMPLE_*
     std::vector<double> feedforward, feedback;  // IIR
     std::shared_ptr<PcmBuffer> buffer;          // ABSN buffer / convolver IR
-    bool normalize = true;                      // convolver
+    bool normalize = true;                      // convolver: the scale the CURRENT buffer was given (taken when the buffer is set)
+    bool normalize_next = true;                 // ConvolverNode::set_normalize: applies to the next set_buffer (convolver.rs:325-328)
     double start_time = 1.7976931348623157e308, stop_time = 1.7976931348623157e308;
     double offset = 0., duration = 1.7976931348623157e308;
     bool loop = false;
