@@ -170,3 +170,35 @@ def test_hrtf_selected_with_set_panning_model(pkg, oracle):
     a, b = build(True), build(False)
     assert np.array_equal(a.get_channel_data(0), b.get_channel_data(0)) and np.array_equal(a.get_channel_data(1), b.get_channel_data(1))
     assert np.abs(a.get_channel_data(1)).max() > 1e-3
+
+
+def test_setters_at_a_suspend_point(pkg, builder):
+    # a control message sent from a suspend_sync callback takes effect at that quantum.  The library plans the two segments separately;
+    # two changes are not lowered (the graph keeps the CPU renderer): loop attributes of a started source, a second impulse response
+    def ctx():
+        c = pkg.OfflineAudioContext(2, 8192 * 3, SR, builder)
+        src = c.create_buffer_source(pkg.AudioBuffer(_noise(3000, 2), SR), loop=True)
+        pan = c.create_panner(position=(2.0, 0.0, -1.0))
+        conv = c.create_convolver(pkg.AudioBuffer(_noise(500, 2, seed=3), SR))
+        src.connect(pan)
+        pan.connect(conv)
+        conv.connect(c.destination())
+        src.start()
+        return c, src, pan, conv
+
+    c, src, pan, conv = ctx()
+    c.suspend_sync(8192 / SR, lambda _c: (pan.set_distance_model(pkg.context.LINEAR), pan.set_rolloff_factor(0.5)))
+    if builder.api.is_product:
+        assert pkg.context.plan_batch([c])["segments"] == 2
+    else:
+        out = c.start_rendering_sync()
+        assert np.abs(out.get_channel_data(0)[8192 + 2000:]).max() > 1e-4
+    for change in (lambda s, p, v: s.set_loop(False), lambda s, p, v: v.set_buffer(pkg.AudioBuffer(_noise(100, 2), SR))):
+        c, src, pan, conv = ctx()
+        c.suspend_sync(8192 / SR, lambda _c, f=change, s=src, p=pan, v=conv: f(s, p, v))
+        if builder.api.is_product:
+            with pytest.raises(pkg.WaeError) as e:
+                pkg.context.plan_batch([c])
+            assert e.value.status == 4  # WAE_UNSUPPORTED
+        else:
+            c.start_rendering_sync()  # the CPU renderer handles both
