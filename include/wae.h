@@ -310,6 +310,14 @@ WAE_API wae_status wae_graph_suspend(wae_graph* graph, double suspend_time);
 WAE_API wae_status wae_connect_param(wae_graph*, wae_node_id from, uint32_t output, wae_node_id to, uint32_t param_index);
 /* AudioNode::disconnect() — removes all outgoing connections of `from`. */
 WAE_API wae_status wae_disconnect(wae_graph*, wae_node_id from);
+/* The selective forms (src/node/audio_node.rs:304-405), all of them ConcreteBaseAudioContext::disconnect(from, Option<output>, Option<to>,
+ * Option<input>) (src/context/concrete_base.rs:474-507): disconnect_output(o) = (from, o, WAE_NODE_NONE, -1); disconnect_dest(d) =
+ * (from, -1, d, -1); disconnect_dest_from_output(d, o) = (from, o, d, -1); disconnect_dest_from_output_to_input(d, o, i) = (from, o, d, i).
+ * Naming a destination that is not connected answers "InvalidAccessError - attempting to disconnect unconnected nodes". */
+#define WAE_NODE_NONE 0xFFFFFFFFu
+WAE_API wae_status wae_disconnect_from(wae_graph*, wae_node_id from, int32_t output, wae_node_id to, int32_t input);
+/* ... and towards an AudioParam of `to` (node.disconnect_dest(&param)) */
+WAE_API wae_status wae_disconnect_param(wae_graph*, wae_node_id from, int32_t output, wae_node_id to, uint32_t param_index);
 
 /* AudioParam methods (src/param.rs:336-662). */
 WAE_API wae_status wae_param_event_push(wae_graph*, wae_node_id node, uint32_t param_index, const wae_param_event* event);

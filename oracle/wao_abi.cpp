@@ -480,6 +480,40 @@ WAO_API wae_status wao_disconnect(wae_graph* g, wae_node_id from) {
     return WAE_OK;
 }
 
+// ConcreteBaseAudioContext::disconnect(from, Option<output>, Option<to>, Option<input>) (src/context/concrete_base.rs:474-507) and the
+// render side Graph::remove_edge (src/render/graph.rs:266-283)
+static wae_status disconnect_matching(wae_graph* g, wae_node_id from, int32_t output, bool has_to, uint32_t to_id, int32_t input) {
+    auto fi = g->info.find(from);
+    if (fi == g->info.end() || fi->second.kind == K_PARAM) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (output >= fi->second.n_outputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port " + std::to_string(output) + " is out of bounds");
+    auto& out = g->graph.get(fi->second.out_id)->outgoing;
+    const size_t before = out.size();
+    out.erase(std::remove_if(out.begin(), out.end(),
+                             [&](const Edge& e) {
+                                 if (e.other_index < 0) return false;
+                                 return (output < 0 || e.self_index == output) && (!has_to || e.other_id == to_id) && (input < 0 || e.other_index == input);
+                             }),
+              out.end());
+    g->graph.ordered.clear();
+    if (has_to && out.size() == before) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - attempting to disconnect unconnected nodes");
+    return WAE_OK;
+}
+WAO_API wae_status wao_disconnect_from(wae_graph* g, wae_node_id from, int32_t output, wae_node_id to, int32_t input) {
+    if (to == WAE_NODE_NONE) return disconnect_matching(g, from, output, false, 0, input);
+    auto ti = g->info.find(to);
+    if (ti == g->info.end() || ti->second.kind == K_PARAM) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (input >= ti->second.n_inputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - input port " + std::to_string(input) + " is out of bounds");
+    return disconnect_matching(g, from, output, true, to, input);
+}
+WAO_API wae_status wao_disconnect_param(wae_graph* g, wae_node_id from, int32_t output, wae_node_id to, uint32_t param_index) {
+    auto ti = g->info.find(to);
+    if (ti == g->info.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (param_index >= ti->second.params.size()) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - param index out of bounds");
+    return disconnect_matching(g, from, output, true, ti->second.params[param_index], -1);
+}
+
 static wae_status push_event(ParamProcessor* p, const wae_param_event* e) {
     ParamEvent ev;
     ev.type = (int)e->type;

@@ -202,3 +202,61 @@ def test_setters_at_a_suspend_point(pkg, builder):
             assert e.value.status == 4  # WAE_UNSUPPORTED
         else:
             c.start_rendering_sync()  # the CPU renderer handles both
+
+
+def test_selective_disconnect(pkg, builder):
+    # src/node/audio_node.rs:304-405 over ConcreteBaseAudioContext::disconnect (concrete_base.rs:474-507)
+    c = pkg.OfflineAudioContext(2, RQ, SR, builder)
+    src = c.create_constant_source()
+    a, b = c.create_gain(0.5), c.create_gain(0.25)
+    split = c.create_channel_splitter(2)
+    merge = c.create_channel_merger(2)
+    lfo = c.create_oscillator()
+    src.connect(a)
+    src.connect(b)
+    a.connect(c.destination())
+    b.connect(c.destination())
+    b.connect(split)
+    split.connect_from_output_to_input(merge, 0, 1)
+    split.connect_from_output_to_input(merge, 1, 0)
+    merge.connect(c.destination())
+    lfo.connect(a.gain)
+    src.start()
+    lfo.start()
+    before = c.render_order()
+    assert a.id in before and b.id in before and merge.id in before
+    src.disconnect_dest(b)                                           # src -> b only
+    with pytest.raises(pkg.WaeError) as e:
+        src.disconnect_dest(b)                                       # not connected any more
+    assert "attempting to disconnect unconnected nodes" in str(e.value)
+    split.disconnect_dest_from_output_to_input(merge, 0, 1)
+    with pytest.raises(pkg.WaeError):
+        split.disconnect_dest_from_output_to_input(merge, 0, 1)
+    with pytest.raises(pkg.WaeError):
+        split.disconnect_dest_from_output(merge, 5)                  # IndexSizeError - output port 5 is out of bounds
+    with pytest.raises(pkg.WaeError):
+        split.disconnect_dest_from_output_to_input(merge, 1, 9)      # IndexSizeError - input port 9 is out of bounds
+    split.disconnect_output(1)                                       # no destination named: nothing to complain about, ever
+    split.disconnect_output(1)
+    lfo.disconnect_dest(a.gain)                                      # towards an AudioParam
+    with pytest.raises(pkg.WaeError):
+        lfo.disconnect_dest(a.gain)
+    other = pkg.OfflineAudioContext(2, RQ, SR, builder)
+    with pytest.raises(pkg.WaeError):
+        src.disconnect_dest(other.destination())                     # different contexts
+
+
+def test_selective_disconnect_renders(pkg, oracle):
+    # two constants into the destination; one is removed selectively at a suspend point
+    c = pkg.OfflineAudioContext(1, RQ * 4, SR, oracle)
+    k1, k2 = c.create_constant_source(offset=0.25), c.create_constant_source(offset=0.5)
+    g = c.create_gain()
+    k1.connect(g)
+    k2.connect(g)
+    k2.connect(c.destination())
+    g.connect(c.destination())
+    k1.start()
+    k2.start()
+    c.suspend_sync(2 * RQ / SR, lambda _c: k2.disconnect_dest(g))
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert np.all(out[:2 * RQ] == 1.25) and np.all(out[2 * RQ:] == 0.75)

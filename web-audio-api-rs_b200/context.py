@@ -198,6 +198,29 @@ class AudioNode:
         api = self._ctx._api
         api.check(api.disconnect(self._ctx._g, self.id))
 
+    # the selective forms, src/node/audio_node.rs:304-405
+    def _disconnect_from(self, output, dest, input):
+        api = self._ctx._api
+        if isinstance(dest, AudioParam):
+            owner = 1 if dest._node == "listener" else dest._node
+            api.check(api.disconnect_param(self._ctx._g, self.id, output, owner, dest._index))
+        else:
+            if dest is not None and dest._ctx is not self._ctx:
+                raise B.WaeError(1, "InvalidAccessError - Attempting to disconnect nodes from different contexts")
+            api.check(api.disconnect_from(self._ctx._g, self.id, output, 0xFFFFFFFF if dest is None else dest.id, input))
+
+    def disconnect_dest(self, dest):
+        self._disconnect_from(-1, dest, -1)
+
+    def disconnect_output(self, output):
+        self._disconnect_from(output, None, -1)
+
+    def disconnect_dest_from_output(self, dest, output):
+        self._disconnect_from(output, dest, -1)
+
+    def disconnect_dest_from_output_to_input(self, dest, output, input):
+        self._disconnect_from(output, dest, input)
+
 
 class AudioScheduledSourceNode(AudioNode):
     def start(self):

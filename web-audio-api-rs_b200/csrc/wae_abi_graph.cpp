@@ -461,6 +461,45 @@ WAE_API wae_status wae_disconnect(wae_graph* g, wae_node_id from) {
     return WAE_OK;
 }
 
+// AudioNode::disconnect_dest / disconnect_output / disconnect_dest_from_output / disconnect_dest_from_output_to_input
+// (src/node/audio_node.rs:304-405) = ConcreteBaseAudioContext::disconnect(from, Option<output>, Option<to>, Option<input>)
+// (src/context/concrete_base.rs:474-507): -1 / WAE_NODE_NONE stand for None.
+static wae_status disconnect_matching(wae_graph* g, wae_node_id from, int32_t output, bool has_to, uint32_t to_id, int32_t input) {
+    auto fi = g->nodes.find(from);
+    if (fi == g->nodes.end() || fi->second.kind == K_PARAM) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (output >= fi->second.n_outputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - output port " + std::to_string(output) + " is out of bounds");
+    std::vector<Edge>& out = g->nodes.at(fi->second.out_id).outgoing;
+    const size_t before = out.size();
+    out.erase(std::remove_if(out.begin(), out.end(),
+                             [&](const Edge& e) {
+                                 if (e.other_index < 0) return false;  // hidden edges (DelayWriter -> reader, listener -> panner) are not the user's
+                                 return (output < 0 || e.self_index == output) && (!has_to || e.other_id == to_id) && (input < 0 || e.other_index == input);
+                             }),
+              out.end());
+    if (has_to && out.size() == before) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - attempting to disconnect unconnected nodes");
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_disconnect_from(wae_graph* g, wae_node_id from, int32_t output, wae_node_id to, int32_t input) {
+    if (!g) return fail(WAE_INVALID_ARGUMENT, "null graph");
+    if (to == WAE_NODE_NONE) return disconnect_matching(g, from, output, false, 0, input);
+    auto ti = g->nodes.find(to);
+    if (ti == g->nodes.end() || ti->second.kind == K_PARAM) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (input >= ti->second.n_inputs)
+        return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - input port " + std::to_string(input) + " is out of bounds");
+    return disconnect_matching(g, from, output, true, to, input);
+}
+
+// the same towards an AudioParam of `to` (AudioParam is an AudioNode in the reference: node.disconnect_dest(param))
+WAE_API wae_status wae_disconnect_param(wae_graph* g, wae_node_id from, int32_t output, wae_node_id to, uint32_t param_index) {
+    if (!g) return fail(WAE_INVALID_ARGUMENT, "null graph");
+    auto ti = g->nodes.find(to);
+    if (ti == g->nodes.end()) return fail(WAE_INVALID_ARGUMENT, "InvalidAccessError - unknown node");
+    if (param_index >= ti->second.params.size()) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - param index out of bounds");
+    return disconnect_matching(g, from, output, true, ti->second.params[param_index], -1);
+}
+
 static wae_status push_event(Param& p, const wae_param_event* e) {
     auto finite = [](float v) { return std::isfinite(v); };
     auto valid_time = [](double t) { return std::isfinite(t) && t >= 0.; };
