@@ -725,6 +725,38 @@ WAO_API wae_status wao_node_set_channel_count(wae_graph* g, wae_node_id node, ui
 WAO_API wae_status wao_node_set_channel_count_mode(wae_graph* g, wae_node_id node, uint32_t mode) { return set_cfg_field(g, node, 1, mode); }
 WAO_API wae_status wao_node_set_channel_interpretation(wae_graph* g, wae_node_id node, uint32_t v) { return set_cfg_field(g, node, 2, v); }
 
+// PeriodicWave::new (src/periodic_wave.rs:104-209), test hook for the wavetable tests (:278-345)
+WAO_API wae_status wao_periodic_wave_table(const float* real, const float* imag, uint32_t len, uint32_t disable_normalization, float* table,
+                                           uint32_t table_len) {
+    const bool has_r = real != nullptr, has_i = imag != nullptr;
+    if ((has_r || has_i) && len < 2) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - `real` and `imag` length should at least 2");
+    if (!table || table_len == 0) return fail(WAE_INVALID_ARGUMENT, "null table");
+    static const float sine_r[2] = {0.f, 0.f}, sine_i[2] = {0.f, 1.f};  // no coefficients: the built-in sine (periodic_wave.rs:143-146)
+    const uint32_t n = (has_r || has_i) ? len : 2;
+    const float pi_2 = 2.f * 3.14159265358979323846f;
+    for (uint32_t i = 0; i < table_len; i++) {
+        float sample = 0.f;
+        const float phase = pi_2 * (float)i / (float)table_len;
+        for (uint32_t j = 1; j < n; j++) {
+            const float re = has_r ? real[j] : ((has_r || has_i) ? 0.f : sine_r[j]);
+            const float im = has_i ? imag[j] : ((has_r || has_i) ? 0.f : sine_i[j]);
+            const float rad = phase * (float)j;
+            const float contrib = re * std::cos(rad) + im * std::sin(rad);
+            sample += contrib;
+        }
+        table[i] = sample;
+    }
+    if (!disable_normalization) {
+        float mx = 0.f;
+        for (uint32_t i = 0; i < table_len; i++) mx = std::fabs(table[i]) > mx ? std::fabs(table[i]) : mx;
+        if (mx > 0.f) {
+            const float norm = 1.f / mx;
+            for (uint32_t i = 0; i < table_len; i++) table[i] *= norm;
+        }
+    }
+    return WAE_OK;
+}
+
 static Analyser* find_analyser(wae_graph* g, wae_node_id node);
 // ---- node attributes set after construction: the onmessage handlers of the renderers ----------------------------------------
 // AudioBufferSourceNode::set_buffer (audio_buffer_source.rs:278-288, onmessage :856-872)

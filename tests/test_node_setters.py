@@ -260,3 +260,33 @@ def test_selective_disconnect_renders(pkg, oracle):
     c.suspend_sync(2 * RQ / SR, lambda _c: k2.disconnect_dest(g))
     out = c.start_rendering_sync().get_channel_data(0)
     assert np.all(out[:2 * RQ] == 1.25) and np.all(out[2 * RQ:] == 0.75)
+
+
+def _wave(api, real, imag, disable_normalization=False, n=2048):
+    import ctypes as C
+    fp = C.POINTER(C.c_float)
+    r = None if real is None else np.ascontiguousarray(real, np.float32)
+    i = None if imag is None else np.ascontiguousarray(imag, np.float32)
+    length = len(r) if r is not None else (len(i) if i is not None else 0)
+    out = np.zeros(n, np.float32)
+    api.check(api.periodic_wave_table(None if r is None else r.ctypes.data_as(fp), None if i is None else i.ctypes.data_as(fp), length,
+                                      1 if disable_normalization else 0, out.ctypes.data_as(fp), n))
+    return out
+
+
+def test_periodic_wave_tables(pkg, host_api):
+    # src/periodic_wave.rs:278-345 wavetable_generate_sine / _2f_not_norm / _2f_norm / normalize, :221-276 the constructor panics
+    i = np.arange(2048, dtype=np.float32)
+    sine = np.sin(i / np.float32(2048) * np.float32(2) * np.float32(np.pi), dtype=np.float32)
+    assert np.abs(_wave(host_api, [0.0, 0.0], [0.0, 1.0]) - sine).max() <= 1e-6
+    assert np.abs(_wave(host_api, None, None) - sine).max() <= 1e-6              # the default is a sine
+    two = (np.float32(0.5) * np.sin(i / np.float32(2048) * np.float32(2) * np.float32(np.pi)) +
+           np.float32(0.5) * np.sin(np.float32(2) * i / np.float32(2048) * np.float32(2) * np.float32(np.pi))).astype(np.float32)
+    assert np.abs(_wave(host_api, [0.0, 0.0, 0.0], [0.0, 0.5, 0.5], disable_normalization=True) - two).max() <= 1e-6
+    assert np.abs(_wave(host_api, [0.0, 0.0, 0.0], [0.0, 0.5, 0.5]) - two / np.abs(two).max()).max() <= 1e-6
+    assert np.abs(_wave(host_api, None, [0.0, 0.5, 0.5]) - two / np.abs(two).max()).max() <= 1e-6   # only `imag`
+    cos = _wave(host_api, [0.0, 1.0], None)                                                       # only `real`
+    assert abs(float(cos[0]) - 1.0) <= 1e-6 and abs(float(cos[512])) <= 1e-6
+    for real, imag in [([0.0], None), (None, [0.0]), ([0.0], [0.0])]:                             # "length should at least 2"
+        with pytest.raises(pkg.WaeError):
+            _wave(host_api, real, imag)

@@ -682,6 +682,39 @@ WAE_API wae_status wae_biquad_set_type(wae_graph* g, wae_node_id node, uint32_t 
     return WAE_OK;
 }
 
+// PeriodicWave::new -> generate_wavetable + normalize (src/periodic_wave.rs:104-209): the wavetable an OscillatorNode of type Custom plays
+// (wae_oscillator_options.periodic_wave / wae_oscillator_set_periodic_wave take it).  real / imag may be NULL (zeros); both NULL = sine.
+WAE_API wae_status wae_periodic_wave_table(const float* real, const float* imag, uint32_t len, uint32_t disable_normalization, float* table,
+                                           uint32_t table_len) {
+    const bool has_r = real != nullptr, has_i = imag != nullptr;
+    if ((has_r || has_i) && len < 2) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - `real` and `imag` length should at least 2");
+    if (!table || table_len == 0) return fail(WAE_INVALID_ARGUMENT, "null table");
+    static const float sine_r[2] = {0.f, 0.f}, sine_i[2] = {0.f, 1.f};  // no coefficients: the built-in sine (periodic_wave.rs:143-146)
+    const uint32_t n = (has_r || has_i) ? len : 2;
+    const float pi_2 = 2.f * 3.14159265358979323846f;
+    for (uint32_t i = 0; i < table_len; i++) {
+        float sample = 0.f;
+        const float phase = pi_2 * (float)i / (float)table_len;
+        for (uint32_t j = 1; j < n; j++) {
+            const float re = has_r ? real[j] : ((has_r || has_i) ? 0.f : sine_r[j]);
+            const float im = has_i ? imag[j] : ((has_r || has_i) ? 0.f : sine_i[j]);
+            const float rad = phase * (float)j;
+            const float contrib = re * std::cos(rad) + im * std::sin(rad);
+            sample += contrib;
+        }
+        table[i] = sample;
+    }
+    if (!disable_normalization) {
+        float mx = 0.f;
+        for (uint32_t i = 0; i < table_len; i++) mx = std::fabs(table[i]) > mx ? std::fabs(table[i]) : mx;
+        if (mx > 0.f) {
+            const float norm = 1.f / mx;
+            for (uint32_t i = 0; i < table_len; i++) table[i] *= norm;
+        }
+    }
+    return WAE_OK;
+}
+
 // ---- node attributes set after construction (the reference posts a control message per setter) ------------------------------
 namespace {
 Node* node_of_kind(wae_graph* g, wae_node_id id, Kind kind) {
