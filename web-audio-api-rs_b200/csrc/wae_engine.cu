@@ -480,14 +480,6 @@ struct Planner {
         BufRef track{nullptr, 0, 0};
     };
     PRef param_ref(wae_graph* g, uint32_t pid);
-    // for renderers whose automated parameters are not lowered yet
-    bool const_param(wae_graph* g, uint32_t pid, float& v) {
-        PRef r = param_ref(g, pid);
-        if (r.dyn) return bail(WAE_UNSUPPORTED, "AudioParam automation / audio-rate input on this parameter is not lowered to the GPU yet");
-        v = r.v;
-        return true;
-    }
-
     bool plan_graph(wae_graph* g, uint32_t gi);
     bool plan_convolver(wae_graph* g, PNode& pn, int level);
 };

@@ -5,6 +5,7 @@
 #pragma once
 #include "wae_spatial.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -108,7 +109,7 @@ struct SincBank {
 inline std::vector<float> hrir_resample(const SincBank& bank, const float* hrir, size_t len, double ratio) {
     const int L = SincBank::kLen, P = SincBank::kPhases;
     std::vector<float> padded(len + 2 * (size_t)L, 0.f);  // two filter lengths of silence before the response
-    std::memcpy(padded.data() + 2 * L, hrir, len * sizeof(float));
+    std::copy(hrir, hrir + len, padded.begin() + 2 * L);
     const double step = 1.0 / ratio, stop = (double)((int64_t)len - (L + 1));
     std::vector<float> out;
     if (!(-(double)(L / 2) < stop)) return out;  // shorter than half a filter: the resampler emits nothing
