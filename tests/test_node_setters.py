@@ -290,3 +290,30 @@ def test_periodic_wave_tables(pkg, host_api):
     for real, imag in [([0.0], None), (None, [0.0]), ([0.0], [0.0])]:                             # "length should at least 2"
         with pytest.raises(pkg.WaeError):
             _wave(host_api, real, imag)
+
+
+def test_buffer_given_after_a_null_buffer_start_is_ignored(pkg, builder):
+    # audio_buffer_source.rs:443-451 / test_null_buffer_start_ends_before_start_time (:1509-1534): started with no buffer and rendered ->
+    # ended for good; a buffer given later (from a suspend callback) is never heard.  Given in the SAME callback as start() it plays.
+    def build(start_in_callback):
+        c = pkg.OfflineAudioContext(1, 48000, SR, builder)
+        src = c.create_buffer_source()
+        src.connect(c.destination())
+        if not start_in_callback:
+            src.start_at(0.75)
+
+        def cb(ctx):
+            if start_in_callback:
+                src.start_at(0.75)
+            src.set_buffer(pkg.AudioBuffer([np.ones(64, np.float32)], SR))
+        c.suspend_sync(0.5, cb)
+        return c
+
+    if builder.api.is_product:
+        dead, live = pkg.context.plan_batch([build(False)]), pkg.context.plan_batch([build(True)])
+        assert set(dead["kinds"]) == {"k_mix"} and dead["source_floats"] == 0          # nothing but silence is rendered
+        assert any(k.startswith("k_buffer_source") or k == "k_chain" for k in live["kinds"]) and live["source_floats"] == 64
+    else:
+        assert not build(False).start_rendering_sync().get_channel_data(0).any()
+        out = build(True).start_rendering_sync().get_channel_data(0)
+        assert out[36000:36064].all() and not out[:36000].any()

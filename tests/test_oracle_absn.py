@@ -237,3 +237,57 @@ def test_loop_out_of_bounds(pkg, oracle, loop_start, loop_end, error):  # :1780-
     want = np.zeros(n, np.float32)
     want[0::500] = 1.0
     assert np.abs(out - want).max() <= error
+
+
+def test_construct_with_options_and_run(pkg, oracle):  # :896-915
+    sr = 44100.0
+    c = pkg.OfflineAudioContext(1, RQ, sr, oracle)
+    src = c.create_buffer_source(pkg.AudioBuffer([np.ones(RQ, np.float32)], sr))
+    src.connect(c.destination())
+    src.start()
+    assert np.array_equal(c.start_rendering_sync().get_channel_data(0), np.ones(RQ, np.float32))
+
+
+def test_null_buffer_start_ends_before_start_time(pkg, oracle):  # :1509-1534: a buffer given after the source has already "ended" stays unheard
+    sr = 48000.0
+    c = pkg.OfflineAudioContext(1, int(sr), sr, oracle)
+    src = c.create_buffer_source()
+    src.connect(c.destination())
+    src.start_at(0.75)
+    c.suspend_sync(0.5, lambda ctx: src.set_buffer(pkg.AudioBuffer([np.ones(1, np.float32)], sr)))
+    out = c.start_rendering_sync().get_channel_data(0)
+    assert not out.any()
+
+
+def test_loop_no_restart_suspend(pkg, oracle):  # :1892-1917: set_loop(true) after the buffer has played out does not restart it
+    sr = 48000.0
+    c = pkg.OfflineAudioContext(1, RQ * 2, sr, oracle)
+    src = c.create_buffer_source()
+    src.connect(c.destination())
+    src.set_buffer(pkg.AudioBuffer([np.ones(1, np.float32)], sr))
+    src.start_at(0.0)
+    c.suspend_sync(RQ / sr, lambda ctx: src.set_loop(True))
+    out = c.start_rendering_sync().get_channel_data(0)
+    want = np.zeros(RQ * 2, np.float32)
+    want[0] = 1.0
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("sample_rate,buffer_rate,threshold", [(44100.0, 44100.0, 9.0957e-5), (44100.0, 43800.0, 3.8986e-3)])
+def test_subsample_buffer_stitching(pkg, oracle, sample_rate, buffer_rate, threshold):
+    # :1987-2043 (ported there from wpt sub-sample-buffer-stitching.html): a sine cut into 30-frame buffers, each started at its
+    # sub-sample time, adds up to the sine again
+    buffer_length, frequency = 30, 440.0
+    length = buffer_length * 15
+    c = pkg.OfflineAudioContext(2, length, sample_rate, oracle)
+    i = np.arange(length, dtype=np.float32)
+    omega = np.float32(2.0) * np.float32(np.pi) / np.float32(buffer_rate) * np.float32(frequency)
+    wave = np.sin(omega * i, dtype=np.float32)
+    for k in range(0, length, buffer_length):
+        src = c.create_buffer_source(pkg.AudioBuffer([wave[k:k + buffer_length].copy()], buffer_rate))
+        src.connect(c.destination())
+        src.start_at(k / buffer_rate)
+    omega = np.float32(2.0) * np.float32(np.pi) / np.float32(sample_rate) * np.float32(frequency)
+    want = np.sin(omega * i, dtype=np.float32)
+    got = c.start_rendering_sync().get_channel_data(0)
+    assert np.abs(got - want).max() <= threshold

@@ -730,6 +730,14 @@ WAE_API wae_status wae_buffer_source_set_buffer(wae_graph* g, wae_node_id node, 
     if (!n || !buffer) return fail(WAE_INVALID_ARGUMENT, "not an AudioBufferSourceNode / null buffer");
     if (n->buffer) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign buffer twice");
     n->buffer = copy_buffer(buffer);
+    // "if start called and buffer is null, should fire ended event and ignore any subsequent buffer assignment"
+    // (audio_buffer_source.rs:443-451): a source that was started before the last suspend point and has been rendered without a
+    // buffer since has ended for good
+    if (!g->epochs.empty()) {
+        const auto& before = g->epochs.back().nodes;
+        auto pi = before.find(node);
+        if (pi != before.end() && pi->second.has_start && !pi->second.buffer) n->start_time = 1.7976931348623157e308;
+    }
     return WAE_OK;
 }
 
