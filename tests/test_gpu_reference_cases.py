@@ -165,3 +165,10 @@ def test_graph_built_with_setters_on_gpu(pkg, engine, oracle):
 @pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
 def test_buffer_source_setters_on_gpu(pkg, engine):
     NS.test_buffer_source_configured_the_way_the_reference_examples_do(pkg, engine.backend)
+
+
+@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
+@pytest.mark.parametrize("rates", [(44100.0, 44100.0, 9.0957e-5), (44100.0, 43800.0, 3.8986e-3)])
+def test_buffer_source_stitching_on_gpu(pkg, engine, rates):
+    A.test_construct_with_options_and_run(pkg, engine.backend)
+    A.test_subsample_buffer_stitching(pkg, engine.backend, *rates)
