@@ -246,3 +246,16 @@ def test_planner_accepts_random_graphs(pkg, be, block):
     for seed in range(1000 + 40 * block, 1000 + 40 * (block + 1)):
         p = plan(pkg, [F.random_graph(pkg, be, seed)])
         assert 1 <= p["stages"] <= 400 and p["segments"] >= 1 and p["chunk_frames"] >= 128, seed
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_the_checker_renders_the_same_random_graphs(pkg, oracle, block):
+    # the oracle side of the fuzz pairs: 4 x 20 of the graphs above rendered on the CPU — finite, not silent, reproducible
+    import test_gpu_fuzz as F
+    for seed in range(1000 + 20 * block, 1000 + 20 * (block + 1)):
+        a = F.random_graph(pkg, oracle, seed).start_rendering_sync()
+        pcm = np.array([a.get_channel_data(0), a.get_channel_data(1)])
+        assert np.isfinite(pcm).all(), seed
+        if seed % 10 == 0:
+            b = F.random_graph(pkg, oracle, seed).start_rendering_sync()
+            assert np.array_equal(pcm[0], b.get_channel_data(0)) and np.array_equal(pcm[1], b.get_channel_data(1))
