@@ -414,8 +414,7 @@ WAE_API wae_status wae_resample_linear(wae_engine* engine, const float* in, uint
                                        uint64_t out_cap, uint64_t* out_len);
 
 /* What wae_batch_prepare would lower `graphs` to, computed on the host only (no engine, no device, default engine options): the planner's
- * sizing pass.  Errors are the ones prepare would report (WAE_UNSUPPORTED for what is not lowered, WAE_INVALID_ARGUMENT ...), except
- * the refusal of a ConvolverNode inside a DelayNode feedback loop, which only the full planning pass detects. */
+ * sizing pass.  Errors are the ones prepare would report (WAE_UNSUPPORTED for what is not lowered, WAE_INVALID_ARGUMENT ...). */
 typedef struct wae_plan_info {
     uint32_t groups;                 /* graph groups of the H2D / render / D2H pipeline                                  */
     uint32_t segments;               /* render segments over all groups (1 per group without wae_graph_suspend points)    */

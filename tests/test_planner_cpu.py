@@ -62,7 +62,7 @@ def test_every_reference_benchmark_scenario_is_lowered(pkg, be, name, build):
         assert p["kinds"] == {"k_chain": 1}
 
 
-def test_feedback_loop_is_scheduled(pkg, be):
+def test_feedback_loop_is_scheduled_and_a_convolver_inside_it_is_refused(pkg, be):
     def echo(with_conv):
         c = pkg.OfflineAudioContext(2, RQ * 16, 48000.0, be)
         src = c.create_constant_source()
@@ -82,9 +82,9 @@ def test_feedback_loop_is_scheduled(pkg, be):
 
     p = plan(pkg, [echo(False)])
     assert p["has_feedback"] and "k_delay_read" in p["kinds"] and "k_ring_write" in p["kinds"]
-    # a ConvolverNode inside the loop is refused by the full planning pass only (it needs the final scheduling classes): the sizing
-    # pass accepts it; tests/test_gpu_parity.py::test_unsupported_is_reported_not_faked checks the refusal on the GPU
-    assert plan(pkg, [echo(True)])["has_feedback"]
+    with pytest.raises(pkg.WaeError) as e:  # a ConvolverNode inside the loop is not lowered
+        plan(pkg, [echo(True)])
+    assert e.value.status == 4 and "feedback cycle" in str(e.value)
 
 
 def test_suspend_points_cut_the_render_into_segments(pkg, be):

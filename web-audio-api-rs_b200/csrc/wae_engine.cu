@@ -543,7 +543,7 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
 bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
-    if (!dry && n.buffer && cur_cls == 1)
+    if (n.buffer && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
         return bail(WAE_UNSUPPORTED, "a ConvolverNode inside a DelayNode feedback cycle is not lowered to the GPU (before or after the cycle it is)");
     if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
         pn.out_ch = {in_ch};
