@@ -3,7 +3,8 @@
  *   gcc -std=c99 -Iinclude examples/c_client.c -Lweb-audio-api-rs_b200 -lwae_b200 -Wl,-rpath,$PWD/web-audio-api-rs_b200 -lm -o c_client
  *
  * Builds N OfflineAudioContexts (Oscillator -> BiquadFilter(lowpass) -> Gain -> destination, the graph of tests/offline.rs with a
- * gain), renders them with ONE wae_render_batch call into host memory and prints the RMS of every render.
+ * gain) WITHOUT a device (graph construction is host work), asks the library what it would lower them to (wae_batch_plan, host only),
+ * then creates the engine, renders them with ONE wae_render_batch call into host memory and prints the RMS of every render.
  * Exit code: 0 = rendered, 2 = no usable CUDA device (the library has no CPU fallback and says so), 1 = any other error. */
 #include <math.h>
 #include <stdio.h>
@@ -24,12 +25,9 @@
 int main(int argc, char** argv) {
     const uint32_t n_graphs = argc > 1 ? (uint32_t)atoi(argv[1]) : 4;
     const uint64_t length = 48000; /* 1 s at 48 kHz */
-    wae_engine* engine = NULL;
-    CHECK(wae_engine_create(0, &engine));
-
     wae_graph** graphs = (wae_graph**)calloc(n_graphs, sizeof(wae_graph*));
     for (uint32_t g = 0; g < n_graphs; g++) {
-        CHECK(wae_graph_create(engine, 2, length, 48000.f, &graphs[g]));
+        CHECK(wae_graph_create(NULL, 2, length, 48000.f, &graphs[g]));
         wae_oscillator_options osc;
         memset(&osc, 0, sizeof osc);
         osc.type = WAE_OSC_SAWTOOTH;
@@ -59,6 +57,13 @@ int main(int argc, char** argv) {
         CHECK(wae_source_start(graphs[g], osc_id, 0.0, 0.0, 0.0));
     }
 
+    wae_plan_info plan;
+    CHECK(wae_batch_plan(graphs, n_graphs, &plan));
+    printf("plan: %u stage(s) per chunk [%s], %llu chunk(s) of %llu frames\n", plan.stages, plan.stage_kinds, (unsigned long long)plan.chunks,
+           (unsigned long long)plan.chunk_frames);
+
+    wae_engine* engine = NULL;
+    CHECK(wae_engine_create(0, &engine));
     float* pcm = (float*)malloc((size_t)n_graphs * 2 * length * sizeof(float)); /* [graph][channel][frame] */
     CHECK(wae_render_batch(engine, graphs, n_graphs, pcm, WAE_RENDER_OUT_HOST));
     for (uint32_t g = 0; g < n_graphs; g++) {

@@ -84,6 +84,8 @@ def test_plain_c_client_links_and_fails_loudly_without_a_gpu(pkg, tmp_path):
     ge.build()
     exe = build_c_client(tmp_path)
     r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=120)
+    # planned on the host, before any device is touched: oscillator -> biquad fused, the gain is automated (ramp): param track + gain + mix
+    assert "plan: 4 stage(s) per chunk [k_mix x 1, k_gain x 1, k_chain x 1, k_param x 1], 1 chunk(s) of 48000 frames" in r.stdout
     if torch.cuda.is_available():
         assert r.returncode == 0, r.stderr
     else:
