@@ -1050,6 +1050,8 @@ WAO_API void wao_iir_frequency_response(const double* ff, uint32_t nff, const do
                                         const float* freq_hz, float* mag, float* phase, uint32_t n) {
     iir_frequency_response(std::vector<double>(ff, ff + nff), std::vector<double>(fb, fb + nfb), sample_rate, freq_hz, mag, phase, (int)n);
 }
+WAO_API float wao_db_to_lin(float v) { return compressor_db_to_lin(v); }
+WAO_API float wao_lin_to_db(float v) { return compressor_lin_to_db(v); }
 WAO_API void wao_blackman(uint32_t size, float* out) {
     auto w = generate_blackman(size);
     std::memcpy(out, w.data(), size * sizeof(float));

@@ -278,6 +278,9 @@ bool StereoPannerRenderer::process(std::vector<Quantum>& inputs, std::vector<Qua
 // dynamics_compressor.rs:13-27
 static inline float db_to_lin(float v) { return powf(10.0f, v / 20.f); }
 static inline float lin_to_db(float v) { return v == 0.f ? -1000.f : 20.f * log10f(v); }
+// test hooks for dynamics_compressor.rs:565-581 (test_db_to_lin / test_lin_to_db)
+float compressor_db_to_lin(float v) { return db_to_lin(v); }
+float compressor_lin_to_db(float v) { return lin_to_db(v); }
 
 // dynamics_compressor.rs:330-478
 bool DynamicsCompressorRenderer::process(std::vector<Quantum>& inputs, std::vector<Quantum>& outputs, const ParamValues& params, const Scope& scope) {

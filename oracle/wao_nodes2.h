@@ -21,6 +21,8 @@ struct WaveShaperRenderer : Processor {
     bool process(std::vector<Quantum>&, std::vector<Quantum>&, const ParamValues&, const Scope&) override;
     const char* name() const override { return "WaveShaperRenderer"; }
 };
+float compressor_db_to_lin(float v);  // dynamics_compressor.rs:13-19
+float compressor_lin_to_db(float v);  // :21-27
 float waveshaper_apply_curve(const std::vector<float>& curve, float input);  // :555-572
 
 // ---- DelayWriter / DelayReader, src/node/delay.rs:376-743 --------------------------------------------------

@@ -244,6 +244,8 @@ class Api:
             f("analyser_get_byte_time_domain_data", C.c_int32, [gp, C.c_uint32, C.POINTER(C.c_uint8), C.c_uint32])
             f("compressor_reduction", C.c_int32, [gp, C.c_uint32, c_float_p])
             f("blackman", None, [C.c_uint32, c_float_p])
+            f("db_to_lin", C.c_float, [C.c_float])
+            f("lin_to_db", C.c_float, [C.c_float])
             f("set_hrir_sphere", C.c_int32, [C.c_void_p, C.c_uint64])
             f("hrtf_locate", C.c_int32, [c_float_p, C.POINTER(C.c_uint32), C.c_uint32, c_float_p, C.POINTER(C.c_uint32), c_float_p])
             f("convolver_normalize", C.c_float, [C.POINTER(AudioBufferDesc)])
