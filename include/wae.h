@@ -299,6 +299,10 @@ WAE_API wae_status wae_param_sim_create(uint32_t a_rate, float default_value, fl
 WAE_API wae_status wae_param_sim_destroy(wae_param_sim* sim);
 WAE_API wae_status wae_param_sim_push(wae_param_sim* sim, const wae_param_event* event);
 WAE_API wae_status wae_param_sim_set_automation_rate(wae_param_sim* sim, uint32_t a_rate);
+/* which implementation of the state machine wae_param_sim_compute runs: 0 = the one the default kernel runs (csrc/wae_param_core.h),
+ * 1 / 2 = the sink-based walker with its serial / recording sink (csrc/wae_param_walk.h; the recording sink is what the opt-in parallel
+ * param kernel uses) */
+WAE_API wae_status wae_param_sim_set_walker(wae_param_sim* sim, uint32_t walker);
 WAE_API wae_status wae_param_sim_compute(wae_param_sim* sim, double block_time, double dt, uint32_t count, float* out, uint32_t* len);
 
 /* OfflineAudioContext::suspend_sync(suspend_time, callback) (src/context/offline.rs:330-387): call this, then run the

@@ -26,7 +26,7 @@ static inline float set_target_sample(double start_time, double time_constant, f
 static inline float value_curve_sample(double start_time, double duration, const std::vector<float>& values, double time) {
     if (time - start_time >= duration) return values[values.size() - 1];
     double position = (double)(values.size() - 1) * (time - start_time) / duration;
-    size_t k = (size_t)position;
+    size_t k = position > 0. ? (size_t)position : 0;  // Rust's `as usize` saturates: a time before the curve's start (negative position) -> 0
     float phase = (float)(position - std::floor(position));
     return std::fma(values[k + 1] - values[k], phase, values[k]);
 }

@@ -67,13 +67,25 @@ class Sim:
         self.api.param_sim_destroy(self.h)
 
 
-@pytest.fixture
-def sim(host_api, pkg):
-    api = host_api
+@pytest.fixture(params=["oracle", "engine", "engine-walk-serial", "engine-walk-record"])
+def sim(request, pkg, oracle):
+    """oracle | the library's param_compute_buffer (what the default kernel and the suspend replay run) | the sink-based walker of
+    csrc/wae_param_walk.h with its serial sink and with the recording sink (what the opt-in parallel param kernel uses)."""
+    import os
+    if request.param == "oracle":
+        api = oracle.api
+    else:
+        so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+        if not os.path.exists(so):
+            pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
+        api = pkg.api()
+    walker = {"engine-walk-serial": 1, "engine-walk-record": 2}.get(request.param, 0)
     made = []
 
     def make(rate, default, mn, mx):
         s = Sim(api, rate, default, mn, mx, pkg)
+        if walker:
+            api.check(api.param_sim_set_walker(s.h, walker))
         made.append(s)
         return s
 
@@ -399,3 +411,73 @@ def test_full_block_ramp_from_set_value(sim):  # :3503-3528 (the intrinsic half 
     p._push(0, 128.0)  # SetValue: stored unclamped, clamped only in mix_to_output
     p.linear(0.0, 128.0)
     eq(p.run(0.0, 128), 128.0 - np.arange(128, dtype=np.float32))
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_the_walker_is_bit_identical_to_the_kernel_code_on_random_timelines(pkg, seed):
+    """csrc/wae_param_walk.h (serial and recording sinks) vs csrc/wae_param_core.h::param_compute_buffer on random event timelines, 128-frame
+    quanta at 48 kHz, events pushed before and during the render: every block, bit for bit (the oracle is compared at f32 resolution)."""
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built")
+    api = pkg.api()
+    rng = np.random.default_rng(seed)
+    sims = []
+    for walker in (0, 1, 2):
+        s = Sim(api, A if seed % 3 else K, 0.5, -10.0, 10.0, pkg)
+        api.check(api.param_sim_set_walker(s.h, walker))
+        sims.append(s)
+    dt, t_end = 1.0 / 48000.0, 60 * 128 / 48000.0
+
+    # identical argument streams: draw once, apply to all three
+    def push_same(t_from):
+        kind = int(rng.integers(7))
+        t = float(rng.uniform(t_from, t_end))
+        v = float(rng.uniform(0.05, 2.0))
+        tc = float(rng.integers(1, 40)) * 1e-4
+        curve = rng.uniform(0.0, 1.0, 5).astype(np.float32)
+        dur = float(rng.uniform(1e-3, 6e-3))
+        for s in sims:
+            try:
+                [lambda: s.set_value_at_time(v, t), lambda: s.linear(v, t), lambda: s.exponential(v, t), lambda: s.target(v, t, tc),
+                 lambda: s.curve(curve, t, dur), lambda: s.cancel_and_hold(t), lambda: s.cancel(t)][kind]()
+            except pkg.WaeError:
+                pass
+
+    for _ in range(int(rng.integers(3, 9))):
+        push_same(0.0)
+    for q in range(60):
+        if rng.random() < 0.15:
+            push_same(q * 128 * dt)
+        outs = []
+        for s in sims:
+            try:
+                outs.append(s.run(q * 128 * dt, 128, dt))
+            except pkg.WaeError:
+                outs.append(None)
+        if outs[0] is None:
+            assert outs[1] is None and outs[2] is None
+            break
+        assert outs[1] is not None and outs[2] is not None
+        assert np.array_equal(outs[0], outs[1], equal_nan=True) and np.array_equal(outs[0], outs[2], equal_nan=True), (seed, q)
+    for s in sims:
+        s.close()
+
+
+def test_a_pending_value_curve_is_sampled_before_its_start(sim):
+    # Found by the fuzz above.  When an event ends inside a block and the next one is a value curve that starts LATER, compute_buffer
+    # still visits the curve branch and leaves compute_set_value_curve_sample(next_block_time) in the intrinsic value (param.rs:1429-1498):
+    # the position on the curve is negative there, Rust's `as usize` saturates it to segment 0 and the phase is the fractional part of the
+    # negative position.  (A C cast would index before the curve.)
+    p = sim(K, 0.0, -10.0, 10.0)
+    p.set_value_at_time(1.0, 0.0)
+    p.linear(2.0, 5.0)                                   # ends inside the first block of 10 frames
+    values = np.array([0.25, 0.75, 0.5], np.float32)
+    p.curve(values, 25.0, 10.0)                          # starts two blocks later
+    eq(p.run(0.0), [0.0])                                # k-rate: the value the block started with
+    position = (len(values) - 1) * (10.0 - 25.0) / 10.0  # at next_block_time = 10
+    phase = F(position - np.floor(position))
+    want = F(values[1] - values[0]) * phase + values[0]
+    eq(p.run(10.0), [want], 1e-7)                        # the k-rate value of the second block is what the first block left behind
+    eq(p.run(20.0), [F(values[1] - values[0]) * F((2 * (20.0 - 25.0) / 10.0) - np.floor(2 * (20.0 - 25.0) / 10.0)) + values[0]], 1e-7)

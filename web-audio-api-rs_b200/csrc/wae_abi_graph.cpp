@@ -6,6 +6,7 @@
 #include "wae_hrtf_host.h"
 #include "wae_param_core.h"
 #include "wae_param_host.h"
+#include "wae_param_walk.h"
 
 #include <algorithm>
 #include <cmath>
@@ -549,7 +550,13 @@ struct wae_param_sim {
     ParamTimeline tl;
     ParamState st{};
     bool started = false;
+    uint32_t walker = 0;  // 0: param_compute_buffer (what the kernel runs); 1 / 2: param_walk with the serial / the recording sink
 };
+WAE_API wae_status wae_param_sim_set_walker(wae_param_sim* s, uint32_t walker) {
+    if (!s || walker > 2) return fail(WAE_INVALID_ARGUMENT, "unknown walker");
+    s->walker = walker;
+    return WAE_OK;
+}
 WAE_API wae_status wae_param_sim_create(uint32_t a_rate, float default_value, float min_value, float max_value, wae_param_sim** out) {
     auto* s = new wae_param_sim;
     s->prm.default_value = default_value;
@@ -604,7 +611,19 @@ WAE_API wae_status wae_param_sim_compute(wae_param_sim* s, double block_time, do
     host.a_rate = s->prm.a_rate ? 1 : 0;
     host.sample_rate = (float)(1. / dt);
     float buf[128];
-    const int n = param_compute_buffer(host, s->st, block_time, buf, (int)count);
+    int n;
+    if (s->walker == 1) {
+        SerialSink sink{buf, 1. / (double)host.sample_rate};
+        n = param_walk(host, s->st, block_time, sink, (int)count);
+    } else if (s->walker == 2) {
+        RecordSink sink;
+        sink.buf = buf;
+        sink.dt = 1. / (double)host.sample_rate;
+        n = param_walk(host, s->st, block_time, sink, (int)count);
+        sink.finish();
+    } else {
+        n = param_compute_buffer(host, s->st, block_time, buf, (int)count);
+    }
     for (int i = 0; i < n; i++) out[i] = buf[i];
     *len = (uint32_t)n;
     return WAE_OK;

@@ -1,56 +1,106 @@
-// AudioParamProcessor::compute_buffer (src/param.rs:1038-1600) — the per-quantum event state machine of one AudioParam:
-// set_value / linear & exponential ramps / setTarget with snap-to-target / value curves / cancel_and_hold over the
-// host-prepared timeline.  Shared by the device (k_param: one thread per automated param) and the host (the planner replays
-// it up to a suspend point to learn the render-side state new events are inserted against, wae_engine.cu).
+// The AudioParam state machine of wae_param_core.h with the per-frame fill loops turned into calls on a sink.
+//
+// Why: in every branch of AudioParamProcessor::compute_buffer (src/param.rs:1093-1498) the intrinsic value left behind is a closed form
+// of the event (its value at next_block_time / end_time / the target) and never the last frame the fill loop produced, so the walk
+// over the events is cheap and serial while the 128 frame values of a quantum are independent of each other.  A sink that records the
+// fills lets a warp evaluate them in parallel (k_param_parallel, off by default: WAE_OPT_PARAM_PARALLEL); a sink that evaluates them on
+// the spot reproduces param_compute_buffer.  Frame times are the reference's running sum (`time += dt` from the fill's first frame), so
+// a lane that starts at frame i re-accumulates i - first additions and gets bit-identical times.
+//
+// STATUS: the walker and both sinks are exercised on the host by the reference's param.rs tests (tests/test_param_timeline.py, third
+// implementation "engine-walk"); the kernel that uses the recording sink has NOT run on a GPU yet — it is opt-in until it has
+// (NEXT.md item 1).  param_compute_buffer stays the code the default k_param kernel and the suspend replay run.
 #pragma once
-#include "../../include/wae.h"
-#include "wae_device.h"
-#include "wae_spatial.h"  // WAE_HD
-
-#include <cmath>
+#include "wae_param_core.h"
 
 namespace wae {
 
-struct ParamCursor {
-    const ParamInst& p;
-    ParamState& s;
-    WAE_HD bool empty() const { return s.head >= p.n_events; }
-    WAE_HD ParamEvDev peek() const { return s.override_valid ? s.override_ev : p.events[s.head]; }
-    WAE_HD bool has_next() const { return s.head + 1 < p.n_events; }
-    WAE_HD ParamEvDev next() const { return p.events[s.head + 1]; }
-    WAE_HD ParamEvDev pop() {
-        ParamEvDev e = peek();
-        s.head++;
-        s.override_valid = 0;
-        return e;
+enum { PF_CONST = 0, PF_LINEAR = 1, PF_EXP = 2, PF_TARGET = 3, PF_CURVE = 4 };
+struct ParamFill {       // frames [first, last) of the quantum
+    int first, last, kind, n;
+    float a, b, pre;     // ramps: v0, k | target: v1, diff, value before the start time | curve: pre = value before the start time
+    double t0, d;        // ramps: start time, duration | target: start time, time constant | curve: start time, duration
+    double time0;        // time of frame `first`
+    const float* values; // curve
+};
+
+WAE_HD float param_fill_at(const ParamFill& f, double time) {
+    switch (f.kind) {
+        case PF_LINEAR: return par_linear(f.t0, f.d, f.a, f.b, time);
+        case PF_EXP: return par_exp(f.t0, f.d, f.a, f.b, time);
+        case PF_TARGET: return (time - f.t0 < 0.) ? f.pre : par_target(f.t0, f.d, f.a, f.b, time);
+        default: return time < f.t0 ? f.pre : par_curve(f.t0, f.d, f.values, f.n, time);
     }
-    WAE_HD void replace_peek(const ParamEvDev& e) {
-        s.override_ev = e;
-        s.override_valid = 1;
+}
+// frames [from, to) of a fill, from >= f.first: the time of `from` is re-accumulated from the fill's first frame
+WAE_HD void param_fill_range(const ParamFill& f, int from, int to, double dt, float* buf) {
+    double time = f.time0;
+    for (int i = f.first; i < from; i++) time += dt;
+    for (int i = from; i < to; i++) {
+        buf[i] = param_fill_at(f, time);
+        time += dt;
+    }
+}
+
+// evaluates every fill on the spot: param_walk<SerialSink> == param_compute_buffer
+struct SerialSink {
+    float* buf;
+    double dt;
+    WAE_HD void constant(int first, int last, float v) {
+        for (int i = first; i < last; i++) buf[i] = v;
+    }
+    WAE_HD void emit(const ParamFill& f) { param_fill_range(f, f.first, f.last, dt, buf); }
+    WAE_HD void ramp(int first, int last, bool lin, double t0, double dur, float v0, float k, double time0, double) {
+        emit(ParamFill{first, last, lin ? PF_LINEAR : PF_EXP, 0, v0, k, 0.f, t0, dur, time0, nullptr});
+    }
+    WAE_HD void target(int first, int last, double t0, double tau, float v1, float diff, float pre, double time0, double) {
+        emit(ParamFill{first, last, PF_TARGET, 0, v1, diff, pre, t0, tau, time0, nullptr});
+    }
+    WAE_HD void curve(int first, int last, double t0, double dur, const float* values, int n, float pre, double time0, double) {
+        emit(ParamFill{first, last, PF_CURVE, n, 0.f, 0.f, pre, t0, dur, time0, values});
+    }
+    WAE_HD void flush_subnormals(int len) {
+        for (int i = 0; i < len; i++)
+            if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
     }
 };
 
-WAE_HD float par_linear(double t0, double dur, float v0, float diff, double t) { return fmaf(diff, (float)((t - t0) / dur), v0); }
-WAE_HD float par_exp(double t0, double dur, float v0, float ratio, double t) { return v0 * powf(ratio, (float)((t - t0) / dur)); }
-WAE_HD float par_target(double t0, double tau, float v1, float diff, double t) { return fmaf(diff, (float)exp(-((t - t0) / tau)), v1); }
-WAE_HD float par_curve(double t0, double dur, const float* values, int n, double t) {
-    if (t - t0 >= dur) return values[n - 1];
-    double position = (double)(n - 1) * (t - t0) / dur;
-    int k = position > 0. ? (int)position : 0;  // Rust's `as usize` saturates: asked for a time before the curve starts -> segment 0
-    float phase = (float)(position - floor(position));
-    return fmaf(values[k + 1] - values[k], phase, values[k]);
-}
-WAE_HD int par_end_index(double end_time, double block_time, double dt, int count) {
-    double r = round(fmax(end_time - block_time, 0.) / dt);
-    if (!(r < 4.0e9)) return count;
-    int idx = (int)r;
-    return idx < count ? idx : count;
-}
+// writes the constant fills, records the computed ones (a quantum rarely holds more than two); when the record is full the fill is
+// evaluated on the spot like SerialSink does.  After the walk: evaluate fills[0..n) in parallel, then apply `flush` to buf[0..flush).
+struct RecordSink {
+    static constexpr int kMax = 4;
+    float* buf;
+    double dt;
+    ParamFill fills[kMax];
+    int n = 0;
+    int flush = 0;
+    WAE_HD void constant(int first, int last, float v) {
+        for (int i = first; i < last; i++) buf[i] = v;
+    }
+    WAE_HD void emit(const ParamFill& f) {
+        if (n < kMax) fills[n++] = f;
+        else param_fill_range(f, f.first, f.last, dt, buf);
+    }
+    WAE_HD void ramp(int first, int last, bool lin, double t0, double dur, float v0, float k, double time0, double) {
+        emit(ParamFill{first, last, lin ? PF_LINEAR : PF_EXP, 0, v0, k, 0.f, t0, dur, time0, nullptr});
+    }
+    WAE_HD void target(int first, int last, double t0, double tau, float v1, float diff, float pre, double time0, double) {
+        emit(ParamFill{first, last, PF_TARGET, 0, v1, diff, pre, t0, tau, time0, nullptr});
+    }
+    WAE_HD void curve(int first, int last, double t0, double dur, const float* values, int n_values, float pre, double time0, double) {
+        emit(ParamFill{first, last, PF_CURVE, n_values, 0.f, 0.f, pre, t0, dur, time0, values});
+    }
+    WAE_HD void flush_subnormals(int len) { flush = len > flush ? len : flush; }
+    // host-side completion (the kernel spreads this over the lanes)
+    WAE_HD void finish() {
+        for (int k = 0; k < n; k++) param_fill_range(fills[k], fills[k].first, fills[k].last, dt, buf);
+        for (int i = 0; i < flush; i++)
+            if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
+    }
+};
 
-
-// Fills buf with the intrinsic values of the quantum starting at block_time; returns how many were written: 1 (constant
-// / k-rate block) or `count` (128 in the render path; the reference's unit tests use shorter blocks).  Advances the state (events popped, last event, intrinsic value).
-WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block_time, float* buf, const int count = 128) {
+template <class Sink>
+WAE_HD int param_walk(const ParamInst& p, ParamState& st, double block_time, Sink& sink, const int count = 128) {
     ParamCursor tl{p, st};
     const double dt = 1. / (double)p.sample_rate;
     const double next_block_time = fma(dt, (double)count, block_time);
@@ -65,13 +115,18 @@ WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block
                                 ? e.time >= next_block_time
                                 : false;
     }
-    if (!p.a_rate || is_constant_block) buf[len++] = st.intrinsic;
+    if (!p.a_rate || is_constant_block) {
+        sink.constant(len, len + 1, st.intrinsic);
+        len++;
+    }
     if (!is_constant_block) {
         for (;;) {
             bool exit_loop;
             if (tl.empty()) {
-                if (p.a_rate)
-                    while (len < count) buf[len++] = st.intrinsic;
+                if (p.a_rate && len < count) {
+                    sink.constant(len, count, st.intrinsic);
+                    len = count;
+                }
                 exit_loop = true;
             } else {
                 ParamEvDev ev = tl.peek();
@@ -81,7 +136,10 @@ WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block
                         double time = ev.time == 0. ? block_time : ev.time;
                         if (p.a_rate) {
                             int e = par_end_index(time, block_time, dt, count);
-                            while (len < e) buf[len++] = st.intrinsic;
+                            if (e > len) {
+                                sink.constant(len, e, st.intrinsic);
+                                len = e;
+                            }
                         }
                         if (time > next_block_time) {
                             exit_loop = true;
@@ -116,14 +174,9 @@ WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block
                         if (p.a_rate) {
                             int e = par_end_index(end_time, block_time, dt, count);
                             if (e > len) {
-                                double time = fma((double)len, dt, block_time);
-                                float value = 0.f;
-                                while (len < e) {
-                                    value = lin ? par_linear(start_time, duration, v0, k, time) : par_exp(start_time, duration, v0, k, time);
-                                    buf[len++] = value;
-                                    time += dt;
-                                }
-                                st.intrinsic = value;
+                                // (the value the loop of compute_buffer leaves in `intrinsic_value` is overwritten below in every path)
+                                sink.ramp(len, e, lin, start_time, duration, v0, k, fma((double)len, dt, block_time), dt);
+                                len = e;
                             }
                         }
                         if (end_time >= next_block_time) {
@@ -171,23 +224,15 @@ WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block
                         if (p.a_rate) {
                             int e = par_end_index(end_time, block_time, dt, count);
                             if (e > len) {
-                                double time = fma((double)len, dt, block_time);
-                                float value = 0.f;
-                                while (len < e) {
-                                    value = (time - start_time < 0.) ? st.intrinsic : par_target(start_time, tau, v1, diff, time);
-                                    buf[len++] = value;
-                                    time += dt;
-                                }
-                                st.intrinsic = value;
+                                sink.target(len, e, start_time, tau, v1, diff, st.intrinsic, fma((double)len, dt, block_time), dt);
+                                len = e;
                             }
                         }
                         if (!ended) {
                             float value = par_target(start_time, tau, v1, diff, next_block_time);
                             if (fabsf(v1 - value) < 1e-10f) {  // SNAP_TO_TARGET, param.rs:22
                                 st.intrinsic = v1;
-                                if (v1 == 0.f)
-                                    for (int i = 0; i < len; i++)
-                                        if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
+                                if (v1 == 0.f) sink.flush_subnormals(len);
                                 ParamEvDev r{};
                                 r.type = WAE_EVENT_SET_VALUE_AT_TIME;
                                 r.time = next_block_time;
@@ -218,14 +263,8 @@ WAE_HD int param_compute_buffer(const ParamInst& p, ParamState& st, double block
                         if (p.a_rate) {
                             int e = par_end_index(end_time, block_time, dt, count);
                             if (e > len) {
-                                double time = fma((double)len, dt, block_time);
-                                float value = 0.f;
-                                while (len < e) {
-                                    value = time < start_time ? st.intrinsic : par_curve(start_time, duration, values, nv, time);
-                                    buf[len++] = value;
-                                    time += dt;
-                                }
-                                st.intrinsic = value;
+                                sink.curve(len, e, start_time, duration, values, nv, st.intrinsic, fma((double)len, dt, block_time), dt);
+                                len = e;
                             }
                         }
                         if (end_time >= next_block_time) {
