@@ -36,3 +36,24 @@ def test_criterion_bench_matches_the_oracle(pkg, engine, oracle, name, build):
     for ch in range(2):
         d = np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch))
         assert d.max() <= 1e-5, (name, ch, float(d.max()))
+
+
+AUTOMATED = ["Granular synthesis", "Synth (Sawtooth with Envelope)", "Substractive Synth", "Stereo panning with automation", "Sawtooth with automation"]
+
+
+@pytest.mark.xfail(strict=False, reason="k_param_parallel (WAE_OPT_PARAM_PARALLEL) was written after the round's GPU time was spent: not yet run on a B200")
+@pytest.mark.parametrize("name", AUTOMATED)
+def test_parallel_param_kernel_matches_the_oracle(pkg, engine, oracle, name):
+    """The opt-in AudioParam kernel (fills of a quantum evaluated by the whole warp, csrc/wae_param_walk.h) on the automation-heavy
+    scenarios of the reference's benchmark suite, against the oracle AND against the default kernel (bit for bit)."""
+    build = dict(BS.SCENARIOS)[name]
+    want = build(pkg, oracle, SECONDS).start_rendering_sync()
+    default = build(pkg, engine.backend, SECONDS).start_rendering_sync()
+    engine.set_option(pkg.OPT_PARAM_PARALLEL, 1)
+    try:
+        got = build(pkg, engine.backend, SECONDS).start_rendering_sync()
+    finally:
+        engine.set_option(pkg.OPT_PARAM_PARALLEL, 0)
+    for ch in range(want.number_of_channels()):
+        assert np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch)).max() <= 1e-5 * max(1.0, float(np.abs(want.get_channel_data(ch)).max()))
+        assert np.array_equal(got.get_channel_data(ch), default.get_channel_data(ch))

@@ -81,4 +81,4 @@ class Engine:
             self.handle = None
 
 
-OPT_CHUNK_FRAMES, OPT_FUSE, OPT_SERIAL_FILTERS, OPT_PIPELINE_GROUPS = 1, 2, 3, 4
+OPT_CHUNK_FRAMES, OPT_FUSE, OPT_SERIAL_FILTERS, OPT_PIPELINE_GROUPS, OPT_PARAM_PARALLEL = 1, 2, 3, 4, 5

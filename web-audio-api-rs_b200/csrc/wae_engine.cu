@@ -45,6 +45,7 @@ struct wae_engine {
     bool fuse = true;
     bool serial_filters = false;
     int pipeline_groups = 0;  // 0 = auto
+    bool param_parallel = false;  // WAE_OPT_PARAM_PARALLEL: k_param_parallel instead of k_param (opt-in until validated on hardware)
     float* d_sine = nullptr;
     wae::HrirSphere* sphere = nullptr;  // wae_engine_set_hrir_sphere
     float* d_sphere_ir = nullptr;
@@ -1809,6 +1810,7 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "pipeline groups must be in [0, 1024]");
             eng->pipeline_groups = (int)value;
             return WAE_OK;
+        case WAE_OPT_PARAM_PARALLEL: eng->param_parallel = value != 0; return WAE_OK;
         default: return fail(WAE_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -2182,7 +2184,7 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_BIQUAD:
             launch_biquad_serial((BiquadInst*)st.d_a, st.n, st.max_ch, ci, s);
             break;
-        case S_PARAM: launch_param((ParamInst*)st.d_a, st.n, ci, s); break;
+        case S_PARAM: launch_param((ParamInst*)st.d_a, st.n, ci, s, b->engine->param_parallel); break;
         case S_OSC_AR: launch_osc_arate((OscArInst*)st.d_a, st.n, ci, s); break;
         case S_ABSN_SLOW: launch_buffer_source_slow((AbsnSlowInst*)st.d_a, st.n, ci, s); break;
         case S_BIQUAD_AR: launch_biquad_arate((BiquadArInst*)st.d_a, st.n, st.max_ch, ci, s); break;

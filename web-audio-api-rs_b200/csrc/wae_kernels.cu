@@ -6,6 +6,7 @@
 // renderer whose arithmetic it reproduces; parity target is 1e-5 absolute on f32 PCM.
 #include "wae_kernels.h"
 #include "wae_param_core.h"
+#include "wae_param_walk.h"
 #include "../../include/wae.h"
 
 #include <cstdlib>
@@ -1861,6 +1862,85 @@ __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param(const ParamInst* __r
     if (lane == 0) *p.state = st;
 }
 
+// OPT-IN variant (WAE_OPT_PARAM_PARALLEL, off by default): lane 0 only WALKS the events of the quantum (wae_param_walk.h, recording sink:
+// constants are written, ramps / set-target / curves are recorded as fills), then the 32 lanes evaluate the recorded fills, 4 consecutive
+// frames each, re-accumulating `time += dt` from the fill's first frame so that the frame times are the reference's running sum.
+// NOT YET RUN ON A GPU (written after the round's GPU time was spent; the walker and the sink are tested on the host, the default stays
+// k_param): profiles/README.md r1_v explains what it is for, NEXT.md item 1 what is left (validate, then make it the default).
+__global__ void __launch_bounds__(32 * PARAM_WARPS) k_param_parallel(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ float s_buf[PARAM_WARPS][128];
+    __shared__ ParamFill s_fill[PARAM_WARPS][RecordSink::kMax];
+    __shared__ int s_meta[PARAM_WARPS][3];  // frames written (1 or 128), recorded fills, frames to flush subnormals in
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ii = blockIdx.x * PARAM_WARPS + w;
+    if (ii >= n_inst) return;
+    const ParamInst p = insts[ii];
+    ParamState st{};
+    if (lane == 0) {
+        st = *p.state;
+        if (!st.inited) {
+            st.intrinsic = p.intrinsic0;
+            st.head = 0;
+            st.has_last = p.has_last0;
+            st.last = p.last0;
+            st.override_valid = 0;
+            st.inited = 1;
+        }
+    }
+    float* out = chan(p.out, 0, ci);
+    float* single = chan(p.out, 1, ci);
+    const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
+    float* buf = s_buf[w];
+    const double dt = 1. / (double)p.sample_rate;  // the walker's own expression
+    auto fix = [&](float v) {
+        if (v != v) return p.def;
+        v = v > p.mn ? v : p.mn;
+        return v < p.mx ? v : p.mx;
+    };
+    for (int q0 = 0; q0 < ci.nf; q0 += 128) {
+        if (lane == 0) {
+            RecordSink sink;
+            sink.buf = buf;
+            sink.dt = dt;
+            const double block_time = (double)(ci.f0 + q0) / (double)p.sample_rate;
+            s_meta[w][0] = param_walk(p, st, block_time, sink);
+            for (int k = 0; k < sink.n; k++) s_fill[w][k] = sink.fills[k];
+            s_meta[w][1] = sink.n;
+            s_meta[w][2] = sink.flush;
+        }
+        __syncwarp();
+        const int len = s_meta[w][0], n_fills = s_meta[w][1], flush = s_meta[w][2];
+        for (int k = 0; k < n_fills; k++) {
+            const ParamFill f = s_fill[w][k];
+            const int from = f.first + 4 * lane, to = min(f.last, from + 4);  // a fill is at most 128 frames = 32 lanes x 4
+            if (from < to) param_fill_range(f, from, to, dt, buf);
+        }
+        __syncwarp();
+        for (int i = lane; i < flush; i += 32)
+            if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
+        __syncwarp();
+        if (len == 1 || !p.a_rate) {
+            const float value = buf[0];
+            if (!in || !p.a_rate) {
+                const float v = fix(value + (in ? in[q0] : 0.f));
+#pragma unroll
+                for (int i = lane; i < 128; i += 32) out[q0 + i] = v;
+                if (lane == 0) single[q0] = 1.f;
+            } else {
+#pragma unroll
+                for (int i = lane; i < 128; i += 32) out[q0 + i] = fix(in[q0 + i] + value);
+                if (lane == 0) single[q0] = 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int i = lane; i < 128; i += 32) out[q0 + i] = fix((in ? in[q0 + i] : 0.f) + buf[i]);
+            if (lane == 0) single[q0] = 0.f;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) *p.state = st;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Convolver — ConvolverRenderer (src/node/convolver.rs:343-490).  The reference runs fft-convolver's uniformly
 // partitioned overlap-save with 1024-frame partitions because it must answer every 128 frames; an offline batch has no
@@ -2358,8 +2438,9 @@ void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, 
 void launch_resample_linear(const float* in, int64_t len, float* out, int64_t target_len, cudaStream_t s) {
     k_resample_linear<<<(unsigned)((target_len + 255) / 256), 256, 0, s>>>(in, len, out, target_len);
 }
-void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s) {
-    k_param<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s, bool parallel_fills) {
+    if (parallel_fills) k_param_parallel<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
+    else k_param<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
 }
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_analyser<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
