@@ -439,6 +439,11 @@ WAE_API wae_status wae_batch_plan(wae_graph* const* graphs, uint32_t n_graphs, w
 WAE_API wae_status wae_periodic_wave_table(const float* real, const float* imag, uint32_t len, uint32_t disable_normalization, float* table,
                                            uint32_t table_len);
 
+/* Test hook: the scheduling clock start / stop times are lowered with.  The reference's renderers compare a start time with a time that is
+ * `frame / sample_rate` at the head of a quantum and then grows by `+= dt` per frame (oscillator.rs:511-557, constant_source.rs:231-246,
+ * audio_buffer_source.rs): the first frame at or after `time` under that clock, and its accumulated time. */
+WAE_API wae_status wae_sched_first_frame_at_or_after(float sample_rate, double time, int64_t* frame, double* frame_time);
+
 /* ---- attributes set after construction (the reference posts one control message per setter) --------------------------------
  * AudioBufferSourceNode::set_buffer (once; src/node/audio_buffer_source.rs:278-288), ConvolverNode::set_buffer (convolver.rs:259-317; the
  * normalisation is decided at this call from the current `normalize` attribute), WaveShaperNode::set_curve (once; waveshaper.rs:203-213),

@@ -99,3 +99,46 @@ def test_scheduled_source_state_machine(pkg, builder, kind):
     c, src = make()
     with pytest.raises(pkg.WaeError):
         src.start_at(-1.0)  # scheduled_source.rs:12-30 assert_valid_time_value / RangeError
+
+
+def test_scheduling_clock_against_a_replay_of_the_reference(pkg):
+    """Start / stop frames of every scheduled source come from csrc/wae_hostmath.h::SchedClock.  The reference never computes them: its
+    renderers compare the start time with a clock that is `current_frame / sample_rate` at the head of each quantum (thread.rs:357-360)
+    and grows by `+= dt` per frame inside it (oscillator.rs:511-557).  Replayed here literally in Python for 6000 random times."""
+    import ctypes as C
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built")
+    api = pkg.api()
+    rng = np.random.default_rng(5)
+    for i in range(6000):
+        sr = float(np.float32(rng.choice([8000.0, 22050.0, 44100.0, 48000.0, 96000.0, 12345.0])))
+        kind = i % 4
+        if kind == 0:
+            t = float(rng.uniform(0.0, 3.0))
+        elif kind == 1:
+            t = int(rng.integers(0, 120000)) / sr                     # exactly on a frame (as computed by a user: k / sr)
+        elif kind == 2:
+            t = int(rng.integers(0, 900)) * 128 / sr                  # exactly on a quantum boundary
+        else:
+            t = np.nextafter(int(rng.integers(1, 900)) * 128 / sr, rng.choice([0.0, 10.0]))  # one ulp off a boundary
+        dt = 1.0 / sr
+        # ---- literal replay
+        q = max(0, int(t * sr / 128) - 2)
+        want = None
+        while want is None:
+            now = (q * 128) / sr
+            if t >= now + dt * 128:                                    # `start_time >= next_block_time`: the block is skipped
+                q += 1
+                continue
+            for f in range(128):
+                if now >= t:
+                    want = (q * 128 + f, now)
+                    break
+                now += dt
+            else:
+                q += 1                                                  # not reached inside the block after all: the next block starts at/after it
+                want = (q * 128, (q * 128) / sr)
+        frame, ftime = C.c_int64(), C.c_double()
+        api.check(api.sched_first_frame_at_or_after(sr, float(t), C.byref(frame), C.byref(ftime)))
+        assert (frame.value, ftime.value) == want, (sr, t, frame.value, want)

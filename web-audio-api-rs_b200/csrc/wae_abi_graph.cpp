@@ -734,6 +734,16 @@ WAE_API wae_status wae_periodic_wave_table(const float* real, const float* imag,
     return WAE_OK;
 }
 
+// Test hook for the scheduling clock every AudioScheduledSourceNode is lowered with (csrc/wae_hostmath.h SchedClock): the first frame
+// whose time, accumulated the way the reference's renderers do (block time = frame / sample_rate, then `+= dt` per frame inside the
+// quantum that contains `time`), is >= `time`; *frame_time = that accumulated time.
+WAE_API wae_status wae_sched_first_frame_at_or_after(float sample_rate, double time, int64_t* frame, double* frame_time) {
+    if (!frame || !frame_time || !(sample_rate > 0.f)) return fail(WAE_INVALID_ARGUMENT, "null / bad argument");
+    hostmath::SchedClock clock(sample_rate);
+    *frame = clock.first_frame_at_or_after(time, frame_time);
+    return WAE_OK;
+}
+
 // ---- node attributes set after construction (the reference posts a control message per setter) ------------------------------
 namespace {
 Node* node_of_kind(wae_graph* g, wae_node_id id, Kind kind) {
