@@ -444,6 +444,11 @@ WAE_API wae_status wae_periodic_wave_table(const float* real, const float* imag,
  * audio_buffer_source.rs): the first frame at or after `time` under that clock, and its accumulated time. */
 WAE_API wae_status wae_sched_first_frame_at_or_after(float sample_rate, double time, int64_t* frame, double* frame_time);
 
+/* Test hook: the spatial math of PannerNode as the planner and the moving-source kernels evaluate it (csrc/wae_spatial.h; panner.rs:927-986,
+ * spatial.rs:205-299).  v15 = source position, source orientation, listener position, forward, up; model6 = refDistance, maxDistance,
+ * rolloffFactor, coneInnerAngle, coneOuterAngle, coneOuterGain; out4 = distance gain, cone gain, azimuth, elevation (degrees). */
+WAE_API wae_status wae_spatial_params(uint32_t distance_model, const double* model6, const float* v15, float* out4);
+
 /* ---- attributes set after construction (the reference posts one control message per setter) --------------------------------
  * AudioBufferSourceNode::set_buffer (once; src/node/audio_buffer_source.rs:278-288), ConvolverNode::set_buffer (convolver.rs:259-317; the
  * normalisation is decided at this call from the current `normalize` attribute), WaveShaperNode::set_curve (once; waveshaper.rs:203-213),

@@ -757,6 +757,18 @@ WAO_API wae_status wao_periodic_wave_table(const float* real, const float* imag,
     return WAE_OK;
 }
 
+// test hook: PannerRenderer's gains and spatial::azimuth_and_elevation for one source / listener configuration (panner.rs:927-986, spatial.rs:205-299)
+WAO_API wae_status wao_spatial_params(uint32_t distance_model, const double* model6, const float* v15, float* out4) {
+    PannerRenderer r;
+    r.distance_model = (int)distance_model;
+    r.ref_distance = model6[0]; r.max_distance = model6[1]; r.rolloff_factor = model6[2];
+    r.cone_inner_angle = model6[3]; r.cone_outer_angle = model6[4]; r.cone_outer_gain = model6[5];
+    out4[0] = r.dist_gain(v15, v15 + 6);
+    out4[1] = r.cone_gain(v15, v15 + 3, v15 + 6);
+    azimuth_and_elevation(v15, v15 + 6, v15 + 9, v15 + 12, out4[2], out4[3]);
+    return WAE_OK;
+}
+
 static Analyser* find_analyser(wae_graph* g, wae_node_id node);
 // ---- node attributes set after construction: the onmessage handlers of the renderers ----------------------------------------
 // AudioBufferSourceNode::set_buffer (audio_buffer_source.rs:278-288, onmessage :856-872)

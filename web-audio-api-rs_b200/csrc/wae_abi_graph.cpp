@@ -744,6 +744,20 @@ WAE_API wae_status wae_sched_first_frame_at_or_after(float sample_rate, double t
     return WAE_OK;
 }
 
+// Test hook for the spatial math of PannerNode (csrc/wae_spatial.h, shared by the planner and the k_panner_dyn / k_hrtf_sel kernels):
+// v = source position xyz, source orientation xyz, listener position xyz, forward xyz, up xyz; model6 = refDistance, maxDistance,
+// rolloffFactor, coneInnerAngle, coneOuterAngle, coneOuterGain; out4 = distance gain, cone gain, azimuth, elevation (degrees)
+WAE_API wae_status wae_spatial_params(uint32_t distance_model, const double* model6, const float* v15, float* out4) {
+    if (!model6 || !v15 || !out4 || distance_model > 2) return fail(WAE_INVALID_ARGUMENT, "null / bad argument");
+    spatial::PanModel m{};
+    m.distance_model = (int32_t)distance_model;
+    m.ref_distance = model6[0]; m.max_distance = model6[1]; m.rolloff_factor = model6[2];
+    m.cone_inner_angle = model6[3]; m.cone_outer_angle = model6[4]; m.cone_outer_gain = model6[5];
+    const spatial::SpatialParams p = spatial::spatial_params(m, v15);
+    out4[0] = p.dist_gain; out4[1] = p.cone_gain; out4[2] = p.azimuth; out4[3] = p.elevation;
+    return WAE_OK;
+}
+
 // ---- node attributes set after construction (the reference posts a control message per setter) ------------------------------
 namespace {
 Node* node_of_kind(wae_graph* g, wae_node_id id, Kind kind) {
