@@ -449,6 +449,10 @@ WAE_API wae_status wae_sched_first_frame_at_or_after(float sample_rate, double t
  * rolloffFactor, coneInnerAngle, coneOuterAngle, coneOuterGain; out4 = distance gain, cone gain, azimuth, elevation (degrees). */
 WAE_API wae_status wae_spatial_params(uint32_t distance_model, const double* model6, const float* v15, float* out4);
 
+/* Test hook: the HRIR-sphere lookup of HRTF panning (the hrtf crate's ray / triangle query + barycentric weights): 1 when `dir` crosses a
+ * face; idx = its 3 vertices, weights = the blend weights of their impulse responses.  pos: [vertex][3], faces: 3 indices per face. */
+WAE_API int32_t wae_hrtf_locate(const float* pos, const uint32_t* faces, uint32_t n_faces, const float* dir, uint32_t* idx, float* weights);
+
 /* ---- attributes set after construction (the reference posts one control message per setter) --------------------------------
  * AudioBufferSourceNode::set_buffer (once; src/node/audio_buffer_source.rs:278-288), ConvolverNode::set_buffer (convolver.rs:259-317; the
  * normalisation is decided at this call from the current `normalize` attribute), WaveShaperNode::set_curve (once; waveshaper.rs:203-213),

@@ -154,7 +154,7 @@ WAE_SYMBOLS = [
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
     "wae_node_set_channel_count", "wae_node_set_channel_count_mode", "wae_node_set_channel_interpretation", "wae_graph_render_order", "wae_hrir_resample", "wae_batch_plan", "wae_buffer_source_set_buffer", "wae_convolver_set_buffer", "wae_wave_shaper_set_curve",
-    "wae_oscillator_set_periodic_wave", "wae_node_set_attribute", "wae_disconnect_from", "wae_disconnect_param", "wae_periodic_wave_table", "wae_param_sim_set_walker", "wae_sched_first_frame_at_or_after", "wae_spatial_params",
+    "wae_oscillator_set_periodic_wave", "wae_node_set_attribute", "wae_disconnect_from", "wae_disconnect_param", "wae_periodic_wave_table", "wae_param_sim_set_walker", "wae_sched_first_frame_at_or_after", "wae_spatial_params", "wae_hrtf_locate",
 ]
 
 
@@ -202,6 +202,7 @@ class Api:
         f("oscillator_set_periodic_wave", C.c_int32, [gp, C.c_uint32, c_float_p, C.c_uint32])
         f("node_set_attribute", C.c_int32, [gp, C.c_uint32, C.c_uint32, C.c_double])
         f("spatial_params", C.c_int32, [C.c_uint32, c_double_p, c_float_p, c_float_p])
+        f("hrtf_locate", C.c_int32, [c_float_p, C.POINTER(C.c_uint32), C.c_uint32, c_float_p, C.POINTER(C.c_uint32), c_float_p])
         f("periodic_wave_table", C.c_int32, [c_float_p, c_float_p, C.c_uint32, C.c_uint32, c_float_p, C.c_uint32])
         f("hrir_resample", C.c_int32, [c_float_p, C.c_uint32, C.c_double, c_float_p, C.c_uint32, C.POINTER(C.c_uint32)])
         for name in ("node_set_channel_count", "node_set_channel_count_mode", "node_set_channel_interpretation"):
@@ -251,7 +252,6 @@ class Api:
             f("db_to_lin", C.c_float, [C.c_float])
             f("lin_to_db", C.c_float, [C.c_float])
             f("set_hrir_sphere", C.c_int32, [C.c_void_p, C.c_uint64])
-            f("hrtf_locate", C.c_int32, [c_float_p, C.POINTER(C.c_uint32), C.c_uint32, c_float_p, C.POINTER(C.c_uint32), c_float_p])
             f("convolver_normalize", C.c_float, [C.POINTER(AudioBufferDesc)])
             f("resample_linear", C.c_uint64, [c_float_p, C.c_uint64, C.c_float, C.c_float, c_float_p, C.c_uint64])
             f("mix", None, [c_float_p, C.c_uint32, C.c_uint32, C.c_uint32, c_float_p])

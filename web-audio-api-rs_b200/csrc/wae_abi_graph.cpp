@@ -758,6 +758,13 @@ WAE_API wae_status wae_spatial_params(uint32_t distance_model, const double* mod
     return WAE_OK;
 }
 
+// Test hook: which sphere triangle a direction crosses and the barycentric weights of the hit (csrc/wae_spatial.h::hrir_locate, shared by
+// the planner for static panners and k_hrtf_sel for moving ones); returns 1 when a face is hit.
+WAE_API int32_t wae_hrtf_locate(const float* pos, const uint32_t* faces, uint32_t n_faces, const float* dir, uint32_t* idx, float* weights) {
+    if (!pos || !faces || !dir || !idx || !weights) return 0;
+    return spatial::hrir_locate(pos, faces, (int)n_faces, dir, idx, weights) ? 1 : 0;
+}
+
 // ---- node attributes set after construction (the reference posts a control message per setter) ------------------------------
 namespace {
 Node* node_of_kind(wae_graph* g, wae_node_id id, Kind kind) {
