@@ -1,5 +1,7 @@
 """The reference's benchmark suite (examples/benchmarks.rs, 24 scenarios) rendered by the CUDA engine and compared with the oracle
 sample by sample at the north_star tolerance (1e-5 absolute, f32)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -41,7 +43,9 @@ def test_criterion_bench_matches_the_oracle(pkg, engine, oracle, name, build):
 AUTOMATED = ["Granular synthesis", "Synth (Sawtooth with Envelope)", "Substractive Synth", "Stereo panning with automation", "Sawtooth with automation"]
 
 
-@pytest.mark.xfail(strict=False, reason="k_param_parallel (WAE_OPT_PARAM_PARALLEL) was written after the round's GPU time was spent: not yet run on a B200")
+# Device code that has never run on hardware is not executed by the default GPU run: a fault in it would poison the CUDA context for every
+# test after it.  First run: WAE_RUN_UNVALIDATED=1 python -m pytest tests/test_gpu_benchmark_scenarios.py -m gpu -k parallel_param
+@pytest.mark.skipif(not os.environ.get("WAE_RUN_UNVALIDATED"), reason="k_param_parallel has not run on a B200 yet: set WAE_RUN_UNVALIDATED=1 for its first run")
 @pytest.mark.parametrize("name", AUTOMATED)
 def test_parallel_param_kernel_matches_the_oracle(pkg, engine, oracle, name):
     """The opt-in AudioParam kernel (fills of a quantum evaluated by the whole warp, csrc/wae_param_walk.h) on the automation-heavy
