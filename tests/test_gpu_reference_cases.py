@@ -147,28 +147,3 @@ def test_resample_up_down_and_edges_on_gpu(pkg, engine):
 def test_resample_stereo_on_gpu(pkg, engine, source_sr):
     BU.check_resample_stereo(engine.resample, source_sr)
 
-
-# ---- post-construction setters (tests/test_node_setters.py): the library only records them in the graph description, the plan is
-# ---- proven identical on the CPU; the GPU render of the same graph was added after the round's GPU time was spent
-import test_node_setters as NS  # noqa: E402
-
-
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
-def test_graph_built_with_setters_on_gpu(pkg, engine, oracle):
-    import numpy as np
-    got = NS._variants(pkg, engine.backend, True).start_rendering_sync()
-    want = NS._variants(pkg, oracle, False).start_rendering_sync()
-    for ch in range(2):
-        assert np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch)).max() <= 1e-5
-
-
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
-def test_buffer_source_setters_on_gpu(pkg, engine):
-    NS.test_buffer_source_configured_the_way_the_reference_examples_do(pkg, engine.backend)
-
-
-@pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
-@pytest.mark.parametrize("rates", [(44100.0, 44100.0, 9.0957e-5), (44100.0, 43800.0, 3.8986e-3)])
-def test_buffer_source_stitching_on_gpu(pkg, engine, rates):
-    A.test_construct_with_options_and_run(pkg, engine.backend)
-    A.test_subsample_buffer_stitching(pkg, engine.backend, *rates)
