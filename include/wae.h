@@ -252,7 +252,7 @@ enum {
     WAE_OPT_FUSE = 2,           /* 1 (default): fuse source->filter->gain chains; 0: one stage/node */
     WAE_OPT_SERIAL_FILTERS = 3, /* 1: bit-faithful serial recurrences (thread per channel)          */
     WAE_OPT_PIPELINE_GROUPS = 4, /* graph groups of the H2D/render/D2H pipeline (0 = auto: 8)       */
-    WAE_OPT_PARAM_PARALLEL = 5   /* 1: AudioParam ramps / set-target / curves evaluated by the whole warp (opt-in, default 0) */
+    WAE_OPT_PARAM_PARALLEL = 5   /* 1 (default): AudioParam ramps / set-target / curves of a quantum evaluated by the whole warp; 0: by one lane */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
 /* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */

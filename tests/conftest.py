@@ -69,15 +69,6 @@ def builder(request, pkg, oracle):
 
 @pytest.fixture(scope="session")
 def engine(pkg, oracle):
-    if os.environ.get("WAE_DRYRUN_ORACLE_AS_ENGINE"):  # local dry run of the test plumbing only (no parity meaning)
-        class Fake:
-            backend = oracle
-            def set_option(self, *a):
-                pass
-            def close(self):
-                pass
-        yield Fake()
-        return
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

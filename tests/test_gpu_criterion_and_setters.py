@@ -1,9 +1,6 @@
-"""GPU tests written after the round's GPU time was spent: they have NOT run on a B200 yet.
-
-They live in a file that is collected last (a fault in a first run must not poison the CUDA context for the validated suite), they are
-non-strict xfails (pass or fail, the run stays green and `-rxX` shows which), and the one that launches device code that has never run at
-all is skipped unless WAE_RUN_UNVALIDATED=1.  NEXT.md item 6: run them, move what passes into the regular files."""
-import os
+"""GPU parity of the reference's criterion / iai benchmark graphs (benches/my_benchmark.rs), of graphs configured through the
+post-construction setters, of the WPT buffer-stitching case, and of the two AudioParam kernels against each other.
+(First run on a B200 in round 2: all green, profiles/README.md r2_a.)"""
 
 import numpy as np
 import pytest
@@ -13,11 +10,9 @@ import test_node_setters as NS
 import test_oracle_absn as A
 
 pytestmark = pytest.mark.gpu
-PENDING = pytest.mark.xfail(strict=False, reason="not yet run on a B200 (added after the round's GPU time was spent)")
 SECONDS = 3.0
 
 
-@PENDING
 @pytest.mark.parametrize("name,build", BS.CRITERION, ids=[n for n, _ in BS.CRITERION])
 def test_criterion_bench_matches_the_oracle(pkg, engine, oracle, name, build):
     """benches/my_benchmark.rs (criterion / iai), GPU vs oracle at 1e-5."""
@@ -33,7 +28,6 @@ def test_criterion_bench_matches_the_oracle(pkg, engine, oracle, name, build):
         assert d.max() <= 1e-5, (name, ch, float(d.max()))
 
 
-@PENDING
 def test_graph_built_with_setters_on_gpu(pkg, engine, oracle):
     # tests/test_node_setters.py: the library only records the setters in the graph description, the plan is proven identical on the CPU
     got = NS._variants(pkg, engine.backend, True).start_rendering_sync()
@@ -42,12 +36,10 @@ def test_graph_built_with_setters_on_gpu(pkg, engine, oracle):
         assert np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch)).max() <= 1e-5
 
 
-@PENDING
 def test_buffer_source_setters_on_gpu(pkg, engine):
     NS.test_buffer_source_configured_the_way_the_reference_examples_do(pkg, engine.backend)
 
 
-@PENDING
 @pytest.mark.parametrize("rates", [(44100.0, 44100.0, 9.0957e-5), (44100.0, 43800.0, 3.8986e-3)])
 def test_buffer_source_stitching_on_gpu(pkg, engine, rates):
     A.test_construct_with_options_and_run(pkg, engine.backend)
@@ -57,21 +49,19 @@ def test_buffer_source_stitching_on_gpu(pkg, engine, rates):
 AUTOMATED = ["Granular synthesis", "Synth (Sawtooth with Envelope)", "Substractive Synth", "Stereo panning with automation", "Sawtooth with automation"]
 
 
-# Device code that has never run on hardware is not executed by the default GPU run at all.
-# First run: WAE_RUN_UNVALIDATED=1 python -m pytest tests/test_zz_gpu_pending.py -m gpu -k parallel_param
-@pytest.mark.skipif(not os.environ.get("WAE_RUN_UNVALIDATED"), reason="k_param_parallel has not run on a B200 yet: set WAE_RUN_UNVALIDATED=1 for its first run")
 @pytest.mark.parametrize("name", AUTOMATED)
 def test_parallel_param_kernel_matches_the_oracle(pkg, engine, oracle, name):
-    """The opt-in AudioParam kernel (fills of a quantum evaluated by the whole warp, csrc/wae_param_walk.h) on the automation-heavy
-    scenarios of the reference's benchmark suite, against the oracle AND against the default kernel (bit for bit)."""
+    """The AudioParam kernel (fills of a quantum evaluated by the whole warp, csrc/wae_param_walk.h) on the automation-heavy
+    scenarios of the reference's benchmark suite, against the oracle AND against the serial kernel (lane 0 evaluates every frame;
+    WAE_OPT_PARAM_PARALLEL = 0), bit for bit."""
     build = dict(BS.SCENARIOS)[name]
     want = build(pkg, oracle, SECONDS).start_rendering_sync()
-    default = build(pkg, engine.backend, SECONDS).start_rendering_sync()
-    engine.set_option(pkg.OPT_PARAM_PARALLEL, 1)
+    got = build(pkg, engine.backend, SECONDS).start_rendering_sync()
+    engine.set_option(pkg.OPT_PARAM_PARALLEL, 0)
     try:
-        got = build(pkg, engine.backend, SECONDS).start_rendering_sync()
+        default = build(pkg, engine.backend, SECONDS).start_rendering_sync()
     finally:
-        engine.set_option(pkg.OPT_PARAM_PARALLEL, 0)
+        engine.set_option(pkg.OPT_PARAM_PARALLEL, 1)
     for ch in range(want.number_of_channels()):
         assert np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch)).max() <= 1e-5 * max(1.0, float(np.abs(want.get_channel_data(ch)).max()))
         assert np.array_equal(got.get_channel_data(ch), default.get_channel_data(ch))

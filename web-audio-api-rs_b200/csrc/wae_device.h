@@ -347,6 +347,27 @@ struct ChainInst {
     ChainBiquad bq[CHAIN_MAX_BIQUADS];
 };
 
+// k_chain work decomposition (see the kernel): time slabs handed out in ticket order, filter state handed from slab to slab
+constexpr int CHAIN_MAX_SLABS = 64;
+struct ChainSched {
+    int32_t n_slabs;         // time slabs per (instance, channel)
+    int32_t tiles_per_slab;  // whole 2048-frame tiles per slab
+    int32_t max_ch;          // channel slots per instance in the item numbering
+    int32_t slab_stride;     // hand-off slots per (instance, channel)
+    uint32_t epoch;          // launch number of this stage: the value a hand-off flag written by this launch carries
+    uint32_t pad;
+    unsigned* ticket;        // one counter per stage (zero between launches); nullptr: item = blockIdx.x
+    double* handoff;         // [(instance * max_ch + channel) * slab_stride + slab][CHAIN_MAX_BIQUADS][4]: state ENTERING the slab
+    unsigned* flags;         // same indexing: == epoch once that state is written
+};
+struct ChainAux {  // per-stage device memory of the slab hand-off (engine-owned)
+    unsigned* ticket = nullptr;
+    double* handoff = nullptr;
+    unsigned* flags = nullptr;
+    int32_t slab_stride = 0;
+    uint32_t epoch = 0;
+};
+
 // ---- convolver (uniformly partitioned overlap-save, block WAE_CONV_BLOCK, time-batched) -----------------
 struct ConvInput {   // one input channel of one convolver instance
     BufRef in;

@@ -45,7 +45,7 @@ struct wae_engine {
     bool fuse = true;
     bool serial_filters = false;
     int pipeline_groups = 0;  // 0 = auto
-    bool param_parallel = false;  // WAE_OPT_PARAM_PARALLEL: k_param_parallel instead of k_param (opt-in until validated on hardware)
+    bool param_parallel = true;  // WAE_OPT_PARAM_PARALLEL: k_param_parallel (the warp evaluates the fills of a quantum); 0: k_param (lane 0 evaluates every frame)
     float* d_sine = nullptr;
     wae::HrirSphere* sphere = nullptr;  // wae_engine_set_hrir_sphere
     float* d_sphere_ir = nullptr;
@@ -123,6 +123,7 @@ struct Stage {
     void* d_a = nullptr;  // instances
     void* d_b = nullptr;  // auxiliary table (mix edges, scan coefficients, conv inputs, panner gains)
     float ms = 0.f;       // accumulated device time of the last run (when timing is enabled)
+    ChainAux chain;       // S_CHAIN with biquads: ticket counter + slab hand-off slots (k_chain)
 };
 
 struct AnalyserRec {
@@ -2079,7 +2080,24 @@ static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32
                     case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
                     case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
                     case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
-                    case S_CHAIN: st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); break;
+                    case S_CHAIN: {
+                        st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef);
+                        const int nb = (s.variant % 6) / 2;
+                        int slabs = 1, tps = 1;
+                        if (nb > 0) chain_plan_slabs(st.n, st.max_ch, (int)std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start), nb, &slabs, &tps);
+                        if (slabs > 1) {  // time slabs of filtered chains hand their state over through device memory
+                            const size_t slots = (size_t)st.n * st.max_ch * slabs;
+                            st.chain.slab_stride = slabs;
+                            st.chain.ticket = b->dalloc<unsigned>(1, true);
+                            st.chain.flags = b->dalloc<unsigned>(slots, true);
+                            st.chain.handoff = b->dalloc<double>(slots * CHAIN_MAX_BIQUADS * 4);
+                            if (!st.chain.ticket || !st.chain.flags || !st.chain.handoff) {
+                                wae_batch_destroy(b);
+                                return fail(WAE_OUT_OF_MEMORY, "out of device memory (chain hand-off)");
+                            }
+                        }
+                        break;
+                    }
                     case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
                     case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
                     case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
@@ -2188,7 +2206,10 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_OSC_AR: launch_osc_arate((OscArInst*)st.d_a, st.n, ci, s); break;
         case S_ABSN_SLOW: launch_buffer_source_slow((AbsnSlowInst*)st.d_a, st.n, ci, s); break;
         case S_BIQUAD_AR: launch_biquad_arate((BiquadArInst*)st.d_a, st.n, st.max_ch, ci, s); break;
-        case S_CHAIN: launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s); break;
+        case S_CHAIN:
+            st.chain.epoch++;  // hand-off flags of this launch carry its number (never reset, never reused)
+            launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s, st.chain);
+            break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;
         case S_SHAPER: launch_shaper((ShaperInst*)st.d_a, st.n, ci, s); break;

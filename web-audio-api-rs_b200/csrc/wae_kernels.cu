@@ -9,6 +9,7 @@
 #include "wae_param_walk.h"
 #include "../../include/wae.h"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -772,6 +773,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     __syncthreads();
     // state entering this warp: chain the previous warps' totals through A^32
     double wa = sm.state[bq][2], wb = sm.state[bq][3];
+    const double in1 = wa, in2 = wb;  // state entering the tile (the serial replay below starts from it)
 #pragma unroll
     for (int k = 0; k < CH_WARPS - 1; k++) {
         if (k < warp) {
@@ -791,14 +793,55 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     // pass 2: the recurrence from the true state
     r1 = e1;
     r2 = e2;
+    unsigned mx = 0;  // largest |output| bit pattern of this thread: >= 0x7f800000 <=> an Inf / NaN came out
 #pragma unroll
     for (int j = 0; j < CH_K; j++) {
         const double y = fma(na1, r1, fma(na2, r2, w[j]));
         r2 = r1;
         r1 = y;
         v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
+        mx = max(mx, __float_as_uint(v[j]) & 0x7fffffffu);
     }
-    __syncthreads();  // everyone has read state / wtot / edge of this step
+    // (barrier: everyone has read state / wtot / edge of this step) + did any thread of the tile see a non-finite output?
+    const int any_bad = __syncthreads_or(active && mx >= 0x7f800000u);
+    if (any_bad) {
+        // Rare: a NaN / Inf reached the recurrence (a NaN in the source PCM, an unstable filter).  The reference flushes every
+        // non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`, biquad_filter.rs:881-883) and so recovers on the next
+        // sample, which no linear scan reproduces: replay this tile serially, thread after thread, from the tile's incoming state.
+        double s1 = in1, s2 = in2;
+#pragma unroll 1
+        for (int wv = 0; wv < CH_WARPS; wv++) {
+            if (warp == wv) {
+#pragma unroll 1
+                for (int l = 0; l < 32; l++) {
+                    double a = s1, b = s2;
+                    if (lane == l && active) {
+#pragma unroll
+                        for (int j = 0; j < CH_K; j++) {
+                            double y = fma(na1, a, fma(na2, b, w[j]));
+                            const double ay = fabs(y);
+                            if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+                            b = a;
+                            a = y;
+                            v[j] = (float)y;
+                        }
+                        r1 = a;
+                        r2 = b;
+                    }
+                    s1 = __shfl_sync(0xffffffffu, a, l);
+                    s2 = __shfl_sync(0xffffffffu, b, l);
+                }
+                if (lane == 31) {
+                    sm.wtot[0][0] = s1;
+                    sm.wtot[0][1] = s2;
+                }
+            }
+            __syncthreads();
+            s1 = sm.wtot[0][0];
+            s2 = sm.wtot[0][1];
+            __syncthreads();
+        }
+    }
     if (active && t == n_active - 1) {
         sm.state[bq][0] = (double)xl1;
         sm.state[bq][1] = (double)xl2;
@@ -807,14 +850,81 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     }
 }
 
-template <int SRC, int NB, bool SHAPER>
-__global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs, int n_inst,
-                                                     ChunkInfo ci) {
+// ---- Blackwell async-copy primitives used by the TMA variant of k_chain (1-D bulk copies, mbarrier completion) ----
+DEVI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+DEVI void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+DEVI void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DEVI void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// global -> shared, completion counted in bytes on `bar` (SASS: UBLKCP)
+DEVI void bulk_load(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-groups
+DEVI void bulk_store(void* gdst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+DEVI void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+DEVI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+DEVI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int CH_STAGES = 4;  // source tiles in flight per CTA (8 KB each)
+
+// conditional exchange of two 16-byte pieces (the un-permutation of the bank-conflict-free access order, see k_chain)
+DEVI void cswap4(bool p, float4& a, float4& b) {
+    const float4 ta = a, tb = b;
+    a.x = p ? tb.x : ta.x; a.y = p ? tb.y : ta.y; a.z = p ? tb.z : ta.z; a.w = p ? tb.w : ta.w;
+    b.x = p ? ta.x : tb.x; b.y = p ? ta.y : tb.y; b.z = p ? ta.z : tb.z; b.w = p ? ta.w : tb.w;
+}
+
+// Work decomposition.  A work item is (time slab, instance, channel); items are numbered slab-major and handed out in
+// order of CTA start (one atomic ticket per CTA), so the slab before a given one of the same (instance, channel) always
+// belongs to a CTA that is already running or done: waiting for the filter state it leaves behind cannot deadlock.
+// With S slabs the launch has S x more, S x shorter CTAs: the tail of the last wave (2000 equal CTAs on 888 slots used to
+// leave the machine a quarter full for a third of the run) shrinks to one short item.  Chains without a filter carry no
+// state: their slabs are independent.  TMA = true: the source tiles arrive through 1-D bulk copies (cp.async.bulk +
+// mbarrier), results leave through bulk stores; TMA = false: 16-byte cp.async pieces / coalesced stores (kept as the
+// reference data path: WAE_OPT_CHAIN_TMA = 0).
+template <int SRC, int NB, bool SHAPER, bool TMA>
+__global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
+                                                                        int n_inst, ChunkInfo ci, ChainSched sc) {
     __shared__ ChainSmem sm;
-    const int c = blockIdx.y;
+    __shared__ int s_item;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int item = (int)blockIdx.x;
+    if (NB > 0 && sc.ticket != nullptr) {
+        if (t == 0) {
+            const unsigned tk = atomicAdd(sc.ticket, 1u);
+            if (tk == gridDim.x - 1) atomicExch(sc.ticket, 0u);  // the last ticket of this launch: leave the counter ready for the next one
+            s_item = (int)tk;
+        }
+        __syncthreads();
+        item = s_item;
+    }
+    const int per_slab = n_inst * sc.max_ch;
+    const int slab = item / per_slab;
+    const int rem = item - slab * per_slab;
+    const int c = rem / n_inst;
+    const int inst = rem - c * n_inst;
     {
-        const int* src = reinterpret_cast<const int*>(insts + blockIdx.x);
+        const int* src = reinterpret_cast<const int*>(insts + inst);
         int* dst = reinterpret_cast<int*>(&sm.q);
         for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = src[i];
     }
@@ -832,74 +942,102 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
     }
     const ChainInst& q = sm.q;
     if (c >= q.ch) return;
-    // A chain without a filter carries nothing from tile to tile (the sources are closed forms of the frame index), so a launch
-    // with few chains but a long chunk is also split along time: gridDim.z slabs of whole tiles.  Filtered chains (NB > 0) carry
-    // their state through the chunk and are always launched with one slab.
-    int slab_begin = 0, slab_end = ci.nf;
-    if (NB == 0 && gridDim.z > 1) {
-        const int n_tiles = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
-        const int per = (n_tiles + (int)gridDim.z - 1) / (int)gridDim.z;
-        slab_begin = (int)blockIdx.z * per * (CH_THREADS * CH_K);
-        slab_end = min(ci.nf, slab_begin + per * (CH_THREADS * CH_K));
-        if (slab_begin >= ci.nf) return;
-    }
+    constexpr int tile = CH_THREADS * CH_K;
+    const int n_tiles = (ci.nf + tile - 1) / tile;
+    const int tile0 = slab * sc.tiles_per_slab;
+    if (tile0 >= n_tiles) return;
+    const int slab_begin = tile0 * tile;
+    const int slab_end = min(ci.nf, (tile0 + sc.tiles_per_slab) * tile);
+    const bool first_slab = slab == 0, last_slab = slab_end >= ci.nf;
+    const size_t ho = ((size_t)inst * sc.max_ch + c) * sc.slab_stride + slab;  // hand-off slot of the state ENTERING this slab
     // per-CTA constants -> registers / shared
     double cb[NB > 0 ? NB : 1][5];
     double plane[NB > 0 ? NB : 1][4];
+    if (NB > 0 && !first_slab) {  // the slab before this one (same instance, channel) publishes the state it ends with
+        if (t == 0) {
+            const unsigned* f = sc.flags + ho;
+            unsigned seen;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(f) : "memory");
+                if (seen == sc.epoch) break;
+                __nanosleep(256);
+            }
+        }
+        __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < NB; k++) {
         const ChainBiquad& bq = q.bq[k];
         cb[k][0] = bq.b0; cb[k][1] = bq.b1; cb[k][2] = bq.b2; cb[k][3] = bq.a1; cb[k][4] = bq.a2;
-        const ScanCoef& sc = coefs[bq.coef];
-        if (t < 20) sm.P[k][t] = (&sc.Pshfl[0][0])[t];
+        const ScanCoef& scf = coefs[bq.coef];
+        if (t < 20) sm.P[k][t] = (&scf.Pshfl[0][0])[t];
         if (t < 4) {
-            sm.P[k][20 + t] = sc.Pwarp[t];
-            sm.state[k][t] = bq.state[4 * c + t];
+            sm.P[k][20 + t] = scf.Pwarp[t];
+            sm.state[k][t] = first_slab ? bq.state[4 * c + t] : __ldcg(sc.handoff + ho * (CHAIN_MAX_BIQUADS * 4) + 4 * k + t);
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) plane[k][i] = lane > 0 ? sc.Plane[lane - 1][i] : 0.;
+        for (int i = 0; i < 4; i++) plane[k][i] = lane > 0 ? scf.Plane[lane - 1][i] : 0.;
     }
     const float g0 = q.g[0], g1 = q.g[1], g2 = q.g[2], g3 = q.g[3];
-    __syncthreads();
 
-    constexpr int tile = CH_THREADS * CH_K;
-    constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;  // PCM read from memory: prefetch with cp.async
-    // Per-warp staging of source / result frames, double buffered.  A warp owns 512 consecutive frames (2 KB) of the
-    // tile; global memory is touched with fully coalesced 512-byte warp accesses (lane l moves the 16-byte piece
-    // f = 32*u + l), while thread tt works on the contiguous pieces f = 4*tt + uu.  The XOR swizzle makes both
-    // access patterns conflict-free for 128-bit shared accesses.
+    constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;  // PCM read from memory: prefetched
+    constexpr bool USE_TMA = TMA && STREAMED;
+    constexpr int NST = STREAMED ? CH_STAGES : 1;
+    // Per-warp staging of source / result frames.  A warp owns 512 consecutive frames (2 KB) of the tile; global memory is
+    // touched with whole 2 KB regions (one bulk copy, or 4 coalesced 512-byte warp accesses), while thread tt works on the
+    // contiguous pieces f = 4*tt + uu.  cp.async path: an XOR swizzle makes both access patterns conflict-free for 128-bit
+    // shared accesses.  Bulk copies are linear, so there a thread visits its own four pieces in the order u ^ xq (conflict-free
+    // for the same reason) and puts them back in place with two conditional exchanges.
     constexpr int WF = 32 * CH_K / 4;  // float4 pieces per warp region (128)
-    __shared__ float4 s_io[2][CH_WARPS][WF];
+    __shared__ __align__(128) float4 s_io[NST][CH_WARPS][WF];
+    __shared__ __align__(8) uint64_t s_bar[USE_TMA ? NST : 1][CH_WARPS];
     // swizzle f -> f ^ ((f >> 3) & 3).  For the coalesced pieces f = 32u + lane it only touches the lane part, for the
     // thread's own pieces f = 4 lane + u only the u part: both reduce to one per-thread constant plus a compile-time offset
     const int lane_sw = lane ^ ((lane >> 3) & 3);  // coalesced piece 32u + lane lives at 32u + lane_sw
     const int xq = (lane >> 1) & 3;                // own piece 4 lane + u lives at 4 lane + (u ^ xq)
     const int wbase = warp * 32 * CH_K;  // first frame of the warp region inside a tile
-    auto stage_source = [&](int buf, int tile_base) {
-        if (!STREAMED) return;
+    if (USE_TMA) {
+        if (t == 0) {
+#pragma unroll
+            for (int s = 0; s < NST; s++)
+#pragma unroll
+                for (int w2 = 0; w2 < CH_WARPS; w2++) mbar_init(&s_bar[s][w2], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+
+    // whole source region of this warp at `tile_base` readable as one aligned 2 KB run?  (warp-uniform, pure function)
+    auto region_src = [&](int tile_base) -> const float* {
+        if (!STREAMED) return nullptr;
         const int nw = tile_base + wbase;  // chunk-relative first frame of this warp's region
-        if (nw >= ci.nf) return;
-        const float* gp = nullptr;  // warp-uniform: whole region readable with aligned 16-byte pieces
+        if (nw + 32 * CH_K > ci.nf) return nullptr;  // nf is a multiple of 128 = 8 threads: the region may be ragged at the end
         if (SRC == CHAIN_SRC_BUFFER) {
-            gp = chan(q.in, c, ci) + nw;  // nf is a multiple of 128 = 8 threads: the warp region may be ragged at the end
-            if (nw + 32 * CH_K > ci.nf) gp = nullptr;
+            const float* gp = chan(q.in, c, ci) + nw;
+            return (reinterpret_cast<uintptr_t>(gp) & 15) == 0 ? gp : nullptr;
         } else {
             const AbsnInst& o = q.absn;
             const float* src = o.buf + (size_t)c * o.buf_stride;
             const int64_t n = ci.f0 + nw;
             const int64_t idx = n - o.n_start + o.buf_offset;
-            if (!o.loop && n >= o.n_start && idx + 32 * CH_K <= o.buf_len && nw + 32 * CH_K <= ci.nf &&
-                ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0))
-                gp = src + idx;
+            if (!o.loop && n >= o.n_start && idx + 32 * CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) return src + idx;
+            return nullptr;
         }
+    };
+    // cp.async path: 16-byte pieces into the swizzled layout, per-thread gather for ragged / looping / unaligned regions
+    auto stage_source = [&](int buf, int tile_base) {
+        if (!STREAMED || tile_base >= slab_end) return;
+        const int nw = tile_base + wbase;
+        if (nw >= ci.nf) return;
+        const float* gp = region_src(tile_base);
         if (gp) {
 #pragma unroll
             for (int u = 0; u < CH_K / 4; u++) {
                 const int f = 32 * u + lane;
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_io[buf][warp][32 * u + lane_sw]);
+                const unsigned dst = smem_u32(&s_io[buf][warp][32 * u + lane_sw]);
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * f) : "memory");
             }
-        } else if (nw + lane * CH_K < ci.nf) {  // ragged start / end, loops, unaligned channel: per-thread gather
+        } else if (nw + lane * CH_K < ci.nf) {
             float tmp[CH_K];
             chain_load_source<SRC>(q, c, ci, nw + lane * CH_K, tmp);
 #pragma unroll
@@ -907,28 +1045,65 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
                 s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
         }
     };
+    // TMA path (lane 0 only): one 2 KB bulk copy per warp region, completion on the region's mbarrier
+    auto issue_bulk = [&](int buf, int tile_base) {
+        if (tile_base >= slab_end) return;
+        const float* gp = region_src(tile_base);
+        if (gp) {
+            mbar_expect_tx(&s_bar[buf][warp], 32 * CH_K * 4);
+            bulk_load(&s_io[buf][warp][0], gp, 32 * CH_K * 4, &s_bar[buf][warp]);
+        }
+    };
     float v[CH_K];
+    unsigned par = 0;  // TMA path: phase parity of every stage's barrier (bit s), flipped each time the stage is consumed
     if (STREAMED) {
-        stage_source(0, slab_begin);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (USE_TMA) {
+            if (lane == 0)
+#pragma unroll
+                for (int s = 0; s < NST - 1; s++) issue_bulk(s, slab_begin + s * tile);
+        } else {
+#pragma unroll
+            for (int s = 0; s < NST - 1; s++) {
+                stage_source(s, slab_begin + s * tile);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+        }
     }
-    int tile_index = 0;
-    for (int base = slab_begin; base < slab_end; base += tile, tile_index++) {
+    int buf = 0;
+    for (int base = slab_begin; base < slab_end; base += tile) {
         const int n0 = base + t * CH_K;
         const bool active = n0 < ci.nf;  // nf is a multiple of 128, K divides 128: a thread is fully in or out
         const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
-        const int buf = tile_index & 1;
-        if (STREAMED) {
-            stage_source(buf ^ 1, base + tile);  // prefetch the next tile while this one is filtered
+        const int pbuf = buf == 0 ? NST - 1 : buf - 1;  // stage of the tile before this one = stage of the tile NST-1 ahead
+        if (STREAMED && !USE_TMA) {
+            stage_source(pbuf, base + (NST - 1) * tile);  // prefetch while this tile is filtered
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 1;" ::: "memory");  // this tile's pieces have landed ...
-            __syncwarp();                                            // ... for every lane of the warp
+            asm volatile("cp.async.wait_group %0;" ::"n"(NST - 1) : "memory");  // this tile's pieces have landed ...
+            __syncwarp();                                                          // ... for every lane of the warp
             if (active) {
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++) {
                     const float4 a = s_io[buf][warp][4 * lane + (u ^ xq)];
                     v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
                 }
+            }
+        } else if (USE_TMA) {
+            if (region_src(base) != nullptr) {  // warp-uniform: the region arrived by bulk copy (all its threads are active)
+                mbar_wait(&s_bar[buf][warp], (par >> buf) & 1u);
+                par ^= 1u << buf;
+                float4 a[CH_K / 4];
+#pragma unroll
+                for (int u = 0; u < CH_K / 4; u++) a[u] = s_io[buf][warp][4 * lane + (u ^ xq)];  // a[u] = piece u ^ xq
+                cswap4((xq & 1) != 0, a[0], a[1]);
+                cswap4((xq & 1) != 0, a[2], a[3]);
+                cswap4((xq & 2) != 0, a[0], a[2]);
+                cswap4((xq & 2) != 0, a[1], a[3]);
+#pragma unroll
+                for (int u = 0; u < CH_K / 4; u++) {
+                    v[4 * u] = a[u].x; v[4 * u + 1] = a[u].y; v[4 * u + 2] = a[u].z; v[4 * u + 3] = a[u].w;
+                }
+            } else if (active) {
+                chain_load_source<SRC>(q, c, ci, n0, v);
             }
         } else if (active) {
             chain_load_source<SRC>(q, c, ci, n0, v);
@@ -964,7 +1139,7 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
         }
         {
             // results: through the warp's staging region (the source pieces of this tile are consumed), so that global
-            // memory sees coalesced 512-byte stores; per-thread stores for ragged / unaligned / length-limited regions
+            // memory sees whole 2 KB regions; per-thread stores for ragged / unaligned / length-limited regions
             const int nw = base + wbase;
             const int n_out = q.out_dup > 1 ? q.out_dup : 1;
             const bool region_full = nw + 32 * CH_K <= ci.nf;
@@ -973,18 +1148,35 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
                                  (q.out_dup <= 1 || (q.out.stride & 3) == 0);
             if (region_full && in_limit && aligned) {  // warp-uniform
                 __syncwarp();
+                if (USE_TMA) {
+                    float4 a[CH_K / 4];
 #pragma unroll
-                for (int u = 0; u < CH_K / 4; u++)
-                    s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                __syncwarp();
-                for (int oc = 0; oc < n_out; oc++) {
-                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+                    for (int u = 0; u < CH_K / 4; u++) a[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    cswap4((xq & 2) != 0, a[0], a[2]);
+                    cswap4((xq & 2) != 0, a[1], a[3]);
+                    cswap4((xq & 1) != 0, a[0], a[1]);
+                    cswap4((xq & 1) != 0, a[2], a[3]);  // a[u] = piece u ^ xq
 #pragma unroll
-                    for (int u = 0; u < CH_K / 4; u++) {
-                        out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
+                    for (int u = 0; u < CH_K / 4; u++) s_io[buf][warp][4 * lane + (u ^ xq)] = a[u];
+                    fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk store's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0)
+                        for (int oc = 0; oc < n_out; oc++)
+                            bulk_store(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw, &s_io[buf][warp][0], 32 * CH_K * 4);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++)
+                        s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                    __syncwarp();
+                    for (int oc = 0; oc < n_out; oc++) {
+                        float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+#pragma unroll
+                        for (int u = 0; u < CH_K / 4; u++) {
+                            out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
             } else if (active) {
                 const int64_t nabs = ci.f0 + n0;
                 for (int oc = 0; oc < n_out; oc++) {
@@ -994,13 +1186,29 @@ __global__ void __launch_bounds__(CH_THREADS) k_chain(const ChainInst* __restric
                         if (q.limit < 0 || nabs + j < q.limit) out[j] = v[j];
                 }
             }
+            if (USE_TMA && lane == 0) {
+                bulk_commit();        // this tile's stores (possibly none) form one group ...
+                bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
+                issue_bulk(pbuf, base + (NST - 1) * tile);
+            }
         }
         if (NB > 0) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
+        buf = buf + 1 == NST ? 0 : buf + 1;
     }
-    // carry the filter state to the next chunk
+    if (USE_TMA && lane == 0) bulk_wait_read<0>();  // shared memory stays valid until the last bulk store has read it
+    // carry the filter state: to the next slab of this launch, or (last slab) to the next chunk
+    if (NB > 0) {
+        if (last_slab) {
 #pragma unroll
-    for (int k = 0; k < NB; k++)
-        if (t < 4) q.bq[k].state[4 * c + t] = sm.state[k][t];
+            for (int k = 0; k < NB; k++)
+                if (t < 4) q.bq[k].state[4 * c + t] = sm.state[k][t];
+        } else {
+            if (t < 4 * NB) __stcg(sc.handoff + (ho + 1) * (CHAIN_MAX_BIQUADS * 4) + t, sm.state[t >> 2][t & 3]);
+            __threadfence();
+            __syncthreads();
+            if (t == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sc.flags + ho + 1), "r"(sc.epoch) : "memory");
+        }
+    }
 }
 
 // Oscillator with automated / audio-rate frequency or detune (oscillator.rs:447-459,511-557): the phase of frame n is
@@ -2358,33 +2566,90 @@ void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, 
     int threads = n * max_ch;
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
 }
-template <int SRC, int NB>
-static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
-    dim3 grid((unsigned)n, (unsigned)max_ch);
-    if (NB == 0) {  // stateless chain: also split along time until the launch fills the machine (4 CTAs per SM)
-        const long ctas = (long)n * max_ch, tiles = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
-        long slabs = (4L * 148 + ctas - 1) / ctas;
-        if (slabs > tiles) slabs = tiles;
-        if (slabs > 1) grid.z = (unsigned)slabs;
+// ---- k_chain launch geometry ---------------------------------------------------------------------------------------
+static int g_chain_tma = -1, g_chain_waves = -1;
+static void chain_env() {
+    if (g_chain_tma < 0) {
+        const char* e = getenv("WAE_CHAIN_TMA");
+        g_chain_tma = e ? (atoi(e) != 0) : 1;
+        e = getenv("WAE_CHAIN_WAVES");
+        g_chain_waves = e ? atoi(e) : 20;
+        if (g_chain_waves < 0) g_chain_waves = 0;
     }
-    if (shaper) k_chain<SRC, NB, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
-    else k_chain<SRC, NB, false><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci);
+}
+void chain_set_tuning(int tma, int waves) {
+    chain_env();
+    if (tma >= 0) g_chain_tma = tma != 0;
+    if (waves >= 0) g_chain_waves = waves;
+}
+// Time slabs of one launch: enough work items for `waves` waves of resident CTAs (148 SMs x 6), at least 8 tiles each.  Filtered
+// chains are only cut when the launch has enough (instance, channel) pairs to fill half the machine without it: the slabs of one
+// pair run one after the other (the state is handed over), so with few pairs more slabs would only add waiting CTAs.
+void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab) {
+    chain_env();
+    const long ctas = (long)n * max_ch, tiles = (nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+    const long slots = 148L * 6;
+    long slabs = 1;
+    if (nb == 0) {
+        slabs = (4L * 148 + ctas - 1) / ctas;  // stateless chain: split along time until the launch fills the machine (4 CTAs per SM)
+        if (g_chain_waves > 0 && ctas * slabs < (long)g_chain_waves * slots) slabs = ((long)g_chain_waves * slots + ctas - 1) / ctas;
+        if (slabs > std::max(1L, tiles / 2)) slabs = std::max(1L, tiles / 2);
+    } else if (g_chain_waves > 0 && 2 * ctas >= slots) {
+        slabs = ((long)g_chain_waves * slots + ctas - 1) / ctas;
+        if (slabs > tiles / 8) slabs = tiles / 8;
+    }
+    if (slabs > CHAIN_MAX_SLABS) slabs = CHAIN_MAX_SLABS;
+    if (slabs < 1) slabs = 1;
+    long tps = (tiles + slabs - 1) / slabs;
+    if (tps < 1) tps = 1;
+    slabs = (tiles + tps - 1) / tps;
+    if (slabs < 1) slabs = 1;
+    *n_slabs = (int)slabs;
+    *tiles_per_slab = (int)tps;
+}
+template <int SRC, int NB>
+static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux) {
+    ChainSched sc{};
+    chain_plan_slabs(n, max_ch, ci.nf, NB, &sc.n_slabs, &sc.tiles_per_slab);
+    if (NB > 0 && (sc.n_slabs > aux.slab_stride || !aux.ticket)) {  // no hand-off memory for that many slabs: one slab
+        sc.n_slabs = 1;
+        sc.tiles_per_slab = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+    }
+    sc.max_ch = max_ch;
+    sc.slab_stride = aux.slab_stride > 0 ? aux.slab_stride : 1;
+    sc.epoch = aux.epoch;
+    sc.ticket = (NB > 0 && sc.n_slabs > 1) ? aux.ticket : nullptr;
+    sc.handoff = aux.handoff;
+    sc.flags = aux.flags;
+    const unsigned grid = (unsigned)n * (unsigned)max_ch * (unsigned)sc.n_slabs;
+    constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;
+    if constexpr (STREAMED) {
+        if (g_chain_tma) {
+            if (shaper) k_chain<SRC, NB, true, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+            else k_chain<SRC, NB, false, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+            return;
+        }
+    }
+    {
+        if (shaper) k_chain<SRC, NB, true, false><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+        else k_chain<SRC, NB, false, false><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+    }
 }
 template <int SRC>
-static void launch_chain_s(int nb, bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
-    if (nb == 0) launch_chain_v<SRC, 0>(shaper, d, c, n, max_ch, ci, s);
-    else if (nb == 1) launch_chain_v<SRC, 1>(shaper, d, c, n, max_ch, ci, s);
-    else launch_chain_v<SRC, 2>(shaper, d, c, n, max_ch, ci, s);
+static void launch_chain_s(int nb, bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux) {
+    if (nb == 0) launch_chain_v<SRC, 0>(shaper, d, c, n, max_ch, ci, s, aux);
+    else if (nb == 1) launch_chain_v<SRC, 1>(shaper, d, c, n, max_ch, ci, s, aux);
+    else launch_chain_v<SRC, 2>(shaper, d, c, n, max_ch, ci, s, aux);
 }
 // variant = src_kind * 6 + n_biquad * 2 + has_shaper (all instances of one launch share the chain shape)
-void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux) {
     const int src = variant / 6, nb = (variant % 6) / 2;
     const bool shaper = (variant & 1) != 0;
     switch (src) {
-        case CHAIN_SRC_BUFFER: launch_chain_s<CHAIN_SRC_BUFFER>(nb, shaper, d, c, n, max_ch, ci, s); break;
-        case CHAIN_SRC_ABSN: launch_chain_s<CHAIN_SRC_ABSN>(nb, shaper, d, c, n, max_ch, ci, s); break;
-        case CHAIN_SRC_OSC: launch_chain_s<CHAIN_SRC_OSC>(nb, shaper, d, c, n, max_ch, ci, s); break;
-        default: launch_chain_s<CHAIN_SRC_CONST>(nb, shaper, d, c, n, max_ch, ci, s); break;
+        case CHAIN_SRC_BUFFER: launch_chain_s<CHAIN_SRC_BUFFER>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
+        case CHAIN_SRC_ABSN: launch_chain_s<CHAIN_SRC_ABSN>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
+        case CHAIN_SRC_OSC: launch_chain_s<CHAIN_SRC_OSC>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
+        default: launch_chain_s<CHAIN_SRC_CONST>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
     }
 }
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
