@@ -252,7 +252,11 @@ enum {
     WAE_OPT_FUSE = 2,           /* 1 (default): fuse source->filter->gain chains; 0: one stage/node */
     WAE_OPT_SERIAL_FILTERS = 3, /* 1: bit-faithful serial recurrences (thread per channel)          */
     WAE_OPT_PIPELINE_GROUPS = 4, /* graph groups of the H2D/render/D2H pipeline (0 = auto: 8)       */
-    WAE_OPT_PARAM_PARALLEL = 5   /* 1 (default): AudioParam ramps / set-target / curves of a quantum evaluated by the whole warp; 0: by one lane */
+    WAE_OPT_PARAM_PARALLEL = 5,  /* 1 (default): AudioParam ramps / set-target / curves of a quantum evaluated by the whole warp; 0: by one lane */
+    WAE_OPT_BIND_NUMA = 6,       /* 1: pin the calling thread and the engine's host workers to the CPUs of the GPU's NUMA node (before the first render) */
+    WAE_OPT_HOST_WORKERS = 7,    /* host worker threads (planning, copy-out to pageable buffers); 0 = auto (hardware threads / 8, 2..16) */
+    WAE_OPT_CHAIN_TMA = 8,       /* process-wide: 1 = the fused chain kernel streams PCM with cp.async.bulk (TMA), 0 = with cp.async */
+    WAE_OPT_CHAIN_WAVES = 9      /* process-wide: time slabs of the fused chain kernel are sized for this many waves of CTAs; 0 = one slab */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
 /* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */
@@ -366,12 +370,18 @@ WAE_API wae_status wae_batch_upload(wae_batch* batch);                    /* asy
 /* per_stage != 0: record CUDA events around every stage (diagnostic: serialises chunks) */
 WAE_API wae_status wae_batch_set_timing(wae_batch* batch, uint32_t per_stage);
 WAE_API wae_status wae_batch_run(wae_batch* batch);                       /* async on the engine stream   */
-/* End-to-end render with HOST buffers: per graph group H2D(source PCM, pinned mirror) -> render -> D2H into host_out
- * ([n_graphs][channels][length] f32, ideally pinned), the three legs of neighbouring groups overlapped on three
- * streams.  Synchronous.  The pinned host mirror of the source PCM is built on the first call.  wae_render_batch(...,
- * WAE_RENDER_OUT_HOST) is prepare (which uploads the sources straight from the graphs' buffers) + group-wise render with
- * overlapped D2H + destroy. */
+/* End-to-end render of a PREPARED batch with HOST buffers: per graph group H2D(source PCM) -> render -> D2H into host_out
+ * ([n_graphs][channels][length] f32, ideally page-locked), the three legs of neighbouring groups overlapped on three
+ * streams.  Synchronous.  Source PCM is copied from where wae_create_buffer_source / set_buffer put it (page-locked when the
+ * graph has an engine; otherwise a pinned mirror is built on the first call).  The one-shot equivalent — planning included and
+ * overlapped, pageable `out` served through staging slots — is wae_render_batch(..., WAE_RENDER_OUT_HOST). */
 WAE_API wae_status wae_batch_run_pipelined(wae_batch* batch, float* host_out);
+/* Graph groups of a prepared batch (contiguous graph ranges [first, last) rendered one after the other) and the render of ONE
+ * group, asynchronous on the engine stream: lets a caller interleave its own work per group — bench.py overlaps the NCCL
+ * all-gather of group k's PCM with the render of group k+1.  Group 0 also resets the per-run node state; call the groups in order. */
+WAE_API wae_status wae_batch_group_count(wae_batch* batch, uint32_t* n_groups);
+WAE_API wae_status wae_batch_group_range(wae_batch* batch, uint32_t group, uint32_t* first_graph, uint32_t* last_graph);
+WAE_API wae_status wae_batch_run_group(wae_batch* batch, uint32_t group);
 WAE_API wae_status wae_batch_sync(wae_batch* batch);                      /* wait for the stream           */
 WAE_API wae_status wae_batch_output_device_ptr(wae_batch* batch, float** out_dev, uint64_t* out_floats);
 WAE_API wae_status wae_batch_fetch(wae_batch* batch, float* host_out);   /* D2H of the whole output       */

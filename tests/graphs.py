@@ -100,13 +100,13 @@ def north_star_voices_convolver(pkg, backend, voices, length, ir, sr=SR, seed=0)
     return c
 
 
-def c5_full_chain(pkg, backend, g, length, ir, sr=SR):
+def c5_full_chain(pkg, backend, g, length, ir, sr=SR, curve_points=257):
     """C5 (configs[4]): Oscillator -> WaveShaper -> Biquad -> Convolver -> PannerNode(HRTF) -> Analyser -> destination.
     The backend must have an HRIR sphere at the context rate (synthetic_hrir_sphere)."""
     rng = np.random.default_rng(5000 + g)
     c = pkg.OfflineAudioContext(2, length, sr, backend)
     osc = c.create_oscillator(type_=[pkg.SAWTOOTH, pkg.SINE, pkg.SQUARE, pkg.TRIANGLE][g % 4], frequency=float(110.0 * 2.0 ** rng.uniform(0, 4)))
-    x = np.linspace(-1.0, 1.0, 257)
+    x = np.linspace(-1.0, 1.0, curve_points)
     sh = c.create_wave_shaper(curve=np.tanh(x * (1.5 + g % 3)).astype(np.float32))
     bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=float(rng.uniform(800, 6000)), q=float(rng.uniform(0.7, 4.0)))
     cv = c.create_convolver(pkg.AudioBuffer(ir, sr))

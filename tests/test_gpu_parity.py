@@ -1012,3 +1012,77 @@ def test_plain_c_client_renders_what_the_oracle_renders(pkg, engine, oracle, tmp
         osc.start()
         left = c.start_rendering_sync().get_channel_data(0).astype(np.float64)
         assert abs(got[g] - float(np.sqrt(np.mean(left * left)))) <= 2e-6
+
+
+def _oneshot_mixed_batch(pkg, be, n_graphs, length, ir):
+    """graphs of four kinds, interleaved: fused buffer chains, voice sums, convolvers sharing one response, a delay loop"""
+    ctxs = []
+    for g in range(n_graphs):
+        k = g % 4
+        if k == 0:
+            ctxs.append(G.c2_buffer_biquad_gain(pkg, be, g, length))
+        elif k == 1:
+            ctxs.append(G.c3_many_voices(pkg, be, 12, length))
+        elif k == 2:
+            ctxs.append(G.c4_convolver(pkg, be, g, length, ir))
+        else:
+            c = pkg.OfflineAudioContext(2, length, G.SR, be)
+            o = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=110.0 + g)
+            d = c.create_delay(max_delay_time=0.05, delay_time=0.011)
+            fb = c.create_gain(0.4)
+            o.connect(d)
+            d.connect(fb)
+            fb.connect(d)
+            d.connect(c.destination())
+            o.start()
+            ctxs.append(c)
+    return ctxs
+
+
+@pytest.mark.parametrize("pinned_out", [False, True])
+def test_one_shot_render_many_groups(pkg, engine, oracle, pinned_out):
+    """wae_render_batch(HOST) on a batch large enough to be cut into graph groups: sizing and planning run on the engine's worker
+    threads, the source PCM goes up from the graphs' page-locked buffers, rendered PCM comes back through the staging slots (pageable
+    `out`) or straight into a page-locked `out` — same PCM as prepare / run / fetch, and as the oracle."""
+    n_graphs, length = 72, 8192 * 2 + 128 * 5 + 3
+    ir = G.synthetic_ir(3000, 2, decay=0.3)
+    want = pkg.Batch(_oneshot_mixed_batch(pkg, engine.backend, n_graphs, length, ir))
+    want.run()
+    want.sync()
+    ref = want.fetch()
+    want.destroy()
+    if pinned_out:
+        import torch
+        t = torch.empty(n_graphs * 2 * length, dtype=torch.float32, pin_memory=True)
+        out = t.numpy().reshape(n_graphs, 2, length)
+    else:
+        out = np.full((n_graphs, 2, length), np.nan, np.float32)
+    for _ in range(2):  # the second call draws its device memory from the engine's cache
+        out[...] = np.nan
+        got = pkg.render_batch_oneshot(_oneshot_mixed_batch(pkg, engine.backend, n_graphs, length, ir), out)
+        assert np.array_equal(got, ref)
+    cpu = G.render(pkg, _oneshot_mixed_batch(pkg, oracle, 8, length, ir))
+    assert maxdiff(got[:8], cpu) <= TOL
+
+
+def test_one_shot_render_reports_planner_refusals(pkg):
+    """an unsupported graph anywhere in the batch fails the whole one-shot call cleanly (status + text), nothing is left running"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    length = 128 * 40
+    eng2 = pkg.Engine(0)  # a fresh engine has no HRIR sphere: HRTF panners are refused
+    try:
+        ctxs = [G.c2_buffer_biquad_gain(pkg, eng2.backend, g, length) for g in range(70)]
+        bad = pkg.OfflineAudioContext(2, length, G.SR, eng2.backend)
+        p = bad.create_panner(panning_model=pkg.context.HRTF)
+        s2 = bad.create_constant_source()
+        s2.connect(p)
+        p.connect(bad.destination())
+        s2.start()
+        with pytest.raises(pkg.WaeError):
+            pkg.render_batch_oneshot(ctxs + [bad])
+        out = pkg.render_batch_oneshot(ctxs[:3])  # the engine is still usable
+        assert np.isfinite(out).all() and np.abs(out).max() > 0
+    finally:
+        eng2.close()

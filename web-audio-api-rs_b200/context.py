@@ -660,6 +660,21 @@ class Batch:
     def sync(self):
         self.api.check(self.api.batch_sync(self.handle))
 
+    def groups(self):
+        """[(first_graph, last_graph)] of the batch's graph groups (rendered one after the other)."""
+        n = C.c_uint32()
+        self.api.check(self.api.batch_group_count(self.handle, C.byref(n)))
+        out = []
+        for k in range(n.value):
+            a, b = C.c_uint32(), C.c_uint32()
+            self.api.check(self.api.batch_group_range(self.handle, k, C.byref(a), C.byref(b)))
+            out.append((a.value, b.value))
+        return out
+
+    def run_group(self, k):
+        """render of ONE graph group, asynchronous on the engine stream (call the groups in order)"""
+        self.api.check(self.api.batch_run_group(self.handle, k))
+
     def run_pipelined(self, host_out_ptr):
         """H2D + render + D2H, overlapped per graph group; `host_out_ptr` = address of [n][ch][length] f32 (pinned)."""
         self.api.check(self.api.batch_run_pipelined(self.handle, host_out_ptr))
@@ -722,6 +737,23 @@ def plan_batch(contexts):
     return {"groups": info.groups, "segments": info.segments, "stages": info.stages, "has_feedback": bool(info.has_feedback),
             "chunk_frames": info.chunk_frames, "chunks": info.chunks, "arena_floats_per_frame": info.arena_floats_per_frame,
             "source_floats": info.source_floats, "kinds": kinds}
+
+
+def render_batch_oneshot(contexts, out=None):
+    """ONE wae_render_batch(engine, graphs, n, out, HOST) call: sizing, planning, H2D of the source PCM, render and D2H overlapped inside
+    the library (csrc/wae_engine.cu: render_oneshot_host) — the call the Rust binding makes from start_rendering_sync
+    (INTEGRATION.md).  `out`: optional [n][channels][length] float32 array (pageable numpy memory, or the numpy view of a pinned torch
+    tensor: the library copies straight into page-locked memory).  Product only."""
+    ctx0 = contexts[0]
+    api = ctx0._api
+    n, ch, length = len(contexts), ctx0._channels, ctx0._length
+    for c in contexts:
+        c._run_suspend_callbacks()
+    if out is None:
+        out = np.empty((n, ch, length), np.float32)
+    arr = (C.c_void_p * n)(*[c._g for c in contexts])
+    api.check(api.render_batch(ctx0._backend.engine, arr, n, out.ctypes.data_as(C.c_void_p), 0))
+    return out
 
 
 def render_batch(contexts, threads=1):

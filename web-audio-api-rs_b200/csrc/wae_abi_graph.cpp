@@ -8,10 +8,15 @@
 #include "wae_param_host.h"
 #include "wae_param_walk.h"
 
+#include <cuda_runtime.h>
+
 #include <algorithm>
 #include <cmath>
 #include <complex>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 
 using namespace wae;
 
@@ -21,6 +26,78 @@ void set_error(const std::string& msg) { g_err = msg; }
 int32_t fail(int32_t code, const std::string& msg) {
     g_err = msg;
     return code;
+}
+
+// ---- page-locked pool of AudioBuffer memory (see PcmBuffer) ---------------------------------------------------------------
+// Slabs of cudaHostAlloc(Portable) memory, carved by bump allocation; freed blocks are recycled by exact (64 KiB-rounded) size,
+// which is what a caller that builds the same kind of graphs again and again produces.  Page-locking costs ~0.3 ms per MiB and
+// happens once per slab, at graph-construction time; the slabs live as long as the process.
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    struct Slab {
+        char* base;
+        size_t size, used;
+    };
+    std::vector<Slab> slabs;
+    std::unordered_map<size_t, std::vector<void*>> free_by_size;
+    bool disabled = false;  // no CUDA device / page-locking refused: stop trying
+    static size_t round(size_t b) { return (b + 65535) / 65536 * 65536; }
+    void* alloc(size_t bytes) {
+        const size_t r = round(bytes);
+        std::lock_guard<std::mutex> lk(mu);
+        if (disabled) return nullptr;
+        auto it = free_by_size.find(r);
+        if (it != free_by_size.end() && !it->second.empty()) {
+            void* p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+        for (auto& s : slabs)
+            if (s.size - s.used >= r) {
+                void* p = s.base + s.used;
+                s.used += r;
+                return p;
+            }
+        const size_t slab_bytes = std::max<size_t>(r, (size_t)256 << 20);
+        void* hp = nullptr;
+        if (cudaHostAlloc(&hp, slab_bytes, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            if (slab_bytes == r || cudaHostAlloc(&hp, r, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                disabled = slabs.empty();
+                return nullptr;
+            }
+            slabs.push_back(Slab{(char*)hp, r, r});
+            return hp;
+        }
+        slabs.push_back(Slab{(char*)hp, slab_bytes, r});
+        return hp;
+    }
+    void free(void* p, size_t bytes) {
+        std::lock_guard<std::mutex> lk(mu);
+        free_by_size[round(bytes)].push_back(p);
+    }
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* pool = new PinnedPool;  // never destroyed: buffers may outlive static destruction order
+    return *pool;
+}
+}  // namespace
+
+void* pcm_host_alloc(size_t bytes, bool want_pinned, bool* pinned) {
+    *pinned = false;
+    if (want_pinned && bytes >= ((size_t)256 << 10)) {
+        if (void* p = pinned_pool().alloc(bytes)) {
+            *pinned = true;
+            return p;
+        }
+    }
+    return std::malloc(bytes);
+}
+void pcm_host_free(void* p, size_t bytes, bool pinned) {
+    if (pinned) pinned_pool().free(p, bytes);
+    else std::free(p);
 }
 
 // AudioParamProcessor::handle_incoming_event for SetValue (src/param.rs:987-990) + mix_to_output clamp (:755-760)
@@ -92,10 +169,29 @@ static ChannelCfg resolve_cfg(const wae_channel_config& c, ChannelCfg def) {
     return ChannelCfg{(int)c.count, (int)c.count_mode, (int)c.interpretation};
 }
 
-static std::shared_ptr<PcmBuffer> copy_buffer(const wae_audio_buffer* b) {
+// `pin`: the buffer will be DMA-ed to a device by a render call (AudioBufferSourceNode assets of a graph that has an engine)
+static std::shared_ptr<PcmBuffer> copy_buffer(const wae_graph* g, const wae_audio_buffer* b, bool pin) {
+    // AudioBuffer::new (src/buffer.rs:96-115): assert_valid_number_of_channels / assert_valid_buffer_length
+    if (b->number_of_channels < 1 || b->number_of_channels > WAE_MAX_CHANNELS || !b->channels) {
+        fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(b->number_of_channels) + " is outside range [1, 32]");
+        return nullptr;
+    }
+    if (b->length == 0) {
+        fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid length: 0 is less than or equal to minimum bound (0)");
+        return nullptr;
+    }
     auto p = std::make_shared<PcmBuffer>();
     p->sample_rate = b->sample_rate;
-    for (uint32_t c = 0; c < b->number_of_channels; c++) p->channels.emplace_back(b->channels[c], b->channels[c] + b->length);
+    bool want = pin && g->engine != nullptr;
+    if (want && cudaSetDevice(engine_device(g->engine)) != cudaSuccess) {
+        cudaGetLastError();
+        want = false;
+    }
+    if (!p->allocate(b->number_of_channels, b->length, want)) {
+        fail(WAE_OUT_OF_MEMORY, "out of host memory (AudioBuffer copy)");
+        return nullptr;
+    }
+    for (uint32_t c = 0; c < b->number_of_channels; c++) std::memcpy(p->channels[c].data(), b->channels[c], (size_t)b->length * sizeof(float));
     return p;
 }
 
@@ -211,7 +307,7 @@ WAE_API wae_status wae_create_buffer_source(wae_graph* g, const wae_buffer_sourc
     n.loop = o->loop != 0;
     n.loop_start = o->loop_start;
     n.loop_end = o->loop_end;
-    if (o->buffer) n.buffer = copy_buffer(o->buffer);
+    if (o->buffer && !(n.buffer = copy_buffer(g, o->buffer, true))) return WAE_NOT_SUPPORTED;
     *out = g->finish_register(std::move(n)).id;
     return WAE_OK;
 }
@@ -246,7 +342,7 @@ WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_option
     n.kind = K_CONV;
     n.cfg = cfg;
     n.normalize = n.normalize_next = !o->disable_normalization;
-    if (o->buffer) n.buffer = copy_buffer(o->buffer);
+    if (o->buffer && !(n.buffer = copy_buffer(g, o->buffer, false))) return WAE_NOT_SUPPORTED;
     *out = g->finish_register(std::move(n)).id;
     return WAE_OK;
 }
@@ -779,7 +875,7 @@ WAE_API wae_status wae_buffer_source_set_buffer(wae_graph* g, wae_node_id node, 
     Node* n = node_of_kind(g, node, K_ABSN);
     if (!n || !buffer) return fail(WAE_INVALID_ARGUMENT, "not an AudioBufferSourceNode / null buffer");
     if (n->buffer) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign buffer twice");
-    n->buffer = copy_buffer(buffer);
+    if (!(n->buffer = copy_buffer(g, buffer, true))) return WAE_NOT_SUPPORTED;
     // "if start called and buffer is null, should fire ended event and ignore any subsequent buffer assignment"
     // (audio_buffer_source.rs:443-451): a source that was started before the last suspend point and has been rendered without a
     // buffer since has ended for good
@@ -801,7 +897,9 @@ WAE_API wae_status wae_convolver_set_buffer(wae_graph* g, wae_node_id node, cons
     if (!(c == 1 || c == 2 || c == 4)) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - the convolution buffer must consist of 1, 2 or 4 channels");
     if (!g->epochs.empty() && n->buffer)  // the reference swaps in fresh convolvers (tail dropped): not lowered mid-render
         return fail(WAE_UNSUPPORTED, "replacing the impulse response of a ConvolverNode at a suspend point is not lowered to the GPU");
-    n->buffer = copy_buffer(buffer);
+    auto fresh = copy_buffer(g, buffer, false);
+    if (!fresh) return WAE_NOT_SUPPORTED;
+    n->buffer = fresh;
     n->normalize = n->normalize_next;
     return WAE_OK;
 }

@@ -16,14 +16,23 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdlib>
+#include <deque>
+#include <fstream>
+#include <mutex>
+#include <sched.h>
+#include <sstream>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <limits>
 #include <map>
+#include <memory>
 #include <set>
 #include <tuple>
 #include <unordered_map>
@@ -38,9 +47,67 @@ namespace hm = wae::hostmath;
         if (_e != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+// host worker threads of an engine: planning of graph groups and the copy-out of rendered PCM to pageable caller memory
+struct WorkerPool {
+    std::vector<std::thread> threads;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> q;
+    bool stop = false;
+    WorkerPool(int n, int device) {
+        for (int i = 0; i < n; i++)
+            threads.emplace_back([this, device] {
+                cudaSetDevice(device);
+                for (;;) {
+                    std::function<void()> f;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [this] { return stop || !q.empty(); });
+                        if (q.empty()) return;
+                        f = std::move(q.front());
+                        q.pop_front();
+                    }
+                    f();
+                }
+            });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto& t : threads) t.join();
+    }
+    void submit(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            q.push_back(std::move(f));
+        }
+        cv.notify_one();
+    }
+    int size() const { return (int)threads.size(); }
+    // fn(i) for i in [0, n), on the workers; returns when all are done
+    void parallel_for(int n, const std::function<void(int)>& fn) {
+        if (n <= 0) return;
+        std::mutex dm;
+        std::condition_variable dcv;
+        int left = n;
+        for (int i = 0; i < n; i++)
+            submit([&, i] {
+                fn(i);
+                std::lock_guard<std::mutex> lk(dm);
+                if (--left == 0) dcv.notify_all();
+            });
+        std::unique_lock<std::mutex> lk(dm);
+        dcv.wait(lk, [&] { return left == 0; });
+    }
+};
+
 struct wae_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined / one-shot paths
     int64_t chunk_frames = 0;  // 0 = auto
     bool fuse = true;
     bool serial_filters = false;
@@ -56,12 +123,105 @@ struct wae_engine {
         uint32_t taps = 0;
     };
     std::map<uint32_t, RateSphere> sphere_rates;
+    std::mutex sphere_mu;
     void drop_rate_spheres() {
         for (auto& kv : sphere_rates)
             if (kv.second.d_ir) cudaFree(kv.second.d_ir);
         sphere_rates.clear();
     }
+    // ---- device memory of finished batches is kept and handed to the next batch (a render call that prepares, renders and drops
+    // its batch would otherwise pay cudaMalloc / cudaFree — both synchronising — for gigabytes of PCM every time)
+    std::mutex mem_mu;
+    std::multimap<size_t, void*> dev_free;          // cached blocks by size
+    std::unordered_map<void*, size_t> dev_size;     // every live block (handed out or cached)
+    size_t dev_cached_bytes = 0;
+    static size_t round_block(size_t b) {
+        if (b < 512) return 512;
+        if (b < ((size_t)1 << 16)) return (b + 511) / 512 * 512;
+        if (b < ((size_t)2 << 20)) return (b + 65535) / 65536 * 65536;
+        return (b + (((size_t)2 << 20) - 1)) / ((size_t)2 << 20) * ((size_t)2 << 20);
+    }
+    void* dev_alloc(size_t bytes, bool* fresh = nullptr) {
+        const size_t r = round_block(bytes);
+        {
+            std::lock_guard<std::mutex> lk(mem_mu);
+            auto it = dev_free.lower_bound(r);
+            if (it != dev_free.end() && it->first <= r + std::max<size_t>(r / 8, 4096)) {
+                void* p = it->second;
+                dev_cached_bytes -= it->first;
+                dev_free.erase(it);
+                if (fresh) *fresh = false;
+                return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaMalloc(&p, r) != cudaSuccess) {
+            cudaGetLastError();
+            dev_trim();  // give the cache back and try once more
+            if (cudaMalloc(&p, r) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+        }
+        std::lock_guard<std::mutex> lk(mem_mu);
+        dev_size[p] = r;
+        if (fresh) *fresh = true;
+        return p;
+    }
+    void dev_release(void* p) {
+        std::lock_guard<std::mutex> lk(mem_mu);
+        auto it = dev_size.find(p);
+        if (it == dev_size.end()) return;
+        dev_free.emplace(it->second, p);
+        dev_cached_bytes += it->second;
+    }
+    void dev_trim() {
+        std::lock_guard<std::mutex> lk(mem_mu);
+        for (auto& kv : dev_free) {
+            cudaFree(kv.second);
+            dev_size.erase(kv.second);
+        }
+        dev_free.clear();
+        dev_cached_bytes = 0;
+    }
+    // ---- host side of the one-shot render: worker threads, page-locked staging slots for pageable output buffers
+    WorkerPool* pool = nullptr;
+    int n_workers = 0;  // 0 = auto
+    WorkerPool* workers() {
+        if (!pool) {
+            int n = n_workers;
+            if (n <= 0) {
+                const unsigned hw = std::thread::hardware_concurrency();
+                n = (int)std::min<unsigned>(16u, std::max<unsigned>(2u, hw / 8u));
+            }
+            pool = new WorkerPool(n, device);
+        }
+        return pool;
+    }
+    static constexpr int kStageSlots = 4;
+    float* h_stage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    size_t h_stage_bytes = 0;
+    bool ensure_stage(size_t bytes) {
+        if (h_stage_bytes >= bytes) return true;
+        for (int i = 0; i < kStageSlots; i++) {
+            if (h_stage[i]) cudaFreeHost(h_stage[i]);
+            h_stage[i] = nullptr;
+        }
+        h_stage_bytes = 0;
+        for (int i = 0; i < kStageSlots; i++)
+            if (cudaHostAlloc((void**)&h_stage[i], bytes, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        h_stage_bytes = bytes;
+        return true;
+    }
+    std::string numa_cpus;  // CPUs this engine's host threads were bound to (WAE_OPT_BIND_NUMA), for the record
 };
+
+namespace wae {
+int engine_device(const wae_engine* eng) { return eng ? eng->device : 0; }
+}  // namespace wae
 
 namespace {
 
@@ -165,10 +325,9 @@ struct wae_batch {
         std::vector<int64_t> seg_bounds;                    // 0 = b0 < b1 < ... < lq: the suspend frames of this group's graphs
         float* d_src = nullptr;         // device slab of source PCM
         float* h_src = nullptr;         // pinned host mirror, built on first use (wae_batch_upload / wae_batch_run_pipelined)
-        struct SrcCopy {                // one channel of one AudioBufferSourceNode's PCM inside the slab
+        struct SrcCopy {                // the PCM of one AudioBufferSourceNode inside the slab: planar [ch][stride], as PcmBuffer holds it
             std::shared_ptr<PcmBuffer> buf;
-            int channel;
-            size_t offset, len;         // floats
+            size_t offset, floats;      // floats
         };
         std::vector<SrcCopy> src_copies;
         size_t src_floats = 0;
@@ -185,7 +344,8 @@ struct wae_batch {
     };
     std::map<StateKey, std::pair<void*, size_t>> state_map;
     std::vector<void*> pinned;
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // the engine's copy streams
+    std::recursive_mutex mu;  // groups are planned on worker threads: allocation, state map, read-out records
     struct Timed {
         size_t stage, e0, e1;
     };
@@ -195,8 +355,8 @@ struct wae_batch {
     std::vector<cudaEvent_t> stage_events;
     bool time_stages = false;
     size_t timed_events_used = 0;
-    uint64_t arena_bytes = 0, asset_bytes = 0;
-    uint64_t n_cuda_malloc = 0;  // prepare-time diagnostics (WAE_PREPARE_PROFILE=1)
+    std::atomic<uint64_t> arena_bytes{0}, asset_bytes{0};
+    uint64_t n_cuda_malloc = 0;  // prepare-time diagnostics (WAE_PREPARE_PROFILE=1): blocks that were not served from the engine's cache
 
     // small per-node state that is zeroed before every run lives in slabs: one memset per slab, not per node
     char* slab = nullptr;
@@ -206,8 +366,10 @@ struct wae_batch {
         if (bytes > (1u << 20)) return nullptr;
         if (!slab || slab_used + bytes > slab_cap) {
             slab_cap = 8u << 20;
-            void* p = nullptr;
-            if (cudaMalloc(&p, slab_cap) != cudaSuccess) return nullptr;
+            bool fresh = false;
+            void* p = engine->dev_alloc(slab_cap, &fresh);
+            if (!p) return nullptr;
+            n_cuda_malloc += fresh ? 1 : 0;
             allocs.push_back(p);
             cudaMemsetAsync(p, 0, slab_cap, engine->stream);
             zero_on_run.push_back({p, slab_cap});
@@ -218,17 +380,46 @@ struct wae_batch {
         slab_used += bytes;
         return r;
     }
+    // small uploads / tables share slabs too (one device block per 4 MiB instead of one per table)
+    char* tslab = nullptr;
+    size_t tslab_used = 0, tslab_cap = 0;
+    void* table_alloc(size_t bytes) {
+        bytes = (bytes + 255) / 256 * 256;
+        if (bytes > (512u << 10)) return nullptr;
+        if (!tslab || tslab_used + bytes > tslab_cap) {
+            tslab_cap = 4u << 20;
+            bool fresh = false;
+            void* p = engine->dev_alloc(tslab_cap, &fresh);
+            if (!p) return nullptr;
+            n_cuda_malloc += fresh ? 1 : 0;
+            allocs.push_back(p);
+            tslab = (char*)p;
+            tslab_used = 0;
+        }
+        void* r = tslab + tslab_used;
+        tslab_used += bytes;
+        return r;
+    }
     template <typename T>
     T* dalloc(size_t count, bool zero = false, bool rezero_on_run = false) {
+        std::lock_guard<std::recursive_mutex> lk(mu);
         if (rezero_on_run && count * sizeof(T) <= (1u << 20)) {
             void* r = slab_alloc(count * sizeof(T));
             if (r) return (T*)r;
         }
-        void* p = nullptr;
         size_t bytes = count * sizeof(T);
         if (bytes == 0) bytes = 16;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
-        n_cuda_malloc++;
+        if (!rezero_on_run) {
+            void* r = table_alloc(bytes);
+            if (r) {
+                if (zero) cudaMemsetAsync(r, 0, bytes, engine->stream);
+                return (T*)r;
+            }
+        }
+        bool fresh = false;
+        void* p = engine->dev_alloc(bytes, &fresh);
+        if (!p) return nullptr;
+        n_cuda_malloc += fresh ? 1 : 0;
         allocs.push_back(p);
         if (zero || rezero_on_run) cudaMemsetAsync(p, 0, bytes, engine->stream);
         if (rezero_on_run) zero_on_run.push_back({p, bytes});
@@ -236,6 +427,7 @@ struct wae_batch {
     }
     template <typename T>
     T* dupload(const std::vector<T>& v) {
+        std::lock_guard<std::recursive_mutex> lk(mu);
         T* p = dalloc<T>(v.size());
         if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, engine->stream);
         return p;
@@ -324,13 +516,14 @@ struct Planner {
     std::string error;
     int error_code = 0;
     uint64_t algorithmic_bytes = 0;
-    // IR spectra cache: content hash -> device spectra
+    // IR spectra cache: content hash -> device spectra (shared by the planners of all groups of a batch, guarded by b->mu)
     struct IrSpectra {
         float2* h;
         int S;
         int channels;
     };
-    std::unordered_map<uint64_t, IrSpectra> ir_cache;
+    std::unordered_map<uint64_t, IrSpectra> own_ir_cache;
+    std::unordered_map<uint64_t, IrSpectra>* ir_cache = &own_ir_cache;
     std::map<int, std::pair<const float2*, const float2*>> os_filters;  // over-sampled shaper: factor -> (up, down) filter bins
 
     bool has_feedback = false;            // some graph has a cycle broken by a DelayNode
@@ -365,6 +558,7 @@ struct Planner {
         if (dry) return reinterpret_cast<T*>(uintptr_t(256));
         const wae_batch::StateKey key{key_graph, key_node, key_seq++, key_salt};
         const size_t bytes = count * sizeof(T);
+        std::lock_guard<std::recursive_mutex> lk(b->mu);
         auto it = b->state_map.find(key);
         if (it != b->state_map.end() && it->second.second == bytes) return (T*)it->second.first;
         T* p = b->dalloc<T>(count, zero, rezero_on_run);
@@ -603,8 +797,9 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     for (int c = 0; c < ir_ch; c++) key = fnv1a(ir.channels[c].data(), ir_len * sizeof(float), key);
     key = fnv1a(&ir_len, sizeof(ir_len), key);
     IrSpectra spec;
-    auto it = ir_cache.find(key);
-    if (it != ir_cache.end()) {
+    std::unique_lock<std::recursive_mutex> ir_lock(b->mu);
+    auto it = ir_cache->find(key);
+    if (it != ir_cache->end()) {
         spec = it->second;
     } else {
         std::vector<float> flat((size_t)ir_ch * ir_len);
@@ -617,8 +812,9 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         if (!d_ir || !spec.h) return bail(WAE_OUT_OF_MEMORY, "out of device memory (IR spectra)");
         if (!dry) launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
         b->asset_bytes += (size_t)ir_ch * Smax * WAE_CONV_SPEC * 8;
-        ir_cache[key] = spec;
+        (*ir_cache)[key] = spec;
     }
+    ir_lock.unlock();
     // inputs: one spectra ring per input channel
     StageBuild& fs = stage(level, S_CONV_FFT);
     int blocks_per_chunk = (int)((b->chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK);
@@ -1112,9 +1308,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (first_use) so = src_offsets.emplace(std::make_pair(gi, id), src_cursor).first;
                 float* d_buf = d_src + so->second;
                 if (first_use) {
-                    if (!dry && src_copies)  // uploaded straight from the graph's buffer after planning (no staging copy)
-                        for (int c = 0; c < ch; c++)
-                            src_copies->push_back(wae_batch::Group::SrcCopy{n.buffer, c, src_cursor + (size_t)c * stride, len});
+                    if (src_copies)  // recorded by the sizing pass: uploaded straight from the graph's buffer, planar [ch][stride] like the slab
+                        src_copies->push_back(wae_batch::Group::SrcCopy{n.buffer, src_cursor, (size_t)ch * stride});
                     src_cursor += (size_t)ch * stride;
                     b->asset_bytes += (size_t)ch * len * 4;
                 }
@@ -1474,6 +1669,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     uint32_t taps = sph->taps;
                     const float* d_ir = eng->d_sphere_ir;
                     if (sr != sph->sample_rate) {  // the crate resamples the responses to the context rate once (wae_hrtf_host.h)
+                        std::lock_guard<std::mutex> slk(eng->sphere_mu);
                         auto it = eng->sphere_rates.find(sr);
                         if (it == eng->sphere_rates.end()) {
                             const HrirSphere rs = sph->at_rate(sr);
@@ -1643,6 +1839,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     float* db = alloc<float>(16384);
                     if (!last || !db) return bail(WAE_OUT_OF_MEMORY, "out of device memory (analyser)");
                     if (!dry) {
+                        std::lock_guard<std::recursive_mutex> lk(b->mu);
                         bool known = false;
                         for (auto& r : b->analysers) known = known || (r.graph_index == gi && r.node == id);
                         if (!known) b->analysers.push_back(AnalyserRec{gi, id, a.ring, n.fft_size, n.smoothing, last, db, false, n.min_db, n.max_db});
@@ -1707,6 +1904,39 @@ struct EpochView {
     EpochView& operator=(const EpochView&) = delete;
 };
 
+// WAE_OPT_BIND_NUMA / WAE_BIND_NUMA=1: restrict the calling thread (and the engine's workers, which inherit the mask) to the CPUs
+// next to this engine's GPU (/sys/bus/pci/devices/<bus id>/local_cpulist), so that page-locked staging memory is allocated and
+// touched on that socket: on a two-socket host the H2D / D2H copies of eight ranks otherwise share one socket's memory
+// controllers and the inter-socket link.
+static bool bind_to_device_numa_node(wae_engine* eng) {
+    char bus[64] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, eng->device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; c++) *c = (char)std::tolower((unsigned char)*c);
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist");
+    std::string list;
+    if (!f || !std::getline(f, list) || list.empty()) return false;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    std::stringstream ss(list);
+    std::string part;
+    int n = 0;
+    while (std::getline(ss, part, ',')) {
+        int a = 0, b2 = 0;
+        if (std::sscanf(part.c_str(), "%d-%d", &a, &b2) == 2) {
+            for (int c = a; c <= b2 && c < CPU_SETSIZE; c++, n++) CPU_SET(c, &set);
+        } else if (std::sscanf(part.c_str(), "%d", &a) == 1 && a < CPU_SETSIZE) {
+            CPU_SET(a, &set);
+            n++;
+        }
+    }
+    if (n == 0 || sched_setaffinity(0, sizeof set, &set) != 0) return false;
+    eng->numa_cpus = list;
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1725,6 +1955,10 @@ WAE_API wae_status wae_engine_create(int32_t device_ordinal, wae_engine** out) {
     auto* eng = new wae_engine;
     eng->device = device_ordinal;
     CUDA_TRY(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&eng->s_d2h, cudaStreamNonBlocking));
+    if (const char* e = getenv("WAE_BIND_NUMA"))
+        if (atoi(e) != 0) bind_to_device_numa_node(eng);
     std::vector<float> sine = hm::sine_table();
     CUDA_TRY(cudaMalloc(&eng->d_sine, sine.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(eng->d_sine, sine.data(), sine.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -1748,7 +1982,13 @@ WAE_API wae_status wae_engine_destroy(wae_engine* eng) {
     if (eng->d_sphere_tri) cudaFree(eng->d_sphere_tri);
     eng->drop_rate_spheres();
     delete eng->sphere;
+    delete eng->pool;  // joins the workers
+    eng->dev_trim();
+    for (int i = 0; i < wae_engine::kStageSlots; i++)
+        if (eng->h_stage[i]) cudaFreeHost(eng->h_stage[i]);
     if (eng->stream) cudaStreamDestroy(eng->stream);
+    if (eng->s_h2d) cudaStreamDestroy(eng->s_h2d);
+    if (eng->s_d2h) cudaStreamDestroy(eng->s_d2h);
     delete eng;
     return WAE_OK;
 }
@@ -1812,6 +2052,20 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             eng->pipeline_groups = (int)value;
             return WAE_OK;
         case WAE_OPT_PARAM_PARALLEL: eng->param_parallel = value != 0; return WAE_OK;
+        case WAE_OPT_BIND_NUMA:
+            if (value != 0 && eng->pool) return fail(WAE_INVALID_STATE, "bind the engine to its NUMA node before its first render (worker threads already run)");
+            if (value != 0 && !bind_to_device_numa_node(eng)) return fail(WAE_UNSUPPORTED, "could not read / apply the CPU list of the GPU's NUMA node");
+            return WAE_OK;
+        case WAE_OPT_HOST_WORKERS:
+            if (value < 0 || value > 256) return fail(WAE_INVALID_ARGUMENT, "host workers must be in [0, 256]");
+            if (eng->pool) return fail(WAE_INVALID_STATE, "the worker threads already run");
+            eng->n_workers = (int)value;
+            return WAE_OK;
+        case WAE_OPT_CHAIN_TMA: chain_set_tuning(value != 0 ? 1 : 0, -1); return WAE_OK;
+        case WAE_OPT_CHAIN_WAVES:
+            if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "chain waves must be in [0, 1024]");
+            chain_set_tuning(-1, (int)value);
+            return WAE_OK;
         default: return fail(WAE_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -1819,15 +2073,17 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
 WAE_API wae_status wae_batch_destroy(wae_batch* b) {
     if (!b) return WAE_OK;
     cudaSetDevice(b->engine->device);
-    cudaStreamSynchronize(b->engine->stream);
+    if (b->engine->stream) {  // (a plan-only batch has no streams)
+        cudaStreamSynchronize(b->engine->stream);
+        cudaStreamSynchronize(b->engine->s_h2d);
+        cudaStreamSynchronize(b->engine->s_d2h);
+    }
     for (void* h : b->pinned) cudaFreeHost(h);
     for (auto& g : b->groups) {
         if (g.ev_h2d) cudaEventDestroy(g.ev_h2d);
         if (g.ev_done) cudaEventDestroy(g.ev_done);
     }
-    if (b->s_h2d) cudaStreamDestroy(b->s_h2d);
-    if (b->s_d2h) cudaStreamDestroy(b->s_d2h);
-    for (void* p : b->allocs) cudaFree(p);
+    for (void* p : b->allocs) b->engine->dev_release(p);  // kept by the engine for the next batch (wae_engine::dev_alloc)
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     for (auto e : b->stage_events) cudaEventDestroy(e);
@@ -1846,19 +2102,42 @@ WAE_API wae_status wae_graph_render_order(wae_graph* g, wae_node_id* ids, uint32
     return WAE_OK;
 }
 
-// `plan` != nullptr: planning only — grouping, the sizing pass of the planner (which touches no device memory) and the chunk choice,
-// reported through *plan; nothing is allocated and no CUDA call is made (wae_batch_plan: runs without a GPU).
-static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out, wae_plan_info* plan) {
-    if (!eng || !graphs || (!out && !plan) || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
+// ---- wae_batch_prepare in phases ------------------------------------------------------------------------------------------
+// A (prep_begin): validation, graph groups, the sizing pass of the planner (no device memory touched; groups in parallel on the
+//   engine's worker threads), chunk size.  B (prep_plan_group): the real plan of ONE group — allocation of its node state / arena,
+//   upload of its instance tables — safe to run for several groups at once (shared structures are guarded by wae_batch::mu).
+//   C (prep_append_group / prep_finish): the groups' stages joined in group order, statistics.
+// wae_batch_prepare runs A, B for every group, C.  The one-shot render (wae_render_batch with a host buffer) runs A, starts the
+// H2D copies of the source PCM, and then overlaps B of group k+1.. with the copies and the render of group k.
+struct PrepState {
+    std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_hint;
+    std::unordered_map<uint64_t, Planner::IrSpectra> ir_cache;
+    uint64_t algorithmic_bytes = 0;
+    std::chrono::steady_clock::time_point t0, t1;
+};
+struct GroupPlan {  // result of phase B for one group
+    std::vector<Stage> stages;
+    std::vector<std::pair<size_t, size_t>> seg_ranges;  // per segment: [first, last) into `stages`
+    uint64_t algorithmic_bytes = 0;
+    int code = WAE_OK;
+    std::string error;
+};
+
+static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_plan_info* plan, wae_batch** out_b, PrepState& ps,
+                             bool want_d_out) {
+    if (!eng || !graphs || n_graphs == 0) return fail(WAE_INVALID_ARGUMENT, "null / empty batch");
     if (!plan) CUDA_TRY(cudaSetDevice(eng->device));
     for (uint32_t i = 0; i < n_graphs; i++) {
+        if (!graphs[i]) return fail(WAE_INVALID_ARGUMENT, "null graph in the batch");
         if (graphs[i]->channels != graphs[0]->channels || graphs[i]->length != graphs[0]->length ||
             graphs[i]->sample_rate != graphs[0]->sample_rate)
             return fail(WAE_INVALID_ARGUMENT, "all graphs of a batch must share number_of_channels, length and sample_rate");
     }
-    const auto t_prep0 = std::chrono::steady_clock::now();
+    ps.t0 = std::chrono::steady_clock::now();
     auto* b = new wae_batch;
     b->engine = eng;
+    b->s_h2d = eng->s_h2d;
+    b->s_d2h = eng->s_d2h;
     b->n_graphs = n_graphs;
     b->channels = graphs[0]->channels;
     b->length = graphs[0]->length;
@@ -1877,7 +2156,7 @@ static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32
         has_conv = has_conv || graph_has_conv[i];
     }
     size_t out_floats = (size_t)n_graphs * b->channels * b->length;
-    if (!plan) {
+    if (!plan && want_d_out) {
         b->d_out = b->dalloc<float>(out_floats, true);
         if (!b->d_out) {
             wae_batch_destroy(b);
@@ -1917,57 +2196,90 @@ static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32
             }
     }
     // Sizing pass (no device memory touched): arena floats per frame of the largest group and the source-PCM slab of
-    // every group.  Chunk size: explicit option, else chosen so that a group's arena stays around 48 MiB — edge
-    // buffers are rewritten every chunk and stay L2-resident (126 MB L2).  A plan without any arena buffer (fully
-    // fused source->...->destination chains) renders the whole length in one launch per group.  Convolvers work on
-    // whole 1024-frame blocks and prefer long chunks (their spectra ring, not the arena, is the traffic that matters).
+    // every group.  Chunk size: explicit option, else chosen so that a group's arena stays around 1 GiB.  A plan without any
+    // arena buffer (fully fused source->...->destination chains) renders the whole length in one launch per group.
+    // Convolvers work on whole 8192-frame blocks and prefer long chunks (their spectra ring, not the arena, is the traffic
+    // that matters).
     b->chunk = 2048;
     uint64_t fpf = 0;
     bool has_feedback = false;
-    std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_hint;
     std::vector<std::vector<int>> plan_stage_lists;  // plan-only: stage kinds per (group, segment) of the last iteration
+    struct SizeOut {
+        uint64_t fpf = 0;
+        bool has_feedback = false;
+        std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_seen;
+        std::vector<std::vector<int>> stage_lists;
+        int code = WAE_OK;
+        std::string error;
+    };
+    WorkerPool* pool = (!plan && n_groups > 1 && n_graphs >= 64) ? eng->workers() : nullptr;
+    bool converged = false;
     for (int iter = 0; iter < 8; iter++) {  // repeated only while the channel layout of in-cycle delays changes
         bool hints_changed = false;
         fpf = 0;
         plan_stage_lists.clear();
-        for (int k = 0; k < n_groups; k++) {
+        std::vector<SizeOut> so(n_groups);
+        auto size_group = [&](int k) {
             Planner sizing{b, eng};
             sizing.dry = true;
-            sizing.delay_ch_hint = &delay_ch_hint;
+            sizing.delay_ch_hint = &ps.delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
+            b->groups[k].src_copies.clear();
+            sizing.src_copies = &b->groups[k].src_copies;
             const std::vector<int64_t>& bounds = b->groups[k].seg_bounds;
             for (size_t sg = 0; sg + 1 < bounds.size(); sg++) {
                 sizing.begin_segment(bounds[sg], bounds[sg + 1]);
                 for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
                     EpochView view(graphs[i], bounds[sg]);
                     if (!sizing.plan_graph(graphs[i], i)) {
-                        int code = sizing.error_code;
-                        std::string msg = sizing.error;
-                        wae_batch_destroy(b);
-                        return fail(code, msg);
+                        so[k].code = sizing.error_code;
+                        so[k].error = sizing.error;
+                        return;
                     }
                 }
-                fpf = std::max(fpf, sizing.arena_floats_per_frame);
+                so[k].fpf = std::max(so[k].fpf, sizing.arena_floats_per_frame);
                 if (plan) {  // the stages (= kernel launches per chunk) this segment of this group lowers to
                     std::vector<int> kinds;
                     for (auto& kv : sizing.builds) kinds.push_back(kv.second.kind);
-                    plan_stage_lists.push_back(std::move(kinds));
+                    so[k].stage_lists.push_back(std::move(kinds));
                 }
             }
             b->groups[k].src_floats = sizing.src_cursor;
-            has_feedback = has_feedback || sizing.has_feedback;
-            for (auto& kv : sizing.delay_ch_seen) {
-                auto it = delay_ch_hint.find(kv.first);
-                int cur = it == delay_ch_hint.end() ? 1 : it->second;
+            so[k].has_feedback = sizing.has_feedback;
+            so[k].delay_ch_seen = std::move(sizing.delay_ch_seen);
+        };
+        if (pool) pool->parallel_for(n_groups, size_group);
+        else
+            for (int k = 0; k < n_groups; k++) size_group(k);
+        for (int k = 0; k < n_groups; k++) {
+            if (so[k].code != WAE_OK) {
+                int code = so[k].code;
+                std::string msg = so[k].error;
+                wae_batch_destroy(b);
+                return fail(code, msg);
+            }
+            fpf = std::max(fpf, so[k].fpf);
+            has_feedback = has_feedback || so[k].has_feedback;
+            for (auto& l : so[k].stage_lists) plan_stage_lists.push_back(std::move(l));
+            for (auto& kv : so[k].delay_ch_seen) {
+                auto it = ps.delay_ch_hint.find(kv.first);
+                int cur = it == ps.delay_ch_hint.end() ? 1 : it->second;
                 if (cur != kv.second) {
-                    delay_ch_hint[kv.first] = kv.second;
+                    ps.delay_ch_hint[kv.first] = kv.second;
                     hints_changed = true;
                 }
             }
         }
-        if (!hints_changed) break;
+        if (!hints_changed) {
+            converged = true;
+            break;
+        }
     }
-    const auto t_prep1 = std::chrono::steady_clock::now();  // sizing pass done
+    if (!converged) {
+        wae_batch_destroy(b);
+        return fail(WAE_UNSUPPORTED, "the channel layout of DelayNodes inside feedback cycles did not settle (graph not lowered to the GPU)");
+    }
+    ps.t1 = std::chrono::steady_clock::now();  // sizing pass done
     b->arena_bytes = 0;
     b->asset_bytes = 0;
     int64_t chunk = eng->chunk_frames;
@@ -2008,150 +2320,156 @@ static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32
             if (per_kind[k]) txt += (txt.empty() ? "" : ", ") + std::string(kStageNames[k]) + " x " + std::to_string(per_kind[k]);
         std::snprintf(plan->stage_kinds, sizeof plan->stage_kinds, "%s", txt.c_str());
         delete b;  // nothing was allocated on the device
+        *out_b = nullptr;
         return WAE_OK;
     }
-    CUDA_TRY(cudaStreamCreateWithFlags(&b->s_h2d, cudaStreamNonBlocking));
-    CUDA_TRY(cudaStreamCreateWithFlags(&b->s_d2h, cudaStreamNonBlocking));
-    uint64_t algorithmic_bytes = 0;
-    std::unordered_map<uint64_t, Planner::IrSpectra> ir_cache;
-    for (int k = 0; k < n_groups; k++) {
-        wae_batch::Group& grp = b->groups[k];
+    for (auto& grp : b->groups) {
         CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_h2d, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_done, cudaEventDisableTiming));
         if (grp.src_floats) {
-            grp.d_src = b->dalloc<float>(grp.src_floats, true);  // zeroed: the channel paddings stay zero
+            // (not zeroed: every float of the slab is covered by a source copy, channel paddings included)
+            grp.d_src = b->dalloc<float>(grp.src_floats, false);
             if (!grp.d_src) {
                 wae_batch_destroy(b);
                 return fail(WAE_OUT_OF_MEMORY, "out of device memory (source PCM slab)");
             }
         }
-        Planner pl{b, eng};
-        pl.d_src = grp.d_src;
-        pl.src_copies = &grp.src_copies;
-        pl.delay_ch_hint = &delay_ch_hint;
-        pl.ir_cache.swap(ir_cache);
-        grp.stage0 = b->stages.size();
-        for (int sg = 0; sg + 1 < (int)grp.seg_bounds.size(); sg++) {
-            pl.begin_segment(grp.seg_bounds[sg], grp.seg_bounds[sg + 1]);
-            const uint64_t alg_before = pl.algorithmic_bytes;
-            for (uint32_t i = grp.g0; i < grp.g1; i++) {
-                EpochView view(graphs[i], grp.seg_bounds[sg]);
-                if (!pl.plan_graph(graphs[i], i)) {
-                    int code = pl.error_code;
-                    std::string msg = pl.error;
-                    wae_batch_destroy(b);
-                    return fail(code, msg);
-                }
-            }
-            // the per-node byte counts assume the whole render: scale to this segment's share of it
-            algorithmic_bytes += (uint64_t)((double)(pl.algorithmic_bytes - alg_before) * (double)(pl.seg_end - pl.seg_start) / (double)b->lq);
-            // materialise the segment's stages in (class, level, kind) order
-            const size_t seg_stage0 = b->stages.size();
-            void* last_conv_inputs = nullptr;
-            for (auto& kv : pl.builds) {
-                StageBuild& s = kv.second;
-                Stage st;
-                st.seg = sg;
-                st.cls = s.cls;
-                st.kind = s.kind;
-                st.variant = s.variant;
-                st.group = k;
-                st.max_ch = s.max_ch;
-                switch (s.kind) {
-                    case S_MIX: {
-                        for (auto& m : s.mix) {  // classify: vector fast path of k_mix
-                            bool simple = true, all_mono = m.n_edges > 0;
-                            for (int e = 0; e < m.n_edges; e++) {
-                                const MixEdge& ed = s.mix_edges[m.edge_offset + e];
-                                bool same = ed.src_ch == m.out_ch;
-                                bool dup = ed.src_ch == 1 && m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS;
-                                if (!(same || dup)) simple = false;
-                                if (ed.src_ch != 1) all_mono = false;
-                                // sources must allow 16-byte loads: arena buffers do; asset / output aliases may not
-                                if (ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) simple = false;
-                            }
-                            m.simple = simple ? 1 : 0;
-                            m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
-                        }
-                        st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
-                        break;
-                    }
-                    case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
-                    case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
-                    case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
-                    case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
-                    case S_CHAIN: {
-                        st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef);
-                        const int nb = (s.variant % 6) / 2;
-                        int slabs = 1, tps = 1;
-                        if (nb > 0) chain_plan_slabs(st.n, st.max_ch, (int)std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start), nb, &slabs, &tps);
-                        if (slabs > 1) {  // time slabs of filtered chains hand their state over through device memory
-                            const size_t slots = (size_t)st.n * st.max_ch * slabs;
-                            st.chain.slab_stride = slabs;
-                            st.chain.ticket = b->dalloc<unsigned>(1, true);
-                            st.chain.flags = b->dalloc<unsigned>(slots, true);
-                            st.chain.handoff = b->dalloc<double>(slots * CHAIN_MAX_BIQUADS * 4);
-                            if (!st.chain.ticket || !st.chain.flags || !st.chain.handoff) {
-                                wae_batch_destroy(b);
-                                return fail(WAE_OUT_OF_MEMORY, "out of device memory (chain hand-off)");
-                            }
-                        }
-                        break;
-                    }
-                    case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
-                    case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
-                    case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
-                    case S_ABSN_SLOW: st.n = (int)s.absn_slow.size(); st.d_a = up(b, s.absn_slow); break;
-                    case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
-                    case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
-                    case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
-                    case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
-                    case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
-                    case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
-                        st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
-                    case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
-                    case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
-                    case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
-                    case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
-                    case S_DELAY:
-                    case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
-                    case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
-                    case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
-                    case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
-                    case S_CONV_MAC:
-                    case S_CONV_MAC_ACC:
-                        st.n = (int)s.conv_path.size();
-                        st.d_a = up(b, s.conv_path);
-                        st.d_b = last_conv_inputs;  // conv-input table of the same level (kinds are ordered FFT < MAC < MAC_ACC)
-                        break;
-                }
-                if (st.n > 0) b->stages.push_back(st);
-            }
-            grp.seg_stages.push_back({seg_stage0, b->stages.size()});
-        }  // segments
-        ir_cache.swap(pl.ir_cache);
-        grp.stage1 = b->stages.size();
-        // first upload of the group's source PCM, straight from the graphs' buffers (a one-shot render never pays for a
-        // pinned staging copy; the pinned mirror of the pipelined path is built on first use)
-        for (auto& sc : grp.src_copies)
-            CUDA_TRY(cudaMemcpyAsync(grp.d_src + sc.offset, sc.buf->channels[sc.channel].data(), sc.len * sizeof(float), cudaMemcpyHostToDevice,
-                                     eng->stream));
     }
-    const auto t_prep2 = std::chrono::steady_clock::now();  // planned, allocated, uploads enqueued
+    *out_b = b;
+    return WAE_OK;
+}
+
+// phase B: plans group k (all its segments) and uploads its tables.  Thread-safe against other groups of the same batch.
+static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepState& ps, GroupPlan& gp) {
+    wae_engine* eng = b->engine;
+    wae_batch::Group& grp = b->groups[k];
+    Planner pl{b, eng};
+    pl.d_src = grp.d_src;
+    pl.src_copies = nullptr;  // recorded by the sizing pass
+    pl.delay_ch_hint = &ps.delay_ch_hint;
+    pl.ir_cache = &ps.ir_cache;
+    auto oom = [&](const char* what) {
+        gp.code = WAE_OUT_OF_MEMORY;
+        gp.error = std::string("out of device memory (") + what + ")";
+    };
+    for (int sg = 0; sg + 1 < (int)grp.seg_bounds.size(); sg++) {
+        pl.begin_segment(grp.seg_bounds[sg], grp.seg_bounds[sg + 1]);
+        const uint64_t alg_before = pl.algorithmic_bytes;
+        for (uint32_t i = grp.g0; i < grp.g1; i++) {
+            EpochView view(graphs[i], grp.seg_bounds[sg]);
+            if (!pl.plan_graph(graphs[i], i)) {
+                gp.code = pl.error_code;
+                gp.error = pl.error;
+                return;
+            }
+        }
+        // the per-node byte counts assume the whole render: scale to this segment's share of it
+        gp.algorithmic_bytes += (uint64_t)((double)(pl.algorithmic_bytes - alg_before) * (double)(pl.seg_end - pl.seg_start) / (double)b->lq);
+        // materialise the segment's stages in (class, level, kind) order
+        const size_t seg_stage0 = gp.stages.size();
+        void* last_conv_inputs = nullptr;
+        for (auto& kv : pl.builds) {
+            StageBuild& s = kv.second;
+            Stage st;
+            st.seg = sg;
+            st.cls = s.cls;
+            st.kind = s.kind;
+            st.variant = s.variant;
+            st.group = k;
+            st.max_ch = s.max_ch;
+            switch (s.kind) {
+                case S_MIX: {
+                    for (auto& m : s.mix) {  // classify: vector fast path of k_mix
+                        bool simple = true, all_mono = m.n_edges > 0;
+                        for (int e = 0; e < m.n_edges; e++) {
+                            const MixEdge& ed = s.mix_edges[m.edge_offset + e];
+                            bool same = ed.src_ch == m.out_ch;
+                            bool dup = ed.src_ch == 1 && m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS;
+                            if (!(same || dup)) simple = false;
+                            if (ed.src_ch != 1) all_mono = false;
+                            // sources must allow 16-byte loads: arena buffers do; asset / output aliases may not
+                            if (ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) simple = false;
+                        }
+                        m.simple = simple ? 1 : 0;
+                        m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
+                    }
+                    st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
+                    break;
+                }
+                case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
+                case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
+                case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
+                case S_BIQUAD: st.n = (int)s.biquad.size(); st.d_a = up(b, s.biquad); break;
+                case S_CHAIN: {
+                    st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef);
+                    const int nb = (s.variant % 6) / 2;
+                    int slabs = 1, tps = 1;
+                    if (nb > 0) chain_plan_slabs(st.n, st.max_ch, (int)std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start), nb, &slabs, &tps);
+                    if (slabs > 1) {  // time slabs of filtered chains hand their state over through device memory
+                        const size_t slots = (size_t)st.n * st.max_ch * slabs;
+                        st.chain.slab_stride = slabs;
+                        st.chain.ticket = b->dalloc<unsigned>(1, true);
+                        st.chain.flags = b->dalloc<unsigned>(slots, true);
+                        st.chain.handoff = b->dalloc<double>(slots * CHAIN_MAX_BIQUADS * 4);
+                        if (!st.chain.ticket || !st.chain.flags || !st.chain.handoff) return oom("chain hand-off");
+                    }
+                    break;
+                }
+                case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
+                case S_OSC_AR: st.n = (int)s.osc_ar.size(); st.d_a = up(b, s.osc_ar); break;
+                case S_BIQUAD_AR: st.n = (int)s.biquad_ar.size(); st.d_a = up(b, s.biquad_ar); break;
+                case S_ABSN_SLOW: st.n = (int)s.absn_slow.size(); st.d_a = up(b, s.absn_slow); break;
+                case S_IIR: st.n = (int)s.iir.size(); st.d_a = up(b, s.iir); break;
+                case S_GAIN: st.n = (int)s.gain.size(); st.d_a = up(b, s.gain); break;
+                case S_SHAPER: st.n = (int)s.shaper.size(); st.d_a = up(b, s.shaper); break;
+                case S_SPAN: st.n = (int)s.span.size(); st.d_a = up(b, s.span); st.d_b = up(b, s.span_gains); break;
+                case S_PAN: st.n = (int)s.pan.size(); st.d_a = up(b, s.pan); break;
+                case S_HRTF: st.n = (int)s.hrtf.size(); st.d_a = up(b, s.hrtf); st.max_ch = s.hrtf.empty() ? 0 : s.hrtf[0].L;
+                    st.n_b = (int)s.hrtf_sel.size(); st.d_b = up(b, s.hrtf_sel); break;
+                case S_PAN_DYN: st.n = (int)s.pan_dyn.size(); st.d_a = up(b, s.pan_dyn); break;
+                case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
+                case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
+                case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
+                case S_DELAY:
+                case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
+                case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
+                case S_ANALYSER: st.n = (int)s.analyser.size(); st.d_a = up(b, s.analyser); break;
+                case S_CONV_FFT: st.n = (int)s.conv_in.size(); st.d_a = up(b, s.conv_in); last_conv_inputs = st.d_a; break;
+                case S_CONV_MAC:
+                case S_CONV_MAC_ACC:
+                    st.n = (int)s.conv_path.size();
+                    st.d_a = up(b, s.conv_path);
+                    st.d_b = last_conv_inputs;  // conv-input table of the same level (kinds are ordered FFT < MAC < MAC_ACC)
+                    break;
+            }
+            if (st.n > 0) {
+                if (!st.d_a) return oom("stage tables");
+                gp.stages.push_back(st);
+            }
+        }
+        gp.seg_ranges.push_back({seg_stage0, gp.stages.size()});
+    }  // segments
+}
+
+static void prep_append_group(wae_batch* b, int k, PrepState& ps, GroupPlan& gp) {
+    wae_batch::Group& grp = b->groups[k];
+    grp.stage0 = b->stages.size();
+    for (auto& r : gp.seg_ranges) grp.seg_stages.push_back({grp.stage0 + r.first, grp.stage0 + r.second});
+    for (auto& st : gp.stages) b->stages.push_back(st);
+    grp.stage1 = b->stages.size();
+    ps.algorithmic_bytes += gp.algorithmic_bytes;
+}
+
+// H2D of a group's source PCM, one copy per AudioBufferSourceNode, straight from the buffers the graphs own
+static wae_status enqueue_source_copies(wae_batch* b, wae_batch::Group& grp, cudaStream_t s) {
+    for (auto& sc : grp.src_copies)
+        CUDA_TRY(cudaMemcpyAsync(grp.d_src + sc.offset, sc.buf->base, sc.floats * sizeof(float), cudaMemcpyHostToDevice, s));
+    return WAE_OK;
+}
+
+static wae_status prep_finish(wae_batch* b, PrepState& ps) {
     CUDA_TRY(cudaEventCreate(&b->ev0));
     CUDA_TRY(cudaEventCreate(&b->ev1));
-    CUDA_TRY(cudaStreamSynchronize(eng->stream));
-    if (getenv("WAE_PREPARE_PROFILE")) {
-        const auto t_prep3 = std::chrono::steady_clock::now();
-        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
-        std::fprintf(stderr, "[wae prepare] sizing %.1f ms, plan+alloc+upload %.1f ms, sync %.1f ms, cudaMalloc calls %llu, stages %zu\n", ms(t_prep0, t_prep1),
-                     ms(t_prep1, t_prep2), ms(t_prep2, t_prep3), (unsigned long long)b->n_cuda_malloc, b->stages.size());
-    }
-    cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) {
-        wae_batch_destroy(b);
-        return fail(WAE_CUDA_ERROR, std::string("prepare: ") + cudaGetErrorString(le));
-    }
     int64_t n_chunks = 0;
     for (auto& grp : b->groups)  // the largest number of chunks any group renders
     {
@@ -2174,8 +2492,58 @@ static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32
     b->stats.chunks = (uint64_t)n_chunks;
     b->stats.arena_bytes = b->arena_bytes;
     b->stats.asset_bytes = b->asset_bytes;
-    b->stats.algorithmic_bytes = algorithmic_bytes;
-    b->stats.graph_quanta = (uint64_t)n_graphs * (uint64_t)(b->lq / 128);
+    b->stats.algorithmic_bytes = ps.algorithmic_bytes;
+    b->stats.graph_quanta = (uint64_t)b->n_graphs * (uint64_t)(b->lq / 128);
+    return WAE_OK;
+}
+
+// `plan` != nullptr: planning only — grouping, the sizing pass of the planner (which touches no device memory) and the chunk choice,
+// reported through *plan; nothing is allocated and no CUDA call is made (wae_batch_plan: runs without a GPU).
+static wae_status prepare_impl(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, wae_batch** out, wae_plan_info* plan) {
+    if (!out && !plan) return fail(WAE_INVALID_ARGUMENT, "null out pointer");
+    PrepState ps;
+    wae_batch* b = nullptr;
+    wae_status st = prep_begin(eng, graphs, n_graphs, plan, &b, ps, true);
+    if (st != WAE_OK || plan) return st;
+    const int n_groups = (int)b->groups.size();
+    std::vector<GroupPlan> gps(n_groups);
+    WorkerPool* pool = (n_groups > 1 && n_graphs >= 64) ? eng->workers() : nullptr;
+    if (pool) pool->parallel_for(n_groups, [&](int k) { prep_plan_group(b, graphs, k, ps, gps[k]); });
+    else
+        for (int k = 0; k < n_groups; k++) prep_plan_group(b, graphs, k, ps, gps[k]);
+    for (int k = 0; k < n_groups; k++) {
+        if (gps[k].code != WAE_OK) {
+            int code = gps[k].code;
+            std::string msg = gps[k].error;
+            wae_batch_destroy(b);
+            return fail(code, msg);
+        }
+        prep_append_group(b, k, ps, gps[k]);
+        // first upload of the group's source PCM, straight from the graphs' buffers (page-locked when the graphs have an engine)
+        wae_status cs = enqueue_source_copies(b, b->groups[k], eng->stream);
+        if (cs != WAE_OK) {
+            wae_batch_destroy(b);
+            return cs;
+        }
+    }
+    const auto t_prep2 = std::chrono::steady_clock::now();  // planned, allocated, uploads enqueued
+    st = prep_finish(b, ps);
+    if (st == WAE_OK && cudaStreamSynchronize(eng->stream) != cudaSuccess) st = fail(WAE_CUDA_ERROR, "prepare: stream synchronisation failed");
+    if (st != WAE_OK) {
+        wae_batch_destroy(b);
+        return st;
+    }
+    if (getenv("WAE_PREPARE_PROFILE")) {
+        const auto t_prep3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point c) { return std::chrono::duration<double, std::milli>(c - a).count(); };
+        std::fprintf(stderr, "[wae prepare] sizing %.1f ms, plan+alloc+upload %.1f ms, sync %.1f ms, fresh device blocks %llu, stages %zu\n", ms(ps.t0, ps.t1),
+                     ms(ps.t1, t_prep2), ms(t_prep2, t_prep3), (unsigned long long)b->n_cuda_malloc, b->stages.size());
+    }
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        wae_batch_destroy(b);
+        return fail(WAE_CUDA_ERROR, std::string("prepare: ") + cudaGetErrorString(le));
+    }
     *out = b;
     return WAE_OK;
 }
@@ -2230,10 +2598,16 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
     }
 }
 
-// pinned host mirror of every group's source-PCM slab: built once, when the PCM is uploaded a second time
+// Groups whose source PCM is not all page-locked (graphs built without an engine, buffers below the pinning threshold) get a pinned
+// mirror of their slab, built once, when the PCM is uploaded a second time; page-locked buffers are copied from where they are.
+static bool group_sources_pinned(const wae_batch::Group& g) {
+    for (auto& sc : g.src_copies)
+        if (!sc.buf->pinned) return false;
+    return true;
+}
 static wae_status ensure_host_mirror(wae_batch* b) {
     for (auto& g : b->groups) {
-        if (!g.src_floats || g.h_src) continue;
+        if (!g.src_floats || g.h_src || group_sources_pinned(g)) continue;
         void* hp = nullptr;
         if (cudaHostAlloc(&hp, g.src_floats * sizeof(float), cudaHostAllocDefault) != cudaSuccess) {
             cudaGetLastError();
@@ -2241,20 +2615,28 @@ static wae_status ensure_host_mirror(wae_batch* b) {
         }
         b->pinned.push_back(hp);
         g.h_src = (float*)hp;
-        std::memset(hp, 0, g.src_floats * sizeof(float));
-        for (auto& sc : g.src_copies) std::memcpy(g.h_src + sc.offset, sc.buf->channels[sc.channel].data(), sc.len * sizeof(float));
+        for (auto& sc : g.src_copies) std::memcpy(g.h_src + sc.offset, sc.buf->base, sc.floats * sizeof(float));
     }
     return WAE_OK;
 }
+static wae_status resend_group_sources(wae_batch* b, wae_batch::Group& g, cudaStream_t s) {
+    if (!g.src_floats) return WAE_OK;
+    if (g.h_src) {
+        CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, s));
+        return WAE_OK;
+    }
+    return enqueue_source_copies(b, g, s);
+}
 
-// re-upload the source PCM of every AudioBufferSourceNode from the pinned host mirror (one copy per group)
+// re-upload the source PCM of every AudioBufferSourceNode (page-locked buffers / pinned mirror)
 WAE_API wae_status wae_batch_upload(wae_batch* b) {
     CUDA_TRY(cudaSetDevice(b->engine->device));
     wae_status ms = ensure_host_mirror(b);
     if (ms != WAE_OK) return ms;
-    for (auto& g : b->groups)
-        if (g.src_floats)
-            CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->engine->stream));
+    for (auto& g : b->groups) {
+        ms = resend_group_sources(b, g, b->engine->stream);
+        if (ms != WAE_OK) return ms;
+    }
     return WAE_OK;
 }
 
@@ -2342,6 +2724,31 @@ WAE_API wae_status wae_batch_run(wae_batch* b) {
     return WAE_OK;
 }
 
+WAE_API wae_status wae_batch_group_count(wae_batch* b, uint32_t* n_groups) {
+    if (!b || !n_groups) return fail(WAE_INVALID_ARGUMENT, "null argument");
+    *n_groups = (uint32_t)b->groups.size();
+    return WAE_OK;
+}
+WAE_API wae_status wae_batch_group_range(wae_batch* b, uint32_t group, uint32_t* first_graph, uint32_t* last_graph) {
+    if (!b || !first_graph || !last_graph || group >= b->groups.size()) return fail(WAE_INVALID_ARGUMENT, "null argument / group out of range");
+    *first_graph = b->groups[group].g0;
+    *last_graph = b->groups[group].g1;
+    return WAE_OK;
+}
+WAE_API wae_status wae_batch_run_group(wae_batch* b, uint32_t group) {
+    if (!b || group >= b->groups.size()) return fail(WAE_INVALID_ARGUMENT, "null batch / group out of range");
+    wae_status st = WAE_OK;
+    if (group == 0) st = begin_run(b);
+    else CUDA_TRY(cudaSetDevice(b->engine->device));
+    if (st != WAE_OK) return st;
+    st = run_group(b, b->groups[group]);
+    if (st != WAE_OK) return st;
+    if (group + 1 == b->groups.size()) CUDA_TRY(cudaEventRecord(b->ev1, b->engine->stream));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(WAE_CUDA_ERROR, std::string("run_group: ") + cudaGetErrorString(le));
+    return WAE_OK;
+}
+
 // End-to-end render with HOST buffers: for every group, H2D of its source PCM (pinned mirror), render, D2H of its
 // rendered PCM into `host_out` ([n_graphs][channels][length] f32; pinned memory gives full PCIe speed) — on three
 // streams, so the copies of neighbouring groups overlap the render.  Synchronous: returns when host_out is complete.
@@ -2354,7 +2761,8 @@ static wae_status run_pipelined(wae_batch* b, float* host_out, bool resend_sourc
     const size_t per_graph = (size_t)b->channels * b->length;
     for (auto& g : b->groups) {
         if (g.src_floats && resend_sources) {
-            CUDA_TRY(cudaMemcpyAsync(g.d_src, g.h_src, g.src_floats * sizeof(float), cudaMemcpyHostToDevice, b->s_h2d));
+            st = resend_group_sources(b, g, b->s_h2d);
+            if (st != WAE_OK) return st;
             CUDA_TRY(cudaEventRecord(g.ev_h2d, b->s_h2d));
             CUDA_TRY(cudaStreamWaitEvent(s, g.ev_h2d, 0));
         }
@@ -2429,28 +2837,175 @@ WAE_API wae_status wae_batch_get_stats(wae_batch* b, wae_batch_stats* out) {
     return WAE_OK;
 }
 
+// ---- one-shot render into a HOST buffer: what `OfflineAudioContext::start_rendering_sync` (src/context/offline.rs:157-185) is for
+// a batch of contexts.  Everything a render needs happens inside this call, overlapped:
+//   sizing pass (workers, all groups at once)
+//   -> H2D of every group's source PCM (copy stream; straight from the graphs' page-locked AudioBuffer memory)
+//   -> per group, in order: plan (workers, running ahead) | render (engine stream, waits for the group's PCM) | D2H (copy stream)
+//   -> D2H lands in `out` directly when `out` is page-locked, else in one of four page-locked staging slots that worker threads
+//      copy out to `out` while the next groups are in flight.
+// Device memory comes from the engine's cache (wae_engine::dev_alloc): after the first call of a given shape no cudaMalloc / cudaFree.
+static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, float* out) {
+    if (!out) return fail(WAE_INVALID_ARGUMENT, "null output buffer");
+    PrepState ps;
+    wae_batch* b = nullptr;
+    wae_status st = prep_begin(eng, graphs, n_graphs, nullptr, &b, ps, true);
+    if (st != WAE_OK) return st;
+    const int n_groups = (int)b->groups.size();
+    const size_t per_graph = (size_t)b->channels * b->length;
+    cudaStream_t s = eng->stream;
+    WorkerPool* pool = eng->workers();
+    // ---- everything below must run to its end before the batch can be destroyed: `pending` counts worker tasks in flight
+    std::mutex mu;
+    std::condition_variable cv;
+    int pending = 0;
+    std::vector<char> planned(n_groups, 0);
+    std::vector<GroupPlan> gps(n_groups);
+    auto task_done = [&] {
+        std::lock_guard<std::mutex> lk(mu);
+        pending--;
+        cv.notify_all();
+    };
+    auto drain = [&] {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return pending == 0; });
+    };
+    wae_status result = WAE_OK;
+    std::string result_msg;
+    auto set_fail = [&](wae_status code, const std::string& msg) {
+        if (result == WAE_OK) {
+            result = code;
+            result_msg = msg;
+        }
+    };
+    // 1. the source PCM of all groups, in group order, on the H2D stream
+    for (int k = 0; k < n_groups && result == WAE_OK; k++) {
+        wae_batch::Group& grp = b->groups[k];
+        if (!grp.src_floats) continue;
+        if (enqueue_source_copies(b, grp, eng->s_h2d) != WAE_OK || cudaEventRecord(grp.ev_h2d, eng->s_h2d) != cudaSuccess)
+            set_fail(WAE_CUDA_ERROR, std::string("one-shot render: H2D of the source PCM failed: ") + wae_last_error());
+    }
+    // 2. plans, running ahead of the render on the workers
+    if (result == WAE_OK) {
+        std::lock_guard<std::mutex> lk(mu);
+        pending += n_groups;
+    }
+    if (result == WAE_OK)
+        for (int k = 0; k < n_groups; k++)
+            pool->submit([&, k] {
+                prep_plan_group(b, graphs, k, ps, gps[k]);
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    planned[k] = 1;
+                }
+                task_done();
+            });
+    // 3. where the rendered PCM lands
+    bool out_pinned = false;
+    {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) out_pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    size_t max_group_bytes = 0;
+    for (auto& grp : b->groups) max_group_bytes = std::max(max_group_bytes, (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float));
+    if (result == WAE_OK && !out_pinned && !eng->ensure_stage(max_group_bytes)) set_fail(WAE_OUT_OF_MEMORY, "out of memory (page-locked staging of the rendered PCM)");
+    constexpr int SLOTS = wae_engine::kStageSlots;
+    bool slot_busy[SLOTS] = {false, false, false, false};
+    std::vector<cudaEvent_t> ev_copy(out_pinned ? 0 : n_groups, nullptr);
+    std::vector<std::unique_ptr<std::atomic<int>>> parts_left;
+    for (auto& e : ev_copy)
+        if (result == WAE_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
+            set_fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+    const int copy_parts = std::max(1, std::min(8, pool->size() / 2));
+    if (result == WAE_OK) {
+        if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventRecord(b->ev0, s) != cudaSuccess)
+            set_fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+    }
+    // 4. group by group: wait for its plan, render, copy back
+    for (int k = 0; k < n_groups && result == WAE_OK; k++) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return planned[k] != 0; });
+        }
+        if (gps[k].code != WAE_OK) {
+            set_fail(gps[k].code, gps[k].error);
+            break;
+        }
+        prep_append_group(b, k, ps, gps[k]);
+        wae_batch::Group& grp = b->groups[k];
+        if (grp.src_floats && cudaStreamWaitEvent(s, grp.ev_h2d, 0) != cudaSuccess) {
+            set_fail(WAE_CUDA_ERROR, "cudaStreamWaitEvent failed");
+            break;
+        }
+        if (run_group(b, grp) != WAE_OK) {
+            set_fail(WAE_CUDA_ERROR, wae_last_error());
+            break;
+        }
+        const size_t off = (size_t)grp.g0 * per_graph, bytes = (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float);
+        if (cudaEventRecord(grp.ev_done, s) != cudaSuccess || cudaStreamWaitEvent(eng->s_d2h, grp.ev_done, 0) != cudaSuccess) {
+            set_fail(WAE_CUDA_ERROR, "event record / wait failed");
+            break;
+        }
+        if (out_pinned) {
+            if (cudaMemcpyAsync(out + off, b->d_out + off, bytes, cudaMemcpyDeviceToHost, eng->s_d2h) != cudaSuccess) set_fail(WAE_CUDA_ERROR, "D2H failed");
+            continue;
+        }
+        const int slot = k % SLOTS;
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !slot_busy[slot]; });
+            slot_busy[slot] = true;
+            pending += copy_parts;
+        }
+        if (cudaMemcpyAsync(eng->h_stage[slot], b->d_out + off, bytes, cudaMemcpyDeviceToHost, eng->s_d2h) != cudaSuccess ||
+            cudaEventRecord(ev_copy[k], eng->s_d2h) != cudaSuccess) {
+            set_fail(WAE_CUDA_ERROR, "D2H failed");
+            std::lock_guard<std::mutex> lk(mu);
+            pending -= copy_parts;
+            slot_busy[slot] = false;
+            break;
+        }
+        parts_left.emplace_back(new std::atomic<int>(copy_parts));
+        std::atomic<int>* left = parts_left.back().get();
+        for (int part = 0; part < copy_parts; part++)
+            pool->submit([&, k, slot, part, left, off, bytes] {
+                cudaEventSynchronize(ev_copy[k]);
+                const size_t chunk = (bytes / copy_parts + 63) / 64 * 64;
+                const size_t a0 = std::min(bytes, (size_t)part * chunk), a1 = std::min(bytes, a0 + chunk);
+                if (a1 > a0) std::memcpy((char*)(out + off) + a0, (const char*)eng->h_stage[slot] + a0, a1 - a0);
+                if (left->fetch_sub(1) == 1) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    slot_busy[slot] = false;
+                }
+                task_done();
+            });
+    }
+    if (result == WAE_OK && cudaEventRecord(b->ev1, s) != cudaSuccess) set_fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+    drain();  // plans and copy-outs
+    if (cudaStreamSynchronize(eng->s_d2h) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess || cudaStreamSynchronize(eng->s_h2d) != cudaSuccess)
+        set_fail(WAE_CUDA_ERROR, std::string("one-shot render: ") + cudaGetErrorString(cudaGetLastError()));
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) set_fail(WAE_CUDA_ERROR, std::string("one-shot render: ") + cudaGetErrorString(le));
+    for (auto& e : ev_copy)
+        if (e) cudaEventDestroy(e);
+    wae_batch_destroy(b);
+    if (result != WAE_OK) return fail(result, result_msg);
+    return WAE_OK;
+}
+
 WAE_API wae_status wae_render_batch(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, float* out, uint32_t flags) {
+    if (!(flags & WAE_RENDER_OUT_DEVICE)) return render_oneshot_host(eng, graphs, n_graphs, out);
     wae_batch* b = nullptr;
     wae_status st = wae_batch_prepare(eng, graphs, n_graphs, &b);
     if (st != WAE_OK) return st;
-    if (!(flags & WAE_RENDER_OUT_DEVICE)) {
-        st = run_pipelined(b, out, false);  // source PCM was uploaded at prepare: render group by group, D2H overlapped
-        std::string saved0 = wae_last_error();
-        wae_batch_destroy(b);
-        if (st != WAE_OK) set_error(saved0);
-        return st;
-    }
     st = wae_batch_run(b);
     if (st == WAE_OK) st = wae_batch_sync(b);
     if (st == WAE_OK) {
-        if (flags & WAE_RENDER_OUT_DEVICE) {
-            size_t bytes = (size_t)b->n_graphs * b->channels * b->length * sizeof(float);
-            cudaError_t e = cudaMemcpyAsync(out, b->d_out, bytes, cudaMemcpyDeviceToDevice, eng->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(eng->stream);
-            if (e != cudaSuccess) st = fail(WAE_CUDA_ERROR, cudaGetErrorString(e));
-        } else {
-            st = wae_batch_fetch(b, out);
-        }
+        size_t bytes = (size_t)b->n_graphs * b->channels * b->length * sizeof(float);
+        cudaError_t e = cudaMemcpyAsync(out, b->d_out, bytes, cudaMemcpyDeviceToDevice, eng->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(eng->stream);
+        if (e != cudaSuccess) st = fail(WAE_CUDA_ERROR, cudaGetErrorString(e));
     }
     std::string saved = wae_last_error();
     wae_batch_destroy(b);

@@ -7,6 +7,7 @@
 #pragma once
 #include "../../include/wae.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -24,9 +25,54 @@ struct ChannelCfg {
     int count = 2, mode = WAE_COUNT_MODE_MAX, interp = WAE_INTERPRETATION_SPEAKERS;
 };
 
-struct PcmBuffer {  // an AudioBuffer asset (src/buffer.rs:69-72), host copy
-    std::vector<std::vector<float>> channels;
+// Host memory of AudioBuffer assets.  When the graph belongs to an engine the samples live in page-locked memory drawn from a
+// process-wide pool (slabs of cudaHostAlloc memory, recycled by size), so that the render call can DMA them to the device at full
+// PCIe speed straight from where `wae_create_buffer_source` / `set_buffer` put them — the counterpart of the reference moving the
+// `Arc<AudioBuffer>` to its render thread (audio_buffer_source.rs:853-866).  Without an engine (CPU-only planning / validation) or
+// when page-locking fails it is ordinary heap memory.
+void* pcm_host_alloc(size_t bytes, bool want_pinned, bool* pinned);
+void pcm_host_free(void* p, size_t bytes, bool pinned);
+
+struct PcmChannel {  // one channel of a PcmBuffer: a view with the std::vector surface the planner uses
+    float* p = nullptr;
+    size_t n = 0;
+    float* data() { return p; }
+    const float* data() const { return p; }
+    size_t size() const { return n; }
+    float& operator[](size_t i) { return p[i]; }
+    const float& operator[](size_t i) const { return p[i]; }
+    float* begin() { return p; }
+    float* end() { return p + n; }
+    const float* begin() const { return p; }
+    const float* end() const { return p + n; }
+};
+
+struct PcmBuffer {  // an AudioBuffer asset (src/buffer.rs:69-72), host copy: ONE block, planar [ch][stride], stride = len rounded up to 4
+                    // floats with zeroed padding — the layout of the device copy (every channel starts 16 B aligned)
+    std::vector<PcmChannel> channels;
     float sample_rate = 0.f;
+    float* base = nullptr;
+    size_t stride = 0, bytes = 0;
+    bool pinned = false;
+    PcmBuffer() = default;
+    PcmBuffer(const PcmBuffer&) = delete;
+    PcmBuffer& operator=(const PcmBuffer&) = delete;
+    ~PcmBuffer() {
+        if (base) pcm_host_free(base, bytes, pinned);
+    }
+    bool allocate(size_t n_channels, size_t len, bool want_pinned) {
+        stride = (len + 3) / 4 * 4;
+        bytes = std::max<size_t>(n_channels * stride, 4) * sizeof(float);
+        base = static_cast<float*>(pcm_host_alloc(bytes, want_pinned, &pinned));
+        if (!base) return false;
+        channels.resize(n_channels);
+        for (size_t c = 0; c < n_channels; c++) {
+            channels[c].p = base + c * stride;
+            channels[c].n = len;
+            for (size_t i = len; i < stride; i++) channels[c].p[i] = 0.f;
+        }
+        return true;
+    }
     size_t length() const { return channels.empty() ? 0 : channels[0].size(); }
     double duration() const { return (double)length() / (double)sample_rate; }
 };
@@ -117,6 +163,7 @@ struct wae_graph {
 };
 
 namespace wae {
+int engine_device(const wae_engine* eng);  // CUDA device ordinal of an engine (wae_engine.cu)
 void set_error(const std::string& msg);
 int32_t fail(int32_t code, const std::string& msg);
 }  // namespace wae

@@ -885,7 +885,10 @@ template <int N>
 DEVI void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 DEVI void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int CH_STAGES = 4;  // source tiles in flight per CTA (8 KB each)
+#ifndef WAE_CH_STAGES
+#define WAE_CH_STAGES 4
+#endif
+constexpr int CH_STAGES = WAE_CH_STAGES;  // source tiles in flight per CTA (8 KB each)
 
 // conditional exchange of two 16-byte pieces (the un-permutation of the bank-conflict-free access order, see k_chain)
 DEVI void cswap4(bool p, float4& a, float4& b) {
@@ -990,7 +993,7 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
     // for the same reason) and puts them back in place with two conditional exchanges.
     constexpr int WF = 32 * CH_K / 4;  // float4 pieces per warp region (128)
     __shared__ __align__(128) float4 s_io[NST][CH_WARPS][WF];
-    __shared__ __align__(8) uint64_t s_bar[USE_TMA ? NST : 1][CH_WARPS];
+    __shared__ __align__(8) uint64_t s_bar[USE_TMA ? NST : 1];  // TMA: one barrier per stage, armed with the tile's 8 KB
     // swizzle f -> f ^ ((f >> 3) & 3).  For the coalesced pieces f = 32u + lane it only touches the lane part, for the
     // thread's own pieces f = 4 lane + u only the u part: both reduce to one per-thread constant plus a compile-time offset
     const int lane_sw = lane ^ ((lane >> 3) & 3);  // coalesced piece 32u + lane lives at 32u + lane_sw
@@ -999,9 +1002,7 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
     if (USE_TMA) {
         if (t == 0) {
 #pragma unroll
-            for (int s = 0; s < NST; s++)
-#pragma unroll
-                for (int w2 = 0; w2 < CH_WARPS; w2++) mbar_init(&s_bar[s][w2], 1);
+            for (int s = 0; s < NST; s++) mbar_init(&s_bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -1045,20 +1046,35 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
                 s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
         }
     };
-    // TMA path (lane 0 only): one 2 KB bulk copy per warp region, completion on the region's mbarrier
+    // TMA path: whole tile (2048 frames, 8 KB) readable as one aligned run?  (CTA-uniform, pure function)
+    auto tile_src = [&](int tile_base) -> const float* {
+        if (!STREAMED || tile_base + tile > ci.nf) return nullptr;
+        if (SRC == CHAIN_SRC_BUFFER) {
+            const float* gp = chan(q.in, c, ci) + tile_base;
+            return (reinterpret_cast<uintptr_t>(gp) & 15) == 0 ? gp : nullptr;
+        } else {
+            const AbsnInst& o = q.absn;
+            const float* src = o.buf + (size_t)c * o.buf_stride;
+            const int64_t n = ci.f0 + tile_base;
+            const int64_t idx = n - o.n_start + o.buf_offset;
+            if (!o.loop && n >= o.n_start && idx + tile <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) return src + idx;
+            return nullptr;
+        }
+    };
+    // TMA path (thread 0 only): one 8 KB bulk copy per tile, completion on the stage's mbarrier
     auto issue_bulk = [&](int buf, int tile_base) {
         if (tile_base >= slab_end) return;
-        const float* gp = region_src(tile_base);
+        const float* gp = tile_src(tile_base);
         if (gp) {
-            mbar_expect_tx(&s_bar[buf][warp], 32 * CH_K * 4);
-            bulk_load(&s_io[buf][warp][0], gp, 32 * CH_K * 4, &s_bar[buf][warp]);
+            mbar_expect_tx(&s_bar[buf], tile * 4);
+            bulk_load(&s_io[buf][0][0], gp, tile * 4, &s_bar[buf]);
         }
     };
     float v[CH_K];
     unsigned par = 0;  // TMA path: phase parity of every stage's barrier (bit s), flipped each time the stage is consumed
     if (STREAMED) {
         if (USE_TMA) {
-            if (lane == 0)
+            if (t == 0)
 #pragma unroll
                 for (int s = 0; s < NST - 1; s++) issue_bulk(s, slab_begin + s * tile);
         } else {
@@ -1088,8 +1104,8 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
                 }
             }
         } else if (USE_TMA) {
-            if (region_src(base) != nullptr) {  // warp-uniform: the region arrived by bulk copy (all its threads are active)
-                mbar_wait(&s_bar[buf][warp], (par >> buf) & 1u);
+            if (tile_src(base) != nullptr) {  // CTA-uniform: the tile arrived by bulk copy (all threads are active)
+                mbar_wait(&s_bar[buf], (par >> buf) & 1u);
                 par ^= 1u << buf;
                 float4 a[CH_K / 4];
 #pragma unroll
@@ -1146,9 +1162,12 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
             const bool in_limit = q.limit < 0 || ci.f0 + nw + 32 * CH_K <= q.limit;
             const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + nw) & 15) == 0 &&
                                  (q.out_dup <= 1 || (q.out.stride & 3) == 0);
-            if (region_full && in_limit && aligned) {  // warp-uniform
-                __syncwarp();
-                if (USE_TMA) {
+            // TMA path: the whole tile leaves as one 8 KB bulk store per output channel (CTA-uniform condition)
+            const bool tile_out = USE_TMA && base + tile <= ci.nf && (q.limit < 0 || ci.f0 + base + tile <= q.limit) &&
+                                  (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + base) & 15) == 0 &&
+                                  (q.out_dup <= 1 || (q.out.stride & 3) == 0);
+            if (USE_TMA) {
+                if (tile_out) {
                     float4 a[CH_K / 4];
 #pragma unroll
                     for (int u = 0; u < CH_K / 4; u++) a[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
@@ -1159,24 +1178,37 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
 #pragma unroll
                     for (int u = 0; u < CH_K / 4; u++) s_io[buf][warp][4 * lane + (u ^ xq)] = a[u];
                     fence_proxy_async_smem();  // generic-proxy writes -> visible to the bulk store's async-proxy reads
-                    __syncwarp();
-                    if (lane == 0)
-                        for (int oc = 0; oc < n_out; oc++)
-                            bulk_store(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw, &s_io[buf][warp][0], 32 * CH_K * 4);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < CH_K / 4; u++)
-                        s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                    __syncwarp();
+                } else if (active) {
+                    const int64_t nabs = ci.f0 + n0;
                     for (int oc = 0; oc < n_out; oc++) {
-                        float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+                        float* out = chan(q.out, q.out_dup > 1 ? oc : c, ci) + n0;
 #pragma unroll
-                        for (int u = 0; u < CH_K / 4; u++) {
-                            out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
-                        }
+                        for (int j = 0; j < CH_K; j++)
+                            if (q.limit < 0 || nabs + j < q.limit) out[j] = v[j];
                     }
-                    __syncwarp();
                 }
+                __syncthreads();  // the tile is staged (and the carried filter state of this tile is visible to the next)
+                if (t == 0) {
+                    if (tile_out)
+                        for (int oc = 0; oc < n_out; oc++) bulk_store(chan(q.out, q.out_dup > 1 ? oc : c, ci) + base, &s_io[buf][0][0], tile * 4);
+                    bulk_commit();        // this tile's stores (possibly none) form one group ...
+                    bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
+                    issue_bulk(pbuf, base + (NST - 1) * tile);
+                }
+            } else if (region_full && in_limit && aligned) {  // warp-uniform
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < CH_K / 4; u++)
+                    s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                __syncwarp();
+                for (int oc = 0; oc < n_out; oc++) {
+                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++) {
+                        out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
+                    }
+                }
+                __syncwarp();
             } else if (active) {
                 const int64_t nabs = ci.f0 + n0;
                 for (int oc = 0; oc < n_out; oc++) {
@@ -1186,16 +1218,11 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
                         if (q.limit < 0 || nabs + j < q.limit) out[j] = v[j];
                 }
             }
-            if (USE_TMA && lane == 0) {
-                bulk_commit();        // this tile's stores (possibly none) form one group ...
-                bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
-                issue_bulk(pbuf, base + (NST - 1) * tile);
-            }
         }
-        if (NB > 0) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
+        if (NB > 0 && !USE_TMA) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
         buf = buf + 1 == NST ? 0 : buf + 1;
     }
-    if (USE_TMA && lane == 0) bulk_wait_read<0>();  // shared memory stays valid until the last bulk store has read it
+    if (USE_TMA && t == 0) bulk_wait_read<0>();  // shared memory stays valid until the last bulk store has read it
     // carry the filter state: to the next slab of this launch, or (last slab) to the next chunk
     if (NB > 0) {
         if (last_slab) {
@@ -2623,6 +2650,17 @@ static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, i
     sc.flags = aux.flags;
     const unsigned grid = (unsigned)n * (unsigned)max_ch * (unsigned)sc.n_slabs;
     constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;
+    // six CTAs of ~35 KB staging each only fit an SM with the shared-memory carve-out at its maximum
+    static bool carved = false;
+    if (!carved) {
+        carved = true;
+        cudaFuncSetAttribute(k_chain<SRC, NB, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_chain<SRC, NB, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if constexpr (STREAMED) {
+            cudaFuncSetAttribute(k_chain<SRC, NB, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(k_chain<SRC, NB, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+    }
     if constexpr (STREAMED) {
         if (g_chain_tma) {
             if (shaper) k_chain<SRC, NB, true, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
