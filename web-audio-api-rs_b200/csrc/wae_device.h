@@ -13,11 +13,23 @@
 
 namespace wae {
 
+// Dynamic layout (src/render/quantum.rs:109-111,179-260): in the reference a node output is a quantum of 1..32 channels whose count
+// can change from one render quantum to the next, and "silent" is a property of the quantum (one shared zero buffer), which
+// processors branch on.  A buffer whose layout the planner cannot prove constant carries a per-quantum META track:
+//   meta[row * meta_stride + qi], rows = the buffer's static (maximum) channel count, qi = quantum index inside the chunk's arena;
+//   low 6 bits = channels of that quantum (row 0 is authoritative), bit 7 = "this row's channel is silent";
+//   the quantum is silent <=> every row has bit 7 (rows let per-channel CTAs / threads report their own filter tail).
+// PCM of channels >= count, and of silent quanta, is unspecified: consumers of a buffer with a meta track read only what the
+// track says exists.  meta == nullptr: the layout is constant (count = static channels, never silent) and nothing is looked up.
 struct BufRef {
     float* p;           // channel 0, frame 0 of the chunk (arena) or of the whole render (absolute)
     uint32_t stride;    // floats between channels
     uint32_t absolute;  // 1: index with f0 + n (final output / assets), 0: index with n (arena)
+    uint8_t* meta;      // per-quantum layout track or nullptr (constant layout)
+    uint32_t meta_stride;
+    uint32_t meta_pad;
 };
+constexpr uint8_t WAE_META_SILENT = 0x80;
 
 struct ChunkInfo {
     int64_t f0;  // first frame of this chunk
@@ -109,6 +121,7 @@ struct BiquadInst {
     double* state;  // [ch][4] = x1, x2, y1, y2 (biquad_filter.rs:761)
     int32_t ch;
     int32_t pad;
+    int32_t* dyn_len;  // [ch] (dynamic input layout only): `xy.len()`, the channel count of the last non-silent input quantum
 };
 
 struct IirInst {
@@ -117,6 +130,7 @@ struct IirInst {
     double* state;        // [ch][20]
     int32_t n;            // number of coefficients
     int32_t ch;
+    int32_t* dyn_len;     // [ch] (dynamic input layout only): `states.len()` of the reference
 };
 
 struct GainInst {
@@ -226,6 +240,12 @@ struct DelayInst {
     float* ring;         // [ch][ring_len]
     uint32_t ring_len;   // power of two
     int32_t ch;
+    // dynamic input layout (static channels <= 2): the reference re-mixes its whole ring whenever the input's channel count changes
+    // (delay.rs:470-488), i.e. a stereo sample collapses to its mono down-mix as soon as a one-channel (or silent) quantum is written
+    // after it.  mono_at[q mod mono_len] = absolute index of the last quantum <= q whose input had one channel (-1: none).
+    int64_t* mono_at;
+    int32_t mono_len;    // power of two >= quanta of the ring + quanta of a chunk
+    int32_t dyn;         // 1: layout tracks in use
     int64_t fl;          // floor(-delay * sr): integer part of the (negative) read offset
     float k;             // fractional part
     int32_t in_cycle;    // 1: the reader runs before the writer (cycle breaker applied): history comes from the ring only
@@ -236,6 +256,7 @@ struct DelayInst {
 
 struct CompInst {
     BufRef in, out;
+    uint8_t* meta_ring;  // dynamic input layout: the layout bytes of the quanta inside the look-ahead ring ([8], index = quantum & 7)
     float* ring;         // [ch][ring_len] input history
     float* state;        // [0] = prev_detector_value, [1] = last reduction (dB)
     uint32_t ring_len;   // power of two
@@ -253,12 +274,54 @@ struct AnalyserInst {
     int32_t pad;
 };
 
+
 struct RouteInst {  // channel merger / splitter: copy one channel
     BufRef in, out;
     int32_t in_channel, out_channel;
     int32_t zero;  // 1: write zeros (splitter output beyond the input's channels)
-    int32_t pad;
+    int32_t in_ch;  // static channels of `in` (rows of its meta track); splitter with a dynamic input: zeros wherever in_channel >= count
 };
+
+// ---- layout tracks of nodes whose PCM does not depend on the layout (or that are handled by their own kernel) ----------------
+// k_meta walks the quanta of a chunk serially, one thread per instance, and writes the output track from the input track(s).
+enum MetaMode : int32_t {
+    META_SOURCE = 0,     // scheduled source: silent outside [n_first, n_stop) (oscillator.rs:382-392, constant_source.rs:197-205,
+                         // audio_buffer_source.rs:430-471), `count` channels inside
+    META_COPY = 1,       // same layout as the input (gain, analyser pass-through, wave-shaper that propagates silence)
+    META_SHAPER = 2,     // wave-shaper whose curve does not map 0 to 0: a silent input still produces sound, on its ONE channel (waveshaper.rs:395-400)
+    META_PAN = 3,        // stereo / equal-power panner: silent in -> silent out, else 2 channels (stereo_panner.rs:230-235, panner.rs:698-708)
+    META_CONV = 4,       // convolver: tail counter (convolver.rs:357-366), output channels from (input count, response channels) (:378-487)
+    META_SPLIT = 5,      // splitter output `aux`: one channel, silent when the input has no such channel (channel_splitter.rs:196-206)
+    META_MERGE = 6,      // merger: `count` channels when any input is not silent, else silent (channel_merger.rs:160-168); inputs in `more`
+    META_CONST = 7,      // constant layout `count`, `aux` != 0: always silent
+};
+struct MetaInst {
+    BufRef in, out;
+    int32_t mode;
+    int32_t in_ch, out_ch;   // static channels (= rows of the tracks)
+    int32_t count;           // META_SOURCE / META_MERGE / META_CONST: channels when not silent
+    int32_t aux;             // META_CONV: response channels; META_SPLIT: channel index; META_CONST: silent flag
+    int32_t n_more;          // META_MERGE: number of inputs
+    int64_t n_first, n_stop; // META_SOURCE
+    int64_t tail_len;        // META_CONV: impulse length in frames
+    int64_t* state;          // META_CONV: tail_count, carried across chunks
+    const BufRef* more;      // META_MERGE: the inputs (device table)
+};
+
+// Mixer with per-quantum layouts: AudioRenderQuantum::add folded over the edges in processing order (quantum.rs:532-569), the
+// running channel count re-mixed edge by edge.  Writes canonical PCM: channels >= count hold the speakers up-mix of the sum
+// (static channels <= 2) so that layout-agnostic consumers (convolver, delay line, compressor ring) can read all static channels.
+struct MixDynInst {
+    BufRef out;
+    int32_t out_ch;    // static channels of the port (maximum)
+    int32_t interp;    // 0 speakers, 1 discrete
+    int32_t mode;      // WAE_COUNT_MODE_*
+    int32_t cfg_count; // channelCount of the node
+    int32_t n_edges;
+    uint32_t edge_offset;
+    int64_t limit;
+};
+
 
 // oscillator with automated / audio-rate frequency or detune (oscillator.rs:447-459): phase = running sum of the
 // per-frame increments
@@ -282,6 +345,7 @@ struct BiquadArInst {
     int32_t type;
     int32_t ch;
     int32_t pad;
+    int32_t* dyn_len;  // see BiquadInst
 };
 
 // ---- AudioParam automation (AudioParamProcessor, src/param.rs:664-1600) -------------------------------------

@@ -20,6 +20,22 @@ namespace wae {
 
 DEVI float* chan(const BufRef& b, int c, const ChunkInfo& ci) { return b.p + (size_t)c * b.stride + (b.absolute ? ci.f0 : ci.sub); }
 
+// ---- dynamic layout tracks (BufRef::meta, wae_device.h) ----------------------------------------------------------------
+DEVI int meta_qi(const ChunkInfo& ci, int n) { return (ci.sub + n) >> 7; }  // quantum slot of chunk frame n inside the chunk's arena
+DEVI bool buf_silent(const BufRef& b, int rows, int qi) {                   // AudioRenderQuantum::is_silent (quantum.rs:257-259)
+    if (!b.meta) return false;
+    for (int r = 0; r < rows; r++)
+        if (!(b.meta[(size_t)r * b.meta_stride + qi] & WAE_META_SILENT)) return false;
+    return true;
+}
+DEVI int buf_count(const BufRef& b, int ch_static, int qi) { return b.meta ? (int)(b.meta[qi] & 0x3f) : ch_static; }
+DEVI void meta_put(const BufRef& b, int row, int qi, int count, bool silent) {
+    b.meta[(size_t)row * b.meta_stride + qi] = (uint8_t)((count & 0x3f) | (silent ? WAE_META_SILENT : 0));
+}
+DEVI void meta_put_all(const BufRef& b, int rows, int qi, int count, bool silent) {
+    for (int r = 0; r < rows; r++) meta_put(b, r, qi, count, silent);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Oscillator — OscillatorRenderer::process + generate_* (src/node/oscillator.rs:364-676), constant
 // frequency/detune.  The reference advances phase by repeated `phase += incr` (f64); here phase is the
@@ -370,6 +386,7 @@ __global__ void __launch_bounds__(32 * ABSN_SERIAL_WARPS) k_buffer_source_serial
                     (!is_looping && ((computed_playback_rate > 0. && buffer_time >= buffer_duration) || (computed_playback_rate < 0. && buffer_time < 0.))))
                     st.ended = 1;  // :826-838
             }
+            if (o.out.meta) meta_put_all(o.out, o.ch, meta_qi(ci, q0), run ? o.ch : 1, !run);  // make_silent: one silent channel (:434-471)
         }
         __syncwarp();
         for (int c = 0; c < o.ch; c++) {
@@ -542,6 +559,27 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
 //         y[j] = y0[j] + h1[j] * y[-1] + h2[j] * y[-2].
 //     Same filter in exact arithmetic; rounding differs from the serial order by ~1e-15 relative.
 // ---------------------------------------------------------------------------------------------------------
+DEVI bool isnormal_d(double v) {
+    const double a = fabs(v);
+    return a >= 2.2250738585072014e-308 && a <= 1.7976931348623157e308;
+}
+// BiquadFilterRenderer / IirFilterRenderer with an input whose layout changes (biquad_filter.rs:778-815, iir_filter.rs:336-376), as seen
+// by the thread of ONE channel `c` at the start of quantum `qi`:
+//   input silent: the filter keeps its channel count `len`; a channel whose state has no normal value left is in its "ended" state —
+//     the reference stops processing once ALL channels are (processing an ended channel yields exact zeros, so deciding per channel
+//     is the same PCM); the quantum is reported silent when every row says so.
+//   input not silent: `len` becomes the input's count; a channel the input does not have loses its state (truncate), one that
+//     appears starts from zeros (push([0.; 4])).
+// skip: write zeros, leave the state alone.  absent: channel c does not exist in this quantum (state zeroed, output don't-care).
+DEVI void filter_layout_step(const BufRef& in, const BufRef& out, int rows, int c, int qi, int& len, bool state_normal, bool& skip, bool& absent) {
+    const bool silent = buf_silent(in, rows, qi);
+    if (!silent) len = buf_count(in, rows, qi);
+    const bool gone = c >= len;
+    skip = (silent && !state_normal) || gone;
+    absent = gone || silent;  // no input samples to read for this channel in this quantum: zeros (`gone` also drops the state, below)
+    if (out.meta) meta_put(out, c, qi, len > 0 ? len : 1, skip);
+}
+
 __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ii = t / max_ch, c = t % max_ch;
@@ -552,8 +590,19 @@ __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restr
     float* out = chan(q.out, c, ci);
     double* st = q.state + 4 * c;
     double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    const bool dyn = q.in.meta != nullptr;
+    int len = dyn ? q.dyn_len[c] : q.ch;  // xy.len() of the reference
+    bool skip = false, absent = false;
     for (int n = 0; n < ci.nf; n++) {
-        double x = (double)in[n];
+        if (dyn && (n & 127) == 0) {  // biquad_filter.rs:778-815, per channel (see filter_layout_step)
+            filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
+            if (c >= len) x1 = x2 = y1 = y2 = 0.;
+        }
+        if (skip) {
+            out[n] = 0.f;
+            continue;
+        }
+        double x = absent ? 0. : (double)in[n];
         // b0*x + b1*x1 + b2*x2 - a1*y1 - a2*y2, left to right, unfused (biquad_filter.rs:878)
         double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.b0, x), __dmul_rn(q.b1, x1)), __dmul_rn(q.b2, x2)),
                                        __dmul_rn(q.a1, y1)),
@@ -571,6 +620,7 @@ __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restr
     st[1] = x2;
     st[2] = y1;
     st[3] = y2;
+    if (dyn) q.dyn_len[c] = len;
 }
 
 DEVI float shaper_apply(const float* curve, int len, float input);
@@ -800,10 +850,20 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         r2 = r1;
         r1 = y;
         v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
+#ifndef WAE_CHAIN_NOFLUSH
         mx = max(mx, __float_as_uint(v[j]) & 0x7fffffffu);
+#endif
     }
     // (barrier: everyone has read state / wtot / edge of this step) + did any thread of the tile see a non-finite output?
+#ifdef WAE_CHAIN_NOFLUSH
+    __syncthreads();
+    const int any_bad = 0;
+    (void)mx;
+    (void)in1;
+    (void)in2;
+#else
     const int any_bad = __syncthreads_or(active && mx >= 0x7f800000u);
+#endif
     if (any_bad) {
         // Rare: a NaN / Inf reached the recurrence (a NaN in the source PCM, an unstable filter).  The reference flushes every
         // non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`, biquad_filter.rs:881-883) and so recovers on the next
@@ -1395,14 +1455,25 @@ __global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restr
     double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
     float pq = 0.f, pd = 0.f, pf = 0.f, pg = 0.f;
     BqC cf{};
+    const bool dyn = q.in.meta != nullptr;
+    int len = dyn ? q.dyn_len[c] : q.ch;
+    bool skip = false, absent = false;
     for (int n = 0; n < ci.nf; n++) {
+        if (dyn && (n & 127) == 0) {
+            filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
+            if (c >= len) x1 = x2 = y1 = y2 = 0.;
+        }
+        if (skip) {
+            out[n] = 0.f;
+            continue;
+        }
         float vq = tq ? tq[n] : q.q_val, vd = td ? td[n] : q.detune_val, vf = tf ? tf[n] : q.freq_val, vg = tg ? tg[n] : q.gain_val;
         if (n == 0 || vq != pq || vd != pd || vf != pf || vg != pg) {
             float computed = vd != 0.f ? vf * exp2f(vd / 1200.f) : vf;  // get_computed_freq, biquad_filter.rs:393-399
             cf = bq_coefs(q.type, (double)q.sample_rate, (double)computed, (double)vg, (double)vq);
             pq = vq; pd = vd; pf = vf; pg = vg;
         }
-        double x = (double)in[n];
+        double x = absent ? 0. : (double)in[n];
         double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf.b0, x), __dmul_rn(cf.b1, x1)), __dmul_rn(cf.b2, x2)),
                                        __dmul_rn(cf.a1, y1)),
                              __dmul_rn(cf.a2, y2));
@@ -1412,6 +1483,7 @@ __global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restr
         out[n] = (float)y;
     }
     st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
+    if (dyn) q.dyn_len[c] = len;
 }
 
 // IIRFilter — IirFilterRenderer::process (src/node/iir_filter.rs:323-414): transposed DF-II in f64, serial
@@ -1426,8 +1498,22 @@ __global__ void __launch_bounds__(64) k_iir_serial(const IirInst* __restrict__ i
     double s[20];
     const int nc = q.n;
     for (int i = 0; i < 20; i++) s[i] = q.state[20 * c + i];
+    const bool dyn = q.in.meta != nullptr;
+    int len = dyn ? q.dyn_len[c] : q.ch;
+    bool skip = false, absent = false;
     for (int n = 0; n < ci.nf; n++) {
-        double x = (double)in[n];
+        if (dyn && (n & 127) == 0) {  // iir_filter.rs:336-376
+            bool normal = false;
+            for (int i = 0; i < 20; i++) normal = normal || isnormal_d(s[i]);
+            filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n), len, normal, skip, absent);
+            if (c >= len)
+                for (int i = 0; i < 20; i++) s[i] = 0.;
+        }
+        if (skip) {
+            out[n] = 0.f;
+            continue;
+        }
+        double x = absent ? 0. : (double)in[n];
         double y = fma(q.b[0], x, s[0]);  // b0.mul_add(input, last_state), :391
         double ay = fabs(y);
         if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
@@ -1437,6 +1523,7 @@ __global__ void __launch_bounds__(64) k_iir_serial(const IirInst* __restrict__ i
         out[n] = (float)y;
     }
     for (int i = 0; i < 20; i++) q.state[20 * c + i] = s[i];
+    if (dyn) q.dyn_len[c] = len;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2652,7 +2739,7 @@ static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, i
     constexpr bool STREAMED = SRC == CHAIN_SRC_BUFFER || SRC == CHAIN_SRC_ABSN;
     // six CTAs of ~35 KB staging each only fit an SM with the shared-memory carve-out at its maximum
     static bool carved = false;
-    if (!carved) {
+    if (!carved && !getenv("WAE_CHAIN_NO_CARVEOUT")) {
         carved = true;
         cudaFuncSetAttribute(k_chain<SRC, NB, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(k_chain<SRC, NB, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
