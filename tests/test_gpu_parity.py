@@ -1086,3 +1086,27 @@ def test_one_shot_render_reports_planner_refusals(pkg):
         assert np.isfinite(out).all() and np.abs(out).max() > 0
     finally:
         eng2.close()
+
+
+@pytest.mark.parametrize("bad", [float("nan"), float("inf")])
+def test_scan_biquad_recovers_from_a_non_finite_sample(pkg, engine, oracle, bad):
+    """biquad_filter.rs:881-883: `if !y.is_normal() { y = 0. }` — a NaN / Inf in the source PCM costs the reference three output samples
+    and its filter state is clean again; the time-parallel scan replays the affected tile serially with the same flush (k_chain)"""
+    length = 128 * 40 + 9
+    def build(be, g):
+        rng = np.random.default_rng(77 + g)
+        pcm = rng.uniform(-0.5, 0.5, (2, length)).astype(np.float32)
+        pcm[0, 1000 + 300 * g] = bad
+        pcm[1, 3000] = -bad if np.isinf(bad) else bad
+        c = pkg.OfflineAudioContext(2, length, G.SR, be)
+        src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=900.0 + 100 * g, q=3.0)
+        b2 = c.create_biquad_filter(type_=pkg.HIGHPASS, frequency=200.0, q=1.0)
+        src.connect(bq)
+        bq.connect(b2)
+        b2.connect(c.destination())
+        src.start()
+        return c
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert np.isfinite(cpu).all() and np.isfinite(gpu).all()
+    assert maxdiff(gpu, cpu) <= TOL

@@ -240,12 +240,20 @@ def test_every_criterion_bench_graph_is_lowered(pkg, be, name, build):
 
 @pytest.mark.parametrize("block", range(8))
 def test_planner_accepts_random_graphs(pkg, be, block):
-    # the generator of tests/test_gpu_fuzz.py (random DAGs of every lowered node kind, automation, feedback loops, suspend points) on the
-    # CPU: 8 x 40 seeds through the planner's sizing pass — no crash, no refusal, a sane plan; the GPU suite renders 120 of them
+    # the generator of tests/test_gpu_fuzz.py (random DAGs of every lowered node kind, stereo sources that end, automation, feedback
+    # loops, suspend points) on the CPU: 8 x 40 seeds through the planner's sizing pass — no crash, a sane plan; the only refusals are the
+    # two documented layout combinations, and they are rare
     import test_gpu_fuzz as F
+    refused = 0
     for seed in range(1000 + 40 * block, 1000 + 40 * (block + 1)):
-        p = plan(pkg, [F.random_graph(pkg, be, seed)])
+        try:
+            p = plan(pkg, [F.random_graph(pkg, be, seed)])
+        except pkg.WaeError as e:
+            assert e.status == 4 and ("mono response" in str(e) or "over-sampled WaveShaperNode" in str(e)), (seed, str(e))
+            refused += 1
+            continue
         assert 1 <= p["stages"] <= 400 and p["segments"] >= 1 and p["chunk_frames"] >= 128, seed
+    assert refused <= 6, refused
 
 
 @pytest.mark.parametrize("block", range(4))

@@ -154,6 +154,10 @@ struct ShaperOsInst {
     const float2* f_up;  // [128] filter bins of the up-sampler
     const float2* f_dn;  // [128] filter bins of the down-sampler
     float* hist;         // [ch][256] the two input quanta before the chunk
+    // dynamic input layout, curve that maps 0 to 0: the reference returns early on a silent input WITHOUT feeding its resamplers
+    // (waveshaper.rs:395-398), so their state is the last PROCESSED quanta, however long ago.  prev[2 q], prev[2 q + 1] = chunk index of
+    // the two processed quanta before quantum q (-1 / -2: the history slots), prev[2 nq], prev[2 nq + 1]: the same after the chunk.
+    int32_t* prev;
     int32_t n;           // curve length
     int32_t ch;
     int32_t factor;      // 2 or 4
@@ -401,6 +405,8 @@ struct ChainInst {
     float g[4];
     int32_t out_dup;     // >1: the (mono) result is written to channels 0..out_dup-1 (speaker up-mix 1->2 by copy)
     int32_t shaper_n;    // curve length
+    int32_t shaper_keeps_silence;  // can_propagate_silence (waveshaper.rs:480-503): the curve maps 0 to 0
+    int32_t pad2;
     const float* curve;  // nullptr: pass-through
     BufRef in;           // CHAIN_SRC_BUFFER
     AbsnInst absn;       // CHAIN_SRC_ABSN (out unused)

@@ -225,13 +225,14 @@ int engine_device(const wae_engine* eng) { return eng ? eng->device : 0; }
 
 namespace {
 
+// (the order of the kinds is the launch order inside one level: mixes first; k_delay_mono before the delay reader that needs it)
 enum StageKind : int {
-    S_MIX = 0, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_SHAPER_OS, S_KINDS
+    S_MIX = 0, S_MIX_DYN, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY_MONO, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_SHAPER_OS, S_META, S_KINDS
 };
-const char* kStageNames[S_KINDS] = {"k_mix", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
-                                    "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial", "k_shaper_os"};
+const char* kStageNames[S_KINDS] = {"k_mix", "k_mix_dyn", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
+                                    "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_mono", "k_delay_read", "k_ring_write", "k_compressor",
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial", "k_shaper_os", "k_meta"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -266,6 +267,8 @@ struct StageBuild {
     std::vector<AnalyserInst> analyser;
     std::vector<MixInst> mix;
     std::vector<MixEdge> mix_edges;
+    std::vector<MixDynInst> mix_dyn;
+    std::vector<MetaInst> meta;
     std::vector<ConvInput> conv_in;
     std::vector<ConvPath> conv_path;
     int max_ch = 1;
@@ -499,14 +502,29 @@ struct PortRef {
     int port;
 };
 
+// What the planner can say about a buffer's layout over the render (see BufRef::meta): the range of its channel count over all quanta
+// (a silent quantum has one channel, quantum.rs:512-517, unless it sits in a port with an explicit count), the range over the quanta
+// that are not silent, and whether it can be silent at all.  A layout that is provably constant needs no track and keeps every
+// kernel on its static path; sources that run from frame 0 to the end of the render (every BASELINE config) are.
+struct Lay {
+    uint8_t lo = 1, hi = 1, nlo = 1, nhi = 1;
+    bool may_silent = false;
+    bool dyn() const { return lo != hi || may_silent; }
+    static Lay fixed(int ch) { return Lay{(uint8_t)ch, (uint8_t)ch, (uint8_t)ch, (uint8_t)ch, false}; }
+    static Lay gated(int ch) { return Lay{1, (uint8_t)ch, (uint8_t)ch, (uint8_t)ch, true}; }  // `ch` channels or silent
+};
+
 struct PNode {
     Node* n = nullptr;
     int level = 0;
     std::vector<std::vector<PortRef>> in_edges;  // per input port, reference summation order
     std::vector<int> in_ch;
     std::vector<BufRef> in_buf;
+    std::vector<Lay> in_lay;
     std::vector<int> out_ch;
     std::vector<BufRef> out_buf;
+    std::vector<Lay> out_lay;  // empty: constant (out_ch channels, never silent)
+    Lay lay_out(int port) const { return port < (int)out_lay.size() ? out_lay[port] : Lay::fixed(out_ch[port]); }
 };
 
 struct Planner {
@@ -533,6 +551,8 @@ struct Planner {
         float* ring;
         uint32_t ring_len;
         int ch;
+        int64_t* mono_at;
+        int32_t mono_len;
     };
     std::map<std::pair<uint32_t, uint32_t>, DelayRing> delay_rings;       // (graph, writer id)
     bool dry = false;                     // sizing pass: count arena floats per frame, touch no device memory
@@ -547,6 +567,7 @@ struct Planner {
         int ch = 1;
         int phase = 0;  // 0: before biquad A, 1: after A, 3: after B, 5: after the shaper (canonical chain order)
         int cls = 0;    // scheduling class of the node that opened the chain (see stage())
+        Lay lay;        // layout of the chain's output over time (the kernel writes the track when it is not constant)
     };
 
     // Node state is allocated through a key (graph, node, n-th allocation of that node, salt): the plans of consecutive
@@ -653,20 +674,45 @@ struct Planner {
         return s;
     }
 
-    BufRef arena_buf(int ch) {
+    // `with_meta`: the buffer's layout is not provably constant: it carries a per-quantum layout track (BufRef::meta), one row per
+    // static channel, stored behind the PCM
+    BufRef arena_buf(int ch, bool with_meta = false) {
         arena_floats_per_frame += (uint64_t)ch;
-        if (dry) return BufRef{reinterpret_cast<float*>(uintptr_t(256)), (uint32_t)b->chunk, 0};
-        std::vector<float*>& pool = arena_pool[ch];
-        size_t& used = arena_used[ch];
-        if (used < pool.size()) return BufRef{pool[used++], (uint32_t)b->chunk, 0};
-        size_t floats = (size_t)ch * (size_t)b->chunk;
-        float* p = b->dalloc<float>(floats);
-        b->arena_bytes += floats * 4;
-        if (p) {
-            pool.push_back(p);
-            used++;
+        const uint32_t mstride = (uint32_t)((b->chunk / 128 + 16) / 16 * 16);
+        BufRef r{reinterpret_cast<float*>(uintptr_t(256)), (uint32_t)b->chunk, 0, nullptr, 0, 0};
+        if (!dry) {
+            std::vector<float*>& pool = arena_pool[ch];
+            size_t& used = arena_used[ch];
+            if (used < pool.size()) {
+                r.p = pool[used++];
+            } else {
+                const size_t floats = (size_t)ch * (size_t)b->chunk;
+                float* p = b->dalloc<float>(floats + ((size_t)ch * mstride + 3) / 4);
+                b->arena_bytes += floats * 4;
+                if (p) {
+                    pool.push_back(p);
+                    used++;
+                }
+                r.p = p;
+            }
         }
-        return BufRef{p, (uint32_t)b->chunk, 0};
+        if (with_meta && r.p) {
+            r.meta = reinterpret_cast<uint8_t*>(r.p + (size_t)ch * (size_t)b->chunk);
+            r.meta_stride = mstride;
+        }
+        return r;
+    }
+    // layout track of a node output from its input's (k_meta)
+    void meta_stage(int L, int mode, const BufRef& in, int in_ch, const BufRef& out, int out_ch, int count = 0, int aux = 0) {
+        MetaInst m{};
+        m.in = in;
+        m.out = out;
+        m.mode = mode;
+        m.in_ch = in_ch;
+        m.out_ch = out_ch;
+        m.count = count;
+        m.aux = aux;
+        stage(L, S_META).meta.push_back(m);
     }
 
     std::map<uint32_t, PNode>* cur_pn = nullptr;
@@ -741,9 +787,11 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     int in_ch = pn.in_ch[0];
     if (n.buffer && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
         return bail(WAE_UNSUPPORTED, "a ConvolverNode inside a DelayNode feedback cycle is not lowered to the GPU (before or after the cycle it is)");
+    const Lay in_lay = pn.in_lay.empty() ? Lay::fixed(in_ch) : pn.in_lay[0];
     if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
         pn.out_ch = {in_ch};
         pn.out_buf = {pn.in_buf[0]};
+        pn.out_lay = {in_lay};
         return true;
     }
     PcmBuffer& ir = *n.buffer;
@@ -786,7 +834,27 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
     }
     int Smax = *std::max_element(S.begin(), S.end());
     pn.out_ch = {ir_ch == 1 && in_ch == 1 ? 1 : 2};
-    pn.out_buf = {arena_buf(pn.out_ch[0])};
+    if (in_lay.dyn() && ir_ch == 1 && in_lay.hi >= 2)
+        return bail(WAE_UNSUPPORTED, "a ConvolverNode with a mono response whose input changes between one and two channels is not lowered to the GPU "
+                                     "(the reference stops feeding its second convolver whenever the input is mono or silent, convolver.rs:378-400)");
+    // silent once the input has been silent for the length of the response (convolver.rs:357-366); channels from the routing table (:378-487)
+    const bool conv_dyn = in_lay.dyn();
+    pn.out_buf = {arena_buf(pn.out_ch[0], conv_dyn && Smax > 0)};
+    if (conv_dyn && Smax > 0) {
+        const int oc = pn.out_ch[0];
+        pn.out_lay = {Lay{(uint8_t)(in_lay.may_silent ? 1 : oc), (uint8_t)oc, (uint8_t)oc, (uint8_t)oc, in_lay.may_silent}};
+        MetaInst m{};
+        m.in = pn.in_buf[0];
+        m.out = pn.out_buf[0];
+        m.mode = META_CONV;
+        m.in_ch = in_ch;
+        m.out_ch = oc;
+        m.aux = ir_ch;
+        m.tail_len = (int64_t)ir_len;
+        m.state = alloc<int64_t>(1, true, true);
+        if (!m.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver tail counter)");
+        stage(level, S_META).meta.push_back(m);
+    }
     if (Smax == 0) {  // all-zero IR: output zeros -> a mix with no edges
         StageBuild& ms = stage(level, S_MIX);
         ms.mix.push_back(MixInst{pn.out_buf[0], pn.out_ch[0], 0, 0, (uint32_t)ms.mix_edges.size(), -1});
@@ -961,7 +1029,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         auto it = pending.find(nid);
         if (it == pending.end()) return true;
         PNode& sp = pn.at(nid);
-        BufRef buf = arena_buf(it->second.ch);
+        BufRef buf = arena_buf(it->second.ch, it->second.lay.dyn());  // (k_chain writes the layout track itself)
         if (!buf.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
         it->second.inst.out = buf;
         it->second.inst.limit = -1;
@@ -1002,18 +1070,37 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             if (!tl.error.empty()) return bail(WAE_NOT_SUPPORTED, tl.error);
             ParamInst pi{};
             if (!edges.empty()) {  // sum of the connected signals, first channel each (1 / explicit / discrete, param.rs:296-310)
-                StageBuild& ms = stage(2 * level, S_MIX);
-                MixInst m;
-                m.out = arena_buf(1);
-                if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                m.out_ch = 1;
-                m.interp = WAE_INTERPRETATION_DISCRETE;
-                m.n_edges = (int)edges.size();
-                m.edge_offset = (uint32_t)ms.mix_edges.size();
-                m.limit = -1;
-                for (auto& r : edges) ms.mix_edges.push_back(MixEdge{pn.at(r.node).out_buf[r.port], pn.at(r.node).out_ch[r.port], 0});
-                ms.mix.push_back(m);
-                pi.in = m.out;
+                bool any_dyn = false;
+                for (auto& r : edges) any_dyn = any_dyn || pn.at(r.node).lay_out(r.port).dyn();
+                if (any_dyn) {  // edges whose layout changes: folded per quantum; a silent sum reads as zeros, which is what the param adds then
+                    StageBuild& ms = stage(2 * level, S_MIX_DYN);
+                    MixDynInst m{};
+                    m.out = arena_buf(1);
+                    if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    m.out_ch = 1;
+                    m.interp = WAE_INTERPRETATION_DISCRETE;
+                    m.mode = WAE_COUNT_MODE_EXPLICIT;
+                    m.cfg_count = 1;
+                    m.n_edges = (int)edges.size();
+                    m.edge_offset = (uint32_t)ms.mix_edges.size();
+                    m.limit = -1;
+                    for (auto& r : edges) ms.mix_edges.push_back(MixEdge{pn.at(r.node).out_buf[r.port], pn.at(r.node).out_ch[r.port], 0});
+                    ms.mix_dyn.push_back(m);
+                    pi.in = m.out;
+                } else {
+                    StageBuild& ms = stage(2 * level, S_MIX);
+                    MixInst m;
+                    m.out = arena_buf(1);
+                    if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    m.out_ch = 1;
+                    m.interp = WAE_INTERPRETATION_DISCRETE;
+                    m.n_edges = (int)edges.size();
+                    m.edge_offset = (uint32_t)ms.mix_edges.size();
+                    m.limit = -1;
+                    for (auto& r : edges) ms.mix_edges.push_back(MixEdge{pn.at(r.node).out_buf[r.port], pn.at(r.node).out_ch[r.port], 0});
+                    ms.mix.push_back(m);
+                    pi.in = m.out;
+                }
             }
             pi.events = tl.events.empty() ? nullptr : upload(tl.events);
             pi.curves = tl.curves.empty() ? nullptr : upload(tl.curves);
@@ -1075,6 +1162,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     if (!materialize(r.node)) return false;
         p.in_ch.assign(n.n_inputs, 1);
         p.in_buf.assign(n.n_inputs, BufRef{nullptr, 0, 0});
+        p.in_lay.assign(n.n_inputs, Lay::fixed(1));
         for (int port = 0; port < n.n_inputs; port++) {
             auto& edges = p.in_edges[port];
             int max_in = 1;
@@ -1084,10 +1172,78 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 ch = max_in;
             }
             p.in_ch[port] = ch;
+            p.in_lay[port] = Lay::fixed(ch);
             bool is_dest = n.kind == K_DEST;
-            if (extend || dest_direct) continue;  // the producer's chain is consumed in registers / written directly
+            if (extend || dest_direct) {  // the producer's chain is consumed in registers / written directly
+                if (extend) p.in_lay[port] = pending.at(fuse_src).lay;
+                continue;
+            }
+            // ---- the port's layout over time: AudioRenderQuantum::add folded over the edges (quantum.rs:532-569)
+            bool any_dyn = false;
+            Lay pl = Lay::fixed(ch);
+            if (!edges.empty()) {
+                int lo = 1, hi = 1, on_nlo = 0, min_nlo = 255;
+                bool all_may_silent = true;
+                for (auto& r : edges) {
+                    const Lay el = pn.at(r.node).lay_out(r.port);
+                    any_dyn = any_dyn || el.dyn();
+                    lo = std::max<int>(lo, el.lo);
+                    hi = std::max<int>(hi, el.hi);
+                    if (!el.may_silent) on_nlo = std::max<int>(on_nlo, el.nlo);
+                    min_nlo = std::min<int>(min_nlo, el.nlo);
+                    all_may_silent = all_may_silent && el.may_silent;
+                }
+                const int nlo = std::max(on_nlo, min_nlo);
+                pl.lo = (uint8_t)computed_channels(n.cfg, lo);
+                pl.hi = (uint8_t)computed_channels(n.cfg, hi);
+                pl.nlo = (uint8_t)computed_channels(n.cfg, nlo);
+                pl.nhi = pl.hi;
+                pl.may_silent = all_may_silent;
+                if (n.kind == K_DELAY_R) pl = pn.at(edges[0].node).lay_out(edges[0].port);
+            }
+            // more than two layouts meeting in a port wider than stereo: the order of the up-mixes matters (mono, stereo, 5.1: the
+            // reference goes 1 -> 2 -> 6): fold edge by edge like it does
+            bool needs_fold = false;
+            if (ch > 2 && n.cfg.mode != WAE_COUNT_MODE_EXPLICIT)
+                for (auto& r : edges) needs_fold = needs_fold || pn.at(r.node).out_ch[r.port] != ch;
             if (!is_dest && edges.size() == 1 && pn.at(edges[0].node).out_ch[edges[0].port] == ch) {
-                p.in_buf[port] = pn.at(edges[0].node).out_buf[edges[0].port];  // alias, no copy
+                const Lay el = pn.at(edges[0].node).lay_out(edges[0].port);
+                // a single edge IS the port when computedNumberOfChannels leaves every count it can have alone
+                const bool identity = !el.dyn() || n.kind == K_DELAY_R || n.cfg.mode == WAE_COUNT_MODE_MAX ||
+                                      (n.cfg.mode == WAE_COUNT_MODE_CLAMPED_MAX && el.hi <= n.cfg.count);
+                // the time-batched convolver reads all static channels of every quantum: it needs the canonical PCM k_mix_dyn writes
+                const bool canonical_needed = el.dyn() && n.kind == K_CONV;
+                if (identity && !canonical_needed) {
+                    p.in_buf[port] = pn.at(edges[0].node).out_buf[edges[0].port];  // alias, no copy
+                    p.in_lay[port] = el;
+                    continue;
+                }
+            }
+            if (any_dyn || needs_fold) {
+                StageBuild& ms = stage(2 * level, S_MIX_DYN);
+                MixDynInst m{};
+                m.out_ch = ch;
+                m.interp = n.cfg.interp;
+                m.mode = n.cfg.mode;
+                m.cfg_count = n.cfg.count;
+                m.n_edges = (int)edges.size();
+                m.edge_offset = (uint32_t)ms.mix_edges.size();
+                m.limit = -1;
+                if (is_dest) {
+                    m.out = BufRef{b->d_out + (size_t)gi * b->channels * b->length, (uint32_t)b->length, 1};
+                    m.limit = (int64_t)b->length;
+                    if (b->length > 0xffffffffull) return bail(WAE_UNSUPPORTED, "render length above 2^32 frames");
+                } else {
+                    m.out = arena_buf(ch, pl.dyn());
+                    if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                }
+                for (auto& r : edges) {
+                    PNode& sn = pn.at(r.node);
+                    ms.mix_edges.push_back(MixEdge{sn.out_buf[r.port], sn.out_ch[r.port], 0});
+                }
+                ms.mix_dyn.push_back(m);
+                p.in_buf[port] = m.out;
+                p.in_lay[port] = pl;
                 continue;
             }
             StageBuild& ms = stage(2 * level, S_MIX);
@@ -1118,10 +1274,43 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             p.out_buf = {arena_buf(ch)};
             return p.out_buf[0].p != nullptr;
         };
+        // the node's (single) output has a layout that is not constant: give its buffer a layout track
+        auto out_dynamic = [&](const Lay& l) {
+            p.out_lay = {l};
+            if (l.dyn() && !p.out_buf.empty() && p.out_buf[0].p && !p.out_buf[0].absolute) {
+                p.out_buf[0].meta = dry ? reinterpret_cast<uint8_t*>(uintptr_t(256)) : reinterpret_cast<uint8_t*>(p.out_buf[0].p + (size_t)p.out_ch[0] * (size_t)b->chunk);
+                p.out_buf[0].meta_stride = (uint32_t)((b->chunk / 128 + 16) / 16 * 16);
+            }
+        };
+        // a scheduled source: `ch` channels inside [n_first, n_stop), one silent channel outside (never silent when it covers the render)
+        auto source_lay = [&](int64_t n_first, int64_t n_stop, int ch) { return (n_first <= 0 && n_stop >= b->lq) ? Lay::fixed(ch) : Lay::gated(ch); };
+        auto source_meta = [&](int64_t n_first, int64_t n_stop, int ch) {
+            MetaInst m{};
+            m.out = p.out_buf[0];
+            m.mode = META_SOURCE;
+            m.out_ch = ch;
+            m.count = ch;
+            m.n_first = n_first;
+            m.n_stop = n_stop;
+            stage(L, S_META).meta.push_back(m);
+        };
+        const Lay in0 = p.in_lay.empty() ? Lay::fixed(1) : p.in_lay[0];
+        // biquad / IIR (biquad_filter.rs:778-815): silent once the input is and the tail has rung out; keeps the channels of the last
+        // input that was not silent
+        auto filter_lay = [](const Lay& l) { return Lay{(uint8_t)(l.may_silent ? 1 : l.lo), l.hi, l.nlo, l.nhi, l.may_silent}; };
+        // output with the input's layout and channel count: share the input's layout track
+        auto out_like_input = [&]() {
+            p.out_lay = {in0};
+            if (in0.dyn() && !p.out_buf.empty() && p.out_buf[0].p) {
+                p.out_buf[0].meta = p.in_buf[0].meta;
+                p.out_buf[0].meta_stride = p.in_buf[0].meta_stride;
+            }
+        };
         // registers this node as the tail of a chain: pending while exactly one consumer may still fuse with it
         auto finish_chain = [&](PendingChain&& pc) -> bool {
             p.out_ch = {pc.ch};
             p.out_buf = {BufRef{nullptr, 0, 0}};
+            p.out_lay = {pc.lay};
             pending[id] = std::move(pc);
             if (!(fuse && consumers(n) == 1)) return materialize(id);
             return true;
@@ -1135,6 +1324,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             for (int i = 0; i < 4; i++) pc.inst.g[i] = 1.f;
             pc.ch = ch;
             pc.cls = cur_cls;
+            pc.lay = Lay::fixed(ch);
             return pc;
         };
         // chain that this biquad / gain / shaper node joins: its producer's pending chain, or a new one reading in_buf
@@ -1146,6 +1336,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             }
             PendingChain pc = source_chain(CHAIN_SRC_BUFFER, p.in_ch[0]);
             pc.inst.in = p.in_buf[0];
+            pc.lay = in0;
             return pc;
         };
         switch (n.kind) {
@@ -1233,12 +1424,19 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     oa.phase = alloc<double>(1, true, true);
                     oa.sample_rate = g->sample_rate;
                     if (!oa.phase) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    out_dynamic(source_lay(o.n_first, o.n_stop, 1));
+                    oa.base.out = p.out_buf[0];
+                    if (p.out_lay[0].dyn()) source_meta(o.n_first, o.n_stop, 1);
                     stage(L, S_OSC_AR).osc_ar.push_back(oa);
                 } else if (fuse_n) {
                     PendingChain pc = source_chain(CHAIN_SRC_OSC, 1);
                     pc.inst.osc = o;
+                    pc.lay = source_lay(o.n_first, o.n_stop, 1);
                     if (!finish_chain(std::move(pc))) return false;
                 } else {
+                    out_dynamic(source_lay(o.n_first, o.n_stop, 1));
+                    o.out = p.out_buf[0];
+                    if (p.out_lay[0].dyn()) source_meta(o.n_first, o.n_stop, 1);
                     stage(L, S_OSC).osc.push_back(o);
                 }
                 break;
@@ -1261,8 +1459,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (fuse_n) {
                     PendingChain pc = source_chain(CHAIN_SRC_CONST, 1);
                     pc.inst.cst = c;
+                    pc.lay = source_lay(c.n_first, c.n_stop, 1);
                     if (!finish_chain(std::move(pc))) return false;
                 } else {
+                    out_dynamic(source_lay(c.n_first, c.n_stop, 1));
+                    c.out = p.out_buf[0];
+                    if (p.out_lay[0].dyn()) source_meta(c.n_first, c.n_stop, 1);
                     stage(L, S_CONST).cst.push_back(c);
                 }
                 break;
@@ -1276,6 +1478,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     if (!need_out(1)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                     StageBuild& ms = stage(L, S_MIX);
                     ms.mix.push_back(MixInst{p.out_buf[0], 1, 0, 0, (uint32_t)ms.mix_edges.size(), -1});
+                    out_dynamic(Lay{1, 1, 1, 1, true});  // silent for good
+                    if (p.out_buf[0].meta) source_meta(0, 0, 1);
                     break;
                 }
                 PcmBuffer& pb = *n.buffer;
@@ -1337,6 +1541,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     a.loop = n.loop ? 1 : 0;
                     a.state = alloc<AbsnSerialState>(1, true, true);
                     if (!a.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (buffer source state)");
+                    out_dynamic(Lay::gated(ch));  // when it plays depends on the automated rate: the kernel writes the layout track
+                    a.out = p.out_buf[0];
                     stage(L, S_ABSN_SERIAL).absn_serial.push_back(a);
                     algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::min<int64_t>(b->lq, (int64_t)len);
                     break;
@@ -1451,6 +1657,18 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     a.n_seg = (int32_t)seg_n.size();
                     a.seg_n = upload(seg_n);
                     a.seg_bt = upload(seg_bt);
+                    {
+                        // layout: silent before the quantum of the first playing frame and after the quantum in which the source ends
+                        // (stop time, explicit duration, or — not looping — the end of the buffer; audio_buffer_source.rs:826-838)
+                        int64_t n_end = a.n_stop;
+                        if (a.step > 0.) {
+                            if (!n.loop) n_end = std::min<int64_t>(n_end, n_first + (int64_t)std::ceil(std::max(0., duration - off) / a.step));
+                            if (n.duration < 1e300) n_end = std::min<int64_t>(n_end, n_first + (int64_t)std::ceil(std::max(0., n.duration - a.elapsed0) / a.step));
+                        }
+                        out_dynamic(source_lay(n_first, n_end, ch));
+                        a.out = p.out_buf[0];
+                        if (p.out_lay[0].dyn()) source_meta(n_first, n_end, ch);
+                    }
                     stage(L, S_ABSN_SLOW).absn_slow.push_back(a);
                     algorithmic_bytes += (uint64_t)ch * 4ull * (uint64_t)std::min<int64_t>(b->lq, (int64_t)len);
                     break;
@@ -1465,11 +1683,29 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 a.buf_offset = 0;
                 a.ch = ch;
                 a.loop = n.loop ? 1 : 0;
+                if (!n.loop) {
+                    // the quantum after which the source has `ended`: the reference accumulates buffer_time += block_duration and stops
+                    // once it reaches the buffer's duration (audio_buffer_source.rs:609,826-838) — replayed, not divided
+                    const double block_duration = clock.dt * 128.;
+                    const int64_t max_q = (b->lq - a.n_start) / 128 + 2;
+                    int64_t played = 0;
+                    double bt = 0.;
+                    while (played < max_q) {
+                        bt += block_duration;
+                        played++;
+                        if (bt >= duration) break;
+                    }
+                    a.n_stop = a.n_start + played * 128;
+                }
                 if (fuse_src) {
                     PendingChain pc = source_chain(CHAIN_SRC_ABSN, ch);
                     pc.inst.absn = a;
+                    pc.lay = source_lay(a.n_start, a.n_stop, ch);
                     if (!finish_chain(std::move(pc))) return false;
                 } else {
+                    out_dynamic(source_lay(a.n_start, a.n_stop, ch));
+                    a.out = p.out_buf[0];
+                    if (p.out_lay[0].dyn()) source_meta(a.n_start, a.n_stop, ch);
                     stage(L, S_ABSN).absn.push_back(a);
                 }
                 // compulsory read of the source PCM that is actually played
@@ -1493,6 +1729,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     ba.q_val = q; ba.detune_val = detune; ba.freq_val = freq; ba.gain_val = gain;
                     ba.state = alloc<double>((size_t)ch * 4, true, true);
                     if (!ba.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    if (in0.dyn()) {
+                        ba.dyn_len = alloc<int32_t>((size_t)ch, true, true);
+                        if (!ba.dyn_len) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                        out_dynamic(filter_lay(in0));
+                        ba.out = p.out_buf[0];
+                    }
                     ba.sample_rate = g->sample_rate;
                     ba.type = n.type;
                     ba.ch = ch;
@@ -1505,9 +1747,17 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 hm::BiquadCoefs c = hm::biquad_coefs(n.type, sr, (double)cf, (double)gain, (double)q);
                 double* state = alloc<double>((size_t)ch * 4, true, true);
                 if (!state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
-                if (eng->serial_filters) {  // bit-faithful serial recurrence, one stage per biquad
+                // An input whose channel COUNT changes while it sounds resets / drops channels of the filter mid-render
+                // (biquad_filter.rs:798-815): the serial kernel follows it quantum by quantum; the scan keeps one state per channel
+                const bool count_varies = !extend && in0.dyn() && !(in0.nlo == in0.nhi && in0.nhi == ch);
+                if (eng->serial_filters || count_varies) {  // bit-faithful serial recurrence, one stage per biquad
                     if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                     BiquadInst bi{};
+                    if (in0.dyn()) {
+                        bi.dyn_len = alloc<int32_t>((size_t)ch, true, true);
+                        if (!bi.dyn_len) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                        out_dynamic(filter_lay(in0));
+                    }
                     bi.in = p.in_buf[0];
                     bi.out = p.out_buf[0];
                     bi.b0 = c.b0; bi.b1 = c.b1; bi.b2 = c.b2; bi.a1 = c.a1; bi.a2 = c.a2;
@@ -1524,6 +1774,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
                 pc.coefs.push_back(make_scan_coef(c));
                 pc.phase = pc.phase == 0 ? 1 : 3;
+                pc.lay = filter_lay(pc.lay);
                 if (!finish_chain(std::move(pc))) return false;
                 break;
             }
@@ -1545,6 +1796,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 }
                 ii.state = alloc<double>((size_t)ch * 20, true, true);
                 if (!ii.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                if (in0.dyn()) {
+                    ii.dyn_len = alloc<int32_t>((size_t)ch, true, true);
+                    if (!ii.dyn_len) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    out_dynamic(filter_lay(in0));
+                    ii.out = p.out_buf[0];
+                }
                 StageBuild& s = stage(L, S_IIR);
                 s.max_ch = std::max(s.max_ch, ch);
                 s.iir.push_back(ii);
@@ -1556,6 +1813,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 int ch = p.in_ch[0];
                 if (pgn.dyn) {  // a-rate gain (gain.rs:189-197)
                     if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    out_like_input();  // silent in -> silent out (gain.rs:155-158); the ~0 / ~1 shortcuts only exist for single values
                     stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch, pgn.track});
                     break;
                 }
@@ -1567,18 +1825,45 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     PendingChain pc = open_chain();
                     // consecutive gains of one slot are folded (differs from two f32 multiplies by <= 1 ulp)
                     pc.inst.g[pc.phase == 0 ? 0 : (pc.phase == 1 ? 1 : (pc.phase == 3 ? 2 : 3))] *= gv;
+                    if (gv == 0.f) pc.lay = Lay{1, 1, 1, 1, true};  // a gain of (about) zero answers with silence (gain.rs:160-163)
                     if (!finish_chain(std::move(pc))) return false;
                     break;
                 }
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (gv == 0.f) {
+                    out_dynamic(Lay{1, 1, 1, 1, true});
+                    if (p.out_buf[0].meta) source_meta(0, 0, 1);
+                } else {
+                    out_like_input();
+                }
                 stage(L, S_GAIN).gain.push_back(GainInst{p.in_buf[0], p.out_buf[0], gv, ch, BufRef{nullptr, 0, 0}});
                 break;
             }
             case K_SHAPER: {
                 int ch = p.in_ch[0];
                 const float* curve = n.has_curve ? upload(n.table) : nullptr;
+                // can_propagate_silence (waveshaper.rs:480-503): the curve maps 0 to 0
+                bool keeps_silence = true;
+                if (n.has_curve && !n.table.empty()) {
+                    const size_t cn = n.table.size();
+                    keeps_silence = cn % 2 == 1 ? std::fabs(n.table[cn / 2]) < 1e-9f : std::fabs((n.table[cn / 2 - 1] + n.table[cn / 2]) / 2.f) < 1e-9f;
+                }
+                // a silent input that still produces sound does so on the ONE channel a silent quantum has (waveshaper.rs:395-400)
+                auto shaper_lay = [&](const Lay& l) {
+                    if (keeps_silence || !l.may_silent) return l;
+                    return Lay{1, l.hi, 1, l.nhi, false};
+                };
                 if (n.oversample && n.has_curve) {  // waveshaper.rs:409-480: up-sample, shape, down-sample
+                    // input that can fall silent: a curve that maps 0 to 0 makes the node return early WITHOUT feeding its resamplers
+                    // (frozen state: the kernel then works on the last processed quanta); a curve that does not keeps processing — on the
+                    // one channel of a silent quantum, which rebuilds the resamplers of a wider node (waveshaper.rs:395-420)
+                    const bool freeze = in0.dyn() && keeps_silence && in0.nlo == in0.nhi && in0.nhi == ch;
+                    const bool as_static = !in0.dyn() || (!keeps_silence && ch == 1 && in0.hi == 1);
+                    if (!freeze && !as_static)
+                        return bail(WAE_UNSUPPORTED, "an over-sampled WaveShaperNode whose input changes its channel count is not lowered to the GPU "
+                                                     "(the reference rebuilds its resamplers then, waveshaper.rs:409-420)");
                     if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                    if (freeze) out_like_input();
                     const int factor = n.oversample == WAE_OVERSAMPLE_X2 ? 2 : 4;
                     auto& filt = os_filters[factor];
                     if (!filt.first) {
@@ -1599,6 +1884,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     so.f_dn = filt.second;
                     so.hist = alloc<float>((size_t)256 * ch, true, true);
                     if (!so.hist || !so.f_up || !so.f_dn) return bail(WAE_OUT_OF_MEMORY, "out of device memory (over-sampled shaper)");
+                    if (freeze) {
+                        so.prev = alloc<int32_t>((size_t)(2 * (b->chunk / 128) + 2));
+                        if (!so.prev) return bail(WAE_OUT_OF_MEMORY, "out of device memory (over-sampled shaper)");
+                    }
                     StageBuild& os = stage(L, S_SHAPER_OS);
                     os.max_ch = std::max(os.max_ch, ch);
                     os.shaper_os.push_back(so);
@@ -1609,12 +1898,20 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     pc.inst.has_shaper = 1;
                     pc.inst.curve = curve;
                     pc.inst.shaper_n = (int)n.table.size();
+                    pc.inst.shaper_keeps_silence = keeps_silence ? 1 : 0;
+                    pc.lay = shaper_lay(pc.lay);
                     pc.phase = 5;
                     if (!finish_chain(std::move(pc))) return false;
                     break;
                 }
                 if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 ShaperInst sh{};
+                if (in0.dyn() && !keeps_silence && n.has_curve) {
+                    out_dynamic(shaper_lay(in0));
+                    if (p.out_buf[0].meta) meta_stage(L, META_SHAPER, p.in_buf[0], ch, p.out_buf[0], ch);
+                } else {
+                    out_like_input();
+                }
                 sh.in = p.in_buf[0];
                 sh.out = p.out_buf[0];
                 sh.ch = ch;
@@ -1628,6 +1925,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 float pan = ppan.v;
                 int ch = p.in_ch[0];
                 if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                // silent in -> silent out, else two channels (stereo_panner.rs:230-235); the kernel picks the mono / stereo law per quantum
+                out_dynamic(in0.may_silent ? Lay{1, 2, 2, 2, true} : Lay::fixed(2));
+                if (p.out_buf[0].meta) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
                 float x = ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);  // stereo_panner.rs:247-249,274-276
                 float gl, gr;
                 hm::stereo_gains(x, gl, gr);
@@ -1646,6 +1946,11 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 }
                 int ch = p.in_ch[0];
                 if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (n.panning_model == WAE_PANNING_HRTF && in0.dyn())
+                    return bail(WAE_UNSUPPORTED, "an HRTF PannerNode whose input can fall silent or change its channel count is not lowered to the GPU "
+                                                 "(tail bookkeeping of panner.rs:697-711)");
+                out_dynamic(in0.may_silent ? Lay{1, 2, 2, 2, true} : Lay::fixed(2));  // panner.rs:698-708
+                if (p.out_buf[0].meta) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
                 spatial::PanModel model{};
                 model.distance_model = n.distance_model;
                 model.ref_distance = n.ref_distance;
@@ -1738,6 +2043,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             case K_DELAY_W: {
                 p.out_ch = {p.in_ch[0]};
                 p.out_buf = {p.in_buf[0]};
+                p.out_lay = {in0};
                 if (Orderer::contains(ord.broken, id)) {
                     // cycle breaker applied (graph.rs:458-466): the hidden writer->reader edge is gone, the reader ran
                     // earlier in this quantum from the ring; record this quantum's input now
@@ -1753,6 +2059,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     d.ch = it->second.ch;
                     d.ring = it->second.ring;
                     d.ring_len = it->second.ring_len;
+                    d.mono_at = it->second.mono_at;
+                    d.mono_len = it->second.mono_len;
+                    d.dyn = it->second.mono_at ? 3 : 0;  // inside a cycle the writer runs after the reader: it extends the one-channel track
                     stage(L, S_DELAY_WRITE).delay.push_back(d);
                 }
                 break;
@@ -1789,8 +2098,21 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 d.ring = alloc<float>((size_t)ch * d.ring_len, true, true);
                 if (!d.ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (delay ring)");
                 b->arena_bytes += (size_t)ch * d.ring_len * 4;
+                if (ch <= 2) {
+                    // The reader reports a quantum without any normal sample as silent (delay.rs:654-664) and the ring follows the
+                    // channel count of the writer's input (:470-488): its output layout is never constant.  (Wider than stereo: the
+                    // static layout is kept, the re-mix of the ring is not followed.)
+                    d.dyn = 1;
+                    d.mono_len = (int32_t)next_pow2((uint64_t)(b->chunk / 128 + 2));
+                    d.mono_at = alloc<int64_t>((size_t)d.mono_len, true, true);
+                    if (!d.mono_at) return bail(WAE_OUT_OF_MEMORY, "out of device memory (delay layout track)");
+                    const Lay wl = in_cycle ? Lay{1, (uint8_t)ch, 1, (uint8_t)ch, true} : in0;
+                    out_dynamic(Lay{1, (uint8_t)ch, (uint8_t)(wl.dyn() ? 1 : ch), (uint8_t)ch, true});
+                    d.out = p.out_buf[0];
+                    if (!in_cycle) stage(L, S_DELAY_MONO).delay.push_back(d);
+                }
                 stage(L, S_DELAY).delay.push_back(d);
-                if (in_cycle) delay_rings[{gi, n.delay_peer}] = DelayRing{d.ring, d.ring_len, ch};
+                if (in_cycle) delay_rings[{gi, n.delay_peer}] = DelayRing{d.ring, d.ring_len, ch, d.mono_at, d.mono_len};
                 else stage(L, S_DELAY_WRITE).delay.push_back(d);  // acyclic: history is recorded right after the read
                 break;
             }
@@ -1809,7 +2131,11 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 c.ring_len = next_pow2((uint64_t)c.delay_frames + 128);
                 c.ring = alloc<float>((size_t)ch * c.ring_len, true, true);
                 c.state = alloc<float>(2, true, true);
-                if (!c.ring || !c.state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (compressor)");
+                c.meta_ring = alloc<uint8_t>(8, true, true);
+                if (!c.ring || !c.state || !c.meta_ring) return bail(WAE_OUT_OF_MEMORY, "out of device memory (compressor)");
+                // the look-ahead ring starts out silent and hands on the layout of the quantum it delays (dynamics_compressor.rs:340-349,452-468)
+                out_dynamic(Lay{1, in0.hi, in0.nlo, in0.nhi, true});
+                c.out = p.out_buf[0];
                 c.threshold = th; c.knee = kn; c.ratio = ra; c.attack = at; c.release = re;
                 for (int i = 0; i < 5; i++) c.track[i] = cp[i].dyn ? cp[i].track : BufRef{nullptr, 0, 0};
                 c.sample_rate = g->sample_rate;
@@ -1827,6 +2153,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 // producer), only the ring is written
                 p.out_ch = {ch};
                 p.out_buf = {p.in_buf[0]};
+                p.out_lay = {in0};
                 AnalyserInst a{};
                 a.in = p.in_buf[0];
                 a.out = BufRef{nullptr, 0, 0};
@@ -1851,15 +2178,44 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             case K_MERGER: {
                 int k = n.n_inputs;
                 if (!need_out(k)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                for (int i = 0; i < k; i++) stage(L, S_ROUTE).route.push_back(RouteInst{p.in_buf[i], p.out_buf[0], 0, i, 0, 0});
+                {
+                    // `k` channels as soon as one input is not silent, else silent (channel_merger.rs:160-168)
+                    bool some_always_on = false, any_dyn = false;
+                    for (int i = 0; i < k; i++) {
+                        some_always_on = some_always_on || !p.in_lay[i].may_silent;
+                        any_dyn = any_dyn || p.in_lay[i].dyn();
+                    }
+                    if (any_dyn && !some_always_on) {
+                        out_dynamic(Lay{1, (uint8_t)k, (uint8_t)k, (uint8_t)k, true});
+                        if (p.out_buf[0].meta) {
+                            MetaInst m{};
+                            m.out = p.out_buf[0];
+                            m.mode = META_MERGE;
+                            m.out_ch = k;
+                            m.count = k;
+                            m.n_more = k;
+                            m.more = upload(p.in_buf);
+                            if (!m.more) return bail(WAE_OUT_OF_MEMORY, "out of device memory (merger inputs)");
+                            stage(L, S_META).meta.push_back(m);
+                        }
+                    }
+                }
+                for (int i = 0; i < k; i++) stage(L, S_ROUTE).route.push_back(RouteInst{p.in_buf[i], p.out_buf[0], 0, i, 0, 1});
                 break;
             }
             case K_SPLITTER: {
                 int k = n.n_outputs;
                 p.out_ch.assign(k, 1);
                 p.out_buf.resize(k);
+                p.out_lay.assign(k, Lay::fixed(1));
                 for (int i = 0; i < k; i++) {
-                    if (i < p.in_ch[0]) {  // alias channel i of the input
+                    if (i < p.in_ch[0] && in0.dyn()) {  // channel i exists only in some quanta: copy it, zeros elsewhere, own layout track
+                        p.out_buf[i] = arena_buf(1, true);
+                        if (!p.out_buf[i].p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                        p.out_lay[i] = Lay{1, 1, 1, 1, true};
+                        stage(L, S_ROUTE).route.push_back(RouteInst{p.in_buf[0], p.out_buf[i], i, 0, 0, p.in_ch[0]});
+                        meta_stage(L, META_SPLIT, p.in_buf[0], p.in_ch[0], p.out_buf[i], 1, 0, i);
+                    } else if (i < p.in_ch[0]) {  // alias channel i of the input
                         BufRef r = p.in_buf[0];
                         r.p += (size_t)i * r.stride;
                         p.out_buf[i] = r;
@@ -2396,6 +2752,8 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                     st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
                     break;
                 }
+                case S_MIX_DYN: st.n = (int)s.mix_dyn.size(); st.d_a = up(b, s.mix_dyn); st.d_b = up(b, s.mix_edges); break;
+                case S_META: st.n = (int)s.meta.size(); st.d_a = up(b, s.meta); break;
                 case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
                 case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
                 case S_ABSN: st.n = (int)s.absn.size(); st.d_a = up(b, s.absn); break;
@@ -2430,6 +2788,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                 case S_ABSN_SERIAL: st.n = (int)s.absn_serial.size(); st.d_a = up(b, s.absn_serial); break;
                 case S_SHAPER_OS: st.n = (int)s.shaper_os.size(); st.d_a = up(b, s.shaper_os); break;
                 case S_ROUTE: st.n = (int)s.route.size(); st.d_a = up(b, s.route); break;
+                case S_DELAY_MONO:
                 case S_DELAY:
                 case S_DELAY_WRITE: st.n = (int)s.delay.size(); st.d_a = up(b, s.delay); break;
                 case S_COMP: st.n = (int)s.comp.size(); st.d_a = up(b, s.comp); break;
@@ -2564,6 +2923,9 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
     cudaStream_t s = b->engine->stream;
     switch (st.kind) {
         case S_MIX: launch_mix((MixInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s); break;
+        case S_MIX_DYN: launch_mix_dyn((MixDynInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s); break;
+        case S_META: launch_meta((MetaInst*)st.d_a, st.n, ci, s); break;
+        case S_DELAY_MONO: launch_delay_mono((DelayInst*)st.d_a, st.n, ci, s); break;
         case S_OSC: launch_oscillator((OscInst*)st.d_a, st.n, ci, s); break;
         case S_CONST: launch_constant((ConstInst*)st.d_a, st.n, ci, s); break;
         case S_ABSN: launch_buffer_source((AbsnInst*)st.d_a, st.n, ci, s); break;

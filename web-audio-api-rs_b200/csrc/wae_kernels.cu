@@ -434,9 +434,9 @@ __global__ void __launch_bounds__(32 * ABSN_SERIAL_WARPS) k_buffer_source_serial
 // are summed in the reference's processing order, each up/down-mixed to the port's computed channel count.
 // One thread per frame; sequential f32 adds over the edges => same summation order as the reference.
 // ---------------------------------------------------------------------------------------------------------
-DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, const ChunkInfo& ci) {
-    const int s = e.src_ch;
-    auto ld = [&](int ch) { return chan(e.src, ch, ci)[n]; };
+// channel c of a quantum of s channels (read through ld) mixed to dst_ch channels (quantum.rs:274-505)
+template <typename LD>
+DEVI float mix_channel(LD ld, int s, int dst_ch, int c, int interp) {
     if (s == dst_ch) return ld(c);
     if (interp == 1 || s > 6 || dst_ch > 6) return c < s ? ld(c) : 0.f;  // discrete: zero-fill / truncate
     const float sqrt05 = 0.70710678118654752440f;                          // (0.5f32).sqrt()
@@ -456,6 +456,118 @@ DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, 
         case 6 * 16 + 4: return c < 2 ? ld(c) + sqrt05 * ld(2) : ld(c + 2);
         default: return c < s ? ld(c) : 0.f;
     }
+}
+DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, const ChunkInfo& ci) {
+    return mix_channel([&](int ch) { return chan(e.src, ch, ci)[n]; }, e.src_ch, dst_ch, c, interp);
+}
+
+// Mixer with per-quantum layouts (MixDynInst): AudioRenderQuantum::add (quantum.rs:532-569) folded over the edges in processing
+// order.  Every add first brings the running sum to computedNumberOfChannels(max(sum's count, edge's count)) — so with three or more
+// layouts the intermediate counts matter (mono, then stereo, then 5.1: 1 -> 2 -> 6, the mono lands in L / R, not in C) — then mixes the
+// edge to that count and adds channel by channel; silent edges only take part in the count.  One thread per frame.
+__global__ void __launch_bounds__(128) k_mix_dyn(const MixDynInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const MixDynInst m = insts[ii];
+        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        const int qi = meta_qi(ci, n);
+        float acc[32], tmp[32];
+        int cnt = 1;
+        bool silent = true;
+        for (int e = 0; e < m.n_edges; e++) {
+            const MixEdge ed = edges[m.edge_offset + e];
+            const int ce = buf_count(ed.src, ed.src_ch, qi);
+            const bool se = buf_silent(ed.src, ed.src_ch, qi);
+            const int mx = cnt > ce ? cnt : ce;
+            const int nw = m.mode == WAE_COUNT_MODE_MAX ? mx : (m.mode == WAE_COUNT_MODE_EXPLICIT ? m.cfg_count : (mx < m.cfg_count ? mx : m.cfg_count));
+            if (!silent && nw != cnt) {  // self.mix(new_channels, interpretation)
+                for (int c = 0; c < nw; c++) tmp[c] = mix_channel([&](int ch) { return acc[ch]; }, cnt, nw, c, m.interp);
+                for (int c = 0; c < nw; c++) acc[c] = tmp[c];
+            }
+            cnt = nw;
+            if (!se) {
+                for (int c = 0; c < nw; c++) {
+                    const float v = mix_channel([&](int ch) { return chan(ed.src, ch, ci)[n]; }, ce, nw, c, m.interp);
+                    acc[c] = silent ? v : acc[c] + v;
+                }
+                silent = false;
+            }
+        }
+        if ((n & 127) == 0 && m.out.meta) meta_put_all(m.out, m.out_ch, qi, cnt, silent);
+        if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
+        for (int c = 0; c < m.out_ch; c++) {
+            float v = 0.f;
+            if (!silent) v = c < cnt ? acc[c] : mix_channel([&](int ch) { return acc[ch]; }, cnt, m.out_ch, c, m.interp);  // canonical fill
+            chan(m.out, c, ci)[n] = v;
+        }
+    }
+}
+
+// Layout tracks of nodes whose PCM path does not look at the layout (MetaInst): one thread per instance walks the chunk's quanta.
+__global__ void __launch_bounds__(64) k_meta(const MetaInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= n_inst) return;
+    const MetaInst m = insts[ii];
+    int64_t tail = m.mode == META_CONV ? *m.state : 0;
+    for (int q = 0; q < ci.nf / 128; q++) {
+        const int qi = meta_qi(ci, q * 128);
+        const int64_t f = ci.f0 + (int64_t)q * 128;
+        bool si = false;
+        int ci_ = m.in_ch;
+        if (m.mode != META_SOURCE && m.mode != META_MERGE && m.mode != META_CONST) {
+            si = buf_silent(m.in, m.in_ch, qi);
+            ci_ = buf_count(m.in, m.in_ch, qi);
+        }
+        int co = 1;
+        bool so = true;
+        switch (m.mode) {
+            case META_SOURCE:
+                so = m.n_stop <= f || m.n_first >= f + 128;
+                co = so ? 1 : m.count;
+                break;
+            case META_COPY:
+                so = si;
+                co = ci_;
+                break;
+            case META_SHAPER:
+                so = false;
+                co = ci_;
+                break;
+            case META_PAN:
+                so = si;
+                co = si ? 1 : 2;
+                break;
+            case META_CONV: {
+                bool out_silent = false;
+                if (si) {
+                    if (tail >= m.tail_len) out_silent = true;
+                    else tail += 128;
+                } else {
+                    tail = 0;
+                }
+                so = out_silent;
+                co = out_silent ? 1 : ((ci_ == 1 && m.aux == 1) ? 1 : 2);
+                break;
+            }
+            case META_SPLIT:
+                so = si || m.aux >= ci_;
+                co = 1;
+                break;
+            case META_MERGE: {
+                bool any = false;
+                for (int k = 0; k < m.n_more; k++) any = any || !buf_silent(m.more[k], 1, qi);
+                so = !any;
+                co = any ? m.count : 1;
+                break;
+            }
+            default:  // META_CONST
+                so = m.aux != 0;
+                co = so ? 1 : m.count;
+                break;
+        }
+        meta_put_all(m.out, m.out_ch, qi, co, so);
+    }
+    if (m.mode == META_CONV) *m.state = tail;
 }
 
 // Fast path (MixInst::simple): every edge either has the port's channel count or is a mono signal up-mixed by
@@ -626,7 +738,10 @@ __global__ void __launch_bounds__(128) k_biquad_serial(const BiquadInst* __restr
 DEVI float shaper_apply(const float* curve, int len, float input);
 
 constexpr int CH_K = WAE_CHAIN_K;  // frames per thread
-constexpr int CH_THREADS = 128;  // threads per CTA -> tile = 2048 frames
+#ifndef WAE_CH_THREADS
+#define WAE_CH_THREADS 128
+#endif
+constexpr int CH_THREADS = WAE_CH_THREADS;  // threads per CTA -> tile = 16 frames per thread
 constexpr int CH_WARPS = CH_THREADS / 32;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -762,12 +877,15 @@ struct ChainSmem {
     double state[CHAIN_MAX_BIQUADS][4];  // x1, x2, y1, y2 carried from tile to tile
     double P[CHAIN_MAX_BIQUADS][24];     // Pshfl[5][4], Pwarp[4]
     double wtot[CH_WARPS][2];            // per-warp end state (zero incoming state)
+    double replay[4];                    // serial replay of a tile (non-finite input): state handed from warp to warp
     float edge[CH_WARPS][2];             // last two step inputs of every warp
 };
 
 // one biquad over the thread's 16 frames (v in/out), see the header comment
+// clean: (threads that start a render quantum) the filter state entering this thread's frames has no normal value — the filter's
+// "tail has ended" test (biquad_filter.rs:778-794), used for the layout track of the chain's output
 DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, const double b2, const double a1, const double a2,
-                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp) {
+                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp, bool& clean) {
     const double* Psh = sm.P[bq];
     const double* Pw = sm.P[bq] + 20;
     // previous two step inputs: neighbour lane, previous warp, or the carried state
@@ -778,7 +896,64 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     }
     const float p1 = __shfl_up_sync(0xffffffffu, xl1, 1);
     const float p2 = __shfl_up_sync(0xffffffffu, xl2, 1);
-    __syncthreads();
+    // NaN / Inf among this thread's inputs?  x * 0 is NaN exactly for those: one FFMA per sample on the otherwise idle FMA pipe
+    float chk = 0.f;
+#pragma unroll
+    for (int j = 0; j < CH_K; j++) chk = fmaf(v[j], 0.f, chk);
+    if (__syncthreads_or(active && chk != chk)) {
+        // Rare: the reference flushes every non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`, biquad_filter.rs:881-883) and
+        // so recovers three samples after a NaN / Inf in its input, which no linear scan reproduces (the state would stay poisoned):
+        // this tile is run serially, thread after thread, in the reference's own operation order.
+        double sx1 = sm.state[bq][0], sx2 = sm.state[bq][1], sy1 = sm.state[bq][2], sy2 = sm.state[bq][3];
+        __syncthreads();
+#pragma unroll 1
+        for (int wv = 0; wv < CH_WARPS; wv++) {
+            if (warp == wv) {
+#pragma unroll 1
+                for (int l = 0; l < 32; l++) {
+                    double qx1 = sx1, qx2 = sx2, qy1 = sy1, qy2 = sy2;
+                    if (lane == l && active) {
+#pragma unroll
+                        for (int j = 0; j < CH_K; j++) {  // (unrolled: v[] must stay in registers)
+                            const double x = (double)v[j];
+                            double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(b0, x), __dmul_rn(b1, qx1)), __dmul_rn(b2, qx2)), __dmul_rn(a1, qy1)),
+                                                 __dmul_rn(a2, qy2));
+                            if (!isnormal_d(y)) y = 0.;
+                            qx2 = qx1;
+                            qx1 = x;
+                            qy2 = qy1;
+                            qy1 = y;
+                            v[j] = (float)y;
+                        }
+                    }
+                    sx1 = __shfl_sync(0xffffffffu, qx1, l);
+                    sx2 = __shfl_sync(0xffffffffu, qx2, l);
+                    sy1 = __shfl_sync(0xffffffffu, qy1, l);
+                    sy2 = __shfl_sync(0xffffffffu, qy2, l);
+                }
+                if (lane == 0) {
+                    sm.replay[0] = sx1;
+                    sm.replay[1] = sx2;
+                    sm.replay[2] = sy1;
+                    sm.replay[3] = sy2;
+                }
+            }
+            __syncthreads();
+            sx1 = sm.replay[0];
+            sx2 = sm.replay[1];
+            sy1 = sm.replay[2];
+            sy2 = sm.replay[3];
+            __syncthreads();
+        }
+        if (t == 0) {
+            sm.state[bq][0] = sx1;
+            sm.state[bq][1] = sx2;
+            sm.state[bq][2] = sy1;
+            sm.state[bq][3] = sy2;
+        }
+        clean = false;
+        return;
+    }
     double x1, x2;
     if (lane == 0) {
         if (warp == 0) {
@@ -792,6 +967,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         x1 = (double)p1;
         x2 = (double)p2;
     }
+    const bool x_normal = isnormal_d(x1) || isnormal_d(x2);
     // FIR part and pass 1 (zero incoming state): end state only
     double w[CH_K];
     double r1 = 0., r2 = 0.;
@@ -823,7 +999,6 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     __syncthreads();
     // state entering this warp: chain the previous warps' totals through A^32
     double wa = sm.state[bq][2], wb = sm.state[bq][3];
-    const double in1 = wa, in2 = wb;  // state entering the tile (the serial replay below starts from it)
 #pragma unroll
     for (int k = 0; k < CH_WARPS - 1; k++) {
         if (k < warp) {
@@ -840,69 +1015,21 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         e2 = eb;
         mat2_fma(Plane, wa, wb, e1, e2);
     }
+    clean = !(x_normal || isnormal_d(e1) || isnormal_d(e2));
     // pass 2: the recurrence from the true state
     r1 = e1;
     r2 = e2;
-    unsigned mx = 0;  // largest |output| bit pattern of this thread: >= 0x7f800000 <=> an Inf / NaN came out
 #pragma unroll
     for (int j = 0; j < CH_K; j++) {
         const double y = fma(na1, r1, fma(na2, r2, w[j]));
         r2 = r1;
         r1 = y;
         v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
-#ifndef WAE_CHAIN_NOFLUSH
-        mx = max(mx, __float_as_uint(v[j]) & 0x7fffffffu);
-#endif
     }
-    // (barrier: everyone has read state / wtot / edge of this step) + did any thread of the tile see a non-finite output?
-#ifdef WAE_CHAIN_NOFLUSH
-    __syncthreads();
-    const int any_bad = 0;
-    (void)mx;
-    (void)in1;
-    (void)in2;
-#else
-    const int any_bad = __syncthreads_or(active && mx >= 0x7f800000u);
-#endif
-    if (any_bad) {
-        // Rare: a NaN / Inf reached the recurrence (a NaN in the source PCM, an unstable filter).  The reference flushes every
-        // non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`, biquad_filter.rs:881-883) and so recovers on the next
-        // sample, which no linear scan reproduces: replay this tile serially, thread after thread, from the tile's incoming state.
-        double s1 = in1, s2 = in2;
-#pragma unroll 1
-        for (int wv = 0; wv < CH_WARPS; wv++) {
-            if (warp == wv) {
-#pragma unroll 1
-                for (int l = 0; l < 32; l++) {
-                    double a = s1, b = s2;
-                    if (lane == l && active) {
-#pragma unroll
-                        for (int j = 0; j < CH_K; j++) {
-                            double y = fma(na1, a, fma(na2, b, w[j]));
-                            const double ay = fabs(y);
-                            if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
-                            b = a;
-                            a = y;
-                            v[j] = (float)y;
-                        }
-                        r1 = a;
-                        r2 = b;
-                    }
-                    s1 = __shfl_sync(0xffffffffu, a, l);
-                    s2 = __shfl_sync(0xffffffffu, b, l);
-                }
-                if (lane == 31) {
-                    sm.wtot[0][0] = s1;
-                    sm.wtot[0][1] = s2;
-                }
-            }
-            __syncthreads();
-            s1 = sm.wtot[0][0];
-            s2 = sm.wtot[0][1];
-            __syncthreads();
-        }
-    }
+    __syncthreads();  // everyone has read state / wtot / edge of this step
     if (active && t == n_active - 1) {
+        // (an unstable filter that has run off to Inf / NaN: the reference's per-sample flush would have reset it; do not carry the poison)
+        if (!(fabs(r1) <= 1.7976931348623157e308) || !(fabs(r2) <= 1.7976931348623157e308)) r1 = r2 = 0.;
         sm.state[bq][0] = (double)xl1;
         sm.state[bq][1] = (double)xl2;
         sm.state[bq][2] = r1;
@@ -966,7 +1093,7 @@ DEVI void cswap4(bool p, float4& a, float4& b) {
 // mbarrier), results leave through bulk stores; TMA = false: 16-byte cp.async pieces / coalesced stores (kept as the
 // reference data path: WAE_OPT_CHAIN_TMA = 0).
 template <int SRC, int NB, bool SHAPER, bool TMA>
-__global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
+__global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
                                                                         int n_inst, ChunkInfo ci, ChainSched sc) {
     __shared__ ChainSmem sm;
     __shared__ int s_item;
@@ -1184,12 +1311,13 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
         } else if (active) {
             chain_load_source<SRC>(q, c, ci, n0, v);
         }
+        bool clean0 = true, clean1 = true;
         if (g0 != 1.f) {  // x * 1.0f == x bit for bit: skip the multiply (uniform branch)
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g0;
         }
         if (NB >= 1) {
-            chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp);
+            chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0);
             if (g1 != 1.f) {
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) v[j] *= g1;
@@ -1197,7 +1325,7 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
         }
         if (NB >= 2) {
             chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], plane[NB - 1], v, active,
-                         n_active, t, lane, warp);
+                         n_active, t, lane, warp, clean1);
             if (g2 != 1.f) {
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) v[j] *= g2;
@@ -1212,6 +1340,50 @@ __global__ void __launch_bounds__(CH_THREADS, NB == 2 ? 5 : 6) k_chain(const Cha
             }
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g3;
+        }
+        if (q.out.meta && active && (n0 & 127) == 0) {
+            // Layout track of the chain's output, row c (this CTA's channel), for the quantum this thread starts: the nodes of the
+            // chain in order.  source: silent outside its schedule; gain: silent in -> silent out, a gain of (about) zero silences
+            // (gain.rs:153-169); biquad: silent once its input is silent AND its state has no normal value left, until then it keeps
+            // its channels (biquad_filter.rs:778-815); wave-shaper: passes silence on only if its curve maps 0 to 0, else it answers
+            // on the one channel a silent quantum has (waveshaper.rs:395-400).
+            const int qi = meta_qi(ci, n0);
+            const int64_t f = ci.f0 + n0;
+            bool sl;
+            int cnt = q.ch;
+            if (SRC == CHAIN_SRC_BUFFER) {
+                sl = buf_silent(q.in, q.ch, qi);
+                cnt = buf_count(q.in, q.ch, qi);
+            } else if (SRC == CHAIN_SRC_OSC) {
+                sl = q.osc.n_stop <= f || q.osc.n_first >= f + 128;
+            } else if (SRC == CHAIN_SRC_CONST) {
+                sl = q.cst.n_stop <= f || q.cst.n_first >= f + 128;
+            } else {
+                sl = q.absn.n_stop <= f || q.absn.n_start >= f + 128;
+            }
+            if (g0 == 0.f) sl = true;
+            if (sl) cnt = 1;
+            if (NB >= 1) {
+                if (sl && !clean0) {
+                    sl = false;
+                    cnt = q.ch;
+                }
+                if (g1 == 0.f) sl = true;
+                if (sl) cnt = 1;
+            }
+            if (NB >= 2) {
+                if (sl && !clean1) {
+                    sl = false;
+                    cnt = q.ch;
+                }
+                if (g2 == 0.f) sl = true;
+                if (sl) cnt = 1;
+            }
+            if (SHAPER) {
+                if (sl && q.curve && !q.shaper_keeps_silence) sl = false;  // (cnt stays 1)
+                if (g3 == 0.f) sl = true;
+            }
+            meta_put(q.out, c, qi, cnt, sl || c >= cnt);
         }
         {
             // results: through the warp's staging region (the source pieces of this tile are consumed), so that global
@@ -1591,16 +1763,28 @@ __global__ void __launch_bounds__(256) k_stereo_panner(const SPanInst* __restric
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
         float pan = s.pan;
-        if (s.pan_track.p) {  // a-rate pan: gains per frame (stereo_panner.rs:259-271, 293-313)
-            pan = chan(s.pan_track, 0, ci)[n];
+        // dynamic input layout: the mono / stereo formulas are chosen per quantum (stereo_panner.rs:242), a silent input gives
+        // a silent output (:230-233; the layout track of the output is written by k_meta)
+        int in_ch = s.in_ch;
+        if (s.in.meta) {
+            const int qi = meta_qi(ci, n);
+            if (buf_silent(s.in, s.in_ch, qi)) {
+                chan(s.out, 0, ci)[n] = 0.f;
+                chan(s.out, 1, ci)[n] = 0.f;
+                continue;
+            }
+            in_ch = buf_count(s.in, s.in_ch, qi);
+        }
+        if (s.pan_track.p || in_ch != s.in_ch) {  // a-rate pan: gains per frame (stereo_panner.rs:259-271, 293-313)
+            if (s.pan_track.p) pan = chan(s.pan_track, 0, ci)[n];
             const float PI32 = 3.14159265358979323846f;
-            float x = s.in_ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);
+            float x = in_ch == 1 ? (pan + 1.f) * 0.5f : (pan <= 0.f ? pan + 1.f : pan);
             gl = sinf((1.f - x) * PI32 / 2.f);
             gr = sinf(x * PI32 / 2.f);
         }
         float* l = chan(s.out, 0, ci);
         float* r = chan(s.out, 1, ci);
-        if (s.in_ch == 1) {
+        if (in_ch == 1) {
             float x = chan(s.in, 0, ci)[n];
             l[n] = x * gl;
             r[n] = x * gr;
@@ -1650,9 +1834,19 @@ __global__ void __launch_bounds__(256) k_panner_eq(const PanInst* __restrict__ i
         int n = blockIdx.x * blockDim.x + threadIdx.x;
         if (n >= ci.nf) continue;
         spatial::SpatialParams sp{p.dist_gain, p.cone_gain, p.azimuth, 0.f};
-        float il = chan(p.in, 0, ci)[n], ir = p.in_ch == 2 ? chan(p.in, 1, ci)[n] : 0.f;
+        int in_ch = p.in_ch;
+        if (p.in.meta) {  // dynamic input layout (panner.rs:698-708,846,872)
+            const int qi = meta_qi(ci, n);
+            if (buf_silent(p.in, p.in_ch, qi)) {
+                chan(p.out, 0, ci)[n] = 0.f;
+                chan(p.out, 1, ci)[n] = 0.f;
+                continue;
+            }
+            in_ch = buf_count(p.in, p.in_ch, qi);
+        }
+        float il = chan(p.in, 0, ci)[n], ir = in_ch == 2 ? chan(p.in, 1, ci)[n] : 0.f;
         float l, r;
-        pan_eq_frame(sp, p.in_ch, il, ir, l, r);
+        pan_eq_frame(sp, in_ch, il, ir, l, r);
         chan(p.out, 0, ci)[n] = l;
         chan(p.out, 1, ci)[n] = r;
     }
@@ -1723,9 +1917,18 @@ __global__ void __launch_bounds__(128) k_shaper_os(const ShaperOsInst* __restric
     const int fo = 128 * p.factor, n2 = 2 * fo, log2n = p.factor == 2 ? 9 : 10;
     const float* in = chan(p.in, c, ci);
     const float* hist = p.hist + 256 * c;
+    int q_of[3] = {q - 2, q - 1, q};
+    if (p.prev) {  // silent quanta are not processed at all (block-uniform): the neighbours are the last processed quanta
+        if (buf_silent(p.in, p.ch, meta_qi(ci, q * 128))) {
+            chan(p.out, c, ci)[q * 128 + t] = 0.f;
+            return;
+        }
+        q_of[0] = p.prev[2 * q + 1];
+        q_of[1] = p.prev[2 * q];
+    }
     // three up-transforms: quanta q-2, q-1, q
     for (int r = 0; r < 3; r++) {
-        const int qq = q - 2 + r;
+        const int qq = q_of[r];
         float x = qq >= 0 ? in[qq * 128 + t] : hist[(qq + 2) * 128 + t];
         z[t] = make_float2(x, 0.f);
         z[128 + t] = make_float2(0.f, 0.f);
@@ -1757,11 +1960,40 @@ __global__ void __launch_bounds__(128) k_shaper_os(const ShaperOsInst* __restric
     }
     chan(p.out, c, ci)[q * 128 + t] = result + dn_prev[t];
 }
+// dynamic input layout: the processed quanta before every quantum of the chunk (ShaperOsInst::prev), one thread per instance
+__global__ void __launch_bounds__(64) k_shaper_os_prev(const ShaperOsInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= n_inst) return;
+    const ShaperOsInst& p = insts[ii];
+    if (!p.prev) return;
+    int last1 = -1, last2 = -2;
+    const int nq = ci.nf / 128;
+    for (int q = 0; q < nq; q++) {
+        p.prev[2 * q] = last1;
+        p.prev[2 * q + 1] = last2;
+        if (!buf_silent(p.in, p.ch, meta_qi(ci, q * 128))) {
+            last2 = last1;
+            last1 = q;
+        }
+    }
+    p.prev[2 * nq] = last1;
+    p.prev[2 * nq + 1] = last2;
+}
 // the two input quanta before the next chunk
 __global__ void __launch_bounds__(256) k_shaper_os_hist(const ShaperOsInst* __restrict__ insts, ChunkInfo ci) {
     const ShaperOsInst& p = insts[blockIdx.x];
     const int t = threadIdx.x;
     for (int c = 0; c < p.ch; c++) {
+        if (p.prev) {  // the two PROCESSED quanta before the next chunk: slot 1 (t >= 128) the latest, slot 0 the one before
+            const int nq = ci.nf / 128;
+            const int qq = t >= 128 ? p.prev[2 * nq] : p.prev[2 * nq + 1];
+            const int i = t & 127;
+            const float v = qq >= 0 ? chan(p.in, c, ci)[qq * 128 + i] : p.hist[256 * c + (qq + 2) * 128 + i];
+            __syncthreads();
+            p.hist[256 * c + t] = v;
+            __syncthreads();
+            continue;
+        }
         const int m = ci.nf - 256 + t;
         const float v = m >= 0 ? chan(p.in, c, ci)[m] : p.hist[256 * c + 128 + t - (128 - ci.nf)];  // nf == 128: shift by one quantum
         __syncthreads();
@@ -1795,7 +2027,16 @@ __global__ void __launch_bounds__(128) k_panner_dyn(const PanDynInst* __restrict
         float v[15];
         spatial_fetch(p.sp, n, listener_single_valued(p.sp, n, ci), ci, v);
         const spatial::SpatialParams sp = spatial::spatial_params(p.model, v);
-        const int in_ch = p.in_ch;
+        int in_ch = p.in_ch;
+        if (p.in.meta) {  // dynamic input layout (panner.rs:698-708,846,872)
+            const int qi = meta_qi(ci, n);
+            if (buf_silent(p.in, p.in_ch, qi)) {
+                chan(p.out, 0, ci)[n] = 0.f;
+                chan(p.out, 1, ci)[n] = 0.f;
+                continue;
+            }
+            in_ch = buf_count(p.in, p.in_ch, qi);
+        }
         float il = chan(p.in, 0, ci)[n], ir = in_ch == 2 ? chan(p.in, 1, ci)[n] : 0.f;
         float l, r;
         pan_eq_frame(sp, in_ch, il, ir, l, r);
@@ -1968,7 +2209,12 @@ __global__ void __launch_bounds__(256) k_route(const RouteInst* __restrict__ ins
         int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
         if (n0 >= ci.nf) continue;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!r.zero) v = *reinterpret_cast<const float4*>(chan(r.in, r.in_channel, ci) + n0);
+        bool zero = r.zero != 0;
+        if (!zero && r.in.meta) {  // dynamic input layout: a channel the input does not have in this quantum (or a silent input) reads as zeros
+            const int qi = meta_qi(ci, n0);
+            zero = buf_silent(r.in, r.in_ch, qi) || r.in_channel >= buf_count(r.in, r.in_ch, qi);
+        }
+        if (!zero) v = *reinterpret_cast<const float4*>(chan(r.in, r.in_channel, ci) + n0);
         *reinterpret_cast<float4*>(chan(r.out, r.out_channel, ci) + n0) = v;
     }
 }
@@ -1990,10 +2236,80 @@ DEVI float delay_fetch(const DelayInst& d, const float* in, const float* ring, i
     }
     return ring[m & (d.ring_len - 1)];
 }
+// Dynamic input layout (static channels <= 2).  Sample of frame m as the reference's ring holds it when the reader runs in quantum
+// `q_read`: the ring stores the canonical two channels of every quantum (a one-channel quantum is stored twice); every time the
+// writer sees a channel count different from the ring's it re-mixes the WHOLE ring (delay.rs:470-488, speakers rules: 2 -> 1 is
+// 0.5 * (L + R), 1 -> 2 a copy), so a stereo sample has collapsed to its mono down-mix iff some quantum in (its own, q_read] had a
+// one-channel input — mono_at[q_read] > quantum of m.  In a feedback cycle the reader runs before the writer: q_read is the quantum
+// before.
+DEVI void delay_fetch2(const DelayInst& d, int64_t m, const ChunkInfo& ci, int64_t mono_last, float& l, float& r) {
+    l = r = 0.f;
+    if (m < 0) return;
+    const float* ring = d.ring;
+    if (!d.in_cycle && m >= ci.f0) {
+        const int64_t rr = m - ci.f0;
+        if (rr >= ci.nf) return;
+        const int qi = meta_qi(ci, (int)rr);
+        if (buf_silent(d.in, d.ch, qi)) return;
+        l = chan(d.in, 0, ci)[rr];
+        r = buf_count(d.in, d.ch, qi) >= 2 ? chan(d.in, 1, ci)[rr] : l;
+    } else {
+        if (d.in_cycle && m >= ci.f0) return;
+        l = ring[m & (d.ring_len - 1)];
+        r = d.ch > 1 ? ring[(size_t)d.ring_len + (m & (d.ring_len - 1))] : l;
+    }
+    if (mono_last > (m >> 7)) l = r = 0.5f * (l + r);
+}
 __global__ void __launch_bounds__(256) k_delay_read(const DelayInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ int s_live[2];
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const DelayInst d = insts[ii];
         int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (d.dyn) {  // whole quanta per block (256 threads = 2 quanta): every thread takes part in the silence vote
+            if (threadIdx.x < 2) s_live[threadIdx.x] = 0;
+            __syncthreads();
+            const bool inside = n < ci.nf;
+            int out_ch = 1;
+            if (inside) {
+                const int64_t q_abs = (ci.f0 + n) >> 7;
+                const int64_t q_read = d.in_cycle ? q_abs - 1 : q_abs;  // newest quantum the ring has seen when the reader runs
+                int64_t mono_last = -1;
+                if (q_read >= 0) {
+                    mono_last = d.mono_at[q_read & (d.mono_len - 1)];
+                    out_ch = mono_last == q_read ? 1 : d.ch;  // ring[0].number_of_channels() (:532-533)
+                }
+                int64_t m = ci.f0 + n + d.fl;
+                float k = d.k;
+                if (d.delay_track.p) {
+                    double delay = (double)chan(d.delay_track, 0, ci)[n];
+                    const double sr = (double)d.sample_rate;
+                    if (d.in_cycle) delay = fmax(delay, 128. / sr);
+                    const int i = (int)((ci.f0 + n) & 127);
+                    double position = (double)i - delay * sr;
+                    double pf = floor(position);
+                    m = (ci.f0 + n - i) + (int64_t)pf;
+                    k = (float)(position - pf);
+                }
+                float pl, pr, nl, nr;
+                delay_fetch2(d, m, ci, mono_last, pl, pr);
+                delay_fetch2(d, m + 1, ci, mono_last, nl, nr);
+                if (out_ch == 1) {  // a one-channel ring: every stereo sample in it has been mixed down
+                    pl = pr = 0.5f * (pl + pr);
+                    nl = nr = 0.5f * (nl + nr);
+                }
+                const float vl = fmaf(1.f - k, pl, k * nl), vr = fmaf(1.f - k, pr, k * nr);
+                chan(d.out, 0, ci)[n] = vl;
+                if (d.ch > 1) chan(d.out, 1, ci)[n] = vr;
+                const float al = fabsf(vl), ar = fabsf(vr);
+                const bool live = (al >= 1.17549435e-38f && al <= 3.40282347e+38f) || (out_ch > 1 && ar >= 1.17549435e-38f && ar <= 3.40282347e+38f);
+                if (live) s_live[threadIdx.x >> 7] = 1;  // is_normal(value) (:654-664)
+            }
+            __syncthreads();
+            if (inside && (threadIdx.x & 127) == 0 && d.out.meta)
+                meta_put_all(d.out, d.ch, meta_qi(ci, n), s_live[threadIdx.x >> 7] ? out_ch : 1, !s_live[threadIdx.x >> 7]);
+            __syncthreads();
+            continue;
+        }
         if (n >= ci.nf) continue;
         for (int c = 0; c < d.ch; c++) {
             const float* in = d.in_cycle ? nullptr : chan(d.in, c, ci);
@@ -2016,11 +2332,37 @@ __global__ void __launch_bounds__(256) k_delay_read(const DelayInst* __restrict_
         }
     }
 }
+// the "last quantum whose input had one channel" track of a delay line for the quanta of this chunk (a running maximum: serial)
+DEVI void delay_mono_scan(const DelayInst& d, const ChunkInfo& ci) {
+    const int64_t q0 = ci.f0 >> 7;
+    int64_t last = q0 > 0 ? d.mono_at[(q0 - 1) & (d.mono_len - 1)] : -1;
+    for (int q = 0; q < ci.nf / 128; q++) {
+        const int qi = meta_qi(ci, q * 128);
+        if (buf_count(d.in, d.ch, qi) <= 1) last = q0 + q;  // (a silent quantum has one channel unless the port's count is explicit)
+        d.mono_at[(q0 + q) & (d.mono_len - 1)] = last;
+    }
+}
+__global__ void __launch_bounds__(64) k_delay_mono(const DelayInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii < n_inst && (insts[ii].dyn & 1)) delay_mono_scan(insts[ii], ci);
+}
 __global__ void __launch_bounds__(256) k_ring_write(const DelayInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const DelayInst d = insts[ii];
         int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if ((d.dyn & 2) && blockIdx.x == 0 && threadIdx.x == 0) delay_mono_scan(d, ci);  // feedback cycle: the writer runs after the reader
         if (n >= ci.nf || ci.nf - n > (int64_t)d.ring_len) continue;  // only the newest ring_len frames (no slot written twice)
+        if (d.dyn) {  // canonical two channels: a one-channel quantum is stored twice, a silent one as zeros
+            const int qi = meta_qi(ci, n);
+            float l = 0.f, r = 0.f;
+            if (!buf_silent(d.in, d.ch, qi)) {
+                l = chan(d.in, 0, ci)[n];
+                r = (d.ch > 1 && buf_count(d.in, d.ch, qi) >= 2) ? chan(d.in, 1, ci)[n] : l;
+            }
+            d.ring[(ci.f0 + n) & (d.ring_len - 1)] = l;
+            if (d.ch > 1) d.ring[(size_t)d.ring_len + ((ci.f0 + n) & (d.ring_len - 1))] = r;
+            continue;
+        }
         for (int c = 0; c < d.ch; c++) d.ring[(size_t)c * d.ring_len + ((ci.f0 + n) & (d.ring_len - 1))] = chan(d.in, c, ci)[n];
     }
 }
@@ -2040,7 +2382,25 @@ __global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ 
     float prev = q.state[0];
     float reduction_gain = q.state[1];
     const uint32_t mask = q.ring_len - 1;
+    // dynamic input layout: the look-ahead ring holds whole quanta WITH their layout (dynamics_compressor.rs:452-461): the output of
+    // quantum q has the channel count / silence of input quantum q - D; the detector reads the channels the current input has
+    const bool dyn = q.in.meta != nullptr || q.out.meta != nullptr;
+    const int D = q.delay_frames / 128;
+    int cur_ch = q.ch, out_ch = q.ch;
+    bool cur_silent = false, out_silent = false;
     for (int n = 0; n < ci.nf; n++) {
+        if (dyn && (n & 127) == 0) {
+            const int qi = meta_qi(ci, n);
+            const int64_t q_abs = (ci.f0 + n) >> 7;
+            cur_silent = buf_silent(q.in, q.ch, qi);
+            cur_ch = buf_count(q.in, q.ch, qi);
+            q.meta_ring[q_abs & 7] = (uint8_t)(cur_ch | (cur_silent ? WAE_META_SILENT : 0));
+            uint8_t dm = (uint8_t)(1 | WAE_META_SILENT);  // the ring starts out as silent quanta (:340-349)
+            if (q_abs - D >= 0) dm = q.meta_ring[(q_abs - D) & 7];
+            out_silent = (dm & WAE_META_SILENT) != 0;
+            out_ch = out_silent ? 1 : (dm & 0x3f);
+            if (q.out.meta) meta_put_all(q.out, q.ch, qi, out_ch, out_silent);
+        }
         if (n == 0 || (automated && (n & 127) == 0)) {  // per-quantum constants (dynamics_compressor.rs:352-391), params are k-rate
             const float attack = q.track[0].p ? chan(q.track[0], 0, ci)[n] : q.attack;
             const float knee = q.track[1].p ? chan(q.track[1], 0, ci)[n] : q.knee;
@@ -2057,8 +2417,8 @@ __global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ 
             makeup_gain = lin_to_db(powf(full_range_makeup, 0.6f));
         }
         float mx = -3.40282347e+38f;
-        for (int c = 0; c < q.ch; c++) {
-            float s = fabsf(chan(q.in, c, ci)[n]);
+        for (int c = 0; c < cur_ch; c++) {
+            float s = cur_silent ? 0.f : fabsf(chan(q.in, c, ci)[n]);
             if (s > mx) mx = s;
         }
         float sample_db = lin_to_db(mx);
@@ -2083,7 +2443,9 @@ __global__ void __launch_bounds__(32) k_compressor(const CompInst* __restrict__ 
         int64_t m = ci.f0 + n - q.delay_frames;
         for (int c = 0; c < q.ch; c++) {
             float x = 0.f;
-            if (m >= ci.f0)
+            if (out_silent || c >= out_ch)
+                x = 0.f;
+            else if (m >= ci.f0)
                 x = chan(q.in, c, ci)[m - ci.f0];
             else if (m >= 0)
                 x = q.ring[(size_t)c * q.ring_len + (m & mask)];
@@ -2108,7 +2470,14 @@ __global__ void __launch_bounds__(256) k_analyser(const AnalyserInst* __restrict
         MixEdge e;
         e.src = a.in;
         e.src_ch = a.ch;
-        float mono = mixed_sample(e, 1, 0, 0, n, ci);  // mono.mix(1, Speakers)
+        float mono;
+        if (a.in.meta) {  // dynamic input layout: the down-mix sees the channels this quantum has
+            const int qi = meta_qi(ci, n);
+            e.src_ch = buf_count(a.in, a.ch, qi);
+            mono = buf_silent(a.in, a.ch, qi) ? 0.f : mixed_sample(e, 1, 0, 0, n, ci);
+        } else {
+            mono = mixed_sample(e, 1, 0, 0, n, ci);  // mono.mix(1, Speakers)
+        }
         if (a.out.p)
             for (int c = 0; c < a.ch; c++) chan(a.out, c, ci)[n] = chan(a.in, c, ci)[n];
         if (ci.nf - n <= RING) a.ring[(ci.f0 + n) % RING] = mono;
@@ -2676,6 +3045,8 @@ void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStr
     if (ctas4 < 2 * 148) k_mix<1><<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci);
     else k_mix<4><<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, e, n, ci);
 }
+void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) { k_mix_dyn<<<grid_tiles(ci.nf, 128, n), 128, 0, s>>>(d, e, n, ci); }
+void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_meta<<<(n + 63) / 64, 64, 0, s>>>(d, n, ci); }
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
@@ -2702,15 +3073,16 @@ void chain_set_tuning(int tma, int waves) {
 void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab) {
     chain_env();
     const long ctas = (long)n * max_ch, tiles = (nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
-    const long slots = 148L * 6;
+    const long slots = 148L * (768 / CH_THREADS);
+    const long min_tiles = std::max(1L, 16384L / (CH_THREADS * CH_K));  // a slab is at least 16384 frames
     long slabs = 1;
     if (nb == 0) {
-        slabs = (4L * 148 + ctas - 1) / ctas;  // stateless chain: split along time until the launch fills the machine (4 CTAs per SM)
+        slabs = (slots * 2 / 3 + ctas - 1) / ctas;  // stateless chain: split along time until the launch fills the machine
         if (g_chain_waves > 0 && ctas * slabs < (long)g_chain_waves * slots) slabs = ((long)g_chain_waves * slots + ctas - 1) / ctas;
-        if (slabs > std::max(1L, tiles / 2)) slabs = std::max(1L, tiles / 2);
+        if (slabs > std::max(1L, tiles / std::max(1L, min_tiles / 4))) slabs = std::max(1L, tiles / std::max(1L, min_tiles / 4));
     } else if (g_chain_waves > 0 && 2 * ctas >= slots) {
         slabs = ((long)g_chain_waves * slots + ctas - 1) / ctas;
-        if (slabs > tiles / 8) slabs = tiles / 8;
+        if (slabs > tiles / min_tiles) slabs = tiles / min_tiles;
     }
     if (slabs > CHAIN_MAX_SLABS) slabs = CHAIN_MAX_SLABS;
     if (slabs < 1) slabs = 1;
@@ -2790,6 +3162,7 @@ void launch_buffer_source_serial(const AbsnSerialInst* d, int n, ChunkInfo ci, c
     k_buffer_source_serial<<<(n + ABSN_SERIAL_WARPS - 1) / ABSN_SERIAL_WARPS, 32 * ABSN_SERIAL_WARPS, 0, s>>>(d, n, ci);
 }
 void launch_shaper_os(const ShaperOsInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    k_shaper_os_prev<<<(n + 63) / 64, 64, 0, s>>>(d, n, ci);
     k_shaper_os<<<dim3((unsigned)(ci.nf / 128), (unsigned)max_ch, (unsigned)n), 128, 0, s>>>(d, ci);
     k_shaper_os_hist<<<n, 256, 0, s>>>(d, ci);
 }
@@ -2811,6 +3184,7 @@ void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, in
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_eq<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_route<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_delay_read(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_delay_read<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
+void launch_delay_mono(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_delay_mono<<<(n + 63) / 64, 64, 0, s>>>(d, n, ci); }
 void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_ring_write<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_osc_arate<<<n, 256, 0, s>>>(d, n, ci); }
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {

@@ -23,6 +23,8 @@ void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source_slow(const AbsnSlowInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
+void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
+void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux);
 void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab);  // launch geometry of k_chain (host)
@@ -38,6 +40,7 @@ void launch_panner_dyn(const PanDynInst* d, int n, ChunkInfo ci, cudaStream_t s)
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_route(const RouteInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_delay_read(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
+void launch_delay_mono(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
