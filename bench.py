@@ -193,7 +193,7 @@ def measure_workload(pkg, eng, D, oracle, name, build, n_gpu, n_cpu, length, ste
                 ev.record(eng_stream)
                 comm.wait_event(ev)
                 with torch.cuda.stream(comm):
-                    dist.all_gather_into_tensor(full[k].view(-1), shard[g0:g1].reshape(-1))
+                    pkg.parallel.all_gather_group(full[k], shard[g0:g1])
             comm.synchronize()
             batch.sync()
 
@@ -214,7 +214,7 @@ def measure_workload(pkg, eng, D, oracle, name, build, n_gpu, n_cpu, length, ste
         with torch.cuda.stream(comm):
             e0.record(comm)
             for k, (g0, g1) in enumerate(groups_r):
-                dist.all_gather_into_tensor(full[k].view(-1), shard[g0:g1].reshape(-1))
+                pkg.parallel.all_gather_group(full[k], shard[g0:g1])
             e1.record(comm)
         torch.cuda.synchronize()
         alone = D.max(e0.elapsed_time(e1))

@@ -44,6 +44,15 @@ def _worker(rank, world, port, out_path):
     g0, g1 = pkg.parallel.shard_range(N_GRAPHS, rank, world)
     _, local = _render_shard(g0, g1)
     full = pkg.parallel.gather_pcm(local, N_GRAPHS, dst=0)
+    # the grouped all-gather of bench.py's "gather inside the step": every rank contributes the same local graph range per group
+    per_rank = N_GRAPHS // world
+    mine = local[:per_rank]
+    for g0, g1 in pkg.parallel.group_ranges(per_rank, 2):
+        full_k = torch.empty((world, g1 - g0) + tuple(mine.shape[1:]), dtype=mine.dtype)
+        pkg.parallel.all_gather_group(full_k, mine[g0:g1])
+        assert torch.equal(full_k[rank], mine[g0:g1])
+        other = torch.tensor([float(full_k[r].abs().sum()) for r in range(world)])
+        assert (other > 0).all()
     slowest = pkg.parallel.max_over_ranks(10.0 + rank)
     assert slowest == 10.0 + world - 1
     if rank == 0:

@@ -194,7 +194,11 @@ struct HrtfInst {
     int32_t L;
     int32_t in_ch;
     float correction;        // 2 for stereo input (panner.rs:805-812)
-    int32_t pad;
+    int32_t dyn;             // 1: the input's layout changes.  A silent input is processed only while the node's tail budget lasts
+                             // (tail_time_counter < L, never reset: panner.rs:697-711); afterwards the node returns early and its
+                             // convolution history FREEZES.  The FIR therefore runs over the PROCESSED quanta only:
+    int32_t* cmap;           // cmap[0] = processed quanta of this chunk, cmap[1 + k] = chunk quantum of the k-th of them
+    int64_t* tail;           // tail_time_counter, carried across chunks
 };
 
 // the 15 spatial params of a panner (source position / orientation, listener position / forward / up); an automated one

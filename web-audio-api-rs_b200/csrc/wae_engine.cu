@@ -1946,11 +1946,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 }
                 int ch = p.in_ch[0];
                 if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                if (n.panning_model == WAE_PANNING_HRTF && in0.dyn())
-                    return bail(WAE_UNSUPPORTED, "an HRTF PannerNode whose input can fall silent or change its channel count is not lowered to the GPU "
-                                                 "(tail bookkeeping of panner.rs:697-711)");
                 out_dynamic(in0.may_silent ? Lay{1, 2, 2, 2, true} : Lay::fixed(2));  // panner.rs:698-708
-                if (p.out_buf[0].meta) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
+                // (the HRTF panner keeps its own tail budget: its layout track is written by k_hrtf_map)
+                if (p.out_buf[0].meta && n.panning_model != WAE_PANNING_HRTF) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
                 spatial::PanModel model{};
                 model.distance_model = n.distance_model;
                 model.ref_distance = n.ref_distance;
@@ -1998,6 +1996,12 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     h.correction = ch == 2 ? 2.f : 1.f;
                     h.hist = alloc<float>(taps, true, true);
                     if (!h.hist) return bail(WAE_OUT_OF_MEMORY, "out of device memory (hrtf history)");
+                    if (in0.dyn()) {  // the node stops processing (and freezes) once its tail budget is used up: panner.rs:697-711
+                        h.dyn = 1;
+                        h.cmap = alloc<int32_t>((size_t)(b->chunk / 128 + 2));
+                        h.tail = alloc<int64_t>(1, true, true);
+                        if (!h.cmap || !h.tail) return bail(WAE_OUT_OF_MEMORY, "out of device memory (hrtf layout)");
+                    }
                     StageBuild& hs = stage(L, S_HRTF);
                     if (moving) {
                         HrtfSelInst si{};

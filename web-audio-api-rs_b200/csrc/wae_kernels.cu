@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -884,8 +885,12 @@ struct ChainSmem {
 // one biquad over the thread's 16 frames (v in/out), see the header comment
 // clean: (threads that start a render quantum) the filter state entering this thread's frames has no normal value — the filter's
 // "tail has ended" test (biquad_filter.rs:778-794), used for the layout track of the chain's output
+struct NoReload {};
+// reload(x): (biquad A of a chain that streams its source) puts the thread's 16 INPUT samples of this tile back into x — the staging
+// region still holds them — for the serial replay of a tile that a NaN / Inf went through.
+template <typename RL>
 DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, const double b2, const double a1, const double a2,
-                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp, bool& clean) {
+                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp, bool& clean, RL reload) {
     const double* Psh = sm.P[bq];
     const double* Pw = sm.P[bq] + 20;
     // previous two step inputs: neighbour lane, previous warp, or the carried state
@@ -896,64 +901,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     }
     const float p1 = __shfl_up_sync(0xffffffffu, xl1, 1);
     const float p2 = __shfl_up_sync(0xffffffffu, xl2, 1);
-    // NaN / Inf among this thread's inputs?  x * 0 is NaN exactly for those: one FFMA per sample on the otherwise idle FMA pipe
-    float chk = 0.f;
-#pragma unroll
-    for (int j = 0; j < CH_K; j++) chk = fmaf(v[j], 0.f, chk);
-    if (__syncthreads_or(active && chk != chk)) {
-        // Rare: the reference flushes every non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`, biquad_filter.rs:881-883) and
-        // so recovers three samples after a NaN / Inf in its input, which no linear scan reproduces (the state would stay poisoned):
-        // this tile is run serially, thread after thread, in the reference's own operation order.
-        double sx1 = sm.state[bq][0], sx2 = sm.state[bq][1], sy1 = sm.state[bq][2], sy2 = sm.state[bq][3];
-        __syncthreads();
-#pragma unroll 1
-        for (int wv = 0; wv < CH_WARPS; wv++) {
-            if (warp == wv) {
-#pragma unroll 1
-                for (int l = 0; l < 32; l++) {
-                    double qx1 = sx1, qx2 = sx2, qy1 = sy1, qy2 = sy2;
-                    if (lane == l && active) {
-#pragma unroll
-                        for (int j = 0; j < CH_K; j++) {  // (unrolled: v[] must stay in registers)
-                            const double x = (double)v[j];
-                            double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(b0, x), __dmul_rn(b1, qx1)), __dmul_rn(b2, qx2)), __dmul_rn(a1, qy1)),
-                                                 __dmul_rn(a2, qy2));
-                            if (!isnormal_d(y)) y = 0.;
-                            qx2 = qx1;
-                            qx1 = x;
-                            qy2 = qy1;
-                            qy1 = y;
-                            v[j] = (float)y;
-                        }
-                    }
-                    sx1 = __shfl_sync(0xffffffffu, qx1, l);
-                    sx2 = __shfl_sync(0xffffffffu, qx2, l);
-                    sy1 = __shfl_sync(0xffffffffu, qy1, l);
-                    sy2 = __shfl_sync(0xffffffffu, qy2, l);
-                }
-                if (lane == 0) {
-                    sm.replay[0] = sx1;
-                    sm.replay[1] = sx2;
-                    sm.replay[2] = sy1;
-                    sm.replay[3] = sy2;
-                }
-            }
-            __syncthreads();
-            sx1 = sm.replay[0];
-            sx2 = sm.replay[1];
-            sy1 = sm.replay[2];
-            sy2 = sm.replay[3];
-            __syncthreads();
-        }
-        if (t == 0) {
-            sm.state[bq][0] = sx1;
-            sm.state[bq][1] = sx2;
-            sm.state[bq][2] = sy1;
-            sm.state[bq][3] = sy2;
-        }
-        clean = false;
-        return;
-    }
+    __syncthreads();
     double x1, x2;
     if (lane == 0) {
         if (warp == 0) {
@@ -1026,10 +974,71 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         r1 = y;
         v[j] = (float)y;  // `*o = y as f32` between nodes (biquad_filter.rs:890)
     }
-    __syncthreads();  // everyone has read state / wtot / edge of this step
-    if (active && t == n_active - 1) {
-        // (an unstable filter that has run off to Inf / NaN: the reference's per-sample flush would have reset it; do not carry the poison)
-        if (!(fabs(r1) <= 1.7976931348623157e308) || !(fabs(r2) <= 1.7976931348623157e308)) r1 = r2 = 0.;
+    // (barrier: everyone has read state / wtot / edge of this step.)  A NaN / Inf that went through the recurrence is still in the state
+    // the tile ends with: the reference flushes every non-normal y to 0 sample by sample (`if !y.is_normal() { y = 0. }`,
+    // biquad_filter.rs:881-883) and recovers three samples after a bad input sample, which no linear scan reproduces.
+    const bool last = active && t == n_active - 1;
+    const bool poisoned = last && (!(fabs(r1) <= 1.7976931348623157e308) || !(fabs(r2) <= 1.7976931348623157e308));
+    if (__syncthreads_or(poisoned)) {
+        if constexpr (!std::is_same<RL, NoReload>::value) {
+            // rare: run the tile again serially, thread after thread, in the reference's own operation order, from the tile's inputs
+            float x[CH_K];
+            reload(x);
+            double sx1 = sm.state[bq][0], sx2 = sm.state[bq][1], sy1 = sm.state[bq][2], sy2 = sm.state[bq][3];
+            __syncthreads();
+#pragma unroll 1
+            for (int wv = 0; wv < CH_WARPS; wv++) {
+                if (warp == wv) {
+#pragma unroll 1
+                    for (int l = 0; l < 32; l++) {
+                        double qx1 = sx1, qx2 = sx2, qy1 = sy1, qy2 = sy2;
+                        if (lane == l && active) {
+#pragma unroll
+                            for (int j = 0; j < CH_K; j++) {  // (unrolled: x[] / v[] stay in registers)
+                                const double xi = (double)x[j];
+                                double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(b0, xi), __dmul_rn(b1, qx1)), __dmul_rn(b2, qx2)), __dmul_rn(a1, qy1)),
+                                                     __dmul_rn(a2, qy2));
+                                if (!isnormal_d(y)) y = 0.;
+                                qx2 = qx1;
+                                qx1 = xi;
+                                qy2 = qy1;
+                                qy1 = y;
+                                v[j] = (float)y;
+                            }
+                        }
+                        sx1 = __shfl_sync(0xffffffffu, qx1, l);
+                        sx2 = __shfl_sync(0xffffffffu, qx2, l);
+                        sy1 = __shfl_sync(0xffffffffu, qy1, l);
+                        sy2 = __shfl_sync(0xffffffffu, qy2, l);
+                    }
+                    if (lane == 0) {
+                        sm.replay[0] = sx1;
+                        sm.replay[1] = sx2;
+                        sm.replay[2] = sy1;
+                        sm.replay[3] = sy2;
+                    }
+                }
+                __syncthreads();
+                sx1 = sm.replay[0];
+                sx2 = sm.replay[1];
+                sy1 = sm.replay[2];
+                sy2 = sm.replay[3];
+                __syncthreads();
+            }
+            if (t == 0) {
+                sm.state[bq][0] = sx1;
+                sm.state[bq][1] = sx2;
+                sm.state[bq][2] = sy1;
+                sm.state[bq][3] = sy2;
+            }
+            return;
+        } else {
+            // (a filter fed by another node of the chain: its input is finite, it has run off by itself — the reference's flush would have
+            // reset it; do not carry the poison)
+            if (last) r1 = r2 = 0.;
+        }
+    }
+    if (last) {
         sm.state[bq][0] = (double)xl1;
         sm.state[bq][1] = (double)xl2;
         sm.state[bq][2] = r1;
@@ -1195,23 +1204,38 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
     }
     __syncthreads();
 
-    // whole source region of this warp at `tile_base` readable as one aligned 2 KB run?  (warp-uniform, pure function)
-    auto region_src = [&](int tile_base) -> const float* {
-        if (!STREAMED) return nullptr;
-        const int nw = tile_base + wbase;  // chunk-relative first frame of this warp's region
-        if (nw + 32 * CH_K > ci.nf) return nullptr;  // nf is a multiple of 128 = 8 threads: the region may be ragged at the end
+    // Per-warp invariants of the slab, so that the hot loop only compares tile bases: the warp's 2 KB source region at tile base `tb` is
+    // one aligned run  s_ptr0 + tb  for  s_lo <= tb <= s_hi  (tile bases are multiples of the tile: the alignment does not change),
+    // and its results leave as coalesced 2 KB stores to  o_ptr0 + tb  (+ channel stride for an up-mixed copy) for  tb <= o_hi.
+    long long s_lo = 1, s_hi = 0;
+    const float* s_ptr0 = nullptr;
+    if (STREAMED) {
         if (SRC == CHAIN_SRC_BUFFER) {
-            const float* gp = chan(q.in, c, ci) + nw;
-            return (reinterpret_cast<uintptr_t>(gp) & 15) == 0 ? gp : nullptr;
+            const float* p0 = chan(q.in, c, ci) + wbase;
+            if ((reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
+                s_ptr0 = p0;
+                s_lo = 0;
+                s_hi = (long long)ci.nf - wbase - 32 * CH_K;  // nf is a multiple of 128 = 8 threads: the region may be ragged at the end
+            }
         } else {
             const AbsnInst& o = q.absn;
-            const float* src = o.buf + (size_t)c * o.buf_stride;
-            const int64_t n = ci.f0 + nw;
-            const int64_t idx = n - o.n_start + o.buf_offset;
-            if (!o.loop && n >= o.n_start && idx + 32 * CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + idx) & 15) == 0)) return src + idx;
-            return nullptr;
+            const long long off = (long long)ci.f0 + wbase - o.n_start + o.buf_offset;  // buffer index of the region's first frame at tb = 0
+            const float* p0 = o.buf + (size_t)c * o.buf_stride + off;
+            if (!o.loop && (reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
+                s_ptr0 = p0;
+                s_lo = max(0ll, (long long)o.n_start - ci.f0 - wbase);
+                s_hi = min((long long)ci.nf - wbase - 32 * CH_K, (long long)o.buf_len - 32 * CH_K - off);
+            }
         }
+    }
+    auto region_src = [&](int tile_base) -> const float* {
+        return ((long long)tile_base >= s_lo && (long long)tile_base <= s_hi) ? s_ptr0 + tile_base : nullptr;
     };
+    const int n_out = q.out_dup > 1 ? q.out_dup : 1;
+    float* const o_ptr0 = chan(q.out, q.out_dup > 1 ? 0 : c, ci) + wbase;
+    long long o_hi = (long long)ci.nf - wbase - 32 * CH_K;
+    if (q.limit >= 0) o_hi = min(o_hi, (long long)q.limit - ci.f0 - wbase - 32 * CH_K);
+    if ((reinterpret_cast<uintptr_t>(o_ptr0) & 15) != 0 || (q.out_dup > 1 && (q.out.stride & 3) != 0)) o_hi = -1;
     // cp.async path: 16-byte pieces into the swizzled layout, per-thread gather for ragged / looping / unaligned regions
     auto stage_source = [&](int buf, int tile_base) {
         if (!STREAMED || tile_base >= slab_end) return;
@@ -1317,7 +1341,27 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             for (int j = 0; j < CH_K; j++) v[j] *= g0;
         }
         if (NB >= 1) {
-            chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0);
+            if constexpr (STREAMED) {
+                // the tile's source samples are still in the staging region (it is overwritten by the results only further down)
+                auto reload = [&](float x[CH_K]) {
+                    float4 a[CH_K / 4];
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++) a[u] = s_io[buf][warp][4 * lane + (u ^ xq)];
+                    if (USE_TMA) {  // linear layout, pieces visited in the order u ^ xq
+                        cswap4((xq & 1) != 0, a[0], a[1]);
+                        cswap4((xq & 1) != 0, a[2], a[3]);
+                        cswap4((xq & 2) != 0, a[0], a[2]);
+                        cswap4((xq & 2) != 0, a[1], a[3]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < CH_K / 4; u++) {
+                        x[4 * u] = a[u].x * g0; x[4 * u + 1] = a[u].y * g0; x[4 * u + 2] = a[u].z * g0; x[4 * u + 3] = a[u].w * g0;
+                    }
+                };
+                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0, reload);
+            } else {
+                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0, NoReload{});
+            }
             if (g1 != 1.f) {
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) v[j] *= g1;
@@ -1325,7 +1369,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
         }
         if (NB >= 2) {
             chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], plane[NB - 1], v, active,
-                         n_active, t, lane, warp, clean1);
+                         n_active, t, lane, warp, clean1, NoReload{});
             if (g2 != 1.f) {
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) v[j] *= g2;
@@ -1389,11 +1433,6 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             // results: through the warp's staging region (the source pieces of this tile are consumed), so that global
             // memory sees whole 2 KB regions; per-thread stores for ragged / unaligned / length-limited regions
             const int nw = base + wbase;
-            const int n_out = q.out_dup > 1 ? q.out_dup : 1;
-            const bool region_full = nw + 32 * CH_K <= ci.nf;
-            const bool in_limit = q.limit < 0 || ci.f0 + nw + 32 * CH_K <= q.limit;
-            const bool aligned = (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + nw) & 15) == 0 &&
-                                 (q.out_dup <= 1 || (q.out.stride & 3) == 0);
             // TMA path: the whole tile leaves as one 8 KB bulk store per output channel (CTA-uniform condition)
             const bool tile_out = USE_TMA && base + tile <= ci.nf && (q.limit < 0 || ci.f0 + base + tile <= q.limit) &&
                                   (reinterpret_cast<uintptr_t>(chan(q.out, q.out_dup > 1 ? 0 : c, ci) + base) & 15) == 0 &&
@@ -1427,14 +1466,14 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
                     bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
                     issue_bulk(pbuf, base + (NST - 1) * tile);
                 }
-            } else if (region_full && in_limit && aligned) {  // warp-uniform
+            } else if ((long long)base <= o_hi) {  // warp-uniform
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++)
                     s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
                 __syncwarp();
                 for (int oc = 0; oc < n_out; oc++) {
-                    float4* out = reinterpret_cast<float4*>(chan(q.out, q.out_dup > 1 ? oc : c, ci) + nw);
+                    float4* out = reinterpret_cast<float4*>(o_ptr0 + (size_t)oc * q.out.stride + base);
 #pragma unroll
                     for (int u = 0; u < CH_K / 4; u++) {
                         out[32 * u + lane] = s_io[buf][warp][32 * u + lane_sw];
@@ -2070,9 +2109,51 @@ constexpr int HRTF_TILE = 1024;  // frames per CTA: 4 warps x 32 lanes x 8 frame
 DEVI int hrtf_pad(int i) { return i + (i >> 3); }  // stride-8 lane access -> 32 distinct banks
 
 DEVI float hrtf_input(const HrtfInst& p, int m, const ChunkInfo& ci) {
+    int in_ch = p.in_ch;
+    if (p.in.meta) {  // dynamic layout: the channels this quantum has; a (processed) silent quantum reads as zeros
+        const int qi = meta_qi(ci, m);
+        if (buf_silent(p.in, p.in_ch, qi)) return 0.f;
+        in_ch = buf_count(p.in, p.in_ch, qi);
+    }
     float v = chan(p.in, 0, ci)[m];
-    if (p.in_ch == 2) v = 0.5f * (v + chan(p.in, 1, ci)[m]);  // output.mix(1, Speakers), quantum.rs 2 -> 1
+    if (in_ch == 2) v = 0.5f * (v + chan(p.in, 1, ci)[m]);  // output.mix(1, Speakers), quantum.rs 2 -> 1
     return v;
+}
+// frame mc of the PROCESSED sequence of this chunk (HrtfInst::cmap) -> chunk frame
+DEVI int hrtf_unmap(const HrtfInst& p, int mc) { return p.dyn ? p.cmap[1 + (mc >> 7)] * 128 + (mc & 127) : mc; }
+// dynamic input layout: which quanta of the chunk the node processes (panner.rs:697-711), its output layout track
+__global__ void __launch_bounds__(64) k_hrtf_map(const HrtfInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    const int ii = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ii >= n_inst) return;
+    const HrtfInst& p = insts[ii];
+    if (!p.dyn) return;
+    int64_t tail = *p.tail;
+    int n_proc = 0;
+    for (int q = 0; q < ci.nf / 128; q++) {
+        const int qi = meta_qi(ci, q * 128);
+        const bool silent = buf_silent(p.in, p.in_ch, qi);
+        bool processed = true;
+        if (silent) {
+            processed = (int64_t)p.L > tail;
+            if (processed) tail += 128;
+        }
+        if (processed) p.cmap[1 + n_proc++] = q;
+        if (p.out.meta) meta_put_all(p.out, 2, qi, processed ? 2 : 1, !processed);
+    }
+    p.cmap[0] = n_proc;
+    *p.tail = tail;
+}
+// quanta the node did not process: silent output, PCM zeroed
+__global__ void __launch_bounds__(256) k_hrtf_fill(const HrtfInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const HrtfInst& p = insts[ii];
+        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (!p.dyn || !p.out.meta || n >= ci.nf) continue;
+        if (p.out.meta[meta_qi(ci, n)] & WAE_META_SILENT) {
+            chan(p.out, 0, ci)[n] = 0.f;
+            chan(p.out, 1, ci)[n] = 0.f;
+        }
+    }
 }
 
 // One lane = 8 consecutive frames x 2 ears (16 accumulators); the input window slides through registers, so 4 taps cost
@@ -2087,11 +2168,14 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
     float* xs = hsm;                           // padded input window: xs[pad(4 + (L4-1) + n)] = x[tile0 + n]
     float* hs = hsm + ((hrtf_pad(nx) + 4) & ~3);  // [8 quanta][2][L4]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (dynamic layout: tile0 and every frame index below count PROCESSED quanta; hrtf_unmap gives the chunk frame)
+    const int nf_proc = p.dyn ? p.cmap[0] * 128 : ci.nf;
+    if (tile0 >= nf_proc) return;
     for (int i = tid; i < nx; i += 128) {
         int m = tile0 + i - 4 - (L4 - 1);  // chunk-relative frame
         float v = 0.f;
         if (m >= 0) {
-            if (m < ci.nf) v = hrtf_input(p, m, ci);
+            if (m < nf_proc) v = hrtf_input(p, hrtf_unmap(p, m), ci);
         } else if (m >= -(L - 1)) {
             v = p.hist[(L - 1) + m];
         }
@@ -2102,9 +2186,10 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
     const bool moving = p.sel != nullptr;
     for (int h = 0; h < 2; h++) {
         const int qi = moving ? warp * 2 + h : 0;
-        const int q0 = tile0 + qi * 128;
-        if (moving && q0 >= ci.nf) break;
+        const int q0c = tile0 + qi * 128;
+        if (moving && q0c >= nf_proc) break;
         if (!moving && h == 1) break;
+        const int q0 = hrtf_unmap(p, q0c);
         const HrtfSel sel = moving ? p.sel[(ci.sub + q0) >> 7] : p.static_sel;
         float* hl = hs + qi * 2 * L4;
         float* hr = hl + L4;
@@ -2123,8 +2208,9 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
     }
     __syncthreads();
     const int qi = warp * 2 + (lane >> 4);
-    const int q0 = tile0 + qi * 128;
-    if (q0 >= ci.nf) return;
+    const int q0c = tile0 + qi * 128;
+    if (q0c >= nf_proc) return;
+    const int q0 = hrtf_unmap(p, q0c);
     const HrtfSel sel = moving ? p.sel[(ci.sub + q0) >> 7] : p.static_sel;
     const float* hl = hs + (moving ? qi : 0) * 2 * L4;
     const float* hr = hl + L4;
@@ -2177,10 +2263,15 @@ __global__ void __launch_bounds__(128) k_hrtf_fir(const HrtfInst* __restrict__ i
         w[7] = w[3]; w[6] = w[2]; w[5] = w[1]; w[4] = w[0];
         w[3] = m1; w[2] = m2; w[1] = m3; w[0] = m4;
     }
-    const int n = tile0 + nrel;
+    const int n = q0 + (nrel & 127);  // (8 frames of a lane never straddle a quantum)
     float* ol = chan(p.out, 0, ci);
     float* orr = chan(p.out, 1, ci);
-    const float g = sel.gain, c = p.correction;
+    float c = p.correction;
+    if (p.in.meta) {  // overall_gain_correction: 2 for a two-channel input quantum (panner.rs:805-812)
+        const int mq = meta_qi(ci, q0);
+        c = (!buf_silent(p.in, p.in_ch, mq) && buf_count(p.in, p.in_ch, mq) == 2) ? 2.f : 1.f;
+    }
+    const float g = sel.gain;
 #pragma unroll
     for (int j = 0; j < 8; j++)
         if (n + j < ci.nf) {
@@ -2194,9 +2285,10 @@ __global__ void __launch_bounds__(128) k_hrtf_hist(const HrtfInst* __restrict__ 
     extern __shared__ float hh[];
     const HrtfInst p = insts[blockIdx.x];
     const int H = p.L - 1;
+    const int nf_proc = p.dyn ? p.cmap[0] * 128 : ci.nf;
     for (int i = threadIdx.x; i < H; i += blockDim.x) {
-        int m = ci.nf - H + i;
-        hh[i] = m >= 0 ? hrtf_input(p, m, ci) : p.hist[H + m];
+        int m = nf_proc - H + i;
+        hh[i] = m >= 0 ? hrtf_input(p, hrtf_unmap(p, m), ci) : p.hist[H + m];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < H; i += blockDim.x) p.hist[i] = hh[i];
@@ -3056,7 +3148,7 @@ static int g_chain_tma = -1, g_chain_waves = -1;
 static void chain_env() {
     if (g_chain_tma < 0) {
         const char* e = getenv("WAE_CHAIN_TMA");
-        g_chain_tma = e ? (atoi(e) != 0) : 1;
+        g_chain_tma = e ? (atoi(e) != 0) : 0;  // measured on C2 (profiles/README.md r2_d): cp.async 1.39 ms, bulk copies 1.58 ms
         e = getenv("WAE_CHAIN_WAVES");
         g_chain_waves = e ? atoi(e) : 20;
         if (g_chain_waves < 0) g_chain_waves = 0;
@@ -3178,7 +3270,9 @@ void launch_hrtf(const HrtfInst* d, int n, const HrtfSelInst* sel, int n_sel, in
         cudaFuncSetAttribute(k_hrtf_fir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = smem;
     }
+    k_hrtf_map<<<(n + 63) / 64, 64, 0, s>>>(d, n, ci);
     k_hrtf_fir<<<dim3((ci.nf + HRTF_TILE - 1) / HRTF_TILE, n), 128, smem, s>>>(d, ci);
+    k_hrtf_fill<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
     k_hrtf_hist<<<n, 128, (size_t)max_taps * sizeof(float), s>>>(d, ci);
 }
 void launch_panner_eq(const PanInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_panner_eq<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }

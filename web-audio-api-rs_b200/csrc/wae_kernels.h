@@ -28,7 +28,7 @@ void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux);
 void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab);  // launch geometry of k_chain (host)
-void chain_set_tuning(int tma, int waves);  // < 0: keep (defaults: WAE_CHAIN_TMA / WAE_CHAIN_WAVES or 1 / 20)
+void chain_set_tuning(int tma, int waves);  // < 0: keep (defaults: WAE_CHAIN_TMA / WAE_CHAIN_WAVES or 0 / 20)
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_shaper(const ShaperInst* d, int n, ChunkInfo ci, cudaStream_t s);

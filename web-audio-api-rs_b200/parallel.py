@@ -38,6 +38,27 @@ def gather_pcm(local, n_graphs_total, dst=0):
     return torch.cat([bufs[r][: sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
 
 
+def all_gather_group(full_k, shard_slice):
+    """One graph group of the pipelined gather bench.py runs (north_star "NCCL gather of rendered PCM"): every rank contributes the
+    PCM of the same local graph range, `full_k` ([world, graphs_in_group, ch, length]) receives all of them.  Called per graph group on
+    a side stream while the next group renders, so that the NVLink transfer hides behind the render instead of following it.
+    NCCL: one all_gather_into_tensor; gloo (CPU tests): the list form."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        full_k[0].copy_(shard_slice)
+        return
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(full_k.view(-1), shard_slice.reshape(-1))
+    else:
+        dist.all_gather([full_k[r] for r in range(full_k.shape[0])], shard_slice.contiguous())
+
+
+def group_ranges(n_graphs, n_groups):
+    """Contiguous graph groups [(first, last)] the way wae_batch_prepare cuts a batch without suspend points (ceil-sized pieces)."""
+    n_groups = max(1, min(n_groups, n_graphs))
+    target = (n_graphs + n_groups - 1) // n_groups
+    return [(g0, min(n_graphs, g0 + target)) for g0 in range(0, n_graphs, target)]
+
+
 def max_over_ranks(value, device="cpu"):
     """Timing reduction used by bench.py: the slowest rank defines the step time."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
