@@ -385,6 +385,7 @@ def main():
     ap.add_argument("--serial-filters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bind-numa", type=int, default=1, help="bind every rank's host threads to its GPU's NUMA node (pinned memory local to the GPU)")
+    ap.add_argument("--kernel-only", action="store_true", help="tuning runs: only the kernel-only leg of C2 (no e2e legs, no other workloads)")
     ap.add_argument("--extra", type=int, default=1, help="also measure the other BASELINE configs (C3 / C4 / north_star / C5 at N=1; C4 at N=2,4; C5 at N=8)")
     args = ap.parse_args()
 
@@ -459,6 +460,19 @@ def main():
     value = total_quanta / (ms_per_step * 1e-3)
     batch.set_timing(False)
     batch.sync()
+    if args.kernel_only:
+        agg = {}
+        for name, ms, _n in stage_times:
+            agg[name] = agg.get(name, 0.0) + ms
+        if rank == 0:
+            peak = load_peaks()[0]
+            k_ms = max(agg.values()) if agg else 0.0
+            print(json.dumps({"kernel_only": True, "ms_per_step": ms_per_step, "kernel_ms": k_ms,
+                              "frac": 2048 * n_graphs * quanta_per_graph / (k_ms * 1e-3) / 1e9 / peak if k_ms else None, "clocks": clocks}))
+        batch.destroy()
+        eng.close()
+        D.close()
+        return
 
     # ---- e2e, the one-shot plugin call: fresh graphs every step, ONE wae_render_batch(engine, graphs, n, out, HOST)
     eng.set_option(pkg.OPT_PIPELINE_GROUPS, 0)  # the library's own choice of graph groups

@@ -873,10 +873,21 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
     }
 }
 
+// ragged / looping / unaligned source regions: the thread's 16 frames gathered one by one and put into the warp's staging region
+// (kept out of line: it is rare, and inlined it is repeated in every prefetch stage of the pipeline)
+template <int SRC>
+__device__ __noinline__ void chain_stage_gather(const ChainInst* q, int c, ChunkInfo ci, int n0, float4* region, int lane, int xq) {
+    float tmp[CH_K];
+    chain_load_source<SRC>(*q, c, ci, n0, tmp);
+#pragma unroll
+    for (int u = 0; u < CH_K / 4; u++) region[4 * lane + (u ^ xq)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
+}
+
 struct ChainSmem {
     ChainInst q;
     double state[CHAIN_MAX_BIQUADS][4];  // x1, x2, y1, y2 carried from tile to tile
     double P[CHAIN_MAX_BIQUADS][24];     // Pshfl[5][4], Pwarp[4]
+    double plane[CHAIN_MAX_BIQUADS][32][4];  // A^(lane+1): carries a warp's incoming state to each lane (read once per tile: not worth registers)
     double wtot[CH_WARPS][2];            // per-warp end state (zero incoming state)
     double replay[4];                    // serial replay of a tile (non-finite input): state handed from warp to warp
     float edge[CH_WARPS][2];             // last two step inputs of every warp
@@ -890,7 +901,8 @@ struct NoReload {};
 // region still holds them — for the serial replay of a tile that a NaN / Inf went through.
 template <typename RL>
 DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, const double b2, const double a1, const double a2,
-                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp, bool& clean, RL reload) {
+                       const double* Plane, float v[CH_K], bool active, int n_active, int t, int lane, int warp, bool want_clean, bool& clean,
+                       RL reload) {
     const double* Psh = sm.P[bq];
     const double* Pw = sm.P[bq] + 20;
     // previous two step inputs: neighbour lane, previous warp, or the carried state
@@ -915,7 +927,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         x1 = (double)p1;
         x2 = (double)p2;
     }
-    const bool x_normal = isnormal_d(x1) || isnormal_d(x2);
+    const bool x_normal = want_clean && (isnormal_d(x1) || isnormal_d(x2));
     // FIR part and pass 1 (zero incoming state): end state only
     double w[CH_K];
     double r1 = 0., r2 = 0.;
@@ -963,7 +975,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
         e2 = eb;
         mat2_fma(Plane, wa, wb, e1, e2);
     }
-    clean = !(x_normal || isnormal_d(e1) || isnormal_d(e2));
+    if (want_clean) clean = !(x_normal || isnormal_d(e1) || isnormal_d(e2));  // (CTA-uniform: only chains that write a layout track)
     // pass 2: the recurrence from the true state
     r1 = e1;
     r2 = e2;
@@ -979,7 +991,12 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
     // biquad_filter.rs:881-883) and recovers three samples after a bad input sample, which no linear scan reproduces.
     const bool last = active && t == n_active - 1;
     const bool poisoned = last && (!(fabs(r1) <= 1.7976931348623157e308) || !(fabs(r2) <= 1.7976931348623157e308));
+#ifdef WAE_CHAIN_NOCHECK  // (tuning builds only: what the non-finite check costs)
+    __syncthreads();
+    if (false) {
+#else
     if (__syncthreads_or(poisoned)) {
+#endif
         if constexpr (!std::is_same<RL, NoReload>::value) {
             // rare: run the tile again serially, thread after thread, in the reference's own operation order, from the tile's inputs
             float x[CH_K];
@@ -1151,7 +1168,6 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
     const size_t ho = ((size_t)inst * sc.max_ch + c) * sc.slab_stride + slab;  // hand-off slot of the state ENTERING this slab
     // per-CTA constants -> registers / shared
     double cb[NB > 0 ? NB : 1][5];
-    double plane[NB > 0 ? NB : 1][4];
     if (NB > 0 && !first_slab) {  // the slab before this one (same instance, channel) publishes the state it ends with
         if (t == 0) {
             const unsigned* f = sc.flags + ho;
@@ -1174,8 +1190,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             sm.P[k][20 + t] = scf.Pwarp[t];
             sm.state[k][t] = first_slab ? bq.state[4 * c + t] : __ldcg(sc.handoff + ho * (CHAIN_MAX_BIQUADS * 4) + 4 * k + t);
         }
-#pragma unroll
-        for (int i = 0; i < 4; i++) plane[k][i] = lane > 0 ? scf.Plane[lane - 1][i] : 0.;
+        for (int i = t; i < 128; i += CH_THREADS) (&sm.plane[k][0][0])[i] = (&scf.Plane[0][0])[i];
     }
     const float g0 = q.g[0], g1 = q.g[1], g2 = q.g[2], g3 = q.g[3];
 
@@ -1207,15 +1222,16 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
     // Per-warp invariants of the slab, so that the hot loop only compares tile bases: the warp's 2 KB source region at tile base `tb` is
     // one aligned run  s_ptr0 + tb  for  s_lo <= tb <= s_hi  (tile bases are multiples of the tile: the alignment does not change),
     // and its results leave as coalesced 2 KB stores to  o_ptr0 + tb  (+ channel stride for an up-mixed copy) for  tb <= o_hi.
-    long long s_lo = 1, s_hi = 0;
+    int s_lo = 1, s_hi = 0;  // (tile bases are ints: the bounds are clamped into the int range)
     const float* s_ptr0 = nullptr;
+    auto clamp_i = [](long long x) { return (int)max(-2000000000ll, min(2000000000ll, x)); };
     if (STREAMED) {
         if (SRC == CHAIN_SRC_BUFFER) {
             const float* p0 = chan(q.in, c, ci) + wbase;
             if ((reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
                 s_ptr0 = p0;
                 s_lo = 0;
-                s_hi = (long long)ci.nf - wbase - 32 * CH_K;  // nf is a multiple of 128 = 8 threads: the region may be ragged at the end
+                s_hi = ci.nf - wbase - 32 * CH_K;  // nf is a multiple of 128 = 8 threads: the region may be ragged at the end
             }
         } else {
             const AbsnInst& o = q.absn;
@@ -1223,18 +1239,18 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             const float* p0 = o.buf + (size_t)c * o.buf_stride + off;
             if (!o.loop && (reinterpret_cast<uintptr_t>(p0) & 15) == 0) {
                 s_ptr0 = p0;
-                s_lo = max(0ll, (long long)o.n_start - ci.f0 - wbase);
-                s_hi = min((long long)ci.nf - wbase - 32 * CH_K, (long long)o.buf_len - 32 * CH_K - off);
+                s_lo = clamp_i(max(0ll, (long long)o.n_start - ci.f0 - wbase));
+                s_hi = clamp_i(min((long long)ci.nf - wbase - 32 * CH_K, (long long)o.buf_len - 32 * CH_K - off));
             }
         }
     }
     auto region_src = [&](int tile_base) -> const float* {
-        return ((long long)tile_base >= s_lo && (long long)tile_base <= s_hi) ? s_ptr0 + tile_base : nullptr;
+        return (tile_base >= s_lo && tile_base <= s_hi) ? s_ptr0 + tile_base : nullptr;
     };
     const int n_out = q.out_dup > 1 ? q.out_dup : 1;
     float* const o_ptr0 = chan(q.out, q.out_dup > 1 ? 0 : c, ci) + wbase;
-    long long o_hi = (long long)ci.nf - wbase - 32 * CH_K;
-    if (q.limit >= 0) o_hi = min(o_hi, (long long)q.limit - ci.f0 - wbase - 32 * CH_K);
+    int o_hi = ci.nf - wbase - 32 * CH_K;
+    if (q.limit >= 0) o_hi = clamp_i(min((long long)o_hi, (long long)q.limit - ci.f0 - wbase - 32 * CH_K));
     if ((reinterpret_cast<uintptr_t>(o_ptr0) & 15) != 0 || (q.out_dup > 1 && (q.out.stride & 3) != 0)) o_hi = -1;
     // cp.async path: 16-byte pieces into the swizzled layout, per-thread gather for ragged / looping / unaligned regions
     auto stage_source = [&](int buf, int tile_base) {
@@ -1250,11 +1266,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gp + 4 * f) : "memory");
             }
         } else if (nw + lane * CH_K < ci.nf) {
-            float tmp[CH_K];
-            chain_load_source<SRC>(q, c, ci, nw + lane * CH_K, tmp);
-#pragma unroll
-            for (int u = 0; u < CH_K / 4; u++)
-                s_io[buf][warp][4 * lane + (u ^ xq)] = make_float4(tmp[4 * u], tmp[4 * u + 1], tmp[4 * u + 2], tmp[4 * u + 3]);
+            chain_stage_gather<SRC>(&sm.q, c, ci, nw + lane * CH_K, &s_io[buf][warp][0], lane, xq);
         }
     };
     // TMA path: whole tile (2048 frames, 8 KB) readable as one aligned run?  (CTA-uniform, pure function)
@@ -1336,6 +1348,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             chain_load_source<SRC>(q, c, ci, n0, v);
         }
         bool clean0 = true, clean1 = true;
+        const bool want_clean = q.out.meta != nullptr;
         if (g0 != 1.f) {  // x * 1.0f == x bit for bit: skip the multiply (uniform branch)
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g0;
@@ -1358,9 +1371,9 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
                         x[4 * u] = a[u].x * g0; x[4 * u + 1] = a[u].y * g0; x[4 * u + 2] = a[u].z * g0; x[4 * u + 3] = a[u].w * g0;
                     }
                 };
-                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0, reload);
+                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], sm.plane[0][lane > 0 ? lane - 1 : 0], v, active, n_active, t, lane, warp, want_clean, clean0, reload);
             } else {
-                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], plane[0], v, active, n_active, t, lane, warp, clean0, NoReload{});
+                chain_biquad(sm, 0, cb[0][0], cb[0][1], cb[0][2], cb[0][3], cb[0][4], sm.plane[0][lane > 0 ? lane - 1 : 0], v, active, n_active, t, lane, warp, want_clean, clean0, NoReload{});
             }
             if (g1 != 1.f) {
 #pragma unroll
@@ -1368,8 +1381,8 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
             }
         }
         if (NB >= 2) {
-            chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], plane[NB - 1], v, active,
-                         n_active, t, lane, warp, clean1, NoReload{});
+            chain_biquad(sm, 1, cb[NB - 1][0], cb[NB - 1][1], cb[NB - 1][2], cb[NB - 1][3], cb[NB - 1][4], sm.plane[1][lane > 0 ? lane - 1 : 0], v, active,
+                         n_active, t, lane, warp, want_clean, clean1, NoReload{});
             if (g2 != 1.f) {
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) v[j] *= g2;
@@ -1466,7 +1479,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS
                     bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
                     issue_bulk(pbuf, base + (NST - 1) * tile);
                 }
-            } else if ((long long)base <= o_hi) {  // warp-uniform
+            } else if (base <= o_hi) {  // warp-uniform
                 __syncwarp();
 #pragma unroll
                 for (int u = 0; u < CH_K / 4; u++)
