@@ -303,6 +303,9 @@ def run_extra_workloads(pkg, eng, D, oracle, cores, steps, peak_gbs):
                                     "configs[4] per-GPU share (2048 graphs / 8 GPUs): Oscillator -> WaveShaper(1024-pt tanh) -> Biquad -> Convolver -> "
                                     "Panner(HRTF, 44.1 kHz / 512-tap sphere resampled to 48 kHz) -> Analyser -> destination, 5 s; HRTF parity is UNPINNED "
                                     "(hrtf crate absent from the reference tree, SURVEY §8c)", model=conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2)))
+    elif D.world > 1 and os.environ.get("WAE_BENCH_EXTRA") == "c5_small":  # validation of the N = 8 leg on fewer GPUs (not a BASELINE size)
+        res.append(measure_workload(pkg, eng, D, None, "C5", c5, 32, 0, c5_len, steps, cores,
+                                    "configs[4] path check: 32 graphs per GPU, with the NCCL gather inside the step", gather=True, groups=4))
     elif D.world in (2, 4):
         n = 512 // D.world
         res.append(measure_workload(pkg, eng, D, None, "C4", c4, n, 0, 480000, steps, cores,

@@ -1119,7 +1119,10 @@ DEVI void cswap4(bool p, float4& a, float4& b) {
 // mbarrier), results leave through bulk stores; TMA = false: 16-byte cp.async pieces / coalesced stores (kept as the
 // reference data path: WAE_OPT_CHAIN_TMA = 0).
 template <int SRC, int NB, bool SHAPER, bool TMA>
-__global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? 640 : 768) / CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
+#ifndef WAE_CH_MINB
+#define WAE_CH_MINB 6
+#endif
+__global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128 : WAE_CH_MINB * 128) / CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
                                                                         int n_inst, ChunkInfo ci, ChainSched sc) {
     __shared__ ChainSmem sm;
     __shared__ int s_item;
@@ -3178,7 +3181,7 @@ void chain_set_tuning(int tma, int waves) {
 void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab) {
     chain_env();
     const long ctas = (long)n * max_ch, tiles = (nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
-    const long slots = 148L * (768 / CH_THREADS);
+    const long slots = 148L * (WAE_CH_MINB * 128 / CH_THREADS);
     const long min_tiles = std::max(1L, 16384L / (CH_THREADS * CH_K));  // a slab is at least 16384 frames
     long slabs = 1;
     if (nb == 0) {
