@@ -322,6 +322,15 @@ def run_extra_workloads(pkg, eng, D, oracle, cores, steps, peak_gbs):
     return res
 
 
+def c2_config(n_graphs, length, seconds):
+    """The `config` object of BOTH arms (ours and --impl reference): same workload, same batch per GPU / per step."""
+    return {"workload": "C2 (BASELINE configs[1]): %d OfflineAudioContexts per GPU (per step for the CPU arm), AudioBufferSource->Biquad->Gain->"
+                        "destination, 48 kHz stereo, %.0f s each" % (n_graphs, seconds),
+            "graphs_per_gpu": n_graphs, "graphs_per_step": n_graphs, "frames_per_graph": length,
+            "l2": "inputs (%.2f GB of source PCM per GPU) larger than L2, no flush" % (n_graphs * 2 * length * 4 / 1e9),
+            "sharding": "independent graphs per rank, no data-path collective"}
+
+
 def load_oracle_only():
     """The checker / CPU arm without mapping the product library: package python + oracle/_build/liboracle.so."""
     import __graft_entry__ as ge
@@ -364,9 +373,7 @@ def run_reference(args, D):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "graph-quanta/s", "n_gpus": D.world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 filter state / f32 PCM", "data": "synthetic",
-        "config": {"workload": "C2 (BASELINE configs[1]): %d OfflineAudioContexts, AudioBufferSource->Biquad->Gain->destination, "
-                               "48 kHz stereo, %.0f s each" % (n, args.seconds),
-                   "graphs_per_step": n, "frames_per_graph": length},
+        "config": c2_config(n, length, args.seconds),
         "cpu_baseline": {"value": value, "unit": "graph-quanta/s", "cores": cores, "kind": "port",
                          "sample": f"{n} graphs x {args.seconds:.0f} s per step (the GPU arm's per-GPU batch), one context per worker thread"},
         "e2e": {"value": value, "unit": "graph-quanta/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -575,12 +582,9 @@ def main():
             "metric": METRIC, "value": value, "unit": "graph-quanta/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 filter state / f32 PCM", "data": "synthetic",
-            "config": {"workload": "C2 (BASELINE configs[1]): %d OfflineAudioContexts/GPU, AudioBufferSource->Biquad->Gain->"
-                                   "destination, 48 kHz stereo, %.0f s each" % (n_graphs, args.seconds),
-                       "graphs_per_gpu": n_graphs, "graphs_per_step": n_graphs, "frames_per_graph": length,
-                       "chunk_frames": int(stats0.chunks and (length + 127) // 128 * 128 // stats0.chunks),
-                       "l2": "inputs (%.2f GB/GPU) larger than L2, no flush" % (stats.asset_bytes / 1e9),
-                       "sharding": "independent graphs per rank, no data-path collective",
+            "config": c2_config(n_graphs, length, args.seconds),
+            "engine": {"chunk_frames": int(stats0.chunks and (length + 127) // 128 * 128 // stats0.chunks),
+                       "source_pcm_gb_per_gpu": stats.asset_bytes / 1e9,
                        "numa_bound_cpus": (f"{numa[0]}..{numa[-1]} ({len(numa)} CPUs)" if numa else None)},
             "samples_per_sec": value * 128, "gpu_launches": int(stats.kernel_launches_per_run) * args.steps,
             "clocks": clocks,

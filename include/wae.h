@@ -359,6 +359,14 @@ enum {
 WAE_API wae_status wae_render_batch(wae_engine* engine, wae_graph* const* graphs, uint32_t n_graphs,
                                     float* out, uint32_t flags);
 
+/* Page-locked host memory for output buffers a caller keeps around: with WAE_RENDER_OUT_HOST the rendered PCM is DMA-ed straight into a
+ * page-locked `out` (pageable memory goes through staging slots and copy-out threads inside the library).  wae_host_register
+ * page-locks memory the caller allocated itself; it must stay allocated until wae_host_unregister. */
+WAE_API wae_status wae_host_alloc(wae_engine* engine, uint64_t bytes, void** out);
+WAE_API wae_status wae_host_free(wae_engine* engine, void* p);
+WAE_API wae_status wae_host_register(wae_engine* engine, void* p, uint64_t bytes);
+WAE_API wae_status wae_host_unregister(wae_engine* engine, void* p);
+
 /* Two-phase variant used by bench.py and by callers that render the same batch repeatedly or keep
  * PCM on the device for the NCCL gather: prepare uploads assets and compiles the stage schedule,
  * run renders (device-resident output owned by the engine), fetch copies to the host. */

@@ -162,6 +162,23 @@ def test_iir_filter(pkg, engine, oracle):
     assert maxdiff(gpu, cpu) <= 1e-7  # same serial f64 order
 
 
+def test_second_order_iir_rides_the_biquad_scan(pkg, engine, oracle):
+    """An IIRFilterNode of order <= 2 fed by a constant layout is lowered to the fused chain's time-parallel biquad (normalised by a0);
+    the reference runs it through its own f64 IIR loop (src/node/iir_filter.rs:206-241), so the two agree to the scan's tolerance."""
+    def build(be, g):
+        pcm = G.c2_source(g, 128 * 40)
+        c = pkg.OfflineAudioContext(2, 128 * 40, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        f = c.create_iir_filter([0.135, 0.2698, 0.135], [2.0, -2.2860, 0.8256]) if g % 2 == 0 else c.create_iir_filter([0.5, 0.5], [1.0, -0.2])
+        s.connect(f)
+        f.connect(c.destination())
+        s.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 4)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
 def test_gain_shaper_panner_chain(pkg, engine, oracle):
     curve = np.tanh(np.linspace(-3, 3, 1024)).astype(np.float32)
 
@@ -1110,3 +1127,18 @@ def test_scan_biquad_recovers_from_a_non_finite_sample(pkg, engine, oracle, bad)
     gpu, cpu = both(pkg, engine, oracle, build, 3)
     assert np.isfinite(cpu).all() and np.isfinite(gpu).all()
     assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_one_shot_render_into_registered_caller_memory(pkg, engine):
+    """wae_host_register: the caller's own buffer page-locked once, D2H of the one-shot render lands in it directly"""
+    import ctypes as C
+    n, length = 70, 128 * 50 + 9
+    api = engine.backend.api
+    out = np.full((n, 2, length), np.nan, np.float32)
+    api.check(api.host_register(engine.backend.engine, out.ctypes.data_as(C.c_void_p), out.nbytes))
+    try:
+        got = pkg.render_batch_oneshot([G.c2_buffer_biquad_gain(pkg, engine.backend, g, length) for g in range(n)], out)
+    finally:
+        api.check(api.host_unregister(engine.backend.engine, out.ctypes.data_as(C.c_void_p)))
+    ref = pkg.render_batch_oneshot([G.c2_buffer_biquad_gain(pkg, engine.backend, g, length) for g in range(n)])
+    assert np.array_equal(got, ref)

@@ -142,3 +142,20 @@ def test_scheduling_clock_against_a_replay_of_the_reference(pkg):
         frame, ftime = C.c_int64(), C.c_double()
         api.check(api.sched_first_frame_at_or_after(sr, float(t), C.byref(frame), C.byref(ftime)))
         assert (frame.value, ftime.value) == want, (sr, t, frame.value, want)
+
+
+def test_constructor_channel_configs_and_audio_buffers_are_validated(pkg, product):
+    """assert_valid_number_of_channels / assert_valid_buffer_length at construction (src/lib.rs:185-228, src/buffer.rs:96-115): a channel
+    count outside [1, 32], an unknown enum value, an AudioBuffer without frames or with more than 32 channels never reach the planner"""
+    c = pkg.OfflineAudioContext(2, 1280, 48000.0, product)
+    with pytest.raises(pkg.WaeError, match="Invalid number of channels"):
+        c.create_gain(1.0, cfg=pkg.context.channel_config(33, pkg.MAX, pkg.SPEAKERS))
+    with pytest.raises(pkg.WaeError, match="unknown channel count mode"):
+        c.create_biquad_filter(cfg=pkg.context.channel_config(2, 7, pkg.SPEAKERS))
+    with pytest.raises(pkg.WaeError, match="unknown channel interpretation"):
+        c.create_delay(cfg=pkg.context.channel_config(2, pkg.MAX, 5))
+    with pytest.raises(pkg.WaeError, match="Invalid length"):
+        c.create_buffer_source(pkg.AudioBuffer([np.zeros(0, np.float32)], 48000.0))
+    with pytest.raises(pkg.WaeError, match="Invalid number of channels"):
+        c.create_buffer_source(pkg.AudioBuffer([np.zeros(8, np.float32)] * 33, 48000.0))
+    c.create_gain(1.0, cfg=pkg.context.channel_config(32, pkg.EXPLICIT, pkg.DISCRETE))  # the limits themselves are fine

@@ -159,7 +159,10 @@ def test_which_kernel_a_node_variant_is_lowered_to(pkg, be):
     k = _one(pkg, be, three_biquads)
     assert k.get("k_chain", 0) == 2 and "k_biquad_serial" not in k
     # IIR filter, compressor, analyser, stereo panner, delay: their own stages
-    assert "k_iir_serial" in _one(pkg, be, lambda c: src_to(c, c.create_iir_filter([0.5, 0.5], [1.0, -0.2])))
+    # an IIR of order <= 2 on a constant layout IS a biquad: it rides the time-parallel scan of k_chain; order >= 3 keeps the serial kernel
+    k = _one(pkg, be, lambda c: src_to(c, c.create_iir_filter([0.5, 0.5], [1.0, -0.2])))
+    assert "k_chain" in k and "k_iir_serial" not in k
+    assert "k_iir_serial" in _one(pkg, be, lambda c: src_to(c, c.create_iir_filter([0.5, 0.5, 0.1, 0.05], [1.0, -0.2, 0.1, 0.01])))
     assert "k_compressor" in _one(pkg, be, lambda c: src_to(c, c.create_dynamics_compressor()))
     assert "k_analyser" in _one(pkg, be, lambda c: src_to(c, c.create_analyser()))
     assert "k_stereo_panner" in _one(pkg, be, lambda c: src_to(c, c.create_stereo_panner(0.3)))

@@ -168,6 +168,15 @@ static ChannelCfg resolve_cfg(const wae_channel_config& c, ChannelCfg def) {
     if (c.count == 0) return def;
     return ChannelCfg{(int)c.count, (int)c.count_mode, (int)c.interpretation};
 }
+// a caller-supplied ChannelConfig: assert_valid_number_of_channels (src/lib.rs:185-192) and the two enums of include/wae.h
+static wae_status check_cfg(const wae_channel_config& c) {
+    if (c.count == 0) return WAE_OK;  // "use the node's default"
+    if (c.count > WAE_MAX_CHANNELS)
+        return fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(c.count) + " is outside range [1, 32]");
+    if (c.count_mode > WAE_COUNT_MODE_EXPLICIT) return fail(WAE_INVALID_ARGUMENT, "unknown channel count mode");
+    if (c.interpretation > WAE_INTERPRETATION_DISCRETE) return fail(WAE_INVALID_ARGUMENT, "unknown channel interpretation");
+    return WAE_OK;
+}
 
 // `pin`: the buffer will be DMA-ed to a device by a render call (AudioBufferSourceNode assets of a graph that has an engine)
 static std::shared_ptr<PcmBuffer> copy_buffer(const wae_graph* g, const wae_audio_buffer* b, bool pin) {
@@ -229,6 +238,7 @@ WAE_API wae_status wae_graph_destroy(wae_graph* g) {
 
 // OscillatorNode::new, src/node/oscillator.rs:211-275
 WAE_API wae_status wae_create_oscillator(wae_graph* g, const wae_oscillator_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     if (o->type > WAE_OSC_CUSTOM) return fail(WAE_INVALID_ARGUMENT, "invalid oscillator type");
     if (o->type == WAE_OSC_CUSTOM && (!o->periodic_wave || o->periodic_wave_len == 0))
         return fail(WAE_INVALID_ARGUMENT, "custom oscillator needs a periodic wave table");
@@ -248,12 +258,14 @@ WAE_API wae_status wae_create_oscillator(wae_graph* g, const wae_oscillator_opti
 
 // BiquadFilterNode::new, src/node/biquad_filter.rs:542-608
 WAE_API wae_status wae_create_biquad_filter(wae_graph* g, const wae_biquad_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     if (o->type > 7) return fail(WAE_INVALID_ARGUMENT, "invalid biquad type");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_BIQUAD;
     n.type = (int)o->type;
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, true, o->q));
     n.params.push_back(g->create_param(n.id, 0.f, -153600.f, 153600.f, true, o->detune));
@@ -265,6 +277,7 @@ WAE_API wae_status wae_create_biquad_filter(wae_graph* g, const wae_biquad_optio
 
 // IIRFilterNode::new, src/node/iir_filter.rs:146-205
 WAE_API wae_status wae_create_iir_filter(wae_graph* g, const wae_iir_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     if (o->feedforward_len == 0 || o->feedforward_len > 20) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - invalid feedforward length");
     if (o->feedback_len == 0 || o->feedback_len > 20) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - invalid feedback length");
     bool all_zero = true;
@@ -276,6 +289,7 @@ WAE_API wae_status wae_create_iir_filter(wae_graph* g, const wae_iir_options* o,
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_IIR;
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     n.feedforward.assign(o->feedforward, o->feedforward + o->feedforward_len);
     n.feedback.assign(o->feedback, o->feedback + o->feedback_len);
@@ -285,10 +299,12 @@ WAE_API wae_status wae_create_iir_filter(wae_graph* g, const wae_iir_options* o,
 
 // GainNode::new, src/node/gain.rs:86-117
 WAE_API wae_status wae_create_gain(wae_graph* g, const wae_gain_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_GAIN;
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     n.params.push_back(g->create_param(n.id, 1.f, -F32_MAX, F32_MAX, true, o->gain));
     *out = g->finish_register(std::move(n)).id;
@@ -297,6 +313,7 @@ WAE_API wae_status wae_create_gain(wae_graph* g, const wae_gain_options* o, wae_
 
 // AudioBufferSourceNode::new, src/node/audio_buffer_source.rs:160-235
 WAE_API wae_status wae_create_buffer_source(wae_graph* g, const wae_buffer_source_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
@@ -314,6 +331,7 @@ WAE_API wae_status wae_create_buffer_source(wae_graph* g, const wae_buffer_sourc
 
 // ConstantSourceNode::new, src/node/constant_source.rs:138-170
 WAE_API wae_status wae_create_constant_source(wae_graph* g, const wae_constant_source_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
@@ -326,6 +344,8 @@ WAE_API wae_status wae_create_constant_source(wae_graph* g, const wae_constant_s
 
 // ConvolverNode::new + set_buffer, src/node/convolver.rs:199-317
 WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
     if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - ConvolverNode channel count cannot be greater than two");
     if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - ConvolverNode channel count mode cannot be set to max");
@@ -349,12 +369,14 @@ WAE_API wae_status wae_create_convolver(wae_graph* g, const wae_convolver_option
 
 // WaveShaperNode::new, src/node/waveshaper.rs:190-260
 WAE_API wae_status wae_create_wave_shaper(wae_graph* g, const wae_wave_shaper_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     if (o->oversample > WAE_OVERSAMPLE_X4) return fail(WAE_INVALID_ARGUMENT, "unknown oversample type");
     Node n;
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_SHAPER;
     n.oversample = (int)o->oversample;
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     if (o->curve) {
         n.has_curve = true;
@@ -366,8 +388,10 @@ WAE_API wae_status wae_create_wave_shaper(wae_graph* g, const wae_wave_shaper_op
 
 // DelayNode::new, src/node/delay.rs:283-368: writer N, reader N+1, delayTime N+2
 WAE_API wae_status wae_create_delay(wae_graph* g, const wae_delay_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     if (!(o->max_delay_time > 0. && o->max_delay_time < 180.))
         return fail(WAE_NOT_SUPPORTED, "NotSupportedError - maxDelayTime MUST be greater than zero and less than three minutes");
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg());
     uint32_t writer_id = g->next_id++;
     uint32_t reader_id = g->next_id++;
@@ -398,6 +422,8 @@ WAE_API wae_status wae_create_delay(wae_graph* g, const wae_delay_options* o, wa
 
 // StereoPannerNode::new, src/node/stereo_panner.rs:163-200
 WAE_API wae_status wae_create_stereo_panner(wae_graph* g, const wae_stereo_panner_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
     if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - StereoPannerNode channel count mode cannot be set to max");
     if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - StereoPannerNode channel count cannot be greater than two");
@@ -413,6 +439,8 @@ WAE_API wae_status wae_create_stereo_panner(wae_graph* g, const wae_stereo_panne
 
 // PannerNode::new, src/node/panner.rs:392-520
 WAE_API wae_status wae_create_panner(wae_graph* g, const wae_panner_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
     if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - PannerNode channel count mode cannot be set to max");
     if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - PannerNode channel count cannot be greater than two");
@@ -444,6 +472,7 @@ WAE_API wae_status wae_create_panner(wae_graph* g, const wae_panner_options* o, 
 
 // AnalyserNode::new, src/node/analyser.rs:130-175 (asserts of src/analysis.rs:33-72)
 WAE_API wae_status wae_create_analyser(wae_graph* g, const wae_analyser_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     uint32_t fft = o->fft_size ? o->fft_size : 2048;
     if ((fft & (fft - 1)) != 0) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: not a power of two");
     if (fft < 32 || fft > 32768) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid fft size: outside range [32, 32768]");
@@ -455,6 +484,7 @@ WAE_API wae_status wae_create_analyser(wae_graph* g, const wae_analyser_options*
     n.id = g->next_id++;
     n.out_id = n.id;
     n.kind = K_ANALYSER;
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     n.cfg = resolve_cfg(o->channel_config, ChannelCfg());
     n.fft_size = fft;
     n.smoothing = stc;
@@ -466,6 +496,8 @@ WAE_API wae_status wae_create_analyser(wae_graph* g, const wae_analyser_options*
 
 // DynamicsCompressorNode::new, src/node/dynamics_compressor.rs:130-260
 WAE_API wae_status wae_create_dynamics_compressor(wae_graph* g, const wae_dynamics_compressor_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
+    if (wae_status cs = check_cfg(o->channel_config)) return cs;
     ChannelCfg cfg = resolve_cfg(o->channel_config, ChannelCfg{2, WAE_COUNT_MODE_CLAMPED_MAX, WAE_INTERPRETATION_SPEAKERS});
     if (cfg.count > 2) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - DynamicsCompressorNode channel count cannot be greater than two");
     if (cfg.mode == WAE_COUNT_MODE_MAX) return fail(WAE_NOT_SUPPORTED, "NotSupportedError - DynamicsCompressorNode channel count mode cannot be set to max");
@@ -485,6 +517,7 @@ WAE_API wae_status wae_create_dynamics_compressor(wae_graph* g, const wae_dynami
 
 // ChannelMergerNode::new, src/node/channel_merger.rs:120-140
 WAE_API wae_status wae_create_channel_merger(wae_graph* g, const wae_channel_merger_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     uint32_t k = o->number_of_inputs ? o->number_of_inputs : 6;
     if (k < 1 || k > WAE_MAX_CHANNELS) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid number of inputs");
     Node n;
@@ -499,6 +532,7 @@ WAE_API wae_status wae_create_channel_merger(wae_graph* g, const wae_channel_mer
 
 // ChannelSplitterNode::new, src/node/channel_splitter.rs:140-180
 WAE_API wae_status wae_create_channel_splitter(wae_graph* g, const wae_channel_splitter_options* o, wae_node_id* out) {
+    if (!g || !o || !out) return fail(WAE_INVALID_ARGUMENT, "null graph / options / out pointer");
     uint32_t k = o->number_of_outputs ? o->number_of_outputs : 6;
     if (k < 1 || k > WAE_MAX_CHANNELS) return fail(WAE_INVALID_ARGUMENT, "IndexSizeError - Invalid number of outputs");
     Node n;

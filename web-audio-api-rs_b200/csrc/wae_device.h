@@ -328,6 +328,8 @@ struct MixDynInst {
     int32_t n_edges;
     uint32_t edge_offset;
     int64_t limit;
+    int32_t stereo4;   // every edge and the port have at most two static channels and 16-byte aligned arena buffers: four frames per thread
+    int32_t pad;
 };
 
 
@@ -354,6 +356,8 @@ struct BiquadArInst {
     int32_t ch;
     int32_t pad;
     int32_t* dyn_len;  // see BiquadInst
+    BufRef coefs;      // [5][chunk frames] f64 (b0, b1, b2, a1, a2 of every frame), written by k_biquad_coefs: the per-frame coefficient
+                       // formulas (sin / cos / pow in f64) run one thread per frame, only the 9-flop recurrence stays serial
 };
 
 // ---- AudioParam automation (AudioParamProcessor, src/param.rs:664-1600) -------------------------------------

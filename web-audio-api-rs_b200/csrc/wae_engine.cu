@@ -1735,6 +1735,13 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                         out_dynamic(filter_lay(in0));
                         ba.out = p.out_buf[0];
                     }
+                    {
+                        // five planes of f64 coefficients per frame of the chunk (an arena buffer of 10 float channels read as doubles)
+                        BufRef cb = arena_buf(10);
+                        if (!cb.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                        cb.stride = (uint32_t)b->chunk;  // in DOUBLES: plane k starts at double index k * chunk
+                        ba.coefs = cb;
+                    }
                     ba.sample_rate = g->sample_rate;
                     ba.type = n.type;
                     ba.ch = ch;
@@ -1780,10 +1787,30 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             }
             case K_IIR: {
                 int ch = p.in_ch[0];
-                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 std::vector<double> ff = n.feedforward, fb = n.feedback;  // iir_filter.rs:282-309
                 if (ff.size() < fb.size()) ff.resize(fb.size(), 0.);
                 if (ff.size() > fb.size()) fb.resize(ff.size(), 0.);
+                if (ff.size() <= 3 && !eng->serial_filters && !in0.dyn()) {
+                    // Order <= 2 with a constant input layout: the same transfer function as a biquad — rendered by the time-parallel scan
+                    // of k_chain (direct form I there, transposed direct form II in iir_filter.rs:386-407: the outputs differ in the last
+                    // bits of the f64 arithmetic only) instead of one serial thread per channel.  With an input that can fall silent the
+                    // serial kernel stays: its tail test looks at the reference's own state variables.
+                    ff.resize(3, 0.);
+                    fb.resize(3, 0.);
+                    const double a0 = fb[0];
+                    hm::BiquadCoefs c{ff[0] / a0, ff[1] / a0, ff[2] / a0, fb[1] / a0, fb[2] / a0};
+                    double* state = alloc<double>((size_t)ch * 4, true, true);
+                    if (!state) return bail(WAE_OUT_OF_MEMORY, "out of device memory (state)");
+                    PendingChain pc = open_chain();
+                    ChainBiquad& st = pc.inst.bq[pc.inst.n_biquad++];
+                    st.state = state;
+                    st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
+                    pc.coefs.push_back(make_scan_coef(c));
+                    pc.phase = 1;
+                    if (!finish_chain(std::move(pc))) return false;
+                    break;
+                }
+                if (!need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 IirInst ii{};
                 ii.in = p.in_buf[0];
                 ii.out = p.out_buf[0];
@@ -2684,8 +2711,12 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
         return WAE_OK;
     }
     for (auto& grp : b->groups) {
-        CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_h2d, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&grp.ev_done, cudaEventDisableTiming));
+        if (cudaEventCreateWithFlags(&grp.ev_h2d, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&grp.ev_done, cudaEventDisableTiming) != cudaSuccess) {
+            const std::string msg = std::string("prepare: cudaEventCreate: ") + cudaGetErrorString(cudaGetLastError());
+            wae_batch_destroy(b);
+            return fail(WAE_CUDA_ERROR, msg);
+        }
         if (grp.src_floats) {
             // (not zeroed: every float of the slab is covered by a source copy, channel paddings included)
             grp.d_src = b->dalloc<float>(grp.src_floats, false);
@@ -2756,7 +2787,18 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                     st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
                     break;
                 }
-                case S_MIX_DYN: st.n = (int)s.mix_dyn.size(); st.d_a = up(b, s.mix_dyn); st.d_b = up(b, s.mix_edges); break;
+                case S_MIX_DYN: {
+                    for (auto& m : s.mix_dyn) {  // classify: the four-frames-per-thread path of k_mix_dyn
+                        bool ok = m.out_ch <= 2;
+                        for (int e = 0; e < m.n_edges && ok; e++) {
+                            const MixEdge& ed = s.mix_edges[m.edge_offset + e];
+                            if (ed.src_ch > 2 || ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) ok = false;
+                        }
+                        m.stereo4 = ok ? 1 : 0;
+                    }
+                    st.n = (int)s.mix_dyn.size(); st.d_a = up(b, s.mix_dyn); st.d_b = up(b, s.mix_edges);
+                    break;
+                }
                 case S_META: st.n = (int)s.meta.size(); st.d_a = up(b, s.meta); break;
                 case S_OSC: st.n = (int)s.osc.size(); st.d_a = up(b, s.osc); break;
                 case S_CONST: st.n = (int)s.cst.size(); st.d_a = up(b, s.cst); break;
@@ -3357,6 +3399,38 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
         if (e) cudaEventDestroy(e);
     wae_batch_destroy(b);
     if (result != WAE_OK) return fail(result, result_msg);
+    return WAE_OK;
+}
+
+// Page-locked host memory for callers that keep their output (or input) buffers around: D2H lands in such a buffer directly instead of
+// going through the staging slots.  wae_host_register page-locks memory the caller allocated itself (it must stay allocated until
+// wae_host_unregister); both are thin wrappers so that a binding needs no CUDA of its own.
+WAE_API wae_status wae_host_alloc(wae_engine* eng, uint64_t bytes, void** out) {
+    if (!eng || !out || bytes == 0) return fail(WAE_INVALID_ARGUMENT, "null engine / out pointer or zero size");
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(WAE_OUT_OF_MEMORY, "out of page-locked host memory");
+    }
+    return WAE_OK;
+}
+WAE_API wae_status wae_host_free(wae_engine* eng, void* p) {
+    if (!eng) return fail(WAE_INVALID_ARGUMENT, "null engine");
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return WAE_OK;
+}
+WAE_API wae_status wae_host_register(wae_engine* eng, void* p, uint64_t bytes) {
+    if (!eng || !p || bytes == 0) return fail(WAE_INVALID_ARGUMENT, "null engine / pointer or zero size");
+    CUDA_TRY(cudaSetDevice(eng->device));
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        const std::string msg = std::string("cudaHostRegister: ") + cudaGetErrorString(cudaGetLastError());
+        return fail(WAE_CUDA_ERROR, msg);
+    }
+    return WAE_OK;
+}
+WAE_API wae_status wae_host_unregister(wae_engine* eng, void* p) {
+    if (!eng || !p) return fail(WAE_INVALID_ARGUMENT, "null engine / pointer");
+    CUDA_TRY(cudaHostUnregister(p));
     return WAE_OK;
 }
 

@@ -466,10 +466,67 @@ DEVI float mixed_sample(const MixEdge& e, int dst_ch, int c, int interp, int n, 
 // order.  Every add first brings the running sum to computedNumberOfChannels(max(sum's count, edge's count)) — so with three or more
 // layouts the intermediate counts matter (mono, then stereo, then 5.1: 1 -> 2 -> 6, the mono lands in L / R, not in C) — then mixes the
 // edge to that count and adds channel by channel; silent edges only take part in the count.  One thread per frame.
+// up to two channels everywhere (the usual case): four frames per thread, the running sum in two float4, the layout bytes read once per
+// four frames.  Same fold, same order of additions as the general path below.
+DEVI void mix_dyn_stereo4(const MixDynInst& m, const MixEdge* __restrict__ edges, int n0, const ChunkInfo& ci) {
+    const int qi = meta_qi(ci, n0);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int cnt = 1;
+    bool silent = true;
+    const bool speakers = m.interp == 0;
+    for (int e = 0; e < m.n_edges; e++) {
+        const MixEdge& ed = edges[m.edge_offset + e];
+        const int ce = buf_count(ed.src, ed.src_ch, qi);
+        const bool se = buf_silent(ed.src, ed.src_ch, qi);
+        const int mx = cnt > ce ? cnt : ce;
+        const int nw = m.mode == WAE_COUNT_MODE_MAX ? mx : (m.mode == WAE_COUNT_MODE_EXPLICIT ? m.cfg_count : (mx < m.cfg_count ? mx : m.cfg_count));
+        if (!silent && nw != cnt) {  // self.mix(new_channels): 1 -> 2 copy (speakers) / zero-fill (discrete); 2 -> 1 half sum / truncate
+            if (nw == 2) a1 = speakers ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);
+            else if (speakers) a0 = make_float4(0.5f * (a0.x + a1.x), 0.5f * (a0.y + a1.y), 0.5f * (a0.z + a1.z), 0.5f * (a0.w + a1.w));
+        }
+        cnt = nw;
+        if (!se) {
+            const float4 v0 = *reinterpret_cast<const float4*>(chan(ed.src, 0, ci) + n0);
+            float4 v1 = v0;
+            if (ce == 2) v1 = *reinterpret_cast<const float4*>(chan(ed.src, 1, ci) + n0);
+            float4 x0 = v0, x1 = v1;  // the edge mixed to nw channels
+            if (nw == 1 && ce == 2 && speakers) x0 = make_float4(0.5f * (v0.x + v1.x), 0.5f * (v0.y + v1.y), 0.5f * (v0.z + v1.z), 0.5f * (v0.w + v1.w));
+            if (nw == 2 && ce == 1 && !speakers) x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (silent) {
+                a0 = x0;
+                a1 = x1;
+            } else {
+                a0.x += x0.x; a0.y += x0.y; a0.z += x0.z; a0.w += x0.w;
+                if (nw == 2) { a1.x += x1.x; a1.y += x1.y; a1.z += x1.z; a1.w += x1.w; }
+            }
+            silent = false;
+        }
+    }
+    if ((n0 & 127) == 0 && m.out.meta) meta_put_all(m.out, m.out_ch, qi, cnt, silent);
+    if (silent) a0 = a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    else if (cnt == 1) a1 = speakers ? a0 : make_float4(0.f, 0.f, 0.f, 0.f);  // canonical fill of the second static channel
+    for (int c = 0; c < m.out_ch; c++) {
+        const float4 v = c == 0 ? a0 : a1;
+        float* out = chan(m.out, c, ci) + n0;
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (m.limit < 0 || ci.f0 + n0 + 4 <= m.limit)) {
+            *reinterpret_cast<float4*>(out) = v;
+        } else {
+            const float w[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4; j++)
+                if (m.limit < 0 || ci.f0 + n0 + j < m.limit) out[j] = w[j];
+        }
+    }
+}
 __global__ void __launch_bounds__(128) k_mix_dyn(const MixDynInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst, ChunkInfo ci) {
     for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
         const MixDynInst m = insts[ii];
-        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (m.stereo4) {  // (instance-uniform)
+            const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+            if (n0 < ci.nf) mix_dyn_stereo4(m, edges, n0, ci);
+            continue;
+        }
+        for (int sub = 0; sub < 4; sub++) {  // (the grid is sized for four frames per thread)
+        const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4 + sub;
         if (n >= ci.nf) continue;
         const int qi = meta_qi(ci, n);
         float acc[32], tmp[32];
@@ -500,6 +557,7 @@ __global__ void __launch_bounds__(128) k_mix_dyn(const MixDynInst* __restrict__ 
             float v = 0.f;
             if (!silent) v = c < cnt ? acc[c] : mix_channel([&](int ch) { return acc[ch]; }, cnt, m.out_ch, c, m.interp);  // canonical fill
             chan(m.out, c, ci)[n] = v;
+        }
         }
     }
 }
@@ -1665,7 +1723,27 @@ DEVI BqC bq_coefs(int type, double sample_rate, double f0, double gain, double q
     }
 }
 
-// BiquadFilter with automated parameters: per-frame coefficients + the reference's serial f64 recurrence
+// BiquadFilter with automated parameters, step 1: the coefficients of every frame (biquad_filter.rs:837-855), one thread per frame.
+// The formulas are a function of the frame's parameter values only, so they do not belong in the serial recurrence.
+__global__ void __launch_bounds__(256) k_biquad_coefs(const BiquadArInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const BiquadArInst& q = insts[ii];
+        const int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= ci.nf) continue;
+        const float vq = q.q.p ? chan(q.q, 0, ci)[n] : q.q_val, vd = q.detune.p ? chan(q.detune, 0, ci)[n] : q.detune_val;
+        const float vf = q.freq.p ? chan(q.freq, 0, ci)[n] : q.freq_val, vg = q.gain.p ? chan(q.gain, 0, ci)[n] : q.gain_val;
+        const float computed = vd != 0.f ? vf * exp2f(vd / 1200.f) : vf;  // get_computed_freq, biquad_filter.rs:393-399
+        const BqC cf = bq_coefs(q.type, (double)q.sample_rate, (double)computed, (double)vg, (double)vq);
+        double* base = reinterpret_cast<double*>(q.coefs.p) + ci.sub + n;
+        const size_t cs = q.coefs.stride;  // doubles between coefficient planes
+        base[0] = cf.b0;
+        base[cs] = cf.b1;
+        base[2 * cs] = cf.b2;
+        base[3 * cs] = cf.a1;
+        base[4 * cs] = cf.a2;
+    }
+}
+// step 2: the reference's serial f64 recurrence with those coefficients
 __global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int ii = t / max_ch, c = t % max_ch;
@@ -1680,7 +1758,9 @@ __global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restr
     const float* tg = q.gain.p ? chan(q.gain, 0, ci) : nullptr;
     double* st = q.state + 4 * c;
     double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
-    float pq = 0.f, pd = 0.f, pf = 0.f, pg = 0.f;
+    const double* cbase = reinterpret_cast<const double*>(q.coefs.p) + ci.sub;
+    const size_t cs = q.coefs.stride;
+    (void)tq; (void)td; (void)tf; (void)tg;
     BqC cf{};
     const bool dyn = q.in.meta != nullptr;
     int len = dyn ? q.dyn_len[c] : q.ch;
@@ -1694,12 +1774,11 @@ __global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restr
             out[n] = 0.f;
             continue;
         }
-        float vq = tq ? tq[n] : q.q_val, vd = td ? td[n] : q.detune_val, vf = tf ? tf[n] : q.freq_val, vg = tg ? tg[n] : q.gain_val;
-        if (n == 0 || vq != pq || vd != pd || vf != pf || vg != pg) {
-            float computed = vd != 0.f ? vf * exp2f(vd / 1200.f) : vf;  // get_computed_freq, biquad_filter.rs:393-399
-            cf = bq_coefs(q.type, (double)q.sample_rate, (double)computed, (double)vg, (double)vq);
-            pq = vq; pd = vd; pf = vf; pg = vg;
-        }
+        cf.b0 = cbase[n];
+        cf.b1 = cbase[cs + n];
+        cf.b2 = cbase[2 * cs + n];
+        cf.a1 = cbase[3 * cs + n];
+        cf.a2 = cbase[4 * cs + n];
         double x = absent ? 0. : (double)in[n];
         double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf.b0, x), __dmul_rn(cf.b1, x1)), __dmul_rn(cf.b2, x2)),
                                        __dmul_rn(cf.a1, y1)),
@@ -2804,11 +2883,13 @@ DEVI void fft_radix8_pass(float2* s, int q, int log_q, int sign) {
         float2 a[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) a[m] = s[cv_pad(base + m * q)];
-        // twiddles exp(-2*pi*i*lo/(8q)), /(4q), /(2q) from the exp(-2*pi*i*k/(2B)) table
+        // twiddles exp(-2*pi*i*lo/(8q)), /(4q), /(2q): the first from the exp(-2*pi*i*k/(2B)) table, the other two are its square and
+        // fourth power (one strided table load per butterfly instead of three: with 3 x 68 KB of shared memory per SM the L1 is
+        // too small for the 64 KB table and every load went to L2 — long_scoreboard 6 - 7 per issue in round 1's profile)
         float2 t1 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 3))]);
-        float2 t2 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 2))]);
-        float2 t3 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 1))]);
-        if (sign > 0) t1.y = -t1.y, t2.y = -t2.y, t3.y = -t3.y;
+        if (sign > 0) t1.y = -t1.y;
+        const float2 t2 = cmul(t1, t1);
+        const float2 t3 = cmul(t2, t2);
         float2 u, v;
         // span 4: twiddle t1 * W8^m
         u = cadd(a[0], a[4]); v = csub(a[0], a[4]); a[0] = u; a[4] = cmul(v, t1);
@@ -3153,7 +3234,7 @@ void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStr
     if (ctas4 < 2 * 148) k_mix<1><<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci);
     else k_mix<4><<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, e, n, ci);
 }
-void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) { k_mix_dyn<<<grid_tiles(ci.nf, 128, n), 128, 0, s>>>(d, e, n, ci); }
+void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) { k_mix_dyn<<<grid_tiles(ci.nf, 512, n), 128, 0, s>>>(d, e, n, ci); }
 void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_meta<<<(n + 63) / 64, 64, 0, s>>>(d, n, ci); }
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;
@@ -3298,6 +3379,7 @@ void launch_delay_mono(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) 
 void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_ring_write<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci); }
 void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_osc_arate<<<n, 256, 0, s>>>(d, n, ci); }
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
+    k_biquad_coefs<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
     int threads = n * max_ch;
     k_biquad_arate<<<(threads + 63) / 64, 64, 0, s>>>(d, n, max_ch, ci);
 }
