@@ -367,6 +367,12 @@ WAE_API wae_status wae_host_free(wae_engine* engine, void* p);
 WAE_API wae_status wae_host_register(wae_engine* engine, void* p, uint64_t bytes);
 WAE_API wae_status wae_host_unregister(wae_engine* engine, void* p);
 
+/* Diagnostics: runs the convolver's 8192-point shared-memory transforms on the HOST with the same butterfly / index / twiddle code the
+ * kernels compile (no GPU needed), in place on 16384 floats.  mode 0: complex forward, natural order in, bit-reversed ("position") order
+ * out; 1: complex inverse (unnormalised), position order in, natural out; 2: 16384 reals -> 8192 packed bins (bin 0 = DC, Nyquist) in
+ * position order; 3: the inverse of 2 (scaled).  tests/test_conv_fft_host.py pins them against numpy. */
+WAE_API wae_status wae_selftest_conv_fft(float* data, uint32_t mode);
+
 /* Two-phase variant used by bench.py and by callers that render the same batch repeatedly or keep
  * PCM on the device for the NCCL gather: prepare uploads assets and compiles the stage schedule,
  * run renders (device-resident output owned by the engine), fetch copies to the host. */

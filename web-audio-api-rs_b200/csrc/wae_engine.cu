@@ -1790,7 +1790,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 std::vector<double> ff = n.feedforward, fb = n.feedback;  // iir_filter.rs:282-309
                 if (ff.size() < fb.size()) ff.resize(fb.size(), 0.);
                 if (ff.size() > fb.size()) fb.resize(ff.size(), 0.);
-                if (ff.size() <= 3 && !eng->serial_filters && !in0.dyn()) {
+                if (ff.size() <= 3 && !eng->serial_filters && !in0.dyn() && !getenv("WAE_DEBUG_NO_IIR_CHAIN")) {
                     // Order <= 2 with a constant input layout: the same transfer function as a biquad — rendered by the time-parallel scan
                     // of k_chain (direct form I there, transposed direct form II in iir_filter.rs:386-407: the outputs differ in the last
                     // bits of the f64 arithmetic only) instead of one serial thread per channel.  With an input that can fall silent the
@@ -2349,12 +2349,7 @@ WAE_API wae_status wae_engine_create(int32_t device_ordinal, wae_engine** out) {
     std::vector<float> sine = hm::sine_table();
     CUDA_TRY(cudaMalloc(&eng->d_sine, sine.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(eng->d_sine, sine.data(), sine.size() * sizeof(float), cudaMemcpyHostToDevice));
-    std::vector<float2> tw(WAE_CONV_BLOCK);
-    for (int k = 0; k < WAE_CONV_BLOCK; k++) {
-        double a = -2.0 * hm::PI64 * (double)k / (2.0 * WAE_CONV_BLOCK);
-        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
-    }
-    upload_twiddles(tw.data());
+    upload_twiddles();
     CUDA_TRY(cudaDeviceSynchronize());
     *out = eng;
     return WAE_OK;
@@ -2794,7 +2789,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                             const MixEdge& ed = s.mix_edges[m.edge_offset + e];
                             if (ed.src_ch > 2 || ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) ok = false;
                         }
-                        m.stereo4 = ok ? 1 : 0;
+                        m.stereo4 = (ok && !getenv("WAE_DEBUG_NO_STEREO4")) ? 1 : 0;
                     }
                     st.n = (int)s.mix_dyn.size(); st.d_a = up(b, s.mix_dyn); st.d_b = up(b, s.mix_edges);
                     break;
@@ -3431,6 +3426,12 @@ WAE_API wae_status wae_host_register(wae_engine* eng, void* p, uint64_t bytes) {
 WAE_API wae_status wae_host_unregister(wae_engine* eng, void* p) {
     if (!eng || !p) return fail(WAE_INVALID_ARGUMENT, "null engine / pointer");
     CUDA_TRY(cudaHostUnregister(p));
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_selftest_conv_fft(float* data, uint32_t mode) {
+    if (!data || mode > 3) return fail(WAE_INVALID_ARGUMENT, "wae_selftest_conv_fft: null data or mode > 3");
+    conv_fft_selftest(data, (int)mode);
     return WAE_OK;
 }
 

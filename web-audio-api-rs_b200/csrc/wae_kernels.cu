@@ -10,7 +10,9 @@
 #include "../../include/wae.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <vector>
 #include <type_traits>
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -2824,33 +2826,53 @@ __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param_parallel(const Param
 // partitioned overlap-save with 1024-frame partitions because it must answer every 128 frames; an offline batch has no
 // such deadline, so the same linear convolution is evaluated time-batched with B = 8192-frame partitions (FFT 16384):
 // 8x fewer partitions => 8x less spectrum traffic and MAC work per output frame.  Per chunk:
-//   k_conv_fft_in : X_j = FFT([block j-1 | block j])                         CTA per (input channel, block), smem FFT
+//   k_conv_fft_in : X_j = FFT([block j-1 | block j])                         CTA per (input channel, block), smem FFT (DIF)
 //   k_conv_mac    : Y_j = sum_i H_i * X_{j-i}  for CV_J output blocks at once  thread per bin, register tiled over j
-//   k_conv_ifft   : out_j = IFFT(Y_j)[B..2B) / 2B                              CTA per (path, block), smem FFT
-// Real FFTs of 2B points are computed as complex FFTs of B points (packed even/odd) in shared memory (64 KB).
+//   k_conv_ifft   : out_j = IFFT(Y_j)[B..2B) / 2B                              CTA per (path, block), smem FFT (DIT)
+// Real FFTs of 2B points are computed as complex FFTs of B points (packed even/odd) in shared memory (64 KB); spectra are kept in
+// bit-reversed ("position") order end to end, see below.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int CV_B = WAE_CONV_BLOCK;    // frames per partition
 constexpr int CV_LOGB = 13;
 static_assert((1 << CV_LOGB) == CV_B, "CV_LOGB");
 constexpr int CV_BINS = CV_B;           // packed half spectrum: bin 0 = (DC, Nyquist), bins 1..B-1 complex
 constexpr int CV_THREADS = 256;
+constexpr int CV_ROWS = CV_B / 32;      // warp rows of a spectrum
 
-__device__ float2 c_tw[CV_B];  // exp(-2*pi*i*k/(2B)), k < B
+__device__ float2 c_tw[CV_B];           // exp(-2*pi*i*k/(2B)), k < B
+__constant__ float2 c_rowtw[CV_ROWS];   // c_tw[brev8(r)]: the warp-uniform factor of a bin's real-FFT twiddle when lanes walk POSITIONS (below)
+static float2 h_tw[CV_B];               // host copy (wae_selftest_conv_fft)
 
-DEVI float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+#define WAE_HD __host__ __device__ __forceinline__
+// the library is built with -fmad=false (the reference's arithmetic is unfused); the transforms are compared at a tolerance against a
+// different FFT anyway (rustfft), so their complex multiply asks for the fused form explicitly: 4 instructions instead of 6
+WAE_HD float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
+WAE_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+WAE_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-// In-place B-point (8192) complex FFT in shared memory, decimation in frequency, radix 8 x 8 x 8 x 16 with the
-// butterflies in registers: 4 passes / 3 barriers instead of 13 radix-2 stages.  The result is left in bit-reversed
-// order (element k at position brev13(k)); consumers index through cv_pos().  Storage is padded by one float2 per 16
-// so that the contiguous radix-16 pass is free of bank conflicts.  sign = -1 forward, +1 inverse (unnormalised).
+// B-point (8192) complex FFTs in shared memory with the butterflies in registers: radix 8 x 8 x 8 x 16, 4 passes / 3 barriers instead of 13
+// radix-2 stages.  Two flow graphs, so that no pass ever permutes:
+//   forward  = decimation in frequency: natural order in, BIT-REVERSED order out (element k at position brev13(k));
+//   inverse  = decimation in time:      bit-reversed order in, natural order out.
+// Spectra therefore live in HBM in POSITION order (X[p] = bin brev13(p)) — the MAC between the two transforms is bin-wise and does not care,
+// and the real-FFT split pairs position p with the position of bin B-k, which for 32 consecutive p is 32 consecutive positions in reverse:
+// both shared-memory reads are conflict free and both HBM accesses coalesced (round 1 indexed bins in natural order through cv_pos(): a
+// 16-way bank conflict on every read, twice the shared-memory wavefronts of the four FFT passes together).
+// Storage is padded by one float2 per 16 so that the contiguous radix-16 pass is free of bank conflicts.  sign = -1 forward, +1 inverse.
 constexpr int CV_SMEM_ELEMS = CV_B + CV_B / 16;
-DEVI int cv_pad(int i) { return i + (i >> 4); }
-DEVI int cv_pos(int k) { return cv_pad((int)(__brev((unsigned)k) >> (32 - CV_LOGB))); }  // where element k of an FFT result lives
-DEVI float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-DEVI float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+WAE_HD int cv_pad(int i) { return i + (i >> 4); }
+WAE_HD int cv_brev(int k) {
+#ifdef __CUDA_ARCH__
+    return (int)(__brev((unsigned)k) >> (32 - CV_LOGB));
+#else
+    int r = 0;
+    for (int b = 0; b < CV_LOGB; b++) r |= ((k >> b) & 1) << (CV_LOGB - 1 - b);
+    return r;
+#endif
+}
 // multiply by exp(sign * 2*pi*i * m / 16)
 template <int M>
-DEVI float2 rot16(float2 v, int sign) {
+WAE_HD float2 rot16(float2 v, int sign) {
     constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f, R = 0.70710678118654752440f;
     constexpr int m = M & 15;
     float c, sn;
@@ -2872,129 +2894,252 @@ DEVI float2 rot16(float2 v, int sign) {
     else if (m == 14) c = R, sn = -R;
     else c = C1, sn = -S1;
     if (sign < 0) sn = -sn;
-    return make_float2(v.x * c - v.y * sn, v.x * sn + v.y * c);
+    return make_float2(fmaf(v.x, c, -(v.y * sn)), fmaf(v.x, sn, v.y * c));
 }
-// one radix-8 DIF butterfly on elements base + m*q (three radix-2 stages with spans 4q, 2q, q)
-DEVI void fft_radix8_pass(float2* s, int q, int log_q, int sign) {
-#pragma unroll 2
-    for (int bf = threadIdx.x; bf < CV_B / 8; bf += CV_THREADS) {
-        const int lo = bf & (q - 1), hi = bf >> log_q;
-        const int base = (hi << (log_q + 3)) + lo;
-        float2 a[8];
+// radix-8 butterfly on elements base + m*q (radix-2 spans 4q, 2q, q) with t1 = exp(sign*2*pi*i*lo/(8q)); the twiddles of the two
+// inner spans are its square and fourth power
+WAE_HD void bf8_dif(float2 (&a)[8], float2 t1, int sign) {
+    const float2 t2 = cmul(t1, t1), t3 = cmul(t2, t2);
+    float2 u, v;
+    u = cadd(a[0], a[4]); v = csub(a[0], a[4]); a[0] = u; a[4] = cmul(v, t1);
+    u = cadd(a[1], a[5]); v = csub(a[1], a[5]); a[1] = u; a[5] = cmul(rot16<2>(v, sign), t1);
+    u = cadd(a[2], a[6]); v = csub(a[2], a[6]); a[2] = u; a[6] = cmul(rot16<4>(v, sign), t1);
+    u = cadd(a[3], a[7]); v = csub(a[3], a[7]); a[3] = u; a[7] = cmul(rot16<6>(v, sign), t1);
 #pragma unroll
-        for (int m = 0; m < 8; m++) a[m] = s[cv_pad(base + m * q)];
-        // twiddles exp(-2*pi*i*lo/(8q)), /(4q), /(2q): the first from the exp(-2*pi*i*k/(2B)) table, the other two are its square and
-        // fourth power (one strided table load per butterfly instead of three: with 3 x 68 KB of shared memory per SM the L1 is
-        // too small for the 64 KB table and every load went to L2 — long_scoreboard 6 - 7 per issue in round 1's profile)
-        float2 t1 = __ldg(&c_tw[lo << (CV_LOGB + 1 - (log_q + 3))]);
-        if (sign > 0) t1.y = -t1.y;
-        const float2 t2 = cmul(t1, t1);
-        const float2 t3 = cmul(t2, t2);
-        float2 u, v;
-        // span 4: twiddle t1 * W8^m
-        u = cadd(a[0], a[4]); v = csub(a[0], a[4]); a[0] = u; a[4] = cmul(v, t1);
-        u = cadd(a[1], a[5]); v = csub(a[1], a[5]); a[1] = u; a[5] = cmul(rot16<2>(v, sign), t1);
-        u = cadd(a[2], a[6]); v = csub(a[2], a[6]); a[2] = u; a[6] = cmul(rot16<4>(v, sign), t1);
-        u = cadd(a[3], a[7]); v = csub(a[3], a[7]); a[3] = u; a[7] = cmul(rot16<6>(v, sign), t1);
-        // span 2: twiddle t2 * W4^m
+    for (int g = 0; g < 8; g += 4) {
+        u = cadd(a[g], a[g + 2]); v = csub(a[g], a[g + 2]); a[g] = u; a[g + 2] = cmul(v, t2);
+        u = cadd(a[g + 1], a[g + 3]); v = csub(a[g + 1], a[g + 3]); a[g + 1] = u; a[g + 3] = cmul(rot16<4>(v, sign), t2);
+    }
 #pragma unroll
-        for (int g = 0; g < 8; g += 4) {
-            u = cadd(a[g], a[g + 2]); v = csub(a[g], a[g + 2]); a[g] = u; a[g + 2] = cmul(v, t2);
-            u = cadd(a[g + 1], a[g + 3]); v = csub(a[g + 1], a[g + 3]); a[g + 1] = u; a[g + 3] = cmul(rot16<4>(v, sign), t2);
-        }
-        // span 1: twiddle t3
-#pragma unroll
-        for (int m = 0; m < 8; m += 2) {
-            u = cadd(a[m], a[m + 1]); v = csub(a[m], a[m + 1]); a[m] = u; a[m + 1] = cmul(v, t3);
-        }
-#pragma unroll
-        for (int m = 0; m < 8; m++) s[cv_pad(base + m * q)] = a[m];
+    for (int m = 0; m < 8; m += 2) {
+        u = cadd(a[m], a[m + 1]); v = csub(a[m], a[m + 1]); a[m] = u; a[m + 1] = cmul(v, t3);
     }
 }
-// the last four radix-2 stages on 16 contiguous elements: all twiddles are 16th roots of unity
-DEVI void fft_radix16_last(float2* s, int sign) {
-    for (int bf = threadIdx.x; bf < CV_B / 16; bf += CV_THREADS) {
-        float2 a[16];
-        float2* p = s + cv_pad(bf * 16);  // 16 contiguous elements never straddle a pad slot
+// the transposed flow graph: twiddle first, spans q, 2q, 4q
+WAE_HD void bf8_dit(float2 (&a)[8], float2 t1, int sign) {
+    const float2 t2 = cmul(t1, t1), t3 = cmul(t2, t2);
+    float2 u, v;
 #pragma unroll
-        for (int m = 0; m < 16; m++) a[m] = p[m];
-        float2 u, v;
+    for (int m = 0; m < 8; m += 2) {
+        v = cmul(a[m + 1], t3); u = a[m]; a[m] = cadd(u, v); a[m + 1] = csub(u, v);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g += 4) {
+        v = cmul(a[g + 2], t2); u = a[g]; a[g] = cadd(u, v); a[g + 2] = csub(u, v);
+        v = rot16<4>(cmul(a[g + 3], t2), sign); u = a[g + 1]; a[g + 1] = cadd(u, v); a[g + 3] = csub(u, v);
+    }
+    v = cmul(a[4], t1); u = a[0]; a[0] = cadd(u, v); a[4] = csub(u, v);
+    v = rot16<2>(cmul(a[5], t1), sign); u = a[1]; a[1] = cadd(u, v); a[5] = csub(u, v);
+    v = rot16<4>(cmul(a[6], t1), sign); u = a[2]; a[2] = cadd(u, v); a[6] = csub(u, v);
+    v = rot16<6>(cmul(a[7], t1), sign); u = a[3]; a[3] = cadd(u, v); a[7] = csub(u, v);
+}
+// four radix-2 stages on 16 contiguous elements: all twiddles are 16th roots of unity
+WAE_HD void bf16_dif(float2 (&a)[16], int sign) {
+    float2 u, v;
 #define WAE_BF(i, j, M) u = cadd(a[i], a[j]); v = csub(a[i], a[j]); a[i] = u; a[j] = rot16<M>(v, sign);
-        WAE_BF(0, 8, 0) WAE_BF(1, 9, 1) WAE_BF(2, 10, 2) WAE_BF(3, 11, 3) WAE_BF(4, 12, 4) WAE_BF(5, 13, 5) WAE_BF(6, 14, 6) WAE_BF(7, 15, 7)
+    WAE_BF(0, 8, 0) WAE_BF(1, 9, 1) WAE_BF(2, 10, 2) WAE_BF(3, 11, 3) WAE_BF(4, 12, 4) WAE_BF(5, 13, 5) WAE_BF(6, 14, 6) WAE_BF(7, 15, 7)
 #pragma unroll
-        for (int g = 0; g < 16; g += 8) {
-            WAE_BF(g, g + 4, 0) WAE_BF(g + 1, g + 5, 2) WAE_BF(g + 2, g + 6, 4) WAE_BF(g + 3, g + 7, 6)
-        }
+    for (int g = 0; g < 16; g += 8) {
+        WAE_BF(g, g + 4, 0) WAE_BF(g + 1, g + 5, 2) WAE_BF(g + 2, g + 6, 4) WAE_BF(g + 3, g + 7, 6)
+    }
 #pragma unroll
-        for (int g = 0; g < 16; g += 4) {
-            WAE_BF(g, g + 2, 0) WAE_BF(g + 1, g + 3, 4)
-        }
+    for (int g = 0; g < 16; g += 4) {
+        WAE_BF(g, g + 2, 0) WAE_BF(g + 1, g + 3, 4)
+    }
 #pragma unroll
-        for (int g = 0; g < 16; g += 2) {
-            WAE_BF(g, g + 1, 0)
-        }
+    for (int g = 0; g < 16; g += 2) {
+        WAE_BF(g, g + 1, 0)
+    }
 #undef WAE_BF
+}
+WAE_HD void bf16_dit(float2 (&a)[16], int sign) {
+    float2 u, v;
+#define WAE_BF(i, j, M) v = rot16<M>(a[j], sign); u = a[i]; a[i] = cadd(u, v); a[j] = csub(u, v);
 #pragma unroll
-        for (int m = 0; m < 16; m++) p[m] = a[m];
+    for (int g = 0; g < 16; g += 2) {
+        WAE_BF(g, g + 1, 0)
+    }
+#pragma unroll
+    for (int g = 0; g < 16; g += 4) {
+        WAE_BF(g, g + 2, 0) WAE_BF(g + 1, g + 3, 4)
+    }
+#pragma unroll
+    for (int g = 0; g < 16; g += 8) {
+        WAE_BF(g, g + 4, 0) WAE_BF(g + 1, g + 5, 2) WAE_BF(g + 2, g + 6, 4) WAE_BF(g + 3, g + 7, 6)
+    }
+    WAE_BF(0, 8, 0) WAE_BF(1, 9, 1) WAE_BF(2, 10, 2) WAE_BF(3, 11, 3) WAE_BF(4, 12, 4) WAE_BF(5, 13, 5) WAE_BF(6, 14, 6) WAE_BF(7, 15, 7)
+#undef WAE_BF
+}
+// Pass twiddles out of registers.  Thread t handles butterflies bf = t + 256*it of a radix-8 pass with span q; lo = bf & (q-1) is
+//   q = 1024: t + 256*it -> exp(s*2*pi*i*t/8192) * exp(s*2*pi*i*it/32)      (one table value + a compile-time rotation per butterfly)
+//   q = 128 : t & 127                                                         (one table value for the whole pass)
+//   q = 16  : t & 15
+// so a thread reads THREE table entries per transform, before its input loads, instead of one L2-latency gather per butterfly (the 64 KB
+// table does not survive in an L1 that shares 256 KB with 3 x 68 KB of shared memory: long_scoreboard 6 - 7 per issue in round 1's profile).
+struct FftTw { float2 w1, w2, w3; };
+static_assert(CV_THREADS == 256 && CV_LOGB == 13, "FftTw assumes 4 radix-8 butterflies per thread and spans 1024 / 128 / 16");
+WAE_HD FftTw fft_tw_of(const float2* tw, int t, int sign) {
+    FftTw w;
+    w.w1 = tw[t << 1];
+    w.w2 = tw[(t & 127) << 4];
+    w.w3 = tw[(t & 15) << 7];
+    if (sign > 0) w.w1.y = -w.w1.y, w.w2.y = -w.w2.y, w.w3.y = -w.w3.y;
+    return w;
+}
+WAE_HD float2 tw_it(float2 w1, int it, int sign) {  // w1 * exp(sign*2*pi*i*it/32)
+    float c, s;
+    if (it == 0) return w1;
+    if (it == 1) c = 0.98078528040323044913f, s = 0.19509032201612826785f;
+    else if (it == 2) c = 0.92387953251128675613f, s = 0.38268343236508977173f;
+    else c = 0.83146961230254523708f, s = 0.55557023301960222474f;
+    return cmul(w1, make_float2(c, sign > 0 ? s : -s));
+}
+template <int LOG_Q, bool DIT>
+WAE_HD void fft_pass8_one(float2* s, int t, int it, const FftTw& w, int sign) {
+    constexpr int q = 1 << LOG_Q;
+    const int bf = t + it * CV_THREADS;
+    const int lo = bf & (q - 1), hi = bf >> LOG_Q;
+    const int base = (hi << (LOG_Q + 3)) + lo;
+    float2 a[8];
+#pragma unroll
+    for (int m = 0; m < 8; m++) a[m] = s[cv_pad(base + m * q)];
+    const float2 t1 = LOG_Q == 10 ? tw_it(w.w1, it, sign) : (LOG_Q == 7 ? w.w2 : w.w3);
+    if (DIT) bf8_dit(a, t1, sign);
+    else bf8_dif(a, t1, sign);
+#pragma unroll
+    for (int m = 0; m < 8; m++) s[cv_pad(base + m * q)] = a[m];
+}
+template <bool DIT>
+WAE_HD void fft_pass16_one(float2* s, int t, int it, int sign) {
+    float2 a[16];
+    float2* p = s + cv_pad((t + it * CV_THREADS) * 16);  // 16 contiguous elements never straddle a pad slot
+#pragma unroll
+    for (int m = 0; m < 16; m++) a[m] = p[m];
+    if (DIT) bf16_dit(a, sign);
+    else bf16_dif(a, sign);
+#pragma unroll
+    for (int m = 0; m < 16; m++) p[m] = a[m];
+}
+#ifndef WAE_CV_UNROLL
+#define WAE_CV_UNROLL 2   // radix-8 butterflies of one thread in flight (4 = all of a pass; registers decide)
+#endif
+template <int LOG_Q, bool DIT>
+DEVI void fft_pass8(float2* s, const FftTw& w, int sign) {
+#pragma unroll 1
+    for (int i0 = 0; i0 < CV_B / 8 / CV_THREADS; i0 += WAE_CV_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < WAE_CV_UNROLL; u++) fft_pass8_one<LOG_Q, DIT>(s, threadIdx.x, i0 + u, w, sign);
     }
 }
-DEVI void fft_smem(float2* s, int sign) {
-    static_assert(CV_LOGB == 13, "pass schedule below is 8 x 8 x 8 x 16");
-    fft_radix8_pass(s, CV_B / 8, CV_LOGB - 3, sign);
+template <bool DIT>
+DEVI void fft_pass16(float2* s, int sign) {
+#pragma unroll 1
+    for (int it = 0; it < CV_B / 16 / CV_THREADS; it++) fft_pass16_one<DIT>(s, threadIdx.x, it, sign);
+}
+DEVI FftTw fft_tw_load(int sign) { return fft_tw_of(c_tw, threadIdx.x, sign); }
+// natural order in -> position order out
+DEVI void fft_dif_smem(float2* s, const FftTw& w) {
+    fft_pass8<10, false>(s, w, -1);
     __syncthreads();
-    fft_radix8_pass(s, CV_B / 64, CV_LOGB - 6, sign);
+    fft_pass8<7, false>(s, w, -1);
     __syncthreads();
-    fft_radix8_pass(s, CV_B / 512, CV_LOGB - 9, sign);
+    fft_pass8<4, false>(s, w, -1);
     __syncthreads();
-    fft_radix16_last(s, sign);
+    fft_pass16<false>(s, -1);
     __syncthreads();
 }
-// FFT result z (bit-reversed, padded) -> the B packed bins of the 2B-point real FFT: X[k] = E[k] + w^k O[k]
-DEVI float2 rfft_bin(const float2* z, int k) {
-    if (k == 0) {
-        const float2 z0 = z[0];
-        return make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
-    }
-    const float2 zk = z[cv_pos(k)], zm = z[cv_pos(CV_B - k)];
+// position order in -> natural order out (unnormalised inverse)
+DEVI void fft_dit_smem(float2* s, const FftTw& w) {
+    fft_pass16<true>(s, +1);
+    __syncthreads();
+    fft_pass8<4, true>(s, w, +1);
+    __syncthreads();
+    fft_pass8<7, true>(s, w, +1);
+    __syncthreads();
+    fft_pass8<10, true>(s, w, +1);
+    __syncthreads();
+}
+// exp(-2*pi*i*k/(2B)) for the bin at position p = lane + 32*row: k = brev13(p) = brev5(lane) << 8 | brev8(row), so the twiddle is the
+// product of a per-lane value (loaded once per thread) and a per-row value that is uniform across the warp (constant cache broadcast)
+DEVI float2 cv_lane_tw() { return c_tw[cv_brev(threadIdx.x & 31)]; }
+DEVI float2 cv_bin_tw(float2 lane_tw, int p) { return cmul(lane_tw, c_rowtw[p >> 5]); }
+// position of the mirror bin B - k of the bin at position p (p > 0)
+WAE_HD int cv_mirror(int p) { return cv_brev(CV_B - cv_brev(p)); }
+// one packed bin of the 2B-point real FFT from the B-point transform of (even, odd): X[k] = E[k] + w^k O[k], zm = Z[B - k], tw = w^k
+WAE_HD float2 rfft_split(float2 zk, float2 zm, float2 tw) {
     const float2 zc = make_float2(zm.x, -zm.y);
     const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
     const float2 d = make_float2(zk.x - zc.x, zk.y - zc.y);
     const float2 o = make_float2(0.5f * d.y, -0.5f * d.x);
-    const float2 tw = cmul(__ldg(&c_tw[k]), o);
-    return make_float2(e.x + tw.x, e.y + tw.y);
+    const float2 r = cmul(tw, o);
+    return make_float2(e.x + r.x, e.y + r.y);
+}
+// and back: the input element of the B-point inverse transform from Y[k], Y[B - k] (twice E + i O; the 1 / 2B scale comes at the end)
+WAE_HD float2 irfft_merge(float2 yk, float2 ym, float2 tw) {
+    const float2 yc = make_float2(ym.x, -ym.y);
+    const float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
+    const float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
+    const float2 o = cmul(make_float2(tw.x, -tw.y), d);
+    return make_float2(e.x - o.y, e.y + o.x);
+}
+// forward transform z (position order, padded) -> the B packed bins of the 2B-point real FFT in position order
+DEVI void rfft_store(const float2* z, float2* __restrict__ X, float2 lane_tw) {
+#pragma unroll 4
+    for (int p = threadIdx.x; p < CV_B; p += CV_THREADS) {
+        float2 r;
+        if (p == 0) {
+            const float2 z0 = z[0];
+            r = make_float2(z0.x + z0.y, z0.x - z0.y);  // (DC, Nyquist)
+        } else {
+            r = rfft_split(z[cv_pad(p)], z[cv_pad(cv_mirror(p))], cv_bin_tw(lane_tw, p));
+        }
+        X[p] = r;
+    }
+}
+// B reals (valid <= B of them readable at src, the rest zero; src == nullptr: all zero) -> B/2 packed complex (even, odd) at z[c0 ..)
+DEVI void conv_load_half(float2* z, int c0, const float* __restrict__ src, int valid) {
+    const int t = threadIdx.x;
+    if (!src || valid <= 0) {
+        for (int i = t; i < CV_B / 2; i += CV_THREADS) z[cv_pad(c0 + i)] = make_float2(0.f, 0.f);
+    } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll 8
+        for (int i4 = t; i4 < CV_B / 4; i4 += CV_THREADS) {
+            const int n = 4 * i4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n + 3 < valid) v = *reinterpret_cast<const float4*>(src + n);
+            else if (n < valid) {
+                v.x = src[n];
+                if (n + 1 < valid) v.y = src[n + 1];
+                if (n + 2 < valid) v.z = src[n + 2];
+            }
+            float2* d = z + cv_pad(c0 + 2 * i4);  // complex 2*i4 and 2*i4 + 1 share a 16-group (c0 is a multiple of 16)
+            d[0] = make_float2(v.x, v.y);
+            d[1] = make_float2(v.z, v.w);
+        }
+    } else {
+        for (int i = t; i < CV_B / 2; i += CV_THREADS) {
+            const int n = 2 * i;
+            z[cv_pad(c0 + i)] = make_float2(n < valid ? src[n] : 0.f, n + 1 < valid ? src[n + 1] : 0.f);
+        }
+    }
 }
 
 // grid: (blocks in chunk, conv inputs).  Builds X_j for every new block of the chunk.
 __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_fft_in(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
     extern __shared__ float2 z[];
+    const FftTw w = fft_tw_load(-1);  // table latency hides behind the input loads
+    const float2 lane_tw = cv_lane_tw();
     const ConvInput ip = inputs[blockIdx.y];
     const int jb = blockIdx.x;                         // block within the chunk
     const int64_t jabs = ci.f0 / CV_B + jb;            // absolute block index
     const float* in = chan(ip.in, ip.in_channel, ci);
-    const int t = threadIdx.x;
-    // frame = [previous block | current block] (2B reals) packed as B complex (even, odd)
-    for (int i = t; i < CV_B; i += CV_THREADS) {
-        float a, b;
-        const int n = 2 * i;
-        if (n < CV_B) {
-            if (jb == 0) {
-                a = ip.prev[n];
-                b = ip.prev[n + 1];
-            } else {
-                a = in[(size_t)(jb - 1) * CV_B + n];
-                b = in[(size_t)(jb - 1) * CV_B + n + 1];
-            }
-        } else {
-            const int64_t m = (int64_t)jb * CV_B + (n - CV_B);
-            a = m < ci.nf ? in[m] : 0.f;
-            b = m + 1 < ci.nf ? in[m + 1] : 0.f;
-        }
-        z[cv_pad(i)] = make_float2(a, b);
-    }
+    // frame = [previous block | current block]
+    const int64_t left = (int64_t)ci.nf - (int64_t)jb * CV_B;
+    conv_load_half(z, 0, jb == 0 ? ip.prev : in + (size_t)(jb - 1) * CV_B, CV_B);
+    conv_load_half(z, CV_B / 2, in + (size_t)jb * CV_B, (int)(left < CV_B ? left : CV_B));
     __syncthreads();
-    fft_smem(z, -1);
-    float2* X = ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS;
-    for (int k = t; k < CV_B; k += CV_THREADS) X[k] = rfft_bin(z, k);
+    fft_dif_smem(z, w);
+    rfft_store(z, ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS, lane_tw);
 }
 
 // saves the last block of the chunk as "previous block" for the next chunk.  grid: (B / 256, conv inputs)
@@ -3011,47 +3156,52 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 // blocks j at once: Y_j = sum_i H_i X_{j-i}.  Register tiling over the block axis: the input blocks are walked in
 // groups of CV_J; a group needs 2*CV_J-1 IR spectrum values and CV_J input spectrum values per bin for CV_J^2 complex
 // MACs (0.36 loads per MAC instead of 2).  No shared memory => many resident warps hide the L2 latency of the loads.
+// The first group only has the lower triangle (i = jj - r >= 0): its upper half is skipped at compile time.
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
 // PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
+template <bool PACKED, bool FIRST>
+DEVI void conv_mac_group(const ConvPath& p, const ConvInput& ip, int k, int i_base, int64_t b0, int slot0, int ring, int64_t jabs_last,
+                         float2 acc[CV_J]) {
+    float2 hw[2 * CV_J - 1];
+#pragma unroll
+    for (int u = FIRST ? CV_J - 1 : 0; u < 2 * CV_J - 1; u++) {
+        const int i = i_base - (CV_J - 1) + u;
+        hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < CV_J; r++) {
+        const int64_t b = b0 + r;
+        float2 x = make_float2(0.f, 0.f);
+        int slot = slot0 + r;
+        slot = slot >= ring ? slot - ring : slot;
+        if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
+        if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)slot * CV_BINS + k];
+#pragma unroll
+        for (int jj = FIRST ? r : 0; jj < CV_J; jj++) {
+            const float2 h = hw[(CV_J - 1) + jj - r];
+            if (PACKED) {
+                acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
+                acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
+            } else {
+                acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
+                acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
+            }
+        }
+    }
+}
 template <bool PACKED>
 DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t jabs0, int64_t jabs_last, float2 acc[CV_J]) {
     const int groups = (p.S - 1 + CV_J - 1) / CV_J + 1;  // i runs up to S-1: i_base - (J-1) <= S-1
     const int ring = ip.xring_blocks;
     // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
     int slot0 = (int)(jabs0 % ring);
+    conv_mac_group<PACKED, true>(p, ip, k, 0, jabs0, slot0, ring, jabs_last, acc);
 #pragma unroll 1
-    for (int g = 0; g < groups; g++) {
-        const int i_base = g * CV_J;
-        const int64_t b0 = jabs0 - i_base;
-        float2 hw[2 * CV_J - 1];
-#pragma unroll
-        for (int u = 0; u < 2 * CV_J - 1; u++) {
-            const int i = i_base - (CV_J - 1) + u;
-            hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
-        }
-#pragma unroll
-        for (int r = 0; r < CV_J; r++) {
-            const int64_t b = b0 + r;
-            float2 x = make_float2(0.f, 0.f);
-            int slot = slot0 + r;
-            slot = slot >= ring ? slot - ring : slot;
-            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
-            if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)slot * CV_BINS + k];
-#pragma unroll
-            for (int jj = 0; jj < CV_J; jj++) {
-                const float2 h = hw[(CV_J - 1) + jj - r];
-                if (PACKED) {
-                    acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
-                    acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
-                } else {
-                    acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
-                    acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
-                }
-            }
-        }
+    for (int g = 1; g < groups; g++) {
         slot0 -= CV_J;
         while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
+        conv_mac_group<PACKED, false>(p, ip, k, g * CV_J, jabs0 - g * CV_J, slot0, ring, jabs_last, acc);
     }
 }
 __global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
@@ -3060,7 +3210,7 @@ __global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* 
     const ConvInput ip = inputs[p.input];
     const int nb = (ci.nf + CV_B - 1) / CV_B;
     constexpr int TILES = CV_B / CV_MAC_THREADS;
-    const int k = (blockIdx.x % TILES) * CV_MAC_THREADS + threadIdx.x;  // bin
+    const int k = (blockIdx.x % TILES) * CV_MAC_THREADS + threadIdx.x;  // bin (position order: index 0 is still the packed DC / Nyquist pair)
     const int j0 = (blockIdx.x / TILES) * CV_J;                         // first output block of this CTA (chunk-relative)
     const int64_t jabs0 = ci.f0 / CV_B + j0;
     const int64_t jabs_last = ci.f0 / CV_B + nb - 1;                    // newest input block transformed so far
@@ -3077,64 +3227,147 @@ __global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* 
 // grid: (blocks in chunk, paths): out_j = IFFT(Y_j)[B..2B) / 2B
 __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __restrict__ paths, int n_paths, ChunkInfo ci) {
     extern __shared__ float2 z[];
+    const FftTw w = fft_tw_load(+1);
+    const float2 lane_tw = cv_lane_tw();
     const ConvPath p = paths[blockIdx.y];
     const int jb = blockIdx.x;
-    const float2* Y = p.y + (size_t)jb * CV_BINS;
+    const float2* __restrict__ Y = p.y + (size_t)jb * CV_BINS;
     const int t = threadIdx.x;
-    // half spectrum -> packed complex input of the B-point inverse transform
-    for (int k = t; k < CV_B; k += CV_THREADS) {
-        const float2 y0 = Y[0];
-        const float2 yk = k == 0 ? make_float2(y0.x, 0.f) : Y[k];
-        const float2 ym = k == 0 ? make_float2(y0.y, 0.f) : Y[CV_B - k];
-        const float2 yc = make_float2(ym.x, -ym.y);
-        const float2 e = make_float2(yk.x + yc.x, yk.y + yc.y);
-        const float2 d = make_float2(yk.x - yc.x, yk.y - yc.y);
-        float2 w = __ldg(&c_tw[k]);
-        w.y = -w.y;
-        const float2 o = cmul(w, d);
-        z[cv_pad(k)] = make_float2(e.x - o.y, e.y + o.x);
+    // half spectrum (position order) -> packed complex input of the B-point inverse transform, same positions
+#pragma unroll 4
+    for (int q = t; q < CV_B; q += CV_THREADS) {
+        float2 yk, ym;
+        if (q == 0) {
+            const float2 y0 = Y[0];
+            yk = make_float2(y0.x, 0.f);
+            ym = make_float2(y0.y, 0.f);
+        } else {
+            yk = Y[q];
+            ym = Y[cv_mirror(q)];
+        }
+        z[cv_pad(q)] = irfft_merge(yk, ym, cv_bin_tw(lane_tw, q));
     }
     __syncthreads();
-    fft_smem(z, +1);
+    fft_dit_smem(z, w);
     const float scale = 1.f / (float)(2 * CV_B);
     float* out = chan(p.out, p.out_channel, ci) + (size_t)jb * CV_B;
-    for (int i = t; i < CV_B / 2; i += CV_THREADS) {  // second half of the 2B frame: complex i in [B/2, B)
-        const int n = 2 * i;
-        if ((int64_t)jb * CV_B + n < ci.nf) {
-            const float2 c = z[cv_pos(CV_B / 2 + i)];
-            float2 v = make_float2(c.x * scale, c.y * scale);
-            float2* dst = reinterpret_cast<float2*>(out + n);
-            if (p.accumulate) {
-                const float2 o = *dst;
-                v.x += o.x;
-                v.y += o.y;
+    const int64_t left = (int64_t)ci.nf - (int64_t)jb * CV_B;
+    const int valid = (int)(left < CV_B ? left : CV_B);
+    // second half of the 2B frame: complex B/2 + i holds frames 2i, 2i+1 of the block (natural order after the DIT transform)
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+#pragma unroll 4
+        for (int i4 = t; i4 < CV_B / 4; i4 += CV_THREADS) {
+            const int n = 4 * i4;
+            const float2* c = z + cv_pad(CV_B / 2 + 2 * i4);
+            float4 v = make_float4(c[0].x * scale, c[0].y * scale, c[1].x * scale, c[1].y * scale);
+            if (n + 3 < valid) {
+                float4* dst = reinterpret_cast<float4*>(out + n);
+                if (p.accumulate) {
+                    const float4 o = *dst;
+                    v.x += o.x, v.y += o.y, v.z += o.z, v.w += o.w;
+                }
+                *dst = v;
+            } else {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (n + u < valid) out[n + u] = p.accumulate ? out[n + u] + vv[u] : vv[u];
             }
-            *dst = v;
+        }
+    } else {
+        for (int i = t; i < CV_B / 2; i += CV_THREADS) {
+            const int n = 2 * i;
+            const float2 c = z[cv_pad(CV_B / 2 + i)];
+            if (n < valid) out[n] = p.accumulate ? out[n] + c.x * scale : c.x * scale;
+            if (n + 1 < valid) out[n + 1] = p.accumulate ? out[n + 1] + c.y * scale : c.y * scale;
         }
     }
 }
 
-// IR segment spectra H_i (host uploads the scaled IR; one CTA per segment).  grid: (S, ir channels)
+// IR segment spectra H_i (host uploads the scaled IR; one CTA per segment), position order like X.  grid: (S, ir channels)
 __global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restrict__ ir, int64_t ir_len, int64_t ir_stride, float2* __restrict__ h,
                                                             int S) {
     extern __shared__ float2 z[];
+    const FftTw w = fft_tw_load(-1);
+    const float2 lane_tw = cv_lane_tw();
     const int seg = blockIdx.x, c = blockIdx.y;
-    const float* src = ir + (size_t)c * ir_stride;
-    const int t = threadIdx.x;
-    for (int i = t; i < CV_B; i += CV_THREADS) {
-        const int n = 2 * i;
-        float a = 0.f, b = 0.f;
-        if (n < CV_B) {  // segment in the first half, zeros in the second
-            const int64_t m = (int64_t)seg * CV_B + n;
-            a = m < ir_len ? src[m] : 0.f;
-            b = m + 1 < ir_len ? src[m + 1] : 0.f;
-        }
-        z[cv_pad(i)] = make_float2(a, b);
-    }
+    const float* src = ir + (size_t)c * ir_stride + (size_t)seg * CV_B;
+    const int64_t left = ir_len - (int64_t)seg * CV_B;
+    conv_load_half(z, 0, src, (int)(left < CV_B ? left : CV_B));  // segment in the first half, zeros in the second
+    conv_load_half(z, CV_B / 2, nullptr, 0);
     __syncthreads();
-    fft_smem(z, -1);
-    float2* H = h + ((size_t)c * S + seg) * CV_BINS;
-    for (int k = t; k < CV_B; k += CV_THREADS) H[k] = rfft_bin(z, k);
+    fft_dif_smem(z, w);
+    rfft_store(z, h + ((size_t)c * S + seg) * CV_BINS, lane_tw);
+}
+
+// Host emulation of the transforms above with the SAME butterfly, index and twiddle code (tests/test_conv_fft_host.py pins them against
+// numpy on a machine without a GPU).  mode 0: complex forward, natural -> position order; 1: complex inverse, position -> natural order
+// (unnormalised); 2: 2B reals -> B packed bins in position order; 3: B packed bins -> 2B reals (scaled by 1 / 2B).  data: 2B floats in place.
+static void host_twiddles() {
+    if (h_tw[0].x == 1.f) return;
+    for (int k = 0; k < CV_B; k++) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)k / (2.0 * CV_B);
+        h_tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+}
+static int brev8(int r) {
+    int o = 0;
+    for (int b = 0; b < 8; b++) o |= ((r >> b) & 1) << (7 - b);
+    return o;
+}
+template <int LOG_Q, bool DIT>
+static void host_pass8(float2* s, int sign) {
+    for (int t = 0; t < CV_THREADS; t++) {
+        const FftTw w = fft_tw_of(h_tw, t, sign);
+        for (int it = 0; it < CV_B / 8 / CV_THREADS; it++) fft_pass8_one<LOG_Q, DIT>(s, t, it, w, sign);
+    }
+}
+template <bool DIT>
+static void host_pass16(float2* s, int sign) {
+    for (int t = 0; t < CV_THREADS; t++)
+        for (int it = 0; it < CV_B / 16 / CV_THREADS; it++) fft_pass16_one<DIT>(s, t, it, sign);
+}
+static void host_fft(float2* s, bool inverse) {
+    if (!inverse) {
+        host_pass8<10, false>(s, -1), host_pass8<7, false>(s, -1), host_pass8<4, false>(s, -1), host_pass16<false>(s, -1);
+    } else {
+        host_pass16<true>(s, +1), host_pass8<4, true>(s, +1), host_pass8<7, true>(s, +1), host_pass8<10, true>(s, +1);
+    }
+}
+void conv_fft_selftest(float* data, int mode) {
+    host_twiddles();
+    std::vector<float2> s(CV_SMEM_ELEMS), x(CV_B);
+    float2* io = reinterpret_cast<float2*>(data);
+    auto bin_tw = [](int p) { return cmul(h_tw[cv_brev(p & 31)], h_tw[brev8(p >> 5)]); };
+    if (mode == 0 || mode == 1) {
+        for (int i = 0; i < CV_B; i++) s[cv_pad(i)] = io[i];
+        host_fft(s.data(), mode == 1);
+        for (int i = 0; i < CV_B; i++) io[i] = s[cv_pad(i)];
+    } else if (mode == 2) {
+        for (int i = 0; i < CV_B; i++) s[cv_pad(i)] = io[i];  // (even, odd) packing is the memory layout of 2B reals
+        host_fft(s.data(), false);
+        for (int p = 0; p < CV_B; p++) {
+            if (p == 0) io[0] = make_float2(s[0].x + s[0].y, s[0].x - s[0].y);
+            else x[p] = rfft_split(s[cv_pad(p)], s[cv_pad(cv_mirror(p))], bin_tw(p));
+        }
+        for (int p = 1; p < CV_B; p++) io[p] = x[p];
+    } else {
+        for (int p = 0; p < CV_B; p++) {
+            const float2 yk = p == 0 ? make_float2(io[0].x, 0.f) : io[p];
+            const float2 ym = p == 0 ? make_float2(io[0].y, 0.f) : io[cv_mirror(p)];
+            s[cv_pad(p)] = irfft_merge(yk, ym, bin_tw(p));
+        }
+        host_fft(s.data(), true);
+        const float scale = 1.f / (float)(2 * CV_B);
+        for (int i = 0; i < CV_B; i++) io[i] = make_float2(s[cv_pad(i)].x * scale, s[cv_pad(i)].y * scale);
+    }
+}
+void upload_twiddles() {
+    host_twiddles();
+    float2 row[CV_ROWS];
+    for (int r = 0; r < CV_ROWS; r++) row[r] = h_tw[brev8(r)];
+    cudaMemcpyToSymbol(c_tw, h_tw, sizeof(float2) * CV_B);
+    cudaMemcpyToSymbol(c_rowtw, row, sizeof(row));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -3220,7 +3453,6 @@ static inline dim3 grid_tiles(int nf, int per_block, int n_inst) {
     return dim3((unsigned)((nf + per_block - 1) / per_block), (unsigned)(n_inst < 32768 ? n_inst : 32768));
 }
 
-void upload_twiddles(const float2* host_tw) { cudaMemcpyToSymbol(c_tw, host_tw, sizeof(float2) * CV_B); }
 
 void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_oscillator<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_constant<<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, n, ci); }

@@ -17,7 +17,8 @@ struct ScanCoef {
     double Pwarp[4];       // A^32: one warp
 };
 
-void upload_twiddles(const float2* host_tw);
+void upload_twiddles();                          // convolver FFT tables (computed in wae_kernels.cu, f64 -> f32)
+void conv_fft_selftest(float* data, int mode);   // host emulation of the convolver transforms (wae_selftest_conv_fft)
 void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s);
