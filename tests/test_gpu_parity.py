@@ -179,6 +179,27 @@ def test_second_order_iir_rides_the_biquad_scan(pkg, engine, oracle):
     assert maxdiff(gpu, cpu) <= TOL
 
 
+def test_second_order_iir_keeps_its_memory_across_a_suspend_point(pkg, engine, oracle):
+    """A render cut by suspend_sync is planned segment by segment; a source that covers the first segment entirely but ends in the second
+    gives the filter a constant layout in one plan and a changing one in the other.  The filter memory has to survive the cut, so such
+    graphs keep the serial IIR kernel in every segment (regression: fuzz seeds 31 / 33 lost the state at the suspend frame)."""
+    def build(be, g):
+        n = 128 * 40
+        pcm = G.c2_source(g, 128 * 30)                       # ends at quantum 30 of 40
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        f = c.create_iir_filter([0.2, 0.3, 0.1], [1.0, -0.4, 0.2])
+        s.connect(f)
+        f.connect(c.destination())
+        s.start()
+        if g != 1:
+            c.suspend_sync(128 * 18 / G.SR, lambda ctx: None)  # graph 1: no cut, same batch
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert maxdiff(gpu, cpu) <= TOL
+
+
 def test_gain_shaper_panner_chain(pkg, engine, oracle):
     curve = np.tanh(np.linspace(-3, 3, 1024)).astype(np.float32)
 
@@ -524,6 +545,32 @@ def test_c4_convolver_long_ir(pkg, engine, oracle, chunk):
         ir = G.synthetic_ir(20000, 2)  # 20 partitions of 1024
         gpu, cpu = both(pkg, engine, oracle, lambda be, g: G.c4_convolver(pkg, be, g, 128 * 250 + 77, ir), 3)
         assert maxdiff(gpu, cpu) <= TOL
+    finally:
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+
+
+@pytest.mark.parametrize("chunk", [8192, 0])
+def test_convolver_reads_the_source_buffer_in_place_and_writes_the_destination(pkg, engine, oracle, chunk):
+    """source -> Convolver -> destination with a buffer that covers the whole (quantum-padded) render: no copy into the arena on the way
+    in, no mix on the way out — the inverse transforms stop at the render length (odd, so the last float4 is cut)."""
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        n = 8192 * 2 + 3001
+        ir = G.synthetic_ir(9000, 2)
+
+        def build(be, g):
+            rng = np.random.default_rng(900 + g)
+            pcm = rng.uniform(-0.3, 0.3, (2, n + 500)).astype(np.float32)   # longer than the padded render
+            c = pkg.OfflineAudioContext(2, n, G.SR, be)
+            src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+            cv = c.create_convolver(pkg.AudioBuffer(ir if g % 2 == 0 else [ir[0]], G.SR))  # stereo / mono response (two paths each)
+            src.connect(cv)
+            cv.connect(c.destination())
+            src.start()
+            return c
+
+        gpu, cpu = both(pkg, engine, oracle, build, 4)
+        assert gpu.shape == (4, 2, n) and maxdiff(gpu, cpu) <= TOL
     finally:
         engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
 

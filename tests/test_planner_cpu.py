@@ -45,7 +45,29 @@ def test_c1_c3_voices_fuse_and_meet_in_one_mix(pkg, be):
 def test_c4_north_star_c5_stage_lists(pkg, be):
     ir = G.synthetic_ir(20000, 2, decay=0.6)
     p = plan(pkg, [G.c4_convolver(pkg, be, g, 8192 * 3, ir) for g in range(4)])
-    assert set(p["kinds"]) == {"k_chain", "k_conv_fft_in", "k_conv_mac_ifft", "k_mix"} and p["chunk_frames"] % 8192 == 0
+    # the source buffer covers the render 1:1 and the convolver is the destination's only input: the forward transforms read the asset,
+    # the inverse transforms write the rendered PCM — no copy stage on either side
+    assert set(p["kinds"]) == {"k_conv_fft_in", "k_conv_mac_ifft"} and p["chunk_frames"] % 8192 == 0 and p["arena_floats_per_frame"] == 0
+    # a second input at the destination needs the mix again ...
+    def two_inputs(g):
+        c = G.c4_convolver(pkg, be, g, 8192 * 3, ir)
+        o = c.create_constant_source()
+        o.connect(c.destination())
+        o.start()
+        return c
+    k = plan(pkg, [two_inputs(g) for g in range(2)])["kinds"]
+    assert "k_mix" in k and k.get("k_chain") == 1   # (that chain is the constant source; the buffer source is still read in place)
+    # ... and a source that does not cover the render 1:1 (here: looping) is copied by the chain kernel as before
+    def looping(g):
+        c = pkg.OfflineAudioContext(2, 8192 * 3, 48000.0, be)
+        src = c.create_buffer_source(pkg.AudioBuffer([np.ones(5000, np.float32)] * 2, 48000.0), loop=True)
+        cv = c.create_convolver(pkg.AudioBuffer(ir, 48000.0))
+        src.connect(cv)
+        cv.connect(c.destination())
+        src.start()
+        return c
+    k = plan(pkg, [looping(g) for g in range(2)])["kinds"]
+    assert "k_chain" in k and "k_mix" not in k
     p = plan(pkg, [G.north_star_voices_convolver(pkg, be, 50, 8192 * 3, ir, seed=g) for g in range(2)])
     assert p["kinds"]["k_chain"] == 1 and "k_conv_mac_ifft" in p["kinds"]
     with pytest.raises(pkg.WaeError) as e:  # an HRTF panner needs the sphere the engine is given (wae_engine_set_hrir_sphere)

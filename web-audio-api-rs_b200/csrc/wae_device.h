@@ -462,6 +462,7 @@ struct ConvPath {    // one FFTConvolver of the reference: (input channel, IR ch
     int32_t S;        // IR segments
     int32_t out_channel;
     int32_t accumulate;  // 1: out += (true-stereo mix-down, convolver.rs:436-452)
+    int64_t limit;       // >= 0: `out` is the rendered PCM itself (the convolver is the destination's only input): frames from `limit` on do not exist
 };
 
 }  // namespace wae

@@ -524,6 +524,7 @@ struct PNode {
     std::vector<int> out_ch;
     std::vector<BufRef> out_buf;
     std::vector<Lay> out_lay;  // empty: constant (out_ch channels, never silent)
+    bool wrote_dest = false;   // out_buf[0] IS the graph's rendered PCM (a convolver that is the destination's only input)
     Lay lay_out(int port) const { return port < (int)out_lay.size() ? out_lay[port] : Lay::fixed(out_ch[port]); }
 };
 
@@ -723,7 +724,7 @@ struct Planner {
     };
     PRef param_ref(wae_graph* g, uint32_t pid);
     bool plan_graph(wae_graph* g, uint32_t gi);
-    bool plan_convolver(wae_graph* g, PNode& pn, int level);
+    bool plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest = nullptr, int64_t dest_limit = -1);
 };
 
 static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
@@ -782,7 +783,7 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
     return sc;
 }
 
-bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
+bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest, int64_t dest_limit) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
     if (n.buffer && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
@@ -839,7 +840,10 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
                                      "(the reference stops feeding its second convolver whenever the input is mono or silent, convolver.rs:378-400)");
     // silent once the input has been silent for the length of the response (convolver.rs:357-366); channels from the routing table (:378-487)
     const bool conv_dyn = in_lay.dyn();
-    pn.out_buf = {arena_buf(pn.out_ch[0], conv_dyn && Smax > 0)};
+    // the destination's only input, same channel count, constant layout: the inverse transforms write the rendered PCM themselves
+    const bool direct = dest && !conv_dyn && Smax > 0 && pn.out_ch[0] == (int)b->channels;
+    pn.out_buf = {direct ? *dest : arena_buf(pn.out_ch[0], conv_dyn && Smax > 0)};
+    pn.wrote_dest = direct;
     if (conv_dyn && Smax > 0) {
         const int oc = pn.out_ch[0];
         pn.out_lay = {Lay{(uint8_t)(in_lay.may_silent ? 1 : oc), (uint8_t)oc, (uint8_t)oc, (uint8_t)oc, in_lay.may_silent}};
@@ -920,6 +924,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level) {
         p.S = Smax;
         p.out_channel = r.out;
         p.accumulate = r.acc;
+        p.limit = direct ? dest_limit : -1;
         p.y = alloc<float2>((size_t)blocks_per_chunk * WAE_CONV_SPEC);
         if (!p.y) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver output spectra)");
         b->arena_bytes += (size_t)blocks_per_chunk * WAE_CONV_SPEC * 8;
@@ -1025,10 +1030,26 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         cs.max_ch = std::max(cs.max_ch, pc.ch);
         cs.chain.push_back(pc.inst);
     };
-    auto materialize = [&](uint32_t nid) -> bool {
+    // may_alias: the consumer reads its input through chan() with any alignment (the convolver's forward transform): a pending chain that
+    // is nothing but an AudioBufferSourceNode playing its buffer 1:1 from frame 0, the buffer covering the whole (quantum-padded) render,
+    // IS that buffer — no copy into the arena
+    auto materialize = [&](uint32_t nid, bool may_alias = false) -> bool {
         auto it = pending.find(nid);
         if (it == pending.end()) return true;
         PNode& sp = pn.at(nid);
+        {
+            const ChainInst& ci = it->second.inst;
+            const AbsnInst& a = ci.absn;
+            bool unit = true;
+            for (int i = 0; i < 4; i++) unit = unit && ci.g[i] == 1.f;
+            if (may_alias && ci.src_kind == CHAIN_SRC_ABSN && ci.n_biquad == 0 && !ci.has_shaper && unit && it->second.phase == 0 &&
+                !it->second.lay.dyn() && a.n_start == 0 && !a.loop && a.buf_offset == 0 && a.buf_len >= b->lq && a.buf_stride <= 0xffffffffll &&
+                seg_start == 0 && seg_end >= b->lq) {
+                sp.out_buf = {BufRef{const_cast<float*>(a.buf), (uint32_t)a.buf_stride, 1}};
+                pending.erase(it);
+                return true;
+            }
+        }
         BufRef buf = arena_buf(it->second.ch, it->second.lay.dyn());  // (k_chain writes the layout track itself)
         if (!buf.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
         it->second.inst.out = buf;
@@ -1159,7 +1180,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         for (auto& port : p.in_edges)
             for (auto& r : port)
                 if (!((extend || dest_direct) && r.node == fuse_src))
-                    if (!materialize(r.node)) return false;
+                    if (!materialize(r.node, n.kind == K_CONV && n.buffer && port.size() == 1)) return false;
         p.in_ch.assign(n.n_inputs, 1);
         p.in_buf.assign(n.n_inputs, BufRef{nullptr, 0, 0});
         p.in_lay.assign(n.n_inputs, Lay::fixed(1));
@@ -1176,6 +1197,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             bool is_dest = n.kind == K_DEST;
             if (extend || dest_direct) {  // the producer's chain is consumed in registers / written directly
                 if (extend) p.in_lay[port] = pending.at(fuse_src).lay;
+                continue;
+            }
+            if (is_dest && edges.size() == 1 && pn.at(edges[0].node).wrote_dest) {  // the producer already wrote the rendered PCM
+                p.in_buf[port] = pn.at(edges[0].node).out_buf[edges[0].port];
                 continue;
             }
             // ---- the port's layout over time: AudioRenderQuantum::add folded over the edges (quantum.rs:532-569)
@@ -1790,11 +1815,13 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 std::vector<double> ff = n.feedforward, fb = n.feedback;  // iir_filter.rs:282-309
                 if (ff.size() < fb.size()) ff.resize(fb.size(), 0.);
                 if (ff.size() > fb.size()) fb.resize(ff.size(), 0.);
-                if (ff.size() <= 3 && !eng->serial_filters && !in0.dyn() && !getenv("WAE_DEBUG_NO_IIR_CHAIN")) {
+                if (ff.size() <= 3 && !eng->serial_filters && !in0.dyn() && seg_start == 0 && seg_end >= b->lq) {
                     // Order <= 2 with a constant input layout: the same transfer function as a biquad — rendered by the time-parallel scan
                     // of k_chain (direct form I there, transposed direct form II in iir_filter.rs:386-407: the outputs differ in the last
                     // bits of the f64 arithmetic only) instead of one serial thread per channel.  With an input that can fall silent the
-                    // serial kernel stays: its tail test looks at the reference's own state variables.
+                    // serial kernel stays: its tail test looks at the reference's own state variables.  Same for a render cut by suspend
+                    // points: the two forms keep different state (x / y history here, the reference's 20 accumulators there) and a later
+                    // segment may see a layout that needs the serial kernel — the filter memory must survive the cut (fuzz seeds 31, 33).
                     ff.resize(3, 0.);
                     fb.resize(3, 0.);
                     const double a0 = fb[0];
@@ -2258,7 +2285,20 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 break;
             }
             case K_CONV: {
-                if (!plan_convolver(g, p, L)) return false;
+                // the destination's only input (and this node's only consumer): the inverse transforms write the rendered PCM
+                const BufRef* dest = nullptr;
+                BufRef fin{b->d_out + (size_t)gi * b->channels * b->length, (uint32_t)b->length, 1};
+                if (fuse && cur_cls == 0 && b->length <= 0xffffffffull) {
+                    int n_out = 0;
+                    uint32_t to = 0;
+                    int to_port = -1;
+                    for (auto& e : ord.edges.at(id))
+                        if (e.other_index >= 0) n_out++, to = e.other_id, to_port = e.other_index;
+                    if (n_out == 1 && to_port == 0 && g->nodes.at(to).kind == K_DEST && pn.at(to).in_edges[0].size() == 1 &&
+                        computed_channels(g->nodes.at(to).cfg, (n.buffer && n.buffer->channels.size() == 1 && p.in_ch[0] == 1) ? 1 : 2) == (int)b->channels)
+                        dest = &fin;
+                }
+                if (!plan_convolver(g, p, L, dest, (int64_t)b->length)) return false;
                 break;
             }
             default: return bail(WAE_UNSUPPORTED, "node kind not lowered to the GPU");
@@ -2789,7 +2829,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                             const MixEdge& ed = s.mix_edges[m.edge_offset + e];
                             if (ed.src_ch > 2 || ed.src.absolute || (ed.src.stride & 3) != 0 || (reinterpret_cast<uintptr_t>(ed.src.p) & 15) != 0) ok = false;
                         }
-                        m.stereo4 = (ok && !getenv("WAE_DEBUG_NO_STEREO4")) ? 1 : 0;
+                        m.stereo4 = ok ? 1 : 0;
                     }
                     st.n = (int)s.mix_dyn.size(); st.d_a = up(b, s.mix_dyn); st.d_b = up(b, s.mix_edges);
                     break;

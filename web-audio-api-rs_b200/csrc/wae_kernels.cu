@@ -2742,11 +2742,11 @@ __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param(const ParamInst* __r
     if (lane == 0) *p.state = st;
 }
 
-// OPT-IN variant (WAE_OPT_PARAM_PARALLEL, off by default): lane 0 only WALKS the events of the quantum (wae_param_walk.h, recording sink:
-// constants are written, ramps / set-target / curves are recorded as fills), then the 32 lanes evaluate the recorded fills, 4 consecutive
-// frames each, re-accumulating `time += dt` from the fill's first frame so that the frame times are the reference's running sum.
-// NOT YET RUN ON A GPU (written after the round's GPU time was spent; the walker and the sink are tested on the host, the default stays
-// k_param): profiles/README.md r1_v explains what it is for, NEXT.md item 1 what is left (validate, then make it the default).
+// The default AudioParam kernel (WAE_OPT_PARAM_PARALLEL = 1; 0 selects k_param above): lane 0 only WALKS the events of the quantum
+// (wae_param_walk.h, recording sink: constants are written, ramps / set-target / curves are recorded as fills), then the 32 lanes evaluate
+// the recorded fills, 4 consecutive frames each, re-accumulating `time += dt` from the fill's first frame so that the frame times are the
+// reference's running sum.  Bit-equal to k_param on hardware (tests/test_gpu_criterion_and_setters.py renders every automation scenario
+// with both and compares the PCM exactly); the walker and the sink are also tested on the host against the reference's event semantics.
 __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param_parallel(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
     __shared__ float s_buf[PARAM_WARPS][128];
     __shared__ ParamFill s_fill[PARAM_WARPS][RecordSink::kMax];
@@ -3156,36 +3156,53 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 // blocks j at once: Y_j = sum_i H_i X_{j-i}.  Register tiling over the block axis: the input blocks are walked in
 // groups of CV_J; a group needs 2*CV_J-1 IR spectrum values and CV_J input spectrum values per bin for CV_J^2 complex
 // MACs (0.36 loads per MAC instead of 2).  No shared memory => many resident warps hide the L2 latency of the loads.
-// The first group only has the lower triangle (i = jj - r >= 0): its upper half is skipped at compile time.
+// The products of a group are taken DIAGONAL by diagonal (d = jj - r selects one H_i, i = i_base + d): a diagonal outside 0 <= i < S is
+// skipped by a warp-uniform branch, so the triangles at the head (i < 0) and at the tail (i >= S) of the walk cost nothing — S = 22
+// used to pay 228 complex MACs per bin for 176.  The group's loads sit at compile-time offsets of two pointers (one ring / range test
+// per group instead of three integer instructions per load: the kernel was bound by issue slots, ALU pipe above the FMA pipe).
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
 // PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
-template <bool PACKED, bool FIRST>
-DEVI void conv_mac_group(const ConvPath& p, const ConvInput& ip, int k, int i_base, int64_t b0, int slot0, int ring, int64_t jabs_last,
-                         float2 acc[CV_J]) {
+template <bool PACKED>
+DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2* __restrict__ xr /* ring[0][k] */, int slot0,
+                         int ring, int64_t b0, int64_t jabs_last, float2 acc[CV_J]) {
+    float2 x[CV_J];
+    if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
+        const float2* xp = xr + (size_t)slot0 * CV_BINS;
+#pragma unroll
+        for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);  // (written by the previous launch: read-only here)
+    } else {
+#pragma unroll
+        for (int r = 0; r < CV_J; r++) {
+            const int64_t bb = b0 + r;
+            int slot = slot0 + r;
+            slot = slot >= ring ? slot - ring : slot;
+            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
+            x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
+        }
+    }
     float2 hw[2 * CV_J - 1];
 #pragma unroll
-    for (int u = FIRST ? CV_J - 1 : 0; u < 2 * CV_J - 1; u++) {
-        const int i = i_base - (CV_J - 1) + u;
-        hw[u] = (i >= 0 && i < p.S) ? __ldg(p.h + (size_t)i * CV_BINS + k) : make_float2(0.f, 0.f);
+    for (int u = 0; u < 2 * CV_J - 1; u++) {
+        const int i = i_lo + u;
+        hw[u] = (i >= 0 && i < S) ? __ldg(hp + (size_t)u * CV_BINS) : make_float2(0.f, 0.f);
     }
 #pragma unroll
-    for (int r = 0; r < CV_J; r++) {
-        const int64_t b = b0 + r;
-        float2 x = make_float2(0.f, 0.f);
-        int slot = slot0 + r;
-        slot = slot >= ring ? slot - ring : slot;
-        if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
-        if (b >= 0 && b <= jabs_last) x = ip.xring[(size_t)slot * CV_BINS + k];
+    for (int u = 0; u < 2 * CV_J - 1; u++) {
+        const int i = i_lo + u;
+        if (i >= 0 && i < S) {  // (uniform)
+            const float2 h = hw[u];
 #pragma unroll
-        for (int jj = FIRST ? r : 0; jj < CV_J; jj++) {
-            const float2 h = hw[(CV_J - 1) + jj - r];
-            if (PACKED) {
-                acc[jj].x = fmaf(h.x, x.x, acc[jj].x);
-                acc[jj].y = fmaf(h.y, x.y, acc[jj].y);
-            } else {
-                acc[jj].x = fmaf(h.x, x.x, fmaf(-h.y, x.y, acc[jj].x));
-                acc[jj].y = fmaf(h.x, x.y, fmaf(h.y, x.x, acc[jj].y));
+            for (int r = 0; r < CV_J; r++) {
+                const int jj = r + u - (CV_J - 1);
+                if (jj < 0 || jj >= CV_J) continue;
+                if (PACKED) {
+                    acc[jj].x = fmaf(h.x, x[r].x, acc[jj].x);
+                    acc[jj].y = fmaf(h.y, x[r].y, acc[jj].y);
+                } else {
+                    acc[jj].x = fmaf(h.x, x[r].x, fmaf(-h.y, x[r].y, acc[jj].x));
+                    acc[jj].y = fmaf(h.x, x[r].y, fmaf(h.y, x[r].x, acc[jj].y));
+                }
             }
         }
     }
@@ -3196,12 +3213,18 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
     const int ring = ip.xring_blocks;
     // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
     int slot0 = (int)(jabs0 % ring);
-    conv_mac_group<PACKED, true>(p, ip, k, 0, jabs0, slot0, ring, jabs_last, acc);
+    int i_lo = -(CV_J - 1);
+    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the i >= 0 test guards it)
+    const float2* xr = ip.xring + k;
+    int64_t b0 = jabs0;
 #pragma unroll 1
-    for (int g = 1; g < groups; g++) {
+    for (int g = 0; g < groups; g++) {
+        conv_mac_group<PACKED>(hp, i_lo, p.S, xr, slot0, ring, b0, jabs_last, acc);
+        hp += (size_t)CV_J * CV_BINS;
+        i_lo += CV_J;
+        b0 -= CV_J;
         slot0 -= CV_J;
         while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
-        conv_mac_group<PACKED, false>(p, ip, k, g * CV_J, jabs0 - g * CV_J, slot0, ring, jabs_last, acc);
     }
 }
 __global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
@@ -3251,8 +3274,9 @@ __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __r
     fft_dit_smem(z, w);
     const float scale = 1.f / (float)(2 * CV_B);
     float* out = chan(p.out, p.out_channel, ci) + (size_t)jb * CV_B;
-    const int64_t left = (int64_t)ci.nf - (int64_t)jb * CV_B;
-    const int valid = (int)(left < CV_B ? left : CV_B);
+    int64_t left = (int64_t)ci.nf - (int64_t)jb * CV_B;
+    if (p.limit >= 0 && p.limit - (ci.f0 + (int64_t)jb * CV_B) < left) left = p.limit - (ci.f0 + (int64_t)jb * CV_B);
+    const int valid = (int)(left < CV_B ? (left > 0 ? left : 0) : CV_B);
     // second half of the 2B frame: complex B/2 + i holds frames 2i, 2i+1 of the block (natural order after the DIT transform)
     if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
 #pragma unroll 4

@@ -3,13 +3,13 @@
 // Why: in every branch of AudioParamProcessor::compute_buffer (src/param.rs:1093-1498) the intrinsic value left behind is a closed form
 // of the event (its value at next_block_time / end_time / the target) and never the last frame the fill loop produced, so the walk
 // over the events is cheap and serial while the 128 frame values of a quantum are independent of each other.  A sink that records the
-// fills lets a warp evaluate them in parallel (k_param_parallel, off by default: WAE_OPT_PARAM_PARALLEL); a sink that evaluates them on
+// fills lets a warp evaluate them in parallel (k_param_parallel, the default: WAE_OPT_PARAM_PARALLEL = 1); a sink that evaluates them on
 // the spot reproduces param_compute_buffer.  Frame times are the reference's running sum (`time += dt` from the fill's first frame), so
 // a lane that starts at frame i re-accumulates i - first additions and gets bit-identical times.
 //
 // STATUS: the walker and both sinks are exercised on the host by the reference's param.rs tests (tests/test_param_timeline.py, third
-// implementation "engine-walk"); the kernel that uses the recording sink has NOT run on a GPU yet — it is opt-in until it has
-// (NEXT.md item 1).  param_compute_buffer stays the code the default k_param kernel and the suspend replay run.
+// implementation "engine-walk"); the kernel that uses the recording sink is the default and is compared bit for bit with k_param on
+// hardware (tests/test_gpu_criterion_and_setters.py).  param_compute_buffer stays the code k_param (option = 0) and the suspend replay run.
 #pragma once
 #include "wae_param_core.h"
 
