@@ -252,7 +252,9 @@ enum {
     WAE_OPT_FUSE = 2,           /* 1 (default): fuse source->filter->gain chains; 0: one stage/node */
     WAE_OPT_SERIAL_FILTERS = 3, /* 1: bit-faithful serial recurrences (thread per channel)          */
     WAE_OPT_PIPELINE_GROUPS = 4, /* graph groups of the H2D/render/D2H pipeline (0 = auto: 8)       */
-    WAE_OPT_PARAM_PARALLEL = 5,  /* 1 (default): AudioParam ramps / set-target / curves of a quantum evaluated by the whole warp; 0: by one lane */
+    WAE_OPT_PARAM_PARALLEL = 5,  /* AudioParam kernel. 2 (default): one CTA per param, 32 quanta walked speculatively at once and verified;
+                                  * 1: one warp per param, the fills of a quantum evaluated by the warp; 0: one lane evaluates every frame.
+                                  * The three are bit-identical (tests/test_gpu_criterion_and_setters.py). */
     WAE_OPT_BIND_NUMA = 6,       /* 1: pin the calling thread and the engine's host workers to the CPUs of the GPU's NUMA node (before the first render) */
     WAE_OPT_HOST_WORKERS = 7,    /* host worker threads (planning, copy-out to pageable buffers); 0 = auto (hardware threads / 8, 2..16) */
     WAE_OPT_CHAIN_TMA = 8,       /* process-wide: 1 = the fused chain kernel streams PCM with cp.async.bulk (TMA), 0 = with cp.async */
@@ -304,10 +306,12 @@ WAE_API wae_status wae_param_sim_create(uint32_t a_rate, float default_value, fl
 WAE_API wae_status wae_param_sim_destroy(wae_param_sim* sim);
 WAE_API wae_status wae_param_sim_push(wae_param_sim* sim, const wae_param_event* event);
 WAE_API wae_status wae_param_sim_set_automation_rate(wae_param_sim* sim, uint32_t a_rate);
-/* which implementation of the state machine wae_param_sim_compute runs: 0 = the one the default kernel runs (csrc/wae_param_core.h),
- * 1 / 2 = the sink-based walker with its serial / recording sink (csrc/wae_param_walk.h; the recording sink is what the opt-in parallel
- * param kernel uses) */
+/* which implementation of the state machine wae_param_sim_compute runs: 0 = csrc/wae_param_core.h (k_param), 1 / 2 = the sink-based
+ * walker with its serial / recording sink (csrc/wae_param_walk.h; k_param_parallel), 3 = the recording sink walked from predicted states
+ * that are verified against the previous quantum's result first, as the default kernel k_param_spec does with 32 quanta at a time.
+ * wae_param_sim_speculation reports how many predictions walker 3 made and how many held. */
 WAE_API wae_status wae_param_sim_set_walker(wae_param_sim* sim, uint32_t walker);
+WAE_API wae_status wae_param_sim_speculation(wae_param_sim* sim, uint64_t* tried, uint64_t* hits);
 WAE_API wae_status wae_param_sim_compute(wae_param_sim* sim, double block_time, double dt, uint32_t count, float* out, uint32_t* len);
 
 /* OfflineAudioContext::suspend_sync(suspend_time, callback) (src/context/offline.rs:330-387): call this, then run the

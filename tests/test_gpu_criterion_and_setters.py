@@ -51,17 +51,21 @@ AUTOMATED = ["Granular synthesis", "Synth (Sawtooth with Envelope)", "Substracti
 
 @pytest.mark.parametrize("name", AUTOMATED)
 def test_parallel_param_kernel_matches_the_oracle(pkg, engine, oracle, name):
-    """The AudioParam kernel (fills of a quantum evaluated by the whole warp, csrc/wae_param_walk.h) on the automation-heavy
-    scenarios of the reference's benchmark suite, against the oracle AND against the serial kernel (lane 0 evaluates every frame;
-    WAE_OPT_PARAM_PARALLEL = 0), bit for bit."""
+    """The AudioParam kernels on the automation-heavy scenarios of the reference's benchmark suite: the default (one CTA per param, 32
+    quanta walked speculatively from predicted states and verified, csrc/wae_kernels.cu k_param_spec) against the oracle AND, bit for
+    bit, against the two kernels that walk quantum after quantum (WAE_OPT_PARAM_PARALLEL = 1: the warp evaluates the fills,
+    csrc/wae_param_walk.h; 0: lane 0 evaluates every frame)."""
     build = dict(BS.SCENARIOS)[name]
     want = build(pkg, oracle, SECONDS).start_rendering_sync()
     got = build(pkg, engine.backend, SECONDS).start_rendering_sync()
-    engine.set_option(pkg.OPT_PARAM_PARALLEL, 0)
+    others = []
     try:
-        default = build(pkg, engine.backend, SECONDS).start_rendering_sync()
+        for mode in (0, 1):
+            engine.set_option(pkg.OPT_PARAM_PARALLEL, mode)
+            others.append(build(pkg, engine.backend, SECONDS).start_rendering_sync())
     finally:
-        engine.set_option(pkg.OPT_PARAM_PARALLEL, 1)
+        engine.set_option(pkg.OPT_PARAM_PARALLEL, 2)
     for ch in range(want.number_of_channels()):
         assert np.abs(got.get_channel_data(ch).astype(np.float64) - want.get_channel_data(ch)).max() <= 1e-5 * max(1.0, float(np.abs(want.get_channel_data(ch)).max()))
-        assert np.array_equal(got.get_channel_data(ch), default.get_channel_data(ch))
+        for o in others:
+            assert np.array_equal(got.get_channel_data(ch), o.get_channel_data(ch))

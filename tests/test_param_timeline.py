@@ -67,10 +67,11 @@ class Sim:
         self.api.param_sim_destroy(self.h)
 
 
-@pytest.fixture(params=["oracle", "engine", "engine-walk-serial", "engine-walk-record"])
+@pytest.fixture(params=["oracle", "engine", "engine-walk-serial", "engine-walk-record", "engine-walk-spec"])
 def sim(request, pkg, oracle):
     """oracle | the library's param_compute_buffer (what the default kernel and the suspend replay run) | the sink-based walker of
-    csrc/wae_param_walk.h with its serial sink and with the recording sink (what the opt-in parallel param kernel uses)."""
+    csrc/wae_param_walk.h with its serial sink, with the recording sink (k_param_parallel), and walked from predicted-then-verified states
+    like the default kernel k_param_spec does."""
     import os
     if request.param == "oracle":
         api = oracle.api
@@ -79,7 +80,7 @@ def sim(request, pkg, oracle):
         if not os.path.exists(so):
             pytest.skip("libwae_b200.so is not built (python -c 'import __graft_entry__ as g; g.build()')")
         api = pkg.api()
-    walker = {"engine-walk-serial": 1, "engine-walk-record": 2}.get(request.param, 0)
+    walker = {"engine-walk-serial": 1, "engine-walk-record": 2, "engine-walk-spec": 3}.get(request.param, 0)
     made = []
 
     def make(rate, default, mn, mx):
@@ -415,7 +416,7 @@ def test_full_block_ramp_from_set_value(sim):  # :3503-3528 (the intrinsic half 
 
 @pytest.mark.parametrize("seed", range(60))
 def test_the_walker_is_bit_identical_to_the_kernel_code_on_random_timelines(pkg, seed):
-    """csrc/wae_param_walk.h (serial and recording sinks) vs csrc/wae_param_core.h::param_compute_buffer on random event timelines, 128-frame
+    """csrc/wae_param_walk.h (serial and recording sinks, and the speculative walk) vs csrc/wae_param_core.h::param_compute_buffer on random event timelines, 128-frame
     quanta at 48 kHz, events pushed before and during the render: every block, bit for bit (the oracle is compared at f32 resolution)."""
     import os
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
@@ -424,7 +425,7 @@ def test_the_walker_is_bit_identical_to_the_kernel_code_on_random_timelines(pkg,
     api = pkg.api()
     rng = np.random.default_rng(seed)
     sims = []
-    for walker in (0, 1, 2):
+    for walker in (0, 1, 2, 3):
         s = Sim(api, A if seed % 3 else K, 0.5, -10.0, 10.0, pkg)
         api.check(api.param_sim_set_walker(s.h, walker))
         sims.append(s)
@@ -457,12 +458,63 @@ def test_the_walker_is_bit_identical_to_the_kernel_code_on_random_timelines(pkg,
             except pkg.WaeError:
                 outs.append(None)
         if outs[0] is None:
-            assert outs[1] is None and outs[2] is None
+            assert all(o is None for o in outs[1:])
             break
-        assert outs[1] is not None and outs[2] is not None
-        assert np.array_equal(outs[0], outs[1], equal_nan=True) and np.array_equal(outs[0], outs[2], equal_nan=True), (seed, q)
+        assert all(o is not None for o in outs[1:])
+        assert all(np.array_equal(outs[0], o, equal_nan=True) for o in outs[1:]), (seed, q)
     for s in sims:
         s.close()
+
+
+def test_speculation_predicts_the_state_inside_every_kind_of_event(pkg):
+    """k_param_spec walks 32 quanta at once from PREDICTED states; a prediction that fails costs a re-walk, so inside a ramp, a set-target,
+    a value curve and a stretch without events nearly all of them have to hold (the host simulator counts them: a window restarts after 32
+    quanta or after a miss, so at most 31 of 32 are predictions)."""
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "web-audio-api-rs_b200", "libwae_b200.so")
+    if not os.path.exists(so):
+        pytest.skip("libwae_b200.so is not built")
+    api = pkg.api()
+    dt = 1.0 / 48000.0
+    quanta = 3000  # 8 s
+
+    def run(setup, rate=A):
+        ref = Sim(api, rate, 0.5, -1000.0, 1000.0, pkg)
+        spec = Sim(api, rate, 0.5, -1000.0, 1000.0, pkg)
+        api.check(api.param_sim_set_walker(spec.h, 3))
+        setup(ref)
+        setup(spec)
+        for q in range(quanta):
+            a, b = ref.run(q * 128 * dt, 128, dt), spec.run(q * 128 * dt, 128, dt)
+            assert np.array_equal(a, b, equal_nan=True), q
+        tried, hits = C.c_uint64(0), C.c_uint64(0)
+        api.check(api.param_sim_speculation(spec.h, C.byref(tried), C.byref(hits)))
+        ref.close()
+        spec.close()
+        return tried.value, hits.value
+
+    def envelope(p):   # examples/benchmarks.rs "Substractive Synth": a set-target restarted every 146 ms
+        t = 0.0
+        while t < quanta * 128 * dt:
+            p.set_value_at_time(1.0, t)
+            p.target(0.0, t, 0.1)
+            t += 140.0 / 60.0 / 16.0
+
+    cases = {
+        "no events": lambda p: None,
+        "events far away": lambda p: (p.set_value_at_time(0.2, 1.0), p.set_value_at_time(0.7, 6.5)),
+        "linear ramp": lambda p: (p.set_value_at_time(100.0, 0.0), p.linear(2000.0, 7.5)),
+        "exponential ramp": lambda p: (p.set_value_at_time(100.0, 0.0), p.exponential(2000.0, 7.0)),
+        "set target": lambda p: p.target(3.0, 0.25, 1.5),
+        "value curve": lambda p: p.curve(np.linspace(0.0, 1.0, 64).astype(np.float32), 0.1, 7.0),
+        "envelope": envelope,
+    }
+    for name, setup in cases.items():
+        for rate in (A, K):
+            tried, hits = run(setup, rate)
+            assert tried >= quanta * 29 // 32, (name, tried)
+            floor = 0.80 if name == "envelope" else 0.97   # (55 events in 8 s: each costs one miss and a short window)
+            assert hits >= floor * tried, (name, rate, tried, hits)
 
 
 def test_a_pending_value_curve_is_sampled_before_its_start(sim):

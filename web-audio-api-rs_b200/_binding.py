@@ -149,7 +149,7 @@ WAE_SYMBOLS = [
 ] + ["wae_" + n for n in CREATE_FUNCS] + [
     "wae_connect", "wae_connect_param", "wae_disconnect", "wae_param_event_push", "wae_param_set_automation_rate",
     "wae_listener_param_event_push", "wae_source_start", "wae_source_stop", "wae_oscillator_set_type",
-    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync", "wae_batch_group_count", "wae_batch_group_range", "wae_batch_run_group", "wae_host_alloc", "wae_host_free", "wae_host_register", "wae_host_unregister", "wae_selftest_conv_fft",
+    "wae_biquad_set_type", "wae_render_batch", "wae_batch_prepare", "wae_batch_upload", "wae_batch_set_timing", "wae_batch_run", "wae_batch_run_pipelined", "wae_batch_sync", "wae_batch_group_count", "wae_batch_group_range", "wae_batch_run_group", "wae_host_alloc", "wae_host_free", "wae_host_register", "wae_host_unregister", "wae_selftest_conv_fft", "wae_param_sim_speculation",
     "wae_batch_output_device_ptr", "wae_batch_fetch", "wae_batch_destroy", "wae_batch_get_stats", "wae_batch_stage_time",
     "wae_analyser_get_float_time_domain_data", "wae_analyser_get_float_frequency_data", "wae_resample_linear", "wae_compressor_reduction", "wae_analyser_get_byte_time_domain_data", "wae_analyser_get_byte_frequency_data", "wae_engine_set_hrir_sphere", "wae_graph_suspend", "wae_param_sim_create", "wae_param_sim_destroy", "wae_param_sim_push",
     "wae_param_sim_set_automation_rate", "wae_param_sim_compute", "wae_biquad_coefs", "wae_biquad_frequency_response", "wae_iir_frequency_response",
@@ -183,6 +183,7 @@ class Api:
         f("param_sim_compute", C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_uint32, c_float_p, C.POINTER(C.c_uint32)])
         if self.is_product:
             f("param_sim_set_walker", C.c_int32, [C.c_void_p, C.c_uint32])
+            f("param_sim_speculation", C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)])
             f("selftest_conv_fft", C.c_int32, [c_float_p, C.c_uint32])
             f("sched_first_frame_at_or_after", C.c_int32, [C.c_float, C.c_double, C.POINTER(C.c_int64), C.POINTER(C.c_double)])
         f("connect", C.c_int32, [gp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32])

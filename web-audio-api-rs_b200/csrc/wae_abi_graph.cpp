@@ -680,10 +680,17 @@ struct wae_param_sim {
     ParamTimeline tl;
     ParamState st{};
     bool started = false;
-    uint32_t walker = 0;  // 0: param_compute_buffer (what the kernel runs); 1 / 2: param_walk with the serial / the recording sink
+    uint32_t walker = 0;  // 0: param_compute_buffer (k_param); 1 / 2: param_walk with the serial / the recording sink (k_param_parallel);
+                          // 3: the recording sink walked from PREDICTED states that are verified first, like k_param_spec does
+    // walker 3: the speculation window of k_param_spec (its lane j walks quantum j from `base` with a predicted intrinsic value)
+    ParamState spec_base{};
+    int spec_j = 0;
+    double spec_prev_block_time = 0.;
+    uint32_t spec_prev_count = 0;
+    uint64_t spec_tried = 0, spec_hits = 0;
 };
 WAE_API wae_status wae_param_sim_set_walker(wae_param_sim* s, uint32_t walker) {
-    if (!s || walker > 2) return fail(WAE_INVALID_ARGUMENT, "unknown walker");
+    if (!s || walker > 3) return fail(WAE_INVALID_ARGUMENT, "unknown walker");
     s->walker = walker;
     return WAE_OK;
 }
@@ -751,11 +758,48 @@ WAE_API wae_status wae_param_sim_compute(wae_param_sim* s, double block_time, do
         sink.dt = 1. / (double)host.sample_rate;
         n = param_walk(host, s->st, block_time, sink, (int)count);
         sink.finish();
+    } else if (s->walker == 3) {
+        // k_param_spec, one quantum per call: lane 0 of a window walks the real state; lane j > 0 walks `base` with the predicted
+        // intrinsic value, and its result is only kept when the state the previous walk left equals that prediction
+        const double sdt = 1. / (double)host.sample_rate;
+        bool speculate = s->spec_j > 0 && s->spec_j < 32 && s->spec_prev_count == count;
+        ParamState from = s->st;
+        if (speculate) {
+            ParamState pred = s->spec_base;
+            pred.intrinsic = param_predict_intrinsic(host, pred, std::fma(sdt, (double)count, s->spec_prev_block_time));
+            s->spec_tried++;
+            if (param_state_equal(s->st, pred)) {
+                s->spec_hits++;
+                from = pred;  // (what the kernel keeps is the walk that started from the prediction)
+            } else {
+                speculate = false;
+            }
+        }
+        if (!speculate) {
+            s->spec_base = s->st;
+            s->spec_j = 0;
+        }
+        RecordSink sink;
+        sink.buf = buf;
+        sink.dt = sdt;
+        n = param_walk(host, from, block_time, sink, (int)count);
+        sink.finish();
+        s->st = from;
+        s->spec_j++;
+        s->spec_prev_block_time = block_time;
+        s->spec_prev_count = count;
     } else {
         n = param_compute_buffer(host, s->st, block_time, buf, (int)count);
     }
     for (int i = 0; i < n; i++) out[i] = buf[i];
     *len = (uint32_t)n;
+    return WAE_OK;
+}
+
+WAE_API wae_status wae_param_sim_speculation(wae_param_sim* s, uint64_t* tried, uint64_t* hits) {
+    if (!s || !tried || !hits) return fail(WAE_INVALID_ARGUMENT, "null argument");
+    *tried = s->spec_tried;
+    *hits = s->spec_hits;
     return WAE_OK;
 }
 

@@ -112,7 +112,7 @@ struct wae_engine {
     bool fuse = true;
     bool serial_filters = false;
     int pipeline_groups = 0;  // 0 = auto
-    bool param_parallel = true;  // WAE_OPT_PARAM_PARALLEL: k_param_parallel (the warp evaluates the fills of a quantum); 0: k_param (lane 0 evaluates every frame)
+    int param_parallel = 2;  // WAE_OPT_PARAM_PARALLEL: 2 k_param_spec (CTA per param, speculative walks of 32 quanta), 1 k_param_parallel (warp per param), 0 k_param (lane 0 evaluates every frame)
     float* d_sine = nullptr;
     wae::HrirSphere* sphere = nullptr;  // wae_engine_set_hrir_sphere
     float* d_sphere_ir = nullptr;
@@ -2473,7 +2473,7 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "pipeline groups must be in [0, 1024]");
             eng->pipeline_groups = (int)value;
             return WAE_OK;
-        case WAE_OPT_PARAM_PARALLEL: eng->param_parallel = value != 0; return WAE_OK;
+        case WAE_OPT_PARAM_PARALLEL: eng->param_parallel = value > 2 ? 2 : (int)value; return WAE_OK;
         case WAE_OPT_BIND_NUMA:
             if (value != 0 && eng->pool) return fail(WAE_INVALID_STATE, "bind the engine to its NUMA node before its first render (worker threads already run)");
             if (value != 0 && !bind_to_device_numa_node(eng)) return fail(WAE_UNSUPPORTED, "could not read / apply the CPU list of the GPU's NUMA node");

@@ -1745,53 +1745,87 @@ __global__ void __launch_bounds__(256) k_biquad_coefs(const BiquadArInst* __rest
         base[4 * cs] = cf.a2;
     }
 }
-// step 2: the reference's serial f64 recurrence with those coefficients
-__global__ void __launch_bounds__(64) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int ii = t / max_ch, c = t % max_ch;
+// step 2: the reference's serial f64 recurrence with those coefficients.  One WARP per (instance, channel): the lanes stage a quantum of
+// coefficients and input in shared memory with coalesced loads (the next quantum's loads are already in flight in registers), lane 0 runs
+// the 128 dependent steps out of shared memory, the lanes store the quantum.  With one THREAD per channel every step waited for five
+// global loads (2 us per frame on a 120 s render: examples/benchmarks.rs "Substractive Synth" took 11 s for 64 graphs).
+constexpr int BQA_WARPS = 2;
+__global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
+    __shared__ double s_cf[BQA_WARPS][5][128];
+    __shared__ float s_x[BQA_WARPS][128];
+    __shared__ float s_y[BQA_WARPS][128];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * BQA_WARPS + wib;
+    const int ii = t / max_ch, c = t % max_ch;
     if (ii >= n_inst) return;
     const BiquadArInst q = insts[ii];
     if (c >= q.ch) return;
     const float* in = chan(q.in, c, ci);
     float* out = chan(q.out, c, ci);
-    const float* tq = q.q.p ? chan(q.q, 0, ci) : nullptr;
-    const float* td = q.detune.p ? chan(q.detune, 0, ci) : nullptr;
-    const float* tf = q.freq.p ? chan(q.freq, 0, ci) : nullptr;
-    const float* tg = q.gain.p ? chan(q.gain, 0, ci) : nullptr;
     double* st = q.state + 4 * c;
-    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    double x1 = 0., x2 = 0., y1 = 0., y2 = 0.;
+    if (lane == 0) x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
     const double* cbase = reinterpret_cast<const double*>(q.coefs.p) + ci.sub;
     const size_t cs = q.coefs.stride;
-    (void)tq; (void)td; (void)tf; (void)tg;
-    BqC cf{};
     const bool dyn = q.in.meta != nullptr;
     int len = dyn ? q.dyn_len[c] : q.ch;
-    bool skip = false, absent = false;
-    for (int n = 0; n < ci.nf; n++) {
-        if (dyn && (n & 127) == 0) {
-            filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
-            if (c >= len) x1 = x2 = y1 = y2 = 0.;
+    double (*cf)[128] = s_cf[wib];
+    float* sx = s_x[wib];
+    float* sy = s_y[wib];
+    // frames lane + 32 k of the quantum at n0 (k < 4), zero past the chunk
+    double pre[5][4];
+    float prex[4];
+    auto fetch = [&](int n0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int n = n0 + lane + 32 * k;
+            const bool ok = n < ci.nf;
+#pragma unroll
+            for (int j = 0; j < 5; j++) pre[j][k] = ok ? cbase[(size_t)j * cs + n] : 0.;
+            prex[k] = ok ? in[n] : 0.f;
         }
-        if (skip) {
-            out[n] = 0.f;
-            continue;
+    };
+    fetch(0);
+    for (int n0 = 0; n0 < ci.nf; n0 += 128) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int j = 0; j < 5; j++) cf[j][lane + 32 * k] = pre[j][k];
+            sx[lane + 32 * k] = prex[k];
         }
-        cf.b0 = cbase[n];
-        cf.b1 = cbase[cs + n];
-        cf.b2 = cbase[2 * cs + n];
-        cf.a1 = cbase[3 * cs + n];
-        cf.a2 = cbase[4 * cs + n];
-        double x = absent ? 0. : (double)in[n];
-        double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf.b0, x), __dmul_rn(cf.b1, x1)), __dmul_rn(cf.b2, x2)),
-                                       __dmul_rn(cf.a1, y1)),
-                             __dmul_rn(cf.a2, y2));
-        double ay = fabs(y);
-        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
-        x2 = x1; x1 = x; y2 = y1; y1 = y;
-        out[n] = (float)y;
+        __syncwarp();
+        if (n0 + 128 < ci.nf) fetch(n0 + 128);  // in flight while lane 0 works
+        const int cnt = min(128, ci.nf - n0);
+        if (lane == 0) {
+            bool skip = false, absent = false;
+            if (dyn) {
+                filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n0), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
+                if (c >= len) x1 = x2 = y1 = y2 = 0.;
+            }
+            if (skip) {
+                for (int i = 0; i < cnt; i++) sy[i] = 0.f;
+            } else {
+#pragma unroll 4
+                for (int i = 0; i < cnt; i++) {
+                    const double x = absent ? 0. : (double)sx[i];
+                    double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf[0][i], x), __dmul_rn(cf[1][i], x1)), __dmul_rn(cf[2][i], x2)),
+                                                   __dmul_rn(cf[3][i], y1)),
+                                         __dmul_rn(cf[4][i], y2));
+                    const double ay = fabs(y);
+                    if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+                    x2 = x1; x1 = x; y2 = y1; y1 = y;
+                    sy[i] = (float)y;
+                }
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) out[n0 + i] = sy[i];
+        __syncwarp();
     }
-    st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
-    if (dyn) q.dyn_len[c] = len;
+    if (lane == 0) {
+        st[0] = x1; st[1] = x2; st[2] = y1; st[3] = y2;
+        if (dyn) q.dyn_len[c] = len;
+    }
 }
 
 // IIRFilter — IirFilterRenderer::process (src/node/iir_filter.rs:323-414): transposed DF-II in f64, serial
@@ -2742,7 +2776,7 @@ __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param(const ParamInst* __r
     if (lane == 0) *p.state = st;
 }
 
-// The default AudioParam kernel (WAE_OPT_PARAM_PARALLEL = 1; 0 selects k_param above): lane 0 only WALKS the events of the quantum
+// WAE_OPT_PARAM_PARALLEL = 1 (0 selects k_param above, 2 = the default k_param_spec below): lane 0 only WALKS the events of the quantum
 // (wae_param_walk.h, recording sink: constants are written, ramps / set-target / curves are recorded as fills), then the 32 lanes evaluate
 // the recorded fills, 4 consecutive frames each, re-accumulating `time += dt` from the fill's first frame so that the frame times are the
 // reference's running sum.  Bit-equal to k_param on hardware (tests/test_gpu_criterion_and_setters.py renders every automation scenario
@@ -2819,6 +2853,122 @@ __global__ void __launch_bounds__(32 * PARAM_WARPS) k_param_parallel(const Param
         __syncwarp();
     }
     if (lane == 0) *p.state = st;
+}
+
+// The default AudioParam kernel (WAE_OPT_PARAM_PARALLEL = 2): one CTA per automated param, SPECULATIVE walks.  The event state machine
+// is serial from quantum to quantum, but almost every quantum leaves it where it was: queue position, last event and override untouched,
+// the intrinsic value a closed form of the event at the head of the queue (param_walk leaves par_linear / par_exp / par_target / par_curve
+// at next_block_time behind, or nothing at all in a constant block).  So the 32 lanes of warp 0 each walk ONE of the next 32 quanta from a
+// PREDICTED state (the current state with that closed form as intrinsic value), and every prediction is then checked against the state
+// the walk of the quantum before it actually left: the verified prefix is kept (always at least one quantum, whose input is the real
+// state), the rest is thrown away and speculated again from the last verified state.  A wrong prediction costs time, never correctness.
+// The recorded fills of the kept quanta are evaluated by all warps.  k_param_parallel walked quantum after quantum with one lane per
+// param: 3 - 25 us per quantum, a second of GPU time for two automated params on a 120 s render.
+constexpr int PSPEC_WARPS = 8;
+constexpr int PSPEC_Q = 32;
+__global__ void __launch_bounds__(32 * PSPEC_WARPS) k_param_spec(const ParamInst* __restrict__ insts, int n_inst, ChunkInfo ci) {
+    __shared__ float s_buf[PSPEC_Q][129];  // (129: the lanes of warp 0 write their rows at the same column)
+    __shared__ ParamFill s_fill[PSPEC_Q][RecordSink::kMax];
+    __shared__ int s_meta[PSPEC_Q][3];     // frames written (1 or 128), recorded fills, frames to flush subnormals in
+    __shared__ ParamState s_after[PSPEC_Q];
+    __shared__ ParamState s_state;
+    __shared__ int s_m;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ii = blockIdx.x;
+    if (ii >= n_inst) return;
+    const ParamInst p = insts[ii];
+    if (threadIdx.x == 0) {
+        ParamState st = *p.state;
+        if (!st.inited) {
+            st.intrinsic = p.intrinsic0;
+            st.head = 0;
+            st.has_last = p.has_last0;
+            st.last = p.last0;
+            st.override_valid = 0;
+            st.inited = 1;
+        }
+        s_state = st;
+    }
+    __syncthreads();
+    float* out = chan(p.out, 0, ci);
+    float* single = chan(p.out, 1, ci);
+    const float* in = p.in.p ? chan(p.in, 0, ci) : nullptr;
+    const double dt = 1. / (double)p.sample_rate;  // the walker's own expression
+    auto fix = [&](float v) {
+        if (v != v) return p.def;
+        v = v > p.mn ? v : p.mn;
+        return v < p.mx ? v : p.mx;
+    };
+    for (int q0 = 0; q0 < ci.nf;) {
+        const int nq = min(PSPEC_Q, (ci.nf - q0 + 127) / 128);
+        if (w == 0) {
+            ParamState st = s_state;
+            const bool active = lane < nq;
+            if (active && lane > 0) {
+                const double prev_block_time = (double)(ci.f0 + q0 + 128 * (lane - 1)) / (double)p.sample_rate;
+                st.intrinsic = param_predict_intrinsic(p, st, fma(dt, 128., prev_block_time));
+            }
+            const ParamState before = st;
+            RecordSink sink;
+            sink.buf = s_buf[lane];
+            sink.dt = dt;
+            int len = 0;
+            if (active) {
+                const double block_time = (double)(ci.f0 + q0 + 128 * lane) / (double)p.sample_rate;
+                len = param_walk(p, st, block_time, sink);
+                s_after[lane] = st;
+            }
+            __syncwarp();
+            const bool ok = active && (lane == 0 || param_state_equal(s_after[lane - 1], before));
+            const unsigned good = __ballot_sync(0xffffffffu, ok);
+            const int m = __ffs(~good) - 1;  // verified prefix (>= 1: lane 0 walked the real state); 32 verified: ~good == 0 -> ffs 0 -> -1
+            const int keep = m < 0 ? 32 : m;
+            if (lane < keep) {
+                for (int k = 0; k < sink.n; k++) s_fill[lane][k] = sink.fills[k];
+                s_meta[lane][0] = len;
+                s_meta[lane][1] = sink.n;
+                s_meta[lane][2] = sink.flush;
+            }
+            if (lane == keep - 1) s_state = st;
+            if (lane == 0) s_m = keep;
+        }
+        __syncthreads();
+        const int m = s_m;
+        for (int j = w; j < m; j += PSPEC_WARPS) {
+            float* buf = s_buf[j];
+            const int qf = q0 + 128 * j;
+            const int len = s_meta[j][0], n_fills = s_meta[j][1], flush = s_meta[j][2];
+            for (int k = 0; k < n_fills; k++) {
+                const ParamFill f = s_fill[j][k];
+                const int from = f.first + 4 * lane, to = min(f.last, from + 4);  // a fill is at most 128 frames = 32 lanes x 4
+                if (from < to) param_fill_range(f, from, to, dt, buf);
+            }
+            __syncwarp();
+            for (int i = lane; i < flush; i += 32)
+                if (buf[i] != 0.f && fabsf(buf[i]) < 1.17549435e-38f) buf[i] = 0.f;
+            __syncwarp();
+            if (len == 1 || !p.a_rate) {
+                const float value = buf[0];
+                if (!in || !p.a_rate) {
+                    const float v = fix(value + (in ? in[qf] : 0.f));
+#pragma unroll
+                    for (int i = lane; i < 128; i += 32) out[qf + i] = v;
+                    if (lane == 0) single[qf] = 1.f;
+                } else {
+#pragma unroll
+                    for (int i = lane; i < 128; i += 32) out[qf + i] = fix(in[qf + i] + value);
+                    if (lane == 0) single[qf] = 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int i = lane; i < 128; i += 32) out[qf + i] = fix((in ? in[qf + i] : 0.f) + buf[i]);
+                if (lane == 0) single[qf] = 0.f;
+            }
+        }
+        __syncthreads();
+        q0 += 128 * m;
+    }
+    if (threadIdx.x == 0) *p.state = s_state;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -3163,34 +3313,27 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
 // PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
-template <bool PACKED>
-DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2* __restrict__ xr /* ring[0][k] */, int slot0,
-                         int ring, int64_t b0, int64_t jabs_last, float2 acc[CV_J]) {
-    float2 x[CV_J];
-    if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
-        const float2* xp = xr + (size_t)slot0 * CV_BINS;
-#pragma unroll
-        for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);  // (written by the previous launch: read-only here)
-    } else {
-#pragma unroll
-        for (int r = 0; r < CV_J; r++) {
-            const int64_t bb = b0 + r;
-            int slot = slot0 + r;
-            slot = slot >= ring ? slot - ring : slot;
-            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
-            x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
-        }
+// MODE 1: every diagonal of the group is inside 0 <= i < S (no tests at all); MODE 2: the first group of a response of at least CV_J
+// partitions (diagonals u >= CV_J - 1, known at compile time); MODE 0: any group, valid diagonals as a bit mask
+template <bool PACKED, int MODE>
+DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2 (&x)[CV_J], float2 acc[CV_J]) {
+    unsigned mask = 0x7fffu;
+    if (MODE == 2) mask = 0x7fffu & ~((1u << (CV_J - 1)) - 1u);
+    if (MODE == 0) {
+        const int u_lo = i_lo < 0 ? -i_lo : 0;
+        const int u_hi = S - i_lo < 2 * CV_J - 1 ? S - i_lo : 2 * CV_J - 1;
+        mask = u_hi > u_lo ? ((1u << (u_hi - u_lo)) - 1u) << u_lo : 0u;
     }
     float2 hw[2 * CV_J - 1];
 #pragma unroll
     for (int u = 0; u < 2 * CV_J - 1; u++) {
-        const int i = i_lo + u;
-        hw[u] = (i >= 0 && i < S) ? __ldg(hp + (size_t)u * CV_BINS) : make_float2(0.f, 0.f);
+        if (MODE != 0 && !((mask >> u) & 1u)) continue;  // (compile time)
+        if (MODE != 0 || ((mask >> u) & 1u)) hw[u] = __ldg(hp + (size_t)u * CV_BINS);
     }
 #pragma unroll
     for (int u = 0; u < 2 * CV_J - 1; u++) {
-        const int i = i_lo + u;
-        if (i >= 0 && i < S) {  // (uniform)
+        if (MODE != 0 && !((mask >> u) & 1u)) continue;  // (compile time)
+        if (MODE != 0 || ((mask >> u) & 1u)) {           // (uniform)
             const float2 h = hw[u];
 #pragma unroll
             for (int r = 0; r < CV_J; r++) {
@@ -3214,12 +3357,34 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
     // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
     int slot0 = (int)(jabs0 % ring);
     int i_lo = -(CV_J - 1);
-    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the i >= 0 test guards it)
-    const float2* xr = ip.xring + k;
+    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the masks guard it)
+    const float2* __restrict__ xr = ip.xring + k;                  // (written by the previous launch: read-only here)
     int64_t b0 = jabs0;
 #pragma unroll 1
     for (int g = 0; g < groups; g++) {
-        conv_mac_group<PACKED>(hp, i_lo, p.S, xr, slot0, ring, b0, jabs_last, acc);
+        float2 x[CV_J];
+        if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
+            const float2* xp = xr + (size_t)slot0 * CV_BINS;
+#pragma unroll
+            for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);
+        } else {
+#pragma unroll
+            for (int r = 0; r < CV_J; r++) {
+                const int64_t bb = b0 + r;
+                int slot = slot0 + r;
+                while (slot >= ring) slot -= ring;  // (rings shorter than CV_J blocks: tiny chunk option + one-partition IR)
+                x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
+            }
+        }
+        if (PACKED) {  // (one thread of the launch: one copy of the code is enough)
+            conv_mac_group<PACKED, 0>(hp, i_lo, p.S, x, acc);
+        } else if (g == 0 && p.S >= CV_J) {
+            conv_mac_group<PACKED, 2>(hp, i_lo, p.S, x, acc);
+        } else if (i_lo >= 0 && i_lo + 2 * CV_J - 1 <= p.S) {
+            conv_mac_group<PACKED, 1>(hp, i_lo, p.S, x, acc);
+        } else {
+            conv_mac_group<PACKED, 0>(hp, i_lo, p.S, x, acc);
+        }
         hp += (size_t)CV_J * CV_BINS;
         i_lo += CV_J;
         b0 -= CV_J;
@@ -3227,7 +3392,10 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
         while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
     }
 }
-__global__ void __launch_bounds__(CV_MAC_THREADS, 3) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
+#ifndef WAE_CV_MAC_MINB
+#define WAE_CV_MAC_MINB 3
+#endif
+__global__ void __launch_bounds__(CV_MAC_THREADS, WAE_CV_MAC_MINB) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
                                                              ChunkInfo ci) {
     const ConvPath p = paths[blockIdx.y];
     const ConvInput ip = inputs[p.input];
@@ -3636,8 +3804,8 @@ void launch_ring_write(const DelayInst* d, int n, ChunkInfo ci, cudaStream_t s) 
 void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_osc_arate<<<n, 256, 0, s>>>(d, n, ci); }
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     k_biquad_coefs<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
-    int threads = n * max_ch;
-    k_biquad_arate<<<(threads + 63) / 64, 64, 0, s>>>(d, n, max_ch, ci);
+    const int warps = n * max_ch;
+    k_biquad_arate<<<(warps + BQA_WARPS - 1) / BQA_WARPS, 32 * BQA_WARPS, 0, s>>>(d, n, max_ch, ci);
 }
 void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, float smoothing, float* last_fft, float* out_db, cudaStream_t s) {
     static bool configured = false;
@@ -3650,8 +3818,9 @@ void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, 
 void launch_resample_linear(const float* in, int64_t len, float* out, int64_t target_len, cudaStream_t s) {
     k_resample_linear<<<(unsigned)((target_len + 255) / 256), 256, 0, s>>>(in, len, out, target_len);
 }
-void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s, bool parallel_fills) {
-    if (parallel_fills) k_param_parallel<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s, int mode) {
+    if (mode >= 2) k_param_spec<<<n, 32 * PSPEC_WARPS, 0, s>>>(d, n, ci);
+    else if (mode == 1) k_param_parallel<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
     else k_param<<<(n + PARAM_WARPS - 1) / PARAM_WARPS, 32 * PARAM_WARPS, 0, s>>>(d, n, ci);
 }
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s) { k_compressor<<<(n + 31) / 32, 32, 0, s>>>(d, n, ci); }

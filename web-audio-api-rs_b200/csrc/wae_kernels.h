@@ -47,7 +47,7 @@ void launch_osc_arate(const OscArInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_arate(const BiquadArInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_analyser_fft(const float* ring, uint32_t write_index, int fft_size, float smoothing, float* last_fft, float* out_db, cudaStream_t s);
 void launch_resample_linear(const float* in, int64_t len, float* out, int64_t target_len, cudaStream_t s);
-void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s, bool parallel_fills = false);
+void launch_param(const ParamInst* d, int n, ChunkInfo ci, cudaStream_t s, int mode);  // 0: k_param, 1: k_param_parallel, 2: k_param_spec
 void launch_compressor(const CompInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_analyser(const AnalyserInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_conv_fft_in(const ConvInput* d, int n, ChunkInfo ci, cudaStream_t s);

@@ -13,6 +13,8 @@
 #pragma once
 #include "wae_param_core.h"
 
+#include <cstring>
+
 namespace wae {
 
 enum { PF_CONST = 0, PF_LINEAR = 1, PF_EXP = 2, PF_TARGET = 3, PF_CURVE = 4 };
@@ -289,6 +291,49 @@ WAE_HD int param_walk(const ParamInst& p, ParamState& st, double block_time, Sin
         }
     }
     return len;
+}
+
+
+// ---- speculation (k_param_spec): the state a quantum is walked from, predicted without walking the quanta before it ------------------
+WAE_HD unsigned par_bits(float v) {
+#ifdef __CUDA_ARCH__
+    return (unsigned)__float_as_int(v);
+#else
+    unsigned u;
+    memcpy(&u, &v, sizeof u);
+    return u;
+#endif
+}
+// The intrinsic value the walk leaves behind after a quantum that ended at `nbt` while the event at the head of the queue stayed there:
+// the closed forms param_walk assigns at next_block_time, or nothing in a constant block.  A wrong guess is harmless: the caller compares
+// the predicted state with the one the walk of the previous quantum really left (param_state_equal) and drops what was built on it.
+WAE_HD float param_predict_intrinsic(const ParamInst& p, ParamState& st, double nbt) {
+    ParamCursor tl{p, st};
+    if (tl.empty()) return st.intrinsic;
+    const ParamEvDev ev = tl.peek();
+    const bool lin = ev.type == WAE_EVENT_LINEAR_RAMP_TO_VALUE_AT_TIME;
+    if (lin || ev.type == WAE_EVENT_EXPONENTIAL_RAMP_TO_VALUE_AT_TIME) {
+        const double start = st.last.time, duration = ev.time - start;
+        const float v0 = st.last.value, v1 = ev.value;
+        if (!lin && (v0 == 0.f || v0 * v1 < 0.f)) return st.intrinsic;
+        return lin ? par_linear(start, duration, v0, v1 - v0, nbt) : par_exp(start, duration, v0, v1 / v0, nbt);
+    }
+    if (ev.time >= nbt) return st.intrinsic;  // the quantum that ended at nbt was a constant block
+    if (ev.type == WAE_EVENT_SET_TARGET_AT_TIME) return par_target(ev.time, ev.aux, ev.value, st.last.value - ev.value, nbt);
+    if (ev.type == WAE_EVENT_SET_VALUE_CURVE_AT_TIME) return par_curve(ev.time, ev.aux, p.curves + ev.values_off, ev.values_len, nbt);
+    return st.intrinsic;
+}
+WAE_HD bool param_ev_equal(const ParamEvDev& a, const ParamEvDev& b) {
+    return a.type == b.type && par_bits(a.value) == par_bits(b.value) && a.time == b.time && a.aux == b.aux &&
+           a.cancel_time == b.cancel_time && a.has_cancel == b.has_cancel && a.values_off == b.values_off && a.values_len == b.values_len;
+}
+// did the walk of the previous quantum leave exactly the state this quantum was walked from?
+WAE_HD bool param_state_equal(const ParamState& a, const ParamState& b) {
+    if (par_bits(a.intrinsic) != par_bits(b.intrinsic) || a.head != b.head || a.has_last != b.has_last || a.override_valid != b.override_valid)
+        return false;
+    if (a.has_last && !param_ev_equal(a.last, b.last)) return false;
+    if (a.override_valid && !param_ev_equal(a.override_ev, b.override_ev)) return false;
+    return true;
 }
 
 }  // namespace wae
