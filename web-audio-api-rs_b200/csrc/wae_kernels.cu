@@ -1751,9 +1751,9 @@ __global__ void __launch_bounds__(256) k_biquad_coefs(const BiquadArInst* __rest
 // global loads (2 us per frame on a 120 s render: examples/benchmarks.rs "Substractive Synth" took 11 s for 64 graphs).
 constexpr int BQA_WARPS = 2;
 __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
-    __shared__ double s_cf[BQA_WARPS][5][128];
-    __shared__ float s_x[BQA_WARPS][128];
-    __shared__ float s_y[BQA_WARPS][128];
+    __shared__ __align__(16) double s_cf[BQA_WARPS][5][128];
+    __shared__ __align__(16) float s_x[BQA_WARPS][128];
+    __shared__ __align__(16) float s_y[BQA_WARPS][128];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * BQA_WARPS + wib;
     const int ii = t / max_ch, c = t % max_ch;
@@ -1805,16 +1805,35 @@ __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArI
             if (skip) {
                 for (int i = 0; i < cnt; i++) sy[i] = 0.f;
             } else {
-#pragma unroll 4
-                for (int i = 0; i < cnt; i++) {
-                    const double x = absent ? 0. : (double)sx[i];
-                    double y = __dsub_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(cf[0][i], x), __dmul_rn(cf[1][i], x1)), __dmul_rn(cf[2][i], x2)),
-                                                   __dmul_rn(cf[3][i], y1)),
-                                         __dmul_rn(cf[4][i], y2));
-                    const double ay = fabs(y);
-                    if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
-                    x2 = x1; x1 = x; y2 = y1; y1 = y;
-                    sy[i] = (float)y;
+                // four frames at a time (cnt is a multiple of 128): everything that does not depend on y — the loads, the conversions, the
+                // feed-forward sum ((b0 x + b1 x1) + b2 x2) — is off the dependent chain, which is one multiply, two subtractions and the
+                // flush per frame; same operation order as biquad_filter.rs:869-883
+                for (int i = 0; i < cnt; i += 4) {
+                    double c[5][4];
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        const double2 lo = *reinterpret_cast<const double2*>(&cf[j][i]), hi = *reinterpret_cast<const double2*>(&cf[j][i + 2]);
+                        c[j][0] = lo.x, c[j][1] = lo.y, c[j][2] = hi.x, c[j][3] = hi.y;
+                    }
+                    const float4 xf = *reinterpret_cast<const float4*>(&sx[i]);
+                    const double xa = absent ? 0. : (double)xf.x, xb = absent ? 0. : (double)xf.y, xc = absent ? 0. : (double)xf.z,
+                                 xd = absent ? 0. : (double)xf.w;
+                    const double t0 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][0], xa), __dmul_rn(c[1][0], x1)), __dmul_rn(c[2][0], x2));
+                    const double t1 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][1], xb), __dmul_rn(c[1][1], xa)), __dmul_rn(c[2][1], x1));
+                    const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][2], xc), __dmul_rn(c[1][2], xb)), __dmul_rn(c[2][2], xa));
+                    const double t3 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][3], xd), __dmul_rn(c[1][3], xc)), __dmul_rn(c[2][3], xb));
+                    auto step = [](double t, double a1, double a2, double ym1, double ym2) {
+                        double y = __dsub_rn(__dsub_rn(t, __dmul_rn(a1, ym1)), __dmul_rn(a2, ym2));
+                        const double ay = fabs(y);
+                        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+                        return y;
+                    };
+                    const double ya = step(t0, c[3][0], c[4][0], y1, y2);
+                    const double yb = step(t1, c[3][1], c[4][1], ya, y1);
+                    const double yc = step(t2, c[3][2], c[4][2], yb, ya);
+                    const double yd = step(t3, c[3][3], c[4][3], yc, yb);
+                    x2 = xc; x1 = xd; y2 = yc; y1 = yd;
+                    *reinterpret_cast<float4*>(&sy[i]) = make_float4((float)ya, (float)yb, (float)yc, (float)yd);
                 }
             }
         }
@@ -3313,27 +3332,34 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
 // PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
-// MODE 1: every diagonal of the group is inside 0 <= i < S (no tests at all); MODE 2: the first group of a response of at least CV_J
-// partitions (diagonals u >= CV_J - 1, known at compile time); MODE 0: any group, valid diagonals as a bit mask
-template <bool PACKED, int MODE>
-DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2 (&x)[CV_J], float2 acc[CV_J]) {
-    unsigned mask = 0x7fffu;
-    if (MODE == 2) mask = 0x7fffu & ~((1u << (CV_J - 1)) - 1u);
-    if (MODE == 0) {
-        const int u_lo = i_lo < 0 ? -i_lo : 0;
-        const int u_hi = S - i_lo < 2 * CV_J - 1 ? S - i_lo : 2 * CV_J - 1;
-        mask = u_hi > u_lo ? ((1u << (u_hi - u_lo)) - 1u) << u_lo : 0u;
+template <bool PACKED>
+DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2* __restrict__ xr /* ring[0][k] */, int slot0,
+                         int ring, int64_t b0, int64_t jabs_last, float2 acc[CV_J]) {
+    float2 x[CV_J];
+    if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
+        const float2* xp = xr + (size_t)slot0 * CV_BINS;
+#pragma unroll
+        for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);  // (written by the previous launch: read-only here)
+    } else {
+#pragma unroll
+        for (int r = 0; r < CV_J; r++) {
+            const int64_t bb = b0 + r;
+            int slot = slot0 + r;
+            slot = slot >= ring ? slot - ring : slot;
+            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
+            x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
+        }
     }
     float2 hw[2 * CV_J - 1];
 #pragma unroll
     for (int u = 0; u < 2 * CV_J - 1; u++) {
-        if (MODE != 0 && !((mask >> u) & 1u)) continue;  // (compile time)
-        if (MODE != 0 || ((mask >> u) & 1u)) hw[u] = __ldg(hp + (size_t)u * CV_BINS);
+        const int i = i_lo + u;
+        hw[u] = (i >= 0 && i < S) ? __ldg(hp + (size_t)u * CV_BINS) : make_float2(0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 2 * CV_J - 1; u++) {
-        if (MODE != 0 && !((mask >> u) & 1u)) continue;  // (compile time)
-        if (MODE != 0 || ((mask >> u) & 1u)) {           // (uniform)
+        const int i = i_lo + u;
+        if (i >= 0 && i < S) {  // (uniform)
             const float2 h = hw[u];
 #pragma unroll
             for (int r = 0; r < CV_J; r++) {
@@ -3357,34 +3383,12 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
     // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
     int slot0 = (int)(jabs0 % ring);
     int i_lo = -(CV_J - 1);
-    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the masks guard it)
-    const float2* __restrict__ xr = ip.xring + k;                  // (written by the previous launch: read-only here)
+    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the i >= 0 test guards it)
+    const float2* xr = ip.xring + k;
     int64_t b0 = jabs0;
 #pragma unroll 1
     for (int g = 0; g < groups; g++) {
-        float2 x[CV_J];
-        if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
-            const float2* xp = xr + (size_t)slot0 * CV_BINS;
-#pragma unroll
-            for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);
-        } else {
-#pragma unroll
-            for (int r = 0; r < CV_J; r++) {
-                const int64_t bb = b0 + r;
-                int slot = slot0 + r;
-                while (slot >= ring) slot -= ring;  // (rings shorter than CV_J blocks: tiny chunk option + one-partition IR)
-                x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
-            }
-        }
-        if (PACKED) {  // (one thread of the launch: one copy of the code is enough)
-            conv_mac_group<PACKED, 0>(hp, i_lo, p.S, x, acc);
-        } else if (g == 0 && p.S >= CV_J) {
-            conv_mac_group<PACKED, 2>(hp, i_lo, p.S, x, acc);
-        } else if (i_lo >= 0 && i_lo + 2 * CV_J - 1 <= p.S) {
-            conv_mac_group<PACKED, 1>(hp, i_lo, p.S, x, acc);
-        } else {
-            conv_mac_group<PACKED, 0>(hp, i_lo, p.S, x, acc);
-        }
+        conv_mac_group<PACKED>(hp, i_lo, p.S, xr, slot0, ring, b0, jabs_last, acc);
         hp += (size_t)CV_J * CV_BINS;
         i_lo += CV_J;
         b0 -= CV_J;
