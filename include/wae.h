@@ -258,7 +258,10 @@ enum {
     WAE_OPT_BIND_NUMA = 6,       /* 1: pin the calling thread and the engine's host workers to the CPUs of the GPU's NUMA node (before the first render) */
     WAE_OPT_HOST_WORKERS = 7,    /* host worker threads (planning, copy-out to pageable buffers); 0 = auto (hardware threads / 8, 2..16) */
     WAE_OPT_CHAIN_TMA = 8,       /* process-wide: 1 = the fused chain kernel streams PCM with cp.async.bulk (TMA), 0 = with cp.async */
-    WAE_OPT_CHAIN_WAVES = 9      /* process-wide: time slabs of the fused chain kernel are sized for this many waves of CTAs; 0 = one slab */
+    WAE_OPT_CHAIN_WAVES = 9,     /* process-wide: time slabs of the fused chain kernel are sized for this many waves of CTAs; 0 = one slab */
+    WAE_OPT_CHAIN_PREPASS = 10   /* process-wide, 1 (default): few (graph, channel) pairs with long renders through one biquad are cut into time slabs
+                                  * that find out what they hand on before they render (one extra read of the source), so that the slabs of
+                                  * a pair run concurrently; 0: one CTA per pair walks the whole render */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
 /* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */

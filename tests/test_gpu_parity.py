@@ -1176,6 +1176,101 @@ def test_scan_biquad_recovers_from_a_non_finite_sample(pkg, engine, oracle, bad)
     assert maxdiff(gpu, cpu) <= TOL
 
 
+@pytest.mark.parametrize("chunk", [0, 2048 * 36])
+def test_few_long_renders_are_cut_into_slabs_that_hand_their_state_on_before_they_render(pkg, engine, oracle, chunk):
+    """A handful of (graph, channel) pairs with a long render through one biquad: k_chain<PRE> (time slabs of 32768 frames; every slab
+    first runs from zero state without storing, publishes G^L s_in + that, then renders).  Against the oracle, and against the same
+    render with one CTA per pair (WAE_OPT_CHAIN_PREPASS = 0); sources: buffer (streamed), oscillator, constant; with / without a
+    wave-shaper behind the filter; a state carried over a chunk boundary."""
+    n = 2048 * 75 + 128 * 5   # 76 tiles, the last one ragged: slabs of 16 tiles
+    curve = np.tanh(np.linspace(-2, 2, 257)).astype(np.float32)
+
+    def build(be, g):
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        if g % 3 == 0:
+            pcm = G.c2_source(g, n)
+            src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        elif g % 3 == 1:
+            src = c.create_oscillator(type_=pkg.SAWTOOTH, frequency=97.0 + 13 * g)
+        else:
+            src = c.create_constant_source(offset=0.25)
+        bq = c.create_biquad_filter(type_=[pkg.LOWPASS, pkg.BANDPASS, pkg.HIGHPASS, pkg.PEAKING][g % 4], frequency=[400.0, 30.0, 2500.0, 1200.0][g % 4],
+                                    q=[0.7, 25.0, 2.0, 4.0][g % 4], gain=3.0)
+        gn = c.create_gain(0.6)
+        src.connect(bq)
+        bq.connect(gn)
+        last = gn
+        if g >= 4:
+            last = c.create_wave_shaper(curve)
+            gn.connect(last)
+        last.connect(c.destination())
+        src.start()
+        return c
+
+    engine.set_option(pkg.OPT_CHUNK_FRAMES, chunk)
+    try:
+        gpu, cpu = both(pkg, engine, oracle, build, 7)
+        engine.set_option(pkg.OPT_CHAIN_PREPASS, 0)
+        one = G.render(pkg, [build(engine.backend, g) for g in range(7)])
+    finally:
+        engine.set_option(pkg.OPT_CHAIN_PREPASS, 1)
+        engine.set_option(pkg.OPT_CHUNK_FRAMES, 0)
+    assert maxdiff(gpu, cpu) <= TOL
+    assert maxdiff(gpu, one) <= 2e-6   # same scan, the state crosses 4 slab boundaries through G^L instead of tile by tile
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf])
+def test_a_non_finite_sample_in_a_slab_that_publishes_its_state_early(pkg, engine, oracle, bad):
+    """k_chain<PRE> + biquad_filter.rs:881-883: a slab that flushed a NaN / Inf ends in the same state wherever it started, so it
+    publishes its zero-state end state alone (the `flushed` flag); bad samples in the first, a middle and the last slab"""
+    n = 2048 * 70
+
+    def build(be, g):
+        rng = np.random.default_rng(170 + g)
+        pcm = rng.uniform(-0.5, 0.5, (2, n)).astype(np.float32)
+        pcm[0, 5000 + 100 * g] = bad
+        pcm[1, 2048 * 16 * 2 + 777] = -bad if np.isinf(bad) else bad
+        pcm[0, n - 3000] = bad
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=700.0 + 150 * g, q=6.0)
+        src.connect(bq)
+        bq.connect(c.destination())
+        src.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert np.isfinite(cpu).all() and np.isfinite(gpu).all()
+    assert maxdiff(gpu, cpu) <= TOL
+
+
+@pytest.mark.parametrize("bad", [np.nan, -np.inf])
+def test_automated_biquad_scan_recovers_from_a_non_finite_sample(pkg, engine, oracle, bad):
+    """k_biquad_arate evaluates a quantum as a scan over affine maps; a NaN / Inf in the input poisons the states handed between the lanes,
+    so that quantum is evaluated again by the reference's serial code with its flush (biquad_filter.rs:881-883)"""
+    length = 128 * 30
+
+    def build(be, g):
+        rng = np.random.default_rng(311 + g)
+        pcm = rng.uniform(-0.5, 0.5, (2, length)).astype(np.float32)
+        pcm[0, 700 + 129 * g] = bad
+        pcm[1, 128 * 11] = bad          # first frame of a quantum
+        pcm[1, 128 * 20 + 127] = bad    # last frame of a quantum
+        c = pkg.OfflineAudioContext(2, length, G.SR, be)
+        src = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        bq = c.create_biquad_filter(type_=pkg.LOWPASS, frequency=300.0, q=4.0)
+        bq.frequency.exponential_ramp_to_value_at_time(6000.0, 0.07)
+        bq.q.linear_ramp_to_value_at_time(0.5, 0.05)
+        src.connect(bq)
+        bq.connect(c.destination())
+        src.start()
+        return c
+
+    gpu, cpu = both(pkg, engine, oracle, build, 3)
+    assert np.isfinite(cpu).all() and np.isfinite(gpu).all()
+    assert maxdiff(gpu, cpu) <= TOL
+
+
 def test_one_shot_render_into_registered_caller_memory(pkg, engine):
     """wae_host_register: the caller's own buffer page-locked once, D2H of the one-shot render lands in it directly"""
     import ctypes as C

@@ -427,13 +427,14 @@ struct ChainInst {
 
 // k_chain work decomposition (see the kernel): time slabs handed out in ticket order, filter state handed from slab to slab
 constexpr int CHAIN_MAX_SLABS = 64;
+constexpr int CHAIN_MAX_PRE_SLABS = 256;  // (PRE: few pairs, long renders)
 struct ChainSched {
     int32_t n_slabs;         // time slabs per (instance, channel)
     int32_t tiles_per_slab;  // whole 2048-frame tiles per slab
     int32_t max_ch;          // channel slots per instance in the item numbering
     int32_t slab_stride;     // hand-off slots per (instance, channel)
     uint32_t epoch;          // launch number of this stage: the value a hand-off flag written by this launch carries
-    uint32_t pad;
+    int32_t pre_log2;        // >= 0: k_chain<..., PRE> — slabs of WAE_CHAIN_PRE_TILES << pre_log2 tiles publish the next slab's state before they render
     unsigned* ticket;        // one counter per stage (zero between launches); nullptr: item = blockIdx.x
     double* handoff;         // [(instance * max_ch + channel) * slab_stride + slab][CHAIN_MAX_BIQUADS][4]: state ENTERING the slab
     unsigned* flags;         // same indexing: == epoch once that state is written

@@ -780,6 +780,19 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
         sc.Plane[l][0] = pl.a; sc.Plane[l][1] = pl.b; sc.Plane[l][2] = pl.c; sc.Plane[l][3] = pl.d;
         pl = mul(A, pl);
     }
+    // one frame with zero input: (x1, x2, y1, y2) -> (0, x1, b1 x1 + b2 x2 - a1 y1 - a2 y2, y1); G^L by squaring (L = 2^15 frames)
+    static_assert(WAE_CHAIN_PRE_TILES * WAE_CHAIN_K * 128 == 1 << 15, "GL below is G^(2^15)");
+    double g[16] = {0., 0., 0., 0., 1., 0., 0., 0., c.b1, c.b2, -c.a1, -c.a2, 0., 0., 1., 0.}, h[16];
+    for (int sq = 0; sq < 15; sq++) {
+        for (int r = 0; r < 4; r++)
+            for (int cc = 0; cc < 4; cc++) {
+                double a = 0.;
+                for (int k = 0; k < 4; k++) a += g[4 * r + k] * g[4 * k + cc];
+                h[4 * r + cc] = a;
+            }
+        std::memcpy(g, h, sizeof g);
+    }
+    std::memcpy(sc.GL, g, sizeof g);
     return sc;
 }
 
@@ -2488,6 +2501,7 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "chain waves must be in [0, 1024]");
             chain_set_tuning(-1, (int)value);
             return WAE_OK;
+        case WAE_OPT_CHAIN_PREPASS: chain_set_prepass(value != 0 ? 1 : 0); return WAE_OK;
         default: return fail(WAE_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -2843,7 +2857,8 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                     st.n = (int)s.chain.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef);
                     const int nb = (s.variant % 6) / 2;
                     int slabs = 1, tps = 1;
-                    if (nb > 0) chain_plan_slabs(st.n, st.max_ch, (int)std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start), nb, &slabs, &tps);
+                    int pre_log2 = -1;
+                    if (nb > 0) chain_plan_slabs(st.n, st.max_ch, (int)std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start), nb, &slabs, &tps, &pre_log2);
                     if (slabs > 1) {  // time slabs of filtered chains hand their state over through device memory
                         const size_t slots = (size_t)st.n * st.max_ch * slabs;
                         st.chain.slab_stride = slabs;

@@ -951,6 +951,7 @@ struct ChainSmem {
     double wtot[CH_WARPS][2];            // per-warp end state (zero incoming state)
     double replay[4];                    // serial replay of a tile (non-finite input): state handed from warp to warp
     float edge[CH_WARPS][2];             // last two step inputs of every warp
+    int flushed;                         // a tile of this slab went through the non-finite handling (its end state no longer depends on the state it started from)
 };
 
 // one biquad over the thread's 16 frames (v in/out), see the header comment
@@ -1057,6 +1058,7 @@ DEVI void chain_biquad(ChainSmem& sm, int bq, const double b0, const double b1, 
 #else
     if (__syncthreads_or(poisoned)) {
 #endif
+        if (t == 0) sm.flushed = 1;
         if constexpr (!std::is_same<RL, NoReload>::value) {
             // rare: run the tile again serially, thread after thread, in the reference's own operation order, from the tile's inputs
             float x[CH_K];
@@ -1178,7 +1180,7 @@ DEVI void cswap4(bool p, float4& a, float4& b) {
 // state: their slabs are independent.  TMA = true: the source tiles arrive through 1-D bulk copies (cp.async.bulk +
 // mbarrier), results leave through bulk stores; TMA = false: 16-byte cp.async pieces / coalesced stores (kept as the
 // reference data path: WAE_OPT_CHAIN_TMA = 0).
-template <int SRC, int NB, bool SHAPER, bool TMA>
+template <int SRC, int NB, bool SHAPER, bool TMA, bool PRE = false>
 #ifndef WAE_CH_MINB
 #define WAE_CH_MINB 6
 #endif
@@ -1231,7 +1233,13 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
     const size_t ho = ((size_t)inst * sc.max_ch + c) * sc.slab_stride + slab;  // hand-off slot of the state ENTERING this slab
     // per-CTA constants -> registers / shared
     double cb[NB > 0 ? NB : 1][5];
-    if (NB > 0 && !first_slab) {  // the slab before this one (same instance, channel) publishes the state it ends with
+    // PRE (few (instance, channel) pairs, long renders: chain_plan_slabs): a slab that is not the last one first runs over its frames from
+    // ZERO state without storing anything, which gives the part of its end state that its own input causes; the rest is the state it
+    // starts from carried through the slab, G^L s_in with a host-computed matrix.  So it can publish the state the NEXT slab starts
+    // from as soon as its own s_in arrives — before it renders — and the slabs of one pair render concurrently instead of one after
+    // the other (one extra read of the source; the chain of hand-offs costs a couple of microseconds per slab).
+    const bool pre = PRE && NB == 1 && sc.pre_log2 >= 0 && !last_slab;
+    auto wait_handoff = [&]() {  // the slab before this one (same instance, channel) publishes the state it ends with
         if (t == 0) {
             const unsigned* f = sc.flags + ho;
             unsigned seen;
@@ -1242,7 +1250,8 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
             }
         }
         __syncthreads();
-    }
+    };
+    if (NB > 0 && !first_slab && !pre) wait_handoff();
 #pragma unroll
     for (int k = 0; k < NB; k++) {
         const ChainBiquad& bq = q.bq[k];
@@ -1251,7 +1260,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
         if (t < 20) sm.P[k][t] = (&scf.Pshfl[0][0])[t];
         if (t < 4) {
             sm.P[k][20 + t] = scf.Pwarp[t];
-            sm.state[k][t] = first_slab ? bq.state[4 * c + t] : __ldcg(sc.handoff + ho * (CHAIN_MAX_BIQUADS * 4) + 4 * k + t);
+            sm.state[k][t] = pre ? 0. : (first_slab ? bq.state[4 * c + t] : __ldcg(sc.handoff + ho * (CHAIN_MAX_BIQUADS * 4) + 4 * k + t));
         }
         for (int i = t; i < 128; i += CH_THREADS) (&sm.plane[k][0][0])[i] = (&scf.Plane[0][0])[i];
     }
@@ -1356,8 +1365,10 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
             bulk_load(&s_io[buf][0][0], gp, tile * 4, &s_bar[buf]);
         }
     };
-    float v[CH_K];
     unsigned par = 0;  // TMA path: phase parity of every stage's barrier (bit s), flipped each time the stage is consumed
+    // the slab, tile by tile.  emit = false (PRE): filter state only — nothing is stored, no layout track written
+    auto run_slab = [&](const bool emit) {
+    float v[CH_K];
     if (STREAMED) {
         if (USE_TMA) {
             if (t == 0)
@@ -1461,7 +1472,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g3;
         }
-        if (q.out.meta && active && (n0 & 127) == 0) {
+        if (emit && q.out.meta && active && (n0 & 127) == 0) {
             // Layout track of the chain's output, row c (this CTA's channel), for the quantum this thread starts: the nodes of the
             // chain in order.  source: silent outside its schedule; gain: silent in -> silent out, a gain of (about) zero silences
             // (gain.rs:153-169); biquad: silent once its input is silent AND its state has no normal value left, until then it keeps
@@ -1505,7 +1516,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
             }
             meta_put(q.out, c, qi, cnt, sl || c >= cnt);
         }
-        {
+        if (emit) {
             // results: through the warp's staging region (the source pieces of this tile are consumed), so that global
             // memory sees whole 2 KB regions; per-thread stores for ragged / unaligned / length-limited regions
             const int nw = base + wbase;
@@ -1569,6 +1580,43 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
         if (NB > 0 && !USE_TMA) __syncthreads();  // the carried state of this tile is visible before the next tile reads it
         buf = buf + 1 == NST ? 0 : buf + 1;
     }
+    if (STREAMED && !USE_TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");  // (prefetches past the slab's end are empty groups)
+    };
+    if constexpr (PRE && NB == 1 && !TMA) {
+        if (pre) {
+            if (t == 0) sm.flushed = 0;
+            __syncthreads();
+            run_slab(false);  // leaves the slab's zero-state end state in sm.state[0]
+            __syncthreads();
+            if (!first_slab) wait_handoff();
+            if (t == 0) {
+                double sin_[4], g[16], h[16];
+                const ScanCoef& scf = coefs[q.bq[0].coef];
+                for (int i = 0; i < 4; i++) sin_[i] = first_slab ? q.bq[0].state[4 * c + i] : __ldcg(sc.handoff + ho * (CHAIN_MAX_BIQUADS * 4) + i);
+                for (int i = 0; i < 16; i++) g[i] = scf.GL[i];
+                for (int sq = 0; sq < sc.pre_log2; sq++) {  // G^(2L) = G^L G^L: slabs of CHAIN_PRE_TILES << pre_log2 tiles
+                    for (int r = 0; r < 4; r++)
+                        for (int cc = 0; cc < 4; cc++) {
+                            double a = 0.;
+                            for (int k = 0; k < 4; k++) a = fma(g[4 * r + k], g[4 * k + cc], a);
+                            h[4 * r + cc] = a;
+                        }
+                    for (int i = 0; i < 16; i++) g[i] = h[i];
+                }
+                for (int r = 0; r < 4; r++) {
+                    double o = sm.state[0][r];  // what the slab's own input leaves behind
+                    if (!sm.flushed)            // (a slab that flushed a NaN / Inf ends in the same state wherever it started)
+                        for (int k = 0; k < 4; k++) o = fma(g[4 * r + k], sin_[k], o);
+                    __stcg(sc.handoff + (ho + 1) * (CHAIN_MAX_BIQUADS * 4) + r, o);
+                }
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sc.flags + ho + 1), "r"(sc.epoch) : "memory");
+                for (int i = 0; i < 4; i++) sm.state[0][i] = sin_[i];
+            }
+            __syncthreads();
+        }
+    }
+    run_slab(true);
     if (USE_TMA && t == 0) bulk_wait_read<0>();  // shared memory stays valid until the last bulk store has read it
     // carry the filter state: to the next slab of this launch, or (last slab) to the next chunk
     if (NB > 0) {
@@ -1576,7 +1624,7 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
 #pragma unroll
             for (int k = 0; k < NB; k++)
                 if (t < 4) q.bq[k].state[4 * c + t] = sm.state[k][t];
-        } else {
+        } else if (!pre) {
             if (t < 4 * NB) __stcg(sc.handoff + (ho + 1) * (CHAIN_MAX_BIQUADS * 4) + t, sm.state[t >> 2][t & 3]);
             __threadfence();
             __syncthreads();
@@ -1745,11 +1793,37 @@ __global__ void __launch_bounds__(256) k_biquad_coefs(const BiquadArInst* __rest
         base[4 * cs] = cf.a2;
     }
 }
-// step 2: the reference's serial f64 recurrence with those coefficients.  One WARP per (instance, channel): the lanes stage a quantum of
-// coefficients and input in shared memory with coalesced loads (the next quantum's loads are already in flight in registers), lane 0 runs
-// the 128 dependent steps out of shared memory, the lanes store the quantum.  With one THREAD per channel every step waited for five
-// global loads (2 us per frame on a 120 s render: examples/benchmarks.rs "Substractive Synth" took 11 s for 64 graphs).
+// step 2: the recurrence with those coefficients, one WARP per (instance, channel), a quantum at a time.  The lanes stage the quantum's
+// coefficients and input in shared memory with coalesced loads (the next quantum's loads are already in flight in registers).  With
+// per-frame coefficients the filter is still linear in its state:  (y[n], y[n-1]) = M_n (y[n-1], y[n-2]) + (t_n, 0),
+// M_n = [[-a1_n, -a2_n], [1, 0]],  t_n = (b0_n x[n] + b1_n x[n-1]) + b2_n x[n-2]  — so the quantum is a scan over affine maps: every lane
+// composes the maps of its four frames, a Kogge-Stone scan over the 32 lanes gives each lane the map from the quantum's start to its
+// first frame, and the lane then runs its four frames from that state in the reference's own operation order (biquad_filter.rs:869-883,
+// with its flush of non-normal values).  About 25 dependent f64 operations per quantum instead of 640 (measured: a dependent f64
+// operation of a lone warp costs ~100 cycles here; "Substractive Synth", 64 graphs x 120 s: 77 s -> 11 s -> 2.8 s -> see profiles r2_o).
+// Differs from the serial evaluation by the re-association of the state carried between lanes (~1e-16 relative); a NaN / Inf going
+// through the recurrence (the reference recovers from it sample by sample) sends the quantum to the serial code, which stays below.
 constexpr int BQA_WARPS = 2;
+struct Aff2 {  // s -> A s + b
+    double a00, a01, a10, a11, b0, b1;
+};
+DEVI Aff2 aff_after(const Aff2& g, const Aff2& f) {  // g o f: first f, then g
+    Aff2 r;
+    r.a00 = fma(g.a00, f.a00, g.a01 * f.a10);
+    r.a01 = fma(g.a00, f.a01, g.a01 * f.a11);
+    r.a10 = fma(g.a10, f.a00, g.a11 * f.a10);
+    r.a11 = fma(g.a10, f.a01, g.a11 * f.a11);
+    r.b0 = fma(g.a00, f.b0, fma(g.a01, f.b1, g.b0));
+    r.b1 = fma(g.a10, f.b0, fma(g.a11, f.b1, g.b1));
+    return r;
+}
+DEVI Aff2 aff_shfl_up(const Aff2& v, int d) {
+    Aff2 r;
+    r.a00 = __shfl_up_sync(0xffffffffu, v.a00, d); r.a01 = __shfl_up_sync(0xffffffffu, v.a01, d);
+    r.a10 = __shfl_up_sync(0xffffffffu, v.a10, d); r.a11 = __shfl_up_sync(0xffffffffu, v.a11, d);
+    r.b0 = __shfl_up_sync(0xffffffffu, v.b0, d);   r.b1 = __shfl_up_sync(0xffffffffu, v.b1, d);
+    return r;
+}
 __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArInst* __restrict__ insts, int n_inst, int max_ch, ChunkInfo ci) {
     __shared__ __align__(16) double s_cf[BQA_WARPS][5][128];
     __shared__ __align__(16) float s_x[BQA_WARPS][128];
@@ -1763,8 +1837,7 @@ __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArI
     const float* in = chan(q.in, c, ci);
     float* out = chan(q.out, c, ci);
     double* st = q.state + 4 * c;
-    double x1 = 0., x2 = 0., y1 = 0., y2 = 0.;
-    if (lane == 0) x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];
+    double x1 = st[0], x2 = st[1], y1 = st[2], y2 = st[3];  // (every lane keeps a copy of the carried state)
     const double* cbase = reinterpret_cast<const double*>(q.coefs.p) + ci.sub;
     const size_t cs = q.coefs.stride;
     const bool dyn = q.in.meta != nullptr;
@@ -1785,6 +1858,13 @@ __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArI
             prex[k] = ok ? in[n] : 0.f;
         }
     };
+    auto step = [](double tt, double a1, double a2, double ym1, double ym2, bool& bad) {
+        double y = __dsub_rn(__dsub_rn(tt, __dmul_rn(a1, ym1)), __dmul_rn(a2, ym2));
+        const double ay = fabs(y);
+        if (!(ay <= 1.7976931348623157e308)) bad = true;  // NaN / Inf: the states handed between the lanes are poisoned too
+        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
+        return y;
+    };
     fetch(0);
     for (int n0 = 0; n0 < ci.nf; n0 += 128) {
 #pragma unroll
@@ -1794,51 +1874,93 @@ __global__ void __launch_bounds__(32 * BQA_WARPS) k_biquad_arate(const BiquadArI
             sx[lane + 32 * k] = prex[k];
         }
         __syncwarp();
-        if (n0 + 128 < ci.nf) fetch(n0 + 128);  // in flight while lane 0 works
-        const int cnt = min(128, ci.nf - n0);
-        if (lane == 0) {
-            bool skip = false, absent = false;
-            if (dyn) {
-                filter_layout_step(q.in, q.out, q.ch, c, meta_qi(ci, n0), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
-                if (c >= len) x1 = x2 = y1 = y2 = 0.;
-            }
-            if (skip) {
-                for (int i = 0; i < cnt; i++) sy[i] = 0.f;
-            } else {
-                // four frames at a time (cnt is a multiple of 128): everything that does not depend on y — the loads, the conversions, the
-                // feed-forward sum ((b0 x + b1 x1) + b2 x2) — is off the dependent chain, which is one multiply, two subtractions and the
-                // flush per frame; same operation order as biquad_filter.rs:869-883
-                for (int i = 0; i < cnt; i += 4) {
-                    double c[5][4];
+        if (n0 + 128 < ci.nf) fetch(n0 + 128);  // in flight while this quantum is filtered
+        const int cnt = min(128, ci.nf - n0);     // (a multiple of 128: the render is padded to whole quanta)
+        bool skip = false, absent = false;
+        if (dyn) {  // (identical in every lane; lane 0 writes the layout track)
+            BufRef none = q.out;
+            if (lane != 0) none.meta = nullptr;
+            filter_layout_step(q.in, none, q.ch, c, meta_qi(ci, n0), len, isnormal_d(x1) || isnormal_d(x2) || isnormal_d(y1) || isnormal_d(y2), skip, absent);
+            if (c >= len) x1 = x2 = y1 = y2 = 0.;
+        }
+        if (skip) {
+            *reinterpret_cast<float4*>(&sy[4 * lane]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int i = 4 * lane;
+            double cq[5][4];
 #pragma unroll
-                    for (int j = 0; j < 5; j++) {
-                        const double2 lo = *reinterpret_cast<const double2*>(&cf[j][i]), hi = *reinterpret_cast<const double2*>(&cf[j][i + 2]);
-                        c[j][0] = lo.x, c[j][1] = lo.y, c[j][2] = hi.x, c[j][3] = hi.y;
-                    }
-                    const float4 xf = *reinterpret_cast<const float4*>(&sx[i]);
-                    const double xa = absent ? 0. : (double)xf.x, xb = absent ? 0. : (double)xf.y, xc = absent ? 0. : (double)xf.z,
-                                 xd = absent ? 0. : (double)xf.w;
-                    const double t0 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][0], xa), __dmul_rn(c[1][0], x1)), __dmul_rn(c[2][0], x2));
-                    const double t1 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][1], xb), __dmul_rn(c[1][1], xa)), __dmul_rn(c[2][1], x1));
-                    const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][2], xc), __dmul_rn(c[1][2], xb)), __dmul_rn(c[2][2], xa));
-                    const double t3 = __dadd_rn(__dadd_rn(__dmul_rn(c[0][3], xd), __dmul_rn(c[1][3], xc)), __dmul_rn(c[2][3], xb));
-                    auto step = [](double t, double a1, double a2, double ym1, double ym2) {
-                        double y = __dsub_rn(__dsub_rn(t, __dmul_rn(a1, ym1)), __dmul_rn(a2, ym2));
-                        const double ay = fabs(y);
-                        if (!(ay >= 2.2250738585072014e-308 && ay <= 1.7976931348623157e308)) y = 0.;
-                        return y;
-                    };
-                    const double ya = step(t0, c[3][0], c[4][0], y1, y2);
-                    const double yb = step(t1, c[3][1], c[4][1], ya, y1);
-                    const double yc = step(t2, c[3][2], c[4][2], yb, ya);
-                    const double yd = step(t3, c[3][3], c[4][3], yc, yb);
-                    x2 = xc; x1 = xd; y2 = yc; y1 = yd;
-                    *reinterpret_cast<float4*>(&sy[i]) = make_float4((float)ya, (float)yb, (float)yc, (float)yd);
-                }
+            for (int j = 0; j < 5; j++) {
+                const double2 lo = *reinterpret_cast<const double2*>(&cf[j][i]), hi = *reinterpret_cast<const double2*>(&cf[j][i + 2]);
+                cq[j][0] = lo.x, cq[j][1] = lo.y, cq[j][2] = hi.x, cq[j][3] = hi.y;
             }
+            const float4 xf = *reinterpret_cast<const float4*>(&sx[i]);
+            const double xa = absent ? 0. : (double)xf.x, xb = absent ? 0. : (double)xf.y, xc = absent ? 0. : (double)xf.z,
+                         xd = absent ? 0. : (double)xf.w;
+            // the two inputs before this lane's frames: the carried state (lane 0) or the neighbour's last two
+            const double pm1 = lane == 0 ? x1 : (absent ? 0. : (double)sx[i - 1]), pm2 = lane == 0 ? x2 : (absent ? 0. : (double)sx[i - 2]);
+            const double t0 = __dadd_rn(__dadd_rn(__dmul_rn(cq[0][0], xa), __dmul_rn(cq[1][0], pm1)), __dmul_rn(cq[2][0], pm2));
+            const double t1 = __dadd_rn(__dadd_rn(__dmul_rn(cq[0][1], xb), __dmul_rn(cq[1][1], xa)), __dmul_rn(cq[2][1], pm1));
+            const double t2 = __dadd_rn(__dadd_rn(__dmul_rn(cq[0][2], xc), __dmul_rn(cq[1][2], xb)), __dmul_rn(cq[2][2], xa));
+            const double t3 = __dadd_rn(__dadd_rn(__dmul_rn(cq[0][3], xd), __dmul_rn(cq[1][3], xc)), __dmul_rn(cq[2][3], xb));
+            const double tt[4] = {t0, t1, t2, t3};
+            // the affine map of this lane's four frames
+            Aff2 m{1., 0., 0., 1., 0., 0.};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const double na1 = -cq[3][j], na2 = -cq[4][j];
+                Aff2 r;
+                r.a00 = fma(na1, m.a00, na2 * m.a10);
+                r.a01 = fma(na1, m.a01, na2 * m.a11);
+                r.a10 = m.a00;
+                r.a11 = m.a01;
+                r.b0 = fma(na1, m.b0, fma(na2, m.b1, tt[j]));
+                r.b1 = m.b0;
+                m = r;
+            }
+            // inclusive scan: lane L ends up with the map from the quantum's start to the end of its frames
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const Aff2 o = aff_shfl_up(m, d);
+                if (lane >= d) m = aff_after(m, o);
+            }
+            const Aff2 e = aff_shfl_up(m, 1);  // ... to the start of its frames (lane 0: the identity)
+            double s1 = y1, s2 = y2;
+            if (lane != 0) {
+                s1 = fma(e.a00, y1, fma(e.a01, y2, e.b0));
+                s2 = fma(e.a10, y1, fma(e.a11, y2, e.b1));
+            }
+            bool bad = !(fabs(s1) <= 1.7976931348623157e308) || !(fabs(s2) <= 1.7976931348623157e308);
+            const double ya = step(t0, cq[3][0], cq[4][0], s1, s2, bad);
+            const double yb = step(t1, cq[3][1], cq[4][1], ya, s1, bad);
+            const double yc = step(t2, cq[3][2], cq[4][2], yb, ya, bad);
+            const double yd = step(t3, cq[3][3], cq[4][3], yc, yb, bad);
+            if (!__any_sync(0xffffffffu, bad)) {
+                *reinterpret_cast<float4*>(&sy[i]) = make_float4((float)ya, (float)yb, (float)yc, (float)yd);
+                y1 = __shfl_sync(0xffffffffu, yd, 31);
+                y2 = __shfl_sync(0xffffffffu, yc, 31);
+            } else if (lane == 0) {
+                // rare: a NaN / Inf went through — the reference's own serial evaluation, sample by sample with its flush
+                double qx1 = x1, qx2 = x2, qy1 = y1, qy2 = y2;
+                bool ignore = false;
+                for (int k = 0; k < cnt; k++) {
+                    const double x = absent ? 0. : (double)sx[k];
+                    const double tk = __dadd_rn(__dadd_rn(__dmul_rn(cf[0][k], x), __dmul_rn(cf[1][k], qx1)), __dmul_rn(cf[2][k], qx2));
+                    const double y = step(tk, cf[3][k], cf[4][k], qy1, qy2, ignore);
+                    qx2 = qx1; qx1 = x; qy2 = qy1; qy1 = y;
+                    sy[k] = (float)y;
+                }
+                y1 = qy1;
+                y2 = qy2;
+            }
+            if (__any_sync(0xffffffffu, bad)) {
+                y1 = __shfl_sync(0xffffffffu, y1, 0);
+                y2 = __shfl_sync(0xffffffffu, y2, 0);
+            }
+            x1 = absent ? 0. : (double)sx[127];
+            x2 = absent ? 0. : (double)sx[126];
         }
         __syncwarp();
-        for (int i = lane; i < cnt; i += 32) out[n0 + i] = sy[i];
+        for (int k = lane; k < cnt; k += 32) out[n0 + k] = sy[k];
         __syncwarp();
     }
     if (lane == 0) {
@@ -3669,7 +3791,8 @@ void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, 
     k_biquad_serial<<<(threads + 127) / 128, 128, 0, s>>>(d, n, max_ch, ci);
 }
 // ---- k_chain launch geometry ---------------------------------------------------------------------------------------
-static int g_chain_tma = -1, g_chain_waves = -1;
+static int g_chain_tma = -1, g_chain_waves = -1, g_chain_prepass = -1;
+void chain_set_prepass(int on) { g_chain_prepass = on != 0; }
 static void chain_env() {
     if (g_chain_tma < 0) {
         const char* e = getenv("WAE_CHAIN_TMA");
@@ -3687,10 +3810,27 @@ void chain_set_tuning(int tma, int waves) {
 // Time slabs of one launch: enough work items for `waves` waves of resident CTAs (148 SMs x 6), at least 8 tiles each.  Filtered
 // chains are only cut when the launch has enough (instance, channel) pairs to fill half the machine without it: the slabs of one
 // pair run one after the other (the state is handed over), so with few pairs more slabs would only add waiting CTAs.
-void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab) {
+void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab, int* pre_log2) {
     chain_env();
     const long ctas = (long)n * max_ch, tiles = (nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
     const long slots = 148L * (WAE_CH_MINB * 128 / CH_THREADS);
+    if (pre_log2) *pre_log2 = -1;
+    // Few (instance, channel) pairs and a long render (64 files of two minutes instead of 1000 of ten seconds): the pairs alone leave
+    // the machine empty and the slabs of one pair would wait for each other — unless every slab first finds out what it hands on
+    // (k_chain PRE).  One filter only: with two, the second one's input history is a rounded function of the first one's state.
+    if (g_chain_prepass < 0) {
+        const char* e = getenv("WAE_CHAIN_PREPASS");
+        g_chain_prepass = (!e || atoi(e) != 0) ? 1 : 0;
+    }
+    if (pre_log2 && g_chain_prepass && nb == 1 && 2 * ctas < slots && tiles >= 2 * WAE_CHAIN_PRE_TILES) {
+        long tps = WAE_CHAIN_PRE_TILES;
+        int j = 0;
+        while ((tiles + tps - 1) / tps > CHAIN_MAX_PRE_SLABS) tps *= 2, j++;
+        *n_slabs = (int)((tiles + tps - 1) / tps);
+        *tiles_per_slab = (int)tps;
+        *pre_log2 = j;
+        return;
+    }
     const long min_tiles = std::max(1L, 16384L / (CH_THREADS * CH_K));  // a slab is at least 16384 frames
     long slabs = 1;
     if (nb == 0) {
@@ -3713,11 +3853,14 @@ void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tile
 template <int SRC, int NB>
 static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux) {
     ChainSched sc{};
-    chain_plan_slabs(n, max_ch, ci.nf, NB, &sc.n_slabs, &sc.tiles_per_slab);
+    int pre_log2 = -1;
+    chain_plan_slabs(n, max_ch, ci.nf, NB, &sc.n_slabs, &sc.tiles_per_slab, &pre_log2);
     if (NB > 0 && (sc.n_slabs > aux.slab_stride || !aux.ticket)) {  // no hand-off memory for that many slabs: one slab
         sc.n_slabs = 1;
         sc.tiles_per_slab = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+        pre_log2 = -1;
     }
+    sc.pre_log2 = sc.n_slabs > 1 ? pre_log2 : -1;
     sc.max_ch = max_ch;
     sc.slab_stride = aux.slab_stride > 0 ? aux.slab_stride : 1;
     sc.epoch = aux.epoch;
@@ -3741,6 +3884,19 @@ static void launch_chain_v(bool shaper, const ChainInst* d, const ScanCoef* c, i
         if (g_chain_tma) {
             if (shaper) k_chain<SRC, NB, true, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
             else k_chain<SRC, NB, false, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+            return;
+        }
+    }
+    if constexpr (NB == 1) {
+        if (sc.pre_log2 >= 0) {
+            static bool carved_pre = false;
+            if (!carved_pre && !getenv("WAE_CHAIN_NO_CARVEOUT")) {
+                carved_pre = true;
+                cudaFuncSetAttribute(k_chain<SRC, NB, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaFuncSetAttribute(k_chain<SRC, NB, false, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
+            if (shaper) k_chain<SRC, NB, true, false, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
+            else k_chain<SRC, NB, false, false, true><<<grid, CH_THREADS, 0, s>>>(d, c, n, ci, sc);
             return;
         }
     }

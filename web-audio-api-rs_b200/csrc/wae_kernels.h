@@ -15,7 +15,9 @@ struct ScanCoef {
     double Pshfl[5][4];    // A^(2^d), d = 0..4: warp-level Kogge-Stone steps
     double Plane[32][4];   // A^(lane+1): carries a warp's incoming state to each lane
     double Pwarp[4];       // A^32: one warp
+    double GL[16];         // G^L, L = WAE_CHAIN_PRE_TILES tiles: (x1, x2, y1, y2) entering a slab of L frames -> its share of the state leaving it
 };
+constexpr int WAE_CHAIN_PRE_TILES = 16;  // 32768 frames (k_chain PRE: slabs of WAE_CHAIN_PRE_TILES << pre_log2 tiles)
 
 void upload_twiddles();                          // convolver FFT tables (computed in wae_kernels.cu, f64 -> f32)
 void conv_fft_selftest(float* data, int mode);   // host emulation of the convolver transforms (wae_selftest_conv_fft)
@@ -28,7 +30,8 @@ void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, 
 void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux);
-void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab);  // launch geometry of k_chain (host)
+void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab, int* pre_log2 = nullptr);  // launch geometry of k_chain (host); *pre_log2 >= 0: slabs publish their end state before they render
+void chain_set_prepass(int on);            // WAE_OPT_CHAIN_PREPASS / WAE_CHAIN_PREPASS (default on)
 void chain_set_tuning(int tma, int waves);  // < 0: keep (defaults: WAE_CHAIN_TMA / WAE_CHAIN_WAVES or 0 / 20)
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_gain(const GainInst* d, int n, ChunkInfo ci, cudaStream_t s);
