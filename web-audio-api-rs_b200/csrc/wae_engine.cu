@@ -893,10 +893,10 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
         if (!dry) cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
         spec.S = Smax;
         spec.channels = ir_ch;
-        spec.h = alloc<float2>((size_t)ir_ch * Smax * WAE_CONV_SPEC);
+        spec.h = alloc<float2>((size_t)ir_ch * (Smax + WAE_CONV_H_PAD) * WAE_CONV_SPEC, true);  // (zeroed: the padding partitions of every channel)
         if (!d_ir || !spec.h) return bail(WAE_OUT_OF_MEMORY, "out of device memory (IR spectra)");
         if (!dry) launch_conv_ir_fft(d_ir, (int64_t)ir_len, (int64_t)ir_len, spec.h, Smax, ir_ch, eng->stream);
-        b->asset_bytes += (size_t)ir_ch * Smax * WAE_CONV_SPEC * 8;
+        b->asset_bytes += (size_t)ir_ch * (Smax + WAE_CONV_H_PAD) * WAE_CONV_SPEC * 8;
         (*ir_cache)[key] = spec;
     }
     ir_lock.unlock();
@@ -932,7 +932,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
     for (auto& r : routes) {
         ConvPath p;
         p.out = pn.out_buf[0];
-        p.h = spec.h + (size_t)r.ir * Smax * WAE_CONV_SPEC;
+        p.h = spec.h + ((size_t)r.ir * (Smax + WAE_CONV_H_PAD) + WAE_CONV_H_PAD_LO) * WAE_CONV_SPEC;
         p.input = in_base + r.in;
         p.S = Smax;
         p.out_channel = r.out;

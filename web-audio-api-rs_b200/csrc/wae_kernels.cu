@@ -847,6 +847,23 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
                 float4 a = __ldg(in + u);
                 v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
             }
+        } else if (o.loop && n >= o.n_start && n + CH_K <= o.n_stop) {
+            // looping, fully active: ONE modulo for the thread's run, then a wrapping index (was: a 64-bit modulo per frame)
+            int64_t pos = idx % o.buf_len;
+            if (pos + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + pos) & 15) == 0)) {
+                const float4* in = reinterpret_cast<const float4*>(src + pos);
+#pragma unroll
+                for (int u = 0; u < CH_K / 4; u++) {
+                    float4 a = __ldg(in + u);
+                    v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) {
+                    v[j] = __ldg(src + pos);
+                    pos = pos + 1 == o.buf_len ? 0 : pos + 1;
+                }
+            }
         } else {
 #pragma unroll
             for (int j = 0; j < CH_K; j++) {
@@ -3453,47 +3470,26 @@ __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restr
 // per group instead of three integer instructions per load: the kernel was bound by issue slots, ALU pipe above the FMA pipe).
 constexpr int CV_J = 8;
 constexpr int CV_MAC_THREADS = 256;
-// PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise
-template <bool PACKED>
-DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_lo}[k] */, int i_lo, int S, const float2* __restrict__ xr /* ring[0][k] */, int slot0,
-                         int ring, int64_t b0, int64_t jabs_last, float2 acc[CV_J]) {
-    float2 x[CV_J];
-    if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
-        const float2* xp = xr + (size_t)slot0 * CV_BINS;
-#pragma unroll
-        for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);  // (written by the previous launch: read-only here)
-    } else {
-#pragma unroll
-        for (int r = 0; r < CV_J; r++) {
-            const int64_t bb = b0 + r;
-            int slot = slot0 + r;
-            slot = slot >= ring ? slot - ring : slot;
-            if (slot >= ring) slot %= ring;  // rings shorter than CV_J blocks (tiny chunk option + one-partition IR)
-            x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
-        }
-    }
+// PACKED: bin 0 holds (DC, Nyquist), two real bins that multiply component-wise.  FIRST: the head group (i_base = 0), only i = jj - r >= 0.
+// The IR spectra are stored with WAE_CONV_H_PAD_LO zero partitions before H_0 and zero partitions behind H_{S-1} up to the end of the
+// last group (plan_convolver): the loads of a group need no range tests at all — 23 loads and 256 FMAs per group, where the tests of
+// the exact walk cost more issue slots than the multiplications with zero they saved (ncu r2_l: ALU pipe 59 % against FMA 32 %).
+template <bool PACKED, bool FIRST>
+DEVI void conv_mac_group(const float2* __restrict__ hp /* H_{i_base - (CV_J - 1)}[k] */, const float2 (&x)[CV_J], float2 acc[CV_J]) {
     float2 hw[2 * CV_J - 1];
 #pragma unroll
-    for (int u = 0; u < 2 * CV_J - 1; u++) {
-        const int i = i_lo + u;
-        hw[u] = (i >= 0 && i < S) ? __ldg(hp + (size_t)u * CV_BINS) : make_float2(0.f, 0.f);
-    }
+    for (int u = FIRST ? CV_J - 1 : 0; u < 2 * CV_J - 1; u++) hw[u] = __ldg(hp + (size_t)u * CV_BINS);
 #pragma unroll
-    for (int u = 0; u < 2 * CV_J - 1; u++) {
-        const int i = i_lo + u;
-        if (i >= 0 && i < S) {  // (uniform)
-            const float2 h = hw[u];
+    for (int r = 0; r < CV_J; r++) {
 #pragma unroll
-            for (int r = 0; r < CV_J; r++) {
-                const int jj = r + u - (CV_J - 1);
-                if (jj < 0 || jj >= CV_J) continue;
-                if (PACKED) {
-                    acc[jj].x = fmaf(h.x, x[r].x, acc[jj].x);
-                    acc[jj].y = fmaf(h.y, x[r].y, acc[jj].y);
-                } else {
-                    acc[jj].x = fmaf(h.x, x[r].x, fmaf(-h.y, x[r].y, acc[jj].x));
-                    acc[jj].y = fmaf(h.x, x[r].y, fmaf(h.y, x[r].x, acc[jj].y));
-                }
+        for (int jj = FIRST ? r : 0; jj < CV_J; jj++) {
+            const float2 h = hw[(CV_J - 1) + jj - r];
+            if (PACKED) {
+                acc[jj].x = fmaf(h.x, x[r].x, acc[jj].x);
+                acc[jj].y = fmaf(h.y, x[r].y, acc[jj].y);
+            } else {
+                acc[jj].x = fmaf(h.x, x[r].x, fmaf(-h.y, x[r].y, acc[jj].x));
+                acc[jj].y = fmaf(h.x, x[r].y, fmaf(h.y, x[r].x, acc[jj].y));
             }
         }
     }
@@ -3504,15 +3500,28 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
     const int ring = ip.xring_blocks;
     // ring slot of input block jabs0 (>= 0), walked backwards by CV_J per group without a division
     int slot0 = (int)(jabs0 % ring);
-    int i_lo = -(CV_J - 1);
-    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (never dereferenced below H_0: the i >= 0 test guards it)
-    const float2* xr = ip.xring + k;
+    const float2* hp = p.h + k - (ptrdiff_t)(CV_J - 1) * CV_BINS;  // (inside the zero partitions in front of H_0)
+    const float2* __restrict__ xr = ip.xring + k;                  // (written by the previous launch: read-only here)
     int64_t b0 = jabs0;
 #pragma unroll 1
     for (int g = 0; g < groups; g++) {
-        conv_mac_group<PACKED>(hp, i_lo, p.S, xr, slot0, ring, b0, jabs_last, acc);
+        float2 x[CV_J];
+        if (slot0 + CV_J <= ring && b0 >= 0 && b0 + (CV_J - 1) <= jabs_last) {  // (uniform) eight produced blocks in eight consecutive slots
+            const float2* xp = xr + (size_t)slot0 * CV_BINS;
+#pragma unroll
+            for (int r = 0; r < CV_J; r++) x[r] = __ldg(xp + (size_t)r * CV_BINS);
+        } else {
+#pragma unroll
+            for (int r = 0; r < CV_J; r++) {
+                const int64_t bb = b0 + r;
+                int slot = slot0 + r;
+                while (slot >= ring) slot -= ring;  // (rings shorter than CV_J blocks: tiny chunk option + one-partition IR)
+                x[r] = (bb >= 0 && bb <= jabs_last) ? __ldg(xr + (size_t)slot * CV_BINS) : make_float2(0.f, 0.f);
+            }
+        }
+        if (g == 0) conv_mac_group<PACKED, true>(hp, x, acc);
+        else conv_mac_group<PACKED, false>(hp, x, acc);
         hp += (size_t)CV_J * CV_BINS;
-        i_lo += CV_J;
         b0 -= CV_J;
         slot0 -= CV_J;
         while (slot0 < 0) slot0 += ring;  // only meaningful while b0 >= 0; older blocks are skipped by the range test
@@ -3615,7 +3624,7 @@ __global__ void __launch_bounds__(CV_THREADS) k_conv_ir_fft(const float* __restr
     conv_load_half(z, CV_B / 2, nullptr, 0);
     __syncthreads();
     fft_dif_smem(z, w);
-    rfft_store(z, h + ((size_t)c * S + seg) * CV_BINS, lane_tw);
+    rfft_store(z, h + ((size_t)c * (S + WAE_CONV_H_PAD) + WAE_CONV_H_PAD_LO + seg) * CV_BINS, lane_tw);  // (padding partitions stay zero)
 }
 
 // Host emulation of the transforms above with the SAME butterfly, index and twiddle code (tests/test_conv_fft_host.py pins them against

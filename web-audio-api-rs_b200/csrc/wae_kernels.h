@@ -11,6 +11,10 @@ namespace wae {
 constexpr int WAE_CHAIN_K = 16;  // frames per thread of k_chain
 constexpr int WAE_CONV_BLOCK = 8192;            // frames per convolver partition (the reference's 1024 is a latency choice, see wae_kernels.cu)
 constexpr int WAE_CONV_SPEC = WAE_CONV_BLOCK;   // float2 per block spectrum (packed real FFT of 2 * block: bin 0 = (DC, Nyquist))
+// IR spectra of one response channel: [WAE_CONV_H_PAD_LO zero partitions][S partitions][zero partitions up to WAE_CONV_H_PAD in total] —
+// k_conv_mac walks the partitions in groups of 8 x 8 products whose first and last group reach 7 / up to 15 partitions past the ends
+constexpr int WAE_CONV_H_PAD_LO = 7;
+constexpr int WAE_CONV_H_PAD = 7 + 16;
 struct ScanCoef {
     double Pshfl[5][4];    // A^(2^d), d = 0..4: warp-level Kogge-Stone steps
     double Plane[32][4];   // A^(lane+1): carries a warp's incoming state to each lane
