@@ -82,4 +82,4 @@ class Engine:
 
 
 OPT_CHUNK_FRAMES, OPT_FUSE, OPT_SERIAL_FILTERS, OPT_PIPELINE_GROUPS, OPT_PARAM_PARALLEL = 1, 2, 3, 4, 5
-OPT_BIND_NUMA, OPT_HOST_WORKERS, OPT_CHAIN_TMA, OPT_CHAIN_WAVES, OPT_CHAIN_PREPASS = 6, 7, 8, 9, 10
+OPT_BIND_NUMA, OPT_HOST_WORKERS, OPT_CHAIN_TMA, OPT_CHAIN_WAVES, OPT_CHAIN_PREPASS, OPT_VOICE_SUM = 6, 7, 8, 9, 10, 11

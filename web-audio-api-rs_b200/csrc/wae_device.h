@@ -447,6 +447,17 @@ struct ChainAux {  // per-stage device memory of the slab hand-off (engine-owned
     uint32_t epoch = 0;
 };
 
+// k_voice_sum: the voices (oscillator -> [biquad] -> gain chains, mono, static layout) of one input port, summed in the port's edge
+// order without ever being written out.  The group's ChainInst records are consecutive in the stage's instance table.
+struct VoiceGroup {
+    int32_t first;     // first ChainInst of the group
+    int32_t n_voices;
+    BufRef out;        // the mono sum (arena buffer or the rendered PCM)
+    int32_t out_dup;   // channels the sum is written to (speaker up-mix 1 -> 2 by copy), >= 1
+    int32_t pad;
+    int64_t limit;     // frames >= limit are not written (destination); < 0: none
+};
+
 // ---- convolver (uniformly partitioned overlap-save, block WAE_CONV_BLOCK, time-batched) -----------------
 struct ConvInput {   // one input channel of one convolver instance
     BufRef in;

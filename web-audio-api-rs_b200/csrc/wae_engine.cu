@@ -110,6 +110,7 @@ struct wae_engine {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined / one-shot paths
     int64_t chunk_frames = 0;  // 0 = auto
     bool fuse = true;
+    int voice_sum = -1;  // WAE_OPT_VOICE_SUM: fused oscillator voices + ordered sum (k_voice_sum); -1: WAE_VOICE_SUM from the environment, default on
     bool serial_filters = false;
     int pipeline_groups = 0;  // 0 = auto
     int param_parallel = 2;  // WAE_OPT_PARAM_PARALLEL: 2 k_param_spec (CTA per param, speculative walks of 32 quanta), 1 k_param_parallel (warp per param), 0 k_param (lane 0 evaluates every frame)
@@ -228,11 +229,11 @@ namespace {
 // (the order of the kinds is the launch order inside one level: mixes first; k_delay_mono before the delay reader that needs it)
 enum StageKind : int {
     S_MIX = 0, S_MIX_DYN, S_OSC, S_CONST, S_ABSN, S_BIQUAD, S_IIR, S_GAIN, S_SHAPER, S_SPAN, S_PAN, S_ROUTE, S_DELAY_MONO, S_DELAY, S_DELAY_WRITE, S_COMP, S_ANALYSER,
-    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_SHAPER_OS, S_META, S_KINDS
+    S_CONV_FFT, S_CONV_MAC, S_CONV_MAC_ACC, S_CHAIN, S_PARAM, S_OSC_AR, S_BIQUAD_AR, S_ABSN_SLOW, S_HRTF, S_PAN_DYN, S_ABSN_SERIAL, S_SHAPER_OS, S_META, S_VSUM, S_KINDS
 };
 const char* kStageNames[S_KINDS] = {"k_mix", "k_mix_dyn", "k_oscillator", "k_constant", "k_buffer_source", "k_biquad_serial", "k_iir_serial", "k_gain",
                                     "k_shaper", "k_stereo_panner", "k_panner_eq", "k_route", "k_delay_mono", "k_delay_read", "k_ring_write", "k_compressor",
-                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial", "k_shaper_os", "k_meta"};
+                                    "k_analyser", "k_conv_fft_in", "k_conv_mac_ifft", "k_conv_mac_ifft(acc)", "k_chain", "k_param", "k_osc_arate", "k_biquad_arate", "k_buffer_source_slow", "k_hrtf_fir", "k_panner_dyn", "k_buffer_source_serial", "k_shaper_os", "k_meta", "k_voice_sum"};
 
 // host-side accumulation of instances for one (level, kind) stage
 struct StageBuild {
@@ -271,6 +272,7 @@ struct StageBuild {
     std::vector<MetaInst> meta;
     std::vector<ConvInput> conv_in;
     std::vector<ConvPath> conv_path;
+    std::vector<VoiceGroup> vgroups;  // S_VSUM: groups of consecutive `chain` records
     int max_ch = 1;
 };
 
@@ -285,6 +287,7 @@ struct Stage {
     int max_ch = 1;
     void* d_a = nullptr;  // instances
     void* d_b = nullptr;  // auxiliary table (mix edges, scan coefficients, conv inputs, panner gains)
+    void* d_c = nullptr;  // S_VSUM: voice groups
     float ms = 0.f;       // accumulated device time of the last run (when timing is enabled)
     ChainAux chain;       // S_CHAIN with biquads: ticket counter + slab hand-off slots (k_chain)
 };
@@ -557,6 +560,12 @@ struct Planner {
     };
     std::map<std::pair<uint32_t, uint32_t>, DelayRing> delay_rings;       // (graph, writer id)
     bool dry = false;                     // sizing pass: count arena floats per frame, touch no device memory
+    int group_graphs = 1;                 // graphs of the group being planned (k_voice_sum: are there enough work items?)
+    int voice_sum_mode() const {  // 0 off, 1 when the launch is large enough, 2 whenever the port has the shape (tests)
+        if (eng->voice_sum >= 0) return eng->voice_sum;
+        static const int env = [] { const char* e = getenv("WAE_VOICE_SUM"); return e ? std::max(0, std::min(2, atoi(e))) : 1; }();
+        return env;
+    }
     uint64_t arena_floats_per_frame = 0;
     // source PCM slab of the group being planned (device pointer, pinned host mirror, cursor in floats)
     float* d_src = nullptr;
@@ -1190,10 +1199,45 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 }
             }
         }
-        for (auto& port : p.in_edges)
+        // ---- k_voice_sum (WAE_OPT_VOICE_SUM): a port fed by many oscillator -> [biquad] -> gain voices, all of them still pending chains
+        // (mono, constant layout, one consumer): the voices are not materialised, one kernel renders them and keeps the running sum in
+        // registers, in the port's edge order.  Only when the launch has enough (2048-frame tile, port) work items to fill the machine
+        // about twice: one graph with thousands of voices and a short render (configs[2]) is better served by k_chain + k_mix, which
+        // take their parallelism from the voices.
+        std::vector<char> port_vsum(p.in_edges.size(), 0);
+        std::vector<int> port_vsum_nb(p.in_edges.size(), 0);
+        if (fuse && voice_sum_mode() != 0 && !extend && !dest_direct && cur_cls == 0 && n.kind != K_DELAY_R) {
+            for (size_t pi = 0; pi < p.in_edges.size() && (int)pi < n.n_inputs; pi++) {
+                const auto& edges = p.in_edges[pi];
+                if ((int)edges.size() < 8) continue;
+                const int ch = computed_channels(n.cfg, 1);
+                if (!(ch == 1 || (ch == 2 && n.cfg.interp == WAE_INTERPRETATION_SPEAKERS))) continue;
+                if (n.kind == K_DEST && b->length > 0xffffffffull) continue;
+                const int64_t tiles = (seg_end - seg_start + 2047) / 2048;
+                if (voice_sum_mode() < 2 && tiles * (int64_t)group_graphs < 2 * (int64_t)voice_sum_slots()) continue;
+                int nb = -1;
+                bool ok = true;
+                std::set<uint32_t> seen_nodes;
+                for (auto& r : edges) {
+                    auto it = pending.find(r.node);
+                    if (r.port != 0 || it == pending.end()) { ok = false; break; }
+                    const PendingChain& pc = it->second;
+                    if (pc.inst.src_kind != CHAIN_SRC_OSC || pc.ch != 1 || pc.inst.has_shaper || pc.inst.n_biquad > 1 || pc.lay.dyn() || pc.cls != cur_cls ||
+                        (nb >= 0 && nb != pc.inst.n_biquad) || !seen_nodes.insert(r.node).second) { ok = false; break; }
+                    nb = pc.inst.n_biquad;
+                }
+                if (!ok) continue;
+                port_vsum[pi] = 1;
+                port_vsum_nb[pi] = nb;
+            }
+        }
+        for (size_t pi = 0; pi < p.in_edges.size(); pi++) {
+            if (port_vsum[pi]) continue;
+            auto& port = p.in_edges[pi];
             for (auto& r : port)
                 if (!((extend || dest_direct) && r.node == fuse_src))
                     if (!materialize(r.node, n.kind == K_CONV && n.buffer && port.size() == 1)) return false;
+        }
         p.in_ch.assign(n.n_inputs, 1);
         p.in_buf.assign(n.n_inputs, BufRef{nullptr, 0, 0});
         p.in_lay.assign(n.n_inputs, Lay::fixed(1));
@@ -1210,6 +1254,35 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             bool is_dest = n.kind == K_DEST;
             if (extend || dest_direct) {  // the producer's chain is consumed in registers / written directly
                 if (extend) p.in_lay[port] = pending.at(fuse_src).lay;
+                continue;
+            }
+            if (port_vsum[port]) {  // the voices of this port and their sum in one kernel
+                StageBuild& vs = stage(2 * level, S_VSUM, port_vsum_nb[port]);
+                VoiceGroup vg{};
+                vg.first = (int32_t)vs.chain.size();
+                vg.n_voices = (int32_t)edges.size();
+                vg.out_dup = ch;
+                vg.limit = -1;
+                if (is_dest) {
+                    vg.out = BufRef{b->d_out + (size_t)gi * b->channels * b->length, (uint32_t)b->length, 1};
+                    vg.limit = (int64_t)b->length;
+                } else {
+                    vg.out = arena_buf(ch);
+                    if (!vg.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                }
+                for (auto& r : edges) {
+                    PendingChain pc = std::move(pending.at(r.node));
+                    pending.erase(r.node);
+                    for (int k = 0; k < pc.inst.n_biquad; k++) {
+                        pc.inst.bq[k].coef = (int32_t)vs.scan_coef.size();
+                        vs.scan_coef.push_back(pc.coefs[k]);
+                    }
+                    pc.inst.limit = -1;
+                    pc.inst.out_dup = 0;
+                    vs.chain.push_back(pc.inst);
+                }
+                vs.vgroups.push_back(vg);
+                p.in_buf[port] = vg.out;
                 continue;
             }
             if (is_dest && edges.size() == 1 && pn.at(edges[0].node).wrote_dest) {  // the producer already wrote the rendered PCM
@@ -2481,6 +2554,7 @@ WAE_API wae_status wae_engine_set_option(wae_engine* eng, uint32_t option, int64
             eng->chunk_frames = value;
             return WAE_OK;
         case WAE_OPT_FUSE: eng->fuse = value != 0; return WAE_OK;
+        case WAE_OPT_VOICE_SUM: eng->voice_sum = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return WAE_OK;
         case WAE_OPT_SERIAL_FILTERS: eng->serial_filters = value != 0; return WAE_OK;
         case WAE_OPT_PIPELINE_GROUPS:
             if (value < 0 || value > 1024) return fail(WAE_INVALID_ARGUMENT, "pipeline groups must be in [0, 1024]");
@@ -2658,6 +2732,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
         auto size_group = [&](int k) {
             Planner sizing{b, eng};
             sizing.dry = true;
+            sizing.group_graphs = (int)(b->groups[k].g1 - b->groups[k].g0);
             sizing.delay_ch_hint = &ps.delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
             b->groups[k].src_copies.clear();
@@ -2785,6 +2860,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
     wae_batch::Group& grp = b->groups[k];
     Planner pl{b, eng};
     pl.d_src = grp.d_src;
+    pl.group_graphs = (int)(grp.g1 - grp.g0);
     pl.src_copies = nullptr;  // recorded by the sizing pass
     pl.delay_ch_hint = &ps.delay_ch_hint;
     pl.ir_cache = &ps.ir_cache;
@@ -2867,6 +2943,17 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                         st.chain.handoff = b->dalloc<double>(slots * CHAIN_MAX_BIQUADS * 4);
                         if (!st.chain.ticket || !st.chain.flags || !st.chain.handoff) return oom("chain hand-off");
                     }
+                    break;
+                }
+                case S_VSUM: {
+                    st.n = (int)s.vgroups.size(); st.d_a = up(b, s.chain); st.d_b = up(b, s.scan_coef); st.d_c = up(b, s.vgroups);
+                    const int64_t nf_max = std::min<int64_t>(b->chunk, pl.seg_end - pl.seg_start);
+                    const int tiles = (int)((nf_max + 2047) / 2048);
+                    st.chain.slab_stride = tiles;  // progress counters per group
+                    st.chain.ticket = b->dalloc<unsigned>(1, true);
+                    st.chain.flags = b->dalloc<unsigned>((size_t)st.n * tiles, true);
+                    st.chain.handoff = b->dalloc<double>(s.chain.size() * 2 * 4);
+                    if (!st.chain.ticket || !st.chain.flags || !st.chain.handoff) return oom("voice-sum hand-off");
                     break;
                 }
                 case S_PARAM: st.n = (int)s.param.size(); st.d_a = up(b, s.param); break;
@@ -3035,6 +3122,10 @@ static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
         case S_CHAIN:
             st.chain.epoch++;  // hand-off flags of this launch carry its number (never reset, never reused)
             launch_chain(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, st.n, st.max_ch, ci, s, st.chain);
+            break;
+        case S_VSUM:
+            st.chain.epoch++;  // (progress counters carry the launch number)
+            launch_voice_sum(st.variant, (ChainInst*)st.d_a, (ScanCoef*)st.d_b, (VoiceGroup*)st.d_c, st.n, ci, s, st.chain);
             break;
         case S_IIR: launch_iir((IirInst*)st.d_a, st.n, st.max_ch, ci, s); break;
         case S_GAIN: launch_gain((GainInst*)st.d_a, st.n, ci, s); break;

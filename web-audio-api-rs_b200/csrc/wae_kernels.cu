@@ -636,7 +636,6 @@ __global__ void __launch_bounds__(64) k_meta(const MetaInst* __restrict__ insts,
 // before the 8 dependent adds, so a 4096-edge fan-in (config C3) is bandwidth-, not latency-bound, while the f32
 // summation order stays the reference's.  When all edges are mono the sum is computed once and written to every
 // output channel (the reference's "all channels identical" fast path, quantum.rs:549-558).
-constexpr int MIX_BATCH = 8;
 template <int VEC>
 struct MixVec;
 template <>
@@ -656,29 +655,44 @@ struct MixVec<1> {
     DEVI float get(int) const { return v; }
 };
 
-template <int VEC, int BATCH>
-DEVI void mix_simple(const MixInst& m, const MixEdge* __restrict__ edges, int c, int n0, const ChunkInfo& ci, MixVec<VEC>& acc) {
-    const MixEdge* e = edges + m.edge_offset;
-    acc.zero();
-    int k = 0;
-    for (; k + BATCH <= m.n_edges; k += BATCH) {
-        MixVec<VEC> v[BATCH];
+// The CTA first resolves the channel pointers of up to MIX_STAGE edges into shared memory (every thread of the CTA follows the same
+// edges: one global read of the edge table per CTA instead of one per thread, and no pointer load in front of every sample load),
+// then each thread walks them in two alternating batches: the loads of one batch are in flight while the other one is added, in edge
+// order, so the f32 summation order stays the reference's.
+constexpr int MIX_STAGE = 256;
+template <int VEC>
+struct MixBatch { static constexpr int N = VEC == 1 ? 16 : 4; };
+
+template <int VEC, int B>
+DEVI void mix_load(MixVec<VEC> (&v)[B], const float* const* src, int k, int n0) {
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            const MixEdge& ed = e[k + u];
-            v[u].load(chan(ed.src, ed.src_ch == 1 ? 0 : c, ci) + n0);
-        }
+    for (int u = 0; u < B; u++) v[u].load(src[k + u] + n0);
+}
+template <int VEC, int B>
+DEVI void mix_add(MixVec<VEC>& acc, const MixVec<VEC> (&v)[B], bool first) {
 #pragma unroll
-        for (int u = 0; u < BATCH; u++) {
-            if (k + u == 0) acc = v[u];
-            else acc.add(v[u]);
-        }
+    for (int u = 0; u < B; u++) {
+        if (u == 0 && first) acc = v[0];  // the first edge is taken as it is (a sum that starts from -0.0 keeps its sign)
+        else acc.add(v[u]);
     }
-    for (; k < m.n_edges; k++) {
-        const MixEdge& ed = e[k];
+}
+// `cnt` edges whose pointers are in src[]; first: src[0] is the port's first edge
+template <int VEC>
+DEVI void mix_run(const float* const* src, int cnt, int n0, bool first, MixVec<VEC>& acc) {
+    constexpr int B = MixBatch<VEC>::N;
+    MixVec<VEC> a[B], b[B];
+    const int nb = cnt / B;
+    if (nb > 0) mix_load<VEC, B>(a, src, 0, n0);
+    for (int bi = 0; bi < nb; bi += 2) {
+        if (bi + 1 < nb) mix_load<VEC, B>(b, src, (bi + 1) * B, n0);
+        mix_add<VEC, B>(acc, a, first && bi == 0);
+        if (bi + 2 < nb) mix_load<VEC, B>(a, src, (bi + 2) * B, n0);
+        if (bi + 1 < nb) mix_add<VEC, B>(acc, b, false);
+    }
+    for (int k = nb * B; k < cnt; k++) {
         MixVec<VEC> v;
-        v.load(chan(ed.src, ed.src_ch == 1 ? 0 : c, ci) + n0);
-        if (k == 0) acc = v;
+        v.load(src[k] + n0);
+        if (k == 0 && first) acc = v;
         else acc.add(v);
     }
 }
@@ -686,15 +700,26 @@ DEVI void mix_simple(const MixInst& m, const MixEdge* __restrict__ edges, int c,
 template <int VEC>
 __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst,
                                              ChunkInfo ci) {
-    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+    __shared__ const float* s_src[MIX_STAGE];
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {  // (CTA-uniform loop: the barriers below are reached by every thread)
         const MixInst m = insts[ii];
         const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
-        if (n0 >= ci.nf) continue;
+        const bool live = n0 < ci.nf;
         if (m.simple) {
             const int n_sum = m.all_mono ? 1 : m.out_ch;
             for (int c = 0; c < n_sum; c++) {
                 MixVec<VEC> acc;
-                mix_simple<VEC, MIX_BATCH>(m, edges, c, n0, ci, acc);  // (32 loads in flight measured slower than 8 on C3)
+                acc.zero();
+                for (int base = 0; base < m.n_edges; base += MIX_STAGE) {
+                    __syncthreads();  // the previous stage's pointers have been used by everyone
+                    if (base + (int)threadIdx.x < m.n_edges) {
+                        const MixEdge& ed = edges[m.edge_offset + base + threadIdx.x];
+                        s_src[threadIdx.x] = chan(ed.src, ed.src_ch == 1 ? 0 : c, ci);
+                    }
+                    __syncthreads();
+                    if (live) mix_run<VEC>(s_src, min(MIX_STAGE, m.n_edges - base), n0, base == 0, acc);
+                }
+                if (!live) continue;
                 for (int oc = c; oc < (m.all_mono ? m.out_ch : c + 1); oc++) {
                     float* out = chan(m.out, oc, ci) + n0;
                     const bool vec = VEC == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (m.limit < 0 || ci.f0 + n0 + 4 <= m.limit);
@@ -708,6 +733,7 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
             }
             continue;
         }
+        if (!live) continue;
         for (int j = 0; j < VEC; j++) {
             const int n = n0 + j;
             if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
@@ -826,7 +852,7 @@ DEVI void mat2_fma(const double* P, double a, double b, double& accA, double& ac
 }
 
 template <int SRC>
-DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int n0, float v[CH_K]) {
+DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int n0, float v[CH_K], const float2* tab2 = nullptr) {
     // n0: first frame (chunk-relative) of this thread's 16 frames; caller guarantees n0 < ci.nf
     if (SRC == CHAIN_SRC_BUFFER) {
         const float4* in = reinterpret_cast<const float4*>(chan(q.in, c, ci) + n0);
@@ -847,33 +873,24 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
                 float4 a = __ldg(in + u);
                 v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
             }
-        } else if (o.loop && n >= o.n_start && n + CH_K <= o.n_stop) {
-            // looping, fully active: ONE modulo for the thread's run, then a wrapping index (was: a 64-bit modulo per frame)
-            int64_t pos = idx % o.buf_len;
-            if (pos + CH_K <= o.buf_len && ((reinterpret_cast<uintptr_t>(src + pos) & 15) == 0)) {
-                const float4* in = reinterpret_cast<const float4*>(src + pos);
-#pragma unroll
-                for (int u = 0; u < CH_K / 4; u++) {
-                    float4 a = __ldg(in + u);
-                    v[4 * u] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = a.z; v[4 * u + 3] = a.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    v[j] = __ldg(src + pos);
-                    pos = pos + 1 == o.buf_len ? 0 : pos + 1;
-                }
-            }
         } else {
+            // ragged / looping runs, frame by frame; a looping buffer costs ONE modulo per thread and then a wrapping index (was: a 64-bit
+            // modulo per frame).  (Kept this small: the out-of-line gather's register needs are saved and restored around every call
+            // in k_chain — a float4 fast path for loops here made the streamed kernel spill, r2_p.)
+            int64_t pos = 0;
+            if (o.loop) {
+                pos = idx % o.buf_len;
+                if (pos < 0) pos += o.buf_len;  // (frames before the start: never read, but the index keeps step)
+            }
 #pragma unroll
             for (int j = 0; j < CH_K; j++) {
-                int64_t m = n + j;
+                const int64_t m = n + j;
                 float s = 0.f;
                 if (m >= o.n_start && m < o.n_stop) {
-                    int64_t id = m - o.n_start + o.buf_offset;
-                    if (o.loop) s = __ldg(src + (id % o.buf_len));
-                    else if (id < o.buf_len) s = __ldg(src + id);
+                    if (o.loop) s = __ldg(src + pos);
+                    else if (idx + j < o.buf_len) s = __ldg(src + idx + j);
                 }
+                if (o.loop) pos = pos + 1 == o.buf_len ? 0 : pos + 1;
                 v[j] = s;
             }
         }
@@ -891,43 +908,79 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
             const unsigned long long HALF = 0x8000000000000000ull;
             const int type = o.type;
             if (type == 0 || type == 4) {  // sine (:571-585) / custom (:622-637): 2048-entry table + lerp with fmaf
+                if (tab2) {  // the CTA's shared copy of the table as (entry, next entry) pairs: one 8-byte shared load per frame
 #pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    const unsigned hi = (unsigned)(ph >> 32), lo = (unsigned)ph;
-                    const int prev = (int)(hi >> 21);
-                    const int next = (prev + 1) & 2047;
-                    const float k = __uint_as_float(0x3f800000u | ((hi << 11 | lo >> 21) >> 9)) - 1.0f;
-                    v[j] = fmaf(o.table[prev], 1.f - k, o.table[next] * k);
-                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
-                }
-            } else if (type == 2) {  // sawtooth (:588-595): 2 * unroll(phase + 0.5) - 1 - polyBLEP
-#pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    const unsigned long long p2 = ph + HALF;
-                    float s;
-                    if (p2 < dph || p2 > 0ull - dph) {  // inside the polyBLEP window (a 2 * incr fraction of the frames)
-                        s = osc_saw_blep(p2, inc, inv);
-                    } else {
-                        s = __ll2float_rn((long long)ph) * 1.08420217248550443e-19f;  // (2 p2 - 1) = signed(ph) / 2^63
+                    for (int j = 0; j < CH_K; j++) {
+                        const unsigned hi = (unsigned)(ph >> 32), lo = (unsigned)ph;
+                        const float2 e = tab2[hi >> 21];
+                        const float k = __uint_as_float(0x3f800000u | ((hi << 11 | lo >> 21) >> 9)) - 1.0f;
+                        v[j] = fmaf(e.x, 1.f - k, e.y * k);
+                        asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
                     }
-                    v[j] = s;
-                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
-                }
-            } else if (type == 1) {  // square (:598-606)
+                } else {
 #pragma unroll
-                for (int j = 0; j < CH_K; j++) {
-                    const unsigned long long p2 = ph + HALF;
-                    float s = (long long)ph >= 0 ? 1.0f : -1.0f;
-                    if (ph < dph || ph > 0ull - dph || p2 < dph || p2 > 0ull - dph) s = osc_square_blep(ph, p2, inc, inv);
-                    v[j] = s;
-                    asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
+                    for (int j = 0; j < CH_K; j++) {
+                        const unsigned hi = (unsigned)(ph >> 32), lo = (unsigned)ph;
+                        const int prev = (int)(hi >> 21);
+                        const int next = (prev + 1) & 2047;
+                        const float k = __uint_as_float(0x3f800000u | ((hi << 11 | lo >> 21) >> 9)) - 1.0f;
+                        v[j] = fmaf(__ldg(o.table + prev), 1.f - k, __ldg(o.table + next) * k);
+                        asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));
+                    }
+                }
+            } else if (type == 2 || type == 1) {
+                // sawtooth (:588-595): 2 * unroll(phase + 0.5) - 1 - polyBLEP;  square (:598-606): +-1 + polyBLEP(phase) - polyBLEP(phase + 0.5).
+                // Pass 1 writes the plain wave and notes, one bit per frame, the frames that MAY lie in a polyBLEP window: with
+                // u = phase + dph the sawtooth's window around the wrap of phase + 0.5 is u + 2^63 < 2 dph, the square's two windows
+                // (around 0 and 0.5) are u mod 2^63 < 2 dph; the test looks at the high words only, so it flags a few frames too many —
+                // the out-of-line evaluation decides exactly, in f64, and returns the plain wave for those.  Pass 2 visits the flagged
+                // frames lane by lane: a warp whose lanes have their windows at different frames runs the f64 evaluation as often as its
+                // busiest lane has flagged frames (1 - 2 times per tile at 440 Hz) instead of once per frame that ANY lane flags (7 of 16;
+                // ncu r2_p: the polyBLEP lines were 32 % of the oscillator chain's instructions).
+                const unsigned long long ph0 = ph;
+                const unsigned thr = (unsigned)((dph + dph) >> 32);
+                unsigned mask = 0;
+                if (type == 2) {
+                    const unsigned long long cw = HALF + dph;
+#pragma unroll
+                    for (int j = 0; j < CH_K; j++) {
+                        v[j] = __ll2float_rn((long long)ph) * 1.08420217248550443e-19f;  // (2 p2 - 1) = signed(ph) / 2^63
+                        if ((unsigned)((ph + cw) >> 32) <= thr) mask |= 1u << j;
+                        asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));
+                    }
+                    while (mask) {
+                        const int jw = __ffs((int)mask) - 1;
+                        mask &= mask - 1;
+                        const unsigned long long pj = ph0 + (unsigned long long)jw * dph;
+                        const float sw = osc_saw_blep(pj + HALF, inc, inv);
+#pragma unroll
+                        for (int j = 0; j < CH_K; j++) v[j] = j == jw ? sw : v[j];
+                    }
+                } else {
+                    const bool wide = dph >= 0x4000000000000000ull;  // incr >= 1/4: the two windows cover every frame
+#pragma unroll
+                    for (int j = 0; j < CH_K; j++) {
+                        v[j] = (long long)ph >= 0 ? 1.0f : -1.0f;
+                        if (((unsigned)((ph + dph) >> 32) & 0x7fffffffu) <= thr) mask |= 1u << j;
+                        asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));
+                    }
+                    if (wide) mask = (1u << CH_K) - 1u;
+                    while (mask) {
+                        const int jw = __ffs((int)mask) - 1;
+                        mask &= mask - 1;
+                        const unsigned long long pj = ph0 + (unsigned long long)jw * dph;
+                        const float sw = osc_square_blep(pj, pj + HALF, inc, inv);
+#pragma unroll
+                        for (int j = 0; j < CH_K; j++) v[j] = j == jw ? sw : v[j];
+                    }
                 }
             } else {  // triangle (:609-619): fold(-4 phase + 2) = 1 - 4 |phase - 1/4| with the difference taken modulo 1
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) {
                     long long q = (long long)(ph - 0x4000000000000000ull);
-                    q = q < 0 ? -q : q;  // |q| * 2^64, < 2^63 (q = -2^63 maps to itself: phase 3/4, value -1)
-                    v[j] = (float)fma((double)(unsigned long long)q, -2.16840434497100887e-19, 1.0);  // 1 - 4 |q| / 2^64, one f32 rounding
+                    q = q < 0 ? -q : q;  // |q| * 2^64, <= 2^63 (q = -2^63 maps to itself: phase 3/4, value -1)
+                    // 1 - 4 |q| / 2^64 = (2^62 - |q|) / 2^62: the integer is exact, its conversion is the one f32 rounding
+                    v[j] = __ll2float_rn((long long)(0x4000000000000000ull - (unsigned long long)q)) * 2.16840434497100887e-19f;
                     asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));  // opaque: keeps ONE running phase instead of 16 precomputed ones
                 }
             }
@@ -1197,11 +1250,21 @@ DEVI void cswap4(bool p, float4& a, float4& b) {
 // state: their slabs are independent.  TMA = true: the source tiles arrive through 1-D bulk copies (cp.async.bulk +
 // mbarrier), results leave through bulk stores; TMA = false: 16-byte cp.async pieces / coalesced stores (kept as the
 // reference data path: WAE_OPT_CHAIN_TMA = 0).
-template <int SRC, int NB, bool SHAPER, bool TMA, bool PRE = false>
 #ifndef WAE_CH_MINB
 #define WAE_CH_MINB 6
 #endif
-__global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128 : WAE_CH_MINB * 128) / CH_THREADS) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
+// resident CTAs per SM the register budget is cut for: 6 (80 registers) for the streamed chains, which live on memory-level parallelism;
+// one fewer with two filters; the oscillator chains are bound by issue slots and latency, not by DRAM, and spill at 80 registers
+// (56 bytes of stack in <OSC, 1>): WAE_CH_MINB_OSC CTAs (96+ registers)
+#ifndef WAE_CH_MINB_OSC
+#define WAE_CH_MINB_OSC 5
+#endif
+constexpr int chain_min_blocks(int src, int nb) {
+    const int base = src == CHAIN_SRC_OSC ? WAE_CH_MINB_OSC : WAE_CH_MINB;
+    return ((nb == 2 ? base - 1 : base) * 128) / CH_THREADS;
+}
+template <int SRC, int NB, bool SHAPER, bool TMA, bool PRE = false>
+__global__ void __launch_bounds__(CH_THREADS, chain_min_blocks(SRC, NB)) k_chain(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
                                                                         int n_inst, ChunkInfo ci, ChainSched sc) {
     __shared__ ChainSmem sm;
     __shared__ int s_item;
@@ -1227,15 +1290,15 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
         for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = src[i];
     }
     __syncthreads();
-    // oscillator wavetable -> shared memory: the 128 threads of a CTA are 16 frames apart, so their table indices fall
-    // in different 128-byte lines (a 32-wavefront global gather per load); shared memory only pays bank conflicts
-    __shared__ float s_table[SRC == CHAIN_SRC_OSC ? 2048 : 1];
-    if (SRC == CHAIN_SRC_OSC && sm.q.osc.table_len <= 2048 && (sm.q.osc.type == 0 || sm.q.osc.type == 4)) {
+    // oscillator wavetable -> shared memory, as (entry, next entry) pairs: the 128 threads of a CTA are 16 frames apart, so their table
+    // indices fall in different 128-byte lines (a 32-wavefront global gather per load); shared memory only pays bank conflicts, and the
+    // pair makes the two taps of the interpolation one 8-byte load
+    __shared__ float2 s_table2[SRC == CHAIN_SRC_OSC ? 2048 : 1];
+    const float2* tab2 = nullptr;
+    if (SRC == CHAIN_SRC_OSC && sm.q.osc.table_len == 2048 && (sm.q.osc.type == 0 || sm.q.osc.type == 4)) {
         const float* gt = sm.q.osc.table;
-        const int len = sm.q.osc.table_len;
-        for (int i = t; i < len; i += CH_THREADS) s_table[i] = __ldg(gt + i);
-        __syncthreads();
-        if (t == 0) sm.q.osc.table = s_table;
+        for (int i = t; i < 2048; i += CH_THREADS) s_table2[i] = make_float2(__ldg(gt + i), __ldg(gt + ((i + 1) & 2047)));
+        tab2 = s_table2;
         __syncthreads();
     }
     const ChainInst& q = sm.q;
@@ -1433,10 +1496,10 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
                     v[4 * u] = a[u].x; v[4 * u + 1] = a[u].y; v[4 * u + 2] = a[u].z; v[4 * u + 3] = a[u].w;
                 }
             } else if (active) {
-                chain_load_source<SRC>(q, c, ci, n0, v);
+                chain_load_source<SRC>(q, c, ci, n0, v, tab2);
             }
         } else if (active) {
-            chain_load_source<SRC>(q, c, ci, n0, v);
+            chain_load_source<SRC>(q, c, ci, n0, v, tab2);
         }
         bool clean0 = true, clean1 = true;
         const bool want_clean = q.out.meta != nullptr;
@@ -1646,6 +1709,151 @@ __global__ void __launch_bounds__(CH_THREADS, (NB == 2 ? (WAE_CH_MINB - 1) * 128
             __threadfence();
             __syncthreads();
             if (t == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(sc.flags + ho + 1), "r"(sc.epoch) : "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// k_voice_sum — Graph::render's edge summation (graph.rs:489-535, AudioRenderQuantum::add, quantum.rs:532-569) for a port fed by
+// many oscillator -> [biquad] -> gain voices (many_oscillators.rs, the north_star graph), fused with the voices themselves: the
+// voices are never written to memory.  f32 addition does not associate and the reference adds the edges one after the other, so the
+// sum of a frame is a serial chain over the voices; the parallelism is over time.  A work item is (2048-frame tile, group): the CTA
+// keeps the tile's partial sum in registers (16 frames per thread) and walks the group's voices in edge order — oscillator into
+// registers, biquad as the block scan of k_chain, gain, add.  The biquad state a voice leaves at the end of tile s is what tile s + 1
+// of the same voice starts from: items are handed out in ticket order, tile-major, so the CTA of tile s - 1 is always running or
+// done when tile s starts, and it publishes, voice by voice, the state it ends with (two slots per voice, indexed by tile parity)
+// and a progress counter "voices finished" that tile s polls — only when its cached copy does not already cover the voice it is at:
+// the CTAs of consecutive tiles follow each other one voice apart, like a pipeline along the time axis.
+// Replaces, for such ports, k_chain (one 8 KB store per voice tile) + k_mix (one 8 KB load per voice tile).
+// ---------------------------------------------------------------------------------------------------------
+#ifndef WAE_VS_MINB
+#define WAE_VS_MINB 5
+#endif
+template <int NB>
+__global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_voice_sum(const ChainInst* __restrict__ insts, const ScanCoef* __restrict__ coefs,
+                                                                                          const VoiceGroup* __restrict__ groups, int n_groups, ChunkInfo ci,
+                                                                                          ChainSched sc) {
+    __shared__ ChainSmem sm;
+    __shared__ int s_item;
+    __shared__ float2 s_table2[2048];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) {
+        const unsigned tk = atomicAdd(sc.ticket, 1u);
+        if (tk == gridDim.x - 1) atomicExch(sc.ticket, 0u);  // the last ticket of this launch: leave the counter ready for the next one
+        s_item = (int)tk;
+    }
+    __syncthreads();
+    const int item = s_item;
+    const int slab = item / n_groups, gi = item - slab * n_groups;
+    const VoiceGroup grp = groups[gi];
+    constexpr int tile = CH_THREADS * CH_K;
+    const int base = slab * tile;
+    if (base >= ci.nf) return;
+    const int n0 = base + t * CH_K;
+    const bool active = n0 < ci.nf;
+    const int n_active = min(CH_THREADS, (ci.nf - base) / CH_K);
+    const bool first_slab = slab == 0, last_slab = base + tile >= ci.nf;
+    const unsigned tag = (sc.epoch & 0xfffu) << 20;
+    const unsigned* prog_prev = sc.flags + (size_t)gi * sc.slab_stride + (slab > 0 ? slab - 1 : 0);
+    unsigned* prog_mine = sc.flags + (size_t)gi * sc.slab_stride + slab;
+    unsigned seen = 0;  // (thread 0) voices the tile before this one is known to have finished
+    const float* cur_table = nullptr;
+    float acc[CH_K];
+#pragma unroll
+    for (int j = 0; j < CH_K; j++) acc[j] = 0.f;
+    for (int vi = 0; vi < grp.n_voices; vi++) {
+        const int inst = grp.first + vi;
+        if (NB > 0 && !first_slab && t == 0 && seen <= (unsigned)vi) {
+            for (;;) {
+                unsigned x;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(prog_prev) : "memory");
+                if ((x & 0xfff00000u) == tag && (x & 0xfffffu) > (unsigned)vi) {
+                    seen = x & 0xfffffu;
+                    break;
+                }
+                __nanosleep(100);
+            }
+        }
+        {
+            const int* src = reinterpret_cast<const int*>(insts + inst);
+            int* dst = reinterpret_cast<int*>(&sm.q);
+            for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();  // (1) the voice's record is in shared memory; thread 0 has seen its incoming state published
+        const ChainInst& q = sm.q;
+        const float2* tab2 = nullptr;
+        if ((q.osc.type == 0 || q.osc.type == 4) && q.osc.table_len == 2048) {
+            if (q.osc.table != cur_table) {  // (CTA-uniform) sine voices share one table: staged once per CTA
+                const float* gt = q.osc.table;
+                for (int i = t; i < 2048; i += CH_THREADS) s_table2[i] = make_float2(__ldg(gt + i), __ldg(gt + ((i + 1) & 2047)));
+                cur_table = gt;
+            }
+            tab2 = s_table2;
+        }
+        double cb[5] = {0., 0., 0., 0., 0.};
+        double* st_ptr = nullptr;
+        if (NB > 0) {
+            const ChainBiquad& bq = q.bq[0];
+            cb[0] = bq.b0; cb[1] = bq.b1; cb[2] = bq.b2; cb[3] = bq.a1; cb[4] = bq.a2;
+            st_ptr = bq.state;
+            const ScanCoef& scf = coefs[bq.coef];
+            if (t < 20) sm.P[0][t] = (&scf.Pshfl[0][0])[t];
+            if (t < 4) {
+                sm.P[0][20 + t] = scf.Pwarp[t];
+                sm.state[0][t] = first_slab ? bq.state[t] : __ldcg(sc.handoff + ((size_t)inst * 2 + (slab & 1)) * 4 + t);
+            }
+            for (int i = t; i < 128; i += CH_THREADS) (&sm.plane[0][0][0])[i] = (&scf.Plane[0][0])[i];
+        }
+        const float g0 = q.g[0], g1 = q.g[1];
+        __syncthreads();  // (2) filter constants, incoming state and (possibly) the table are in place
+        float v[CH_K];
+        if (active) chain_load_source<CHAIN_SRC_OSC>(q, 0, ci, n0, v, tab2);
+        if (g0 != 1.f) {
+#pragma unroll
+            for (int j = 0; j < CH_K; j++) v[j] *= g0;
+        }
+        if (NB > 0) {
+            bool clean = true;
+            chain_biquad(sm, 0, cb[0], cb[1], cb[2], cb[3], cb[4], sm.plane[0][lane > 0 ? lane - 1 : 0], v, active, n_active, t, lane, warp, false, clean, NoReload{});
+            if (g1 != 1.f) {
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) v[j] *= g1;
+            }
+        }
+        if (active) {
+            if (vi == 0) {  // the first edge is taken as it is (AudioRenderQuantum::add onto a silent input = copy)
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) acc[j] = v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < CH_K; j++) acc[j] += v[j];
+            }
+        }
+        __syncthreads();  // (3) everyone is done with the voice's record and constants; its end state is in sm.state[0]
+        if (NB > 0 && warp == 0) {
+            if (lane < 4) {
+                const double e = sm.state[0][lane];
+                if (last_slab) st_ptr[lane] = e;  // carried to the next chunk
+                else __stcg(sc.handoff + ((size_t)inst * 2 + ((slab + 1) & 1)) * 4 + lane, e);
+            }
+            if (!last_slab) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_mine), "r"(tag | (unsigned)(vi + 1)) : "memory");
+            }
+        }
+    }
+    if (!active) return;
+    const int64_t nabs = ci.f0 + n0;
+    for (int oc = 0; oc < grp.out_dup; oc++) {
+        float* out = chan(grp.out, oc, ci) + n0;
+        if ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (grp.limit < 0 || nabs + CH_K <= grp.limit)) {
+#pragma unroll
+            for (int u = 0; u < CH_K / 4; u++) reinterpret_cast<float4*>(out)[u] = make_float4(acc[4 * u], acc[4 * u + 1], acc[4 * u + 2], acc[4 * u + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < CH_K; j++)
+                if (grp.limit < 0 || nabs + j < grp.limit) out[j] = acc[j];
         }
     }
 }
@@ -3930,6 +4138,29 @@ void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int
         case CHAIN_SRC_OSC: launch_chain_s<CHAIN_SRC_OSC>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
         default: launch_chain_s<CHAIN_SRC_CONST>(nb, shaper, d, c, n, max_ch, ci, s, aux); break;
     }
+}
+int voice_sum_slots() { return 148 * (WAE_VS_MINB * 128 / CH_THREADS); }
+void launch_voice_sum(int nb, const ChainInst* d, const ScanCoef* c, const VoiceGroup* g, int n_groups, ChunkInfo ci, cudaStream_t s, ChainAux aux) {
+    ChainSched sc{};
+    const int n_tiles = (ci.nf + CH_THREADS * CH_K - 1) / (CH_THREADS * CH_K);
+    sc.n_slabs = n_tiles;
+    sc.tiles_per_slab = 1;
+    sc.max_ch = 1;
+    sc.slab_stride = aux.slab_stride;  // progress counters per group (>= n_tiles: sized for a whole chunk)
+    sc.epoch = aux.epoch;
+    sc.pre_log2 = -1;
+    sc.ticket = aux.ticket;
+    sc.handoff = aux.handoff;
+    sc.flags = aux.flags;
+    const unsigned grid = (unsigned)n_tiles * (unsigned)n_groups;
+    static bool carved = false;
+    if (!carved) {
+        carved = true;
+        cudaFuncSetAttribute(k_voice_sum<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_voice_sum<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    if (nb == 0) k_voice_sum<0><<<grid, CH_THREADS, 0, s>>>(d, c, g, n_groups, ci, sc);
+    else k_voice_sum<1><<<grid, CH_THREADS, 0, s>>>(d, c, g, n_groups, ci, sc);
 }
 void launch_iir(const IirInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s) {
     int threads = n * max_ch;

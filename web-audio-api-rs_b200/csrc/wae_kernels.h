@@ -34,6 +34,10 @@ void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, 
 void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
 void launch_chain(int variant, const ChainInst* d, const ScanCoef* c, int n, int max_ch, ChunkInfo ci, cudaStream_t s, ChainAux aux);
+// voices summed in edge order inside one kernel (k_voice_sum); nb = biquads per voice (0 / 1).  aux: ticket, progress counters
+// [n_groups][aux.slab_stride tiles], state hand-off [voices][2][4]
+void launch_voice_sum(int nb, const ChainInst* d, const ScanCoef* c, const VoiceGroup* g, int n_groups, ChunkInfo ci, cudaStream_t s, ChainAux aux);
+int voice_sum_slots();  // resident CTAs of k_voice_sum on the machine (host: is a launch big enough to be worth it?)
 void chain_plan_slabs(int n, int max_ch, int nf, int nb, int* n_slabs, int* tiles_per_slab, int* pre_log2 = nullptr);  // launch geometry of k_chain (host); *pre_log2 >= 0: slabs publish their end state before they render
 void chain_set_prepass(int on);            // WAE_OPT_CHAIN_PREPASS / WAE_CHAIN_PREPASS (default on)
 void chain_set_tuning(int tma, int waves);  // < 0: keep (defaults: WAE_CHAIN_TMA / WAE_CHAIN_WAVES or 0 / 20)
