@@ -251,6 +251,11 @@ def measure_workload(pkg, eng, D, oracle, name, build, n_gpu, n_cpu, length, ste
         out["cpu_port"] = {"value": n_cpu * ((length + 127) // 128) / secs.value, "cores_used": min(cores, n_cpu),
                            "sample": f"{n_cpu} graphs, {secs.value:.2f} s wall", "max_abs_diff_vs_gpu": float(np.abs(got - ref).max()),
                            "ref_abs_max": float(np.abs(ref).max())}
+        # the batch the kernel-only figure was timed on may be lowered differently from the one-shot call's one-graph groups (k_voice_sum
+        # needs a whole group's work items): check its PCM as well
+        timed = batch.fetch()[:n_cpu]
+        out["cpu_port"]["max_abs_diff_vs_timed_batch"] = float(np.abs(timed - ref).max())
+        del timed
     batch.destroy()
     return out
 

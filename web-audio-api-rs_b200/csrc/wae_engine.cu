@@ -1273,6 +1273,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 for (auto& r : edges) {
                     PendingChain pc = std::move(pending.at(r.node));
                     pending.erase(r.node);
+                    // (k_voice_sum prefetches the constants of voice k as coefficient set k: one set per voice, in voice order)
+                    if (pc.inst.n_biquad == 1 && vs.scan_coef.size() != vs.chain.size()) return bail(WAE_UNSUPPORTED, "internal: voice-sum coefficient table out of step");
                     for (int k = 0; k < pc.inst.n_biquad; k++) {
                         pc.inst.bq[k].coef = (int32_t)vs.scan_coef.size();
                         vs.scan_coef.push_back(pc.coefs[k]);

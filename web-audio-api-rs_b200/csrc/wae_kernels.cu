@@ -1761,25 +1761,61 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
     float acc[CH_K];
 #pragma unroll
     for (int j = 0; j < CH_K; j++) acc[j] = 0.f;
+    // The record and the filter constants of the NEXT voice are loaded into registers while the current voice is computed (one 4-byte
+    // word of the 512-byte record, one or two doubles of the 152 scan constants per thread) and put into shared memory at the top of
+    // the next iteration: the voice loop never waits for a table read.  Voice k of the stage owns coefficient set k (plan_graph).
+    constexpr int REC_W = (int)(sizeof(ChainInst) / 4 + CH_THREADS - 1) / CH_THREADS;
+    constexpr int PL_W = (128 + CH_THREADS - 1) / CH_THREADS;
+    static_assert(CH_THREADS >= 24, "scan constants: one of Pshfl / Pwarp per thread");
+    int rec_n[REC_W];
+    double pl_n[PL_W], pw_n = 0.;
+    auto prefetch = [&](int vi) {
+        const int inst = grp.first + vi;
+        const int* src = reinterpret_cast<const int*>(insts + inst);
+#pragma unroll
+        for (int i = 0; i < REC_W; i++) rec_n[i] = (t + i * CH_THREADS) < (int)(sizeof(ChainInst) / 4) ? __ldg(src + t + i * CH_THREADS) : 0;
+        if (NB > 0) {
+            const ScanCoef& scf = coefs[inst];
+#pragma unroll
+            for (int i = 0; i < PL_W; i++) pl_n[i] = (t + i * CH_THREADS) < 128 ? (&scf.Plane[0][0])[t + i * CH_THREADS] : 0.;
+            if (t < 20) pw_n = (&scf.Pshfl[0][0])[t];
+            else if (t < 24) pw_n = scf.Pwarp[t - 20];
+        }
+    };
+    prefetch(0);
     for (int vi = 0; vi < grp.n_voices; vi++) {
         const int inst = grp.first + vi;
-        if (NB > 0 && !first_slab && t == 0 && seen <= (unsigned)vi) {
-            for (;;) {
-                unsigned x;
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(prog_prev) : "memory");
-                if ((x & 0xfff00000u) == tag && (x & 0xfffffu) > (unsigned)vi) {
-                    seen = x & 0xfffffu;
-                    break;
+        // (everyone is past barrier (3) of the voice before: its record and constants are dead)
+#pragma unroll
+        for (int i = 0; i < REC_W; i++)
+            if ((t + i * CH_THREADS) < (int)(sizeof(ChainInst) / 4)) reinterpret_cast<int*>(&sm.q)[t + i * CH_THREADS] = rec_n[i];
+        if (NB > 0) {
+#pragma unroll
+            for (int i = 0; i < PL_W; i++)
+                if ((t + i * CH_THREADS) < 128) (&sm.plane[0][0][0])[t + i * CH_THREADS] = pl_n[i];
+            if (t < 24) sm.P[0][t] = pw_n;  // [0, 20): Pshfl, [20, 24): Pwarp
+            if (warp == 0) {  // the state this voice enters the tile with
+                if (first_slab) {
+                    if (lane < 4) sm.state[0][lane] = insts[inst].bq[0].state[lane];  // (carried from the chunk before)
+                } else {
+                    if (lane == 0 && seen <= (unsigned)vi) {
+                        for (;;) {
+                            unsigned x;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(prog_prev) : "memory");
+                            if ((x & 0xfff00000u) == tag && (x & 0xfffffu) > (unsigned)vi) {
+                                seen = x & 0xfffffu;
+                                break;
+                            }
+                            __nanosleep(100);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < 4) sm.state[0][lane] = __ldcg(sc.handoff + ((size_t)inst * 2 + (slab & 1)) * 4 + lane);
                 }
-                __nanosleep(100);
             }
         }
-        {
-            const int* src = reinterpret_cast<const int*>(insts + inst);
-            int* dst = reinterpret_cast<int*>(&sm.q);
-            for (int i = t; i < (int)(sizeof(ChainInst) / 4); i += CH_THREADS) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();  // (1) the voice's record is in shared memory; thread 0 has seen its incoming state published
+        __syncthreads();  // (1) record, constants and incoming state of the voice are in shared memory
+        if (vi + 1 < grp.n_voices) prefetch(vi + 1);
         const ChainInst& q = sm.q;
         const float2* tab2 = nullptr;
         if ((q.osc.type == 0 || q.osc.type == 4) && q.osc.table_len == 2048) {
@@ -1787,6 +1823,7 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
                 const float* gt = q.osc.table;
                 for (int i = t; i < 2048; i += CH_THREADS) s_table2[i] = make_float2(__ldg(gt + i), __ldg(gt + ((i + 1) & 2047)));
                 cur_table = gt;
+                __syncthreads();
             }
             tab2 = s_table2;
         }
@@ -1796,16 +1833,8 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
             const ChainBiquad& bq = q.bq[0];
             cb[0] = bq.b0; cb[1] = bq.b1; cb[2] = bq.b2; cb[3] = bq.a1; cb[4] = bq.a2;
             st_ptr = bq.state;
-            const ScanCoef& scf = coefs[bq.coef];
-            if (t < 20) sm.P[0][t] = (&scf.Pshfl[0][0])[t];
-            if (t < 4) {
-                sm.P[0][20 + t] = scf.Pwarp[t];
-                sm.state[0][t] = first_slab ? bq.state[t] : __ldcg(sc.handoff + ((size_t)inst * 2 + (slab & 1)) * 4 + t);
-            }
-            for (int i = t; i < 128; i += CH_THREADS) (&sm.plane[0][0][0])[i] = (&scf.Plane[0][0])[i];
         }
         const float g0 = q.g[0], g1 = q.g[1];
-        __syncthreads();  // (2) filter constants, incoming state and (possibly) the table are in place
         float v[CH_K];
         if (active) chain_load_source<CHAIN_SRC_OSC>(q, 0, ci, n0, v, tab2);
         if (g0 != 1.f) {
