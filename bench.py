@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 SR = 48000.0
 METRIC = "offline render-quanta/sec (48kHz stereo, 128-frame)"
+FP64_PEAK_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # B200 non-tensor FP64 (nominal)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # B200 non-tensor FP32: 148 SMs x 128 lanes x FMA at the 1965 MHz boost clock
 PARKING_GARAGE_IR_FRAMES = 178899  # samples/parking-garage-response.wav (164 363 frames @ 44.1 kHz) resampled to 48 kHz
 
@@ -273,6 +274,19 @@ def kernel_rooflines(w, peak_gbs):
             res.append({"kernels": "k_conv_fft_in + k_conv_mac_ifft", "ms": round(conv_ms, 4), "bound": "fp32 (FFT butterflies + spectrum MACs)",
                         "achieved_tflops": tf, "peak_tflops": FP32_PEAK_TFLOPS, "frac": tf / FP32_PEAK_TFLOPS,
                         "hbm_gbs_vs_compulsory_io": gbs, "hbm_frac": gbs / peak_gbs})
+    vf = w.get("voice_frames")
+    if vf:
+        # oscillator -> biquad voices: SURVEY §8(d) counts 0 HBM bytes for them (state in registers), so the bound is arithmetic.  Model: the
+        # biquad of one voice frame = 3 feed-forward + 2 x 2 recurrence DFMA (the time-parallel scan runs the recurrence twice) = 14 f64
+        # flops; oscillator, conversions and the warp scan come on top and are not counted.  Peak: 148 SMs x 64 f64 lanes x FMA at 1965 MHz
+        # (nominal, not in MEASURED_PEAKS.json).
+        names = [k for k in st if k in ("k_voice_sum", "k_chain", "k_mix")]
+        ms = sum(st[k] for k in names)
+        if ms > 0:
+            tf = vf * 14 / (ms * 1e-3) / 1e12
+            res.append({"kernels": " + ".join(names), "ms": round(ms, 4), "bound": "issue slots / f64 pipe (no compulsory HBM bytes)",
+                        "voice_frames_per_s": vf / (ms * 1e-3), "achieved_tflops": tf, "peak_tflops": FP64_PEAK_TFLOPS, "frac": tf / FP64_PEAK_TFLOPS,
+                        "peak_source": "nominal"})
     return res
 
 
@@ -323,6 +337,10 @@ def run_extra_workloads(pkg, eng, D, oracle, cores, steps, peak_gbs):
                                     "with the NCCL gather of the PCM inside the step", model=conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2),
                                     gather=True, groups=8))
     for w in res:
+        if w["workload"] == "north_star":
+            w["voice_frames"] = w["graphs_per_gpu"] * 1000 * w["frames_per_graph"]
+        elif w["workload"] == "C3":
+            w["voice_frames"] = 4096 * w["frames_per_graph"]
         w["kernel_rooflines"] = kernel_rooflines(w, peak_gbs)
     return res
 
