@@ -85,7 +85,7 @@ def test_a_port_the_shape_does_not_fit_keeps_the_mixer(pkg, engine, oracle):
             bq.connect(c.destination())
             osc.start()
             if v == 3:
-                osc.stop(0.02)
+                osc.stop_at(0.02)
         return c
     engine.set_option(pkg.OPT_VOICE_SUM, 2)
     try:

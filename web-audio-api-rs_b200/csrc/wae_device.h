@@ -47,7 +47,7 @@ struct OscInst {
     int64_t n_first, n_stop;  // active frames [n_first, n_stop)
     const float* table;       // sine table (2048) or periodic wave
     int32_t table_len;
-    int32_t pad;
+    int32_t fast;             // (host) 0 < incr < 1/2, inside Nyquist, table of 2048 entries or no table: the fixed-point phase paths of k_chain apply
     double inv_incr;          // 1 / incr (polyBLEP of constant-frequency oscillators)
 };
 

@@ -1526,6 +1526,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     o.table = eng->d_sine;
                     o.table_len = 2048;
                 }
+                o.fast = (!o.outside_nyquist && o.incr > 0. && o.incr < 0.5 && (o.table_len == 2048 || (o.type != WAE_OSC_SINE && o.type != WAE_OSC_CUSTOM))) ? 1 : 0;
                 if (dyn_params) {  // automated / audio-rate frequency or detune: running-sum phase
                     OscArInst oa{};
                     oa.base = o;

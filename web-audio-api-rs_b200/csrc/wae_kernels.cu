@@ -710,6 +710,17 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
             for (int c = 0; c < n_sum; c++) {
                 MixVec<VEC> acc;
                 acc.zero();
+                if (m.n_edges < 16) {  // a handful of edges (the usual port): straight from the edge table, no staging, no barriers
+                    if (live) {
+                        const MixEdge* e = edges + m.edge_offset;
+                        for (int k = 0; k < m.n_edges; k++) {
+                            MixVec<VEC> v;
+                            v.load(chan(e[k].src, e[k].src_ch == 1 ? 0 : c, ci) + n0);
+                            if (k == 0) acc = v;
+                            else acc.add(v);
+                        }
+                    }
+                } else
                 for (int base = 0; base < m.n_edges; base += MIX_STAGE) {
                     __syncthreads();  // the previous stage's pointers have been used by everyone
                     if (base + (int)threadIdx.x < m.n_edges) {
@@ -897,7 +908,7 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
     } else if (SRC == CHAIN_SRC_OSC) {
         const OscInst& o = q.osc;
         const int64_t na = ci.f0 + n0;
-        if (na >= o.n_first && na + CH_K <= o.n_stop && !o.outside_nyquist && o.incr > 0. && o.incr < 0.5 && (o.table_len == 2048 || (o.type != 0 && o.type != 4))) {
+        if (o.fast && na >= o.n_first && na + CH_K <= o.n_stop) {
             // Fully active run.  The reference accumulates `phase += incr` (wrapping at 1) in f64; here the phase of the
             // first frame comes from the closed form and then runs as a 64-bit fixed-point fraction of a cycle (wraps for
             // free, 2^-64 resolution): |phase - reference phase| stays ~1e-14, far below the f32 output resolution, and the
@@ -1783,6 +1794,34 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
         }
     };
     prefetch(0);
+    // No hand-off duty sits in front of a CTA barrier.  Incoming (warp 0): the state a voice enters the tile with is needed only inside
+    // chain_biquad (behind ITS first barrier), so it is fetched after barrier (1), while the other warps already compute their
+    // oscillator frames; whether the tile before this one has finished voice vi + 1 as well is asked at the start of voice vi (a load
+    // whose result is not waited for) and looked at when voice vi is done: if so — the usual case once the CTAs of consecutive tiles
+    // have settled a voice apart — the state of vi + 1 is loaded right then, a whole voice before it is needed; only when it has not
+    // does warp 0 poll at the start of vi + 1.  Outgoing (lane 0 of warp 1): two 16-byte stores + a release store of the progress
+    // counter, after barrier (1) of the next voice.  The counter is read with relaxed loads (no L1 invalidation per poll) and the
+    // state with L2 loads issued only once the counter's value is known: the writer's release orders state before counter at L2.
+    const bool handoff_in = NB > 0 && !first_slab, handoff_out = NB > 0 && !last_slab;
+    auto poll_ok = [&](unsigned x, int v) { return (x & 0xfff00000u) == tag && (x & 0xfffffu) > (unsigned)v; };
+    double st_next = 0.;        // (lanes 0-3 of warp 0) incoming state of the next voice, when it could be loaded early
+    bool st_next_valid = false;
+    constexpr int PUB_T = CH_WARPS > 1 ? 32 : 0;     // the publishing thread
+    double pe0 = 0., pe1 = 0., pe2 = 0., pe3 = 0.;  // (thread PUB_T) end state of the voice before, not yet published
+    double* pub_ptr = nullptr;
+    int pub_vi = -1;
+    auto publish = [&]() {  // thread PUB_T
+        if (pub_vi < 0) return;
+        if (last_slab) {  // carried to the next chunk
+            pub_ptr[0] = pe0; pub_ptr[1] = pe1; pub_ptr[2] = pe2; pub_ptr[3] = pe3;
+        } else {
+            double* dst = sc.handoff + ((size_t)(grp.first + pub_vi) * 2 + ((slab + 1) & 1)) * 4;
+            asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(dst), "d"(pe0), "d"(pe1) : "memory");
+            asm volatile("st.global.cg.v2.f64 [%0], {%1, %2};" ::"l"(dst + 2), "d"(pe2), "d"(pe3) : "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_mine), "r"(tag | (unsigned)(pub_vi + 1)) : "memory");
+        }
+        pub_vi = -1;
+    };
     for (int vi = 0; vi < grp.n_voices; vi++) {
         const int inst = grp.first + vi;
         // (everyone is past barrier (3) of the voice before: its record and constants are dead)
@@ -1794,29 +1833,37 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
             for (int i = 0; i < PL_W; i++)
                 if ((t + i * CH_THREADS) < 128) (&sm.plane[0][0][0])[t + i * CH_THREADS] = pl_n[i];
             if (t < 24) sm.P[0][t] = pw_n;  // [0, 20): Pshfl, [20, 24): Pwarp
-            if (warp == 0) {  // the state this voice enters the tile with
-                if (first_slab) {
-                    if (lane < 4) sm.state[0][lane] = insts[inst].bq[0].state[lane];  // (carried from the chunk before)
-                } else {
-                    if (lane == 0 && seen <= (unsigned)vi) {
-                        for (;;) {
-                            unsigned x;
-                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(prog_prev) : "memory");
-                            if ((x & 0xfff00000u) == tag && (x & 0xfffffu) > (unsigned)vi) {
-                                seen = x & 0xfffffu;
-                                break;
-                            }
-                            __nanosleep(100);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane < 4) sm.state[0][lane] = __ldcg(sc.handoff + ((size_t)inst * 2 + (slab & 1)) * 4 + lane);
-                }
-            }
         }
-        __syncthreads();  // (1) record, constants and incoming state of the voice are in shared memory
+        __syncthreads();  // (1) record and constants of the voice are in shared memory (nothing global was waited for)
         if (vi + 1 < grp.n_voices) prefetch(vi + 1);
         const ChainInst& q = sm.q;
+        double st_cur = 0.;
+        unsigned xa = 0;
+        if (NB > 0 && t == PUB_T) publish();  // the voice before this one
+        if (NB > 0 && warp == 0) {
+            if (first_slab) {
+                if (lane < 4) st_cur = q.bq[0].state[lane];  // (carried from the chunk before)
+            } else if (st_next_valid) {
+                st_cur = st_next;
+            } else {
+                if (lane == 0 && seen <= (unsigned)vi) {
+                    for (;;) {
+                        unsigned x;
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(x) : "l"(prog_prev) : "memory");
+                        if (poll_ok(x, vi)) {
+                            seen = x & 0xfffffu;
+                            break;
+                        }
+                        __nanosleep(20);
+                    }
+                }
+                __syncwarp();
+                if (lane < 4) st_cur = __ldcg(sc.handoff + ((size_t)inst * 2 + (slab & 1)) * 4 + lane);
+            }
+            // has the tile before this one finished the NEXT voice as well?  asked now, looked at when this voice is done
+            if (handoff_in && lane == 0 && vi + 1 < grp.n_voices && seen <= (unsigned)(vi + 1))
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(xa) : "l"(prog_prev));
+        }
         const float2* tab2 = nullptr;
         if ((q.osc.type == 0 || q.osc.type == 4) && q.osc.table_len == 2048) {
             if (q.osc.table != cur_table) {  // (CTA-uniform) sine voices share one table: staged once per CTA
@@ -1842,6 +1889,7 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
             for (int j = 0; j < CH_K; j++) v[j] *= g0;
         }
         if (NB > 0) {
+            if (warp == 0 && lane < 4) sm.state[0][lane] = st_cur;  // (read behind chain_biquad's first barrier)
             bool clean = true;
             chain_biquad(sm, 0, cb[0], cb[1], cb[2], cb[3], cb[4], sm.plane[0][lane > 0 ? lane - 1 : 0], v, active, n_active, t, lane, warp, false, clean, NoReload{});
             if (g1 != 1.f) {
@@ -1858,20 +1906,23 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
                 for (int j = 0; j < CH_K; j++) acc[j] += v[j];
             }
         }
-        __syncthreads();  // (3) everyone is done with the voice's record and constants; its end state is in sm.state[0]
-        if (NB > 0 && warp == 0) {
-            if (lane < 4) {
-                const double e = sm.state[0][lane];
-                if (last_slab) st_ptr[lane] = e;  // carried to the next chunk
-                else __stcg(sc.handoff + ((size_t)inst * 2 + ((slab + 1) & 1)) * 4 + lane, e);
-            }
-            if (!last_slab) {
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(prog_mine), "r"(tag | (unsigned)(vi + 1)) : "memory");
+        if (handoff_in && warp == 0) {
+            st_next_valid = false;
+            if (vi + 1 < grp.n_voices) {
+                if (lane == 0 && seen <= (unsigned)(vi + 1) && poll_ok(xa, vi + 1)) seen = xa & 0xfffffu;
+                st_next_valid = __shfl_sync(0xffffffffu, seen > (unsigned)(vi + 1) ? 1 : 0, 0) != 0;
+                if (st_next_valid && lane < 4) st_next = __ldcg(sc.handoff + ((size_t)(inst + 1) * 2 + (slab & 1)) * 4 + lane);
             }
         }
+        __syncthreads();  // (3) everyone is done with the voice's record and constants; its end state is in sm.state[0]
+        if (NB > 0 && t == PUB_T) {
+            pe0 = sm.state[0][0]; pe1 = sm.state[0][1]; pe2 = sm.state[0][2]; pe3 = sm.state[0][3];
+            pub_ptr = st_ptr;
+            pub_vi = vi;
+        }
     }
+    if (NB > 0 && t == PUB_T) publish();
+    (void)handoff_out;
     if (!active) return;
     const int64_t nabs = ci.f0 + n0;
     for (int oc = 0; oc < grp.out_dup; oc++) {
