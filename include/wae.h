@@ -262,10 +262,11 @@ enum {
     WAE_OPT_CHAIN_PREPASS = 10,  /* process-wide, 1 (default): few (graph, channel) pairs with long renders through one biquad are cut into time slabs
                                   * that find out what they hand on before they render (one extra read of the source), so that the slabs of
                                   * a pair run concurrently; 0: one CTA per pair walks the whole render */
-    WAE_OPT_VOICE_SUM = 11       /* 1 (default): an input fed by many oscillator -> [biquad] -> gain voices is rendered by one kernel that keeps
-                                  * the running sum in registers and walks the voices in edge order (no voice is written to memory);
-                                  * 0: the voices are rendered into buffers and summed by the mixer kernel; 2: also when the launch is too
-                                  * small to fill the machine that way (tests) */
+    WAE_OPT_VOICE_SUM = 11       /* 0 (default): oscillator voices are rendered into buffers by the chain kernel and summed by the mixer kernel;
+                                  * 1: an input fed by many oscillator -> [biquad] -> gain voices is rendered by ONE kernel that keeps the running
+                                  * sum in registers and walks the voices in edge order (no voice is written to memory) when the launch has enough
+                                  * (time tile, port) work items; 2: whenever the port has the shape (tests).  Measured slower than the two
+                                  * kernels it replaces: kept as an option */
 };
 WAE_API wae_status wae_engine_set_option(wae_engine* engine, uint32_t option, int64_t value);
 /* the cudaStream_t every kernel of this engine is launched on (callers that time with their own CUDA events) */

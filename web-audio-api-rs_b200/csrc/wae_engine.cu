@@ -561,10 +561,16 @@ struct Planner {
     std::map<std::pair<uint32_t, uint32_t>, DelayRing> delay_rings;       // (graph, writer id)
     bool dry = false;                     // sizing pass: count arena floats per frame, touch no device memory
     int group_graphs = 1;                 // graphs of the group being planned (k_voice_sum: are there enough work items?)
-    int voice_sum_mode() const {  // 0 off, 1 when the launch is large enough, 2 whenever the port has the shape (tests)
+    // 0 off (default: measured slower than k_chain + k_mix on north_star, profiles/README.md r2_q / r2_r), 1 when the launch is large enough,
+    // 2 whenever the port has the shape (tests).  WAE_OPT_VOICE_SUM, else WAE_VOICE_SUM from the environment (read per plan).
+    int vs_mode = -1;
+    int voice_sum_mode() {
         if (eng->voice_sum >= 0) return eng->voice_sum;
-        static const int env = [] { const char* e = getenv("WAE_VOICE_SUM"); return e ? std::max(0, std::min(2, atoi(e))) : 1; }();
-        return env;
+        if (vs_mode < 0) {
+            const char* e = getenv("WAE_VOICE_SUM");
+            vs_mode = e ? std::max(0, std::min(2, atoi(e))) : 0;
+        }
+        return vs_mode;
     }
     uint64_t arena_floats_per_frame = 0;
     // source PCM slab of the group being planned (device pointer, pinned host mirror, cursor in floats)

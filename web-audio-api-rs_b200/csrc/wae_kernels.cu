@@ -697,6 +697,29 @@ DEVI void mix_run(const float* const* src, int cnt, int n0, bool first, MixVec<V
     }
 }
 
+// few edges: the loads of up to 8 edges are issued together, then added in edge order
+template <int VEC>
+DEVI void mix_direct(const MixInst& m, const MixEdge* __restrict__ edges, int c, int n0, const ChunkInfo& ci, MixVec<VEC>& acc) {
+    const MixEdge* e = edges + m.edge_offset;
+    int k = 0;
+    for (; k + 8 <= m.n_edges; k += 8) {
+        MixVec<VEC> v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u].load(chan(e[k + u].src, e[k + u].src_ch == 1 ? 0 : c, ci) + n0);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            if (k + u == 0) acc = v[u];
+            else acc.add(v[u]);
+        }
+    }
+    for (; k < m.n_edges; k++) {
+        MixVec<VEC> v;
+        v.load(chan(e[k].src, e[k].src_ch == 1 ? 0 : c, ci) + n0);
+        if (k == 0) acc = v;
+        else acc.add(v);
+    }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst,
                                              ChunkInfo ci) {
@@ -711,15 +734,7 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
                 MixVec<VEC> acc;
                 acc.zero();
                 if (m.n_edges < 16) {  // a handful of edges (the usual port): straight from the edge table, no staging, no barriers
-                    if (live) {
-                        const MixEdge* e = edges + m.edge_offset;
-                        for (int k = 0; k < m.n_edges; k++) {
-                            MixVec<VEC> v;
-                            v.load(chan(e[k].src, e[k].src_ch == 1 ? 0 : c, ci) + n0);
-                            if (k == 0) acc = v;
-                            else acc.add(v);
-                        }
-                    }
+                    if (live) mix_direct<VEC>(m, edges, c, n0, ci, acc);
                 } else
                 for (int base = 0; base < m.n_edges; base += MIX_STAGE) {
                     __syncthreads();  // the previous stage's pointers have been used by everyone
@@ -1841,10 +1856,10 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
         unsigned xa = 0;
         if (NB > 0 && t == PUB_T) publish();  // the voice before this one
         if (NB > 0 && warp == 0) {
-            if (first_slab) {
-                if (lane < 4) st_cur = q.bq[0].state[lane];  // (carried from the chunk before)
-            } else if (st_next_valid) {
+            if (st_next_valid) {
                 st_cur = st_next;
+            } else if (first_slab) {
+                if (lane < 4) st_cur = q.bq[0].state[lane];  // (carried from the chunk before)
             } else {
                 if (lane == 0 && seen <= (unsigned)vi) {
                     for (;;) {
@@ -1905,6 +1920,10 @@ __global__ void __launch_bounds__(CH_THREADS, WAE_VS_MINB * 128 / CH_THREADS) k_
 #pragma unroll
                 for (int j = 0; j < CH_K; j++) acc[j] += v[j];
             }
+        }
+        if (NB > 0 && first_slab && warp == 0) {  // the head of the pipeline sets everyone's pace: its next state is loaded a voice early too
+            st_next_valid = vi + 1 < grp.n_voices;
+            if (st_next_valid && lane < 4) st_next = insts[inst + 1].bq[0].state[lane];
         }
         if (handoff_in && warp == 0) {
             st_next_valid = false;
