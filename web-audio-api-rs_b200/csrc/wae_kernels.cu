@@ -963,18 +963,15 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
                 // frames lane by lane: a warp whose lanes have their windows at different frames runs the f64 evaluation as often as its
                 // busiest lane has flagged frames (1 - 2 times per tile at 440 Hz) instead of once per frame that ANY lane flags (7 of 16;
                 // ncu r2_p: the polyBLEP lines were 32 % of the oscillator chain's instructions).
-                // (the flag test adds high words only: hi(ph + c) is hi(ph) + hi(c) or one more, so "hi(ph) + hi(c) + 1 <= thr + 1" in wrapping
-                // 32-bit arithmetic covers both, one frame in 2^32 / thr too many)
                 const unsigned long long ph0 = ph;
-                const unsigned thr0 = (unsigned)((dph + dph) >> 32);
-                const unsigned thr1 = thr0 + (thr0 != 0xffffffffu ? 1u : 0u);  // (saturating: incr just below 1/2 flags every frame)
+                const unsigned thr = (unsigned)((dph + dph) >> 32);
                 unsigned mask = 0;
                 if (type == 2) {
-                    const unsigned cw1 = (unsigned)((HALF + dph) >> 32) + 1u;
+                    const unsigned long long cw = HALF + dph;
 #pragma unroll
                     for (int j = 0; j < CH_K; j++) {
                         v[j] = __ll2float_rn((long long)ph) * 1.08420217248550443e-19f;  // (2 p2 - 1) = signed(ph) / 2^63
-                        if ((unsigned)(ph >> 32) + cw1 <= thr1) mask |= 1u << j;
+                        if ((unsigned)((ph + cw) >> 32) <= thr) mask |= 1u << j;
                         asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));
                     }
                     while (mask) {
@@ -986,12 +983,11 @@ DEVI void chain_load_source(const ChainInst& q, int c, const ChunkInfo& ci, int 
                         for (int j = 0; j < CH_K; j++) v[j] = j == jw ? sw : v[j];
                     }
                 } else {
-                    const bool wide = dph >= 0x3fffffff00000000ull;  // incr ~>= 1/4: the two windows cover every frame (and thr1 stays below 2^31)
-                    const unsigned dw1 = (unsigned)(dph >> 32) + 1u;
+                    const bool wide = dph >= 0x4000000000000000ull;  // incr >= 1/4: the two windows cover every frame
 #pragma unroll
                     for (int j = 0; j < CH_K; j++) {
                         v[j] = (long long)ph >= 0 ? 1.0f : -1.0f;
-                        if ((((unsigned)(ph >> 32) + dw1) & 0x7fffffffu) <= thr1) mask |= 1u << j;
+                        if (((unsigned)((ph + dph) >> 32) & 0x7fffffffu) <= thr) mask |= 1u << j;
                         asm("add.u64 %0, %0, %1;" : "+l"(ph) : "l"(dph));
                     }
                     if (wide) mask = (1u << CH_K) - 1u;
@@ -1290,7 +1286,7 @@ DEVI void cswap4(bool p, float4& a, float4& b) {
 #define WAE_CH_MINB_OSC 5
 #endif
 constexpr int chain_min_blocks(int src, int nb) {
-    const int base = (src == CHAIN_SRC_OSC || src == CHAIN_SRC_CONST) ? WAE_CH_MINB_OSC : WAE_CH_MINB;  // (the constant-source chains spill at 80 registers too)
+    const int base = src == CHAIN_SRC_OSC ? WAE_CH_MINB_OSC : WAE_CH_MINB;
     return ((nb == 2 ? base - 1 : base) * 128) / CH_THREADS;
 }
 template <int SRC, int NB, bool SHAPER, bool TMA, bool PRE = false>
@@ -1477,7 +1473,6 @@ __global__ void __launch_bounds__(CH_THREADS, chain_min_blocks(SRC, NB)) k_chain
     };
     unsigned par = 0;  // TMA path: phase parity of every stage's barrier (bit s), flipped each time the stage is consumed
     // the slab, tile by tile.  emit = false (PRE): filter state only — nothing is stored, no layout track written
-    const bool want_clean = q.out.meta != nullptr;  // (CTA constant: read once, not per tile)
     auto run_slab = [&](const bool emit) {
     float v[CH_K];
     if (STREAMED) {
@@ -1533,6 +1528,7 @@ __global__ void __launch_bounds__(CH_THREADS, chain_min_blocks(SRC, NB)) k_chain
             chain_load_source<SRC>(q, c, ci, n0, v, tab2);
         }
         bool clean0 = true, clean1 = true;
+        const bool want_clean = q.out.meta != nullptr;
         if (g0 != 1.f) {  // x * 1.0f == x bit for bit: skip the multiply (uniform branch)
 #pragma unroll
             for (int j = 0; j < CH_K; j++) v[j] *= g0;
@@ -1662,17 +1658,6 @@ __global__ void __launch_bounds__(CH_THREADS, chain_min_blocks(SRC, NB)) k_chain
                     bulk_commit();        // this tile's stores (possibly none) form one group ...
                     bulk_wait_read<1>();  // ... and the group of the tile before has finished reading its stage: refill it
                     issue_bulk(pbuf, base + (NST - 1) * tile);
-                }
-            } else if (!STREAMED && base <= o_hi) {
-                // computed sources (oscillator, constant): these chains are bound by issue slots, not by DRAM — the thread's 64 bytes leave
-                // as four 16-byte stores (a warp's four stores fill its 2 KB region; the sectors meet in L2) instead of ~50 instructions
-                // of staging for whole-line stores
-                if (active) {
-                    for (int oc = 0; oc < n_out; oc++) {
-                        float4* out = reinterpret_cast<float4*>(o_ptr0 + (size_t)oc * q.out.stride + base) + 4 * lane;
-#pragma unroll
-                        for (int u = 0; u < CH_K / 4; u++) out[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                    }
                 }
             } else if (base <= o_hi) {  // warp-uniform
                 __syncwarp();
