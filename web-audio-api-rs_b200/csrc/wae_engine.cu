@@ -122,6 +122,7 @@ struct wae_engine {
     struct RateSphere {  // the sphere's responses resampled to a context rate (HrirSphere::new of the crate), built on first use
         float* d_ir = nullptr;
         uint32_t taps = 0;
+        std::vector<float> ir_host;  // [vertex][2][taps] (static panners: blended on the host into the response of a convolution)
     };
     std::map<uint32_t, RateSphere> sphere_rates;
     std::mutex sphere_mu;
@@ -739,7 +740,8 @@ struct Planner {
     };
     PRef param_ref(wae_graph* g, uint32_t pid);
     bool plan_graph(wae_graph* g, uint32_t gi);
-    bool plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest = nullptr, int64_t dest_limit = -1);
+    // ir_override: the response of a STATIC HRTF panner (blended, gain folded in): no normalisation, no trimming of small trailing taps
+    bool plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest = nullptr, int64_t dest_limit = -1, const PcmBuffer* ir_override = nullptr);
 };
 
 static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934665603ull) {
@@ -811,24 +813,24 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
     return sc;
 }
 
-bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest, int64_t dest_limit) {
+bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest, int64_t dest_limit, const PcmBuffer* ir_override) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
-    if (n.buffer && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
+    if ((n.buffer || ir_override) && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
         return bail(WAE_UNSUPPORTED, "a ConvolverNode inside a DelayNode feedback cycle is not lowered to the GPU (before or after the cycle it is)");
     const Lay in_lay = pn.in_lay.empty() ? Lay::fixed(in_ch) : pn.in_lay[0];
-    if (!n.buffer) {  // no buffer: pass-through (convolver.rs:368-375)
+    if (!n.buffer && !ir_override) {  // no buffer: pass-through (convolver.rs:368-375)
         pn.out_ch = {in_ch};
         pn.out_buf = {pn.in_buf[0]};
         pn.out_lay = {in_lay};
         return true;
     }
-    PcmBuffer& ir = *n.buffer;
+    const PcmBuffer& ir = ir_override ? *ir_override : *n.buffer;
     int ir_ch = (int)ir.channels.size();
     size_t ir_len = ir.length();
     // normalize_buffer, src/node/convolver.rs:16-53 (f32, channel by channel)
     float scale = 1.f;
-    if (n.normalize) {
+    if (n.normalize && !ir_override) {
         float power = 0.f;
         for (auto& c : ir.channels) {
             float s = 0.f;
@@ -855,7 +857,8 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
     std::vector<int> S(ir_ch);
     for (int c = 0; c < ir_ch; c++) {
         size_t m = ir_len;
-        while (m > 0 && std::fabs(scaled[c][m - 1]) < 0.000001f) m--;
+        while (!ir_override && m > 0 && std::fabs(scaled[c][m - 1]) < 0.000001f) m--;
+        while (ir_override && m > 0 && scaled[c][m - 1] == 0.f) m--;  // (exact zeros only)
         S[c] = (int)((m + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK);
         trimmed_len = std::max(trimmed_len, m);
         // zero the ignored tail so that a shared segment count reproduces the per-convolver trimming
@@ -960,7 +963,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
     }
     // S*1025*8 B of input-history spectra per convolver-block of 1024 frames
     // (the reference's 1024-frame partitioning defines the algorithmic figure, whatever block size the kernels use)
-    algorithmic_bytes += (uint64_t)routes.size() * (uint64_t)((trimmed_len + 1023) / 1024) * 1025ull * 8ull * (uint64_t)((b->lq + 1023) / 1024);
+    if (!ir_override) algorithmic_bytes += (uint64_t)routes.size() * (uint64_t)((trimmed_len + 1023) / 1024) * 1025ull * 8ull * (uint64_t)((b->lq + 1023) / 1024);
     return true;
 }
 
@@ -2094,10 +2097,15 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     moving = moving || pr[i].dyn;
                 }
                 int ch = p.in_ch[0];
-                if (!need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
-                out_dynamic(in0.may_silent ? Lay{1, 2, 2, 2, true} : Lay::fixed(2));  // panner.rs:698-708
+                // (a static HRTF panner with a constant-layout input is lowered to the convolver kernels, which take their own output buffer)
+                static const bool hrtf_fft_on = [] { const char* e = getenv("WAE_HRTF_FFT"); return !e || atoi(e) != 0; }();
+                const bool hrtf_as_conv = n.panning_model == WAE_PANNING_HRTF && hrtf_fft_on && eng->sphere && !moving && !in0.dyn() && cur_cls != 1 &&
+                                          seg_start == 0 && seg_end >= b->lq && (ch == 1 || ch == 2);
+                if (!hrtf_as_conv && !need_out(2)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
+                if (hrtf_as_conv) p.out_lay = {Lay::fixed(2)};
+                else out_dynamic(in0.may_silent ? Lay{1, 2, 2, 2, true} : Lay::fixed(2));  // panner.rs:698-708
                 // (the HRTF panner keeps its own tail budget: its layout track is written by k_hrtf_map)
-                if (p.out_buf[0].meta && n.panning_model != WAE_PANNING_HRTF) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
+                if (!hrtf_as_conv && p.out_buf[0].meta && n.panning_model != WAE_PANNING_HRTF) meta_stage(L, META_PAN, p.in_buf[0], ch, p.out_buf[0], 2);
                 spatial::PanModel model{};
                 model.distance_model = n.distance_model;
                 model.ref_distance = n.ref_distance;
@@ -2120,6 +2128,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     if (sr < 27000) sr = 27000;  // panner.rs:46
                     uint32_t taps = sph->taps;
                     const float* d_ir = eng->d_sphere_ir;
+                    const float* h_ir = sph->ir.data();  // [vertex][2][taps] on the host
                     if (sr != sph->sample_rate) {  // the crate resamples the responses to the context rate once (wae_hrtf_host.h)
                         std::lock_guard<std::mutex> slk(eng->sphere_mu);
                         auto it = eng->sphere_rates.find(sr);
@@ -2130,10 +2139,43 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                             if (r.taps < 2) return bail(WAE_UNSUPPORTED, "HRTF panning: the HRIR sphere is too short to be resampled to the context rate");
                             if (cudaMalloc(&r.d_ir, rs.ir.size() * sizeof(float)) != cudaSuccess) return bail(WAE_OUT_OF_MEMORY, "out of device memory (resampled HRIR sphere)");
                             cudaMemcpy(r.d_ir, rs.ir.data(), rs.ir.size() * sizeof(float), cudaMemcpyHostToDevice);
+                            r.ir_host = rs.ir;
                             it = eng->sphere_rates.emplace(sr, r).first;
                         }
                         taps = it->second.taps;
                         d_ir = it->second.d_ir;
+                        h_ir = it->second.ir_host.data();  // (map nodes are stable; entries are only dropped with the sphere)
+                    }
+                    // A static source heard by a static listener through a constant-layout input is ONE fixed pair of impulse responses:
+                    // out_ear = gain * (h_ear * mono(in)).  The crate evaluates that by FFT overlap-save per 128-frame block (hrtf 0.8.1
+                    // process_samples); here it is handed to the time-batched convolver kernels as a ConvolverNode-shaped problem —
+                    // response = the blended pair with the gain (and, for a two-channel input, the 0.5 of the mono down-mix times the
+                    // reference's correction of 2, panner.rs:805-812) folded in, routed like a "true stereo" response for stereo inputs —
+                    // instead of 2 x taps multiply-adds per output frame in k_hrtf_fir.  WAE_HRTF_FFT=0: keep the FIR kernel.
+                    if (hrtf_as_conv) {
+                        float proj[3];
+                        spatial::projected_source(sp0, proj);
+                        const float dir[3] = {proj[0], proj[2], proj[1]};  // HrtfState::process swaps y / z (panner.rs:248-252)
+                        HrtfSel sel{{0, 0, 0}, {0.f, 0.f, 0.f}, sp0.cone_gain * sp0.dist_gain, 0.f};
+                        sph->locate(dir, sel.v, sel.w);  // no face: all-zero weights (silence)
+                        PcmBuffer resp;
+                        if (!resp.allocate(ch == 2 ? 4 : 2, taps, false)) return bail(WAE_OUT_OF_MEMORY, "out of host memory (hrtf response)");
+                        const float* A = h_ir + (size_t)sel.v[0] * 2 * taps;
+                        const float* B = h_ir + (size_t)sel.v[1] * 2 * taps;
+                        const float* C = h_ir + (size_t)sel.v[2] * 2 * taps;
+                        for (uint32_t k = 0; k < taps; k++) {  // (the blend k_hrtf_fir does, same f32 operations)
+                            const float l = (A[k] * sel.w[0] + B[k] * sel.w[1]) + C[k] * sel.w[2];
+                            const float r = (A[taps + k] * sel.w[0] + B[taps + k] * sel.w[1]) + C[taps + k] * sel.w[2];
+                            resp.channels[0].p[k] = l * sel.gain;
+                            resp.channels[1].p[k] = r * sel.gain;
+                            if (ch == 2) {  // 2 (correction) * 0.5 (down-mix) = 1
+                                resp.channels[2].p[k] = resp.channels[0].p[k];
+                                resp.channels[3].p[k] = resp.channels[1].p[k];
+                            }
+                        }
+                        resp.sample_rate = (float)sr;
+                        if (!plan_convolver(g, p, L, nullptr, -1, &resp)) return false;
+                        break;
                     }
                     HrtfInst h{};
                     h.in = p.in_buf[0];
@@ -2661,12 +2703,14 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
     b->channels = graphs[0]->channels;
     b->length = graphs[0]->length;
     b->lq = (int64_t)((b->length + 127) / 128 * 128);
-    bool has_conv = false;
+    bool has_conv = false, has_hrtf = false;
     std::vector<char> graph_has_conv(n_graphs, 0);
     std::vector<std::vector<int64_t>> cuts(n_graphs);  // per graph: its suspend frames inside the render
     for (uint32_t i = 0; i < n_graphs; i++) {
-        for (auto& kv : graphs[i]->nodes)
+        for (auto& kv : graphs[i]->nodes) {
             if (kv.second.kind == K_CONV && kv.second.buffer) graph_has_conv[i] = 1;
+            if (kv.second.kind == K_PANNER && kv.second.panning_model == WAE_PANNING_HRTF) has_hrtf = true;  // (static ones ride the convolver kernels)
+        }
         for (auto& ep : graphs[i]->epochs) {
             if ((int64_t)ep.frame > 0 && (int64_t)ep.frame < b->lq) cuts[i].push_back((int64_t)ep.frame);
             for (auto& kv : ep.nodes)
@@ -2811,13 +2855,13 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             chunk = std::max<int64_t>(8192, std::min<int64_t>(chunk, 1 << 20));  // >= 8192: keeps per-chunk launches and serial tails amortised
             chunk = chunk / 2048 * 2048;
         }
-        if (has_conv) chunk = std::max<int64_t>(chunk, 8 * WAE_CONV_BLOCK);  // k_conv_mac tiles 8 output blocks
+        if (has_conv || has_hrtf) chunk = std::max<int64_t>(chunk, 8 * WAE_CONV_BLOCK);  // k_conv_mac tiles 8 output blocks
     }
     // feedback through a DelayNode: the stages up to the cycle are replayed one render quantum at a time INSIDE each chunk
     // (run_group), so the chunk size does not depend on it
     (void)has_feedback;
-    if (has_conv) chunk = (chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK;
-    if (chunk > b->lq) chunk = has_conv ? (b->lq + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK : b->lq;
+    if (has_conv || has_hrtf) chunk = (chunk + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK;
+    if (chunk > b->lq) chunk = (has_conv || has_hrtf) ? (b->lq + WAE_CONV_BLOCK - 1) / WAE_CONV_BLOCK * WAE_CONV_BLOCK : b->lq;
     b->chunk = chunk;
     if (plan) {
         std::memset(plan, 0, sizeof *plan);
