@@ -145,6 +145,15 @@ def conv_model(n_graphs, length, ir_frames, in_ch=2, paths=2):
             "flops": flops, "compulsory_bytes": bytes_io}
 
 
+def add_models(a, b2):
+    """Two convolution stages of one graph (C5: the ConvolverNode and the static HRTF panner lowered to the same kernels)."""
+    out = dict(a)
+    out["flops"] = a["flops"] + b2["flops"]
+    out["compulsory_bytes"] = a["compulsory_bytes"] + b2["compulsory_bytes"]
+    out["second_convolution"] = {k: b2[k] for k in ("blocks_per_graph", "ir_partitions_8192", "flops", "compulsory_bytes")}
+    return out
+
+
 def measure_workload(pkg, eng, D, oracle, name, build, n_gpu, n_cpu, length, steps, cores, note, model=None, gather=False, groups=0):
     """One additional BASELINE workload: kernel-only (max over ranks), one-shot e2e, optional NCCL gather inside the step, CPU port."""
     import torch
@@ -321,7 +330,7 @@ def run_extra_workloads(pkg, eng, D, oracle, cores, steps, peak_gbs):
         res.append(measure_workload(pkg, eng, D, oracle, "C5", c5, 256, min(cores, 64), c5_len, steps, cores,
                                     "configs[4] per-GPU share (2048 graphs / 8 GPUs): Oscillator -> WaveShaper(1024-pt tanh) -> Biquad -> Convolver -> "
                                     "Panner(HRTF, 44.1 kHz / 512-tap sphere resampled to 48 kHz) -> Analyser -> destination, 5 s; HRTF parity is UNPINNED "
-                                    "(hrtf crate absent from the reference tree, SURVEY §8c)", model=conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2)))
+                                    "(hrtf crate absent from the reference tree, SURVEY §8c)", model=add_models(conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2), conv_model(256, c5_len, 558, in_ch=2, paths=4))))
     elif D.world > 1 and os.environ.get("WAE_BENCH_EXTRA") == "c5_small":  # validation of the N = 8 leg on fewer GPUs (not a BASELINE size)
         res.append(measure_workload(pkg, eng, D, None, "C5", c5, 32, 0, c5_len, steps, cores,
                                     "configs[4] path check: 32 graphs per GPU, with the NCCL gather inside the step", gather=True, groups=4))
@@ -334,7 +343,7 @@ def run_extra_workloads(pkg, eng, D, oracle, cores, steps, peak_gbs):
     elif D.world == 8:
         res.append(measure_workload(pkg, eng, D, None, "C5", c5, 256, 0, c5_len, steps, cores,
                                     "configs[4]: 2048 graphs over 8 GPUs (256 per GPU), full chain with HRTF panner (parity unpinned, SURVEY §8c), 5 s; also "
-                                    "with the NCCL gather of the PCM inside the step", model=conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2),
+                                    "with the NCCL gather of the PCM inside the step", model=add_models(conv_model(256, c5_len, PARKING_GARAGE_IR_FRAMES, in_ch=1, paths=2), conv_model(256, c5_len, 558, in_ch=2, paths=4)),
                                     gather=True, groups=8))
     for w in res:
         if w["workload"] == "north_star":

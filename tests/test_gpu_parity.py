@@ -281,6 +281,42 @@ def test_hrtf_panner(pkg, engine, oracle, taps, chunk):
     assert maxdiff(gpu, cpu) <= TOL
 
 
+def test_static_hrtf_panner_is_lowered_to_the_convolver_kernels(pkg, engine, oracle):
+    """A static source heard by a static listener through a constant-layout input is one fixed pair of impulse responses: the planner hands
+    it to the time-batched convolver kernels (the hrtf crate itself convolves by FFT overlap-save); a moving source, or an input whose layout
+    changes (a source that ends), keeps the per-quantum FIR kernel.  Same PCM as the oracle either way."""
+    data = G.synthetic_hrir_sphere(int(G.SR), 256)
+    oracle.set_hrir_sphere(data)
+    engine.backend.set_hrir_sphere(data)
+    n = 128 * 40
+
+    def build(be, kind):
+        c = pkg.OfflineAudioContext(2, n, G.SR, be)
+        pcm = G.c2_source(kind, n) * np.float32(0.5)
+        s = c.create_buffer_source(pkg.AudioBuffer([pcm[0], pcm[1]], G.SR))
+        p = c.create_panner(panning_model=pkg.context.HRTF, position=(2.0, 0.5, -1.5))
+        s.connect(p)
+        p.connect(c.destination())
+        s.start()
+        if kind == 1:
+            p.position_x.linear_ramp_to_value_at_time(-3.0, n / G.SR)  # moving source
+        if kind == 2:
+            s.stop_at(0.03)  # the input goes silent: per-quantum layout
+        return c
+
+    import os
+    want = {0: os.environ.get("WAE_HRTF_FFT", "1") != "0", 1: False, 2: False}
+    for kind in (0, 1, 2):
+        batch = pkg.Batch([build(engine.backend, kind)])
+        names = {name for name, _t, _k in batch.stage_times()}
+        batch.destroy()
+        assert ("k_conv_mac_ifft" in names) == want[kind], (kind, names)
+        assert ("k_hrtf_fir" in names) == (not want[kind]), (kind, names)
+        gpu = G.render(pkg, [build(engine.backend, kind)])
+        cpu = G.render(pkg, [build(oracle, kind)])
+        assert maxdiff(gpu, cpu) <= TOL, kind
+
+
 @pytest.mark.parametrize("model", ["equalpower", "hrtf"])
 @pytest.mark.parametrize("who", ["source", "listener", "both", "audio_rate"])
 def test_panner_moving_source_and_listener(pkg, engine, oracle, model, who):

@@ -740,7 +740,8 @@ struct Planner {
     };
     PRef param_ref(wae_graph* g, uint32_t pid);
     bool plan_graph(wae_graph* g, uint32_t gi);
-    // ir_override: the response of a STATIC HRTF panner (blended, gain folded in): no normalisation, no trimming of small trailing taps
+    // ir_override: the response of a STATIC HRTF panner (blended, gain folded in): no normalisation, no trimming of small trailing taps;
+    // a two-channel input is mixed down to mono by the forward transform's loads (ConvInput::in_channel = -1)
     bool plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest = nullptr, int64_t dest_limit = -1, const PcmBuffer* ir_override = nullptr);
 };
 
@@ -816,6 +817,8 @@ static ScanCoef make_scan_coef(const hm::BiquadCoefs& c) {
 bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* dest, int64_t dest_limit, const PcmBuffer* ir_override) {
     Node& n = *pn.n;
     int in_ch = pn.in_ch[0];
+    const bool mono_mix = ir_override && in_ch == 2;
+    if (mono_mix) in_ch = 1;
     if ((n.buffer || ir_override) && cur_cls == 1)  // (the class is a property of the graph: the sizing pass already knows it)
         return bail(WAE_UNSUPPORTED, "a ConvolverNode inside a DelayNode feedback cycle is not lowered to the GPU (before or after the cycle it is)");
     const Lay in_lay = pn.in_lay.empty() ? Lay::fixed(in_ch) : pn.in_lay[0];
@@ -926,7 +929,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
     for (int c = 0; c < in_ch; c++) {
         ConvInput ci;
         ci.in = pn.in_buf[0];
-        ci.in_channel = c;
+        ci.in_channel = mono_mix ? -1 : c;
         ci.prev = alloc<float>(WAE_CONV_BLOCK, true, true);
         ci.xring = alloc<float2>((size_t)ring_blocks * WAE_CONV_SPEC);
         ci.xring_blocks = ring_blocks;
@@ -956,9 +959,12 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
         p.out_channel = r.out;
         p.accumulate = r.acc;
         p.limit = direct ? dest_limit : -1;
-        p.y = alloc<float2>((size_t)blocks_per_chunk * WAE_CONV_SPEC);
-        if (!p.y) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver output spectra)");
-        b->arena_bytes += (size_t)blocks_per_chunk * WAE_CONV_SPEC * 8;
+        p.y = nullptr;
+        if (Smax > 1) {  // (one partition: k_conv_ifft forms the product itself, there are no output spectra)
+            p.y = alloc<float2>((size_t)blocks_per_chunk * WAE_CONV_SPEC);
+            if (!p.y) return bail(WAE_OUT_OF_MEMORY, "out of device memory (convolver output spectra)");
+            b->arena_bytes += (size_t)blocks_per_chunk * WAE_CONV_SPEC * 8;
+        }
         stage(level, r.acc ? S_CONV_MAC_ACC : S_CONV_MAC).conv_path.push_back(p);
     }
     // S*1025*8 B of input-history spectra per convolver-block of 1024 frames
@@ -2149,9 +2155,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     // A static source heard by a static listener through a constant-layout input is ONE fixed pair of impulse responses:
                     // out_ear = gain * (h_ear * mono(in)).  The crate evaluates that by FFT overlap-save per 128-frame block (hrtf 0.8.1
                     // process_samples); here it is handed to the time-batched convolver kernels as a ConvolverNode-shaped problem —
-                    // response = the blended pair with the gain (and, for a two-channel input, the 0.5 of the mono down-mix times the
-                    // reference's correction of 2, panner.rs:805-812) folded in, routed like a "true stereo" response for stereo inputs —
-                    // instead of 2 x taps multiply-adds per output frame in k_hrtf_fir.  WAE_HRTF_FFT=0: keep the FIR kernel.
+                    // response = the blended pair with the gain (and the reference's correction of 2 for a two-channel input,
+                    // panner.rs:805-812) folded in; a two-channel input is mixed down to mono by the forward transform's loads; one
+                    // partition, so the product is formed inside the inverse transform — instead of 2 x taps multiply-adds per output
+                    // frame in k_hrtf_fir.  WAE_HRTF_FFT=0: keep the FIR kernel.
                     if (hrtf_as_conv) {
                         float proj[3];
                         spatial::projected_source(sp0, proj);
@@ -2159,19 +2166,16 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                         HrtfSel sel{{0, 0, 0}, {0.f, 0.f, 0.f}, sp0.cone_gain * sp0.dist_gain, 0.f};
                         sph->locate(dir, sel.v, sel.w);  // no face: all-zero weights (silence)
                         PcmBuffer resp;
-                        if (!resp.allocate(ch == 2 ? 4 : 2, taps, false)) return bail(WAE_OUT_OF_MEMORY, "out of host memory (hrtf response)");
+                        if (!resp.allocate(2, taps, false)) return bail(WAE_OUT_OF_MEMORY, "out of host memory (hrtf response)");
+                        const float corr = ch == 2 ? 2.f : 1.f;  // overall_gain_correction of a two-channel input (panner.rs:805-812)
                         const float* A = h_ir + (size_t)sel.v[0] * 2 * taps;
                         const float* B = h_ir + (size_t)sel.v[1] * 2 * taps;
                         const float* C = h_ir + (size_t)sel.v[2] * 2 * taps;
                         for (uint32_t k = 0; k < taps; k++) {  // (the blend k_hrtf_fir does, same f32 operations)
                             const float l = (A[k] * sel.w[0] + B[k] * sel.w[1]) + C[k] * sel.w[2];
                             const float r = (A[taps + k] * sel.w[0] + B[taps + k] * sel.w[1]) + C[taps + k] * sel.w[2];
-                            resp.channels[0].p[k] = l * sel.gain;
-                            resp.channels[1].p[k] = r * sel.gain;
-                            if (ch == 2) {  // 2 (correction) * 0.5 (down-mix) = 1
-                                resp.channels[2].p[k] = resp.channels[0].p[k];
-                                resp.channels[3].p[k] = resp.channels[1].p[k];
-                            }
+                            resp.channels[0].p[k] = corr * (l * sel.gain);
+                            resp.channels[1].p[k] = corr * (r * sel.gain);
                         }
                         resp.sample_rate = (float)sr;
                         if (!plan_convolver(g, p, L, nullptr, -1, &resp)) return false;

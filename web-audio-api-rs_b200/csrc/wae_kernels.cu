@@ -3712,10 +3712,16 @@ DEVI void rfft_store(const float2* z, float2* __restrict__ X, float2 lane_tw) {
     }
 }
 // B reals (valid <= B of them readable at src, the rest zero; src == nullptr: all zero) -> B/2 packed complex (even, odd) at z[c0 ..)
-DEVI void conv_load_half(float2* z, int c0, const float* __restrict__ src, int valid) {
+// src2 != nullptr: the speakers down-mix of two channels, 0.5 * (a + b) (quantum.rs 2 -> 1; ConvInput::in_channel = -1)
+DEVI void conv_load_half(float2* z, int c0, const float* __restrict__ src, int valid, const float* __restrict__ src2 = nullptr) {
     const int t = threadIdx.x;
     if (!src || valid <= 0) {
         for (int i = t; i < CV_B / 2; i += CV_THREADS) z[cv_pad(c0 + i)] = make_float2(0.f, 0.f);
+    } else if (src2) {
+        for (int i = t; i < CV_B / 2; i += CV_THREADS) {
+            const int n = 2 * i;
+            z[cv_pad(c0 + i)] = make_float2(n < valid ? 0.5f * (src[n] + src2[n]) : 0.f, n + 1 < valid ? 0.5f * (src[n + 1] + src2[n + 1]) : 0.f);
+        }
     } else if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
 #pragma unroll 8
         for (int i4 = t; i4 < CV_B / 4; i4 += CV_THREADS) {
@@ -3747,11 +3753,14 @@ __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_fft_in(const ConvInput* 
     const ConvInput ip = inputs[blockIdx.y];
     const int jb = blockIdx.x;                         // block within the chunk
     const int64_t jabs = ci.f0 / CV_B + jb;            // absolute block index
-    const float* in = chan(ip.in, ip.in_channel, ci);
+    const bool mix = ip.in_channel < 0;
+    const float* in = chan(ip.in, mix ? 0 : ip.in_channel, ci);
+    const float* in2 = mix ? chan(ip.in, 1, ci) : nullptr;
     // frame = [previous block | current block]
     const int64_t left = (int64_t)ci.nf - (int64_t)jb * CV_B;
-    conv_load_half(z, 0, jb == 0 ? ip.prev : in + (size_t)(jb - 1) * CV_B, CV_B);
-    conv_load_half(z, CV_B / 2, in + (size_t)jb * CV_B, (int)(left < CV_B ? left : CV_B));
+    if (jb == 0) conv_load_half(z, 0, ip.prev, CV_B);  // (already mixed)
+    else conv_load_half(z, 0, in + (size_t)(jb - 1) * CV_B, CV_B, mix ? in2 + (size_t)(jb - 1) * CV_B : nullptr);
+    conv_load_half(z, CV_B / 2, in + (size_t)jb * CV_B, (int)(left < CV_B ? left : CV_B), mix ? in2 + (size_t)jb * CV_B : nullptr);
     __syncthreads();
     fft_dif_smem(z, w);
     rfft_store(z, ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS, lane_tw);
@@ -3760,11 +3769,14 @@ __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_fft_in(const ConvInput* 
 // saves the last block of the chunk as "previous block" for the next chunk.  grid: (B / 256, conv inputs)
 __global__ void __launch_bounds__(256) k_conv_save_prev(const ConvInput* __restrict__ inputs, int n_inputs, ChunkInfo ci) {
     const ConvInput ip = inputs[blockIdx.y];
-    const float* in = chan(ip.in, ip.in_channel, ci);
+    const bool mix = ip.in_channel < 0;
+    const float* in = chan(ip.in, mix ? 0 : ip.in_channel, ci);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int nblocks = (ci.nf + CV_B - 1) / CV_B;
     const int64_t m = (int64_t)(nblocks - 1) * CV_B + i;
-    ip.prev[i] = m < ci.nf ? in[m] : 0.f;
+    float v = m < ci.nf ? in[m] : 0.f;
+    if (mix && m < ci.nf) v = 0.5f * (v + chan(ip.in, 1, ci)[m]);
+    ip.prev[i] = v;
 }
 
 // grid: (B / 256 * ceil(blocks in chunk / CV_J), paths), 256 threads, one bin per thread.  For CV_J consecutive output
@@ -3840,6 +3852,7 @@ DEVI void conv_mac_bin(const ConvPath& p, const ConvInput& ip, int k, int64_t ja
 __global__ void __launch_bounds__(CV_MAC_THREADS, WAE_CV_MAC_MINB) k_conv_mac(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths,
                                                              ChunkInfo ci) {
     const ConvPath p = paths[blockIdx.y];
+    if (p.S == 1) return;  // one partition: the product is formed by k_conv_ifft while it loads (Y never exists)
     const ConvInput ip = inputs[p.input];
     const int nb = (ci.nf + CV_B - 1) / CV_B;
     constexpr int TILES = CV_B / CV_MAC_THREADS;
@@ -3858,7 +3871,9 @@ __global__ void __launch_bounds__(CV_MAC_THREADS, WAE_CV_MAC_MINB) k_conv_mac(co
 }
 
 // grid: (blocks in chunk, paths): out_j = IFFT(Y_j)[B..2B) / 2B
-__global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __restrict__ paths, int n_paths, ChunkInfo ci) {
+// A response of ONE partition (a static HRTF panner's: ~560 taps) needs no k_conv_mac pass: Y_j = H_0 X_j is formed here, from the
+// input spectra ring, while the half spectrum is loaded (k_conv_mac skips such paths).
+__global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __restrict__ paths, const ConvInput* __restrict__ inputs, int n_paths, ChunkInfo ci) {
     extern __shared__ float2 z[];
     const FftTw w = fft_tw_load(+1);
     const float2 lane_tw = cv_lane_tw();
@@ -3866,6 +3881,29 @@ __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __r
     const int jb = blockIdx.x;
     const float2* __restrict__ Y = p.y + (size_t)jb * CV_BINS;
     const int t = threadIdx.x;
+    if (p.S == 1) {
+        const ConvInput ip = inputs[p.input];
+        const int64_t jabs = ci.f0 / CV_B + jb;
+        const float2* __restrict__ X = ip.xring + (size_t)(jabs % ip.xring_blocks) * CV_BINS;
+        const float2* __restrict__ H = p.h;
+        auto prod = [&](int q) {
+            const float2 h = __ldg(H + q), x = __ldg(X + q);
+            return make_float2(fmaf(h.x, x.x, __fmul_rn(-h.y, x.y)), fmaf(h.x, x.y, __fmul_rn(h.y, x.x)));
+        };
+#pragma unroll 4
+        for (int q = t; q < CV_B; q += CV_THREADS) {
+            float2 yk, ym;
+            if (q == 0) {  // (DC, Nyquist): two real bins that multiply component-wise
+                const float2 h = __ldg(H), x = __ldg(X);
+                yk = make_float2(h.x * x.x, 0.f);
+                ym = make_float2(h.y * x.y, 0.f);
+            } else {
+                yk = prod(q);
+                ym = prod(cv_mirror(q));
+            }
+            z[cv_pad(q)] = irfft_merge(yk, ym, cv_bin_tw(lane_tw, q));
+        }
+    } else {
     // half spectrum (position order) -> packed complex input of the B-point inverse transform, same positions
 #pragma unroll 4
     for (int q = t; q < CV_B; q += CV_THREADS) {
@@ -3879,6 +3917,7 @@ __global__ void __launch_bounds__(CV_THREADS, 3) k_conv_ifft(const ConvPath* __r
             ym = Y[cv_mirror(q)];
         }
         z[cv_pad(q)] = irfft_merge(yk, ym, cv_bin_tw(lane_tw, q));
+    }
     }
     __syncthreads();
     fft_dit_smem(z, w);
@@ -4343,7 +4382,7 @@ void launch_conv_mac_ifft(const ConvPath* p, const ConvInput* in, int n, ChunkIn
     conv_configure();
     const int nb = (ci.nf + CV_B - 1) / CV_B;
     k_conv_mac<<<dim3((unsigned)((CV_B / CV_MAC_THREADS) * ((nb + CV_J - 1) / CV_J)), (unsigned)n), CV_MAC_THREADS, 0, s>>>(p, in, n, ci);
-    k_conv_ifft<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, CV_SMEM_ELEMS * sizeof(float2), s>>>(p, n, ci);
+    k_conv_ifft<<<dim3((unsigned)nb, (unsigned)n), CV_THREADS, CV_SMEM_ELEMS * sizeof(float2), s>>>(p, in, n, ci);
 }
 void launch_conv_ir_fft(const float* ir, int64_t ir_len, int64_t ir_stride, float2* h, int S, int channels, cudaStream_t s) {
     conv_configure();
