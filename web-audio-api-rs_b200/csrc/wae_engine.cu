@@ -2967,6 +2967,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
                         m.all_mono = (simple && all_mono && (m.out_ch == 1 || (m.out_ch == 2 && m.interp == WAE_INTERPRETATION_SPEAKERS))) ? 1 : 0;
                     }
                     st.n = (int)s.mix.size(); st.d_a = up(b, s.mix); st.d_b = up(b, s.mix_edges);
+                    for (auto& m : s.mix) st.n_b = std::max(st.n_b, (int)m.n_edges);  // widest port: picks the mixer kernel
                     break;
                 }
                 case S_MIX_DYN: {
@@ -3162,7 +3163,7 @@ WAE_API wae_status wae_batch_plan(wae_graph* const* graphs, uint32_t n_graphs, w
 static void launch_stage(wae_batch* b, Stage& st, ChunkInfo ci) {
     cudaStream_t s = b->engine->stream;
     switch (st.kind) {
-        case S_MIX: launch_mix((MixInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s); break;
+        case S_MIX: launch_mix((MixInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s, st.n_b); break;
         case S_MIX_DYN: launch_mix_dyn((MixDynInst*)st.d_a, (MixEdge*)st.d_b, st.n, ci, s); break;
         case S_META: launch_meta((MetaInst*)st.d_a, st.n, ci, s); break;
         case S_DELAY_MONO: launch_delay_mono((DelayInst*)st.d_a, st.n, ci, s); break;

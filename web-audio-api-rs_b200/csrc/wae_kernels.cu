@@ -775,6 +775,48 @@ __global__ void __launch_bounds__(256) k_mix(const MixInst* __restrict__ insts, 
     }
 }
 
+// stages whose ports all have fewer than 16 edges (the usual graph): no staging, no barriers, 40 registers — the mixer is memory-bound and
+// lives on resident warps (the staged kernel above needs 64+)
+template <int VEC>
+__global__ void __launch_bounds__(256) k_mix_narrow(const MixInst* __restrict__ insts, const MixEdge* __restrict__ edges, int n_inst, ChunkInfo ci) {
+    for (int ii = blockIdx.y; ii < n_inst; ii += gridDim.y) {
+        const MixInst m = insts[ii];
+        const int n0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+        if (n0 >= ci.nf) continue;
+        if (m.simple) {
+            const int n_sum = m.all_mono ? 1 : m.out_ch;
+            for (int c = 0; c < n_sum; c++) {
+                MixVec<VEC> acc;
+                acc.zero();
+                mix_direct<VEC>(m, edges, c, n0, ci, acc);
+                for (int oc = c; oc < (m.all_mono ? m.out_ch : c + 1); oc++) {
+                    float* out = chan(m.out, oc, ci) + n0;
+                    const bool vec = VEC == 4 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (m.limit < 0 || ci.f0 + n0 + 4 <= m.limit);
+                    if (vec) {
+                        *reinterpret_cast<float4*>(out) = make_float4(acc.get(0), acc.get(1), acc.get(2), acc.get(3));
+                    } else {
+                        for (int j = 0; j < VEC; j++)
+                            if (m.limit < 0 || ci.f0 + n0 + j < m.limit) out[j] = acc.get(j);
+                    }
+                }
+            }
+            continue;
+        }
+        for (int j = 0; j < VEC; j++) {
+            const int n = n0 + j;
+            if (m.limit >= 0 && ci.f0 + n >= m.limit) continue;
+            for (int c = 0; c < m.out_ch; c++) {
+                float acc = 0.f;
+                for (int e = 0; e < m.n_edges; e++) {
+                    float v = mixed_sample(edges[m.edge_offset + e], m.out_ch, c, m.interp, n, ci);
+                    acc = e == 0 ? v : acc + v;
+                }
+                chan(m.out, c, ci)[n] = acc;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // BiquadFilter — BiquadFilterRenderer::process (src/node/biquad_filter.rs:764-899), constant coefficients.
 // (1) serial: one thread per (instance, channel), the reference's exact f64 operation order (bit-faithful).
@@ -3717,6 +3759,23 @@ DEVI void conv_load_half(float2* z, int c0, const float* __restrict__ src, int v
     const int t = threadIdx.x;
     if (!src || valid <= 0) {
         for (int i = t; i < CV_B / 2; i += CV_THREADS) z[cv_pad(c0 + i)] = make_float2(0.f, 0.f);
+    } else if (src2 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(src2)) & 15) == 0) {
+#pragma unroll 8
+        for (int i4 = t; i4 < CV_B / 4; i4 += CV_THREADS) {
+            const int n = 4 * i4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n + 3 < valid) {
+                const float4 a = *reinterpret_cast<const float4*>(src + n), c = *reinterpret_cast<const float4*>(src2 + n);
+                v = make_float4(0.5f * (a.x + c.x), 0.5f * (a.y + c.y), 0.5f * (a.z + c.z), 0.5f * (a.w + c.w));
+            } else if (n < valid) {
+                v.x = 0.5f * (src[n] + src2[n]);
+                if (n + 1 < valid) v.y = 0.5f * (src[n + 1] + src2[n + 1]);
+                if (n + 2 < valid) v.z = 0.5f * (src[n + 2] + src2[n + 2]);
+            }
+            float2* d = z + cv_pad(c0 + 2 * i4);
+            d[0] = make_float2(v.x, v.y);
+            d[1] = make_float2(v.z, v.w);
+        }
     } else if (src2) {
         for (int i = t; i < CV_B / 2; i += CV_THREADS) {
             const int n = 2 * i;
@@ -4133,9 +4192,14 @@ void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s
 void launch_buffer_source_slow(const AbsnSlowInst* d, int n, ChunkInfo ci, cudaStream_t s) {
     k_buffer_source_slow<<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, n, ci);
 }
-void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s) {
+void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s, int max_edges) {
     // few instances x few frames (one graph with a huge fan-in): one frame per thread keeps more loads in flight
     const long ctas4 = (long)((ci.nf + 1023) / 1024) * n;
+    if (max_edges < 16) {  // no port of this stage is wide enough for the staged kernel
+        if (ctas4 < 2 * 148) k_mix_narrow<1><<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci);
+        else k_mix_narrow<4><<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, e, n, ci);
+        return;
+    }
     if (ctas4 < 2 * 148) k_mix<1><<<grid_tiles(ci.nf, 256, n), 256, 0, s>>>(d, e, n, ci);
     else k_mix<4><<<grid_tiles(ci.nf, 1024, n), 256, 0, s>>>(d, e, n, ci);
 }

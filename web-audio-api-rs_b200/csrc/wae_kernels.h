@@ -29,7 +29,7 @@ void launch_oscillator(const OscInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_constant(const ConstInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source(const AbsnInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_buffer_source_slow(const AbsnSlowInst* d, int n, ChunkInfo ci, cudaStream_t s);
-void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
+void launch_mix(const MixInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s, int max_edges);  // max_edges: widest port of the stage (host)
 void launch_mix_dyn(const MixDynInst* d, const MixEdge* e, int n, ChunkInfo ci, cudaStream_t s);
 void launch_meta(const MetaInst* d, int n, ChunkInfo ci, cudaStream_t s);
 void launch_biquad_serial(const BiquadInst* d, int n, int max_ch, ChunkInfo ci, cudaStream_t s);
