@@ -14,6 +14,7 @@
 #include "wae_param_host.h"
 
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <atomic>
@@ -216,6 +217,21 @@ struct wae_engine {
                 return false;
             }
         h_stage_bytes = bytes;
+        return true;
+    }
+    // small ring of page-locked pieces for the copy-out to pageable caller memory (render_oneshot_host)
+    char* h_ring = nullptr;
+    size_t h_ring_bytes = 0;
+    bool ensure_ring(size_t bytes) {
+        if (h_ring_bytes >= bytes) return true;
+        if (h_ring) cudaFreeHost(h_ring);
+        h_ring = nullptr;
+        h_ring_bytes = 0;
+        if (cudaHostAlloc((void**)&h_ring, bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        h_ring_bytes = bytes;
         return true;
     }
     std::string numa_cpus;  // CPUs this engine's host threads were bound to (WAE_OPT_BIND_NUMA), for the record
@@ -2549,6 +2565,7 @@ WAE_API wae_status wae_engine_destroy(wae_engine* eng) {
     eng->dev_trim();
     for (int i = 0; i < wae_engine::kStageSlots; i++)
         if (eng->h_stage[i]) cudaFreeHost(eng->h_stage[i]);
+    if (eng->h_ring) cudaFreeHost(eng->h_ring);
     if (eng->stream) cudaStreamDestroy(eng->stream);
     if (eng->s_h2d) cudaStreamDestroy(eng->s_h2d);
     if (eng->s_d2h) cudaStreamDestroy(eng->s_d2h);
@@ -3452,6 +3469,37 @@ WAE_API wae_status wae_batch_get_stats(wae_batch* b, wae_batch_stats* out) {
 //   -> D2H lands in `out` directly when `out` is page-locked, else in one of four page-locked staging slots that worker threads
 //      copy out to `out` while the next groups are in flight.
 // Device memory comes from the engine's cache (wae_engine::dev_alloc): after the first call of a given shape no cudaMalloc / cudaFree.
+// copy with non-temporal stores: the destination (the caller's pageable buffer) is written once and not read here, so its lines are
+// not fetched first (a plain memcpy of a few MB stays below glibc's non-temporal threshold and pays a read for every line it writes)
+static void copy_streaming(void* dst, const void* src, size_t n) {
+    char* d = static_cast<char*>(dst);
+    const char* sp = static_cast<const char*>(src);
+    const size_t head = std::min(n, (size_t)((64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63));
+    if (head) std::memcpy(d, sp, head);
+    d += head; sp += head; n -= head;
+    if ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) {
+        for (; n >= 64; n -= 64, d += 64, sp += 64) {
+            const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i*>(sp)), b2 = _mm_load_si128(reinterpret_cast<const __m128i*>(sp + 16));
+            const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i*>(sp + 32)), e = _mm_load_si128(reinterpret_cast<const __m128i*>(sp + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b2);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+        }
+    } else {
+        for (; n >= 64; n -= 64, d += 64, sp += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sp)), b2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sp + 16));
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sp + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(sp + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d), a);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b2);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+        }
+    }
+    _mm_sfence();
+    if (n) std::memcpy(d, sp, n);
+}
+
 static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs, uint32_t n_graphs, float* out) {
     if (!out) return fail(WAE_INVALID_ARGUMENT, "null output buffer");
     PrepState ps;
@@ -3516,10 +3564,79 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
     }
     size_t max_group_bytes = 0;
     for (auto& grp : b->groups) max_group_bytes = std::max(max_group_bytes, (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float));
-    if (result == WAE_OK && !out_pinned && !eng->ensure_stage(max_group_bytes)) set_fail(WAE_OUT_OF_MEMORY, "out of memory (page-locked staging of the rendered PCM)");
+    // Pageable `out`: the rendered PCM comes down in PIECES of a couple of MB through a small ring of page-locked slots, each piece is
+    // copied out by a worker (non-temporal stores) as soon as it has landed, and its slot goes back to the ring.  The ring is small on
+    // purpose: inbound DMA writes allocate in the last-level cache on the hosts this runs on, the copy-out reads them back from there and
+    // the next piece overwrites the same lines — the staging costs (almost) no DRAM traffic, where whole-group slots (120 MB each on C2)
+    // cost a DRAM write, a DRAM read and a read-for-ownership per byte.  That is what made the call lose a third of its throughput when
+    // two ranks shared a socket (profiles/README.md r2_w).  WAE_STAGE_RING=0: the whole-group slots of before.
+    static const bool use_ring = [] { const char* e = getenv("WAE_STAGE_RING"); return !e || atoi(e) != 0; }();
+    static const size_t piece_bytes = [] { const char* e = getenv("WAE_STAGE_PIECE_KB"); long kb = e ? atol(e) : 2048; return (size_t)std::max(64l, std::min(65536l, kb)) * 1024; }();
+    static const int ring_slots = [] { const char* e = getenv("WAE_STAGE_SLOTS"); int n = e ? atoi(e) : 8; return std::max(2, std::min(64, n)); }();
+    const bool ring = !out_pinned && use_ring;
+    if (result == WAE_OK && ring && !eng->ensure_ring(piece_bytes * (size_t)ring_slots)) set_fail(WAE_OUT_OF_MEMORY, "out of memory (page-locked staging ring of the rendered PCM)");
+    if (result == WAE_OK && !out_pinned && !ring && !eng->ensure_stage(max_group_bytes)) set_fail(WAE_OUT_OF_MEMORY, "out of memory (page-locked staging of the rendered PCM)");
+    // ring state (guarded by `mu`): slot i is free again once its copy-out is done; groups are handed to the pump thread in order
+    std::vector<char> ring_busy(ring ? ring_slots : 0, 0);
+    std::vector<cudaEvent_t> ring_ev(ring ? ring_slots : 0, nullptr);
+    for (auto& e : ring_ev)
+        if (result == WAE_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) set_fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
+    int issued_groups = 0;       // groups whose render has been launched and whose ev_done is recorded
+    bool pump_abort = false;     // the main thread gave up: no more groups will come
+    std::string pump_error;
+    std::thread pump;
+    if (result == WAE_OK && ring)
+        pump = std::thread([&] {
+            cudaSetDevice(eng->device);
+            size_t piece_no = 0;
+            for (int k = 0; k < n_groups; k++) {
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return issued_groups > k || pump_abort; });
+                    if (issued_groups <= k) return;
+                }
+                wae_batch::Group& grp = b->groups[k];
+                if (cudaStreamWaitEvent(eng->s_d2h, grp.ev_done, 0) != cudaSuccess) {
+                    std::lock_guard<std::mutex> lk(mu);
+                    pump_error = "cudaStreamWaitEvent failed";
+                    return;
+                }
+                const size_t off = (size_t)grp.g0 * per_graph * sizeof(float), bytes = (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float);
+                for (size_t a0 = 0; a0 < bytes; a0 += piece_bytes, piece_no++) {
+                    const size_t nb = std::min(piece_bytes, bytes - a0);
+                    const int slot = (int)(piece_no % (size_t)ring_slots);
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return !ring_busy[slot]; });
+                        ring_busy[slot] = 1;
+                        pending++;
+                    }
+                    char* stage = eng->h_ring + (size_t)slot * piece_bytes;
+                    if (cudaMemcpyAsync(stage, (const char*)b->d_out + off + a0, nb, cudaMemcpyDeviceToHost, eng->s_d2h) != cudaSuccess ||
+                        cudaEventRecord(ring_ev[slot], eng->s_d2h) != cudaSuccess) {
+                        std::lock_guard<std::mutex> lk(mu);
+                        pump_error = "D2H failed";
+                        ring_busy[slot] = 0;
+                        pending--;
+                        cv.notify_all();
+                        return;
+                    }
+                    char* dst = (char*)out + off + a0;
+                    pool->submit([&, slot, stage, dst, nb] {
+                        cudaEventSynchronize(ring_ev[slot]);
+                        copy_streaming(dst, stage, nb);
+                        {
+                            std::lock_guard<std::mutex> lk(mu);
+                            ring_busy[slot] = 0;
+                        }
+                        task_done();  // (notifies: the pump may be waiting for this slot)
+                    });
+                }
+            }
+        });
     constexpr int SLOTS = wae_engine::kStageSlots;
     bool slot_busy[SLOTS] = {false, false, false, false};
-    std::vector<cudaEvent_t> ev_copy(out_pinned ? 0 : n_groups, nullptr);
+    std::vector<cudaEvent_t> ev_copy((out_pinned || ring) ? 0 : n_groups, nullptr);
     std::vector<std::unique_ptr<std::atomic<int>>> parts_left;
     for (auto& e : ev_copy)
         if (result == WAE_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
@@ -3550,12 +3667,20 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
             break;
         }
         const size_t off = (size_t)grp.g0 * per_graph, bytes = (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float);
-        if (cudaEventRecord(grp.ev_done, s) != cudaSuccess || cudaStreamWaitEvent(eng->s_d2h, grp.ev_done, 0) != cudaSuccess) {
+        // (ring: the pump thread makes the copy stream wait, in group order — a wait queued from here could land between the pieces of
+        // the group before)
+        if (cudaEventRecord(grp.ev_done, s) != cudaSuccess || (!ring && cudaStreamWaitEvent(eng->s_d2h, grp.ev_done, 0) != cudaSuccess)) {
             set_fail(WAE_CUDA_ERROR, "event record / wait failed");
             break;
         }
         if (out_pinned) {
             if (cudaMemcpyAsync(out + off, b->d_out + off, bytes, cudaMemcpyDeviceToHost, eng->s_d2h) != cudaSuccess) set_fail(WAE_CUDA_ERROR, "D2H failed");
+            continue;
+        }
+        if (ring) {  // the pump thread brings this group down piece by piece
+            std::lock_guard<std::mutex> lk(mu);
+            issued_groups = k + 1;
+            cv.notify_all();
             continue;
         }
         const int slot = k % SLOTS;
@@ -3589,12 +3714,23 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
             });
     }
     if (result == WAE_OK && cudaEventRecord(b->ev1, s) != cudaSuccess) set_fail(WAE_CUDA_ERROR, "cudaEventRecord failed");
+    if (pump.joinable()) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (issued_groups < n_groups) pump_abort = true;  // (a failure above: the groups that were launched are still brought down)
+            cv.notify_all();
+        }
+        pump.join();
+        if (!pump_error.empty()) set_fail(WAE_CUDA_ERROR, "one-shot render: " + pump_error);
+    }
     drain();  // plans and copy-outs
     if (cudaStreamSynchronize(eng->s_d2h) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess || cudaStreamSynchronize(eng->s_h2d) != cudaSuccess)
         set_fail(WAE_CUDA_ERROR, std::string("one-shot render: ") + cudaGetErrorString(cudaGetLastError()));
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) set_fail(WAE_CUDA_ERROR, std::string("one-shot render: ") + cudaGetErrorString(le));
     for (auto& e : ev_copy)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : ring_ev)
         if (e) cudaEventDestroy(e);
     wae_batch_destroy(b);
     if (result != WAE_OK) return fail(result, result_msg);
