@@ -3564,13 +3564,12 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
     }
     size_t max_group_bytes = 0;
     for (auto& grp : b->groups) max_group_bytes = std::max(max_group_bytes, (size_t)(grp.g1 - grp.g0) * per_graph * sizeof(float));
-    // Pageable `out`: the rendered PCM comes down in PIECES of a couple of MB through a small ring of page-locked slots, each piece is
-    // copied out by a worker (non-temporal stores) as soon as it has landed, and its slot goes back to the ring.  The ring is small on
-    // purpose: inbound DMA writes allocate in the last-level cache on the hosts this runs on, the copy-out reads them back from there and
-    // the next piece overwrites the same lines — the staging costs (almost) no DRAM traffic, where whole-group slots (120 MB each on C2)
-    // cost a DRAM write, a DRAM read and a read-for-ownership per byte.  That is what made the call lose a third of its throughput when
-    // two ranks shared a socket (profiles/README.md r2_w).  WAE_STAGE_RING=0: the whole-group slots of before.
-    static const bool use_ring = [] { const char* e = getenv("WAE_STAGE_RING"); return !e || atoi(e) != 0; }();
+    // Pageable `out`, default: whole-group page-locked staging slots, copied out in parts by the workers (below).  WAE_STAGE_RING=1 (an
+    // experiment that lost, kept for the record: profiles/README.md r2_x): the PCM comes down in PIECES of a couple of MB through a small
+    // ring of page-locked slots meant to stay in the last-level cache (inbound DMA writes allocate there), each piece copied out as soon
+    // as it has landed.  Two ranks on one socket: 414 - 1117 ms per call against 184 ms with the group slots — a piece pays a blocking
+    // event wait and two thread wake-ups, and 2 MB is not enough work to hide them.
+    static const bool use_ring = [] { const char* e = getenv("WAE_STAGE_RING"); return e && atoi(e) != 0; }();
     static const size_t piece_bytes = [] { const char* e = getenv("WAE_STAGE_PIECE_KB"); long kb = e ? atol(e) : 2048; return (size_t)std::max(64l, std::min(65536l, kb)) * 1024; }();
     static const int ring_slots = [] { const char* e = getenv("WAE_STAGE_SLOTS"); int n = e ? atoi(e) : 8; return std::max(2, std::min(64, n)); }();
     const bool ring = !out_pinned && use_ring;
@@ -3705,7 +3704,13 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
                 cudaEventSynchronize(ev_copy[k]);
                 const size_t chunk = (bytes / copy_parts + 63) / 64 * 64;
                 const size_t a0 = std::min(bytes, (size_t)part * chunk), a1 = std::min(bytes, a0 + chunk);
-                if (a1 > a0) std::memcpy((char*)(out + off) + a0, (const char*)eng->h_stage[slot] + a0, a1 - a0);
+                // (non-temporal stores: a 15 MB part is far below glibc's non-temporal threshold — 3/4 of a 260 MB L3 — and a plain memcpy
+                // would fetch every destination line before overwriting it; WAE_STAGE_NT=0: memcpy)
+                static const bool nt = [] { const char* e = getenv("WAE_STAGE_NT"); return !e || atoi(e) != 0; }();
+                if (a1 > a0) {
+                    if (nt) copy_streaming((char*)(out + off) + a0, (const char*)eng->h_stage[slot] + a0, a1 - a0);
+                    else std::memcpy((char*)(out + off) + a0, (const char*)eng->h_stage[slot] + a0, a1 - a0);
+                }
                 if (left->fetch_sub(1) == 1) {
                     std::lock_guard<std::mutex> lk(mu);
                     slot_busy[slot] = false;
