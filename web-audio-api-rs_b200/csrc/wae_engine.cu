@@ -2750,6 +2750,10 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
     // graph groups for the H2D / render / D2H pipeline
     int n_groups = eng->pipeline_groups;
     if (n_groups == 0) n_groups = n_graphs >= 512 ? 32 : (n_graphs >= 64 ? 8 : 1);  // measured on C2: 8 groups 88 ms, 16: 83.7, 32: 80.6 (fill / drain of the 3-stage pipeline)
+    if (eng->pipeline_groups == 0 && n_graphs >= 512) {  // (tuning: WAE_AUTO_GROUPS overrides the automatic choice for large batches)
+        static const int env_groups = [] { const char* e = getenv("WAE_AUTO_GROUPS"); return e ? atoi(e) : 0; }();
+        if (env_groups > 0) n_groups = env_groups;
+    }
     n_groups = std::max(1, std::min<int>(n_groups, (int)n_graphs));
     {
         // contiguous runs of graphs with the same suspend frames, cut further into about n_groups pieces
@@ -3640,7 +3644,8 @@ static wae_status render_oneshot_host(wae_engine* eng, wae_graph* const* graphs,
     for (auto& e : ev_copy)
         if (result == WAE_OK && cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
             set_fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
-    const int copy_parts = std::max(1, std::min(8, pool->size() / 2));
+    static const int env_parts = [] { const char* e = getenv("WAE_COPY_PARTS"); return e ? atoi(e) : 0; }();  // (tuning)
+    const int copy_parts = env_parts > 0 ? std::min(env_parts, 32) : std::max(1, std::min(8, pool->size() / 2));
     if (result == WAE_OK) {
         if (cudaEventCreate(&b->ev0) != cudaSuccess || cudaEventCreate(&b->ev1) != cudaSuccess || cudaEventRecord(b->ev0, s) != cudaSuccess)
             set_fail(WAE_CUDA_ERROR, "cudaEventCreate failed");
