@@ -460,14 +460,47 @@ struct wae_batch {
 namespace {
 
 // ---- topological order: Graph::order_nodes / visit (src/render/graph.rs:331-487) ---------------------------
+// node id -> outgoing edges (ids are dense: a vector with presence flags; iteration in id order like the std::map it replaces)
+struct EdgeTable {
+    std::vector<std::vector<Edge>> v;
+    std::vector<char> has;
+    void reserve_ids(uint32_t max_id) {
+        v.resize((size_t)max_id + 1);
+        has.resize((size_t)max_id + 1, 0);
+    }
+    std::vector<Edge>& operator[](uint32_t id) {
+        if (id >= v.size()) reserve_ids(id);
+        has[id] = 1;
+        return v[id];
+    }
+    bool count(uint32_t id) const { return id < v.size() && has[id]; }
+    const std::vector<Edge>* find(uint32_t id) const { return count(id) ? &v[id] : nullptr; }
+    const std::vector<Edge>& at(uint32_t id) const {
+        if (!count(id)) throw std::out_of_range("orderer: unknown node id");
+        return v[id];
+    }
+};
+
 struct Orderer {
     wae_graph* g;
-    std::map<uint32_t, std::vector<Edge>> edges;  // working copy: cycle breakers clear a DelayWriter's edges
+    EdgeTable edges;  // working copy: cycle breakers clear a DelayWriter's edges
     std::vector<uint32_t> ordered, marked, marked_temp, in_cycle, cycle_breakers, broken;
     static bool contains(const std::vector<uint32_t>& v, uint32_t x) { return std::find(v.begin(), v.end(), x) != v.end(); }
     // returns true when a cycle breaker was applied (the ordering is then restarted), graph.rs:331-403.  Same visiting order
-    // as the reference; membership tests use hash sets instead of its linear `contains` (O(n^2) on 10^4-node graphs).
-    std::unordered_set<uint32_t> marked_set, temp_set;
+    // as the reference; membership tests use flag vectors indexed by node id instead of its linear `contains` (O(n^2) on 10^4-node graphs).
+    struct IdSet {
+        std::vector<char> f;
+        void reset(size_t n) { f.assign(n, 0); }
+        bool count(uint32_t id) const { return id < f.size() && f[id]; }
+        bool insert(uint32_t id) {  // true: newly inserted
+            if (id >= f.size()) f.resize((size_t)id + 1, 0);
+            const bool fresh = !f[id];
+            f[id] = 1;
+            return fresh;
+        }
+        void erase(uint32_t id) { if (id < f.size()) f[id] = 0; }
+    };
+    IdSet marked_set, temp_set;
     bool visit(uint32_t id) {
         if (temp_set.count(id)) {
             auto it = std::find(marked_temp.begin(), marked_temp.end(), id);
@@ -479,12 +512,12 @@ struct Orderer {
             in_cycle.insert(in_cycle.end(), it, marked_temp.end());  // no DelayNode in the cycle: its nodes are muted
             return false;
         }
-        if (!marked_set.insert(id).second) return false;
+        if (!marked_set.insert(id)) return false;
         marked_temp.push_back(id);
         temp_set.insert(id);
         const std::vector<Edge>& out = edges.at(id);
         for (size_t i = 0; i < out.size(); i++)
-            if (g->nodes.count(out[i].other_id) && visit(out[i].other_id)) return true;
+            if (edges.count(out[i].other_id) && visit(out[i].other_id)) return true;  // (every node of the graph has an entry)
         ordered.push_back(id);
         // `id` is the innermost node still being visited: it is the last entry of the stack unless an unbroken cycle was
         // recorded below it, in which case the reference's `retain` removes it wherever it is
@@ -494,10 +527,12 @@ struct Orderer {
         return false;
     }
     void run() {  // graph.rs:418-487
+        if (!g->nodes.empty()) edges.reserve_ids(g->nodes.rbegin()->first);
         for (auto& kv : g->nodes) edges[kv.first] = kv.second.outgoing;
+        ordered.reserve(g->nodes.size());
         for (;;) {
             ordered.clear(); marked.clear(); marked_temp.clear(); in_cycle.clear(); cycle_breakers.clear();
-            marked_set.clear(); temp_set.clear();
+            marked_set.reset(edges.v.size()); temp_set.reset(edges.v.size());
             bool applied = false;
             for (auto& kv : g->nodes) {
                 applied = visit(kv.first);
@@ -546,6 +581,29 @@ struct PNode {
     std::vector<Lay> out_lay;  // empty: constant (out_ch channels, never silent)
     bool wrote_dest = false;   // out_buf[0] IS the graph's rendered PCM (a convolver that is the destination's only input)
     Lay lay_out(int port) const { return port < (int)out_lay.size() ? out_lay[port] : Lay::fixed(out_ch[port]); }
+};
+
+// node id -> PNode; ids are handed out densely (wae_graph::next_id), so this is a vector, not a tree (the planner looks nodes up
+// several times per edge)
+struct NodeTable {
+    std::vector<PNode> v;
+    std::vector<char> has;
+    void reserve_ids(uint32_t max_id) {
+        v.resize((size_t)max_id + 1);
+        has.assign((size_t)max_id + 1, 0);
+    }
+    PNode& put(uint32_t id, PNode&& p) {
+        if (id >= v.size()) reserve_ids(id);
+        v[id] = std::move(p);
+        has[id] = 1;
+        return v[id];
+    }
+    PNode* find(uint32_t id) { return id < v.size() && has[id] ? &v[id] : nullptr; }
+    bool count(uint32_t id) const { return id < v.size() && has[id]; }
+    PNode& at(uint32_t id) {
+        if (!(id < v.size() && has[id])) throw std::out_of_range("planner: unknown node id");
+        return v[id];
+    }
 };
 
 struct Planner {
@@ -631,15 +689,16 @@ struct Planner {
         ParamTimeline tl;
         int64_t init_frame = 0;
     };
-    std::map<std::pair<uint32_t, uint32_t>, ParamRecord> param_records;
+    std::unordered_map<uint64_t, ParamRecord> param_records;  // (graph << 32 | param id); element addresses survive rehashing
     const ParamTimeline* param_timeline(uint32_t gi, uint32_t pid, const Param& prm, float sample_rate) {
-        auto it = param_records.find({gi, pid});
+        const uint64_t rec_key = (uint64_t)gi << 32 | pid;
+        auto it = param_records.find(rec_key);
         if (it == param_records.end()) {
             ParamRecord r;
             r.tl = build_param_timeline(prm);
             r.n_source_events = prm.events.size();
             r.init_frame = seg_start;
-            return &param_records.emplace(std::make_pair(gi, pid), std::move(r)).first->second.tl;
+            return &param_records.emplace(rec_key, std::move(r)).first->second.tl;
         }
         ParamRecord& r = it->second;
         if (r.n_source_events == prm.events.size() || !r.tl.error.empty()) return &r.tl;
@@ -748,7 +807,7 @@ struct Planner {
         stage(L, S_META).meta.push_back(m);
     }
 
-    std::map<uint32_t, PNode>* cur_pn = nullptr;
+    NodeTable* cur_pn = nullptr;
     struct PRef {
         bool dyn = false;  // automated / audio-rate driven: one value per frame in `track`
         float v = 0.f;
@@ -991,11 +1050,11 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
 
 Planner::PRef Planner::param_ref(wae_graph* g, uint32_t pid) {
     PRef r;
-    r.v = g->nodes.at(pid).param.constant_value();
-    auto it = cur_pn->find(pid);
-    if (it != cur_pn->end() && !it->second.out_buf.empty()) {
+    PNode* it = cur_pn->find(pid);
+    r.v = (it ? *it->n : g->nodes.at(pid)).param.constant_value();
+    if (it && !it->out_buf.empty()) {
         r.dyn = true;
-        r.track = it->second.out_buf[0];
+        r.track = it->out_buf[0];
     }
     return r;
 }
@@ -1009,8 +1068,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     std::set<uint32_t> feeds_cycle;
     if (!ord.broken.empty()) {
         std::map<uint32_t, std::vector<uint32_t>> rev;
-        for (auto& kv : ord.edges)
-            for (auto& e : kv.second) rev[e.other_id].push_back(kv.first);
+        for (uint32_t src = 0; src < (uint32_t)ord.edges.v.size(); src++)
+            if (ord.edges.has[src])
+                for (auto& e : ord.edges.v[src]) rev[e.other_id].push_back(src);
         std::vector<uint32_t> todo(ord.broken.begin(), ord.broken.end());
         while (!todo.empty()) {
             uint32_t x = todo.back();
@@ -1029,31 +1089,32 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             uint32_t x = todo.back();
             todo.pop_back();
             if (!fed_by_cycle.insert(x).second) continue;
-            auto it = ord.edges.find(x);
-            if (it == ord.edges.end()) continue;
-            for (auto& e : it->second) todo.push_back(e.other_id);
+            const std::vector<Edge>* it = ord.edges.find(x);
+            if (!it) continue;
+            for (auto& e : *it) todo.push_back(e.other_id);
         }
     }
     auto node_class = [&](uint32_t id) {
         if (ord.broken.empty() || !feeds_cycle.count(id)) return ord.broken.empty() ? 0 : 2;
         return fed_by_cycle.count(id) ? 1 : 0;
     };
-    std::map<uint32_t, PNode> pn;
+    NodeTable pn;
     cur_pn = &pn;
+    if (!g->nodes.empty()) pn.reserve_ids(g->nodes.rbegin()->first);
     for (auto& kv : g->nodes) {
         PNode p;
         p.n = &kv.second;
         p.in_edges.resize(kv.second.n_inputs);
-        pn[kv.first] = std::move(p);
+        pn.put(kv.first, std::move(p));
     }
     // Graph::render (graph.rs:500-535): walk the order, append each audio edge to its destination port
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
         for (auto& e : ord.edges.at(id)) {
             if (e.other_index < 0) continue;
-            auto it = pn.find(e.other_id);
-            if (it == pn.end()) continue;
-            it->second.in_edges[e.other_index].push_back(PortRef{id, e.self_index});
+            PNode* it = pn.find(e.other_id);
+            if (!it) continue;
+            it->in_edges[e.other_index].push_back(PortRef{id, e.self_index});
         }
     }
     hm::SchedClock clock(g->sample_rate);
