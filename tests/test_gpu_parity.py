@@ -1320,3 +1320,41 @@ def test_one_shot_render_into_registered_caller_memory(pkg, engine):
         api.check(api.host_unregister(engine.backend.engine, out.ctypes.data_as(C.c_void_p)))
     ref = pkg.render_batch_oneshot([G.c2_buffer_biquad_gain(pkg, engine.backend, g, length) for g in range(n)])
     assert np.array_equal(got, ref)
+
+
+def test_one_audio_buffer_played_by_many_sources(pkg, engine, oracle):
+    # one AudioBuffer (one copy in the device slab) played by sources on every track at once: the aligned fast track (fused chain), offsets and
+    # durations, a resampling playback rate, a loop with custom points, a rate ramp (serial track), a second buffer in between, two suspend-free
+    # graphs per batch — each node must find its samples at the shared offset
+    rng = np.random.default_rng(77)
+    length = 128 * 60 + 17
+
+    def build(be, g):
+        c = pkg.OfflineAudioContext(2, length, 48000.0, be)
+        pcm = rng.uniform(-1, 1, (2, 3000)).astype(np.float32) if be is engine.backend else build.pcm[g]
+        build.pcm[g] = pcm
+        buf = pkg.AudioBuffer(list(pcm), 48000.0)
+        mono = pkg.AudioBuffer([pcm[0, :1777] * 0.5], 44100.0)
+        s = c.create_buffer_source(buf)
+        s.connect(c.destination())
+        s.start()                                            # fast track
+        for i in range(6):
+            gn = c.create_gain()
+            gn.gain.value = 0.3 + 0.1 * i
+            gn.connect(c.destination())
+            s = c.create_buffer_source(buf if i != 3 else mono, playback_rate=1.0 if i % 2 == 0 else 0.77 + 0.1 * i)
+            s.connect(gn)
+            s.start_at_with_offset_and_duration(0.002 * i + 0.0001 * g, 0.004 * i, 0.03 + 0.01 * i)
+        lp = c.create_buffer_source(buf, loop=True, loop_start=0.01, loop_end=0.03)
+        lp.connect(c.destination())
+        lp.start_at(0.01)
+        rp = c.create_buffer_source(buf)
+        rp.playback_rate.set_value_at_time(0.5, 0.0)
+        rp.playback_rate.linear_ramp_to_value_at_time(2.0, 0.1)
+        rp.connect(c.destination())
+        rp.start_at(0.005)
+        return c
+    build.pcm = {}
+    gpu, cpu = both(pkg, engine, oracle, build, 2)
+    assert np.abs(cpu).max() > 1.0
+    assert maxdiff(gpu, cpu) <= TOL

@@ -306,3 +306,35 @@ def test_the_checker_renders_the_same_random_graphs(pkg, oracle, block):
         if seed % 10 == 0:
             b = F.random_graph(pkg, oracle, seed).start_rendering_sync()
             assert np.array_equal(pcm[0], b.get_channel_data(0)) and np.array_equal(pcm[1], b.get_channel_data(1))
+
+
+def test_an_audio_buffer_played_by_many_nodes_is_held_once(pkg, be):
+    # the reference clones an Arc<AudioBuffer> into every AudioBufferSourceNode (src/buffer.rs:69-72): the grains of
+    # examples/benchmarks.rs:351-388 all play ONE buffer.  The graph keeps one host copy per distinct PCM (copy_buffer) and the planner
+    # one copy per buffer in the device slab — same samples in another array count as the same buffer, different samples do not
+    rng = np.random.default_rng(3)
+    pcm = rng.uniform(-1, 1, (2, 1000)).astype(np.float32)   # stride 1000 floats per channel
+    other = pcm.copy()
+    other[1, 999] += 0.5                                       # same shape, differs in the very last sample
+
+    def graph(buffers):
+        c = pkg.OfflineAudioContext(2, 128 * 20, 48000.0, be)
+        for i, bufr in enumerate(buffers):
+            s = c.create_buffer_source(pkg.AudioBuffer(list(bufr), 48000.0))
+            s.connect(c.destination())
+            s.start_at_with_offset_and_duration(i * 0.001, 0.0005 * i, 0.01)
+        return c
+    assert plan(pkg, [graph([pcm] * 12)])["source_floats"] == 2 * 1000
+    assert plan(pkg, [graph([pcm, pcm.copy(), other, pcm, other.copy()])])["source_floats"] == 2 * 2 * 1000
+    # not shared across graphs (each context owns its assets) ...
+    assert plan(pkg, [graph([pcm] * 3), graph([pcm] * 3)])["source_floats"] == 2 * 2 * 1000
+    # ... and a shorter buffer with the same leading samples is its own asset
+    assert plan(pkg, [graph([pcm, pcm[:, :996]])])["source_floats"] == 2 * 1000 + 2 * 996
+    # set_buffer goes through the same door
+    c = pkg.OfflineAudioContext(2, 128 * 20, 48000.0, be)
+    for _ in range(4):
+        s = c.create_buffer_source()
+        s.set_buffer(pkg.AudioBuffer(list(pcm), 48000.0))
+        s.connect(c.destination())
+        s.start()
+    assert plan(pkg, [c])["source_floats"] == 2 * 1000

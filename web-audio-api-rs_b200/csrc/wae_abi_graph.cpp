@@ -179,7 +179,7 @@ static wae_status check_cfg(const wae_channel_config& c) {
 }
 
 // `pin`: the buffer will be DMA-ed to a device by a render call (AudioBufferSourceNode assets of a graph that has an engine)
-static std::shared_ptr<PcmBuffer> copy_buffer(const wae_graph* g, const wae_audio_buffer* b, bool pin) {
+static std::shared_ptr<PcmBuffer> copy_buffer(wae_graph* g, const wae_audio_buffer* b, bool pin) {
     // AudioBuffer::new (src/buffer.rs:96-115): assert_valid_number_of_channels / assert_valid_buffer_length
     if (b->number_of_channels < 1 || b->number_of_channels > WAE_MAX_CHANNELS || !b->channels) {
         fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(b->number_of_channels) + " is outside range [1, 32]");
@@ -188,6 +188,22 @@ static std::shared_ptr<PcmBuffer> copy_buffer(const wae_graph* g, const wae_audi
     if (b->length == 0) {
         fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid length: 0 is less than or equal to minimum bound (0)");
         return nullptr;
+    }
+    // the same PCM again (same shape, same samples): share the copy the graph already holds.  PcmBuffers are never written after this
+    // function; only shape-equal candidates are compared, newest first, and memcmp stops at the first difference — a graph with one
+    // buffer (C2) pays nothing, one with a hundred different buffers a few cache lines per candidate
+    auto& assets = g->assets[pin ? 1 : 0];
+    {
+        int looked = 0;
+        for (size_t i = assets.size(); i-- > 0 && looked < 16;) {
+            std::shared_ptr<PcmBuffer> have = assets[i].lock();
+            if (!have || have->channels.size() != b->number_of_channels || have->length() != b->length || have->sample_rate != b->sample_rate) continue;
+            looked++;
+            bool same = true;
+            for (uint32_t c = 0; c < b->number_of_channels && same; c++)
+                same = std::memcmp(have->channels[c].data(), b->channels[c], (size_t)b->length * sizeof(float)) == 0;
+            if (same) return have;
+        }
     }
     auto p = std::make_shared<PcmBuffer>();
     p->sample_rate = b->sample_rate;
@@ -201,6 +217,13 @@ static std::shared_ptr<PcmBuffer> copy_buffer(const wae_graph* g, const wae_audi
         return nullptr;
     }
     for (uint32_t c = 0; c < b->number_of_channels; c++) std::memcpy(p->channels[c].data(), b->channels[c], (size_t)b->length * sizeof(float));
+    if (assets.size() >= 64 && (assets.size() & (assets.size() - 1)) == 0) {  // at 64, 128, ...: drop the entries whose buffer is gone
+        size_t w = 0;
+        for (auto& a : assets)
+            if (!a.expired()) assets[w++] = a;
+        assets.resize(w);
+    }
+    assets.push_back(p);
     return p;
 }
 

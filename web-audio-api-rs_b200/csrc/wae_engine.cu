@@ -681,6 +681,7 @@ struct Planner {
     std::map<int, std::vector<float*>> arena_pool;
     std::map<int, size_t> arena_used;
     std::map<std::pair<uint32_t, uint32_t>, size_t> src_offsets;  // (graph, buffer source node) -> offset in the group's PCM slab
+    std::unordered_map<const PcmBuffer*, size_t> buf_offsets;       // one copy per AudioBuffer in the slab, whatever number of nodes play it
     // render-side view of every AudioParam: the event queue it (re)started with at `init_frame`.  When a suspend callback
     // pushed more events, the state machine is replayed on the host up to the suspend frame and the new events are folded
     // into what is left of the queue — handle_incoming_event against the live state, like the reference's render thread.
@@ -1712,10 +1713,16 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 if (!fuse_src && !need_out(ch)) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                 size_t len = pb.length();
                 size_t stride = (len + 3) / 4 * 4;  // every channel starts 16 B aligned (LDG.128)
-                // one copy of the PCM per (graph, node) in the group's slab, shared by the plans of all render segments
+                // one copy of the PCM per AudioBuffer in the group's slab (the grains of a granular patch all play the same one: the graph
+                // holds it once, wae_abi_graph.cpp copy_buffer), shared by the plans of all render segments
                 auto so = src_offsets.find({gi, id});
-                const bool first_use = so == src_offsets.end();
-                if (first_use) so = src_offsets.emplace(std::make_pair(gi, id), src_cursor).first;
+                bool first_use = so == src_offsets.end();
+                if (first_use) {
+                    auto bo = buf_offsets.find(n.buffer.get());
+                    if (bo != buf_offsets.end()) first_use = false;  // (already in the slab for another node)
+                    else bo = buf_offsets.emplace(n.buffer.get(), src_cursor).first;
+                    so = src_offsets.emplace(std::make_pair(gi, id), bo->second).first;
+                }
                 float* d_buf = d_src + so->second;
                 if (first_use) {
                     if (src_copies)  // recorded by the sizing pass: uploaded straight from the graph's buffer, planar [ch][stride] like the slab

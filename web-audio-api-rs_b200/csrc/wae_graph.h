@@ -154,6 +154,9 @@ struct wae_graph {
         std::map<uint32_t, wae::Node> nodes;
     };
     std::vector<Epoch> epochs;
+    // AudioBuffer assets of this graph, by pin mode: a buffer handed in again (the reference clones an Arc: one `AudioBuffer` played by
+    // hundreds of grains, src/buffer.rs:69-72) shares ONE host copy — and so one copy in the device slab (Planner::buf_offsets)
+    std::vector<std::weak_ptr<wae::PcmBuffer>> assets[2];
 
     uint32_t create_param(uint32_t owner, float def, float mn, float mx, bool a_rate, float initial, bool send_set_value = true,
                           bool fixed_id = false, uint32_t id = 0, bool constrained = false);
