@@ -527,7 +527,7 @@ struct Orderer {
         return false;
     }
     void run() {  // graph.rs:418-487
-        if (!g->nodes.empty()) edges.reserve_ids(g->nodes.rbegin()->first);
+        if (!g->nodes.empty()) edges.reserve_ids(g->nodes.max_id());
         for (auto& kv : g->nodes) edges[kv.first] = kv.second.outgoing;
         ordered.reserve(g->nodes.size());
         for (;;) {
@@ -838,6 +838,43 @@ static uint64_t fnv1a(const void* data, size_t bytes, uint64_t h = 1469598103934
 }
 
 // computedNumberOfChannels for one input port (src/render/quantum.rs:543-547), static channel counts
+// Developer check of planner refactorings (WAE_PLAN_DIGEST=1, wae_batch_plan only): a hash over every instance record the sizing pass
+// builds (records are value-initialised, device pointers are the dry pass's placeholders), printed per group — equal digests before and
+// after a change of the planner's data structures mean the same tables would be uploaded.
+static bool plan_digest_wanted() {
+    static const bool on = [] { const char* e = getenv("WAE_PLAN_DIGEST"); return e && atoi(e) != 0; }();
+    return on;
+}
+template <typename T>
+static uint64_t digest_vec(const std::vector<T>& v, uint64_t h) {
+    const uint64_t n = v.size();
+    h = fnv1a(&n, sizeof n, h);
+    if (v.empty()) return h;
+    static const bool dump = [] { const char* e = getenv("WAE_PLAN_DIGEST"); return e && atoi(e) >= 2; }();
+    if (dump) {  // which 8-byte word of which record type differs between two runs
+        std::fprintf(stderr, "  [%s] n %zu size %zu:", __PRETTY_FUNCTION__, v.size(), sizeof(T));
+        const uint64_t* q = (const uint64_t*)v.data();
+        for (size_t i = 0; i < sizeof(T) / 8 && i < 400; i++) std::fprintf(stderr, " %llx", (unsigned long long)q[i]);
+        std::fprintf(stderr, "\n");
+    }
+    return fnv1a(v.data(), v.size() * sizeof(T), h);
+}
+static uint64_t digest_builds(const std::map<std::pair<int, int>, StageBuild>& builds, uint64_t h) {
+    for (auto& kv : builds) {
+        const StageBuild& s = kv.second;
+        const int key[6] = {kv.first.first, kv.first.second, s.cls, s.level, s.kind * 64 + s.variant, s.max_ch};
+        h = fnv1a(key, sizeof key, h);
+        h = digest_vec(s.osc, h); h = digest_vec(s.cst, h); h = digest_vec(s.absn, h); h = digest_vec(s.biquad, h); h = digest_vec(s.chain, h);
+        h = digest_vec(s.param, h); h = digest_vec(s.osc_ar, h); h = digest_vec(s.biquad_ar, h); h = digest_vec(s.absn_slow, h);
+        h = digest_vec(s.scan_coef, h); h = digest_vec(s.iir, h); h = digest_vec(s.gain, h); h = digest_vec(s.shaper, h); h = digest_vec(s.span, h);
+        h = digest_vec(s.span_gains, h); h = digest_vec(s.pan, h); h = digest_vec(s.hrtf, h); h = digest_vec(s.hrtf_sel, h); h = digest_vec(s.pan_dyn, h);
+        h = digest_vec(s.absn_serial, h); h = digest_vec(s.shaper_os, h); h = digest_vec(s.route, h); h = digest_vec(s.delay, h); h = digest_vec(s.comp, h);
+        h = digest_vec(s.analyser, h); h = digest_vec(s.mix, h); h = digest_vec(s.mix_edges, h); h = digest_vec(s.mix_dyn, h); h = digest_vec(s.meta, h);
+        h = digest_vec(s.conv_in, h); h = digest_vec(s.conv_path, h); h = digest_vec(s.vgroups, h);
+    }
+    return h;
+}
+
 static int computed_channels(const ChannelCfg& cfg, int max_in) {
     switch (cfg.mode) {
         case WAE_COUNT_MODE_MAX: return max_in;
@@ -1101,7 +1138,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     };
     NodeTable pn;
     cur_pn = &pn;
-    if (!g->nodes.empty()) pn.reserve_ids(g->nodes.rbegin()->first);
+    if (!g->nodes.empty()) pn.reserve_ids(g->nodes.max_id());
     for (auto& kv : g->nodes) {
         PNode p;
         p.n = &kv.second;
@@ -2865,6 +2902,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
         bool has_feedback = false;
         std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_seen;
         std::vector<std::vector<int>> stage_lists;
+        uint64_t digest = 1469598103934665603ull;
         int code = WAE_OK;
         std::string error;
     };
@@ -2899,6 +2937,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
                     std::vector<int> kinds;
                     for (auto& kv : sizing.builds) kinds.push_back(kv.second.kind);
                     so[k].stage_lists.push_back(std::move(kinds));
+                    if (plan_digest_wanted()) so[k].digest = digest_builds(sizing.builds, so[k].digest);
                 }
             }
             b->groups[k].src_floats = sizing.src_cursor;
@@ -2918,6 +2957,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             fpf = std::max(fpf, so[k].fpf);
             has_feedback = has_feedback || so[k].has_feedback;
             for (auto& l : so[k].stage_lists) plan_stage_lists.push_back(std::move(l));
+            if (plan && plan_digest_wanted()) std::fprintf(stderr, "[wae plan digest] group %d fpf %llu src %zu: %016llx\n", k, (unsigned long long)so[k].fpf, b->groups[k].src_floats, (unsigned long long)so[k].digest);
             for (auto& kv : so[k].delay_ch_seen) {
                 auto it = ps.delay_ch_hint.find(kv.first);
                 int cur = it == ps.delay_ch_hint.end() ? 1 : it->second;

@@ -11,6 +11,9 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <stdexcept>
+#include <type_traits>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -136,6 +139,90 @@ struct Node {
     Param param;  // K_PARAM only
 };
 
+// node id -> Node.  Ids are handed out densely (wae_graph::next_id), so this is a table indexed by id, not a tree: the planner walks all
+// nodes of every graph several times per pass and looks them up per edge.  Surface of the std::map it replaces where the code uses it
+// (iteration in id order yielding (id, node) pairs, find / at / operator[]); every node is its own allocation, so references to nodes
+// stay valid while nodes are added (the graph-building calls hold some across create_param).
+class NodeMap {
+  public:
+    using value_type = std::pair<const uint32_t, Node>;
+    template <bool Const>
+    class Iter {
+        using Map = typename std::conditional<Const, const NodeMap, NodeMap>::type;
+        using Ref = typename std::conditional<Const, const value_type, value_type>::type;
+        Map* m = nullptr;
+        size_t i = 0;
+        void skip() {
+            while (i < m->slots.size() && !m->slots[i]) i++;
+        }
+        friend class NodeMap;
+        Iter(Map* map, size_t at) : m(map), i(at) { skip(); }
+
+      public:
+        Iter() = default;
+        Ref& operator*() const { return *m->slots[i]; }
+        Ref* operator->() const { return m->slots[i].get(); }
+        Iter& operator++() {
+            i++;
+            skip();
+            return *this;
+        }
+        bool operator==(const Iter& o) const { return i == o.i; }
+        bool operator!=(const Iter& o) const { return i != o.i; }
+    };
+    using iterator = Iter<false>;
+    using const_iterator = Iter<true>;
+    NodeMap() = default;
+    NodeMap(NodeMap&&) = default;
+    NodeMap& operator=(NodeMap&&) = default;
+    NodeMap(const NodeMap& o) : slots(o.slots.size()), count_(o.count_), max_id_(o.max_id_) {  // (suspend_sync keeps the graph as it was: a deep copy)
+        for (size_t i = 0; i < o.slots.size(); i++)
+            if (o.slots[i]) slots[i] = std::make_unique<value_type>(*o.slots[i]);
+    }
+    NodeMap& operator=(const NodeMap& o) {
+        if (this != &o) {
+            NodeMap c(o);
+            *this = std::move(c);
+        }
+        return *this;
+    }
+    iterator begin() { return iterator(this, 0); }
+    iterator end() { return iterator(this, slots.size()); }
+    const_iterator begin() const { return const_iterator(this, 0); }
+    const_iterator end() const { return const_iterator(this, slots.size()); }
+    iterator find(uint32_t id) { return id < slots.size() && slots[id] ? iterator(this, id) : end(); }
+    const_iterator find(uint32_t id) const { return id < slots.size() && slots[id] ? const_iterator(this, id) : end(); }
+    Node* get(uint32_t id) { return id < slots.size() && slots[id] ? &slots[id]->second : nullptr; }
+    const Node* get(uint32_t id) const { return id < slots.size() && slots[id] ? &slots[id]->second : nullptr; }
+    Node& at(uint32_t id) {
+        Node* n = get(id);
+        if (!n) throw std::out_of_range("unknown node id");
+        return *n;
+    }
+    const Node& at(uint32_t id) const {
+        const Node* n = get(id);
+        if (!n) throw std::out_of_range("unknown node id");
+        return *n;
+    }
+    Node& operator[](uint32_t id) {
+        if (id >= slots.size()) slots.resize(std::max<size_t>((size_t)id + 1, slots.size() * 2));
+        if (!slots[id]) {
+            slots[id] = std::make_unique<value_type>(id, Node{});
+            count_++;
+            if (id > max_id_ || count_ == 1) max_id_ = id;
+        }
+        return slots[id]->second;
+    }
+    size_t size() const { return count_; }
+    bool empty() const { return count_ == 0; }
+    uint32_t max_id() const { return max_id_; }  // (of a non-empty map)
+
+  private:
+    std::vector<std::unique_ptr<value_type>> slots;
+    size_t count_ = 0;
+    uint32_t max_id_ = 0;
+};
+
 }  // namespace wae
 
 struct wae_graph {
@@ -144,14 +231,14 @@ struct wae_graph {
     uint64_t length = 0;
     float sample_rate = 0.f;
     uint32_t next_id = 11;  // src/context/mod.rs:24-40
-    std::map<uint32_t, wae::Node> nodes;
+    wae::NodeMap nodes;
     std::vector<std::pair<uint32_t, uint32_t>> pending_param_edges;
     bool listener_present = false;
     // OfflineAudioContext::suspend_sync (src/context/offline.rs:330-387): `epochs[k]` is the graph as it was before the k-th
     // suspend point, valid for the frames before `frame`; the live `nodes` describe the frames after the last suspend point
     struct Epoch {
         uint64_t frame;
-        std::map<uint32_t, wae::Node> nodes;
+        wae::NodeMap nodes;
     };
     std::vector<Epoch> epochs;
     // AudioBuffer assets of this graph, by pin mode: a buffer handed in again (the reference clones an Arc: one `AudioBuffer` played by
