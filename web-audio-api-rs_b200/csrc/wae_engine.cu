@@ -460,24 +460,33 @@ struct wae_batch {
 namespace {
 
 // ---- topological order: Graph::order_nodes / visit (src/render/graph.rs:331-487) ---------------------------
-// node id -> outgoing edges (ids are dense: a vector with presence flags; iteration in id order like the std::map it replaces)
+// node id -> outgoing edges (ids are dense: a vector with presence flags; iteration in id order like the std::map it replaces).  The lists
+// are the graph's own (no copies); a cycle breaker's list is replaced by the empty one.
 struct EdgeTable {
-    std::vector<std::vector<Edge>> v;
+    std::vector<const std::vector<Edge>*> v;
     std::vector<char> has;
-    void reserve_ids(uint32_t max_id) {
-        v.resize((size_t)max_id + 1);
-        has.resize((size_t)max_id + 1, 0);
+    static const std::vector<Edge>& none() {
+        static const std::vector<Edge> e;
+        return e;
     }
-    std::vector<Edge>& operator[](uint32_t id) {
-        if (id >= v.size()) reserve_ids(id);
+    void reset(uint32_t max_id) {
+        v.assign((size_t)max_id + 1, &none());
+        has.assign((size_t)max_id + 1, 0);
+    }
+    void set(uint32_t id, const std::vector<Edge>* edges) {
+        if (id >= v.size()) {
+            v.resize((size_t)id + 1, &none());
+            has.resize((size_t)id + 1, 0);
+        }
         has[id] = 1;
-        return v[id];
+        v[id] = edges;
     }
+    void clear(uint32_t id) { set(id, &none()); }
     bool count(uint32_t id) const { return id < v.size() && has[id]; }
-    const std::vector<Edge>* find(uint32_t id) const { return count(id) ? &v[id] : nullptr; }
+    const std::vector<Edge>* find(uint32_t id) const { return count(id) ? v[id] : nullptr; }
     const std::vector<Edge>& at(uint32_t id) const {
         if (!count(id)) throw std::out_of_range("orderer: unknown node id");
-        return v[id];
+        return *v[id];
     }
 };
 
@@ -527,8 +536,8 @@ struct Orderer {
         return false;
     }
     void run() {  // graph.rs:418-487
-        if (!g->nodes.empty()) edges.reserve_ids(g->nodes.max_id());
-        for (auto& kv : g->nodes) edges[kv.first] = kv.second.outgoing;
+        edges.reset(g->nodes.empty() ? 0 : g->nodes.max_id());
+        for (auto& kv : g->nodes) edges.set(kv.first, &kv.second.outgoing);
         ordered.reserve(g->nodes.size());
         for (;;) {
             ordered.clear(); marked.clear(); marked_temp.clear(); in_cycle.clear(); cycle_breakers.clear();
@@ -540,7 +549,7 @@ struct Orderer {
             }
             if (!applied) break;
             for (uint32_t id : cycle_breakers) {
-                edges[id].clear();
+                edges.clear(id);
                 if (!contains(broken, id)) broken.push_back(id);
             }
         }
@@ -584,19 +593,34 @@ struct PNode {
 };
 
 // node id -> PNode; ids are handed out densely (wae_graph::next_id), so this is a vector, not a tree (the planner looks nodes up
-// several times per edge)
+// several times per edge).  One table per Planner, reset from graph to graph: the per-node vectors keep their capacity, so the graphs
+// of a batch after the first are planned without allocating them again (seven vectors per node).
 struct NodeTable {
     std::vector<PNode> v;
     std::vector<char> has;
-    void reserve_ids(uint32_t max_id) {
-        v.resize((size_t)max_id + 1);
-        has.assign((size_t)max_id + 1, 0);
+    void reset(uint32_t max_id) {
+        if (v.size() < (size_t)max_id + 1) v.resize((size_t)max_id + 1);
+        has.assign(v.size(), 0);
     }
-    PNode& put(uint32_t id, PNode&& p) {
-        if (id >= v.size()) reserve_ids(id);
-        v[id] = std::move(p);
+    PNode& put(uint32_t id, Node* n) {
+        if (id >= v.size()) {
+            v.resize((size_t)id + 1);
+            has.resize((size_t)id + 1, 0);
+        }
+        PNode& p = v[id];
+        p.n = n;
+        p.level = 0;
+        p.in_edges.resize((size_t)n->n_inputs);
+        for (auto& port : p.in_edges) port.clear();
+        p.in_ch.clear();
+        p.in_buf.clear();
+        p.in_lay.clear();
+        p.out_ch.clear();
+        p.out_buf.clear();
+        p.out_lay.clear();
+        p.wrote_dest = false;
         has[id] = 1;
-        return v[id];
+        return p;
     }
     PNode* find(uint32_t id) { return id < v.size() && has[id] ? &v[id] : nullptr; }
     bool count(uint32_t id) const { return id < v.size() && has[id]; }
@@ -808,6 +832,7 @@ struct Planner {
         stage(L, S_META).meta.push_back(m);
     }
 
+    NodeTable node_table;  // of the graph being planned (reused from graph to graph)
     NodeTable* cur_pn = nullptr;
     struct PRef {
         bool dyn = false;  // automated / audio-rate driven: one value per frame in `track`
@@ -1108,7 +1133,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         std::map<uint32_t, std::vector<uint32_t>> rev;
         for (uint32_t src = 0; src < (uint32_t)ord.edges.v.size(); src++)
             if (ord.edges.has[src])
-                for (auto& e : ord.edges.v[src]) rev[e.other_id].push_back(src);
+                for (auto& e : *ord.edges.v[src]) rev[e.other_id].push_back(src);
         std::vector<uint32_t> todo(ord.broken.begin(), ord.broken.end());
         while (!todo.empty()) {
             uint32_t x = todo.back();
@@ -1136,15 +1161,10 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         if (ord.broken.empty() || !feeds_cycle.count(id)) return ord.broken.empty() ? 0 : 2;
         return fed_by_cycle.count(id) ? 1 : 0;
     };
-    NodeTable pn;
+    NodeTable& pn = node_table;
     cur_pn = &pn;
-    if (!g->nodes.empty()) pn.reserve_ids(g->nodes.max_id());
-    for (auto& kv : g->nodes) {
-        PNode p;
-        p.n = &kv.second;
-        p.in_edges.resize(kv.second.n_inputs);
-        pn.put(kv.first, std::move(p));
-    }
+    pn.reset(g->nodes.empty() ? 0 : g->nodes.max_id());
+    for (auto& kv : g->nodes) pn.put(kv.first, &kv.second);
     // Graph::render (graph.rs:500-535): walk the order, append each audio edge to its destination port
     for (uint32_t id : ord.ordered) {
         Node& n = g->nodes.at(id);
@@ -1232,6 +1252,8 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
             // AudioParamProcessor (param.rs:685-797): only params with automation events or audio-rate inputs become
             // GPU work; a constant param is a scalar in its owner's instance
             auto& edges = p.in_edges[0];
+            // (a render without suspend points never replays a timeline: a constant param needs no record at all — most params are)
+            if (seg_start == 0 && seg_end >= b->lq && edges.empty() && n.param.constant()) continue;
             const ParamTimeline* tlp = param_timeline(gi, id, n.param, g->sample_rate);
             if (n.param.constant() && edges.empty()) continue;
             int level = 0;
@@ -1262,7 +1284,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     pi.in = m.out;
                 } else {
                     StageBuild& ms = stage(2 * level, S_MIX);
-                    MixInst m;
+                    MixInst m{};
                     m.out = arena_buf(1);
                     if (!m.out.p) return bail(WAE_OUT_OF_MEMORY, "out of device memory (arena)");
                     m.out_ch = 1;
@@ -1490,7 +1512,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 continue;
             }
             StageBuild& ms = stage(2 * level, S_MIX);
-            MixInst m;
+            MixInst m{};
             m.out_ch = ch;
             m.interp = n.cfg.interp;
             m.n_edges = (int)edges.size();

@@ -117,8 +117,10 @@ inline void fold_param_events(ParamTimeline& tl, const ParamEv* evs, size_t n) {
             sv.time = 0.;
             q.push_back(sv);
         }
+        // (the queue is sorted at this point: an event that arrives in time order — nearly all do — is in place where it was appended)
+        const bool in_order = q.empty() || !(ev.time < q.back().time);
         q.push_back(ev);
-        sort_q();
+        if (!in_order) sort_q();
     }
 }
 
