@@ -268,6 +268,13 @@ struct StageBuild {
     std::vector<BiquadArInst> biquad_ar;
     std::vector<AbsnSlowInst> absn_slow;
     std::vector<ScanCoef> scan_coef;
+    size_t n_scan_coef = 0;  // sets appended (the sizing pass counts them without building them)
+    // one set of scan constants per biquad of a chain instance, in instance order; returns its index
+    template <typename MakeFn>
+    int32_t add_scan_coef(bool build, MakeFn&& make) {
+        if (build) scan_coef.push_back(make());
+        return (int32_t)n_scan_coef++;
+    }
     std::vector<IirInst> iir;
     std::vector<GainInst> gain;
     std::vector<ShaperInst> shaper;
@@ -678,7 +685,7 @@ struct Planner {
     size_t src_cursor = 0;
     struct PendingChain {
         ChainInst inst;
-        std::vector<ScanCoef> coefs;
+        hm::BiquadCoefs coefs[CHAIN_MAX_BIQUADS] = {};  // of inst.bq[k]: the scan constants (1.3 KB a set) are derived when the chain is emitted
         int ch = 1;
         int phase = 0;  // 0: before biquad A, 1: after A, 3: after B, 5: after the shaper (canonical chain order)
         int cls = 0;    // scheduling class of the node that opened the chain (see stage())
@@ -1182,6 +1189,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
     // edge) or forces it to be materialised into an arena buffer.  A chain that ends at a destination whose only
     // input it is writes the final PCM directly.
     const bool fuse = eng->fuse;
+    const bool want_scan_coefs = !dry || plan_digest_wanted();  // (the sizing pass needs their number only)
     std::map<uint32_t, PendingChain> pending;
     auto consumers = [&](const Node& nd) {
         int k = 0;
@@ -1196,8 +1204,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
         StageBuild& cs = stage(L, S_CHAIN, variant);
         cur_cls = consumer_cls;
         for (int k = 0; k < pc.inst.n_biquad; k++) {
-            pc.inst.bq[k].coef = (int32_t)cs.scan_coef.size();
-            cs.scan_coef.push_back(pc.coefs[k]);
+            pc.inst.bq[k].coef = cs.add_scan_coef(want_scan_coefs, [&] { return make_scan_coef(pc.coefs[k]); });
         }
         cs.max_ch = std::max(cs.max_ch, pc.ch);
         cs.chain.push_back(pc.inst);
@@ -1426,11 +1433,9 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     PendingChain pc = std::move(pending.at(r.node));
                     pending.erase(r.node);
                     // (k_voice_sum prefetches the constants of voice k as coefficient set k: one set per voice, in voice order)
-                    if (pc.inst.n_biquad == 1 && vs.scan_coef.size() != vs.chain.size()) return bail(WAE_UNSUPPORTED, "internal: voice-sum coefficient table out of step");
-                    for (int k = 0; k < pc.inst.n_biquad; k++) {
-                        pc.inst.bq[k].coef = (int32_t)vs.scan_coef.size();
-                        vs.scan_coef.push_back(pc.coefs[k]);
-                    }
+                    if (pc.inst.n_biquad == 1 && vs.n_scan_coef != vs.chain.size()) return bail(WAE_UNSUPPORTED, "internal: voice-sum coefficient table out of step");
+                    for (int k = 0; k < pc.inst.n_biquad; k++)
+                        pc.inst.bq[k].coef = vs.add_scan_coef(want_scan_coefs, [&] { return make_scan_coef(pc.coefs[k]); });
                     pc.inst.limit = -1;
                     pc.inst.out_dup = 0;
                     vs.chain.push_back(pc.inst);
@@ -2051,7 +2056,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 ChainBiquad& st = pc.inst.bq[pc.inst.n_biquad++];
                 st.state = state;
                 st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
-                pc.coefs.push_back(make_scan_coef(c));
+                pc.coefs[pc.inst.n_biquad - 1] = c;
                 pc.phase = pc.phase == 0 ? 1 : 3;
                 pc.lay = filter_lay(pc.lay);
                 if (!finish_chain(std::move(pc))) return false;
@@ -2079,7 +2084,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                     ChainBiquad& st = pc.inst.bq[pc.inst.n_biquad++];
                     st.state = state;
                     st.b0 = c.b0; st.b1 = c.b1; st.b2 = c.b2; st.a1 = c.a1; st.a2 = c.a2;
-                    pc.coefs.push_back(make_scan_coef(c));
+                    pc.coefs[pc.inst.n_biquad - 1] = c;
                     pc.phase = 1;
                     if (!finish_chain(std::move(pc))) return false;
                     break;
