@@ -338,3 +338,40 @@ def test_an_audio_buffer_played_by_many_nodes_is_held_once(pkg, be):
         s.connect(c.destination())
         s.start()
     assert plan(pkg, [c])["source_floats"] == 2 * 1000
+
+
+def test_split_sizing_of_a_group_agrees_with_the_serial_pass():
+    # one-shot renders size a group of few, large graphs on several workers (prep_begin: size_group_split); with WAE_PLAN_PARALLEL=1
+    # wae_batch_plan sizes every multi-graph group both ways and refuses with "internal: ..." when arena floats, slab size, the recorded
+    # source copies, feedback or the in-cycle delay layouts differ.  (The switch is read once per process: a child process.)
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import conftest, graphs as G, test_gpu_fuzz as F, benchmark_scenarios as BS
+pkg = conftest.load_package()
+be = pkg.context.Backend(pkg.api(), None)
+ir = G.synthetic_ir(20000, 2, decay=0.6)
+batches = [[G.c2_buffer_biquad_gain(pkg, be, g, 12800) for g in range(5)],
+           [G.c2_buffer_biquad_gain(pkg, be, g, 2560) for g in range(70)],
+           [G.north_star_voices_convolver(pkg, be, 40, 48000, ir, seed=g) for g in range(4)],
+           [G.c3_many_voices(pkg, be, 50, 4800) for _ in range(3)]]
+batches += [[fn(pkg, be, 2.0) for _ in range(3)] for _name, fn in BS.SCENARIOS]
+n = refused = 0
+for seed in range(3000, 3120, 4):
+    batches.append([F.random_graph(pkg, be, seed + i) for i in range(4)])
+for ctxs in batches:
+    try:
+        pkg.context.plan_batch(ctxs)
+        n += 1
+    except pkg.WaeError as e:
+        assert "internal" not in str(e), str(e)
+        refused += 1
+print("planned", n, "refused", refused)
+""" % os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, WAE_PLAN_PARALLEL="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    planned = int(r.stdout.split()[1])
+    assert planned >= 40, r.stdout

@@ -699,6 +699,7 @@ struct Planner {
     template <typename T>
     T* alloc(size_t count, bool zero = false, bool rezero_on_run = false) {
         if (dry) return reinterpret_cast<T*>(uintptr_t(256));
+        if (seg_start == 0 && seg_end >= b->lq) return b->dalloc<T>(count, zero, rezero_on_run);  // no suspend point: no later plan looks it up
         const wae_batch::StateKey key{key_graph, key_node, key_seq++, key_salt};
         const size_t bytes = count * sizeof(T);
         std::lock_guard<std::recursive_mutex> lk(b->mu);
@@ -2940,10 +2941,91 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
         fpf = 0;
         plan_stage_lists.clear();
         std::vector<SizeOut> so(n_groups);
-        auto size_group = [&](int k) {
+        // A group without suspend points whose graphs are large is sized by several workers, each with its own dry planner over a
+        // contiguous run of the group's graphs: the graphs of a group share nothing in this pass but the running totals — arena floats per
+        // frame (summed) and the cursor into the source-PCM slab (the copies are recorded relative to the run and rebased in graph order,
+        // which is the order the planning pass walks).  WAE_PLAN_PARALLEL=1 lets wae_batch_plan (no engine, no GPU) size every group
+        // both ways and compare — the check of this path in the CPU suite.
+        struct RangeOut {
+            uint64_t fpf = 0;
+            size_t src_floats = 0;
+            bool has_feedback = false;
+            std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_seen;
+            std::vector<wae_batch::Group::SrcCopy> copies;
+            int code = WAE_OK;
+            std::string error;
+        };
+        auto size_range = [&](int k, uint32_t i0, uint32_t i1, RangeOut& ro) {  // single-segment groups only
             Planner sizing{b, eng};
             sizing.dry = true;
             sizing.group_graphs = (int)(b->groups[k].g1 - b->groups[k].g0);
+            sizing.delay_ch_hint = &ps.delay_ch_hint;
+            sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
+            sizing.src_copies = &ro.copies;
+            sizing.begin_segment(0, b->lq);
+            for (uint32_t i = i0; i < i1; i++) {
+                EpochView view(graphs[i], 0);
+                if (!sizing.plan_graph(graphs[i], i)) {
+                    ro.code = sizing.error_code;
+                    ro.error = sizing.error;
+                    return;
+                }
+            }
+            ro.fpf = sizing.arena_floats_per_frame;
+            ro.src_floats = sizing.src_cursor;
+            ro.has_feedback = sizing.has_feedback;
+            ro.delay_ch_seen = std::move(sizing.delay_ch_seen);
+        };
+        // (RangeOut of the whole group) from `parts` runs sized on `wp`; false: a run failed (first failing graph's error in `out`)
+        auto size_group_split = [&](int k, WorkerPool* wp, int parts, RangeOut& out) {
+            const uint32_t g0 = b->groups[k].g0, n = b->groups[k].g1 - g0;
+            std::vector<RangeOut> ro((size_t)parts);
+            auto run = [&](int t) { size_range(k, g0 + (uint32_t)((uint64_t)n * t / parts), g0 + (uint32_t)((uint64_t)n * (t + 1) / parts), ro[t]); };
+            if (wp) wp->parallel_for(parts, run);
+            else
+                for (int t = 0; t < parts; t++) run(t);
+            for (auto& r : ro) {
+                if (r.code != WAE_OK) {
+                    out.code = r.code;
+                    out.error = r.error;
+                    return false;
+                }
+                for (auto& c : r.copies) out.copies.push_back(wae_batch::Group::SrcCopy{c.buf, c.offset + out.src_floats, c.floats});
+                out.fpf += r.fpf;
+                out.src_floats += r.src_floats;
+                out.has_feedback = out.has_feedback || r.has_feedback;
+                for (auto& kv : r.delay_ch_seen) out.delay_ch_seen[kv.first] = kv.second;
+            }
+            return true;
+        };
+        auto group_nodes = [&](int k) {
+            size_t nn = 0;
+            for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) nn += graphs[i]->nodes.size();
+            return nn;
+        };
+        static const bool check_split = [] { const char* e = getenv("WAE_PLAN_PARALLEL"); return e && atoi(e) != 0; }();
+        auto size_group = [&](int k) {
+            const uint32_t n_in_group = b->groups[k].g1 - b->groups[k].g0;
+            const bool one_segment = b->groups[k].seg_bounds.size() == 2;
+            // groups are sized one after the other on this thread (no group-level pool): its workers are free for the runs of a group
+            if (!plan && !pool && one_segment && n_in_group >= 2 && group_nodes(k) >= 4096) {
+                WorkerPool* wp = eng->workers();
+                RangeOut out;
+                if (!size_group_split(k, wp, (int)std::min<uint32_t>(n_in_group, (uint32_t)wp->size()), out)) {
+                    so[k].code = out.code;
+                    so[k].error = out.error;
+                    return;
+                }
+                b->groups[k].src_copies = std::move(out.copies);
+                b->groups[k].src_floats = out.src_floats;
+                so[k].fpf = out.fpf;
+                so[k].has_feedback = out.has_feedback;
+                so[k].delay_ch_seen = std::move(out.delay_ch_seen);
+                return;
+            }
+            Planner sizing{b, eng};
+            sizing.dry = true;
+            sizing.group_graphs = (int)n_in_group;
             sizing.delay_ch_hint = &ps.delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
             b->groups[k].src_copies.clear();
@@ -2970,6 +3052,21 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             b->groups[k].src_floats = sizing.src_cursor;
             so[k].has_feedback = sizing.has_feedback;
             so[k].delay_ch_seen = std::move(sizing.delay_ch_seen);
+            if (plan && check_split && one_segment && n_in_group >= 2) {  // the split sizing of the same group must say the same
+                RangeOut out;
+                const bool ok = size_group_split(k, nullptr, (int)std::min<uint32_t>(n_in_group, 3u), out);
+                bool same = ok && out.fpf == so[k].fpf && out.src_floats == b->groups[k].src_floats && out.has_feedback == so[k].has_feedback &&
+                            out.delay_ch_seen == so[k].delay_ch_seen && out.copies.size() == b->groups[k].src_copies.size();
+                for (size_t c = 0; same && c < out.copies.size(); c++) {
+                    const auto& x = out.copies[c];
+                    const auto& y = b->groups[k].src_copies[c];
+                    same = x.buf == y.buf && x.offset == y.offset && x.floats == y.floats;
+                }
+                if (!same) {
+                    so[k].code = WAE_INVALID_STATE;
+                    so[k].error = "internal: the split sizing pass disagrees with the serial one";
+                }
+            }
         };
         if (pool) pool->parallel_for(n_groups, size_group);
         else
