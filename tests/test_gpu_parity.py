@@ -1358,3 +1358,26 @@ def test_one_audio_buffer_played_by_many_sources(pkg, engine, oracle):
     gpu, cpu = both(pkg, engine, oracle, build, 2)
     assert np.abs(cpu).max() > 1.0
     assert maxdiff(gpu, cpu) <= TOL
+
+
+def test_a_batch_of_few_large_graphs_is_planned_by_several_workers(pkg, engine, oracle):
+    # >= 4096 nodes in a batch of few graphs without suspend points: the sizing pass and the planning pass are split over the host workers
+    # (prep_begin: size_group_split, prep_plan_group: merge_builds) — the merged tables must be the ones a single planner builds: buffer
+    # sources between the voice graphs (slab offsets per run), biquad chains (scan-constant indices), a convolver per voice graph (conv-input
+    # indices), mixes (edge offsets).  Rendered through prepare / run / fetch AND through the one-shot call (planned on a worker there).
+    length = 128 * 37 + 11
+    ir = G.synthetic_ir(9000, 2, decay=0.5)
+
+    def build(be, g):
+        if g % 2 == 0:
+            return G.c2_buffer_biquad_gain(pkg, be, g, length)
+        return G.north_star_voices_convolver(pkg, be, 260, length, ir, seed=g)
+    n = 5
+    # (5 graphs, 5237 nodes in processing order: above the 4096-node threshold of the split)
+    ctxs = [build(engine.backend, g) for g in range(n)]
+    gpu = G.render(pkg, ctxs)
+    cpu = G.render(pkg, [build(oracle, g) for g in range(n)])
+    assert maxdiff(gpu, cpu) <= TOL
+    host = np.zeros((n, 2, length), np.float32)
+    pkg.render_batch_oneshot([build(engine.backend, g) for g in range(n)], host)
+    assert np.array_equal(host, gpu)

@@ -360,6 +360,7 @@ struct wae_batch {
             size_t offset, floats;      // floats
         };
         std::vector<SrcCopy> src_copies;
+        std::vector<size_t> graph_src_base;  // groups without suspend points: the slab cursor each graph starts at (split planning)
         size_t src_floats = 0;
         cudaEvent_t ev_h2d = nullptr, ev_done = nullptr;
     };
@@ -906,6 +907,61 @@ static uint64_t digest_builds(const std::map<std::pair<int, int>, StageBuild>& b
         h = digest_vec(s.conv_in, h); h = digest_vec(s.conv_path, h); h = digest_vec(s.vgroups, h);
     }
     return h;
+}
+
+// Split planning (a group of few, large graphs planned by several workers, each with its own Planner over a contiguous run of the
+// group's graphs): the runs' stage builds are appended to one another in graph order, which is the order a single planner would have
+// produced.  Records that index a sibling table of their stage are rebased: mix instances -> mix edges, chain biquads -> scan constants,
+// voice groups -> chain records, convolver paths -> the conv-input table of the forward-transform stage of their level.
+using Builds = std::map<std::pair<int, int>, StageBuild>;
+template <typename T>
+static void append_vec(std::vector<T>& d, std::vector<T>& s) {
+    if (d.empty()) d = std::move(s);
+    else d.insert(d.end(), s.begin(), s.end());
+}
+static void merge_builds(Builds& dst, Builds& src) {
+    struct Base {
+        size_t mix_edges = 0, scan = 0, chain = 0, conv_in = 0;
+    };
+    std::map<std::pair<int, int>, Base> base;  // table sizes of `dst` before anything of `src` is appended
+    for (auto& kv : src) {
+        auto it = dst.find(kv.first);
+        if (it != dst.end()) base[kv.first] = Base{it->second.mix_edges.size(), it->second.n_scan_coef, it->second.chain.size(), it->second.conv_in.size()};
+        else base[kv.first] = Base{};
+    }
+    for (auto& kv : src) {
+        StageBuild& s = kv.second;
+        const Base bs = base[kv.first];
+        for (auto& m : s.mix) m.edge_offset += (uint32_t)bs.mix_edges;
+        for (auto& m : s.mix_dyn) m.edge_offset += (uint32_t)bs.mix_edges;
+        for (auto& c : s.chain)
+            for (int k = 0; k < c.n_biquad; k++) c.bq[k].coef += (int32_t)bs.scan;
+        for (auto& v : s.vgroups) v.first += (int32_t)bs.chain;
+        if (s.kind == S_CONV_MAC || s.kind == S_CONV_MAC_ACC) {
+            const std::pair<int, int> fft_key{kv.first.first, S_CONV_FFT * 64};
+            size_t off = 0;
+            auto bi = base.find(fft_key);
+            if (bi != base.end()) off = bi->second.conv_in;
+            else if (dst.count(fft_key)) off = dst[fft_key].conv_in.size();
+            for (auto& cp : s.conv_path) cp.input += (int32_t)off;
+        }
+        auto it = dst.find(kv.first);
+        if (it == dst.end()) {
+            dst.emplace(kv.first, std::move(s));
+            continue;
+        }
+        StageBuild& d = it->second;
+        append_vec(d.osc, s.osc); append_vec(d.cst, s.cst); append_vec(d.absn, s.absn); append_vec(d.biquad, s.biquad); append_vec(d.chain, s.chain);
+        append_vec(d.param, s.param); append_vec(d.osc_ar, s.osc_ar); append_vec(d.biquad_ar, s.biquad_ar); append_vec(d.absn_slow, s.absn_slow);
+        append_vec(d.scan_coef, s.scan_coef); append_vec(d.iir, s.iir); append_vec(d.gain, s.gain); append_vec(d.shaper, s.shaper); append_vec(d.span, s.span);
+        append_vec(d.span_gains, s.span_gains); append_vec(d.pan, s.pan); append_vec(d.hrtf, s.hrtf); append_vec(d.hrtf_sel, s.hrtf_sel);
+        append_vec(d.pan_dyn, s.pan_dyn); append_vec(d.absn_serial, s.absn_serial); append_vec(d.shaper_os, s.shaper_os); append_vec(d.route, s.route);
+        append_vec(d.delay, s.delay); append_vec(d.comp, s.comp); append_vec(d.analyser, s.analyser); append_vec(d.mix, s.mix);
+        append_vec(d.mix_edges, s.mix_edges); append_vec(d.mix_dyn, s.mix_dyn); append_vec(d.meta, s.meta); append_vec(d.conv_in, s.conv_in);
+        append_vec(d.conv_path, s.conv_path); append_vec(d.vgroups, s.vgroups);
+        d.n_scan_coef += s.n_scan_coef;
+        d.max_ch = std::max(d.max_ch, s.max_ch);
+    }
 }
 
 static int computed_channels(const ChannelCfg& cfg, int max_in) {
@@ -2489,6 +2545,7 @@ bool Planner::plan_graph(wae_graph* g, uint32_t gi) {
                 c.sample_rate = g->sample_rate;
                 stage(L, S_COMP).comp.push_back(c);
                 if (!dry) {
+                    std::lock_guard<std::recursive_mutex> lk(b->mu);  // (groups are planned on worker threads)
                     bool known = false;
                     for (auto& r : b->compressors) known = known || (r.graph == gi && r.node == id);
                     if (!known) b->compressors.push_back(wae_batch::CompRec{gi, id, c.state});
@@ -2952,35 +3009,45 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             bool has_feedback = false;
             std::map<std::pair<uint32_t, uint32_t>, int> delay_ch_seen;
             std::vector<wae_batch::Group::SrcCopy> copies;
+            std::vector<size_t> graph_base;  // slab cursor before each graph (relative to the run, rebased by the merge)
+            Builds builds;                   // kept for the self-check only
             int code = WAE_OK;
             std::string error;
         };
-        auto size_range = [&](int k, uint32_t i0, uint32_t i1, RangeOut& ro) {  // single-segment groups only
+        // `cursor0`: where the run starts in the slab — 0 while that is not known yet (the sizing pass proper: rebased by the merge), the
+        // recorded base of graph i0 once it is (the planning pass and the self-check of the merged stage builds)
+        auto size_range = [&](int k, uint32_t i0, uint32_t i1, RangeOut& ro, size_t cursor0) {  // single-segment groups only
             Planner sizing{b, eng};
             sizing.dry = true;
             sizing.group_graphs = (int)(b->groups[k].g1 - b->groups[k].g0);
             sizing.delay_ch_hint = &ps.delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
             sizing.src_copies = &ro.copies;
+            sizing.src_cursor = cursor0;
             sizing.begin_segment(0, b->lq);
             for (uint32_t i = i0; i < i1; i++) {
                 EpochView view(graphs[i], 0);
+                ro.graph_base.push_back(sizing.src_cursor);
                 if (!sizing.plan_graph(graphs[i], i)) {
                     ro.code = sizing.error_code;
                     ro.error = sizing.error;
                     return;
                 }
             }
+            if (plan) ro.builds = std::move(sizing.builds);
             ro.fpf = sizing.arena_floats_per_frame;
-            ro.src_floats = sizing.src_cursor;
+            ro.src_floats = sizing.src_cursor - cursor0;
             ro.has_feedback = sizing.has_feedback;
             ro.delay_ch_seen = std::move(sizing.delay_ch_seen);
         };
         // (RangeOut of the whole group) from `parts` runs sized on `wp`; false: a run failed (first failing graph's error in `out`)
-        auto size_group_split = [&](int k, WorkerPool* wp, int parts, RangeOut& out) {
+        auto size_group_split = [&](int k, WorkerPool* wp, int parts, RangeOut& out, const std::vector<size_t>* known_base = nullptr) {
             const uint32_t g0 = b->groups[k].g0, n = b->groups[k].g1 - g0;
             std::vector<RangeOut> ro((size_t)parts);
-            auto run = [&](int t) { size_range(k, g0 + (uint32_t)((uint64_t)n * t / parts), g0 + (uint32_t)((uint64_t)n * (t + 1) / parts), ro[t]); };
+            auto run = [&](int t) {
+                const uint32_t i0 = (uint32_t)((uint64_t)n * t / parts), i1 = (uint32_t)((uint64_t)n * (t + 1) / parts);
+                size_range(k, g0 + i0, g0 + i1, ro[t], known_base ? (*known_base)[i0] : 0);
+            };
             if (wp) wp->parallel_for(parts, run);
             else
                 for (int t = 0; t < parts; t++) run(t);
@@ -2990,7 +3057,10 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
                     out.error = r.error;
                     return false;
                 }
-                for (auto& c : r.copies) out.copies.push_back(wae_batch::Group::SrcCopy{c.buf, c.offset + out.src_floats, c.floats});
+                const size_t rebase = known_base ? 0 : out.src_floats;
+                for (auto& c : r.copies) out.copies.push_back(wae_batch::Group::SrcCopy{c.buf, c.offset + rebase, c.floats});
+                for (size_t gb : r.graph_base) out.graph_base.push_back(gb + rebase);
+                if (plan) merge_builds(out.builds, r.builds);
                 out.fpf += r.fpf;
                 out.src_floats += r.src_floats;
                 out.has_feedback = out.has_feedback || r.has_feedback;
@@ -3017,6 +3087,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
                     return;
                 }
                 b->groups[k].src_copies = std::move(out.copies);
+                b->groups[k].graph_src_base = std::move(out.graph_base);
                 b->groups[k].src_floats = out.src_floats;
                 so[k].fpf = out.fpf;
                 so[k].has_feedback = out.has_feedback;
@@ -3029,12 +3100,15 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             sizing.delay_ch_hint = &ps.delay_ch_hint;
             sizing.d_src = reinterpret_cast<float*>(uintptr_t(256));
             b->groups[k].src_copies.clear();
+            b->groups[k].graph_src_base.clear();
             sizing.src_copies = &b->groups[k].src_copies;
             const std::vector<int64_t>& bounds = b->groups[k].seg_bounds;
+            uint64_t serial_digest = 0;
             for (size_t sg = 0; sg + 1 < bounds.size(); sg++) {
                 sizing.begin_segment(bounds[sg], bounds[sg + 1]);
                 for (uint32_t i = b->groups[k].g0; i < b->groups[k].g1; i++) {
                     EpochView view(graphs[i], bounds[sg]);
+                    if (one_segment) b->groups[k].graph_src_base.push_back(sizing.src_cursor);
                     if (!sizing.plan_graph(graphs[i], i)) {
                         so[k].code = sizing.error_code;
                         so[k].error = sizing.error;
@@ -3047,6 +3121,7 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
                     for (auto& kv : sizing.builds) kinds.push_back(kv.second.kind);
                     so[k].stage_lists.push_back(std::move(kinds));
                     if (plan_digest_wanted()) so[k].digest = digest_builds(sizing.builds, so[k].digest);
+                    if (check_split && one_segment) serial_digest = digest_builds(sizing.builds, 1469598103934665603ull);
                 }
             }
             b->groups[k].src_floats = sizing.src_cursor;
@@ -3056,7 +3131,13 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
                 RangeOut out;
                 const bool ok = size_group_split(k, nullptr, (int)std::min<uint32_t>(n_in_group, 3u), out);
                 bool same = ok && out.fpf == so[k].fpf && out.src_floats == b->groups[k].src_floats && out.has_feedback == so[k].has_feedback &&
-                            out.delay_ch_seen == so[k].delay_ch_seen && out.copies.size() == b->groups[k].src_copies.size();
+                            out.delay_ch_seen == so[k].delay_ch_seen && out.copies.size() == b->groups[k].src_copies.size() &&
+                            out.graph_base == b->groups[k].graph_src_base;
+                if (same) {  // with the runs started at their place in the slab the merged stage builds ARE the serial ones
+                    RangeOut abs_out;
+                    same = size_group_split(k, nullptr, (int)std::min<uint32_t>(n_in_group, 3u), abs_out, &b->groups[k].graph_src_base) &&
+                           abs_out.graph_base == b->groups[k].graph_src_base && digest_builds(abs_out.builds, 1469598103934665603ull) == serial_digest;
+                }
                 for (size_t c = 0; same && c < out.copies.size(); c++) {
                     const auto& x = out.copies[c];
                     const auto& y = b->groups[k].src_copies[c];
@@ -3178,9 +3259,65 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
         gp.code = WAE_OUT_OF_MEMORY;
         gp.error = std::string("out of device memory (") + what + ")";
     };
+    // The only group of a batch of few, large graphs, no suspend points (north_star: 8 graphs of 3000 nodes): planned by several workers,
+    // one Planner per contiguous run of graphs starting at the slab cursor the sizing pass recorded for its first graph; the runs' stage
+    // builds are merged in graph order (merge_builds) — the tables a single planner would have built (wae_batch_plan checks that on the
+    // CPU under WAE_PLAN_PARALLEL=1).  This function may itself run on a worker (one-shot render), which then waits for the others: only
+    // with one group in the batch, and never with fewer than two workers left.
+    int split_parts = 0;
+    {
+        static const bool split_on = [] { const char* e = getenv("WAE_PLAN_SPLIT"); return !e || atoi(e) != 0; }();
+        const uint32_t n_in_group = grp.g1 - grp.g0;
+        size_t nn = 0;
+        for (uint32_t i = grp.g0; i < grp.g1; i++) nn += graphs[i]->nodes.size();
+        if (split_on && b->groups.size() == 1 && grp.seg_bounds.size() == 2 && n_in_group >= 2 && nn >= 4096 && grp.graph_src_base.size() == n_in_group) {
+            const int free_workers = eng->workers()->size() - 1;
+            if (free_workers >= 2) split_parts = (int)std::min<uint32_t>(n_in_group, (uint32_t)free_workers);
+        }
+    }
     for (int sg = 0; sg + 1 < (int)grp.seg_bounds.size(); sg++) {
         pl.begin_segment(grp.seg_bounds[sg], grp.seg_bounds[sg + 1]);
         const uint64_t alg_before = pl.algorithmic_bytes;
+        if (split_parts >= 2) {
+            struct Run {
+                Builds builds;
+                uint64_t algorithmic_bytes = 0;
+                int code = WAE_OK;
+                std::string error;
+            };
+            std::vector<Run> runs((size_t)split_parts);
+            const uint32_t n = grp.g1 - grp.g0;
+            eng->workers()->parallel_for(split_parts, [&](int t) {
+                const uint32_t i0 = (uint32_t)((uint64_t)n * t / split_parts), i1 = (uint32_t)((uint64_t)n * (t + 1) / split_parts);
+                Planner rp{b, eng};
+                rp.d_src = grp.d_src;
+                rp.group_graphs = (int)n;
+                rp.src_copies = nullptr;
+                rp.delay_ch_hint = &ps.delay_ch_hint;
+                rp.ir_cache = &ps.ir_cache;
+                rp.src_cursor = grp.graph_src_base[i0];
+                rp.begin_segment(grp.seg_bounds[sg], grp.seg_bounds[sg + 1]);
+                for (uint32_t i = grp.g0 + i0; i < grp.g0 + i1; i++) {
+                    EpochView view(graphs[i], grp.seg_bounds[sg]);
+                    if (!rp.plan_graph(graphs[i], i)) {
+                        runs[t].code = rp.error_code;
+                        runs[t].error = rp.error;
+                        return;
+                    }
+                }
+                runs[t].builds = std::move(rp.builds);
+                runs[t].algorithmic_bytes = rp.algorithmic_bytes;
+            });
+            for (auto& r : runs) {
+                if (r.code != WAE_OK) {
+                    gp.code = r.code;
+                    gp.error = r.error;
+                    return;
+                }
+                merge_builds(pl.builds, r.builds);
+                pl.algorithmic_bytes += r.algorithmic_bytes;
+            }
+        } else
         for (uint32_t i = grp.g0; i < grp.g1; i++) {
             EpochView view(graphs[i], grp.seg_bounds[sg]);
             if (!pl.plan_graph(graphs[i], i)) {
