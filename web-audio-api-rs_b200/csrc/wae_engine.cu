@@ -456,8 +456,55 @@ struct wae_batch {
         if (rezero_on_run) zero_on_run.push_back({p, bytes});
         return (T*)p;
     }
+    // Small uploads (instance tables, AudioParam timelines) have 4 MiB slabs of their own, are written into a host shadow of the slab and
+    // sent with ONE copy per slab: flush_uploads(), at the end of a group's planning — before its first launch, on the stream the
+    // launches go to.  (One cudaMemcpyAsync per table before: a plan with thousands of automated params issued thousands of them, each
+    // a driver call that syncs the stream first because the source is pageable.)  Ranges are flushed once; tables of a group that is
+    // still being planned by another worker may travel with this group's flush — they are complete (written under `mu`) and their
+    // group flushes whatever it adds later.
+    char* uslab = nullptr;
+    std::vector<char> uslab_host;
+    size_t uslab_used = 0, uslab_cap = 0, uslab_flushed = 0;
+    void flush_uploads() {
+        std::lock_guard<std::recursive_mutex> lk(mu);
+        if (uslab && uslab_used > uslab_flushed) {
+            cudaMemcpyAsync(uslab + uslab_flushed, uslab_host.data() + uslab_flushed, uslab_used - uslab_flushed, cudaMemcpyHostToDevice, engine->stream);
+            uslab_flushed = uslab_used;
+        }
+    }
+    void* upload_alloc(size_t bytes) {  // (under `mu`)
+        bytes = (bytes + 255) / 256 * 256;
+        if (bytes > (512u << 10)) return nullptr;
+        if (!uslab || uslab_used + bytes > uslab_cap) {
+            flush_uploads();  // what is left of the slab that is full
+            bool fresh = false;
+            void* p = engine->dev_alloc(4u << 20, &fresh);
+            if (!p) return nullptr;
+            n_cuda_malloc += fresh ? 1 : 0;
+            allocs.push_back(p);
+            uslab = (char*)p;
+            uslab_cap = 4u << 20;
+            uslab_used = uslab_flushed = 0;
+            if (uslab_host.size() != uslab_cap) uslab_host.assign(uslab_cap, 0);  // (one shadow: the copy above has left it when cudaMemcpyAsync returns)
+        }
+        void* r = uslab + uslab_used;
+        uslab_used += bytes;
+        return r;
+    }
     template <typename T>
     T* dupload(const std::vector<T>& v) {
+        std::lock_guard<std::recursive_mutex> lk(mu);
+        const size_t bytes = v.size() * sizeof(T);
+        if (bytes > 0)
+            if (void* r = upload_alloc(bytes)) {
+                std::memcpy(uslab_host.data() + ((char*)r - uslab), v.data(), bytes);
+                return (T*)r;
+            }
+        return dupload_now(v);
+    }
+    // ... and the direct form, for large tables and for data a kernel launched by the planner itself reads (the response of a convolver)
+    template <typename T>
+    T* dupload_now(const std::vector<T>& v) {
         std::lock_guard<std::recursive_mutex> lk(mu);
         T* p = dalloc<T>(v.size());
         if (p && !v.empty()) cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, engine->stream);
@@ -1112,7 +1159,7 @@ bool Planner::plan_convolver(wae_graph* g, PNode& pn, int level, const BufRef* d
     } else {
         std::vector<float> flat((size_t)ir_ch * ir_len);
         for (int c = 0; c < ir_ch; c++) std::memcpy(flat.data() + (size_t)c * ir_len, scaled[c].data(), ir_len * sizeof(float));
-        float* d_ir = upload(flat);
+        float* d_ir = dry ? upload(flat) : b->dupload_now(flat);  // (read by launch_conv_ir_fft below: not through the deferred upload slabs)
         if (!dry) cudaStreamSynchronize(eng->stream);  // `flat` is about to go out of scope
         spec.S = Smax;
         spec.channels = ir_ch;
@@ -3439,6 +3486,7 @@ static void prep_plan_group(wae_batch* b, wae_graph* const* graphs, int k, PrepS
         }
         gp.seg_ranges.push_back({seg_stage0, gp.stages.size()});
     }  // segments
+    b->flush_uploads();  // the group's tables, before anything of it is launched
 }
 
 static void prep_append_group(wae_batch* b, int k, PrepState& ps, GroupPlan& gp) {
