@@ -222,6 +222,18 @@ WAO_API wae_status wao_create_gain(wae_graph* g, const wae_gain_options* o, wae_
     return WAE_OK;
 }
 
+// AudioBuffer::new / ::from (src/buffer.rs:96-131): assert_valid_number_of_channels, assert_valid_buffer_length
+static bool valid_buffer(const wae_audio_buffer* b) {
+    if (b->number_of_channels < 1 || b->number_of_channels > 32 || !b->channels) {
+        fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid number of channels: " + std::to_string(b->number_of_channels) + " is outside range [1, 32]");
+        return false;
+    }
+    if (b->length == 0) {
+        fail(WAE_NOT_SUPPORTED, "NotSupportedError - Invalid length: 0 is less than or equal to minimum bound (0)");
+        return false;
+    }
+    return true;
+}
 static std::shared_ptr<AudioBuffer> copy_buffer(const wae_audio_buffer* b) {
     auto ab = std::make_shared<AudioBuffer>();
     ab->sample_rate = b->sample_rate;
@@ -231,6 +243,7 @@ static std::shared_ptr<AudioBuffer> copy_buffer(const wae_audio_buffer* b) {
 
 // AudioBufferSourceNode::new, src/node/audio_buffer_source.rs:160-235
 WAO_API wae_status wao_create_buffer_source(wae_graph* g, const wae_buffer_source_options* o, wae_node_id* out) {
+    if (o->buffer && !valid_buffer(o->buffer)) return WAE_NOT_SUPPORTED;
     uint32_t id = g->next_id++;
     uint32_t d = g->create_param(id, ParamDescriptor{0.f, -F32_MAX, F32_MAX, false}, o->detune);
     uint32_t pr = g->create_param(id, ParamDescriptor{1.f, -F32_MAX, F32_MAX, false}, o->playback_rate);
@@ -777,6 +790,7 @@ WAO_API wae_status wao_buffer_source_set_buffer(wae_graph* g, wae_node_id node, 
     if (ni == g->info.end() || ni->second.kind != K_ABSN || !buffer) return fail(WAE_INVALID_ARGUMENT, "not an AudioBufferSourceNode / null buffer");
     auto* r = static_cast<AudioBufferSourceRenderer*>(ni->second.proc);
     if (r->buffer) return fail(WAE_INVALID_STATE, "InvalidStateError - cannot assign buffer twice");
+    if (!valid_buffer(buffer)) return WAE_NOT_SUPPORTED;
     r->buffer = copy_buffer(buffer);
     r->clamp_loop_boundaries();
     return WAE_OK;
