@@ -152,3 +152,105 @@ def test_audioparam_curves_vs_closed_forms(pkg, oracle):
     waiting = (t < t0 - 0.5 / sr) & (np.arange(n) >= RQ)
     quirk = 2.0 + (0.25 - 2.0) * np.exp(-(RQ / sr - t0) / tc)
     assert waiting.sum() > 300 and quirk < -0.5 and np.abs(got - quirk)[waiting].max() <= 2e-6
+
+
+def _render_channels(pkg, be, sr, channels, make_node, out_channels=2):
+    n = -(-len(channels[0]) // RQ) * RQ
+    c = pkg.OfflineAudioContext(out_channels, n, sr, be)
+    src = c.create_buffer_source(pkg.AudioBuffer([np.asarray(ch, np.float32) for ch in channels], sr))
+    node = make_node(c)
+    src.connect(node)
+    node.connect(c.destination())
+    src.start()
+    a = c.start_rendering_sync()
+    return np.array([a.get_channel_data(i)[:len(channels[0])] for i in range(out_channels)], np.float64)
+
+
+@pytest.mark.parametrize("delay_frames", [0.0, 1.0, 40.25, 127.5, 128.0, 300.75, 1000.5])
+def test_delay_vs_linear_interpolation(pkg, oracle, delay_frames):
+    # spec: y(t) = x(t - delayTime); between samples the reference interpolates linearly (delay.rs:640-700)
+    rng = np.random.default_rng(5)
+    sr = 48000.0
+    x = rng.uniform(-1, 1, 2048).astype(np.float32)
+    got = _render_through(pkg, oracle, sr, x, lambda c: c.create_delay(1.0, delay_frames / sr))
+    d = float(np.float32(delay_frames / sr)) * sr   # delayTime is an f32 AudioParam
+    k = int(np.floor(d))
+    f = d - k
+    xp = np.concatenate([np.zeros(k + 2), x.astype(np.float64)])
+    idx = np.arange(len(x)) + 2
+    want = (1 - f) * xp[idx] + f * xp[idx - 1]
+    assert np.abs(got - want).max() <= 2e-6, delay_frames
+
+
+@pytest.mark.parametrize("pan", [-1.0, -0.3, 0.0, 0.45, 1.0])
+def test_stereo_panner_vs_the_specification(pkg, oracle, pan):
+    # https://webaudio.github.io/web-audio-api/#stereopanner-algorithm
+    rng = np.random.default_rng(6)
+    sr = 48000.0
+    left, right = rng.uniform(-1, 1, (2, 512)).astype(np.float32)
+    got = _render_channels(pkg, oracle, sr, [left], lambda c: c.create_stereo_panner(pan))
+    x = (pan + 1) / 2
+    assert np.abs(got[0] - left * np.cos(x * np.pi / 2)).max() <= 2e-7 and np.abs(got[1] - left * np.sin(x * np.pi / 2)).max() <= 2e-7
+    got = _render_channels(pkg, oracle, sr, [left, right], lambda c: c.create_stereo_panner(pan))
+    x = pan + 1 if pan <= 0 else pan
+    gl, gr = np.cos(x * np.pi / 2), np.sin(x * np.pi / 2)
+    if pan <= 0:
+        want = [left + right * gl, right * gr]
+    else:
+        want = [left * gl, right + left * gr]
+    assert np.abs(got[0] - want[0]).max() <= 4e-7 and np.abs(got[1] - want[1]).max() <= 4e-7
+
+
+@pytest.mark.parametrize("points", [2, 3, 64, 1025])
+def test_wave_shaper_vs_the_specification(pkg, oracle, points):
+    # https://webaudio.github.io/web-audio-api/#WaveShaperNode-attributes: v = (N - 1) / 2 * (x + 1), k = floor(v), f = v - k,
+    # y = (1 - f) curve[k] + f curve[k + 1]; x <= -1 -> curve[0], x >= 1 -> curve[N - 1]
+    rng = np.random.default_rng(points)
+    sr = 48000.0
+    curve = rng.uniform(-1, 1, points).astype(np.float32)
+    x = np.concatenate([rng.uniform(-1.3, 1.3, 1000), [-1.0, 1.0, 0.0, -2.0, 2.0]]).astype(np.float32)
+    got = _render_through(pkg, oracle, sr, x, lambda c: c.create_wave_shaper(curve=curve))
+    v = (points - 1) / 2 * (x.astype(np.float64) + 1)
+    k = np.clip(np.floor(v).astype(int), 0, points - 2)
+    f = v - k
+    want = (1 - f) * curve[k] + f * curve[k + 1]
+    want = np.where(x <= -1, curve[0], np.where(x >= 1, curve[-1], want))
+    # the reference computes v in f32: half an ulp of v (up to N - 1) times the local slope of the curve (up to 2 per point)
+    assert np.abs(got - want).max() <= 1e-6 + 2.5e-7 * points
+
+
+@pytest.mark.parametrize("model", ["linear", "inverse", "exponential"])
+def test_panner_distance_gain_vs_the_specification(pkg, oracle, model):
+    # https://webaudio.github.io/web-audio-api/#enumdef-distancemodeltype; source straight ahead of the default listener (azimuth 0): the
+    # equal-power law gives a mono input cos(pi / 4) on both sides
+    sr = 48000.0
+    x = np.full(256, 0.5, np.float32)
+    ref, mx, roll = 2.0, 40.0, 0.8 if model == "linear" else 1.7
+    for d in [0.5, 2.0, 7.0, 39.0, 90.0]:
+        got = _render_channels(pkg, oracle, sr, [x], lambda c: c.create_panner(distance_model={"linear": pkg.LINEAR, "inverse": pkg.INVERSE, "exponential": pkg.EXPONENTIAL}[model],
+                                                                           position=(0.0, 0.0, -d), ref_distance=ref, max_distance=mx, rolloff_factor=roll))
+        if model == "linear":
+            g = 1 - roll * (min(max(d, ref), mx) - ref) / (mx - ref)
+        elif model == "inverse":
+            g = ref / (ref + roll * (max(d, ref) - ref))
+        else:
+            g = (max(d, ref) / ref) ** (-roll)
+        want = 0.5 * np.cos(np.pi / 4) * g
+        assert np.abs(got - want).max() <= 1e-6, (model, d)
+
+
+def test_convolver_normalisation_vs_the_specification(pkg, oracle):
+    # https://webaudio.github.io/web-audio-api/#dom-convolvernode-normalize (calculateNormalizationScale)
+    import ctypes as C
+    import importlib
+    B = importlib.import_module(pkg.__name__ + "._binding")
+    rng = np.random.default_rng(12)
+    for n_ch, length, sr, amp in [(1, 1000, 44100.0, 0.3), (2, 4096, 48000.0, 1.0), (4, 777, 96000.0, 0.01), (1, 64, 48000.0, 1e-7)]:
+        data = (amp * rng.uniform(-1, 1, (n_ch, length))).astype(np.float32)
+        rows = [np.ascontiguousarray(r) for r in data]
+        ptrs = (C.POINTER(C.c_float) * n_ch)(*[B.fptr(r) for r in rows])
+        got = oracle.api.convolver_normalize(C.byref(B.AudioBufferDesc(n_ch, length, sr, ptrs)))
+        power = np.sqrt(np.sum(data.astype(np.float64) ** 2) / (n_ch * length))
+        power = max(power, 0.000125)
+        want = 1 / power * 0.00125 * (44100.0 / sr) * (0.5 if n_ch == 4 else 1.0)
+        assert abs(got - want) <= 2e-6 * want, (n_ch, length)
