@@ -370,7 +370,7 @@ for ctxs in batches:
         refused += 1
 print("planned", n, "refused", refused)
 """ % os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, WAE_PLAN_PARALLEL="1")
+    env = dict(os.environ, WAE_PLAN_PARALLEL="2")  # 2: the runs of the check on real worker threads
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     planned = int(r.stdout.split()[1])

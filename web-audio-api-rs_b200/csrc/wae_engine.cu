@@ -3176,7 +3176,10 @@ static wae_status prep_begin(wae_engine* eng, wae_graph* const* graphs, uint32_t
             so[k].delay_ch_seen = std::move(sizing.delay_ch_seen);
             if (plan && check_split && one_segment && n_in_group >= 2) {  // the split sizing of the same group must say the same
                 RangeOut out;
-                const bool ok = size_group_split(k, nullptr, (int)std::min<uint32_t>(n_in_group, 3u), out);
+                // (WAE_PLAN_PARALLEL=2: the runs on real worker threads, as the one-shot render sizes them — for the sanitizers)
+                static const bool threaded = [] { const char* e = getenv("WAE_PLAN_PARALLEL"); return e && atoi(e) >= 2; }();
+                std::unique_ptr<WorkerPool> tmp_pool(threaded ? new WorkerPool(3, 0) : nullptr);
+                const bool ok = size_group_split(k, tmp_pool.get(), (int)std::min<uint32_t>(n_in_group, 3u), out);
                 bool same = ok && out.fpf == so[k].fpf && out.src_floats == b->groups[k].src_floats && out.has_feedback == so[k].has_feedback &&
                             out.delay_ch_seen == so[k].delay_ch_seen && out.copies.size() == b->groups[k].src_copies.size() &&
                             out.graph_base == b->groups[k].graph_src_base;
