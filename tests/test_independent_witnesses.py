@@ -254,3 +254,71 @@ def test_convolver_normalisation_vs_the_specification(pkg, oracle):
         power = max(power, 0.000125)
         want = 1 / power * 0.00125 * (44100.0 / sr) * (0.5 if n_ch == 4 else 1.0)
         assert abs(got - want) <= 2e-6 * want, (n_ch, length)
+
+
+def _spec_azimuth(src, listener=(0.0, 0.0, 0.0), forward=(0.0, 0.0, -1.0), up=(0.0, 1.0, 0.0)):
+    """https://webaudio.github.io/web-audio-api/#azimuth-elevation"""
+    s = np.array(src, float) - np.array(listener, float)
+    if not s.any():
+        return 0.0
+    s /= np.linalg.norm(s)
+    f, u = np.array(forward, float), np.array(up, float)
+    right = np.cross(f, u)
+    right /= np.linalg.norm(right)
+    f /= np.linalg.norm(f)
+    up2 = np.cross(right, f)
+    proj = s - np.dot(s, up2) * up2
+    if not proj.any():
+        return 0.0
+    proj /= np.linalg.norm(proj)
+    az = np.degrees(np.arccos(np.clip(np.dot(proj, right), -1, 1)))
+    if np.dot(proj, f) < 0:
+        az = 360 - az
+    return 90 - az if 0 <= az <= 270 else 450 - az
+
+
+@pytest.mark.parametrize("stereo", [False, True])
+def test_equal_power_panner_vs_the_specification(pkg, oracle, stereo):
+    # https://webaudio.github.io/web-audio-api/#Spatialization-equal-power-panning; sources on the unit circle and off the horizontal plane
+    # (distance 1 = refDistance: no distance attenuation, full cones)
+    rng = np.random.default_rng(21)
+    sr = 48000.0
+    left, right = (0.5 * rng.uniform(-1, 1, (2, 256))).astype(np.float32)
+    for pos in [(0.0, 0.0, -1.0), (1.0, 0.0, 0.0), (-1.0, 0.0, 0.0), (0.6, 0.0, -0.8), (-0.6, 0.0, 0.8), (0.0, 0.0, 1.0), (0.5, 0.7, -0.5), (-0.3, -0.4, 0.2)]:
+        p = np.array(pos) / np.linalg.norm(pos)
+        got = _render_channels(pkg, oracle, sr, [left, right] if stereo else [left], lambda c: c.create_panner(position=tuple(float(v) for v in p)))
+        az = float(np.clip(_spec_azimuth(p), -180, 180))
+        az = -180 - az if az < -90 else (180 - az if az > 90 else az)
+        if not stereo:
+            x = (az + 90) / 180
+            want = [left * np.cos(x * np.pi / 2), left * np.sin(x * np.pi / 2)]
+        else:
+            x = (az + 90) / 90 if az <= 0 else az / 90
+            gl, gr = np.cos(x * np.pi / 2), np.sin(x * np.pi / 2)
+            want = [left + right * gl, right * gr] if az <= 0 else [left * gl, right + left * gr]
+        assert np.abs(got[0] - want[0]).max() <= 2e-6 and np.abs(got[1] - want[1]).max() <= 2e-6, (pos, az)
+
+
+def test_panner_cone_gain_vs_the_specification(pkg, oracle):
+    # https://webaudio.github.io/web-audio-api/#Spatialization-sound-cones — the gain law as specified, the ANGLE as the reference measures it:
+    # spatial.rs:277-299 takes the angle between the source's orientation and the vector from the LISTENER to the SOURCE (source_position -
+    # listener_position), where the specification uses the vector from the source to the listener: a source facing away from the listener is
+    # "on axis" for the reference.  Oracle and engine follow the reference (the first attempt at this test, written from the specification,
+    # found the outer gain at angle 0).  Source at (0, 0, -1); `angle` degrees between its orientation and (0, 0, -1).
+    sr = 48000.0
+    x = np.full(256, 0.5, np.float32)
+    inner, outer, outer_gain = 60.0, 200.0, 0.25
+    for angle in [0.0, 20.0, 30.0, 65.0, 99.9, 100.0, 150.0, 180.0]:
+        a = np.radians(angle)
+        orientation = (float(np.sin(a)), 0.0, float(-np.cos(a)))
+        got = _render_channels(pkg, oracle, sr, [x], lambda c: c.create_panner(position=(0.0, 0.0, -1.0), orientation=orientation, cone_inner_angle=inner,
+                                                                           cone_outer_angle=outer, cone_outer_gain=outer_gain))
+        if angle <= inner / 2:
+            g = 1.0
+        elif angle >= outer / 2:
+            g = outer_gain
+        else:
+            t = (angle - inner / 2) / (outer / 2 - inner / 2)
+            g = (1 - t) + outer_gain * t
+        want = 0.5 * np.cos(np.pi / 4) * g
+        assert np.abs(got - want).max() <= 3e-6, (angle, g)
