@@ -322,3 +322,64 @@ def test_panner_cone_gain_vs_the_specification(pkg, oracle):
             g = (1 - t) + outer_gain * t
         want = 0.5 * np.cos(np.pi / 4) * g
         assert np.abs(got - want).max() <= 3e-6, (angle, g)
+
+
+def test_value_curve_vs_the_specification(pkg, oracle):
+    # https://webaudio.github.io/web-audio-api/#dom-audioparam-setvaluecurveattime: k = floor((N - 1) / T_D (t - T_0)),
+    # v(t) = V[k] + (V[k + 1] - V[k]) ((N - 1) / T_D (t - T_0) - k); after T_0 + T_D the last value holds
+    sr = 48000.0
+    n = RQ * 30
+    t = np.arange(n) / sr
+    values = np.array([0.0, 1.0, -0.5, 0.25, 0.75], np.float32)
+    t0, dur = 0.001, 0.045   # (starts inside the first quantum: a curve that is still pending at the end of a quantum is sampled early by the
+    #                           reference, like the pending setTarget above — tests/test_param_timeline.py::test_a_pending_value_curve_...)
+    c = pkg.OfflineAudioContext(1, n, sr, oracle)
+    s = c.create_constant_source(1.0)
+    g = c.create_gain(0.5)
+    g.gain.set_value_curve_at_time(values, t0, dur)
+    s.connect(g)
+    g.connect(c.destination())
+    s.start()
+    got = c.start_rendering_sync().get_channel_data(0).astype(np.float64)
+    pos = (len(values) - 1) / dur * (t - t0)
+    k = np.clip(np.floor(pos).astype(int), 0, len(values) - 2)
+    curve = values[k] + (values[k + 1] - values[k]) * (pos - k)
+    inside = (t > t0 + 1 / sr) & (t < t0 + dur - 1 / sr)
+    assert np.all(got[t < t0 - 1 / sr] == 0.5)
+    assert np.abs(got - curve)[inside].max() <= 1e-5
+    assert np.all(got[t > t0 + dur + 1 / sr] == values[-1])
+
+
+def test_sine_oscillator_and_detune_vs_numpy(pkg, oracle):
+    # computedOscFrequency = frequency * 2^(detune / 1200); a sine of that frequency from phase 0 (the reference reads a 2048-point table with
+    # linear interpolation: 2.4e-6 worst case for a sine + the f32 phase accumulation over the render)
+    sr = 48000.0
+    n = RQ * 32
+    for f, det in [(440.0, 0.0), (1000.0, 700.0), (93.7, -1200.0)]:
+        c = pkg.OfflineAudioContext(1, n, sr, oracle)
+        o = c.create_oscillator(frequency=f, detune=det)
+        o.connect(c.destination())
+        o.start()
+        got = c.start_rendering_sync().get_channel_data(0).astype(np.float64)
+        want = np.sin(2 * np.pi * f * 2.0 ** (det / 1200.0) * np.arange(n) / sr)
+        assert np.abs(got - want).max() <= 2e-4, (f, det)
+
+
+def test_looping_buffer_source_vs_modular_indexing(pkg, oracle):
+    # https://webaudio.github.io/web-audio-api/#playback-AudioBufferSourceNode at playbackRate 1 with sample-aligned loop points: the
+    # playhead runs to loopEnd and wraps to loopStart
+    rng = np.random.default_rng(31)
+    sr = 48000.0
+    buf = rng.uniform(-1, 1, 700).astype(np.float32)
+    ls, le = 100, 420
+    n = RQ * 12
+    c = pkg.OfflineAudioContext(1, n, sr, oracle)
+    s = c.create_buffer_source(pkg.AudioBuffer([buf], sr), loop=True, loop_start=ls / sr, loop_end=le / sr)
+    s.connect(c.destination())
+    s.start()
+    got = c.start_rendering_sync().get_channel_data(0)
+    idx = np.arange(n)
+    idx = np.where(idx < le, idx, ls + (idx - le) % (le - ls))
+    # (the frame AT every wrap belongs to whichever side the reference's accumulated f64 playhead puts it, interpolated: not asserted)
+    at_wrap = (np.arange(n) >= le) & ((np.arange(n) - le) % (le - ls) == 0)
+    assert at_wrap.sum() == 4 and np.array_equal(got[~at_wrap], buf[idx][~at_wrap])
