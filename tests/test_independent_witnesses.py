@@ -383,3 +383,34 @@ def test_looping_buffer_source_vs_modular_indexing(pkg, oracle):
     # (the frame AT every wrap belongs to whichever side the reference's accumulated f64 playhead puts it, interpolated: not asserted)
     at_wrap = (np.arange(n) >= le) & ((np.arange(n) - le) % (le - ls) == 0)
     assert at_wrap.sum() == 4 and np.array_equal(got[~at_wrap], buf[idx][~at_wrap])
+
+
+def test_dynamics_compressor_vs_the_published_design(pkg, oracle):
+    # The node's design is public: the specification's compression curve and makeup gain (full-range gain = the curve applied to 1.0, makeup =
+    # its inverse to the power 0.6), the gain computer and the branching peak detector of Giannoulis, Massberg and Reiss, "Digital Dynamic Range
+    # Compressor Design" (JAES 2012: eq. 4, 7, 16 — the paper dynamics_compressor.rs:355-360 cites), a 6 ms look-ahead in whole render quanta.
+    # Restated in f64 from the paper and the spec (the reference works in f32: 1e-4 relative).
+    rng = np.random.default_rng(77)
+    sr = 48000.0
+    n = RQ * 60
+    t = np.arange(n) / sr
+    x = (np.where((t > 0.02) & (t < 0.09), 0.9, 0.05) * np.sin(2 * np.pi * 330.0 * t) + 0.01 * rng.uniform(-1, 1, n)).astype(np.float32)
+    for thr, knee, ratio, att, rel in [(-24.0, 30.0, 12.0, 0.003, 0.25), (-30.0, 0.0, 4.0, 0.01, 0.05), (-12.0, 6.0, 20.0, 0.001, 0.1)]:
+        got = _render_through(pkg, oracle, sr, x, lambda c: c.create_dynamics_compressor(attack=att, knee=knee, ratio=ratio, release=rel, threshold=thr))
+        T = thr + knee / 2 if knee > 0 else thr            # the knee is centred on the shifted threshold (paper's W around T)
+        a_tau, r_tau = np.exp(-1 / (att * sr)), np.exp(-1 / (rel * sr))
+        makeup_db = 20 * np.log10((1 / 10 ** ((T - T / ratio) / 20)) ** 0.6)
+        xs = np.abs(x.astype(np.float64))
+        xg = np.where(xs == 0, -1000.0, 20 * np.log10(np.maximum(xs, 1e-300)))
+        yg = np.where(2 * (xg - T) < -knee, xg, np.where(2 * np.abs(xg - T) <= knee, xg + (1 / ratio - 1) * (xg - T + knee / 2) ** 2 / (2 * knee if knee > 0 else 1), T + (xg - T) / ratio))
+        xl = xg - yg
+        gain = np.empty(n)
+        yl = 0.0
+        for i in range(n):
+            yl = a_tau * yl + (1 - a_tau) * xl[i] if xl[i] > yl else r_tau * yl + (1 - r_tau) * xl[i]
+            gain[i] = 10 ** ((-yl + makeup_db) / 20)
+        delay = (int(np.ceil(sr * 0.006 / RQ)) + 1 - 1) * RQ   # ring of ceil(6 ms / quantum) + 1 quanta, read one slot ahead of the write
+        delayed = np.concatenate([np.zeros(delay), x.astype(np.float64)])[:n]
+        want = delayed * gain
+        assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), (thr, knee, ratio)
+        assert np.abs(want).max() > 0.3   # (the loud burst came through, attenuated)
