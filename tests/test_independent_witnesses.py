@@ -414,3 +414,43 @@ def test_dynamics_compressor_vs_the_published_design(pkg, oracle):
         want = delayed * gain
         assert np.abs(got - want).max() <= 2e-4 * max(1.0, np.abs(want).max()), (thr, knee, ratio)
         assert np.abs(want).max() > 0.3   # (the loud burst came through, attenuated)
+
+
+def _spec_mix(x, m):
+    """https://webaudio.github.io/web-audio-api/#channel-up-mixing-and-down-mixing, "speakers": x [k][n] -> [m][n]; layouts 1, 2, 4 (L R SL SR),
+    6 (L R C LFE SL SR); other combinations are "discrete" (copy what fits, zero the rest)"""
+    k = len(x)
+    z = np.zeros_like(x[0])
+    s = np.sqrt(0.5)
+    if k == m:
+        return list(x)
+    table = {
+        (1, 2): lambda: [x[0], x[0]], (1, 4): lambda: [x[0], x[0], z, z], (1, 6): lambda: [z, z, x[0], z, z, z],
+        (2, 4): lambda: [x[0], x[1], z, z], (2, 6): lambda: [x[0], x[1], z, z, z, z], (4, 6): lambda: [x[0], x[1], z, z, x[2], x[3]],
+        (2, 1): lambda: [0.5 * (x[0] + x[1])], (4, 1): lambda: [0.25 * (x[0] + x[1] + x[2] + x[3])],
+        (6, 1): lambda: [s * (x[0] + x[1]) + x[2] + 0.5 * (x[4] + x[5])],
+        (4, 2): lambda: [0.5 * (x[0] + x[2]), 0.5 * (x[1] + x[3])],
+        (6, 2): lambda: [x[0] + s * (x[2] + x[4]), x[1] + s * (x[2] + x[5])],
+        (6, 4): lambda: [x[0] + s * x[2], x[1] + s * x[2], x[4], x[5]],
+    }
+    if (k, m) in table:
+        return table[(k, m)]()
+    return [x[i] if i < k else z for i in range(m)]
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 6])
+def test_speaker_mixing_vs_the_specification(pkg, oracle, k):
+    rng = np.random.default_rng(40 + k)
+    sr = 48000.0
+    x = rng.uniform(-1, 1, (k, RQ * 2)).astype(np.float32)
+    for m in [1, 2, 3, 4, 6]:
+        c = pkg.OfflineAudioContext(m, RQ * 2, sr, oracle)
+        src = c.create_buffer_source(pkg.AudioBuffer(list(x), sr))
+        port = c.create_gain(1.0, cfg=pkg.channel_config(m, pkg.EXPLICIT, pkg.SPEAKERS))
+        src.connect(port)
+        port.connect(c.destination())
+        src.start()
+        a = c.start_rendering_sync()
+        got = np.array([a.get_channel_data(i) for i in range(m)], np.float64)
+        want = np.array(_spec_mix(x.astype(np.float64), m))
+        assert np.abs(got - want).max() <= 3e-7, (k, m)
