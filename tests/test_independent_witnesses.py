@@ -454,3 +454,22 @@ def test_speaker_mixing_vs_the_specification(pkg, oracle, k):
         got = np.array([a.get_channel_data(i) for i in range(m)], np.float64)
         want = np.array(_spec_mix(x.astype(np.float64), m))
         assert np.abs(got - want).max() <= 3e-7, (k, m)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_biquad_frequency_response_of_both_libraries_vs_the_specification(pkg, host_api, kind):
+    # BiquadFilterNode::get_frequency_response — the coefficient code of the oracle AND of the product (csrc/wae_hostmath.h: what the planner
+    # feeds the kernels with) — against H(e^{jw}) of the specification's coefficients (scipy.signal.freqz)
+    import ctypes as C
+    sr = 44100.0
+    f = np.geomspace(20.0, 20000.0, 64).astype(np.float32)
+    fp = C.POINTER(C.c_float)
+    for f0, q, gain, det in [(350.0, 1.0, 0.0, 0.0), (2000.0, 7.0, 9.0, 300.0), (80.0, 0.5, -12.0, -700.0)]:
+        mag = np.zeros(len(f), np.float32)
+        phase = np.zeros(len(f), np.float32)
+        host_api.biquad_frequency_response(KINDS.index(kind), sr, f0, det, q, gain, f.ctypes.data_as(fp), mag.ctypes.data_as(fp), phase.ctypes.data_as(fp), len(f))
+        b, a = w3c_biquad(kind, sr, f0 * 2.0 ** (det / 1200.0), q, gain)
+        _w, h = scipy_signal.freqz(np.array(b) / a[0], np.array(a) / a[0], worN=2 * np.pi * f.astype(np.float64) / sr)
+        assert np.abs(mag - np.abs(h)).max() <= 2e-5 * max(1.0, np.abs(h).max()), (kind, f0)
+        dphi = np.angle(np.exp(1j * (phase.astype(np.float64) - np.angle(h))))
+        assert np.abs(dphi[np.abs(h) > 1e-4]).max() <= 2e-4, (kind, f0)
