@@ -473,3 +473,47 @@ def test_biquad_frequency_response_of_both_libraries_vs_the_specification(pkg, h
         assert np.abs(mag - np.abs(h)).max() <= 2e-5 * max(1.0, np.abs(h).max()), (kind, f0)
         dphi = np.angle(np.exp(1j * (phase.astype(np.float64) - np.angle(h))))
         assert np.abs(dphi[np.abs(h) > 1e-4]).max() <= 2e-4, (kind, f0)
+
+
+def test_spatial_math_of_both_libraries_vs_the_specification(host_api):
+    # wae_spatial_params / wao_spatial_params: what the planner and the moving-source kernels evaluate (csrc/wae_spatial.h) and what the oracle's
+    # PannerNode evaluates — against the specification's azimuth / elevation algorithm and distance models, random sources and listeners
+    import ctypes as C
+    dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+    rng = np.random.default_rng(404)
+    worst_az = worst_el = 0.0
+    for _ in range(400):
+        src = rng.uniform(-5, 5, 3)
+        lp = rng.uniform(-2, 2, 3)
+        fwd = rng.uniform(-1, 1, 3)
+        fwd /= np.linalg.norm(fwd)
+        up = np.cross(np.cross(fwd, rng.uniform(-1, 1, 3)), fwd)   # perpendicular to forward
+        if np.linalg.norm(up) < 0.2 or np.linalg.norm(src - lp) < 0.3:
+            continue
+        up /= np.linalg.norm(up)
+        ref, mx, roll = 0.5 + rng.uniform(0, 2), 6.0 + rng.uniform(0, 4), rng.uniform(0.1, 1.0)
+        model = int(rng.integers(0, 3))   # 0 linear, 1 inverse, 2 exponential (include/wae.h)
+        m6 = np.array([ref, mx, roll, 360.0, 360.0, 0.0], np.float64)
+        v15 = np.concatenate([src, [0.0, 0.0, 0.0], lp, fwd, up]).astype(np.float32)
+        out = np.zeros(4, np.float32)
+        host_api.check(host_api.spatial_params(model, m6.ctypes.data_as(dp), v15.ctypes.data_as(fp), out.ctypes.data_as(fp)))
+        s64, l64, f64, u64 = (v15[0:3].astype(np.float64), v15[6:9].astype(np.float64), v15[9:12].astype(np.float64), v15[12:15].astype(np.float64))
+        d = np.linalg.norm(s64 - l64)
+        if model == 0:
+            g = 1 - roll * (min(max(d, ref), mx) - ref) / (mx - ref)
+        elif model == 1:
+            g = ref / (ref + roll * (max(d, ref) - ref))
+        else:
+            g = (max(d, ref) / ref) ** (-roll)
+        assert abs(out[0] - g) <= 2e-5, (model, d, out[0], g)
+        az = _spec_azimuth(s64, l64, f64, u64)
+        right = np.cross(f64, u64)
+        up2 = np.cross(right / np.linalg.norm(right), f64 / np.linalg.norm(f64))
+        sl = (s64 - l64) / d
+        el = 90 - np.degrees(np.arccos(np.clip(np.dot(sl, up2), -1, 1)))   # spec: 90 - angle(sourceListener, up), folded into [-90, 90]
+        el = 180 - el if el > 90 else (-180 - el if el < -90 else el)
+        horizontal = np.linalg.norm(sl - np.dot(sl, up2) * up2)
+        if horizontal > 0.2:   # (the azimuth is ill-conditioned right above / below the listener)
+            worst_az = max(worst_az, abs(np.angle(np.exp(1j * np.radians(out[2] - az)))))
+        worst_el = max(worst_el, abs(out[3] - el))
+    assert worst_az <= np.radians(0.02) and worst_el <= 0.02, (worst_az, worst_el)
