@@ -517,3 +517,23 @@ def test_spatial_math_of_both_libraries_vs_the_specification(host_api):
             worst_az = max(worst_az, abs(np.angle(np.exp(1j * np.radians(out[2] - az)))))
         worst_el = max(worst_el, abs(out[3] - el))
     assert worst_az <= np.radians(0.02) and worst_el <= 0.02, (worst_az, worst_el)
+
+
+def test_periodic_wave_tables_of_both_libraries_vs_fourier_synthesis(host_api):
+    # https://webaudio.github.io/web-audio-api/#waveform-generation: x(t) = sum_{k >= 1} real[k] cos(2 pi k t) + imag[k] sin(2 pi k t) (the
+    # DC terms are ignored), normalised to a peak of 1 unless disabled — numpy's inverse FFT against both libraries' wavetables
+    import test_node_setters as NS
+    rng = np.random.default_rng(77)
+    n = 2048
+    for harmonics in (2, 5, 33, 200):
+        real = rng.uniform(-1, 1, harmonics).astype(np.float32)
+        imag = rng.uniform(-1, 1, harmonics).astype(np.float32)
+        spec = np.zeros(n // 2 + 1, np.complex128)
+        spec[1:harmonics] = (real[1:].astype(np.float64) - 1j * imag[1:].astype(np.float64)) * n / 2
+        want = np.fft.irfft(spec, n)
+        got = NS._wave(host_api, real, imag, disable_normalization=True, n=n) if "n" in NS._wave.__code__.co_varnames else NS._wave(host_api, real, imag, disable_normalization=True)
+        # the reference accumulates in f32 with phases up to 2 pi k: an ulp of the phase (k * 1.2e-7 * 2 pi) per term, k terms
+        tol = 2e-5 + 2e-7 * harmonics * harmonics
+        assert np.abs(got - want).max() <= tol, harmonics
+        got = NS._wave(host_api, real, imag)
+        assert np.abs(got - want / np.abs(want).max()).max() <= tol, harmonics
