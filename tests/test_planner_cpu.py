@@ -375,3 +375,35 @@ print("planned", n, "refused", refused)
     assert r.returncode == 0, r.stderr[-2000:]
     planned = int(r.stdout.split()[1])
     assert planned >= 40, r.stdout
+
+
+def test_plan_digests_are_reproducible_across_processes():
+    # WAE_PLAN_DIGEST=1 hashes every instance record the sizing pass builds (tools/plan_digest_corpus.py compares them across library versions):
+    # that only works when no record carries uninitialised bytes or host addresses — two processes must print the same digests
+    import subprocess
+    import sys
+    code = r"""
+import sys
+sys.path.insert(0, %r)
+import conftest, graphs as G, test_gpu_fuzz as F, benchmark_scenarios as BS
+pkg = conftest.load_package()
+be = pkg.context.Backend(pkg.api(), None)
+ir = G.synthetic_ir(20000, 2, decay=0.6)
+for ctxs in ([G.c1_osc_biquad(pkg, be, 4800)], [G.c2_buffer_biquad_gain(pkg, be, g, 2560) for g in range(6)], [G.c3_many_voices(pkg, be, 40, 4800)],
+             [G.north_star_voices_convolver(pkg, be, 30, 24576, ir, seed=g) for g in range(2)]):
+    pkg.context.plan_batch(ctxs)
+for name, fn in BS.SCENARIOS:
+    pkg.context.plan_batch([fn(pkg, be, 2.0)])
+for seed in range(6000, 6060):
+    try:
+        pkg.context.plan_batch([F.random_graph(pkg, be, seed)])
+    except pkg.WaeError:
+        pass
+""" % os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, WAE_PLAN_DIGEST="1")
+    outs = []
+    for _ in range(2):
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append([ln for ln in r.stderr.splitlines() if "plan digest" in ln])
+    assert len(outs[0]) >= 80 and outs[0] == outs[1]
