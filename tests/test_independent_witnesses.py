@@ -537,3 +537,22 @@ def test_periodic_wave_tables_of_both_libraries_vs_fourier_synthesis(host_api):
         assert np.abs(got - want).max() <= tol, harmonics
         got = NS._wave(host_api, real, imag)
         assert np.abs(got - want / np.abs(want).max()).max() <= tol, harmonics
+
+
+@pytest.mark.parametrize("rate,buffer_sr", [(0.5, 48000.0), (1.37, 48000.0), (2.0, 48000.0), (1.0, 32000.0), (0.8, 44100.0)])
+def test_buffer_source_resampling_vs_linear_interpolation(pkg, oracle, rate, buffer_sr):
+    # the playhead advances by playbackRate * bufferRate / contextRate buffer frames per output frame; between frames the reference interpolates
+    # linearly (audio_buffer_source.rs:727-800) — numpy.interp at the same positions
+    rng = np.random.default_rng(int(rate * 100))
+    sr = 48000.0
+    buf = np.cumsum(rng.uniform(-0.05, 0.05, 6000)).astype(np.float32)   # smooth enough that a 1e-9 playhead error stays below 1e-6
+    n = RQ * 16
+    c = pkg.OfflineAudioContext(1, n, sr, oracle)
+    s = c.create_buffer_source(pkg.AudioBuffer([buf], buffer_sr), playback_rate=rate)
+    s.connect(c.destination())
+    s.start()
+    got = c.start_rendering_sync().get_channel_data(0).astype(np.float64)
+    pos = np.arange(n) * rate * buffer_sr / sr
+    inside = pos < len(buf) - 1
+    want = np.interp(pos[inside], np.arange(len(buf)), buf.astype(np.float64))
+    assert inside.sum() > 1500 and np.abs(got[inside] - want).max() <= 2e-6
